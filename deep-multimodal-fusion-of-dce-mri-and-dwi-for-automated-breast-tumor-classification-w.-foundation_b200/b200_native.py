@@ -1,0 +1,233 @@
+"""ctypes binding of libb200fusion.so - the C ABI declared in include/b200_fusion.h.
+
+This is the only place the Python host layer touches native code.  There is no CPU
+fallback: if the shared library is missing, or a tensor is not on a CUDA device, the
+call raises.  PyTorch is used for device memory and streams only; every arithmetic
+operation of the hot path runs in the hand-written sm_100a kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
+ABI_VERSION = 1
+
+_lib = None
+
+
+class B200NativeError(RuntimeError):
+    pass
+
+
+class FusionWeights(C.Structure):
+    """Mirror of `struct b200_fusion_weights` (include/b200_fusion.h)."""
+
+    _fields_ = [
+        ("C", C.c_int), ("T", C.c_int), ("heads", C.c_int), ("se_mid", C.c_int), ("num_classes", C.c_int),
+        ("use_cross_attention", C.c_int), ("use_mask_attention", C.c_int), ("use_se", C.c_int),
+        ("ln_eps", C.c_float),
+        ("gate_w", C.c_void_p), ("gate_b", C.c_void_p),
+        ("in_proj_wt", C.c_void_p), ("in_proj_b", C.c_void_p),
+        ("out_proj_wt", C.c_void_p), ("out_proj_b", C.c_void_p),
+        ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
+        ("ffn1_wt", C.c_void_p), ("ffn1_b", C.c_void_p),
+        ("ffn2_wt", C.c_void_p), ("ffn2_b", C.c_void_p),
+        ("up_coef", C.c_void_p),
+        ("se_w1t", C.c_void_p), ("se_b1", C.c_void_p), ("se_w2t", C.c_void_p), ("se_b2", C.c_void_p),
+        ("cls_w", C.c_void_p), ("cls_b", C.c_void_p),
+    ]
+
+
+_P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> argtypes; must list every symbol include/b200_fusion.h declares (tests check this).
+SIGNATURES = {
+    "b200_abi_version": [],
+    "b200_conv_gemm": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b200_dwi_normalize": [_P, _P, _I, _I, _I, _I, _F, _F, _P, _P],
+    "b200_nyul_transform": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "b200_plane_mean": [_P, _I, _I, _P, _P],
+    "b200_stem": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P],
+    "b200_se_gate": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "b200_scale_map": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "b200_conv3x3_c1": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "b200_mask_tail": [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _F, _P, _P],
+    "b200_lift_c1": [_P, _LL, _I, _P, _P, _P, _P, _P],
+    "b200_cls_head": [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P],
+    "b200_fusion_tokens": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "b200_fusion_core": [C.POINTER(FusionWeights), _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+    "b200_fusion_mix": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+}
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200NativeError(
+                f"{LIB_PATH} is missing: build it with csrc/build.sh (or __graft_entry__.build()); "
+                "this package has no CPU or PyTorch fallback")
+        handle = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        if handle.b200_abi_version() != ABI_VERSION:
+            raise B200NativeError("libb200fusion.so ABI version mismatch; rebuild it")
+        _lib = handle
+    return _lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise B200NativeError("b200 native ops need CUDA tensors (there is no CPU path)")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(rc, name):
+    if rc != 0:
+        kind = "invalid argument" if rc < 0 else "CUDA error"
+        raise B200NativeError(f"{name} failed: {kind} {rc}")
+
+
+def _bf16_map(t, name):
+    if t.dtype != torch.bfloat16 or not t.is_contiguous():
+        raise B200NativeError(f"{name} must be a contiguous bfloat16 NHWC tensor")
+
+
+def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0, out=None, up2=False, gap=None,
+              cin=None, store=True):
+    """x [B,H,W,ld] bf16 NHWC (channels [0,cin) used); w [Cout, taps*cin] bf16.  Returns `out`."""
+    _bf16_map(x, "x")
+    B, H, W, x_ld = x.shape
+    cin = x_ld if cin is None else cin
+    cout = w.shape[0]
+    assert w.dtype == torch.bfloat16 and w.is_contiguous() and w.shape[1] == taps * cin
+    if out is None and store:
+        oh, ow = (2 * H, 2 * W) if up2 else (H, W)
+        out = torch.empty((B, oh, ow, cout), dtype=torch.bfloat16, device=x.device)
+    out_ld = out.shape[-1] if out is not None else 0
+    if out is not None:
+        _bf16_map(out, "out")
+    if res is not None:
+        _bf16_map(res, "res")
+    rc = lib().b200_conv_gemm(_ptr(x), x_ld, _ptr(w), _ptr(scale), _ptr(bias), _ptr(res),
+                              res.shape[-1] if res is not None else 0, res_mode, act, _ptr(out), out_ld,
+                              1 if up2 else 0, _ptr(gap), B, H, W, cin, cout, taps, _stream())
+    _check(rc, "b200_conv_gemm")
+    return out
+
+
+def linear(x2d, w, *, scale=None, bias=None, res=None, res_mode=0, act=0, out=None):
+    """Plain GEMM: x2d [M,K] bf16, w [N,K] bf16 -> [M,N] bf16 with the same fused epilogue."""
+    M, K = x2d.shape
+    y = conv_gemm(x2d.view(1, 1, M, K), w, taps=1, scale=scale, bias=bias,
+                  res=None if res is None else res.view(1, 1, M, -1), res_mode=res_mode, act=act,
+                  out=None if out is None else out.view(1, 1, M, -1))
+    return y.view(M, -1)
+
+
+def dwi_normalize(x, out, C_, n, skip_last, z_lo, z_hi, plane_mean=None):
+    planes = x.numel() // n
+    _check(lib().b200_dwi_normalize(_ptr(x), _ptr(out), planes, C_, n, 1 if skip_last else 0, float(z_lo),
+                                    float(z_hi), _ptr(plane_mean), _stream()), "b200_dwi_normalize")
+    return out
+
+
+def nyul_transform(x, out, C_, n, avg_landmarks, standard_scale, prev_index, gamma, plane_mean=None):
+    planes = x.numel() // n
+    L = standard_scale.numel()
+    _check(lib().b200_nyul_transform(_ptr(x), _ptr(out), planes, C_, n, L, _ptr(avg_landmarks),
+                                     _ptr(standard_scale), _ptr(prev_index), _ptr(gamma), _ptr(plane_mean),
+                                     _stream()), "b200_nyul_transform")
+    return out
+
+
+def plane_mean(x, planes, n, out):
+    _check(lib().b200_plane_mean(_ptr(x), planes, n, _ptr(out), _stream()), "b200_plane_mean")
+    return out
+
+
+def stem(x, stride, pm, se, wcat, scale, bias, n_skip, n_mid, skip_out, mid_out, mod_attn):
+    B, C_, H, W = x.shape
+    w1, b1, w2, b2 = se if se is not None else (None, None, None, None)
+    cm = w1.shape[0] if w1 is not None else 0
+    _check(lib().b200_stem(_ptr(x), B, C_, H, W, stride, _ptr(pm), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), cm,
+                           _ptr(wcat), _ptr(scale), _ptr(bias), n_skip, n_mid, _ptr(skip_out), _ptr(mid_out),
+                           _ptr(mod_attn), _stream()), "b200_stem")
+
+
+def se_gate(gap_sum, npix, w1t, b1, w2t, b2, gate):
+    B, C_ = gap_sum.shape
+    _check(lib().b200_se_gate(_ptr(gap_sum), B, C_, w1t.shape[1], npix, _ptr(w1t), _ptr(b1), _ptr(w2t), _ptr(b2),
+                              _ptr(gate), _stream()), "b200_se_gate")
+    return gate
+
+
+def scale_map(x, y, gate=None, attn=None, gamma=None):
+    B, H, W, C_ = x.shape
+    _check(lib().b200_scale_map(_ptr(x), _ptr(y), B, H * W, C_, _ptr(gate), _ptr(attn), _ptr(gamma), _stream()),
+           "b200_scale_map")
+    return y
+
+
+def conv3x3_c1(x, w, bias, out):
+    B, H, W, C_ = x.shape
+    _check(lib().b200_conv3x3_c1(_ptr(x), B, H, W, C_, _ptr(w), _ptr(bias), _ptr(out), _stream()),
+           "b200_conv3x3_c1")
+    return out
+
+
+def mask_tail(pre, w_out, b_out, mask_pred, attn_params=None, attn=None):
+    B, H, W, Cm = pre.shape
+    if attn_params is None:
+        hc, wa, gw, gb, wb, bb, eps = 0, None, None, None, None, None, 0.0
+    else:
+        hc, wa, gw, gb, wb, bb, eps = attn_params
+    _check(lib().b200_mask_tail(_ptr(pre), B, H * W, Cm, _ptr(w_out), _ptr(b_out), _ptr(mask_pred), hc, _ptr(wa),
+                                _ptr(gw), _ptr(gb), _ptr(wb), _ptr(bb), float(eps), _ptr(attn), _stream()),
+           "b200_mask_tail")
+
+
+def lift_c1(r, w, scale, bias, y):
+    _check(lib().b200_lift_c1(_ptr(r), r.numel(), w.numel(), _ptr(w), _ptr(scale), _ptr(bias), _ptr(y), _stream()),
+           "b200_lift_c1")
+    return y
+
+
+def cls_head(gap_sum, gate, npix, fc_w, fc_b, normalize, logits, pooled_out=None):
+    B, C_ = gap_sum.shape
+    _check(lib().b200_cls_head(_ptr(gap_sum), _ptr(gate), B, C_, npix, fc_w.shape[0], _ptr(fc_w), _ptr(fc_b),
+                               1 if normalize else 0, _ptr(logits), _ptr(pooled_out), _stream()), "b200_cls_head")
+    return logits
+
+
+def fusion_tokens(p, hp, wp, tokens):
+    B, H, W, C_ = p.shape
+    _check(lib().b200_fusion_tokens(_ptr(p), B, H, W, C_, hp, wp, _ptr(tokens), _stream()), "b200_fusion_tokens")
+    return tokens
+
+
+def fusion_core(wts, B, pvec_dwi_sum, pvec_dce_sum, npix, mask_dwi, mask_dce, npix_mask, tok_dwi, tok_dce,
+                gating, attn, lowres, gate, logits):
+    _check(lib().b200_fusion_core(C.byref(wts), B, _ptr(pvec_dwi_sum), _ptr(pvec_dce_sum), npix, _ptr(mask_dwi),
+                                  _ptr(mask_dce), npix_mask, _ptr(tok_dwi), _ptr(tok_dce), _ptr(gating), _ptr(attn),
+                                  _ptr(lowres), _ptr(gate), _ptr(logits), _stream()), "b200_fusion_core")
+
+
+def fusion_mix(p_dwi, p_dce, gating, lowres, gate, hp, wp, out):
+    B, H, W, C_ = p_dwi.shape
+    _check(lib().b200_fusion_mix(_ptr(p_dwi), _ptr(p_dce), _ptr(gating), _ptr(lowres), _ptr(gate), B, H, W, C_, hp,
+                                 wp, _ptr(out), _stream()), "b200_fusion_mix")
+    return out

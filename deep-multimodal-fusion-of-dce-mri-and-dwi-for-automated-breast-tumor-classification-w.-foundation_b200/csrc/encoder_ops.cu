@@ -1,0 +1,406 @@
+// SIMT kernels of the DWI / DCE encoder that are not GEMM-shaped (K < 64, N == 1, or
+// per-case vectors): modality-attention + first strided 1x1 convolutions ("stem"),
+// squeeze-excite gates, channel rescaling, N=1 convolutions, the mask head tail with the
+// mask-guided spatial attention, the 1->C projector lift and the classification head.
+// Reference: code/model_module.py (line ranges cited per kernel).
+#include "b200_fusion.h"
+#include "common.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------- stem -----
+// model_module.py:649-650 (modality SE, SEBlock :25-43) followed by the two stride-s 1x1
+// convolutions of block1 that read the raw input: skip (:276-280) and the first
+// bottleneck conv + BN + GELU (:260-262).  Input is fp32 NCHW (what the normalisers
+// emit), outputs are NHWC bf16.  One CTA = one case x `kStemPix` output pixels, one
+// thread per output channel with its weight column in registers.
+constexpr int kStemPix = 64;
+constexpr int kStemMaxC = 32;
+
+__global__ void stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
+                            const float* __restrict__ plane_mean,  // [B, C]
+                            const float* __restrict__ se_w1, const float* __restrict__ se_b1,  // [Cm, C], [Cm]
+                            const float* __restrict__ se_w2, const float* __restrict__ se_b2,  // [C, Cm], [C]
+                            int Cm,
+                            const float* __restrict__ wcat,   // [n_skip + n_mid, C]
+                            const float* __restrict__ scale,  // [n_skip + n_mid]
+                            const float* __restrict__ bias, int n_skip, int n_mid,
+                            __nv_bfloat16* __restrict__ skip_out, __nv_bfloat16* __restrict__ mid_out,
+                            float* __restrict__ mod_attn) {
+    __shared__ float s_gate[kStemMaxC];
+    __shared__ float s_hidden[kStemMaxC];
+    __shared__ float s_x[kStemMaxC][kStemPix];
+    const int b = blockIdx.y;
+    const int Ho = H / stride, Wo = W / stride;
+    const int pix0 = blockIdx.x * kStemPix;
+    const int npix = Ho * Wo;
+    const int tid = threadIdx.x;
+
+    if (se_w1 != nullptr) {
+        if (tid < Cm) {
+            float a = se_b1[tid];
+            for (int c = 0; c < C; ++c) a += se_w1[tid * C + c] * plane_mean[b * C + c];
+            s_hidden[tid] = gelu_exact(a);
+        }
+        __syncthreads();
+        if (tid < C) {
+            float a = se_b2[tid];
+            for (int m = 0; m < Cm; ++m) a += se_w2[tid * Cm + m] * s_hidden[m];
+            const float g = sigmoidf_(a);
+            s_gate[tid] = g;
+            if (blockIdx.x == 0 && mod_attn != nullptr) mod_attn[b * C + tid] = g;
+        }
+    } else if (tid < C) {
+        s_gate[tid] = 1.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < C * kStemPix; i += blockDim.x) {
+        const int c = i / kStemPix, pp = i % kStemPix;
+        const int pix = pix0 + pp;
+        float v = 0.f;
+        if (pix < npix) {
+            const int ho = pix / Wo, wo = pix % Wo;
+            v = x[((static_cast<size_t>(b) * C + c) * H + ho * stride) * W + wo * stride] * s_gate[c];
+        }
+        s_x[c][pp] = v;
+    }
+    __syncthreads();
+    const int n = tid;
+    if (n >= n_skip + n_mid) return;
+    float wreg[kStemMaxC];
+#pragma unroll
+    for (int c = 0; c < kStemMaxC; ++c) wreg[c] = c < C ? wcat[n * C + c] : 0.f;
+    const float sc = scale[n], bi = bias[n];
+    const bool is_mid = n >= n_skip;
+    __nv_bfloat16* dst = is_mid ? mid_out : skip_out;
+    const int ld = is_mid ? n_mid : n_skip;
+    const int nn = is_mid ? n - n_skip : n;
+    for (int pp = 0; pp < kStemPix; pp += 4) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < kStemMaxC; ++c) {
+            if (c < C) {
+                const float4 xv = *reinterpret_cast<const float4*>(&s_x[c][pp]);
+                a0 += wreg[c] * xv.x;
+                a1 += wreg[c] * xv.y;
+                a2 += wreg[c] * xv.z;
+                a3 += wreg[c] * xv.w;
+            }
+        }
+        float r[4] = {a0 * sc + bi, a1 * sc + bi, a2 * sc + bi, a3 * sc + bi};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int pix = pix0 + pp + k;
+            if (pix < npix) {
+                const float y = is_mid ? gelu_exact(r[k]) : r[k];
+                dst[(static_cast<size_t>(b) * npix + pix) * ld + nn] = __float2bfloat16(y);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------- SE gate -----
+// SEBlock.fc on the pooled vector (model_module.py:34-40): gate = sigmoid(W2 gelu(W1 m + b1) + b2)
+// with m = gap_sum / npix.  One CTA per case; weights are passed transposed
+// (w1t [C, Cm], w2t [Cm, C]) so that consecutive threads read consecutive addresses.
+__global__ void se_gate_kernel(const float* __restrict__ gap_sum, float inv_npix, int C, int Cm,
+                               const float* __restrict__ w1t, const float* __restrict__ b1,
+                               const float* __restrict__ w2t, const float* __restrict__ b2,
+                               float* __restrict__ gate) {
+    extern __shared__ float sm[];  // C + Cm floats
+    float* s_m = sm;
+    float* s_h = sm + C;
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s_m[c] = gap_sum[static_cast<size_t>(b) * C + c] * inv_npix;
+    __syncthreads();
+    for (int m = threadIdx.x; m < Cm; m += blockDim.x) {
+        float a = b1[m];
+        for (int c = 0; c < C; ++c) a += w1t[c * Cm + m] * s_m[c];
+        s_h[m] = gelu_exact(a);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = b2[c];
+        for (int m = 0; m < Cm; ++m) a += w2t[m * C + c] * s_h[m];
+        gate[static_cast<size_t>(b) * C + c] = sigmoidf_(a);
+    }
+}
+
+// ------------------------------------------------- channel / pixel scale ---
+// y[b,p,c] = x[b,p,c] * gate[b,c] * (1 + gamma * attn[b,p]); either factor optional.
+// SE rescale (model_module.py:43) and mask-guided modulation (:96).
+__global__ void scale_map_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int npix,
+                                 size_t total_vec, const float* __restrict__ gate, const float* __restrict__ attn,
+                                 const float* __restrict__ gamma_ptr) {
+    const int cv = C >> 3;
+    const float gamma = gamma_ptr != nullptr ? *gamma_ptr : 0.f;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total_vec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c0 = static_cast<int>(i % cv) << 3;
+        const size_t bp = i / cv;
+        const size_t b = bp / npix;
+        float f[8];
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
+        float m = 1.f;
+        if (attn != nullptr) m = 1.f + gamma * attn[bp];
+        if (gate != nullptr) {
+            const float4 g0 = *reinterpret_cast<const float4*>(gate + b * C + c0);
+            const float4 g1 = *reinterpret_cast<const float4*>(gate + b * C + c0 + 4);
+            f[0] *= g0.x * m; f[1] *= g0.y * m; f[2] *= g0.z * m; f[3] *= g0.w * m;
+            f[4] *= g1.x * m; f[5] *= g1.y * m; f[6] *= g1.z * m; f[7] *= g1.w * m;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] *= m;
+        }
+        reinterpret_cast<uint4*>(y)[i] = pack_bf16x8(f);
+    }
+}
+
+// ------------------------------------------------------- conv 3x3, N=1 -----
+// ReconHead's last conv (model_module.py:117): C -> 1, 3x3, pad 1, with bias, fp32 output
+// [B,H,W].  One warp per output pixel; lanes split the channels, taps are L1/L2 re-reads.
+__global__ void conv3x3_c1_kernel(const __nv_bfloat16* __restrict__ x, int H, int W, int C,
+                                  const float* __restrict__ w,  // [9, C]
+                                  const float* __restrict__ bias, float* __restrict__ out, size_t total_pix) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp_global = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+    if (warp_global >= total_pix) return;
+    const int wq = static_cast<int>(warp_global % W);
+    const int hq = static_cast<int>((warp_global / W) % H);
+    const size_t b = warp_global / (static_cast<size_t>(W) * H);
+    float acc = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+        const int hh = hq + tap / 3 - 1, ww = wq + tap % 3 - 1;
+        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+        const __nv_bfloat16* px = x + ((b * H + hh) * W + ww) * C;
+        for (int c0 = lane * 8; c0 < C; c0 += 256) {
+            float f[8];
+            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(px + c0)), f);
+            const float4 w0 = *reinterpret_cast<const float4*>(w + tap * C + c0);
+            const float4 w1 = *reinterpret_cast<const float4*>(w + tap * C + c0 + 4);
+            acc += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y + f[6] * w1.z +
+                   f[7] * w1.w;
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[warp_global] = acc + bias[0];
+}
+
+// ------------------------------------------- mask head tail + attention ----
+// MaskHeadResize.out (model_module.py:187, 1x1 Cm->1 + bias) on the `pre` activations, then
+// MaskGuidedSpatialAttention.mask_processor (:67-73, :92-93): 1x1 1->Hc (no bias),
+// GroupNorm(1,Hc), GELU, 1x1 Hc->1 (+bias), sigmoid, clamp to [1e-4, 1-1e-4].
+// GroupNorm(1,Hc) of u[c,p] = wa[c]*m[p] has mean = mean(wa)*mean(m) and
+// E[u^2] = mean(wa^2)*mean(m^2), so two plane statistics of m suffice.  One CTA per case.
+constexpr int kMaskHidden = 32;
+
+__global__ void mask_tail_kernel(const __nv_bfloat16* __restrict__ pre, int Cm, int npix,
+                                 const float* __restrict__ w_out, const float* __restrict__ b_out,
+                                 float* __restrict__ mask_pred,  // [B, npix]
+                                 int Hc, const float* __restrict__ wa, const float* __restrict__ gn_w,
+                                 const float* __restrict__ gn_b, const float* __restrict__ wb,
+                                 const float* __restrict__ bb, float gn_eps,
+                                 float* __restrict__ attn) {  // [B, npix] or nullptr
+    extern __shared__ float s_m[];  // npix floats
+    __shared__ double scratch[33];
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // each warp handles pixels warp, warp+nwarps, ...; lanes split the Cm channels
+    for (int p = warp; p < npix; p += nwarps) {
+        const __nv_bfloat16* px = pre + (static_cast<size_t>(b) * npix + p) * Cm;
+        float acc = 0.f;
+        for (int c0 = lane * 2; c0 < Cm; c0 += 64) {
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(px + c0);
+            acc += __low2float(h) * w_out[c0] + __high2float(h) * w_out[c0 + 1];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float m = acc + b_out[0];
+            s_m[p] = m;
+            mask_pred[static_cast<size_t>(b) * npix + p] = m;
+        }
+    }
+    __syncthreads();
+    if (attn == nullptr) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+        const double m = s_m[p];
+        s1 += m;
+        s2 += m * m;
+    }
+    const double mean_m = block_sum<double>(s1, scratch) / npix;
+    const double mean_m2 = block_sum<double>(s2, scratch) / npix;
+    double wa1 = 0.0, wa2 = 0.0;
+    for (int c = 0; c < Hc; ++c) {
+        wa1 += wa[c];
+        wa2 += static_cast<double>(wa[c]) * wa[c];
+    }
+    wa1 /= Hc;
+    wa2 /= Hc;
+    const double mu = wa1 * mean_m;
+    const double var = fmax(wa2 * mean_m2 - mu * mu, 0.0);
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(gn_eps)));
+    const float muf = static_cast<float>(mu);
+    for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+        const float m = s_m[p];
+        float a = bb[0];
+        for (int c = 0; c < Hc; ++c) a += wb[c] * gelu_exact((wa[c] * m - muf) * rstd * gn_w[c] + gn_b[c]);
+        const float A = fminf(fmaxf(sigmoidf_(a), 1e-4f), 1.0f - 1e-4f);
+        attn[static_cast<size_t>(b) * npix + p] = A;
+    }
+}
+
+// ----------------------------------------------- 1 -> C pointwise lift -----
+// First layer of Projector(1, proj_dim) (model_module.py:338-340) on a 1-channel fp32
+// map: y[p, n] = gelu(r[p] * w[n] * scale[n] + bias[n]) as NHWC bf16.
+__global__ void lift_c1_kernel(const float* __restrict__ r, size_t total_pix, int N, const float* __restrict__ w,
+                               const float* __restrict__ scale, const float* __restrict__ bias,
+                               __nv_bfloat16* __restrict__ y) {
+    const int nv = N >> 3;
+    const size_t total = total_pix * nv;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int n0 = static_cast<int>(i % nv) << 3;
+        const float rv = r[i / nv];
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = gelu_exact(rv * w[n0 + k] * scale[n0 + k] + bias[n0 + k]);
+        reinterpret_cast<uint4*>(y)[i] = pack_bf16x8(f);
+    }
+}
+
+// ------------------------------------------------- classification head -----
+// ClassificationHead.forward (model_module.py:364-369): GAP -> L2 normalise -> Linear.
+// The pooled vector comes from the fp32 channel sums of the producing GEMM epilogue,
+// rescaled by the SE gate (GAP(x*g) = g*GAP(x)).  One warp per case.
+__global__ void cls_head_kernel(const float* __restrict__ gap_sum, const float* __restrict__ gate, float inv_npix,
+                                int C, int K, const float* __restrict__ fc_w, const float* __restrict__ fc_b,
+                                int normalize, int B, float* __restrict__ logits, float* __restrict__ pooled_out) {
+    const int lane = threadIdx.x & 31;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        float v = gap_sum[static_cast<size_t>(b) * C + c] * inv_npix;
+        if (gate != nullptr) v *= gate[static_cast<size_t>(b) * C + c];
+        ss += v * v;
+    }
+    ss = warp_sum(ss);
+    const float inv = normalize ? 1.0f / fmaxf(sqrtf(ss), 1e-12f) : 1.0f;
+    for (int k = 0; k < K; ++k) {
+        float a = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            float v = gap_sum[static_cast<size_t>(b) * C + c] * inv_npix;
+            if (gate != nullptr) v *= gate[static_cast<size_t>(b) * C + c];
+            a += v * inv * fc_w[k * C + c];
+        }
+        a = warp_sum(a);
+        if (lane == 0) logits[static_cast<size_t>(b) * K + k] = a + fc_b[k];
+    }
+    if (pooled_out != nullptr) {
+        for (int c = lane; c < C; c += 32) {
+            float v = gap_sum[static_cast<size_t>(b) * C + c] * inv_npix;
+            if (gate != nullptr) v *= gate[static_cast<size_t>(b) * C + c];
+            pooled_out[static_cast<size_t>(b) * C + c] = v * inv;
+        }
+    }
+}
+
+static inline int grid_for(size_t work_items, int threads, int max_blocks = 148 * 16) {
+    size_t g = (work_items + threads - 1) / threads;
+    if (g > static_cast<size_t>(max_blocks)) g = max_blocks;
+    if (g == 0) g = 1;
+    return static_cast<int>(g);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_stem(const float* x, int B, int C, int H, int W, int stride, const float* plane_mean,
+                         const float* se_w1, const float* se_b1, const float* se_w2, const float* se_b2, int Cm,
+                         const float* wcat, const float* scale, const float* bias, int n_skip, int n_mid,
+                         void* skip_out, void* mid_out, float* mod_attn, void* stream) {
+    if (B < 0 || C <= 0 || C > kStemMaxC || Cm > kStemMaxC || H % stride != 0 || W % stride != 0) return -1;
+    if (B == 0) return 0;
+    if (x == nullptr || wcat == nullptr || scale == nullptr || bias == nullptr) return -2;
+    if (se_w1 != nullptr && plane_mean == nullptr) return -3;
+    const int n_out = n_skip + n_mid;
+    if (n_out <= 0 || n_out > 1024) return -4;
+    const int npix = (H / stride) * (W / stride);
+    const int threads = ((n_out + 31) / 32) * 32;
+    dim3 grid((npix + kStemPix - 1) / kStemPix, B);
+    stem_kernel<<<grid, threads < 64 ? 64 : threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, C, H, W, stride, plane_mean, se_w1, se_b1, se_w2, se_b2, Cm, wcat, scale, bias, n_skip, n_mid,
+        static_cast<__nv_bfloat16*>(skip_out), static_cast<__nv_bfloat16*>(mid_out), mod_attn);
+    return launch_status();
+}
+
+extern "C" int b200_se_gate(const float* gap_sum, int B, int C, int Cm, int npix, const float* w1t, const float* b1,
+                            const float* w2t, const float* b2, float* gate, void* stream) {
+    if (B < 0 || C <= 0 || Cm <= 0 || npix <= 0) return -1;
+    if (B == 0) return 0;
+    if (gap_sum == nullptr || gate == nullptr) return -2;
+    se_gate_kernel<<<B, 256, (C + Cm) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        gap_sum, 1.0f / npix, C, Cm, w1t, b1, w2t, b2, gate);
+    return launch_status();
+}
+
+extern "C" int b200_scale_map(const void* x, void* y, int B, int npix, int C, const float* gate, const float* attn,
+                              const float* gamma, void* stream) {
+    if (B < 0 || C % 8 != 0 || npix <= 0) return -1;
+    if (B == 0) return 0;
+    if (x == nullptr || y == nullptr) return -2;
+    const size_t total_vec = static_cast<size_t>(B) * npix * (C / 8);
+    scale_map_kernel<<<grid_for(total_vec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), C, npix, total_vec, gate, attn, gamma);
+    return launch_status();
+}
+
+extern "C" int b200_conv3x3_c1(const void* x, int B, int H, int W, int C, const float* w, const float* bias,
+                               float* out, void* stream) {
+    if (B < 0 || C % 8 != 0 || H <= 0 || W <= 0) return -1;
+    if (B == 0) return 0;
+    if (x == nullptr || w == nullptr || bias == nullptr || out == nullptr) return -2;
+    const size_t total_pix = static_cast<size_t>(B) * H * W;
+    const size_t blocks = (total_pix * 32 + 255) / 256;
+    conv3x3_c1_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), H, W, C, w, bias, out, total_pix);
+    return launch_status();
+}
+
+extern "C" int b200_mask_tail(const void* pre, int B, int npix, int Cm, const float* w_out, const float* b_out,
+                              float* mask_pred, int Hc, const float* wa, const float* gn_w, const float* gn_b,
+                              const float* wb, const float* bb, float gn_eps, float* attn, void* stream) {
+    if (B < 0 || npix <= 0 || Cm % 2 != 0 || npix > 12 * 1024) return -1;
+    if (B == 0) return 0;
+    if (pre == nullptr || w_out == nullptr || b_out == nullptr || mask_pred == nullptr) return -2;
+    if (attn != nullptr && (wa == nullptr || gn_w == nullptr || gn_b == nullptr || wb == nullptr || bb == nullptr))
+        return -3;
+    mask_tail_kernel<<<B, 256, npix * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(pre), Cm, npix, w_out, b_out, mask_pred, Hc, wa, gn_w, gn_b, wb, bb, gn_eps,
+        attn);
+    return launch_status();
+}
+
+extern "C" int b200_lift_c1(const float* r, long long total_pix, int N, const float* w, const float* scale,
+                            const float* bias, void* y, void* stream) {
+    if (total_pix < 0 || N % 8 != 0) return -1;
+    if (total_pix == 0) return 0;
+    if (r == nullptr || w == nullptr || scale == nullptr || bias == nullptr || y == nullptr) return -2;
+    lift_c1_kernel<<<grid_for(static_cast<size_t>(total_pix) * (N / 8), 256), 256, 0,
+                     static_cast<cudaStream_t>(stream)>>>(r, static_cast<size_t>(total_pix), N, w, scale, bias,
+                                                          static_cast<__nv_bfloat16*>(y));
+    return launch_status();
+}
+
+extern "C" int b200_cls_head(const float* gap_sum, const float* gate, int B, int C, int npix, int K, const float* fc_w,
+                             const float* fc_b, int normalize, float* logits, float* pooled_out, void* stream) {
+    if (B < 0 || C <= 0 || K <= 0 || npix <= 0) return -1;
+    if (B == 0) return 0;
+    if (gap_sum == nullptr || fc_w == nullptr || fc_b == nullptr || logits == nullptr) return -2;
+    const int blocks = (B * 32 + 127) / 128;
+    cls_head_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(gap_sum, gate, 1.0f / npix, C, K, fc_w,
+                                                                           fc_b, normalize, B, logits, pooled_out);
+    return launch_status();
+}

@@ -1,0 +1,181 @@
+/*
+ * C ABI of the B200-native DWI+DCE fusion-classifier hot path.
+ *
+ * The reference (simhelgithub/Deep-Multimodal-Fusion-of-DCE-MRI-and-DWI-...) has no FFI:
+ * its boundary is the Python module surface.  Every entry point
+ * below is therefore the native half of one reference Python function or nn.Module
+ * forward; the Python mirror of that function (same name and arguments) lives in the
+ * package directory and calls these through ctypes.  Each declaration cites the
+ * reference code it replaces (paths relative to /root/reference/).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - the caller allocates every output and workspace; nothing is retained between calls
+ *     except immutable cached launch attributes;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it;
+ *   - return value: 0 = launched, <0 = invalid argument (nothing launched),
+ *     >0 = cudaError_t from the launch;
+ *   - activations ("maps") are NHWC bfloat16 unless stated; `*_ld` is the element
+ *     stride between consecutive pixels (>= channels, multiple of 8).
+ */
+#ifndef B200_FUSION_H
+#define B200_FUSION_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Library/ABI version; bumped whenever a signature changes. */
+int b200_abi_version(void);
+
+/*
+ * Implicit-GEMM convolution (1x1 or 3x3/pad 1, stride 1) or linear layer with fused
+ * epilogue, tcgen05/TMEM + TMA.  Replaces nn.Conv2d+BatchNorm2d(eval)+GELU(+residual)
+ * stacks: code/model_module.py:259-269 (bottleneck), :276-280 (skip), :113-118
+ * (ReconHead), :150 (MaskHeadResize.pre), :337-345 (Projector), :386-390
+ * (FeatureDownAlign), :857-858 (FusionModel.proj_in_*), and nn.Linear at
+ * code/transformer_model.py:93,95,123,125.
+ *   x      [B,H,W,x_ld] bf16, channels [0,Cin) are read; H==1 selects plain-GEMM mode
+ *          (W = number of rows, any value)
+ *   w      [Cout, taps*Cin] bf16, k = tap*Cin + c, tap = ky*3+kx
+ *   scale, bias  fp32 [Cout] per-output-channel affine (folded BatchNorm or conv bias); NULL = 1 / 0
+ *   res    optional residual map (bf16, res_ld); res_mode 0 none, 1 add before the
+ *          activation, 2 add after it
+ *   act    0 none, 1 exact (erf) GELU
+ *   out    bf16 map (out_ld), or NULL to skip the store; up2 != 0 replicates every pixel
+ *          into a 2x2 block of a [B,2H,2W,out_ld] map (AdaptiveAvgPool2d to twice the
+ *          size, model_module.py:534,707-710, commuted past the 1x1 projector)
+ *   gap    optional fp32 [B,Cout]; the per-case sum over pixels of the epilogue result is
+ *          ACCUMULATED into it (caller zeroes it)
+ * Requires Cin % 64 == 0, Cout % 64 == 0, and for convolutions 128 % W == 0, H % (128/W) == 0.
+ */
+int b200_conv_gemm(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
+                   const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
+                   float* gap, int B, int H, int W, int Cin, int Cout, int taps, void* stream);
+
+/*
+ * DWINormalize.__call__ (code/dataset.py:14-41), batched over `planes` = cases*C image
+ * planes of n = H*W fp32 samples (NCHW): per plane z-score with unbiased std clamped at
+ * 1e-6, clip to [z_lo, z_hi], map to [0,1]; when skip_last != 0 the last channel of every
+ * case is written as zeros (adc=True).  plane_mean (optional, fp32 [planes]) receives the
+ * mean of each OUTPUT plane - the pooled vector the modality SE block needs
+ * (code/model_module.py:35, :649-650).
+ */
+int b200_dwi_normalize(const float* x, float* out, int planes, int C, int n, int skip_last, float z_lo,
+                       float z_hi, float* plane_mean, void* stream);
+
+/*
+ * NyulStandardizer.transform (code/preprocess_helpers.py:85-120), batched like the above.
+ *   avg_landmarks  fp64 [C, L]  fitted channel_landmarks (preprocess_helpers.py:77-80)
+ *   standard_scale fp64 [L]     np.linspace(target_range) (:60)
+ *   prev_index int32 [L], gamma fp64 [L]: floor and fractional part of q/100*(n-1), the
+ *   "linear" percentile rule of np.percentile (:100), computed on the host in float64.
+ * n must be <= 32768 samples per plane in this version.
+ */
+int b200_nyul_transform(const float* x, float* out, int planes, int C, int n, int L, const double* avg_landmarks,
+                        const double* standard_scale, const int* prev_index, const double* gamma,
+                        float* plane_mean, void* stream);
+
+/* Mean of each fp32 plane (AdaptiveAvgPool2d(1) of SEBlock, code/model_module.py:35). */
+int b200_plane_mean(const float* x, int planes, int n, float* plane_mean, void* stream);
+
+/*
+ * Encoder stem: modality SE gate (code/model_module.py:25-43, :649-650) applied to the fp32
+ * NCHW input, then the two stride-`stride` 1x1 convolutions of block1 that read it - skip
+ * conv + BN (:276-280) and first bottleneck conv + BN + GELU (:260-262).
+ *   se_w1 [Cm,C], se_b1 [Cm], se_w2 [C,Cm], se_b2 [C] fp32, or se_w1 == NULL for no gate
+ *   wcat [n_skip+n_mid, C] fp32, scale/bias [n_skip+n_mid] folded BatchNorm
+ *   skip_out [B,H/s,W/s,n_skip] bf16, mid_out [B,H/s,W/s,n_mid] bf16, mod_attn [B,C] fp32
+ */
+int b200_stem(const float* x, int B, int C, int H, int W, int stride, const float* plane_mean, const float* se_w1,
+              const float* se_b1, const float* se_w2, const float* se_b2, int Cm, const float* wcat,
+              const float* scale, const float* bias, int n_skip, int n_mid, void* skip_out, void* mid_out,
+              float* mod_attn, void* stream);
+
+/*
+ * SEBlock.fc on pooled sums (code/model_module.py:34-40): gate[b,:] =
+ * sigmoid(W2 gelu(W1 (gap_sum[b,:]/npix) + b1) + b2); w1t [C,Cm] and w2t [Cm,C] are the
+ * conv weights transposed.
+ */
+int b200_se_gate(const float* gap_sum, int B, int C, int Cm, int npix, const float* w1t, const float* b1,
+                 const float* w2t, const float* b2, float* gate, void* stream);
+
+/*
+ * y = x * gate[b,c] * (1 + gamma * attn[b,p]) on a bf16 NHWC map (in place allowed).
+ * SE rescale (code/model_module.py:43) and MaskGuidedSpatialAttention modulation (:96);
+ * gate / attn may be NULL; gamma is a device scalar.
+ */
+int b200_scale_map(const void* x, void* y, int B, int npix, int C, const float* gate, const float* attn,
+                   const float* gamma, void* stream);
+
+/* ReconHead last conv (code/model_module.py:117): 3x3 pad 1, C -> 1, bias; w [9,C] fp32; out fp32 [B,H,W]. */
+int b200_conv3x3_c1(const void* x, int B, int H, int W, int C, const float* w, const float* bias, float* out,
+                    void* stream);
+
+/*
+ * MaskHeadResize.out (code/model_module.py:187) on the `pre` activations [B,npix,Cm] bf16
+ * -> mask_pred fp32 [B,npix]; when attn != NULL also MaskGuidedSpatialAttention's
+ * mask_processor (:67-73, :92-93) -> attention map fp32 [B,npix] in [1e-4, 1-1e-4].
+ */
+int b200_mask_tail(const void* pre, int B, int npix, int Cm, const float* w_out, const float* b_out,
+                   float* mask_pred, int Hc, const float* wa, const float* gn_w, const float* gn_b, const float* wb,
+                   const float* bb, float gn_eps, float* attn, void* stream);
+
+/* First Projector layer on a 1-channel map (code/model_module.py:338-340, :639-640). */
+int b200_lift_c1(const float* r, long long total_pix, int N, const float* w, const float* scale, const float* bias,
+                 void* y, void* stream);
+
+/*
+ * ClassificationHead.forward (code/model_module.py:364-369) from pooled sums:
+ * v = gap_sum/npix * gate; v /= max(||v||,1e-12) if normalize; logits = fc_w v + fc_b.
+ */
+int b200_cls_head(const float* gap_sum, const float* gate, int B, int C, int npix, int K, const float* fc_w,
+                  const float* fc_b, int normalize, float* logits, float* pooled_out, void* stream);
+
+/* FusionModel._to_tokens (code/model_module.py:903-917): adaptive average pool to Hp x Wp tokens, fp32 [B,Hp*Wp,C]. */
+int b200_fusion_tokens(const void* p, int B, int H, int W, int C, int Hp, int Wp, float* tokens, void* stream);
+
+/* Device pointers to the small fusion-head parameters (all fp32; *_wt are transposed [in,out]). */
+typedef struct b200_fusion_weights {
+    int C, T, heads, se_mid, num_classes;
+    int use_cross_attention, use_mask_attention, use_se;
+    float ln_eps;
+    const float* gate_w;      /* GatingAttention.fc.weight [2, 2C(+2)]   model_module.py:755 */
+    const float* gate_b;      /* [2] */
+    const float* in_proj_wt;  /* MultiheadAttention.in_proj_weight^T [C,3C] model_module.py:806 */
+    const float* in_proj_b;   /* [3C] */
+    const float* out_proj_wt; /* out_proj.weight^T [C,C] */
+    const float* out_proj_b;  /* [C] */
+    const float* ln_w;        /* attn_ffn.0 LayerNorm model_module.py:808 */
+    const float* ln_b;
+    const float* ffn1_wt;     /* attn_ffn.1.weight^T [C,C] */
+    const float* ffn1_b;
+    const float* ffn2_wt;     /* attn_ffn.3.weight^T [C,C] */
+    const float* ffn2_b;
+    const float* up_coef;     /* [T] mean bilinear weight of each token cell (GAP of the upsample) */
+    const float* se_w1t;      /* fusion_se.fc.1.weight^T [C,Cm] model_module.py:867 */
+    const float* se_b1;
+    const float* se_w2t;      /* fusion_se.fc.3.weight^T [Cm,C] */
+    const float* se_b2;
+    const float* cls_w;       /* classifier.2.weight [K,C] model_module.py:895-899 */
+    const float* cls_b;
+} b200_fusion_weights;
+
+/*
+ * Per-case part of FusionModel.forward (code/model_module.py:942-986): gating softmax,
+ * cross-attention + FFN on pooled tokens, SE gate and classifier on the pooled fused map.
+ * pvec_*_sum are per-case channel SUMS of p_dwi / p_dce over npix pixels.
+ */
+int b200_fusion_core(const b200_fusion_weights* wts, int B, const float* pvec_dwi_sum, const float* pvec_dce_sum,
+                     int npix, const float* mask_dwi, const float* mask_dce, int npix_mask, const float* tok_dwi,
+                     const float* tok_dce, float* gating_out, float* attn_out, float* lowres_out, float* gate_out,
+                     float* logits_out, void* stream);
+
+/* fused_refined = (a0*p_dwi + a1*p_dce + bilinear_up(lowres)) * gate (code/model_module.py:958-978). */
+int b200_fusion_mix(const void* p_dwi, const void* p_dce, const float* gating, const float* lowres,
+                    const float* gate, int B, int H, int W, int C, int Hp, int Wp, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_FUSION_H */

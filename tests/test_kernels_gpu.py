@@ -1,0 +1,83 @@
+"""Kernel-level numerics on the GPU: every C-ABI op against a plain PyTorch fp32 restatement
+of the same op on the same (bf16-rounded) operands.  Tolerances are stated per test."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import b200_native as nat
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel(a, b):
+    return (a.float() - b.float()).abs().max().item() / max(b.float().abs().max().item(), 1e-12)
+
+
+def _conv_ref(x, w, taps, scale, bias, res, res_mode, act):
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    xf = x.float().permute(0, 3, 1, 2)
+    k = 3 if taps == 9 else 1
+    wf = w.float().view(Cout, taps, Cin).permute(0, 2, 1).reshape(Cout, Cin, k, k)
+    y = F.conv2d(xf, wf, padding=k // 2)
+    if scale is not None:
+        y = y * scale.view(1, -1, 1, 1)
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1)
+    r = res.float().permute(0, 3, 1, 2) if res is not None else None
+    if res_mode == 1:
+        y = y + r
+    if act:
+        y = F.gelu(y)
+    if res_mode == 2:
+        y = y + r
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps,res_mode,act,gap,up2", [
+    (2, 32, 32, 64, 64, 1, 0, 0, False, False),
+    (2, 32, 32, 64, 64, 9, 0, 1, False, False),
+    (3, 32, 32, 64, 128, 1, 1, 1, True, False),
+    (2, 32, 32, 128, 128, 9, 0, 1, False, False),
+    (2, 32, 32, 128, 256, 1, 2, 1, False, False),
+    (5, 32, 32, 256, 256, 9, 0, 1, True, False),
+    (2, 32, 32, 256, 512, 1, 1, 1, True, False),
+    (2, 32, 32, 128, 64, 1, 0, 1, False, True),
+    (1, 64, 64, 64, 64, 9, 0, 1, False, False),
+    (40, 32, 32, 256, 256, 9, 0, 1, True, False),   # > 148 tiles: persistent loop + both TMEM stages
+])
+def test_conv_gemm(B, H, W, Cin, Cout, taps, res_mode, act, gap, up2):
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + Cin + Cout + taps)
+    x = (torch.randn(B, H, W, Cin, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(Cout, taps * Cin, generator=g) / math.sqrt(taps * Cin)).to(DEV).bfloat16()
+    scale = (torch.rand(Cout, generator=g) + 0.5).to(DEV)
+    bias = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    res = (torch.randn(B, H, W, Cout, generator=g) * 0.5).to(DEV).bfloat16() if res_mode else None
+    gap_buf = torch.zeros(B, Cout, device=DEV) if gap else None
+    y = nat.conv_gemm(x, w, taps=taps, scale=scale, bias=bias, res=res, res_mode=res_mode, act=act, gap=gap_buf,
+                      up2=up2)
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, w, taps, scale, bias, res, res_mode, act)
+    if up2:
+        ref = ref.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    # bf16 output rounding: 2^-9 relative per element; accumulation is fp32
+    assert _rel(y, ref) < 1e-2
+    assert (y.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    if gap:
+        gref = _conv_ref(x, w, taps, scale, bias, res, res_mode, act).sum(dim=(1, 2))
+        assert _rel(gap_buf, gref) < 1e-3
+
+
+@pytest.mark.parametrize("M,K,N", [(197, 768, 768), (1000, 128, 64), (128, 64, 256), (77, 3072, 768)])
+def test_linear_ragged_rows(M, K, N):
+    g = torch.Generator(device="cpu").manual_seed(M + K + N)
+    x = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).bfloat16()
+    bias = (torch.randn(N, generator=g) * 0.1).to(DEV)
+    y = nat.linear(x, w, bias=bias, act=1)
+    torch.cuda.synchronize()
+    ref = F.gelu(x.float() @ w.float().t() + bias)
+    assert _rel(y, ref) < 1e-2
