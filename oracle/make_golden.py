@@ -1,0 +1,157 @@
+"""Generates tests/golden/* by running the UNMODIFIED reference modules (authoring container only).
+
+    python oracle/make_golden.py            # needs /root/reference (read-only)
+
+The reference cannot travel to the GPU box, so its outputs on seeded inputs and seeded
+weights are committed as small fixtures: full small tensors (logits, gates, masks) and
+strided probes + sums of the large feature maps.  Inputs and weights are NOT stored - they
+are regenerated from seeds by oracle/params.py.  Nothing here is imported by the product.
+"""
+from __future__ import annotations
+
+import copy
+import json
+import os
+import runpy
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/code"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from oracle import params as op  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+PROBE_STRIDE = 997
+PROBE_N = 256
+
+
+def probe(t):
+    """Compact fingerprint of a tensor: strided samples, sum, sum of |x|."""
+    f = t.detach().double().reshape(-1)
+    return {"shape": list(t.shape), "samples": f[::PROBE_STRIDE][:PROBE_N].float().numpy(),
+            "sum": float(f.sum()), "abs_sum": float(f.abs().sum())}
+
+
+def reference_parameters():
+    """Execute code/parameters_generate.py with torch.save stubbed (it writes to Drive paths)."""
+    saved = torch.save
+    torch.save = lambda *a, **k: None
+    try:
+        ns = runpy.run_path(os.path.join(REF, "parameters_generate.py"))
+    finally:
+        torch.save = saved
+    p = copy.deepcopy(ns["parameters"])
+    for m in ("dwi", "dce", "fusion"):  # break the aliasing (parameters_generate.py:174, :183)
+        p[f"{m}_model_parameters"] = copy.deepcopy(p[f"{m}_model_parameters"])
+    return p
+
+
+def configure(p, hybrid=False):
+    p["dwi_channel_num"], p["dce_channel_num"] = 16, 6
+    for m in ("dwi", "dce", "fusion"):
+        mp = p[f"{m}_model_parameters"]
+        mp["use_backbone"] = False
+        mp["input_size"] = 64
+        mp["use_hybrid_transformer"] = hybrid and m != "fusion"
+    return p
+
+
+def flatten(prefix, obj, out):
+    if obj is None:
+        return
+    if torch.is_tensor(obj):
+        pr = probe(obj)
+        out[prefix + "/samples"] = pr["samples"]
+        out[prefix + "/meta"] = np.array(pr["shape"] + [0], dtype=np.float64)
+        out[prefix + "/sums"] = np.array([pr["sum"], pr["abs_sum"]])
+        if obj.numel() <= 8192:
+            out[prefix + "/full"] = obj.detach().float().numpy()
+    elif isinstance(obj, (list, tuple)):
+        for i, o in enumerate(obj):
+            flatten(f"{prefix}.{i}", o, out)
+    elif isinstance(obj, dict):
+        for k, o in obj.items():
+            flatten(f"{prefix}.{k}", o, out)
+
+
+def model_goldens(tag, hybrid):
+    import model_module as mm  # the reference module, imported from /root/reference/code
+
+    p = configure(reference_parameters(), hybrid)
+    torch.manual_seed(0)
+    models = {"dwi": mm.ModelMaskHeadBackbone("dwi", p, None), "dce": mm.ModelMaskHeadBackbone("dce", p, None),
+              "fusion": mm.FusionModel(p)}
+    shapes = {}
+    for name, m in models.items():
+        sh = op.shapes_of(m.state_dict())
+        shapes[name] = {k: list(v) for k, v in sh.items()}
+        m.load_state_dict(op.seeded_state_dict(sh, seed=7))
+        m.eval()
+    out = {}
+    for kind in ("U", "S"):
+        dwi_raw, dce_raw, _, _ = op.synthetic_raw(2, seed=1234, kind=kind)
+        # model inputs are the normalised tensors; any fp32 tensor in [0,1] does for model parity
+        dwi = dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)
+        dce = dce_raw
+        with torch.no_grad():
+            ld, ad, md = models["dwi"](dwi)
+            lc, ac, mc = models["dce"](dce)
+            lf, mf, af = models["fusion"](ad["raw_feats"], ac["raw_feats"], md, mc)
+        flatten(f"{kind}/dwi/logits", ld, out)
+        flatten(f"{kind}/dwi/aux", ad, out)
+        flatten(f"{kind}/dwi/mask", md, out)
+        flatten(f"{kind}/dce/logits", lc, out)
+        flatten(f"{kind}/dce/aux", ac, out)
+        flatten(f"{kind}/dce/mask", mc, out)
+        flatten(f"{kind}/fusion/logits", lf, out)
+        flatten(f"{kind}/fusion/mask", mf, out)
+        flatten(f"{kind}/fusion/aux", af, out)
+    np.savez_compressed(os.path.join(GOLD, f"model_{tag}.npz"), **out)
+    with open(os.path.join(GOLD, f"state_shapes_{tag}.json"), "w") as f:
+        json.dump(shapes, f, indent=0, sort_keys=True)
+    print(tag, "fusion logits", lf)
+
+
+def normalizer_goldens():
+    import dataset as ref_dataset
+    import preprocess_helpers as ref_pre
+
+    out = {}
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(12, seed=1234, kind="S")
+    dwi_u, dce_u, _, _ = op.synthetic_raw(3, seed=77, kind="U")
+    norm = ref_dataset.DWINormalize()
+    for name, x in (("S", dwi_raw[:3]), ("U", dwi_u), ("E", op.edge_cases())):
+        y = torch.stack([norm(c) for c in x])
+        flatten(f"dwi/{name}", y, out)
+    y = torch.stack([ref_dataset.DWINormalize(clip_z=(-2, 2.5), adc=False)(c) for c in dwi_u])
+    flatten("dwi/U_noadc", y, out)
+    import contextlib
+    import io
+    nyul = ref_pre.NyulStandardizer()
+    with contextlib.redirect_stdout(io.StringIO()):
+        nyul.fit(list(dce_raw[:8]), num_channels=6)
+    lm = np.stack([nyul.channel_landmarks[c] for c in range(6)])
+    out["nyul/landmarks"] = lm
+    for name, x in (("S", dce_raw[8:]), ("U", dce_u)):
+        y = torch.stack([ref_dataset.DCENormalize(nyul)(c) for c in x])
+        flatten(f"nyul/{name}", y, out)
+    ties = torch.round(dce_u * 20) / 20  # tied percentiles
+    y = torch.stack([nyul.transform(c) for c in ties])
+    flatten("nyul/ties", y, out)
+    adc = ref_pre.compute_adc_map(dwi_raw[0, :13], list(range(13)))
+    out["adc/map"] = adc.numpy()
+    np.savez_compressed(os.path.join(GOLD, "normalizers.npz"), **out)
+    print("normalizers done")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    normalizer_goldens()
+    model_goldens("cnn", hybrid=False)
+    model_goldens("hybrid", hybrid=True)

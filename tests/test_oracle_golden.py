@@ -1,0 +1,80 @@
+"""CPU: the oracle restatement against the fixtures produced by the unmodified reference
+(oracle/make_golden.py).  Tolerances: the model restatement reorders no arithmetic, so it
+must agree to fp32 round-off (1e-5 of the tensor's max); normalisers to 1e-6."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import parameters_default as pd
+from oracle import model_oracle as mo
+from oracle import normalize_oracle as no
+from oracle import params as op
+
+
+def _params(hybrid):
+    p = pd.default_parameters()
+    for m in ("dwi", "dce"):
+        p[f"{m}_model_parameters"]["use_hybrid_transformer"] = hybrid
+    return p
+
+
+@pytest.mark.parametrize("tag,hybrid", [("cnn", False), ("hybrid", True)])
+def test_model_oracle_matches_reference(tag, hybrid):
+    gold = gu.load(f"model_{tag}.npz")
+    shapes = gu.load_shapes(tag)
+    p = _params(hybrid)
+    sds = {m: op.seeded_state_dict(shapes[m], seed=7) for m in ("dwi", "dce", "fusion")}
+    torch.set_num_threads(8)
+    for kind in ("U", "S"):
+        dwi_raw, dce_raw, _, _ = op.synthetic_raw(2, seed=1234, kind=kind)
+        dwi = dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)
+        with torch.no_grad():
+            ld, ad, md = mo.encoder_forward(sds["dwi"], "dwi", p, dwi)
+            lc, ac, mc = mo.encoder_forward(sds["dce"], "dce", p, dce_raw)
+            lf, mf, af = mo.fusion_forward(sds["fusion"], p, ad["raw_feats"], ac["raw_feats"], md, mc)
+        outs = {f"{kind}/dwi/logits": ld, f"{kind}/dwi/aux": ad, f"{kind}/dwi/mask": md,
+                f"{kind}/dce/logits": lc, f"{kind}/dce/aux": ac, f"{kind}/dce/mask": mc,
+                f"{kind}/fusion/logits": lf, f"{kind}/fusion/mask": mf, f"{kind}/fusion/aux": af}
+        n = 0
+        for prefix, obj in outs.items():
+            for key, t in gu.walk(prefix, obj):
+                gu.check(gold, key, t, rtol=2e-5)
+                n += 1
+        assert n == 34
+
+
+def test_dwi_normalize_oracle_matches_reference():
+    gold = gu.load("normalizers.npz")
+    dwi_raw, _, _, _ = op.synthetic_raw(12, seed=1234, kind="S")
+    dwi_u, _, _, _ = op.synthetic_raw(3, seed=77, kind="U")
+    gu.check(gold, "dwi/S", no.dwi_normalize_batch(dwi_raw[:3]), rtol=1e-6)
+    gu.check(gold, "dwi/U", no.dwi_normalize_batch(dwi_u), rtol=1e-6)
+    gu.check(gold, "dwi/E", no.dwi_normalize_batch(op.edge_cases()), rtol=1e-6)
+    gu.check(gold, "dwi/U_noadc", no.dwi_normalize_batch(dwi_u, clip_z=(-2, 2.5), adc=False), rtol=1e-6)
+
+
+def test_nyul_oracle_matches_reference():
+    gold = gu.load("normalizers.npz")
+    _, dce_raw, _, _ = op.synthetic_raw(12, seed=1234, kind="S")
+    _, dce_u, _, _ = op.synthetic_raw(3, seed=77, kind="U")
+    lm = no.nyul_fit(list(dce_raw[:8]), num_channels=6)
+    assert np.array_equal(lm, gold["nyul/landmarks"])  # float64, bit-exact
+    gu.check(gold, "nyul/S", no.nyul_transform_batch(dce_raw[8:], lm), rtol=1e-7)
+    gu.check(gold, "nyul/U", no.nyul_transform_batch(dce_u, lm), rtol=1e-7)
+    gu.check(gold, "nyul/ties", no.nyul_transform_batch(torch.round(dce_u * 20) / 20, lm), rtol=1e-7)
+
+
+def test_adc_oracle_matches_reference():
+    gold = gu.load("normalizers.npz")
+    dwi_raw, _, _, _ = op.synthetic_raw(12, seed=1234, kind="S")
+    adc = no.compute_adc_map(dwi_raw[0, :13], list(range(13)))
+    assert np.allclose(adc.numpy(), gold["adc/map"], rtol=1e-6, atol=1e-9)
+
+
+def test_percentile_rule_is_numpy_percentile():
+    g = np.random.default_rng(0)
+    for n in (4096, 50176, 17):
+        x = g.random(n).astype(np.float32)
+        ref = np.percentile(x, no.DEFAULT_LANDMARKS)
+        assert np.array_equal(no.percentile_linear(np.sort(x), no.DEFAULT_LANDMARKS), ref)
