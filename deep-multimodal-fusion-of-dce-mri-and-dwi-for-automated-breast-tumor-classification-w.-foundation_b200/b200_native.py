@@ -101,6 +101,42 @@ def _check(rc, name):
         raise B200NativeError(f"{name} failed: {kind} {rc}")
 
 
+LAUNCH_COUNT = 0   # kernels launched through this binding (bench.py reports it as gpu_launches)
+_profile = None    # list of (name, key, start_event, end_event) while profiling
+
+
+def start_profile():
+    """Bracket every subsequent native launch with CUDA events on the launching stream."""
+    global _profile
+    _profile = []
+
+
+def stop_profile():
+    """-> {(name, key): [ms, ...]} for the launches since start_profile() (synchronises)."""
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, key, s, e in rec or []:
+        out.setdefault((name, key), []).append(s.elapsed_time(e))
+    return out
+
+
+def _call(name, key, *args):
+    global LAUNCH_COUNT
+    fn = getattr(lib(), name)
+    if _profile is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        _profile.append((name, key, s, e))
+    else:
+        rc = fn(*args)
+    LAUNCH_COUNT += 1
+    _check(rc, name)
+
+
 def _bf16_map(t, name):
     if t.dtype != torch.bfloat16 or not t.is_contiguous():
         raise B200NativeError(f"{name} must be a contiguous bfloat16 NHWC tensor")
@@ -122,10 +158,9 @@ def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0,
         _bf16_map(out, "out")
     if res is not None:
         _bf16_map(res, "res")
-    rc = lib().b200_conv_gemm(_ptr(x), x_ld, _ptr(w), _ptr(scale), _ptr(bias), _ptr(res),
-                              res.shape[-1] if res is not None else 0, res_mode, act, _ptr(out), out_ld,
-                              1 if up2 else 0, _ptr(gap), B, H, W, cin, cout, taps, _stream())
-    _check(rc, "b200_conv_gemm")
+    _call("b200_conv_gemm", (B, H, W, cin, cout, taps), _ptr(x), x_ld, _ptr(w), _ptr(scale), _ptr(bias), _ptr(res),
+          res.shape[-1] if res is not None else 0, res_mode, act, _ptr(out), out_ld,
+          1 if up2 else 0, _ptr(gap), B, H, W, cin, cout, taps, _stream())
     return out
 
 
@@ -140,22 +175,22 @@ def linear(x2d, w, *, scale=None, bias=None, res=None, res_mode=0, act=0, out=No
 
 def dwi_normalize(x, out, C_, n, skip_last, z_lo, z_hi, plane_mean=None):
     planes = x.numel() // n
-    _check(lib().b200_dwi_normalize(_ptr(x), _ptr(out), planes, C_, n, 1 if skip_last else 0, float(z_lo),
-                                    float(z_hi), _ptr(plane_mean), _stream()), "b200_dwi_normalize")
+    _call("b200_dwi_normalize", None, _ptr(x), _ptr(out), planes, C_, n, 1 if skip_last else 0, float(z_lo),
+                                    float(z_hi), _ptr(plane_mean), _stream())
     return out
 
 
 def nyul_transform(x, out, C_, n, avg_landmarks, standard_scale, prev_index, gamma, plane_mean=None):
     planes = x.numel() // n
     L = standard_scale.numel()
-    _check(lib().b200_nyul_transform(_ptr(x), _ptr(out), planes, C_, n, L, _ptr(avg_landmarks),
+    _call("b200_nyul_transform", None, _ptr(x), _ptr(out), planes, C_, n, L, _ptr(avg_landmarks),
                                      _ptr(standard_scale), _ptr(prev_index), _ptr(gamma), _ptr(plane_mean),
-                                     _stream()), "b200_nyul_transform")
+                                     _stream())
     return out
 
 
 def plane_mean(x, planes, n, out):
-    _check(lib().b200_plane_mean(_ptr(x), planes, n, _ptr(out), _stream()), "b200_plane_mean")
+    _call("b200_plane_mean", None, _ptr(x), planes, n, _ptr(out), _stream())
     return out
 
 
@@ -163,29 +198,27 @@ def stem(x, stride, pm, se, wcat, scale, bias, n_skip, n_mid, skip_out, mid_out,
     B, C_, H, W = x.shape
     w1, b1, w2, b2 = se if se is not None else (None, None, None, None)
     cm = w1.shape[0] if w1 is not None else 0
-    _check(lib().b200_stem(_ptr(x), B, C_, H, W, stride, _ptr(pm), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), cm,
+    _call("b200_stem", None, _ptr(x), B, C_, H, W, stride, _ptr(pm), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), cm,
                            _ptr(wcat), _ptr(scale), _ptr(bias), n_skip, n_mid, _ptr(skip_out), _ptr(mid_out),
-                           _ptr(mod_attn), _stream()), "b200_stem")
+                           _ptr(mod_attn), _stream())
 
 
 def se_gate(gap_sum, npix, w1t, b1, w2t, b2, gate):
     B, C_ = gap_sum.shape
-    _check(lib().b200_se_gate(_ptr(gap_sum), B, C_, w1t.shape[1], npix, _ptr(w1t), _ptr(b1), _ptr(w2t), _ptr(b2),
-                              _ptr(gate), _stream()), "b200_se_gate")
+    _call("b200_se_gate", None, _ptr(gap_sum), B, C_, w1t.shape[1], npix, _ptr(w1t), _ptr(b1), _ptr(w2t), _ptr(b2),
+                              _ptr(gate), _stream())
     return gate
 
 
 def scale_map(x, y, gate=None, attn=None, gamma=None):
     B, H, W, C_ = x.shape
-    _check(lib().b200_scale_map(_ptr(x), _ptr(y), B, H * W, C_, _ptr(gate), _ptr(attn), _ptr(gamma), _stream()),
-           "b200_scale_map")
+    _call("b200_scale_map", None, _ptr(x), _ptr(y), B, H * W, C_, _ptr(gate), _ptr(attn), _ptr(gamma), _stream())
     return y
 
 
 def conv3x3_c1(x, w, bias, out):
     B, H, W, C_ = x.shape
-    _check(lib().b200_conv3x3_c1(_ptr(x), B, H, W, C_, _ptr(w), _ptr(bias), _ptr(out), _stream()),
-           "b200_conv3x3_c1")
+    _call("b200_conv3x3_c1", None, _ptr(x), B, H, W, C_, _ptr(w), _ptr(bias), _ptr(out), _stream())
     return out
 
 
@@ -195,39 +228,37 @@ def mask_tail(pre, w_out, b_out, mask_pred, attn_params=None, attn=None):
         hc, wa, gw, gb, wb, bb, eps = 0, None, None, None, None, None, 0.0
     else:
         hc, wa, gw, gb, wb, bb, eps = attn_params
-    _check(lib().b200_mask_tail(_ptr(pre), B, H * W, Cm, _ptr(w_out), _ptr(b_out), _ptr(mask_pred), hc, _ptr(wa),
-                                _ptr(gw), _ptr(gb), _ptr(wb), _ptr(bb), float(eps), _ptr(attn), _stream()),
-           "b200_mask_tail")
+    _call("b200_mask_tail", None, _ptr(pre), B, H * W, Cm, _ptr(w_out), _ptr(b_out), _ptr(mask_pred), hc, _ptr(wa),
+                                _ptr(gw), _ptr(gb), _ptr(wb), _ptr(bb), float(eps), _ptr(attn), _stream())
 
 
 def lift_c1(r, w, scale, bias, y):
-    _check(lib().b200_lift_c1(_ptr(r), r.numel(), w.numel(), _ptr(w), _ptr(scale), _ptr(bias), _ptr(y), _stream()),
-           "b200_lift_c1")
+    _call("b200_lift_c1", None, _ptr(r), r.numel(), w.numel(), _ptr(w), _ptr(scale), _ptr(bias), _ptr(y), _stream())
     return y
 
 
 def cls_head(gap_sum, gate, npix, fc_w, fc_b, normalize, logits, pooled_out=None):
     B, C_ = gap_sum.shape
-    _check(lib().b200_cls_head(_ptr(gap_sum), _ptr(gate), B, C_, npix, fc_w.shape[0], _ptr(fc_w), _ptr(fc_b),
-                               1 if normalize else 0, _ptr(logits), _ptr(pooled_out), _stream()), "b200_cls_head")
+    _call("b200_cls_head", None, _ptr(gap_sum), _ptr(gate), B, C_, npix, fc_w.shape[0], _ptr(fc_w), _ptr(fc_b),
+                               1 if normalize else 0, _ptr(logits), _ptr(pooled_out), _stream())
     return logits
 
 
 def fusion_tokens(p, hp, wp, tokens):
     B, H, W, C_ = p.shape
-    _check(lib().b200_fusion_tokens(_ptr(p), B, H, W, C_, hp, wp, _ptr(tokens), _stream()), "b200_fusion_tokens")
+    _call("b200_fusion_tokens", None, _ptr(p), B, H, W, C_, hp, wp, _ptr(tokens), _stream())
     return tokens
 
 
 def fusion_core(wts, B, pvec_dwi_sum, pvec_dce_sum, npix, mask_dwi, mask_dce, npix_mask, tok_dwi, tok_dce,
                 gating, attn, lowres, gate, logits):
-    _check(lib().b200_fusion_core(C.byref(wts), B, _ptr(pvec_dwi_sum), _ptr(pvec_dce_sum), npix, _ptr(mask_dwi),
+    _call("b200_fusion_core", None, C.byref(wts), B, _ptr(pvec_dwi_sum), _ptr(pvec_dce_sum), npix, _ptr(mask_dwi),
                                   _ptr(mask_dce), npix_mask, _ptr(tok_dwi), _ptr(tok_dce), _ptr(gating), _ptr(attn),
-                                  _ptr(lowres), _ptr(gate), _ptr(logits), _stream()), "b200_fusion_core")
+                                  _ptr(lowres), _ptr(gate), _ptr(logits), _stream())
 
 
 def fusion_mix(p_dwi, p_dce, gating, lowres, gate, hp, wp, out):
     B, H, W, C_ = p_dwi.shape
-    _check(lib().b200_fusion_mix(_ptr(p_dwi), _ptr(p_dce), _ptr(gating), _ptr(lowres), _ptr(gate), B, H, W, C_, hp,
-                                 wp, _ptr(out), _stream()), "b200_fusion_mix")
+    _call("b200_fusion_mix", None, _ptr(p_dwi), _ptr(p_dce), _ptr(gating), _ptr(lowres), _ptr(gate), B, H, W, C_, hp,
+                                 wp, _ptr(out), _stream())
     return out

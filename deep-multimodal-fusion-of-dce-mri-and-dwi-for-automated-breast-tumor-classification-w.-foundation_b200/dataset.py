@@ -1,0 +1,153 @@
+"""B200-native drop-in for the reference's ``dataset`` module (code/dataset.py).
+
+``DWINormalize`` / ``DCENormalize`` keep the reference call signature (a callable on one
+[C,H,W] image, code/dataset.py:9-53) and add a batched entry ``batch(x[B,C,H,W])`` - one
+kernel launch for a whole batch, which is how the B200 pipeline uses them (normalisation
+happens on the device after collation instead of per sample in DataLoader workers).
+The arithmetic runs in csrc/normalize.cu; there is no CPU implementation here: CPU
+tensors are staged through the GPU and returned on their original device.
+The dataset / fold-splitting classes are host-side indexing and keep the reference behaviour.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+import b200_native as nat
+
+__all__ = ["DWINormalize", "DCENormalize", "SingleInputDataset", "LoadedFusionDataset", "data_segmentation",
+           "data_segmentation_mask"]
+
+
+def _to_device(img):
+    if img.is_cuda:
+        return img, None
+    if not torch.cuda.is_available():
+        raise nat.B200NativeError("normalisers run on the GPU only (no CPU path); no CUDA device is visible")
+    return img.cuda(non_blocking=True), img.device
+
+
+class DWINormalize(object):
+    """Per-channel z-score -> clip -> [0,1]; the last channel is zeroed when adc=True (dataset.py:9-41)."""
+
+    def __init__(self, clip_z=(-3, 3), adc=True):
+        self.z_lo, self.z_hi = clip_z
+        self.adc = adc
+
+    def batch(self, x, plane_mean=None):
+        """x [B,C,H,W] fp32 CUDA -> normalised fp32 [B,C,H,W]; optionally fills plane_mean [B*C]."""
+        if x.dim() != 4:
+            raise ValueError("expected [B,C,H,W]")
+        x = x.contiguous().float()
+        out = torch.empty_like(x)
+        B, C, H, W = x.shape
+        nat.dwi_normalize(x, out, C, H * W, self.adc, self.z_lo, self.z_hi, plane_mean)
+        return out
+
+    def __call__(self, img):
+        dev_img, home = _to_device(img)
+        out = self.batch(dev_img.unsqueeze(0))[0]
+        return out if home is None else out.to(home)
+
+
+class DCENormalize(object):
+    """Nyul standardisation of one image through the fitted standardiser (dataset.py:46-53)."""
+
+    def __init__(self, nyul_standardizer):
+        self.nyul = nyul_standardizer
+
+    def batch(self, x, plane_mean=None):
+        return self.nyul.transform_batch(x, plane_mean=plane_mean)
+
+    def __call__(self, img):
+        norm = self.nyul.transform(img)
+        return norm.to(img.device)
+
+
+class SingleInputDataset(torch.utils.data.Dataset):
+    """(img[, mask][, label]) samples with optional transforms and ADC channel (dataset.py:56-98)."""
+
+    def __init__(self, imgs, masks=None, labels=None, transforms=None, modality="dwi", nyul_standardizer=None,
+                 adc_min=None, adc_map=None):
+        self.imgs, self.masks, self.labels = imgs, masks, labels
+        self.transforms, self.modality, self.adc_map = transforms, modality, adc_map
+
+    def __len__(self):
+        return len(self.imgs)
+
+    def __getitem__(self, index):
+        img = self.imgs[index].clone()
+        label = self.labels[index] if self.labels is not None else None
+        mask = self.masks[index] if self.masks is not None else None
+        if self.transforms:
+            img = self.transforms(img)
+        if self.adc_map is not None:
+            adc = F.interpolate(self.adc_map.unsqueeze(0), size=img.shape[-2:], mode="bilinear",
+                                align_corners=False).squeeze(0)
+            img = torch.cat([img, adc.to(img.device)], dim=0)
+        items = [img.float()]
+        if mask is not None:
+            items.append(mask.float())
+        if label is not None:
+            items.append(label)
+        return items[0] if len(items) == 1 else tuple(items)
+
+
+class LoadedFusionDataset(torch.utils.data.Dataset):
+    """Pre-processed (dwi, dce[, mask][, label]) tuples (dataset.py:100-140)."""
+
+    def __init__(self, dwi, dce, masks=None, labels=None):
+        self.dwi, self.dce, self.masks, self.labels = dwi, dce, masks, labels
+        self.length = len(dwi)
+        assert len(dwi) == len(dce), "DWI and DCE must have same length"
+        if masks is not None:
+            assert len(masks) == len(dwi), "Masks must match DWI length"
+        if labels is not None:
+            assert len(labels) == len(dwi), "Labels must match DWI length"
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, index):
+        x1, x2 = self.dwi[index].clone().float(), self.dce[index].clone().float()
+        m = self.masks[index] if self.masks is not None else None
+        y = self.labels[index] if self.labels is not None else None
+        if m is not None and y is not None:
+            return x1, x2, m.float(), y
+        if y is not None:
+            return x1, x2, y
+        if m is not None:
+            return x1, x2, m.float()
+        return x1, x2
+
+
+def _fold_indices(labels, segnum, classnum, fold):
+    """Index form of the reference's stratified K-fold (dataset.py:142-176, :178-235): seed numpy once
+    with 42, permute every class's indices in class order, cut each class into `segnum` slices of
+    floor(n/segnum) (the last slice takes the remainder), segment i = concat over classes of slice i;
+    segment `fold` is validation, the others (in order) are training."""
+    np.random.seed(42)
+    per_class = []
+    for c in range(classnum):
+        idx = torch.where(labels == c)[0]
+        per_class.append(idx[np.random.permutation(idx.size(0))].tolist())
+    segments = []
+    for i in range(segnum):
+        seg = []
+        for idx in per_class:
+            step = len(idx) // segnum
+            seg += idx[i * step:(i + 1) * step] if i != segnum - 1 else idx[(segnum - 1) * step:]
+        segments.append(seg)
+    train = [j for i, seg in enumerate(segments) if i != fold for j in seg]
+    return train, segments[fold]
+
+
+def data_segmentation(imgs, labels, segnum, classnum, fold):
+    tr, va = _fold_indices(labels, segnum, classnum, fold)
+    return [imgs[tr], imgs[va]], [labels[tr].float(), labels[va].float()]
+
+
+def data_segmentation_mask(imgs, masks, labels, segnum, classnum, fold):
+    tr, va = _fold_indices(labels, segnum, classnum, fold)
+    return [imgs[tr], imgs[va]], [masks[tr], masks[va]], [labels[tr], labels[va]]

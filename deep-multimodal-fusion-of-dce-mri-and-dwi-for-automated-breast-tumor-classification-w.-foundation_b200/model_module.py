@@ -1,0 +1,821 @@
+"""B200-native drop-in for the reference's ``model_module`` (DWI / DCE encoders + late fusion).
+
+Same class names, constructor arguments, parameter names / shapes (``state_dict`` compatible,
+so checkpoints and the reference's name-based optimiser grouping keep working) and the
+same ``forward`` contracts as /root/reference/code/model_module.py:
+
+    ModelMaskHeadBackbone(method, parameters_dict, backbone=None).forward(x, masks=None)
+        -> (logits[B,K], aux, mask_pred[B,1,32,32])                    (reference :481-733)
+    FusionModel(parameters_dict).forward(raw_feats_dwi, raw_feats_dce, dwi_mask_pred, dce_mask_pred)
+        -> (logits[B,K], fused_mask_logits[B,1,32,32], aux)            (reference :821-1000)
+
+The sub-modules are parameter containers; the arithmetic of an eval-mode forward runs in
+the hand-written sm_100a kernels behind include/b200_fusion.h (tcgen05/TMEM implicit-GEMM
+convolutions fed by TMA, SIMT kernels for the K<64 / N=1 / per-case pieces).  Activations
+live in HBM as NHWC bf16; the feature maps handed back in ``aux`` are zero-copy NCHW-shaped
+(channels_last) bf16 views of those buffers, 1-channel maps / gates / logits are fp32.
+
+There is no CPU or PyTorch fallback: a forward on a non-CUDA tensor, or without the
+compiled library, raises.  Training-mode forward (batch-statistics BatchNorm, dropout,
+autograd) is not built yet and raises NotImplementedError - see DESIGN.md.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+from torch.nn import init
+
+import b200_native as nat
+
+__all__ = [
+    "FeatureSpec", "SEBlock", "TemporalAttention", "ChannelAttention", "MaskGuidedSpatialAttention", "ReconHead",
+    "MaskHeadResize", "ResNetLiteBlock_withRecon", "Projector", "ClassificationHead", "FeatureDownAlign",
+    "BackboneAdapter", "ModelMaskHeadBackbone", "GatingAttention", "FusionReduce", "CrossAttentionBlock",
+    "FusionModel", "init_parameter", "initialize_model", "smooth_l1_loss",
+]
+
+
+def smooth_l1_loss(a, b):
+    return torch.nn.functional.smooth_l1_loss(a, b)
+
+
+@dataclass
+class FeatureSpec:
+    channels: int
+    stride: int
+
+
+def _only_2d(dim):
+    if dim != 2:
+        raise NotImplementedError("the B200 path covers dim=2 only (all BASELINE configs are 2-D)")
+
+
+def _container_only(name):
+    raise NotImplementedError(
+        f"{name} is a parameter container in the B200 build; its arithmetic runs inside "
+        "ModelMaskHeadBackbone.forward / FusionModel.forward")
+
+
+# --------------------------------------------------------------------------------------
+# parameter containers (names mirror the reference so state_dict keys are identical)
+# --------------------------------------------------------------------------------------
+class SEBlock(nn.Module):
+    """Squeeze-excite: keys fc.1.*, fc.3.* (reference :25-43)."""
+
+    def __init__(self, channels, reduction=2, dim=2):
+        super().__init__()
+        _only_2d(dim)
+        mid = max(channels // reduction, 1)
+        self.fc = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(channels, mid, 1), nn.GELU(),
+                                nn.Conv2d(mid, channels, 1), nn.Sigmoid())
+
+    def forward(self, x):
+        _container_only("SEBlock")
+
+
+class TemporalAttention(SEBlock):
+    pass
+
+
+class ChannelAttention(SEBlock):
+    pass
+
+
+class MaskGuidedSpatialAttention(nn.Module):
+    """keys gamma, mask_processor.{0,1,3}.* (reference :49-97)."""
+
+    def __init__(self, in_channels_img, in_channels_mask, hidden_channels=16, dim=2):
+        super().__init__()
+        _only_2d(dim)
+        self.dim = dim
+        self.interp_mode = "bilinear"
+        self.gamma = nn.Parameter(torch.tensor(0.1))
+        self.mask_processor = nn.Sequential(
+            nn.Conv2d(in_channels_mask, hidden_channels, 1, bias=False), nn.GroupNorm(1, hidden_channels), nn.GELU(),
+            nn.Conv2d(hidden_channels, 1, 1), nn.Sigmoid())
+
+    def forward(self, img_features, mask_features):
+        _container_only("MaskGuidedSpatialAttention")
+
+
+class ReconHead(nn.Module):
+    """keys conv.{0,1,3}.* (reference :100-125)."""
+
+    def __init__(self, in_ch, recon_ch=1, upsample=False, dim=2):
+        super().__init__()
+        _only_2d(dim)
+        self.upsample, self.dim = upsample, dim
+        self.conv = nn.Sequential(nn.Conv2d(in_ch, in_ch, 3, padding=1, bias=False), nn.BatchNorm2d(in_ch), nn.GELU(),
+                                  nn.Conv2d(in_ch, recon_ch, 3, padding=1))
+
+    def forward(self, x):
+        _container_only("ReconHead")
+
+
+class MaskHeadResize(nn.Module):
+    """keys pre.*, down_{64,128,256,512}_to_32.*, out.* (reference :131-215)."""
+
+    def __init__(self, in_ch, mid_ch=64, out_ch=1, out_size=32, dim=2):
+        super().__init__()
+        _only_2d(dim)
+        self.dim, self.out_size, self.interp_mode = dim, out_size, "bilinear"
+        self.pre = nn.Conv2d(in_ch, mid_ch, 1)
+
+        def chain(n):
+            layers = []
+            for _ in range(n):
+                layers += [nn.Conv2d(mid_ch, mid_ch, 3, stride=2, padding=1), nn.GELU()]
+            return nn.Sequential(*layers)
+
+        self.down_64_to_32, self.down_128_to_32 = chain(1), chain(2)
+        self.down_256_to_32, self.down_512_to_32 = chain(3), chain(4)
+        self.out = nn.Conv2d(mid_ch, out_ch, 1)
+
+    def forward(self, x):
+        _container_only("MaskHeadResize")
+
+
+class ResNetLiteBlock_withRecon(nn.Module):
+    """keys bottlenecks.N.{0,1,4,5,7,8}.*, skip.{0,1}.*, se.*, reconstruct.* (reference :220-316)."""
+
+    def __init__(self, in_ch, out_ch, downsample=False, recon_ch=1, use_se=False, se_reduction=2, dropout=0.4, dim=2,
+                 num_repeats=1, downsample_each_repeat=False, mid_squeeze=2):
+        super().__init__()
+        _only_2d(dim)
+        self.dim, self.num_repeats = dim, num_repeats
+        self.stride = 2 if downsample else 1
+        self.downsample_each_repeat = downsample_each_repeat
+        mid = max(out_ch // mid_squeeze, 1)
+        self.bottlenecks = nn.ModuleList()
+        for i in range(num_repeats):
+            s = self.stride if (i == 0 or downsample_each_repeat) else 1
+            self.bottlenecks.append(nn.Sequential(
+                nn.Conv2d(in_ch if i == 0 else out_ch, mid, 1, stride=s, bias=False), nn.BatchNorm2d(mid), nn.GELU(),
+                nn.Dropout(p=dropout),
+                nn.Conv2d(mid, mid, 3, padding=1, bias=False), nn.BatchNorm2d(mid), nn.GELU(),
+                nn.Conv2d(mid, out_ch, 1, bias=False), nn.BatchNorm2d(out_ch)))
+        self.act = nn.GELU()
+        self.dropout = nn.Dropout(p=dropout)
+        if self.stride > 1 or in_ch != out_ch:
+            self.skip = nn.Sequential(nn.Conv2d(in_ch, out_ch, 1, stride=self.stride, bias=False),
+                                      nn.BatchNorm2d(out_ch))
+        else:
+            self.skip = None
+        self.use_se = use_se
+        self.se = SEBlock(out_ch, reduction=se_reduction, dim=dim) if use_se else None
+        self.recon_ch = int(recon_ch)
+        self.reconstruct = ReconHead(out_ch, recon_ch, upsample=False, dim=dim) if self.recon_ch > 0 else None
+
+    def forward(self, x):
+        _container_only("ResNetLiteBlock_withRecon")
+
+
+class Projector(nn.Module):
+    """keys proj.{0,1,3,4}.* (reference :323-348)."""
+
+    def __init__(self, in_ch, proj_dim=64, dim=2):
+        super().__init__()
+        _only_2d(dim)
+        self.dim = dim
+        self.proj = nn.Sequential(nn.Conv2d(in_ch, proj_dim, 1, bias=False), nn.BatchNorm2d(proj_dim), nn.GELU(),
+                                  nn.Conv2d(proj_dim, proj_dim, 1, bias=False), nn.BatchNorm2d(proj_dim), nn.GELU())
+
+    def forward(self, x):
+        _container_only("Projector")
+
+
+class ClassificationHead(nn.Module):
+    """keys fc.* (reference :355-369)."""
+
+    def __init__(self, in_ch, num_classes, dim=2, normalize=True):
+        super().__init__()
+        _only_2d(dim)
+        self.pool, self.flatten = nn.AdaptiveAvgPool2d((1, 1)), nn.Flatten()
+        self.fc = nn.Linear(in_ch, num_classes)
+        self.normalize = normalize
+
+    def forward(self, x):
+        _container_only("ClassificationHead")
+
+
+class FeatureDownAlign(nn.Module):
+    """keys proj.{0,1}.* (reference :371-396)."""
+
+    def __init__(self, in_ch, out_ch, dim=2, downsample=True):
+        super().__init__()
+        _only_2d(dim)
+        self.downsample = downsample
+        if in_ch != out_ch or downsample:
+            k, s, p = (3, 2, 1) if downsample else (1, 1, 0)
+            self.proj = nn.Sequential(nn.Conv2d(in_ch, out_ch, k, stride=s, padding=p, bias=False),
+                                      nn.BatchNorm2d(out_ch), nn.GELU())
+        else:
+            self.proj = nn.Identity()
+
+    def forward(self, x):
+        _container_only("FeatureDownAlign")
+
+
+class BackboneAdapter(nn.Module):
+    """keys backbone.*, necks.f{1,2,3}.{0,1,3,4}.* (reference :401-476)."""
+
+    def __init__(self, backbone, selected_indices_chains, out_channels=(64, 128, 256), dim=2, is_transformer=False):
+        super().__init__()
+        _only_2d(dim)
+        assert len(selected_indices_chains) == 3, "Must provide 3 chains for f1/f2/f3"
+        assert len(out_channels) == 3, "Must provide 3 output channels for f1/f2/f3"
+        self.backbone = backbone
+        self.selected_indices_chains = selected_indices_chains
+        self.dim, self.is_transformer = dim, is_transformer
+        info = backbone.feature_info
+        self.features = [FeatureSpec(c, s) for c, s in zip(info.channels(), info.reduction())]
+        self.necks = nn.ModuleDict()
+        for i, chain in enumerate(selected_indices_chains):
+            cin, cout = sum(self.features[j].channels for j in chain), out_channels[i]
+            self.necks[f"f{i + 1}"] = nn.Sequential(
+                nn.Conv2d(cin, cout, 3, padding=1), nn.BatchNorm2d(cout), nn.GELU(),
+                nn.Conv2d(cout, cout, 3, padding=1), nn.BatchNorm2d(cout), nn.GELU())
+
+    def forward(self, x):
+        _container_only("BackboneAdapter")
+
+
+class GatingAttention(nn.Module):
+    """keys fc.* (reference :745-780)."""
+
+    def __init__(self, feat_dim, use_mask_attention=True, dim=2):
+        super().__init__()
+        self.use_mask_attention, self.dim = use_mask_attention, dim
+        self.fc = nn.Linear(feat_dim * 2 + (2 if use_mask_attention else 0), 2)
+
+    def forward(self, pvec_dwi, pvec_dce, dwi_mask=None, dce_mask=None):
+        _container_only("GatingAttention")
+
+
+class FusionReduce(nn.Module):
+    """keys reduce.{0,1}.* (reference :782-794)."""
+
+    def __init__(self, in_ch, out_ch, dim=2):
+        super().__init__()
+        _only_2d(dim)
+        self.reduce = nn.Sequential(nn.Conv2d(in_ch, out_ch, 1, bias=False), nn.BatchNorm2d(out_ch), nn.GELU())
+
+    def forward(self, x):
+        _container_only("FusionReduce")
+
+
+class CrossAttentionBlock(nn.Module):
+    """keys cross_attn.*, attn_ffn.{0,1,3}.* (reference :799-818)."""
+
+    def __init__(self, channels, num_heads=4):
+        super().__init__()
+        self.cross_attn = nn.MultiheadAttention(embed_dim=channels, num_heads=num_heads, batch_first=True)
+        self.attn_ffn = nn.Sequential(nn.LayerNorm(channels), nn.Linear(channels, channels), nn.GELU(),
+                                      nn.Linear(channels, channels))
+
+    def forward(self, query_tokens, key_value_tokens):
+        _container_only("CrossAttentionBlock")
+
+
+# --------------------------------------------------------------------------------------
+# weight packing helpers (one-off layout transforms; not on the per-batch path)
+# --------------------------------------------------------------------------------------
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _conv_w_bf16(conv, dev):
+    """[Cout,Cin,kh,kw] -> [Cout, kh*kw*Cin] bf16 (k = tap*Cin + c)."""
+    w = conv.weight.detach().to(dev)
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+
+
+def _bn_fold(bn, dev, conv_bias=None):
+    """Eval-mode BatchNorm as a per-channel affine; a preceding conv bias folds into the shift."""
+    g, b = _f32(bn.weight, dev), _f32(bn.bias, dev)
+    m, v = _f32(bn.running_mean, dev), _f32(bn.running_var, dev)
+    scale = g / torch.sqrt(v + bn.eps)
+    shift = b - m * scale
+    if conv_bias is not None:
+        shift = shift + _f32(conv_bias, dev) * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def _se_pack(se, dev):
+    c1, c2 = se.fc[1], se.fc[3]
+    return {"w1": _f32(c1.weight.flatten(1), dev), "b1": _f32(c1.bias, dev),
+            "w2": _f32(c2.weight.flatten(1), dev), "b2": _f32(c2.bias, dev),
+            "w1t": _f32(c1.weight.flatten(1).t(), dev), "w2t": _f32(c2.weight.flatten(1).t(), dev)}
+
+
+def _recon_pack(rh, dev):
+    s, b = _bn_fold(rh.conv[1], dev)
+    w3 = rh.conv[3].weight.detach().to(dev)  # [1,C,3,3]
+    if w3.shape[0] != 1:
+        raise NotImplementedError("reconstruction heads with recon_ch != 1")
+    return {"w0": _conv_w_bf16(rh.conv[0], dev), "s0": s, "b0": b,
+            "w3": w3[0].permute(1, 2, 0).reshape(9, -1).float().contiguous(), "b3": _f32(rh.conv[3].bias, dev)}
+
+
+def _proj_pack(pr, dev):
+    s0, b0 = _bn_fold(pr.proj[1], dev)
+    s3, b3 = _bn_fold(pr.proj[4], dev)
+    p = {"s0": s0, "b0": b0, "w3": _conv_w_bf16(pr.proj[3], dev), "s3": s3, "b3": b3}
+    if pr.proj[0].in_channels == 1:
+        p["w0_vec"] = _f32(pr.proj[0].weight.flatten(), dev)
+    else:
+        p["w0"] = _conv_w_bf16(pr.proj[0], dev)
+    return p
+
+
+def _block_pack(blk, dev):
+    p = {"bott": []}
+    for bt in blk.bottlenecks:
+        s1, b1 = _bn_fold(bt[1], dev)
+        s5, b5 = _bn_fold(bt[5], dev)
+        s8, b8 = _bn_fold(bt[8], dev)
+        p["bott"].append({"conv0": bt[0], "s1": s1, "b1": b1, "w4": _conv_w_bf16(bt[4], dev), "s5": s5, "b5": b5,
+                          "w7": _conv_w_bf16(bt[7], dev), "s8": s8, "b8": b8})
+    if blk.skip is not None:
+        ss, sb = _bn_fold(blk.skip[1], dev)
+        p["skip"] = {"conv": blk.skip[0], "s": ss, "b": sb}
+    if blk.se is not None:
+        p["se"] = _se_pack(blk.se, dev)
+    if blk.reconstruct is not None:
+        p["recon"] = _recon_pack(blk.reconstruct, dev)
+    return p
+
+
+def _state_signature(module):
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+def _as_nhwc_bf16(t):
+    """NCHW-shaped tensor -> NHWC bf16 contiguous buffer (zero-copy for our own channels_last views)."""
+    if not t.is_cuda:
+        raise nat.B200NativeError("feature maps must be CUDA tensors (no CPU path)")
+    v = t.permute(0, 2, 3, 1)
+    if v.dtype == torch.bfloat16 and v.is_contiguous():
+        return v
+    return v.to(torch.bfloat16).contiguous()
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+# --------------------------------------------------------------------------------------
+# encoder
+# --------------------------------------------------------------------------------------
+class ModelMaskHeadBackbone(nn.Module):
+    """DWI / DCE encoder (reference :481-733).  ``aux_mode``: "full" materialises every output of
+    the reference API; "logits" skips what the fusion logits do not depend on (reconstruction heads,
+    projectors, the encoder's own classifier) and returns None for those entries."""
+
+    def __init__(self, method, parameters_dict, backbone=None):
+        super().__init__()
+        self.method = method
+        self.channel_num = parameters_dict[f"{method}_channel_num"]
+        self.num_classes = parameters_dict["class_num"]
+        self.dim = parameters_dict["dim"]
+        _only_2d(self.dim)
+        mp = parameters_dict[f"{method}_model_parameters"]
+        self.enable_modality_attention = mp["enable_modality_attention"]
+        self.use_se = mp["use_se"]
+        self.use_hybrid_transformer = mp["use_hybrid_transformer"]
+        self.use_backbone = mp["use_backbone"]
+        self.channels = mp["channels"]
+        self.proj_dim = mp["proj_dim"]
+        self.dropout = mp["dropout"]
+        self.num_repeats = mp["repeat_blocks"]
+        self.mid_squeeze = mp["mid_squeeze"]
+        self.downsample = mp["downsample"]
+        self.downsample_each_repeat = mp["downsample_each_repeat"]
+        self.selected_indices_chains = mp["backbone_index_lists"]
+        self.backbone_out_channels = mp["backbone_out_channels"]
+        self.transformer_backbone = mp["transformer_backbone"]
+        maskp = mp["mask_parameters"]
+        self.mask_enabled = maskp["mask"]
+        self.mask_stage = maskp["mask_stage"].lower()
+        self.mask_size = maskp["mask_target_size"][0]
+        self.aux_mode = "full"
+        c1, c2, c3 = self.channels
+
+        self.proj_pool = nn.AdaptiveAvgPool2d((self.proj_dim, self.proj_dim))
+        self.backbone = backbone
+        if self.use_backbone:
+            self.backbone_adapter = BackboneAdapter(backbone=backbone, selected_indices_chains=self.selected_indices_chains,
+                                                    out_channels=(c1, c1, c2), is_transformer=self.transformer_backbone)
+            block1_in = c1
+        else:
+            block1_in = self.channel_num
+
+        def block(cin, cout, i, recon):
+            return ResNetLiteBlock_withRecon(cin, cout, downsample=self.downsample[i], recon_ch=recon,
+                                             use_se=self.use_se, dim=self.dim, dropout=self.dropout,
+                                             num_repeats=self.num_repeats[i],
+                                             downsample_each_repeat=self.downsample_each_repeat,
+                                             mid_squeeze=self.mid_squeeze)
+
+        self.block1 = block(block1_in, c1, 0, 1)
+        self.block2 = block(c1, c2, 1, 1)
+        if not self.use_hybrid_transformer:
+            self.block3 = block(c2, c3, 2, 0)
+        else:
+            from transformer_model import TransformerStage
+            self.transformer = TransformerStage(in_ch=c2, embed_dim=mp["transformer_embed_dim"],
+                                                depth=mp["transformer_depth"], heads=mp["transformer_heads"],
+                                                patch_size=mp["transformer_patch_size"], dim=self.dim)
+            self.trans_out_proj = nn.Conv2d(mp["transformer_embed_dim"], c3, kernel_size=1)
+
+        self.modality_attention = None
+        if self.enable_modality_attention:
+            if method == "dce":
+                self.modality_attention = TemporalAttention(self.channel_num, reduction=2)
+            elif method == "dwi":
+                self.modality_attention = ChannelAttention(self.channel_num, reduction=2)
+            else:
+                raise ValueError("Unknown method for modality attention.")
+        self.f2_weight = nn.Parameter(torch.tensor(0.5))
+        self.f3_weight = nn.Parameter(torch.tensor(0.5))
+        self.norm_f2 = nn.GroupNorm(c1, c1)
+        self.norm_f3 = nn.GroupNorm(c2, c2)
+        if self.mask_enabled:
+            self.f1_to_f2 = FeatureDownAlign(c1, c2, dim=self.dim, downsample=False)
+            self.f2_to_f3 = FeatureDownAlign(c2, c3, dim=self.dim, downsample=False)
+            mask_in = {"f1": c1, "f2": c2, "f3": c3}[self.mask_stage]
+            self.mask_head = MaskHeadResize(in_ch=mask_in, out_size=self.mask_size, dim=self.dim)
+            self.mask_spatial_attention = MaskGuidedSpatialAttention(in_channels_img=c3, in_channels_mask=1,
+                                                                     dim=self.dim)
+            if self.use_hybrid_transformer and self.mask_stage == "f3":
+                raise ValueError("mask_stage='f3' not supported with hybrid transformer")
+        self.classification_head = ClassificationHead(in_ch=c3, num_classes=self.num_classes, dim=self.dim)
+        self.proj_f1 = Projector(c1, self.proj_dim, dim=self.dim)
+        self.proj_f2 = Projector(c2, self.proj_dim, dim=self.dim)
+        self.proj_r1 = Projector(1, self.proj_dim, dim=self.dim)
+        self.proj_r2 = Projector(1, self.proj_dim, dim=self.dim)
+        self._pack_cache = None
+
+    # ---------------------------------------------------------------- packing ----
+    def _packed(self, dev):
+        sig = (str(dev), _state_signature(self))
+        if self._pack_cache is not None and self._pack_cache[0] == sig:
+            return self._pack_cache[1]
+        if self.use_backbone or self.use_hybrid_transformer:
+            raise NotImplementedError("backbone-adapter / hybrid-transformer encoders are not wired to the "
+                                      "B200 kernels yet (SURVEY.md section 8 rows a11-a14)")
+        if self.mask_enabled and self.mask_stage != "f2":
+            raise NotImplementedError("only mask_stage='f2' (the reference default) is built")
+        b1 = self.block1
+        if b1.stride not in (1, 2) or b1.skip is None or self.channel_num > 32:
+            raise NotImplementedError("block1 must read the raw (<=32 channel) input through a skip conv")
+        for blk in (self.block2, self.block3):
+            if blk.stride != 1:
+                raise NotImplementedError("stride-2 block2/block3 are not built (reference default is stride 1)")
+        pk = {"b1": _block_pack(self.block1, dev), "b2": _block_pack(self.block2, dev),
+              "b3": _block_pack(self.block3, dev)}
+        # stem: skip conv and first bottleneck conv of block1 concatenated, fp32
+        bt0 = pk["b1"]["bott"][0]
+        wskip = pk["b1"]["skip"]["conv"].weight.detach().to(dev).flatten(1).float()
+        wmid = bt0["conv0"].weight.detach().to(dev).flatten(1).float()
+        pk["stem"] = {"w": torch.cat([wskip, wmid], 0).contiguous(),
+                      "s": torch.cat([pk["b1"]["skip"]["s"], bt0["s1"]]).contiguous(),
+                      "b": torch.cat([pk["b1"]["skip"]["b"], bt0["b1"]]).contiguous(),
+                      "n_skip": wskip.shape[0], "n_mid": wmid.shape[0]}
+        for name in ("b2", "b3"):
+            blk = pk[name]
+            if "skip" in blk:
+                blk["skip"]["w"] = _conv_w_bf16(blk["skip"]["conv"], dev)
+            for bt in blk["bott"]:
+                bt["w0"] = _conv_w_bf16(bt["conv0"], dev)
+        for bt in pk["b1"]["bott"][1:]:
+            bt["w0"] = _conv_w_bf16(bt["conv0"], dev)
+        if self.modality_attention is not None:
+            pk["mod_se"] = _se_pack(self.modality_attention, dev)
+        if self.mask_enabled:
+            al = self.f1_to_f2.proj
+            if isinstance(al, nn.Identity):
+                raise NotImplementedError("f1_to_f2 identity (c1 == c2)")
+            s, b = _bn_fold(al[1], dev)
+            mh, ma = self.mask_head, self.mask_spatial_attention
+            mproc = ma.mask_processor
+            pk["mask"] = {
+                "align_w": _conv_w_bf16(al[0], dev), "align_s": s, "align_b": b,
+                "pre_w": _conv_w_bf16(mh.pre, dev), "pre_b": _f32(mh.pre.bias, dev),
+                "out_w": _f32(mh.out.weight.flatten(), dev), "out_b": _f32(mh.out.bias, dev),
+                "attn": (mproc[0].out_channels, _f32(mproc[0].weight.flatten(), dev), _f32(mproc[1].weight, dev),
+                         _f32(mproc[1].bias, dev), _f32(mproc[3].weight.flatten(), dev), _f32(mproc[3].bias, dev),
+                         mproc[1].eps),
+                "gamma": _f32(ma.gamma, dev).reshape(1),
+            }
+        pk["head"] = {"w": _f32(self.classification_head.fc.weight, dev), "b": _f32(self.classification_head.fc.bias, dev)}
+        pk["proj"] = {n: _proj_pack(getattr(self, n), dev) for n in ("proj_f1", "proj_f2", "proj_r1", "proj_r2")}
+        self._pack_cache = (sig, pk)
+        return pk
+
+    # ---------------------------------------------------------------- forward ----
+    def _run_block(self, pk, mid, skip, need_recon):
+        """`mid` = output of the first bottleneck conv (+BN+GELU); `skip` = identity branch (both NHWC bf16)."""
+        bt = pk["bott"][0]
+        B, H, W, _ = mid.shape
+        dev = mid.device
+        t = nat.conv_gemm(mid, bt["w4"], taps=9, scale=bt["s5"], bias=bt["b5"], act=1)
+        cout = bt["w7"].shape[0]
+        gap = torch.zeros((B, cout), dtype=torch.float32, device=dev)
+        if len(pk["bott"]) > 1:
+            raise NotImplementedError("repeat_blocks > 1")
+        out = nat.conv_gemm(t, bt["w7"], taps=1, scale=bt["s8"], bias=bt["b8"], res=skip, res_mode=1, act=1, gap=gap)
+        gate = None
+        if "se" in pk:
+            se = pk["se"]
+            gate = torch.empty((B, cout), dtype=torch.float32, device=dev)
+            nat.se_gate(gap, H * W, se["w1t"], se["b1"], se["w2t"], se["b2"], gate)
+            nat.scale_map(out, out, gate=gate)
+        rec = None
+        if need_recon and "recon" in pk:
+            rc = pk["recon"]
+            t2 = nat.conv_gemm(out, rc["w0"], taps=9, scale=rc["s0"], bias=rc["b0"], act=1)
+            rec = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+            nat.conv3x3_c1(t2, rc["w3"], rc["b3"], rec)
+        return out, rec, gap, gate
+
+    def _block_from_map(self, pk, x, need_recon):
+        bt = pk["bott"][0]
+        skip = nat.conv_gemm(x, pk["skip"]["w"], taps=1, scale=pk["skip"]["s"], bias=pk["skip"]["b"]) \
+            if "skip" in pk else x
+        mid = nat.conv_gemm(x, bt["w0"], taps=1, scale=bt["s1"], bias=bt["b1"], act=1)
+        return self._run_block(pk, mid, skip, need_recon)
+
+    def _project(self, pp, src, up2):
+        if "w0_vec" in pp:  # 1-channel fp32 source map
+            B, H, W = src.shape
+            g = torch.empty((B, H, W, pp["w0_vec"].numel()), dtype=torch.bfloat16, device=src.device)
+            nat.lift_c1(src, pp["w0_vec"], pp["s0"], pp["b0"], g)
+        else:
+            g = nat.conv_gemm(src, pp["w0"], taps=1, scale=pp["s0"], bias=pp["b0"], act=1)
+        return nat.conv_gemm(g, pp["w3"], taps=1, scale=pp["s3"], bias=pp["b3"], act=1, up2=up2)
+
+    def forward(self, x, masks=None, plane_mean=None):
+        """x [B,C,H,W] normalised fp32.  `plane_mean` (optional, [B*C] fp32) is the per-plane mean the
+        normaliser kernels can emit, which saves one pass over x."""
+        if self.training:
+            raise NotImplementedError("training-mode forward is not built in the B200 path yet; call .eval()")
+        if not x.is_cuda:
+            raise nat.B200NativeError("ModelMaskHeadBackbone.forward needs a CUDA tensor (no CPU path)")
+        full = self.aux_mode == "full"
+        dev = x.device
+        pk = self._packed(dev)
+        x = x.contiguous().float()
+        B, C, H, W = x.shape
+        st = pk["stem"]
+        stride = self.block1.stride
+        Ho, Wo = H // stride, W // stride
+        se = None
+        mod_attn = None
+        if "mod_se" in pk:
+            if plane_mean is None:
+                plane_mean = torch.empty(B * C, dtype=torch.float32, device=dev)
+                nat.plane_mean(x, B * C, H * W, plane_mean)
+            ms = pk["mod_se"]
+            se = (ms["w1"], ms["b1"], ms["w2"], ms["b2"])
+            mod_attn = torch.empty((B, C), dtype=torch.float32, device=dev)
+        skip1 = torch.empty((B, Ho, Wo, st["n_skip"]), dtype=torch.bfloat16, device=dev)
+        mid1 = torch.empty((B, Ho, Wo, st["n_mid"]), dtype=torch.bfloat16, device=dev)
+        nat.stem(x, stride, plane_mean, se, st["w"], st["s"], st["b"], st["n_skip"], st["n_mid"], skip1, mid1, mod_attn)
+
+        f1, r1, _, _ = self._run_block(pk["b1"], mid1, skip1, full)
+        f2, r2, _, _ = self._block_from_map(pk["b2"], f1, full)
+        mask_pred = attn_map = None
+        if self.mask_enabled:
+            mk = pk["mask"]
+            m_in = nat.conv_gemm(f1, mk["align_w"], taps=1, scale=mk["align_s"], bias=mk["align_b"], act=1, res=f2,
+                                 res_mode=2)
+            mpre = nat.conv_gemm(m_in, mk["pre_w"], taps=1, bias=mk["pre_b"])
+            if mpre.shape[1] != self.mask_size:
+                raise NotImplementedError("mask head resize paths (input != 32x32) are not built")
+            mask_pred = torch.empty((B, 1, Ho, Wo), dtype=torch.float32, device=dev)
+            attn_map = torch.empty((B, 1, Ho, Wo), dtype=torch.float32, device=dev)
+            nat.mask_tail(mpre, mk["out_w"], mk["out_b"], mask_pred, mk["attn"], attn_map)
+            nat.scale_map(f2, f2, attn=attn_map, gamma=mk["gamma"])
+        f3, _, gap3, gate3 = self._block_from_map(pk["b3"], f2, False)
+
+        logits = None
+        p1 = p1r = p2 = p2r = None
+        if full:
+            logits = torch.empty((B, self.num_classes), dtype=torch.float32, device=dev)
+            nat.cls_head(gap3, gate3, Ho * Wo, pk["head"]["w"], pk["head"]["b"], self.classification_head.normalize,
+                         logits)
+            if self.proj_dim == 2 * Ho:
+                up2 = True
+            elif self.proj_dim == Ho:
+                up2 = False
+            else:
+                raise NotImplementedError("proj_pool ratios other than 1x / 2x")
+            pj = pk["proj"]
+            p1 = _nchw(self._project(pj["proj_f1"], f1, up2))
+            p2 = _nchw(self._project(pj["proj_f2"], f2, up2))
+            p1r = _nchw(self._project(pj["proj_r1"], r1, up2))
+            p2r = _nchw(self._project(pj["proj_r2"], r2, up2))
+        aux = {
+            "raw_feats": [_nchw(f1), _nchw(f2), _nchw(f3)],
+            "recon_feats": [r1.unsqueeze(1) if r1 is not None else None, r2.unsqueeze(1) if r2 is not None else None],
+            "proj_pairs": [p1, p1r, p2, p2r],
+            "mask_attn_map": attn_map,
+            "mod_attn_map": mod_attn.view(B, C, 1, 1) if mod_attn is not None else None,
+        }
+        return logits, aux, mask_pred
+
+
+# --------------------------------------------------------------------------------------
+# fusion
+# --------------------------------------------------------------------------------------
+def _bilinear_axis_weights(n_in, n_out):
+    """Mean weight each source cell receives under F.interpolate(bilinear, align_corners=False)."""
+    w = [0.0] * n_in
+    scale = n_in / n_out
+    for d in range(n_out):
+        s = max((d + 0.5) * scale - 0.5, 0.0)
+        i0 = int(s)
+        i1 = min(i0 + 1, n_in - 1)
+        lam = s - i0
+        w[i0] += (1.0 - lam) / n_out
+        w[i1] += lam / n_out
+    return w
+
+
+class FusionModel(nn.Module):
+    """Late-fusion head (reference :821-1000).  The reference's cat -> fusion_conv_reduce -> refine
+    branch (:935-940) never reaches an output, so it is not evaluated (its parameters exist for
+    state_dict compatibility)."""
+
+    def __init__(self, parameters_dict):
+        super().__init__()
+        fc = parameters_dict["fusion_model_parameters"]
+        fs = fc["fusion_specific_parameters"]
+        self.dim = parameters_dict["dim"]
+        _only_2d(self.dim)
+        self.num_classes = parameters_dict["class_num"]
+        self.fusion_channels = fs["fusion_channels"]
+        self.token_pool = fs["token_pool"]
+        self.mha_heads = fs["mha_heads"]
+        self.dwi_ch, self.dce_ch = fs["dwi_out_channels"], fs["dce_out_channels"]
+        self.use_cross_attention = fs["use_cross_attention"]
+        self.use_mask_attention = fs["use_mask_attention"]
+        self.fusion_recon_ch = fs["fusion_recon_ch"]
+        self.proj_dim = fc["proj_dim"]
+        self.mask_size = fc["mask_parameters"]["mask_target_size"][0]
+        self.dropout = fc["dropout"]
+        self.use_se_in_fusion = fc["use_se"]
+        self.aux_mode = "full"
+        c = self.fusion_channels
+        self.proj_in_dwi = nn.Conv2d(self.dwi_ch, c, 1, bias=False) if self.dwi_ch != c else nn.Identity()
+        self.proj_in_dce = nn.Conv2d(self.dce_ch, c, 1, bias=False) if self.dce_ch != c else nn.Identity()
+        self.fusion_conv_reduce = FusionReduce(2 * c, c, dim=self.dim)
+        self.refine_act = nn.GELU()
+        self.fusion_se = SEBlock(c, reduction=2, dim=self.dim) if self.use_se_in_fusion else None
+        self.gating = GatingAttention(feat_dim=c, use_mask_attention=self.use_mask_attention, dim=self.dim)
+        self.refine = ResNetLiteBlock_withRecon(in_ch=c, out_ch=c, dim=self.dim, dropout=self.dropout, mid_squeeze=2)
+        if self.use_cross_attention:
+            self.cross_attn_block = CrossAttentionBlock(c, num_heads=self.mha_heads)
+        self.mask_head = MaskHeadResize(in_ch=c, out_size=self.mask_size, dim=self.dim)
+        self.fusion_reconstruct = ReconHead(in_ch=c, recon_ch=self.fusion_recon_ch, upsample=False, dim=self.dim)
+        self.classifier = nn.Sequential(nn.AdaptiveAvgPool2d((1, 1)), nn.Flatten(), nn.Linear(c, self.num_classes))
+        self.projF = Projector(in_ch=c, proj_dim=self.proj_dim, dim=self.dim)
+        self._pack_cache = None
+
+    def _packed(self, dev, H, W):
+        sig = (str(dev), H, W, _state_signature(self))
+        if self._pack_cache is not None and self._pack_cache[0] == sig:
+            return self._pack_cache[1]
+        if isinstance(self.proj_in_dwi, nn.Identity) or isinstance(self.proj_in_dce, nn.Identity):
+            raise NotImplementedError("encoder channels == fusion_channels (identity proj_in) is not built")
+        c = self.fusion_channels
+        hp, wp = self.token_pool
+        keep = {}
+        w = nat.FusionWeights()
+        w.C, w.T, w.heads, w.num_classes = c, hp * wp, self.mha_heads, self.num_classes
+        w.use_cross_attention = int(self.use_cross_attention)
+        w.use_mask_attention = int(self.use_mask_attention)
+        w.use_se = int(self.fusion_se is not None)
+
+        def put(name, t):
+            keep[name] = _f32(t, dev)
+            setattr(w, name, keep[name].data_ptr())
+
+        put("gate_w", self.gating.fc.weight)
+        put("gate_b", self.gating.fc.bias)
+        if self.use_cross_attention:
+            ca = self.cross_attn_block
+            put("in_proj_wt", ca.cross_attn.in_proj_weight.t())
+            put("in_proj_b", ca.cross_attn.in_proj_bias)
+            put("out_proj_wt", ca.cross_attn.out_proj.weight.t())
+            put("out_proj_b", ca.cross_attn.out_proj.bias)
+            put("ln_w", ca.attn_ffn[0].weight)
+            put("ln_b", ca.attn_ffn[0].bias)
+            w.ln_eps = ca.attn_ffn[0].eps
+            put("ffn1_wt", ca.attn_ffn[1].weight.t())
+            put("ffn1_b", ca.attn_ffn[1].bias)
+            put("ffn2_wt", ca.attn_ffn[3].weight.t())
+            put("ffn2_b", ca.attn_ffn[3].bias)
+            ah, aw = _bilinear_axis_weights(hp, H), _bilinear_axis_weights(wp, W)
+            put("up_coef", torch.tensor([ah[i] * aw[j] for i in range(hp) for j in range(wp)]))
+        if self.fusion_se is not None:
+            se = _se_pack(self.fusion_se, dev)
+            w.se_mid = se["b1"].numel()
+            put("se_w1t", se["w1t"])
+            put("se_b1", se["b1"])
+            put("se_w2t", se["w2t"])
+            put("se_b2", se["b2"])
+        put("cls_w", self.classifier[2].weight)
+        put("cls_b", self.classifier[2].bias)
+        mh = self.mask_head
+        pk = {"w": w, "keep": keep,
+              "in_dwi": _conv_w_bf16(self.proj_in_dwi, dev), "in_dce": _conv_w_bf16(self.proj_in_dce, dev),
+              "mask_pre_w": _conv_w_bf16(mh.pre, dev), "mask_pre_b": _f32(mh.pre.bias, dev),
+              "mask_out_w": _f32(mh.out.weight.flatten(), dev), "mask_out_b": _f32(mh.out.bias, dev),
+              "recon": _recon_pack(self.fusion_reconstruct, dev), "projF": _proj_pack(self.projF, dev)}
+        self._pack_cache = (sig, pk)
+        return pk
+
+    def forward(self, raw_feats_dwi, raw_feats_dce, dwi_mask_pred=None, dce_mask_pred=None):
+        if self.training:
+            raise NotImplementedError("training-mode forward is not built in the B200 path yet; call .eval()")
+        f3d, f3c = _as_nhwc_bf16(raw_feats_dwi[-1]), _as_nhwc_bf16(raw_feats_dce[-1])
+        B, H, W, _ = f3d.shape
+        dev = f3d.device
+        pk = self._packed(dev, H, W)
+        c = self.fusion_channels
+        hp, wp = self.token_pool
+        full = self.aux_mode == "full"
+        if self.use_mask_attention and (dwi_mask_pred is None or dce_mask_pred is None):
+            # the reference feeds a 2C vector into a (2C+2)-input Linear in this case and raises too
+            raise RuntimeError("use_mask_attention needs both encoder mask predictions")
+        pv_d = torch.zeros((B, c), dtype=torch.float32, device=dev)
+        pv_c = torch.zeros((B, c), dtype=torch.float32, device=dev)
+        p_dwi = nat.conv_gemm(f3d, pk["in_dwi"], taps=1, gap=pv_d)
+        p_dce = nat.conv_gemm(f3c, pk["in_dce"], taps=1, gap=pv_c)
+        tok_d = tok_c = attn_w = lowres = None
+        if self.use_cross_attention:
+            tok_d = torch.empty((B, hp * wp, c), dtype=torch.float32, device=dev)
+            tok_c = torch.empty_like(tok_d)
+            nat.fusion_tokens(p_dwi, hp, wp, tok_d)
+            nat.fusion_tokens(p_dce, hp, wp, tok_c)
+            attn_w = torch.empty((B, hp * wp, hp * wp), dtype=torch.float32, device=dev)
+            lowres = torch.empty((B, hp * wp, c), dtype=torch.float32, device=dev)
+        gating = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        gate = torch.empty((B, c), dtype=torch.float32, device=dev)
+        logits = torch.empty((B, self.num_classes), dtype=torch.float32, device=dev)
+        md = mc = None
+        npix_mask = 0
+        if self.use_mask_attention:
+            md = dwi_mask_pred.contiguous().float()
+            mc = dce_mask_pred.contiguous().float()
+            npix_mask = md[0].numel()
+        nat.fusion_core(pk["w"], B, pv_d, pv_c, H * W, md, mc, npix_mask, tok_d, tok_c, gating, attn_w, lowres, gate,
+                        logits)
+        fused = torch.empty((B, H, W, c), dtype=torch.bfloat16, device=dev)
+        nat.fusion_mix(p_dwi, p_dce, gating, lowres, gate if self.fusion_se is not None else None, hp, wp, fused)
+        mask_logits = recon = proj = None
+        if full:
+            mpre = nat.conv_gemm(fused, pk["mask_pre_w"], taps=1, bias=pk["mask_pre_b"])
+            if H != self.mask_size:
+                raise NotImplementedError("mask head resize paths (input != 32x32) are not built")
+            mask_logits = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+            nat.mask_tail(mpre, pk["mask_out_w"], pk["mask_out_b"], mask_logits)
+            rc = pk["recon"]
+            t = nat.conv_gemm(fused, rc["w0"], taps=9, scale=rc["s0"], bias=rc["b0"], act=1)
+            recon = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+            nat.conv3x3_c1(t, rc["w3"], rc["b3"], recon)
+            pj = pk["projF"]
+            g = nat.conv_gemm(fused, pj["w0"], taps=1, scale=pj["s0"], bias=pj["b0"], act=1)
+            proj = _nchw(nat.conv_gemm(g, pj["w3"], taps=1, scale=pj["s3"], bias=pj["b3"], act=1))
+        aux = {"proj_fused": proj, "recon_fused": recon, "gating_weights": gating, "attn_weights": attn_w,
+               "p_dwi": _nchw(p_dwi), "p_dce": _nchw(p_dce)}
+        return logits, mask_logits, aux
+
+
+# --------------------------------------------------------------------------------------
+# initialisation (reference :1002-1023)
+# --------------------------------------------------------------------------------------
+def init_parameter(model):
+    """Linear: Kaiming-uniform weight, zero bias.  BatchNorm: weight ~ N(1, 0.02), zero bias."""
+    if isinstance(model, nn.Linear):
+        if model.weight is not None:
+            init.kaiming_uniform_(model.weight.data)
+        if model.bias is not None:
+            init.constant_(model.bias.data, 0)
+    elif isinstance(model, (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)):
+        if model.weight is not None:
+            init.normal_(model.weight.data, mean=1, std=0.02)
+        if model.bias is not None:
+            init.constant_(model.bias.data, 0)
+
+
+def initialize_model(model, requires_grad):
+    for param in model.parameters():
+        param.requires_grad = requires_grad
+    model.apply(init_parameter)
+    return model

@@ -1,0 +1,97 @@
+"""Batched dual-modality classification pipeline: raw ROIs -> logits.
+
+This is the B200 arrangement of the reference's inference path: per-sample CPU normalisation
+in the dataset (code/dataset.py:70-98) + `fusion_model_test`'s per-batch loop
+(code/model_test.py:114-155) / `LightningFusionModel.forward_from_inputs`
+(code/train_fusion.py:670-677) become one device-resident step:
+
+    DWINormalize.batch, DCENormalize.batch  ->  dwi_model, dce_model  ->  fusion_model
+
+The per-plane means the normaliser kernels emit feed the encoders' modality SE block, so the
+normalised inputs are read once.  `classify_host` is the end-to-end entry: pinned host
+tensors in, host logits out, with the next batch's upload overlapped on a copy stream.
+"""
+from __future__ import annotations
+
+import torch
+
+import b200_native as nat
+from dataset import DCENormalize, DWINormalize
+
+
+class FusionPipeline:
+    def __init__(self, dwi_model, dce_model, fusion_model, nyul_standardizer, dwi_normalize=None, aux_mode="full"):
+        self.dwi_model, self.dce_model, self.fusion_model = dwi_model, dce_model, fusion_model
+        self.dwi_norm = dwi_normalize if dwi_normalize is not None else DWINormalize()
+        self.dce_norm = DCENormalize(nyul_standardizer)
+        self.set_aux_mode(aux_mode)
+        self._copy_stream = None
+
+    def set_aux_mode(self, mode):
+        if mode not in ("full", "logits"):
+            raise ValueError("aux_mode must be 'full' or 'logits'")
+        self.aux_mode = mode
+        for m in (self.dwi_model, self.dce_model, self.fusion_model):
+            m.aux_mode = mode
+
+    def eval(self):
+        for m in (self.dwi_model, self.dce_model, self.fusion_model):
+            m.eval()
+        return self
+
+    @torch.no_grad()
+    def forward_raw(self, dwi_raw, dce_raw, return_all=False):
+        """dwi_raw [B,Cd,H,W], dce_raw [B,Cc,H,W] fp32 CUDA (DCE already divided by the case max,
+        code/prepare_single_model.py:338-339).  Returns fusion logits [B,K] (fp32)."""
+        B = dwi_raw.shape[0]
+        dev = dwi_raw.device
+        pm_d = torch.empty(B * dwi_raw.shape[1], dtype=torch.float32, device=dev)
+        pm_c = torch.empty(B * dce_raw.shape[1], dtype=torch.float32, device=dev)
+        dwi = self.dwi_norm.batch(dwi_raw, plane_mean=pm_d)
+        dce = self.dce_norm.batch(dce_raw, plane_mean=pm_c)
+        out_d = self.dwi_model(dwi, None, plane_mean=pm_d)
+        out_c = self.dce_model(dce, None, plane_mean=pm_c)
+        out_f = self.fusion_model(out_d[1]["raw_feats"], out_c[1]["raw_feats"], out_d[2], out_c[2])
+        if return_all:
+            return out_d, out_c, out_f
+        return out_f[0]
+
+    @torch.no_grad()
+    def classify_host(self, batches, device="cuda"):
+        """End-to-end: iterable of (dwi_host, dce_host) PINNED fp32 CPU tensors -> list of host logits.
+        Upload of batch i+1 runs on a copy stream while batch i computes."""
+        dev = torch.device(device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        compute = torch.cuda.current_stream(dev)
+        results, staged = [], None
+
+        def upload(pair):
+            with torch.cuda.stream(self._copy_stream):
+                d = pair[0].to(dev, non_blocking=True)
+                c = pair[1].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            return d, c, ev
+
+        it = iter(batches)
+        try:
+            staged = upload(next(it))
+        except StopIteration:
+            return results
+        while staged is not None:
+            d, c, ev = staged
+            try:
+                nxt = upload(next(it))
+            except StopIteration:
+                nxt = None
+            compute.wait_event(ev)
+            d.record_stream(compute)
+            c.record_stream(compute)
+            logits = self.forward_raw(d, c)
+            host = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
+            host.copy_(logits, non_blocking=True)
+            results.append(host)
+            staged = nxt
+        compute.synchronize()
+        return results
