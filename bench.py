@@ -302,7 +302,7 @@ def main():
         for (name, key), times in prof.items():
             table[(name, key)] = (statistics.mean(times), len(times))
             total_ms += sum(times)
-        dom_key = ("b200_conv_gemm", (B, 32, 32, 256, 256, 9))
+        dom_key = ("b200_conv_gemm_ex", (B, 32, 32, 256, 256, 9))
         dom_ms, _ = table.get(dom_key, (None, 0))
         roofline = None
         if dom_ms:
@@ -313,7 +313,7 @@ def main():
                         "kernel": "conv_gemm_kernel<256> 3x3 256->256 @32x32",
                         "ms_per_launch": dom_ms, "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
                         "share_of_step": sum(prof[dom_key]) / total_ms if total_ms else None}
-        conv_ms = sum(sum(t) for (n, _), t in prof.items() if n == "b200_conv_gemm")
+        conv_ms = sum(sum(t) for (n, _), t in prof.items() if n == "b200_conv_gemm_ex")
         kernels = sorted(((sum(t), n, k, len(t)) for (n, k), t in prof.items()), reverse=True)[:8]
         nsteps_prof = max(2, min(args.steps, 5))
         flop_case = FLOP_PER_CASE_FULL if args.aux == "full" else FLOP_PER_CASE_LOGITS

@@ -48,6 +48,9 @@ _P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 SIGNATURES = {
     "b200_abi_version": [],
     "b200_conv_gemm": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b200_conv_gemm_ex": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I,
+                          _I, _P],
+    "b200_tapsum": [_P, _I, _I, _I, _P, _P, _P],
     "b200_dwi_normalize": [_P, _P, _I, _I, _I, _I, _F, _F, _P, _P],
     "b200_nyul_transform": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "b200_plane_mean": [_P, _I, _I, _P, _P],
@@ -143,24 +146,35 @@ def _bf16_map(t, name):
 
 
 def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0, out=None, up2=False, gap=None,
-              cin=None, store=True):
-    """x [B,H,W,ld] bf16 NHWC (channels [0,cin) used); w [Cout, taps*cin] bf16.  Returns `out`."""
+              cin=None, store=True, n_split=None, act2=0, out2=None, dot_w=None, dot_out=None):
+    """x [B,H,W,ld] bf16 NHWC (channels [0,cin) used); w [Cout, taps*cin] bf16.  Returns `out`
+    (or (out, out2) when n_split is given: channels [n_split, Cout) form a second layer on the same input)."""
     _bf16_map(x, "x")
     B, H, W, x_ld = x.shape
     cin = x_ld if cin is None else cin
     cout = w.shape[0]
     assert w.dtype == torch.bfloat16 and w.is_contiguous() and w.shape[1] == taps * cin
+    n1 = cout if n_split is None else n_split
     if out is None and store:
         oh, ow = (2 * H, 2 * W) if up2 else (H, W)
-        out = torch.empty((B, oh, ow, cout), dtype=torch.bfloat16, device=x.device)
+        out = torch.empty((B, oh, ow, n1), dtype=torch.bfloat16, device=x.device)
+    if n_split is not None and out2 is None:
+        out2 = torch.empty((B, H, W, cout - n_split), dtype=torch.bfloat16, device=x.device)
     out_ld = out.shape[-1] if out is not None else 0
     if out is not None:
         _bf16_map(out, "out")
     if res is not None:
         _bf16_map(res, "res")
-    _call("b200_conv_gemm", (B, H, W, cin, cout, taps), _ptr(x), x_ld, _ptr(w), _ptr(scale), _ptr(bias), _ptr(res),
+    _call("b200_conv_gemm_ex", (B, H, W, cin, cout, taps), _ptr(x), x_ld, _ptr(w), _ptr(scale), _ptr(bias), _ptr(res),
           res.shape[-1] if res is not None else 0, res_mode, act, _ptr(out), out_ld,
-          1 if up2 else 0, _ptr(gap), B, H, W, cin, cout, taps, _stream())
+          1 if up2 else 0, _ptr(gap), n1, _ptr(out2), out2.shape[-1] if out2 is not None else 0, act2,
+          _ptr(dot_w), _ptr(dot_out), B, H, W, cin, cout, taps, _stream())
+    return out if n_split is None else (out, out2)
+
+
+def tapsum(d, bias, out):
+    B, H, W, _ = d.shape
+    _call("b200_tapsum", None, _ptr(d), B, H, W, _ptr(bias), _ptr(out), _stream())
     return out
 
 

@@ -43,8 +43,17 @@ struct ConvGemmParams {
     int act;               // 0 none, 1 GELU(erf)
     __nv_bfloat16* out;
     int out_ld;
+    int tma_epi;           // 1: outputs / residual go through shared memory + TMA (coalesced); 0: direct
     int up2;               // replicate every output pixel into a 2x2 block of a [B,2H,2W,ld] map
     float* gap;            // [B, Cout] fp32 sums over the pixels of each case, or nullptr
+    // second output segment: channels [n_split, Cout) go to out2 with their own activation flag
+    int n_split;           // == Cout when unused
+    __nv_bfloat16* out2;
+    int out2_ld;
+    int act2;
+    // fused N=9 pointwise projection of the epilogue result (tap dot-products of a following 3x3, C->1 conv)
+    const float* dot_w;    // [9, Cout] fp32 or nullptr
+    float* dot_out;        // [pixels, 9] fp32
 };
 
 constexpr int kBlockM = 128;
@@ -58,17 +67,41 @@ template <int BN>
 struct Tile {
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (192 * 1024) / kStageBytes;
+    static constexpr int kStages = (176 * 1024) / kStageBytes;  // 3 / 5 / 7 stages for BN = 256 / 128 / 64
     static constexpr int kTmemCols = 2 * BN;  // two accumulator stages: 128 / 256 / 512 columns
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kDotWBytes = 9 * BN * 4;          // dot weights staged once per CTA
+    static constexpr int kDotSBytes = 2 * kBlockM * 9 * 4;  // half-1 partial sums, double buffered
+    // per epilogue warp: one 32x32 bf16 box (2 KB, 64-byte swizzle) for the output and one for the residual
+    static constexpr int kStageOutBytes = kNumEpiWarps * 2048;
+    static constexpr int kStageResBytes = kNumEpiWarps * 2048;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                      kDotWBytes + kDotSBytes + kStageOutBytes + kStageResBytes + 1024;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf(z) ~= z * P(z^2) on |z| <= 3 (odd minimax polynomial,
+// 8 terms, |erf error| < 9e-5, P(9)*3 == 1 so the clamp is continuous with +-1).  The result is rounded to
+// bf16 (relative step 4e-3), so the 1.8e-4 worst-case absolute deviation from the exact-erf GELU is below
+// one output ulp for |x| >= 0.05; it costs 14 issue slots against ~30 for erff().
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fminf(fmaxf(x * 0.70710678118654752f, -3.0f), 3.0f);
+    const float t = z * z;
+    float p = -3.901667185e-07f;
+    p = fmaf(p, t, 1.668003461e-05f);
+    p = fmaf(p, t, -3.086500801e-04f);
+    p = fmaf(p, t, 3.281538375e-03f);
+    p = fmaf(p, t, -2.256273106e-02f);
+    p = fmaf(p, t, 1.075116023e-01f);
+    p = fmaf(p, t, -3.730817735e-01f);
+    p = fmaf(p, t, 1.127865076e+00f);
+    const float h = 0.5f * x;
+    return fmaf(h, z * p, h);
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                 const __grid_constant__ CUtensorMap tmRes, const ConvGemmParams p) {
     using T = Tile<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -78,7 +111,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* empty = full + T::kStages;
     uint64_t* tfull = empty + T::kStages;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* resbar = tempty + 2;  // [kNumEpiWarps] residual-box arrival, one per epilogue warp
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resbar + kNumEpiWarps);
+    float* s_dotw = reinterpret_cast<float*>(smem + T::kStages * T::kStageBytes + 256);  // [9][BN]
+    float* s_dots = s_dotw + 9 * BN;                                                      // [2][128][9]
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(s_dots + 2 * kBlockM * 9) + 1023) & ~uintptr_t(1023));  // out boxes, then res boxes
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -87,6 +125,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (p.tma_epi) {
+            tma_prefetch_desc(&tmOut);
+            if (p.n_split < p.Cout) tma_prefetch_desc(&tmOut2);
+            if (p.res_mode != 0) tma_prefetch_desc(&tmRes);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < T::kStages; ++s) {
@@ -97,9 +140,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], kNumEpiWarps);
         }
+        for (int s = 0; s < kNumEpiWarps; ++s) mbar_init(&resbar[s], 1);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<T::kTmemCols>(tmem_slot);
+    if (p.dot_w != nullptr && warp >= kEpiWarp0) {
+        for (int i = threadIdx.x - kEpiWarp0 * 32; i < 9 * BN; i += kNumEpiWarps * 32) s_dotw[i] = p.dot_w[i];
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -170,6 +217,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;                  // TMEM lane quadrant this warp may read
         const int half = (warp - kEpiWarp0) >> 2;  // which half of the BLOCK_N columns
         constexpr int kChunks = BN / 64;         // 32-column chunks per warp
+        const int ew = warp - kEpiWarp0;
+        uint8_t* const obuf = s_stage + ew * 2048;
+        uint8_t* const rbuf = s_stage + T::kStageOutBytes + ew * 2048;
+        uint64_t* const rbar = &resbar[ew];
+        uint32_t rphase = 0;
+        // 64-byte swizzle of a 32x32 bf16 box: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)
+        const int swz = (lane >> 1) & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -183,20 +237,50 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int w = w0 + row % p.BW;
             const bool valid = (w < p.W) && (h < p.H);
             const long long pix = (static_cast<long long>(b) * p.H + h) * p.W + w;
+            // first output row of this warp's 32-row slab (rows of a tile are consecutive pixels)
+            const int slab_row0 = (b * p.H + h0) * p.W + w0 + q * 32;
 
+            const bool seg2 = n_tile * BN >= p.n_split;
+            __nv_bfloat16* const out_ptr = seg2 ? p.out2 : p.out;
+            const int out_ld = seg2 ? p.out2_ld : p.out_ld;
+            const int act = seg2 ? p.act2 : p.act;
+            const int res_mode = seg2 ? 0 : p.res_mode;
+            const int out_col_base = seg2 ? n_tile * BN - p.n_split : n_tile * BN;
+            const CUtensorMap* const tm_out = seg2 ? &tmOut2 : &tmOut;
+            const bool tma_res = p.tma_epi && res_mode != 0;
+            float dsum[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) dsum[k] = 0.f;
+
+            if (tma_res && lane == 0) {  // residual box of the first chunk: in flight while the MMAs finish
+                mbar_arrive_expect_tx(rbar, 2048);
+                tma_load_2d(rbuf, &tmRes, rbar, n_tile * BN + half * (BN / 2), slab_row0);
+            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
             for (int ch = 0; ch < kChunks; ++ch) {
                 const int col0 = half * (BN / 2) + ch * 32;
                 const int n0 = n_tile * BN + col0;
+                const int oc0 = out_col_base + col0;
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0, r);
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (p.scale != nullptr) {
+                if (p.scale != nullptr && p.bias != nullptr) {
+                    const float4* s4 = reinterpret_cast<const float4*>(p.scale + n0);
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 s = __ldg(s4 + j), t = __ldg(b4 + j);
+                        v[4 * j + 0] = fmaf(v[4 * j + 0], s.x, t.x);
+                        v[4 * j + 1] = fmaf(v[4 * j + 1], s.y, t.y);
+                        v[4 * j + 2] = fmaf(v[4 * j + 2], s.z, t.z);
+                        v[4 * j + 3] = fmaf(v[4 * j + 3], s.w, t.w);
+                    }
+                } else if (p.scale != nullptr) {
                     const float4* s4 = reinterpret_cast<const float4*>(p.scale + n0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -206,8 +290,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         v[4 * j + 2] *= s.z;
                         v[4 * j + 3] *= s.w;
                     }
-                }
-                if (p.bias != nullptr) {
+                } else if (p.bias != nullptr) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -218,39 +301,72 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         v[4 * j + 3] += s.w;
                     }
                 }
-                float rres[32];
-                if (p.res_mode != 0) {
-                    if (valid) {
+                if (res_mode != 0) {
+                    uint4 u[4];
+                    if (tma_res) {
+                        mbar_wait(rbar, rphase);
+                        rphase ^= 1;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            u[j] = *reinterpret_cast<const uint4*>(rbuf + lane * 64 + ((j ^ swz) << 4));
+                        __syncwarp();  // every lane has read the box before it is refilled
+                        if (ch + 1 < kChunks && lane == 0) {
+                            mbar_arrive_expect_tx(rbar, 2048);
+                            tma_load_2d(rbuf, &tmRes, rbar, n0 + 32, slab_row0);
+                        }
+                    } else if (valid) {
                         const uint4* r4 = reinterpret_cast<const uint4*>(p.res + pix * p.res_ld + n0);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint4 u = __ldg(r4 + j);
-                            const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&uu[t]);
-                                rres[8 * j + 2 * t + 0] = __low2float(h2);
-                                rres[8 * j + 2 * t + 1] = __high2float(h2);
-                            }
-                        }
+                        for (int j = 0; j < 4; ++j) u[j] = __ldg(r4 + j);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) rres[j] = 0.f;
+                        for (int j = 0; j < 4; ++j) u[j] = make_uint4(0u, 0u, 0u, 0u);
                     }
-                }
-                if (p.res_mode == 1) {
+                    float rres[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += rres[j];
-                }
-                if (p.act == 1) {
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t uu[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&uu[t]);
+                            rres[8 * j + 2 * t + 0] = __low2float(h2);
+                            rres[8 * j + 2 * t + 1] = __high2float(h2);
+                        }
+                    }
+                    if (res_mode == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += rres[j];
+                        if (act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                        }
+                    } else {
+                        if (act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += rres[j];
+                    }
+                } else if (act == 1) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                 }
-                if (p.res_mode == 2) {
+                if (p.dot_w != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += rres[j];
+                    for (int k = 0; k < 9; ++k) {
+                        const float4* w4 = reinterpret_cast<const float4*>(s_dotw + k * BN + col0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 wv = w4[j];
+                            dsum[k] = fmaf(v[4 * j + 0], wv.x, dsum[k]);
+                            dsum[k] = fmaf(v[4 * j + 1], wv.y, dsum[k]);
+                            dsum[k] = fmaf(v[4 * j + 2], wv.z, dsum[k]);
+                            dsum[k] = fmaf(v[4 * j + 3], wv.w, dsum[k]);
+                        }
+                    }
                 }
-                if (valid && p.out != nullptr) {
+                if (out_ptr != nullptr) {
                     uint4 o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -262,18 +378,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                         o[j] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
                     }
-                    if (!p.up2) {
-                        uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.out_ld + n0);
+                    if (p.tma_epi) {
+                        // stage the warp's 32x32 box in shared memory (conflict-free under the 64-byte swizzle)
+                        // and let the TMA write it: full 64-byte row segments, rows past the end are clipped
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) dst[j] = o[j];
-                    } else {
-#pragma unroll
-                        for (int rep = 0; rep < 4; ++rep) {
-                            const long long opix =
-                                (static_cast<long long>(b) * (2 * p.H) + 2 * h + (rep >> 1)) * (2 * p.W) + 2 * w + (rep & 1);
-                            uint4* dst = reinterpret_cast<uint4*>(p.out + opix * p.out_ld + n0);
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(obuf + lane * 64 + ((j ^ swz) << 4)) = o[j];
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(tm_out, obuf, oc0, slab_row0);
+                            tma_store_commit();
+                        }
+                    } else if (valid) {
+                        if (!p.up2) {
+                            uint4* dst = reinterpret_cast<uint4*>(out_ptr + pix * out_ld + oc0);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) dst[j] = o[j];
+                        } else {
+#pragma unroll
+                            for (int rep = 0; rep < 4; ++rep) {
+                                const long long opix =
+                                    (static_cast<long long>(b) * (2 * p.H) + 2 * h + (rep >> 1)) * (2 * p.W) + 2 * w +
+                                    (rep & 1);
+                                uint4* dst = reinterpret_cast<uint4*>(out_ptr + opix * out_ld + oc0);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) dst[j] = o[j];
+                            }
                         }
                     }
                 }
@@ -300,9 +433,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (p.dot_w != nullptr) {
+                // The two column halves of a row live in different warps: half 1 parks its 9 partial sums in
+                // shared memory (double buffered by accumulator stage), one named barrier over the 8 epilogue
+                // warps, half 0 adds its own and writes the row.  Deterministic, no atomics.
+                float* buf = s_dots + (acc * kBlockM + row) * 9;
+                if (half == 1) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) buf[k] = dsum[k];
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (half == 0 && valid) {
+                    float* dst = p.dot_out + pix * 9;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) dst[k] = dsum[k] + buf[k];
+                }
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (p.tma_epi && lane == 0) tma_store_wait_all<0>();  // global writes done before the CTA retires
     }
 
     tc_fence_before();
@@ -334,7 +484,8 @@ static EncodeTiledFn get_encode_fn() {
 static int g_num_sms = 0;
 
 template <int BN>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmOut2,
+                  const CUtensorMap& tmRes, const ConvGemmParams& p, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -344,15 +495,28 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemm
     }
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < g_num_sms ? total : g_num_sms;
-    conv_gemm_kernel<BN><<<grid, kThreads, Tile<BN>::kSmemBytes, stream>>>(tmA, tmB, p);
+    conv_gemm_kernel<BN><<<grid, kThreads, Tile<BN>::kSmemBytes, stream>>>(tmA, tmB, tmOut, tmOut2, tmRes, p);
     return static_cast<int>(cudaGetLastError());
 }
 
 }  // namespace b200
 
+extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
+                                 const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
+                                 float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w,
+                                 float* dot_out, int B, int H, int W, int Cin, int Cout, int taps, void* stream);
+
 extern "C" int b200_conv_gemm(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
                               const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
                               float* gap, int B, int H, int W, int Cin, int Cout, int taps, void* stream) {
+    return b200_conv_gemm_ex(x, x_ld, w, scale, bias, res, res_ld, res_mode, act, out, out_ld, up2, gap, Cout, nullptr,
+                             0, 0, nullptr, nullptr, B, H, W, Cin, Cout, taps, stream);
+}
+
+extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
+                                 const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
+                                 float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w,
+                                 float* dot_out, int B, int H, int W, int Cin, int Cout, int taps, void* stream) {
     using namespace b200;
     if (x == nullptr || w == nullptr || B <= 0 || H <= 0 || W <= 0) return -1;
     if (Cin % 64 != 0 || Cout % 64 != 0 || (taps != 1 && taps != 9)) return -2;
@@ -380,7 +544,15 @@ extern "C" int b200_conv_gemm(const void* x, int x_ld, const void* w, const floa
     p.H = H;
     p.W = W;
     p.Cout = Cout;
-    const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    if (n_split <= 0 || n_split > Cout || n_split % 64 != 0) return -10;
+    const bool two = n_split < Cout;
+    if (two && (out2 == nullptr || out2_ld % 8 != 0 || (reinterpret_cast<uintptr_t>(out2) & 15) || gap != nullptr ||
+                up2 || dot_w != nullptr))
+        return -11;
+    const int seg2 = Cout - n_split;
+    auto divides = [&](int bn) { return Cout % bn == 0 && n_split % bn == 0 && (!two || seg2 % bn == 0); };
+    const int BN = divides(256) ? 256 : (divides(128) ? 128 : 64);
+    if (dot_w != nullptr && (dot_out == nullptr || BN != Cout || H == 1)) return -12;  // needs one N tile per row
     p.n_tiles = Cout / BN;
     p.m_tiles = B * p.tiles_w * p.tiles_h;
     p.kc = Cin / 64;
@@ -396,6 +568,12 @@ extern "C" int b200_conv_gemm(const void* x, int x_ld, const void* w, const floa
     p.out_ld = out_ld;
     p.up2 = up2;
     p.gap = gap;
+    p.n_split = n_split;
+    p.out2 = static_cast<__nv_bfloat16*>(out2);
+    p.out2_ld = out2_ld;
+    p.act2 = act2;
+    p.dot_w = dot_w;
+    p.dot_out = dot_out;
 
     EncodeTiledFn encode = get_encode_fn();
     if (encode == nullptr) return -8;
@@ -430,8 +608,29 @@ extern "C" int b200_conv_gemm(const void* x, int x_ld, const void* w, const floa
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return -200 - static_cast<int>(r);
     }
+    // Row-major [rows, ld] views of the output(s) and the residual for the staged (TMA) epilogue: 32x32 boxes,
+    // 64-byte swizzle.  The 2x2-replicating store keeps the direct path (its rows are not consecutive).
+    CUtensorMap tmOut = tmA, tmOut2 = tmA, tmRes = tmA;
+    p.tma_epi = up2 ? 0 : 1;
+    if (p.tma_epi) {
+        const cuuint64_t rows = static_cast<cuuint64_t>(B) * H * W;
+        auto encode2d = [&](CUtensorMap* tm, const void* base, int cols, int ld) -> int {
+            const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), rows};
+            const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+            const cuuint32_t box[2] = {32, 32};
+            const cuuint32_t estr[2] = {1, 1};
+            CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            return r == CUDA_SUCCESS ? 0 : -300 - static_cast<int>(r);
+        };
+        int rc = 0;
+        if (out != nullptr && (rc = encode2d(&tmOut, out, n_split, out_ld)) != 0) return rc;
+        if (two && (rc = encode2d(&tmOut2, out2, seg2, out2_ld)) != 0) return rc;
+        if (res_mode != 0 && (rc = encode2d(&tmRes, res, n_split, res_ld)) != 0) return rc;
+    }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (BN == 256) return launch<256>(tmA, tmB, p, s);
-    if (BN == 128) return launch<128>(tmA, tmB, p, s);
-    return launch<64>(tmA, tmB, p, s);
+    if (BN == 256) return launch<256>(tmA, tmB, tmOut, tmOut2, tmRes, p, s);
+    if (BN == 128) return launch<128>(tmA, tmB, tmOut, tmOut2, tmRes, p, s);
+    return launch<64>(tmA, tmB, tmOut, tmOut2, tmRes, p, s);
 }

@@ -186,6 +186,26 @@ __global__ void conv3x3_c1_kernel(const __nv_bfloat16* __restrict__ x, int H, in
     if (lane == 0) out[warp_global] = acc + bias[0];
 }
 
+// ------------------------------------------------------ tap shift-sum ------
+// Second half of a 3x3, C -> 1 convolution whose per-tap dot products d[p][k] = sum_c x[p,c] w[k,c]
+// were produced by the preceding GEMM's epilogue (b200_conv_gemm_ex, dot_w):
+// out[b,h,w] = bias + sum_k d[(b, h+ky-1, w+kx-1)][k] with zero padding.
+__global__ void tapsum_kernel(const float* __restrict__ d, int H, int W, const float* __restrict__ bias,
+                              float* __restrict__ out, size_t total_pix) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= total_pix) return;
+    const int w = static_cast<int>(i % W);
+    const int h = static_cast<int>((i / W) % H);
+    float acc = bias[0];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int hh = h + k / 3 - 1, ww = w + k % 3 - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+            acc += d[(i + static_cast<long long>(k / 3 - 1) * W + (k % 3 - 1)) * 9 + k];
+    }
+    out[i] = acc;
+}
+
 // ------------------------------------------- mask head tail + attention ----
 // MaskHeadResize.out (model_module.py:187, 1x1 Cm->1 + bias) on the `pre` activations, then
 // MaskGuidedSpatialAttention.mask_processor (:67-73, :92-93): 1x1 1->Hc (no bias),
@@ -366,6 +386,16 @@ extern "C" int b200_conv3x3_c1(const void* x, int B, int H, int W, int C, const 
     const size_t blocks = (total_pix * 32 + 255) / 256;
     conv3x3_c1_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), H, W, C, w, bias, out, total_pix);
+    return launch_status();
+}
+
+extern "C" int b200_tapsum(const float* d, int B, int H, int W, const float* bias, float* out, void* stream) {
+    if (B < 0 || H <= 0 || W <= 0) return -1;
+    if (B == 0) return 0;
+    if (d == nullptr || bias == nullptr || out == nullptr) return -2;
+    const size_t total_pix = static_cast<size_t>(B) * H * W;
+    tapsum_kernel<<<static_cast<unsigned>((total_pix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d, H, W, bias, out, total_pix);
     return launch_status();
 }
 

@@ -367,6 +367,17 @@ def _nchw(t):
     return t.permute(0, 3, 1, 2)
 
 
+def _recon(rc, x):
+    """ReconHead (reference :113-118): 3x3 conv + BN + GELU on the tensor cores with the final 3x3, C->1
+    conv folded in - the GEMM epilogue emits the 9 per-tap dot products of its result, a shift-sum finishes
+    the convolution, and the intermediate C-channel map is never written to HBM."""
+    B, H, W, _ = x.shape
+    d = torch.empty((B, H, W, 9), dtype=torch.float32, device=x.device)
+    nat.conv_gemm(x, rc["w0"], taps=9, scale=rc["s0"], bias=rc["b0"], act=1, store=False, dot_w=rc["w3"], dot_out=d)
+    rec = torch.empty((B, H, W), dtype=torch.float32, device=x.device)
+    return nat.tapsum(d, rc["b3"], rec)
+
+
 # --------------------------------------------------------------------------------------
 # encoder
 # --------------------------------------------------------------------------------------
@@ -487,10 +498,15 @@ class ModelMaskHeadBackbone(nn.Module):
                       "n_skip": wskip.shape[0], "n_mid": wmid.shape[0]}
         for name in ("b2", "b3"):
             blk = pk[name]
-            if "skip" in blk:
-                blk["skip"]["w"] = _conv_w_bf16(blk["skip"]["conv"], dev)
             for bt in blk["bott"]:
                 bt["w0"] = _conv_w_bf16(bt["conv0"], dev)
+            if "skip" in blk:
+                blk["skip"]["w"] = _conv_w_bf16(blk["skip"]["conv"], dev)
+                b0 = blk["bott"][0]
+                blk["fused_in"] = {"w": torch.cat([blk["skip"]["w"], b0["w0"]], 0).contiguous(),
+                                   "s": torch.cat([blk["skip"]["s"], b0["s1"]]).contiguous(),
+                                   "b": torch.cat([blk["skip"]["b"], b0["b1"]]).contiguous(),
+                                   "n_split": blk["skip"]["w"].shape[0]}
         for bt in pk["b1"]["bott"][1:]:
             bt["w0"] = _conv_w_bf16(bt["conv0"], dev)
         if self.modality_attention is not None:
@@ -534,19 +550,19 @@ class ModelMaskHeadBackbone(nn.Module):
             gate = torch.empty((B, cout), dtype=torch.float32, device=dev)
             nat.se_gate(gap, H * W, se["w1t"], se["b1"], se["w2t"], se["b2"], gate)
             nat.scale_map(out, out, gate=gate)
-        rec = None
-        if need_recon and "recon" in pk:
-            rc = pk["recon"]
-            t2 = nat.conv_gemm(out, rc["w0"], taps=9, scale=rc["s0"], bias=rc["b0"], act=1)
-            rec = torch.empty((B, H, W), dtype=torch.float32, device=dev)
-            nat.conv3x3_c1(t2, rc["w3"], rc["b3"], rec)
+        rec = _recon(pk["recon"], out) if (need_recon and "recon" in pk) else None
         return out, rec, gap, gate
 
     def _block_from_map(self, pk, x, need_recon):
         bt = pk["bott"][0]
-        skip = nat.conv_gemm(x, pk["skip"]["w"], taps=1, scale=pk["skip"]["s"], bias=pk["skip"]["b"]) \
-            if "skip" in pk else x
-        mid = nat.conv_gemm(x, bt["w0"], taps=1, scale=bt["s1"], bias=bt["b1"], act=1)
+        if "skip" in pk:
+            # skip conv and first bottleneck conv read the same map: one GEMM, two output segments
+            f = pk["fused_in"]
+            skip, mid = nat.conv_gemm(x, f["w"], taps=1, scale=f["s"], bias=f["b"], act=0, n_split=f["n_split"],
+                                      act2=1)
+        else:
+            skip = x
+            mid = nat.conv_gemm(x, bt["w0"], taps=1, scale=bt["s1"], bias=bt["b1"], act=1)
         return self._run_block(pk, mid, skip, need_recon)
 
     def _project(self, pp, src, up2):
@@ -785,10 +801,7 @@ class FusionModel(nn.Module):
                 raise NotImplementedError("mask head resize paths (input != 32x32) are not built")
             mask_logits = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
             nat.mask_tail(mpre, pk["mask_out_w"], pk["mask_out_b"], mask_logits)
-            rc = pk["recon"]
-            t = nat.conv_gemm(fused, rc["w0"], taps=9, scale=rc["s0"], bias=rc["b0"], act=1)
-            recon = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
-            nat.conv3x3_c1(t, rc["w3"], rc["b3"], recon)
+            recon = _recon(pk["recon"], fused).unsqueeze(1)
             pj = pk["projF"]
             g = nat.conv_gemm(fused, pj["w0"], taps=1, scale=pj["s0"], bias=pj["b0"], act=1)
             proj = _nchw(nat.conv_gemm(g, pj["w3"], taps=1, scale=pj["s3"], bias=pj["b3"], act=1))

@@ -54,6 +54,25 @@ int b200_conv_gemm(const void* x, int x_ld, const void* w, const float* scale, c
                    float* gap, int B, int H, int W, int Cin, int Cout, int taps, void* stream);
 
 /*
+ * b200_conv_gemm with two extensions used to fuse neighbouring layers of the reference graph:
+ *   n_split/out2/out2_ld/act2: output channels [n_split, Cout) are a second layer that reads the same
+ *     input (e.g. a block's skip conv and first bottleneck conv, code/model_module.py:299 and :303) and
+ *     go to out2 with their own activation flag (no residual / gap / up2 on either segment then);
+ *     n_split == Cout disables it.
+ *   dot_w [9,Cout] fp32 / dot_out [pixels,9] fp32: additionally emits, per pixel, the 9 dot products of
+ *     the epilogue result with dot_w[k,:] - the per-tap partial sums of the ReconHead's final 3x3,
+ *     C -> 1 convolution (code/model_module.py:117); b200_tapsum finishes it.  Requires Cout in
+ *     {64,128,256} (one N tile) and H > 1; `out` may then be NULL so the C-channel map never reaches HBM.
+ */
+int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
+                      const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
+                      float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w,
+                      float* dot_out, int B, int H, int W, int Cin, int Cout, int taps, void* stream);
+
+/* out[b,h,w] = bias + sum_k d[(b,h+ky-1,w+kx-1)][k], zero padded: finishes a 3x3 C->1 conv from tap dots. */
+int b200_tapsum(const float* d, int B, int H, int W, const float* bias, float* out, void* stream);
+
+/*
  * DWINormalize.__call__ (code/dataset.py:14-41), batched over `planes` = cases*C image
  * planes of n = H*W fp32 samples (NCHW): per plane z-score with unbiased std clamped at
  * 1e-6, clip to [z_lo, z_hi], map to [0,1]; when skip_last != 0 the last channel of every

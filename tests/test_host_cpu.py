@@ -1,0 +1,222 @@
+"""CPU-only checks: the C-ABI library exports what include/b200_fusion.h declares, the Python
+mirror keeps the reference's parameter names/shapes, host-side logic, loud failure without CUDA."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import b200path
+import golden_util as gu
+
+ROOT = b200path.ROOT
+
+
+def _header_decls():
+    text = open(os.path.join(ROOT, "include", "b200_fusion.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"\bint\s+(b200_\w+)\s*\((.*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        decls[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    return decls
+
+
+def test_library_exports_every_declared_symbol():
+    import b200_native as nat
+
+    decls = _header_decls()
+    assert len(decls) >= 15
+    lib = nat.lib()  # loads the .so built by __graft_entry__.build(); no GPU needed to load it
+    for name, nargs in decls.items():
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in nat.SIGNATURES, f"{name} has no ctypes signature"
+        assert len(nat.SIGNATURES[name]) == nargs, f"{name}: ctypes arity != header arity"
+    assert set(nat.SIGNATURES) == set(decls)
+    assert lib.b200_abi_version() == nat.ABI_VERSION
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu():
+    import b200_native as nat
+
+    lib = nat.lib()
+    # negative return = invalid argument, nothing launched (no CUDA call is reached)
+    assert lib.b200_conv_gemm(None, 64, None, None, None, None, 0, 0, 0, None, 0, 0, None, 1, 32, 32, 64, 64, 1, None) < 0
+    assert lib.b200_dwi_normalize(None, None, 5, 4, 16, 1, -3.0, 3.0, None, None) < 0   # planes % C != 0
+    assert lib.b200_dwi_normalize(None, None, 0, 4, 16, 1, -3.0, 3.0, None, None) == 0  # empty batch is a no-op
+    assert lib.b200_nyul_transform(None, None, 6, 6, 16, 40, None, None, None, None, None, None) < 0  # L too large
+    assert lib.b200_stem(None, 1, 64, 8, 8, 2, None, None, None, None, None, 0, None, None, None, 8, 8, None, None, None, None) < 0
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    import b200_native as nat
+
+    monkeypatch.setattr(nat, "_lib", None)
+    monkeypatch.setattr(nat, "LIB_PATH", "/nonexistent/libb200fusion.so")
+    with pytest.raises(nat.B200NativeError):
+        nat.lib()
+
+
+@pytest.mark.parametrize("tag,hybrid", [("cnn", False), ("hybrid", True)])
+def test_state_dict_matches_reference_names_and_shapes(tag, hybrid):
+    import model_module as mm
+    import parameters_default as pd
+
+    p = pd.default_parameters()
+    for m in ("dwi", "dce"):
+        p[f"{m}_model_parameters"]["use_hybrid_transformer"] = hybrid
+    ref = gu.load_shapes(tag)
+    mods = {"dwi": mm.ModelMaskHeadBackbone("dwi", p), "dce": mm.ModelMaskHeadBackbone("dce", p),
+            "fusion": mm.FusionModel(p)}
+    for k, m in mods.items():
+        mine = {a: tuple(b.shape) for a, b in m.state_dict().items()}
+        assert mine == ref[k]
+
+
+def test_no_cpu_fallback():
+    import b200_native as nat
+    import dataset as ds
+    import model_module as mm
+    import parameters_default as pd
+
+    p = pd.default_parameters()
+    enc = mm.ModelMaskHeadBackbone("dwi", p).eval()
+    with pytest.raises(nat.B200NativeError):
+        enc(torch.zeros(1, 16, 64, 64))
+    enc.train()
+    with pytest.raises(NotImplementedError):
+        enc(torch.zeros(1, 16, 64, 64))
+    if not torch.cuda.is_available():
+        with pytest.raises(nat.B200NativeError):
+            ds.DWINormalize()(torch.zeros(4, 8, 8))
+    with pytest.raises(NotImplementedError):
+        mm.SEBlock(8)(torch.zeros(1, 8, 4, 4))
+
+
+def test_initialize_model_rules():
+    import model_module as mm
+
+    lin, bn = torch.nn.Linear(8, 4), torch.nn.BatchNorm2d(16)
+    seq = mm.initialize_model(torch.nn.Sequential(lin, bn), False)
+    assert all(not q.requires_grad for q in seq.parameters())
+    assert torch.count_nonzero(lin.bias) == 0 and torch.count_nonzero(bn.bias) == 0
+    assert abs(bn.weight.mean().item() - 1) < 0.05
+
+
+def test_bilinear_axis_weights_equal_gap_of_interpolate():
+    import model_module as mm
+
+    for n_in, n_out in ((4, 32), (4, 14), (3, 7)):
+        w = torch.tensor(mm._bilinear_axis_weights(n_in, n_out))
+        for i in range(n_in):
+            e = torch.zeros(1, 1, n_in, 1)
+            e[0, 0, i, 0] = 1.0
+            up = F.interpolate(e, size=(n_out, 1), mode="bilinear", align_corners=False)
+            assert abs(up.mean().item() - w[i].item()) < 1e-6
+
+
+def test_nyul_fit_and_tables_are_numpy_exact():
+    import preprocess_helpers as pre
+    from oracle import normalize_oracle as no
+    from oracle import params as op
+
+    gold = gu.load("normalizers.npz")
+    _, dce, _, _ = op.synthetic_raw(12, seed=1234, kind="S")
+    nyul = pre.NyulStandardizer()
+    assert not nyul.fitted
+    with pytest.raises(RuntimeError):
+        nyul.transform(dce[0])
+    nyul.fit(list(dce[:8]), num_channels=6)
+    lm = np.stack([nyul.channel_landmarks[c] for c in range(6)])
+    assert np.array_equal(lm, gold["nyul/landmarks"]) and np.array_equal(lm, no.nyul_fit(list(dce[:8]), 6))
+    prev, gamma = no.percentile_indices(4096, nyul.landmarks)
+    x = np.sort(np.random.default_rng(1).random(4096).astype(np.float32))
+    manual = np.where(gamma >= 0.5, x[prev + 1] - (x[prev + 1] - x[prev]) * (1 - gamma),
+                      x[prev] + (x[prev + 1] - x[prev]).astype(np.float64) * gamma)
+    assert np.allclose(manual, np.percentile(x, nyul.landmarks), rtol=0, atol=1e-9)
+
+
+def test_nyul_save_load_roundtrip(tmp_path):
+    import preprocess_helpers as pre
+
+    a = pre.NyulStandardizer()
+    a.fit([torch.rand(6, 8, 8) for _ in range(3)], num_channels=6)
+    path = str(tmp_path / "lm.npy")
+    a.save(path)
+    b = pre.NyulStandardizer()
+    b.load(path)
+    assert b.fitted and all(np.array_equal(a.channel_landmarks[c], b.channel_landmarks[c]) for c in range(6))
+
+
+def test_collate_and_fold_split():
+    import dataset as ds
+    import prepare_fusion_model as pf
+
+    items = [(torch.zeros(16, 4, 4), torch.zeros(6, 4, 4), torch.zeros(1, 2, 2), torch.tensor(i % 4)) for i in range(5)]
+    d, c, m, y = pf.custom_double_input_collate_fn(items)
+    assert d.shape == (5, 16, 4, 4) and c.shape == (5, 6, 4, 4) and m.shape == (5, 1, 2, 2) and y.tolist() == [0, 1, 2, 3, 0]
+    d, c, m, y = pf.custom_double_input_collate_fn([it[:2] + it[3:] for it in items])
+    assert m is None
+    with pytest.raises(RuntimeError):
+        pf.custom_double_input_collate_fn([(torch.zeros(1),)])
+    labels = torch.arange(40) % 4
+    imgs = torch.arange(40).float().view(40, 1, 1, 1)
+    seen = []
+    for fold in range(5):
+        (tr, va), (ltr, lva) = ds.data_segmentation(imgs, labels, 5, 4, fold)
+        assert len(tr) + len(va) == 40 and set(tr.flatten().tolist()).isdisjoint(va.flatten().tolist())
+        assert sorted(labels[va.flatten().long()].tolist()) == sorted(lva.long().tolist())
+        assert [int((lva == k).sum()) for k in range(4)] == [2, 2, 2, 2]
+        seen += va.flatten().tolist()
+    assert sorted(seen) == list(range(40))
+
+
+def test_shard_bounds_cover_every_case_once():
+    import sharding
+
+    for n, world in ((1024, 8), (10, 4), (3, 8), (0, 2)):
+        spans = [sharding.shard_bounds(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); import b200path, sharding
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+n = 7
+lo, hi = sharding.shard_bounds(n, dist.get_rank(), 2)
+full = torch.arange(n * 4, dtype=torch.float32).view(n, 4)
+got = sharding.gather_logits(full[lo:hi].clone(), n)
+assert torch.equal(got, full), got
+t = sharding.max_over_ranks(1.0 + dist.get_rank(), "cpu")
+assert t == 2.0
+dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_logit_gather_two_ranks_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 500)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
+def test_reference_arm_prints_one_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--ref-batch", "2"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "cases/s" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"

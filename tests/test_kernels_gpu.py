@@ -81,3 +81,56 @@ def test_linear_ragged_rows(M, K, N):
     torch.cuda.synchronize()
     ref = F.gelu(x.float() @ w.float().t() + bias)
     assert _rel(y, ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,Cin,n1,n2", [(3, 128, 256, 128), (2, 256, 512, 256), (2, 64, 64, 64)])
+def test_conv_gemm_two_segments(B, Cin, n1, n2):
+    """Skip conv (no activation) and first bottleneck conv (GELU) on the same input in one launch."""
+    g = torch.Generator(device="cpu").manual_seed(Cin + n1)
+    x = (torch.randn(B, 32, 32, Cin, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(n1 + n2, Cin, generator=g) / math.sqrt(Cin)).to(DEV).bfloat16()
+    scale = (torch.rand(n1 + n2, generator=g) + 0.5).to(DEV)
+    bias = (torch.randn(n1 + n2, generator=g) * 0.1).to(DEV)
+    y1, y2 = nat.conv_gemm(x, w, taps=1, scale=scale, bias=bias, act=0, n_split=n1, act2=1)
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, w, 1, scale, bias, None, 0, 0)
+    assert y1.shape[-1] == n1 and y2.shape[-1] == n2
+    assert _rel(y1, ref[..., :n1]) < 1e-2
+    assert _rel(y2, F.gelu(ref[..., n1:])) < 1e-2
+
+
+@pytest.mark.parametrize("B,C", [(2, 128), (3, 256), (1, 64)])
+def test_recon_head_fused_tap_dots(B, C):
+    """3x3 conv + affine + GELU with the following 3x3, C->1 conv folded into the epilogue + tapsum."""
+    g = torch.Generator(device="cpu").manual_seed(C)
+    x = (torch.randn(B, 32, 32, C, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(C, 9 * C, generator=g) / math.sqrt(9 * C)).to(DEV).bfloat16()
+    scale = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    bias = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    w3 = (torch.randn(9, C, generator=g) / math.sqrt(9 * C)).to(DEV)
+    b3 = torch.tensor([0.3], device=DEV)
+    d = torch.empty(B, 32, 32, 9, device=DEV)
+    nat.conv_gemm(x, w, taps=9, scale=scale, bias=bias, act=1, store=False, dot_w=w3, dot_out=d)
+    out = nat.tapsum(d, b3, torch.empty(B, 32, 32, device=DEV))
+    torch.cuda.synchronize()
+    t = _conv_ref(x, w, 9, scale, bias, None, 0, 1)  # fp32, not rounded to bf16 (the fused path keeps fp32 too)
+    ref = F.conv2d(t.permute(0, 3, 1, 2), w3.view(9, C).t().reshape(1, C, 3, 3), b3, padding=1)[:, 0]
+    assert _rel(out, ref) < 5e-3
+    # and the stand-alone N=1 kernel on a bf16 map agrees with torch as well
+    tb = t.bfloat16()
+    out2 = nat.conv3x3_c1(tb, w3, b3, torch.empty(B, 32, 32, device=DEV))
+    ref2 = F.conv2d(tb.float().permute(0, 3, 1, 2), w3.view(9, C).t().reshape(1, C, 3, 3), b3, padding=1)[:, 0]
+    assert _rel(out2, ref2) < 1e-3
+
+
+def test_fast_gelu_deviation_is_below_bf16_resolution():
+    """The epilogue GELU uses an 8-term odd polynomial for erf: compare with exact GELU through an
+    identity 1x1 'convolution' (weights = I)."""
+    C = 64
+    xs = torch.linspace(-9, 9, 2 * 32 * 32 * C).view(2, 32, 32, C).to(DEV).bfloat16()
+    w = torch.eye(C, device=DEV).bfloat16()
+    y = nat.conv_gemm(xs, w, taps=1, act=1)
+    torch.cuda.synchronize()
+    ref = F.gelu(xs.float())
+    err = (y.float() - ref).abs()
+    assert (err <= 4e-3 * ref.abs() + 2.5e-4).all(), err.max()
