@@ -2,25 +2,29 @@
 //
 //   out[pixel, n] = epilogue( sum_{tap, c} x[pixel + offset(tap), c] * w[n, tap*Cin + c] )
 //
-// Activations are NHWC bf16, weights are [Cout, taps*Cin] bf16 (K-major), the
-// accumulator lives in TMEM (fp32).  One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer: one 4-D box {64 ch, BW, BH, 1} of the input per
-//               (tap, 64-channel slice) - the tap shift is a coordinate offset and
-//               the zero padding is the TMA out-of-bounds fill - plus one 2-D box
-//               {64, BLOCK_N} of the weights, both written with the 128-byte swizzle
+// Activations are NHWC bf16, weights are [Cout, taps*Cin] bf16 (K-major), the accumulator lives in
+// TMEM (fp32).  One persistent CTA per SM, warp-specialised, 640 threads:
+//   warp 0      TMA producer: one 4-D box {64 ch, BW, BH, 1} of the input per (tap, 64-channel slice) -
+//               the tap shift is a coordinate offset, the zero padding is the TMA out-of-bounds fill -
+//               plus one 2-D box {64, BLOCK_N} of the weights, both written with the 128-byte swizzle
 //   warp 1      tcgen05.mma issuer (single thread), M=128, N=BLOCK_N, K=16 per instruction
-//   warp 2      TMEM allocation / release (2 accumulator stages)
-//   warps 4-11  epilogue: tcgen05.ld -> folded-BN scale/bias, residual, GELU,
-//               bf16 store (optionally replicated 2x2), per-case channel sums (GAP)
+//   warp 2      TMEM allocation / release (2 accumulator stages: the epilogue of tile i overlaps the
+//               MMAs of tile i+1)
+//   warps 4-19  epilogue (4 warps per scheduler so fixed-latency stalls are covered): each warp owns 32
+//               accumulator rows (its TMEM lane quadrant) x BLOCK_N/4 columns and walks them in
+//               16-column chunks: tcgen05.ld -> folded-BN FMA -> residual (TMA-loaded box) -> GELU ->
+//               bf16 -> swizzled shared-memory box -> TMA store.  Optional fused products: per-case
+//               channel sums, a second output segment with its own activation, the 9 per-tap dot
+//               products of a following 3x3 C->1 convolution, 2x2-replicated (strided TMA) stores.
 //
-// Covers the reference's conv/BN/GELU stacks (model_module.py:259-269, :113-118,
-// :150, :337-345, :386-390, :857-858) and nn.Linear layers (transformer_model.py:93-125).
+// Covers the reference's conv/BN/GELU stacks (model_module.py:259-269, :113-118, :150, :337-345,
+// :386-390, :857-858) and nn.Linear layers (transformer_model.py:93-125).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
-#include <cstdio>
+#include <cstdlib>
 
 #include "b200_fusion.h"
 #include "ptx.cuh"
@@ -43,45 +47,54 @@ struct ConvGemmParams {
     int act;               // 0 none, 1 GELU(erf)
     __nv_bfloat16* out;
     int out_ld;
-    int tma_epi;           // 1: outputs / residual go through shared memory + TMA (coalesced); 0: direct
     int up2;               // replicate every output pixel into a 2x2 block of a [B,2H,2W,ld] map
+    int tma_epi;           // outputs / residual go through shared memory + TMA (coalesced); else direct
     float* gap;            // [B, Cout] fp32 sums over the pixels of each case, or nullptr
-    // second output segment: channels [n_split, Cout) go to out2 with their own activation flag
-    int n_split;           // == Cout when unused
+    int n_split;           // channels [n_split, Cout) are a second output segment (== Cout when unused)
     __nv_bfloat16* out2;
     int out2_ld;
     int act2;
-    // fused N=9 pointwise projection of the epilogue result (tap dot-products of a following 3x3, C->1 conv)
-    const float* dot_w;    // [9, Cout] fp32 or nullptr
+    const float* dot_w;    // [9, Cout] fp32 or nullptr: fused per-pixel projection of the epilogue result
     float* dot_out;        // [pixels, 9] fp32
+    int total_rows;        // B*H*W
+    int stages;            // operand ring depth
+    int off_ring, off_bar, off_union, off_rbox;  // shared-memory plan (bytes from the 1 KB-aligned base)
 };
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;
-constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiWarps = 8;
+constexpr int kThreads = (kEpiWarp0 + kNumEpiWarps) * 32;
+constexpr int kChunk = 32;  // accumulator columns per epilogue step (one tcgen05.ld.32x32b.x32)
+constexpr int kMaxStages = 12;
+constexpr int kBarBytes = 512;
 
+// Shared-memory plan, computed on the host (plan_smem) and passed in ConvGemmParams:
+//   [ resident weights (weight-stationary mode) | operand ring | barriers | union{output boxes, tap-dot
+//     buffers} | residual boxes ]
+// Weight-stationary mode (1x1 layers whose whole [BN, K] weight slab fits): the CTA owns one N tile, loads
+// its weights once and only streams activations, so the ring holds 16 KB stages and runs several tiles
+// ahead (the activations of a 1x1 layer come from DRAM, and a 3-stage ring cannot cover that latency).
 template <int BN>
 struct Tile {
     static constexpr int kBBytes = BN * kBlockK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (176 * 1024) / kStageBytes;  // 3 / 5 / 7 stages for BN = 256 / 128 / 64
-    static constexpr int kTmemCols = 2 * BN;  // two accumulator stages: 128 / 256 / 512 columns
-    static constexpr int kDotWBytes = 9 * BN * 4;          // dot weights staged once per CTA
-    static constexpr int kDotSBytes = 2 * kBlockM * 9 * 4;  // half-1 partial sums, double buffered
-    // per epilogue warp: one 32x32 bf16 box (2 KB, 64-byte swizzle) for the output and one for the residual
-    static constexpr int kStageOutBytes = kNumEpiWarps * 2048;
-    static constexpr int kStageResBytes = kNumEpiWarps * 2048;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                      kDotWBytes + kDotSBytes + kStageOutBytes + kStageResBytes + 1024;
+    static constexpr int kTmemCols = 2 * BN;             // two accumulator stages: 128 / 256 / 512 columns
+    static constexpr int kColsPerWarp = BN / 2;           // each epilogue warp: 32 rows x BN/2 columns
+    static constexpr int kChunksPerWarp = kColsPerWarp / kChunk;
+    static constexpr int kBoxCols = kColsPerWarp < 64 ? kColsPerWarp : 64;  // TMA box width (<= 128 B rows)
+    static constexpr int kBoxesPerWarp = kColsPerWarp / kBoxCols;
+    static constexpr int kRowBytes = kBoxCols * 2;
+    static constexpr int kBoxBytes = 32 * kRowBytes;      // 2 KB (64-byte swizzle) or 4 KB (128-byte swizzle)
+    static constexpr int kWarpBoxBytes = kBoxesPerWarp * kBoxBytes;
+    static constexpr int kDotBytes = 9 * BN * 4 + 2 * kBlockM * 9 * 4;
 };
 
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf(z) ~= z * P(z^2) on |z| <= 3 (odd minimax polynomial,
 // 8 terms, |erf error| < 9e-5, P(9)*3 == 1 so the clamp is continuous with +-1).  The result is rounded to
 // bf16 (relative step 4e-3), so the 1.8e-4 worst-case absolute deviation from the exact-erf GELU is below
-// one output ulp for |x| >= 0.05; it costs 14 issue slots against ~30 for erff().
+// one output ulp for |x| >= 0.05; it costs 15 issue slots against ~30 for erff().
 __device__ __forceinline__ float gelu_erf(float x) {
     const float z = fminf(fmaxf(x * 0.70710678118654752f, -3.0f), 3.0f);
     const float t = z * z;
@@ -97,7 +110,29 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(h, z * p, h);
 }
 
-template <int BN>
+// Two elements at a time on the packed fp32x2 pipe (FFMA2 / FMUL2, new in sm_100): the polynomial, the
+// scaling and the final blend are packed, only the clamp stays scalar - 8 issue slots per element.
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+    float2 z = __fmul2_rn(x, make_float2(0.70710678118654752f, 0.70710678118654752f));
+    z.x = fminf(fmaxf(z.x, -3.0f), 3.0f);
+    z.y = fminf(fmaxf(z.y, -3.0f), 3.0f);
+    const float2 t = __fmul2_rn(z, z);
+    float2 p = make_float2(-3.901667185e-07f, -3.901667185e-07f);
+    p = __ffma2_rn(p, t, make_float2(1.668003461e-05f, 1.668003461e-05f));
+    p = __ffma2_rn(p, t, make_float2(-3.086500801e-04f, -3.086500801e-04f));
+    p = __ffma2_rn(p, t, make_float2(3.281538375e-03f, 3.281538375e-03f));
+    p = __ffma2_rn(p, t, make_float2(-2.256273106e-02f, -2.256273106e-02f));
+    p = __ffma2_rn(p, t, make_float2(1.075116023e-01f, 1.075116023e-01f));
+    p = __ffma2_rn(p, t, make_float2(-3.730817735e-01f, -3.730817735e-01f));
+    p = __ffma2_rn(p, t, make_float2(1.127865076e+00f, 1.127865076e+00f));
+    const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+    return __ffma2_rn(h, __fmul2_rn(z, p), h);
+}
+
+// Epilogue features are compile-time so that the per-element instruction stream carries no flag tests:
+//   RES  0 none, 1 residual added before the activation, 2 after it
+//   GAP  per-case channel sums          DOT  fused 9-tap dot products (no map store)
+template <int BN, bool WS, int RES, bool GAP, bool DOT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
@@ -105,34 +140,45 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     using T = Tile<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + T::kStages * kABytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + T::kStages * T::kStageBytes);
-    uint64_t* empty = full + T::kStages;
-    uint64_t* tfull = empty + T::kStages;
+    uint8_t* sW = smem;  // resident weights [k_blocks][BN x 64] (WS only)
+    uint8_t* sRing = smem + p.off_ring;
+    constexpr int kStageBytes = WS ? kABytes : kABytes + T::kBBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* tfull = empty + kMaxStages;
     uint64_t* tempty = tfull + 2;
     uint64_t* resbar = tempty + 2;  // [kNumEpiWarps] residual-box arrival, one per epilogue warp
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resbar + kNumEpiWarps);
-    float* s_dotw = reinterpret_cast<float*>(smem + T::kStages * T::kStageBytes + 256);  // [9][BN]
-    float* s_dots = s_dotw + 9 * BN;                                                      // [2][128][9]
-    uint8_t* s_stage = reinterpret_cast<uint8_t*>(
-        (reinterpret_cast<uintptr_t>(s_dots + 2 * kBlockM * 9) + 1023) & ~uintptr_t(1023));  // out boxes, then res boxes
+    uint64_t* wbar = resbar + kNumEpiWarps;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    uint8_t* s_union = smem + p.off_union;
+    float* s_dotw = reinterpret_cast<float*>(s_union);  // [9][BN]        (tap-dot mode)
+    float* s_dots = s_dotw + 9 * BN;                    // [2][128][9]    (tap-dot mode)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int stages = p.stages;
+    // tile walk: WS CTAs keep one N tile and stride over M tiles; otherwise tiles are dealt round-robin, N fastest
+    const int my_n = WS ? static_cast<int>(blockIdx.x) % p.n_tiles : 0;
+    const int m_first = WS ? static_cast<int>(blockIdx.x) / p.n_tiles : 0;
+    const int m_step = WS ? static_cast<int>(gridDim.x) / p.n_tiles : 0;
     const int total_tiles = p.m_tiles * p.n_tiles;
+    const int n_iters = WS ? (p.m_tiles > m_first ? (p.m_tiles - m_first + m_step - 1) / m_step : 0)
+                           : (total_tiles > static_cast<int>(blockIdx.x)
+                                  ? (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                        static_cast<int>(gridDim.x)
+                                  : 0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (p.tma_epi) {
-            tma_prefetch_desc(&tmOut);
+            if (p.out != nullptr) tma_prefetch_desc(&tmOut);
             if (p.n_split < p.Cout) tma_prefetch_desc(&tmOut2);
-            if (p.res_mode != 0) tma_prefetch_desc(&tmRes);
+            if (RES != 0) tma_prefetch_desc(&tmRes);
         }
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < T::kStages; ++s) {
+        for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -141,10 +187,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&tempty[s], kNumEpiWarps);
         }
         for (int s = 0; s < kNumEpiWarps; ++s) mbar_init(&resbar[s], 1);
+        mbar_init(wbar, 1);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<T::kTmemCols>(tmem_slot);
-    if (p.dot_w != nullptr && warp >= kEpiWarp0) {
+    if (DOT && warp >= kEpiWarp0) {
         for (int i = threadIdx.x - kEpiWarp0 * 32; i < 9 * BN; i += kNumEpiWarps * 32) s_dotw[i] = p.dot_w[i];
     }
     tc_fence_before();
@@ -153,15 +200,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane == 0 && n_iters > 0) {
+            if (WS) {  // the CTA's whole weight slab, once
+                mbar_arrive_expect_tx(wbar, p.k_blocks * T::kBBytes);
+                for (int kb = 0; kb < p.k_blocks; ++kb)
+                    tma_load_2d(sW + kb * T::kBBytes, &tmB, wbar, kb * kBlockK, my_n * BN);
+            }
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n_tile = tile % p.n_tiles;
-                const int m_tile = tile / p.n_tiles;
-                const int w0 = (m_tile % p.tiles_w) * p.BW;
-                const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.BH;
-                const int b = m_tile / (p.tiles_w * p.tiles_h);
+            int tile = blockIdx.x, m_tile = m_first;
+            for (int it = 0; it < n_iters; ++it, tile += gridDim.x, m_tile += m_step) {
+                const int n_tile = WS ? my_n : tile % p.n_tiles;
+                const int mt = WS ? m_tile : tile / p.n_tiles;
+                const int w0 = (mt % p.tiles_w) * p.BW;
+                const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.BH;
+                const int b = mt / (p.tiles_w * p.tiles_h);
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     const int tap = kb / p.kc;
                     const int c0 = (kb - tap * p.kc) * kBlockK;
@@ -171,10 +224,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         dx = tap % 3 - 1;
                     }
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], T::kStageBytes);
-                    tma_load_4d(sA + stage * kABytes, &tmA, &full[stage], c0, w0 + dx, h0 + dy, b);
-                    tma_load_2d(sB + stage * T::kBBytes, &tmB, &full[stage], kb * kBlockK, n_tile * BN);
-                    if (++stage == T::kStages) {
+                    mbar_arrive_expect_tx(&full[stage], kStageBytes);
+                    uint8_t* dst = sRing + stage * kStageBytes;
+                    tma_load_4d(dst, &tmA, &full[stage], c0, w0 + dx, h0 + dy, b);
+                    if (!WS) tma_load_2d(dst + kABytes, &tmB, &full[stage], kb * kBlockK, n_tile * BN);
+                    if (++stage == stages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -182,28 +236,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (lane == 0 && n_iters > 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            if (WS) mbar_wait(wbar, 0);
+            for (int it = 0; it < n_iters; ++it) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * kABytes));
-                    const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * T::kBBytes));
+                    const uint8_t* a_src = sRing + stage * kStageBytes;
+                    const uint64_t da = umma_desc_sw128(smem_u32(a_src));
+                    const uint64_t db = umma_desc_sw128(smem_u32(WS ? sW + kb * T::kBBytes : a_src + kABytes));
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // 16 bf16 = 32 bytes along K inside the 128-byte swizzle row -> +2 in 16-byte units
                         umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);
-                    if (++stage == T::kStages) {
+                    if (++stage == stages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -214,150 +270,128 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp >= kEpiWarp0) {
-        const int q = warp & 3;                  // TMEM lane quadrant this warp may read
-        const int half = (warp - kEpiWarp0) >> 2;  // which half of the BLOCK_N columns
-        constexpr int kChunks = BN / 64;         // 32-column chunks per warp
         const int ew = warp - kEpiWarp0;
-        uint8_t* const obuf = s_stage + ew * 2048;
-        uint8_t* const rbuf = s_stage + T::kStageOutBytes + ew * 2048;
+        const int q = warp & 3;    // TMEM lane quadrant this warp may read (rows q*32 .. q*32+31 of the tile)
+        const int half = ew >> 2;  // column half: columns [half*BN/2, (half+1)*BN/2)
+        const int colw0 = half * T::kColsPerWarp;
+        uint8_t* const obuf = s_union + ew * T::kWarpBoxBytes;
+        uint8_t* const rbuf = smem + p.off_rbox + ew * T::kWarpBoxBytes;
         uint64_t* const rbar = &resbar[ew];
         uint32_t rphase = 0;
-        // 64-byte swizzle of a 32x32 bf16 box: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)
-        const int swz = (lane >> 1) & 3;
+        // A staged box is 32 rows x kBoxCols bf16 under the TMA swizzle of its row width (64 or 128 B):
+        // 16-byte chunk c of row r sits at chunk c ^ (((r * rowBytes) >> 7) & (rowBytes/16 - 1)).
+        const int swz = ((lane * T::kRowBytes) >> 7) & (T::kRowBytes / 16 - 1);
+        const int row_off = lane * T::kRowBytes;
+        const bool tma_epi = p.tma_epi != 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n_tile = tile % p.n_tiles;
-            const int m_tile = tile / p.n_tiles;
-            const int w0 = (m_tile % p.tiles_w) * p.BW;
-            const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.BH;
-            const int b = m_tile / (p.tiles_w * p.tiles_h);
-            const int row = q * 32 + lane;
-            const int h = h0 + row / p.BW;
-            const int w = w0 + row % p.BW;
-            const bool valid = (w < p.W) && (h < p.H);
-            const long long pix = (static_cast<long long>(b) * p.H + h) * p.W + w;
-            // first output row of this warp's 32-row slab (rows of a tile are consecutive pixels)
-            const int slab_row0 = (b * p.H + h0) * p.W + w0 + q * 32;
+        int tile = blockIdx.x, m_walk = m_first;
+        for (int it = 0; it < n_iters; ++it, tile += gridDim.x, m_walk += m_step) {
+            const int n_tile = WS ? my_n : tile % p.n_tiles;
+            const int m_tile = WS ? m_walk : tile / p.n_tiles;
+            // rows of a tile are 128 consecutive pixels of the flattened [B*H*W] map (GEMM mode: rows)
+            const int slab_row0 = m_tile * kBlockM + q * 32;
+            const int pix = slab_row0 + lane;
+            const bool valid = pix < p.total_rows;
 
             const bool seg2 = n_tile * BN >= p.n_split;
             __nv_bfloat16* const out_ptr = seg2 ? p.out2 : p.out;
-            const int out_ld = seg2 ? p.out2_ld : p.out_ld;
             const int act = seg2 ? p.act2 : p.act;
-            const int res_mode = seg2 ? 0 : p.res_mode;
-            const int out_col_base = seg2 ? n_tile * BN - p.n_split : n_tile * BN;
+            const bool use_res = RES != 0 && !seg2;
+            const int out_col0 = (seg2 ? n_tile * BN - p.n_split : n_tile * BN) + colw0;
             const CUtensorMap* const tm_out = seg2 ? &tmOut2 : &tmOut;
-            const bool tma_res = p.tma_epi && res_mode != 0;
+            const int nbase = n_tile * BN + colw0;
             float dsum[9];
+            if (DOT) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) dsum[k] = 0.f;
-
-            if (tma_res && lane == 0) {  // residual box of the first chunk: in flight while the MMAs finish
-                mbar_arrive_expect_tx(rbar, 2048);
-                tma_load_2d(rbuf, &tmRes, rbar, n_tile * BN + half * (BN / 2), slab_row0);
+                for (int k = 0; k < 9; ++k) dsum[k] = 0.f;
+            }
+            if (RES != 0 && use_res && tma_epi && lane == 0) {  // whole residual slab: in flight during the MMAs
+                mbar_arrive_expect_tx(rbar, T::kWarpBoxBytes);
+#pragma unroll
+                for (int bx = 0; bx < T::kBoxesPerWarp; ++bx)
+                    tma_load_2d(rbuf + bx * T::kBoxBytes, &tmRes, rbar, nbase + bx * T::kBoxCols, slab_row0);
+            }
+            if (!DOT && tma_epi && out_ptr != nullptr) {  // last tile's store has finished reading this warp's boxes
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
             }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-#pragma unroll 1
-            for (int ch = 0; ch < kChunks; ++ch) {
-                const int col0 = half * (BN / 2) + ch * 32;
-                const int n0 = n_tile * BN + col0;
-                const int oc0 = out_col_base + col0;
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0, r);
+            const uint32_t tm_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + colw0;
+            if (RES != 0 && use_res && tma_epi) {
+                mbar_wait(rbar, rphase);
+                rphase ^= 1;
+            }
+#pragma unroll
+            for (int ch = 0; ch < T::kChunksPerWarp; ++ch) {
+                const int n0 = nbase + ch * kChunk;
+                uint32_t r[kChunk];
+                tmem_ld_32x32(tm_row + ch * kChunk, r);
                 tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (p.scale != nullptr && p.bias != nullptr) {
+                float v[kChunk];
+                float2* const v2 = reinterpret_cast<float2*>(v);
+                {
                     const float4* s4 = reinterpret_cast<const float4*>(p.scale + n0);
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < kChunk / 4; ++j) {
                         const float4 s = __ldg(s4 + j), t = __ldg(b4 + j);
-                        v[4 * j + 0] = fmaf(v[4 * j + 0], s.x, t.x);
-                        v[4 * j + 1] = fmaf(v[4 * j + 1], s.y, t.y);
-                        v[4 * j + 2] = fmaf(v[4 * j + 2], s.z, t.z);
-                        v[4 * j + 3] = fmaf(v[4 * j + 3], s.w, t.w);
-                    }
-                } else if (p.scale != nullptr) {
-                    const float4* s4 = reinterpret_cast<const float4*>(p.scale + n0);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 s = __ldg(s4 + j);
-                        v[4 * j + 0] *= s.x;
-                        v[4 * j + 1] *= s.y;
-                        v[4 * j + 2] *= s.z;
-                        v[4 * j + 3] *= s.w;
-                    }
-                } else if (p.bias != nullptr) {
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 s = __ldg(b4 + j);
-                        v[4 * j + 0] += s.x;
-                        v[4 * j + 1] += s.y;
-                        v[4 * j + 2] += s.z;
-                        v[4 * j + 3] += s.w;
+                        v2[2 * j + 0] = __ffma2_rn(make_float2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])),
+                                                   make_float2(s.x, s.y), make_float2(t.x, t.y));
+                        v2[2 * j + 1] = __ffma2_rn(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])),
+                                                   make_float2(s.z, s.w), make_float2(t.z, t.w));
                     }
                 }
-                if (res_mode != 0) {
-                    uint4 u[4];
-                    if (tma_res) {
-                        mbar_wait(rbar, rphase);
-                        rphase ^= 1;
+                // box / chunk position of these 32 columns inside the warp's staged boxes
+                const int bx = (ch * kChunk) / T::kBoxCols;
+                const int c16 = ((ch * kChunk) % T::kBoxCols) / 8;  // first 16-byte chunk inside the box row
+                if (RES != 0) {
+                    if (use_res) {
+                        uint4 u[4];
+                        if (tma_epi) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            u[j] = *reinterpret_cast<const uint4*>(rbuf + lane * 64 + ((j ^ swz) << 4));
-                        __syncwarp();  // every lane has read the box before it is refilled
-                        if (ch + 1 < kChunks && lane == 0) {
-                            mbar_arrive_expect_tx(rbar, 2048);
-                            tma_load_2d(rbuf, &tmRes, rbar, n0 + 32, slab_row0);
+                            for (int j = 0; j < 4; ++j)
+                                u[j] = *reinterpret_cast<const uint4*>(rbuf + bx * T::kBoxBytes + row_off +
+                                                                       (((c16 + j) ^ swz) << 4));
+                        } else if (valid) {
+                            const uint4* r4 = reinterpret_cast<const uint4*>(p.res + static_cast<long long>(pix) * p.res_ld + n0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) u[j] = __ldg(r4 + j);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) u[j] = make_uint4(0u, 0u, 0u, 0u);
                         }
-                    } else if (valid) {
-                        const uint4* r4 = reinterpret_cast<const uint4*>(p.res + pix * p.res_ld + n0);
+                        if (RES == 2 && act == 1) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) u[j] = __ldg(r4 + j);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) u[j] = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                    float rres[32];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t uu[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&uu[t]);
-                            rres[8 * j + 2 * t + 0] = __low2float(h2);
-                            rres[8 * j + 2 * t + 1] = __high2float(h2);
-                        }
-                    }
-                    if (res_mode == 1) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += rres[j];
-                        if (act == 1) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                        }
-                    } else {
-                        if (act == 1) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                            for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
                         }
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += rres[j];
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t uu[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)  // bf16 pair -> fp32 pair, packed add
+                                v2[4 * j + t] = __fadd2_rn(v2[4 * j + t], make_float2(__uint_as_float(uu[t] << 16),
+                                                                                     __uint_as_float(uu[t] & 0xffff0000u)));
+                        }
+                        if (RES == 1 && act == 1) {
+#pragma unroll
+                            for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+                        }
+                    } else if (act == 1) {
+#pragma unroll
+                        for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
                     }
                 } else if (act == 1) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
                 }
-                if (p.dot_w != nullptr) {
+                if (DOT) {
 #pragma unroll
                     for (int k = 0; k < 9; ++k) {
-                        const float4* w4 = reinterpret_cast<const float4*>(s_dotw + k * BN + col0);
+                        const float4* w4 = reinterpret_cast<const float4*>(s_dotw + k * BN + colw0 + ch * kChunk);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
+                        for (int j = 0; j < kChunk / 4; ++j) {
                             const float4 wv = w4[j];
                             dsum[k] = fmaf(v[4 * j + 0], wv.x, dsum[k]);
                             dsum[k] = fmaf(v[4 * j + 1], wv.y, dsum[k]);
@@ -365,8 +399,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             dsum[k] = fmaf(v[4 * j + 3], wv.w, dsum[k]);
                         }
                     }
-                }
-                if (out_ptr != nullptr) {
+                } else if (out_ptr != nullptr) {
                     uint4 o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -378,45 +411,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                         o[j] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
                     }
-                    if (p.tma_epi) {
-                        // stage the warp's 32x32 box in shared memory (conflict-free under the 64-byte swizzle)
-                        // and let the TMA write it: full 64-byte row segments, rows past the end are clipped
-                        if (lane == 0) tma_store_wait_read<0>();
-                        __syncwarp();
+                    if (tma_epi) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(obuf + lane * 64 + ((j ^ swz) << 4)) = o[j];
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_2d(tm_out, obuf, oc0, slab_row0);
-                            tma_store_commit();
-                        }
-                    } else if (valid) {
-                        if (!p.up2) {
-                            uint4* dst = reinterpret_cast<uint4*>(out_ptr + pix * out_ld + oc0);
+                            *reinterpret_cast<uint4*>(obuf + bx * T::kBoxBytes + row_off + (((c16 + j) ^ swz) << 4)) = o[j];
+                    } else if (valid) {  // direct 2x2-replicated store (only when the strided TMA form does not apply)
+                        const int hw = p.H * p.W;
+                        const int b = pix / hw, rem = pix - b * hw;
+                        const int h = rem / p.W, w = rem - h * p.W;
+                        const int out_ld = seg2 ? p.out2_ld : p.out_ld;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) dst[j] = o[j];
-                        } else {
-#pragma unroll
-                            for (int rep = 0; rep < 4; ++rep) {
-                                const long long opix =
-                                    (static_cast<long long>(b) * (2 * p.H) + 2 * h + (rep >> 1)) * (2 * p.W) + 2 * w +
-                                    (rep & 1);
-                                uint4* dst = reinterpret_cast<uint4*>(out_ptr + opix * out_ld + oc0);
+                        for (int rep = 0; rep < 4; ++rep) {
+                            const long long opix = p.up2 ? (static_cast<long long>(b) * (2 * p.H) + 2 * h + (rep >> 1)) *
+                                                                   (2 * p.W) + 2 * w + (rep & 1)
+                                                         : static_cast<long long>(pix);
+                            if (p.up2 || rep == 0) {
+                                uint4* dst = reinterpret_cast<uint4*>(out_ptr + opix * out_ld + out_col0 + ch * kChunk);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) dst[j] = o[j];
                             }
                         }
                     }
                 }
-                if (p.gap != nullptr) {
+                if (GAP) {
                     if (!valid) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        for (int j = 0; j < kChunk; ++j) v[j] = 0.f;
                     }
-                    // Transposed warp reduction: after the 5 halving steps lane L holds the
-                    // sum over the warp's 32 rows of column L.
+                    // Transposed warp reduction: after the 5 halving steps lane L holds the sum over the warp's
+                    // 32 rows of column L.
 #pragma unroll
                     for (int s = 16; s >= 1; s >>= 1) {
                         const bool upper = (lane & s) != 0;
@@ -427,24 +450,51 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
                         }
                     }
+                    const int b = slab_row0 / (p.H * p.W);  // a 32-row slab never straddles two cases
                     atomicAdd(p.gap + static_cast<long long>(b) * p.Cout + n0 + lane, v[0]);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (p.dot_w != nullptr) {
+            if (!DOT && tma_epi && out_ptr != nullptr) {
+                // one TMA store per staged box: full 64/128-byte row segments, rows past the end are clipped
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (!p.up2) {
+#pragma unroll
+                        for (int bx = 0; bx < T::kBoxesPerWarp; ++bx)
+                            tma_store_2d(tm_out, obuf + bx * T::kBoxBytes, out_col0 + bx * T::kBoxCols, slab_row0);
+                    } else {
+                        // [B*2H*2W, C] map walked with traversal stride 2 along pixels: the same 32 source
+                        // pixels land on (2h+i, 2w+j) for the four (i, j)
+                        const int hw = p.H * p.W;
+                        const int b = slab_row0 / hw, rem = slab_row0 - b * hw;
+                        const int sh = rem / p.W, sw = rem - sh * p.W;
+#pragma unroll
+                        for (int rep = 0; rep < 4; ++rep) {
+                            const int orow = (b * 2 * p.H + 2 * sh + (rep >> 1)) * (2 * p.W) + 2 * sw + (rep & 1);
+#pragma unroll
+                            for (int bx = 0; bx < T::kBoxesPerWarp; ++bx)
+                                tma_store_2d(tm_out, obuf + bx * T::kBoxBytes, out_col0 + bx * T::kBoxCols, orow);
+                        }
+                    }
+                    tma_store_commit();
+                }
+            }
+            if (DOT) {
                 // The two column halves of a row live in different warps: half 1 parks its 9 partial sums in
                 // shared memory (double buffered by accumulator stage), one named barrier over the 8 epilogue
                 // warps, half 0 adds its own and writes the row.  Deterministic, no atomics.
-                float* buf = s_dots + (acc * kBlockM + row) * 9;
+                float* buf = s_dots + (acc * kBlockM + q * 32 + lane) * 9;
                 if (half == 1) {
 #pragma unroll
                     for (int k = 0; k < 9; ++k) buf[k] = dsum[k];
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (half == 0 && valid) {
-                    float* dst = p.dot_out + pix * 9;
+                    float* dst = p.dot_out + static_cast<long long>(pix) * 9;
 #pragma unroll
                     for (int k = 0; k < 9; ++k) dst[k] = dsum[k] + buf[k];
                 }
@@ -452,7 +502,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-        if (p.tma_epi && lane == 0) tma_store_wait_all<0>();  // global writes done before the CTA retires
+        if (tma_epi && lane == 0) tma_store_wait_all<0>();  // global writes done before the CTA retires
     }
 
     tc_fence_before();
@@ -482,29 +532,91 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int g_num_sms = 0;
+constexpr int kSmemLimit = 227 * 1024;
 
-template <int BN>
+template <int BN, bool WS, int RES, bool GAP, bool DOT>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmOut2,
-                  const CUtensorMap& tmRes, const ConvGemmParams& p, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Tile<BN>::kSmemBytes);
+                  const CUtensorMap& tmRes, const ConvGemmParams& p, int smem_bytes, int grid, cudaStream_t stream) {
+    static int configured = 0;
+    if (smem_bytes > configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, WS, RES, GAP, DOT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return static_cast<int>(e);
-        configured = true;
+        configured = smem_bytes;
     }
-    const int total = p.m_tiles * p.n_tiles;
-    const int grid = total < g_num_sms ? total : g_num_sms;
-    conv_gemm_kernel<BN><<<grid, kThreads, Tile<BN>::kSmemBytes, stream>>>(tmA, tmB, tmOut, tmOut2, tmRes, p);
+    conv_gemm_kernel<BN, WS, RES, GAP, DOT><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmOut, tmOut2, tmRes, p);
     return static_cast<int>(cudaGetLastError());
 }
 
-}  // namespace b200
+template <int BN, bool WS>
+static int dispatch(int res_mode, bool gap, bool dot, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                    const CUtensorMap& tmOut, const CUtensorMap& tmOut2, const CUtensorMap& tmRes,
+                    const ConvGemmParams& p, int smem_bytes, int grid, cudaStream_t s) {
+#define B200_GO(RES, GAP, DOT) \
+    return launch<BN, WS, RES, GAP, DOT>(tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s)
+    if (dot) {
+        if constexpr (!WS) {
+            if (res_mode == 0 && !gap) B200_GO(0, false, true);
+        }
+        return -14;
+    }
+    if (res_mode == 0) {
+        if (gap) B200_GO(0, true, false);
+        B200_GO(0, false, false);
+    }
+    if (res_mode == 1) {
+        if (gap) B200_GO(1, true, false);
+        B200_GO(1, false, false);
+    }
+    if (res_mode == 2 && !gap) B200_GO(2, false, false);
+    return -14;
+#undef B200_GO
+}
 
-extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
-                                 const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
-                                 float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w,
-                                 float* dot_out, int B, int H, int W, int Cin, int Cout, int taps, void* stream);
+// Identity scale / zero bias for callers that pass NULL (immutable, allocated once per process).
+static const float* identity_affine(bool ones) {
+    static float* buf = nullptr;
+    constexpr int kN = 8192;
+    if (buf == nullptr) {
+        float* d = nullptr;
+        if (cudaMalloc(&d, 2 * kN * sizeof(float)) != cudaSuccess) return nullptr;
+        float* h = static_cast<float*>(std::malloc(2 * kN * sizeof(float)));
+        for (int i = 0; i < kN; ++i) {
+            h[i] = 1.f;
+            h[kN + i] = 0.f;
+        }
+        cudaMemcpy(d, h, 2 * kN * sizeof(float), cudaMemcpyHostToDevice);
+        std::free(h);
+        buf = d;
+    }
+    return ones ? buf : buf + kN;
+}
+
+static inline int align1k(int v) { return (v + 1023) & ~1023; }
+
+// Lays out shared memory for (BN, weight-stationary?) and returns the total dynamic size, or -1 if the
+// configuration does not fit / leaves fewer than 3 ring stages.
+static int plan_smem(ConvGemmParams& p, int BN, bool ws, bool has_out, bool has_res, bool dot) {
+    const int b_bytes = BN * kBlockK * 2;
+    const int stage_bytes = ws ? kABytes : kABytes + b_bytes;
+    const int box_all = kBlockM * BN * 2;  // 8 warps x (32 rows x BN/2 columns) of bf16
+    const int dot_bytes = 9 * BN * 4 + 2 * kBlockM * 9 * 4;
+    const int union_bytes = align1k(dot ? dot_bytes : (has_out ? box_all : 0));
+    const int rbox_bytes = has_res ? align1k(box_all) : 0;
+    const int resident = ws ? align1k(p.k_blocks * b_bytes) : 0;
+    const int fixed = resident + align1k(kBarBytes) + union_bytes + rbox_bytes + 1024 /*base alignment slack*/;
+    int stages = (kSmemLimit - fixed) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 3) return -1;
+    p.stages = stages;
+    p.off_ring = resident;
+    p.off_bar = resident + stages * stage_bytes;
+    p.off_union = p.off_bar + align1k(kBarBytes);
+    p.off_rbox = p.off_union + union_bytes;
+    return fixed + stages * stage_bytes;
+}
+
+}  // namespace b200
 
 extern "C" int b200_conv_gemm(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
                               const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
@@ -527,13 +639,12 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
         return -5;
 
     ConvGemmParams p{};
-    if (H == 1) {  // plain GEMM over W rows: 128-row boxes, ragged tail handled by TMA OOB fill + row mask
+    if (H == 1) {  // plain GEMM over W rows: 128-row boxes, ragged tail handled by TMA OOB fill / clipping
         if (taps != 1 || up2) return -6;
         p.BW = 128;
         p.BH = 1;
         p.tiles_w = (W + 127) / 128;
         p.tiles_h = 1;
-        if (gap != nullptr && p.tiles_w * 128 != W && B > 1) { /* per-case sums stay per-case: fine */ }
     } else {
         if (W > 128 || 128 % W != 0 || H % (128 / W) != 0) return -7;
         p.BW = W;
@@ -550,14 +661,51 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
                 up2 || dot_w != nullptr))
         return -11;
     const int seg2 = Cout - n_split;
-    auto divides = [&](int bn) { return Cout % bn == 0 && n_split % bn == 0 && (!two || seg2 % bn == 0); };
-    const int BN = divides(256) ? 256 : (divides(128) ? 128 : 64);
-    if (dot_w != nullptr && (dot_out == nullptr || BN != Cout || H == 1)) return -12;  // needs one N tile per row
-    p.n_tiles = Cout / BN;
+    if (dot_w != nullptr && (dot_out == nullptr || H == 1 || out != nullptr)) return -12;
     p.m_tiles = B * p.tiles_w * p.tiles_h;
     p.kc = Cin / 64;
     p.taps = taps;
     p.k_blocks = taps * p.kc;
+
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) return -9;
+    }
+    // Tile shape: weight-stationary (BN <= 128, the CTA's weight slab resident) for 1x1 layers when it fits,
+    // otherwise the widest BN that divides the channel counts and fits shared memory.
+    // Measured on B200 (tools/kbench.py): the weight-stationary variant is slower than the streamed one for
+    // every layer of this model (it needs BN <= 128, i.e. twice the tiles and activation re-reads), so it
+    // is opt-in (B200_WS=1) until a 2-CTA / multicast version makes it pay.
+    static const bool no_ws = std::getenv("B200_WS") == nullptr;
+    auto divides = [&](int bn) { return Cout % bn == 0 && n_split % bn == 0 && (!two || seg2 % bn == 0); };
+    const bool has_out = out != nullptr, has_res = res_mode != 0, dot = dot_w != nullptr;
+    int BN = 0, smem_bytes = -1;
+    bool ws = false;
+    if (taps == 1 && !dot && !no_ws) {
+        for (int bn : {128, 64}) {
+            if (!divides(bn) || Cout / bn > g_num_sms || p.k_blocks * bn * kBlockK * 2 > 128 * 1024) continue;
+            smem_bytes = plan_smem(p, bn, true, has_out, has_res, false);
+            if (smem_bytes > 0) {
+                BN = bn;
+                ws = true;
+                break;
+            }
+        }
+    }
+    if (!ws) {
+        for (int bn : {256, 128, 64}) {
+            if (!divides(bn) || (dot && bn != Cout)) continue;
+            smem_bytes = plan_smem(p, bn, false, has_out, has_res, dot);
+            if (smem_bytes > 0) {
+                BN = bn;
+                break;
+            }
+        }
+    }
+    if (BN == 0) return -13;
+    p.n_tiles = Cout / BN;
     p.scale = scale;
     p.bias = bias;
     p.res = static_cast<const __nv_bfloat16*>(res);
@@ -574,15 +722,14 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
     p.act2 = act2;
     p.dot_w = dot_w;
     p.dot_out = dot_out;
+    p.total_rows = B * H * W;
+    if (Cout > 8192) return -15;
+    if (p.scale == nullptr) p.scale = identity_affine(true);
+    if (p.bias == nullptr) p.bias = identity_affine(false);
+    if (p.scale == nullptr || p.bias == nullptr) return -16;
 
     EncodeTiledFn encode = get_encode_fn();
     if (encode == nullptr) return -8;
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) return -9;
-    }
 
     CUtensorMap tmA, tmB;
     {
@@ -594,7 +741,7 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return -100 - static_cast<int>(r);
     }
     {
@@ -608,29 +755,47 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return -200 - static_cast<int>(r);
     }
-    // Row-major [rows, ld] views of the output(s) and the residual for the staged (TMA) epilogue: 32x32 boxes,
-    // 64-byte swizzle.  The 2x2-replicating store keeps the direct path (its rows are not consecutive).
+    // Row-major [rows, ld] views of the output(s) and the residual for the staged (TMA) epilogue: one box of
+    // 32 rows x BN/4 columns per epilogue warp, swizzled by its row width.  The 2x2-replicating store walks
+    // the [B*2H*2W, ld] output with a traversal stride of 2 along the pixel dimension (needs the warp's 32
+    // pixels inside one image row).
+    static const bool no_tma_up2 = std::getenv("B200_NO_TMA_UP2") != nullptr;
     CUtensorMap tmOut = tmA, tmOut2 = tmA, tmRes = tmA;
-    p.tma_epi = up2 ? 0 : 1;
+    p.tma_epi = (up2 && (W % 32 != 0 || no_tma_up2)) ? 0 : 1;
     if (p.tma_epi) {
         const cuuint64_t rows = static_cast<cuuint64_t>(B) * H * W;
-        auto encode2d = [&](CUtensorMap* tm, const void* base, int cols, int ld) -> int {
-            const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), rows};
+        const int cw = BN / 2 < 64 ? BN / 2 : 64;  // box width: 32 columns (64-byte rows) or 64 (128-byte rows)
+        const CUtensorMapSwizzle swz = cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+        auto encode2d = [&](CUtensorMap* tm, const void* base, int cols, int ld, cuuint64_t nrows, int pstride) -> int {
+            const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), nrows};
             const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-            const cuuint32_t box[2] = {32, 32};
-            const cuuint32_t estr[2] = {1, 1};
+            const cuuint32_t box[2] = {static_cast<cuuint32_t>(cw), static_cast<cuuint32_t>(32 * pstride)};
+            const cuuint32_t estr[2] = {1, static_cast<cuuint32_t>(pstride)};
             CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
-                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             return r == CUDA_SUCCESS ? 0 : -300 - static_cast<int>(r);
         };
         int rc = 0;
-        if (out != nullptr && (rc = encode2d(&tmOut, out, n_split, out_ld)) != 0) return rc;
-        if (two && (rc = encode2d(&tmOut2, out2, seg2, out2_ld)) != 0) return rc;
-        if (res_mode != 0 && (rc = encode2d(&tmRes, res, n_split, res_ld)) != 0) return rc;
+        if (out != nullptr && (rc = encode2d(&tmOut, out, n_split, out_ld, up2 ? rows * 4 : rows, up2 ? 2 : 1)) != 0)
+            return rc;
+        if (two && (rc = encode2d(&tmOut2, out2, seg2, out2_ld, rows, 1)) != 0) return rc;
+        if (res_mode != 0 && (rc = encode2d(&tmRes, res, n_split, res_ld, rows, 1)) != 0) return rc;
+    }
+    const int total = p.m_tiles * p.n_tiles;
+    int grid = total < g_num_sms ? total : g_num_sms;
+    if (ws) {  // every CTA keeps one N tile: the grid is a whole number of N-tile groups
+        const int groups = g_num_sms / p.n_tiles < p.m_tiles ? g_num_sms / p.n_tiles : p.m_tiles;
+        grid = groups * p.n_tiles;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (BN == 256) return launch<256>(tmA, tmB, tmOut, tmOut2, tmRes, p, s);
-    if (BN == 128) return launch<128>(tmA, tmB, tmOut, tmOut2, tmRes, p, s);
-    return launch<64>(tmA, tmB, tmOut, tmOut2, tmRes, p, s);
+    const bool g = gap != nullptr;
+    if (ws) {
+        if (BN == 128)
+            return dispatch<128, true>(res_mode, g, dot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
+        return dispatch<64, true>(res_mode, g, dot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
+    }
+    if (BN == 256) return dispatch<256, false>(res_mode, g, dot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
+    if (BN == 128) return dispatch<128, false>(res_mode, g, dot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
+    return dispatch<64, false>(res_mode, g, dot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
 }
