@@ -314,7 +314,7 @@ def main():
                         "ms_per_launch": dom_ms, "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
                         "share_of_step": sum(prof[dom_key]) / total_ms if total_ms else None}
         conv_ms = sum(sum(t) for (n, _), t in prof.items() if n == "b200_conv_gemm_ex")
-        kernels = sorted(((sum(t), n, k, len(t)) for (n, k), t in prof.items()), reverse=True)[:8]
+        kernels = sorted(((sum(t), n, k, len(t)) for (n, k), t in prof.items()), reverse=True)[:40]
         nsteps_prof = max(2, min(args.steps, 5))
         flop_case = FLOP_PER_CASE_FULL if args.aux == "full" else FLOP_PER_CASE_LOGITS
         line = {

@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 
@@ -48,8 +48,9 @@ _P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 SIGNATURES = {
     "b200_abi_version": [],
     "b200_conv_gemm": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
-    "b200_conv_gemm_ex": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I,
-                          _I, _P],
+    "b200_conv_gemm_ex": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _F, _P, _I, _I, _I,
+                          _I, _I, _I, _P],
+    "b200_mask_attention": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P],
     "b200_tapsum": [_P, _I, _I, _I, _P, _P, _P],
     "b200_dwi_normalize": [_P, _P, _I, _I, _I, _I, _F, _F, _P, _P],
     "b200_nyul_transform": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
@@ -146,7 +147,7 @@ def _bf16_map(t, name):
 
 
 def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0, out=None, up2=False, gap=None,
-              cin=None, store=True, n_split=None, act2=0, out2=None, dot_w=None, dot_out=None):
+              cin=None, store=True, n_split=None, act2=0, out2=None, dot_w=None, dot_out=None, dot_bias=0.0):
     """x [B,H,W,ld] bf16 NHWC (channels [0,cin) used); w [Cout, taps*cin] bf16.  Returns `out`
     (or (out, out2) when n_split is given: channels [n_split, Cout) form a second layer on the same input)."""
     _bf16_map(x, "x")
@@ -168,7 +169,8 @@ def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0,
     _call("b200_conv_gemm_ex", (B, H, W, cin, cout, taps), _ptr(x), x_ld, _ptr(w), _ptr(scale), _ptr(bias), _ptr(res),
           res.shape[-1] if res is not None else 0, res_mode, act, _ptr(out), out_ld,
           1 if up2 else 0, _ptr(gap), n1, _ptr(out2), out2.shape[-1] if out2 is not None else 0, act2,
-          _ptr(dot_w), _ptr(dot_out), B, H, W, cin, cout, taps, _stream())
+          _ptr(dot_w), dot_w.shape[0] if dot_w is not None else 0, float(dot_bias), _ptr(dot_out), B, H, W, cin, cout,
+          taps, _stream())
     return out if n_split is None else (out, out2)
 
 
@@ -244,6 +246,14 @@ def mask_tail(pre, w_out, b_out, mask_pred, attn_params=None, attn=None):
         hc, wa, gw, gb, wb, bb, eps = attn_params
     _call("b200_mask_tail", None, _ptr(pre), B, H * W, Cm, _ptr(w_out), _ptr(b_out), _ptr(mask_pred), hc, _ptr(wa),
                                 _ptr(gw), _ptr(gb), _ptr(wb), _ptr(bb), float(eps), _ptr(attn), _stream())
+
+
+def mask_attention(mask, attn_params, attn):
+    B = mask.shape[0]
+    hc, wa, gw, gb, wb, bb, eps = attn_params
+    _call("b200_mask_attention", None, _ptr(mask), B, mask[0].numel(), hc, _ptr(wa), _ptr(gw), _ptr(gb), _ptr(wb),
+          _ptr(bb), float(eps), _ptr(attn), _stream())
+    return attn
 
 
 def lift_c1(r, w, scale, bias, y):

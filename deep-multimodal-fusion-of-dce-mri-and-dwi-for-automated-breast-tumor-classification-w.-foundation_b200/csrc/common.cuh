@@ -10,6 +10,26 @@ namespace b200 {
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// GELU with erf(z) ~= z * P(z^2) on |z| <= 3 (8-term odd minimax polynomial, |erf error| < 9e-5, continuous
+// with +-1 at the clamp), two elements per instruction on the packed fp32x2 pipe (FFMA2 / FMUL2, sm_100).
+// Same function as the GEMM epilogue uses, so every stored activation goes through one GELU.
+__device__ __forceinline__ float2 gelu_poly2(float2 x) {
+    float2 z = __fmul2_rn(x, make_float2(0.70710678118654752f, 0.70710678118654752f));
+    z.x = fminf(fmaxf(z.x, -3.0f), 3.0f);
+    z.y = fminf(fmaxf(z.y, -3.0f), 3.0f);
+    const float2 t = __fmul2_rn(z, z);
+    float2 p = make_float2(-3.901667185e-07f, -3.901667185e-07f);
+    p = __ffma2_rn(p, t, make_float2(1.668003461e-05f, 1.668003461e-05f));
+    p = __ffma2_rn(p, t, make_float2(-3.086500801e-04f, -3.086500801e-04f));
+    p = __ffma2_rn(p, t, make_float2(3.281538375e-03f, 3.281538375e-03f));
+    p = __ffma2_rn(p, t, make_float2(-2.256273106e-02f, -2.256273106e-02f));
+    p = __ffma2_rn(p, t, make_float2(1.075116023e-01f, 1.075116023e-01f));
+    p = __ffma2_rn(p, t, make_float2(-3.730817735e-01f, -3.730817735e-01f));
+    p = __ffma2_rn(p, t, make_float2(1.127865076e+00f, 1.127865076e+00f));
+    const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+    return __ffma2_rn(h, __fmul2_rn(z, p), h);
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

@@ -54,8 +54,9 @@ struct ConvGemmParams {
     __nv_bfloat16* out2;
     int out2_ld;
     int act2;
-    const float* dot_w;    // [9, Cout] fp32 or nullptr: fused per-pixel projection of the epilogue result
-    float* dot_out;        // [pixels, 9] fp32
+    const float* dot_w;    // [ndot, Cout] fp32 or nullptr: fused per-pixel projection of the epilogue result
+    float* dot_out;        // [pixels, ndot] fp32 (+ dot_bias)
+    float dot_bias;
     int total_rows;        // B*H*W
     int stages;            // operand ring depth
     int off_ring, off_bar, off_union, off_rbox;  // shared-memory plan (bytes from the 1 KB-aligned base)
@@ -131,13 +132,14 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
 
 // Epilogue features are compile-time so that the per-element instruction stream carries no flag tests:
 //   RES  0 none, 1 residual added before the activation, 2 after it
-//   GAP  per-case channel sums          DOT  fused 9-tap dot products (no map store)
-template <int BN, bool WS, int RES, bool GAP, bool DOT>
+//   GAP  per-case channel sums          NDOT 0, or 1 / 9 fused per-pixel dot products (no map store)
+template <int BN, bool WS, int RES, bool GAP, int NDOT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
                  const __grid_constant__ CUtensorMap tmRes, const ConvGemmParams p) {
     using T = Tile<BN>;
+    constexpr bool DOT = NDOT > 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sW = smem;  // resident weights [k_blocks][BN x 64] (WS only)
@@ -147,12 +149,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* empty = full + kMaxStages;
     uint64_t* tfull = empty + kMaxStages;
     uint64_t* tempty = tfull + 2;
-    uint64_t* resbar = tempty + 2;  // [kNumEpiWarps] residual-box arrival, one per epilogue warp
-    uint64_t* wbar = resbar + kNumEpiWarps;
+    uint64_t* resbar = tempty + 2;  // [kNumEpiWarps][2] residual-box arrival, one per epilogue warp and box
+    uint64_t* wbar = resbar + 2 * kNumEpiWarps;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
     uint8_t* s_union = smem + p.off_union;
-    float* s_dotw = reinterpret_cast<float*>(s_union);  // [9][BN]        (tap-dot mode)
-    float* s_dots = s_dotw + 9 * BN;                    // [2][128][9]    (tap-dot mode)
+    float* s_dotw = reinterpret_cast<float*>(s_union);  // [NDOT][BN]       (dot mode)
+    float* s_dots = s_dotw + NDOT * BN;                 // [2][128][NDOT]   (dot mode)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -186,13 +188,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], kNumEpiWarps);
         }
-        for (int s = 0; s < kNumEpiWarps; ++s) mbar_init(&resbar[s], 1);
+        for (int s = 0; s < 2 * kNumEpiWarps; ++s) mbar_init(&resbar[s], 1);
         mbar_init(wbar, 1);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<T::kTmemCols>(tmem_slot);
     if (DOT && warp >= kEpiWarp0) {
-        for (int i = threadIdx.x - kEpiWarp0 * 32; i < 9 * BN; i += kNumEpiWarps * 32) s_dotw[i] = p.dot_w[i];
+        for (int i = threadIdx.x - kEpiWarp0 * 32; i < NDOT * BN; i += kNumEpiWarps * 32) s_dotw[i] = p.dot_w[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -276,8 +278,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int colw0 = half * T::kColsPerWarp;
         uint8_t* const obuf = s_union + ew * T::kWarpBoxBytes;
         uint8_t* const rbuf = smem + p.off_rbox + ew * T::kWarpBoxBytes;
-        uint64_t* const rbar = &resbar[ew];
-        uint32_t rphase = 0;
+        uint64_t* const rbar = &resbar[2 * ew];  // one barrier per staged residual box
+        uint32_t rphase = 0;                     // bit bx = phase of box bx
         // A staged box is 32 rows x kBoxCols bf16 under the TMA swizzle of its row width (64 or 128 B):
         // 16-byte chunk c of row r sits at chunk c ^ (((r * rowBytes) >> 7) & (rowBytes/16 - 1)).
         const int swz = ((lane * T::kRowBytes) >> 7) & (T::kRowBytes / 16 - 1);
@@ -286,6 +288,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int acc = 0;
         uint32_t acc_phase = 0;
         int tile = blockIdx.x, m_walk = m_first;
+        // Residual boxes are fetched one tile ahead: box bx of tile i+1 is requested as soon as the last lane
+        // has read box bx of tile i, so its DRAM latency hides behind the rest of tile i's epilogue.
+        auto res_fetch = [&](int t_idx, int m_idx, int bx) {
+            const int nt = WS ? my_n : t_idx % p.n_tiles;
+            const int mt = WS ? m_idx : t_idx / p.n_tiles;
+            mbar_arrive_expect_tx(&rbar[bx], T::kBoxBytes);
+            tma_load_2d(rbuf + bx * T::kBoxBytes, &tmRes, &rbar[bx], nt * BN + colw0 + bx * T::kBoxCols,
+                        mt * kBlockM + q * 32);
+        };
+        if (RES != 0 && tma_epi && lane == 0 && n_iters > 0) {
+#pragma unroll
+            for (int bx = 0; bx < T::kBoxesPerWarp; ++bx) res_fetch(tile, m_walk, bx);
+        }
         for (int it = 0; it < n_iters; ++it, tile += gridDim.x, m_walk += m_step) {
             const int n_tile = WS ? my_n : tile % p.n_tiles;
             const int m_tile = WS ? m_walk : tile / p.n_tiles;
@@ -297,20 +312,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool seg2 = n_tile * BN >= p.n_split;
             __nv_bfloat16* const out_ptr = seg2 ? p.out2 : p.out;
             const int act = seg2 ? p.act2 : p.act;
-            const bool use_res = RES != 0 && !seg2;
+            constexpr bool use_res = RES != 0;  // (the host rejects a residual together with two segments)
             const int out_col0 = (seg2 ? n_tile * BN - p.n_split : n_tile * BN) + colw0;
             const CUtensorMap* const tm_out = seg2 ? &tmOut2 : &tmOut;
             const int nbase = n_tile * BN + colw0;
-            float dsum[9];
+            float dsum[DOT ? NDOT : 1];
             if (DOT) {
 #pragma unroll
-                for (int k = 0; k < 9; ++k) dsum[k] = 0.f;
-            }
-            if (RES != 0 && use_res && tma_epi && lane == 0) {  // whole residual slab: in flight during the MMAs
-                mbar_arrive_expect_tx(rbar, T::kWarpBoxBytes);
-#pragma unroll
-                for (int bx = 0; bx < T::kBoxesPerWarp; ++bx)
-                    tma_load_2d(rbuf + bx * T::kBoxBytes, &tmRes, rbar, nbase + bx * T::kBoxCols, slab_row0);
+                for (int k = 0; k < NDOT; ++k) dsum[k] = 0.f;
             }
             if (!DOT && tma_epi && out_ptr != nullptr) {  // last tile's store has finished reading this warp's boxes
                 if (lane == 0) tma_store_wait_read<0>();
@@ -319,10 +328,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t tm_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + colw0;
-            if (RES != 0 && use_res && tma_epi) {
-                mbar_wait(rbar, rphase);
-                rphase ^= 1;
-            }
 #pragma unroll
             for (int ch = 0; ch < T::kChunksPerWarp; ++ch) {
                 const int n0 = nbase + ch * kChunk;
@@ -350,10 +355,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (use_res) {
                         uint4 u[4];
                         if (tma_epi) {
+                            constexpr int kChunksPerBox = T::kBoxCols / kChunk;
+                            if (ch % kChunksPerBox == 0) {  // first use of this box in this tile
+                                mbar_wait(&rbar[bx], (rphase >> bx) & 1u);
+                                rphase ^= 1u << bx;
+                            }
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 u[j] = *reinterpret_cast<const uint4*>(rbuf + bx * T::kBoxBytes + row_off +
                                                                        (((c16 + j) ^ swz) << 4));
+                            if (ch % kChunksPerBox == kChunksPerBox - 1) {  // last use: refill it for the next tile
+                                __syncwarp();
+                                if (lane == 0 && it + 1 < n_iters) res_fetch(tile + gridDim.x, m_walk + m_step, bx);
+                            }
                         } else if (valid) {
                             const uint4* r4 = reinterpret_cast<const uint4*>(p.res + static_cast<long long>(pix) * p.res_ld + n0);
 #pragma unroll
@@ -388,7 +402,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 if (DOT) {
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) {
+                    for (int k = 0; k < NDOT; ++k) {
                         const float4* w4 = reinterpret_cast<const float4*>(s_dotw + k * BN + colw0 + ch * kChunk);
 #pragma unroll
                         for (int j = 0; j < kChunk / 4; ++j) {
@@ -433,26 +447,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     }
                 }
-                if (GAP) {
-                    if (!valid) {
-#pragma unroll
-                        for (int j = 0; j < kChunk; ++j) v[j] = 0.f;
-                    }
-                    // Transposed warp reduction: after the 5 halving steps lane L holds the sum over the warp's
-                    // 32 rows of column L.
-#pragma unroll
-                    for (int s = 16; s >= 1; s >>= 1) {
-                        const bool upper = (lane & s) != 0;
-#pragma unroll
-                        for (int i = 0; i < s; ++i) {
-                            const float send = upper ? v[i] : v[i + s];
-                            const float keep = upper ? v[i + s] : v[i];
-                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-                        }
-                    }
-                    const int b = slab_row0 / (p.H * p.W);  // a 32-row slab never straddles two cases
-                    atomicAdd(p.gap + static_cast<long long>(b) * p.Cout + n0 + lane, v[0]);
-                }
             }
             tc_fence_before();
             __syncwarp();
@@ -483,20 +477,44 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tma_store_commit();
                 }
             }
+            if (GAP) {
+                // Per-case channel sums from the staged bf16 boxes (exactly the values the map holds): lane L
+                // adds columns 2L, 2L+1 of each box over the slab's valid rows; one atomic per column and warp.
+                const int n_valid = min(32, p.total_rows - slab_row0);
+                const int b = slab_row0 / (p.H * p.W);  // a 32-row slab never straddles two cases
+                constexpr int kLanes = T::kBoxCols / 2;
+                if (lane < kLanes) {
+#pragma unroll
+                    for (int bx = 0; bx < T::kBoxesPerWarp; ++bx) {
+                        float s0 = 0.f, s1 = 0.f;
+                        const uint8_t* base = obuf + bx * T::kBoxBytes + (lane & 3) * 4;
+#pragma unroll 8
+                        for (int rr = 0; rr < n_valid; ++rr) {
+                            const int phys = (lane >> 2) ^ (((rr * T::kRowBytes) >> 7) & (T::kRowBytes / 16 - 1));
+                            const uint32_t wv = *reinterpret_cast<const uint32_t*>(base + rr * T::kRowBytes + (phys << 4));
+                            s0 += __uint_as_float(wv << 16);
+                            s1 += __uint_as_float(wv & 0xffff0000u);
+                        }
+                        float* g = p.gap + static_cast<long long>(b) * p.Cout + nbase + bx * T::kBoxCols + 2 * lane;
+                        atomicAdd(g, s0);
+                        atomicAdd(g + 1, s1);
+                    }
+                }
+            }
             if (DOT) {
                 // The two column halves of a row live in different warps: half 1 parks its 9 partial sums in
                 // shared memory (double buffered by accumulator stage), one named barrier over the 8 epilogue
                 // warps, half 0 adds its own and writes the row.  Deterministic, no atomics.
-                float* buf = s_dots + (acc * kBlockM + q * 32 + lane) * 9;
+                float* buf = s_dots + (acc * kBlockM + q * 32 + lane) * NDOT;
                 if (half == 1) {
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) buf[k] = dsum[k];
+                    for (int k = 0; k < NDOT; ++k) buf[k] = dsum[k];
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (half == 0 && valid) {
-                    float* dst = p.dot_out + static_cast<long long>(pix) * 9;
+                    float* dst = p.dot_out + static_cast<long long>(pix) * NDOT;
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) dst[k] = dsum[k] + buf[k];
+                    for (int k = 0; k < NDOT; ++k) dst[k] = dsum[k] + buf[k] + p.dot_bias;
                 }
             }
             acc ^= 1;
@@ -534,41 +552,42 @@ static EncodeTiledFn get_encode_fn() {
 static int g_num_sms = 0;
 constexpr int kSmemLimit = 227 * 1024;
 
-template <int BN, bool WS, int RES, bool GAP, bool DOT>
+template <int BN, bool WS, int RES, bool GAP, int NDOT>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmOut2,
                   const CUtensorMap& tmRes, const ConvGemmParams& p, int smem_bytes, int grid, cudaStream_t stream) {
     static int configured = 0;
     if (smem_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, WS, RES, GAP, DOT>,
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, WS, RES, GAP, NDOT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return static_cast<int>(e);
         configured = smem_bytes;
     }
-    conv_gemm_kernel<BN, WS, RES, GAP, DOT><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmOut, tmOut2, tmRes, p);
+    conv_gemm_kernel<BN, WS, RES, GAP, NDOT><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmOut, tmOut2, tmRes, p);
     return static_cast<int>(cudaGetLastError());
 }
 
 template <int BN, bool WS>
-static int dispatch(int res_mode, bool gap, bool dot, const CUtensorMap& tmA, const CUtensorMap& tmB,
+static int dispatch(int res_mode, bool gap, int ndot, const CUtensorMap& tmA, const CUtensorMap& tmB,
                     const CUtensorMap& tmOut, const CUtensorMap& tmOut2, const CUtensorMap& tmRes,
                     const ConvGemmParams& p, int smem_bytes, int grid, cudaStream_t s) {
 #define B200_GO(RES, GAP, DOT) \
     return launch<BN, WS, RES, GAP, DOT>(tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s)
-    if (dot) {
+    if (ndot != 0) {
         if constexpr (!WS) {
-            if (res_mode == 0 && !gap) B200_GO(0, false, true);
+            if (res_mode == 0 && !gap && ndot == 9) B200_GO(0, false, 9);
+            if (res_mode == 0 && !gap && ndot == 1) B200_GO(0, false, 1);
         }
         return -14;
     }
     if (res_mode == 0) {
-        if (gap) B200_GO(0, true, false);
-        B200_GO(0, false, false);
+        if (gap) B200_GO(0, true, 0);
+        B200_GO(0, false, 0);
     }
     if (res_mode == 1) {
-        if (gap) B200_GO(1, true, false);
-        B200_GO(1, false, false);
+        if (gap) B200_GO(1, true, 0);
+        B200_GO(1, false, 0);
     }
-    if (res_mode == 2 && !gap) B200_GO(2, false, false);
+    if (res_mode == 2 && !gap) B200_GO(2, false, 0);
     return -14;
 #undef B200_GO
 }
@@ -596,12 +615,12 @@ static inline int align1k(int v) { return (v + 1023) & ~1023; }
 
 // Lays out shared memory for (BN, weight-stationary?) and returns the total dynamic size, or -1 if the
 // configuration does not fit / leaves fewer than 3 ring stages.
-static int plan_smem(ConvGemmParams& p, int BN, bool ws, bool has_out, bool has_res, bool dot) {
+static int plan_smem(ConvGemmParams& p, int BN, bool ws, bool has_out, bool has_res, int ndot) {
     const int b_bytes = BN * kBlockK * 2;
     const int stage_bytes = ws ? kABytes : kABytes + b_bytes;
     const int box_all = kBlockM * BN * 2;  // 8 warps x (32 rows x BN/2 columns) of bf16
-    const int dot_bytes = 9 * BN * 4 + 2 * kBlockM * 9 * 4;
-    const int union_bytes = align1k(dot ? dot_bytes : (has_out ? box_all : 0));
+    const int dot_bytes = ndot * BN * 4 + 2 * kBlockM * ndot * 4;
+    const int union_bytes = align1k(ndot ? dot_bytes : (has_out ? box_all : 0));
     const int rbox_bytes = has_res ? align1k(box_all) : 0;
     const int resident = ws ? align1k(p.k_blocks * b_bytes) : 0;
     const int fixed = resident + align1k(kBarBytes) + union_bytes + rbox_bytes + 1024 /*base alignment slack*/;
@@ -622,14 +641,17 @@ extern "C" int b200_conv_gemm(const void* x, int x_ld, const void* w, const floa
                               const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
                               float* gap, int B, int H, int W, int Cin, int Cout, int taps, void* stream) {
     return b200_conv_gemm_ex(x, x_ld, w, scale, bias, res, res_ld, res_mode, act, out, out_ld, up2, gap, Cout, nullptr,
-                             0, 0, nullptr, nullptr, B, H, W, Cin, Cout, taps, stream);
+                             0, 0, nullptr, 0, 0.f, nullptr, B, H, W, Cin, Cout, taps, stream);
 }
 
 extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
                                  const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
                                  float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w,
-                                 float* dot_out, int B, int H, int W, int Cin, int Cout, int taps, void* stream) {
+                                 int ndot, float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout,
+                                 int taps, void* stream) {
     using namespace b200;
+    if (dot_w == nullptr) ndot = 0;
+    if (ndot != 0 && ndot != 1 && ndot != 9) return -18;
     if (x == nullptr || w == nullptr || B <= 0 || H <= 0 || W <= 0) return -1;
     if (Cin % 64 != 0 || Cout % 64 != 0 || (taps != 1 && taps != 9)) return -2;
     if (x_ld % 8 != 0 || x_ld < Cin || (out != nullptr && out_ld % 8 != 0)) return -3;
@@ -658,8 +680,9 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
     if (n_split <= 0 || n_split > Cout || n_split % 64 != 0) return -10;
     const bool two = n_split < Cout;
     if (two && (out2 == nullptr || out2_ld % 8 != 0 || (reinterpret_cast<uintptr_t>(out2) & 15) || gap != nullptr ||
-                up2 || dot_w != nullptr))
+                up2 || dot_w != nullptr || res_mode != 0))
         return -11;
+    if (gap != nullptr && (out == nullptr || up2)) return -17;  // channel sums are taken from the staged output boxes
     const int seg2 = Cout - n_split;
     if (dot_w != nullptr && (dot_out == nullptr || H == 1 || out != nullptr)) return -12;
     p.m_tiles = B * p.tiles_w * p.tiles_h;
@@ -680,13 +703,13 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
     // is opt-in (B200_WS=1) until a 2-CTA / multicast version makes it pay.
     static const bool no_ws = std::getenv("B200_WS") == nullptr;
     auto divides = [&](int bn) { return Cout % bn == 0 && n_split % bn == 0 && (!two || seg2 % bn == 0); };
-    const bool has_out = out != nullptr, has_res = res_mode != 0, dot = dot_w != nullptr;
+    const bool has_out = out != nullptr, has_res = res_mode != 0, dot = ndot != 0;
     int BN = 0, smem_bytes = -1;
     bool ws = false;
     if (taps == 1 && !dot && !no_ws) {
         for (int bn : {128, 64}) {
             if (!divides(bn) || Cout / bn > g_num_sms || p.k_blocks * bn * kBlockK * 2 > 128 * 1024) continue;
-            smem_bytes = plan_smem(p, bn, true, has_out, has_res, false);
+            smem_bytes = plan_smem(p, bn, true, has_out, has_res, 0);
             if (smem_bytes > 0) {
                 BN = bn;
                 ws = true;
@@ -697,7 +720,7 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
     if (!ws) {
         for (int bn : {256, 128, 64}) {
             if (!divides(bn) || (dot && bn != Cout)) continue;
-            smem_bytes = plan_smem(p, bn, false, has_out, has_res, dot);
+            smem_bytes = plan_smem(p, bn, false, has_out, has_res, ndot);
             if (smem_bytes > 0) {
                 BN = bn;
                 break;
@@ -722,6 +745,7 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
     p.act2 = act2;
     p.dot_w = dot_w;
     p.dot_out = dot_out;
+    p.dot_bias = dot_bias;
     p.total_rows = B * H * W;
     if (Cout > 8192) return -15;
     if (p.scale == nullptr) p.scale = identity_affine(true);
@@ -792,10 +816,10 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
     const bool g = gap != nullptr;
     if (ws) {
         if (BN == 128)
-            return dispatch<128, true>(res_mode, g, dot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
-        return dispatch<64, true>(res_mode, g, dot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
+            return dispatch<128, true>(res_mode, g, ndot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
+        return dispatch<64, true>(res_mode, g, ndot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
     }
-    if (BN == 256) return dispatch<256, false>(res_mode, g, dot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
-    if (BN == 128) return dispatch<128, false>(res_mode, g, dot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
-    return dispatch<64, false>(res_mode, g, dot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
+    if (BN == 256) return dispatch<256, false>(res_mode, g, ndot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
+    if (BN == 128) return dispatch<128, false>(res_mode, g, ndot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
+    return dispatch<64, false>(res_mode, g, ndot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
 }

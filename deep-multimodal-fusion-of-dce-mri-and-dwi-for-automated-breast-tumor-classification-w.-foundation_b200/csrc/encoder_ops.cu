@@ -12,28 +12,40 @@ namespace b200 {
 // model_module.py:649-650 (modality SE, SEBlock :25-43) followed by the two stride-s 1x1
 // convolutions of block1 that read the raw input: skip (:276-280) and the first
 // bottleneck conv + BN + GELU (:260-262).  Input is fp32 NCHW (what the normalisers
-// emit), outputs are NHWC bf16.  One CTA = one case x `kStemPix` output pixels, one
-// thread per output channel with its weight column in registers.
+// emit), outputs are NHWC bf16.  K = C <= 32 is far too thin for the tensor cores and the
+// layer is write-bound, so this is fp32 SIMT: one CTA = one case x 64 consecutive output
+// pixels; every thread owns one pixel and a quarter of the output channels, weights are
+// broadcast from shared memory, and the [64 px][n_out] bf16 tile is staged in shared memory
+// so that both maps leave the SM as fully coalesced 16-byte stores.
 constexpr int kStemPix = 64;
 constexpr int kStemMaxC = 32;
+constexpr int kStemThreads = 256;
+constexpr int kStemCB = 16;  // output channels per register block
 
-__global__ void stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
-                            const float* __restrict__ plane_mean,  // [B, C]
-                            const float* __restrict__ se_w1, const float* __restrict__ se_b1,  // [Cm, C], [Cm]
-                            const float* __restrict__ se_w2, const float* __restrict__ se_b2,  // [C, Cm], [C]
-                            int Cm,
-                            const float* __restrict__ wcat,   // [n_skip + n_mid, C]
-                            const float* __restrict__ scale,  // [n_skip + n_mid]
-                            const float* __restrict__ bias, int n_skip, int n_mid,
-                            __nv_bfloat16* __restrict__ skip_out, __nv_bfloat16* __restrict__ mid_out,
-                            float* __restrict__ mod_attn) {
+template <int CMAX>
+__global__ void __launch_bounds__(kStemThreads)
+stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
+            const float* __restrict__ plane_mean,  // [B, C]
+            const float* __restrict__ se_w1, const float* __restrict__ se_b1,  // [Cm, C], [Cm]
+            const float* __restrict__ se_w2, const float* __restrict__ se_b2,  // [C, Cm], [C]
+            int Cm,
+            const float* __restrict__ wcat,   // [n_out, C], n_out = n_skip + n_mid
+            const float* __restrict__ scale,  // [n_out]
+            const float* __restrict__ bias, int n_skip, int n_mid, __nv_bfloat16* __restrict__ skip_out,
+            __nv_bfloat16* __restrict__ mid_out, float* __restrict__ mod_attn) {
+    extern __shared__ float s_dyn[];
     __shared__ float s_gate[kStemMaxC];
     __shared__ float s_hidden[kStemMaxC];
-    __shared__ float s_x[kStemMaxC][kStemPix];
+    const int n_out = n_skip + n_mid;       // multiple of 4 * kStemCB (host-checked)
+    const int row_words = n_out / 2 + 1;    // staged row: n_out bf16 + one pad word -> odd stride, no bank conflicts
+    float* s_w = s_dyn;                     // [C][n_out] transposed weights
+    float* s_sc = s_w + C * n_out;          // [n_out]
+    float* s_bi = s_sc + n_out;             // [n_out]
+    uint32_t* s_out = reinterpret_cast<uint32_t*>(s_bi + n_out);  // [kStemPix][row_words]
     const int b = blockIdx.y;
     const int Ho = H / stride, Wo = W / stride;
-    const int pix0 = blockIdx.x * kStemPix;
     const int npix = Ho * Wo;
+    const int pix0 = blockIdx.x * kStemPix;
     const int tid = threadIdx.x;
 
     if (se_w1 != nullptr) {
@@ -53,48 +65,76 @@ __global__ void stem_kernel(const float* __restrict__ x, int C, int H, int W, in
     } else if (tid < C) {
         s_gate[tid] = 1.f;
     }
-    __syncthreads();
-    for (int i = tid; i < C * kStemPix; i += blockDim.x) {
-        const int c = i / kStemPix, pp = i % kStemPix;
-        const int pix = pix0 + pp;
-        float v = 0.f;
-        if (pix < npix) {
-            const int ho = pix / Wo, wo = pix % Wo;
-            v = x[((static_cast<size_t>(b) * C + c) * H + ho * stride) * W + wo * stride] * s_gate[c];
-        }
-        s_x[c][pp] = v;
+    for (int i = tid; i < C * n_out; i += kStemThreads) {
+        const int c = i / n_out, n = i - c * n_out;
+        s_w[i] = wcat[n * C + c];
+    }
+    for (int i = tid; i < n_out; i += kStemThreads) {
+        s_sc[i] = scale[i];
+        s_bi[i] = bias[i];
     }
     __syncthreads();
-    const int n = tid;
-    if (n >= n_skip + n_mid) return;
-    float wreg[kStemMaxC];
+
+    const int pp = tid % kStemPix;
+    const int quarter = tid / kStemPix;  // 0..3
+    const int pix = pix0 + pp;
+    float2 xv[CMAX];  // the pixel's gated input, duplicated into both halves of a packed operand
+    {
+        const int ho = pix / Wo, wo = pix - ho * Wo;
+        const float* src = x + (static_cast<size_t>(b) * C * H + static_cast<size_t>(ho) * stride) * W + wo * stride;
 #pragma unroll
-    for (int c = 0; c < kStemMaxC; ++c) wreg[c] = c < C ? wcat[n * C + c] : 0.f;
-    const float sc = scale[n], bi = bias[n];
-    const bool is_mid = n >= n_skip;
-    __nv_bfloat16* dst = is_mid ? mid_out : skip_out;
-    const int ld = is_mid ? n_mid : n_skip;
-    const int nn = is_mid ? n - n_skip : n;
-    for (int pp = 0; pp < kStemPix; pp += 4) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int c = 0; c < CMAX; ++c) {
+            const float v = (c < C && pix < npix) ? __ldg(src + static_cast<size_t>(c) * H * W) * s_gate[c] : 0.f;
+            xv[c] = make_float2(v, v);
+        }
+    }
+    const int per_quarter = n_out / 4;
+    for (int n0 = quarter * per_quarter; n0 < (quarter + 1) * per_quarter; n0 += kStemCB) {
+        float2 acc[kStemCB / 2];
 #pragma unroll
-        for (int c = 0; c < kStemMaxC; ++c) {
+        for (int j = 0; j < kStemCB / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
             if (c < C) {
-                const float4 xv = *reinterpret_cast<const float4*>(&s_x[c][pp]);
-                a0 += wreg[c] * xv.x;
-                a1 += wreg[c] * xv.y;
-                a2 += wreg[c] * xv.z;
-                a3 += wreg[c] * xv.w;
+                const float4* w4 = reinterpret_cast<const float4*>(s_w + c * n_out + n0);
+#pragma unroll
+                for (int j = 0; j < kStemCB / 4; ++j) {
+                    const float4 wv = w4[j];
+                    acc[2 * j + 0] = __ffma2_rn(xv[c], make_float2(wv.x, wv.y), acc[2 * j + 0]);
+                    acc[2 * j + 1] = __ffma2_rn(xv[c], make_float2(wv.z, wv.w), acc[2 * j + 1]);
+                }
             }
         }
-        float r[4] = {a0 * sc + bi, a1 * sc + bi, a2 * sc + bi, a3 * sc + bi};
+        const bool is_mid = n0 >= n_skip;  // a 16-channel block never straddles the two maps (host-checked)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int pix = pix0 + pp + k;
-            if (pix < npix) {
-                const float y = is_mid ? gelu_exact(r[k]) : r[k];
-                dst[(static_cast<size_t>(b) * npix + pix) * ld + nn] = __float2bfloat16(y);
-            }
+        for (int j = 0; j < kStemCB / 2; ++j) {
+            const float2 sc = *reinterpret_cast<const float2*>(s_sc + n0 + 2 * j);
+            const float2 bi = *reinterpret_cast<const float2*>(s_bi + n0 + 2 * j);
+            float2 y = __ffma2_rn(acc[j], sc, bi);
+            if (is_mid) y = gelu_poly2(y);
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(y.x, y.y);
+            s_out[pp * row_words + n0 / 2 + j] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+    }
+    __syncthreads();
+    // copy out: the CTA's pixels are consecutive, so each map's slice is one contiguous block in HBM
+    const int valid_pix = min(kStemPix, npix - pix0);
+    {
+        const int vec_per_pix = n_skip / 8;
+        uint4* dst = reinterpret_cast<uint4*>(skip_out + (static_cast<size_t>(b) * npix + pix0) * n_skip);
+        for (int i = tid; i < valid_pix * vec_per_pix; i += kStemThreads) {
+            const int pq = i / vec_per_pix, v = i - pq * vec_per_pix;
+            const uint32_t* src = s_out + pq * row_words + v * 4;
+            dst[i] = make_uint4(src[0], src[1], src[2], src[3]);
+        }
+    }
+    {
+        const int vec_per_pix = n_mid / 8;
+        uint4* dst = reinterpret_cast<uint4*>(mid_out + (static_cast<size_t>(b) * npix + pix0) * n_mid);
+        for (int i = tid; i < valid_pix * vec_per_pix; i += kStemThreads) {
+            const int pq = i / vec_per_pix, v = i - pq * vec_per_pix;
+            const uint32_t* src = s_out + pq * row_words + n_skip / 2 + v * 4;
+            dst[i] = make_uint4(src[0], src[1], src[2], src[3]);
         }
     }
 }
@@ -115,13 +155,29 @@ __global__ void se_gate_kernel(const float* __restrict__ gap_sum, float inv_npix
     __syncthreads();
     for (int m = threadIdx.x; m < Cm; m += blockDim.x) {
         float a = b1[m];
-        for (int c = 0; c < C; ++c) a += w1t[c * Cm + m] * s_m[c];
+        int c = 0;
+        for (; c + 8 <= C; c += 8) {  // 8 independent loads in flight per thread
+            float wv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) wv[k] = __ldg(w1t + (c + k) * Cm + m);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a = fmaf(wv[k], s_m[c + k], a);
+        }
+        for (; c < C; ++c) a = fmaf(__ldg(w1t + c * Cm + m), s_m[c], a);
         s_h[m] = gelu_exact(a);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float a = b2[c];
-        for (int m = 0; m < Cm; ++m) a += w2t[m * C + c] * s_h[m];
+        int m = 0;
+        for (; m + 8 <= Cm; m += 8) {
+            float wv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) wv[k] = __ldg(w2t + (m + k) * C + c);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a = fmaf(wv[k], s_h[m + k], a);
+        }
+        for (; m < Cm; ++m) a = fmaf(__ldg(w2t + m * C + c), s_h[m], a);
         gate[static_cast<size_t>(b) * C + c] = sigmoidf_(a);
     }
 }
@@ -224,21 +280,23 @@ __global__ void mask_tail_kernel(const __nv_bfloat16* __restrict__ pre, int Cm, 
     extern __shared__ float s_m[];  // npix floats
     __shared__ double scratch[33];
     const int b = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    // each warp handles pixels warp, warp+nwarps, ...; lanes split the Cm channels
-    for (int p = warp; p < npix; p += nwarps) {
-        const __nv_bfloat16* px = pre + (static_cast<size_t>(b) * npix + p) * Cm;
-        float acc = 0.f;
-        for (int c0 = lane * 2; c0 < Cm; c0 += 64) {
-            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(px + c0);
-            acc += __low2float(h) * w_out[c0] + __high2float(h) * w_out[c0 + 1];
+    // one thread per pixel: its Cm bf16 activations are one contiguous 2*Cm-byte row (16-byte loads);
+    // with pre == nullptr the mask is already there (emitted by the producing GEMM's fused dot product)
+    for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+        if (pre == nullptr) {
+            s_m[p] = mask_pred[static_cast<size_t>(b) * npix + p];
+            continue;
         }
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            const float m = acc + b_out[0];
-            s_m[p] = m;
-            mask_pred[static_cast<size_t>(b) * npix + p] = m;
+        const uint4* px = reinterpret_cast<const uint4*>(pre + (static_cast<size_t>(b) * npix + p) * Cm);
+        float acc = b_out[0];
+        for (int v = 0; v < Cm / 8; ++v) {
+            float f[8];
+            unpack_bf16x8(__ldg(px + v), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc = fmaf(f[k], __ldg(w_out + v * 8 + k), acc);
         }
+        s_m[p] = acc;
+        mask_pred[static_cast<size_t>(b) * npix + p] = acc;
     }
     __syncthreads();
     if (attn == nullptr) return;
@@ -264,7 +322,12 @@ __global__ void mask_tail_kernel(const __nv_bfloat16* __restrict__ pre, int Cm, 
     for (int p = threadIdx.x; p < npix; p += blockDim.x) {
         const float m = s_m[p];
         float a = bb[0];
-        for (int c = 0; c < Hc; ++c) a += wb[c] * gelu_exact((wa[c] * m - muf) * rstd * gn_w[c] + gn_b[c]);
+        for (int c = 0; c + 1 < Hc; c += 2) {
+            const float2 g = gelu_poly2(make_float2((wa[c] * m - muf) * rstd * gn_w[c] + gn_b[c],
+                                                    (wa[c + 1] * m - muf) * rstd * gn_w[c + 1] + gn_b[c + 1]));
+            a += wb[c] * g.x + wb[c + 1] * g.y;
+        }
+        if (Hc & 1) a += wb[Hc - 1] * gelu_exact((wa[Hc - 1] * m - muf) * rstd * gn_w[Hc - 1] + gn_b[Hc - 1]);
         const float A = fminf(fmaxf(sigmoidf_(a), 1e-4f), 1.0f - 1e-4f);
         attn[static_cast<size_t>(b) * npix + p] = A;
     }
@@ -284,7 +347,12 @@ __global__ void lift_c1_kernel(const float* __restrict__ r, size_t total_pix, in
         const float rv = r[i / nv];
         float f[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = gelu_exact(rv * w[n0 + k] * scale[n0 + k] + bias[n0 + k]);
+        for (int k = 0; k < 8; k += 2) {
+            const float2 g = gelu_poly2(make_float2(rv * w[n0 + k] * scale[n0 + k] + bias[n0 + k],
+                                                    rv * w[n0 + k + 1] * scale[n0 + k + 1] + bias[n0 + k + 1]));
+            f[k] = g.x;
+            f[k + 1] = g.y;
+        }
         reinterpret_cast<uint4*>(y)[i] = pack_bf16x8(f);
     }
 }
@@ -346,13 +414,23 @@ extern "C" int b200_stem(const float* x, int B, int C, int H, int W, int stride,
     if (x == nullptr || wcat == nullptr || scale == nullptr || bias == nullptr) return -2;
     if (se_w1 != nullptr && plane_mean == nullptr) return -3;
     const int n_out = n_skip + n_mid;
-    if (n_out <= 0 || n_out > 1024) return -4;
+    // register blocks of 16 channels per quarter of the outputs, none straddling the skip / mid boundary
+    if (n_out <= 0 || n_out % (4 * kStemCB) != 0 || n_skip % kStemCB != 0 || n_skip % 8 != 0 || n_mid % 8 != 0)
+        return -4;
+    if (skip_out == nullptr || mid_out == nullptr) return -5;
     const int npix = (H / stride) * (W / stride);
-    const int threads = ((n_out + 31) / 32) * 32;
+    const size_t smem = (static_cast<size_t>(C) * n_out + 2 * n_out) * sizeof(float) +
+                        static_cast<size_t>(kStemPix) * (n_out / 2 + 1) * sizeof(uint32_t);
+    if (smem > 48 * 1024) return -6;  // all supported shapes stay inside the default dynamic limit
     dim3 grid((npix + kStemPix - 1) / kStemPix, B);
-    stem_kernel<<<grid, threads < 64 ? 64 : threads, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, C, H, W, stride, plane_mean, se_w1, se_b1, se_w2, se_b2, Cm, wcat, scale, bias, n_skip, n_mid,
-        static_cast<__nv_bfloat16*>(skip_out), static_cast<__nv_bfloat16*>(mid_out), mod_attn);
+    auto go = [&](auto kern) {
+        kern<<<grid, kStemThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+            x, C, H, W, stride, plane_mean, se_w1, se_b1, se_w2, se_b2, Cm, wcat, scale, bias, n_skip, n_mid,
+            static_cast<__nv_bfloat16*>(skip_out), static_cast<__nv_bfloat16*>(mid_out), mod_attn);
+    };
+    if (C <= 8) go(stem_kernel<8>);
+    else if (C <= 16) go(stem_kernel<16>);
+    else go(stem_kernel<32>);
     return launch_status();
 }
 
@@ -402,7 +480,7 @@ extern "C" int b200_tapsum(const float* d, int B, int H, int W, const float* bia
 extern "C" int b200_mask_tail(const void* pre, int B, int npix, int Cm, const float* w_out, const float* b_out,
                               float* mask_pred, int Hc, const float* wa, const float* gn_w, const float* gn_b,
                               const float* wb, const float* bb, float gn_eps, float* attn, void* stream) {
-    if (B < 0 || npix <= 0 || Cm % 2 != 0 || npix > 12 * 1024) return -1;
+    if (B < 0 || npix <= 0 || Cm % 8 != 0 || npix > 12 * 1024) return -1;
     if (B == 0) return 0;
     if (pre == nullptr || w_out == nullptr || b_out == nullptr || mask_pred == nullptr) return -2;
     if (attn != nullptr && (wa == nullptr || gn_w == nullptr || gn_b == nullptr || wb == nullptr || bb == nullptr))
@@ -410,6 +488,19 @@ extern "C" int b200_mask_tail(const void* pre, int B, int npix, int Cm, const fl
     mask_tail_kernel<<<B, 256, npix * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(pre), Cm, npix, w_out, b_out, mask_pred, Hc, wa, gn_w, gn_b, wb, bb, gn_eps,
         attn);
+    return launch_status();
+}
+
+extern "C" int b200_mask_attention(const float* mask, int B, int npix, int Hc, const float* wa, const float* gn_w,
+                                   const float* gn_b, const float* wb, const float* bb, float gn_eps, float* attn,
+                                   void* stream) {
+    if (B < 0 || npix <= 0 || npix > 12 * 1024 || Hc <= 0) return -1;
+    if (B == 0) return 0;
+    if (mask == nullptr || attn == nullptr || wa == nullptr || gn_w == nullptr || gn_b == nullptr || wb == nullptr ||
+        bb == nullptr)
+        return -2;
+    mask_tail_kernel<<<B, 256, npix * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        nullptr, 0, npix, nullptr, nullptr, const_cast<float*>(mask), Hc, wa, gn_w, gn_b, wb, bb, gn_eps, attn);
     return launch_status();
 }
 

@@ -47,6 +47,7 @@ __device__ __forceinline__ void linear_tokens(const float* X, int ldx, const flo
         float acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 8
         for (int i = 0; i < Cin; ++i) {
             const float w = __ldg(Wt + static_cast<size_t>(i) * ldw + o);
 #pragma unroll

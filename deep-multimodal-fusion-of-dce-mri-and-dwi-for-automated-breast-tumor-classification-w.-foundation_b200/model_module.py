@@ -522,6 +522,7 @@ class ModelMaskHeadBackbone(nn.Module):
                 "align_w": _conv_w_bf16(al[0], dev), "align_s": s, "align_b": b,
                 "pre_w": _conv_w_bf16(mh.pre, dev), "pre_b": _f32(mh.pre.bias, dev),
                 "out_w": _f32(mh.out.weight.flatten(), dev), "out_b": _f32(mh.out.bias, dev),
+                "out_b_host": float(mh.out.bias.detach().float().cpu().item()),
                 "attn": (mproc[0].out_channels, _f32(mproc[0].weight.flatten(), dev), _f32(mproc[1].weight, dev),
                          _f32(mproc[1].bias, dev), _f32(mproc[3].weight.flatten(), dev), _f32(mproc[3].bias, dev),
                          mproc[1].eps),
@@ -609,12 +610,15 @@ class ModelMaskHeadBackbone(nn.Module):
             mk = pk["mask"]
             m_in = nat.conv_gemm(f1, mk["align_w"], taps=1, scale=mk["align_s"], bias=mk["align_b"], act=1, res=f2,
                                  res_mode=2)
-            mpre = nat.conv_gemm(m_in, mk["pre_w"], taps=1, bias=mk["pre_b"])
-            if mpre.shape[1] != self.mask_size:
+            if Ho != self.mask_size:
                 raise NotImplementedError("mask head resize paths (input != 32x32) are not built")
+            # mask head: `pre` (1x1, bias) with `out` (1x1 -> 1 channel) folded into its epilogue as an fp32
+            # dot product, so the 64-channel map is neither rounded to bf16 nor written to HBM
             mask_pred = torch.empty((B, 1, Ho, Wo), dtype=torch.float32, device=dev)
+            nat.conv_gemm(m_in, mk["pre_w"], taps=1, bias=mk["pre_b"], store=False, dot_w=mk["out_w"].view(1, -1),
+                          dot_out=mask_pred, dot_bias=mk["out_b_host"])
             attn_map = torch.empty((B, 1, Ho, Wo), dtype=torch.float32, device=dev)
-            nat.mask_tail(mpre, mk["out_w"], mk["out_b"], mask_pred, mk["attn"], attn_map)
+            nat.mask_attention(mask_pred, mk["attn"], attn_map)
             nat.scale_map(f2, f2, attn=attn_map, gamma=mk["gamma"])
         f3, _, gap3, gate3 = self._block_from_map(pk["b3"], f2, False)
 
@@ -752,6 +756,7 @@ class FusionModel(nn.Module):
               "in_dwi": _conv_w_bf16(self.proj_in_dwi, dev), "in_dce": _conv_w_bf16(self.proj_in_dce, dev),
               "mask_pre_w": _conv_w_bf16(mh.pre, dev), "mask_pre_b": _f32(mh.pre.bias, dev),
               "mask_out_w": _f32(mh.out.weight.flatten(), dev), "mask_out_b": _f32(mh.out.bias, dev),
+              "mask_out_b_host": float(mh.out.bias.detach().float().cpu().item()),
               "recon": _recon_pack(self.fusion_reconstruct, dev), "projF": _proj_pack(self.projF, dev)}
         self._pack_cache = (sig, pk)
         return pk
@@ -796,11 +801,11 @@ class FusionModel(nn.Module):
         nat.fusion_mix(p_dwi, p_dce, gating, lowres, gate if self.fusion_se is not None else None, hp, wp, fused)
         mask_logits = recon = proj = None
         if full:
-            mpre = nat.conv_gemm(fused, pk["mask_pre_w"], taps=1, bias=pk["mask_pre_b"])
             if H != self.mask_size:
                 raise NotImplementedError("mask head resize paths (input != 32x32) are not built")
             mask_logits = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
-            nat.mask_tail(mpre, pk["mask_out_w"], pk["mask_out_b"], mask_logits)
+            nat.conv_gemm(fused, pk["mask_pre_w"], taps=1, bias=pk["mask_pre_b"], store=False,
+                          dot_w=pk["mask_out_w"].view(1, -1), dot_out=mask_logits, dot_bias=pk["mask_out_b_host"])
             recon = _recon(pk["recon"], fused).unsqueeze(1)
             pj = pk["projF"]
             g = nat.conv_gemm(fused, pj["w0"], taps=1, scale=pj["s0"], bias=pj["b0"], act=1)

@@ -59,15 +59,18 @@ int b200_conv_gemm(const void* x, int x_ld, const void* w, const float* scale, c
  *     input (e.g. a block's skip conv and first bottleneck conv, code/model_module.py:299 and :303) and
  *     go to out2 with their own activation flag (no residual / gap / up2 on either segment then);
  *     n_split == Cout disables it.
- *   dot_w [9,Cout] fp32 / dot_out [pixels,9] fp32: additionally emits, per pixel, the 9 dot products of
- *     the epilogue result with dot_w[k,:] - the per-tap partial sums of the ReconHead's final 3x3,
- *     C -> 1 convolution (code/model_module.py:117); b200_tapsum finishes it.  Requires Cout in
- *     {64,128,256} (one N tile) and H > 1; `out` may then be NULL so the C-channel map never reaches HBM.
+ *   dot_w [ndot,Cout] fp32 / dot_out [pixels,ndot] fp32, ndot in {1, 9}: instead of storing the map, emits
+ *     per pixel the ndot dot products of the fp32 epilogue result with dot_w[k,:] (+ dot_bias).  ndot = 9:
+ *     the per-tap partial sums of the ReconHead's final 3x3, C -> 1 convolution
+ *     (code/model_module.py:117), finished by b200_tapsum.  ndot = 1: a following 1x1, C -> 1 convolution
+ *     (MaskHeadResize.out, code/model_module.py:187).  Requires Cout in {64,128,256} (one N tile), H > 1
+ *     and out == NULL: the C-channel map never reaches HBM and is never rounded to bf16.
  */
 int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
                       const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
-                      float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w,
-                      float* dot_out, int B, int H, int W, int Cin, int Cout, int taps, void* stream);
+                      float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w, int ndot,
+                      float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout, int taps,
+                      void* stream);
 
 /* out[b,h,w] = bias + sum_k d[(b,h+ky-1,w+kx-1)][k], zero padded: finishes a 3x3 C->1 conv from tap dots. */
 int b200_tapsum(const float* d, int B, int H, int W, const float* bias, float* out, void* stream);
@@ -136,6 +139,14 @@ int b200_conv3x3_c1(const void* x, int B, int H, int W, int C, const float* w, c
  * -> mask_pred fp32 [B,npix]; when attn != NULL also MaskGuidedSpatialAttention's
  * mask_processor (:67-73, :92-93) -> attention map fp32 [B,npix] in [1e-4, 1-1e-4].
  */
+/*
+ * MaskGuidedSpatialAttention.mask_processor (code/model_module.py:67-73, :92-93) on an fp32 1-channel map
+ * mask [B,npix] -> attention map fp32 [B,npix] clamped to [1e-4, 1-1e-4].
+ */
+int b200_mask_attention(const float* mask, int B, int npix, int Hc, const float* wa, const float* gn_w,
+                        const float* gn_b, const float* wb, const float* bb, float gn_eps, float* attn,
+                        void* stream);
+
 int b200_mask_tail(const void* pre, int B, int npix, int Cm, const float* w_out, const float* b_out,
                    float* mask_pred, int Hc, const float* wa, const float* gn_w, const float* gn_b, const float* wb,
                    const float* bb, float gn_eps, float* attn, void* stream);

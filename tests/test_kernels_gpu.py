@@ -134,3 +134,18 @@ def test_fast_gelu_deviation_is_below_bf16_resolution():
     ref = F.gelu(xs.float())
     err = (y.float() - ref).abs()
     assert (err <= 4e-3 * ref.abs() + 2.5e-4).all(), err.max()
+
+
+def test_fused_single_dot_is_a_following_1x1_conv_to_one_channel():
+    """Mask head: `pre` 1x1 conv + bias with `out` (C -> 1) folded into the epilogue (ndot = 1)."""
+    g = torch.Generator(device="cpu").manual_seed(3)
+    B, Cin, C = 3, 256, 64
+    x = (torch.randn(B, 32, 32, Cin, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(C, Cin, generator=g) / math.sqrt(Cin)).to(DEV).bfloat16()
+    bias = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    wo = (torch.randn(1, C, generator=g) / math.sqrt(C)).to(DEV)
+    out = torch.empty(B, 32, 32, 1, device=DEV)
+    nat.conv_gemm(x, w, taps=1, bias=bias, store=False, dot_w=wo, dot_out=out, dot_bias=0.25)
+    torch.cuda.synchronize()
+    ref = (x.float() @ w.float().t() + bias) @ wo.t() + 0.25
+    assert _rel(out, ref) < 1e-4

@@ -22,10 +22,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 NORM_TOL = 1e-5
 MODEL_TOL = 2e-2
-# Single-channel reconstruction maps (3x3, C->1) are cancellation-heavy sums over 9*C bf16
-# activations: their max-normalised error is larger than that of the wide maps.  north_star
-# states a tolerance for logits only; this one is ours and is reported, not hidden.
-RECON_TOL = 4e-2
+# Single-channel maps (reconstruction heads, mask logits) are cancellation-heavy sums over up to 9*C
+# activations; their producers keep those sums in fp32 (fused dot-product epilogues), which keeps them
+# inside the same 2e-2 as every other output.
+RECON_TOL = MODEL_TOL
 
 
 def _tol(key):
