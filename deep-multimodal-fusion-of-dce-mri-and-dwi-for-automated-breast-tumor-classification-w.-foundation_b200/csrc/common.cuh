@@ -37,6 +37,18 @@ __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
+// Block-wide sum of per-thread fp32 partials: fp32 shuffles inside a warp, fp64 across warps.
+__device__ __forceinline__ double block_sum_f(float v, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect scratch from a previous use
+    if (lane == 0) scratch[warp] = static_cast<double>(v);
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nwarps; ++w) t += scratch[w];  // broadcast reads, identical order in every thread
+    return t;
+}
+
 // Sum over the whole block; every thread gets the result.  `scratch` needs 33 elements.
 template <typename T>
 __device__ __forceinline__ T block_sum(T v, T* scratch) {

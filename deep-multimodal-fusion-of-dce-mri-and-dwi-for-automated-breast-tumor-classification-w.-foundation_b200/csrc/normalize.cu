@@ -22,60 +22,75 @@ constexpr int kNormThreads = 256;
 // ------------------------------------------------------------------ DWI ----
 template <int VEC>  // float4 values per thread kept in registers
 __global__ void __launch_bounds__(kNormThreads)
-dwi_normalize_reg_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int n, int skip_last,
-                         float z_lo, float z_hi, float* __restrict__ plane_mean) {
+dwi_normalize_reg_kernel(const float* __restrict__ x, float* __restrict__ out, int planes, int C, int n,
+                         int skip_last, float z_lo, float z_hi, float* __restrict__ plane_mean) {
     __shared__ double scratch[33];
-    const int plane = blockIdx.x;
-    const int c = plane % C;
     const int n4 = n >> 2;
-    const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(plane) * n);
-    float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(plane) * n);
-    if (skip_last && c == C - 1) {
-        for (int i = threadIdx.x; i < n4; i += kNormThreads) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (plane_mean != nullptr && threadIdx.x == 0) plane_mean[plane] = 0.f;
-        return;
-    }
-    float4 v[VEC];
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        const int i = threadIdx.x + j * kNormThreads;
-        v[j] = i < n4 ? __ldcs(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-    const double total = block_sum<double>(static_cast<double>(s), scratch);
-    const float mean = static_cast<float>(total / n);
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        const int i = threadIdx.x + j * kNormThreads;
-        if (i < n4) {
-            const float a = v[j].x - mean, b = v[j].y - mean, cc = v[j].z - mean, d = v[j].w - mean;
-            q += (a * a + b * b) + (cc * cc + d * d);
-        }
-    }
-    const double ss = block_sum<double>(static_cast<double>(q), scratch);
-    // torch.std(): unbiased (n-1); n == 1 gives NaN there as well.
-    const float sd = fmaxf(static_cast<float>(sqrt(ss / static_cast<double>(n - 1))), 1e-6f);
     const float range = z_hi - z_lo;
-    float osum = 0.f;
+    // Persistent CTAs: the next plane's loads are issued before the current plane's reductions, so HBM
+    // reads stay in flight across the block-wide barriers.
+    auto skipped = [&](int pl) { return skip_last && (pl % C) == C - 1; };
+    auto load = [&](int pl, float4 (&v)[VEC]) {
+        const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(pl) * n);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        const int i = threadIdx.x + j * kNormThreads;
-        if (i < n4) {
-            float4 o;
-            o.x = (fminf(fmaxf((v[j].x - mean) / sd, z_lo), z_hi) - z_lo) / range;
-            o.y = (fminf(fmaxf((v[j].y - mean) / sd, z_lo), z_hi) - z_lo) / range;
-            o.z = (fminf(fmaxf((v[j].z - mean) / sd, z_lo), z_hi) - z_lo) / range;
-            o.w = (fminf(fmaxf((v[j].w - mean) / sd, z_lo), z_hi) - z_lo) / range;
-            osum += (o.x + o.y) + (o.z + o.w);
-            __stcs(dst + i, o);
+        for (int j = 0; j < VEC; ++j) {
+            const int i = threadIdx.x + j * kNormThreads;
+            v[j] = (i < n4) ? __ldcs(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    }
-    if (plane_mean != nullptr) {
-        const double om = block_sum<double>(static_cast<double>(osum), scratch);
-        if (threadIdx.x == 0) plane_mean[plane] = static_cast<float>(om / n);
+    };
+    int plane = blockIdx.x;
+    float4 v[VEC], vn[VEC];
+    if (plane < planes && !skipped(plane)) load(plane, v);
+    for (; plane < planes; plane += gridDim.x) {
+        const int next = plane + gridDim.x;
+        if (next < planes && !skipped(next)) load(next, vn);
+        float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(plane) * n);
+        if (skipped(plane)) {
+            for (int i = threadIdx.x; i < n4; i += kNormThreads) __stcs(dst + i, make_float4(0.f, 0.f, 0.f, 0.f));
+            if (plane_mean != nullptr && threadIdx.x == 0) plane_mean[plane] = 0.f;
+        } else {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+            const double total = block_sum_f(s, scratch);
+            const float mean = static_cast<float>(total / n);
+            float q = 0.f;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const int i = threadIdx.x + j * kNormThreads;
+                if (i < n4) {
+                    const float a = v[j].x - mean, b = v[j].y - mean, cc = v[j].z - mean, d = v[j].w - mean;
+                    q += (a * a + b * b) + (cc * cc + d * d);
+                }
+            }
+            const double ss = block_sum_f(q, scratch);
+            // torch.std(): unbiased (n-1); n == 1 gives NaN there as well.
+            const float sd = fmaxf(static_cast<float>(sqrt(ss / static_cast<double>(n - 1))), 1e-6f);
+            // The two divisions of the reference become multiplications by correctly rounded reciprocals
+            // (<= 2 ulp from the divided form, far inside the 1e-5 tolerance): IEEE fp32 division costs ~10
+            // issue slots and would make this HBM-bound kernel ALU-bound.
+            const float inv_sd = 1.0f / sd, inv_range = 1.0f / range, off = -z_lo * inv_range;
+            float osum = 0.f;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const int i = threadIdx.x + j * kNormThreads;
+                if (i < n4) {
+                    float4 o;
+                    o.x = fmaf(fminf(fmaxf((v[j].x - mean) * inv_sd, z_lo), z_hi), inv_range, off);
+                    o.y = fmaf(fminf(fmaxf((v[j].y - mean) * inv_sd, z_lo), z_hi), inv_range, off);
+                    o.z = fmaf(fminf(fmaxf((v[j].z - mean) * inv_sd, z_lo), z_hi), inv_range, off);
+                    o.w = fmaf(fminf(fmaxf((v[j].w - mean) * inv_sd, z_lo), z_hi), inv_range, off);
+                    osum += (o.x + o.y) + (o.z + o.w);
+                    __stcs(dst + i, o);
+                }
+            }
+            if (plane_mean != nullptr) {
+                const double om = block_sum_f(osum, scratch);
+                if (threadIdx.x == 0) plane_mean[plane] = static_cast<float>(om / n);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v[j] = vn[j];
     }
 }
 
@@ -140,6 +155,17 @@ __device__ __forceinline__ double np_interp(double xv, const double* xp, const d
     return r;
 }
 
+constexpr int kNyulBins = 4096;   // linear bins over [min, max] of the plane
+constexpr int kNyulListCap = 64;   // candidates kept per landmark rank
+constexpr int kNyulMaxRanks = 2 * kMaxLandmarks;
+
+// One CTA per (case, channel) plane.  The 2L order statistics numpy's "linear" percentile rule needs are
+// found WITHOUT sorting the plane: a monotone linear binning of [min, max] into 4096 bins, an exclusive
+// scan, then for each wanted rank the (typically 1-3) samples of its bin are gathered and the in-bin rank
+// is resolved by counting.  Monotone binning preserves order, so the selected values are exactly the
+// sorted array's entries.  A bin holding more than 64 samples (heavy ties) falls back to a full in-shared-
+// memory bitonic sort of the plane.  Interpolation then runs from the shared-memory copy, so the plane is
+// read from HBM once and written once.
 __global__ void __launch_bounds__(kNyulThreads)
 nyul_transform_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int n, int npad, int L,
                       const double* __restrict__ avg_landmarks,  // [C, L]
@@ -147,57 +173,194 @@ nyul_transform_kernel(const float* __restrict__ x, float* __restrict__ out, int 
                       const int* __restrict__ prev_index,         // [L] floor(q*(n-1))
                       const double* __restrict__ gamma,           // [L] fractional part
                       float* __restrict__ plane_mean) {
-    extern __shared__ float sorted[];  // npad floats
+    extern __shared__ float s_x[];  // npad floats: the plane (later sorted in place on the fallback path)
+    __shared__ int s_hist[kNyulBins];
+    __shared__ unsigned char s_mark[kNyulBins];
+    __shared__ float s_list[kNyulMaxRanks][kNyulListCap];
+    __shared__ int s_cnt[kNyulMaxRanks];
+    __shared__ int s_rank[kNyulMaxRanks], s_bin[kNyulMaxRanks], s_inbin[kNyulMaxRanks], s_lid[kNyulMaxRanks];
+    __shared__ float s_val[kNyulMaxRanks];
+    __shared__ int s_flags[2];  // [0] overflow -> sort fallback, [1] number of distinct target bins
+    __shared__ float s_red[2 * (kNyulThreads / 32)];
+    __shared__ int s_scan[kNyulThreads / 32];
     __shared__ double s_orig[kMaxLandmarks], s_avg[kMaxLandmarks], s_std[kMaxLandmarks];
     __shared__ double s_slope1[kMaxLandmarks], s_slope2[kMaxLandmarks];
     __shared__ double scratch[33];
     const int plane = blockIdx.x;
     const int c = plane % C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* src = x + static_cast<size_t>(plane) * n;
     float* dst = out + static_cast<size_t>(plane) * n;
+    const int R = 2 * L;
 
-    for (int i = threadIdx.x; i < npad; i += kNyulThreads) sorted[i] = i < n ? __ldcs(src + i) : FLT_MAX;
-    __syncthreads();
-    // Bitonic sort, ascending.
-    for (int k = 2; k <= npad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (npad >> 1); t += kNyulThreads) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
-                const int l = i | j;
-                const bool up = (i & k) == 0;
-                const float a = sorted[i], b = sorted[l];
-                if ((a > b) == up) {
-                    sorted[i] = b;
-                    sorted[l] = a;
-                }
-            }
-            __syncthreads();
+    // ---- load, min / max ----
+    float mn = FLT_MAX, mx = -FLT_MAX;
+    for (int i = tid; i < npad; i += kNyulThreads) {
+        const float v = i < n ? __ldcs(src + i) : FLT_MAX;
+        s_x[i] = v;
+        if (i < n) {
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
         }
     }
-    if (threadIdx.x < L) {
-        const int t = threadIdx.x;
-        const int lo = prev_index[t];
-        const int hi = min(lo + 1, n - 1);
-        const float a = sorted[lo], b = sorted[hi];
-        const float diff = b - a;  // numpy subtracts in the array dtype (float32) first
+    for (int i = tid; i < kNyulBins; i += kNyulThreads) {
+        s_hist[i] = 0;
+        s_mark[i] = 0;
+    }
+    if (tid < kNyulMaxRanks) s_cnt[tid] = 0;
+    if (tid < 2) s_flags[tid] = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) {
+        s_red[warp] = mn;
+        s_red[kNyulThreads / 32 + warp] = mx;
+    }
+    __syncthreads();
+    mn = s_red[0];
+    mx = s_red[kNyulThreads / 32];
+    for (int w = 1; w < kNyulThreads / 32; ++w) {
+        mn = fminf(mn, s_red[w]);
+        mx = fmaxf(mx, s_red[kNyulThreads / 32 + w]);
+    }
+    const float range = mx - mn;
+    const float inv = range > 0.f ? static_cast<float>(kNyulBins) / range : 0.f;
+    auto bin_of = [&](float v) { return min(kNyulBins - 1, static_cast<int>((v - mn) * inv)); };
+
+    // ---- histogram + exclusive scan (s_hist becomes the count of samples in lower bins) ----
+    for (int i = tid; i < n; i += kNyulThreads) atomicAdd(&s_hist[bin_of(s_x[i])], 1);
+    __syncthreads();
+    {
+        constexpr int kPer = kNyulBins / kNyulThreads;  // 8 consecutive bins per thread
+        int local[kPer], sum = 0;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            local[k] = s_hist[tid * kPer + k];
+            sum += local[k];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < warp; ++w) base += s_scan[w];
+        int run = base + incl - sum;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            s_hist[tid * kPer + k] = run;
+            run += local[k];
+        }
+    }
+    __syncthreads();
+    // ---- locate the bin of every wanted rank ----
+    if (tid < R) {
+        const int l = tid >> 1;
+        const int lo = prev_index[l];
+        const int rank = (tid & 1) ? min(lo + 1, n - 1) : lo;
+        int a = 0, bnd = kNyulBins - 1;  // last bin whose exclusive prefix is <= rank
+        while (a < bnd) {
+            const int mid = (a + bnd + 1) >> 1;
+            if (s_hist[mid] <= rank) a = mid;
+            else bnd = mid - 1;
+        }
+        s_rank[tid] = rank;
+        s_bin[tid] = a;
+        s_inbin[tid] = rank - s_hist[a];
+    }
+    __syncthreads();
+    if (tid == 0) {  // distinct target bins -> candidate lists
+        int nl = 0;
+        for (int t = 0; t < R; ++t) {
+            int id = -1;
+            for (int u = 0; u < t; ++u)
+                if (s_bin[u] == s_bin[t]) {
+                    id = s_lid[u];
+                    break;
+                }
+            if (id < 0) {
+                id = nl++;
+                s_mark[s_bin[t]] = static_cast<unsigned char>(id + 1);
+            }
+            s_lid[t] = id;
+        }
+        s_flags[1] = nl;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kNyulThreads) {
+        const float v = s_x[i];
+        const int m = s_mark[bin_of(v)];
+        if (m != 0) {
+            const int pos = atomicAdd(&s_cnt[m - 1], 1);
+            if (pos < kNyulListCap) s_list[m - 1][pos] = v;
+            else s_flags[0] = 1;
+        }
+    }
+    __syncthreads();
+    const bool fallback = s_flags[0] != 0;
+    if (!fallback) {
+        // in-bin rank by counting: the wanted value e has (#smaller) <= r < (#smaller + #equal)
+        for (int t = warp; t < R; t += kNyulThreads / 32) {
+            const int id = s_lid[t], m = s_cnt[id], r = s_inbin[t];
+            for (int j = lane; j < m; j += 32) {
+                const float e = s_list[id][j];
+                int less = 0, eq = 0;
+                for (int k = 0; k < m; ++k) {
+                    const float f = s_list[id][k];
+                    less += f < e;
+                    eq += f == e;
+                }
+                if (less <= r && r < less + eq) s_val[t] = e;
+            }
+        }
+    } else {
+        // Bitonic sort of the padded plane, ascending (padding = FLT_MAX sorts to the end).
+        for (int k = 2; k <= npad; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (npad >> 1); t += kNyulThreads) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
+                    const int l2 = i | j;
+                    const bool up = (i & k) == 0;
+                    const float a = s_x[i], b2 = s_x[l2];
+                    if ((a > b2) == up) {
+                        s_x[i] = b2;
+                        s_x[l2] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (tid < R) s_val[tid] = s_x[s_rank[tid]];
+    }
+    __syncthreads();
+    if (tid < L) {
+        const int t = tid;
+        const float a = s_val[2 * t], b2 = s_val[2 * t + 1];
+        const float diff = b2 - a;  // numpy subtracts in the array dtype (float32) first
         const double g = gamma[t];
         double pv;
-        if (g >= 0.5) pv = __dadd_rn(static_cast<double>(b), -__dmul_rn(static_cast<double>(diff), __dadd_rn(1.0, -g)));
+        if (g >= 0.5) pv = __dadd_rn(static_cast<double>(b2), -__dmul_rn(static_cast<double>(diff), __dadd_rn(1.0, -g)));
         else pv = __dadd_rn(static_cast<double>(a), __dmul_rn(static_cast<double>(diff), g));
         s_orig[t] = pv;
         s_avg[t] = avg_landmarks[c * L + t];
         s_std[t] = standard_scale[t];
     }
     __syncthreads();
-    if (threadIdx.x < L - 1) {
-        const int t = threadIdx.x;
+    if (tid < L - 1) {
+        const int t = tid;
         s_slope1[t] = __ddiv_rn(__dadd_rn(s_avg[t + 1], -s_avg[t]), __dadd_rn(s_orig[t + 1], -s_orig[t]));
         s_slope2[t] = __ddiv_rn(__dadd_rn(s_std[t + 1], -s_std[t]), __dadd_rn(s_avg[t + 1], -s_avg[t]));
     }
     __syncthreads();
     double osum = 0.0;
-    for (int i = threadIdx.x; i < n; i += kNyulThreads) {
-        const double xv = static_cast<double>(src[i]);  // second read of the plane: L2/L1 hit
+    for (int i = tid; i < n; i += kNyulThreads) {
+        // the sort fallback permuted the shared copy: re-read the plane (an L2 hit) on that path only
+        const double xv = static_cast<double>(fallback ? src[i] : s_x[i]);
         const double mid = np_interp(xv, s_orig, s_avg, s_slope1, L);
         const float o = static_cast<float>(np_interp(mid, s_avg, s_std, s_slope2, L));
         osum += static_cast<double>(o);
@@ -205,7 +368,7 @@ nyul_transform_kernel(const float* __restrict__ x, float* __restrict__ out, int 
     }
     if (plane_mean != nullptr) {
         const double om = block_sum<double>(osum, scratch);
-        if (threadIdx.x == 0) plane_mean[plane] = static_cast<float>(om / n);
+        if (tid == 0) plane_mean[plane] = static_cast<float>(om / n);
     }
 }
 
@@ -230,10 +393,21 @@ extern "C" int b200_dwi_normalize(const float* x, float* out, int planes, int C,
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool aligned = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    // persistent grid = resident CTAs (64 / 114 registers per thread -> 4 / 2 CTAs of 256 threads per SM)
+    int grid = planes < sms * 4 ? planes : sms * 4;
     if (aligned && n <= kNormThreads * 4 * 4)
-        dwi_normalize_reg_kernel<4><<<planes, kNormThreads, 0, s>>>(x, out, C, n, skip_last, z_lo, z_hi, plane_mean);
+        dwi_normalize_reg_kernel<4><<<grid, kNormThreads, 0, s>>>(x, out, planes, C, n, skip_last, z_lo, z_hi,
+                                                                  plane_mean);
     else if (aligned && n <= kNormThreads * 4 * 8)
-        dwi_normalize_reg_kernel<8><<<planes, kNormThreads, 0, s>>>(x, out, C, n, skip_last, z_lo, z_hi, plane_mean);
+        dwi_normalize_reg_kernel<8><<<(grid = planes < sms * 2 ? planes : sms * 2), kNormThreads, 0, s>>>(x, out, planes, C, n, skip_last, z_lo, z_hi,
+                                                                  plane_mean);
     else
         dwi_normalize_stream_kernel<<<planes, kNormThreads, 0, s>>>(x, out, C, n, skip_last, z_lo, z_hi, plane_mean);
     return launch_status();

@@ -72,6 +72,17 @@ def main():
         conv_case("1x1 64->64 gelu up2 (proj out)", B, 32, 32, 64, 64, 1, up2=True),
         conv_case("1x1 64->64 gelu", B, 32, 32, 64, 64, 1),
     ]
+    import numpy as np
+    import dataset as b_dataset
+    import preprocess_helpers as b_pre
+    dwi = torch.rand(B, 16, 64, 64, device=DEV) * 1000 + 1
+    dce = torch.rand(B, 6, 64, 64, device=DEV)
+    pm = torch.empty(B * 16, device=DEV)
+    norm = b_dataset.DWINormalize()
+    nyul = b_pre.NyulStandardizer()
+    nyul.fit(list(dce[:16].cpu()), num_channels=6)
+    cases.insert(0, ("DWI normalise 16x64x64 (+plane means)", lambda: norm.batch(dwi, plane_mean=pm), B * 31 * 16384, 0.0))
+    cases.insert(1, ("DCE Nyul 6x64x64", lambda: nyul.transform_batch(dce), B * 12 * 16384, 0.0))
     print(f"{'case':42s} {'ms':>8s} {'GB/s':>8s} {'TFLOP/s':>8s}")
     for name, run, byts, flops in cases:
         if a.only and a.only not in name:
