@@ -42,6 +42,26 @@ class FusionWeights(C.Structure):
     ]
 
 
+class GemmDesc(C.Structure):
+    """Mirror of `struct b200_gemm_desc` (include/b200_fusion.h)."""
+
+    _fields_ = [
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("heads", C.c_int), ("batch", C.c_int),
+        ("a", C.c_void_p), ("a_row_stride", C.c_longlong), ("a_head_stride", C.c_longlong),
+        ("a_batch_stride", C.c_longlong), ("a_shared", C.c_int),
+        ("b", C.c_void_p), ("b_row_stride", C.c_longlong), ("b_head_stride", C.c_longlong),
+        ("b_batch_stride", C.c_longlong),
+        ("out", C.c_void_p), ("out_row_stride", C.c_longlong), ("out_head_stride", C.c_longlong),
+        ("out_batch_stride", C.c_longlong),
+        ("res", C.c_void_p), ("res_row_stride", C.c_longlong), ("res_head_stride", C.c_longlong),
+        ("res_batch_stride", C.c_longlong),
+        ("res_mode", C.c_int), ("act", C.c_int),
+        ("scale", C.c_void_p), ("bias", C.c_void_p), ("vec_h_stride", C.c_int),
+        ("rowscale", C.c_void_p), ("mode", C.c_int), ("alpha", C.c_float), ("n_valid", C.c_int),
+        ("rowsum_inv", C.c_void_p),
+    ]
+
+
 _P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
 # name -> argtypes; must list every symbol include/b200_fusion.h declares (tests check this).
@@ -52,6 +72,8 @@ SIGNATURES = {
                           _I, _I, _I, _P],
     "b200_mask_attention": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P],
     "b200_tapsum": [_P, _I, _I, _I, _P, _P, _P],
+    "b200_gemm_batched": [C.POINTER(GemmDesc), _P],
+    "b200_layernorm": [_P, _LL, _I, _P, _P, _F, _P, _P],
     "b200_dwi_normalize": [_P, _P, _I, _I, _I, _I, _F, _F, _P, _P],
     "b200_nyul_transform": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "b200_plane_mean": [_P, _I, _I, _P, _P],
@@ -157,10 +179,12 @@ def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0,
     assert w.dtype == torch.bfloat16 and w.is_contiguous() and w.shape[1] == taps * cin
     n1 = cout if n_split is None else n_split
     if out is None and store:
-        oh, ow = (2 * H, 2 * W) if up2 else (H, W)
+        oh, ow = (2 * H, 2 * W) if up2 else ((H // 2, W // 2) if taps == 4 else (H, W))
         out = torch.empty((B, oh, ow, n1), dtype=torch.bfloat16, device=x.device)
     if n_split is not None and out2 is None:
         out2 = torch.empty((B, H, W, cout - n_split), dtype=torch.bfloat16, device=x.device)
+    if gap is not None and taps == 4:
+        raise B200NativeError("gap with the strided patch-embedding conv is not supported")
     out_ld = out.shape[-1] if out is not None else 0
     if out is not None:
         _bf16_map(out, "out")
@@ -172,6 +196,32 @@ def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0,
           _ptr(dot_w), dot_w.shape[0] if dot_w is not None else 0, float(dot_bias), _ptr(dot_out), B, H, W, cin, cout,
           taps, _stream())
     return out if n_split is None else (out, out2)
+
+
+def gemm_batched(*, M, N, K, heads, batch, a, a_strides, b, b_strides, out, out_strides, a_shared=False, res=None,
+                 res_strides=(0, 0, 0), res_mode=0, act=0, scale=None, bias=None, vec_h_stride=0, rowscale=None,
+                 mode=0, alpha=1.0, n_valid=0, rowsum_inv=None):
+    """Batched K-major GEMM (see b200_gemm_batched).  a / b / out / res are data pointers (ints) so that views
+    with channel offsets can be passed; strides are (row, head, batch) in elements."""
+    d = GemmDesc()
+    d.M, d.N, d.K, d.heads, d.batch = M, N, K, heads, batch
+    d.a, (d.a_row_stride, d.a_head_stride, d.a_batch_stride), d.a_shared = a, a_strides, int(a_shared)
+    d.b, (d.b_row_stride, d.b_head_stride, d.b_batch_stride) = b, b_strides
+    d.out, (d.out_row_stride, d.out_head_stride, d.out_batch_stride) = out, out_strides
+    d.res, (d.res_row_stride, d.res_head_stride, d.res_batch_stride) = res, res_strides
+    d.res_mode, d.act = res_mode, act
+    d.scale, d.bias, d.vec_h_stride = _ptr(scale), _ptr(bias), vec_h_stride
+    d.rowscale, d.mode, d.alpha, d.n_valid, d.rowsum_inv = _ptr(rowscale), mode, float(alpha), n_valid, _ptr(rowsum_inv)
+    _call("b200_gemm_batched", (batch, heads, M, K, N, mode), C.byref(d), _stream())
+
+
+def layernorm(x, w, b, eps, out=None):
+    """x [rows, C] bf16 contiguous -> LayerNorm over C, bf16."""
+    rows, C_ = x.numel() // x.shape[-1], x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    _call("b200_layernorm", None, _ptr(x), rows, C_, _ptr(w), _ptr(b), float(eps), _ptr(out), _stream())
+    return out
 
 
 def tapsum(d, bias, out):

@@ -57,9 +57,17 @@ struct ConvGemmParams {
     const float* dot_w;    // [ndot, Cout] fp32 or nullptr: fused per-pixel projection of the epilogue result
     float* dot_out;        // [pixels, ndot] fp32 (+ dot_bias)
     float dot_bias;
-    int total_rows;        // B*H*W
+    int ndot;
+    int cstride;           // convolution stride (1, or 2 for the 2x2 / stride-2 patch embedding: taps == 4)
+    int a_batched;         // 0: the A operand is shared by every (h, b) (weights on the A side)
+    int b_mode;            // 0: B operand = 2-D weights [N, K]; 1: 4-D batched {K, N, H, B}
+    int bias_h_stride;     // scale / bias index = n + h * bias_h_stride (per-head vectors in batched GEMMs)
+    const float* rowscale; // optional per-row multiplier [B, H, W] applied before scale / bias (1 / softmax sum)
+    float* rowsum_inv;     // MODE 1: receives 1 / sum_j exp(...) per row, [B, H, W]
+    float alpha;           // MODE 1: logits = alpha * acc
+    int n_valid;           // MODE 1: number of real columns (keys); the rest are masked out
     int stages;            // operand ring depth
-    int off_ring, off_bar, off_union, off_rbox;  // shared-memory plan (bytes from the 1 KB-aligned base)
+    int off_ring, off_bar, off_union, off_rbox, off_sm;  // shared-memory plan (bytes from the 1 KB-aligned base)
 };
 
 constexpr int kBlockM = 128;
@@ -133,7 +141,9 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
 // Epilogue features are compile-time so that the per-element instruction stream carries no flag tests:
 //   RES  0 none, 1 residual added before the activation, 2 after it
 //   GAP  per-case channel sums          NDOT 0, or 1 / 9 fused per-pixel dot products (no map store)
-template <int BN, bool WS, int RES, bool GAP, int NDOT>
+//   MODE 0 standard; 1 row softmax numerator: out = exp(alpha*acc - rowmax) as bf16, 1/rowsum to rowsum_inv
+//        (the whole row lives in one N tile; the division is deferred to the consumer GEMM's rowscale)
+template <int BN, bool WS, int RES, bool GAP, int NDOT, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
@@ -224,12 +234,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (p.taps == 9) {
                         dy = tap / 3 - 1;
                         dx = tap % 3 - 1;
+                    } else if (p.taps == 4) {
+                        dy = tap >> 1;
+                        dx = tap & 1;
                     }
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], kStageBytes);
                     uint8_t* dst = sRing + stage * kStageBytes;
-                    tma_load_4d(dst, &tmA, &full[stage], c0, w0 + dx, h0 + dy, b);
-                    if (!WS) tma_load_2d(dst + kABytes, &tmB, &full[stage], kb * kBlockK, n_tile * BN);
+                    if (p.a_batched) tma_load_4d(dst, &tmA, &full[stage], c0, p.cstride * w0 + dx, p.cstride * h0 + dy, b);
+                    else tma_load_4d(dst, &tmA, &full[stage], c0, w0, 0, 0);
+                    if (!WS) {
+                        if (p.b_mode == 0) tma_load_2d(dst + kABytes, &tmB, &full[stage], kb * kBlockK, n_tile * BN);
+                        else tma_load_4d(dst + kABytes, &tmB, &full[stage], kb * kBlockK, n_tile * BN, h0, b);
+                    }
                     if (++stage == stages) {
                         stage = 0;
                         phase ^= 1;
@@ -293,9 +310,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         auto res_fetch = [&](int t_idx, int m_idx, int bx) {
             const int nt = WS ? my_n : t_idx % p.n_tiles;
             const int mt = WS ? m_idx : t_idx / p.n_tiles;
+            const int fw = (mt % p.tiles_w) * p.BW + (q * 32) % p.BW;
+            const int fh = ((mt / p.tiles_w) % p.tiles_h) * p.BH + (q * 32) / p.BW;
+            const int fb = mt / (p.tiles_w * p.tiles_h);
             mbar_arrive_expect_tx(&rbar[bx], T::kBoxBytes);
-            tma_load_2d(rbuf + bx * T::kBoxBytes, &tmRes, &rbar[bx], nt * BN + colw0 + bx * T::kBoxCols,
-                        mt * kBlockM + q * 32);
+            tma_load_4d(rbuf + bx * T::kBoxBytes, &tmRes, &rbar[bx], nt * BN + colw0 + bx * T::kBoxCols, fw, fh, fb);
         };
         if (RES != 0 && tma_epi && lane == 0 && n_iters > 0) {
 #pragma unroll
@@ -304,10 +323,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int it = 0; it < n_iters; ++it, tile += gridDim.x, m_walk += m_step) {
             const int n_tile = WS ? my_n : tile % p.n_tiles;
             const int m_tile = WS ? m_walk : tile / p.n_tiles;
-            // rows of a tile are 128 consecutive pixels of the flattened [B*H*W] map (GEMM mode: rows)
-            const int slab_row0 = m_tile * kBlockM + q * 32;
-            const int pix = slab_row0 + lane;
-            const bool valid = pix < p.total_rows;
+            // tile -> (w0, h0, b); this warp's slab = 32 consecutive rows of the tile = a {bw, bh} box in (w, h)
+            const int w0 = (m_tile % p.tiles_w) * p.BW;
+            const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.BH;
+            const int b = m_tile / (p.tiles_w * p.tiles_h);
+            const int slab_w = w0 + (q * 32) % p.BW, slab_h = h0 + (q * 32) / p.BW;
+            const int trow = q * 32 + lane;
+            const int pw = w0 + trow % p.BW, ph = h0 + trow / p.BW;
+            const bool valid = pw < p.W && ph < p.H;
+            const long long pix = (static_cast<long long>(b) * p.H + ph) * p.W + pw;
 
             const bool seg2 = n_tile * BN >= p.n_split;
             __nv_bfloat16* const out_ptr = seg2 ? p.out2 : p.out;
@@ -328,6 +352,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t tm_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + colw0;
+            const int vec_off = h0 * p.bias_h_stride;  // per-head scale / bias vectors (0 for convolutions)
+            const float row_mul = (MODE == 0 && p.rowscale != nullptr && valid) ? p.rowscale[pix] : 1.f;
+            float row_max2 = 0.f;  // MODE 1: row maximum of the logits, in log2 units
+            float* const s_sm = reinterpret_cast<float*>(smem + p.off_sm);  // [2 acc][2 halves][128] max, then sums
+            if (MODE == 1) {
+                const float k2 = p.alpha * 1.4426950408889634f;
+                float m = -INFINITY;
+#pragma unroll
+                for (int ch = 0; ch < T::kChunksPerWarp; ++ch) {
+                    uint32_t rr[kChunk];
+                    tmem_ld_32x32(tm_row + ch * kChunk, rr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j)
+                        if (colw0 + ch * kChunk + j < p.n_valid) m = fmaxf(m, __uint_as_float(rr[j]) * k2);
+                }
+                s_sm[(acc * 2 + half) * kBlockM + trow] = m;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                row_max2 = fmaxf(m, s_sm[(acc * 2 + (half ^ 1)) * kBlockM + trow]);
+            }
+            float row_sum = 0.f;
 #pragma unroll
             for (int ch = 0; ch < T::kChunksPerWarp; ++ch) {
                 const int n0 = nbase + ch * kChunk;
@@ -336,9 +381,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tmem_ld_wait();
                 float v[kChunk];
                 float2* const v2 = reinterpret_cast<float2*>(v);
-                {
-                    const float4* s4 = reinterpret_cast<const float4*>(p.scale + n0);
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+                if (MODE == 1) {
+                    // softmax numerator: logits = alpha * acc (columns >= n_valid masked), e = exp(logit - rowmax)
+                    const float k2 = p.alpha * 1.4426950408889634f;  // work in log2 units: exp(x) = exp2(x*log2 e)
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j) {
+                        const bool real = n0 + j < p.n_valid;
+                        const float e = real ? exp2f(fmaf(__uint_as_float(r[j]), k2, -row_max2)) : 0.f;
+                        v[j] = __bfloat162float(__float2bfloat16_rn(e));  // the sum must match what P.V will read
+                        row_sum += v[j];
+                    }
+                } else {
+                    if (p.rowscale != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < kChunk; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * row_mul);
+                    }
+                    const float4* s4 = reinterpret_cast<const float4*>(p.scale + n0 + vec_off);
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + vec_off);
 #pragma unroll
                     for (int j = 0; j < kChunk / 4; ++j) {
                         const float4 s = __ldg(s4 + j), t = __ldg(b4 + j);
@@ -430,9 +489,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int j = 0; j < 4; ++j)
                             *reinterpret_cast<uint4*>(obuf + bx * T::kBoxBytes + row_off + (((c16 + j) ^ swz) << 4)) = o[j];
                     } else if (valid) {  // direct 2x2-replicated store (only when the strided TMA form does not apply)
-                        const int hw = p.H * p.W;
-                        const int b = pix / hw, rem = pix - b * hw;
-                        const int h = rem / p.W, w = rem - h * p.W;
+                        const int h = ph, w = pw;
                         const int out_ld = seg2 ? p.out2_ld : p.out_ld;
 #pragma unroll
                         for (int rep = 0; rep < 4; ++rep) {
@@ -451,6 +508,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (MODE == 1) {
+                float* const s_sum = s_sm + 4 * kBlockM;
+                s_sum[(acc * 2 + half) * kBlockM + trow] = row_sum;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (half == 0 && valid)
+                    p.rowsum_inv[pix] = 1.0f / (row_sum + s_sum[(acc * 2 + 1) * kBlockM + trow]);
+            }
             if (!DOT && tma_epi && out_ptr != nullptr) {
                 // one TMA store per staged box: full 64/128-byte row segments, rows past the end are clipped
                 fence_proxy_async_smem();
@@ -459,19 +523,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (!p.up2) {
 #pragma unroll
                         for (int bx = 0; bx < T::kBoxesPerWarp; ++bx)
-                            tma_store_2d(tm_out, obuf + bx * T::kBoxBytes, out_col0 + bx * T::kBoxCols, slab_row0);
+                            tma_store_4d(tm_out, obuf + bx * T::kBoxBytes, out_col0 + bx * T::kBoxCols, slab_w, slab_h, b);
                     } else {
-                        // [B*2H*2W, C] map walked with traversal stride 2 along pixels: the same 32 source
-                        // pixels land on (2h+i, 2w+j) for the four (i, j)
-                        const int hw = p.H * p.W;
-                        const int b = slab_row0 / hw, rem = slab_row0 - b * hw;
-                        const int sh = rem / p.W, sw = rem - sh * p.W;
+                        // [B, 2H, 2W, C] map walked with traversal stride 2 along w and h: the slab's pixels
+                        // land on (2h+i, 2w+j) for the four (i, j)
 #pragma unroll
                         for (int rep = 0; rep < 4; ++rep) {
-                            const int orow = (b * 2 * p.H + 2 * sh + (rep >> 1)) * (2 * p.W) + 2 * sw + (rep & 1);
 #pragma unroll
                             for (int bx = 0; bx < T::kBoxesPerWarp; ++bx)
-                                tma_store_2d(tm_out, obuf + bx * T::kBoxBytes, out_col0 + bx * T::kBoxCols, orow);
+                                tma_store_4d(tm_out, obuf + bx * T::kBoxBytes, out_col0 + bx * T::kBoxCols,
+                                             2 * slab_w + (rep & 1), 2 * slab_h + (rep >> 1), b);
                         }
                     }
                     tma_store_commit();
@@ -480,8 +541,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (GAP) {
                 // Per-case channel sums from the staged bf16 boxes (exactly the values the map holds): lane L
                 // adds columns 2L, 2L+1 of each box over the slab's valid rows; one atomic per column and warp.
-                const int n_valid = min(32, p.total_rows - slab_row0);
-                const int b = slab_row0 / (p.H * p.W);  // a 32-row slab never straddles two cases
+                const int n_valid = __popc(__ballot_sync(0xffffffffu, valid));  // valid rows are a prefix of the slab
                 constexpr int kLanes = T::kBoxCols / 2;
                 if (lane < kLanes) {
 #pragma unroll
@@ -552,42 +612,49 @@ static EncodeTiledFn get_encode_fn() {
 static int g_num_sms = 0;
 constexpr int kSmemLimit = 227 * 1024;
 
-template <int BN, bool WS, int RES, bool GAP, int NDOT>
+template <int BN, bool WS, int RES, bool GAP, int NDOT, int MODE>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmOut2,
                   const CUtensorMap& tmRes, const ConvGemmParams& p, int smem_bytes, int grid, cudaStream_t stream) {
     static int configured = 0;
     if (smem_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, WS, RES, GAP, NDOT>,
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, WS, RES, GAP, NDOT, MODE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return static_cast<int>(e);
         configured = smem_bytes;
     }
-    conv_gemm_kernel<BN, WS, RES, GAP, NDOT><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmOut, tmOut2, tmRes, p);
+    conv_gemm_kernel<BN, WS, RES, GAP, NDOT, MODE>
+        <<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmOut, tmOut2, tmRes, p);
     return static_cast<int>(cudaGetLastError());
 }
 
 template <int BN, bool WS>
-static int dispatch(int res_mode, bool gap, int ndot, const CUtensorMap& tmA, const CUtensorMap& tmB,
+static int dispatch(int res_mode, bool gap, int ndot, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB,
                     const CUtensorMap& tmOut, const CUtensorMap& tmOut2, const CUtensorMap& tmRes,
                     const ConvGemmParams& p, int smem_bytes, int grid, cudaStream_t s) {
-#define B200_GO(RES, GAP, DOT) \
-    return launch<BN, WS, RES, GAP, DOT>(tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s)
+#define B200_GO(RES, GAP, DOT, MODE) \
+    return launch<BN, WS, RES, GAP, DOT, MODE>(tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s)
+    if (mode == 1) {
+        if constexpr (!WS && BN == 256) {
+            if (res_mode == 0 && !gap && ndot == 0) B200_GO(0, false, 0, 1);
+        }
+        return -14;
+    }
     if (ndot != 0) {
         if constexpr (!WS) {
-            if (res_mode == 0 && !gap && ndot == 9) B200_GO(0, false, 9);
-            if (res_mode == 0 && !gap && ndot == 1) B200_GO(0, false, 1);
+            if (res_mode == 0 && !gap && ndot == 9) B200_GO(0, false, 9, 0);
+            if (res_mode == 0 && !gap && ndot == 1) B200_GO(0, false, 1, 0);
         }
         return -14;
     }
     if (res_mode == 0) {
-        if (gap) B200_GO(0, true, 0);
-        B200_GO(0, false, 0);
+        if (gap) B200_GO(0, true, 0, 0);
+        B200_GO(0, false, 0, 0);
     }
     if (res_mode == 1) {
-        if (gap) B200_GO(1, true, 0);
-        B200_GO(1, false, 0);
+        if (gap) B200_GO(1, true, 0, 0);
+        B200_GO(1, false, 0, 0);
     }
-    if (res_mode == 2 && !gap) B200_GO(2, false, 0);
+    if (res_mode == 2 && !gap) B200_GO(2, false, 0, 0);
     return -14;
 #undef B200_GO
 }
@@ -615,15 +682,16 @@ static inline int align1k(int v) { return (v + 1023) & ~1023; }
 
 // Lays out shared memory for (BN, weight-stationary?) and returns the total dynamic size, or -1 if the
 // configuration does not fit / leaves fewer than 3 ring stages.
-static int plan_smem(ConvGemmParams& p, int BN, bool ws, bool has_out, bool has_res, int ndot) {
+static int plan_smem(ConvGemmParams& p, int BN, bool ws, bool has_out, bool has_res, int ndot, int mode) {
     const int b_bytes = BN * kBlockK * 2;
     const int stage_bytes = ws ? kABytes : kABytes + b_bytes;
     const int box_all = kBlockM * BN * 2;  // 8 warps x (32 rows x BN/2 columns) of bf16
     const int dot_bytes = ndot * BN * 4 + 2 * kBlockM * ndot * 4;
     const int union_bytes = align1k(ndot ? dot_bytes : (has_out ? box_all : 0));
     const int rbox_bytes = has_res ? align1k(box_all) : 0;
+    const int sm_bytes = mode == 1 ? align1k(8 * kBlockM * 4) : 0;  // row max / row sum exchange
     const int resident = ws ? align1k(p.k_blocks * b_bytes) : 0;
-    const int fixed = resident + align1k(kBarBytes) + union_bytes + rbox_bytes + 1024 /*base alignment slack*/;
+    const int fixed = resident + align1k(kBarBytes) + union_bytes + rbox_bytes + sm_bytes + 1024 /*alignment slack*/;
     int stages = (kSmemLimit - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 3) return -1;
@@ -632,7 +700,160 @@ static int plan_smem(ConvGemmParams& p, int BN, bool ws, bool has_out, bool has_
     p.off_bar = resident + stages * stage_bytes;
     p.off_union = p.off_bar + align1k(kBarBytes);
     p.off_rbox = p.off_union + union_bytes;
+    p.off_sm = p.off_rbox + rbox_bytes;
     return fixed + stages * stage_bytes;
+}
+
+// A 4-D bf16 view {cols, W, H, B} (element strides) for cuTensorMapEncodeTiled.
+struct View4 {
+    const void* base;
+    long long dims[4];
+    long long strides[3];  // elements: W-step, H-step, B-step (cols are contiguous)
+};
+
+static int encode_view(EncodeTiledFn encode, CUtensorMap* tm, const View4& v, const int box[4], const int estr[4],
+                       CUtensorMapSwizzle swz, CUtensorMapL2promotion promo) {
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t bx[4], es[4];
+    for (int i = 0; i < 4; ++i) {
+        dims[i] = static_cast<cuuint64_t>(v.dims[i] > 0 ? v.dims[i] : 1);
+        bx[i] = static_cast<cuuint32_t>(box[i]);
+        es[i] = static_cast<cuuint32_t>(estr[i]);
+    }
+    for (int i = 0; i < 3; ++i) {
+        // a degenerate dimension still needs a legal (16-byte multiple, non-zero) stride
+        long long st = v.strides[i] > 0 ? v.strides[i] : v.dims[0];
+        strides[i] = static_cast<cuuint64_t>(st) * 2;
+        if (strides[i] % 16 != 0) return -400;
+    }
+    if (reinterpret_cast<uintptr_t>(v.base) & 15) return -401;
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.base), dims, strides, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -300 - static_cast<int>(r);
+}
+
+// Everything the two C entry points hand to the common launcher.
+struct GemmJob {
+    View4 a;       // {K, W, H, B}: K-major rows of the A operand (activations, or weights when !a_batched)
+    View4 b4;      // batched B operand {K, N, H, B} (b_mode 1)
+    const void* w; // 2-D weights [N, K] (b_mode 0)
+    View4 out, out2, res;  // {cols, W', H', B}
+    int K;         // reduction length = taps * Cin
+};
+
+static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, cudaStream_t stream) {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) return -9;
+    }
+    EncodeTiledFn encode = get_encode_fn();
+    if (encode == nullptr) return -8;
+    const int Cout = p.Cout, n_split = p.n_split;
+    const bool two = n_split < Cout;
+    const int seg2 = Cout - n_split;
+    const bool has_out = p.out != nullptr, has_res = p.res_mode != 0;
+    const int ndot = p.dot_w != nullptr ? p.ndot : 0;
+    auto divides = [&](int bn) { return Cout % bn == 0 && n_split % bn == 0 && (!two || seg2 % bn == 0); };
+    int BN = 0, smem_bytes = -1;
+    bool ws = false;
+    if (want_ws && p.taps == 1 && ndot == 0 && mode == 0 && p.b_mode == 0) {
+        for (int bn : {128, 64}) {
+            if (!divides(bn) || Cout / bn > g_num_sms || p.k_blocks * bn * kBlockK * 2 > 128 * 1024) continue;
+            smem_bytes = plan_smem(p, bn, true, has_out, has_res, 0, 0);
+            if (smem_bytes > 0) {
+                BN = bn;
+                ws = true;
+                break;
+            }
+        }
+    }
+    if (!ws) {
+        for (int bn : {256, 128, 64}) {
+            if (!divides(bn) || ((ndot != 0 || mode == 1) && bn != Cout)) continue;
+            smem_bytes = plan_smem(p, bn, false, has_out, has_res, ndot, mode);
+            if (smem_bytes > 0) {
+                BN = bn;
+                break;
+            }
+        }
+    }
+    if (BN == 0) return -13;
+    p.n_tiles = Cout / BN;
+    if (Cout > 8192) return -15;
+    if (p.scale == nullptr) p.scale = identity_affine(true);
+    if (p.bias == nullptr) p.bias = identity_affine(false);
+    if (p.scale == nullptr || p.bias == nullptr) return -16;
+
+    CUtensorMap tmA, tmB, tmOut, tmOut2, tmRes;
+    int rc;
+    {
+        const int s = p.cstride;
+        const int box[4] = {64, p.BW * s, p.BH * s, 1};
+        const int estr[4] = {1, s, s, 1};
+        if ((rc = encode_view(encode, &tmA, j.a, box, estr, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != 0)
+            return rc - 1000;
+    }
+    if (p.b_mode == 0) {
+        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(j.K), static_cast<cuuint64_t>(Cout)};
+        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(j.K) * 2};
+        const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(BN)};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(j.w), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return -200 - static_cast<int>(r);
+    } else {
+        const int box[4] = {64, BN, 1, 1};
+        const int estr[4] = {1, 1, 1, 1};
+        if ((rc = encode_view(encode, &tmB, j.b4, box, estr, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != 0)
+            return rc - 2000;
+    }
+    // Staged (TMA) epilogue: per epilogue warp one {cw columns, bw, bh} box = its 32 rows x BN/2 columns
+    // (two boxes when BN = 256), swizzled by the row width.  The 2x2-replicating store walks a
+    // [B, 2H, 2W, ld] map with a traversal stride of 2 along w and h.
+    static const bool no_tma_up2 = std::getenv("B200_NO_TMA_UP2") != nullptr;
+    tmOut = tmA;
+    tmOut2 = tmA;
+    tmRes = tmA;
+    p.tma_epi = (p.up2 && no_tma_up2) ? 0 : 1;
+    if (p.tma_epi) {
+        const int cw = BN / 2 < 64 ? BN / 2 : 64;
+        const CUtensorMapSwizzle swz = cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+        const int bw = p.BW < 32 ? p.BW : 32, bh = 32 / bw;
+        const int us = p.up2 ? 2 : 1;
+        const int obox[4] = {cw, bw * us, bh * us, 1};
+        const int oestr[4] = {1, us, us, 1};
+        const int rbox[4] = {cw, bw, bh, 1};
+        const int one[4] = {1, 1, 1, 1};
+        if (has_out && (rc = encode_view(encode, &tmOut, j.out, obox, oestr, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE)) != 0)
+            return rc - 3000;
+        if (two && (rc = encode_view(encode, &tmOut2, j.out2, rbox, one, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE)) != 0)
+            return rc - 4000;
+        if (has_res && (rc = encode_view(encode, &tmRes, j.res, rbox, one, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE)) != 0)
+            return rc - 5000;
+    }
+    const int total = p.m_tiles * p.n_tiles;
+    int grid = total < g_num_sms ? total : g_num_sms;
+    if (ws) {  // every CTA keeps one N tile: the grid is a whole number of N-tile groups
+        const int groups = g_num_sms / p.n_tiles < p.m_tiles ? g_num_sms / p.n_tiles : p.m_tiles;
+        grid = groups * p.n_tiles;
+    }
+    const bool g = p.gap != nullptr;
+    const int rm = p.res_mode;
+    if (ws) {
+        if (BN == 128)
+            return dispatch<128, true>(rm, g, ndot, mode, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, stream);
+        return dispatch<64, true>(rm, g, ndot, mode, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, stream);
+    }
+    if (BN == 256)
+        return dispatch<256, false>(rm, g, ndot, mode, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, stream);
+    if (BN == 128)
+        return dispatch<128, false>(rm, g, ndot, mode, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, stream);
+    return dispatch<64, false>(rm, g, ndot, mode, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, stream);
 }
 
 }  // namespace b200
@@ -653,7 +874,7 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
     if (dot_w == nullptr) ndot = 0;
     if (ndot != 0 && ndot != 1 && ndot != 9) return -18;
     if (x == nullptr || w == nullptr || B <= 0 || H <= 0 || W <= 0) return -1;
-    if (Cin % 64 != 0 || Cout % 64 != 0 || (taps != 1 && taps != 9)) return -2;
+    if (Cin % 64 != 0 || Cout % 64 != 0 || (taps != 1 && taps != 9 && taps != 4)) return -2;
     if (x_ld % 8 != 0 || x_ld < Cin || (out != nullptr && out_ld % 8 != 0)) return -3;
     if (res_mode != 0 && (res == nullptr || res_ld % 8 != 0)) return -4;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
@@ -661,6 +882,9 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
         return -5;
 
     ConvGemmParams p{};
+    const int cs = taps == 4 ? 2 : 1;  // taps == 4: 2x2 kernel, stride 2, no padding (patch embedding)
+    if (cs == 2 && (H % 2 != 0 || W % 2 != 0 || up2 || H == 1)) return -6;
+    const int Ho = H / cs, Wo = W / cs;  // output map
     if (H == 1) {  // plain GEMM over W rows: 128-row boxes, ragged tail handled by TMA OOB fill / clipping
         if (taps != 1 || up2) return -6;
         p.BW = 128;
@@ -668,14 +892,14 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
         p.tiles_w = (W + 127) / 128;
         p.tiles_h = 1;
     } else {
-        if (W > 128 || 128 % W != 0 || H % (128 / W) != 0) return -7;
-        p.BW = W;
-        p.BH = 128 / W;
+        if (Wo > 128 || 128 % Wo != 0 || Ho % (128 / Wo) != 0) return -7;
+        p.BW = Wo;
+        p.BH = 128 / Wo;
         p.tiles_w = 1;
-        p.tiles_h = H / p.BH;
+        p.tiles_h = Ho / p.BH;
     }
-    p.H = H;
-    p.W = W;
+    p.H = Ho;
+    p.W = Wo;
     p.Cout = Cout;
     if (n_split <= 0 || n_split > Cout || n_split % 64 != 0) return -10;
     const bool two = n_split < Cout;
@@ -683,52 +907,17 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
                 up2 || dot_w != nullptr || res_mode != 0))
         return -11;
     if (gap != nullptr && (out == nullptr || up2)) return -17;  // channel sums are taken from the staged output boxes
-    const int seg2 = Cout - n_split;
     if (dot_w != nullptr && (dot_out == nullptr || H == 1 || out != nullptr)) return -12;
     p.m_tiles = B * p.tiles_w * p.tiles_h;
     p.kc = Cin / 64;
     p.taps = taps;
     p.k_blocks = taps * p.kc;
-
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) return -9;
-    }
-    // Tile shape: weight-stationary (BN <= 128, the CTA's weight slab resident) for 1x1 layers when it fits,
-    // otherwise the widest BN that divides the channel counts and fits shared memory.
-    // Measured on B200 (tools/kbench.py): the weight-stationary variant is slower than the streamed one for
-    // every layer of this model (it needs BN <= 128, i.e. twice the tiles and activation re-reads), so it
-    // is opt-in (B200_WS=1) until a 2-CTA / multicast version makes it pay.
-    static const bool no_ws = std::getenv("B200_WS") == nullptr;
-    auto divides = [&](int bn) { return Cout % bn == 0 && n_split % bn == 0 && (!two || seg2 % bn == 0); };
-    const bool has_out = out != nullptr, has_res = res_mode != 0, dot = ndot != 0;
-    int BN = 0, smem_bytes = -1;
-    bool ws = false;
-    if (taps == 1 && !dot && !no_ws) {
-        for (int bn : {128, 64}) {
-            if (!divides(bn) || Cout / bn > g_num_sms || p.k_blocks * bn * kBlockK * 2 > 128 * 1024) continue;
-            smem_bytes = plan_smem(p, bn, true, has_out, has_res, 0);
-            if (smem_bytes > 0) {
-                BN = bn;
-                ws = true;
-                break;
-            }
-        }
-    }
-    if (!ws) {
-        for (int bn : {256, 128, 64}) {
-            if (!divides(bn) || (dot && bn != Cout)) continue;
-            smem_bytes = plan_smem(p, bn, false, has_out, has_res, ndot);
-            if (smem_bytes > 0) {
-                BN = bn;
-                break;
-            }
-        }
-    }
-    if (BN == 0) return -13;
-    p.n_tiles = Cout / BN;
+    p.cstride = cs;
+    p.a_batched = 1;
+    p.b_mode = 0;
+    p.bias_h_stride = 0;
+    p.rowscale = nullptr;
+    p.rowsum_inv = nullptr;
     p.scale = scale;
     p.bias = bias;
     p.res = static_cast<const __nv_bfloat16*>(res);
@@ -744,82 +933,77 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
     p.out2_ld = out2_ld;
     p.act2 = act2;
     p.dot_w = dot_w;
+    p.ndot = ndot;
     p.dot_out = dot_out;
     p.dot_bias = dot_bias;
-    p.total_rows = B * H * W;
-    if (Cout > 8192) return -15;
-    if (p.scale == nullptr) p.scale = identity_affine(true);
-    if (p.bias == nullptr) p.bias = identity_affine(false);
-    if (p.scale == nullptr || p.bias == nullptr) return -16;
 
-    EncodeTiledFn encode = get_encode_fn();
-    if (encode == nullptr) return -8;
+    GemmJob j{};
+    j.K = taps * Cin;
+    j.w = w;
+    j.a = View4{x, {Cin, W, H, B}, {x_ld, static_cast<long long>(x_ld) * W, static_cast<long long>(x_ld) * W * H}};
+    const int us = up2 ? 2 : 1;
+    j.out = View4{out, {n_split, static_cast<long long>(Wo) * us, static_cast<long long>(Ho) * us, B},
+                  {out_ld, static_cast<long long>(out_ld) * Wo * us, static_cast<long long>(out_ld) * Wo * us * Ho * us}};
+    j.out2 = View4{out2, {Cout - n_split, Wo, Ho, B},
+                   {out2_ld, static_cast<long long>(out2_ld) * Wo, static_cast<long long>(out2_ld) * Wo * Ho}};
+    j.res = View4{res, {n_split, Wo, Ho, B},
+                  {res_ld, static_cast<long long>(res_ld) * Wo, static_cast<long long>(res_ld) * Wo * Ho}};
+    // Measured on B200 (tools/kbench.py): the weight-stationary variant is slower than the streamed one for
+    // every layer of this model (it needs BN <= 128, i.e. twice the tiles and activation re-reads), so it
+    // is opt-in (B200_WS=1) until a 2-CTA / multicast version makes it pay.
+    static const bool want_ws = std::getenv("B200_WS") != nullptr;
+    return run_job(p, j, 0, want_ws, static_cast<cudaStream_t>(stream));
+}
 
-    CUtensorMap tmA, tmB;
-    {
-        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(Cin), static_cast<cuuint64_t>(W),
-                                    static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
-        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(x_ld) * 2, static_cast<cuuint64_t>(x_ld) * 2 * W,
-                                       static_cast<cuuint64_t>(x_ld) * 2 * W * H};
-        const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.BW), static_cast<cuuint32_t>(p.BH), 1};
-        const cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return -100 - static_cast<int>(r);
-    }
-    {
-        const cuuint64_t K = static_cast<cuuint64_t>(taps) * Cin;
-        const cuuint64_t dims[2] = {K, static_cast<cuuint64_t>(Cout)};
-        const cuuint64_t strides[1] = {K * 2};
-        const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(BN)};
-        const cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return -200 - static_cast<int>(r);
-    }
-    // Row-major [rows, ld] views of the output(s) and the residual for the staged (TMA) epilogue: one box of
-    // 32 rows x BN/4 columns per epilogue warp, swizzled by its row width.  The 2x2-replicating store walks
-    // the [B*2H*2W, ld] output with a traversal stride of 2 along the pixel dimension (needs the warp's 32
-    // pixels inside one image row).
-    static const bool no_tma_up2 = std::getenv("B200_NO_TMA_UP2") != nullptr;
-    CUtensorMap tmOut = tmA, tmOut2 = tmA, tmRes = tmA;
-    p.tma_epi = (up2 && (W % 32 != 0 || no_tma_up2)) ? 0 : 1;
-    if (p.tma_epi) {
-        const cuuint64_t rows = static_cast<cuuint64_t>(B) * H * W;
-        const int cw = BN / 2 < 64 ? BN / 2 : 64;  // box width: 32 columns (64-byte rows) or 64 (128-byte rows)
-        const CUtensorMapSwizzle swz = cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-        auto encode2d = [&](CUtensorMap* tm, const void* base, int cols, int ld, cuuint64_t nrows, int pstride) -> int {
-            const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), nrows};
-            const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-            const cuuint32_t box[2] = {static_cast<cuuint32_t>(cw), static_cast<cuuint32_t>(32 * pstride)};
-            const cuuint32_t estr[2] = {1, static_cast<cuuint32_t>(pstride)};
-            CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
-                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            return r == CUDA_SUCCESS ? 0 : -300 - static_cast<int>(r);
-        };
-        int rc = 0;
-        if (out != nullptr && (rc = encode2d(&tmOut, out, n_split, out_ld, up2 ? rows * 4 : rows, up2 ? 2 : 1)) != 0)
-            return rc;
-        if (two && (rc = encode2d(&tmOut2, out2, seg2, out2_ld, rows, 1)) != 0) return rc;
-        if (res_mode != 0 && (rc = encode2d(&tmRes, res, n_split, res_ld, rows, 1)) != 0) return rc;
-    }
-    const int total = p.m_tiles * p.n_tiles;
-    int grid = total < g_num_sms ? total : g_num_sms;
-    if (ws) {  // every CTA keeps one N tile: the grid is a whole number of N-tile groups
-        const int groups = g_num_sms / p.n_tiles < p.m_tiles ? g_num_sms / p.n_tiles : p.m_tiles;
-        grid = groups * p.n_tiles;
-    }
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const bool g = gap != nullptr;
-    if (ws) {
-        if (BN == 128)
-            return dispatch<128, true>(res_mode, g, ndot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
-        return dispatch<64, true>(res_mode, g, ndot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
-    }
-    if (BN == 256) return dispatch<256, false>(res_mode, g, ndot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
-    if (BN == 128) return dispatch<128, false>(res_mode, g, ndot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
-    return dispatch<64, false>(res_mode, g, ndot, tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
+extern "C" int b200_gemm_batched(const b200_gemm_desc* d, void* stream) {
+    using namespace b200;
+    if (d == nullptr || d->a == nullptr || d->b == nullptr) return -1;
+    if (d->M <= 0 || d->N <= 0 || d->K <= 0 || d->heads <= 0 || d->batch <= 0) return -1;
+    if (d->K % 8 != 0 || d->N % 64 != 0) return -2;  // K tail handled by TMA zero fill, rows by clipping
+    if (d->mode != 0 && d->mode != 1) return -2;
+    if (d->mode == 1 && (d->N != 256 || d->rowsum_inv == nullptr || d->out == nullptr)) return -3;
+    if (d->res_mode != 0 && d->res == nullptr) return -4;
+    ConvGemmParams p{};
+    p.H = d->heads;
+    p.W = d->M;
+    p.BW = 128;
+    p.BH = 1;
+    p.tiles_w = (d->M + 127) / 128;
+    p.tiles_h = d->heads;
+    p.Cout = d->N;
+    p.n_split = d->N;
+    p.m_tiles = d->batch * p.tiles_w * p.tiles_h;
+    p.kc = 0;  // unused when taps == 1 (tap = kb / kc is never evaluated with kc = k_blocks)
+    p.taps = 1;
+    p.k_blocks = (d->K + 63) / 64;
+    p.kc = p.k_blocks;
+    p.cstride = 1;
+    p.a_batched = d->a_shared ? 0 : 1;
+    p.b_mode = 1;
+    p.bias_h_stride = d->vec_h_stride;
+    p.rowscale = d->rowscale;
+    p.rowsum_inv = d->rowsum_inv;
+    p.alpha = d->alpha;
+    p.n_valid = d->n_valid > 0 ? d->n_valid : d->N;
+    p.scale = d->scale;
+    p.bias = d->bias;
+    p.res = static_cast<const __nv_bfloat16*>(d->res);
+    p.res_ld = static_cast<int>(d->res_row_stride);
+    p.res_mode = d->res_mode;
+    p.act = d->act;
+    p.out = static_cast<__nv_bfloat16*>(d->out);
+    p.out_ld = static_cast<int>(d->out_row_stride);
+    p.up2 = 0;
+    p.gap = nullptr;
+    p.out2 = nullptr;
+    p.dot_w = nullptr;
+    p.ndot = 0;
+    GemmJob j{};
+    j.K = d->K;
+    if (d->a_shared) j.a = View4{d->a, {d->K, d->M, 1, 1}, {d->a_row_stride, 0, 0}};
+    else j.a = View4{d->a, {d->K, d->M, d->heads, d->batch}, {d->a_row_stride, d->a_head_stride, d->a_batch_stride}};
+    j.b4 = View4{d->b, {d->K, d->N, d->heads, d->batch}, {d->b_row_stride, d->b_head_stride, d->b_batch_stride}};
+    j.out = View4{d->out, {d->N, d->M, d->heads, d->batch}, {d->out_row_stride, d->out_head_stride, d->out_batch_stride}};
+    j.res = View4{d->res, {d->N, d->M, d->heads, d->batch}, {d->res_row_stride, d->res_head_stride, d->res_batch_stride}};
+    return run_job(p, j, d->mode, false, static_cast<cudaStream_t>(stream));
 }

@@ -47,7 +47,9 @@ int b200_abi_version(void);
  *          size, model_module.py:534,707-710, commuted past the 1x1 projector)
  *   gap    optional fp32 [B,Cout]; the per-case sum over pixels of the epilogue result is
  *          ACCUMULATED into it (caller zeroes it)
- * Requires Cin % 64 == 0, Cout % 64 == 0, and for convolutions 128 % W == 0, H % (128/W) == 0.
+ * taps may also be 4: a 2x2 kernel with stride 2 and no padding (PatchEmbed, code/transformer_model.py:18-23),
+ * k = (ky*2+kx)*Cin + c; the output map is then [B,H/2,W/2,*].
+ * Requires Cin % 64 == 0, Cout % 64 == 0, and for convolutions 128 % Wout == 0, Hout % (128/Wout) == 0.
  */
 int b200_conv_gemm(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
                    const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
@@ -71,6 +73,46 @@ int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale
                       float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w, int ndot,
                       float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout, int taps,
                       void* stream);
+
+/*
+ * Batched GEMM on the same tcgen05 kernel: for every (batch, head)
+ *     out[m, n] = epilogue( sum_k A[m, k] * B[n, k] ),   A, B bf16 K-major, fp32 accumulation.
+ * This is how the transformer blocks run (code/transformer_model.py:98-116): Q.K^T per head
+ * (mode 1: the epilogue writes exp(alpha*acc - rowmax) as bf16 and 1/rowsum to rowsum_inv - the softmax
+ * numerator of :108; columns >= n_valid are masked), P.V^T per head (rowscale = that 1/rowsum, so the
+ * division of the softmax is applied to the fp32 accumulator), and V^T = W_v X^T with the weights on the A
+ * side (a_shared).  Strides are in elements; rows of A / B must be 16-byte aligned; K tails are zero-filled
+ * and ragged M tails clipped by the TMA.  mode 1 needs N == 256 (one tile holds a whole row).
+ * scale / bias are indexed n + head * vec_h_stride.
+ */
+typedef struct b200_gemm_desc {
+    int M, N, K, heads, batch;
+    const void* a;
+    long long a_row_stride, a_head_stride, a_batch_stride;
+    int a_shared;
+    const void* b;
+    long long b_row_stride, b_head_stride, b_batch_stride;
+    void* out;
+    long long out_row_stride, out_head_stride, out_batch_stride;
+    const void* res;
+    long long res_row_stride, res_head_stride, res_batch_stride;
+    int res_mode, act;
+    const float* scale;
+    const float* bias;
+    int vec_h_stride;
+    const float* rowscale; /* [batch, heads, M] or NULL */
+    int mode;              /* 0 standard, 1 softmax numerator */
+    float alpha;
+    int n_valid;
+    float* rowsum_inv;     /* [batch, heads, M] (mode 1) */
+} b200_gemm_desc;
+
+int b200_gemm_batched(const b200_gemm_desc* d, void* stream);
+
+/* nn.LayerNorm over the last dimension of a bf16 token matrix [rows, C] (code/transformer_model.py:16, :71, :73),
+ * C a multiple of 256 up to 1024, fp32 statistics, bf16 output. */
+int b200_layernorm(const void* x, long long rows, int C, const float* w, const float* b, float eps, void* y,
+                   void* stream);
 
 /* out[b,h,w] = bias + sum_k d[(b,h+ky-1,w+kx-1)][k], zero padded: finishes a 3x3 C->1 conv from tap dots. */
 int b200_tapsum(const float* d, int B, int H, int W, const float* bias, float* out, void* stream);

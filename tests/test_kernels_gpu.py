@@ -149,3 +149,70 @@ def test_fused_single_dot_is_a_following_1x1_conv_to_one_channel():
     torch.cuda.synchronize()
     ref = (x.float() @ w.float().t() + bias) @ wo.t() + 0.25
     assert _rel(out, ref) < 1e-4
+
+
+def test_patch_embed_conv_2x2_stride2():
+    """PatchEmbed.proj (transformer_model.py:18-23): 2x2 kernel, stride 2, bias -> tokens."""
+    g = torch.Generator(device="cpu").manual_seed(8)
+    B, Cin, Cout = 3, 256, 512
+    x = (torch.randn(B, 32, 32, Cin, generator=g) * 0.5).to(DEV).bfloat16()
+    w4 = (torch.randn(Cout, Cin, 2, 2, generator=g) / math.sqrt(4 * Cin)).to(DEV)
+    bias = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    w = w4.permute(0, 2, 3, 1).reshape(Cout, -1).bfloat16().contiguous()
+    y = nat.conv_gemm(x, w, taps=4, bias=bias)
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == (B, 16, 16, Cout)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w4.bfloat16().float(), bias, stride=2).permute(0, 2, 3, 1)
+    assert _rel(y, ref) < 1e-2
+
+
+@pytest.mark.parametrize("C", [256, 512, 768])
+def test_layernorm(C):
+    g = torch.Generator(device="cpu").manual_seed(C)
+    x = (torch.randn(1000, C, generator=g) * 2 + 0.3).to(DEV).bfloat16()
+    w = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    b = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    y = nat.layernorm(x, w, b, 1e-5)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.float(), (C,), w, b, 1e-5)
+    assert _rel(y, ref) < 6e-3  # one bf16 rounding of the output
+
+
+def test_batched_gemm_weights_on_a_side():
+    """V^T = W_v X^T per case: A shared (weights), B batched (tokens), ragged nothing."""
+    g = torch.Generator(device="cpu").manual_seed(12)
+    B, N, C = 3, 256, 512
+    x = (torch.randn(B, N, C, generator=g) * 0.5).to(DEV).bfloat16()
+    wv = (torch.randn(C, C, generator=g) / math.sqrt(C)).to(DEV).bfloat16()
+    out = torch.empty(B, C, N, device=DEV, dtype=torch.bfloat16)
+    nat.gemm_batched(M=C, N=N, K=C, heads=1, batch=B, a=wv.data_ptr(), a_strides=(C, 0, 0), a_shared=True,
+                     b=x.data_ptr(), b_strides=(C, 0, N * C), out=out.data_ptr(), out_strides=(N, 0, C * N))
+    torch.cuda.synchronize()
+    ref = torch.einsum("oc,bnc->bon", wv.float(), x.float())
+    assert _rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,heads,N,dh", [(2, 4, 256, 128), (3, 2, 256, 64)])
+def test_attention_from_batched_gemms(B, heads, N, dh):
+    """softmax(Q K^T / sqrt d) V per head (transformer_model.py:107-111) from two batched GEMMs: mode 1 writes
+    exp(logit - rowmax) and 1/rowsum, the P.V GEMM applies 1/rowsum to its accumulator and adds the V bias."""
+    g = torch.Generator(device="cpu").manual_seed(B * heads)
+    C = heads * dh
+    qk = (torch.randn(B, N, 2 * C, generator=g) * 0.7).to(DEV).bfloat16()
+    vt = (torch.randn(B, C, N, generator=g) * 0.5).to(DEV).bfloat16()     # V^T, channel-major
+    bv = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    P = torch.empty(B, heads, N, N, device=DEV, dtype=torch.bfloat16)
+    rs = torch.empty(B, heads, N, device=DEV)
+    nat.gemm_batched(M=N, N=N, K=dh, heads=heads, batch=B, a=qk.data_ptr(), a_strides=(2 * C, dh, N * 2 * C),
+                     b=qk.data_ptr() + 2 * C, b_strides=(2 * C, dh, N * 2 * C), out=P.data_ptr(),
+                     out_strides=(N, N * N, heads * N * N), mode=1, alpha=dh ** -0.5, n_valid=N, rowsum_inv=rs)
+    O = torch.empty(B, N, C, device=DEV, dtype=torch.bfloat16)
+    nat.gemm_batched(M=N, N=dh, K=N, heads=heads, batch=B, a=P.data_ptr(), a_strides=(N, N * N, heads * N * N),
+                     b=vt.data_ptr(), b_strides=(N, dh * N, C * N), out=O.data_ptr(), out_strides=(C, dh, N * C),
+                     rowscale=rs, bias=bv, vec_h_stride=dh)
+    torch.cuda.synchronize()
+    q = qk[..., :C].float().view(B, N, heads, dh).permute(0, 2, 1, 3)
+    k = qk[..., C:].float().view(B, N, heads, dh).permute(0, 2, 1, 3)
+    v = vt.float().view(B, heads, dh, N).permute(0, 1, 3, 2) + bv.view(1, heads, 1, dh)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B, N, C)
+    assert _rel(O, ref) < 1.5e-2
