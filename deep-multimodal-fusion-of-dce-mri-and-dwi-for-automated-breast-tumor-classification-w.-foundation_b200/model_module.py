@@ -349,6 +349,83 @@ def _block_pack(blk, dev):
     return p
 
 
+def _transformer_pack(stage, out_proj, dev):
+    """TransformerStage + trans_out_proj (reference transformer_model.py:137-175, model_module.py:568-579)."""
+    pe = stage.patch_embed
+    if pe.proj.kernel_size != (2, 2) or pe.proj.stride != (2, 2):
+        raise NotImplementedError("only patch_size=2 (the reference default) is built")
+    E = pe.proj.out_channels
+    tr = {"E": E, "pe_w": _conv_w_bf16(pe.proj, dev), "pe_b": _f32(pe.proj.bias, dev),
+          "pe_ln": (_f32(pe.norm.weight, dev), _f32(pe.norm.bias, dev), pe.norm.eps), "layers": [],
+          "out_w": _conv_w_bf16(out_proj, dev), "out_b": _f32(out_proj.bias, dev)}
+    for blk in stage.transformer.layers:
+        at = blk.attn
+        wqkv = at.qkv.weight.detach().to(dev)
+        bqkv = at.qkv.bias.detach().to(dev).float() if at.qkv.bias is not None else torch.zeros(3 * E, device=dev)
+        g1, g2 = _f32(blk.gamma1, dev), _f32(blk.gamma2, dev)
+        tr["layers"].append({
+            "heads": at.num_heads, "dh": at.head_dim,
+            "ln1": (_f32(blk.norm1.weight, dev), _f32(blk.norm1.bias, dev), blk.norm1.eps),
+            "ln2": (_f32(blk.norm2.weight, dev), _f32(blk.norm2.bias, dev), blk.norm2.eps),
+            "wqk": wqkv[:2 * E].to(torch.bfloat16).contiguous(), "bqk": bqkv[:2 * E].contiguous(),
+            "wv": wqkv[2 * E:].to(torch.bfloat16).contiguous(), "bv": bqkv[2 * E:].contiguous(),
+            # x + gamma * (W y + b)  ==  (acc * gamma + gamma * b) + x : LayerScale folds into the epilogue affine
+            "wproj": at.proj.weight.detach().to(dev, torch.bfloat16).contiguous(), "sproj": g1,
+            "bproj": (g1 * _f32(at.proj.bias, dev)).contiguous(),
+            "wfc1": blk.mlp.fc1.weight.detach().to(dev, torch.bfloat16).contiguous(), "bfc1": _f32(blk.mlp.fc1.bias, dev),
+            "wfc2": blk.mlp.fc2.weight.detach().to(dev, torch.bfloat16).contiguous(), "sfc2": g2,
+            "bfc2": (g2 * _f32(blk.mlp.fc2.bias, dev)).contiguous(),
+        })
+    return tr
+
+
+def _transformer_stage(tr, x):
+    """x [B,H,W,C] bf16 NHWC -> (f3 [B,H/2,W/2,c3] bf16, per-case channel sums of f3).
+
+    Pre-norm blocks exactly as transformer_model.py:68-133 (eval: dropout is identity); every matmul runs on
+    the tcgen05 GEMM kernel: the patch embedding as a 2x2/stride-2 implicit GEMM, Q.K^T per head with the
+    softmax numerator fused into its epilogue, P.V per head with the 1/rowsum applied to the fp32
+    accumulator (V is produced transposed by putting W_v on the A side; its bias commutes past the
+    row-stochastic P), LayerScale + residual folded into the proj / fc2 epilogues."""
+    B, H, W, _ = x.shape
+    E = tr["E"]
+    dev = x.device
+    tok = nat.conv_gemm(x, tr["pe_w"], taps=4, bias=tr["pe_b"])  # [B, H/2, W/2, E]
+    Ht, Wt = tok.shape[1], tok.shape[2]
+    N = Ht * Wt
+    if N != 256:
+        raise NotImplementedError("the fused softmax epilogue needs 256 tokens per case (32x32 maps, patch 2)")
+    M = B * N
+    t = nat.layernorm(tok.view(M, E), *tr["pe_ln"])
+    h = torch.empty_like(t)
+    qk = torch.empty((M, 2 * E), dtype=torch.bfloat16, device=dev)
+    vt = torch.empty((B, E, N), dtype=torch.bfloat16, device=dev)
+    o = torch.empty((M, E), dtype=torch.bfloat16, device=dev)
+    u = torch.empty((M, 4 * E), dtype=torch.bfloat16, device=dev)
+    for ly in tr["layers"]:
+        heads, dh = ly["heads"], ly["dh"]
+        p_buf = torch.empty((B, heads, N, N), dtype=torch.bfloat16, device=dev)
+        rs = torch.empty((B, heads, N), dtype=torch.float32, device=dev)
+        nat.layernorm(t, *ly["ln1"], out=h)
+        nat.linear(h, ly["wqk"], bias=ly["bqk"], out=qk)
+        nat.gemm_batched(M=E, N=N, K=E, heads=1, batch=B, a=ly["wv"].data_ptr(), a_strides=(E, 0, 0), a_shared=True,
+                         b=h.data_ptr(), b_strides=(E, 0, N * E), out=vt.data_ptr(), out_strides=(N, 0, E * N))
+        nat.gemm_batched(M=N, N=N, K=dh, heads=heads, batch=B, a=qk.data_ptr(), a_strides=(2 * E, dh, N * 2 * E),
+                         b=qk.data_ptr() + 2 * E, b_strides=(2 * E, dh, N * 2 * E), out=p_buf.data_ptr(),
+                         out_strides=(N, N * N, heads * N * N), mode=1, alpha=dh ** -0.5, n_valid=N, rowsum_inv=rs)
+        nat.gemm_batched(M=N, N=dh, K=N, heads=heads, batch=B, a=p_buf.data_ptr(),
+                         a_strides=(N, N * N, heads * N * N), b=vt.data_ptr(), b_strides=(N, dh * N, E * N),
+                         out=o.data_ptr(), out_strides=(E, dh, N * E), rowscale=rs, bias=ly["bv"], vec_h_stride=dh)
+        t2 = nat.linear(o, ly["wproj"], scale=ly["sproj"], bias=ly["bproj"], res=t, res_mode=2)
+        nat.layernorm(t2, *ly["ln2"], out=h)
+        nat.linear(h, ly["wfc1"], bias=ly["bfc1"], act=1, out=u)
+        t = nat.linear(u, ly["wfc2"], scale=ly["sfc2"], bias=ly["bfc2"], res=t2, res_mode=2)
+    c3 = tr["out_w"].shape[0]
+    gap = torch.zeros((B, c3), dtype=torch.float32, device=dev)
+    f3 = nat.conv_gemm(t.view(B, Ht, Wt, E), tr["out_w"], taps=1, bias=tr["out_b"], gap=gap)
+    return f3, gap
+
+
 def _state_signature(module):
     return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
 
@@ -475,19 +552,23 @@ class ModelMaskHeadBackbone(nn.Module):
         sig = (str(dev), _state_signature(self))
         if self._pack_cache is not None and self._pack_cache[0] == sig:
             return self._pack_cache[1]
-        if self.use_backbone or self.use_hybrid_transformer:
-            raise NotImplementedError("backbone-adapter / hybrid-transformer encoders are not wired to the "
-                                      "B200 kernels yet (SURVEY.md section 8 rows a11-a14)")
+        if self.use_backbone:
+            raise NotImplementedError("backbone-adapter encoders (ViT-B/16 + necks) are not wired to the B200 "
+                                      "kernels yet (SURVEY.md section 8 rows a11-a13)")
         if self.mask_enabled and self.mask_stage != "f2":
             raise NotImplementedError("only mask_stage='f2' (the reference default) is built")
         b1 = self.block1
         if b1.stride not in (1, 2) or b1.skip is None or self.channel_num > 32:
             raise NotImplementedError("block1 must read the raw (<=32 channel) input through a skip conv")
-        for blk in (self.block2, self.block3):
-            if blk.stride != 1:
+        blocks = {"b1": self.block1, "b2": self.block2}
+        if not self.use_hybrid_transformer:
+            blocks["b3"] = self.block3
+        for name, blk in blocks.items():
+            if name != "b1" and blk.stride != 1:
                 raise NotImplementedError("stride-2 block2/block3 are not built (reference default is stride 1)")
-        pk = {"b1": _block_pack(self.block1, dev), "b2": _block_pack(self.block2, dev),
-              "b3": _block_pack(self.block3, dev)}
+        pk = {name: _block_pack(blk, dev) for name, blk in blocks.items()}
+        if self.use_hybrid_transformer:
+            pk["tr"] = _transformer_pack(self.transformer, self.trans_out_proj, dev)
         # stem: skip conv and first bottleneck conv of block1 concatenated, fp32
         bt0 = pk["b1"]["bott"][0]
         wskip = pk["b1"]["skip"]["conv"].weight.detach().to(dev).flatten(1).float()
@@ -497,6 +578,8 @@ class ModelMaskHeadBackbone(nn.Module):
                       "b": torch.cat([pk["b1"]["skip"]["b"], bt0["b1"]]).contiguous(),
                       "n_skip": wskip.shape[0], "n_mid": wmid.shape[0]}
         for name in ("b2", "b3"):
+            if name not in pk:
+                continue
             blk = pk[name]
             for bt in blk["bott"]:
                 bt["w0"] = _conv_w_bf16(bt["conv0"], dev)
@@ -620,13 +703,18 @@ class ModelMaskHeadBackbone(nn.Module):
             attn_map = torch.empty((B, 1, Ho, Wo), dtype=torch.float32, device=dev)
             nat.mask_attention(mask_pred, mk["attn"], attn_map)
             nat.scale_map(f2, f2, attn=attn_map, gamma=mk["gamma"])
-        f3, _, gap3, gate3 = self._block_from_map(pk["b3"], f2, False)
+        if self.use_hybrid_transformer:
+            f3, gap3 = _transformer_stage(pk["tr"], f2)  # reference :702-703
+            gate3 = None
+        else:
+            f3, _, gap3, gate3 = self._block_from_map(pk["b3"], f2, False)
+        npix3 = f3.shape[1] * f3.shape[2]
 
         logits = None
         p1 = p1r = p2 = p2r = None
         if full:
             logits = torch.empty((B, self.num_classes), dtype=torch.float32, device=dev)
-            nat.cls_head(gap3, gate3, Ho * Wo, pk["head"]["w"], pk["head"]["b"], self.classification_head.normalize,
+            nat.cls_head(gap3, gate3, npix3, pk["head"]["w"], pk["head"]["b"], self.classification_head.normalize,
                          logits)
             if self.proj_dim == 2 * Ho:
                 up2 = True

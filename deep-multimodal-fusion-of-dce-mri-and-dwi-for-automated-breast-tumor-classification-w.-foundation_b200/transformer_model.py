@@ -5,8 +5,8 @@ pre-norm transformer stage (PatchEmbed :7-32, TokensToFeatureMap :34-52, Transfo
 :54-66, TransformerBlock :68-81, MultiHeadSelfAttention :83-116, MLP :118-134,
 TransformerStage :137-175).  The modules are parameter containers; the stage's arithmetic is
 scheduled by ModelMaskHeadBackbone.forward on the sm_100a kernels (linears through
-b200_conv_gemm's GEMM mode).  The fused attention / LayerNorm kernels for this stage are the
-next SURVEY.md section-8 row (a14) and are not wired yet: a hybrid-transformer forward raises.
+b200_conv_gemm / b200_gemm_batched, LayerNorm through b200_layernorm; see
+model_module._transformer_stage).  Calling a sub-module's forward on its own raises.
 """
 from __future__ import annotations
 
@@ -18,7 +18,7 @@ __all__ = ["PatchEmbed", "TokensToFeatureMap", "TransformerEncoder", "Transforme
 
 
 def _not_wired(name):
-    raise NotImplementedError(f"{name}: the hybrid transformer stage is not wired to the B200 kernels yet")
+    raise NotImplementedError(f"{name} is a parameter container; the stage runs inside ModelMaskHeadBackbone.forward")
 
 
 class PatchEmbed(nn.Module):

@@ -104,9 +104,11 @@ def test_nyul_requires_fit_and_odd_sizes():
 
 
 # ----------------------------------------------------------------------- models ----
-def _build(seed=7):
+def _build(seed=7, hybrid=False):
     p = pd.default_parameters()
-    shapes = gu.load_shapes("cnn")
+    for m in ("dwi", "dce"):
+        p[f"{m}_model_parameters"]["use_hybrid_transformer"] = hybrid
+    shapes = gu.load_shapes("hybrid" if hybrid else "cnn")
     sds = {m: op.seeded_state_dict(shapes[m], seed=seed) for m in ("dwi", "dce", "fusion")}
     mods = {"dwi": b_mm.ModelMaskHeadBackbone("dwi", p), "dce": b_mm.ModelMaskHeadBackbone("dce", p),
             "fusion": b_mm.FusionModel(p)}
@@ -173,6 +175,31 @@ def test_models_vs_oracle_batch():
     assert agree[decided].all()
     print(f"fusion logits rel err {errs['fusion.0']:.2e}; argmax agreement {agree.float().mean():.3f} "
           f"(margins min {margin.min():.3f} median {margin.median():.3f})")
+
+
+def test_hybrid_transformer_encoders_vs_golden_and_oracle():
+    """use_hybrid_transformer=True: block3 is replaced by the in-house TransformerStage (6 pre-norm blocks,
+    4 heads x 128, 256 tokens) + 1x1 projection.  Encoder outputs against the reference fixtures and the oracle."""
+    gold = gu.load("model_hybrid.npz")
+    p, sds, mods = _build(hybrid=True)
+    worst = {}
+    for kind in ("U", "S"):
+        dwi_raw, dce_raw, _, _ = op.synthetic_raw(2, seed=1234, kind=kind)
+        dwi = dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)
+        with torch.no_grad():
+            ld, ad, md = mods["dwi"](dwi.to(DEV))
+            lc, ac, mc = mods["dce"](dce_raw.to(DEV))
+        torch.cuda.synchronize()
+        outs = {f"{kind}/dwi/logits": ld, f"{kind}/dwi/aux": ad, f"{kind}/dwi/mask": md,
+                f"{kind}/dce/logits": lc, f"{kind}/dce/aux": ac, f"{kind}/dce/mask": mc}
+        for prefix, obj in outs.items():
+            for key, t in gu.walk(prefix, obj):
+                worst[key] = gu.check(gold, key, t, rtol=_tol(key))
+    assert tuple(ad["raw_feats"][2].shape) == (2, 512, 16, 16)
+    print("hybrid worst relative errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:6])
+    with torch.no_grad():
+        o_d = mo.encoder_forward(sds["dwi"], "dwi", p, dwi)
+    assert _relmax(ld, o_d[0]) <= MODEL_TOL and _relmax(ad["raw_feats"][2], o_d[1]["raw_feats"][2]) <= MODEL_TOL
 
 
 def test_logits_mode_matches_full_mode():
