@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lib = None
 
@@ -70,10 +70,12 @@ SIGNATURES = {
     "b200_conv_gemm": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_conv_gemm_ex": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _F, _P, _I, _I, _I,
                           _I, _I, _I, _P],
+    "b200_resize_bilinear_c1": [_P, _I, _I, _I, _P, _I, _I, _P],
     "b200_mask_attention": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P],
     "b200_tapsum": [_P, _I, _I, _I, _P, _P, _P],
     "b200_gemm_batched": [C.POINTER(GemmDesc), _P],
-    "b200_layernorm": [_P, _LL, _I, _P, _P, _F, _P, _P],
+    "b200_layernorm": [_P, _I, _LL, _I, _P, _P, _F, _P, _I, _P],
+    "b200_linear": [_P, _LL, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _P],
     "b200_dwi_normalize": [_P, _P, _I, _I, _I, _I, _F, _F, _P, _P],
     "b200_nyul_transform": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "b200_plane_mean": [_P, _I, _I, _P, _P],
@@ -215,12 +217,25 @@ def gemm_batched(*, M, N, K, heads, batch, a, a_strides, b, b_strides, out, out_
     _call("b200_gemm_batched", (batch, heads, M, K, N, mode), C.byref(d), _stream())
 
 
-def layernorm(x, w, b, eps, out=None):
-    """x [rows, C] bf16 contiguous -> LayerNorm over C, bf16."""
+def layernorm(x, w, b, eps, out=None, out_dtype=torch.bfloat16):
+    """x [rows, C] bf16 or fp32 contiguous -> LayerNorm over C, bf16 (default) or fp32."""
     rows, C_ = x.numel() // x.shape[-1], x.shape[-1]
     if out is None:
-        out = torch.empty_like(x)
-    _call("b200_layernorm", None, _ptr(x), rows, C_, _ptr(w), _ptr(b), float(eps), _ptr(out), _stream())
+        out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    _call("b200_layernorm", None, _ptr(x), int(x.dtype == torch.float32), rows, C_, _ptr(w), _ptr(b), float(eps),
+          _ptr(out), int(out.dtype == torch.float32), _stream())
+    return out
+
+
+def linear_f32(x2d, w, *, scale=None, bias=None, res=None, res_mode=0, act=0, out=None, out_dtype=torch.bfloat16):
+    """x2d [M,K] bf16, w [N,K] bf16; residual / output may be fp32 [M,N] (the transformer residual stream)."""
+    M, K = x2d.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=x2d.device)
+    _call("b200_linear", (M, K, N), _ptr(x2d), M, K, _ptr(w), N, _ptr(scale), _ptr(bias), _ptr(res),
+          int(res is not None and res.dtype == torch.float32), res_mode, act, _ptr(out),
+          int(out.dtype == torch.float32), _stream())
     return out
 
 
@@ -304,6 +319,13 @@ def mask_attention(mask, attn_params, attn):
     _call("b200_mask_attention", None, _ptr(mask), B, mask[0].numel(), hc, _ptr(wa), _ptr(gw), _ptr(gb), _ptr(wb),
           _ptr(bb), float(eps), _ptr(attn), _stream())
     return attn
+
+
+def resize_bilinear_c1(src, out):
+    """src [B,h,w] fp32 -> out [B,H,W] fp32, F.interpolate(bilinear, align_corners=False)."""
+    B, h, w = src.shape
+    _call("b200_resize_bilinear_c1", None, _ptr(src), B, h, w, _ptr(out), out.shape[-2], out.shape[-1], _stream())
+    return out
 
 
 def lift_c1(r, w, scale, bias, y):

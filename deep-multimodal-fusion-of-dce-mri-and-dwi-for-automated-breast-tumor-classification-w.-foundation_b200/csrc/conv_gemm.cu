@@ -66,6 +66,7 @@ struct ConvGemmParams {
     float* rowsum_inv;     // MODE 1: receives 1 / sum_j exp(...) per row, [B, H, W]
     float alpha;           // MODE 1: logits = alpha * acc
     int n_valid;           // MODE 1: number of real columns (keys); the rest are masked out
+    int res_f32, out_f32;  // residual / output are fp32 row-major (transformer residual stream); direct path
     int stages;            // operand ring depth
     int off_ring, off_bar, off_union, off_rbox, off_sm;  // shared-memory plan (bytes from the 1 KB-aligned base)
 };
@@ -411,7 +412,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int bx = (ch * kChunk) / T::kBoxCols;
                 const int c16 = ((ch * kChunk) % T::kBoxCols) / 8;  // first 16-byte chunk inside the box row
                 if (RES != 0) {
-                    if (use_res) {
+                    if (use_res && p.res_f32) {
+                        // fp32 residual stream: every thread owns one 128-byte row segment per chunk
+                        if (RES == 2 && act == 1) {
+#pragma unroll
+                            for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+                        }
+                        if (valid) {
+                            const float4* r4 = reinterpret_cast<const float4*>(
+                                reinterpret_cast<const float*>(p.res) + pix * p.res_ld + n0);
+#pragma unroll
+                            for (int j = 0; j < kChunk / 4; ++j) {
+                                const float4 f = __ldg(r4 + j);
+                                v2[2 * j + 0] = __fadd2_rn(v2[2 * j + 0], make_float2(f.x, f.y));
+                                v2[2 * j + 1] = __fadd2_rn(v2[2 * j + 1], make_float2(f.z, f.w));
+                            }
+                        }
+                        if (RES == 1 && act == 1) {
+#pragma unroll
+                            for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+                        }
+                    } else if (use_res) {
                         uint4 u[4];
                         if (tma_epi) {
                             constexpr int kChunksPerBox = T::kBoxCols / kChunk;
@@ -471,6 +492,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             dsum[k] = fmaf(v[4 * j + 2], wv.z, dsum[k]);
                             dsum[k] = fmaf(v[4 * j + 3], wv.w, dsum[k]);
                         }
+                    }
+                } else if (out_ptr != nullptr && p.out_f32) {
+                    if (valid) {
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_ptr) + pix * p.out_ld +
+                                                                out_col0 + ch * kChunk);
+#pragma unroll
+                        for (int j = 0; j < kChunk / 4; ++j)
+                            dst[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
                 } else if (out_ptr != nullptr) {
                     uint4 o[4];
@@ -819,7 +848,7 @@ static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, 
     tmOut = tmA;
     tmOut2 = tmA;
     tmRes = tmA;
-    p.tma_epi = (p.up2 && no_tma_up2) ? 0 : 1;
+    p.tma_epi = ((p.up2 && no_tma_up2) || p.res_f32 || p.out_f32) ? 0 : 1;
     if (p.tma_epi) {
         const int cw = BN / 2 < 64 ? BN / 2 : 64;
         const CUtensorMapSwizzle swz = cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -953,6 +982,48 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
     // is opt-in (B200_WS=1) until a 2-CTA / multicast version makes it pay.
     static const bool want_ws = std::getenv("B200_WS") != nullptr;
     return run_job(p, j, 0, want_ws, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_linear(const void* x, long long M, int K, const void* w, int N, const float* scale, const float* bias,
+                           const void* res, int res_f32, int res_mode, int act, void* out, int out_f32,
+                           void* stream) {
+    using namespace b200;
+    if (x == nullptr || w == nullptr || out == nullptr || M <= 0 || M > 0x7fffffffLL) return -1;
+    if (K % 64 != 0 || N % 64 != 0) return -2;
+    if (res_mode != 0 && res == nullptr) return -4;
+    ConvGemmParams p{};
+    p.H = 1;
+    p.W = static_cast<int>(M);
+    p.BW = 128;
+    p.BH = 1;
+    p.tiles_w = static_cast<int>((M + 127) / 128);
+    p.tiles_h = 1;
+    p.Cout = N;
+    p.n_split = N;
+    p.m_tiles = p.tiles_w;
+    p.kc = K / 64;
+    p.taps = 1;
+    p.k_blocks = p.kc;
+    p.cstride = 1;
+    p.a_batched = 1;
+    p.b_mode = 0;
+    p.scale = scale;
+    p.bias = bias;
+    p.res = static_cast<const __nv_bfloat16*>(res);
+    p.res_ld = N;
+    p.res_mode = res_mode;
+    p.res_f32 = res_mode != 0 ? res_f32 : 0;
+    p.act = act;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.out_ld = N;
+    p.out_f32 = out_f32;
+    GemmJob j{};
+    j.K = K;
+    j.w = w;
+    j.a = View4{x, {K, M, 1, 1}, {K, 0, 0}};
+    j.out = View4{out, {N, M, 1, 1}, {N, 0, 0}};
+    j.res = View4{res, {N, M, 1, 1}, {N, 0, 0}};
+    return run_job(p, j, 0, false, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b200_gemm_batched(const b200_gemm_desc* d, void* stream) {

@@ -262,6 +262,26 @@ __global__ void tapsum_kernel(const float* __restrict__ d, int H, int W, const f
     out[i] = acc;
 }
 
+// ------------------------------------------------ 1-channel bilinear resize -
+// F.interpolate(mode='bilinear', align_corners=False) of an fp32 1-channel map (MaskHeadResize's fallback
+// path, model_module.py:205-211; it commutes with the 1x1 `out` convolution that follows it there, so it is
+// applied to the 1-channel logits instead of the 64-channel map).
+__global__ void resize_bilinear_c1_kernel(const float* __restrict__ in, int h, int w, float* __restrict__ out, int H,
+                                          int W, size_t total) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= total) return;
+    const int ox = static_cast<int>(i % W), oy = static_cast<int>((i / W) % H);
+    const size_t b = i / (static_cast<size_t>(W) * H);
+    const float sy = fmaxf((oy + 0.5f) * (static_cast<float>(h) / H) - 0.5f, 0.f);
+    const float sx = fmaxf((ox + 0.5f) * (static_cast<float>(w) / W) - 0.5f, 0.f);
+    const int y0 = min(static_cast<int>(sy), h - 1), x0 = min(static_cast<int>(sx), w - 1);
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly = sy - y0, lx = sx - x0;
+    const float* src = in + b * h * w;
+    out[i] = (1.f - ly) * ((1.f - lx) * src[y0 * w + x0] + lx * src[y0 * w + x1]) +
+             ly * ((1.f - lx) * src[y1 * w + x0] + lx * src[y1 * w + x1]);
+}
+
 // ------------------------------------------- mask head tail + attention ----
 // MaskHeadResize.out (model_module.py:187, 1x1 Cm->1 + bias) on the `pre` activations, then
 // MaskGuidedSpatialAttention.mask_processor (:67-73, :92-93): 1x1 1->Hc (no bias),
@@ -501,6 +521,16 @@ extern "C" int b200_mask_attention(const float* mask, int B, int npix, int Hc, c
         return -2;
     mask_tail_kernel<<<B, 256, npix * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
         nullptr, 0, npix, nullptr, nullptr, const_cast<float*>(mask), Hc, wa, gn_w, gn_b, wb, bb, gn_eps, attn);
+    return launch_status();
+}
+
+extern "C" int b200_resize_bilinear_c1(const float* in, int B, int h, int w, float* out, int H, int W, void* stream) {
+    if (B < 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return -1;
+    if (B == 0) return 0;
+    if (in == nullptr || out == nullptr) return -2;
+    const size_t total = static_cast<size_t>(B) * H * W;
+    resize_bilinear_c1_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, h, w, out, H, W, total);
     return launch_status();
 }
 

@@ -6,19 +6,26 @@
 
 namespace b200 {
 
-template <int VEC>  // uint4 (8 x bf16) vectors per lane: C = 256 * VEC
+template <int VEC, bool IN32, bool OUT32>  // 8-element vectors per lane: C = 256 * VEC
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, const float* __restrict__ w,
-                 const float* __restrict__ b, float eps, __nv_bfloat16* __restrict__ y) {
+layernorm_kernel(const void* __restrict__ xv, long long rows, int C, const float* __restrict__ w,
+                 const float* __restrict__ b, float eps, void* __restrict__ yv) {
     const int lane = threadIdx.x & 31;
     const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
     if (row >= rows) return;
-    const uint4* src = reinterpret_cast<const uint4*>(x + row * C);
     float f[VEC][8];
     float s = 0.f;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-        unpack_bf16x8(__ldg(src + v * 32 + lane), f[v]);
+        if (IN32) {
+            const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(xv) + row * C) + (v * 32 + lane) * 2;
+            const float4 a = __ldg(src), c = __ldg(src + 1);
+            f[v][0] = a.x; f[v][1] = a.y; f[v][2] = a.z; f[v][3] = a.w;
+            f[v][4] = c.x; f[v][5] = c.y; f[v][6] = c.z; f[v][7] = c.w;
+        } else {
+            const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(xv) + row * C);
+            unpack_bf16x8(__ldg(src + v * 32 + lane), f[v]);
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) s += f[v][k];
     }
@@ -32,7 +39,6 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, con
             q += d * d;
         }
     const float rstd = rsqrtf(warp_sum(q) / C + eps);
-    uint4* dst = reinterpret_cast<uint4*>(y + row * C);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
         const int c0 = (v * 32 + lane) * 8;
@@ -47,27 +53,40 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, con
         o[5] = (f[v][5] - mean) * rstd * w1.y + b1.y;
         o[6] = (f[v][6] - mean) * rstd * w1.z + b1.z;
         o[7] = (f[v][7] - mean) * rstd * w1.w + b1.w;
-        dst[v * 32 + lane] = pack_bf16x8(o);
+        if (OUT32) {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(yv) + row * C) + (v * 32 + lane) * 2;
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+            reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(yv) + row * C)[v * 32 + lane] = pack_bf16x8(o);
+        }
     }
 }
 
 }  // namespace b200
 
-extern "C" int b200_layernorm(const void* x, long long rows, int C, const float* w, const float* b, float eps, void* y,
-                              void* stream) {
+template <bool IN32, bool OUT32>
+static void ln_launch(int vec, unsigned blocks, cudaStream_t s, const void* x, long long rows, int C, const float* w,
+                      const float* b, float eps, void* y) {
+    switch (vec) {
+        case 1: b200::layernorm_kernel<1, IN32, OUT32><<<blocks, 256, 0, s>>>(x, rows, C, w, b, eps, y); break;
+        case 2: b200::layernorm_kernel<2, IN32, OUT32><<<blocks, 256, 0, s>>>(x, rows, C, w, b, eps, y); break;
+        case 3: b200::layernorm_kernel<3, IN32, OUT32><<<blocks, 256, 0, s>>>(x, rows, C, w, b, eps, y); break;
+        default: b200::layernorm_kernel<4, IN32, OUT32><<<blocks, 256, 0, s>>>(x, rows, C, w, b, eps, y); break;
+    }
+}
+
+extern "C" int b200_layernorm(const void* x, int x_f32, long long rows, int C, const float* w, const float* b, float eps,
+                              void* y, int y_f32, void* stream) {
     using namespace b200;
     if (rows < 0 || C <= 0 || C % 256 != 0 || C > 1024) return -1;
     if (rows == 0) return 0;
     if (x == nullptr || w == nullptr || b == nullptr || y == nullptr) return -2;
-    const long long blocks = (rows * 32 + 255) / 256;
+    const unsigned blocks = static_cast<unsigned>((rows * 32 + 255) / 256);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const __nv_bfloat16* xi = static_cast<const __nv_bfloat16*>(x);
-    __nv_bfloat16* yo = static_cast<__nv_bfloat16*>(y);
-    switch (C / 256) {
-        case 1: layernorm_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, s>>>(xi, rows, C, w, b, eps, yo); break;
-        case 2: layernorm_kernel<2><<<static_cast<unsigned>(blocks), 256, 0, s>>>(xi, rows, C, w, b, eps, yo); break;
-        case 3: layernorm_kernel<3><<<static_cast<unsigned>(blocks), 256, 0, s>>>(xi, rows, C, w, b, eps, yo); break;
-        default: layernorm_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, s>>>(xi, rows, C, w, b, eps, yo); break;
-    }
+    if (x_f32 && y_f32) ln_launch<true, true>(C / 256, blocks, s, x, rows, C, w, b, eps, y);
+    else if (x_f32) ln_launch<true, false>(C / 256, blocks, s, x, rows, C, w, b, eps, y);
+    else if (y_f32) ln_launch<false, true>(C / 256, blocks, s, x, rows, C, w, b, eps, y);
+    else ln_launch<false, false>(C / 256, blocks, s, x, rows, C, w, b, eps, y);
     return launch_status();
 }

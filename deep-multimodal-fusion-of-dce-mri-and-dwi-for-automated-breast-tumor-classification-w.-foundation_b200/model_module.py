@@ -396,8 +396,10 @@ def _transformer_stage(tr, x):
     if N != 256:
         raise NotImplementedError("the fused softmax epilogue needs 256 tokens per case (32x32 maps, patch 2)")
     M = B * N
-    t = nat.layernorm(tok.view(M, E), *tr["pe_ln"])
-    h = torch.empty_like(t)
+    # the residual stream t is kept in fp32 across the blocks (12 bf16 roundings of it would dominate the error);
+    # everything that feeds a tensor-core GEMM is bf16
+    t = nat.layernorm(tok.view(M, E), *tr["pe_ln"], out_dtype=torch.float32)
+    h = torch.empty((M, E), dtype=torch.bfloat16, device=dev)
     qk = torch.empty((M, 2 * E), dtype=torch.bfloat16, device=dev)
     vt = torch.empty((B, E, N), dtype=torch.bfloat16, device=dev)
     o = torch.empty((M, E), dtype=torch.bfloat16, device=dev)
@@ -416,10 +418,13 @@ def _transformer_stage(tr, x):
         nat.gemm_batched(M=N, N=dh, K=N, heads=heads, batch=B, a=p_buf.data_ptr(),
                          a_strides=(N, N * N, heads * N * N), b=vt.data_ptr(), b_strides=(N, dh * N, E * N),
                          out=o.data_ptr(), out_strides=(E, dh, N * E), rowscale=rs, bias=ly["bv"], vec_h_stride=dh)
-        t2 = nat.linear(o, ly["wproj"], scale=ly["sproj"], bias=ly["bproj"], res=t, res_mode=2)
+        last = ly is tr["layers"][-1]
+        t2 = nat.linear_f32(o, ly["wproj"], scale=ly["sproj"], bias=ly["bproj"], res=t, res_mode=2,
+                            out_dtype=torch.float32)
         nat.layernorm(t2, *ly["ln2"], out=h)
         nat.linear(h, ly["wfc1"], bias=ly["bfc1"], act=1, out=u)
-        t = nat.linear(u, ly["wfc2"], scale=ly["sfc2"], bias=ly["bfc2"], res=t2, res_mode=2)
+        t = nat.linear_f32(u, ly["wfc2"], scale=ly["sfc2"], bias=ly["bfc2"], res=t2, res_mode=2,
+                           out_dtype=torch.bfloat16 if last else torch.float32)
     c3 = tr["out_w"].shape[0]
     gap = torch.zeros((B, c3), dtype=torch.float32, device=dev)
     f3 = nat.conv_gemm(t.view(B, Ht, Wt, E), tr["out_w"], taps=1, bias=tr["out_b"], gap=gap)
@@ -889,11 +894,17 @@ class FusionModel(nn.Module):
         nat.fusion_mix(p_dwi, p_dce, gating, lowres, gate if self.fusion_se is not None else None, hp, wp, fused)
         mask_logits = recon = proj = None
         if full:
-            if H != self.mask_size:
-                raise NotImplementedError("mask head resize paths (input != 32x32) are not built")
+            if H != self.mask_size and H in (64, 128, 256, 512):
+                raise NotImplementedError("the strided-conv mask head paths (64..512 inputs) are not built")
             mask_logits = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
             nat.conv_gemm(fused, pk["mask_pre_w"], taps=1, bias=pk["mask_pre_b"], store=False,
                           dot_w=pk["mask_out_w"].view(1, -1), dot_out=mask_logits, dot_bias=pk["mask_out_b_host"])
+            if H != self.mask_size:
+                # reference :205-211: bilinear resize of the 64-channel map, then the 1x1 `out` conv; both are
+                # linear and the resize acts per channel, so resizing the 1-channel logits is the same map
+                small = mask_logits
+                mask_logits = torch.empty((B, 1, self.mask_size, self.mask_size), dtype=torch.float32, device=dev)
+                nat.resize_bilinear_c1(small.view(B, H, W), mask_logits.view(B, self.mask_size, self.mask_size))
             recon = _recon(pk["recon"], fused).unsqueeze(1)
             pj = pk["projF"]
             g = nat.conv_gemm(fused, pj["w0"], taps=1, scale=pj["s0"], bias=pj["b0"], act=1)

@@ -109,10 +109,19 @@ typedef struct b200_gemm_desc {
 
 int b200_gemm_batched(const b200_gemm_desc* d, void* stream);
 
-/* nn.LayerNorm over the last dimension of a bf16 token matrix [rows, C] (code/transformer_model.py:16, :71, :73),
- * C a multiple of 256 up to 1024, fp32 statistics, bf16 output. */
-int b200_layernorm(const void* x, long long rows, int C, const float* w, const float* b, float eps, void* y,
-                   void* stream);
+/* nn.LayerNorm over the last dimension of a token matrix [rows, C] (code/transformer_model.py:16, :71, :73),
+ * C a multiple of 256 up to 1024, fp32 statistics; x / y are bf16, or fp32 when x_f32 / y_f32 (the
+ * transformer residual stream is kept in fp32). */
+int b200_layernorm(const void* x, int x_f32, long long rows, int C, const float* w, const float* b, float eps,
+                   void* y, int y_f32, void* stream);
+
+/*
+ * nn.Linear on a token matrix (code/transformer_model.py:93, :95, :123, :125): out[M,N] = epilogue(x[M,K] w[N,K]^T)
+ * with the b200_conv_gemm epilogue (scale, bias, GELU, residual).  The residual and / or the output may be
+ * fp32 row-major [M,N] (res_f32 / out_f32): x + gamma * (W y + b) then accumulates into an fp32 stream.
+ */
+int b200_linear(const void* x, long long M, int K, const void* w, int N, const float* scale, const float* bias,
+                const void* res, int res_f32, int res_mode, int act, void* out, int out_f32, void* stream);
 
 /* out[b,h,w] = bias + sum_k d[(b,h+ky-1,w+kx-1)][k], zero padded: finishes a 3x3 C->1 conv from tap dots. */
 int b200_tapsum(const float* d, int B, int H, int W, const float* bias, float* out, void* stream);
@@ -188,6 +197,10 @@ int b200_conv3x3_c1(const void* x, int B, int H, int W, int C, const float* w, c
 int b200_mask_attention(const float* mask, int B, int npix, int Hc, const float* wa, const float* gn_w,
                         const float* gn_b, const float* wb, const float* bb, float gn_eps, float* attn,
                         void* stream);
+
+/* F.interpolate(bilinear, align_corners=False) of an fp32 1-channel map [B,h,w] -> [B,H,W]
+ * (MaskHeadResize fallback, code/model_module.py:205-211, commuted past the 1x1 `out` conv). */
+int b200_resize_bilinear_c1(const float* in, int B, int h, int w, float* out, int H, int W, void* stream);
 
 int b200_mask_tail(const void* pre, int B, int npix, int Cm, const float* w_out, const float* b_out,
                    float* mask_pred, int Hc, const float* wa, const float* gn_w, const float* gn_b, const float* wb,

@@ -173,9 +173,11 @@ def test_layernorm(C):
     w = (torch.rand(C, generator=g) + 0.5).to(DEV)
     b = (torch.randn(C, generator=g) * 0.1).to(DEV)
     y = nat.layernorm(x, w, b, 1e-5)
+    y32 = nat.layernorm(x.float(), w, b, 1e-5, out_dtype=torch.float32)
     torch.cuda.synchronize()
     ref = F.layer_norm(x.float(), (C,), w, b, 1e-5)
     assert _rel(y, ref) < 6e-3  # one bf16 rounding of the output
+    assert _rel(y32, ref) < 1e-5
 
 
 def test_batched_gemm_weights_on_a_side():
@@ -216,3 +218,20 @@ def test_attention_from_batched_gemms(B, heads, N, dh):
     v = vt.float().view(B, heads, dh, N).permute(0, 1, 3, 2) + bv.view(1, heads, 1, dh)
     ref = (torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B, N, C)
     assert _rel(O, ref) < 1.5e-2
+
+
+def test_linear_fp32_residual_stream():
+    """x + gamma * (W y + b) with the residual read and the result written in fp32 (transformer blocks)."""
+    g = torch.Generator(device="cpu").manual_seed(21)
+    M, K, N = 1000, 2048, 512
+    y = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).bfloat16()
+    gamma = (0.1 * (1 + 0.1 * torch.randn(N, generator=g))).to(DEV)
+    bias = (torch.randn(N, generator=g) * 0.1).to(DEV)
+    x = torch.randn(M, N, generator=g).to(DEV)
+    out = nat.linear_f32(y, w, scale=gamma, bias=gamma * bias, res=x, res_mode=2, out_dtype=torch.float32)
+    out_b = nat.linear_f32(y, w, scale=gamma, bias=gamma * bias, res=x, res_mode=2, out_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    ref = x + gamma * (y.float() @ w.float().t() + bias)
+    assert out.dtype == torch.float32 and _rel(out, ref) < 1e-5
+    assert _rel(out_b, ref) < 6e-3

@@ -195,7 +195,17 @@ def test_hybrid_transformer_encoders_vs_golden_and_oracle():
         for prefix, obj in outs.items():
             for key, t in gu.walk(prefix, obj):
                 worst[key] = gu.check(gold, key, t, rtol=_tol(key))
-    assert tuple(ad["raw_feats"][2].shape) == (2, 512, 16, 16)
+        with torch.no_grad():
+            lf, mf, af = mods["fusion"](ad["raw_feats"], ac["raw_feats"], md, mc)  # 16x16 encoder maps
+        torch.cuda.synchronize()
+        # The fusion head on these 16x16 maps amplifies input perturbations ~5x for this seeded weight draw
+        # (fed identical inputs it matches the oracle to 1.7e-3 - tools/dbg_hybrid.py): the encoders' 0.7 %
+        # bf16 error on f3 becomes up to 3.5 % on the fused logits.  Encoder outputs keep the 2e-2 bound above;
+        # the fused outputs of this non-default configuration are held to 5e-2.
+        for prefix, obj in {f"{kind}/fusion/logits": lf, f"{kind}/fusion/mask": mf, f"{kind}/fusion/aux": af}.items():
+            for key, t in gu.walk(prefix, obj):
+                worst[key] = gu.check(gold, key, t, rtol=5e-2)
+    assert tuple(ad["raw_feats"][2].shape) == (2, 512, 16, 16) and tuple(mf.shape) == (2, 1, 32, 32)
     print("hybrid worst relative errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:6])
     with torch.no_grad():
         o_d = mo.encoder_forward(sds["dwi"], "dwi", p, dwi)
