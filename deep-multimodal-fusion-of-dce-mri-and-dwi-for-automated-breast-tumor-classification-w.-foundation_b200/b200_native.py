@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lib = None
 
@@ -58,7 +58,7 @@ class GemmDesc(C.Structure):
         ("res_mode", C.c_int), ("act", C.c_int),
         ("scale", C.c_void_p), ("bias", C.c_void_p), ("vec_h_stride", C.c_int),
         ("rowscale", C.c_void_p), ("mode", C.c_int), ("alpha", C.c_float), ("n_valid", C.c_int),
-        ("rowsum_inv", C.c_void_p),
+        ("rowsum_inv", C.c_void_p), ("b_rows", C.c_int),
     ]
 
 
@@ -75,6 +75,9 @@ SIGNATURES = {
     "b200_tapsum": [_P, _I, _I, _I, _P, _P, _P],
     "b200_gemm_batched": [C.POINTER(GemmDesc), _P],
     "b200_layernorm": [_P, _I, _LL, _I, _P, _P, _F, _P, _I, _P],
+    "b200_patchify": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "b200_vit_tokens": [_P, _P, _P, _I, _I, _I, _P, _P],
+    "b200_vit_feature": [_P, _I, _I, _I, _P, _P],
     "b200_linear": [_P, _LL, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _P],
     "b200_dwi_normalize": [_P, _P, _I, _I, _I, _I, _F, _F, _P, _P],
     "b200_nyul_transform": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
@@ -202,7 +205,7 @@ def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0,
 
 def gemm_batched(*, M, N, K, heads, batch, a, a_strides, b, b_strides, out, out_strides, a_shared=False, res=None,
                  res_strides=(0, 0, 0), res_mode=0, act=0, scale=None, bias=None, vec_h_stride=0, rowscale=None,
-                 mode=0, alpha=1.0, n_valid=0, rowsum_inv=None):
+                 mode=0, alpha=1.0, n_valid=0, rowsum_inv=None, b_rows=0):
     """Batched K-major GEMM (see b200_gemm_batched).  a / b / out / res are data pointers (ints) so that views
     with channel offsets can be passed; strides are (row, head, batch) in elements."""
     d = GemmDesc()
@@ -214,6 +217,7 @@ def gemm_batched(*, M, N, K, heads, batch, a, a_strides, b, b_strides, out, out_
     d.res_mode, d.act = res_mode, act
     d.scale, d.bias, d.vec_h_stride = _ptr(scale), _ptr(bias), vec_h_stride
     d.rowscale, d.mode, d.alpha, d.n_valid, d.rowsum_inv = _ptr(rowscale), mode, float(alpha), n_valid, _ptr(rowsum_inv)
+    d.b_rows = b_rows
     _call("b200_gemm_batched", (batch, heads, M, K, N, mode), C.byref(d), _stream())
 
 
@@ -236,6 +240,22 @@ def linear_f32(x2d, w, *, scale=None, bias=None, res=None, res_mode=0, act=0, ou
     _call("b200_linear", (M, K, N), _ptr(x2d), M, K, _ptr(w), N, _ptr(scale), _ptr(bias), _ptr(res),
           int(res is not None and res.dtype == torch.float32), res_mode, act, _ptr(out),
           int(out.dtype == torch.float32), _stream())
+    return out
+
+
+def patchify(x, P, out):
+    B, C_, H, W = x.shape
+    _call("b200_patchify", None, _ptr(x), B, C_, H, W, P, _ptr(out), _stream())
+    return out
+
+
+def vit_tokens(patches, cls, pos, B, n_patch, E, t):
+    _call("b200_vit_tokens", None, _ptr(patches), _ptr(cls), _ptr(pos), B, n_patch, E, _ptr(t), _stream())
+    return t
+
+
+def vit_feature(t, B, n_patch, E, out):
+    _call("b200_vit_feature", None, _ptr(t), B, n_patch, E, _ptr(out), _stream())
     return out
 
 

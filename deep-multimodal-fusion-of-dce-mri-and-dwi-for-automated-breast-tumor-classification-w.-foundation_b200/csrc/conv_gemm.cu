@@ -1073,7 +1073,9 @@ extern "C" int b200_gemm_batched(const b200_gemm_desc* d, void* stream) {
     j.K = d->K;
     if (d->a_shared) j.a = View4{d->a, {d->K, d->M, 1, 1}, {d->a_row_stride, 0, 0}};
     else j.a = View4{d->a, {d->K, d->M, d->heads, d->batch}, {d->a_row_stride, d->a_head_stride, d->a_batch_stride}};
-    j.b4 = View4{d->b, {d->K, d->N, d->heads, d->batch}, {d->b_row_stride, d->b_head_stride, d->b_batch_stride}};
+    // b_rows < N: the missing rows of the B operand are zero-filled by the TMA (ragged key / token counts)
+    j.b4 = View4{d->b, {d->K, d->b_rows > 0 ? d->b_rows : d->N, d->heads, d->batch},
+                 {d->b_row_stride, d->b_head_stride, d->b_batch_stride}};
     j.out = View4{d->out, {d->N, d->M, d->heads, d->batch}, {d->out_row_stride, d->out_head_stride, d->out_batch_stride}};
     j.res = View4{d->res, {d->N, d->M, d->heads, d->batch}, {d->res_row_stride, d->res_head_stride, d->res_batch_stride}};
     return run_job(p, j, d->mode, false, static_cast<cudaStream_t>(stream));

@@ -63,7 +63,106 @@ layernorm_kernel(const void* __restrict__ xv, long long rows, int C, const float
     }
 }
 
+// ---------------------------------------------------------------- ViT glue -
+// patchify: fp32 NCHW image -> bf16 patch matrix [B * gh * gw, C * P * P], k = (c*P + ky)*P + kx, i.e. the
+// flattening of Conv2d(C, E, P, P).weight, so the patch embedding (timm PatchEmbed / foundation_model.py
+// :388-412) becomes one tcgen05 GEMM.  One thread moves one 8-pixel run of a patch row.
+__global__ void patchify_kernel(const float* __restrict__ x, int C, int H, int W, int P,
+                                __nv_bfloat16* __restrict__ out, size_t total_runs) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= total_runs) return;
+    const int runs_per_row = P / 8;
+    const int gw = W / P, gh = H / P;
+    size_t r = i;
+    const int run = static_cast<int>(r % runs_per_row); r /= runs_per_row;
+    const int ky = static_cast<int>(r % P); r /= P;
+    const int c = static_cast<int>(r % C); r /= C;
+    const int px = static_cast<int>(r % gw); r /= gw;
+    const int py = static_cast<int>(r % gh);
+    const size_t b = r / gh;
+    const float* src = x + ((b * C + c) * H + py * P + ky) * W + px * P + run * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src)), d = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    const float f[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+    const size_t token = (b * gh + py) * gw + px;
+    __nv_bfloat16* dst = out + token * (static_cast<size_t>(C) * P * P) + (static_cast<size_t>(c) * P + ky) * P + run * 8;
+    *reinterpret_cast<uint4*>(dst) = pack_bf16x8(f);
+}
+
+// tokens: t[b,0,:] = cls + pos[0]; t[b,1+i,:] = patch[b,i,:] + pos[1+i]  (fp32 residual stream)
+__global__ void vit_tokens_kernel(const __nv_bfloat16* __restrict__ patches, const float* __restrict__ cls,
+                                  const float* __restrict__ pos, int n_patch, int E, float* __restrict__ t,
+                                  size_t total_vec) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= total_vec) return;
+    const int ev = E / 8;
+    const int e0 = static_cast<int>(i % ev) * 8;
+    const size_t row = i / ev;
+    const int tok = static_cast<int>(row % (n_patch + 1));
+    const size_t b = row / (n_patch + 1);
+    float f[8];
+    if (tok == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = cls[e0 + k];
+    } else {
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(patches + (b * n_patch + tok - 1) * E + e0)), f);
+    }
+    float* dst = t + row * E + e0;
+    const float* pp = pos + static_cast<size_t>(tok) * E + e0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dst[k] = f[k] + pp[k];
+}
+
+// feature map of one block: fp32 stream [B, 1+n, E] -> bf16 [B, n, E] (cls token stripped; NHWC map)
+__global__ void vit_feature_kernel(const float* __restrict__ t, int n_patch, int E, __nv_bfloat16* __restrict__ out,
+                                   size_t total_vec) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= total_vec) return;
+    const int ev = E / 8;
+    const int e0 = static_cast<int>(i % ev) * 8;
+    const size_t row = i / ev;
+    const int tok = static_cast<int>(row % n_patch);
+    const size_t b = row / n_patch;
+    const float4* src = reinterpret_cast<const float4*>(t + (b * (n_patch + 1) + tok + 1) * E + e0);
+    const float4 a = __ldg(src), d = __ldg(src + 1);
+    const float f[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+    reinterpret_cast<uint4*>(out)[i] = pack_bf16x8(f);
+}
+
 }  // namespace b200
+
+extern "C" int b200_patchify(const float* x, int B, int C, int H, int W, int P, void* out, void* stream) {
+    using namespace b200;
+    if (B < 0 || C <= 0 || P <= 0 || P % 8 != 0 || H % P != 0 || W % P != 0) return -1;
+    if (B == 0) return 0;
+    if (x == nullptr || out == nullptr || (reinterpret_cast<uintptr_t>(x) & 15)) return -2;
+    const size_t total = static_cast<size_t>(B) * (H / P) * (W / P) * C * P * (P / 8);
+    patchify_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, C, H, W, P, static_cast<__nv_bfloat16*>(out), total);
+    return launch_status();
+}
+
+extern "C" int b200_vit_tokens(const void* patches, const float* cls, const float* pos, int B, int n_patch, int E,
+                               float* t, void* stream) {
+    using namespace b200;
+    if (B < 0 || n_patch <= 0 || E % 8 != 0) return -1;
+    if (B == 0) return 0;
+    if (patches == nullptr || cls == nullptr || pos == nullptr || t == nullptr) return -2;
+    const size_t total = static_cast<size_t>(B) * (n_patch + 1) * (E / 8);
+    vit_tokens_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(patches), cls, pos, n_patch, E, t, total);
+    return launch_status();
+}
+
+extern "C" int b200_vit_feature(const float* t, int B, int n_patch, int E, void* out, void* stream) {
+    using namespace b200;
+    if (B < 0 || n_patch <= 0 || E % 8 != 0) return -1;
+    if (B == 0) return 0;
+    if (t == nullptr || out == nullptr) return -2;
+    const size_t total = static_cast<size_t>(B) * n_patch * (E / 8);
+    vit_feature_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        t, n_patch, E, static_cast<__nv_bfloat16*>(out), total);
+    return launch_status();
+}
 
 template <bool IN32, bool OUT32>
 static void ln_launch(int vec, unsigned blocks, cudaStream_t s, const void* x, long long rows, int C, const float* w,

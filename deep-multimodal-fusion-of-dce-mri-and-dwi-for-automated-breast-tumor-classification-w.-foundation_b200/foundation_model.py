@@ -1,0 +1,217 @@
+"""B200-native drop-in for the ViT branch of the reference's ``foundation_model``.
+
+``build_medical_backbone(parameters, device, method, in_channels)`` keeps the reference contract
+(/root/reference/code/foundation_model.py:490-577): it returns an ``nn.Module`` with
+``.feature_info.channels()/.reduction()``, ``.output_dims`` and ``forward(x) -> list[NCHW maps]`` and
+mutates ``parameters[f"{method}_model_parameters"]`` the way the ViT branch does (:526-545:
+``backbone_index_lists=[[0,1,2],[3,4,5,6],[7,8,9,10,11]]``, ``downsample=(False,)*3``,
+``channels=(768,)*3``, ``transformer_backbone=True``).
+
+The reference gets the network itself from ``timm.create_model("vit_base_patch16_224",
+features_only=True, out_indices=0..11, img_size=..., in_chans=C)`` (:371-431).  timm is an un-vendored,
+un-pinned dependency that is absent here, so this module carries its own ViT-B/16 feature extractor with
+timm's parameter names (``patch_embed.proj``, ``cls_token``, ``pos_embed``, ``blocks.N.{norm1,attn.qkv,
+attn.proj,norm2,mlp.fc1,mlp.fc2}``, ``norm``) - a timm checkpoint's ``state_dict`` loads unchanged - and
+runs it on the sm_100a kernels: patchify + one GEMM for the patch embedding, an fp32 residual stream,
+LayerNorm (eps 1e-6), per-head Q.K^T with the softmax numerator fused into the GEMM epilogue (197 keys
+masked inside a 256-wide tile), P.V with the 1/rowsum applied to the fp32 accumulator, MLP with a
+fused GELU.  Parity for this backbone is UNPINNED (no timm to compare with); the oracle is a restatement
+cross-checked against torchvision's VisionTransformer (oracle/backbone_oracle.py).
+
+Only the ViT names are built ("vit_base_patch16_224", "dino_vitbase16_pretrained" - the reference builds the
+same timm model for both, :526, :538-545); the ResNet / RadImageNet / UNI2-h branches need network access and
+are out of scope.  No pretrained weights can be fetched offline: parameters are
+randomly initialised unless a state dict is loaded.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+import b200_native as nat
+
+__all__ = ["build_medical_backbone", "build_vit_dino_backbone", "B200ViTBackbone"]
+
+VIT_NAMES = ("vit_base_patch16_224", "dino_vitbase16_pretrain", "dino_vitbase16_pretrained")
+
+
+class _FeatureInfo:
+    def __init__(self, channels, reductions):
+        self._c, self._r = list(channels), list(reductions)
+
+    def channels(self):
+        return list(self._c)
+
+    def reduction(self):
+        return list(self._r)
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, in_chans, embed, patch):
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, embed, kernel_size=patch, stride=patch)
+
+
+class _Attention(nn.Module):
+    def __init__(self, embed, heads):
+        super().__init__()
+        self.num_heads = heads
+        self.qkv = nn.Linear(embed, 3 * embed, bias=True)
+        self.proj = nn.Linear(embed, embed)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, embed, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(embed, hidden)
+        self.fc2 = nn.Linear(hidden, embed)
+
+
+class _Block(nn.Module):
+    def __init__(self, embed, heads, hidden):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(embed, eps=1e-6)
+        self.attn = _Attention(embed, heads)
+        self.norm2 = nn.LayerNorm(embed, eps=1e-6)
+        self.mlp = _Mlp(embed, hidden)
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _bf16(t, dev):
+    return t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+
+
+class B200ViTBackbone(nn.Module):
+    """ViT-B/16 `features_only` backbone: forward(x[B,C,H,W]) -> 12 maps [B,768,H/16,W/16] (bf16,
+    channels_last views), cls token stripped, no final norm - what timm's FeatureGetterNet returns."""
+
+    def __init__(self, in_chans=3, img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4.0,
+                 out_indices=None):
+        super().__init__()
+        self.patch_size, self.embed_dim, self.img_size = patch_size, embed_dim, img_size
+        self.grid = img_size // patch_size
+        self.out_indices = list(range(depth)) if out_indices is None else list(out_indices)
+        self.patch_embed = _PatchEmbed(in_chans, embed_dim, patch_size)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.randn(1, self.grid * self.grid + 1, embed_dim) * 0.02)
+        self.blocks = nn.ModuleList([_Block(embed_dim, num_heads, int(embed_dim * mlp_ratio)) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=1e-6)  # present in timm's model; not applied to features
+        self.feature_info = _FeatureInfo([embed_dim] * len(self.out_indices), [patch_size] * len(self.out_indices))
+        self.output_dims = [embed_dim] * len(self.out_indices)
+        self._pack_cache = None
+
+    def _packed(self, dev):
+        sig = (str(dev), tuple((t.data_ptr(), t._version) for t in self.parameters()))
+        if self._pack_cache is not None and self._pack_cache[0] == sig:
+            return self._pack_cache[1]
+        E = self.embed_dim
+        pk = {"pe_w": _bf16(self.patch_embed.proj.weight.flatten(1), dev), "pe_b": _f32(self.patch_embed.proj.bias, dev),
+              "cls": _f32(self.cls_token.flatten(), dev), "pos": _f32(self.pos_embed[0], dev), "layers": []}
+        for blk in self.blocks:
+            wqkv, bqkv = blk.attn.qkv.weight, blk.attn.qkv.bias
+            pk["layers"].append({
+                "heads": blk.attn.num_heads, "dh": E // blk.attn.num_heads,
+                "ln1": (_f32(blk.norm1.weight, dev), _f32(blk.norm1.bias, dev), blk.norm1.eps),
+                "ln2": (_f32(blk.norm2.weight, dev), _f32(blk.norm2.bias, dev), blk.norm2.eps),
+                "wqk": _bf16(wqkv[:2 * E], dev), "bqk": _f32(bqkv[:2 * E], dev),
+                "wv": _bf16(wqkv[2 * E:], dev), "bv": _f32(bqkv[2 * E:], dev),
+                "wproj": _bf16(blk.attn.proj.weight, dev), "bproj": _f32(blk.attn.proj.bias, dev),
+                "wfc1": _bf16(blk.mlp.fc1.weight, dev), "bfc1": _f32(blk.mlp.fc1.bias, dev),
+                "wfc2": _bf16(blk.mlp.fc2.weight, dev), "bfc2": _f32(blk.mlp.fc2.bias, dev)})
+        self._pack_cache = (sig, pk)
+        return pk
+
+    @torch.no_grad()
+    def forward(self, x):
+        if self.training:
+            raise NotImplementedError("training-mode forward is not built in the B200 path yet; call .eval()")
+        if not x.is_cuda:
+            raise nat.B200NativeError("B200ViTBackbone.forward needs a CUDA tensor (no CPU path)")
+        x = x.contiguous().float()
+        B, C, H, W = x.shape
+        P, E = self.patch_size, self.embed_dim
+        if H != self.img_size or W != self.img_size:
+            raise ValueError(f"expected {self.img_size}x{self.img_size} inputs (fixed position embedding)")
+        g = self.grid
+        n = g * g          # patch tokens
+        N = n + 1          # + cls
+        if N > 256:
+            raise NotImplementedError("more than 256 tokens per image (the fused softmax tile is 256 keys wide)")
+        dev = x.device
+        pk = self._packed(dev)
+        K0 = C * P * P
+        if K0 % 64 != 0:
+            raise NotImplementedError("in_chans * patch^2 must be a multiple of 64")
+        patches = torch.empty((B * n, K0), dtype=torch.bfloat16, device=dev)
+        nat.patchify(x, P, patches)
+        emb = nat.linear(patches, pk["pe_w"], bias=pk["pe_b"])            # [B*n, E] bf16
+        t = torch.empty((B * N, E), dtype=torch.float32, device=dev)      # fp32 residual stream
+        nat.vit_tokens(emb, pk["cls"], pk["pos"], B, n, E, t)
+        M = B * N
+        h = torch.empty((M, E), dtype=torch.bfloat16, device=dev)
+        qk = torch.empty((M, 2 * E), dtype=torch.bfloat16, device=dev)
+        vt = torch.empty((B, E, 256), dtype=torch.bfloat16, device=dev)   # V^T, key axis padded to the tile
+        o = torch.empty((M, E), dtype=torch.bfloat16, device=dev)
+        u = torch.empty((M, pk["layers"][0]["wfc1"].shape[0]), dtype=torch.bfloat16, device=dev)
+        heads, dh = pk["layers"][0]["heads"], pk["layers"][0]["dh"]
+        p_buf = torch.empty((B, heads, N, 256), dtype=torch.bfloat16, device=dev)
+        rs = torch.empty((B, heads, N), dtype=torch.float32, device=dev)
+        feats = []
+        for i, ly in enumerate(pk["layers"]):
+            nat.layernorm(t, *ly["ln1"], out=h)
+            nat.linear(h, ly["wqk"], bias=ly["bqk"], out=qk)
+            # V^T[b] = W_v h[b]^T (weights on the A side); token rows >= N of the B operand are zero-filled
+            nat.gemm_batched(M=E, N=256, K=E, heads=1, batch=B, a=ly["wv"].data_ptr(), a_strides=(E, 0, 0),
+                             a_shared=True, b=h.data_ptr(), b_strides=(E, 0, N * E), b_rows=N, out=vt.data_ptr(),
+                             out_strides=(256, 0, E * 256))
+            # P = exp(q.k^T / sqrt(d) - rowmax) over the N real keys of a 256-wide tile; rs = 1 / rowsum
+            nat.gemm_batched(M=N, N=256, K=dh, heads=heads, batch=B, a=qk.data_ptr(),
+                             a_strides=(2 * E, dh, N * 2 * E), b=qk.data_ptr() + 2 * E,
+                             b_strides=(2 * E, dh, N * 2 * E), b_rows=N, out=p_buf.data_ptr(),
+                             out_strides=(256, N * 256, heads * N * 256), mode=1, alpha=dh ** -0.5, n_valid=N,
+                             rowsum_inv=rs)
+            # O = (P V) * rs + b_v  (the V bias commutes past the row-stochastic attention matrix)
+            nat.gemm_batched(M=N, N=dh, K=256, heads=heads, batch=B, a=p_buf.data_ptr(),
+                             a_strides=(256, N * 256, heads * N * 256), b=vt.data_ptr(), b_strides=(256, dh * 256, E * 256),
+                             out=o.data_ptr(), out_strides=(E, dh, N * E), rowscale=rs, bias=ly["bv"], vec_h_stride=dh)
+            t2 = nat.linear_f32(o, ly["wproj"], bias=ly["bproj"], res=t, res_mode=2, out_dtype=torch.float32)
+            nat.layernorm(t2, *ly["ln2"], out=h)
+            nat.linear(h, ly["wfc1"], bias=ly["bfc1"], act=1, out=u)
+            t = nat.linear_f32(u, ly["wfc2"], bias=ly["bfc2"], res=t2, res_mode=2, out_dtype=torch.float32)
+            if i in self.out_indices:
+                f = torch.empty((B, g, g, E), dtype=torch.bfloat16, device=dev)
+                nat.vit_feature(t, B, n, E, f)
+                feats.append(f.permute(0, 3, 1, 2))  # NCHW-shaped view of the NHWC buffer
+        return feats
+
+
+def build_vit_dino_backbone(model_name="vit_base_patch16_224", in_channels=3, img_size=224, device=None, **_):
+    """Reference :371-431 without the timm dependency: a ViT-B/16 feature extractor for `in_channels` inputs."""
+    if model_name not in VIT_NAMES:
+        raise ValueError(f"unsupported ViT name {model_name!r}")
+    size = img_size[0] if isinstance(img_size, (tuple, list)) else img_size
+    model = B200ViTBackbone(in_chans=in_channels, img_size=size)
+    return model.to(device) if device is not None else model
+
+
+def build_medical_backbone(parameters, device, method, in_channels):
+    """Reference :490-577, ViT branch (:526-545).  Mutates parameters[f"{method}_model_parameters"]."""
+    mp = parameters[f"{method}_model_parameters"]
+    name = mp["backbone_str"]
+    if name not in VIT_NAMES:
+        raise NotImplementedError(
+            f"backbone {name!r}: only the ViT-B/16 branch is built (ResNet / RadImageNet / UNI2-h need network "
+            "access and timm; SURVEY.md section 2)")
+    backbone = build_vit_dino_backbone("vit_base_patch16_224", in_channels=in_channels, img_size=mp["input_size"],
+                                       device=device)
+    mp["backbone_index_lists"] = [[0, 1, 2], [3, 4, 5, 6], [7, 8, 9, 10, 11]]
+    mp["downsample"] = (False, False, False)
+    mp["channels"] = (backbone.embed_dim,) * 3
+    mp["transformer_backbone"] = True
+    backbone.eval()
+    return backbone

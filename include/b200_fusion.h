@@ -105,6 +105,7 @@ typedef struct b200_gemm_desc {
     float alpha;
     int n_valid;
     float* rowsum_inv;     /* [batch, heads, M] (mode 1) */
+    int b_rows;            /* valid rows of B per (head, batch); 0 = N.  Rows beyond are read as zeros */
 } b200_gemm_desc;
 
 int b200_gemm_batched(const b200_gemm_desc* d, void* stream);
@@ -114,6 +115,18 @@ int b200_gemm_batched(const b200_gemm_desc* d, void* stream);
  * transformer residual stream is kept in fp32). */
 int b200_layernorm(const void* x, int x_f32, long long rows, int C, const float* w, const float* b, float eps,
                    void* y, int y_f32, void* stream);
+
+/*
+ * ViT-B/16 glue (timm VisionTransformer as used by code/foundation_model.py:371-431):
+ *   b200_patchify    fp32 NCHW image -> bf16 patch matrix [B*gh*gw, C*P*P] in Conv2d-weight order, so the patch
+ *                    embedding is one GEMM
+ *   b200_vit_tokens  prepend the cls token and add the position embedding -> fp32 stream [B, 1+n, E]
+ *   b200_vit_feature one block's feature map: fp32 stream -> bf16 [B, n, E] with the cls token stripped
+ */
+int b200_patchify(const float* x, int B, int C, int H, int W, int P, void* out, void* stream);
+int b200_vit_tokens(const void* patches, const float* cls, const float* pos, int B, int n_patch, int E, float* t,
+                    void* stream);
+int b200_vit_feature(const float* t, int B, int n_patch, int E, void* out, void* stream);
 
 /*
  * nn.Linear on a token matrix (code/transformer_model.py:93, :95, :123, :125): out[M,N] = epilogue(x[M,K] w[N,K]^T)

@@ -78,3 +78,31 @@ def test_percentile_rule_is_numpy_percentile():
         x = g.random(n).astype(np.float32)
         ref = np.percentile(x, no.DEFAULT_LANDMARKS)
         assert np.array_equal(no.percentile_linear(np.sort(x), no.DEFAULT_LANDMARKS), ref)
+
+
+def test_vit_oracle_matches_torchvision_stand_in():
+    """timm is absent (parity unpinned); the restated ViT-B/16 feature extractor is cross-checked against
+    torchvision's VisionTransformer - the same architecture - with the weights mapped across (small depth)."""
+    from torchvision.models.vision_transformer import VisionTransformer
+
+    from oracle import backbone_oracle as bo
+
+    shapes = bo.vit_shapes(in_chans=6, depth=2)
+    sd = op.seeded_state_dict(shapes, seed=3)
+    tv = VisionTransformer(image_size=224, patch_size=16, num_layers=2, num_heads=12, hidden_dim=768, mlp_dim=3072)
+    tv.conv_proj = torch.nn.Conv2d(6, 768, 16, 16)
+    for blk in tv.encoder.layers:
+        blk.ln_1.eps = blk.ln_2.eps = 1e-6
+    tvsd = bo.to_torchvision(sd)
+    tvsd["heads.head.weight"], tvsd["heads.head.bias"] = tv.heads.head.weight.data, tv.heads.head.bias.data
+    tv.load_state_dict(tvsd)
+    tv.eval()
+    x = torch.rand(2, 6, 224, 224, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        feats = bo.vit_features(sd, x)
+        t = tv._process_input(x)
+        t = torch.cat([tv.class_token.expand(2, -1, -1), t], dim=1) + tv.encoder.pos_embedding
+        for i, blk in enumerate(tv.encoder.layers):
+            t = blk(t)
+            ref = t[:, 1:].transpose(1, 2).reshape(2, 768, 14, 14)
+            assert torch.allclose(feats[i], ref, rtol=1e-4, atol=1e-4), i

@@ -232,3 +232,32 @@ def test_cpu_input_fails_loudly():
     mods["dwi"].train()
     with pytest.raises(NotImplementedError):
         mods["dwi"](torch.zeros(1, 16, 64, 64, device=DEV))
+
+
+def test_vit_backbone_features_vs_oracle():
+    """ViT-B/16 features_only backbone (foundation_model.build_medical_backbone) against the restated oracle
+    (parity with timm itself is unpinned - timm is absent; the oracle is cross-checked with torchvision)."""
+    import foundation_model as fm
+    from oracle import backbone_oracle as bo
+
+    p = pd.default_parameters(input_size=224)
+    p["dce_model_parameters"]["backbone_str"] = "vit_base_patch16_224"
+    p["dce_model_parameters"]["use_backbone"] = True
+    bb = fm.build_medical_backbone(p, torch.device(DEV), "dce", in_channels=6)
+    mp = p["dce_model_parameters"]
+    assert mp["backbone_index_lists"] == [[0, 1, 2], [3, 4, 5, 6], [7, 8, 9, 10, 11]] and mp["transformer_backbone"]
+    assert mp["channels"] == (768, 768, 768) and bb.feature_info.channels() == [768] * 12
+    shapes = {k: tuple(v.shape) for k, v in bb.state_dict().items()}
+    assert shapes == bo.vit_shapes(in_chans=6)
+    sd = op.seeded_state_dict(shapes, seed=5)
+    bb.load_state_dict(sd)
+    x = torch.rand(2, 6, 224, 224, generator=torch.Generator().manual_seed(2))
+    feats = bb(x.to(DEV))
+    torch.cuda.synchronize()
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    with torch.no_grad():
+        ref = bo.vit_features(sd, x)
+    assert len(feats) == 12 and tuple(feats[0].shape) == (2, 768, 14, 14)
+    errs = [_relmax(a, b) for a, b in zip(feats, ref)]
+    print("ViT feature errors per block:", [f"{e:.1e}" for e in errs])
+    assert max(errs) <= MODEL_TOL
