@@ -43,12 +43,43 @@ def conv_case(name, B, H, W, cin, cout, taps, res_mode=0, act=1, gap=False, n_sp
     return name, run, byts, flops
 
 
+def vit_bench(batch, iters):
+    """ViT-B/16 features_only backbone (foundation_model.B200ViTBackbone), DCE-shaped input (6 x 224 x 224)."""
+    import foundation_model as fm
+
+    bb = fm.B200ViTBackbone(in_chans=6).to(DEV).eval()
+    x = torch.rand(batch, 6, 224, 224, device=DEV)
+    for _ in range(2):
+        bb(x)
+    torch.cuda.synchronize()
+    nat.start_profile()
+    bb(x)
+    prof = nat.stop_profile()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        bb(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    gf_case = 35.36  # SURVEY.md row a13: 2*MAC of the matmuls, per case, C=6
+    print(f"ViT-B/16 backbone, batch {batch}: {ms:.2f} ms/forward, {batch / ms * 1e3:.0f} cases/s, "
+          f"{batch * gf_case / ms:.0f} TFLOP/s algorithmic")
+    tot = sum(sum(t) for t in prof.values())
+    for (name, key), t in sorted(prof.items(), key=lambda kv: -sum(kv[1]))[:12]:
+        print(f"   {sum(t):8.3f} ms {100 * sum(t) / tot:5.1f}%  x{len(t):3d}  {name} {key}")
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--vit", type=int, default=0, help="benchmark the ViT-B/16 backbone at this batch size instead")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--only", default="")
     ap.add_argument("--batch", type=int, default=1024)
     a = ap.parse_args()
+    if a.vit:
+        vit_bench(a.vit, a.iters)
+        return
     B = a.batch
     cases = [
         conv_case("3x3 256->256 gelu", B, 32, 32, 256, 256, 9),
