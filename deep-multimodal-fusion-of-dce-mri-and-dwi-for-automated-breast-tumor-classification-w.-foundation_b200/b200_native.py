@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _lib = None
 
@@ -75,9 +75,9 @@ SIGNATURES = {
     "b200_tapsum": [_P, _I, _I, _I, _P, _P, _P],
     "b200_gemm_batched": [C.POINTER(GemmDesc), _P],
     "b200_layernorm": [_P, _I, _LL, _I, _P, _P, _F, _P, _I, _P],
-    "b200_patchify": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "b200_patchify": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "b200_vit_tokens": [_P, _P, _P, _I, _I, _I, _P, _P],
-    "b200_vit_feature": [_P, _I, _I, _I, _P, _P],
+    "b200_vit_feature": [_P, _I, _I, _I, _P, _I, _P],
     "b200_linear": [_P, _LL, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _P],
     "b200_dwi_normalize": [_P, _P, _I, _I, _I, _I, _F, _F, _P, _P],
     "b200_nyul_transform": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
@@ -89,6 +89,10 @@ SIGNATURES = {
     "b200_mask_tail": [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _F, _P, _P],
     "b200_lift_c1": [_P, _LL, _I, _P, _P, _P, _P, _P],
     "b200_cls_head": [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P],
+    "b200_channel_sums": [_P, _I, _I, _I, _I, _P, _P],
+    "b200_mix_instnorm": [_P, _P, _I, _I, _I, _P, _P, _P, _F, _P, _P],
+    "b200_adaptive_pool": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "b200_add_maps": [_P, _P, _LL, _P, _P],
     "b200_fusion_tokens": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "b200_fusion_core": [C.POINTER(FusionWeights), _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "b200_fusion_mix": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
@@ -243,9 +247,10 @@ def linear_f32(x2d, w, *, scale=None, bias=None, res=None, res_mode=0, act=0, ou
     return out
 
 
-def patchify(x, P, out):
+def patchify(x, P, out, gate=None):
+    """`gate` [B,C] fp32 (optional) multiplies plane (b, c) on the way in (modality attention)."""
     B, C_, H, W = x.shape
-    _call("b200_patchify", None, _ptr(x), B, C_, H, W, P, _ptr(out), _stream())
+    _call("b200_patchify", None, _ptr(x), _ptr(gate), B, C_, H, W, P, _ptr(out), _stream())
     return out
 
 
@@ -254,8 +259,48 @@ def vit_tokens(patches, cls, pos, B, n_patch, E, t):
     return t
 
 
-def vit_feature(t, B, n_patch, E, out):
-    _call("b200_vit_feature", None, _ptr(t), B, n_patch, E, _ptr(out), _stream())
+def vit_feature(t, B, n_patch, E, out, out_ld=None):
+    """`out` may be a channel slice of a wider [B, n, out_ld] buffer (pass its row stride as out_ld)."""
+    _call("b200_vit_feature", None, _ptr(t), B, n_patch, E, _ptr(out), E if out_ld is None else out_ld, _stream())
+    return out
+
+
+def channel_sums(x, out=None):
+    """x [B,H,W,C] bf16 NHWC (the last dim may be a channel slice of a wider row) -> [B,C] fp32 sums."""
+    B, H, W, C_ = x.shape
+    if out is None:
+        out = torch.empty((B, C_), dtype=torch.float32, device=x.device)
+    _call("b200_channel_sums", None, _ptr(x), x.stride(2), B, H * W, C_, _ptr(out), _stream())
+    return out
+
+
+def mix_instnorm(fb, f, weight_logit, gn_w, gn_b, eps, out=None):
+    """GroupNorm(C, C)(sigmoid(w) * fb + (1 - sigmoid(w)) * f) on contiguous NHWC bf16 maps."""
+    B, H, W, C_ = f.shape
+    if out is None:
+        out = torch.empty_like(f)
+    _call("b200_mix_instnorm", None, _ptr(fb), _ptr(f), B, H * W, C_, _ptr(weight_logit), _ptr(gn_w), _ptr(gn_b),
+          float(eps), _ptr(out), _stream())
+    return out
+
+
+def adaptive_pool(x, size, act=0):
+    """x [B,H,W,C] bf16 NHWC -> [B,size,size,C] bf16 (optional GELU), or x [B,H,W] fp32 -> [B,size,size] fp32."""
+    if x.dim() == 3:
+        B, H, W = x.shape
+        out = torch.empty((B, size, size), dtype=torch.float32, device=x.device)
+        _call("b200_adaptive_pool", None, _ptr(x), 1, B, H, W, 1, size, size, 0, _ptr(out), _stream())
+        return out
+    B, H, W, C_ = x.shape
+    out = torch.empty((B, size, size, C_), dtype=torch.bfloat16, device=x.device)
+    _call("b200_adaptive_pool", None, _ptr(x), 0, B, H, W, C_, size, size, act, _ptr(out), _stream())
+    return out
+
+
+def add_maps(a, b, out=None):
+    if out is None:
+        out = torch.empty_like(a)
+    _call("b200_add_maps", None, _ptr(a), _ptr(b), a.numel(), _ptr(out), _stream())
     return out
 
 

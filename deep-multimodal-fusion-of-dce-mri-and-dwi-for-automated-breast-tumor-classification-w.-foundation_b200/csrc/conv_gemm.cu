@@ -58,6 +58,7 @@ struct ConvGemmParams {
     float* dot_out;        // [pixels, ndot] fp32 (+ dot_bias)
     float dot_bias;
     int ndot;
+    int a_box_bytes;       // bytes one A box really delivers (BW*BH rows x 128 B; < 16 KB when BW*BH < 128)
     int cstride;           // convolution stride (1, or 2 for the 2x2 / stride-2 patch embedding: taps == 4)
     int a_batched;         // 0: the A operand is shared by every (h, b) (weights on the A side)
     int b_mode;            // 0: B operand = 2-D weights [N, K]; 1: 4-D batched {K, N, H, B}
@@ -240,7 +241,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         dx = tap & 1;
                     }
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], kStageBytes);
+                    mbar_arrive_expect_tx(&full[stage], p.a_box_bytes + (WS ? 0 : T::kBBytes));
                     uint8_t* dst = sRing + stage * kStageBytes;
                     if (p.a_batched) tma_load_4d(dst, &tmA, &full[stage], c0, p.cstride * w0 + dx, p.cstride * h0 + dy, b);
                     else tma_load_4d(dst, &tmA, &full[stage], c0, w0, 0, 0);
@@ -331,7 +332,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int slab_w = w0 + (q * 32) % p.BW, slab_h = h0 + (q * 32) / p.BW;
             const int trow = q * 32 + lane;
             const int pw = w0 + trow % p.BW, ph = h0 + trow / p.BW;
-            const bool valid = pw < p.W && ph < p.H;
+            const bool valid = trow < p.BW * p.BH && pw < p.W && ph < p.H;
             const long long pix = (static_cast<long long>(b) * p.H + ph) * p.W + pw;
 
             const bool seg2 = n_tile * BN >= p.n_split;
@@ -848,7 +849,10 @@ static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, 
     tmOut = tmA;
     tmOut2 = tmA;
     tmRes = tmA;
-    p.tma_epi = ((p.up2 && no_tma_up2) || p.res_f32 || p.out_f32) ? 0 : 1;
+    const bool slab_is_box = p.BW * p.BH == kBlockM && (p.BW % 32 == 0 || 32 % p.BW == 0) &&
+                             (p.H == 1 || p.b_mode == 1 || p.H % p.BH == 0);
+    p.tma_epi = ((p.up2 && no_tma_up2) || p.res_f32 || p.out_f32 || !slab_is_box) ? 0 : 1;
+    p.a_box_bytes = p.BW * p.BH * kBlockK * 2;
     if (p.tma_epi) {
         const int cw = BN / 2 < 64 ? BN / 2 : 64;
         const CUtensorMapSwizzle swz = cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -921,11 +925,16 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
         p.tiles_w = (W + 127) / 128;
         p.tiles_h = 1;
     } else {
-        if (Wo > 128 || 128 % Wo != 0 || Ho % (128 / Wo) != 0) return -7;
+        // A tile is BW x BH output pixels of one case with BW = W.  Maps whose width does not divide 128
+        // (the 14 x 14 ViT grid: 14 x 9 = 126-row tiles, two per case) leave the last MMA rows unused and
+        // take the direct (non-TMA) epilogue; rows past the map come back as zeros from the TMA OOB fill.
+        if (Wo > 128) return -7;
         p.BW = Wo;
         p.BH = 128 / Wo;
         p.tiles_w = 1;
-        p.tiles_h = Ho / p.BH;
+        p.tiles_h = (Ho + p.BH - 1) / p.BH;
+        const bool ragged = p.BW * p.BH != 128 || Ho % p.BH != 0;
+        if (ragged && (up2 || gap != nullptr)) return -7;
     }
     p.H = Ho;
     p.W = Wo;

@@ -67,7 +67,7 @@ layernorm_kernel(const void* __restrict__ xv, long long rows, int C, const float
 // patchify: fp32 NCHW image -> bf16 patch matrix [B * gh * gw, C * P * P], k = (c*P + ky)*P + kx, i.e. the
 // flattening of Conv2d(C, E, P, P).weight, so the patch embedding (timm PatchEmbed / foundation_model.py
 // :388-412) becomes one tcgen05 GEMM.  One thread moves one 8-pixel run of a patch row.
-__global__ void patchify_kernel(const float* __restrict__ x, int C, int H, int W, int P,
+__global__ void patchify_kernel(const float* __restrict__ x, const float* __restrict__ gate, int C, int H, int W, int P,
                                 __nv_bfloat16* __restrict__ out, size_t total_runs) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (i >= total_runs) return;
@@ -82,7 +82,8 @@ __global__ void patchify_kernel(const float* __restrict__ x, int C, int H, int W
     const size_t b = r / gh;
     const float* src = x + ((b * C + c) * H + py * P + ky) * W + px * P + run * 8;
     const float4 a = __ldg(reinterpret_cast<const float4*>(src)), d = __ldg(reinterpret_cast<const float4*>(src) + 1);
-    const float f[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+    const float g = gate != nullptr ? __ldg(gate + b * C + c) : 1.f;  // modality-attention gate of this plane
+    const float f[8] = {a.x * g, a.y * g, a.z * g, a.w * g, d.x * g, d.y * g, d.z * g, d.w * g};
     const size_t token = (b * gh + py) * gw + px;
     __nv_bfloat16* dst = out + token * (static_cast<size_t>(C) * P * P) + (static_cast<size_t>(c) * P + ky) * P + run * 8;
     *reinterpret_cast<uint4*>(dst) = pack_bf16x8(f);
@@ -114,7 +115,7 @@ __global__ void vit_tokens_kernel(const __nv_bfloat16* __restrict__ patches, con
 
 // feature map of one block: fp32 stream [B, 1+n, E] -> bf16 [B, n, E] (cls token stripped; NHWC map)
 __global__ void vit_feature_kernel(const float* __restrict__ t, int n_patch, int E, __nv_bfloat16* __restrict__ out,
-                                   size_t total_vec) {
+                                   int out_ld, size_t total_vec) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (i >= total_vec) return;
     const int ev = E / 8;
@@ -125,19 +126,20 @@ __global__ void vit_feature_kernel(const float* __restrict__ t, int n_patch, int
     const float4* src = reinterpret_cast<const float4*>(t + (b * (n_patch + 1) + tok + 1) * E + e0);
     const float4 a = __ldg(src), d = __ldg(src + 1);
     const float f[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
-    reinterpret_cast<uint4*>(out)[i] = pack_bf16x8(f);
+    *reinterpret_cast<uint4*>(out + row * out_ld + e0) = pack_bf16x8(f);
 }
 
 }  // namespace b200
 
-extern "C" int b200_patchify(const float* x, int B, int C, int H, int W, int P, void* out, void* stream) {
+extern "C" int b200_patchify(const float* x, const float* gate, int B, int C, int H, int W, int P, void* out,
+                             void* stream) {
     using namespace b200;
     if (B < 0 || C <= 0 || P <= 0 || P % 8 != 0 || H % P != 0 || W % P != 0) return -1;
     if (B == 0) return 0;
     if (x == nullptr || out == nullptr || (reinterpret_cast<uintptr_t>(x) & 15)) return -2;
     const size_t total = static_cast<size_t>(B) * (H / P) * (W / P) * C * P * (P / 8);
     patchify_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, C, H, W, P, static_cast<__nv_bfloat16*>(out), total);
+        x, gate, C, H, W, P, static_cast<__nv_bfloat16*>(out), total);
     return launch_status();
 }
 
@@ -153,14 +155,15 @@ extern "C" int b200_vit_tokens(const void* patches, const float* cls, const floa
     return launch_status();
 }
 
-extern "C" int b200_vit_feature(const float* t, int B, int n_patch, int E, void* out, void* stream) {
+extern "C" int b200_vit_feature(const float* t, int B, int n_patch, int E, void* out, int out_ld, void* stream) {
     using namespace b200;
-    if (B < 0 || n_patch <= 0 || E % 8 != 0) return -1;
+    if (B < 0 || n_patch <= 0 || E % 8 != 0 || out_ld % 8 != 0 || out_ld < E) return -1;
+    if (reinterpret_cast<uintptr_t>(out) & 15) return -2;
     if (B == 0) return 0;
     if (t == nullptr || out == nullptr) return -2;
     const size_t total = static_cast<size_t>(B) * n_patch * (E / 8);
     vit_feature_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        t, n_patch, E, static_cast<__nv_bfloat16*>(out), total);
+        t, n_patch, E, static_cast<__nv_bfloat16*>(out), out_ld, total);
     return launch_status();
 }
 

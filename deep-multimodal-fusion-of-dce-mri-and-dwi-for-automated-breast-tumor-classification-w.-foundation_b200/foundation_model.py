@@ -128,6 +128,17 @@ class B200ViTBackbone(nn.Module):
 
     @torch.no_grad()
     def forward(self, x):
+        return self._run(x, None, None)
+
+    @torch.no_grad()
+    def forward_chains(self, x, chains, gate=None):
+        """What BackboneAdapter needs (reference model_module.py:452-471): for every index chain the channel
+        concatenation of its feature maps, as one NHWC bf16 buffer [B, g, g, len(chain)*E] that the blocks'
+        outputs are written straight into (no torch.cat pass).  `gate` [B,C] fp32 is the modality-attention
+        weight, applied while the image is cut into patches."""
+        return self._run(x, gate, [list(c) for c in chains])
+
+    def _run(self, x, gate, chains):
         if self.training:
             raise NotImplementedError("training-mode forward is not built in the B200 path yet; call .eval()")
         if not x.is_cuda:
@@ -148,7 +159,7 @@ class B200ViTBackbone(nn.Module):
         if K0 % 64 != 0:
             raise NotImplementedError("in_chans * patch^2 must be a multiple of 64")
         patches = torch.empty((B * n, K0), dtype=torch.bfloat16, device=dev)
-        nat.patchify(x, P, patches)
+        nat.patchify(x, P, patches, gate)
         emb = nat.linear(patches, pk["pe_w"], bias=pk["pe_b"])            # [B*n, E] bf16
         t = torch.empty((B * N, E), dtype=torch.float32, device=dev)      # fp32 residual stream
         nat.vit_tokens(emb, pk["cls"], pk["pos"], B, n, E, t)
@@ -162,6 +173,9 @@ class B200ViTBackbone(nn.Module):
         p_buf = torch.empty((B, heads, N, 256), dtype=torch.bfloat16, device=dev)
         rs = torch.empty((B, heads, N), dtype=torch.float32, device=dev)
         feats = []
+        bufs = None
+        if chains is not None:
+            bufs = [torch.empty((B, g, g, len(c) * E), dtype=torch.bfloat16, device=dev) for c in chains]
         for i, ly in enumerate(pk["layers"]):
             nat.layernorm(t, *ly["ln1"], out=h)
             nat.linear(h, ly["wqk"], bias=ly["bqk"], out=qk)
@@ -183,11 +197,16 @@ class B200ViTBackbone(nn.Module):
             nat.layernorm(t2, *ly["ln2"], out=h)
             nat.linear(h, ly["wfc1"], bias=ly["bfc1"], act=1, out=u)
             t = nat.linear_f32(u, ly["wfc2"], bias=ly["bfc2"], res=t2, res_mode=2, out_dtype=torch.float32)
-            if i in self.out_indices:
+            if chains is not None:
+                for ci, chain in enumerate(chains):
+                    for slot, idx in enumerate(chain):
+                        if self.out_indices[idx] == i:  # feats[idx] is block out_indices[idx]
+                            nat.vit_feature(t, B, n, E, bufs[ci][..., slot * E:(slot + 1) * E], out_ld=len(chain) * E)
+            elif i in self.out_indices:
                 f = torch.empty((B, g, g, E), dtype=torch.bfloat16, device=dev)
                 nat.vit_feature(t, B, n, E, f)
                 feats.append(f.permute(0, 3, 1, 2))  # NCHW-shaped view of the NHWC buffer
-        return feats
+        return feats if chains is None else bufs
 
 
 def build_vit_dino_backbone(model_name="vit_base_patch16_224", in_channels=3, img_size=224, device=None, **_):

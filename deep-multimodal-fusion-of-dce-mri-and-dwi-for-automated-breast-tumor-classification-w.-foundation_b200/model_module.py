@@ -219,6 +219,25 @@ class FeatureDownAlign(nn.Module):
         _container_only("FeatureDownAlign")
 
 
+class _DynamoDisabled(nn.Module):
+    """Stands in for the wrapper `torch._dynamo.disable(backbone)` returns (reference :539): the wrapped module
+    sits under `_orig_mod`, which is what puts `backbone._orig_mod.*` / `backbone_adapter.backbone._orig_mod.*`
+    keys into the reference's checkpoints.  Everything else is forwarded to the wrapped module."""
+
+    def __init__(self, module):
+        super().__init__()
+        self._orig_mod = module
+
+    def forward(self, *args, **kwargs):
+        return self._orig_mod(*args, **kwargs)
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            return getattr(self._modules["_orig_mod"], name)
+
+
 class BackboneAdapter(nn.Module):
     """keys backbone.*, necks.f{1,2,3}.{0,1,3,4}.* (reference :401-476)."""
 
@@ -449,14 +468,36 @@ def _nchw(t):
     return t.permute(0, 3, 1, 2)
 
 
+def _staged_tiles(H, W):
+    """True when the GEMM kernel tiles an H x W map into whole 128-pixel boxes (W divides 128 and the rows per
+    tile divide H): only then can its epilogue stage tiles in shared memory, which the fused per-case channel
+    sums rely on.  The 14 x 14 ViT grid does not; its pools go through b200_channel_sums."""
+    return W <= 128 and 128 % W == 0 and H % (128 // W) == 0
+
+
+def _conv_gap(x, w, **kw):
+    """conv_gemm that also returns the per-case channel sums of its output (global average pool)."""
+    B, H, W, _ = x.shape
+    if _staged_tiles(H, W):
+        gap = torch.zeros((B, w.shape[0]), dtype=torch.float32, device=x.device)
+        return nat.conv_gemm(x, w, gap=gap, **kw), gap
+    out = nat.conv_gemm(x, w, **kw)
+    return out, nat.channel_sums(out)
+
+
 def _recon(rc, x):
     """ReconHead (reference :113-118): 3x3 conv + BN + GELU on the tensor cores with the final 3x3, C->1
     conv folded in - the GEMM epilogue emits the 9 per-tap dot products of its result, a shift-sum finishes
     the convolution, and the intermediate C-channel map is never written to HBM."""
-    B, H, W, _ = x.shape
+    B, H, W, C = x.shape
+    rec = torch.empty((B, H, W), dtype=torch.float32, device=x.device)
+    if C > 256:
+        # the fused form needs all C output channels in one 256-wide accumulator tile; wider heads (768 on the
+        # ViT path) write the intermediate map and finish with the stand-alone C->1 kernel
+        t = nat.conv_gemm(x, rc["w0"], taps=9, scale=rc["s0"], bias=rc["b0"], act=1)
+        return nat.conv3x3_c1(t, rc["w3"], rc["b3"], rec)
     d = torch.empty((B, H, W, 9), dtype=torch.float32, device=x.device)
     nat.conv_gemm(x, rc["w0"], taps=9, scale=rc["s0"], bias=rc["b0"], act=1, store=False, dot_w=rc["w3"], dot_out=d)
-    rec = torch.empty((B, H, W), dtype=torch.float32, device=x.device)
     return nat.tapsum(d, rc["b3"], rec)
 
 
@@ -498,9 +539,9 @@ class ModelMaskHeadBackbone(nn.Module):
         c1, c2, c3 = self.channels
 
         self.proj_pool = nn.AdaptiveAvgPool2d((self.proj_dim, self.proj_dim))
-        self.backbone = backbone
+        self.backbone = _DynamoDisabled(backbone) if isinstance(backbone, nn.Module) else None
         if self.use_backbone:
-            self.backbone_adapter = BackboneAdapter(backbone=backbone, selected_indices_chains=self.selected_indices_chains,
+            self.backbone_adapter = BackboneAdapter(backbone=self.backbone, selected_indices_chains=self.selected_indices_chains,
                                                     out_channels=(c1, c1, c2), is_transformer=self.transformer_backbone)
             block1_in = c1
         else:
@@ -557,13 +598,16 @@ class ModelMaskHeadBackbone(nn.Module):
         sig = (str(dev), _state_signature(self))
         if self._pack_cache is not None and self._pack_cache[0] == sig:
             return self._pack_cache[1]
-        if self.use_backbone:
-            raise NotImplementedError("backbone-adapter encoders (ViT-B/16 + necks) are not wired to the B200 "
-                                      "kernels yet (SURVEY.md section 8 rows a11-a13)")
+        if self.use_backbone and not hasattr(self.backbone, "forward_chains"):
+            raise NotImplementedError("use_backbone needs a B200ViTBackbone (foundation_model.build_medical_backbone); "
+                                      "the ResNet / RadImageNet / UNI2-h backbones are not built")
         if self.mask_enabled and self.mask_stage != "f2":
             raise NotImplementedError("only mask_stage='f2' (the reference default) is built")
         b1 = self.block1
-        if b1.stride not in (1, 2) or b1.skip is None or self.channel_num > 32:
+        if self.use_backbone:
+            if b1.stride != 1 or self.use_hybrid_transformer:
+                raise NotImplementedError("backbone encoders: stride-1 CNN blocks only (what the ViT branch configures)")
+        elif b1.stride not in (1, 2) or b1.skip is None or self.channel_num > 32:
             raise NotImplementedError("block1 must read the raw (<=32 channel) input through a skip conv")
         blocks = {"b1": self.block1, "b2": self.block2}
         if not self.use_hybrid_transformer:
@@ -574,15 +618,29 @@ class ModelMaskHeadBackbone(nn.Module):
         pk = {name: _block_pack(blk, dev) for name, blk in blocks.items()}
         if self.use_hybrid_transformer:
             pk["tr"] = _transformer_pack(self.transformer, self.trans_out_proj, dev)
-        # stem: skip conv and first bottleneck conv of block1 concatenated, fp32
-        bt0 = pk["b1"]["bott"][0]
-        wskip = pk["b1"]["skip"]["conv"].weight.detach().to(dev).flatten(1).float()
-        wmid = bt0["conv0"].weight.detach().to(dev).flatten(1).float()
-        pk["stem"] = {"w": torch.cat([wskip, wmid], 0).contiguous(),
-                      "s": torch.cat([pk["b1"]["skip"]["s"], bt0["s1"]]).contiguous(),
-                      "b": torch.cat([pk["b1"]["skip"]["b"], bt0["b1"]]).contiguous(),
-                      "n_skip": wskip.shape[0], "n_mid": wmid.shape[0]}
-        for name in ("b2", "b3"):
+        if self.use_backbone:
+            # necks (reference :440-447): conv bias folds into the BatchNorm shift
+            pk["necks"] = []
+            for i in range(3):
+                nk = self.backbone_adapter.necks[f"f{i + 1}"]
+                s0, b0 = _bn_fold(nk[1], dev, nk[0].bias)
+                s3, b3 = _bn_fold(nk[4], dev, nk[3].bias)
+                pk["necks"].append({"w0": _conv_w_bf16(nk[0], dev), "s0": s0, "b0": b0,
+                                    "w3": _conv_w_bf16(nk[3], dev), "s3": s3, "b3": b3})
+            pk["mix"] = {"f2": (_f32(self.f2_weight, dev).reshape(1), _f32(self.norm_f2.weight, dev),
+                                _f32(self.norm_f2.bias, dev), self.norm_f2.eps),
+                         "f3": (_f32(self.f3_weight, dev).reshape(1), _f32(self.norm_f3.weight, dev),
+                                _f32(self.norm_f3.bias, dev), self.norm_f3.eps)}
+        else:
+            # stem: skip conv and first bottleneck conv of block1 concatenated, fp32
+            bt0 = pk["b1"]["bott"][0]
+            wskip = pk["b1"]["skip"]["conv"].weight.detach().to(dev).flatten(1).float()
+            wmid = bt0["conv0"].weight.detach().to(dev).flatten(1).float()
+            pk["stem"] = {"w": torch.cat([wskip, wmid], 0).contiguous(),
+                          "s": torch.cat([pk["b1"]["skip"]["s"], bt0["s1"]]).contiguous(),
+                          "b": torch.cat([pk["b1"]["skip"]["b"], bt0["b1"]]).contiguous(),
+                          "n_skip": wskip.shape[0], "n_mid": wmid.shape[0]}
+        for name in (("b1", "b2", "b3") if self.use_backbone else ("b2", "b3")):
             if name not in pk:
                 continue
             blk = pk[name]
@@ -595,19 +653,22 @@ class ModelMaskHeadBackbone(nn.Module):
                                    "s": torch.cat([blk["skip"]["s"], b0["s1"]]).contiguous(),
                                    "b": torch.cat([blk["skip"]["b"], b0["b1"]]).contiguous(),
                                    "n_split": blk["skip"]["w"].shape[0]}
-        for bt in pk["b1"]["bott"][1:]:
-            bt["w0"] = _conv_w_bf16(bt["conv0"], dev)
+        if not self.use_backbone:
+            for bt in pk["b1"]["bott"][1:]:
+                bt["w0"] = _conv_w_bf16(bt["conv0"], dev)
         if self.modality_attention is not None:
             pk["mod_se"] = _se_pack(self.modality_attention, dev)
         if self.mask_enabled:
             al = self.f1_to_f2.proj
-            if isinstance(al, nn.Identity):
-                raise NotImplementedError("f1_to_f2 identity (c1 == c2)")
-            s, b = _bn_fold(al[1], dev)
+            if isinstance(al, nn.Identity):  # c1 == c2 (the ViT path): f1_aligned = f1
+                aw = s = b = None
+            else:
+                aw = _conv_w_bf16(al[0], dev)
+                s, b = _bn_fold(al[1], dev)
             mh, ma = self.mask_head, self.mask_spatial_attention
             mproc = ma.mask_processor
             pk["mask"] = {
-                "align_w": _conv_w_bf16(al[0], dev), "align_s": s, "align_b": b,
+                "align_w": aw, "align_s": s, "align_b": b,
                 "pre_w": _conv_w_bf16(mh.pre, dev), "pre_b": _f32(mh.pre.bias, dev),
                 "out_w": _f32(mh.out.weight.flatten(), dev), "out_b": _f32(mh.out.bias, dev),
                 "out_b_host": float(mh.out.bias.detach().float().cpu().item()),
@@ -629,10 +690,9 @@ class ModelMaskHeadBackbone(nn.Module):
         dev = mid.device
         t = nat.conv_gemm(mid, bt["w4"], taps=9, scale=bt["s5"], bias=bt["b5"], act=1)
         cout = bt["w7"].shape[0]
-        gap = torch.zeros((B, cout), dtype=torch.float32, device=dev)
         if len(pk["bott"]) > 1:
             raise NotImplementedError("repeat_blocks > 1")
-        out = nat.conv_gemm(t, bt["w7"], taps=1, scale=bt["s8"], bias=bt["b8"], res=skip, res_mode=1, act=1, gap=gap)
+        out, gap = _conv_gap(t, bt["w7"], taps=1, scale=bt["s8"], bias=bt["b8"], res=skip, res_mode=1, act=1)
         gate = None
         if "se" in pk:
             se = pk["se"]
@@ -663,6 +723,40 @@ class ModelMaskHeadBackbone(nn.Module):
             g = nat.conv_gemm(src, pp["w0"], taps=1, scale=pp["s0"], bias=pp["b0"], act=1)
         return nat.conv_gemm(g, pp["w3"], taps=1, scale=pp["s3"], bias=pp["b3"], act=1, up2=up2)
 
+    def _project_pooled(self, pp, src):
+        """proj(AdaptiveAvgPool2d(proj_dim)(src)) for any map size (reference :707-715).  The pool is an average
+        and the projector's first 1x1 conv + BatchNorm is affine per pixel, so they commute: the conv runs on
+        the small map, the pool (fused with the GELU) writes proj_dim^2 x 64 channels instead of
+        proj_dim^2 x C, and the second 1x1 layer runs at the pooled size."""
+        pd = self.proj_dim
+        if "w0_vec" in pp:
+            r = nat.adaptive_pool(src, pd)                      # [B,pd,pd] fp32
+            g = torch.empty((*r.shape, pp["w0_vec"].numel()), dtype=torch.bfloat16, device=src.device)
+            nat.lift_c1(r, pp["w0_vec"], pp["s0"], pp["b0"], g)
+        else:
+            y = nat.conv_gemm(src, pp["w0"], taps=1, scale=pp["s0"], bias=pp["b0"], act=0)
+            g = nat.adaptive_pool(y, pd, act=1)
+        return nat.conv_gemm(g, pp["w3"], taps=1, scale=pp["s3"], bias=pp["b3"], act=1)
+
+    def _backbone_features(self, pk, x, plane_mean):
+        """Modality attention + BackboneAdapter (reference :645-657, :401-476): returns (f1_b, f2_b, f3_b, gate)."""
+        B, C, H, W = x.shape
+        dev = x.device
+        gate = None
+        if "mod_se" in pk:
+            if plane_mean is None:
+                plane_mean = torch.empty(B * C, dtype=torch.float32, device=dev)
+                nat.plane_mean(x, B * C, H * W, plane_mean)
+            ms = pk["mod_se"]
+            gate = torch.empty((B, C), dtype=torch.float32, device=dev)
+            nat.se_gate(plane_mean.view(B, C), 1, ms["w1t"], ms["b1"], ms["w2t"], ms["b2"], gate)
+        cats = self.backbone.forward_chains(x, self.selected_indices_chains, gate)
+        outs = []
+        for nk, cat in zip(pk["necks"], cats):
+            t = nat.conv_gemm(cat, nk["w0"], taps=9, scale=nk["s0"], bias=nk["b0"], act=1)
+            outs.append(nat.conv_gemm(t, nk["w3"], taps=9, scale=nk["s3"], bias=nk["b3"], act=1))
+        return outs[0], outs[1], outs[2], gate
+
     def forward(self, x, masks=None, plane_mean=None):
         """x [B,C,H,W] normalised fp32.  `plane_mean` (optional, [B*C] fp32) is the per-plane mean the
         normaliser kernels can emit, which saves one pass over x."""
@@ -675,44 +769,70 @@ class ModelMaskHeadBackbone(nn.Module):
         pk = self._packed(dev)
         x = x.contiguous().float()
         B, C, H, W = x.shape
-        st = pk["stem"]
-        stride = self.block1.stride
-        Ho, Wo = H // stride, W // stride
-        se = None
         mod_attn = None
-        if "mod_se" in pk:
-            if plane_mean is None:
-                plane_mean = torch.empty(B * C, dtype=torch.float32, device=dev)
-                nat.plane_mean(x, B * C, H * W, plane_mean)
-            ms = pk["mod_se"]
-            se = (ms["w1"], ms["b1"], ms["w2"], ms["b2"])
-            mod_attn = torch.empty((B, C), dtype=torch.float32, device=dev)
-        skip1 = torch.empty((B, Ho, Wo, st["n_skip"]), dtype=torch.bfloat16, device=dev)
-        mid1 = torch.empty((B, Ho, Wo, st["n_mid"]), dtype=torch.bfloat16, device=dev)
-        nat.stem(x, stride, plane_mean, se, st["w"], st["s"], st["b"], st["n_skip"], st["n_mid"], skip1, mid1, mod_attn)
+        f2_b = f3_b = None
+        if self.use_backbone:
+            f1_b, f2_b, f3_b, mod_attn = self._backbone_features(pk, x, plane_mean)
+            f1, r1, _, _ = self._block_from_map(pk["b1"], f1_b, full)
+            Ho, Wo = f1.shape[1], f1.shape[2]
+        else:
+            st = pk["stem"]
+            stride = self.block1.stride
+            Ho, Wo = H // stride, W // stride
+            se = None
+            if "mod_se" in pk:
+                if plane_mean is None:
+                    plane_mean = torch.empty(B * C, dtype=torch.float32, device=dev)
+                    nat.plane_mean(x, B * C, H * W, plane_mean)
+                ms = pk["mod_se"]
+                se = (ms["w1"], ms["b1"], ms["w2"], ms["b2"])
+                mod_attn = torch.empty((B, C), dtype=torch.float32, device=dev)
+            skip1 = torch.empty((B, Ho, Wo, st["n_skip"]), dtype=torch.bfloat16, device=dev)
+            mid1 = torch.empty((B, Ho, Wo, st["n_mid"]), dtype=torch.bfloat16, device=dev)
+            nat.stem(x, stride, plane_mean, se, st["w"], st["s"], st["b"], st["n_skip"], st["n_mid"], skip1, mid1,
+                     mod_attn)
+            f1, r1, _, _ = self._run_block(pk["b1"], mid1, skip1, full)
 
-        f1, r1, _, _ = self._run_block(pk["b1"], mid1, skip1, full)
-        f2, r2, _, _ = self._block_from_map(pk["b2"], f1, full)
+        f2_in = f1
+        if self.use_backbone:  # reference :673-675
+            f2_in = nat.mix_instnorm(f2_b, f1, *pk["mix"]["f2"])
+        f2, r2, _, _ = self._block_from_map(pk["b2"], f2_in, full)
         mask_pred = attn_map = None
         if self.mask_enabled:
             mk = pk["mask"]
-            m_in = nat.conv_gemm(f1, mk["align_w"], taps=1, scale=mk["align_s"], bias=mk["align_b"], act=1, res=f2,
-                                 res_mode=2)
-            if Ho != self.mask_size:
-                raise NotImplementedError("mask head resize paths (input != 32x32) are not built")
+            if mk["align_w"] is None:
+                m_in = nat.add_maps(f2, f1)
+            else:
+                m_in = nat.conv_gemm(f1, mk["align_w"], taps=1, scale=mk["align_s"], bias=mk["align_b"], act=1,
+                                     res=f2, res_mode=2)
+            ms_ = self.mask_size
+            if Ho != ms_ and Ho in (64, 128, 256, 512):
+                raise NotImplementedError("the strided-conv mask head paths (64..512 maps) are not built")
             # mask head: `pre` (1x1, bias) with `out` (1x1 -> 1 channel) folded into its epilogue as an fp32
             # dot product, so the 64-channel map is neither rounded to bf16 nor written to HBM
             mask_pred = torch.empty((B, 1, Ho, Wo), dtype=torch.float32, device=dev)
             nat.conv_gemm(m_in, mk["pre_w"], taps=1, bias=mk["pre_b"], store=False, dot_w=mk["out_w"].view(1, -1),
                           dot_out=mask_pred, dot_bias=mk["out_b_host"])
+            mask_at_map = mask_pred
+            if Ho != ms_:
+                # reference :205-211 resizes the 64-channel map bilinearly before the 1x1 `out` conv; both are
+                # linear and the resize acts per channel, so resizing the 1-channel logits is the same map.
+                # MaskGuidedSpatialAttention then resizes the prediction back to the feature grid (:80-88).
+                mask_pred = torch.empty((B, 1, ms_, ms_), dtype=torch.float32, device=dev)
+                nat.resize_bilinear_c1(mask_at_map.view(B, Ho, Wo), mask_pred.view(B, ms_, ms_))
+                mask_at_map = torch.empty((B, 1, Ho, Wo), dtype=torch.float32, device=dev)
+                nat.resize_bilinear_c1(mask_pred.view(B, ms_, ms_), mask_at_map.view(B, Ho, Wo))
             attn_map = torch.empty((B, 1, Ho, Wo), dtype=torch.float32, device=dev)
-            nat.mask_attention(mask_pred, mk["attn"], attn_map)
+            nat.mask_attention(mask_at_map, mk["attn"], attn_map)
             nat.scale_map(f2, f2, attn=attn_map, gamma=mk["gamma"])
         if self.use_hybrid_transformer:
             f3, gap3 = _transformer_stage(pk["tr"], f2)  # reference :702-703
             gate3 = None
         else:
-            f3, _, gap3, gate3 = self._block_from_map(pk["b3"], f2, False)
+            f3_in = f2
+            if self.use_backbone:  # reference :688-690
+                f3_in = nat.mix_instnorm(f3_b, f2, *pk["mix"]["f3"])
+            f3, _, gap3, gate3 = self._block_from_map(pk["b3"], f3_in, False)
         npix3 = f3.shape[1] * f3.shape[2]
 
         logits = None
@@ -721,17 +841,16 @@ class ModelMaskHeadBackbone(nn.Module):
             logits = torch.empty((B, self.num_classes), dtype=torch.float32, device=dev)
             nat.cls_head(gap3, gate3, npix3, pk["head"]["w"], pk["head"]["b"], self.classification_head.normalize,
                          logits)
-            if self.proj_dim == 2 * Ho:
-                up2 = True
-            elif self.proj_dim == Ho:
-                up2 = False
-            else:
-                raise NotImplementedError("proj_pool ratios other than 1x / 2x")
             pj = pk["proj"]
-            p1 = _nchw(self._project(pj["proj_f1"], f1, up2))
-            p2 = _nchw(self._project(pj["proj_f2"], f2, up2))
-            p1r = _nchw(self._project(pj["proj_r1"], r1, up2))
-            p2r = _nchw(self._project(pj["proj_r2"], r2, up2))
+            if self.proj_dim in (Ho, 2 * Ho) and Ho == Wo and _staged_tiles(Ho, Wo):
+                up2 = self.proj_dim == 2 * Ho  # AdaptiveAvgPool2d to 2x the size replicates each pixel 2x2
+                proj = lambda pp, src: self._project(pp, src, up2)
+            else:
+                proj = self._project_pooled
+            p1 = _nchw(proj(pj["proj_f1"], f1))
+            p2 = _nchw(proj(pj["proj_f2"], f2))
+            p1r = _nchw(proj(pj["proj_r1"], r1))
+            p2r = _nchw(proj(pj["proj_r2"], r2))
         aux = {
             "raw_feats": [_nchw(f1), _nchw(f2), _nchw(f3)],
             "recon_feats": [r1.unsqueeze(1) if r1 is not None else None, r2.unsqueeze(1) if r2 is not None else None],
@@ -867,10 +986,8 @@ class FusionModel(nn.Module):
         if self.use_mask_attention and (dwi_mask_pred is None or dce_mask_pred is None):
             # the reference feeds a 2C vector into a (2C+2)-input Linear in this case and raises too
             raise RuntimeError("use_mask_attention needs both encoder mask predictions")
-        pv_d = torch.zeros((B, c), dtype=torch.float32, device=dev)
-        pv_c = torch.zeros((B, c), dtype=torch.float32, device=dev)
-        p_dwi = nat.conv_gemm(f3d, pk["in_dwi"], taps=1, gap=pv_d)
-        p_dce = nat.conv_gemm(f3c, pk["in_dce"], taps=1, gap=pv_c)
+        p_dwi, pv_d = _conv_gap(f3d, pk["in_dwi"], taps=1)
+        p_dce, pv_c = _conv_gap(f3c, pk["in_dce"], taps=1)
         tok_d = tok_c = attn_w = lowres = None
         if self.use_cross_attention:
             tok_d = torch.empty((B, hp * wp, c), dtype=torch.float32, device=dev)

@@ -119,14 +119,17 @@ int b200_layernorm(const void* x, int x_f32, long long rows, int C, const float*
 /*
  * ViT-B/16 glue (timm VisionTransformer as used by code/foundation_model.py:371-431):
  *   b200_patchify    fp32 NCHW image -> bf16 patch matrix [B*gh*gw, C*P*P] in Conv2d-weight order, so the patch
- *                    embedding is one GEMM
+ *                    embedding is one GEMM; `gate` (nullable, [B, C]) multiplies plane (b, c) - the modality
+ *                    attention x * w of code/model_module.py:41-43, :649-650 applied on the way in
  *   b200_vit_tokens  prepend the cls token and add the position embedding -> fp32 stream [B, 1+n, E]
- *   b200_vit_feature one block's feature map: fp32 stream -> bf16 [B, n, E] with the cls token stripped
+ *   b200_vit_feature one block's feature map: fp32 stream -> bf16 [B, n, E] with the cls token stripped; rows are
+ *                    written `out_ld` elements apart, so a block's map can land directly in its slot of the
+ *                    channel-concatenated neck input (torch.cat of code/model_module.py:471)
  */
-int b200_patchify(const float* x, int B, int C, int H, int W, int P, void* out, void* stream);
+int b200_patchify(const float* x, const float* gate, int B, int C, int H, int W, int P, void* out, void* stream);
 int b200_vit_tokens(const void* patches, const float* cls, const float* pos, int B, int n_patch, int E, float* t,
                     void* stream);
-int b200_vit_feature(const float* t, int B, int n_patch, int E, void* out, void* stream);
+int b200_vit_feature(const float* t, int B, int n_patch, int E, void* out, int out_ld, void* stream);
 
 /*
  * nn.Linear on a token matrix (code/transformer_model.py:93, :95, :123, :125): out[M,N] = epilogue(x[M,K] w[N,K]^T)
@@ -229,6 +232,27 @@ int b200_lift_c1(const float* r, long long total_pix, int N, const float* w, con
  */
 int b200_cls_head(const float* gap_sum, const float* gate, int B, int C, int npix, int K, const float* fc_w,
                   const float* fc_b, int normalize, float* logits, float* pooled_out, void* stream);
+
+/*
+ * Backbone-adapter helpers (the ViT-B/16 path, 14 x 14 maps; all maps NHWC bf16, C a multiple of 8):
+ *   b200_channel_sums   per-case channel sums [B, C] fp32 of a map with row stride x_ld - the global average
+ *                       pools of SEBlock / ClassificationHead (code/model_module.py:35, :364) for maps whose
+ *                       width does not divide 128, where the GEMM epilogue cannot take them from staged tiles
+ *   b200_mix_instnorm   GroupNorm(C, C)(alpha * f_b + (1 - alpha) * f), alpha = sigmoid(*weight_logit)
+ *                       (code/model_module.py:592-597, :673-675, :688-690): per (case, channel) mean / biased
+ *                       variance over the npix pixels, affine gn_w / gn_b
+ *   b200_adaptive_pool  nn.AdaptiveAvgPool2d((Ho, Wo)) (code/model_module.py:531-534, :707-710); x_f32 = 1:
+ *                       1-channel fp32 map -> fp32; else bf16 -> bf16 with an optional GELU (act = 1) applied
+ *                       to the pooled value (the pool is moved behind the Projector's first 1x1 conv + BN,
+ *                       with which it commutes)
+ *   b200_add_maps       out = a + b element-wise (f2 + f1_aligned with an identity FeatureDownAlign, :682-683)
+ */
+int b200_channel_sums(const void* x, int x_ld, int B, int npix, int C, float* out, void* stream);
+int b200_mix_instnorm(const void* fb, const void* f, int B, int npix, int C, const float* weight_logit,
+                      const float* gn_w, const float* gn_b, float eps, void* out, void* stream);
+int b200_adaptive_pool(const void* x, int x_f32, int B, int H, int W, int C, int Ho, int Wo, int act, void* out,
+                       void* stream);
+int b200_add_maps(const void* a, const void* b, long long n_elems, void* out, void* stream);
 
 /* FusionModel._to_tokens (code/model_module.py:903-917): adaptive average pool to Hp x Wp tokens, fp32 [B,Hp*Wp,C]. */
 int b200_fusion_tokens(const void* p, int B, int H, int W, int C, int Hp, int Wp, float* tokens, void* stream);

@@ -117,6 +117,93 @@ def model_goldens(tag, hybrid):
     print(tag, "fusion logits", lf)
 
 
+class _StandInInfo:
+    def __init__(self, channels, reduction):
+        self._c, self._r = channels, reduction
+
+    def channels(self):
+        return self._c
+
+    def reduction(self):
+        return self._r
+
+
+def standin_vit(in_chans, depth=12):
+    """timm is absent here (and un-pinned in the reference): the backbone handed to the reference's
+    ModelMaskHeadBackbone is a parameter container with timm's ViT key names whose forward is the restated
+    oracle/backbone_oracle.vit_features (itself cross-checked against torchvision's VisionTransformer)."""
+    import torch.nn as nn
+    from oracle import backbone_oracle as bo
+
+    class StandInViT(nn.Module):
+        def __init__(self):
+            super().__init__()
+            for key, shape in bo.vit_shapes(in_chans, depth=depth).items():
+                mod = self
+                *path, leaf = key.split(".")
+                for name in path:
+                    if not hasattr(mod, name):
+                        mod.add_module(name, nn.Module())
+                    mod = getattr(mod, name)
+                mod.register_parameter(leaf, nn.Parameter(torch.zeros(shape)))
+            self.feature_info = _StandInInfo([768] * depth, [16] * depth)
+
+        def forward(self, x):
+            return bo.vit_features(dict(self.state_dict()), x)
+
+    return StandInViT()
+
+
+def configure_vit(p):
+    """What foundation_model.build_medical_backbone writes for the ViT branch (foundation_model.py:526-545),
+    plus the fusion input width that has to follow by hand (SURVEY.md note 9)."""
+    p["dwi_channel_num"], p["dce_channel_num"] = 16, 6
+    for m in ("dwi", "dce", "fusion"):
+        mp = p[f"{m}_model_parameters"]
+        mp["input_size"] = 224
+        mp["use_hybrid_transformer"] = False
+        mp["use_backbone"] = m != "fusion"
+        if m != "fusion":
+            mp["backbone_index_lists"] = [[0, 1, 2], [3, 4, 5, 6], [7, 8, 9, 10, 11]]
+            mp["downsample"] = (False, False, False)
+            mp["channels"] = (768, 768, 768)
+            mp["transformer_backbone"] = True
+    fs = p["fusion_model_parameters"]["fusion_specific_parameters"]
+    fs["dwi_out_channels"] = fs["dce_out_channels"] = 768
+    return p
+
+
+def vit_goldens():
+    """C4: both encoders with the ViT-B/16 backbone adapter at 224 x 224 + the fusion head on 14 x 14 maps."""
+    import model_module as mm
+
+    p = configure_vit(reference_parameters())
+    torch.manual_seed(0)
+    models = {"dwi": mm.ModelMaskHeadBackbone("dwi", p, standin_vit(16)),
+              "dce": mm.ModelMaskHeadBackbone("dce", p, standin_vit(6)), "fusion": mm.FusionModel(p)}
+    shapes = {}
+    for name, m in models.items():
+        sh = op.shapes_of(m.state_dict())
+        shapes[name] = {k: list(v) for k, v in sh.items()}
+        m.load_state_dict(op.seeded_state_dict(sh, seed=11))
+        m.eval()
+    out = {}
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(2, seed=4321, size=224, kind="S")
+    dwi = dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)
+    dce = dce_raw
+    with torch.no_grad():
+        ld, ad, md = models["dwi"](dwi)
+        lc, ac, mc = models["dce"](dce)
+        lf, mf, af = models["fusion"](ad["raw_feats"], ac["raw_feats"], md, mc)
+    for tag, val in (("dwi/logits", ld), ("dwi/aux", ad), ("dwi/mask", md), ("dce/logits", lc), ("dce/aux", ac),
+                     ("dce/mask", mc), ("fusion/logits", lf), ("fusion/mask", mf), ("fusion/aux", af)):
+        flatten(f"S/{tag}", val, out)
+    np.savez_compressed(os.path.join(GOLD, "model_vit.npz"), **out)
+    with open(os.path.join(GOLD, "state_shapes_vit.json"), "w") as f:
+        json.dump(shapes, f, indent=0, sort_keys=True)
+    print("vit fusion logits", lf)
+
+
 def normalizer_goldens():
     import dataset as ref_dataset
     import preprocess_helpers as ref_pre
@@ -155,3 +242,4 @@ if __name__ == "__main__":
     normalizer_goldens()
     model_goldens("cnn", hybrid=False)
     model_goldens("hybrid", hybrid=True)
+    vit_goldens()

@@ -158,9 +158,29 @@ def _mhsa(x, s: SD, heads):
     return F.linear(y, s["proj.weight"], s["proj.bias"])
 
 
+# ----------------------------------------------------------- backbone adapter ----
+def backbone_adapter(x, s: SD, chains, feats=None):
+    """BackboneAdapter.forward, model_module.py:452-476: backbone features -> per chain channel concat ->
+    neck (3x3 conv + BN + GELU, twice, :440-447).  The backbone is the ViT-B/16 restated in
+    oracle/backbone_oracle.py (its weights sit under `backbone.`); `feats` overrides it."""
+    if feats is None:
+        from oracle.backbone_oracle import vit_features
+        pre = s.prefix + "backbone."
+        if any(k.startswith(pre + "_orig_mod.") for k in s.sd):  # torch._dynamo.disable wrapper, model_module.py:539
+            pre += "_orig_mod."
+        feats = vit_features({k[len(pre):]: v for k, v in s.sd.items() if k.startswith(pre)}, x)
+    outs = []
+    for i, chain in enumerate(chains):
+        n = s.sub(f"necks.f{i + 1}")
+        y = torch.cat([feats[j] for j in chain], dim=1)                        # :471
+        y = F.gelu(_bn(_conv(y, n.sub("0"), padding=1), n.sub("1")))
+        outs.append(F.gelu(_bn(_conv(y, n.sub("3"), padding=1), n.sub("4"))))
+    return outs
+
+
 # -------------------------------------------------------------------- encoder ----
 def encoder_forward(sd, method, params, x, backbone_feats=None):
-    """ModelMaskHeadBackbone.forward, model_module.py:645-733 (no backbone unless feats are given).
+    """ModelMaskHeadBackbone.forward, model_module.py:645-733 (use_backbone: the ViT-B/16 adapter path).
 
     Returns (logits, aux, mask_pred) with the reference's aux keys.
     """
@@ -177,20 +197,29 @@ def encoder_forward(sd, method, params, x, backbone_feats=None):
     mod_attn = None
     if mp["enable_modality_attention"]:
         x, mod_attn = se_block(x, s.sub("modality_attention"))                 # :649-650
+    f2_b = f3_b = None
     if mp["use_backbone"]:
-        raise NotImplementedError("backbone adapter path is restated in oracle/backbone_oracle.py")
+        x, f2_b, f3_b = backbone_adapter(x, s.sub("backbone_adapter"), mp["backbone_index_lists"], backbone_feats)
     f1, r1 = res_block(x, s.sub("block1"), strides[0], reps[0], der, use_se)   # :666
     mask_pred = attn_map = None
     if mask_on and stage == "f1":
         mask_pred = mask_head(f1, s.sub("mask_head"), size)
         f1, attn_map = mask_spatial_attention(f1, mask_pred, s.sub("mask_spatial_attention"))
-    f2, r2 = res_block(f1, s.sub("block2"), strides[1], reps[1], der, use_se)  # :679
+    f2_in = f1
+    if mp["use_backbone"]:                                                      # :673-675
+        a = torch.sigmoid(s["f2_weight"])
+        f2_in = F.group_norm(a * f2_b + (1 - a) * f1, f1.shape[1], s["norm_f2.weight"], s["norm_f2.bias"], 1e-5)
+    f2, r2 = res_block(f2_in, s.sub("block2"), strides[1], reps[1], der, use_se)  # :679
     if mask_on and stage == "f2":
         m_in = f2 + feature_down_align(f1, s.sub("f1_to_f2"))                  # :682-683
         mask_pred = mask_head(m_in, s.sub("mask_head"), size)                  # :684
         f2, attn_map = mask_spatial_attention(f2, mask_pred, s.sub("mask_spatial_attention"))
     if not mp["use_hybrid_transformer"]:
-        f3, _ = res_block(f2, s.sub("block3"), strides[2], reps[2], der, use_se)   # :694
+        f3_in = f2
+        if mp["use_backbone"]:                                                  # :688-690
+            a = torch.sigmoid(s["f3_weight"])
+            f3_in = F.group_norm(a * f3_b + (1 - a) * f2, f2.shape[1], s["norm_f3.weight"], s["norm_f3.bias"], 1e-5)
+        f3, _ = res_block(f3_in, s.sub("block3"), strides[2], reps[2], der, use_se)   # :694
         if mask_on and stage == "f3":
             m_in = f3 + feature_down_align(f2, s.sub("f2_to_f3"))
             mask_pred = mask_head(m_in, s.sub("mask_head"), size)

@@ -78,6 +78,22 @@ def test_state_dict_matches_reference_names_and_shapes(tag, hybrid):
         assert mine == ref[k]
 
 
+def test_vit_state_dict_matches_reference_names_and_shapes():
+    """use_backbone encoders: same keys as the reference, including the `_orig_mod` level its
+    torch._dynamo.disable(backbone) wrapper introduces (model_module.py:539) - checkpoints load unchanged."""
+    import model_module as mm
+    from test_oracle_golden import vit_parameters
+
+    p, backbones = vit_parameters()
+    ref = gu.load_shapes("vit")
+    mods = {"dwi": mm.ModelMaskHeadBackbone("dwi", p, backbones["dwi"]),
+            "dce": mm.ModelMaskHeadBackbone("dce", p, backbones["dce"]), "fusion": mm.FusionModel(p)}
+    for k, m in mods.items():
+        mine = {a: tuple(b.shape) for a, b in m.state_dict().items()}
+        assert mine == ref[k]
+        assert any(a.startswith("backbone._orig_mod.") for a in mine) == (k != "fusion")
+
+
 def test_no_cpu_fallback():
     import b200_native as nat
     import dataset as ds

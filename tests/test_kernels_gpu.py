@@ -235,3 +235,108 @@ def test_linear_fp32_residual_stream():
     ref = x + gamma * (y.float() @ w.float().t() + bias)
     assert out.dtype == torch.float32 and _rel(out, ref) < 1e-5
     assert _rel(out_b, ref) < 6e-3
+
+
+# ------------------------------------------------------------------ 14 x 14 maps (ViT grid) ----
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps,res_mode,act", [
+    (2, 14, 14, 64, 64, 1, 0, 0),
+    (3, 14, 14, 128, 256, 9, 0, 1),
+    (2, 14, 14, 768, 768, 1, 1, 1),      # block tail: 1x1 + residual + GELU, 3 N tiles
+    (2, 14, 14, 2304, 768, 9, 0, 1),     # neck conv on 3 concatenated ViT maps (K = 20 736)
+    (90, 14, 14, 384, 384, 9, 0, 1),     # > 148 tiles
+    (2, 10, 10, 64, 128, 9, 2, 1),       # 10 x 12-row tiles (120 rows used), single ragged tile per case
+    (2, 20, 24, 64, 64, 9, 0, 1),        # 24 x 5 tiles, 4 per case
+])
+def test_conv_gemm_ragged_tiles(B, H, W, Cin, Cout, taps, res_mode, act):
+    """Maps whose width does not divide 128: BW x floor(128/BW) tiles, unused MMA rows masked, direct stores."""
+    g = torch.Generator(device="cpu").manual_seed(B + H * 7 + Cin + Cout + taps)
+    x = (torch.randn(B, H, W, Cin, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(Cout, taps * Cin, generator=g) / math.sqrt(taps * Cin)).to(DEV).bfloat16()
+    scale = (torch.rand(Cout, generator=g) + 0.5).to(DEV)
+    bias = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    res = (torch.randn(B, H, W, Cout, generator=g) * 0.5).to(DEV).bfloat16() if res_mode else None
+    y = torch.full((B, H, W, Cout), 7.0, device=DEV, dtype=torch.bfloat16)
+    nat.conv_gemm(x, w, taps=taps, scale=scale, bias=bias, res=res, res_mode=res_mode, act=act, out=y)
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, w, taps, scale, bias, res, res_mode, act)
+    assert _rel(y, ref) < 1e-2
+    with pytest.raises(nat.B200NativeError):  # fused pooling needs staged tiles
+        nat.conv_gemm(x, w, taps=taps, scale=scale, bias=bias, gap=torch.zeros(B, Cout, device=DEV))
+
+
+def test_ragged_tiles_two_segments_and_dots():
+    g = torch.Generator(device="cpu").manual_seed(14)
+    B, C = 3, 128
+    x = (torch.randn(B, 14, 14, C, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(256 + 128, C, generator=g) / math.sqrt(C)).to(DEV).bfloat16()
+    scale = (torch.rand(384, generator=g) + 0.5).to(DEV)
+    bias = (torch.randn(384, generator=g) * 0.1).to(DEV)
+    y1, y2 = nat.conv_gemm(x, w, taps=1, scale=scale, bias=bias, act=0, n_split=256, act2=1)
+    ref = _conv_ref(x, w, 1, scale, bias, None, 0, 0)
+    assert _rel(y1, ref[..., :256]) < 1e-2 and _rel(y2, F.gelu(ref[..., 256:])) < 1e-2
+    # recon head (3x3 + GELU, then 3x3 C->1 folded in) on a 14 x 14 map
+    w9 = (torch.randn(C, 9 * C, generator=g) / math.sqrt(9 * C)).to(DEV).bfloat16()
+    w3 = (torch.randn(9, C, generator=g) / math.sqrt(9 * C)).to(DEV)
+    b3 = torch.tensor([0.3], device=DEV)
+    d = torch.empty(B, 14, 14, 9, device=DEV)
+    nat.conv_gemm(x, w9, taps=9, scale=scale[:C], bias=bias[:C], act=1, store=False, dot_w=w3, dot_out=d)
+    out = nat.tapsum(d, b3, torch.empty(B, 14, 14, device=DEV))
+    torch.cuda.synchronize()
+    t = _conv_ref(x, w9, 9, scale[:C], bias[:C], None, 0, 1)
+    ref = F.conv2d(t.permute(0, 3, 1, 2), w3.view(9, C).t().reshape(1, C, 3, 3), b3, padding=1)[:, 0]
+    assert _rel(out, ref) < 5e-3
+
+
+@pytest.mark.parametrize("B,H,W,C", [(3, 14, 14, 768), (2, 32, 32, 128), (5, 7, 9, 72)])
+def test_channel_sums_mix_instnorm_add(B, H, W, C):
+    g = torch.Generator(device="cpu").manual_seed(C + H)
+    a = (torch.randn(B, H, W, C, generator=g) * 0.7 + 0.2).to(DEV).bfloat16()
+    b = (torch.randn(B, H, W, C, generator=g) * 0.4 - 0.1).to(DEV).bfloat16()
+    s = nat.channel_sums(a)
+    assert _rel(s, a.float().sum(dim=(1, 2))) < 1e-5
+    # channel slice of a wider buffer (row stride > C)
+    if C % 16 == 0:
+        s2 = nat.channel_sums(a[..., C // 2:])
+        assert _rel(s2, a[..., C // 2:].float().sum(dim=(1, 2))) < 1e-5
+    wl = torch.tensor([0.3], device=DEV)
+    gw = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    gb = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    y = nat.mix_instnorm(a, b, wl, gw, gb, 1e-5)
+    al = torch.sigmoid(wl)
+    m = (al * a.float() + (1 - al) * b.float()).permute(0, 3, 1, 2)
+    ref = F.group_norm(m, C, gw, gb, 1e-5).permute(0, 2, 3, 1)
+    assert _rel(y, ref) < 1e-2          # bf16 output rounding
+    z = nat.add_maps(a, b)
+    torch.cuda.synchronize()
+    assert _rel(z, a.float() + b.float()) < 1e-2
+
+
+@pytest.mark.parametrize("H,size,C", [(14, 64, 64), (32, 64, 64), (14, 4, 128), (64, 64, 8)])
+def test_adaptive_pool(H, size, C):
+    g = torch.Generator(device="cpu").manual_seed(H + size)
+    x = (torch.randn(2, H, H, C, generator=g)).to(DEV).bfloat16()
+    ref = F.adaptive_avg_pool2d(x.float().permute(0, 3, 1, 2), (size, size)).permute(0, 2, 3, 1)
+    assert _rel(nat.adaptive_pool(x, size), ref) < 1e-2
+    assert _rel(nat.adaptive_pool(x, size, act=1), F.gelu(ref)) < 1e-2
+    r = torch.randn(3, H, H, generator=g).to(DEV)
+    ref1 = F.adaptive_avg_pool2d(r.unsqueeze(1), (size, size))[:, 0]
+    out1 = nat.adaptive_pool(r, size)
+    torch.cuda.synchronize()
+    assert _rel(out1, ref1) < 1e-6
+
+
+def test_patchify_gate_and_feature_slices():
+    g = torch.Generator(device="cpu").manual_seed(3)
+    B, C, P, E, n = 2, 6, 16, 768, 196
+    x = torch.rand(B, C, 224, 224, generator=g).to(DEV)
+    gate = torch.rand(B, C, generator=g).to(DEV)
+    out = torch.empty(B * n, C * P * P, dtype=torch.bfloat16, device=DEV)
+    nat.patchify(x, P, out, gate)
+    ref = F.unfold(x * gate.view(B, C, 1, 1), P, stride=P).transpose(1, 2).reshape(B * n, -1)
+    assert _rel(out, ref) < 5e-3
+    t = torch.randn(B, n + 1, E, generator=g).to(DEV)
+    buf = torch.zeros(B, 14, 14, 3 * E, dtype=torch.bfloat16, device=DEV)
+    nat.vit_feature(t, B, n, E, buf[..., E:2 * E], out_ld=3 * E)
+    torch.cuda.synchronize()
+    assert _rel(buf[..., E:2 * E].reshape(B, n, E), t[:, 1:]) < 5e-3
+    assert buf[..., :E].abs().max().item() == 0 and buf[..., 2 * E:].abs().max().item() == 0

@@ -44,6 +44,50 @@ def test_model_oracle_matches_reference(tag, hybrid):
         assert n == 34
 
 
+def vit_parameters():
+    """C4 configuration: foundation_model.build_medical_backbone rewrites the encoder parameters exactly as the
+    reference does (foundation_model.py:526-545); the fusion input widths follow by hand (SURVEY.md note 9)."""
+    import foundation_model as fm
+
+    p = pd.default_parameters(input_size=224)
+    backbones = {}
+    for m, c in (("dwi", 16), ("dce", 6)):
+        mp = p[f"{m}_model_parameters"]
+        mp["backbone_str"], mp["use_backbone"] = "vit_base_patch16_224", True
+        backbones[m] = fm.build_medical_backbone(p, None, m, in_channels=c)
+    fs = p["fusion_model_parameters"]["fusion_specific_parameters"]
+    fs["dwi_out_channels"] = fs["dce_out_channels"] = 768
+    return p, backbones
+
+
+def vit_inputs():
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(2, seed=4321, size=224, kind="S")
+    return dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True), dce_raw
+
+
+def test_vit_adapter_oracle_matches_reference():
+    """use_backbone encoders (ViT-B/16 stand-in + BackboneAdapter necks + GroupNorm mix) and the fusion head on
+    14 x 14 maps: the restatement against the unmodified reference modules' outputs (model_vit.npz)."""
+    gold = gu.load("model_vit.npz")
+    shapes = gu.load_shapes("vit")
+    p, _ = vit_parameters()
+    sds = {m: op.seeded_state_dict(shapes[m], seed=11) for m in ("dwi", "dce", "fusion")}
+    dwi, dce = vit_inputs()
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        ld, ad, md = mo.encoder_forward(sds["dwi"], "dwi", p, dwi)
+        lc, ac, mc = mo.encoder_forward(sds["dce"], "dce", p, dce)
+        lf, mf, af = mo.fusion_forward(sds["fusion"], p, ad["raw_feats"], ac["raw_feats"], md, mc)
+    outs = {"S/dwi/logits": ld, "S/dwi/aux": ad, "S/dwi/mask": md, "S/dce/logits": lc, "S/dce/aux": ac,
+            "S/dce/mask": mc, "S/fusion/logits": lf, "S/fusion/mask": mf, "S/fusion/aux": af}
+    n = 0
+    for prefix, obj in outs.items():
+        for key, t in gu.walk(prefix, obj):
+            gu.check(gold, key, t, rtol=2e-5)
+            n += 1
+    assert n == 34
+
+
 def test_dwi_normalize_oracle_matches_reference():
     gold = gu.load("normalizers.npz")
     dwi_raw, _, _, _ = op.synthetic_raw(12, seed=1234, kind="S")

@@ -261,3 +261,45 @@ def test_vit_backbone_features_vs_oracle():
     errs = [_relmax(a, b) for a, b in zip(feats, ref)]
     print("ViT feature errors per block:", [f"{e:.1e}" for e in errs])
     assert max(errs) <= MODEL_TOL
+
+
+# Tolerance of the ViT-adapter path.  With the seeded random weights the two GroupNorm(C, C) backbone mixes
+# (per-channel instance norms over 196 pixels) and the heavy-tailed maps they feed (max/rms ~ 25) amplify bf16
+# operand rounding: the fp32 oracle with nothing but its GEMM operands rounded to bf16 (tools/bf16_floor.py)
+# already deviates from itself by 1.2-1.7 % on f1, 3-7 % on f2 / f3, 2.7 % on the DWI logits and 3.7 % on the
+# DWI mask.  The product is held to that floor: 8e-2 of the tensor's max on maps downstream of a mix, and the
+# usual 2e-2 on everything upstream of the first one.
+VIT_TOL = 8e-2
+VIT_UPSTREAM = ("aux.raw_feats.0", "aux.recon_feats.0", "aux.proj_pairs.0", "aux.proj_pairs.1", "aux.mod_attn_map")
+
+
+def test_vit_adapter_pipeline_vs_golden_reference():
+    """C4 path: use_backbone encoders (modality SE -> ViT-B/16 -> BackboneAdapter necks -> blocks with the
+    GroupNorm backbone mix -> mask stage / heads / pooled projectors on 14 x 14 maps) and the fusion head on
+    768-channel inputs, against the outputs of the unmodified reference modules (tests/golden/model_vit.npz;
+    the backbone the reference was given is the torchvision-checked ViT restatement, timm being absent)."""
+    from test_oracle_golden import vit_inputs, vit_parameters
+
+    gold = gu.load("model_vit.npz")
+    shapes = gu.load_shapes("vit")
+    p, backbones = vit_parameters()
+    mods = {"dwi": b_mm.ModelMaskHeadBackbone("dwi", p, backbones["dwi"]),
+            "dce": b_mm.ModelMaskHeadBackbone("dce", p, backbones["dce"]), "fusion": b_mm.FusionModel(p)}
+    for k, m in mods.items():
+        m.load_state_dict(op.seeded_state_dict(shapes[k], seed=11))
+        m.to(DEV).eval()
+    dwi, dce = vit_inputs()
+    (ld, ad, md), (lc, ac, mc), (lf, mf, af) = _run_product(mods, dwi, dce)
+    outs = {"S/dwi/logits": ld, "S/dwi/aux": ad, "S/dwi/mask": md, "S/dce/logits": lc, "S/dce/aux": ac,
+            "S/dce/mask": mc, "S/fusion/logits": lf, "S/fusion/mask": mf, "S/fusion/aux": af}
+    worst = {}
+    for prefix, obj in outs.items():
+        for key, t in gu.walk(prefix, obj):
+            tol = MODEL_TOL if key.endswith(VIT_UPSTREAM) else VIT_TOL
+            worst[key] = gu.check(gold, key, t, rtol=tol)
+    print("ViT path relative errors:", sorted(worst.items(), key=lambda kv: -kv[1]))
+    assert len(worst) == 34
+    assert worst["S/fusion/aux.gating_weights"] < 1e-3 and worst["S/dwi/aux.mod_attn_map"] < 1e-5
+    # class decisions agree with the reference
+    ref_logits = torch.from_numpy(gold["S/fusion/logits/full"])
+    assert torch.equal(lf.float().cpu().argmax(1), ref_logits.argmax(1))
