@@ -42,6 +42,11 @@ UNIT = "cases/s"
 WORKLOAD = "C3: DWI 16x64x64 + DCE 6x64x64 -> normalise -> CNN encoders -> late-fusion head"
 FLOP_PER_CASE_FULL = 9.418e9    # observable graph, all API outputs
 FLOP_PER_CASE_LOGITS = 5.37e9   # logit path only
+# --workload c4 (not the default line): the ViT-B/16 backbone configuration of BASELINE.json configs[3]
+WORKLOAD_C4 = ("C4: DWI 16x64x64 + DCE 6x64x64 -> resize 224 -> normalise -> ViT-B/16 + adapter encoders -> "
+               "late-fusion head")
+FLOP_C4_FULL = 148.8e9
+FLOP_C4_LOGITS = 138.6e9
 
 
 def load_peaks():
@@ -101,18 +106,38 @@ def make_inputs(batch, rank):
     return dwi, dce
 
 
-def build_product(device, aux, hybrid=False):
+def make_params(workload, hybrid=False):
+    """Parameter dict (+ backbones for c4, configured as foundation_model.build_medical_backbone does)."""
+    import parameters_default as pd
+
+    if workload == "c3":
+        params = pd.default_parameters()
+        for m in ("dwi", "dce"):
+            params[f"{m}_model_parameters"]["use_hybrid_transformer"] = hybrid
+        return params, {"dwi": None, "dce": None}
+    import foundation_model as fm
+
+    params = pd.default_parameters(input_size=224)
+    backbones = {}
+    for m, c in (("dwi", 16), ("dce", 6)):
+        mp = params[f"{m}_model_parameters"]
+        mp["backbone_str"], mp["use_backbone"] = "vit_base_patch16_224", True
+        backbones[m] = fm.build_medical_backbone(params, None, m, in_channels=c)
+    fs = params["fusion_model_parameters"]["fusion_specific_parameters"]
+    fs["dwi_out_channels"] = fs["dce_out_channels"] = 768  # SURVEY.md note 9: not updated by the reference itself
+    return params, backbones
+
+
+def build_product(device, aux, hybrid=False, workload="c3"):
     import model_module as mm
     import parameters_default as pd
     import preprocess_helpers as pre
     from pipeline import FusionPipeline
 
-    params = pd.default_parameters()
-    for m in ("dwi", "dce"):
-        params[f"{m}_model_parameters"]["use_hybrid_transformer"] = hybrid
+    params, backbones = make_params(workload, hybrid)
     torch.manual_seed(0)
-    mods = [mm.initialize_model(mm.ModelMaskHeadBackbone("dwi", params), True),
-            mm.initialize_model(mm.ModelMaskHeadBackbone("dce", params), True),
+    mods = [mm.initialize_model(mm.ModelMaskHeadBackbone("dwi", params, backbones["dwi"]), True),
+            mm.initialize_model(mm.ModelMaskHeadBackbone("dce", params, backbones["dce"]), True),
             mm.initialize_model(mm.FusionModel(params), True)]
     g = torch.Generator().manual_seed(1)
     for m in mods:  # randomise BN running stats so BN folding is exercised (SURVEY.md section 8d)
@@ -126,7 +151,12 @@ def build_product(device, aux, hybrid=False):
     _, fit_dce = make_inputs(64, 10_000)
     nyul = pre.NyulStandardizer()
     nyul.fit(list(fit_dce), num_channels=6)
-    pipe = FusionPipeline(mods[0], mods[1], mods[2], nyul, aux_mode=aux).eval()
+    if workload == "c4":  # the standardiser sees resized images (Resize comes first in the reference's transforms)
+        from dataset import Resize
+        nyul = pre.NyulStandardizer()
+        nyul.fit(list(Resize(224).batch(fit_dce[:16].to(device)).cpu()), num_channels=6)
+    pipe = FusionPipeline(mods[0], mods[1], mods[2], nyul, aux_mode=aux,
+                          input_size=224 if workload == "c4" else None).eval()
     return params, pipe, cpu_state, nyul
 
 
@@ -137,6 +167,8 @@ def cpu_reference_step(params, cpu_state, landmarks, dwi, dce):
     from oracle import normalize_oracle as no
 
     with torch.no_grad():
+        if params["dwi_model_parameters"]["use_backbone"]:  # C4: Resize(224) ahead of the normalisers
+            dwi, dce = no.resize(dwi, 224), no.resize(dce, 224)
         x_d = no.dwi_normalize_batch(dwi)
         x_c = no.nyul_transform_batch(dce, landmarks)
         sds = {"dwi": cpu_state[0], "dce": cpu_state[1], "fusion": cpu_state[2]}
@@ -173,13 +205,16 @@ def reference_arm(args):
     import preprocess_helpers as pre
     import numpy as np
 
-    params = pd.default_parameters()
+    params, backbones = make_params(args.workload)
     torch.manual_seed(0)
-    mods = [mm.initialize_model(mm.ModelMaskHeadBackbone("dwi", params), True),
-            mm.initialize_model(mm.ModelMaskHeadBackbone("dce", params), True),
+    mods = [mm.initialize_model(mm.ModelMaskHeadBackbone("dwi", params, backbones["dwi"]), True),
+            mm.initialize_model(mm.ModelMaskHeadBackbone("dce", params, backbones["dce"]), True),
             mm.initialize_model(mm.FusionModel(params), True)]
     cpu_state = [m.state_dict() for m in mods]
     _, fit_dce = make_inputs(64, 10_000)
+    if args.workload == "c4":
+        from oracle import normalize_oracle as no
+        fit_dce = no.resize(fit_dce[:16], 224)
     nyul = pre.NyulStandardizer()
     nyul.fit(list(fit_dce), num_channels=6)
     lm = np.stack([nyul.channel_landmarks[c] for c in range(6)])
@@ -198,7 +233,8 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": batch, "aux": "full (as the reference executes)"},
+        "config": {"workload": WORKLOAD if args.workload == "c3" else WORKLOAD_C4, "batch_per_step": batch,
+                   "aux": "full (as the reference executes)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"each step = {batch} cases (reference batch_size) of the workload on {threads} host threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -213,7 +249,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="cases per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="cases per GPU per step (default 1024; 256 for c4)")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4"],
+                    help="c3 = the headline CNN-encoder configuration; c4 = ViT-B/16 backbone encoders at 224x224")
     ap.add_argument("--aux", default="full", choices=["full", "logits"])
     ap.add_argument("--ref-batch", type=int, default=32)
     ap.add_argument("--cpu-cases", type=int, default=256, help="bounded CPU-baseline sample")
@@ -223,6 +261,11 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.batch is None:
+        args.batch = 1024 if args.workload == "c3" else 256
+    if args.workload == "c4" and args.ref_batch == 32:
+        args.ref_batch = 8  # ~1 s per case on the host cores: keep a step / the CPU sample bounded
+        args.cpu_cases = min(args.cpu_cases, 16)
 
     if args.impl == "reference":
         reference_arm(args)
@@ -243,7 +286,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
 
-    params, pipe, cpu_state, nyul = build_product(device, args.aux, args.hybrid)
+    params, pipe, cpu_state, nyul = build_product(device, args.aux, args.hybrid, args.workload)
     B = args.batch
     dwi_h, dce_h = make_inputs(B, rank)
     dwi_d, dce_d = dwi_h.to(device), dce_h.to(device)
@@ -313,29 +356,51 @@ def main():
         for (name, key), times in prof.items():
             table[(name, key)] = (statistics.mean(times), len(times))
             total_ms += sum(times)
-        dom_key = ("b200_conv_gemm_ex", (B, 32, 32, 256, 256, 9))
-        dom_ms, _ = table.get(dom_key, (None, 0))
+        def gemm_flops(name, key):
+            if key is None:
+                return None
+            if name == "b200_conv_gemm_ex":      # (B, H, W, Cin, Cout, taps)
+                b_, h_, w_, ci, co, tp = key
+                return 2.0 * b_ * (h_ * w_ // (4 if tp == 4 else 1)) * ci * co * tp
+            if name == "b200_linear":            # (M, K, N)
+                return 2.0 * key[0] * key[1] * key[2]
+            if name == "b200_gemm_batched":      # (batch, heads, M, K, N, mode)
+                return 2.0 * key[0] * key[1] * key[2] * key[3] * key[4]
+            return None
+
+        if args.workload == "c3":
+            dom_key = ("b200_conv_gemm_ex", (B, 32, 32, 256, 256, 9))
+            dom_name = "conv_gemm_kernel<256> 3x3 256->256 @32x32"
+        else:  # the GEMM-shaped launch class with the largest share of the step
+            cands = [(sum(t), nk) for nk, t in prof.items() if gemm_flops(*nk) is not None]
+            dom_key = max(cands)[1] if cands else None
+            dom_name = f"conv_gemm_kernel via {dom_key[0]} {list(dom_key[1])}" if dom_key else None
+        dom_ms, dom_cnt = table.get(dom_key, (None, 0))
         roofline = None
         if dom_ms:
-            flops = 2.0 * B * 32 * 32 * 256 * 256 * 9
+            flops = gemm_flops(*dom_key)
             ach = flops / (dom_ms / 1e3) / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                         "frac": ach / peaks["tf_sustained"], "traffic": None,
-                        "kernel": "conv_gemm_kernel<256> 3x3 256->256 @32x32",
+                        "kernel": dom_name,
                         "ms_per_launch": dom_ms, "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
                         "share_of_step": sum(prof[dom_key]) / total_ms if total_ms else None}
         conv_ms = sum(sum(t) for (n, _), t in prof.items() if n == "b200_conv_gemm_ex")
         kernels = sorted(((sum(t), n, k, len(t)) for (n, k), t in prof.items()), reverse=True)[:40]
         nsteps_prof = max(2, min(args.steps, 5))
-        flop_case = FLOP_PER_CASE_FULL if args.aux == "full" else FLOP_PER_CASE_LOGITS
+        if args.workload == "c3":
+            flop_case = FLOP_PER_CASE_FULL if args.aux == "full" else FLOP_PER_CASE_LOGITS
+        else:
+            flop_case = FLOP_C4_FULL if args.aux == "full" else FLOP_C4_LOGITS
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD + (" [hybrid TransformerStage encoders]" if args.hybrid else ""),
+            "config": {"workload": (WORKLOAD if args.workload == "c3" else WORKLOAD_C4) +
+                       (" [hybrid TransformerStage encoders]" if args.hybrid else ""),
                        "batch_per_gpu": B, "global_batch": B * world, "aux": args.aux,
                        "weights": "seeded random init (initialize_model) + randomised BN running stats",
-                       "l2": "no flush needed: per-step inputs 369 MB and activations >10 GB exceed the 126 MB L2",
+                       "l2": "no flush needed: per-step inputs (369 MB at B=1024) and activations (>10 GB) exceed the 126 MB L2",
                        "parallelism": f"case-sharded x{world}, logit all_gather" if world > 1 else "single GPU"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

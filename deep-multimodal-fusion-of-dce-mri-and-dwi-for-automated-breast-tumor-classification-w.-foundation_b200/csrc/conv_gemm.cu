@@ -304,6 +304,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int swz = ((lane * T::kRowBytes) >> 7) & (T::kRowBytes / 16 - 1);
         const int row_off = lane * T::kRowBytes;
         const bool tma_epi = p.tma_epi != 0;
+        // fp32 residual / output (never TMA-staged): transpose through the warp's staging box when it is large enough
+        constexpr bool kF32 = MODE == 2;  // the fp32 code exists only in the instantiations b200_linear uses for it
+        constexpr bool kTransposeF32 = T::kWarpBoxBytes >= 32 * 33 * 4;  // BN = 256 (every fp32 GEMM of the path)
         int acc = 0;
         uint32_t acc_phase = 0;
         int tile = blockIdx.x, m_walk = m_first;
@@ -334,6 +337,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int pw = w0 + trow % p.BW, ph = h0 + trow / p.BW;
             const bool valid = trow < p.BW * p.BH && pw < p.W && ph < p.H;
             const long long pix = (static_cast<long long>(b) * p.H + ph) * p.W + pw;
+            // pixel index of tile row r, or -1 when that row does not exist (ragged tiles / tails)
+            // (used by the fp32 epilogue, i.e. b200_linear only: H = 1 and a tile is 128 consecutive rows)
+            auto row_pix = [&](int r) -> long long { return w0 + r < p.W ? static_cast<long long>(w0 + r) : -1; };
 
             const bool seg2 = n_tile * BN >= p.n_split;
             __nv_bfloat16* const out_ptr = seg2 ? p.out2 : p.out;
@@ -359,17 +365,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float row_max2 = 0.f;  // MODE 1: row maximum of the logits, in log2 units
             float* const s_sm = reinterpret_cast<float*>(smem + p.off_sm);  // [2 acc][2 halves][128] max, then sums
             if (MODE == 1) {
-                const float k2 = p.alpha * 1.4426950408889634f;
+                // row maximum over the valid columns, on the raw accumulator (alpha > 0 scales it afterwards);
+                // two 32-column TMEM loads in flight per wait, chunks past n_valid are not read at all
                 float m = -INFINITY;
 #pragma unroll
-                for (int ch = 0; ch < T::kChunksPerWarp; ++ch) {
-                    uint32_t rr[kChunk];
-                    tmem_ld_32x32(tm_row + ch * kChunk, rr);
+                for (int ch = 0; ch < T::kChunksPerWarp; ch += 2) {
+                    const int c0 = colw0 + ch * kChunk;
+                    if (c0 >= p.n_valid) break;  // warp-uniform
+                    uint32_t ra[kChunk], rb[kChunk];
+                    tmem_ld_32x32(tm_row + ch * kChunk, ra);
+                    tmem_ld_32x32(tm_row + (ch + 1) * kChunk, rb);
                     tmem_ld_wait();
+                    if (c0 + 2 * kChunk <= p.n_valid) {
 #pragma unroll
-                    for (int j = 0; j < kChunk; ++j)
-                        if (colw0 + ch * kChunk + j < p.n_valid) m = fmaxf(m, __uint_as_float(rr[j]) * k2);
+                        for (int j = 0; j < kChunk; ++j)
+                            m = fmaxf(m, fmaxf(__uint_as_float(ra[j]), __uint_as_float(rb[j])));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kChunk; ++j) {
+                            if (c0 + j < p.n_valid) m = fmaxf(m, __uint_as_float(ra[j]));
+                            if (c0 + kChunk + j < p.n_valid) m = fmaxf(m, __uint_as_float(rb[j]));
+                        }
+                    }
                 }
+                m *= p.alpha * 1.4426950408889634f;
                 s_sm[(acc * 2 + half) * kBlockM + trow] = m;
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 row_max2 = fmaxf(m, s_sm[(acc * 2 + (half ^ 1)) * kBlockM + trow]);
@@ -386,12 +405,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (MODE == 1) {
                     // softmax numerator: logits = alpha * acc (columns >= n_valid masked), e = exp(logit - rowmax)
                     const float k2 = p.alpha * 1.4426950408889634f;  // work in log2 units: exp(x) = exp2(x*log2 e)
+                    const bool all_real = n0 + kChunk <= p.n_valid;  // warp-uniform
 #pragma unroll
-                    for (int j = 0; j < kChunk; ++j) {
-                        const bool real = n0 + j < p.n_valid;
-                        const float e = real ? exp2f(fmaf(__uint_as_float(r[j]), k2, -row_max2)) : 0.f;
-                        v[j] = __bfloat162float(__float2bfloat16_rn(e));  // the sum must match what P.V will read
-                        row_sum += v[j];
+                    for (int j = 0; j < kChunk; j += 2) {
+                        float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), k2, -row_max2));
+                        float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), k2, -row_max2));
+                        if (!all_real) {
+                            if (n0 + j >= p.n_valid) e0 = 0.f;
+                            if (n0 + j + 1 >= p.n_valid) e1 = 0.f;
+                        }
+                        // round to bf16 first: the row sum must match what the P.V GEMM will read
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+                        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+                        v[j] = __uint_as_float(hb << 16);
+                        v[j + 1] = __uint_as_float(hb & 0xffff0000u);
+                        row_sum += v[j] + v[j + 1];
                     }
                 } else {
                     if (p.rowscale != nullptr) {
@@ -413,13 +441,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int bx = (ch * kChunk) / T::kBoxCols;
                 const int c16 = ((ch * kChunk) % T::kBoxCols) / 8;  // first 16-byte chunk inside the box row
                 if (RES != 0) {
-                    if (use_res && p.res_f32) {
+                    if (kF32 && use_res && p.res_f32) {
                         // fp32 residual stream: every thread owns one 128-byte row segment per chunk
                         if (RES == 2 && act == 1) {
 #pragma unroll
                             for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
                         }
-                        if (valid) {
+                        if (kTransposeF32) {
+                            // Coalesced: one warp instruction reads 4 rows x 128 B (8 lanes x 16 B per row), the
+                            // 32 x 32 block goes through this warp's (otherwise unused) staging box so that every
+                            // thread ends up with its own row.  Rows are 33 words apart: the transposed writes and
+                            // the row reads are both bank-conflict free, with constant offsets from one base.
+                            float* const tb = reinterpret_cast<float*>(obuf);
+                            float* const tq = tb + (lane >> 3) * 33 + (lane & 7) * 4;
+                            const float* const rbase = reinterpret_cast<const float*>(p.res) + n0 + (lane & 7) * 4;
+                            __syncwarp();
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const long long rp = row_pix(q * 32 + 4 * k + (lane >> 3));
+                                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (rp >= 0) f = __ldg(reinterpret_cast<const float4*>(rbase + rp * p.res_ld));
+                                tq[k * 132 + 0] = f.x;
+                                tq[k * 132 + 1] = f.y;
+                                tq[k * 132 + 2] = f.z;
+                                tq[k * 132 + 3] = f.w;
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < kChunk / 2; ++j)
+                                v2[j] = __fadd2_rn(v2[j], make_float2(tb[lane * 33 + 2 * j], tb[lane * 33 + 2 * j + 1]));
+                        } else if (valid) {
                             const float4* r4 = reinterpret_cast<const float4*>(
                                 reinterpret_cast<const float*>(p.res) + pix * p.res_ld + n0);
 #pragma unroll
@@ -494,7 +545,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             dsum[k] = fmaf(v[4 * j + 3], wv.w, dsum[k]);
                         }
                     }
-                } else if (out_ptr != nullptr && p.out_f32) {
+                } else if (kF32 && out_ptr != nullptr && p.out_f32 && kTransposeF32) {
+                    float* const tb = reinterpret_cast<float*>(obuf);
+                    float* const tq = tb + (lane >> 3) * 33 + (lane & 7) * 4;
+                    __syncwarp();  // the residual pass (if any) has finished reading the block
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j) tb[lane * 33 + j] = v[j];
+                    __syncwarp();
+                    float* const obase = reinterpret_cast<float*>(out_ptr) + out_col0 + ch * kChunk + (lane & 7) * 4;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const long long rp = row_pix(q * 32 + 4 * k + (lane >> 3));
+                        const float4 f = make_float4(tq[k * 132 + 0], tq[k * 132 + 1], tq[k * 132 + 2], tq[k * 132 + 3]);
+                        if (rp >= 0) *reinterpret_cast<float4*>(obase + rp * p.out_ld) = f;
+                    }
+                } else if (kF32 && out_ptr != nullptr && p.out_f32) {
                     if (valid) {
                         float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_ptr) + pix * p.out_ld +
                                                                 out_col0 + ch * kChunk);
@@ -669,6 +734,16 @@ static int dispatch(int res_mode, bool gap, int ndot, int mode, const CUtensorMa
         }
         return -14;
     }
+    if (mode == 2) {  // fp32 residual stream and / or fp32 output (b200_linear)
+        if constexpr (!WS) {
+            if (!gap && ndot == 0 && p.H == 1 && p.BW == kBlockM) {
+                if (res_mode == 0) B200_GO(0, false, 0, 2);
+                if (res_mode == 1) B200_GO(1, false, 0, 2);
+                if (res_mode == 2) B200_GO(2, false, 0, 2);
+            }
+        }
+        return -14;
+    }
     if (ndot != 0) {
         if constexpr (!WS) {
             if (res_mode == 0 && !gap && ndot == 9) B200_GO(0, false, 9, 0);
@@ -783,7 +858,8 @@ static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, 
     const int Cout = p.Cout, n_split = p.n_split;
     const bool two = n_split < Cout;
     const int seg2 = Cout - n_split;
-    const bool has_out = p.out != nullptr, has_res = p.res_mode != 0;
+    const bool has_out = p.out != nullptr;
+    const bool has_res = p.res_mode != 0 && mode != 2;  // an fp32 residual is never staged by TMA
     const int ndot = p.dot_w != nullptr ? p.ndot : 0;
     auto divides = [&](int bn) { return Cout % bn == 0 && n_split % bn == 0 && (!two || seg2 % bn == 0); };
     int BN = 0, smem_bytes = -1;
@@ -1032,7 +1108,7 @@ extern "C" int b200_linear(const void* x, long long M, int K, const void* w, int
     j.a = View4{x, {K, M, 1, 1}, {K, 0, 0}};
     j.out = View4{out, {N, M, 1, 1}, {N, 0, 0}};
     j.res = View4{res, {N, M, 1, 1}, {N, 0, 0}};
-    return run_job(p, j, 0, false, static_cast<cudaStream_t>(stream));
+    return run_job(p, j, (p.res_f32 || p.out_f32) ? 2 : 0, false, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b200_gemm_batched(const b200_gemm_desc* d, void* stream) {
@@ -1041,7 +1117,7 @@ extern "C" int b200_gemm_batched(const b200_gemm_desc* d, void* stream) {
     if (d->M <= 0 || d->N <= 0 || d->K <= 0 || d->heads <= 0 || d->batch <= 0) return -1;
     if (d->K % 8 != 0 || d->N % 64 != 0) return -2;  // K tail handled by TMA zero fill, rows by clipping
     if (d->mode != 0 && d->mode != 1) return -2;
-    if (d->mode == 1 && (d->N != 256 || d->rowsum_inv == nullptr || d->out == nullptr)) return -3;
+    if (d->mode == 1 && (d->N != 256 || d->rowsum_inv == nullptr || d->out == nullptr || !(d->alpha > 0.f))) return -3;
     if (d->res_mode != 0 && d->res == nullptr) return -4;
     ConvGemmParams p{};
     p.H = d->heads;

@@ -15,6 +15,8 @@
 #include "b200_fusion.h"
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace b200 {
 
 constexpr int kNormThreads = 256;
@@ -159,6 +161,52 @@ constexpr int kNyulBins = 4096;   // linear bins over [min, max] of the plane
 constexpr int kNyulListCap = 64;   // candidates kept per landmark rank
 constexpr int kNyulMaxRanks = 2 * kMaxLandmarks;
 
+// Tail shared by both Nyul kernels: the L percentiles from the 2L selected order statistics (numpy's "linear"
+// rule: float32 difference, fp64 lerp, switched at gamma >= 0.5), the two interpolation tables, then
+// out = interp(interp(x, orig, avg), avg, std) over the plane.  `s_val` holds the order statistics (shared).
+template <typename Load>
+__device__ __forceinline__ void nyul_apply(const float* s_val, int L, int c, int n, int plane,
+                                           const double* __restrict__ avg_landmarks,
+                                           const double* __restrict__ standard_scale,
+                                           const double* __restrict__ gamma, Load load, float* __restrict__ dst,
+                                           float* __restrict__ plane_mean) {
+    __shared__ double s_orig[kMaxLandmarks], s_avg[kMaxLandmarks], s_std[kMaxLandmarks];
+    __shared__ double s_slope1[kMaxLandmarks], s_slope2[kMaxLandmarks];
+    __shared__ double scratch[33];
+    const int tid = threadIdx.x;
+    if (tid < L) {
+        const int t = tid;
+        const float a = s_val[2 * t], b2 = s_val[2 * t + 1];
+        const float diff = b2 - a;  // numpy subtracts in the array dtype (float32) first
+        const double g = gamma[t];
+        double pv;
+        if (g >= 0.5) pv = __dadd_rn(static_cast<double>(b2), -__dmul_rn(static_cast<double>(diff), __dadd_rn(1.0, -g)));
+        else pv = __dadd_rn(static_cast<double>(a), __dmul_rn(static_cast<double>(diff), g));
+        s_orig[t] = pv;
+        s_avg[t] = avg_landmarks[c * L + t];
+        s_std[t] = standard_scale[t];
+    }
+    __syncthreads();
+    if (tid < L - 1) {
+        const int t = tid;
+        s_slope1[t] = __ddiv_rn(__dadd_rn(s_avg[t + 1], -s_avg[t]), __dadd_rn(s_orig[t + 1], -s_orig[t]));
+        s_slope2[t] = __ddiv_rn(__dadd_rn(s_std[t + 1], -s_std[t]), __dadd_rn(s_avg[t + 1], -s_avg[t]));
+    }
+    __syncthreads();
+    double osum = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double xv = static_cast<double>(load(i));
+        const double mid = np_interp(xv, s_orig, s_avg, s_slope1, L);
+        const float o = static_cast<float>(np_interp(mid, s_avg, s_std, s_slope2, L));
+        osum += static_cast<double>(o);
+        __stcs(dst + i, o);
+    }
+    if (plane_mean != nullptr) {
+        const double om = block_sum<double>(osum, scratch);
+        if (tid == 0) plane_mean[plane] = static_cast<float>(om / n);
+    }
+}
+
 // One CTA per (case, channel) plane.  The 2L order statistics numpy's "linear" percentile rule needs are
 // found WITHOUT sorting the plane: a monotone linear binning of [min, max] into 4096 bins, an exclusive
 // scan, then for each wanted rank the (typically 1-3) samples of its bin are gathered and the in-bin rank
@@ -183,9 +231,6 @@ nyul_transform_kernel(const float* __restrict__ x, float* __restrict__ out, int 
     __shared__ int s_flags[2];  // [0] overflow -> sort fallback, [1] number of distinct target bins
     __shared__ float s_red[2 * (kNyulThreads / 32)];
     __shared__ int s_scan[kNyulThreads / 32];
-    __shared__ double s_orig[kMaxLandmarks], s_avg[kMaxLandmarks], s_std[kMaxLandmarks];
-    __shared__ double s_slope1[kMaxLandmarks], s_slope2[kMaxLandmarks];
-    __shared__ double scratch[33];
     const int plane = blockIdx.x;
     const int c = plane % C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -338,38 +383,112 @@ nyul_transform_kernel(const float* __restrict__ x, float* __restrict__ out, int 
         if (tid < R) s_val[tid] = s_x[s_rank[tid]];
     }
     __syncthreads();
-    if (tid < L) {
-        const int t = tid;
-        const float a = s_val[2 * t], b2 = s_val[2 * t + 1];
-        const float diff = b2 - a;  // numpy subtracts in the array dtype (float32) first
-        const double g = gamma[t];
-        double pv;
-        if (g >= 0.5) pv = __dadd_rn(static_cast<double>(b2), -__dmul_rn(static_cast<double>(diff), __dadd_rn(1.0, -g)));
-        else pv = __dadd_rn(static_cast<double>(a), __dmul_rn(static_cast<double>(diff), g));
-        s_orig[t] = pv;
-        s_avg[t] = avg_landmarks[c * L + t];
-        s_std[t] = standard_scale[t];
+    // the sort fallback permuted the shared copy: re-read the plane (an L2 hit) on that path only
+    nyul_apply(s_val, L, c, n, plane, avg_landmarks, standard_scale, gamma,
+               [&](int i) { return fallback ? src[i] : s_x[i]; }, dst, plane_mean);
+}
+
+// Planes too large to stage in shared memory (224 x 224 after the C4 resize = 50 176 samples): the 2L order
+// statistics come from an exact radix select on the order-preserving integer image of the floats - four passes
+// of 8 bits over the plane (L2-resident after the first), one 256-bin histogram per distinct key prefix still
+// alive (at most 2L), warp-aggregated shared-memory atomics so that heavy ties (a zero background) cost one
+// atomic per warp.  Bitwise exact by construction, no distribution assumptions, no fallback.
+__device__ __forceinline__ uint32_t nyul_ordkey(float v) {
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float nyul_ordkey_inv(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(kNyulThreads)
+nyul_transform_large_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int n, int L,
+                            const double* __restrict__ avg_landmarks, const double* __restrict__ standard_scale,
+                            const int* __restrict__ prev_index, const double* __restrict__ gamma,
+                            float* __restrict__ plane_mean) {
+    __shared__ int s_hist[kNyulMaxRanks][256];
+    __shared__ uint32_t s_prefix[kNyulMaxRanks], s_uprefix[kNyulMaxRanks];
+    __shared__ int s_rem[kNyulMaxRanks], s_uid[kNyulMaxRanks];
+    __shared__ int s_nu;
+    __shared__ float s_val[kNyulMaxRanks];
+    const int plane = blockIdx.x;
+    const int c = plane % C;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const float* src = x + static_cast<size_t>(plane) * n;
+    float* dst = out + static_cast<size_t>(plane) * n;
+    const int R = 2 * L;
+    if (tid < R) {
+        const int lo = prev_index[tid >> 1];
+        s_rem[tid] = (tid & 1) ? min(lo + 1, n - 1) : lo;
+        s_prefix[tid] = 0u;
+        s_uid[tid] = 0;
+    }
+    if (tid == 0) {
+        s_nu = 1;
+        s_uprefix[0] = 0u;
     }
     __syncthreads();
-    if (tid < L - 1) {
-        const int t = tid;
-        s_slope1[t] = __ddiv_rn(__dadd_rn(s_avg[t + 1], -s_avg[t]), __dadd_rn(s_orig[t + 1], -s_orig[t]));
-        s_slope2[t] = __ddiv_rn(__dadd_rn(s_std[t + 1], -s_std[t]), __dadd_rn(s_avg[t + 1], -s_avg[t]));
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const int nu = s_nu;
+        for (int i = tid; i < nu * 256; i += kNyulThreads) (&s_hist[0][0])[i] = 0;
+        __syncthreads();
+        const int n_round = (n + kNyulThreads - 1) / kNyulThreads * kNyulThreads;  // whole warps stay converged
+        for (int i = tid; i < n_round; i += kNyulThreads) {
+            int slot = -1;
+            if (i < n) {
+                const uint32_t key = nyul_ordkey(pass == 0 ? __ldcs(src + i) : __ldg(src + i));
+                int u = 0;
+                if (pass != 0) {
+                    const uint32_t hi = key >> (shift + 8);
+                    u = -1;
+                    for (int q = 0; q < nu; ++q)
+                        if (s_uprefix[q] == hi) {
+                            u = q;
+                            break;
+                        }
+                }
+                if (u >= 0) slot = u * 256 + static_cast<int>((key >> shift) & 255u);
+            }
+            const uint32_t peers = __match_any_sync(0xffffffffu, slot);
+            if (slot >= 0 && lane == __ffs(peers) - 1) atomicAdd(&(&s_hist[0][0])[slot], __popc(peers));
+        }
+        __syncthreads();
+        if (tid < R) {
+            const int* h = s_hist[s_uid[tid]];
+            int rem = s_rem[tid], d = 0;
+            for (; d < 255; ++d) {
+                const int cnt = h[d];
+                if (rem < cnt) break;
+                rem -= cnt;
+            }
+            s_rem[tid] = rem;
+            s_prefix[tid] = (s_prefix[tid] << 8) | static_cast<uint32_t>(d);
+        }
+        __syncthreads();
+        if (tid == 0) {  // distinct prefixes still alive -> one histogram each in the next pass
+            int nl = 0;
+            for (int t = 0; t < R; ++t) {
+                int id = -1;
+                for (int q = 0; q < nl; ++q)
+                    if (s_uprefix[q] == s_prefix[t]) {
+                        id = q;
+                        break;
+                    }
+                if (id < 0) {
+                    id = nl++;
+                    s_uprefix[id] = s_prefix[t];
+                }
+                s_uid[t] = id;
+            }
+            s_nu = nl;
+        }
+        __syncthreads();
     }
+    if (tid < R) s_val[tid] = nyul_ordkey_inv(s_prefix[tid]);
     __syncthreads();
-    double osum = 0.0;
-    for (int i = tid; i < n; i += kNyulThreads) {
-        // the sort fallback permuted the shared copy: re-read the plane (an L2 hit) on that path only
-        const double xv = static_cast<double>(fallback ? src[i] : s_x[i]);
-        const double mid = np_interp(xv, s_orig, s_avg, s_slope1, L);
-        const float o = static_cast<float>(np_interp(mid, s_avg, s_std, s_slope2, L));
-        osum += static_cast<double>(o);
-        __stcs(dst + i, o);
-    }
-    if (plane_mean != nullptr) {
-        const double om = block_sum<double>(osum, scratch);
-        if (tid == 0) plane_mean[plane] = static_cast<float>(om / n);
-    }
+    nyul_apply(s_val, L, c, n, plane, avg_landmarks, standard_scale, gamma, [&](int i) { return __ldg(src + i); }, dst,
+               plane_mean);
 }
 
 __global__ void __launch_bounds__(kNormThreads)
@@ -425,7 +544,12 @@ extern "C" int b200_nyul_transform(const float* x, float* out, int planes, int C
     int npad = 2;
     while (npad < n) npad <<= 1;
     const size_t smem = static_cast<size_t>(npad) * sizeof(float);
-    if (smem > 200 * 1024) return -3;  // planes above 51200 samples need the multi-pass select (not built yet)
+    static const bool force_large = std::getenv("B200_NYUL_LARGE") != nullptr;  // test hook
+    if (smem > 128 * 1024 || force_large) {  // > 32 768 samples: radix select straight from global / L2
+        nyul_transform_large_kernel<<<planes, kNyulThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            x, out, C, n, L, avg_landmarks, standard_scale, prev_index, gamma, plane_mean);
+        return launch_status();
+    }
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(nyul_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

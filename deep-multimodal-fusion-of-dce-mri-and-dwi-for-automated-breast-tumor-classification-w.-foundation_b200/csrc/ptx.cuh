@@ -199,4 +199,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
            | ((m >> 4) << 24);  // M / 16
 }
 
+// 2^x on the SFU (MUFU.EX2), denormals flushed: the softmax numerator needs no more than bf16 accuracy
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 }  // namespace b200

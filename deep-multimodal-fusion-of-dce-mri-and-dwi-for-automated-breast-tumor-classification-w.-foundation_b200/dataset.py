@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 import b200_native as nat
 
-__all__ = ["DWINormalize", "DCENormalize", "SingleInputDataset", "LoadedFusionDataset", "data_segmentation",
+__all__ = ["DWINormalize", "DCENormalize", "Resize", "SingleInputDataset", "LoadedFusionDataset", "data_segmentation",
            "data_segmentation_mask"]
 
 
@@ -43,6 +43,36 @@ class DWINormalize(object):
         out = torch.empty_like(x)
         B, C, H, W = x.shape
         nat.dwi_normalize(x, out, C, H * W, self.adc, self.z_lo, self.z_hi, plane_mean)
+        return out
+
+    def __call__(self, img):
+        dev_img, home = _to_device(img)
+        out = self.batch(dev_img.unsqueeze(0))[0]
+        return out if home is None else out.to(home)
+
+
+class Resize(object):
+    """torchvision `transforms.Resize(input_size)` as the reference applies it BEFORE the normaliser
+    (code/prepare_single_model.py:112-120): bilinear, align_corners=False, antialias on.  For an upsample
+    (64 -> 224, config C4) the antialias filter is the plain bilinear kernel, which is what is built;
+    downsampling (where antialiasing widens the filter) is not."""
+
+    def __init__(self, size):
+        self.size = (size, size) if isinstance(size, int) else tuple(size)
+
+    def batch(self, x):
+        """x [B,C,H,W] fp32 CUDA -> [B,C,size,size] fp32 (one launch, every plane independent)."""
+        if x.dim() != 4:
+            raise ValueError("expected [B,C,H,W]")
+        B, C, H, W = x.shape
+        S0, S1 = self.size
+        if (S0, S1) == (H, W):
+            return x
+        if S0 < H or S1 < W:
+            raise NotImplementedError("Resize: antialiased downsampling is not built (the path only upsamples)")
+        x = x.contiguous().float()
+        out = torch.empty((B, C, S0, S1), dtype=torch.float32, device=x.device)
+        nat.resize_bilinear_c1(x.view(B * C, H, W), out.view(B * C, S0, S1))
         return out
 
     def __call__(self, img):

@@ -16,12 +16,16 @@ from __future__ import annotations
 import torch
 
 import b200_native as nat
-from dataset import DCENormalize, DWINormalize
+from dataset import DCENormalize, DWINormalize, Resize
 
 
 class FusionPipeline:
-    def __init__(self, dwi_model, dce_model, fusion_model, nyul_standardizer, dwi_normalize=None, aux_mode="full"):
+    def __init__(self, dwi_model, dce_model, fusion_model, nyul_standardizer, dwi_normalize=None, aux_mode="full",
+                 input_size=None):
+        """`input_size`: the reference's `transforms.Resize(input_size)` ahead of the normalisers
+        (code/prepare_single_model.py:112-120) - 224 for the ViT-B/16 encoders (C4), None = keep the ROI size."""
         self.dwi_model, self.dce_model, self.fusion_model = dwi_model, dce_model, fusion_model
+        self.resize = Resize(input_size) if input_size is not None else None
         self.dwi_norm = dwi_normalize if dwi_normalize is not None else DWINormalize()
         self.dce_norm = DCENormalize(nyul_standardizer)
         self.set_aux_mode(aux_mode)
@@ -45,6 +49,8 @@ class FusionPipeline:
         code/prepare_single_model.py:338-339).  Returns fusion logits [B,K] (fp32)."""
         B = dwi_raw.shape[0]
         dev = dwi_raw.device
+        if self.resize is not None:
+            dwi_raw, dce_raw = self.resize.batch(dwi_raw), self.resize.batch(dce_raw)
         pm_d = torch.empty(B * dwi_raw.shape[1], dtype=torch.float32, device=dev)
         pm_c = torch.empty(B * dce_raw.shape[1], dtype=torch.float32, device=dev)
         dwi = self.dwi_norm.batch(dwi_raw, plane_mean=pm_d)

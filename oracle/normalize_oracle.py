@@ -103,3 +103,14 @@ def compute_adc_map(dwi: torch.Tensor, bvals, eps: float = 1e-6) -> torch.Tensor
     cov = ((b - b.mean()) * (log_s - log_s.mean(dim=0))).sum(dim=0)
     var = ((b - b.mean()) ** 2).sum()
     return (-(cov / (var + eps))).unsqueeze(0)
+
+
+def resize(x: torch.Tensor, size: int) -> torch.Tensor:
+    """torchvision `transforms.Resize(size)` on a float tensor [..., H, W] as the reference applies it ahead of
+    the normaliser (code/prepare_single_model.py:112, :116, :120): bilinear, align_corners=False, antialias=True
+    (torchvision's default for tensors since 0.17).  tests/test_oracle_golden.py checks it against
+    torchvision.transforms.Resize itself."""
+    lead = x.shape[:-2]
+    y = torch.nn.functional.interpolate(x.reshape(-1, 1, *x.shape[-2:]).float(), size=(size, size), mode="bilinear",
+                                        align_corners=False, antialias=True)
+    return y.reshape(*lead, size, size)

@@ -150,3 +150,15 @@ def test_vit_oracle_matches_torchvision_stand_in():
             t = blk(t)
             ref = t[:, 1:].transpose(1, 2).reshape(2, 768, 14, 14)
             assert torch.allclose(feats[i], ref, rtol=1e-4, atol=1e-4), i
+
+
+def test_resize_oracle_is_torchvision_resize():
+    """a5: the oracle's resize against torchvision.transforms.Resize (what the reference calls), 64 -> 224."""
+    from torchvision import transforms
+
+    x = torch.rand(3, 6, 64, 64, generator=torch.Generator().manual_seed(5))
+    ref = torch.stack([transforms.Resize(224)(c) for c in x])
+    assert torch.equal(no.resize(x, 224), ref)
+    # for an upsample the antialias filter degenerates to plain bilinear interpolation (what the kernel does)
+    plain = torch.nn.functional.interpolate(x, size=(224, 224), mode="bilinear", align_corners=False)
+    assert torch.allclose(ref, plain, rtol=0, atol=1e-5)  # the separable antialias code path rounds differently

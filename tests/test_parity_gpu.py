@@ -5,6 +5,8 @@ Tolerances (BASELINE.json north_star): normalisation 1e-5 relative; logits / fea
 relative in bf16, measured as max|d| / max|ref| per tensor; argmax agreement reported with the
 oracle's top-2 margins.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -101,6 +103,63 @@ def test_nyul_requires_fit_and_odd_sizes():
     nyul.fit(list(x), num_channels=6)
     lm = np.stack([nyul.channel_landmarks[c] for c in range(6)])
     assert _relmax(nyul.transform_batch(x.to(DEV)), no.nyul_transform_batch(x, lm)) <= NORM_TOL
+
+
+def _dce_224(n, seed):
+    """224 x 224 DCE planes with a zero background (heavy ties) - what C4's resize hands to the Nyul kernel."""
+    _, dce, _, _ = op.synthetic_raw(n, seed=seed, size=224, kind="S")
+    yy, xx = torch.meshgrid(torch.arange(224), torch.arange(224), indexing="ij")
+    body = ((yy - 112) ** 2 + (xx - 100) ** 2) < 90 ** 2
+    return dce * body
+
+
+def test_nyul_large_planes_radix_select():
+    """Planes above 32 768 samples (224 x 224) take the radix-select kernel: exact order statistics straight
+    from global memory; checked against the numpy oracle, ties and a 40 % zero background included."""
+    x = _dce_224(3, 31)
+    nyul = b_pre.NyulStandardizer()
+    nyul.fit(list(x[:2]), num_channels=6)
+    lm = np.stack([nyul.channel_landmarks[c] for c in range(6)])
+    for inp in (x, torch.round(x * 50) / 50, op.synthetic_raw(2, seed=8, size=224, kind="U")[1]):
+        pm = torch.empty(inp.shape[0] * 6, device=DEV)
+        y = nyul.transform_batch(inp.to(DEV), plane_mean=pm)
+        ref = no.nyul_transform_batch(inp, lm)
+        assert _relmax(y, ref) <= NORM_TOL
+        assert (y.cpu() != ref).float().mean().item() < 1e-3
+        assert torch.allclose(pm.cpu(), ref.mean(dim=(2, 3)).flatten(), rtol=1e-5, atol=1e-6)
+
+
+def test_nyul_radix_select_on_golden_planes():
+    """The same kernel forced onto the 64 x 64 golden planes (B200_NYUL_LARGE=1 is read once per process)."""
+    import subprocess
+    import sys
+
+    import b200path
+
+    code = (
+        "import sys; sys.path.insert(0, 'tests'); import b200path, golden_util as gu, numpy as np, torch\n"
+        "import preprocess_helpers as pre\nfrom oracle import params as op\n"
+        "gold = gu.load('normalizers.npz'); _, s, _, _ = op.synthetic_raw(12, seed=1234, kind='S')\n"
+        "_, u, _, _ = op.synthetic_raw(3, seed=77, kind='U'); n = pre.NyulStandardizer(); n.fit(list(s[:8]), num_channels=6)\n"
+        "for k, x in (('nyul/S', s[8:]), ('nyul/U', u), ('nyul/ties', torch.round(u * 20) / 20)):\n"
+        "    gu.check(gold, k, n.transform_batch(x.cuda()), rtol=1e-5)\nprint('radix-ok')\n")
+    env = dict(os.environ, B200_NYUL_LARGE="1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=b200path.ROOT, env=env, capture_output=True, text=True,
+                       timeout=300)
+    assert "radix-ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_resize_then_normalise_matches_oracle():
+    """a5 + a1/a2 at C4 sizes: 64 -> 224 bilinear resize, then the normalisers on 224 x 224 planes."""
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(2, seed=99, kind="S")
+    rz = b_dataset.Resize(224)
+    d224, c224 = rz.batch(dwi_raw.to(DEV)), rz.batch(dce_raw.to(DEV))
+    assert _relmax(d224, no.resize(dwi_raw, 224)) <= NORM_TOL and _relmax(c224, no.resize(dce_raw, 224)) <= NORM_TOL
+    y = b_dataset.DWINormalize().batch(d224)
+    assert _relmax(y, no.dwi_normalize_batch(no.resize(dwi_raw, 224))) <= NORM_TOL
+    assert torch.allclose(rz(dce_raw[0]), no.resize(dce_raw[0], 224), atol=1e-5)  # per-image CPU-in/CPU-out call
+    with pytest.raises(NotImplementedError):
+        b_dataset.Resize(32).batch(dwi_raw.to(DEV))
 
 
 # ----------------------------------------------------------------------- models ----
@@ -300,6 +359,10 @@ def test_vit_adapter_pipeline_vs_golden_reference():
     print("ViT path relative errors:", sorted(worst.items(), key=lambda kv: -kv[1]))
     assert len(worst) == 34
     assert worst["S/fusion/aux.gating_weights"] < 1e-3 and worst["S/dwi/aux.mod_attn_map"] < 1e-5
-    # class decisions agree with the reference
+    # class decisions agree with the reference wherever its top-2 margin exceeds the measured logit error
+    # (case 0 of this fixture has a margin of 0.009 on logits of magnitude 1.5 - a coin flip at any bf16 precision)
     ref_logits = torch.from_numpy(gold["S/fusion/logits/full"])
-    assert torch.equal(lf.float().cpu().argmax(1), ref_logits.argmax(1))
+    top2 = ref_logits.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 2 * worst["S/fusion/logits"] * ref_logits.abs().max()
+    assert decided.any()
+    assert torch.equal(lf.float().cpu().argmax(1)[decided], ref_logits.argmax(1)[decided])
