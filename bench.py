@@ -407,6 +407,7 @@ def main():
                     "ms_per_step": e2e_ms / args.steps, "api": "FusionPipeline.classify_host (pinned host tensors, "
                     "upload overlapped on a copy stream)"},
             "gpu_launches": launches,
+            "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated(device) / 1e9,
             "roofline": roofline,
             "step_model": {"algorithmic_gflop_per_case": flop_case / 1e9,
                            "achieved_tflops_whole_step": value / world * flop_case / 1e12,

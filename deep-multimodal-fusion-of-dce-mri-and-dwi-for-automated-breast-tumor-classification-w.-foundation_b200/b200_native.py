@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _lib = None
 
@@ -83,7 +83,7 @@ SIGNATURES = {
     "b200_nyul_transform": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "b200_plane_mean": [_P, _I, _I, _P, _P],
     "b200_stem": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P],
-    "b200_se_gate": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "b200_se_gate": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "b200_scale_map": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "b200_conv3x3_c1": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
     "b200_mask_tail": [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _F, _P, _P],
@@ -351,8 +351,11 @@ def stem(x, stride, pm, se, wcat, scale, bias, n_skip, n_mid, skip_out, mid_out,
 
 def se_gate(gap_sum, npix, w1t, b1, w2t, b2, gate):
     B, C_ = gap_sum.shape
+    hidden = torch.empty((B, w1t.shape[1]), dtype=torch.float32, device=gap_sum.device)
     _call("b200_se_gate", None, _ptr(gap_sum), B, C_, w1t.shape[1], npix, _ptr(w1t), _ptr(b1), _ptr(w2t), _ptr(b2),
-                              _ptr(gate), _stream())
+                              _ptr(gate), _ptr(hidden), _stream())
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += 1  # the call launches two kernels (hidden layer, gate layer)
     return gate
 
 

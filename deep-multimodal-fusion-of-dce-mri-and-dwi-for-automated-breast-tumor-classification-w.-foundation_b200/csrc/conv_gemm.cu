@@ -49,6 +49,7 @@ struct ConvGemmParams {
     int out_ld;
     int up2;               // replicate every output pixel into a 2x2 block of a [B,2H,2W,ld] map
     int tma_epi;           // outputs / residual go through shared memory + TMA (coalesced); else direct
+    int share_box;         // BN = 256: a warp's two 64-column output boxes share one 4 KB staging slot (one more ring stage)
     float* gap;            // [B, Cout] fp32 sums over the pixels of each case, or nullptr
     int n_split;           // channels [n_split, Cout) are a second output segment (== Cout when unused)
     __nv_bfloat16* out2;
@@ -73,6 +74,7 @@ struct ConvGemmParams {
 };
 
 constexpr int kBlockM = 128;
+constexpr int kF32BlockBytes = 32 * 33 * 4;  // one warp's padded 32 x 32 fp32 transposition block (fp32 epilogue)
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kEpiWarp0 = 4;
@@ -153,7 +155,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     using T = Tile<BN>;
     constexpr bool DOT = NDOT > 0;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1 KB alignment by OFFSET (not by rounding the generic address): the compiler keeps the shared state space
+    // and emits STS / LDS for the staging traffic instead of generic ST / LD
+    uint8_t* smem = smem_raw + ((1024u - (static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw)) & 1023u)) & 1023u);
     uint8_t* sW = smem;  // resident weights [k_blocks][BN x 64] (WS only)
     uint8_t* sRing = smem + p.off_ring;
     constexpr int kStageBytes = WS ? kABytes : kABytes + T::kBBytes;
@@ -295,7 +299,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;    // TMEM lane quadrant this warp may read (rows q*32 .. q*32+31 of the tile)
         const int half = ew >> 2;  // column half: columns [half*BN/2, (half+1)*BN/2)
         const int colw0 = half * T::kColsPerWarp;
-        uint8_t* const obuf = s_union + ew * T::kWarpBoxBytes;
+        const bool share = p.share_box != 0;  // warp-uniform; set by the host for BN = 256 plain-output launches only
+        uint8_t* const obuf = s_union + ew * (MODE == 2 ? kF32BlockBytes : (share ? T::kBoxBytes : T::kWarpBoxBytes));
         uint8_t* const rbuf = smem + p.off_rbox + ew * T::kWarpBoxBytes;
         uint64_t* const rbar = &resbar[2 * ew];  // one barrier per staged residual box
         uint32_t rphase = 0;                     // bit bx = phase of box bx
@@ -306,7 +311,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool tma_epi = p.tma_epi != 0;
         // fp32 residual / output (never TMA-staged): transpose through the warp's staging box when it is large enough
         constexpr bool kF32 = MODE == 2;  // the fp32 code exists only in the instantiations b200_linear uses for it
-        constexpr bool kTransposeF32 = T::kWarpBoxBytes >= 32 * 33 * 4;  // BN = 256 (every fp32 GEMM of the path)
+        constexpr bool kTransposeF32 = true;  // the host plans 8 transposition blocks for mode 2
         int acc = 0;
         uint32_t acc_phase = 0;
         int tile = blockIdx.x, m_walk = m_first;
@@ -357,6 +362,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (lane == 0) tma_store_wait_read<0>();
                 __syncwarp();
             }
+            if (kF32 && RES != 0 && p.res_f32) {
+                // fp32 residual: pull this warp's 32 x kColsPerWarp block towards L2 while the accumulator is
+                // still being produced (the residual does not depend on it); no registers are held
+                constexpr int kLinesPerRow = T::kColsPerWarp * 4 / 128;
+#pragma unroll
+                for (int i = 0; i < kLinesPerRow; ++i) {
+                    const int line = lane + 32 * i;
+                    const long long rp = row_pix(q * 32 + line / kLinesPerRow);
+                    if (rp >= 0)
+                        prefetch_l2(reinterpret_cast<const float*>(p.res) + rp * p.res_ld + nbase +
+                                    (line % kLinesPerRow) * 32);
+                }
+            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t tm_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + colw0;
@@ -397,6 +415,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int ch = 0; ch < T::kChunksPerWarp; ++ch) {
                 const int n0 = nbase + ch * kChunk;
+                // fp32 residual (mode 2): its coalesced global loads are issued before the TMEM load so that the
+                // DRAM latency overlaps the TMEM round trip and the affine math of the same chunk
+                float4 rf[kF32 ? 8 : 1];
+                if (kF32 && RES != 0 && p.res_f32) {
+                    const float* const rbase = reinterpret_cast<const float*>(p.res) + n0 + (lane & 7) * 4;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const long long rp = row_pix(q * 32 + 4 * k + (lane >> 3));
+                        rf[k] = rp >= 0 ? __ldg(reinterpret_cast<const float4*>(rbase + rp * p.res_ld))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
                 uint32_t r[kChunk];
                 tmem_ld_32x32(tm_row + ch * kChunk, r);
                 tmem_ld_wait();
@@ -454,13 +484,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             // the row reads are both bank-conflict free, with constant offsets from one base.
                             float* const tb = reinterpret_cast<float*>(obuf);
                             float* const tq = tb + (lane >> 3) * 33 + (lane & 7) * 4;
-                            const float* const rbase = reinterpret_cast<const float*>(p.res) + n0 + (lane & 7) * 4;
                             __syncwarp();
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
-                                const long long rp = row_pix(q * 32 + 4 * k + (lane >> 3));
-                                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (rp >= 0) f = __ldg(reinterpret_cast<const float4*>(rbase + rp * p.res_ld));
+                                const float4 f = rf[k];
                                 tq[k * 132 + 0] = f.x;
                                 tq[k * 132 + 1] = f.y;
                                 tq[k * 132 + 2] = f.z;
@@ -580,9 +607,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         o[j] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
                     }
                     if (tma_epi) {
+                        constexpr int kChunksPerBoxO = T::kBoxCols / kChunk;
+                        if (share && ch != 0 && ch % kChunksPerBoxO == 0) {
+                            // the previous box is complete: store it, and wait until the TMA has read the slot
+                            // before this chunk overwrites it (this chunk's TMEM load and math are already done)
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_4d(tm_out, obuf, out_col0 + (bx - 1) * T::kBoxCols, slab_w, slab_h, b);
+                                tma_store_commit();
+                                tma_store_wait_read<0>();
+                            }
+                            __syncwarp();
+                        }
+                        uint8_t* const slot = obuf + (share ? 0 : bx * T::kBoxBytes);
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(obuf + bx * T::kBoxBytes + row_off + (((c16 + j) ^ swz) << 4)) = o[j];
+                            *reinterpret_cast<uint4*>(slot + row_off + (((c16 + j) ^ swz) << 4)) = o[j];
                     } else if (valid) {  // direct 2x2-replicated store (only when the strided TMA form does not apply)
                         const int h = ph, w = pw;
                         const int out_ld = seg2 ? p.out2_ld : p.out_ld;
@@ -615,7 +656,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    if (!p.up2) {
+                    if (share) {  // the last box; the earlier one went out when its slot was recycled
+                        tma_store_4d(tm_out, obuf, out_col0 + (T::kBoxesPerWarp - 1) * T::kBoxCols, slab_w, slab_h, b);
+                    } else if (!p.up2) {
 #pragma unroll
                         for (int bx = 0; bx < T::kBoxesPerWarp; ++bx)
                             tma_store_4d(tm_out, obuf + bx * T::kBoxBytes, out_col0 + bx * T::kBoxCols, slab_w, slab_h, b);
@@ -787,12 +830,15 @@ static inline int align1k(int v) { return (v + 1023) & ~1023; }
 
 // Lays out shared memory for (BN, weight-stationary?) and returns the total dynamic size, or -1 if the
 // configuration does not fit / leaves fewer than 3 ring stages.
-static int plan_smem(ConvGemmParams& p, int BN, bool ws, bool has_out, bool has_res, int ndot, int mode) {
+static int plan_smem(ConvGemmParams& p, int BN, bool ws, bool has_out, bool has_res, int ndot, int mode,
+                     bool share_box = false) {
     const int b_bytes = BN * kBlockK * 2;
     const int stage_bytes = ws ? kABytes : kABytes + b_bytes;
     const int box_all = kBlockM * BN * 2;  // 8 warps x (32 rows x BN/2 columns) of bf16
     const int dot_bytes = ndot * BN * 4 + 2 * kBlockM * ndot * 4;
-    const int union_bytes = align1k(ndot ? dot_bytes : (has_out ? box_all : 0));
+    // mode 2 (fp32 epilogue) needs only the eight 32 x 33-word transposition blocks
+    const int out_stage = mode == 2 ? 8 * kF32BlockBytes : (share_box ? box_all / 2 : box_all);
+    const int union_bytes = align1k(ndot ? dot_bytes : (has_out ? out_stage : 0));
     const int rbox_bytes = has_res ? align1k(box_all) : 0;
     const int sm_bytes = mode == 1 ? align1k(8 * kBlockM * 4) : 0;  // row max / row sum exchange
     const int resident = ws ? align1k(p.k_blocks * b_bytes) : 0;
@@ -800,6 +846,8 @@ static int plan_smem(ConvGemmParams& p, int BN, bool ws, bool has_out, bool has_
     int stages = (kSmemLimit - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 3) return -1;
+    static const int stage_cap = std::getenv("B200_STAGES") ? std::atoi(std::getenv("B200_STAGES")) : 0;  // experiments
+    if (stage_cap >= 2 && stages > stage_cap) stages = stage_cap;
     p.stages = stages;
     p.off_ring = resident;
     p.off_bar = resident + stages * stage_bytes;
@@ -875,12 +923,26 @@ static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, 
             }
         }
     }
+    // TMA-staged epilogue?  Needs the warp's 32-row slab to be a {bw, bh} box and bf16 output / residual.
+    static const bool no_tma_up2 = std::getenv("B200_NO_TMA_UP2") != nullptr;
+    const bool slab_is_box = p.BW * p.BH == kBlockM && (p.BW % 32 == 0 || 32 % p.BW == 0) &&
+                             (p.H == 1 || p.b_mode == 1 || p.H % p.BH == 0);
+    p.tma_epi = ((p.up2 && no_tma_up2) || p.res_f32 || p.out_f32 || !slab_is_box) ? 0 : 1;
+    p.share_box = 0;
     if (!ws) {
+        static const bool no_share = std::getenv("B200_NO_SHARE_BOX") != nullptr;  // experiments
         for (int bn : {256, 128, 64}) {
             if (!divides(bn) || ((ndot != 0 || mode == 1) && bn != Cout)) continue;
-            smem_bytes = plan_smem(p, bn, false, has_out, has_res, ndot, mode);
+            // BN = 256 with a plain staged output: one 4 KB slot per warp instead of two buys a 4th ring stage,
+            // and the kernel is TMA-latency bound with three (measured: 2 -> 3 stages = +17..32 %)
+            const bool share = bn == 256 && p.tma_epi && has_out && !has_res && p.gap == nullptr && ndot == 0 &&
+                               mode == 0 && !p.up2 && !no_share;
+            // staging boxes exist only for the TMA epilogue (mode 2 keeps its transposition blocks)
+            const bool st_out = has_out && (p.tma_epi || mode == 2), st_res = has_res && p.tma_epi;
+            smem_bytes = plan_smem(p, bn, false, st_out, st_res, ndot, mode, share);
             if (smem_bytes > 0) {
                 BN = bn;
+                p.share_box = share ? 1 : 0;
                 break;
             }
         }
@@ -921,13 +983,9 @@ static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, 
     // Staged (TMA) epilogue: per epilogue warp one {cw columns, bw, bh} box = its 32 rows x BN/2 columns
     // (two boxes when BN = 256), swizzled by the row width.  The 2x2-replicating store walks a
     // [B, 2H, 2W, ld] map with a traversal stride of 2 along w and h.
-    static const bool no_tma_up2 = std::getenv("B200_NO_TMA_UP2") != nullptr;
     tmOut = tmA;
     tmOut2 = tmA;
     tmRes = tmA;
-    const bool slab_is_box = p.BW * p.BH == kBlockM && (p.BW % 32 == 0 || 32 % p.BW == 0) &&
-                             (p.H == 1 || p.b_mode == 1 || p.H % p.BH == 0);
-    p.tma_epi = ((p.up2 && no_tma_up2) || p.res_f32 || p.out_f32 || !slab_is_box) ? 0 : 1;
     p.a_box_bytes = p.BW * p.BH * kBlockK * 2;
     if (p.tma_epi) {
         const int cw = BN / 2 < 64 ? BN / 2 : 64;

@@ -140,45 +140,59 @@ stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
 }
 
 // ------------------------------------------------------------- SE gate -----
-// SEBlock.fc on the pooled vector (model_module.py:34-40): gate = sigmoid(W2 gelu(W1 m + b1) + b2)
-// with m = gap_sum / npix.  One CTA per case; weights are passed transposed
-// (w1t [C, Cm], w2t [Cm, C]) so that consecutive threads read consecutive addresses.
-__global__ void se_gate_kernel(const float* __restrict__ gap_sum, float inv_npix, int C, int Cm,
-                               const float* __restrict__ w1t, const float* __restrict__ b1,
-                               const float* __restrict__ w2t, const float* __restrict__ b2,
-                               float* __restrict__ gate) {
-    extern __shared__ float sm[];  // C + Cm floats
-    float* s_m = sm;
-    float* s_h = sm + C;
-    const int b = blockIdx.x;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) s_m[c] = gap_sum[static_cast<size_t>(b) * C + c] * inv_npix;
-    __syncthreads();
-    for (int m = threadIdx.x; m < Cm; m += blockDim.x) {
-        float a = b1[m];
-        int c = 0;
-        for (; c + 8 <= C; c += 8) {  // 8 independent loads in flight per thread
-            float wv[8];
+// SEBlock.fc on the pooled vector (model_module.py:34-40): gate = sigmoid(W2 gelu(W1 m + b1) + b2) with
+// m = gap_sum / npix, as two small fp32 dense layers.  One CTA = 8 cases x 64 outputs; its 256 threads are
+// 64 output columns x 4 quarters of every 128-long K slice, so a thread issues 32 independent weight loads
+// per slice (the layer is L2-latency bound, not bandwidth bound) and reuses each for 8 cases; the four
+// partial sums meet in shared memory.  Weights are passed transposed ([in, out]): consecutive threads read
+// consecutive addresses.  ACT: 0 = GELU (hidden layer), 1 = sigmoid (gate).
+constexpr int kSeCases = 8;
+
+template <int ACT>
+__global__ void __launch_bounds__(256)
+se_dense_kernel(const float* __restrict__ in, float in_scale, int B, int K, int N, const float* __restrict__ wt,
+                const float* __restrict__ bias, float* __restrict__ out) {
+    __shared__ float s_in[kSeCases][128];
+    __shared__ float s_part[4][kSeCases][64];
+    const int tx = threadIdx.x & 63, kq = (threadIdx.x >> 6) * 32;
+    const int n = blockIdx.x * 64 + tx;
+    const int b0 = blockIdx.y * kSeCases;
+    float acc[kSeCases];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) wv[k] = __ldg(w1t + (c + k) * Cm + m);
+    for (int c = 0; c < kSeCases; ++c) acc[c] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 128) {
+        __syncthreads();
 #pragma unroll
-            for (int k = 0; k < 8; ++k) a = fmaf(wv[k], s_m[c + k], a);
+        for (int i = 0; i < 4; ++i) {
+            const int idx = threadIdx.x + i * 256;  // 8 cases x 128 k
+            const int r = idx >> 7, kk = idx & 127;
+            s_in[r][kk] = (b0 + r < B && k0 + kk < K) ? in[static_cast<size_t>(b0 + r) * K + k0 + kk] * in_scale : 0.f;
         }
-        for (; c < C; ++c) a = fmaf(__ldg(w1t + c * Cm + m), s_m[c], a);
-        s_h[m] = gelu_exact(a);
+        __syncthreads();
+        if (n < N && k0 + kq < K) {
+            float w[32];
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk)
+                w[kk] = k0 + kq + kk < K ? __ldg(wt + static_cast<size_t>(k0 + kq + kk) * N + n) : 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) {
+#pragma unroll
+                for (int c = 0; c < kSeCases; ++c) acc[c] = fmaf(w[kk], s_in[c][kq + kk], acc[c]);
+            }
+        }
     }
+#pragma unroll
+    for (int c = 0; c < kSeCases; ++c) s_part[kq >> 5][c][tx] = acc[c];
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a = b2[c];
-        int m = 0;
-        for (; m + 8 <= Cm; m += 8) {
-            float wv[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) wv[k] = __ldg(w2t + (m + k) * C + c);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a = fmaf(wv[k], s_h[m + k], a);
+    for (int i = 0; i < 2; ++i) {
+        const int idx = threadIdx.x + i * 256;  // 8 cases x 64 columns
+        const int c = idx >> 6, col = idx & 63;
+        const int nn = blockIdx.x * 64 + col, bb = b0 + c;
+        if (nn < N && bb < B) {
+            const float v = s_part[0][c][col] + s_part[1][c][col] + s_part[2][c][col] + s_part[3][c][col] + bias[nn];
+            out[static_cast<size_t>(bb) * N + nn] = ACT == 0 ? gelu_exact(v) : sigmoidf_(v);
         }
-        for (; m < Cm; ++m) a = fmaf(__ldg(w2t + m * C + c), s_h[m], a);
-        gate[static_cast<size_t>(b) * C + c] = sigmoidf_(a);
     }
 }
 
@@ -266,20 +280,40 @@ __global__ void tapsum_kernel(const float* __restrict__ d, int H, int W, const f
 // F.interpolate(mode='bilinear', align_corners=False) of an fp32 1-channel map (MaskHeadResize's fallback
 // path, model_module.py:205-211; it commutes with the 1x1 `out` convolution that follows it there, so it is
 // applied to the 1-channel logits instead of the 64-channel map).
-__global__ void resize_bilinear_c1_kernel(const float* __restrict__ in, int h, int w, float* __restrict__ out, int H,
-                                          int W, size_t total) {
-    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    if (i >= total) return;
-    const int ox = static_cast<int>(i % W), oy = static_cast<int>((i / W) % H);
-    const size_t b = i / (static_cast<size_t>(W) * H);
+// block (64, 4): thread (tx, ty) produces outputs x = 4 tx .. 4 tx + 3 of row blockIdx.y * 4 + ty of plane blockIdx.z
+// (grid.x strides over rows wider than 256); one 16-byte store per thread when the row allows it.
+__global__ void __launch_bounds__(256)
+resize_bilinear_c1_kernel(const float* __restrict__ in, int h, int w, float* __restrict__ out, int H, int W) {
+    const int oy = blockIdx.y * 4 + threadIdx.y;
+    const int ox0 = (blockIdx.x * 64 + threadIdx.x) * 4;
+    if (oy >= H || ox0 >= W) return;
+    const size_t plane = blockIdx.z;
     const float sy = fmaxf((oy + 0.5f) * (static_cast<float>(h) / H) - 0.5f, 0.f);
-    const float sx = fmaxf((ox + 0.5f) * (static_cast<float>(w) / W) - 0.5f, 0.f);
-    const int y0 = min(static_cast<int>(sy), h - 1), x0 = min(static_cast<int>(sx), w - 1);
-    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-    const float ly = sy - y0, lx = sx - x0;
-    const float* src = in + b * h * w;
-    out[i] = (1.f - ly) * ((1.f - lx) * src[y0 * w + x0] + lx * src[y0 * w + x1]) +
-             ly * ((1.f - lx) * src[y1 * w + x0] + lx * src[y1 * w + x1]);
+    const int y0 = min(static_cast<int>(sy), h - 1);
+    const int y1 = min(y0 + 1, h - 1);
+    const float ly = sy - y0;
+    const float* r0 = in + (plane * h + y0) * w;
+    const float* r1 = in + (plane * h + y1) * w;
+    const float sxs = static_cast<float>(w) / W;
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ox = min(ox0 + k, W - 1);
+        const float sx = fmaxf((ox + 0.5f) * sxs - 0.5f, 0.f);
+        const int x0 = min(static_cast<int>(sx), w - 1);
+        const int x1 = min(x0 + 1, w - 1);
+        const float lx = sx - x0;
+        o[k] = (1.f - ly) * ((1.f - lx) * __ldg(r0 + x0) + lx * __ldg(r0 + x1)) +
+               ly * ((1.f - lx) * __ldg(r1 + x0) + lx * __ldg(r1 + x1));
+    }
+    float* dst = out + (plane * H + oy) * W + ox0;
+    if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (ox0 + k < W) dst[k] = o[k];
+    }
 }
 
 // ------------------------------------------- mask head tail + attention ----
@@ -455,12 +489,14 @@ extern "C" int b200_stem(const float* x, int B, int C, int H, int W, int stride,
 }
 
 extern "C" int b200_se_gate(const float* gap_sum, int B, int C, int Cm, int npix, const float* w1t, const float* b1,
-                            const float* w2t, const float* b2, float* gate, void* stream) {
+                            const float* w2t, const float* b2, float* gate, float* hidden, void* stream) {
     if (B < 0 || C <= 0 || Cm <= 0 || npix <= 0) return -1;
     if (B == 0) return 0;
-    if (gap_sum == nullptr || gate == nullptr) return -2;
-    se_gate_kernel<<<B, 256, (C + Cm) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-        gap_sum, 1.0f / npix, C, Cm, w1t, b1, w2t, b2, gate);
+    if (gap_sum == nullptr || gate == nullptr || hidden == nullptr) return -2;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned rows = (B + kSeCases - 1) / kSeCases;
+    se_dense_kernel<0><<<dim3((Cm + 63) / 64, rows), 256, 0, s>>>(gap_sum, 1.0f / npix, B, C, Cm, w1t, b1, hidden);
+    se_dense_kernel<1><<<dim3((C + 63) / 64, rows), 256, 0, s>>>(hidden, 1.0f, B, Cm, C, w2t, b2, gate);
     return launch_status();
 }
 
@@ -528,9 +564,13 @@ extern "C" int b200_resize_bilinear_c1(const float* in, int B, int h, int w, flo
     if (B < 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return -1;
     if (B == 0) return 0;
     if (in == nullptr || out == nullptr) return -2;
-    const size_t total = static_cast<size_t>(B) * H * W;
-    resize_bilinear_c1_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        in, h, w, out, H, W, total);
+    if (B > 65535 * 64 || (H + 3) / 4 > 65535) return -3;
+    for (int b0 = 0; b0 < B; b0 += 65535) {  // gridDim.z limit
+        const int nb = B - b0 < 65535 ? B - b0 : 65535;
+        const dim3 grid((W + 255) / 256, (H + 3) / 4, nb);
+        resize_bilinear_c1_kernel<<<grid, dim3(64, 4), 0, static_cast<cudaStream_t>(stream)>>>(
+            in + static_cast<size_t>(b0) * h * w, h, w, out + static_cast<size_t>(b0) * H * W, H, W);
+    }
     return launch_status();
 }
 

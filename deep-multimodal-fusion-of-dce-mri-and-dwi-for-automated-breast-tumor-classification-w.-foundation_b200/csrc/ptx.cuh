@@ -206,4 +206,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
 }  // namespace b200

@@ -184,10 +184,10 @@ int b200_stem(const float* x, int B, int C, int H, int W, int stride, const floa
 /*
  * SEBlock.fc on pooled sums (code/model_module.py:34-40): gate[b,:] =
  * sigmoid(W2 gelu(W1 (gap_sum[b,:]/npix) + b1) + b2); w1t [C,Cm] and w2t [Cm,C] are the
- * conv weights transposed.
+ * conv weights transposed; `hidden` is caller-provided scratch [B, Cm] fp32 (the GELU layer's output).
  */
 int b200_se_gate(const float* gap_sum, int B, int C, int Cm, int npix, const float* w1t, const float* b1,
-                 const float* w2t, const float* b2, float* gate, void* stream);
+                 const float* w2t, const float* b2, float* gate, float* hidden, void* stream);
 
 /*
  * y = x * gate[b,c] * (1 + gamma * attn[b,p]) on a bf16 NHWC map (in place allowed).

@@ -340,3 +340,18 @@ def test_patchify_gate_and_feature_slices():
     torch.cuda.synchronize()
     assert _rel(buf[..., E:2 * E].reshape(B, n, E), t[:, 1:]) < 5e-3
     assert buf[..., :E].abs().max().item() == 0 and buf[..., 2 * E:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("B,C,Cm", [(256, 768, 384), (37, 128, 64), (5, 16, 8), (3, 6, 3)])
+def test_se_gate(B, C, Cm):
+    g = torch.Generator(device="cpu").manual_seed(B + C)
+    gap = (torch.randn(B, C, generator=g) * 50).to(DEV)
+    w1 = (torch.randn(Cm, C, generator=g) / math.sqrt(C)).to(DEV)
+    b1 = (torch.randn(Cm, generator=g) * 0.1).to(DEV)
+    w2 = (torch.randn(C, Cm, generator=g) / math.sqrt(Cm)).to(DEV)
+    b2 = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    gate = torch.empty(B, C, device=DEV)
+    nat.se_gate(gap, 196, w1.t().contiguous(), b1, w2.t().contiguous(), b2, gate)
+    torch.cuda.synchronize()
+    ref = torch.sigmoid(F.linear(F.gelu(F.linear(gap / 196, w1, b1)), w2, b2))
+    assert _rel(gate, ref) < 1e-5
