@@ -380,8 +380,11 @@ def main():
         if dom_ms:
             flops = gemm_flops(*dom_key)
             ach = flops / (dom_ms / 1e3) / 1e12
+            # DRAM bytes of this launch from the committed ncu --set full capture (profiles/r1_conv_gemm_ncu_full.csv:
+            # dram__bytes_read.sum + dram__bytes_write.sum at B = 1024, scaled by the batch); algorithmic = 2 maps
+            traffic = 1.03e9 * B / 1024 if args.workload == "c3" else None
             roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tf_sustained"], "traffic": None,
+                        "frac": ach / peaks["tf_sustained"], "traffic": traffic,
                         "kernel": dom_name,
                         "ms_per_launch": dom_ms, "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
                         "share_of_step": sum(prof[dom_key]) / total_ms if total_ms else None}

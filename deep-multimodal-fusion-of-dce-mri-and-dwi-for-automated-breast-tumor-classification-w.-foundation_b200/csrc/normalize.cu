@@ -22,57 +22,87 @@ namespace b200 {
 constexpr int kNormThreads = 256;
 
 // ------------------------------------------------------------------ DWI ----
-template <int VEC>  // float4 values per thread kept in registers
+template <int VEC>
 __global__ void __launch_bounds__(kNormThreads)
 dwi_normalize_reg_kernel(const float* __restrict__ x, float* __restrict__ out, int planes, int C, int n,
                          int skip_last, float z_lo, float z_hi, float* __restrict__ plane_mean) {
-    __shared__ double scratch[33];
+    // One block-wide barrier per plane.  Each thread accumulates sum(d) and sum(d^2) of d = x - pivot in fp64
+    // (pivot = the plane's first sample: shifting makes the one-pass variance as safe as the reference's two
+    // passes; fp64 removes what cancellation is left), the block reduces both together with the OUTPUT sum of
+    // the previous plane (the plane_mean by-product), and the scratch area is double buffered so that no
+    // second barrier is needed before it is rewritten.
+    constexpr int kWarps = kNormThreads / 32;
+    __shared__ double red[2][kWarps][3];
     const int n4 = n >> 2;
     const float range = z_hi - z_lo;
-    // Persistent CTAs: the next plane's loads are issued before the current plane's reductions, so HBM
-    // reads stay in flight across the block-wide barriers.
+    const float inv_range = 1.0f / range, off = -z_lo * inv_range;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     auto skipped = [&](int pl) { return skip_last && (pl % C) == C - 1; };
-    auto load = [&](int pl, float4 (&v)[VEC]) {
+    auto load = [&](int pl, float4 (&v)[VEC], float& pivot) {
         const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(pl) * n);
+        pivot = __ldg(reinterpret_cast<const float*>(src));
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             const int i = threadIdx.x + j * kNormThreads;
-            v[j] = (i < n4) ? __ldcs(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j] = (i < n4) ? __ldcs(src + i) : make_float4(pivot, pivot, pivot, pivot);  // d = 0 for padding lanes
         }
     };
     int plane = blockIdx.x;
     float4 v[VEC], vn[VEC];
-    if (plane < planes && !skipped(plane)) load(plane, v);
+    float pivot = 0.f, pivot_n = 0.f;
+    if (plane < planes && !skipped(plane)) load(plane, v, pivot);
+    double osum_prev = 0.0;  // this thread's share of the previous plane's output sum
+    int prev_plane = -1;     // plane whose output mean is still to be written (-1: none)
+    int buf = 0;
     for (; plane < planes; plane += gridDim.x) {
+        // the next plane's loads are issued before this plane's barrier, so HBM reads stay in flight across it
         const int next = plane + gridDim.x;
-        if (next < planes && !skipped(next)) load(next, vn);
+        if (next < planes && !skipped(next)) load(next, vn, pivot_n);
         float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(plane) * n);
-        if (skipped(plane)) {
-            for (int i = threadIdx.x; i < n4; i += kNormThreads) __stcs(dst + i, make_float4(0.f, 0.f, 0.f, 0.f));
-            if (plane_mean != nullptr && threadIdx.x == 0) plane_mean[plane] = 0.f;
-        } else {
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-            const double total = block_sum_f(s, scratch);
-            const float mean = static_cast<float>(total / n);
-            float q = 0.f;
+        const bool skip = skipped(plane);
+        double sd = 0.0, sq = 0.0;
+        if (!skip) {
+            const double pv = static_cast<double>(pivot);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                const int i = threadIdx.x + j * kNormThreads;
-                if (i < n4) {
-                    const float a = v[j].x - mean, b = v[j].y - mean, cc = v[j].z - mean, d = v[j].w - mean;
-                    q += (a * a + b * b) + (cc * cc + d * d);
-                }
+                const double a = static_cast<double>(v[j].x) - pv, b = static_cast<double>(v[j].y) - pv;
+                const double c = static_cast<double>(v[j].z) - pv, d = static_cast<double>(v[j].w) - pv;
+                sd += (a + b) + (c + d);
+                sq = fma(a, a, sq);
+                sq = fma(b, b, sq);
+                sq = fma(c, c, sq);
+                sq = fma(d, d, sq);
             }
-            const double ss = block_sum_f(q, scratch);
+        }
+        double r0 = warp_sum(sd), r1 = warp_sum(sq), r2 = warp_sum(osum_prev);
+        if (lane == 0) {
+            red[buf][warp][0] = r0;
+            red[buf][warp][1] = r1;
+            red[buf][warp][2] = r2;
+        }
+        __syncthreads();
+        r0 = r1 = r2 = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {  // broadcast reads, identical order in every thread
+            r0 += red[buf][w][0];
+            r1 += red[buf][w][1];
+            r2 += red[buf][w][2];
+        }
+        buf ^= 1;
+        if (plane_mean != nullptr && threadIdx.x == 0 && prev_plane >= 0) plane_mean[prev_plane] = static_cast<float>(r2 / n);
+        float osum = 0.f;
+        if (skip) {
+            for (int i = threadIdx.x; i < n4; i += kNormThreads) __stcs(dst + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else {
+            const double md = r0 / n;
+            const float mean = static_cast<float>(static_cast<double>(pivot) + md);
             // torch.std(): unbiased (n-1); n == 1 gives NaN there as well.
-            const float sd = fmaxf(static_cast<float>(sqrt(ss / static_cast<double>(n - 1))), 1e-6f);
+            const double var = (r1 - r0 * md) / static_cast<double>(n - 1);
+            const float sdev = fmaxf(static_cast<float>(sqrt(fmax(var, 0.0))), 1e-6f);
             // The two divisions of the reference become multiplications by correctly rounded reciprocals
             // (<= 2 ulp from the divided form, far inside the 1e-5 tolerance): IEEE fp32 division costs ~10
             // issue slots and would make this HBM-bound kernel ALU-bound.
-            const float inv_sd = 1.0f / sd, inv_range = 1.0f / range, off = -z_lo * inv_range;
-            float osum = 0.f;
+            const float inv_sd = 1.0f / sdev;
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 const int i = threadIdx.x + j * kNormThreads;
@@ -86,13 +116,22 @@ dwi_normalize_reg_kernel(const float* __restrict__ x, float* __restrict__ out, i
                     __stcs(dst + i, o);
                 }
             }
-            if (plane_mean != nullptr) {
-                const double om = block_sum_f(osum, scratch);
-                if (threadIdx.x == 0) plane_mean[plane] = static_cast<float>(om / n);
-            }
         }
+        osum_prev = static_cast<double>(osum);
+        prev_plane = plane;
+        pivot = pivot_n;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) v[j] = vn[j];
+    }
+    if (plane_mean != nullptr && prev_plane >= 0) {  // the last plane's output mean
+        const double r2 = warp_sum(osum_prev);
+        if (lane == 0) red[buf][warp][2] = r2;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kWarps; ++w) t += red[buf][w][2];
+            plane_mean[prev_plane] = static_cast<float>(t / n);
+        }
     }
 }
 
@@ -100,35 +139,57 @@ dwi_normalize_reg_kernel(const float* __restrict__ x, float* __restrict__ out, i
 __global__ void __launch_bounds__(kNormThreads)
 dwi_normalize_stream_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int n, int skip_last,
                             float z_lo, float z_hi, float* __restrict__ plane_mean) {
+    // Planes too large for registers (224 x 224 after the C4 resize): one statistics pass (pivot-shifted fp64
+    // sum / sum of squares, see the register kernel) and one apply pass that re-reads the plane from L2;
+    // 16-byte accesses when the plane allows it.
     __shared__ double scratch[33];
     const int plane = blockIdx.x;
     const int c = plane % C;
     const float* src = x + static_cast<size_t>(plane) * n;
     float* dst = out + static_cast<size_t>(plane) * n;
+    const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    const int n4 = vec ? n >> 2 : 0;
     if (skip_last && c == C - 1) {
-        for (int i = threadIdx.x; i < n; i += kNormThreads) dst[i] = 0.f;
+        for (int i = threadIdx.x; i < n4; i += kNormThreads)
+            __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int i = n4 * 4 + threadIdx.x; i < n; i += kNormThreads) dst[i] = 0.f;
         if (plane_mean != nullptr && threadIdx.x == 0) plane_mean[plane] = 0.f;
         return;
     }
-    double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += kNormThreads) s += static_cast<double>(src[i]);
-    const float mean = static_cast<float>(block_sum<double>(s, scratch) / n);
-    double q = 0.0;
-    for (int i = threadIdx.x; i < n; i += kNormThreads) {
-        const float d = src[i] - mean;
-        q += static_cast<double>(d * d);
+    const double pv = static_cast<double>(__ldg(src));
+    double sd = 0.0, sq = 0.0;
+    for (int i = threadIdx.x; i < n4; i += kNormThreads) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(src) + i);
+        const double a = f.x - pv, b = f.y - pv, cc = f.z - pv, d = f.w - pv;
+        sd += (a + b) + (cc + d);
+        sq = fma(a, a, fma(b, b, fma(cc, cc, fma(d, d, sq))));
     }
-    const double ss = block_sum<double>(q, scratch);
-    const float sd = fmaxf(static_cast<float>(sqrt(ss / static_cast<double>(n - 1))), 1e-6f);
-    const float range = z_hi - z_lo;
-    double osum = 0.0;
-    for (int i = threadIdx.x; i < n; i += kNormThreads) {
-        const float o = (fminf(fmaxf((src[i] - mean) / sd, z_lo), z_hi) - z_lo) / range;
-        osum += static_cast<double>(o);
+    for (int i = n4 * 4 + threadIdx.x; i < n; i += kNormThreads) {
+        const double a = src[i] - pv;
+        sd += a;
+        sq = fma(a, a, sq);
+    }
+    const double r0 = block_sum<double>(sd, scratch);
+    const double r1 = block_sum<double>(sq, scratch);
+    const double md = r0 / n;
+    const float mean = static_cast<float>(pv + md);
+    const float sdev = fmaxf(static_cast<float>(sqrt(fmax((r1 - r0 * md) / static_cast<double>(n - 1), 0.0))), 1e-6f);
+    const float inv_sd = 1.0f / sdev, inv_range = 1.0f / (z_hi - z_lo), off = -z_lo * inv_range;
+    auto map = [&](float v) { return fmaf(fminf(fmaxf((v - mean) * inv_sd, z_lo), z_hi), inv_range, off); };
+    float osum = 0.f;
+    for (int i = threadIdx.x; i < n4; i += kNormThreads) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(src) + i);
+        const float4 o = make_float4(map(f.x), map(f.y), map(f.z), map(f.w));
+        osum += (o.x + o.y) + (o.z + o.w);
+        __stcs(reinterpret_cast<float4*>(dst) + i, o);
+    }
+    for (int i = n4 * 4 + threadIdx.x; i < n; i += kNormThreads) {
+        const float o = map(src[i]);
+        osum += o;
         dst[i] = o;
     }
     if (plane_mean != nullptr) {
-        const double om = block_sum<double>(osum, scratch);
+        const double om = block_sum<double>(static_cast<double>(osum), scratch);
         if (threadIdx.x == 0) plane_mean[plane] = static_cast<float>(om / n);
     }
 }
@@ -139,14 +200,23 @@ constexpr int kNyulThreads = 512;
 
 // numpy.interp for one sample: xp ascending (ties allowed), float64 throughout, no FMA
 // contraction (matches the C loop in numpy's compiled_base.c).
-__device__ __forceinline__ double np_interp(double xv, const double* xp, const double* fp, const double* slope, int L) {
+__device__ __forceinline__ double np_interp(double xv, const double* xp, const float* xpf, const double* fp,
+                                            const double* slope, int L) {
     if (xv != xv) return xv;
     if (xv < xp[0]) return fp[0];
     if (xv > xp[L - 1]) return fp[L - 1];
-    int j = 0;  // largest j with xp[j] <= xv
-#pragma unroll 1
-    for (int i = 1; i < L; ++i)
-        if (xp[i] <= xv) j = i;
+    // largest j with xp[j] <= xv: a 4-step binary search on fp32 copies of the landmarks (L <= 16), then an
+    // exact fp64 fix-up (the fp32 guess is off by at most one when xv sits within rounding of a landmark), so
+    // the segment is the one numpy picks while ~20 fp64 compare/select pairs per sample are saved
+    const float xf = static_cast<float>(xv);
+    int j = 0;
+#pragma unroll
+    for (int step = 8; step >= 1; step >>= 1) {
+        const int t = j + step;
+        if (t < L && xpf[t] <= xf) j = t;
+    }
+    while (j > 0 && xp[j] > xv) --j;
+    while (j + 1 < L && xp[j + 1] <= xv) ++j;
     if (j == L - 1) return fp[j];
     if (xp[j] == xv) return fp[j];
     double r = __dadd_rn(__dmul_rn(slope[j], __dadd_rn(xv, -xp[j])), fp[j]);
@@ -172,6 +242,7 @@ __device__ __forceinline__ void nyul_apply(const float* s_val, int L, int c, int
                                            float* __restrict__ plane_mean) {
     __shared__ double s_orig[kMaxLandmarks], s_avg[kMaxLandmarks], s_std[kMaxLandmarks];
     __shared__ double s_slope1[kMaxLandmarks], s_slope2[kMaxLandmarks];
+    __shared__ float s_origf[kMaxLandmarks], s_avgf[kMaxLandmarks];
     __shared__ double scratch[33];
     const int tid = threadIdx.x;
     if (tid < L) {
@@ -185,6 +256,8 @@ __device__ __forceinline__ void nyul_apply(const float* s_val, int L, int c, int
         s_orig[t] = pv;
         s_avg[t] = avg_landmarks[c * L + t];
         s_std[t] = standard_scale[t];
+        s_origf[t] = static_cast<float>(pv);
+        s_avgf[t] = static_cast<float>(s_avg[t]);
     }
     __syncthreads();
     if (tid < L - 1) {
@@ -196,8 +269,8 @@ __device__ __forceinline__ void nyul_apply(const float* s_val, int L, int c, int
     double osum = 0.0;
     for (int i = tid; i < n; i += blockDim.x) {
         const double xv = static_cast<double>(load(i));
-        const double mid = np_interp(xv, s_orig, s_avg, s_slope1, L);
-        const float o = static_cast<float>(np_interp(mid, s_avg, s_std, s_slope2, L));
+        const double mid = np_interp(xv, s_orig, s_origf, s_avg, s_slope1, L);
+        const float o = static_cast<float>(np_interp(mid, s_avg, s_avgf, s_std, s_slope2, L));
         osum += static_cast<double>(o);
         __stcs(dst + i, o);
     }

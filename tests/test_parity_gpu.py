@@ -366,3 +366,33 @@ def test_vit_adapter_pipeline_vs_golden_reference():
     decided = (top2[:, 0] - top2[:, 1]) > 2 * worst["S/fusion/logits"] * ref_logits.abs().max()
     assert decided.any()
     assert torch.equal(lf.float().cpu().argmax(1)[decided], ref_logits.argmax(1)[decided])
+
+
+def test_full_size_batch_is_the_small_batches_stacked():
+    """BASELINE.json's full C3 size (B = 1024 per GPU), through a size-independent property: inference has no
+    cross-case operation, so every case of the 1024-batch must come out as it does in a 16-case batch (and the
+    16-case batches are the ones checked against the oracle above).  Covers the persistent-kernel tile loops,
+    the > 65 535-row grids and the channel-sum atomics at full size."""
+    from pipeline import FusionPipeline
+
+    p, sds, mods = _build()
+    n = 1024
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(64, seed=99, kind="S")
+    reps = n // 64
+    scale = torch.linspace(0.5, 1.5, reps).repeat_interleave(64).view(n, 1, 1, 1)  # no two cases identical
+    dwi_raw, dce_raw = dwi_raw.repeat(reps, 1, 1, 1) * scale, dce_raw.repeat(reps, 1, 1, 1) * scale.clamp(max=1.0)
+    nyul = b_pre.NyulStandardizer()
+    nyul.fit(list(dce_raw[:8]), num_channels=6)
+    pipe = FusionPipeline(mods["dwi"], mods["dce"], mods["fusion"], nyul).eval()
+    big_d, big_c, big_f = pipe.forward_raw(dwi_raw.to(DEV), dce_raw.to(DEV), return_all=True)
+    torch.cuda.synchronize()
+    assert big_f[0].shape == (n, 4) and torch.isfinite(big_f[0]).all()
+    for lo in (0, 496, 1008):  # first, middle and last 16 cases
+        sl = slice(lo, lo + 16)
+        s_d, s_c, s_f = pipe.forward_raw(dwi_raw[sl].to(DEV), dce_raw[sl].to(DEV), return_all=True)
+        # float atomics (channel sums) make runs agree to fp32 round-off rather than bitwise
+        assert torch.allclose(big_f[0][sl], s_f[0], rtol=1e-3, atol=1e-4)
+        assert torch.allclose(big_f[1][sl], s_f[1], rtol=1e-3, atol=1e-3)
+        assert torch.allclose(big_d[1]["raw_feats"][2][sl].float(), s_d[1]["raw_feats"][2].float(), rtol=2e-2, atol=2e-2)
+        assert torch.equal(big_d[2][sl], s_d[2]) or torch.allclose(big_d[2][sl], s_d[2], rtol=1e-3, atol=1e-4)
+        assert torch.allclose(big_c[0][sl], s_c[0], rtol=1e-3, atol=1e-4)
