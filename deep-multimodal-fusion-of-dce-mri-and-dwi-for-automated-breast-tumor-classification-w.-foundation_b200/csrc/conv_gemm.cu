@@ -202,7 +202,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], kNumEpiWarps);
+            mbar_init(&tempty[s], MODE == 1 ? kNumEpiWarps / 2 : kNumEpiWarps);  // mode 1: one warp set per stage
         }
         for (int s = 0; s < 2 * kNumEpiWarps; ++s) mbar_init(&resbar[s], 1);
         mbar_init(wbar, 1);
@@ -294,6 +294,125 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (acc == 0) acc_phase ^= 1;
             }
         }
+    } else if (MODE == 1 && warp >= kEpiWarp0) {
+        // Softmax-numerator epilogue (Q.K^T): out = bf16(exp(alpha * acc - rowmax)) over the n_valid real columns,
+        // zeros beyond, and 1 / rowsum per row.  The MMA side of these launches is tiny (K = head_dim), so the
+        // epilogue is the whole cost: each accumulator stage belongs to ONE set of four warps (one per TMEM lane
+        // quadrant), a warp owns complete rows - no row max / row sum exchange between warps, no named barriers -
+        // and the two sets work on consecutive tiles concurrently.  A warp's four 64-column output boxes rotate
+        // through its two 4 KB staging slots.
+        const int ew = warp - kEpiWarp0;
+        const int q = warp & 3;
+        const int set = ew >> 2;  // accumulator stage this warp serves
+        uint8_t* const obuf = s_union + ew * T::kWarpBoxBytes;
+        const int swz = ((lane * T::kRowBytes) >> 7) & (T::kRowBytes / 16 - 1);
+        const int row_off = lane * T::kRowBytes;
+        const float k2 = p.alpha * 1.4426950408889634f;  // exp(x) = exp2(x * log2 e)
+        constexpr int kChunks = BN / kChunk;             // 8 chunks of 32 columns
+        constexpr int kChunksPerBox = T::kBoxCols / kChunk;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int tile = blockIdx.x;
+        for (int it = 0; it < n_iters; ++it, tile += gridDim.x) {
+            if (acc == set) {
+                const int m_tile = tile / p.n_tiles;
+                const int w0 = (m_tile % p.tiles_w) * p.BW;
+                const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.BH;
+                const int b = m_tile / (p.tiles_w * p.tiles_h);
+                const int slab_w = w0 + (q * 32) % p.BW, slab_h = h0 + (q * 32) / p.BW;
+                const int trow = q * 32 + lane;
+                const int pw = w0 + trow % p.BW, ph = h0 + trow / p.BW;
+                const bool valid = pw < p.W && ph < p.H;
+                const long long pix = (static_cast<long long>(b) * p.H + ph) * p.W + pw;
+                if (lane == 0) tma_store_wait_read<0>();  // the previous tile's boxes have left the staging slots
+                __syncwarp();
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t tm_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+                // pass 1: row maximum of the raw accumulator over the valid columns (alpha > 0 scales it afterwards)
+                float m = -INFINITY;
+#pragma unroll
+                for (int ch = 0; ch < kChunks; ch += 2) {
+                    const int c0 = ch * kChunk;
+                    if (c0 >= p.n_valid) break;  // warp-uniform
+                    uint32_t ra[kChunk], rb[kChunk];
+                    tmem_ld_32x32(tm_row + c0, ra);
+                    tmem_ld_32x32(tm_row + c0 + kChunk, rb);
+                    tmem_ld_wait();
+                    if (c0 + 2 * kChunk <= p.n_valid) {
+#pragma unroll
+                        for (int j = 0; j < kChunk; ++j)
+                            m = fmaxf(m, fmaxf(__uint_as_float(ra[j]), __uint_as_float(rb[j])));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kChunk; ++j) {
+                            if (c0 + j < p.n_valid) m = fmaxf(m, __uint_as_float(ra[j]));
+                            if (c0 + kChunk + j < p.n_valid) m = fmaxf(m, __uint_as_float(rb[j]));
+                        }
+                    }
+                }
+                const float row_max2 = m * k2;
+                // pass 2: numerators, bf16 rounding, row sum, staged stores
+                float row_sum = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < kChunks; ++ch) {
+                    const int n0 = ch * kChunk;
+                    const int bx = ch / kChunksPerBox;
+                    uint8_t* const slot = obuf + (bx & 1) * T::kBoxBytes;
+                    const int c16 = (ch % kChunksPerBox) * (kChunk / 8);
+                    uint4 o[4];
+                    if (n0 < p.n_valid) {  // warp-uniform
+                        uint32_t r[kChunk];
+                        tmem_ld_32x32(tm_row + n0, r);
+                        tmem_ld_wait();
+                        const bool all_real = n0 + kChunk <= p.n_valid;
+                        uint32_t hb[kChunk / 2];
+#pragma unroll
+                        for (int j = 0; j < kChunk; j += 2) {
+                            float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), k2, -row_max2));
+                            float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), k2, -row_max2));
+                            if (!all_real) {
+                                if (n0 + j >= p.n_valid) e0 = 0.f;
+                                if (n0 + j + 1 >= p.n_valid) e1 = 0.f;
+                            }
+                            // round to bf16 first: the row sum must match what the P.V GEMM will read
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+                            hb[j / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+                            row_sum += __uint_as_float(hb[j / 2] << 16) + __uint_as_float(hb[j / 2] & 0xffff0000u);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o[j] = make_uint4(hb[4 * j], hb[4 * j + 1], hb[4 * j + 2], hb[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o[j] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    if (ch % kChunksPerBox == 0 && bx >= 2) {  // the slot still holds box bx - 2: wait for its TMA read
+                        if (lane == 0) tma_store_wait_read<1>();
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(slot + row_off + (((c16 + j) ^ swz) << 4)) = o[j];
+                    if (ch % kChunksPerBox == kChunksPerBox - 1) {  // box complete
+                        if (ch == kChunks - 1) {  // last TMEM read of the tile is done: release the accumulator stage
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty[acc]);
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_4d(&tmOut, slot, bx * T::kBoxCols, slab_w, slab_h, b);
+                            tma_store_commit();
+                        }
+                    }
+                }
+                if (valid) p.rowsum_inv[pix] = 1.0f / row_sum;
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (lane == 0) tma_store_wait_all<0>();
     } else if (warp >= kEpiWarp0) {
         const int ew = warp - kEpiWarp0;
         const int q = warp & 3;    // TMEM lane quadrant this warp may read (rows q*32 .. q*32+31 of the tile)

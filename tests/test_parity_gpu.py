@@ -390,9 +390,11 @@ def test_full_size_batch_is_the_small_batches_stacked():
     for lo in (0, 496, 1008):  # first, middle and last 16 cases
         sl = slice(lo, lo + 16)
         s_d, s_c, s_f = pipe.forward_raw(dwi_raw[sl].to(DEV), dce_raw[sl].to(DEV), return_all=True)
-        # float atomics (channel sums) make runs agree to fp32 round-off rather than bitwise
-        assert torch.allclose(big_f[0][sl], s_f[0], rtol=1e-3, atol=1e-4)
-        assert torch.allclose(big_f[1][sl], s_f[1], rtol=1e-3, atol=1e-3)
-        assert torch.allclose(big_d[1]["raw_feats"][2][sl].float(), s_d[1]["raw_feats"][2].float(), rtol=2e-2, atol=2e-2)
-        assert torch.equal(big_d[2][sl], s_d[2]) or torch.allclose(big_d[2][sl], s_d[2], rtol=1e-3, atol=1e-4)
-        assert torch.allclose(big_c[0][sl], s_c[0], rtol=1e-3, atol=1e-4)
+        # float atomics (channel sums) make two runs agree to fp32 round-off in the gates, which flips the bf16
+        # rounding of an occasional feature-map element (one bf16 ulp = 0.4 %): outputs agree to well below the
+        # parity tolerance, not bitwise
+        assert _relmax(big_f[0][sl], s_f[0]) <= 2e-3
+        assert _relmax(big_f[1][sl], s_f[1]) <= 5e-3
+        assert _relmax(big_d[1]["raw_feats"][2][sl], s_d[1]["raw_feats"][2]) <= 1e-2
+        assert _relmax(big_d[2][sl], s_d[2]) <= 5e-3
+        assert _relmax(big_c[0][sl], s_c[0]) <= 2e-3
