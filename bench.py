@@ -380,9 +380,12 @@ def main():
         if dom_ms:
             flops = gemm_flops(*dom_key)
             ach = flops / (dom_ms / 1e3) / 1e12
-            # DRAM bytes of this launch from the committed ncu --set full capture (profiles/r1_conv_gemm_ncu_full.csv:
-            # dram__bytes_read.sum + dram__bytes_write.sum at B = 1024, scaled by the batch); algorithmic = 2 maps
-            traffic = 1.03e9 * B / 1024 if args.workload == "c3" else None
+            # DRAM bytes of this launch from the committed ncu --set full captures (dram__bytes_read.sum +
+            # dram__bytes_write.sum, scaled by the batch)
+            # profiles/r1_conv_gemm_ncu_full.csv: 539 + 495 MB (C3 conv, B = 1024); 82 + 252 MB (C4 fc1, 50 432 rows)
+            traffic = 1.034e9 * B / 1024 if args.workload == "c3" else None
+            if args.workload == "c4" and dom_key[0] == "b200_conv_gemm_ex" and tuple(dom_key[1][3:]) == (768, 3072, 1):
+                traffic = 334.5e6 * dom_key[1][2] / 50432
             roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                         "frac": ach / peaks["tf_sustained"], "traffic": traffic,
                         "kernel": dom_name,
