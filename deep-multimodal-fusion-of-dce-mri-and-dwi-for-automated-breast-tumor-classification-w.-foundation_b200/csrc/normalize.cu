@@ -239,7 +239,7 @@ __device__ __forceinline__ void nyul_apply(const float* s_val, int L, int c, int
                                            const double* __restrict__ avg_landmarks,
                                            const double* __restrict__ standard_scale,
                                            const double* __restrict__ gamma, Load load, float* __restrict__ dst,
-                                           float* __restrict__ plane_mean) {
+                                           float* __restrict__ plane_mean, const float* __restrict__ gsrc = nullptr) {
     __shared__ double s_orig[kMaxLandmarks], s_avg[kMaxLandmarks], s_std[kMaxLandmarks];
     __shared__ double s_slope1[kMaxLandmarks], s_slope2[kMaxLandmarks];
     __shared__ float s_origf[kMaxLandmarks], s_avgf[kMaxLandmarks];
@@ -267,12 +267,24 @@ __device__ __forceinline__ void nyul_apply(const float* s_val, int L, int c, int
     }
     __syncthreads();
     double osum = 0.0;
-    for (int i = tid; i < n; i += blockDim.x) {
-        const double xv = static_cast<double>(load(i));
-        const double mid = np_interp(xv, s_orig, s_origf, s_avg, s_slope1, L);
-        const float o = static_cast<float>(np_interp(mid, s_avg, s_avgf, s_std, s_slope2, L));
-        osum += static_cast<double>(o);
-        __stcs(dst + i, o);
+    auto map = [&](float v) {
+        const double mid = np_interp(static_cast<double>(v), s_orig, s_origf, s_avg, s_slope1, L);
+        return static_cast<float>(np_interp(mid, s_avg, s_avgf, s_std, s_slope2, L));
+    };
+    if (gsrc != nullptr && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(gsrc) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        // plane read straight from global / L2: 16-byte loads and stores, four independent interpolations per trip
+        for (int i = tid; i < (n >> 2); i += blockDim.x) {
+            const float4 q4 = __ldg(reinterpret_cast<const float4*>(gsrc) + i);
+            const float4 o = make_float4(map(q4.x), map(q4.y), map(q4.z), map(q4.w));
+            osum += (static_cast<double>(o.x) + static_cast<double>(o.y)) + (static_cast<double>(o.z) + static_cast<double>(o.w));
+            __stcs(reinterpret_cast<float4*>(dst) + i, o);
+        }
+    } else {
+        for (int i = tid; i < n; i += blockDim.x) {
+            const float o = map(load(i));
+            osum += static_cast<double>(o);
+            __stcs(dst + i, o);
+        }
     }
     if (plane_mean != nullptr) {
         const double om = block_sum<double>(osum, scratch);
@@ -506,25 +518,52 @@ nyul_transform_large_kernel(const float* __restrict__ x, float* __restrict__ out
         const int nu = s_nu;
         for (int i = tid; i < nu * 256; i += kNyulThreads) (&s_hist[0][0])[i] = 0;
         __syncthreads();
-        const int n_round = (n + kNyulThreads - 1) / kNyulThreads * kNyulThreads;  // whole warps stay converged
-        for (int i = tid; i < n_round; i += kNyulThreads) {
-            int slot = -1;
-            if (i < n) {
-                const uint32_t key = nyul_ordkey(pass == 0 ? __ldcs(src + i) : __ldg(src + i));
-                int u = 0;
-                if (pass != 0) {
-                    const uint32_t hi = key >> (shift + 8);
-                    u = -1;
-                    for (int q = 0; q < nu; ++q)
-                        if (s_uprefix[q] == hi) {
-                            u = q;
-                            break;
-                        }
-                }
-                if (u >= 0) slot = u * 256 + static_cast<int>((key >> shift) & 255u);
+        // four samples per thread and trip (one 16-byte load when the plane allows it): the passes are bound by the
+        // L2 round trip of the load, not by arithmetic
+        const bool vec = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+        const int n_trip = (n + 4 * kNyulThreads - 1) / (4 * kNyulThreads);  // whole warps stay converged
+        for (int t = 0; t < n_trip; ++t) {
+            const int i0 = (t * kNyulThreads + tid) * 4;
+            float f[4];
+            if (vec && i0 + 3 < n) {
+                const float4 q4 = __ldg(reinterpret_cast<const float4*>(src + i0));
+                f[0] = q4.x; f[1] = q4.y; f[2] = q4.z; f[3] = q4.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) f[e] = i0 + e < n ? __ldg(src + i0 + e) : 0.f;
             }
-            const uint32_t peers = __match_any_sync(0xffffffffu, slot);
-            if (slot >= 0 && lane == __ffs(peers) - 1) atomicAdd(&(&s_hist[0][0])[slot], __popc(peers));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int slot = -1;
+                if (i0 + e < n) {
+                    const uint32_t key = nyul_ordkey(f[e]);
+                    int u = 0;
+                    if (pass != 0) {
+                        const uint32_t hi = key >> (shift + 8);
+                        u = -1;
+                        for (int q = 0; q < nu; ++q)
+                            if (s_uprefix[q] == hi) {
+                                u = q;
+                                break;
+                            }
+                    }
+                    if (u >= 0) slot = u * 256 + static_cast<int>((key >> shift) & 255u);
+                }
+                // Histogram update.  Two rounds of warp aggregation (the lowest active lane's slot, everybody who
+                // shares it, one atomic for the group) catch the heavy ties - a zero background puts most of a warp
+                // on one slot - and whoever is left adds individually: distinct slots do not contend.
+                uint32_t active = __ballot_sync(0xffffffffu, slot >= 0);
+#pragma unroll
+                for (int round = 0; round < 2; ++round) {
+                    if (active == 0u) break;  // warp-uniform
+                    const int leader = __ffs(active) - 1;
+                    const int s0 = __shfl_sync(0xffffffffu, slot, leader);
+                    const uint32_t same = __ballot_sync(0xffffffffu, slot == s0) & active;
+                    if (lane == leader) atomicAdd(&(&s_hist[0][0])[s0], __popc(same));
+                    active &= ~same;
+                }
+                if ((active >> lane) & 1u) atomicAdd(&(&s_hist[0][0])[slot], 1);
+            }
         }
         __syncthreads();
         if (tid < R) {
@@ -561,7 +600,7 @@ nyul_transform_large_kernel(const float* __restrict__ x, float* __restrict__ out
     if (tid < R) s_val[tid] = nyul_ordkey_inv(s_prefix[tid]);
     __syncthreads();
     nyul_apply(s_val, L, c, n, plane, avg_landmarks, standard_scale, gamma, [&](int i) { return __ldg(src + i); }, dst,
-               plane_mean);
+               plane_mean, src);
 }
 
 __global__ void __launch_bounds__(kNormThreads)
