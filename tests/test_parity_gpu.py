@@ -398,3 +398,35 @@ def test_full_size_batch_is_the_small_batches_stacked():
         assert _relmax(big_d[1]["raw_feats"][2][sl], s_d[1]["raw_feats"][2]) <= 1e-2
         assert _relmax(big_d[2][sl], s_d[2]) <= 5e-3
         assert _relmax(big_c[0][sl], s_c[0]) <= 2e-3
+
+
+@pytest.mark.parametrize("sizes", [(1, 3, 5)])
+def test_odd_batch_sizes_match_the_16_case_batch(sizes):
+    """Ragged tails everywhere (row tiles, persistent-grid remainders, SE / head CTAs): batches of 1, 3 and 5 cases
+    give what the same cases give inside a 16-case batch, for the CNN path and for the ViT-adapter path."""
+    from test_oracle_golden import vit_parameters
+
+    p, sds, mods = _build()
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(16, seed=55, kind="S")
+    dwi = (dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)).to(DEV)
+    dce = dce_raw.to(DEV)
+    ref = _run_product(mods, dwi, dce)
+    for n in sizes:
+        got = _run_product(mods, dwi[:n], dce[:n])
+        assert _relmax(got[2][0], ref[2][0][:n]) <= 2e-3                       # fusion logits
+        assert _relmax(got[2][1], ref[2][1][:n]) <= 5e-3                       # fusion mask logits
+        assert _relmax(got[0][1]["proj_pairs"][3], ref[0][1]["proj_pairs"][3][:n]) <= 1e-2
+    # ViT-adapter encoders (DCE): 1 and 3 cases against a 4-case batch
+    shapes = gu.load_shapes("vit")
+    pv, backbones = vit_parameters()
+    enc = b_mm.ModelMaskHeadBackbone("dce", pv, backbones["dce"])
+    enc.load_state_dict(op.seeded_state_dict(shapes["dce"], seed=11))
+    enc.to(DEV).eval()
+    x = op.synthetic_raw(4, seed=56, size=224, kind="S")[1].to(DEV)
+    with torch.no_grad():
+        l4, a4, m4 = enc(x)
+        for n in (1, 3):
+            ln, an, mn = enc(x[:n])
+            assert _relmax(ln, l4[:n]) <= 2e-3 and _relmax(mn, m4[:n]) <= 5e-3
+            assert _relmax(an["raw_feats"][2], a4["raw_feats"][2][:n]) <= 1e-2
+    torch.cuda.synchronize()
