@@ -360,8 +360,9 @@ def main():
             if key is None:
                 return None
             if name == "b200_conv_gemm_ex":      # (B, H, W, Cin, Cout, taps)
-                b_, h_, w_, ci, co, tp = key
-                return 2.0 * b_ * (h_ * w_ // (4 if tp == 4 else 1)) * ci * co * tp
+                b_, h_, w_, ci, co, tp = key[:6]
+                st = 2 if tp == 4 else (key[6] if len(key) > 6 else 1)
+                return 2.0 * b_ * (h_ * w_ // (st * st)) * ci * co * tp
             if name == "b200_linear":            # (M, K, N)
                 return 2.0 * key[0] * key[1] * key[2]
             if name == "b200_gemm_batched":      # (batch, heads, M, K, N, mode)

@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _lib = None
 
@@ -69,7 +69,7 @@ SIGNATURES = {
     "b200_abi_version": [],
     "b200_conv_gemm": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_conv_gemm_ex": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _F, _P, _I, _I, _I,
-                          _I, _I, _I, _P],
+                          _I, _I, _I, _I, _P],
     "b200_resize_bilinear_c1": [_P, _I, _I, _I, _P, _I, _I, _P],
     "b200_mask_attention": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P],
     "b200_tapsum": [_P, _I, _I, _I, _P, _P, _P],
@@ -178,7 +178,7 @@ def _bf16_map(t, name):
 
 
 def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0, out=None, up2=False, gap=None,
-              cin=None, store=True, n_split=None, act2=0, out2=None, dot_w=None, dot_out=None, dot_bias=0.0):
+              cin=None, store=True, n_split=None, act2=0, out2=None, dot_w=None, dot_out=None, dot_bias=0.0, stride=1):
     """x [B,H,W,ld] bf16 NHWC (channels [0,cin) used); w [Cout, taps*cin] bf16.  Returns `out`
     (or (out, out2) when n_split is given: channels [n_split, Cout) form a second layer on the same input)."""
     _bf16_map(x, "x")
@@ -187,11 +187,12 @@ def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0,
     cout = w.shape[0]
     assert w.dtype == torch.bfloat16 and w.is_contiguous() and w.shape[1] == taps * cin
     n1 = cout if n_split is None else n_split
+    cs = 2 if taps == 4 else stride
     if out is None and store:
-        oh, ow = (2 * H, 2 * W) if up2 else ((H // 2, W // 2) if taps == 4 else (H, W))
+        oh, ow = (2 * H, 2 * W) if up2 else (H // cs, W // cs)
         out = torch.empty((B, oh, ow, n1), dtype=torch.bfloat16, device=x.device)
     if n_split is not None and out2 is None:
-        out2 = torch.empty((B, H, W, cout - n_split), dtype=torch.bfloat16, device=x.device)
+        out2 = torch.empty((B, H // cs, W // cs, cout - n_split), dtype=torch.bfloat16, device=x.device)
     if gap is not None and taps == 4:
         raise B200NativeError("gap with the strided patch-embedding conv is not supported")
     out_ld = out.shape[-1] if out is not None else 0
@@ -199,11 +200,11 @@ def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0,
         _bf16_map(out, "out")
     if res is not None:
         _bf16_map(res, "res")
-    _call("b200_conv_gemm_ex", (B, H, W, cin, cout, taps), _ptr(x), x_ld, _ptr(w), _ptr(scale), _ptr(bias), _ptr(res),
+    _call("b200_conv_gemm_ex", (B, H, W, cin, cout, taps) if stride == 1 else (B, H, W, cin, cout, taps, stride), _ptr(x), x_ld, _ptr(w), _ptr(scale), _ptr(bias), _ptr(res),
           res.shape[-1] if res is not None else 0, res_mode, act, _ptr(out), out_ld,
           1 if up2 else 0, _ptr(gap), n1, _ptr(out2), out2.shape[-1] if out2 is not None else 0, act2,
           _ptr(dot_w), dot_w.shape[0] if dot_w is not None else 0, float(dot_bias), _ptr(dot_out), B, H, W, cin, cout,
-          taps, _stream())
+          taps, stride, _stream())
     return out if n_split is None else (out, out2)
 
 

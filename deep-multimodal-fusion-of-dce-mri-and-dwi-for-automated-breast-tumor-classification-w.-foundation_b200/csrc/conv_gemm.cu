@@ -1148,14 +1148,14 @@ extern "C" int b200_conv_gemm(const void* x, int x_ld, const void* w, const floa
                               const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
                               float* gap, int B, int H, int W, int Cin, int Cout, int taps, void* stream) {
     return b200_conv_gemm_ex(x, x_ld, w, scale, bias, res, res_ld, res_mode, act, out, out_ld, up2, gap, Cout, nullptr,
-                             0, 0, nullptr, 0, 0.f, nullptr, B, H, W, Cin, Cout, taps, stream);
+                             0, 0, nullptr, 0, 0.f, nullptr, B, H, W, Cin, Cout, taps, 1, stream);
 }
 
 extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
                                  const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
                                  float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w,
                                  int ndot, float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout,
-                                 int taps, void* stream) {
+                                 int taps, int stride, void* stream) {
     using namespace b200;
     if (dot_w == nullptr) ndot = 0;
     if (ndot != 0 && ndot != 1 && ndot != 9) return -18;
@@ -1168,7 +1168,10 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
         return -5;
 
     ConvGemmParams p{};
-    const int cs = taps == 4 ? 2 : 1;  // taps == 4: 2x2 kernel, stride 2, no padding (patch embedding)
+    if (stride != 1 && stride != 2) return -6;
+    // taps == 4: 2x2 kernel, stride 2, no padding (patch embedding); taps 1 / 9 with stride 2: the strided 1x1 and
+    // 3x3 (padding 1) convolutions of down-sampling blocks and of the mask head (input pixel 2*o + tap - pad)
+    const int cs = taps == 4 ? 2 : stride;
     if (cs == 2 && (H % 2 != 0 || W % 2 != 0 || up2 || H == 1)) return -6;
     const int Ho = H / cs, Wo = W / cs;  // output map
     if (H == 1) {  // plain GEMM over W rows: 128-row boxes, ragged tail handled by TMA OOB fill / clipping

@@ -350,6 +350,46 @@ def _proj_pack(pr, dev):
     return p
 
 
+def _mask_down_pack(mh, dev):
+    """MaskHeadResize's strided stacks (reference :153-181): map size -> [(weight [64, 9*64] bf16, bias)] of its
+    3x3 / stride-2 convs (each followed by GELU)."""
+    out = {}
+    for size, name in ((64, "down_64_to_32"), (128, "down_128_to_32"), (256, "down_256_to_32"), (512, "down_512_to_32")):
+        seq = getattr(mh, name, None)
+        if seq is not None:
+            out[size] = [(_conv_w_bf16(m, dev), _f32(m.bias, dev)) for m in seq if isinstance(m, nn.Conv2d)]
+    return out
+
+
+def _mask_head(mk, m_in, mask_size):
+    """MaskHeadResize.forward (reference :197-215) on an NHWC bf16 map -> mask logits [B,1,S,S] fp32 at the
+    head's output size and, when the `pre` map is not resized (32 x 32 input), nothing else.  The final 1x1
+    `out` conv (64 -> 1) always runs as an fp32 dot product inside the epilogue of the GEMM before it."""
+    B, H, W, _ = m_in.shape
+    dev = m_in.device
+    out_w, out_b = mk["out_w"].view(1, -1), mk["out_b_host"]
+    if H == mask_size or H not in mk["down"]:
+        # identity path, or the bilinear fallback (:205-211): resize and the 1x1 `out` conv are both linear and the
+        # resize acts per channel, so the 1-channel logits are resized instead of the 64-channel map
+        small = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+        nat.conv_gemm(m_in, mk["pre_w"], taps=1, bias=mk["pre_b"], store=False, dot_w=out_w, dot_out=small, dot_bias=out_b)
+        if H == mask_size:
+            return small
+        mask = torch.empty((B, 1, mask_size, mask_size), dtype=torch.float32, device=dev)
+        nat.resize_bilinear_c1(small.view(B, H, W), mask.view(B, mask_size, mask_size))
+        return mask
+    # strided stacks: pre (1x1, bias) -> [3x3 stride 2 + GELU] x n -> out
+    t = nat.conv_gemm(m_in, mk["pre_w"], taps=1, bias=mk["pre_b"])
+    stack = mk["down"][H]
+    for w, b in stack[:-1]:
+        t = nat.conv_gemm(t, w, taps=9, bias=b, act=1, stride=2)
+    w, b = stack[-1]
+    S = t.shape[1] // 2
+    mask = torch.empty((B, 1, S, S), dtype=torch.float32, device=dev)
+    nat.conv_gemm(t, w, taps=9, bias=b, act=1, stride=2, store=False, dot_w=out_w, dot_out=mask, dot_bias=out_b)
+    return mask
+
+
 def _block_pack(blk, dev):
     p = {"bott": []}
     for bt in blk.bottlenecks:
@@ -612,10 +652,11 @@ class ModelMaskHeadBackbone(nn.Module):
         blocks = {"b1": self.block1, "b2": self.block2}
         if not self.use_hybrid_transformer:
             blocks["b3"] = self.block3
-        for name, blk in blocks.items():
-            if name != "b1" and blk.stride != 1:
-                raise NotImplementedError("stride-2 block2/block3 are not built (reference default is stride 1)")
         pk = {name: _block_pack(blk, dev) for name, blk in blocks.items()}
+        for name, blk in blocks.items():
+            pk[name]["stride"] = blk.stride
+            if blk.stride not in (1, 2) or (blk.stride == 2 and blk.skip is None):
+                raise NotImplementedError("block strides other than 1 / 2")
         if self.use_hybrid_transformer:
             pk["tr"] = _transformer_pack(self.transformer, self.trans_out_proj, dev)
         if self.use_backbone:
@@ -670,6 +711,7 @@ class ModelMaskHeadBackbone(nn.Module):
             pk["mask"] = {
                 "align_w": aw, "align_s": s, "align_b": b,
                 "pre_w": _conv_w_bf16(mh.pre, dev), "pre_b": _f32(mh.pre.bias, dev),
+                "down": _mask_down_pack(mh, dev),
                 "out_w": _f32(mh.out.weight.flatten(), dev), "out_b": _f32(mh.out.bias, dev),
                 "out_b_host": float(mh.out.bias.detach().float().cpu().item()),
                 "attn": (mproc[0].out_channels, _f32(mproc[0].weight.flatten(), dev), _f32(mproc[1].weight, dev),
@@ -708,7 +750,7 @@ class ModelMaskHeadBackbone(nn.Module):
             # skip conv and first bottleneck conv read the same map: one GEMM, two output segments
             f = pk["fused_in"]
             skip, mid = nat.conv_gemm(x, f["w"], taps=1, scale=f["s"], bias=f["b"], act=0, n_split=f["n_split"],
-                                      act2=1)
+                                      act2=1, stride=pk.get("stride", 1))
         else:
             skip = x
             mid = nat.conv_gemm(x, bt["w0"], taps=1, scale=bt["s1"], bias=bt["b1"], act=1)
@@ -805,24 +847,14 @@ class ModelMaskHeadBackbone(nn.Module):
             else:
                 m_in = nat.conv_gemm(f1, mk["align_w"], taps=1, scale=mk["align_s"], bias=mk["align_b"], act=1,
                                      res=f2, res_mode=2)
-            ms_ = self.mask_size
-            if Ho != ms_ and Ho in (64, 128, 256, 512):
-                raise NotImplementedError("the strided-conv mask head paths (64..512 maps) are not built")
-            # mask head: `pre` (1x1, bias) with `out` (1x1 -> 1 channel) folded into its epilogue as an fp32
-            # dot product, so the 64-channel map is neither rounded to bf16 nor written to HBM
-            mask_pred = torch.empty((B, 1, Ho, Wo), dtype=torch.float32, device=dev)
-            nat.conv_gemm(m_in, mk["pre_w"], taps=1, bias=mk["pre_b"], store=False, dot_w=mk["out_w"].view(1, -1),
-                          dot_out=mask_pred, dot_bias=mk["out_b_host"])
+            Hm, Wm = f2.shape[1], f2.shape[2]
+            mask_pred = _mask_head(mk, m_in, self.mask_size)
             mask_at_map = mask_pred
-            if Ho != ms_:
-                # reference :205-211 resizes the 64-channel map bilinearly before the 1x1 `out` conv; both are
-                # linear and the resize acts per channel, so resizing the 1-channel logits is the same map.
-                # MaskGuidedSpatialAttention then resizes the prediction back to the feature grid (:80-88).
-                mask_pred = torch.empty((B, 1, ms_, ms_), dtype=torch.float32, device=dev)
-                nat.resize_bilinear_c1(mask_at_map.view(B, Ho, Wo), mask_pred.view(B, ms_, ms_))
-                mask_at_map = torch.empty((B, 1, Ho, Wo), dtype=torch.float32, device=dev)
-                nat.resize_bilinear_c1(mask_pred.view(B, ms_, ms_), mask_at_map.view(B, Ho, Wo))
-            attn_map = torch.empty((B, 1, Ho, Wo), dtype=torch.float32, device=dev)
+            if mask_pred.shape[-1] != Wm or mask_pred.shape[-2] != Hm:
+                # MaskGuidedSpatialAttention resizes the prediction to the feature grid (:80-88)
+                mask_at_map = torch.empty((B, 1, Hm, Wm), dtype=torch.float32, device=dev)
+                nat.resize_bilinear_c1(mask_pred.view(B, *mask_pred.shape[-2:]), mask_at_map.view(B, Hm, Wm))
+            attn_map = torch.empty((B, 1, Hm, Wm), dtype=torch.float32, device=dev)
             nat.mask_attention(mask_at_map, mk["attn"], attn_map)
             nat.scale_map(f2, f2, attn=attn_map, gamma=mk["gamma"])
         if self.use_hybrid_transformer:
@@ -842,11 +874,14 @@ class ModelMaskHeadBackbone(nn.Module):
             nat.cls_head(gap3, gate3, npix3, pk["head"]["w"], pk["head"]["b"], self.classification_head.normalize,
                          logits)
             pj = pk["proj"]
-            if self.proj_dim in (Ho, 2 * Ho) and Ho == Wo and _staged_tiles(Ho, Wo):
-                up2 = self.proj_dim == 2 * Ho  # AdaptiveAvgPool2d to 2x the size replicates each pixel 2x2
-                proj = lambda pp, src: self._project(pp, src, up2)
-            else:
-                proj = self._project_pooled
+
+            def proj(pp, src):
+                hs, ws = src.shape[1], src.shape[2]
+                if self.proj_dim in (hs, 2 * hs) and hs == ws and _staged_tiles(hs, ws):
+                    # AdaptiveAvgPool2d to the same size is the identity, to 2x the size a 2x2 replication
+                    return self._project(pp, src, self.proj_dim == 2 * hs)
+                return self._project_pooled(pp, src)
+
             p1 = _nchw(proj(pj["proj_f1"], f1))
             p2 = _nchw(proj(pj["proj_f2"], f2))
             p1r = _nchw(proj(pj["proj_r1"], r1))
@@ -966,9 +1001,9 @@ class FusionModel(nn.Module):
         mh = self.mask_head
         pk = {"w": w, "keep": keep,
               "in_dwi": _conv_w_bf16(self.proj_in_dwi, dev), "in_dce": _conv_w_bf16(self.proj_in_dce, dev),
-              "mask_pre_w": _conv_w_bf16(mh.pre, dev), "mask_pre_b": _f32(mh.pre.bias, dev),
-              "mask_out_w": _f32(mh.out.weight.flatten(), dev), "mask_out_b": _f32(mh.out.bias, dev),
-              "mask_out_b_host": float(mh.out.bias.detach().float().cpu().item()),
+              "mask": {"pre_w": _conv_w_bf16(mh.pre, dev), "pre_b": _f32(mh.pre.bias, dev),
+                       "down": _mask_down_pack(mh, dev), "out_w": _f32(mh.out.weight.flatten(), dev),
+                       "out_b_host": float(mh.out.bias.detach().float().cpu().item())},
               "recon": _recon_pack(self.fusion_reconstruct, dev), "projF": _proj_pack(self.projF, dev)}
         self._pack_cache = (sig, pk)
         return pk
@@ -1011,17 +1046,7 @@ class FusionModel(nn.Module):
         nat.fusion_mix(p_dwi, p_dce, gating, lowres, gate if self.fusion_se is not None else None, hp, wp, fused)
         mask_logits = recon = proj = None
         if full:
-            if H != self.mask_size and H in (64, 128, 256, 512):
-                raise NotImplementedError("the strided-conv mask head paths (64..512 inputs) are not built")
-            mask_logits = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
-            nat.conv_gemm(fused, pk["mask_pre_w"], taps=1, bias=pk["mask_pre_b"], store=False,
-                          dot_w=pk["mask_out_w"].view(1, -1), dot_out=mask_logits, dot_bias=pk["mask_out_b_host"])
-            if H != self.mask_size:
-                # reference :205-211: bilinear resize of the 64-channel map, then the 1x1 `out` conv; both are
-                # linear and the resize acts per channel, so resizing the 1-channel logits is the same map
-                small = mask_logits
-                mask_logits = torch.empty((B, 1, self.mask_size, self.mask_size), dtype=torch.float32, device=dev)
-                nat.resize_bilinear_c1(small.view(B, H, W), mask_logits.view(B, self.mask_size, self.mask_size))
+            mask_logits = _mask_head(pk["mask"], fused, self.mask_size)
             recon = _recon(pk["recon"], fused).unsqueeze(1)
             pj = pk["projF"]
             g = nat.conv_gemm(fused, pj["w0"], taps=1, scale=pj["s0"], bias=pj["b0"], act=1)

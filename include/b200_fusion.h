@@ -67,12 +67,15 @@ int b200_conv_gemm(const void* x, int x_ld, const void* w, const float* scale, c
  *     (code/model_module.py:117), finished by b200_tapsum.  ndot = 1: a following 1x1, C -> 1 convolution
  *     (MaskHeadResize.out, code/model_module.py:187).  Requires Cout in {64,128,256} (one N tile), H > 1
  *     and out == NULL: the C-channel map never reaches HBM and is never rounded to bf16.
+  * `stride` (1 or 2) applies to taps 1 / 9: the strided 1x1 convs of a down-sampling ResNetLiteBlock
+ * (code/model_module.py:259-262, :276-280) and the 3x3 / stride-2 / padding-1 stacks of MaskHeadResize (:153-181);
+ * H and W are the INPUT size, the output map is H/stride x W/stride.
  */
 int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
                       const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
                       float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w, int ndot,
                       float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout, int taps,
-                      void* stream);
+                      int stride, void* stream);
 
 /*
  * Batched GEMM on the same tcgen05 kernel: for every (batch, head)

@@ -51,13 +51,15 @@ def reference_parameters():
     return p
 
 
-def configure(p, hybrid=False):
+def configure(p, hybrid=False, input_size=64, downsample=None):
     p["dwi_channel_num"], p["dce_channel_num"] = 16, 6
     for m in ("dwi", "dce", "fusion"):
         mp = p[f"{m}_model_parameters"]
         mp["use_backbone"] = False
-        mp["input_size"] = 64
+        mp["input_size"] = input_size
         mp["use_hybrid_transformer"] = hybrid and m != "fusion"
+        if downsample is not None and m != "fusion":
+            mp["downsample"] = downsample
     return p
 
 
@@ -79,10 +81,10 @@ def flatten(prefix, obj, out):
             flatten(f"{prefix}.{k}", o, out)
 
 
-def model_goldens(tag, hybrid):
+def model_goldens(tag, hybrid, input_size=64, downsample=None, kinds=("U", "S")):
     import model_module as mm  # the reference module, imported from /root/reference/code
 
-    p = configure(reference_parameters(), hybrid)
+    p = configure(reference_parameters(), hybrid, input_size, downsample)
     torch.manual_seed(0)
     models = {"dwi": mm.ModelMaskHeadBackbone("dwi", p, None), "dce": mm.ModelMaskHeadBackbone("dce", p, None),
               "fusion": mm.FusionModel(p)}
@@ -93,8 +95,8 @@ def model_goldens(tag, hybrid):
         m.load_state_dict(op.seeded_state_dict(sh, seed=7))
         m.eval()
     out = {}
-    for kind in ("U", "S"):
-        dwi_raw, dce_raw, _, _ = op.synthetic_raw(2, seed=1234, kind=kind)
+    for kind in kinds:
+        dwi_raw, dce_raw, _, _ = op.synthetic_raw(2, seed=1234, size=input_size, kind=kind)
         # model inputs are the normalised tensors; any fp32 tensor in [0,1] does for model parity
         dwi = dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)
         dce = dce_raw
@@ -112,8 +114,9 @@ def model_goldens(tag, hybrid):
         flatten(f"{kind}/fusion/mask", mf, out)
         flatten(f"{kind}/fusion/aux", af, out)
     np.savez_compressed(os.path.join(GOLD, f"model_{tag}.npz"), **out)
-    with open(os.path.join(GOLD, f"state_shapes_{tag}.json"), "w") as f:
-        json.dump(shapes, f, indent=0, sort_keys=True)
+    if input_size == 64 and downsample is None:  # the geometry variants share the parameter shapes of "cnn"
+        with open(os.path.join(GOLD, f"state_shapes_{tag}.json"), "w") as f:
+            json.dump(shapes, f, indent=0, sort_keys=True)
     print(tag, "fusion logits", lf)
 
 
@@ -242,4 +245,8 @@ if __name__ == "__main__":
     normalizer_goldens()
     model_goldens("cnn", hybrid=False)
     model_goldens("hybrid", hybrid=True)
+    # non-default geometries: 128 x 128 ROIs (64 x 64 maps, strided mask head, 2x2-averaging projector pool) and a
+    # stride-2 block3 (16 x 16 f3, fusion head with the bilinear mask path)
+    model_goldens("cnn128", hybrid=False, input_size=128, kinds=("S",))
+    model_goldens("cnn_s2", hybrid=False, downsample=(True, False, True), kinds=("S",))
     vit_goldens()

@@ -355,3 +355,20 @@ def test_se_gate(B, C, Cm):
     torch.cuda.synchronize()
     ref = torch.sigmoid(F.linear(F.gelu(F.linear(gap / 196, w1, b1)), w2, b2))
     assert _rel(gate, ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps", [(3, 64, 64, 64, 64, 9), (2, 128, 128, 64, 64, 9), (2, 32, 32, 128, 256, 1),
+                                                 (2, 64, 64, 64, 128, 1)])
+def test_conv_gemm_stride2(B, H, W, Cin, Cout, taps):
+    """Strided 3x3 (padding 1) and 1x1 convolutions through the TMA traversal stride (mask-head stacks, stride-2 blocks)."""
+    g = torch.Generator(device="cpu").manual_seed(H + Cin + taps)
+    x = (torch.randn(B, H, W, Cin, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(Cout, taps * Cin, generator=g) / math.sqrt(taps * Cin)).to(DEV).bfloat16()
+    bias = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    y = nat.conv_gemm(x, w, taps=taps, bias=bias, act=1, stride=2)
+    torch.cuda.synchronize()
+    k = 3 if taps == 9 else 1
+    wf = w.float().view(Cout, taps, Cin).permute(0, 2, 1).reshape(Cout, Cin, k, k)
+    ref = F.gelu(F.conv2d(x.float().permute(0, 3, 1, 2), wf, bias, stride=2, padding=k // 2)).permute(0, 2, 3, 1)
+    assert tuple(y.shape) == (B, H // 2, W // 2, Cout)
+    assert _rel(y, ref) < 1e-2

@@ -88,6 +88,47 @@ def test_vit_adapter_oracle_matches_reference():
     assert n == 34
 
 
+GEOMETRY_VARIANTS = {"cnn128": dict(input_size=128, downsample=None), "cnn_s2": dict(input_size=64, downsample=(True, False, True))}
+
+
+def variant_parameters(tag):
+    """Non-default geometries: 128 x 128 ROIs (64 x 64 maps: strided mask-head stack, 2x2-averaging projector
+    pool) and a stride-2 block3 (16 x 16 f3; the fusion head takes the bilinear mask path)."""
+    v = GEOMETRY_VARIANTS[tag]
+    p = pd.default_parameters(input_size=v["input_size"])
+    if v["downsample"] is not None:
+        for m in ("dwi", "dce"):
+            p[f"{m}_model_parameters"]["downsample"] = v["downsample"]
+    return p, v["input_size"]
+
+
+def variant_inputs(size):
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(2, seed=1234, size=size, kind="S")
+    return dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True), dce_raw
+
+
+@pytest.mark.parametrize("tag", sorted(GEOMETRY_VARIANTS))
+def test_geometry_variant_oracle_matches_reference(tag):
+    gold = gu.load(f"model_{tag}.npz")
+    shapes = gu.load_shapes("cnn")
+    p, size = variant_parameters(tag)
+    sds = {m: op.seeded_state_dict(shapes[m], seed=7) for m in ("dwi", "dce", "fusion")}
+    dwi, dce = variant_inputs(size)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        ld, ad, md = mo.encoder_forward(sds["dwi"], "dwi", p, dwi)
+        lc, ac, mc = mo.encoder_forward(sds["dce"], "dce", p, dce)
+        lf, mf, af = mo.fusion_forward(sds["fusion"], p, ad["raw_feats"], ac["raw_feats"], md, mc)
+    outs = {"S/dwi/logits": ld, "S/dwi/aux": ad, "S/dwi/mask": md, "S/dce/logits": lc, "S/dce/aux": ac,
+            "S/dce/mask": mc, "S/fusion/logits": lf, "S/fusion/mask": mf, "S/fusion/aux": af}
+    n = 0
+    for prefix, obj in outs.items():
+        for key, t in gu.walk(prefix, obj):
+            gu.check(gold, key, t, rtol=2e-5)
+            n += 1
+    assert n == 34
+
+
 def test_dwi_normalize_oracle_matches_reference():
     gold = gu.load("normalizers.npz")
     dwi_raw, _, _, _ = op.synthetic_raw(12, seed=1234, kind="S")

@@ -430,3 +430,31 @@ def test_odd_batch_sizes_match_the_16_case_batch(sizes):
             assert _relmax(ln, l4[:n]) <= 2e-3 and _relmax(mn, m4[:n]) <= 5e-3
             assert _relmax(an["raw_feats"][2], a4["raw_feats"][2][:n]) <= 1e-2
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("tag", ["cnn128", "cnn_s2"])
+def test_geometry_variants_vs_golden_reference(tag):
+    """128 x 128 ROIs (64 x 64 maps: the strided 3x3 mask-head stack, 2x2-averaging projector pool) and a stride-2
+    block3 (strided 1x1 convs, 16 x 16 f3, fusion with the bilinear mask path) against the unmodified reference."""
+    from test_oracle_golden import variant_inputs, variant_parameters
+
+    gold = gu.load(f"model_{tag}.npz")
+    shapes = gu.load_shapes("cnn")
+    p, size = variant_parameters(tag)
+    mods = {"dwi": b_mm.ModelMaskHeadBackbone("dwi", p), "dce": b_mm.ModelMaskHeadBackbone("dce", p),
+            "fusion": b_mm.FusionModel(p)}
+    for k, m in mods.items():
+        m.load_state_dict(op.seeded_state_dict(shapes[k], seed=7))
+        m.to(DEV).eval()
+    dwi, dce = variant_inputs(size)
+    (ld, ad, md), (lc, ac, mc), (lf, mf, af) = _run_product(mods, dwi, dce)
+    outs = {"S/dwi/logits": ld, "S/dwi/aux": ad, "S/dwi/mask": md, "S/dce/logits": lc, "S/dce/aux": ac,
+            "S/dce/mask": mc, "S/fusion/logits": lf, "S/fusion/mask": mf, "S/fusion/aux": af}
+    worst = {}
+    for prefix, obj in outs.items():
+        for key, t in gu.walk(prefix, obj):
+            worst[key] = gu.check(gold, key, t, rtol=1.0)
+    print(tag, "relative errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:10])
+    assert len(worst) == 34
+    bad = {k: v for k, v in worst.items() if v > MODEL_TOL}
+    assert not bad, bad
