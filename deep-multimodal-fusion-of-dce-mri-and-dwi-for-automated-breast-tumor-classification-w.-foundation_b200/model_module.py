@@ -641,8 +641,6 @@ class ModelMaskHeadBackbone(nn.Module):
         if self.use_backbone and not hasattr(self.backbone, "forward_chains"):
             raise NotImplementedError("use_backbone needs a B200ViTBackbone (foundation_model.build_medical_backbone); "
                                       "the ResNet / RadImageNet / UNI2-h backbones are not built")
-        if self.mask_enabled and self.mask_stage != "f2":
-            raise NotImplementedError("only mask_stage='f2' (the reference default) is built")
         b1 = self.block1
         if self.use_backbone:
             if b1.stride != 1 or self.use_hybrid_transformer:
@@ -655,6 +653,10 @@ class ModelMaskHeadBackbone(nn.Module):
         pk = {name: _block_pack(blk, dev) for name, blk in blocks.items()}
         for name, blk in blocks.items():
             pk[name]["stride"] = blk.stride
+            pk[name]["downsample_each_repeat"] = bool(self.downsample_each_repeat) and len(blk.bottlenecks) > 1
+            if pk[name]["downsample_each_repeat"] and blk.stride != 1:
+                raise NotImplementedError("downsample_each_repeat with a strided block (the identity branch would "
+                                          "not match in the reference either)")
             if blk.stride not in (1, 2) or (blk.stride == 2 and blk.skip is None):
                 raise NotImplementedError("block strides other than 1 / 2")
         if self.use_hybrid_transformer:
@@ -700,8 +702,9 @@ class ModelMaskHeadBackbone(nn.Module):
         if self.modality_attention is not None:
             pk["mod_se"] = _se_pack(self.modality_attention, dev)
         if self.mask_enabled:
-            al = self.f1_to_f2.proj
-            if isinstance(al, nn.Identity):  # c1 == c2 (the ViT path): f1_aligned = f1
+            # the aligner feeding the mask head: f1 -> f2 for mask_stage f2, f2 -> f3 for f3, none for f1
+            al = {"f1": nn.Identity(), "f2": self.f1_to_f2.proj, "f3": self.f2_to_f3.proj}[self.mask_stage]
+            if isinstance(al, nn.Identity):  # equal channel counts (the ViT path) or mask_stage f1
                 aw = s = b = None
             else:
                 aw = _conv_w_bf16(al[0], dev)
@@ -727,13 +730,19 @@ class ModelMaskHeadBackbone(nn.Module):
     # ---------------------------------------------------------------- forward ----
     def _run_block(self, pk, mid, skip, need_recon):
         """`mid` = output of the first bottleneck conv (+BN+GELU); `skip` = identity branch (both NHWC bf16)."""
-        bt = pk["bott"][0]
-        B, H, W, _ = mid.shape
+        botts = pk["bott"]
         dev = mid.device
-        t = nat.conv_gemm(mid, bt["w4"], taps=9, scale=bt["s5"], bias=bt["b5"], act=1)
+        t = mid
+        for i, bt in enumerate(botts):  # repeat_blocks bottlenecks in sequence (reference :298-310)
+            if i > 0:  # later repeats start from the previous repeat's (un-activated) output
+                st = pk.get("stride", 1) if pk.get("downsample_each_repeat", False) else 1
+                t = nat.conv_gemm(t, bt["w0"], taps=1, scale=bt["s1"], bias=bt["b1"], act=1, stride=st)
+            t = nat.conv_gemm(t, bt["w4"], taps=9, scale=bt["s5"], bias=bt["b5"], act=1)
+            if i + 1 < len(botts):
+                t = nat.conv_gemm(t, bt["w7"], taps=1, scale=bt["s8"], bias=bt["b8"], act=0)
+        bt = botts[-1]
+        B, H, W, _ = t.shape
         cout = bt["w7"].shape[0]
-        if len(pk["bott"]) > 1:
-            raise NotImplementedError("repeat_blocks > 1")
         out, gap = _conv_gap(t, bt["w7"], taps=1, scale=bt["s8"], bias=bt["b8"], res=skip, res_mode=1, act=1)
         gate = None
         if "se" in pk:
@@ -755,6 +764,29 @@ class ModelMaskHeadBackbone(nn.Module):
             skip = x
             mid = nat.conv_gemm(x, bt["w0"], taps=1, scale=bt["s1"], bias=bt["b1"], act=1)
         return self._run_block(pk, mid, skip, need_recon)
+
+    def _mask_stage(self, mk, feat, prev):
+        """Mask head on `feat` (+ the aligned previous-stage map, reference :682-684 / :696-698) and the mask-guided
+        modulation feat *= 1 + gamma * A in place (:75-97).  Returns (mask_pred [B,1,S,S], attention map)."""
+        B, Hm, Wm, _ = feat.shape
+        dev = feat.device
+        if prev is None:
+            m_in = feat
+        elif mk["align_w"] is None:
+            m_in = nat.add_maps(feat, prev)
+        else:
+            m_in = nat.conv_gemm(prev, mk["align_w"], taps=1, scale=mk["align_s"], bias=mk["align_b"], act=1,
+                                 res=feat, res_mode=2)
+        mask_pred = _mask_head(mk, m_in, self.mask_size)
+        mask_at_map = mask_pred
+        if mask_pred.shape[-1] != Wm or mask_pred.shape[-2] != Hm:
+            # MaskGuidedSpatialAttention resizes the prediction to the feature grid (:80-88)
+            mask_at_map = torch.empty((B, 1, Hm, Wm), dtype=torch.float32, device=dev)
+            nat.resize_bilinear_c1(mask_pred.view(B, *mask_pred.shape[-2:]), mask_at_map.view(B, Hm, Wm))
+        attn_map = torch.empty((B, 1, Hm, Wm), dtype=torch.float32, device=dev)
+        nat.mask_attention(mask_at_map, mk["attn"], attn_map)
+        nat.scale_map(feat, feat, attn=attn_map, gamma=mk["gamma"])
+        return mask_pred, attn_map
 
     def _project(self, pp, src, up2):
         if "w0_vec" in pp:  # 1-channel fp32 source map
@@ -835,28 +867,15 @@ class ModelMaskHeadBackbone(nn.Module):
                      mod_attn)
             f1, r1, _, _ = self._run_block(pk["b1"], mid1, skip1, full)
 
+        mask_pred = attn_map = None
+        if self.mask_enabled and self.mask_stage == "f1":                       # reference :668-670
+            mask_pred, attn_map = self._mask_stage(pk["mask"], f1, None)
         f2_in = f1
         if self.use_backbone:  # reference :673-675
             f2_in = nat.mix_instnorm(f2_b, f1, *pk["mix"]["f2"])
         f2, r2, _, _ = self._block_from_map(pk["b2"], f2_in, full)
-        mask_pred = attn_map = None
-        if self.mask_enabled:
-            mk = pk["mask"]
-            if mk["align_w"] is None:
-                m_in = nat.add_maps(f2, f1)
-            else:
-                m_in = nat.conv_gemm(f1, mk["align_w"], taps=1, scale=mk["align_s"], bias=mk["align_b"], act=1,
-                                     res=f2, res_mode=2)
-            Hm, Wm = f2.shape[1], f2.shape[2]
-            mask_pred = _mask_head(mk, m_in, self.mask_size)
-            mask_at_map = mask_pred
-            if mask_pred.shape[-1] != Wm or mask_pred.shape[-2] != Hm:
-                # MaskGuidedSpatialAttention resizes the prediction to the feature grid (:80-88)
-                mask_at_map = torch.empty((B, 1, Hm, Wm), dtype=torch.float32, device=dev)
-                nat.resize_bilinear_c1(mask_pred.view(B, *mask_pred.shape[-2:]), mask_at_map.view(B, Hm, Wm))
-            attn_map = torch.empty((B, 1, Hm, Wm), dtype=torch.float32, device=dev)
-            nat.mask_attention(mask_at_map, mk["attn"], attn_map)
-            nat.scale_map(f2, f2, attn=attn_map, gamma=mk["gamma"])
+        if self.mask_enabled and self.mask_stage == "f2":                       # reference :681-685
+            mask_pred, attn_map = self._mask_stage(pk["mask"], f2, f1)
         if self.use_hybrid_transformer:
             f3, gap3 = _transformer_stage(pk["tr"], f2)  # reference :702-703
             gate3 = None
@@ -865,6 +884,9 @@ class ModelMaskHeadBackbone(nn.Module):
             if self.use_backbone:  # reference :688-690
                 f3_in = nat.mix_instnorm(f3_b, f2, *pk["mix"]["f3"])
             f3, _, gap3, gate3 = self._block_from_map(pk["b3"], f3_in, False)
+            if self.mask_enabled and self.mask_stage == "f3":                   # reference :695-699
+                mask_pred, attn_map = self._mask_stage(pk["mask"], f3, f2)
+                gap3, gate3 = nat.channel_sums(f3), None  # the classifier pools the modulated map
         npix3 = f3.shape[1] * f3.shape[2]
 
         logits = None

@@ -51,7 +51,7 @@ def reference_parameters():
     return p
 
 
-def configure(p, hybrid=False, input_size=64, downsample=None):
+def configure(p, hybrid=False, input_size=64, downsample=None, mask_stage=None, repeat_blocks=None):
     p["dwi_channel_num"], p["dce_channel_num"] = 16, 6
     for m in ("dwi", "dce", "fusion"):
         mp = p[f"{m}_model_parameters"]
@@ -60,6 +60,10 @@ def configure(p, hybrid=False, input_size=64, downsample=None):
         mp["use_hybrid_transformer"] = hybrid and m != "fusion"
         if downsample is not None and m != "fusion":
             mp["downsample"] = downsample
+        if mask_stage is not None and m != "fusion":
+            mp["mask_parameters"] = dict(mp["mask_parameters"], mask_stage=mask_stage)
+        if repeat_blocks is not None and m != "fusion":
+            mp["repeat_blocks"] = repeat_blocks
     return p
 
 
@@ -81,10 +85,10 @@ def flatten(prefix, obj, out):
             flatten(f"{prefix}.{k}", o, out)
 
 
-def model_goldens(tag, hybrid, input_size=64, downsample=None, kinds=("U", "S")):
+def model_goldens(tag, hybrid, input_size=64, downsample=None, kinds=("U", "S"), mask_stage=None, repeat_blocks=None):
     import model_module as mm  # the reference module, imported from /root/reference/code
 
-    p = configure(reference_parameters(), hybrid, input_size, downsample)
+    p = configure(reference_parameters(), hybrid, input_size, downsample, mask_stage, repeat_blocks)
     torch.manual_seed(0)
     models = {"dwi": mm.ModelMaskHeadBackbone("dwi", p, None), "dce": mm.ModelMaskHeadBackbone("dce", p, None),
               "fusion": mm.FusionModel(p)}
@@ -249,4 +253,8 @@ if __name__ == "__main__":
     # stride-2 block3 (16 x 16 f3, fusion head with the bilinear mask path)
     model_goldens("cnn128", hybrid=False, input_size=128, kinds=("S",))
     model_goldens("cnn_s2", hybrid=False, downsample=(True, False, True), kinds=("S",))
+    # mask head on f1 / f3 and repeated bottlenecks
+    model_goldens("cnn_mf1", hybrid=False, kinds=("S",), mask_stage="f1")
+    model_goldens("cnn_mf3", hybrid=False, kinds=("S",), mask_stage="f3")
+    model_goldens("cnn_r2", hybrid=False, kinds=("S",), repeat_blocks=(2, 1, 2))
     vit_goldens()

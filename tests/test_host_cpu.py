@@ -78,6 +78,17 @@ def test_state_dict_matches_reference_names_and_shapes(tag, hybrid):
         assert mine == ref[k]
 
 
+@pytest.mark.parametrize("tag", ["cnn_mf1", "cnn_mf3", "cnn_r2"])
+def test_variant_state_dicts_match_reference(tag):
+    import model_module as mm
+    from test_oracle_golden import variant_parameters
+
+    p, _, shape_tag = variant_parameters(tag)
+    ref = gu.load_shapes(shape_tag)
+    for k, m in {"dwi": mm.ModelMaskHeadBackbone("dwi", p), "dce": mm.ModelMaskHeadBackbone("dce", p)}.items():
+        assert {a: tuple(b.shape) for a, b in m.state_dict().items()} == ref[k]
+
+
 def test_vit_state_dict_matches_reference_names_and_shapes():
     """use_backbone encoders: same keys as the reference, including the `_orig_mod` level its
     torch._dynamo.disable(backbone) wrapper introduces (model_module.py:539) - checkpoints load unchanged."""

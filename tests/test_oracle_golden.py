@@ -88,18 +88,31 @@ def test_vit_adapter_oracle_matches_reference():
     assert n == 34
 
 
-GEOMETRY_VARIANTS = {"cnn128": dict(input_size=128, downsample=None), "cnn_s2": dict(input_size=64, downsample=(True, False, True))}
+GEOMETRY_VARIANTS = {
+    "cnn128": dict(input_size=128, shapes="cnn"),
+    "cnn_s2": dict(downsample=(True, False, True), shapes="cnn"),
+    "cnn_mf1": dict(mask_stage="f1", shapes="cnn_mf1"),
+    "cnn_mf3": dict(mask_stage="f3", shapes="cnn_mf3"),
+    "cnn_r2": dict(repeat_blocks=(2, 1, 2), shapes="cnn_r2"),
+}
 
 
 def variant_parameters(tag):
-    """Non-default geometries: 128 x 128 ROIs (64 x 64 maps: strided mask-head stack, 2x2-averaging projector
-    pool) and a stride-2 block3 (16 x 16 f3; the fusion head takes the bilinear mask path)."""
+    """Non-default configurations: 128 x 128 ROIs (64 x 64 maps: strided mask-head stack, 2x2-averaging projector
+    pool), a stride-2 block3 (16 x 16 f3; the fusion head takes the bilinear mask path), the mask head on f1 / f3,
+    repeated bottlenecks.  Returns (parameters, input size, tag of the state-shape table)."""
     v = GEOMETRY_VARIANTS[tag]
-    p = pd.default_parameters(input_size=v["input_size"])
-    if v["downsample"] is not None:
-        for m in ("dwi", "dce"):
-            p[f"{m}_model_parameters"]["downsample"] = v["downsample"]
-    return p, v["input_size"]
+    size = v.get("input_size", 64)
+    p = pd.default_parameters(input_size=size)
+    for m in ("dwi", "dce"):
+        mp = p[f"{m}_model_parameters"]
+        if "downsample" in v:
+            mp["downsample"] = v["downsample"]
+        if "mask_stage" in v:
+            mp["mask_parameters"] = dict(mp["mask_parameters"], mask_stage=v["mask_stage"])
+        if "repeat_blocks" in v:
+            mp["repeat_blocks"] = v["repeat_blocks"]
+    return p, size, v["shapes"]
 
 
 def variant_inputs(size):
@@ -110,8 +123,8 @@ def variant_inputs(size):
 @pytest.mark.parametrize("tag", sorted(GEOMETRY_VARIANTS))
 def test_geometry_variant_oracle_matches_reference(tag):
     gold = gu.load(f"model_{tag}.npz")
-    shapes = gu.load_shapes("cnn")
-    p, size = variant_parameters(tag)
+    p, size, shape_tag = variant_parameters(tag)
+    shapes = gu.load_shapes(shape_tag)
     sds = {m: op.seeded_state_dict(shapes[m], seed=7) for m in ("dwi", "dce", "fusion")}
     dwi, dce = variant_inputs(size)
     torch.set_num_threads(8)
