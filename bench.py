@@ -60,15 +60,48 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons of this rank's GPU while the timed region runs: NVML in-process
+    (10 ms period, so even a 0.2 s region gets ~20 samples), `nvidia-smi -lms` as the fallback."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.stop = threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            props = torch.cuda.get_device_properties(index)
+            try:
+                bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        while not self.stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append([str(sm), str(mx)] + ["Active" if bits & b else "Not Active"
+                                                       for b in (0x8, 0x40, 0x20, 0x4)])
+            except Exception:
+                pass
+            self.stop.wait(0.01)
 
     def __enter__(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -84,8 +117,10 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
+        self.stop.set()
         if self.proc is not None:
             self.proc.terminate()
+        if self.thread is not None:
             self.thread.join(timeout=2)
 
     def summary(self):
@@ -94,7 +129,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
         return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------ data ----
