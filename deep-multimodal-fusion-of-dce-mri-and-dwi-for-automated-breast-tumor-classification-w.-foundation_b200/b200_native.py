@@ -172,9 +172,21 @@ def _call(name, key, *args):
     _check(rc, name)
 
 
-def _bf16_map(t, name):
-    if t.dtype != torch.bfloat16 or not t.is_contiguous():
-        raise B200NativeError(f"{name} must be a contiguous bfloat16 NHWC tensor")
+def _bf16_map(t, name, allow_slice=False):
+    """NHWC bf16 map; with allow_slice also a channel slice [..., a:b] of a contiguous NHWC buffer (its row stride
+    is then the wider buffer's channel count)."""
+    if t.dtype != torch.bfloat16:
+        raise B200NativeError(f"{name} must be a bfloat16 NHWC tensor")
+    if t.is_contiguous():
+        return
+    B, H, W, _ = t.shape
+    ld = t.stride(2)
+    if not (allow_slice and t.stride(3) == 1 and t.stride(1) == W * ld and t.stride(0) == H * W * ld and ld % 8 == 0):
+        raise B200NativeError(f"{name} must be a contiguous bfloat16 NHWC tensor (or a channel slice of one)")
+
+
+def _ld(t):
+    return t.stride(2) if t.dim() == 4 else t.shape[-1]
 
 
 def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0, out=None, up2=False, gap=None,
@@ -195,14 +207,16 @@ def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0,
         out2 = torch.empty((B, H // cs, W // cs, cout - n_split), dtype=torch.bfloat16, device=x.device)
     if gap is not None and taps == 4:
         raise B200NativeError("gap with the strided patch-embedding conv is not supported")
-    out_ld = out.shape[-1] if out is not None else 0
+    out_ld = _ld(out) if out is not None else 0
     if out is not None:
-        _bf16_map(out, "out")
+        _bf16_map(out, "out", allow_slice=True)
+    if out2 is not None:
+        _bf16_map(out2, "out2", allow_slice=True)
     if res is not None:
         _bf16_map(res, "res")
     _call("b200_conv_gemm_ex", (B, H, W, cin, cout, taps) if stride == 1 else (B, H, W, cin, cout, taps, stride), _ptr(x), x_ld, _ptr(w), _ptr(scale), _ptr(bias), _ptr(res),
           res.shape[-1] if res is not None else 0, res_mode, act, _ptr(out), out_ld,
-          1 if up2 else 0, _ptr(gap), n1, _ptr(out2), out2.shape[-1] if out2 is not None else 0, act2,
+          1 if up2 else 0, _ptr(gap), n1, _ptr(out2), _ld(out2) if out2 is not None else 0, act2,
           _ptr(dot_w), dot_w.shape[0] if dot_w is not None else 0, float(dot_bias), _ptr(dot_out), B, H, W, cin, cout,
           taps, stride, _stream())
     return out if n_split is None else (out, out2)

@@ -24,6 +24,8 @@ from __future__ import annotations
 import math
 from dataclasses import dataclass
 
+import os
+
 import torch
 import torch.nn as nn
 from torch.nn import init
@@ -397,7 +399,8 @@ def _block_pack(blk, dev):
         s5, b5 = _bn_fold(bt[5], dev)
         s8, b8 = _bn_fold(bt[8], dev)
         p["bott"].append({"conv0": bt[0], "s1": s1, "b1": b1, "w4": _conv_w_bf16(bt[4], dev), "s5": s5, "b5": b5,
-                          "w7": _conv_w_bf16(bt[7], dev), "s8": s8, "b8": b8})
+                          "w7": _conv_w_bf16(bt[7], dev), "s8": s8, "b8": b8,
+                          "conv7_f32": bt[7].weight.detach().to(dev).flatten(1).float()})
     if blk.skip is not None:
         ss, sb = _bn_fold(blk.skip[1], dev)
         p["skip"] = {"conv": blk.skip[0], "s": ss, "b": sb}
@@ -506,6 +509,11 @@ def _as_nhwc_bf16(t):
 
 def _nchw(t):
     return t.permute(0, 3, 1, 2)
+
+
+# Residual of a block's tail conv folded into its contraction (see _packed); B200_NO_TAIL_CAT=1 restores the
+# residual-in-the-epilogue form for A/B measurements.
+_TAIL_CAT = os.environ.get("B200_NO_TAIL_CAT") is None
 
 
 def _staged_tiles(H, W):
@@ -692,6 +700,17 @@ class ModelMaskHeadBackbone(nn.Module):
             if "skip" in blk:
                 blk["skip"]["w"] = _conv_w_bf16(blk["skip"]["conv"], dev)
                 b0 = blk["bott"][0]
+                # Tail conv with the residual folded into the contraction: out = [s*W7 | I] . [t ; skip] + b, i.e. the
+                # identity branch enters as extra K channels with exact unit weights (fp32 accumulation, so the sum is
+                # what an fp32 residual add gives).  The epilogue then has no residual to fetch and the 256-wide tile
+                # becomes available.  Used while the widened contraction stays short (mid + Cout <= 512: block2,
+                # 0.32 ms instead of 0.39 per launch at B = 1024); block3's 768-long contraction would make its tail
+                # tensor bound (0.91 ms against 0.84 with the residual in the epilogue), so it keeps the epilogue form.
+                last = blk["bott"][-1]
+                w7 = last["conv7_f32"] * last["s8"][:, None]
+                co = w7.shape[0]
+                blk["tail_cat"] = {"w": torch.cat([w7, torch.eye(co, device=dev)], 1).to(torch.bfloat16).contiguous(),
+                                   "b": last["b8"], "mid": w7.shape[1]}
                 blk["fused_in"] = {"w": torch.cat([blk["skip"]["w"], b0["w0"]], 0).contiguous(),
                                    "s": torch.cat([blk["skip"]["s"], b0["s1"]]).contiguous(),
                                    "b": torch.cat([blk["skip"]["b"], b0["b1"]]).contiguous(),
@@ -728,8 +747,9 @@ class ModelMaskHeadBackbone(nn.Module):
         return pk
 
     # ---------------------------------------------------------------- forward ----
-    def _run_block(self, pk, mid, skip, need_recon):
-        """`mid` = output of the first bottleneck conv (+BN+GELU); `skip` = identity branch (both NHWC bf16)."""
+    def _run_block(self, pk, mid, skip, need_recon, cat=None):
+        """`mid` = output of the first bottleneck conv (+BN+GELU); `skip` = identity branch (both NHWC bf16), or
+        `cat` = the tail GEMM's K-concatenated input whose upper channels already hold the identity branch."""
         botts = pk["bott"]
         dev = mid.device
         t = mid
@@ -737,13 +757,18 @@ class ModelMaskHeadBackbone(nn.Module):
             if i > 0:  # later repeats start from the previous repeat's (un-activated) output
                 st = pk.get("stride", 1) if pk.get("downsample_each_repeat", False) else 1
                 t = nat.conv_gemm(t, bt["w0"], taps=1, scale=bt["s1"], bias=bt["b1"], act=1, stride=st)
-            t = nat.conv_gemm(t, bt["w4"], taps=9, scale=bt["s5"], bias=bt["b5"], act=1)
+            last_into_cat = cat is not None and i + 1 == len(botts)
+            t = nat.conv_gemm(t, bt["w4"], taps=9, scale=bt["s5"], bias=bt["b5"], act=1,
+                              out=cat[..., :pk["tail_cat"]["mid"]] if last_into_cat else None)
             if i + 1 < len(botts):
                 t = nat.conv_gemm(t, bt["w7"], taps=1, scale=bt["s8"], bias=bt["b8"], act=0)
         bt = botts[-1]
         B, H, W, _ = t.shape
         cout = bt["w7"].shape[0]
-        out, gap = _conv_gap(t, bt["w7"], taps=1, scale=bt["s8"], bias=bt["b8"], res=skip, res_mode=1, act=1)
+        if cat is not None:
+            out, gap = _conv_gap(cat, pk["tail_cat"]["w"], taps=1, bias=pk["tail_cat"]["b"], act=1)
+        else:
+            out, gap = _conv_gap(t, bt["w7"], taps=1, scale=bt["s8"], bias=bt["b8"], res=skip, res_mode=1, act=1)
         gate = None
         if "se" in pk:
             se = pk["se"]
@@ -758,8 +783,17 @@ class ModelMaskHeadBackbone(nn.Module):
         if "skip" in pk:
             # skip conv and first bottleneck conv read the same map: one GEMM, two output segments
             f = pk["fused_in"]
+            st = pk.get("stride", 1)
+            if "tail_cat" in pk and _TAIL_CAT and pk["tail_cat"]["w"].shape[1] <= 512:
+                # the skip segment lands in the upper channels of the tail GEMM's K-concatenated input
+                tc = pk["tail_cat"]
+                B, H, W, _ = x.shape
+                cat = torch.empty((B, H // st, W // st, tc["mid"] + f["n_split"]), dtype=torch.bfloat16, device=x.device)
+                _, mid = nat.conv_gemm(x, f["w"], taps=1, scale=f["s"], bias=f["b"], act=0, n_split=f["n_split"],
+                                       act2=1, stride=st, out=cat[..., tc["mid"]:])
+                return self._run_block(pk, mid, None, need_recon, cat=cat)
             skip, mid = nat.conv_gemm(x, f["w"], taps=1, scale=f["s"], bias=f["b"], act=0, n_split=f["n_split"],
-                                      act2=1, stride=pk.get("stride", 1))
+                                      act2=1, stride=st)
         else:
             skip = x
             mid = nat.conv_gemm(x, bt["w0"], taps=1, scale=bt["s1"], bias=bt["b1"], act=1)

@@ -1,7 +1,7 @@
 """Run one GEMM shape of the path a few times (target for `ncu -k regex:conv_gemm -s N -c 1`).
 
     python tools/one_gemm.py M K N [gelu|f32res]
-    python tools/one_gemm.py conv B H W Cin Cout taps
+    python tools/one_gemm.py conv B H W Cin Cout taps [gap]
 """
 import os
 import sys
@@ -18,15 +18,16 @@ if sys.argv[1] == "conv":
     x = (torch.randn(B, H, W, CI, device="cuda") * 0.5).bfloat16()
     w = (torch.randn(CO, TAPS * CI, device="cuda") / (TAPS * CI) ** 0.5).bfloat16()
     sc, bi = torch.rand(CO, device="cuda") + 0.5, torch.randn(CO, device="cuda") * 0.1
+    gap = torch.zeros(B, CO, device="cuda") if len(sys.argv) > 8 and sys.argv[8] == "gap" else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(6):
         if i == 3:
             e0.record()
-        nat.conv_gemm(x, w, taps=TAPS, scale=sc, bias=bi, act=1)
+        nat.conv_gemm(x, w, taps=TAPS, scale=sc, bias=bi, act=1, gap=gap)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
-    print(f"conv {B}x{H}x{W} {CI}->{CO} taps={TAPS}: {ms * 1e3:.1f} us  {2.0 * B * H * W * CI * CO * TAPS / ms / 1e9:.0f} TFLOP/s")
+    print(f"conv {B}x{H}x{W} {CI}->{CO} taps={TAPS} gap={gap is not None}: {ms * 1e3:.1f} us  {2.0 * B * H * W * CI * CO * TAPS / ms / 1e9:.0f} TFLOP/s")
     sys.exit(0)
 M, K, N = (int(a) for a in sys.argv[1:4])
 kind = sys.argv[4] if len(sys.argv) > 4 else "gelu"
