@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _lib = None
 
@@ -93,6 +93,8 @@ SIGNATURES = {
     "b200_mix_instnorm": [_P, _P, _I, _I, _I, _P, _P, _P, _F, _P, _P],
     "b200_adaptive_pool": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "b200_add_maps": [_P, _P, _LL, _P, _P],
+    "b200_set_dropout": [_F, C.c_ulonglong, _I],
+    "b200_flip_planes": [_P, _P, _LL, _I, _I, _I, _I, _P],
     "b200_fusion_tokens": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "b200_fusion_core": [C.POINTER(FusionWeights), _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "b200_fusion_mix": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
@@ -190,7 +192,8 @@ def _ld(t):
 
 
 def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0, out=None, up2=False, gap=None,
-              cin=None, store=True, n_split=None, act2=0, out2=None, dot_w=None, dot_out=None, dot_bias=0.0, stride=1):
+              cin=None, store=True, n_split=None, act2=0, out2=None, dot_w=None, dot_out=None, dot_bias=0.0, stride=1,
+              dropout=None):
     """x [B,H,W,ld] bf16 NHWC (channels [0,cin) used); w [Cout, taps*cin] bf16.  Returns `out`
     (or (out, out2) when n_split is given: channels [n_split, Cout) form a second layer on the same input)."""
     _bf16_map(x, "x")
@@ -214,6 +217,8 @@ def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0,
         _bf16_map(out2, "out2", allow_slice=True)
     if res is not None:
         _bf16_map(res, "res")
+    if dropout is not None:  # (p, seed, segments): arms the one-shot MC-dropout epilogue of this launch
+        set_dropout(*dropout)
     _call("b200_conv_gemm_ex", (B, H, W, cin, cout, taps) if stride == 1 else (B, H, W, cin, cout, taps, stride), _ptr(x), x_ld, _ptr(w), _ptr(scale), _ptr(bias), _ptr(res),
           res.shape[-1] if res is not None else 0, res_mode, act, _ptr(out), out_ld,
           1 if up2 else 0, _ptr(gap), n1, _ptr(out2), _ld(out2) if out2 is not None else 0, act2,
@@ -355,7 +360,25 @@ def plane_mean(x, planes, n, out):
     return out
 
 
-def stem(x, stride, pm, se, wcat, scale, bias, n_skip, n_mid, skip_out, mid_out, mod_attn):
+def set_dropout(p, seed, segments=1):
+    """One-shot: the next conv_gemm / stem launch drops elements of the selected output segments with probability p."""
+    rc = lib().b200_set_dropout(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(segments))
+    if rc:
+        raise B200NativeError(f"b200_set_dropout -> {rc}")
+
+
+def flip_planes(x, flip_w, flip_h):
+    """torch.flip over the last / second-last dimension of an fp32 CUDA tensor [..., H, W] (out of place)."""
+    x = x.contiguous().float()
+    out = torch.empty_like(x)
+    H, W = x.shape[-2], x.shape[-1]
+    _call("b200_flip_planes", None, _ptr(x), _ptr(out), x.numel() // (H * W), H, W, int(flip_w), int(flip_h), _stream())
+    return out
+
+
+def stem(x, stride, pm, se, wcat, scale, bias, n_skip, n_mid, skip_out, mid_out, mod_attn, dropout=None):
+    if dropout is not None:
+        set_dropout(dropout[0], dropout[1], 1)
     B, C_, H, W = x.shape
     w1, b1, w2, b2 = se if se is not None else (None, None, None, None)
     cm = w1.shape[0] if w1 is not None else 0

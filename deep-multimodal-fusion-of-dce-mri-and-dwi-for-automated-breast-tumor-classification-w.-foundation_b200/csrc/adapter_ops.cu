@@ -184,6 +184,18 @@ __global__ void add_maps_kernel(const uint4* __restrict__ a, const uint4* __rest
     }
 }
 
+// Test-time-augmentation flips (reference train.py:916-923: torch.flip over the last and / or second-last
+// dimension): every [H, W] plane of a [planes, H, W] fp32 tensor, one output row per (blockIdx.y, plane).
+__global__ void flip_planes_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W, int flip_w,
+                                   int flip_h) {
+    const int h = blockIdx.y;
+    const size_t plane = blockIdx.z;
+    const float* src = x + (plane * H + (flip_h ? H - 1 - h : h)) * W;
+    float* dst = out + (plane * H + h) * W;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x)
+        dst[w] = __ldg(src + (flip_w ? W - 1 - w : w));
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -242,5 +254,19 @@ extern "C" int b200_add_maps(const void* a, const void* b, long long n_elems, vo
     if (blocks > 148 * 16) blocks = 148 * 16;
     add_maps_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), total_vec);
+    return launch_status();
+}
+
+extern "C" int b200_flip_planes(const float* x, float* out, long long planes, int H, int W, int flip_w, int flip_h,
+                                void* stream) {
+    if (planes < 0 || H <= 0 || W <= 0 || H > 65535) return -1;
+    if (planes == 0) return 0;
+    if (x == nullptr || out == nullptr || x == out) return -2;
+    const int threads = W >= 256 ? 256 : (W >= 128 ? 128 : 64);
+    for (long long p0 = 0; p0 < planes; p0 += 65535) {  // gridDim.z limit
+        const unsigned nz = static_cast<unsigned>(planes - p0 < 65535 ? planes - p0 : 65535);
+        flip_planes_kernel<<<dim3((W + threads - 1) / threads, H, nz), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+            x + p0 * H * W, out + p0 * H * W, H, W, flip_w, flip_h);
+    }
     return launch_status();
 }

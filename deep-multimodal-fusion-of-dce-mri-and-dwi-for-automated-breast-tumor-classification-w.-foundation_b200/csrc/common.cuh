@@ -87,4 +87,35 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
 
 inline int launch_status() { return static_cast<int>(cudaGetLastError()); }
 
+// Philox4x32 with 7 rounds (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"; 7 rounds pass BigCrush):
+// counter-based, so a dropout decision is a pure function of (seed, element index) - no state, any launch shape.
+__device__ __forceinline__ uint4 philox4x32_7(unsigned long long ctr, uint32_t key0, uint32_t key1) {
+    uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32), c2 = 0x2545f491u, c3 = 0x9e3779b9u;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ key0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ key1;
+        c3 = lo0;
+        key0 += 0x9E3779B9u;
+        key1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// Host side of b200_set_dropout: the one-shot request armed for the next dropout-capable launch of this thread
+// (defined in conv_gemm.cu; taking it clears it).
+struct PendingDropout {
+    float p = 0.f;
+    unsigned long long seed = 0;
+    int seg = 0;
+};
+PendingDropout take_pending_dropout();
+inline unsigned int dropout_threshold(float p) {
+    const double t = static_cast<double>(p) * 4294967296.0;
+    return t >= 4294967295.0 ? 4294967295u : static_cast<unsigned int>(t);
+}
+
 }  // namespace b200

@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "b200_fusion.h"
+#include "common.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -50,6 +51,13 @@ struct ConvGemmParams {
     int up2;               // replicate every output pixel into a 2x2 block of a [B,2H,2W,ld] map
     int tma_epi;           // outputs / residual go through shared memory + TMA (coalesced); else direct
     int share_box;         // BN = 256: a warp's two 64-column output boxes share one 4 KB staging slot (one more ring stage)
+    // MC-dropout (mode 3): element (pixel, channel) of the segments selected by drop_seg (bit 0 = first output,
+    // bit 1 = second) is zeroed when Philox4x32-7(seed; pixel * Cout + channel) < drop_thresh, else scaled by
+    // drop_scale = 1 / (1 - p).  Applied after the activation, before the store / channel sums.
+    unsigned int drop_thresh;
+    float drop_scale;
+    unsigned int drop_seed_lo, drop_seed_hi;
+    int drop_seg;
     float* gap;            // [B, Cout] fp32 sums over the pixels of each case, or nullptr
     int n_split;           // channels [n_split, Cout) are a second output segment (== Cout when unused)
     __nv_bfloat16* out2;
@@ -678,6 +686,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
                 }
+                if (MODE == 3 && (p.drop_seg & (seg2 ? 2 : 1))) {
+                    // nn.Dropout in MC-dropout inference (reference train_fusion.py:478-481: dropout modules in train
+                    // mode, BatchNorm frozen): one Philox call yields the keep decisions of 4 consecutive channels
+                    const unsigned long long e0 = static_cast<unsigned long long>(pix) * p.Cout + n0;
+#pragma unroll
+                    for (int j = 0; j < kChunk / 4; ++j) {
+                        const uint4 rnd = philox4x32_7(e0 / 4 + j, p.drop_seed_lo, p.drop_seed_hi);
+                        v[4 * j + 0] = rnd.x < p.drop_thresh ? 0.f : v[4 * j + 0] * p.drop_scale;
+                        v[4 * j + 1] = rnd.y < p.drop_thresh ? 0.f : v[4 * j + 1] * p.drop_scale;
+                        v[4 * j + 2] = rnd.z < p.drop_thresh ? 0.f : v[4 * j + 2] * p.drop_scale;
+                        v[4 * j + 3] = rnd.w < p.drop_thresh ? 0.f : v[4 * j + 3] * p.drop_scale;
+                    }
+                }
                 if (DOT) {
 #pragma unroll
                     for (int k = 0; k < NDOT; ++k) {
@@ -893,6 +914,17 @@ static int dispatch(int res_mode, bool gap, int ndot, int mode, const CUtensorMa
     if (mode == 1) {
         if constexpr (!WS && BN == 256) {
             if (res_mode == 0 && !gap && ndot == 0) B200_GO(0, false, 0, 1);
+        }
+        return -14;
+    }
+    if (mode == 3) {  // MC-dropout epilogue (plain / residual, with or without channel sums)
+        if constexpr (!WS) {
+            if (ndot == 0) {
+                if (res_mode == 0 && gap) B200_GO(0, true, 0, 3);
+                if (res_mode == 0) B200_GO(0, false, 0, 3);
+                if (res_mode == 1 && gap) B200_GO(1, true, 0, 3);
+                if (res_mode == 1) B200_GO(1, false, 0, 3);
+            }
         }
         return -14;
     }
@@ -1151,6 +1183,24 @@ extern "C" int b200_conv_gemm(const void* x, int x_ld, const void* w, const floa
                              0, 0, nullptr, 0, 0.f, nullptr, B, H, W, Cin, Cout, taps, 1, stream);
 }
 
+// One-shot MC-dropout request for the next dropout-capable launch of this thread (see b200_fusion.h).
+namespace b200 {
+static thread_local PendingDropout g_pending_dropout;
+PendingDropout take_pending_dropout() {
+    const PendingDropout d = g_pending_dropout;
+    g_pending_dropout = PendingDropout{};
+    return d;
+}
+}  // namespace b200
+
+extern "C" int b200_set_dropout(float p, unsigned long long seed, int segments) {
+    if (!(p >= 0.f && p < 1.f) || segments < 0 || segments > 3) return -1;
+    b200::g_pending_dropout.p = p;
+    b200::g_pending_dropout.seed = seed;
+    b200::g_pending_dropout.seg = p > 0.f ? segments : 0;
+    return 0;
+}
+
 extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
                                  const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
                                  float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w,
@@ -1246,7 +1296,18 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
     // every layer of this model (it needs BN <= 128, i.e. twice the tiles and activation re-reads), so it
     // is opt-in (B200_WS=1) until a 2-CTA / multicast version makes it pay.
     static const bool want_ws = std::getenv("B200_WS") != nullptr;
-    return run_job(p, j, 0, want_ws, static_cast<cudaStream_t>(stream));
+    int mode = 0;
+    const PendingDropout drop = take_pending_dropout();  // one shot
+    if (drop.seg != 0) {
+        if (dot_w != nullptr || up2 || res_mode == 2) return -19;  // dropout variants: plain / residual (+ channel sums)
+        mode = 3;
+        p.drop_thresh = dropout_threshold(drop.p);
+        p.drop_scale = 1.0f / (1.0f - drop.p);
+        p.drop_seed_lo = static_cast<unsigned int>(drop.seed);
+        p.drop_seed_hi = static_cast<unsigned int>(drop.seed >> 32);
+        p.drop_seg = drop.seg;
+    }
+    return run_job(p, j, mode, mode == 0 && want_ws, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b200_linear(const void* x, long long M, int K, const void* w, int N, const float* scale, const float* bias,

@@ -32,7 +32,8 @@ stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
             const float* __restrict__ wcat,   // [n_out, C], n_out = n_skip + n_mid
             const float* __restrict__ scale,  // [n_out]
             const float* __restrict__ bias, int n_skip, int n_mid, __nv_bfloat16* __restrict__ skip_out,
-            __nv_bfloat16* __restrict__ mid_out, float* __restrict__ mod_attn) {
+            __nv_bfloat16* __restrict__ mid_out, float* __restrict__ mod_attn, unsigned int drop_thresh,
+            float drop_scale, unsigned int seed_lo, unsigned int seed_hi) {
     extern __shared__ float s_dyn[];
     __shared__ float s_gate[kStemMaxC];
     __shared__ float s_hidden[kStemMaxC];
@@ -106,12 +107,20 @@ stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
             }
         }
         const bool is_mid = n0 >= n_skip;  // a 16-channel block never straddles the two maps (host-checked)
+        // MC-dropout on the bottleneck's first activation (model_module.py:260): element index in the mid map
+        const unsigned long long e0 = (static_cast<unsigned long long>(b) * npix + pix) * n_mid + (n0 - n_skip);
 #pragma unroll
         for (int j = 0; j < kStemCB / 2; ++j) {
             const float2 sc = *reinterpret_cast<const float2*>(s_sc + n0 + 2 * j);
             const float2 bi = *reinterpret_cast<const float2*>(s_bi + n0 + 2 * j);
             float2 y = __ffma2_rn(acc[j], sc, bi);
             if (is_mid) y = gelu_poly2(y);
+            if (is_mid && drop_thresh != 0u) {
+                const uint4 rnd = philox4x32_7(e0 / 4 + (j >> 1), seed_lo, seed_hi);  // 4 channels per call
+                const unsigned int r0 = (j & 1) ? rnd.z : rnd.x, r1 = (j & 1) ? rnd.w : rnd.y;
+                y.x = r0 < drop_thresh ? 0.f : y.x * drop_scale;
+                y.y = r1 < drop_thresh ? 0.f : y.y * drop_scale;
+            }
             const __nv_bfloat162 h2 = __floats2bfloat162_rn(y.x, y.y);
             s_out[pp * row_words + n0 / 2 + j] = *reinterpret_cast<const uint32_t*>(&h2);
         }
@@ -477,10 +486,14 @@ extern "C" int b200_stem(const float* x, int B, int C, int H, int W, int stride,
                         static_cast<size_t>(kStemPix) * (n_out / 2 + 1) * sizeof(uint32_t);
     if (smem > 48 * 1024) return -6;  // all supported shapes stay inside the default dynamic limit
     dim3 grid((npix + kStemPix - 1) / kStemPix, B);
+    const b200::PendingDropout drop = b200::take_pending_dropout();  // MC-dropout on the mid map, if armed
+    const unsigned int thresh = drop.seg != 0 ? b200::dropout_threshold(drop.p) : 0u;
+    const float dscale = drop.seg != 0 ? 1.0f / (1.0f - drop.p) : 1.0f;
     auto go = [&](auto kern) {
         kern<<<grid, kStemThreads, smem, static_cast<cudaStream_t>(stream)>>>(
             x, C, H, W, stride, plane_mean, se_w1, se_b1, se_w2, se_b2, Cm, wcat, scale, bias, n_skip, n_mid,
-            static_cast<__nv_bfloat16*>(skip_out), static_cast<__nv_bfloat16*>(mid_out), mod_attn);
+            static_cast<__nv_bfloat16*>(skip_out), static_cast<__nv_bfloat16*>(mid_out), mod_attn, thresh, dscale,
+            static_cast<unsigned int>(drop.seed), static_cast<unsigned int>(drop.seed >> 32));
     };
     if (C <= 8) go(stem_kernel<8>);
     else if (C <= 16) go(stem_kernel<16>);

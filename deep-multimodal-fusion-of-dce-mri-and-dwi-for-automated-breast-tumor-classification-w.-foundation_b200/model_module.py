@@ -640,6 +640,21 @@ class ModelMaskHeadBackbone(nn.Module):
         self.proj_r1 = Projector(1, self.proj_dim, dim=self.dim)
         self.proj_r2 = Projector(1, self.proj_dim, dim=self.dim)
         self._pack_cache = None
+        self._mc_seed, self._mc_calls, self._drop = 0x5EED, 0, None
+
+    # ------------------------------------------------------------- MC dropout ----
+    def set_mc_seed(self, seed):
+        """Seed of the in-kernel dropout generator (Philox, counter based): one forward consumes one seed step, so
+        a fixed seed reproduces a sequence of MC passes."""
+        self._mc_seed, self._mc_calls = int(seed), 0
+
+    def _mc_dropout_p(self):
+        """MC-dropout inference as the reference arms it (train_fusion.py:445-481): the module is in eval mode,
+        BatchNorm frozen, but its nn.Dropout sub-modules have been put in train mode.  Returns p (0 = off)."""
+        for mod in self.modules():
+            if isinstance(mod, nn.Dropout) and mod.training and mod.p > 0:
+                return float(mod.p)
+        return 0.0
 
     # ---------------------------------------------------------------- packing ----
     def _packed(self, dev):
@@ -756,7 +771,8 @@ class ModelMaskHeadBackbone(nn.Module):
         for i, bt in enumerate(botts):  # repeat_blocks bottlenecks in sequence (reference :298-310)
             if i > 0:  # later repeats start from the previous repeat's (un-activated) output
                 st = pk.get("stride", 1) if pk.get("downsample_each_repeat", False) else 1
-                t = nat.conv_gemm(t, bt["w0"], taps=1, scale=bt["s1"], bias=bt["b1"], act=1, stride=st)
+                t = nat.conv_gemm(t, bt["w0"], taps=1, scale=bt["s1"], bias=bt["b1"], act=1, stride=st,
+                                  dropout=self._drop(1) if self._drop else None)
             last_into_cat = cat is not None and i + 1 == len(botts)
             t = nat.conv_gemm(t, bt["w4"], taps=9, scale=bt["s5"], bias=bt["b5"], act=1,
                               out=cat[..., :pk["tail_cat"]["mid"]] if last_into_cat else None)
@@ -765,10 +781,12 @@ class ModelMaskHeadBackbone(nn.Module):
         bt = botts[-1]
         B, H, W, _ = t.shape
         cout = bt["w7"].shape[0]
+        drop = self._drop(1) if self._drop else None  # Dropout after GELU(out + identity), before SE (:305-306)
         if cat is not None:
-            out, gap = _conv_gap(cat, pk["tail_cat"]["w"], taps=1, bias=pk["tail_cat"]["b"], act=1)
+            out, gap = _conv_gap(cat, pk["tail_cat"]["w"], taps=1, bias=pk["tail_cat"]["b"], act=1, dropout=drop)
         else:
-            out, gap = _conv_gap(t, bt["w7"], taps=1, scale=bt["s8"], bias=bt["b8"], res=skip, res_mode=1, act=1)
+            out, gap = _conv_gap(t, bt["w7"], taps=1, scale=bt["s8"], bias=bt["b8"], res=skip, res_mode=1, act=1,
+                                 dropout=drop)
         gate = None
         if "se" in pk:
             se = pk["se"]
@@ -790,13 +808,15 @@ class ModelMaskHeadBackbone(nn.Module):
                 B, H, W, _ = x.shape
                 cat = torch.empty((B, H // st, W // st, tc["mid"] + f["n_split"]), dtype=torch.bfloat16, device=x.device)
                 _, mid = nat.conv_gemm(x, f["w"], taps=1, scale=f["s"], bias=f["b"], act=0, n_split=f["n_split"],
-                                       act2=1, stride=st, out=cat[..., tc["mid"]:])
+                                       act2=1, stride=st, out=cat[..., tc["mid"]:],
+                                       dropout=self._drop(2) if self._drop else None)
                 return self._run_block(pk, mid, None, need_recon, cat=cat)
             skip, mid = nat.conv_gemm(x, f["w"], taps=1, scale=f["s"], bias=f["b"], act=0, n_split=f["n_split"],
-                                      act2=1, stride=st)
+                                      act2=1, stride=st, dropout=self._drop(2) if self._drop else None)
         else:
             skip = x
-            mid = nat.conv_gemm(x, bt["w0"], taps=1, scale=bt["s1"], bias=bt["b1"], act=1)
+            mid = nat.conv_gemm(x, bt["w0"], taps=1, scale=bt["s1"], bias=bt["b1"], act=1,
+                                dropout=self._drop(1) if self._drop else None)
         return self._run_block(pk, mid, skip, need_recon)
 
     def _mask_stage(self, mk, feat, prev):
@@ -872,6 +892,20 @@ class ModelMaskHeadBackbone(nn.Module):
             raise NotImplementedError("training-mode forward is not built in the B200 path yet; call .eval()")
         if not x.is_cuda:
             raise nat.B200NativeError("ModelMaskHeadBackbone.forward needs a CUDA tensor (no CPU path)")
+        p_drop = self._mc_dropout_p()
+        if p_drop > 0 and self.use_hybrid_transformer:
+            raise NotImplementedError("MC dropout with the hybrid transformer stage (its attention / MLP dropouts)")
+        self._drop = None
+        if p_drop > 0:  # per-launch seeds: (model seed, forward count, launch count)
+            self._mc_calls += 1
+            base = (self._mc_seed * 0x9E3779B97F4A7C15 + self._mc_calls * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+            counter = [0]
+
+            def _drop(segments=1):
+                counter[0] += 1
+                return (p_drop, (base + counter[0] * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF, segments)
+
+            self._drop = _drop
         full = self.aux_mode == "full"
         dev = x.device
         pk = self._packed(dev)
@@ -898,7 +932,7 @@ class ModelMaskHeadBackbone(nn.Module):
             skip1 = torch.empty((B, Ho, Wo, st["n_skip"]), dtype=torch.bfloat16, device=dev)
             mid1 = torch.empty((B, Ho, Wo, st["n_mid"]), dtype=torch.bfloat16, device=dev)
             nat.stem(x, stride, plane_mean, se, st["w"], st["s"], st["b"], st["n_skip"], st["n_mid"], skip1, mid1,
-                     mod_attn)
+                     mod_attn, dropout=self._drop(1)[:2] if self._drop else None)
             f1, r1, _, _ = self._run_block(pk["b1"], mid1, skip1, full)
 
         mask_pred = attn_map = None

@@ -56,6 +56,16 @@ int b200_conv_gemm(const void* x, int x_ld, const void* w, const float* scale, c
                    float* gap, int B, int H, int W, int Cin, int Cout, int taps, void* stream);
 
 /*
+ * MC-dropout inference (code/train_fusion.py:478-536: nn.Dropout modules in train mode, BatchNorm frozen; the
+ * dropouts of ResNetLiteBlock_withRecon, code/model_module.py:260, :271, :306).  One-shot: arms the NEXT
+ * b200_conv_gemm_ex or b200_stem call of the calling thread (b200_stem drops its `mid` map), whose epilogue then zeroes each element of the selected output
+ * segments (bit 0 = first, bit 1 = second) with probability p and scales the survivors by 1 / (1 - p), after the
+ * activation and before the store / channel sums.  Decisions are Philox4x32-7(seed; pixel * Cout + channel):
+ * reproducible for a given seed, statistically (not bitwise) comparable with torch's generator.
+ */
+int b200_set_dropout(float p, unsigned long long seed, int segments);
+
+/*
  * b200_conv_gemm with two extensions used to fuse neighbouring layers of the reference graph:
  *   n_split/out2/out2_ld/act2: output channels [n_split, Cout) are a second layer that reads the same
  *     input (e.g. a block's skip conv and first bottleneck conv, code/model_module.py:299 and :303) and
@@ -256,6 +266,11 @@ int b200_mix_instnorm(const void* fb, const void* f, int B, int npix, int C, con
 int b200_adaptive_pool(const void* x, int x_f32, int B, int H, int W, int C, int Ho, int Wo, int act, void* out,
                        void* stream);
 int b200_add_maps(const void* a, const void* b, long long n_elems, void* out, void* stream);
+
+/* Test-time-augmentation flips (code/train.py:916-923, used by code/train_fusion.py:543-632): out = flip of every
+ * [H, W] plane of x [planes, H, W] fp32 along W and / or H.  Out of place. */
+int b200_flip_planes(const float* x, float* out, long long planes, int H, int W, int flip_w, int flip_h,
+                     void* stream);
 
 /* FusionModel._to_tokens (code/model_module.py:903-917): adaptive average pool to Hp x Wp tokens, fp32 [B,Hp*Wp,C]. */
 int b200_fusion_tokens(const void* p, int B, int H, int W, int C, int Hp, int Wp, float* tokens, void* stream);

@@ -58,17 +58,20 @@ def recon_head(x, s: SD):
     return _conv(y, s.sub("conv.3"), padding=1)
 
 
-def res_block(x, s: SD, stride, num_repeats, downsample_each_repeat, use_se):
-    """model_module.py:298-316."""
+def res_block(x, s: SD, stride, num_repeats, downsample_each_repeat, use_se, drop_p=0.0):
+    """model_module.py:298-316.  drop_p > 0: the block's nn.Dropout layers active (MC-dropout inference,
+    train_fusion.py:445-481) with torch's global generator; BatchNorm stays in eval mode."""
     identity = _bn(_conv(x, s.sub("skip.0"), stride=stride), s.sub("skip.1")) if s.has("skip.0.weight") else x
     out = x
     for i in range(num_repeats):
         b = s.sub(f"bottlenecks.{i}")
         st = stride if (i == 0 or downsample_each_repeat) else 1
         out = F.gelu(_bn(_conv(out, b.sub("0"), stride=st), b.sub("1")))
+        out = F.dropout(out, drop_p, training=drop_p > 0)                      # :260
         out = F.gelu(_bn(_conv(out, b.sub("4"), padding=1), b.sub("5")))
         out = _bn(_conv(out, b.sub("7")), b.sub("8"))
     out = F.gelu(out + identity)
+    out = F.dropout(out, drop_p, training=drop_p > 0)                          # :305-306
     if use_se:
         out, _ = se_block(out, s.sub("se"))
     rec = recon_head(out, s.sub("reconstruct")) if s.has("reconstruct.conv.0.weight") else None
@@ -179,7 +182,7 @@ def backbone_adapter(x, s: SD, chains, feats=None):
 
 
 # -------------------------------------------------------------------- encoder ----
-def encoder_forward(sd, method, params, x, backbone_feats=None):
+def encoder_forward(sd, method, params, x, backbone_feats=None, mc_dropout=False):
     """ModelMaskHeadBackbone.forward, model_module.py:645-733 (use_backbone: the ViT-B/16 adapter path).
 
     Returns (logits, aux, mask_pred) with the reference's aux keys.
@@ -193,6 +196,7 @@ def encoder_forward(sd, method, params, x, backbone_feats=None):
     maskp = mp["mask_parameters"]
     mask_on, stage = maskp["mask"], maskp["mask_stage"].lower()
     size = maskp["mask_target_size"][0]
+    dp = float(mp["dropout"]) if mc_dropout else 0.0
 
     mod_attn = None
     if mp["enable_modality_attention"]:
@@ -200,7 +204,7 @@ def encoder_forward(sd, method, params, x, backbone_feats=None):
     f2_b = f3_b = None
     if mp["use_backbone"]:
         x, f2_b, f3_b = backbone_adapter(x, s.sub("backbone_adapter"), mp["backbone_index_lists"], backbone_feats)
-    f1, r1 = res_block(x, s.sub("block1"), strides[0], reps[0], der, use_se)   # :666
+    f1, r1 = res_block(x, s.sub("block1"), strides[0], reps[0], der, use_se, dp)   # :666
     mask_pred = attn_map = None
     if mask_on and stage == "f1":
         mask_pred = mask_head(f1, s.sub("mask_head"), size)
@@ -209,7 +213,7 @@ def encoder_forward(sd, method, params, x, backbone_feats=None):
     if mp["use_backbone"]:                                                      # :673-675
         a = torch.sigmoid(s["f2_weight"])
         f2_in = F.group_norm(a * f2_b + (1 - a) * f1, f1.shape[1], s["norm_f2.weight"], s["norm_f2.bias"], 1e-5)
-    f2, r2 = res_block(f2_in, s.sub("block2"), strides[1], reps[1], der, use_se)  # :679
+    f2, r2 = res_block(f2_in, s.sub("block2"), strides[1], reps[1], der, use_se, dp)  # :679
     if mask_on and stage == "f2":
         m_in = f2 + feature_down_align(f1, s.sub("f1_to_f2"))                  # :682-683
         mask_pred = mask_head(m_in, s.sub("mask_head"), size)                  # :684
@@ -219,7 +223,7 @@ def encoder_forward(sd, method, params, x, backbone_feats=None):
         if mp["use_backbone"]:                                                  # :688-690
             a = torch.sigmoid(s["f3_weight"])
             f3_in = F.group_norm(a * f3_b + (1 - a) * f2, f2.shape[1], s["norm_f3.weight"], s["norm_f3.bias"], 1e-5)
-        f3, _ = res_block(f3_in, s.sub("block3"), strides[2], reps[2], der, use_se)   # :694
+        f3, _ = res_block(f3_in, s.sub("block3"), strides[2], reps[2], der, use_se, dp)   # :694
         if mask_on and stage == "f3":
             m_in = f3 + feature_down_align(f2, s.sub("f2_to_f3"))
             mask_pred = mask_head(m_in, s.sub("mask_head"), size)

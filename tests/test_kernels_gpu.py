@@ -372,3 +372,44 @@ def test_conv_gemm_stride2(B, H, W, Cin, Cout, taps):
     ref = F.gelu(F.conv2d(x.float().permute(0, 3, 1, 2), wf, bias, stride=2, padding=k // 2)).permute(0, 2, 3, 1)
     assert tuple(y.shape) == (B, H // 2, W // 2, Cout)
     assert _rel(y, ref) < 1e-2
+
+
+def test_mc_dropout_epilogue_properties():
+    """Philox dropout in the GEMM epilogue: survivors are the undropped values x 1/(1-p), the drop rate is p, the
+    decisions depend on the seed only, segment selection and the fused channel sums follow the dropped map."""
+    g = torch.Generator(device="cpu").manual_seed(77)
+    B, H, W, Cin, n1, n2, p = 4, 32, 32, 128, 128, 128, 0.2
+    x = (torch.randn(B, H, W, Cin, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(n1 + n2, Cin, generator=g) / math.sqrt(Cin)).to(DEV).bfloat16()
+    bias = (torch.randn(n1 + n2, generator=g) * 0.1 + 1.0).to(DEV)   # keeps outputs away from 0
+    a1, a2 = nat.conv_gemm(x, w, taps=1, bias=bias, act=0, n_split=n1, act2=1)
+    d1, d2 = nat.conv_gemm(x, w, taps=1, bias=bias, act=0, n_split=n1, act2=1, dropout=(p, 1234, 2))
+    e1, e2 = nat.conv_gemm(x, w, taps=1, bias=bias, act=0, n_split=n1, act2=1, dropout=(p, 1234, 2))
+    f1, f2 = nat.conv_gemm(x, w, taps=1, bias=bias, act=0, n_split=n1, act2=1, dropout=(p, 99, 2))
+    z1, _ = nat.conv_gemm(x, w, taps=1, bias=bias, act=0, n_split=n1, act2=1)   # the request is one-shot
+    torch.cuda.synchronize()
+    assert torch.equal(a1, d1) and torch.equal(a1, z1)       # segment 1 untouched
+    assert torch.equal(d2, e2) and not torch.equal(d2, f2)   # same seed -> same mask; other seed -> other mask
+    dropped = d2 == 0
+    rate = dropped.float().mean().item()
+    n = d2.numel()
+    assert abs(rate - p) < 5 * math.sqrt(p * (1 - p) / n) + 1e-3
+    keep = ~dropped
+    assert _rel(d2[keep], a2[keep].float() / (1 - p)) < 1e-2
+    # no structure along channels / pixels: per-channel and per-pixel drop rates stay near p
+    assert (dropped.float().mean(dim=(0, 1, 2)) - p).abs().max().item() < 0.03
+    assert (dropped.float().mean(dim=3) - p).abs().max().item() < 0.2
+    # residual + GELU + fused channel sums on a dropped map
+    res = (torch.randn(B, H, W, 256, generator=g) * 0.5 + 1.0).to(DEV).bfloat16()
+    gap = torch.zeros(B, 256, device=DEV)
+    y = nat.conv_gemm(x, w, taps=1, bias=bias, res=res, res_mode=1, act=1, gap=gap, dropout=(0.5, 7, 1))
+    torch.cuda.synchronize()
+    assert abs((y == 0).float().mean().item() - 0.5) < 0.01
+    assert _rel(gap, y.float().sum(dim=(1, 2))) < 1e-3
+
+
+def test_flip_planes():
+    x = torch.randn(5, 6, 24, 40, device=DEV)
+    assert torch.equal(nat.flip_planes(x, True, False), torch.flip(x, dims=[-1]))
+    assert torch.equal(nat.flip_planes(x, False, True), torch.flip(x, dims=[-2]))
+    assert torch.equal(nat.flip_planes(x, True, True), torch.flip(x, dims=[-1, -2]))

@@ -465,3 +465,73 @@ def test_geometry_variants_vs_golden_reference(tag):
                      5e-2 if (tag == "cnn_r2" and k == "S/fusion/mask") else MODEL_TOL)
     bad = {k: v for k, v in worst.items() if v > tol(k)}
     assert not bad, bad
+
+
+def _lightning(p, mods):
+    import train_fusion as b_tf
+
+    return b_tf.LightningFusionModel(mods["dwi"], mods["dce"], mods["fusion"], p)
+
+
+def test_tta_prediction_vs_oracle():
+    """predict_tta (train_fusion.py:543-587): softmax probabilities averaged over identity / lr / ud / lr+ud flips."""
+    p, sds, mods = _build()
+    lm = _lightning(p, mods)
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(6, seed=21, kind="S")
+    dwi = dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)
+    mean_p, std_p, aux = lm.predict_tta(dwi.to(DEV), dce_raw.to(DEV))
+    torch.cuda.synchronize()
+    probs = []
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    with torch.no_grad():
+        for dims in ([], [-1], [-2], [-1, -2]):
+            fd = torch.flip(dwi, dims) if dims else dwi
+            fc = torch.flip(dce_raw, dims) if dims else dce_raw
+            probs.append(torch.softmax(mo.pipeline_forward(sds, p, fd, fc)[0], dim=1))
+    ref = torch.stack(probs)
+    assert _relmax(mean_p, ref.mean(0)) <= MODEL_TOL
+    assert (std_p.cpu() - ref.std(0)).abs().max().item() <= 2e-2 * ref.mean(0).max().item()
+    assert aux["gating_weights"].shape == (6, 2)
+    out = lm.predict_custom((dwi, dce_raw, torch.zeros(6, dtype=torch.long)), mode="normal")
+    assert out[0].shape == (6, 4)
+
+
+def test_mc_dropout_prediction_is_statistically_the_reference():
+    """predict_mc_dropout (train_fusion.py:484-536): dropout active in both encoders, BatchNorm frozen.  The kernel
+    draws its own Philox stream, so parity is statistical: the mean over N passes must agree with the oracle's mean
+    over N passes (torch generator) within the Monte-Carlo error of the two estimates, and the pass-to-pass spread
+    must match.  Also: fixed seed -> reproducible, module train flags restored."""
+    p, sds, mods = _build()
+    lm = _lightning(p, mods)
+    n, passes = 4, 48
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(n, seed=22, kind="S")
+    dwi = dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)
+    lm.set_mc_seed(5)
+    mean_a, std_a, aux = lm.predict_mc_dropout(dwi.to(DEV), dce_raw.to(DEV), passes=passes)
+    lm.set_mc_seed(5)
+    mean_b, _, _ = lm.predict_mc_dropout(dwi.to(DEV), dce_raw.to(DEV), passes=passes)
+    torch.cuda.synchronize()
+    assert _relmax(mean_a, mean_b) <= 2e-3                      # same seed, same passes (up to fp32 atomics)
+    assert std_a.max().item() > 1e-4                            # dropout really was active
+    assert not any(m.training for m in mods["dwi"].modules())   # train flags restored
+    eval_logits = _run_product(mods, dwi, dce_raw)[2][0]
+    assert _relmax(torch.softmax(eval_logits, 1), mean_a) < 0.5  # and switched off again
+    torch.manual_seed(3)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    ref = []
+    with torch.no_grad():
+        for _ in range(passes):
+            _, ad, md = mo.encoder_forward(sds["dwi"], "dwi", p, dwi, mc_dropout=True)
+            _, ac, mc = mo.encoder_forward(sds["dce"], "dce", p, dce_raw, mc_dropout=True)
+            ref.append(torch.softmax(mo.fusion_forward(sds["fusion"], p, ad["raw_feats"], ac["raw_feats"], md, mc)[0], 1))
+    ref = torch.stack(ref)
+    ref_mean, ref_std = ref.mean(0), ref.std(0)
+    # both means are Monte-Carlo estimates with standard error std / sqrt(passes); allow 5 combined standard errors
+    # plus the deterministic bf16 tolerance
+    se = torch.sqrt(ref_std ** 2 + std_a.cpu() ** 2) / passes ** 0.5
+    diff = (mean_a.cpu() - ref_mean).abs()
+    assert (diff <= 5 * se + MODEL_TOL * ref_mean.max()).all(), (diff, se)
+    ratio = (std_a.cpu().mean() / ref_std.mean()).item()
+    assert 0.6 < ratio < 1.6, ratio
+    mean_t, std_t, _ = lm.predict_tta_mc(dwi.to(DEV), dce_raw.to(DEV), passes=4)
+    assert mean_t.shape == (n, 4) and torch.isfinite(mean_t).all() and abs(mean_t.sum(1).mean().item() - 1) < 1e-3
