@@ -291,6 +291,9 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=32)
     ap.add_argument("--cpu-cases", type=int, default=256, help="bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--predict-mode", default="normal", choices=["normal", "tta", "mc", "tta_mc"],
+                    help="reference test-time modes (train_fusion.py:682-702); tta_mc = 4 flips x 10 MC-dropout passes, "
+                         "the reference's default test_mode.  Not the headline workload.")
     ap.add_argument("--hybrid", action="store_true",
                     help="encoders with the in-house TransformerStage instead of block3 (not the headline workload)")
     args = ap.parse_args()
@@ -327,7 +330,26 @@ def main():
     dwi_d, dce_d = dwi_h.to(device), dce_h.to(device)
     gathered = [torch.empty((B, 4), device=device) for _ in range(world)] if world > 1 else None
 
+    lightning = None
+    if args.predict_mode != "normal":
+        import train_fusion as tf_mod
+        lightning = tf_mod.LightningFusionModel(pipe.dwi_model, pipe.dce_model, pipe.fusion_model, params)
+
     def step():
+        if lightning is not None:  # normalise once, then the reference's multi-pass prediction mode
+            d, c = dwi_d, dce_d
+            if pipe.resize is not None:
+                d, c = pipe.resize.batch(d), pipe.resize.batch(c)
+            d, c = pipe.dwi_norm.batch(d), pipe.dce_norm.batch(c)
+            if args.predict_mode == "tta":
+                logits = lightning.predict_tta(d, c)[0]
+            elif args.predict_mode == "mc":
+                logits = lightning.predict_mc_dropout(d, c, passes=10)[0]
+            else:
+                logits = lightning.predict_tta_mc(d, c, passes=10)[0]
+            if world > 1:
+                dist.all_gather(gathered, logits)
+            return logits
         logits = pipe.forward_raw(dwi_d, dce_d)
         if world > 1:  # the path's only exchange: final logit gather (16 B/case)
             dist.all_gather(gathered, logits)
@@ -439,7 +461,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": (WORKLOAD if args.workload == "c3" else WORKLOAD_C4) +
-                       (" [hybrid TransformerStage encoders]" if args.hybrid else ""),
+                       (" [hybrid TransformerStage encoders]" if args.hybrid else "") +
+                       (f" [predict mode {args.predict_mode}: {dict(tta=4, mc=10, tta_mc=40)[args.predict_mode]} forwards per case]"
+                        if args.predict_mode != "normal" else ""),
                        "batch_per_gpu": B, "global_batch": B * world, "aux": args.aux,
                        "weights": "seeded random init (initialize_model) + randomised BN running stats",
                        "l2": "no flush needed: per-step inputs (369 MB at B=1024) and activations (>10 GB) exceed the 126 MB L2",
