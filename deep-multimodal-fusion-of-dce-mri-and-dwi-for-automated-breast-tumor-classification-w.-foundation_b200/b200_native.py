@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _lib = None
 
@@ -94,6 +94,7 @@ SIGNATURES = {
     "b200_adaptive_pool": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "b200_add_maps": [_P, _P, _LL, _P, _P],
     "b200_set_dropout": [_F, C.c_ulonglong, _I],
+    "b200_adc_map": [_P, _I, _I, _I, _P, _F, _P, _P],
     "b200_flip_planes": [_P, _P, _LL, _I, _I, _I, _I, _P],
     "b200_fusion_tokens": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "b200_fusion_core": [C.POINTER(FusionWeights), _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -365,6 +366,15 @@ def set_dropout(p, seed, segments=1):
     rc = lib().b200_set_dropout(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(segments))
     if rc:
         raise B200NativeError(f"b200_set_dropout -> {rc}")
+
+
+def adc_map(x, bvals, eps=1e-6):
+    """x [B,C,H,W] fp32 CUDA, bvals [C] fp32 CUDA -> [B,1,H,W] ADC maps."""
+    x = x.contiguous().float()
+    B, C_, H, W = x.shape
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+    _call("b200_adc_map", None, _ptr(x), B, C_, H * W, _ptr(bvals), float(eps), _ptr(out), _stream())
+    return out
 
 
 def flip_planes(x, flip_w, flip_h):

@@ -603,6 +603,44 @@ nyul_transform_large_kernel(const float* __restrict__ x, float* __restrict__ out
                plane_mean, src);
 }
 
+// ADC map (reference preprocess_helpers.py:133-167): per pixel, minus the least-squares slope of log(max(S, eps))
+// over the b-values: adc = -sum_c (b_c - mean b)(log S_c - mean log S) / (sum_c (b_c - mean b)^2 + eps).
+// One thread per pixel, the C planes read with unit stride across threads; C <= 32.
+__global__ void __launch_bounds__(kNormThreads)
+adc_map_kernel(const float* __restrict__ x, const float* __restrict__ bvals, int C, int n, float eps,
+               float* __restrict__ out, size_t total) {
+    __shared__ float s_db[32];
+    __shared__ float s_inv_var;
+    if (threadIdx.x == 0) {
+        float mb = 0.f;
+        for (int c = 0; c < C; ++c) mb += bvals[c];
+        mb /= C;
+        float var = 0.f;
+        for (int c = 0; c < C; ++c) {
+            s_db[c] = bvals[c] - mb;
+            var += s_db[c] * s_db[c];
+        }
+        s_inv_var = 1.0f / (var + eps);
+    }
+    __syncthreads();
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= total) return;
+    const size_t b = i / n;
+    const int pix = static_cast<int>(i - b * n);
+    const float* src = x + b * static_cast<size_t>(C) * n + pix;
+    float ls[32];
+    float mean = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) {
+        ls[c] = logf(fmaxf(__ldg(src + static_cast<size_t>(c) * n), eps));
+        mean += ls[c];
+    }
+    mean /= C;
+    float cov = 0.f;
+    for (int c = 0; c < C; ++c) cov += s_db[c] * (ls[c] - mean);
+    out[i] = -(cov * s_inv_var);
+}
+
 __global__ void __launch_bounds__(kNormThreads)
 plane_mean_kernel(const float* __restrict__ x, int n, float* __restrict__ plane_mean) {
     __shared__ double scratch[33];
@@ -680,5 +718,16 @@ extern "C" int b200_plane_mean(const float* x, int planes, int n, float* plane_m
     if (planes == 0) return 0;
     if (x == nullptr || plane_mean == nullptr) return -2;
     plane_mean_kernel<<<planes, kNormThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, n, plane_mean);
+    return launch_status();
+}
+
+extern "C" int b200_adc_map(const float* x, int B, int C, int n, const float* bvals, float eps, float* out, void* stream) {
+    using namespace b200;
+    if (B < 0 || C <= 0 || C > 32 || n <= 0) return -1;
+    if (B == 0) return 0;
+    if (x == nullptr || bvals == nullptr || out == nullptr) return -2;
+    const size_t total = static_cast<size_t>(B) * n;
+    adc_map_kernel<<<static_cast<unsigned>((total + kNormThreads - 1) / kNormThreads), kNormThreads, 0,
+                     static_cast<cudaStream_t>(stream)>>>(x, bvals, C, n, eps, out, total);
     return launch_status();
 }

@@ -112,9 +112,13 @@ class SingleInputDataset(torch.utils.data.Dataset):
         mask = self.masks[index] if self.masks is not None else None
         if self.transforms:
             img = self.transforms(img)
-        if self.adc_map is not None:
-            adc = F.interpolate(self.adc_map.unsqueeze(0), size=img.shape[-2:], mode="bilinear",
-                                align_corners=False).squeeze(0)
+        if self.adc_map is not None:  # the ADC channel is resized to the (transformed) image (reference :79-88)
+            adc = self.adc_map
+            if tuple(adc.shape[-2:]) != tuple(img.shape[-2:]):
+                dev_adc, home = _to_device(adc)
+                out = torch.empty((adc.shape[0], *img.shape[-2:]), dtype=torch.float32, device=dev_adc.device)
+                nat.resize_bilinear_c1(dev_adc.contiguous().float(), out)
+                adc = out if home is None else out.to(home)
             img = torch.cat([img, adc.to(img.device)], dim=0)
         items = [img.float()]
         if mask is not None:

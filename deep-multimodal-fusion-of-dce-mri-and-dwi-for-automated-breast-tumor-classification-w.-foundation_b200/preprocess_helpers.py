@@ -114,11 +114,17 @@ def preprocess_adc(adc_map):
 
 
 def compute_adc_map(dwi_imgs, bvals, eps=1e-6):
-    """-slope of the per-pixel least-squares line of log S over b (:133-167).  Host-side helper that
-    precedes the hot path; a fused device kernel is a 'next' row."""
-    C = dwi_imgs.shape[0]
-    b = torch.tensor(bvals, dtype=torch.float32, device=dwi_imgs.device).view(C, 1, 1)
-    log_s = torch.log(torch.clamp(dwi_imgs, min=eps))
-    db = b - b.mean()
-    slope = (db * (log_s - log_s.mean(dim=0))).sum(dim=0) / ((db ** 2).sum() + eps)
-    return (-slope).unsqueeze(0)
+    """-slope of the per-pixel least-squares line of log S over b (:133-167) -> [1,H,W].  Runs on the device
+    (b200_adc_map); a CPU tensor is staged through the GPU and returned on the CPU, like the normalisers."""
+    home = None if dwi_imgs.is_cuda else dwi_imgs.device
+    if home is not None and not torch.cuda.is_available():
+        raise nat.B200NativeError("compute_adc_map runs on the GPU only (no CPU path)")
+    x = dwi_imgs if dwi_imgs.is_cuda else dwi_imgs.cuda()
+    b = torch.as_tensor(bvals, dtype=torch.float32).to(x.device)
+    out = nat.adc_map(x.unsqueeze(0), b, eps)[0]
+    return out if home is None else out.to(home)
+
+
+def compute_adc_map_batch(dwi, bvals, eps=1e-6):
+    """Batched form: dwi [B,C,H,W] CUDA -> [B,1,H,W] (one launch)."""
+    return nat.adc_map(dwi, torch.as_tensor(bvals, dtype=torch.float32).to(dwi.device), eps)

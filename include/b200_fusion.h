@@ -267,6 +267,10 @@ int b200_adaptive_pool(const void* x, int x_f32, int B, int H, int W, int C, int
                        void* stream);
 int b200_add_maps(const void* a, const void* b, long long n_elems, void* out, void* stream);
 
+/* compute_adc_map (code/preprocess_helpers.py:133-167): x [B, C, n] fp32 DWI stacks (n = H*W), bvals [C] on the
+ * device -> out [B, n]: minus the per-pixel least-squares slope of log(max(S, eps)) over b.  C <= 32. */
+int b200_adc_map(const float* x, int B, int C, int n, const float* bvals, float eps, float* out, void* stream);
+
 /* Test-time-augmentation flips (code/train.py:916-923, used by code/train_fusion.py:543-632): out = flip of every
  * [H, W] plane of x [planes, H, W] fp32 along W and / or H.  Out of place. */
 int b200_flip_planes(const float* x, float* out, long long planes, int H, int W, int flip_w, int flip_h,

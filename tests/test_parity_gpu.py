@@ -535,3 +535,28 @@ def test_mc_dropout_prediction_is_statistically_the_reference():
     assert 0.6 < ratio < 1.6, ratio
     mean_t, std_t, _ = lm.predict_tta_mc(dwi.to(DEV), dce_raw.to(DEV), passes=4)
     assert mean_t.shape == (n, 4) and torch.isfinite(mean_t).all() and abs(mean_t.sum(1).mean().item() - 1) < 1e-3
+
+
+def test_adc_map_vs_oracle_and_golden():
+    """compute_adc_map (preprocess_helpers.py:133-167) on the device, against the reference fixture and the oracle;
+    and the dataset's ADC channel (resized to the image, dataset.py:79-88)."""
+    gold = gu.load("normalizers.npz")
+    dwi_raw, _, _, _ = op.synthetic_raw(12, seed=1234, kind="S")
+    bvals = list(range(13))
+    adc = b_pre.compute_adc_map(dwi_raw[0, :13].to(DEV), bvals)
+    ref = torch.from_numpy(gold["adc/map"])
+    assert tuple(adc.shape) == (1, 64, 64)
+    assert _relmax(adc, ref) <= NORM_TOL
+    batch = b_pre.compute_adc_map_batch(dwi_raw[:, :13].to(DEV), bvals)
+    for i in (0, 5, 11):
+        assert _relmax(batch[i], no.compute_adc_map(dwi_raw[i, :13], bvals)) <= NORM_TOL
+    zeros = torch.zeros(1, 13, 8, 8, device=DEV)             # log(max(0, eps)) on every plane: slope 0
+    assert b_pre.compute_adc_map_batch(zeros, bvals).abs().max().item() < 1e-6
+    cpu_adc = b_pre.compute_adc_map(dwi_raw[0, :13], bvals)  # CPU in -> CPU out, staged through the GPU
+    assert not cpu_adc.is_cuda and _relmax(cpu_adc, ref) <= NORM_TOL
+    ds = b_dataset.SingleInputDataset(dwi_raw[:2, :13], labels=torch.tensor([0, 1]), transforms=b_dataset.Resize(128),
+                                      adc_map=cpu_adc)
+    img, label = ds[1]
+    assert tuple(img.shape) == (14, 128, 128)
+    ref_adc = torch.nn.functional.interpolate(ref.unsqueeze(0), size=(128, 128), mode="bilinear", align_corners=False)[0]
+    assert _relmax(img[13:], ref_adc) <= NORM_TOL
