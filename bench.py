@@ -449,6 +449,17 @@ def main():
                         "kernel": dom_name,
                         "ms_per_launch": dom_ms, "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
                         "share_of_step": sum(prof[dom_key]) / total_ms if total_ms else None}
+        # the HBM-bound side of the path: the DWI normaliser against the measured copy bandwidth
+        # (algorithmic bytes per case: 15 planes read + 16 written, SURVEY.md section 8(d) / DESIGN.md 4.2)
+        hbm_roofline = None
+        nm = table.get(("b200_dwi_normalize", None))
+        if nm:
+            side = 224 if args.workload == "c4" else 64
+            nbytes = B * (15 + 16) * side * side * 4
+            gbs = nbytes / (nm[0] / 1e3) / 1e9
+            hbm_roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": gbs / peaks["hbm_gbs"], "traffic": None, "kernel": "dwi_normalize (inside the step)",
+                            "ms_per_launch": nm[0]}
         conv_ms = sum(sum(t) for (n, _), t in prof.items() if n == "b200_conv_gemm_ex")
         kernels = sorted(((sum(t), n, k, len(t)) for (n, k), t in prof.items()), reverse=True)[:40]
         nsteps_prof = max(2, min(args.steps, 5))
@@ -475,6 +486,7 @@ def main():
             "gpu_launches": launches,
             "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated(device) / 1e9,
             "roofline": roofline,
+            "roofline_hbm_kernel": hbm_roofline,
             "step_model": {"algorithmic_gflop_per_case": flop_case / 1e9,
                            "achieved_tflops_whole_step": value / world * flop_case / 1e12,
                            "frac_of_sustained_peak": value / world * flop_case / 1e12 / peaks["tf_sustained"],
