@@ -201,25 +201,32 @@ constexpr int kNyulThreads = 512;
 // numpy.interp for one sample: xp ascending (ties allowed), float64 throughout, no FMA
 // contraction (matches the C loop in numpy's compiled_base.c).
 __device__ __forceinline__ double np_interp(double xv, const double* xp, const float* xpf, const double* fp,
-                                            const double* slope, int L) {
-    if (xv != xv) return xv;
-    if (xv < xp[0]) return fp[0];
-    if (xv > xp[L - 1]) return fp[L - 1];
-    // largest j with xp[j] <= xv: a 4-step binary search on fp32 copies of the landmarks (L <= 16), then an
-    // exact fp64 fix-up (the fp32 guess is off by at most one when xv sits within rounding of a landmark), so
-    // the segment is the one numpy picks while ~20 fp64 compare/select pairs per sample are saved
-    const float xf = static_cast<float>(xv);
-    int j = 0;
+                                            const double* slope, int L, int hint, int& j_out) {
+    if (xv != xv) {
+        j_out = 0;
+        return xv;
+    }
+    // Segment j = largest index with xp[j] <= xv (0 when xv < xp[0]).  First guess: the caller's hint (the second
+    // interpolation of a sample almost always lands in the segment of the first), else a 4-step binary search on
+    // fp32 copies of the landmarks (L <= 16); then an exact fp64 fix-up, normally two compares that change nothing.
+    int j = hint;
+    if (hint < 0) {
+        const float xf = static_cast<float>(xv);
+        j = 0;
 #pragma unroll
-    for (int step = 8; step >= 1; step >>= 1) {
-        const int t = j + step;
-        if (t < L && xpf[t] <= xf) j = t;
+        for (int step = 8; step >= 1; step >>= 1) {
+            const int t = j + step;
+            if (t < L && xpf[t] <= xf) j = t;
+        }
     }
     while (j > 0 && xp[j] > xv) --j;
     while (j + 1 < L && xp[j + 1] <= xv) ++j;
-    if (j == L - 1) return fp[j];
-    if (xp[j] == xv) return fp[j];
-    double r = __dadd_rn(__dmul_rn(slope[j], __dadd_rn(xv, -xp[j])), fp[j]);
+    j_out = j;
+    // numpy.interp: left / right fill, exact hits, then slope * (x - xp[j]) + fp[j] with its NaN fallbacks
+    if (j == L - 1) return fp[j];            // xv >= xp[L-1]
+    const double x0 = xp[j];
+    if (!(xv > x0)) return fp[j];            // xv == xp[j], or xv < xp[0] (j == 0)
+    double r = __dadd_rn(__dmul_rn(slope[j], __dadd_rn(xv, -x0)), fp[j]);
     if (r != r) {
         r = __dadd_rn(__dmul_rn(slope[j], __dadd_rn(xv, -xp[j + 1])), fp[j + 1]);
         if (r != r && fp[j] == fp[j + 1]) r = fp[j];
@@ -268,8 +275,9 @@ __device__ __forceinline__ void nyul_apply(const float* s_val, int L, int c, int
     __syncthreads();
     double osum = 0.0;
     auto map = [&](float v) {
-        const double mid = np_interp(static_cast<double>(v), s_orig, s_origf, s_avg, s_slope1, L);
-        return static_cast<float>(np_interp(mid, s_avg, s_avgf, s_std, s_slope2, L));
+        int j1, j2;
+        const double mid = np_interp(static_cast<double>(v), s_orig, s_origf, s_avg, s_slope1, L, -1, j1);
+        return static_cast<float>(np_interp(mid, s_avg, s_avgf, s_std, s_slope2, L, j1, j2));
     };
     if (gsrc != nullptr && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(gsrc) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
         // plane read straight from global / L2: 16-byte loads and stores, four independent interpolations per trip
