@@ -46,7 +46,6 @@ stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
     const int b = blockIdx.y;
     const int Ho = H / stride, Wo = W / stride;
     const int npix = Ho * Wo;
-    const int pix0 = blockIdx.x * kStemPix;
     const int tid = threadIdx.x;
 
     if (se_w1 != nullptr) {
@@ -78,6 +77,11 @@ stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
 
     const int pp = tid % kStemPix;
     const int quarter = tid / kStemPix;  // 0..3
+    // A CTA walks several 64-pixel tiles of its case: the weight staging / transposition and the SE gate above are
+    // paid once per CTA, not once per tile (they cost about as much as one tile's arithmetic).
+    const int n_tiles = (npix + kStemPix - 1) / kStemPix;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int pix0 = tile * kStemPix;
     const int pix = pix0 + pp;
     float2 xv[CMAX];  // the pixel's gated input, duplicated into both halves of a packed operand
     {
@@ -146,6 +150,8 @@ stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
             dst[i] = make_uint4(src[0], src[1], src[2], src[3]);
         }
     }
+    __syncthreads();  // s_out is rewritten by the next tile
+    }  // tile loop
 }
 
 // ------------------------------------------------------------- SE gate -----
@@ -485,7 +491,11 @@ extern "C" int b200_stem(const float* x, int B, int C, int H, int W, int stride,
     const size_t smem = (static_cast<size_t>(C) * n_out + 2 * n_out) * sizeof(float) +
                         static_cast<size_t>(kStemPix) * (n_out / 2 + 1) * sizeof(uint32_t);
     if (smem > 48 * 1024) return -6;  // all supported shapes stay inside the default dynamic limit
-    dim3 grid((npix + kStemPix - 1) / kStemPix, B);
+    const int n_tiles = (npix + kStemPix - 1) / kStemPix;
+    // tiles per CTA: as many as keeps >= ~8 CTAs per SM in the grid
+    int gx = n_tiles;
+    while (gx > 1 && static_cast<long long>(gx / 2) * B >= 148LL * 8) gx = (gx + 1) / 2;
+    dim3 grid(gx, B);
     const b200::PendingDropout drop = b200::take_pending_dropout();  // MC-dropout on the mid map, if armed
     const unsigned int thresh = drop.seg != 0 ? b200::dropout_threshold(drop.p) : 0u;
     const float dscale = drop.seg != 0 ? 1.0f / (1.0f - drop.p) : 1.0f;
