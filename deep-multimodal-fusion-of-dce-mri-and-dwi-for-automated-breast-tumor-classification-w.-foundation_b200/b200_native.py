@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _lib = None
 
@@ -69,7 +69,7 @@ SIGNATURES = {
     "b200_abi_version": [],
     "b200_conv_gemm": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_conv_gemm_ex": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _F, _P, _I, _I, _I,
-                          _I, _I, _I, _I, _P],
+                          _I, _I, _I, _I, _I, _P],
     "b200_resize_bilinear_c1": [_P, _I, _I, _I, _P, _I, _I, _P],
     "b200_mask_attention": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P],
     "b200_tapsum": [_P, _I, _I, _I, _P, _P, _P],
@@ -95,6 +95,8 @@ SIGNATURES = {
     "b200_add_maps": [_P, _P, _LL, _P, _P],
     "b200_set_dropout": [_F, C.c_ulonglong, _I],
     "b200_adc_map": [_P, _I, _I, _I, _P, _F, _P, _P],
+    "b200_conv7x7_s2": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "b200_maxpool3x3_s2": [_P, _I, _I, _I, _I, _P, _P],
     "b200_flip_planes": [_P, _P, _LL, _I, _I, _I, _I, _P],
     "b200_fusion_tokens": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "b200_fusion_core": [C.POINTER(FusionWeights), _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -194,12 +196,13 @@ def _ld(t):
 
 def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0, out=None, up2=False, gap=None,
               cin=None, store=True, n_split=None, act2=0, out2=None, dot_w=None, dot_out=None, dot_bias=0.0, stride=1,
-              dropout=None):
+              dropout=None, dilation=1):
     """x [B,H,W,ld] bf16 NHWC (channels [0,cin) used); w [Cout, taps*cin] bf16.  Returns `out`
     (or (out, out2) when n_split is given: channels [n_split, Cout) form a second layer on the same input)."""
-    _bf16_map(x, "x")
-    B, H, W, x_ld = x.shape
-    cin = x_ld if cin is None else cin
+    _bf16_map(x, "x", allow_slice=True)
+    B, H, W, _ = x.shape
+    x_ld = _ld(x)
+    cin = x.shape[-1] if cin is None else cin
     cout = w.shape[0]
     assert w.dtype == torch.bfloat16 and w.is_contiguous() and w.shape[1] == taps * cin
     n1 = cout if n_split is None else n_split
@@ -224,7 +227,7 @@ def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0,
           res.shape[-1] if res is not None else 0, res_mode, act, _ptr(out), out_ld,
           1 if up2 else 0, _ptr(gap), n1, _ptr(out2), _ld(out2) if out2 is not None else 0, act2,
           _ptr(dot_w), dot_w.shape[0] if dot_w is not None else 0, float(dot_bias), _ptr(dot_out), B, H, W, cin, cout,
-          taps, stride, _stream())
+          taps, stride, dilation, _stream())
     return out if n_split is None else (out, out2)
 
 
@@ -375,6 +378,22 @@ def adc_map(x, bvals, eps=1e-6):
     out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
     _call("b200_adc_map", None, _ptr(x), B, C_, H * W, _ptr(bvals), float(eps), _ptr(out), _stream())
     return out
+
+
+def conv7x7_s2(x, gate, wt, scale, bias):
+    """ResNet stem: x [B,C,H,W] fp32 -> relu(bn(conv7x7/s2)) as bf16 NHWC [B,H/2,W/2,64]; wt [C,49,64] fp32."""
+    x = x.contiguous().float()
+    B, C_, H, W = x.shape
+    y = torch.empty((B, H // 2, W // 2, 64), dtype=torch.bfloat16, device=x.device)
+    _call("b200_conv7x7_s2", None, _ptr(x), _ptr(gate), B, C_, H, W, _ptr(wt), _ptr(scale), _ptr(bias), _ptr(y), _stream())
+    return y
+
+
+def maxpool3x3_s2(x):
+    B, H, W, C_ = x.shape
+    y = torch.empty((B, H // 2, W // 2, C_), dtype=torch.bfloat16, device=x.device)
+    _call("b200_maxpool3x3_s2", None, _ptr(x), B, H, W, C_, _ptr(y), _stream())
+    return y
 
 
 def flip_planes(x, flip_w, flip_h):

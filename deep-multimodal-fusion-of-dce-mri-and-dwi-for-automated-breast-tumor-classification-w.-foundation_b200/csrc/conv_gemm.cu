@@ -68,7 +68,8 @@ struct ConvGemmParams {
     float dot_bias;
     int ndot;
     int a_box_bytes;       // bytes one A box really delivers (BW*BH rows x 128 B; < 16 KB when BW*BH < 128)
-    int cstride;           // convolution stride (1, or 2 for the 2x2 / stride-2 patch embedding: taps == 4)
+    int cstride;           // convolution stride
+    int dil;               // dilation of the 3x3 taps (1 = dense) (1, or 2 for the 2x2 / stride-2 patch embedding: taps == 4)
     int a_batched;         // 0: the A operand is shared by every (h, b) (weights on the A side)
     int b_mode;            // 0: B operand = 2-D weights [N, K]; 1: 4-D batched {K, N, H, B}
     int bias_h_stride;     // scale / bias index = n + h * bias_h_stride (per-head vectors in batched GEMMs)
@@ -246,8 +247,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int c0 = (kb - tap * p.kc) * kBlockK;
                     int dy = 0, dx = 0;
                     if (p.taps == 9) {
-                        dy = tap / 3 - 1;
-                        dx = tap % 3 - 1;
+                        dy = (tap / 3 - 1) * p.dil;
+                        dx = (tap % 3 - 1) * p.dil;
                     } else if (p.taps == 4) {
                         dy = tap >> 1;
                         dx = tap & 1;
@@ -600,9 +601,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (RES != 0) {
                     if (kF32 && use_res && p.res_f32) {
                         // fp32 residual stream: every thread owns one 128-byte row segment per chunk
-                        if (RES == 2 && act == 1) {
+                        if (RES == 2 && act != 0) {
+
+                            if (act == 1) {
 #pragma unroll
-                            for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+
+                                for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+
+                            } else {  // act == 2: ReLU (ResNet backbones)
+#pragma unroll
+
+                                for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.f);
+
+                            }
                         }
                         if (kTransposeF32) {
                             // Coalesced: one warp instruction reads 4 rows x 128 B (8 lanes x 16 B per row), the
@@ -634,9 +645,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 v2[2 * j + 1] = __fadd2_rn(v2[2 * j + 1], make_float2(f.z, f.w));
                             }
                         }
-                        if (RES == 1 && act == 1) {
+                        if (RES == 1 && act != 0) {
+
+                            if (act == 1) {
 #pragma unroll
-                            for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+
+                                for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+
+                            } else {  // act == 2: ReLU (ResNet backbones)
+#pragma unroll
+
+                                for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.f);
+
+                            }
                         }
                     } else if (use_res) {
                         uint4 u[4];
@@ -662,9 +683,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                             for (int j = 0; j < 4; ++j) u[j] = make_uint4(0u, 0u, 0u, 0u);
                         }
-                        if (RES == 2 && act == 1) {
+                        if (RES == 2 && act != 0) {
+
+                            if (act == 1) {
 #pragma unroll
-                            for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+
+                                for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+
+                            } else {  // act == 2: ReLU (ResNet backbones)
+#pragma unroll
+
+                                for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.f);
+
+                            }
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -674,17 +705,47 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 v2[4 * j + t] = __fadd2_rn(v2[4 * j + t], make_float2(__uint_as_float(uu[t] << 16),
                                                                                      __uint_as_float(uu[t] & 0xffff0000u)));
                         }
-                        if (RES == 1 && act == 1) {
+                        if (RES == 1 && act != 0) {
+
+                            if (act == 1) {
 #pragma unroll
-                            for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+
+                                for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+
+                            } else {  // act == 2: ReLU (ResNet backbones)
+#pragma unroll
+
+                                for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.f);
+
+                            }
                         }
-                    } else if (act == 1) {
+                    } else if (act != 0) {
+
+                        if (act == 1) {
 #pragma unroll
-                        for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+
+                            for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+
+                        } else {  // act == 2: ReLU (ResNet backbones)
+#pragma unroll
+
+                            for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.f);
+
+                        }
                     }
-                } else if (act == 1) {
+                } else if (act != 0) {
+
+                    if (act == 1) {
 #pragma unroll
-                    for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+
+                        for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+
+                    } else {  // act == 2: ReLU (ResNet backbones)
+#pragma unroll
+
+                        for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.f);
+
+                    }
                 }
                 if (MODE == 3 && (p.drop_seg & (seg2 ? 2 : 1))) {
                     // nn.Dropout in MC-dropout inference (reference train_fusion.py:478-481: dropout modules in train
@@ -1180,7 +1241,7 @@ extern "C" int b200_conv_gemm(const void* x, int x_ld, const void* w, const floa
                               const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
                               float* gap, int B, int H, int W, int Cin, int Cout, int taps, void* stream) {
     return b200_conv_gemm_ex(x, x_ld, w, scale, bias, res, res_ld, res_mode, act, out, out_ld, up2, gap, Cout, nullptr,
-                             0, 0, nullptr, 0, 0.f, nullptr, B, H, W, Cin, Cout, taps, 1, stream);
+                             0, 0, nullptr, 0, 0.f, nullptr, B, H, W, Cin, Cout, taps, 1, 1, stream);
 }
 
 // One-shot MC-dropout request for the next dropout-capable launch of this thread (see b200_fusion.h).
@@ -1205,8 +1266,9 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
                                  const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
                                  float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w,
                                  int ndot, float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout,
-                                 int taps, int stride, void* stream) {
+                                 int taps, int stride, int dilation, void* stream) {
     using namespace b200;
+    if (dilation < 1 || dilation > 8 || (dilation != 1 && taps != 9)) return -6;
     if (dot_w == nullptr) ndot = 0;
     if (ndot != 0 && ndot != 1 && ndot != 9) return -18;
     if (x == nullptr || w == nullptr || B <= 0 || H <= 0 || W <= 0) return -1;
@@ -1257,6 +1319,7 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
     p.taps = taps;
     p.k_blocks = taps * p.kc;
     p.cstride = cs;
+    p.dil = dilation;
     p.a_batched = 1;
     p.b_mode = 0;
     p.bias_h_stride = 0;

@@ -32,9 +32,11 @@ import torch.nn as nn
 
 import b200_native as nat
 
-__all__ = ["build_medical_backbone", "build_vit_dino_backbone", "B200ViTBackbone"]
+__all__ = ["build_medical_backbone", "build_vit_dino_backbone", "build_radimagenet_backbone", "build_imagenet_backbone",
+           "B200ViTBackbone", "B200ResNetBackbone"]
 
 VIT_NAMES = ("vit_base_patch16_224", "dino_vitbase16_pretrain", "dino_vitbase16_pretrained")
+RESNET_NAMES = ("resnet50", "radimagenet", "radimagenet_resnet50")
 
 
 class _FeatureInfo:
@@ -209,6 +211,209 @@ class B200ViTBackbone(nn.Module):
         return feats if chains is None else bufs
 
 
+# --------------------------------------------------------------------------------------
+# ResNet-50 (timm / torchvision `resnet50`, v1.5: the stride sits on the 3x3 conv)
+# --------------------------------------------------------------------------------------
+class _Bottleneck(nn.Module):
+    """keys conv1, bn1, conv2, bn2, conv3, bn3, downsample.{0,1} (timm / torchvision Bottleneck)."""
+
+    def __init__(self, cin, planes, stride, dilation, downsample):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=dilation, dilation=dilation, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.downsample = None
+        if downsample:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, planes * 4, 1, stride=stride, bias=False),
+                                            nn.BatchNorm2d(planes * 4))
+        self.stride, self.dilation = stride, dilation
+
+
+def _bn_affine(bn, dev):
+    g, b = _f32(bn.weight, dev), _f32(bn.bias, dev)
+    m, v = _f32(bn.running_mean, dev), _f32(bn.running_var, dev)
+    scale = g / torch.sqrt(v + bn.eps)
+    return scale.contiguous(), (b - m * scale).contiguous()
+
+
+def _conv_k_major(conv, dev):
+    w = conv.weight.detach().to(dev)
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+
+
+class B200ResNetBackbone(nn.Module):
+    """ResNet-50 `features_only` backbone as the reference builds it with timm (foundation_model.py:15-68, :220-312:
+    `timm.create_model("resnet50", features_only=True, output_stride=8, out_indices=(1, 2, 3, 4), in_chans=C)`):
+    forward(x[B,C,H,W]) -> [C2 (256, /4), C3 (512, /8), C4 (1024, /8, dilated), C5 (2048, /8, dilated)] as bf16
+    channels_last views.  Parameter names are timm's / torchvision's (conv1, bn1, layerN.M.{conv1..bn3, downsample}),
+    so resnet50 and (re-keyed, see map_rasool_to_timm_keys) RadImageNet checkpoints load unchanged.  Eval-mode only:
+    BatchNorm is folded into the GEMM epilogues."""
+
+    def __init__(self, in_chans=3, layers=(3, 4, 6, 3), output_stride=8, out_indices=(1, 2, 3, 4)):
+        super().__init__()
+        if output_stride not in (8, 16, 32):
+            raise ValueError("output_stride must be 8, 16 or 32")
+        self.conv1 = nn.Conv2d(in_chans, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.out_indices = list(out_indices)
+        if any(i not in (1, 2, 3, 4) for i in self.out_indices):
+            raise NotImplementedError("only the C2..C5 features (out_indices 1..4) are built")
+        cin, net_stride, dilation, prev_dilation = 64, 4, 1, 1
+        reductions = []
+        for li, (planes, n_blocks, stride) in enumerate(zip((64, 128, 256, 512), layers, (1, 2, 2, 2))):
+            if net_stride >= output_stride:  # timm: trade the stride for dilation once the target stride is reached
+                dilation *= stride
+                stride = 1
+            else:
+                net_stride *= stride
+            blocks = []
+            for bi in range(n_blocks):
+                blocks.append(_Bottleneck(cin, planes, stride if bi == 0 else 1, prev_dilation if bi == 0 else dilation,
+                                          downsample=(bi == 0)))
+                cin = planes * 4
+            prev_dilation = dilation
+            setattr(self, f"layer{li + 1}", nn.Sequential(*blocks))
+            reductions.append(net_stride)
+        chans = [256, 512, 1024, 2048]
+        self.feature_info = _FeatureInfo([chans[i - 1] for i in self.out_indices], [reductions[i - 1] for i in self.out_indices])
+        self.output_dims = self.feature_info.channels()
+        self.expected_input, self.is_3d, self.foundation_model, self.transformer_backbone = "B, C, H, W", False, True, False
+        self._pack_cache = None
+
+    def _packed(self, dev):
+        sig = (str(dev), tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers())))
+        if self._pack_cache is not None and self._pack_cache[0] == sig:
+            return self._pack_cache[1]
+        s0, b0 = _bn_affine(self.bn1, dev)
+        w = self.conv1.weight.detach().to(dev).float()
+        pk = {"stem": (w.permute(1, 2, 3, 0).reshape(w.shape[1], 49, 64).contiguous(), s0, b0), "layers": []}
+        for li in range(4):
+            blocks = []
+            for blk in getattr(self, f"layer{li + 1}"):
+                d = {"w1": _conv_k_major(blk.conv1, dev), "a1": _bn_affine(blk.bn1, dev),
+                     "w2": _conv_k_major(blk.conv2, dev), "a2": _bn_affine(blk.bn2, dev),
+                     "w3": _conv_k_major(blk.conv3, dev), "a3": _bn_affine(blk.bn3, dev),
+                     "stride": blk.stride, "dilation": blk.dilation}
+                if blk.downsample is not None:
+                    d["wd"] = _conv_k_major(blk.downsample[0], dev)
+                    d["ad"] = _bn_affine(blk.downsample[1], dev)
+                blocks.append(d)
+            pk["layers"].append(blocks)
+        self._pack_cache = (sig, pk)
+        return pk
+
+    @torch.no_grad()
+    def forward(self, x):
+        return [f.permute(0, 3, 1, 2) for f in self._run(x, None, None)]
+
+    @torch.no_grad()
+    def forward_chains(self, x, chains, gate=None):
+        """Per index chain the channel concatenation of its feature maps (BackboneAdapter, model_module.py:452-471),
+        written in place: a layer's last bottleneck stores straight into its slice of the chain buffer."""
+        return self._run(x, gate, [list(c) for c in chains])
+
+    def _run(self, x, gate, chains):
+        if self.training:
+            raise NotImplementedError("training-mode forward is not built in the B200 path yet; call .eval()")
+        if not x.is_cuda:
+            raise nat.B200NativeError("B200ResNetBackbone.forward needs a CUDA tensor (no CPU path)")
+        x = x.contiguous().float()
+        dev = x.device
+        pk = self._packed(dev)
+        B = x.shape[0]
+        t = nat.maxpool3x3_s2(nat.conv7x7_s2(x, gate, *pk["stem"]))   # [B, H/4, W/4, 64]
+        chans = [256, 512, 1024, 2048]
+        # where does feature fi (position in the returned list) have to land?
+        dest = {}
+        bufs = None
+        if chains is not None:
+            sizes = []
+            for chain in chains:
+                sizes.append(sum(self.feature_info.channels()[i] for i in chain))
+            bufs = [None] * len(chains)
+            for ci, chain in enumerate(chains):
+                off = 0
+                for fi in chain:
+                    dest[fi] = (ci, off, sizes[ci])
+                    off += self.feature_info.channels()[fi]
+        feats = []
+        for li, blocks in enumerate(pk["layers"]):
+            fi = self.out_indices.index(li + 1) if (li + 1) in self.out_indices else None
+            for bi, blk in enumerate(blocks):
+                last = bi == len(blocks) - 1
+                h = nat.conv_gemm(t, blk["w1"], taps=1, scale=blk["a1"][0], bias=blk["a1"][1], act=2)
+                h = nat.conv_gemm(h, blk["w2"], taps=9, scale=blk["a2"][0], bias=blk["a2"][1], act=2,
+                                  stride=blk["stride"], dilation=blk["dilation"])
+                idn = t
+                if "wd" in blk:
+                    idn = nat.conv_gemm(t, blk["wd"], taps=1, scale=blk["ad"][0], bias=blk["ad"][1], act=0,
+                                        stride=blk["stride"])
+                elif not idn.is_contiguous():
+                    idn = idn.contiguous()   # (never: a sliced feature is only ever a first-block input)
+                out = None
+                if last and fi is not None and fi in dest:
+                    ci, off, total = dest[fi]
+                    if bufs[ci] is None:
+                        bufs[ci] = torch.empty((B, h.shape[1], h.shape[2], total), dtype=torch.bfloat16, device=dev)
+                    if tuple(bufs[ci].shape[1:3]) != tuple(h.shape[1:3]):
+                        raise ValueError("features of one chain must share their spatial size (torch.cat would fail too)")
+                    out = bufs[ci][..., off:off + chans[li]]
+                t = nat.conv_gemm(h, blk["w3"], taps=1, scale=blk["a3"][0], bias=blk["a3"][1], res=idn, res_mode=1,
+                                  act=2, out=out)
+            if fi is not None:
+                feats.append(t)
+        if chains is not None:
+            return bufs
+        return feats
+
+
+def build_radimagenet_backbone(name="resnet50", device="cuda", in_channels=6, output_stride=8, out_indices=(1, 2, 3, 4),
+                               use_advanced_adapt=True, pretrained_path=None):
+    """Reference :220-312 without timm / the checkpoint download (no network): the same ResNet-50 feature extractor;
+    `pretrained_path` (a local RadImageNet or timm state dict) is loaded when given, re-keyed as the reference does."""
+    if name != "resnet50":
+        raise NotImplementedError("RadImageNet ResNet-101 is not built")
+    model = B200ResNetBackbone(in_chans=in_channels, output_stride=output_stride, out_indices=out_indices)
+    if pretrained_path is not None:
+        ckpt = torch.load(pretrained_path, map_location="cpu")
+        for key in ("state_dict", "model_state_dict", "model", "encoder"):
+            if isinstance(ckpt, dict) and key in ckpt and isinstance(ckpt[key], dict):
+                ckpt = ckpt[key]
+                break
+        ckpt = map_rasool_to_timm_keys(ckpt)
+        own = model.state_dict()
+        w = ckpt.get("conv1.weight")
+        if w is not None and w.shape[1] != in_channels:  # adapt_first_conv (:70-95): mean over RGB, repeated
+            ckpt["conv1.weight"] = w.mean(dim=1, keepdim=True).repeat(1, in_channels, 1, 1)
+        model.load_state_dict({k: v for k, v in ckpt.items() if k in own and own[k].shape == v.shape}, strict=False)
+    model.eval()
+    return model.to(device) if device is not None else model
+
+
+build_imagenet_backbone = build_radimagenet_backbone
+
+
+def map_rasool_to_timm_keys(rasool_state_dict):
+    """Reference :180-218: RadImageNet (Rasool) ResNet-50 keys -> timm resnet50 keys."""
+    layer_map = {"4": "layer1", "5": "layer2", "6": "layer3", "7": "layer4"}
+    mapped = {}
+    for k, v in rasool_state_dict.items():
+        nk = k[len("backbone."):] if k.startswith("backbone.") else k
+        if nk == "0.weight":
+            nk = "conv1.weight"
+        elif nk.startswith("1."):
+            nk = "bn1." + nk[2:]
+        elif nk[:1] in layer_map and nk[1:2] == ".":
+            nk = f"{layer_map[nk[0]]}.{nk[2:]}"
+        if nk.startswith("fc."):
+            continue
+        mapped[nk] = v
+    return mapped
+
+
 def build_vit_dino_backbone(model_name="vit_base_patch16_224", in_channels=3, img_size=224, device=None, **_):
     """Reference :371-431 without the timm dependency: a ViT-B/16 feature extractor for `in_channels` inputs."""
     if model_name not in VIT_NAMES:
@@ -222,6 +427,14 @@ def build_medical_backbone(parameters, device, method, in_channels):
     """Reference :490-577, ViT branch (:526-545).  Mutates parameters[f"{method}_model_parameters"]."""
     mp = parameters[f"{method}_model_parameters"]
     name = mp["backbone_str"]
+    if name in RESNET_NAMES:
+        # reference :503-524 (resnet50) and :547-569 (radimagenet): C2 / C3 / C4+C5 chains, block1 down-samples
+        backbone = build_radimagenet_backbone("resnet50", device=device, in_channels=in_channels,
+                                              output_stride=mp.get("backbone_stride", 8))
+        mp["backbone_index_lists"] = [[0], [1], [2, 3]]
+        mp["downsample"] = (True, False, False)
+        mp["downsample_each_repeat"] = False
+        return backbone
     if name not in VIT_NAMES:
         raise NotImplementedError(
             f"backbone {name!r}: only the ViT-B/16 branch is built (ResNet / RadImageNet / UNI2-h need network "

@@ -662,12 +662,12 @@ class ModelMaskHeadBackbone(nn.Module):
         if self._pack_cache is not None and self._pack_cache[0] == sig:
             return self._pack_cache[1]
         if self.use_backbone and not hasattr(self.backbone, "forward_chains"):
-            raise NotImplementedError("use_backbone needs a B200ViTBackbone (foundation_model.build_medical_backbone); "
-                                      "the ResNet / RadImageNet / UNI2-h backbones are not built")
+            raise NotImplementedError("use_backbone needs a backbone from foundation_model.build_medical_backbone "
+                                      "(B200ViTBackbone / B200ResNetBackbone); UNI2-h is not built")
         b1 = self.block1
         if self.use_backbone:
-            if b1.stride != 1 or self.use_hybrid_transformer:
-                raise NotImplementedError("backbone encoders: stride-1 CNN blocks only (what the ViT branch configures)")
+            if self.use_hybrid_transformer or (b1.stride != 1 and b1.skip is None):
+                raise NotImplementedError("backbone encoders with the hybrid transformer stage")
         elif b1.stride not in (1, 2) or b1.skip is None or self.channel_num > 32:
             raise NotImplementedError("block1 must read the raw (<=32 channel) input through a skip conv")
         blocks = {"b1": self.block1, "b2": self.block2}

@@ -79,13 +79,15 @@ int b200_set_dropout(float p, unsigned long long seed, int segments);
  *     and out == NULL: the C-channel map never reaches HBM and is never rounded to bf16.
   * `stride` (1 or 2) applies to taps 1 / 9: the strided 1x1 convs of a down-sampling ResNetLiteBlock
  * (code/model_module.py:259-262, :276-280) and the 3x3 / stride-2 / padding-1 stacks of MaskHeadResize (:153-181);
- * H and W are the INPUT size, the output map is H/stride x W/stride.
+ * H and W are the INPUT size, the output map is H/stride x W/stride.  `dilation` (>= 1, taps 9 only; padding =
+ * dilation) serves the dilated layer3 / layer4 of the ResNet-50 backbones built with output_stride 8
+ * (code/foundation_model.py:243-250).  `act`: 0 none, 1 GELU, 2 ReLU.
  */
 int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
                       const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
                       float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w, int ndot,
                       float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout, int taps,
-                      int stride, void* stream);
+                      int stride, int dilation, void* stream);
 
 /*
  * Batched GEMM on the same tcgen05 kernel: for every (batch, head)
@@ -266,6 +268,18 @@ int b200_mix_instnorm(const void* fb, const void* f, int B, int npix, int C, con
 int b200_adaptive_pool(const void* x, int x_f32, int B, int H, int W, int C, int Ho, int Wo, int act, void* out,
                        void* stream);
 int b200_add_maps(const void* a, const void* b, long long n_elems, void* out, void* stream);
+
+/*
+ * ResNet-50 backbone stem (timm / torchvision `resnet50` as built by code/foundation_model.py:15-68, :220-312):
+ *   b200_conv7x7_s2     conv1 (7x7, stride 2, padding 3) + folded bn1 + ReLU on the fp32 NCHW input, optionally
+ *                       scaled per (case, channel) by the modality-attention gate; wt is the weight transposed to
+ *                       [C][49][64]; y bf16 NHWC [B, H/2, W/2, 64]
+ *   b200_maxpool3x3_s2  nn.MaxPool2d(3, 2, 1) on an NHWC bf16 map
+ * The bottlenecks run on b200_conv_gemm_ex (act = 2, stride, dilation, residual).
+ */
+int b200_conv7x7_s2(const float* x, const float* gate, int B, int C, int H, int W, const float* wt, const float* scale,
+                    const float* bias, void* y, void* stream);
+int b200_maxpool3x3_s2(const void* x, int B, int H, int W, int C, void* y, void* stream);
 
 /* compute_adc_map (code/preprocess_helpers.py:133-167): x [B, C, n] fp32 DWI stacks (n = H*W), bvals [C] on the
  * device -> out [B, n]: minus the per-pixel least-squares slope of log(max(S, eps)) over b.  C <= 32. */

@@ -82,3 +82,39 @@ def to_torchvision(sd):
                     q + "mlp.3.weight": sd[p + "mlp.fc2.weight"], q + "mlp.3.bias": sd[p + "mlp.fc2.bias"]})
         i += 1
     return out
+
+
+# ------------------------------------------------------------------------- ResNet-50 ----
+def resnet_features(sd, x, layers=(3, 4, 6, 3), output_stride=8):
+    """fp32 restatement of timm / torchvision `resnet50` (v1.5) as a feature extractor - what the reference builds
+    at /root/reference/code/foundation_model.py:15-68 and :243-250 (`timm.create_model("resnet50",
+    features_only=True, output_stride=8, out_indices=(1, 2, 3, 4), in_chans=C)`): returns [C2, C3, C4, C5].
+    timm is absent (PARITY UNPINNED for the backbone itself); tests/test_oracle_golden.py cross-checks this
+    restatement against torchvision's ResNet with `replace_stride_with_dilation`, whose parameter names it shares."""
+    def bn(t, p):
+        return F.batch_norm(t, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                            False, 0.0, 1e-5)
+
+    t = F.relu(bn(F.conv2d(x, sd["conv1.weight"], stride=2, padding=3), "bn1"))
+    t = F.max_pool2d(t, 3, stride=2, padding=1)
+    feats = []
+    net_stride, dilation, prev_dilation = 4, 1, 1
+    for li, (n_blocks, stride) in enumerate(zip(layers, (1, 2, 2, 2))):
+        if net_stride >= output_stride:
+            dilation *= stride
+            stride = 1
+        else:
+            net_stride *= stride
+        for bi in range(n_blocks):
+            p = f"layer{li + 1}.{bi}."
+            s, d = (stride, prev_dilation) if bi == 0 else (1, dilation)
+            h = F.relu(bn(F.conv2d(t, sd[p + "conv1.weight"]), p + "bn1"))
+            h = F.relu(bn(F.conv2d(h, sd[p + "conv2.weight"], stride=s, padding=d, dilation=d), p + "bn2"))
+            h = bn(F.conv2d(h, sd[p + "conv3.weight"]), p + "bn3")
+            idn = t
+            if p + "downsample.0.weight" in sd:
+                idn = bn(F.conv2d(t, sd[p + "downsample.0.weight"], stride=s), p + "downsample.1")
+            t = F.relu(h + idn)
+        prev_dilation = dilation
+        feats.append(t)
+    return feats

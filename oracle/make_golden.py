@@ -211,6 +211,78 @@ def vit_goldens():
     print("vit fusion logits", lf)
 
 
+def standin_resnet(in_chans):
+    """timm is absent: the ResNet-50 feature extractor handed to the reference is torchvision's ResNet (same
+    architecture and parameter names as timm's resnet50; dilated to output stride 8 like the reference's
+    `output_stride=8`), with the classifier removed and `feature_info` added."""
+    import torch.nn as nn
+    import torchvision
+
+    class StandInResNet(torchvision.models.ResNet):
+        def __init__(self):
+            super().__init__(torchvision.models.resnet.Bottleneck, [3, 4, 6, 3],
+                             replace_stride_with_dilation=[False, True, True])
+            self.conv1 = nn.Conv2d(in_chans, 64, 7, stride=2, padding=3, bias=False)
+            del self.fc
+            self.feature_info = _StandInInfo([256, 512, 1024, 2048], [4, 8, 8, 8])
+
+        def forward(self, x):
+            t = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+            feats = []
+            for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+                t = layer(t)
+                feats.append(t)
+            return feats
+
+    return StandInResNet()
+
+
+def configure_resnet(p):
+    """What foundation_model.build_medical_backbone writes for the radimagenet / resnet50 branches (:503-524, :547-569)."""
+    p["dwi_channel_num"], p["dce_channel_num"] = 16, 6
+    for m in ("dwi", "dce", "fusion"):
+        mp = p[f"{m}_model_parameters"]
+        mp["input_size"] = 224
+        mp["use_hybrid_transformer"] = False
+        mp["use_backbone"] = m != "fusion"
+        if m != "fusion":
+            mp["backbone_index_lists"] = [[0], [1], [2, 3]]
+            mp["downsample"] = (True, False, False)
+            mp["downsample_each_repeat"] = False
+            mp["transformer_backbone"] = False
+    return p
+
+
+def resnet_goldens():
+    """The reference's default backbone family: ResNet-50 (RadImageNet) encoders at 224 x 224 + the fusion head."""
+    import model_module as mm
+
+    p = configure_resnet(reference_parameters())
+    torch.manual_seed(0)
+    models = {"dwi": mm.ModelMaskHeadBackbone("dwi", p, standin_resnet(16)),
+              "dce": mm.ModelMaskHeadBackbone("dce", p, standin_resnet(6)), "fusion": mm.FusionModel(p)}
+    shapes = {}
+    for name, m in models.items():
+        sh = op.shapes_of(m.state_dict())
+        shapes[name] = {k: list(v) for k, v in sh.items()}
+        m.load_state_dict(op.seeded_state_dict(sh, seed=13))
+        m.eval()
+    out = {}
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(2, seed=4321, size=224, kind="S")
+    dwi = dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)
+    with torch.no_grad():
+        ld, ad, md = models["dwi"](dwi)
+        lc, ac, mc = models["dce"](dce_raw)
+        lf, mf, af = models["fusion"](ad["raw_feats"], ac["raw_feats"], md, mc)
+    for tag, val in (("dwi/logits", ld), ("dwi/aux", ad), ("dwi/mask", md), ("dce/logits", lc), ("dce/aux", ac),
+                     ("dce/mask", mc), ("fusion/logits", lf), ("fusion/mask", mf), ("fusion/aux", af)):
+        flatten(f"S/{tag}", val, out)
+    np.savez_compressed(os.path.join(GOLD, "model_resnet.npz"), **out)
+    with open(os.path.join(GOLD, "state_shapes_resnet.json"), "w") as f:
+        json.dump(shapes, f, indent=0, sort_keys=True)
+    print("resnet fusion logits", lf, [tuple(t.shape) for t in ad["raw_feats"]])
+
+
 def normalizer_goldens():
     import dataset as ref_dataset
     import preprocess_helpers as ref_pre
@@ -258,3 +330,4 @@ if __name__ == "__main__":
     model_goldens("cnn_mf3", hybrid=False, kinds=("S",), mask_stage="f3")
     model_goldens("cnn_r2", hybrid=False, kinds=("S",), repeat_blocks=(2, 1, 2))
     vit_goldens()
+    resnet_goldens()

@@ -167,11 +167,12 @@ def backbone_adapter(x, s: SD, chains, feats=None):
     neck (3x3 conv + BN + GELU, twice, :440-447).  The backbone is the ViT-B/16 restated in
     oracle/backbone_oracle.py (its weights sit under `backbone.`); `feats` overrides it."""
     if feats is None:
-        from oracle.backbone_oracle import vit_features
+        from oracle.backbone_oracle import resnet_features, vit_features
         pre = s.prefix + "backbone."
         if any(k.startswith(pre + "_orig_mod.") for k in s.sd):  # torch._dynamo.disable wrapper, model_module.py:539
             pre += "_orig_mod."
-        feats = vit_features({k[len(pre):]: v for k, v in s.sd.items() if k.startswith(pre)}, x)
+        bsd = {k[len(pre):]: v for k, v in s.sd.items() if k.startswith(pre)}
+        feats = resnet_features(bsd, x) if "layer1.0.conv1.weight" in bsd else vit_features(bsd, x)
     outs = []
     for i, chain in enumerate(chains):
         n = s.sub(f"necks.f{i + 1}")

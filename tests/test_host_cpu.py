@@ -105,6 +105,19 @@ def test_vit_state_dict_matches_reference_names_and_shapes():
         assert any(a.startswith("backbone._orig_mod.") for a in mine) == (k != "fusion")
 
 
+def test_resnet_state_dict_matches_reference_names_and_shapes():
+    import model_module as mm
+    from test_oracle_golden import resnet_parameters
+
+    p, backbones = resnet_parameters()
+    assert p["dce_model_parameters"]["backbone_index_lists"] == [[0], [1], [2, 3]]
+    assert p["dce_model_parameters"]["downsample"] == (True, False, False)
+    ref = gu.load_shapes("resnet")
+    for k in ("dwi", "dce"):
+        m = mm.ModelMaskHeadBackbone(k, p, backbones[k])
+        assert {a: tuple(b.shape) for a, b in m.state_dict().items()} == ref[k]
+
+
 def test_no_cpu_fallback():
     import b200_native as nat
     import dataset as ds

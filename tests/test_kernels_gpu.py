@@ -413,3 +413,37 @@ def test_flip_planes():
     assert torch.equal(nat.flip_planes(x, True, False), torch.flip(x, dims=[-1]))
     assert torch.equal(nat.flip_planes(x, False, True), torch.flip(x, dims=[-2]))
     assert torch.equal(nat.flip_planes(x, True, True), torch.flip(x, dims=[-1, -2]))
+
+
+def test_resnet_stem_kernels_and_dilated_relu_conv():
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = torch.rand(3, 6, 64, 80, generator=g).to(DEV)
+    gate = (torch.rand(3, 6, generator=g) + 0.5).to(DEV)
+    w = (torch.randn(64, 6, 7, 7, generator=g) / math.sqrt(6 * 49)).to(DEV)
+    scale = (torch.rand(64, generator=g) + 0.5).to(DEV)
+    bias = (torch.randn(64, generator=g) * 0.1).to(DEV)
+    y = nat.conv7x7_s2(x, gate, w.permute(1, 2, 3, 0).reshape(6, 49, 64).contiguous(), scale, bias)
+    ref = F.relu(F.conv2d(x * gate.view(3, 6, 1, 1), w, stride=2, padding=3) * scale.view(1, -1, 1, 1) +
+                 bias.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    assert tuple(y.shape) == (3, 32, 40, 64) and _rel(y, ref) < 5e-3
+    p = nat.maxpool3x3_s2(y)
+    refp = F.max_pool2d(y.float().permute(0, 3, 1, 2), 3, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert torch.equal(p.float(), refp)
+    # dilated 3x3 + ReLU on a 28 x 28 map (ragged 112-row tiles), residual + ReLU on a channel slice
+    a = (torch.randn(2, 28, 28, 128, generator=g) * 0.5).to(DEV).bfloat16()
+    w3 = (torch.randn(128, 9 * 128, generator=g) / math.sqrt(9 * 128)).to(DEV).bfloat16()
+    for dil in (2, 4):
+        o = nat.conv_gemm(a, w3, taps=9, bias=bias.repeat(2), act=2, dilation=dil)
+        wf = w3.float().view(128, 9, 128).permute(0, 2, 1).reshape(128, 128, 3, 3)
+        r = F.relu(F.conv2d(a.float().permute(0, 3, 1, 2), wf, bias.repeat(2), padding=dil, dilation=dil)).permute(0, 2, 3, 1)
+        assert _rel(o, r) < 1e-2
+    buf = torch.zeros(2, 28, 28, 384, dtype=torch.bfloat16, device=DEV)
+    w1 = (torch.randn(256, 128, generator=g) / math.sqrt(128)).to(DEV).bfloat16()
+    res = (torch.randn(2, 28, 28, 256, generator=g) * 0.5).to(DEV).bfloat16()
+    nat.conv_gemm(a, w1, taps=1, res=res, res_mode=1, act=2, out=buf[..., 128:])
+    torch.cuda.synchronize()
+    r = F.relu(a.float() @ w1.float().t() + res.float())
+    assert _rel(buf[..., 128:], r) < 1e-2 and buf[..., :128].abs().max().item() == 0
+    # a channel slice as the A operand
+    o2 = nat.conv_gemm(buf[..., 128:], (torch.randn(64, 256, generator=g) / 16).to(DEV).bfloat16(), taps=1)
+    assert tuple(o2.shape) == (2, 28, 28, 64)

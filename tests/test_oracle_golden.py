@@ -142,6 +142,65 @@ def test_geometry_variant_oracle_matches_reference(tag):
     assert n == 34
 
 
+def resnet_parameters():
+    """The reference's default backbone family (RadImageNet / resnet50 branches of build_medical_backbone)."""
+    import foundation_model as fm
+
+    p = pd.default_parameters(input_size=224)
+    backbones = {}
+    for m, c in (("dwi", 16), ("dce", 6)):
+        mp = p[f"{m}_model_parameters"]
+        mp["backbone_str"], mp["use_backbone"] = "radimagenet", True
+        backbones[m] = fm.build_medical_backbone(p, None, m, in_channels=c)
+    return p, backbones
+
+
+def test_resnet_oracle_matches_torchvision_stand_in():
+    """timm is absent (parity unpinned for the backbone itself): the restated ResNet-50 feature extractor against
+    torchvision's ResNet dilated to output stride 8, same parameter names."""
+    import torchvision
+    from oracle import backbone_oracle as bo
+
+    tv = torchvision.models.resnet50(replace_stride_with_dilation=[False, True, True])
+    tv.conv1 = torch.nn.Conv2d(6, 64, 7, stride=2, padding=3, bias=False)
+    shapes = {k: tuple(v.shape) for k, v in tv.state_dict().items() if not k.startswith("fc.")}
+    sd = op.seeded_state_dict(shapes, seed=3)
+    tv.load_state_dict(sd, strict=False)
+    tv.eval()
+    x = torch.rand(1, 6, 96, 96, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        t = tv.maxpool(tv.relu(tv.bn1(tv.conv1(x))))
+        ref = []
+        for layer in (tv.layer1, tv.layer2, tv.layer3, tv.layer4):
+            t = layer(t)
+            ref.append(t)
+        got = bo.resnet_features(sd, x)
+    assert [tuple(f.shape) for f in got] == [(1, 256, 24, 24), (1, 512, 12, 12), (1, 1024, 12, 12), (1, 2048, 12, 12)]
+    for a, b in zip(got, ref):
+        assert (a - b).abs().max().item() <= 1e-5 * b.abs().max().item()
+
+
+def test_resnet_adapter_oracle_matches_reference():
+    gold = gu.load("model_resnet.npz")
+    shapes = gu.load_shapes("resnet")
+    p, _ = resnet_parameters()
+    sds = {m: op.seeded_state_dict(shapes[m], seed=13) for m in ("dwi", "dce", "fusion")}
+    dwi, dce = vit_inputs()
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        ld, ad, md = mo.encoder_forward(sds["dwi"], "dwi", p, dwi)
+        lc, ac, mc = mo.encoder_forward(sds["dce"], "dce", p, dce)
+        lf, mf, af = mo.fusion_forward(sds["fusion"], p, ad["raw_feats"], ac["raw_feats"], md, mc)
+    outs = {"S/dwi/logits": ld, "S/dwi/aux": ad, "S/dwi/mask": md, "S/dce/logits": lc, "S/dce/aux": ac,
+            "S/dce/mask": mc, "S/fusion/logits": lf, "S/fusion/mask": mf, "S/fusion/aux": af}
+    n = 0
+    for prefix, obj in outs.items():
+        for key, t in gu.walk(prefix, obj):
+            gu.check(gold, key, t, rtol=2e-5)
+            n += 1
+    assert n == 34
+
+
 def test_dwi_normalize_oracle_matches_reference():
     gold = gu.load("normalizers.npz")
     dwi_raw, _, _, _ = op.synthetic_raw(12, seed=1234, kind="S")
