@@ -45,6 +45,9 @@ FLOP_PER_CASE_LOGITS = 5.37e9   # logit path only
 # --workload c4 (not the default line): the ViT-B/16 backbone configuration of BASELINE.json configs[3]
 WORKLOAD_C4 = ("C4: DWI 16x64x64 + DCE 6x64x64 -> resize 224 -> normalise -> ViT-B/16 + adapter encoders -> "
                "late-fusion head")
+WORKLOAD_RESNET = ("DWI 16x64x64 + DCE 6x64x64 -> resize 224 -> normalise -> ResNet-50 (output stride 8) + adapter "
+                   "encoders -> late-fusion head")
+FLOP_RESNET = 116.9e9   # per case, observable graph: hook count on the reference modules (58.6 + 57.8 + 0.84 GF) minus the dead fusion branch
 FLOP_C4_FULL = 148.8e9
 FLOP_C4_LOGITS = 138.6e9
 
@@ -156,10 +159,11 @@ def make_params(workload, hybrid=False):
     backbones = {}
     for m, c in (("dwi", 16), ("dce", 6)):
         mp = params[f"{m}_model_parameters"]
-        mp["backbone_str"], mp["use_backbone"] = "vit_base_patch16_224", True
+        mp["backbone_str"], mp["use_backbone"] = ("vit_base_patch16_224" if workload == "c4" else "radimagenet"), True
         backbones[m] = fm.build_medical_backbone(params, None, m, in_channels=c)
-    fs = params["fusion_model_parameters"]["fusion_specific_parameters"]
-    fs["dwi_out_channels"] = fs["dce_out_channels"] = 768  # SURVEY.md note 9: not updated by the reference itself
+    if workload == "c4":
+        fs = params["fusion_model_parameters"]["fusion_specific_parameters"]
+        fs["dwi_out_channels"] = fs["dce_out_channels"] = 768  # SURVEY.md note 9: not updated by the reference itself
     return params, backbones
 
 
@@ -186,12 +190,12 @@ def build_product(device, aux, hybrid=False, workload="c3"):
     _, fit_dce = make_inputs(64, 10_000)
     nyul = pre.NyulStandardizer()
     nyul.fit(list(fit_dce), num_channels=6)
-    if workload == "c4":  # the standardiser sees resized images (Resize comes first in the reference's transforms)
+    if workload != "c3":  # the standardiser sees resized images (Resize comes first in the reference's transforms)
         from dataset import Resize
         nyul = pre.NyulStandardizer()
         nyul.fit(list(Resize(224).batch(fit_dce[:16].to(device)).cpu()), num_channels=6)
     pipe = FusionPipeline(mods[0], mods[1], mods[2], nyul, aux_mode=aux,
-                          input_size=224 if workload == "c4" else None).eval()
+                          input_size=224 if workload != "c3" else None).eval()
     return params, pipe, cpu_state, nyul
 
 
@@ -247,7 +251,7 @@ def reference_arm(args):
             mm.initialize_model(mm.FusionModel(params), True)]
     cpu_state = [m.state_dict() for m in mods]
     _, fit_dce = make_inputs(64, 10_000)
-    if args.workload == "c4":
+    if args.workload != "c3":
         from oracle import normalize_oracle as no
         fit_dce = no.resize(fit_dce[:16], 224)
     nyul = pre.NyulStandardizer()
@@ -268,7 +272,7 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD if args.workload == "c3" else WORKLOAD_C4, "batch_per_step": batch,
+        "config": {"workload": {"c3": WORKLOAD, "c4": WORKLOAD_C4, "resnet": WORKLOAD_RESNET}[args.workload], "batch_per_step": batch,
                    "aux": "full (as the reference executes)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"each step = {batch} cases (reference batch_size) of the workload on {threads} host threads"},
@@ -285,8 +289,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="cases per GPU per step (default 1024; 256 for c4)")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4"],
-                    help="c3 = the headline CNN-encoder configuration; c4 = ViT-B/16 backbone encoders at 224x224")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "resnet"],
+                    help="c3 = the headline CNN-encoder configuration; c4 = ViT-B/16 backbone encoders at 224x224; "
+                         "resnet = ResNet-50 (RadImageNet branch, output stride 8) backbone encoders at 224x224")
     ap.add_argument("--aux", default="full", choices=["full", "logits"])
     ap.add_argument("--ref-batch", type=int, default=32)
     ap.add_argument("--cpu-cases", type=int, default=256, help="bounded CPU-baseline sample")
@@ -301,7 +306,7 @@ def main():
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.batch is None:
         args.batch = 1024 if args.workload == "c3" else 256
-    if args.workload == "c4" and args.ref_batch == 32:
+    if args.workload != "c3" and args.ref_batch == 32:
         args.ref_batch = 8  # ~1 s per case on the host cores: keep a step / the CPU sample bounded
         args.cpu_cases = min(args.cpu_cases, 16)
 
@@ -454,7 +459,7 @@ def main():
         hbm_roofline = None
         nm = table.get(("b200_dwi_normalize", None))
         if nm:
-            side = 224 if args.workload == "c4" else 64
+            side = 224 if args.workload != "c3" else 64
             nbytes = B * (15 + 16) * side * side * 4
             gbs = nbytes / (nm[0] / 1e3) / 1e9
             hbm_roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -465,13 +470,15 @@ def main():
         nsteps_prof = max(2, min(args.steps, 5))
         if args.workload == "c3":
             flop_case = FLOP_PER_CASE_FULL if args.aux == "full" else FLOP_PER_CASE_LOGITS
-        else:
+        elif args.workload == "c4":
             flop_case = FLOP_C4_FULL if args.aux == "full" else FLOP_C4_LOGITS
+        else:
+            flop_case = FLOP_RESNET
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": (WORKLOAD if args.workload == "c3" else WORKLOAD_C4) +
+            "config": {"workload": {"c3": WORKLOAD, "c4": WORKLOAD_C4, "resnet": WORKLOAD_RESNET}[args.workload] +
                        (" [hybrid TransformerStage encoders]" if args.hybrid else "") +
                        (f" [predict mode {args.predict_mode}: {dict(tta=4, mc=10, tta_mc=40)[args.predict_mode]} forwards per case]"
                         if args.predict_mode != "normal" else ""),

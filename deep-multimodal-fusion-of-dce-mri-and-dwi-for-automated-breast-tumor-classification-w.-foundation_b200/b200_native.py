@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _lib = None
 
@@ -97,6 +97,7 @@ SIGNATURES = {
     "b200_adc_map": [_P, _I, _I, _I, _P, _F, _P, _P],
     "b200_conv7x7_s2": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "b200_maxpool3x3_s2": [_P, _I, _I, _I, _I, _P, _P],
+    "b200_im2col7x7_s2": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "b200_flip_planes": [_P, _P, _LL, _I, _I, _I, _I, _P],
     "b200_fusion_tokens": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "b200_fusion_core": [C.POINTER(FusionWeights), _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -387,6 +388,15 @@ def conv7x7_s2(x, gate, wt, scale, bias):
     y = torch.empty((B, H // 2, W // 2, 64), dtype=torch.bfloat16, device=x.device)
     _call("b200_conv7x7_s2", None, _ptr(x), _ptr(gate), B, C_, H, W, _ptr(wt), _ptr(scale), _ptr(bias), _ptr(y), _stream())
     return y
+
+
+def im2col7x7_s2(x, gate, kp):
+    """x [B,C,H,W] fp32 -> bf16 patch matrix [B*H/2*W/2, kp] of the 7x7 / stride-2 stem."""
+    x = x.contiguous().float()
+    B, C_, H, W = x.shape
+    out = torch.empty((B * (H // 2) * (W // 2), kp), dtype=torch.bfloat16, device=x.device)
+    _call("b200_im2col7x7_s2", None, _ptr(x), _ptr(gate), B, C_, H, W, kp, _ptr(out), _stream())
+    return out
 
 
 def maxpool3x3_s2(x):

@@ -275,11 +275,15 @@ int b200_add_maps(const void* a, const void* b, long long n_elems, void* out, vo
  *                       scaled per (case, channel) by the modality-attention gate; wt is the weight transposed to
  *                       [C][49][64]; y bf16 NHWC [B, H/2, W/2, 64]
  *   b200_maxpool3x3_s2  nn.MaxPool2d(3, 2, 1) on an NHWC bf16 map
+ *   b200_im2col7x7_s2   (below) the stem as a GEMM operand
  * The bottlenecks run on b200_conv_gemm_ex (act = 2, stride, dilation, residual).
  */
 int b200_conv7x7_s2(const float* x, const float* gate, int B, int C, int H, int W, const float* wt, const float* scale,
                     const float* bias, void* y, void* stream);
 int b200_maxpool3x3_s2(const void* x, int B, int H, int W, int C, void* y, void* stream);
+/* The same stem for the tensor cores: bf16 patch matrix [B * H/2 * W/2, Kp] (column c*49 + ky*7 + kx, zero padded to
+ * Kp, a multiple of 64), gate applied; conv1 + bn1 + ReLU is then one b200_linear call. */
+int b200_im2col7x7_s2(const float* x, const float* gate, int B, int C, int H, int W, int Kp, void* out, void* stream);
 
 /* compute_adc_map (code/preprocess_helpers.py:133-167): x [B, C, n] fp32 DWI stacks (n = H*W), bvals [C] on the
  * device -> out [B, n]: minus the per-pixel least-squares slope of log(max(S, eps)) over b.  C <= 32. */

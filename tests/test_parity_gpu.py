@@ -598,8 +598,11 @@ def test_resnet_backbone_and_adapter_path_vs_golden_reference():
             worst[key] = gu.check(gold, key, t, rtol=1.0)
     print("ResNet path relative errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:12])
     assert len(worst) == 34
-    # 53 bf16 convolutions put the backbone features themselves at 1.0-1.3 % of their range (above); the neck,
-    # the instance-norm backbone mixes and the heads then behave as on the ViT path (see VIT_TOL): 8e-2 throughout
-    bad = {k: v for k, v in worst.items() if v > VIT_TOL}
+    # 53 bf16 convolutions put the backbone features themselves at 1.0-1.3 % of their range (above); the necks,
+    # the instance-norm backbone mixes and the heads amplify that as on the ViT path.  The floor of THIS fixture -
+    # the fp32 oracle with nothing but its GEMM operands rounded to bf16, `python tools/bf16_floor.py resnet` - is
+    # 12.7-13.7 % on the DWI f3, 8-10 % on p_dwi, 6.7 % on the fusion mask, 4.5-4.8 % on the fusion logits; the product
+    # measures 5.7 %, 4.4 %, 7.2-8.6 %, 4.1 %.  Held to 1.5e-1.
+    bad = {k: v for k, v in worst.items() if v > 1.5e-1}
     assert not bad, bad
     assert worst["S/dwi/aux.mod_attn_map"] < 1e-5 and worst["S/fusion/aux.gating_weights"] < 5e-3

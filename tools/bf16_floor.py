@@ -7,7 +7,8 @@ weights the two GroupNorm(C, C) backbone mixes (instance norms over 196 pixels) 
 maps they produce amplify bf16 operand rounding to 2-7 % on the downstream maps; this is the floor the
 tolerance of tests/test_parity_gpu.py::test_vit_adapter_pipeline_vs_golden_reference is set against.
 
-    python tools/bf16_floor.py
+    python tools/bf16_floor.py            # ViT-adapter fixture (model_vit.npz configuration)
+    python tools/bf16_floor.py resnet     # ResNet-50 fixture (model_resnet.npz configuration)
 """
 import os
 import sys
@@ -19,9 +20,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import b200path, golden_util as gu
 from oracle import model_oracle as mo, params as op, backbone_oracle as bo
-from test_oracle_golden import vit_inputs, vit_parameters
+from test_oracle_golden import resnet_parameters, vit_inputs, vit_parameters
 torch.set_num_threads(8)
-shapes = gu.load_shapes("vit"); p, _ = vit_parameters()
+RESNET = len(sys.argv) > 1 and sys.argv[1] == "resnet"
+shapes = gu.load_shapes("resnet" if RESNET else "vit"); p, _ = resnet_parameters() if RESNET else vit_parameters()
+SEED = 13 if RESNET else 11
 dwi, dce = vit_inputs()
 bf = lambda t: t.bfloat16().float()
 class Emu:
@@ -38,9 +41,9 @@ def run(emu):
     out = {}
     with torch.no_grad():
         for m, x in (("dwi", dwi), ("dce", dce)):
-            sd = op.seeded_state_dict(shapes[m], seed=11)
+            sd = op.seeded_state_dict(shapes[m], seed=SEED)
             out[m] = mo.encoder_forward(sd, m, p, x)
-        sdf = op.seeded_state_dict(shapes["fusion"], seed=11)
+        sdf = op.seeded_state_dict(shapes["fusion"], seed=SEED)
         out["fusion"] = mo.fusion_forward(sdf, p, out["dwi"][1]["raw_feats"], out["dce"][1]["raw_feats"], out["dwi"][2], out["dce"][2])
     return out
 a = run(False); b = run(True)
