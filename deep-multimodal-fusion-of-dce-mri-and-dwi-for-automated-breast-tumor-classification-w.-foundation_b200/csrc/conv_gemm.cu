@@ -1268,6 +1268,8 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
                                  int ndot, float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout,
                                  int taps, int stride, int dilation, void* stream) {
     using namespace b200;
+    // consume the one-shot dropout request first: a call that fails validation must not leave it armed for the next
+    const PendingDropout drop = take_pending_dropout();
     if (dilation < 1 || dilation > 8 || (dilation != 1 && taps != 9)) return -6;
     if (dot_w == nullptr) ndot = 0;
     if (ndot != 0 && ndot != 1 && ndot != 9) return -18;
@@ -1360,7 +1362,6 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
     // is opt-in (B200_WS=1) until a 2-CTA / multicast version makes it pay.
     static const bool want_ws = std::getenv("B200_WS") != nullptr;
     int mode = 0;
-    const PendingDropout drop = take_pending_dropout();  // one shot
     if (drop.seg != 0) {
         if (dot_w != nullptr || up2 || res_mode == 2) return -19;  // dropout variants: plain / residual (+ channel sums)
         mode = 3;

@@ -478,6 +478,7 @@ extern "C" int b200_stem(const float* x, int B, int C, int H, int W, int stride,
                          const float* se_w1, const float* se_b1, const float* se_w2, const float* se_b2, int Cm,
                          const float* wcat, const float* scale, const float* bias, int n_skip, int n_mid,
                          void* skip_out, void* mid_out, float* mod_attn, void* stream) {
+    const b200::PendingDropout drop = b200::take_pending_dropout();  // one shot, consumed even if validation fails
     if (B < 0 || C <= 0 || C > kStemMaxC || Cm > kStemMaxC || H % stride != 0 || W % stride != 0) return -1;
     if (B == 0) return 0;
     if (x == nullptr || wcat == nullptr || scale == nullptr || bias == nullptr) return -2;
@@ -496,7 +497,6 @@ extern "C" int b200_stem(const float* x, int B, int C, int H, int W, int stride,
     int gx = n_tiles;
     while (gx > 1 && static_cast<long long>(gx / 2) * B >= 148LL * 8) gx = (gx + 1) / 2;
     dim3 grid(gx, B);
-    const b200::PendingDropout drop = b200::take_pending_dropout();  // MC-dropout on the mid map, if armed
     const unsigned int thresh = drop.seg != 0 ? b200::dropout_threshold(drop.p) : 0u;
     const float dscale = drop.seg != 0 ? 1.0f / (1.0f - drop.p) : 1.0f;
     auto go = [&](auto kern) {

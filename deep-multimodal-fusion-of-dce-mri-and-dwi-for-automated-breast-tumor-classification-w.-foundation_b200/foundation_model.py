@@ -1,27 +1,29 @@
-"""B200-native drop-in for the ViT branch of the reference's ``foundation_model``.
+"""B200-native drop-in for the reference's ``foundation_model``: the ViT-B/16 and ResNet-50 backbone branches.
 
 ``build_medical_backbone(parameters, device, method, in_channels)`` keeps the reference contract
 (/root/reference/code/foundation_model.py:490-577): it returns an ``nn.Module`` with
 ``.feature_info.channels()/.reduction()``, ``.output_dims`` and ``forward(x) -> list[NCHW maps]`` and
-mutates ``parameters[f"{method}_model_parameters"]`` the way the ViT branch does (:526-545:
-``backbone_index_lists=[[0,1,2],[3,4,5,6],[7,8,9,10,11]]``, ``downsample=(False,)*3``,
-``channels=(768,)*3``, ``transformer_backbone=True``).
+mutates ``parameters[f"{method}_model_parameters"]`` the way the reference's branches do - ViT (:526-545):
+``backbone_index_lists=[[0,1,2],[3,4,5,6],[7,8,9,10,11]]``, ``downsample=(False,)*3``, ``channels=(768,)*3``,
+``transformer_backbone=True``; resnet50 / radimagenet (:503-524, :547-569): ``backbone_index_lists=[[0],[1],[2,3]]``,
+``downsample=(True, False, False)``, ``downsample_each_repeat=False``.
 
-The reference gets the network itself from ``timm.create_model("vit_base_patch16_224",
-features_only=True, out_indices=0..11, img_size=..., in_chans=C)`` (:371-431).  timm is an un-vendored,
-un-pinned dependency that is absent here, so this module carries its own ViT-B/16 feature extractor with
-timm's parameter names (``patch_embed.proj``, ``cls_token``, ``pos_embed``, ``blocks.N.{norm1,attn.qkv,
-attn.proj,norm2,mlp.fc1,mlp.fc2}``, ``norm``) - a timm checkpoint's ``state_dict`` loads unchanged - and
-runs it on the sm_100a kernels: patchify + one GEMM for the patch embedding, an fp32 residual stream,
-LayerNorm (eps 1e-6), per-head Q.K^T with the softmax numerator fused into the GEMM epilogue (197 keys
-masked inside a 256-wide tile), P.V with the 1/rowsum applied to the fp32 accumulator, MLP with a
-fused GELU.  Parity for this backbone is UNPINNED (no timm to compare with); the oracle is a restatement
-cross-checked against torchvision's VisionTransformer (oracle/backbone_oracle.py).
+The reference gets the networks from timm (``timm.create_model("vit_base_patch16_224", features_only=True,
+out_indices=0..11, ...)`` :371-431; ``timm.create_model("resnet50", features_only=True, output_stride=8,
+out_indices=(1,2,3,4), ...)`` :15-68, :243-250).  timm is an un-vendored, un-pinned dependency that is absent
+here, so this module carries its own feature extractors with timm's parameter names - a timm (or, re-keyed,
+RadImageNet) checkpoint's ``state_dict`` loads unchanged - and runs them on the sm_100a kernels:
 
-Only the ViT names are built ("vit_base_patch16_224", "dino_vitbase16_pretrained" - the reference builds the
-same timm model for both, :526, :538-545); the ResNet / RadImageNet / UNI2-h branches need network access and
-are out of scope.  No pretrained weights can be fetched offline: parameters are
-randomly initialised unless a state dict is loaded.
+* ``B200ViTBackbone``: patchify + one GEMM for the patch embedding, an fp32 residual stream, LayerNorm (eps 1e-6),
+  per-head Q.K^T with the softmax numerator fused into the GEMM epilogue (197 keys masked inside a 256-wide tile),
+  P.V with the 1/rowsum applied to the fp32 accumulator, MLP with a fused GELU.
+* ``B200ResNetBackbone``: the 7x7 stem as shared-memory im2col + one GEMM, max-pool, then the 16 bottlenecks as
+  implicit GEMMs with folded BatchNorm, ReLU, stride / dilation and the residual in the epilogue.
+
+Parity for the backbones themselves is UNPINNED (no timm to compare with); the oracles are restatements
+cross-checked against torchvision's VisionTransformer / ResNet (oracle/backbone_oracle.py).  ResNet-50d,
+ResNet-101 and UNI2-h are not built.  No pretrained weights can be fetched offline: parameters are randomly
+initialised unless a state dict (or a local ``pretrained_path``) is loaded.
 """
 from __future__ import annotations
 
