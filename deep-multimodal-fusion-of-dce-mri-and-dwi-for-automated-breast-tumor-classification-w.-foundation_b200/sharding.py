@@ -41,3 +41,54 @@ def max_over_ranks(value: float, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_device_numa_node(device_index: int):
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off (sysfs), so that the pinned host buffers
+    it allocates afterwards - and the thread that issues the copies - sit next to the PCIe root of that GPU.  On a
+    two-socket host a buffer on the far socket caps host-to-device copies at the inter-socket link (measured on this
+    pool: 10.7 GB/s instead of > 18 GB/s, which makes the end-to-end path copy bound).  Returns a dict describing
+    what was done; never raises (containers often hide the topology: then nothing is changed)."""
+    import os
+
+    info = {"node": None, "cpus": None, "bound": False}
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        target = cpus & allowed
+        info["cpus"] = len(target)
+        if target and target != allowed:
+            os.sched_setaffinity(0, target)
+            info["bound"] = True
+            info["previous"] = allowed
+    except Exception as exc:  # topology not visible: leave the affinity alone
+        info["error"] = type(exc).__name__
+    return info
+
+
+def restore_affinity(info):
+    import os
+
+    if info.get("bound") and info.get("previous"):
+        try:
+            os.sched_setaffinity(0, info["previous"])
+        except Exception:
+            pass
