@@ -281,6 +281,182 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+
+# --------------------------------------------------------------- fusion-head fine-tuning (C5 slice) ----
+WORKLOAD_C5 = ("C5 (frozen-encoder phase): DWI 16x64x64 + DCE 6x64x64 -> normalise -> frozen CNN encoders -> "
+               "fusion-head forward + backward (smoothed focal loss) -> gradient all-reduce -> AdamW")
+METRIC_C5 = "fusion-head fine-tuning cases/sec"
+
+
+def train_arm(args):
+    """--workload c5: one optimisation step of the fusion head per batch (fusion_train.FusionHeadTrainer), data
+    parallel over the ranks with ONE NCCL all-reduce of the flat gradient buffer per step."""
+    import b200_native as nat
+    from fusion_train import FusionHeadTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import datetime
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
+    params, pipe, cpu_state, nyul = build_product(device, "logits", False, "c3")
+    trainer = FusionHeadTrainer(pipe.fusion_model, lr=1e-4, weight_decay=4e-5, smoothing=0.1, gamma=1.5)
+    B = args.batch
+    dwi_h, dce_h = make_inputs(B, rank)
+    lab_h = torch.randint(0, 4, (B,), generator=torch.Generator().manual_seed(99 + rank))
+    dwi_d, dce_d, lab_d = dwi_h.to(device), dce_h.to(device), lab_h.to(device)
+
+    def step(d=dwi_d, c=dce_d, lab=lab_d):
+        with torch.no_grad():
+            pm_d = torch.empty(B * 16, dtype=torch.float32, device=device)
+            pm_c = torch.empty(B * 6, dtype=torch.float32, device=device)
+            xd = pipe.dwi_norm.batch(d, plane_mean=pm_d)
+            xc = pipe.dce_norm.batch(c, plane_mean=pm_c)
+            out_d = pipe.dwi_model(xd, None, plane_mean=pm_d)
+            out_c = pipe.dce_model(xc, None, plane_mean=pm_c)
+        loss, _ = trainer.train_step(out_d[1]["raw_feats"][-1], out_c[1]["raw_feats"][-1], out_d[2], out_c[2], lab)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = nat.LAUNCH_COUNT
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        barrier()
+    launches = nat.LAUNCH_COUNT - launches0
+    ms = e0.elapsed_time(e1)
+    # end to end: pinned host batch (inputs + labels) uploaded every step, the loss read back every step
+    dwi_p, dce_p, lab_p = dwi_h.pin_memory(), dce_h.pin_memory(), lab_h.pin_memory()
+    loss_host = torch.empty(1, dtype=torch.float32, pin_memory=True)
+
+    def e2e_step():
+        d, c, lab = dwi_p.to(device, non_blocking=True), dce_p.to(device, non_blocking=True), lab_p.to(device, non_blocking=True)
+        loss_host.copy_(step(d, c, lab), non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t[0].item(), t[1].item()
+    value = world * B * args.steps / (ms / 1e3)
+    line = None
+    if rank == 0:
+        peaks = load_peaks()
+        nsp = max(2, min(args.steps, 5))
+        nat.start_profile()
+        for _ in range(nsp):
+            step() if world == 1 else None
+        prof = nat.stop_profile()
+        total_ms = sum(sum(t) for t in prof.values())
+        head = {n: 0.0 for n in ("b200_sgemm", "b200_colsum", "b200_mha_fwd", "b200_mha_bwd", "b200_ln_fwd",
+                                 "b200_ln_bwd", "b200_gelu_bwd", "b200_head_loss", "b200_adamw", "b200_fusion_tokens")}
+        sg_flops = sg_ms = 0.0
+        for (n, k), t in prof.items():
+            if n in head:
+                head[n] += sum(t) / nsp
+            if n == "b200_sgemm" and k is not None:
+                sg_flops += 2.0 * k[0] * k[1] * k[2] * len(t) / nsp
+                sg_ms += sum(t) / nsp
+        dom_key = ("b200_conv_gemm_ex", (B, 32, 32, 256, 256, 9))
+        roofline = None
+        if dom_key in prof:
+            dom_ms = statistics.mean(prof[dom_key])
+            ach = 2.0 * B * 1024 * 256 * 256 * 9 / (dom_ms / 1e3) / 1e12
+            roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["tf_sustained"], "traffic": 1.034e9 * B / 1024,
+                        "kernel": "conv_gemm_kernel<256> 3x3 256->256 @32x32 (frozen encoders: still the dominant launch)",
+                        "ms_per_launch": dom_ms, "share_of_step": sum(prof[dom_key]) / total_ms if total_ms else None,
+                        "peak_source": peaks["source"] + " sustained bf16"}
+        line = {
+            "metric": METRIC_C5, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 encoders (frozen) / f32 head forward, backward and optimiser",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD_C5, "batch_per_gpu": B, "global_batch": B * world,
+                       "objective": "classification term only (label smoothing 0.1, focal gamma 1.5)",
+                       "trainable_parameters": trainer.numel, "allreduce_bytes_per_step": 4 * (trainer.numel + 1),
+                       "l2": "no flush needed: per-step inputs and activations exceed the 126 MB L2",
+                       "parallelism": f"data parallel x{world}, one NCCL all-reduce of the flat gradient buffer per step"
+                       if world > 1 else "single GPU"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": dwi_p.numel() * 4 + dce_p.numel() * 4 + lab_p.numel() * 8,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+                    "api": "normalisers + frozen encoders + FusionHeadTrainer.train_step, pinned host batch, loss read back"},
+            "gpu_launches": launches, "final_loss": float(loss.item()),
+            "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated(device) / 1e9,
+            "roofline": roofline,
+            "step_model": {"head_kernels_ms_per_step": {k: round(v, 4) for k, v in head.items()},
+                           "head_share_of_step": sum(head.values()) / (total_ms / nsp) if total_ms else None,
+                           "sgemm_fp32_tflops": sg_flops / (sg_ms / 1e3) / 1e12 if sg_ms else None},
+            "cpu_baseline": None,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = run_cpu_train_baseline(params, cpu_state, nyul, args.ref_batch)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def run_cpu_train_baseline(params, cpu_state, nyul, batch, steps=3):
+    """The same step on the host cores: oracle encoders (eval, no grad) + oracle/train_oracle.py (autograd over the
+    full-resolution FusionModel forward + AdamW)."""
+    import numpy as np
+    from oracle import model_oracle as mo
+    from oracle import normalize_oracle as no
+    from oracle import train_oracle as to
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    lm = np.stack([nyul.channel_landmarks[c] for c in range(6)])
+    dwi, dce = make_inputs(batch, 777)
+    labels = torch.randint(0, 4, (batch,), generator=torch.Generator().manual_seed(5))
+    sd = {k: v.clone() for k, v in cpu_state[2].items()}
+
+    def one(sd):
+        with torch.no_grad():
+            x_d, x_c = no.dwi_normalize_batch(dwi), no.nyul_transform_batch(dce, lm)
+            _, aux_d, m_d = mo.encoder_forward(cpu_state[0], "dwi", params, x_d)
+            _, aux_c, m_c = mo.encoder_forward(cpu_state[1], "dce", params, x_c)
+        b = (aux_d["raw_feats"][-1], aux_c["raw_feats"][-1], m_d, m_c, labels)
+        return to.train_steps(sd, params, b, 1, 0.1, 1.5, None, 1e-4, (0.9, 0.999), 1e-8, 4e-5)[1]
+
+    sd = one(sd)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sd = one(sd)
+    dt = time.perf_counter() - t0
+    return {"value": steps * batch / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{steps} optimisation steps of {batch} cases, fp32, torch CPU threads={threads}, 1 warm-up step, "
+                      f"{dt:.1f} s"}
+
 # ------------------------------------------------------------------------- B200 arm ----
 def main():
     ap = argparse.ArgumentParser()
@@ -289,7 +465,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="cases per GPU per step (default 1024; 256 for c4)")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "resnet"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "resnet", "c5"],
                     help="c3 = the headline CNN-encoder configuration; c4 = ViT-B/16 backbone encoders at 224x224; "
                          "resnet = ResNet-50 (RadImageNet branch, output stride 8) backbone encoders at 224x224")
     ap.add_argument("--aux", default="full", choices=["full", "logits"])
@@ -305,11 +481,17 @@ def main():
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.batch is None:
-        args.batch = 1024 if args.workload == "c3" else 256
-    if args.workload != "c3" and args.ref_batch == 32:
+        args.batch = 1024 if args.workload in ("c3", "c5") else 256
+    if args.workload not in ("c3", "c5") and args.ref_batch == 32:
         args.ref_batch = 8  # ~1 s per case on the host cores: keep a step / the CPU sample bounded
         args.cpu_cases = min(args.cpu_cases, 16)
 
+    if args.workload == "c5":
+        if args.impl == "reference":
+            raise SystemExit("--impl reference times the headline inference workload; the c5 line carries its own "
+                             "cpu_baseline")
+        train_arm(args)
+        return
     if args.impl == "reference":
         reference_arm(args)
         return

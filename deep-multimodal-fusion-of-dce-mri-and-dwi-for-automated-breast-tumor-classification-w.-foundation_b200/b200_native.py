@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _lib = None
 
@@ -62,6 +62,25 @@ class GemmDesc(C.Structure):
     ]
 
 
+class HeadTrain(C.Structure):
+    """Mirror of `struct b200_head_train` (include/b200_fusion.h)."""
+
+    _fields_ = [
+        ("C", C.c_int), ("T", C.c_int), ("se_mid", C.c_int), ("num_classes", C.c_int),
+        ("use_mask_attention", C.c_int), ("use_se", C.c_int), ("npix_mask", C.c_int),
+        ("smoothing", C.c_float), ("gamma", C.c_float), ("loss_scale", C.c_float),
+        ("class_weights", C.c_void_p), ("tok_dwi", C.c_void_p), ("tok_dce", C.c_void_p), ("lowres", C.c_void_p),
+        ("mask_dwi", C.c_void_p), ("mask_dce", C.c_void_p), ("labels", C.c_void_p),
+        ("gate_w", C.c_void_p), ("gate_b", C.c_void_p), ("up_coef", C.c_void_p),
+        ("se_w1", C.c_void_p), ("se_b1", C.c_void_p), ("se_w2", C.c_void_p), ("se_b2", C.c_void_p),
+        ("cls_w", C.c_void_p), ("cls_b", C.c_void_p),
+        ("loss_out", C.c_void_p), ("logits_out", C.c_void_p), ("gating_out", C.c_void_p),
+        ("dlogits_out", C.c_void_p), ("z_out", C.c_void_p), ("gf_out", C.c_void_p), ("h_out", C.c_void_p),
+        ("da1_out", C.c_void_p), ("da2_out", C.c_void_p), ("gx_out", C.c_void_p), ("dgl_out", C.c_void_p),
+        ("dpd_out", C.c_void_p), ("dpc_out", C.c_void_p), ("dlowres_out", C.c_void_p),
+    ]
+
+
 _P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
 # name -> argtypes; must list every symbol include/b200_fusion.h declares (tests check this).
@@ -102,6 +121,15 @@ SIGNATURES = {
     "b200_fusion_tokens": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "b200_fusion_core": [C.POINTER(FusionWeights), _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "b200_fusion_mix": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "b200_sgemm": [_P, _LL, _I, _P, _LL, _I, _P, _LL, _I, _I, _I, _P, _P, _LL, _I, _P, _I, _I, _I, _P],
+    "b200_colsum": [_P, _LL, _I, _I, _P, _P],
+    "b200_mha_fwd": [_P, _LL, _P, _P, _LL, _I, _I, _I, _I, _I, _P, _P, _LL, _P],
+    "b200_mha_bwd": [_P, _LL, _P, _P, _LL, _P, _P, _LL, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "b200_ln_fwd": [_P, _I, _I, _P, _P, _F, _P, _P, _P, _P],
+    "b200_ln_bwd": [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P],
+    "b200_gelu_bwd": [_P, _P, _LL, _P, _P],
+    "b200_head_loss": [C.POINTER(HeadTrain), _I, _P],
+    "b200_adamw": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P],
 }
 
 
@@ -503,3 +531,95 @@ def fusion_mix(p_dwi, p_dce, gating, lowres, gate, hp, wp, out):
     _call("b200_fusion_mix", None, _ptr(p_dwi), _ptr(p_dce), _ptr(gating), _ptr(lowres), _ptr(gate), B, H, W, C_, hp,
                                  wp, _ptr(out), _stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fusion-head fine-tuning step (csrc/train_ops.cu); every tensor is fp32 and row-major
+# ---------------------------------------------------------------------------------------------------------------
+def _f32_rows(t, name):
+    if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+        raise B200NativeError(f"{name} must be a 2-D float32 tensor with unit column stride")
+    return t
+
+
+def sgemm(a, b, out, *, trans_a=False, trans_b=False, bias=None, res=None, res_div=1, pre=None, act=0, beta=0,
+          split_k=1):
+    """out = op(a) @ op(b) (+ bias, + res broadcast over res_div rows; pre <- value before GELU; beta=1 accumulates).
+    a, b, out (and res) are 2-D fp32 tensors or row-strided views of them."""
+    _f32_rows(a, "a"), _f32_rows(b, "b"), _f32_rows(out, "out")
+    M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    Kb, N = (b.shape[1], b.shape[0]) if trans_b else b.shape
+    if K != Kb or tuple(out.shape) != (M, N):
+        raise B200NativeError(f"sgemm shape mismatch: op(a) {M}x{K}, op(b) {Kb}x{N}, out {tuple(out.shape)}")
+    if res is not None:
+        _f32_rows(res, "res")
+        if res.shape[1] != N or res.shape[0] * res_div != M:
+            raise B200NativeError("sgemm residual shape mismatch")
+    if pre is not None and (pre.shape != out.shape or pre.stride(0) != out.stride(0)):
+        raise B200NativeError("sgemm pre-activation output must have the layout of out")
+    if bias is not None and bias.numel() != N:
+        raise B200NativeError("sgemm bias length mismatch")
+    _call("b200_sgemm", (M, N, K, int(trans_a), int(trans_b)), _ptr(a), a.stride(0), int(trans_a), _ptr(b), b.stride(0), int(trans_b), _ptr(out),
+          out.stride(0), M, N, K, _ptr(bias), _ptr(res), res.stride(0) if res is not None else 0, res_div, _ptr(pre),
+          act, beta, split_k, _stream())
+    return out
+
+
+def colsum(x, out):
+    """out[n] += sum_r x[r, n]."""
+    _f32_rows(x, "x")
+    if out.numel() != x.shape[1] or out.dtype != torch.float32:
+        raise B200NativeError("colsum output mismatch")
+    _call("b200_colsum", None, _ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(out), _stream())
+    return out
+
+
+def mha_fwd(q, k, v, B, heads, probs, ctx):
+    """q [B*Tq, C] and k / v [B*Tk, C] (row-strided views allowed, k and v with the same row stride)."""
+    Tq, Tk, DH = q.shape[0] // B, k.shape[0] // B, q.shape[1] // heads
+    if k.stride(0) != v.stride(0):
+        raise B200NativeError("k and v must share a row stride")
+    _call("b200_mha_fwd", None, _ptr(q), q.stride(0), _ptr(k), _ptr(v), k.stride(0), B, heads, Tq, Tk, DH,
+          _ptr(probs), _ptr(ctx), ctx.stride(0), _stream())
+    return probs, ctx
+
+
+def mha_bwd(q, k, v, probs, dctx, B, heads, dq, dk, dv):
+    Tq, Tk, DH = q.shape[0] // B, k.shape[0] // B, q.shape[1] // heads
+    if k.stride(0) != v.stride(0) or dk.stride(0) != k.stride(0) or dv.stride(0) != k.stride(0) or \
+            dq.stride(0) != q.stride(0):
+        raise B200NativeError("mha_bwd gradients must have the layouts of q / k / v")
+    _call("b200_mha_bwd", None, _ptr(q), q.stride(0), _ptr(k), _ptr(v), k.stride(0), _ptr(probs), _ptr(dctx),
+          dctx.stride(0), B, heads, Tq, Tk, DH, _ptr(dq), _ptr(dk), _ptr(dv), _stream())
+    return dq, dk, dv
+
+
+def ln_fwd(x, w, b, eps, y, mean, rstd):
+    R, C_ = x.shape
+    _call("b200_ln_fwd", None, _ptr(x), R, C_, _ptr(w), _ptr(b), float(eps), _ptr(y), _ptr(mean), _ptr(rstd),
+          _stream())
+    return y
+
+
+def ln_bwd(x, dy, dres, w, mean, rstd, dx, dyxhat):
+    R, C_ = x.shape
+    _call("b200_ln_bwd", None, _ptr(x), _ptr(dy), _ptr(dres), R, C_, _ptr(w), _ptr(mean), _ptr(rstd), _ptr(dx),
+          _ptr(dyxhat), _stream())
+    return dx
+
+
+def gelu_bwd(pre, dg, out):
+    _call("b200_gelu_bwd", None, _ptr(pre), _ptr(dg), pre.numel(), _ptr(out), _stream())
+    return out
+
+
+def head_loss(args, B):
+    _call("b200_head_loss", None, C.byref(args), B, _stream())
+
+
+def adamw(p, g, m, v, *, lr, betas, eps, weight_decay, step, grad_scale=1.0):
+    for t in (p, g, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != p.numel():
+            raise B200NativeError("adamw needs equally sized contiguous float32 buffers")
+    _call("b200_adamw", None, _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(betas[0]),
+          float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale), _stream())

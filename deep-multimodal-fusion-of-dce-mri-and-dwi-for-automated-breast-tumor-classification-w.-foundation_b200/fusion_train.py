@@ -1,0 +1,331 @@
+"""Fusion-head fine-tuning step on the B200 kernels (BASELINE config C5, frozen-encoder phase).
+
+What the reference does in that phase (code/train_fusion.py:203-321 with the optimiser factory of
+code/selector_helpers.py:356-520, `backbone_freeze_on_start`): both encoders are frozen, the fusion head is the one
+trainable parameter group, and every step is  encoders -> FusionModel.forward -> loss -> backward -> AdamW.
+This module is the classification-objective part of that step:
+
+    loss = Soft(Weighted)FocalLoss(logits, LabelSmoothing(logits, labels))       train_fusion.py:238-242
+
+The logits of FusionModel.forward (code/model_module.py:919-1000) depend on the encoder maps only through their
+4x4-pooled tokens (proj_in_* are bias-free 1x1 convolutions, GAP and the bilinear up-sample are linear), so one
+pooling pass over each f3 map is the only map-sized work; forward, backward and the weight gradients then run as
+fp32 kernels on [B*16, C] token matrices (csrc/train_ops.cu).  The parameters that receive a gradient - the same
+20 tensors torch autograd finds on the reference module (tests/golden/train_head.npz) - live in ONE flat fp32
+buffer (the nn.Parameters are views of it, so state_dict / load_state_dict keep working), their gradients in a
+second one: a data-parallel step is one all-reduce of that buffer (NCCL over NVLink on the GPUs, gloo in the CPU
+tests of the host logic) and one fused AdamW launch.  Parameters off the logits path (mask head, reconstruction
+head, projector, the reference's dead reduce/refine branch) get no gradient and are left untouched, exactly like
+torch.optim.AdamW skips parameters whose .grad is None.
+
+Not built: the mask / reconstruction / mimic terms of the reference's total loss (they need the training-mode
+BatchNorm backward of the mask, reconstruction and projector heads) and unfrozen encoders.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+import b200_native as nat
+from model_module import _as_nhwc_bf16, _bilinear_axis_weights
+
+__all__ = ["FusionHeadTrainer", "flat_views", "average_gradients"]
+
+
+def flat_views(tensors, flat):
+    """Views of `flat` with the shapes of `tensors`, packed back to back (the layout of both flat buffers)."""
+    out, off = [], 0
+    for t in tensors:
+        n = t.numel()
+        out.append(flat[off:off + n].view(t.shape))
+        off += n
+    return out
+
+
+def average_gradients(flat_grads, group=None):
+    """Data-parallel exchange of one step: SUM all-reduce of the flat gradient buffer; returns the factor the
+    optimiser kernel must apply (1 / world size).  One collective per step."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 1.0
+    dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
+def _split_k(m, n, k):
+    tiles = ((m + 63) // 64) * ((n + 63) // 64)
+    return max(1, min((2 * 148 + tiles - 1) // tiles, max(1, k // 64)))
+
+
+class FusionHeadTrainer:
+    """Owns the flat parameter / gradient / AdamW-moment buffers of a `model_module.FusionModel` and runs its
+    classification fine-tuning step.  `lr`, `betas`, `eps`, `weight_decay` as torch.optim.AdamW
+    (code/selector_helpers.py:222-229); `smoothing` = label_smoothing_alpha, `gamma` / `class_weights` as
+    Soft(Weighted)FocalLoss (code/selector_helpers.py:14-46)."""
+
+    def __init__(self, fusion_model, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=4e-5, smoothing=0.1,
+                 gamma=1.5, class_weights=None, process_group=None):
+        fm = fusion_model
+        if not fm.use_cross_attention:
+            raise NotImplementedError("fusion-head training without the cross-attention block is not built")
+        if isinstance(fm.proj_in_dwi, nn.Identity) or isinstance(fm.proj_in_dce, nn.Identity):
+            raise NotImplementedError("encoder channels == fusion_channels (identity proj_in) is not built")
+        hp, wp = fm.token_pool
+        if hp * wp > 32 or fm.fusion_channels % fm.mha_heads != 0 or fm.fusion_channels // fm.mha_heads > 128:
+            raise NotImplementedError("token_pool / head size outside the attention kernel's range")
+        self.model = fm
+        self.lr, self.betas, self.eps, self.weight_decay = lr, tuple(betas), eps, weight_decay
+        self.smoothing, self.gamma = float(smoothing), float(gamma)
+        self.class_weights = class_weights
+        self.group = process_group
+        self.step_count = 0
+        ca = fm.cross_attn_block
+        named = [("proj_in_dwi.weight", fm.proj_in_dwi.weight), ("proj_in_dce.weight", fm.proj_in_dce.weight),
+                 ("gating.fc.weight", fm.gating.fc.weight), ("gating.fc.bias", fm.gating.fc.bias),
+                 ("cross_attn_block.cross_attn.in_proj_weight", ca.cross_attn.in_proj_weight),
+                 ("cross_attn_block.cross_attn.in_proj_bias", ca.cross_attn.in_proj_bias),
+                 ("cross_attn_block.cross_attn.out_proj.weight", ca.cross_attn.out_proj.weight),
+                 ("cross_attn_block.cross_attn.out_proj.bias", ca.cross_attn.out_proj.bias),
+                 ("cross_attn_block.attn_ffn.0.weight", ca.attn_ffn[0].weight),
+                 ("cross_attn_block.attn_ffn.0.bias", ca.attn_ffn[0].bias),
+                 ("cross_attn_block.attn_ffn.1.weight", ca.attn_ffn[1].weight),
+                 ("cross_attn_block.attn_ffn.1.bias", ca.attn_ffn[1].bias),
+                 ("cross_attn_block.attn_ffn.3.weight", ca.attn_ffn[3].weight),
+                 ("cross_attn_block.attn_ffn.3.bias", ca.attn_ffn[3].bias)]
+        if fm.fusion_se is not None:
+            se = fm.fusion_se
+            named += [("fusion_se.fc.1.weight", se.fc[1].weight), ("fusion_se.fc.1.bias", se.fc[1].bias),
+                      ("fusion_se.fc.3.weight", se.fc[3].weight), ("fusion_se.fc.3.bias", se.fc[3].bias)]
+        named += [("classifier.2.weight", fm.classifier[2].weight), ("classifier.2.bias", fm.classifier[2].bias)]
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        self.numel = sum(p.numel() for p in self.params)
+        self._flat = None
+        self._ws = {}
+
+    # ------------------------------------------------------------------------------------------ buffers ----
+    def _bind(self):
+        """(Re)create the flat buffers on the parameters' device and make the parameters views of them."""
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise nat.B200NativeError("FusionHeadTrainer needs the fusion model on a CUDA device (no CPU path)")
+        bound = self._flat is not None and self._flat["p"].device == dev
+        if bound:
+            base, off = self._flat["p"].data_ptr(), 0
+            for p in self.params:
+                bound = bound and p.data_ptr() == base + 4 * off and p.dtype == torch.float32
+                off += p.numel()
+        if bound:
+            return self._flat
+        old = self._flat
+        flat = {"p": torch.empty(self.numel, dtype=torch.float32, device=dev),
+                "g": torch.zeros(self.numel + 1, dtype=torch.float32, device=dev),  # last element: the loss
+                "m": torch.zeros(self.numel, dtype=torch.float32, device=dev),
+                "v": torch.zeros(self.numel, dtype=torch.float32, device=dev)}
+        if old is not None:  # the model was moved / reloaded: keep the optimiser state
+            flat["m"].copy_(old["m"])
+            flat["v"].copy_(old["v"])
+        for p, view in zip(self.params, flat_views(self.params, flat["p"])):
+            view.copy_(p.data.float())
+            p.data = view
+        self.grads = flat_views(self.params, flat["g"])
+        for p, g in zip(self.params, self.grads):
+            p.grad = g
+        cw = self.class_weights
+        flat["cw"] = None if cw is None else torch.as_tensor(cw, dtype=torch.float32).to(dev).contiguous()
+        self._flat = flat
+        self._ws = {}
+        return flat
+
+    def _workspace(self, B, H, W):
+        key = (B, H, W)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        fm = self.model
+        dev = self.params[0].device
+        hp, wp = fm.token_pool
+        T, C = hp * wp, fm.fusion_channels
+        R = B * T
+        Cm = fm.fusion_se.fc[1].weight.shape[0] if fm.fusion_se is not None else 0
+        in_dim = 2 * C + (2 if fm.use_mask_attention else 0)
+        K = fm.num_classes
+
+        def z(*shape):
+            return torch.empty(shape, dtype=torch.float32, device=dev)
+
+        ws = {"Xd": z(R, fm.dwi_ch), "Xc": z(R, fm.dce_ch), "Td": z(R, C), "Tc": z(R, C), "Q": z(R, C),
+              "KV": z(R, 2 * C), "P": z(B, fm.mha_heads, T, T), "CTX": z(R, C), "AO": z(R, C), "LN": z(R, C),
+              "mean": z(R), "rstd": z(R), "H1": z(R, C), "G1": z(R, C), "LOW": z(R, C),
+              "logits": z(B, K), "gating": z(B, 2), "dlogits": z(B, K), "zvec": z(B, C), "gf": z(B, C),
+              "h": z(B, max(Cm, 1)), "da1": z(B, max(Cm, 1)), "da2": z(B, C), "gx": z(B, in_dim), "dgl": z(B, 2),
+              "dpd": z(B, C), "dpc": z(B, C), "dLOW": z(R, C), "dG1": z(R, C), "dH1": z(R, C), "dLN": z(R, C),
+              "dAO": z(R, C), "tmp": z(R, C), "dCTX": z(R, C), "dQ": z(R, C), "dKV": z(R, 2 * C), "dTd": z(R, C),
+              "dTc": z(R, C)}
+        ah, aw = _bilinear_axis_weights(hp, H), _bilinear_axis_weights(wp, W)
+        ws["up"] = torch.tensor([ah[i] * aw[j] for i in range(hp) for j in range(wp)], dtype=torch.float32,
+                                device=dev)
+        self._ws = {key: ws}  # one batch geometry at a time
+        return ws
+
+    # ---------------------------------------------------------------------------------------- the step ----
+    def zero_grad(self):
+        self._bind()["g"].zero_()
+
+    def loss_and_grads(self, f3_dwi, f3_dce, dwi_mask_pred, dce_mask_pred, labels):
+        """Forward + backward of the classification objective on one batch; ACCUMULATES into the flat gradient
+        buffer (call zero_grad first).  f3_* are the encoders' deepest maps ([B,C,H,W]-shaped, bf16 channels-last as
+        the B200 encoders emit them), *_mask_pred their mask logits.  Returns (loss, logits) - device tensors, the
+        loss being this rank's batch mean."""
+        fm = self.model
+        flat = self._bind()
+        f3d, f3c = _as_nhwc_bf16(f3_dwi), _as_nhwc_bf16(f3_dce)
+        B, H, W, _ = f3d.shape
+        hp, wp = fm.token_pool
+        if H % hp or W % wp:
+            raise NotImplementedError("token pooling with unequal bins (map size not a multiple of token_pool)")
+        if fm.use_mask_attention and (dwi_mask_pred is None or dce_mask_pred is None):
+            raise RuntimeError("use_mask_attention needs both encoder mask predictions")
+        T, C, NH = hp * wp, fm.fusion_channels, fm.mha_heads
+        R = B * T
+        ws = self._workspace(B, H, W)
+        par = dict(zip(self.names, self.params))
+        grd = dict(zip(self.names, self.grads))
+        ca = "cross_attn_block."
+        Wd, Wc = par["proj_in_dwi.weight"].view(C, -1), par["proj_in_dce.weight"].view(C, -1)
+        Win, b_in = par[ca + "cross_attn.in_proj_weight"], par[ca + "cross_attn.in_proj_bias"]
+        Wo, bo = par[ca + "cross_attn.out_proj.weight"], par[ca + "cross_attn.out_proj.bias"]
+        lnw, lnb = par[ca + "attn_ffn.0.weight"], par[ca + "attn_ffn.0.bias"]
+        W1, b1 = par[ca + "attn_ffn.1.weight"], par[ca + "attn_ffn.1.bias"]
+        W2, b2 = par[ca + "attn_ffn.3.weight"], par[ca + "attn_ffn.3.bias"]
+
+        # ---- forward on pooled tokens ----
+        nat.fusion_tokens(f3d, hp, wp, ws["Xd"])
+        nat.fusion_tokens(f3c, hp, wp, ws["Xc"])
+        nat.sgemm(ws["Xd"], Wd, ws["Td"], trans_b=True)
+        nat.sgemm(ws["Xc"], Wc, ws["Tc"], trans_b=True)
+        nat.sgemm(ws["Td"], Win[:C], ws["Q"], trans_b=True, bias=b_in[:C])
+        nat.sgemm(ws["Tc"], Win[C:], ws["KV"], trans_b=True, bias=b_in[C:])
+        Kt, Vt = ws["KV"][:, :C], ws["KV"][:, C:]
+        nat.mha_fwd(ws["Q"], Kt, Vt, B, NH, ws["P"], ws["CTX"])
+        nat.sgemm(ws["CTX"], Wo, ws["AO"], trans_b=True, bias=bo)
+        nat.ln_fwd(ws["AO"], lnw, lnb, fm.cross_attn_block.attn_ffn[0].eps, ws["LN"], ws["mean"], ws["rstd"])
+        nat.sgemm(ws["LN"], W1, ws["G1"], trans_b=True, bias=b1, pre=ws["H1"], act=1)
+        nat.sgemm(ws["G1"], W2, ws["LOW"], trans_b=True, bias=b2, res=ws["AO"])
+
+        # ---- per-case tail, loss, and the backward of the tail ----
+        a = nat.HeadTrain()
+        a.C, a.T, a.num_classes = C, T, fm.num_classes
+        a.use_mask_attention, a.use_se = int(fm.use_mask_attention), int(fm.fusion_se is not None)
+        a.smoothing, a.gamma, a.loss_scale = self.smoothing, self.gamma, 1.0 / B
+        keep = []
+
+        def ptr(t):
+            keep.append(t)
+            return t.data_ptr()
+
+        if flat["cw"] is not None:
+            a.class_weights = ptr(flat["cw"])
+        a.tok_dwi, a.tok_dce, a.lowres = ptr(ws["Td"]), ptr(ws["Tc"]), ptr(ws["LOW"])
+        if fm.use_mask_attention:
+            md, mc = dwi_mask_pred.contiguous().float(), dce_mask_pred.contiguous().float()
+            a.npix_mask = md[0].numel()
+            a.mask_dwi, a.mask_dce = ptr(md), ptr(mc)
+        lab = labels.to(device=f3d.device, dtype=torch.int64).contiguous()
+        if lab.numel() != B:
+            raise ValueError("one label per case is required")
+        a.labels = ptr(lab)
+        a.gate_w, a.gate_b = ptr(par["gating.fc.weight"]), ptr(par["gating.fc.bias"])
+        a.up_coef = ptr(ws["up"])
+        if fm.fusion_se is not None:
+            a.se_mid = par["fusion_se.fc.1.weight"].shape[0]
+            a.se_w1, a.se_b1 = ptr(par["fusion_se.fc.1.weight"]), ptr(par["fusion_se.fc.1.bias"])
+            a.se_w2, a.se_b2 = ptr(par["fusion_se.fc.3.weight"]), ptr(par["fusion_se.fc.3.bias"])
+            a.h_out, a.da1_out, a.da2_out = ptr(ws["h"]), ptr(ws["da1"]), ptr(ws["da2"])
+        a.cls_w, a.cls_b = ptr(par["classifier.2.weight"]), ptr(par["classifier.2.bias"])
+        loss = flat["g"][self.numel:]
+        a.loss_out, a.logits_out, a.gating_out = ptr(loss), ptr(ws["logits"]), ptr(ws["gating"])
+        a.dlogits_out, a.z_out, a.gf_out = ptr(ws["dlogits"]), ptr(ws["zvec"]), ptr(ws["gf"])
+        a.gx_out, a.dgl_out = ptr(ws["gx"]), ptr(ws["dgl"])
+        a.dpd_out, a.dpc_out, a.dlowres_out = ptr(ws["dpd"]), ptr(ws["dpc"]), ptr(ws["dLOW"])
+        nat.head_loss(a, B)
+
+        def wgrad(dy, x, name, rows=None):
+            g = grd[name] if rows is None else grd[name][rows]
+            g = g.view(g.shape[0], -1)
+            nat.sgemm(dy, x, g, trans_a=True, beta=1, split_k=_split_k(g.shape[0], g.shape[1], dy.shape[0]))
+
+        def bgrad(dy, name, rows=None):
+            nat.colsum(dy, grd[name] if rows is None else grd[name][rows])
+
+        wgrad(ws["dlogits"], ws["zvec"], "classifier.2.weight")
+        bgrad(ws["dlogits"], "classifier.2.bias")
+        if fm.fusion_se is not None:
+            wgrad(ws["da1"], ws["gf"], "fusion_se.fc.1.weight")
+            bgrad(ws["da1"], "fusion_se.fc.1.bias")
+            wgrad(ws["da2"], ws["h"], "fusion_se.fc.3.weight")
+            bgrad(ws["da2"], "fusion_se.fc.3.bias")
+        wgrad(ws["dgl"], ws["gx"], "gating.fc.weight")
+        bgrad(ws["dgl"], "gating.fc.bias")
+
+        # ---- backward through the cross-attention block ----
+        dLOW = ws["dLOW"]
+        wgrad(dLOW, ws["G1"], ca + "attn_ffn.3.weight")
+        bgrad(dLOW, ca + "attn_ffn.3.bias")
+        nat.sgemm(dLOW, W2, ws["dG1"])
+        nat.gelu_bwd(ws["H1"], ws["dG1"], ws["dH1"])
+        wgrad(ws["dH1"], ws["LN"], ca + "attn_ffn.1.weight")
+        bgrad(ws["dH1"], ca + "attn_ffn.1.bias")
+        nat.sgemm(ws["dH1"], W1, ws["dLN"])
+        nat.ln_bwd(ws["AO"], ws["dLN"], dLOW, lnw, ws["mean"], ws["rstd"], ws["dAO"], ws["tmp"])
+        bgrad(ws["tmp"], ca + "attn_ffn.0.weight")
+        bgrad(ws["dLN"], ca + "attn_ffn.0.bias")
+        wgrad(ws["dAO"], ws["CTX"], ca + "cross_attn.out_proj.weight")
+        bgrad(ws["dAO"], ca + "cross_attn.out_proj.bias")
+        nat.sgemm(ws["dAO"], Wo, ws["dCTX"])
+        dK, dV = ws["dKV"][:, :C], ws["dKV"][:, C:]
+        nat.mha_bwd(ws["Q"], Kt, Vt, ws["P"], ws["dCTX"], B, NH, ws["dQ"], dK, dV)
+        q_rows, kv_rows = slice(0, C), slice(C, 3 * C)
+        wgrad(ws["dQ"], ws["Td"], ca + "cross_attn.in_proj_weight", q_rows)
+        bgrad(ws["dQ"], ca + "cross_attn.in_proj_bias", q_rows)
+        wgrad(ws["dKV"], ws["Tc"], ca + "cross_attn.in_proj_weight", kv_rows)
+        bgrad(ws["dKV"], ca + "cross_attn.in_proj_bias", kv_rows)
+        nat.sgemm(ws["dQ"], Win[:C], ws["dTd"], res=ws["dpd"], res_div=T)
+        nat.sgemm(ws["dKV"], Win[C:], ws["dTc"], res=ws["dpc"], res_div=T)
+        wgrad(ws["dTd"], ws["Xd"], "proj_in_dwi.weight")
+        wgrad(ws["dTc"], ws["Xc"], "proj_in_dce.weight")
+        return loss, ws["logits"]
+
+    def step(self):
+        """Gradient all-reduce (when torch.distributed is initialised) + one fused AdamW launch."""
+        flat = self._bind()
+        scale = average_gradients(flat["g"], self.group)
+        self.step_count += 1
+        nat.adamw(flat["p"], flat["g"][:self.numel], flat["m"], flat["v"], lr=self.lr, betas=self.betas, eps=self.eps,
+                  weight_decay=self.weight_decay, step=self.step_count, grad_scale=scale)
+        for p in self.params:  # the kernel wrote through raw pointers: tell torch (packed-weight caches key on it)
+            torch.autograd.graph.increment_version(p)
+        return flat["g"][self.numel:] * scale  # the loss averaged over ranks
+
+    def train_step(self, f3_dwi, f3_dce, dwi_mask_pred, dce_mask_pred, labels):
+        """zero_grad -> loss_and_grads -> all-reduce -> AdamW.  Returns (loss averaged over ranks, logits)."""
+        self.zero_grad()
+        _, logits = self.loss_and_grads(f3_dwi, f3_dce, dwi_mask_pred, dce_mask_pred, labels)
+        return self.step(), logits
+
+    # torch.optim-like surface for harnesses that treat the object returned by configure_optimizers as one
+    def state_dict(self):
+        flat = self._bind()
+        return {"step": self.step_count, "names": list(self.names), "exp_avg": flat["m"].clone(),
+                "exp_avg_sq": flat["v"].clone()}
+
+    def load_state_dict(self, sd):
+        flat = self._bind()
+        if list(sd["names"]) != list(self.names):
+            raise ValueError("optimizer state was saved for a different parameter set")
+        self.step_count = int(sd["step"])
+        flat["m"].copy_(sd["exp_avg"])
+        flat["v"].copy_(sd["exp_avg_sq"])

@@ -2,7 +2,9 @@
 one object, `forward` / `forward_from_inputs` (:200-201, :670-677) and the prediction modes its test loop runs -
 `predict_tta`, `predict_mc_dropout`, `predict_tta_mc`, `predict_custom` (:484-632, :682-702; the default test mode
 is "tta_mc": 4 flips x 10 dropout passes).  Same method names, arguments and return structure; no Lightning
-dependency.  Training (`_shared_step`, optimisers, losses) is not built and raises.
+dependency.  Training: `_shared_step("train")` / `training_step` / `configure_optimizers` run the fusion-head
+fine-tuning step of the frozen-encoder phase under the classification objective (fusion_train.FusionHeadTrainer);
+the mask / reconstruction / mimic loss terms and unfrozen encoders are not built and raise.
 
 MC dropout follows the reference's switch exactly: `enable_dropout` puts the nn.Dropout sub-modules of the two
 encoders in train mode, `set_batchnorm_eval` keeps BatchNorm frozen, and the encoders' forward then arms the
@@ -142,7 +144,112 @@ class LightningFusionModel(nn.Module):
         raise ValueError(f"Unknown predict mode: {mode}")
 
     # --------------------------------------------------------------- training ----
-    def _shared_step(self, batch, phase="train", return_preds=False):
-        raise NotImplementedError("the fusion training step (losses, backward, optimiser) is not built in the B200 path")
+    _UNBUILT_TERMS = (("recon_enabled", "reconstruction (train_fusion.py:271-284)"),
+                      ("mimic_enabled", "mimic (train_fusion.py:287-292)"),
+                      ("attn_reg_enabled", "attention regularisation (train_fusion.py:259-262)"))
 
-    training_step = validation_step = test_step = configure_optimizers = _shared_step
+    def _objective_check(self):
+        """The B200 step computes the classification term of the reference's total loss (train_fusion.py:238-242).
+        Anything else the configuration enables raises unless the caller opted into the classification-only
+        objective with parameters_dict["b200_classification_objective_only"] = True."""
+        if self.parameters_dict.get("b200_classification_objective_only", False):
+            return
+        fp = self.parameters_dict.get("fusion_model_parameters", {})
+        on = [what for key, what in self._UNBUILT_TERMS if fp.get(key, False)]
+        mp = fp.get("mask_parameters", {})
+        if mp.get("mask", False) and mp.get("lambda_mask", 0.0):
+            on.append("mask dice (train_fusion.py:245-255)")
+        if on:
+            raise NotImplementedError(
+                "loss terms not built in the B200 training step: " + "; ".join(on) + " - disable them or set "
+                "parameters_dict['b200_classification_objective_only'] = True")
+
+    def configure_optimizers(self):
+        """The fusion-head parameter group of LightningFusionOptimizerFactory (selector_helpers.py:356-520, the only
+        group in the optimiser while `backbone_freeze_on_start`), as a FusionHeadTrainer (flat buffers + fused
+        AdamW).  Loss settings: label_smoothing_alpha, classification_loss_parameters.gamma; `class_weights` (the
+        'wfl' inverse-frequency weights of selector_helpers.py:25-41) via set_class_weights."""
+        from fusion_train import FusionHeadTrainer
+
+        fp = self.parameters_dict.get("fusion_model_parameters", {})
+        op = fp.get("optimizer_parameters", {})
+        if op.get("name", "adamw").lower() != "adamw" or op.get("amsgrad", False):
+            raise NotImplementedError("only AdamW without amsgrad is built")
+        if not fp.get("label_smoothing_enabled", True):
+            # the reference's train branch reads `smoothed` unconditionally (train_fusion.py:240-241): NameError
+            raise RuntimeError("the reference training step requires label_smoothing_enabled")
+        cl = fp.get("classification_loss_parameters", {})
+        gamma = cl.get("gamma", None)
+        self.head_trainer = FusionHeadTrainer(
+            self.fusion_model, lr=op.get("lr", 1e-4), betas=op.get("betas", (0.9, 0.999)), eps=op.get("eps", 1e-8),
+            weight_decay=op.get("weight_decay", 4e-5), smoothing=fp.get("label_smoothing_alpha", 0.1),
+            gamma=2 if gamma is None else gamma, class_weights=getattr(self, "_class_weights", None))
+        return self.head_trainer
+
+    def set_class_weights(self, train_labels):
+        """Inverse class frequency weights of the 'wfl' loss (selector_helpers.py:25-41)."""
+        counts = torch.bincount(train_labels.long().cpu(), minlength=self.fusion_model.num_classes).float()
+        self._class_weights = train_labels.numel() / (len(counts) * (counts + 1e-6))
+        return self._class_weights
+
+    def _unpack(self, batch):
+        if len(batch) == 4:
+            dwi, dce, _masks, labels = batch
+        else:
+            dwi, dce, labels = batch
+        dev = self.device
+        return dwi.to(dev), dce.to(dev), labels.long().to(dev)
+
+    def _shared_step(self, batch, phase="train", return_preds=False):
+        """train: frozen encoders (eval-mode BatchNorm, no dropout) -> fusion head forward + backward; the gradients
+        are left in the trainer's flat buffer (there is no autograd graph: `optimizer_step` / `fit_batch` apply
+        them).  val / test: inference forward and the hard-label loss (train_fusion.py:241)."""
+        self._objective_check()
+        dwi, dce, labels = self._unpack(batch)
+        if phase == "train":
+            if getattr(self, "head_trainer", None) is None:
+                self.configure_optimizers()
+            if any(p.requires_grad for m in (self.dwi_model, self.dce_model) for p in m.parameters()):
+                raise NotImplementedError("training with unfrozen encoders is not built (freeze them: "
+                                          "backbone_freeze_on_start)")
+            with torch.no_grad():
+                _, dwi_aux, dwi_mask = self.dwi_model(dwi)
+                _, dce_aux, dce_mask = self.dce_model(dce)
+            self.head_trainer.zero_grad()
+            loss, logits = self.head_trainer.loss_and_grads(dwi_aux["raw_feats"][-1], dce_aux["raw_feats"][-1],
+                                                            dwi_mask, dce_mask, labels)
+            loss = loss.clone().squeeze(0)
+            if return_preds:
+                return loss, logits.clone(), None, None
+            return loss
+        with torch.no_grad():
+            logits, fused_mask, aux = self.forward_from_inputs(dwi, dce)
+            tr = getattr(self, "head_trainer", None)
+            gamma = tr.gamma if tr is not None else 2.0
+            lp = torch.log_softmax(logits, dim=1)  # [B, K] metric arithmetic on the logits
+            fw = (1 - lp.exp()) ** gamma
+            if getattr(self, "_class_weights", None) is not None:
+                fw = fw * self._class_weights.to(lp.device).view(1, -1)
+            onehot = torch.nn.functional.one_hot(labels, logits.shape[1]).float()
+            loss = (-(onehot * fw * lp).sum(dim=1)).mean()
+        if return_preds:
+            return loss, logits, aux, fused_mask
+        return loss
+
+    def training_step(self, batch, batch_idx=0):
+        return self._shared_step(batch, "train")
+
+    def validation_step(self, batch, batch_idx=0):
+        return self._shared_step(batch, "val")
+
+    def test_step(self, batch, batch_idx=0):
+        return self._shared_step(batch, "test")
+
+    def optimizer_step(self):
+        """Gradient all-reduce over the data-parallel ranks + AdamW; returns the rank-averaged loss."""
+        return self.head_trainer.step()
+
+    def fit_batch(self, batch):
+        """One whole optimisation step: training_step + optimizer_step."""
+        self.training_step(batch)
+        return self.optimizer_step()

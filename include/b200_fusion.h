@@ -337,6 +337,96 @@ int b200_fusion_core(const b200_fusion_weights* wts, int B, const float* pvec_dw
 int b200_fusion_mix(const void* p_dwi, const void* p_dce, const float* gating, const float* lowres,
                     const float* gate, int B, int H, int W, int C, int Hp, int Wp, void* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Fusion-head fine-tuning step (BASELINE config C5, frozen-encoder phase of code/train_fusion.py:203-321 with
+ * code/selector_helpers.py:356-520: the fusion head is the always-trainable parameter group).  All fp32.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* C = op(A) op(B): op(A) is [M,K] (A is [M,K] with row stride lda, or [K,M] when trans_a), op(B) is [K,N] (B is
+ * [K,N], or [N,K] when trans_b - an nn.Linear weight used as stored).  Epilogue (split_k == 1 only): + bias[N],
+ * + res[(row / res_div) * ldres + col] (res_div > 1 broadcasts one residual row over res_div consecutive rows),
+ * pre (optional, row stride ldc) receives the value before the activation, act 1 = exact GELU, beta 1 adds the
+ * previous C.  split_k > 1 splits K over grid.z and ACCUMULATES into C atomically (beta must be 1; the caller
+ * zeroes C for a plain product).  Serves nn.Linear forward / data gradient / weight gradient of
+ * FusionModel.proj_in_* (code/model_module.py:857-858, 929-930, applied to pooled tokens),
+ * nn.MultiheadAttention's projections (:806) and attn_ffn (:807-812). */
+int b200_sgemm(const float* A, long long lda, int trans_a, const float* B, long long ldb, int trans_b, float* C,
+               long long ldc, int M, int N, int K, const float* bias, const float* res, long long ldres, int res_div,
+               float* pre, int act, int beta, int split_k, void* stream);
+
+/* out[n] += sum over rows of X[R,N] (bias gradients; the caller zeroes out). */
+int b200_colsum(const float* X, long long ld, int R, int N, float* out, void* stream);
+
+/* nn.MultiheadAttention core (code/model_module.py:806, :816; no dropout, no mask) for Tq, Tk <= 32 tokens:
+ * probs[B,heads,Tq,Tk] = softmax(q k^T / sqrt(DH)), ctx = probs v.  q [B*Tq, ldq], k / v [B*Tk, ldkv], head h in
+ * columns [h*DH, (h+1)*DH).  The backward writes dq (layout of q) and dk / dv (layout of k / v). */
+int b200_mha_fwd(const float* q, long long ldq, const float* k, const float* v, long long ldkv, int B, int heads,
+                 int Tq, int Tk, int DH, float* probs, float* ctx, long long ldc, void* stream);
+int b200_mha_bwd(const float* q, long long ldq, const float* k, const float* v, long long ldkv, const float* probs,
+                 const float* dctx, long long ldc, int B, int heads, int Tq, int Tk, int DH, float* dq, float* dk,
+                 float* dv, void* stream);
+
+/* nn.LayerNorm of attn_ffn (code/model_module.py:808) on [R,C] rows with saved statistics, and its backward:
+ * dx = dres (optional residual-path gradient) + LN'(dy); dyxhat = dy * xhat, whose column sums are the weight
+ * gradient (dy's column sums are the bias gradient). */
+int b200_ln_fwd(const float* x, int R, int C, const float* w, const float* b, float eps, float* y, float* mean,
+                float* rstd, void* stream);
+int b200_ln_bwd(const float* x, const float* dy, const float* dres, int R, int C, const float* w, const float* mean,
+                const float* rstd, float* dx, float* dyxhat, void* stream);
+
+/* out = dg * gelu'(pre), exact (erf) GELU (nn.GELU of attn_ffn, code/model_module.py:810). */
+int b200_gelu_bwd(const float* pre, const float* dg, long long n, float* out, void* stream);
+
+/* Per-case tail of the head's logits path and its backward.  Weights in their nn.Module layouts. */
+typedef struct b200_head_train {
+    int C, T, se_mid, num_classes;
+    int use_mask_attention, use_se;
+    int npix_mask;
+    float smoothing;            /* LabelSmoothing alpha (code/loss.py:190-213) */
+    float gamma;                /* focal exponent (code/loss.py:133-188) */
+    float loss_scale;           /* 1 / batch: reduction "mean" */
+    const float* class_weights; /* [K] or NULL (SoftWeightedFocalLoss) */
+    const float* tok_dwi;       /* [B,T,C] projected pooled tokens */
+    const float* tok_dce;
+    const float* lowres;        /* [B,T,C] cross-attention block output, or NULL (use_cross_attention False) */
+    const float* mask_dwi;      /* [B,npix_mask] encoder mask logits (GatingAttention confidences) */
+    const float* mask_dce;
+    const long long* labels;    /* [B] int64 */
+    const float* gate_w;        /* gating.fc.weight [2, 2C(+2)] */
+    const float* gate_b;
+    const float* up_coef;       /* [T] mean bilinear weight of each token cell */
+    const float* se_w1;         /* fusion_se.fc.1.weight [Cm,C] */
+    const float* se_b1;
+    const float* se_w2;         /* fusion_se.fc.3.weight [C,Cm] */
+    const float* se_b2;
+    const float* cls_w;         /* classifier.2.weight [K,C] */
+    const float* cls_b;
+    float* loss_out;            /* scalar, ACCUMULATED (caller zeroes) */
+    float* logits_out;          /* [B,K] or NULL */
+    float* gating_out;          /* [B,2] or NULL */
+    float* dlogits_out;         /* [B,K]   -> classifier weight / bias gradients */
+    float* z_out;               /* [B,C]   gated pooled vector (classifier input) */
+    float* gf_out;              /* [B,C]   pooled fused vector (SE input) */
+    float* h_out;               /* [B,Cm]  SE hidden activation */
+    float* da1_out;             /* [B,Cm]  gradient at the SE hidden pre-activation */
+    float* da2_out;             /* [B,C]   gradient at the SE output pre-activation */
+    float* gx_out;              /* [B,2C(+2)] gating input */
+    float* dgl_out;             /* [B,2]   gradient at the gating logits */
+    float* dpd_out;             /* [B,C]   gradient of each DWI token coming through the pooled vector (already / T) */
+    float* dpc_out;             /* [B,C]   same for DCE */
+    float* dlowres_out;         /* [B,T,C] gradient of lowres, or NULL with lowres */
+} b200_head_train;
+
+/* FusionModel.forward tail (code/model_module.py:942-986: gating :952-958, GAP of the fused map, fusion_se :977,
+ * classifier :986) + LabelSmoothing and Soft(Weighted)FocalLoss with mean reduction (code/train_fusion.py:238-242)
+ * + the backward of that chain, one CTA per case. */
+int b200_head_loss(const b200_head_train* args, int B, void* stream);
+
+/* torch.optim.AdamW step (code/selector_helpers.py:222-229) on flat fp32 buffers; g is multiplied by grad_scale
+ * first (1 / world_size after the summing gradient all-reduce).  step >= 1 is the update count. */
+int b200_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+               float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

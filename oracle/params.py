@@ -97,3 +97,17 @@ def edge_cases(size=64, dwi_channels=16):
     x[3] = x[3] - 50.0                             # negatives
     x[4, 2, 5, 5] = 1e6                            # one huge outlier
     return x
+
+
+def synthetic_head_batch(n, seed=11, channels=512, size=32, num_classes=4):
+    """Inputs of the fusion-head training step: encoder f3 maps (values exactly representable in bf16, the dtype the
+    product's encoders emit), encoder mask logits and labels.  Returns (f3_dwi, f3_dce [n,C,S,S], mask_dwi, mask_dce
+    [n,1,S,S], labels [n] int64)."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn(n, 1, size, size, generator=g)
+    f3d = (0.6 * torch.randn(n, channels, size, size, generator=g) + 0.3 * base).bfloat16().float()
+    f3c = (0.6 * torch.randn(n, channels, size, size, generator=g) - 0.2 * base).bfloat16().float()
+    md = torch.randn(n, 1, size, size, generator=g)
+    mc = torch.randn(n, 1, size, size, generator=g)
+    labels = torch.randint(0, num_classes, (n,), generator=g)
+    return f3d, f3c, md, mc, labels

@@ -1,0 +1,170 @@
+"""CPU checks of the fusion-head training step: the oracle (oracle/train_oracle.py) against the fixture generated
+from the UNMODIFIED reference (tests/golden/train_head.npz, oracle/make_golden_train.py), and the host logic of the
+step (flat buffers, gradient all-reduce on 2 gloo ranks, configuration checks, loud failure without CUDA)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import b200path
+import golden_util as gu
+from oracle import params as op
+from oracle import train_oracle as to
+
+ROOT = b200path.ROOT
+
+
+def _setup():
+    gold = gu.load("train_head.npz")
+    hp = json.loads(str(gold["hp"]))
+    import parameters_default as pd
+
+    params = pd.default_parameters()
+    shapes = gu.load_shapes("cnn")["fusion"]
+    sd = op.seeded_state_dict(shapes, seed=hp["weight_seed"])
+    batch = op.synthetic_head_batch(hp["n"], seed=hp["seed"])
+    return gold, hp, params, sd, batch
+
+
+def check_updated_parameter(gold, name, got, rtol):
+    """Parameters after the AdamW steps.  The key bias of nn.MultiheadAttention has a mathematically zero gradient
+    (softmax is invariant to a per-query shift of the scores); Adam normalises its rounding noise (1e-10) to full
+    +-lr steps, so that third of in_proj_bias is a random walk in the reference too and is not compared."""
+    if name.endswith("cross_attn.in_proj_bias"):
+        ref = torch.from_numpy(gold[f"param/{name}/full"])
+        c = ref.numel() // 3
+        keep = torch.cat([torch.arange(0, c), torch.arange(2 * c, 3 * c)])
+        got = got.detach().float().cpu()
+        err = (got[keep] - ref[keep]).abs().max().item() / ref[keep].abs().max().item()
+        assert err <= rtol, f"{name} (query / value thirds): {err:.3e} > {rtol:.1e}"
+        return err
+    return gu.check(gold, f"param/{name}", got, rtol, what="updated parameter ")
+
+
+def test_oracle_loss_and_gradients_match_the_reference():
+    gold, hp, params, sd, batch = _setup()
+    loss, logits, grads = to.head_loss_and_grads(sd, params, *batch, hp["smoothing"], hp["gamma"],
+                                                 torch.tensor(hp["class_weights"]))
+    assert abs(float(loss) - gold["losses"][0]) <= 1e-5 * abs(gold["losses"][0])
+    gu.check(gold, "logits", logits, 1e-5)
+    names = sorted(k[len("grad/"):-len("/meta")] for k in gold.files if k.startswith("grad/") and k.endswith("/meta"))
+    assert names == sorted(grads) == sorted(hp["updated"])  # the same 20 tensors receive a gradient
+    for k in names:
+        gu.check(gold, f"grad/{k}", grads[k], 2e-4, what="gradient ")
+
+
+def test_oracle_adamw_steps_match_the_reference():
+    gold, hp, params, sd, batch = _setup()
+    losses, new_sd, names = to.train_steps(sd, params, batch, hp["steps"], hp["smoothing"], hp["gamma"],
+                                           torch.tensor(hp["class_weights"]), hp["lr"], tuple(hp["betas"]),
+                                           hp["eps"], hp["weight_decay"])
+    assert sorted(names) == sorted(hp["updated"])
+    for a, b in zip(losses, gold["losses"]):
+        assert abs(a - b) <= 2e-4 * abs(b), (losses, gold["losses"])
+    assert losses[-1] < losses[0]
+    for k in names:
+        check_updated_parameter(gold, k, new_sd[k], 1e-4)
+    untouched = [k for k in sd if k not in names and sd[k].is_floating_point()]
+    assert untouched and all(torch.equal(sd[k], new_sd[k]) for k in untouched)
+
+
+def test_flat_views_pack_back_to_back():
+    from fusion_train import flat_views
+
+    ts = [torch.zeros(2, 3), torch.zeros(5), torch.zeros(1, 1, 4)]
+    flat = torch.arange(15, dtype=torch.float32)
+    v = flat_views(ts, flat)
+    assert [tuple(x.shape) for x in v] == [(2, 3), (5,), (1, 1, 4)]
+    assert v[1][0] == 6 and v[2].flatten()[0] == 11
+    v[0].zero_()
+    assert flat[:6].abs().sum() == 0  # views, not copies
+
+
+def test_split_k_fills_the_machine_without_empty_slices():
+    from fusion_train import _split_k
+
+    assert _split_k(128, 512, 16384) == 19          # 16 output tiles -> ~296 CTAs
+    assert _split_k(4, 128, 1024) == 16             # capped by K / 64
+    assert _split_k(4096, 4096, 64) == 1
+
+
+def test_trainer_refuses_cpu_and_unbuilt_configurations():
+    import b200_native as nat
+    import model_module as mm
+    import parameters_default as pd
+    from fusion_train import FusionHeadTrainer
+
+    params = pd.default_parameters()
+    tr = FusionHeadTrainer(mm.FusionModel(params))
+    assert len(tr.names) == 20 and tr.numel == sum(p.numel() for p in tr.params)
+    with pytest.raises(nat.B200NativeError):
+        tr.zero_grad()  # parameters live on the CPU: no CPU path
+    params["fusion_model_parameters"]["fusion_specific_parameters"]["use_cross_attention"] = False
+    with pytest.raises(NotImplementedError):
+        FusionHeadTrainer(mm.FusionModel(params))
+
+
+def test_shared_step_rejects_unbuilt_loss_terms():
+    import model_module as mm
+    import parameters_default as pd
+    from train_fusion import LightningFusionModel
+
+    params = pd.default_parameters()
+    params["fusion_model_parameters"]["recon_enabled"] = True
+    lm = LightningFusionModel(mm.ModelMaskHeadBackbone("dwi", params), mm.ModelMaskHeadBackbone("dce", params),
+                              mm.FusionModel(params), params)
+    batch = (torch.zeros(2, 16, 64, 64), torch.zeros(2, 6, 64, 64), torch.zeros(2, dtype=torch.long))
+    with pytest.raises(NotImplementedError, match="reconstruction"):
+        lm.training_step(batch)
+    params["fusion_model_parameters"]["label_smoothing_enabled"] = False
+    params["b200_classification_objective_only"] = True
+    with pytest.raises(RuntimeError, match="label_smoothing"):
+        lm.configure_optimizers()
+    w = lm.set_class_weights(torch.tensor([0, 0, 1, 2, 3, 3, 3, 3]))
+    assert torch.allclose(w, torch.tensor([1.0, 2.0, 2.0, 0.5]), atol=1e-5)
+
+
+_WORKER = r"""
+import sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); import b200path
+from fusion_train import average_gradients, flat_views
+rank = int(sys.argv[3])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=2)
+shapes = [torch.zeros(3, 2), torch.zeros(4)]
+flat = torch.zeros(11)                      # 10 gradient elements + the loss slot
+g = flat_views(shapes, flat)
+g[0].fill_(1.0 + rank); g[1].fill_(10.0 * (1 + rank)); flat[10] = 0.5 + rank
+scale = average_gradients(flat)
+assert scale == 0.5
+avg = flat * scale
+assert torch.allclose(avg[:6], torch.full((6,), 1.5)) and torch.allclose(avg[6:10], torch.full((4,), 15.0))
+assert abs(float(avg[10]) - 1.0) < 1e-6     # the loss is averaged by the same collective
+dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_gradient_allreduce_two_ranks_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(30100 + os.getpid() % 500)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
+def test_training_entry_points_reject_bad_arguments_without_a_gpu():
+    import b200_native as nat
+
+    lib = nat.lib()
+    assert lib.b200_sgemm(None, 1, 0, None, 1, 0, None, 1, 4, 4, 4, None, None, 0, 1, None, 0, 0, 1, None) < 0
+    assert lib.b200_sgemm(None, 1, 0, None, 1, 0, None, 1, 0, 4, 4, None, None, 0, 1, None, 0, 0, 1, None) == 0
+    assert lib.b200_mha_fwd(None, 1, None, None, 1, 2, 4, 64, 16, 32, None, None, 1, None) < 0   # Tq > 32
+    assert lib.b200_adamw(None, None, None, None, 8, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0, 1.0, None) < 0  # step < 1
+    assert lib.b200_head_loss(None, 4, None) < 0
+    assert lib.b200_colsum(None, 1, 0, 4, None, None) == 0
