@@ -31,12 +31,12 @@ def test_sgemm_matches_matmul(M, N, K, ta, tb):
     ref = (a.t() if ta else a).double() @ (b.t() if tb else b).double()
     out = torch.empty(M, N, device=DEV)
     nat.sgemm(a, b, out, trans_a=bool(ta), trans_b=bool(tb))
-    assert _rel(out, ref) < 2e-6
+    assert _rel(out, ref) < 5e-6   # fp32 accumulation over up to 4 096 terms against an fp64 product
     # split-K accumulates into the existing contents
     base = torch.randn(M, N, generator=g, device=DEV)
     out2 = base.clone()
     nat.sgemm(a, b, out2, trans_a=bool(ta), trans_b=bool(tb), beta=1, split_k=max(1, min(7, K // 16)))
-    assert _rel(out2, ref + base.double()) < 2e-6
+    assert _rel(out2, ref + base.double()) < 5e-6
 
 
 def test_sgemm_epilogue_and_strided_views():
