@@ -53,40 +53,41 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+    // global -> register prefetch of the next k-slab while the current one is consumed from shared memory
+    constexpr int NA = BM * SG_BK / 256, NB = SG_BN * SG_BK / 256;
+    float ra[NA], rb[NB];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const int idx = tid + i * 256;
+            const int m = TA ? idx % BM : idx / SG_BK, k = TA ? idx / BM : idx % SG_BK;
+            const int gm = m0 + m, gk = k0 + k;
+            ra[i] = (gm < a.M && gk < kend) ? (TA ? __ldg(a.A + gk * a.lda + gm) : __ldg(a.A + gm * a.lda + gk)) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int idx = tid + i * 256;
+            const int n = TB ? idx / SG_BK : idx % SG_BN, k = TB ? idx % SG_BK : idx / SG_BN;
+            const int gn = n0 + n, gk = k0 + k;
+            rb[i] = (gn < a.N && gk < kend) ? (TB ? __ldg(a.B + gn * a.ldb + gk) : __ldg(a.B + gk * a.ldb + gn)) : 0.f;
+        }
+    };
+    if (kbeg < kend) fetch(kbeg);
     for (int k0 = kbeg; k0 < kend; k0 += SG_BK) {
 #pragma unroll
-        for (int i = 0; i < BM * SG_BK / 256; ++i) {
+        for (int i = 0; i < NA; ++i) {
             const int idx = tid + i * 256;
-            int m, k;
-            if (TA) {
-                k = idx / BM;
-                m = idx % BM;
-            } else {
-                m = idx / SG_BK;
-                k = idx % SG_BK;
-            }
-            const int gm = m0 + m, gk = k0 + k;
-            float v = 0.f;
-            if (gm < a.M && gk < kend) v = TA ? __ldg(a.A + gk * a.lda + gm) : __ldg(a.A + gm * a.lda + gk);
-            As[k][m] = v;
+            const int m = TA ? idx % BM : idx / SG_BK, k = TA ? idx / BM : idx % SG_BK;
+            As[k][m] = ra[i];
         }
 #pragma unroll
-        for (int i = 0; i < SG_BN * SG_BK / 256; ++i) {
+        for (int i = 0; i < NB; ++i) {
             const int idx = tid + i * 256;
-            int n, k;
-            if (TB) {
-                n = idx / SG_BK;
-                k = idx % SG_BK;
-            } else {
-                k = idx / SG_BN;
-                n = idx % SG_BN;
-            }
-            const int gn = n0 + n, gk = k0 + k;
-            float v = 0.f;
-            if (gn < a.N && gk < kend) v = TB ? __ldg(a.B + gn * a.ldb + gk) : __ldg(a.B + gk * a.ldb + gn);
-            Bs[k][n] = v;
+            const int n = TB ? idx / SG_BK : idx % SG_BN, k = TB ? idx % SG_BK : idx / SG_BN;
+            Bs[k][n] = rb[i];
         }
         __syncthreads();
+        if (k0 + SG_BK < kend) fetch(k0 + SG_BK);
 #pragma unroll
         for (int k = 0; k < SG_BK; ++k) {
             float av[TM];
@@ -589,7 +590,8 @@ extern "C" int b200_sgemm(const float* A, long long lda, int trans_a, const floa
     a.kchunk = kchunk;
     const int splits = K == 0 ? 1 : (K + kchunk - 1) / kchunk;
     if (splits > 1 && split_k == 1) return -6;
-    const bool big = M >= 2048;
+    // 128-row tiles only when they still fill the machine several times over (4 CTAs per SM)
+    const bool big = static_cast<long long>((M + 127) / 128) * ((N + SG_BN - 1) / SG_BN) >= 4 * 148;
     dim3 grid((N + SG_BN - 1) / SG_BN, (M + (big ? 128 : 64) - 1) / (big ? 128 : 64), splits);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return big ? launch_sgemm<8>(a, trans_a, trans_b, grid, s) : launch_sgemm<4>(a, trans_a, trans_b, grid, s);

@@ -62,42 +62,77 @@ class FusionPipeline:
             return out_d, out_c, out_f
         return out_f[0]
 
-    @torch.no_grad()
-    def classify_host(self, batches, device="cuda"):
-        """End-to-end: iterable of (dwi_host, dce_host) PINNED fp32 CPU tensors -> list of host logits.
-        Upload of batch i+1 runs on a copy stream while batch i computes."""
-        dev = torch.device(device)
+    def _staged(self, batches, dev):
+        """Yield device copies of the host batches; batch i+1 is uploaded on a copy stream while batch i is in use."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
         compute = torch.cuda.current_stream(dev)
-        results, staged = [], None
 
-        def upload(pair):
+        def upload(items):
             with torch.cuda.stream(self._copy_stream):
-                d = pair[0].to(dev, non_blocking=True)
-                c = pair[1].to(dev, non_blocking=True)
+                out = tuple(t.to(dev, non_blocking=True) for t in items)
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
-            return d, c, ev
+            return out, ev
 
         it = iter(batches)
         try:
             staged = upload(next(it))
         except StopIteration:
-            return results
+            return
         while staged is not None:
-            d, c, ev = staged
+            tensors, ev = staged
             try:
                 nxt = upload(next(it))
             except StopIteration:
                 nxt = None
             compute.wait_event(ev)
-            d.record_stream(compute)
-            c.record_stream(compute)
+            for t in tensors:
+                t.record_stream(compute)
+            yield tensors
+            staged = nxt
+
+    @torch.no_grad()
+    def classify_host(self, batches, device="cuda"):
+        """End-to-end: iterable of (dwi_host, dce_host) PINNED fp32 CPU tensors -> list of host logits.
+        Upload of batch i+1 runs on a copy stream while batch i computes."""
+        dev = torch.device(device)
+        results = []
+        for d, c in self._staged(batches, dev):
             logits = self.forward_raw(d, c)
             host = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
             host.copy_(logits, non_blocking=True)
             results.append(host)
-            staged = nxt
-        compute.synchronize()
+        torch.cuda.current_stream(dev).synchronize()
         return results
+
+    @torch.no_grad()
+    def encode_raw(self, dwi_raw, dce_raw):
+        """Normalisers + the two (frozen) encoders: -> (f3_dwi, f3_dce, dwi_mask_pred, dce_mask_pred), the inputs of
+        the fusion head (code/train_fusion.py:226-236)."""
+        B = dwi_raw.shape[0]
+        dev = dwi_raw.device
+        if self.resize is not None:
+            dwi_raw, dce_raw = self.resize.batch(dwi_raw), self.resize.batch(dce_raw)
+        pm_d = torch.empty(B * dwi_raw.shape[1], dtype=torch.float32, device=dev)
+        pm_c = torch.empty(B * dce_raw.shape[1], dtype=torch.float32, device=dev)
+        dwi = self.dwi_norm.batch(dwi_raw, plane_mean=pm_d)
+        dce = self.dce_norm.batch(dce_raw, plane_mean=pm_c)
+        out_d = self.dwi_model(dwi, None, plane_mean=pm_d)
+        out_c = self.dce_model(dce, None, plane_mean=pm_c)
+        return out_d[1]["raw_feats"][-1], out_c[1]["raw_feats"][-1], out_d[2], out_c[2]
+
+    def fit_host(self, batches, trainer, device="cuda"):
+        """End-to-end fine-tuning of the fusion head: iterable of (dwi_host, dce_host, labels_host) PINNED CPU
+        tensors, one optimisation step per batch with `trainer` (fusion_train.FusionHeadTrainer: forward, backward,
+        gradient all-reduce over the data-parallel ranks, AdamW).  Returns the per-step rank-averaged losses as
+        pinned host tensors; the upload of batch i+1 overlaps the step on batch i."""
+        dev = torch.device(device)
+        losses = []
+        for d, c, lab in self._staged(batches, dev):
+            loss, _ = trainer.train_step(*self.encode_raw(d, c), lab)
+            host = torch.empty(1, dtype=torch.float32, pin_memory=True)
+            host.copy_(loss, non_blocking=True)
+            losses.append(host)
+        torch.cuda.current_stream(dev).synchronize()
+        return losses

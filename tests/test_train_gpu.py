@@ -256,3 +256,43 @@ def test_lightning_surface_trains_and_inference_sees_the_new_weights():
         p.requires_grad = True
     with pytest.raises(NotImplementedError):
         lm.training_step(batch)
+
+
+def test_fit_host_equals_step_by_step_training():
+    """FusionPipeline.fit_host (pinned host batches, uploads overlapped with the previous step) gives the losses of
+    the same steps run one by one on device-resident inputs."""
+    import copy
+
+    import model_module as mm
+    import parameters_default as pd
+    import preprocess_helpers as pre
+    from fusion_train import FusionHeadTrainer
+    from pipeline import FusionPipeline
+
+    params = pd.default_parameters()
+    base = {"dwi": mm.ModelMaskHeadBackbone("dwi", params), "dce": mm.ModelMaskHeadBackbone("dce", params),
+            "fusion": mm.FusionModel(params)}
+    for m in base.values():
+        m.load_state_dict(op.seeded_state_dict(op.shapes_of(m.state_dict()), seed=7))
+    nyul = pre.NyulStandardizer()
+    nyul.fit(list(op.synthetic_raw(8, seed=6, kind="S")[1]), num_channels=6)
+    batches = []
+    for i in range(3):
+        dwi, dce, _, lab = op.synthetic_raw(8, seed=40 + i, kind="S")
+        batches.append((dwi.pin_memory(), dce.pin_memory(), lab.pin_memory()))
+    losses = []
+    for mode in ("host", "device"):
+        mods = {k: copy.deepcopy(m).to(DEV).eval() for k, m in base.items()}
+        pipe = FusionPipeline(mods["dwi"], mods["dce"], mods["fusion"], nyul, aux_mode="logits").eval()
+        tr = FusionHeadTrainer(mods["fusion"], lr=1e-3)
+        if mode == "host":
+            losses.append([l.item() for l in pipe.fit_host(batches, tr)])
+        else:
+            out = []
+            for d, c, lab in batches:
+                loss, _ = tr.train_step(*pipe.encode_raw(d.to(DEV), c.to(DEV)), lab.to(DEV))
+                out.append(loss.item())
+            losses.append(out)
+    assert len(losses[0]) == 3
+    for a, b in zip(*losses):
+        assert abs(a - b) <= 1e-4 * abs(b), losses
