@@ -387,7 +387,7 @@ def train_arm(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD_C5, "batch_per_gpu": B, "global_batch": B * world,
                        "objective": "classification term only (label smoothing 0.1, focal gamma 1.5)",
-                       "trainable_parameters": trainer.numel, "allreduce_bytes_per_step": 4 * (trainer.numel + 1),
+                       "trainable_parameters": trainer.numel, "allreduce_bytes_per_step": 4 * (trainer.flat_numel + 1),
                        "l2": "no flush needed: per-step inputs and activations exceed the 126 MB L2",
                        "parallelism": f"data parallel x{world}, one NCCL all-reduce of the flat gradient buffer per step"
                        if world > 1 else "single GPU"},

@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _lib = None
 
@@ -78,6 +78,9 @@ class HeadTrain(C.Structure):
         ("dlogits_out", C.c_void_p), ("z_out", C.c_void_p), ("gf_out", C.c_void_p), ("h_out", C.c_void_p),
         ("da1_out", C.c_void_p), ("da2_out", C.c_void_p), ("gx_out", C.c_void_p), ("dgl_out", C.c_void_p),
         ("dpd_out", C.c_void_p), ("dpc_out", C.c_void_p), ("dlowres_out", C.c_void_p),
+        ("forward_only", C.c_int), ("mask_v", C.c_void_p), ("mk_tmpd", C.c_void_p), ("mk_tmpc", C.c_void_p),
+        ("mk_q", C.c_void_p), ("gate_out", C.c_void_p), ("u_out", C.c_void_p), ("dug_out", C.c_void_p),
+        ("aud_out", C.c_void_p), ("auc_out", C.c_void_p),
     ]
 
 
@@ -130,6 +133,11 @@ SIGNATURES = {
     "b200_gelu_bwd": [_P, _P, _LL, _P, _P],
     "b200_head_loss": [C.POINTER(HeadTrain), _I, _P],
     "b200_adamw": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P],
+    "b200_mask_dot": [_P, _P, _I, _I, _I, _P, _P],
+    "b200_mask_dice": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P,
+                       _P, _P],
+    "b200_mask_wsum": [_P, _P, _I, _I, _I, _P, _P],
+    "b200_mask_head_grads": [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
 }
 
 
@@ -623,3 +631,36 @@ def adamw(p, g, m, v, *, lr, betas, eps, weight_decay, step, grad_scale=1.0):
             raise B200NativeError("adamw needs equally sized contiguous float32 buffers")
     _call("b200_adamw", None, _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(betas[0]),
           float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale), _stream())
+
+
+def mask_dot(f3, omega, out):
+    """f3 NHWC bf16 [B,H,W,Cin] (contiguous), omega [B,Cin] fp32 -> out [B,H*W] fp32."""
+    _bf16_map(f3, "f3")
+    if not f3.is_contiguous():
+        raise B200NativeError("mask_dot needs a contiguous NHWC map")
+    B, H, W, Cin = f3.shape
+    _call("b200_mask_dot", None, _ptr(f3), _ptr(omega), B, H * W, Cin, _ptr(out), _stream())
+    return out
+
+
+def mask_wsum(f3, dm, out):
+    """out[b,:] = sum_p dm[b,p] * f3[b,p,:]."""
+    if f3.dtype != torch.bfloat16 or not f3.is_contiguous():
+        raise B200NativeError("mask_wsum needs a contiguous bfloat16 NHWC map")
+    B, H, W, Cin = f3.shape
+    _call("b200_mask_wsum", None, _ptr(f3), _ptr(dm), B, H * W, Cin, _ptr(out), _stream())
+    return out
+
+
+def mask_dice(D_dwi, D_dce, gating, u, lowres, pre_b, out_w, out_b, target, enc_dwi, enc_dce, H, W, hp, wp, scale,
+              eps, m_out, dm_out, q_out, dc0_out, loss_out):
+    B, C_ = u.shape
+    _call("b200_mask_dice", None, _ptr(D_dwi), _ptr(D_dce), _ptr(gating), _ptr(u), _ptr(lowres), _ptr(pre_b),
+          _ptr(out_w), _ptr(out_b), pre_b.numel(), _ptr(target), _ptr(enc_dwi), _ptr(enc_dce), B, H, W, hp, wp, C_,
+          float(scale), float(eps), _ptr(m_out), _ptr(dm_out), _ptr(q_out), _ptr(dc0_out), _ptr(loss_out), _stream())
+
+
+def mask_head_grads(dv, dc0, pre_w, pre_b, out_w, g_pre_w, g_pre_b, g_out_w, g_out_b):
+    mid, C_ = pre_b.numel(), dv.numel()
+    _call("b200_mask_head_grads", None, _ptr(dv), _ptr(dc0), _ptr(pre_w), _ptr(pre_b), _ptr(out_w), mid, C_,
+          _ptr(g_pre_w), _ptr(g_pre_b), _ptr(g_out_w), _ptr(g_out_b), _stream())

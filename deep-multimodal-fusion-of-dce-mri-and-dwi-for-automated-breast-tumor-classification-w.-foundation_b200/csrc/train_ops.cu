@@ -441,7 +441,11 @@ __global__ void __launch_bounds__(128) head_loss_kernel(const b200_head_train a)
         for (int c = tid; c < C; c += blockDim.x) s_g[c] = 1.f;
     }
     __syncthreads();
-    for (int c = tid; c < C; c += blockDim.x) a.z_out[static_cast<long long>(b) * C + c] = s_gf[c] * s_g[c];
+    for (int c = tid; c < C; c += blockDim.x) {
+        a.z_out[static_cast<long long>(b) * C + c] = s_gf[c] * s_g[c];
+        if (a.gate_out != nullptr) a.gate_out[static_cast<long long>(b) * C + c] = s_g[c];
+        if (a.u_out != nullptr && a.mask_v != nullptr) a.u_out[static_cast<long long>(b) * C + c] = a.mask_v[c] * s_g[c];
+    }
     // ---- classifier (:895-899) ----
     for (int k = warp; k < K; k += nwarps) {
         float acc = 0.f;
@@ -450,6 +454,11 @@ __global__ void __launch_bounds__(128) head_loss_kernel(const b200_head_train a)
         if (lane == 0) s_dl[k] = acc + a.cls_b[k];
     }
     __syncthreads();
+    if (a.forward_only) {
+        if (a.logits_out != nullptr)
+            for (int k = tid; k < K; k += blockDim.x) a.logits_out[static_cast<long long>(b) * K + k] = s_dl[k];
+        return;
+    }
     // ---- LabelSmoothing (loss.py:190-213) + Soft(Weighted)FocalLoss (loss.py:133-188), mean over the batch ----
     if (tid == 0) {
         const int label = static_cast<int>(a.labels[b]);
@@ -483,15 +492,35 @@ __global__ void __launch_bounds__(128) head_loss_kernel(const b200_head_train a)
         atomicAdd(a.loss_out, loss * a.loss_scale);
     }
     __syncthreads();
-    // ---- backward: classifier, SE ----
+    // ---- backward: classifier, SE (+ the fused-mask dice term arriving through u = v * gate) ----
+    const bool mask_term = a.mask_v != nullptr && a.mk_tmpd != nullptr;
+    float e0 = 0.f, e1 = 0.f;  // gradient of the gating weights coming from the mask term
     for (int c = tid; c < C; c += blockDim.x) {
         float dz = 0.f;
         for (int k = 0; k < K; ++k) dz = fmaf(a.cls_w[k * C + c], s_dl[k], dz);
         const float g = s_g[c];
         s_dgf[c] = dz * g;
-        const float da2 = a.use_se ? dz * s_gf[c] * g * (1.0f - g) : 0.f;
+        float dg = dz * s_gf[c];
+        if (mask_term) {
+            const long long bc = static_cast<long long>(b) * C + c;
+            const float v = a.mask_v[c], u = v * g, td = a.mk_tmpd[bc], tc = a.mk_tmpc[bc];
+            float du = al0 * td + al1 * tc;
+            if (a.lowres != nullptr)
+                for (int t = 0; t < T; ++t) du = fmaf(a.mk_q[b * T + t], a.lowres[tokbase + t * C + c], du);
+            dg = fmaf(du, v, dg);
+            a.dug_out[bc] = du * g;
+            a.aud_out[bc] = al0 * u;
+            a.auc_out[bc] = al1 * u;
+            e0 = fmaf(u, td, e0);
+            e1 = fmaf(u, tc, e1);
+        }
+        const float da2 = a.use_se ? dg * g * (1.0f - g) : 0.f;
         s_da2[c] = da2;
         if (a.use_se) a.da2_out[static_cast<long long>(b) * C + c] = da2;
+    }
+    if (mask_term) {
+        e0 = static_cast<float>(block_sum<double>(e0, scratch));
+        e1 = static_cast<float>(block_sum<double>(e1, scratch));
     }
     __syncthreads();
     if (a.use_se) {
@@ -516,8 +545,8 @@ __global__ void __launch_bounds__(128) head_loss_kernel(const b200_head_train a)
         q0 = fmaf(s_dgf[c], s_pd[c], q0);
         q1 = fmaf(s_dgf[c], s_pc[c], q1);
     }
-    const float da0 = static_cast<float>(block_sum<double>(q0, scratch));
-    const float da1g = static_cast<float>(block_sum<double>(q1, scratch));
+    const float da0 = static_cast<float>(block_sum<double>(q0, scratch)) + e0;
+    const float da1g = static_cast<float>(block_sum<double>(q1, scratch)) + e1;
     const float dots = al0 * da0 + al1 * da1g;
     const float dgl0 = al0 * (da0 - dots), dgl1 = al1 * (da1g - dots);
     if (tid == 0) {
@@ -530,9 +559,194 @@ __global__ void __launch_bounds__(128) head_loss_kernel(const b200_head_train a)
             (al0 * dgf + a.gate_w[c] * dgl0 + a.gate_w[in_dim + c] * dgl1) * invT;
         a.dpc_out[static_cast<long long>(b) * C + c] =
             (al1 * dgf + a.gate_w[C + c] * dgl0 + a.gate_w[in_dim + C + c] * dgl1) * invT;
-        if (a.dlowres_out != nullptr)
-            for (int t = 0; t < T; ++t) a.dlowres_out[tokbase + t * C + c] = a.up_coef[t] * dgf;
+        if (a.dlowres_out != nullptr) {
+            const float u = mask_term ? a.mask_v[c] * s_g[c] : 0.f;
+            for (int t = 0; t < T; ++t)
+                a.dlowres_out[tokbase + t * C + c] =
+                    a.up_coef[t] * dgf + (mask_term ? a.mk_q[b * T + t] * u : 0.f);
+        }
     }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// fused-mask dice term (see b200_fusion.h)
+// --------------------------------------------------------------------------------------------------------------
+// D[b,p] = omega[b] . f3[b,p,:]; one warp per pixel, omega[b] in registers (Cin <= 1024)
+__global__ void __launch_bounds__(256)
+mask_dot_kernel(const __nv_bfloat16* __restrict__ f3, const float* __restrict__ omega, int npix, int Cin,
+                float* __restrict__ D) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nvec = Cin >> 3;  // uint4 = 8 channels
+    float w[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = (lane + 32 * j) * 8 + k;
+            w[j][k] = (lane + 32 * j) < nvec ? omega[static_cast<long long>(b) * Cin + c] : 0.f;
+        }
+    for (int p = blockIdx.x * nwarps + warp; p < npix; p += gridDim.x * nwarps) {
+        const uint4* row = reinterpret_cast<const uint4*>(f3 + (static_cast<long long>(b) * npix + p) * Cin);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (lane + 32 * j < nvec) {
+                float f[8];
+                unpack_bf16x8(__ldg(row + lane + 32 * j), f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc = fmaf(w[j][k], f[k], acc);
+            }
+        acc = warp_sum(acc);
+        if (lane == 0) D[static_cast<long long>(b) * npix + p] = acc;
+    }
+}
+
+// s[b,c] = sum_p dm[b,p] f3[b,p,c]; grid (chunks, B): each CTA sums a pixel chunk, 8 channels per thread
+__global__ void __launch_bounds__(128)
+mask_wsum_kernel(const __nv_bfloat16* __restrict__ f3, const float* __restrict__ dm, int npix, int Cin,
+                 float* __restrict__ s) {
+    const int b = blockIdx.y, nvec = Cin >> 3;
+    const int per = (npix + gridDim.x - 1) / gridDim.x;
+    const int p0 = blockIdx.x * per, p1 = min(npix, p0 + per);
+    for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 4
+        for (int p = p0; p < p1; ++p) {
+            const float d = __ldg(dm + static_cast<long long>(b) * npix + p);
+            float f[8];
+            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(f3 + (static_cast<long long>(b) * npix + p) * Cin) + vi), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fmaf(d, f[k], acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(s + static_cast<long long>(b) * Cin + vi * 8 + k, acc[k]);
+    }
+}
+
+__device__ __forceinline__ float dice_of(const float* __restrict__ logits, const float* __restrict__ target, int npix,
+                                         float eps, double* scratch) {
+    float si = 0.f, sp = 0.f, st = 0.f;
+    for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+        const float pr = sigmoidf_(logits[p]), t = target[p];
+        si = fmaf(pr, t, si);
+        sp += pr;
+        st += t;
+    }
+    const double I = block_sum<double>(si, scratch), P = block_sum<double>(sp, scratch),
+                 Tt = block_sum<double>(st, scratch);
+    return static_cast<float>((2.0 * I + eps) / (P + Tt + eps));
+}
+
+__global__ void __launch_bounds__(256)
+mask_dice_kernel(const float* __restrict__ D_dwi, const float* __restrict__ D_dce, const float* __restrict__ gating,
+                 const float* __restrict__ u, const float* __restrict__ lowres, const float* __restrict__ pre_b,
+                 const float* __restrict__ out_w, const float* __restrict__ out_b, int mid,
+                 const float* __restrict__ target, const float* __restrict__ enc_dwi,
+                 const float* __restrict__ enc_dce, int H, int W, int Hp, int Wp, int C, float scale, float eps,
+                 float* __restrict__ m_out, float* __restrict__ dm_out, float* __restrict__ q_out,
+                 float* __restrict__ dc0_out, float* __restrict__ loss_out) {
+    extern __shared__ float sm[];
+    const int npix = H * W, T = Hp * Wp;
+    float* s_m = sm;          // [npix] logits, then probabilities
+    float* s_r = s_m + npix;  // [T] u . lowres[t]
+    float* s_q = s_r + T;     // [T]
+    __shared__ double scratch[33];
+    __shared__ float s_c0;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const long long pb = static_cast<long long>(b) * npix;
+    for (int t = warp; t < T; t += nwarps) {
+        float acc = 0.f;
+        if (lowres != nullptr)
+            for (int c = lane; c < C; c += 32)
+                acc = fmaf(u[static_cast<long long>(b) * C + c], lowres[(static_cast<long long>(b) * T + t) * C + c], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            s_r[t] = acc;
+            s_q[t] = 0.f;
+        }
+    }
+    if (warp == 0) {
+        float acc = 0.f;
+        for (int i = lane; i < mid; i += 32) acc = fmaf(out_w[i], pre_b[i], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) s_c0 = acc + out_b[0];
+    }
+    __syncthreads();
+    const float a0 = gating[b * 2], a1 = gating[b * 2 + 1], c0 = s_c0;
+    const float sh = static_cast<float>(Hp) / H, sw = static_cast<float>(Wp) / W;
+    float si = 0.f, sp = 0.f, st = 0.f;
+    for (int p = tid; p < npix; p += blockDim.x) {
+        const int h = p / W, w = p % W;
+        // F.interpolate(mode='bilinear', align_corners=False) source coordinates (model_module.py:972-973)
+        const float sy = fmaxf((h + 0.5f) * sh - 0.5f, 0.f), sx = fmaxf((w + 0.5f) * sw - 0.5f, 0.f);
+        const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+        const int y1 = min(y0 + 1, Hp - 1), x1 = min(x0 + 1, Wp - 1);
+        const float ly = sy - y0, lx = sx - x0;
+        const float up = (1.f - ly) * ((1.f - lx) * s_r[y0 * Wp + x0] + lx * s_r[y0 * Wp + x1]) +
+                         ly * ((1.f - lx) * s_r[y1 * Wp + x0] + lx * s_r[y1 * Wp + x1]);
+        const float m = c0 + a0 * D_dwi[pb + p] + a1 * D_dce[pb + p] + up;
+        m_out[pb + p] = m;
+        const float pr = sigmoidf_(m), t = target[pb + p];
+        s_m[p] = pr;
+        si = fmaf(pr, t, si);
+        sp += pr;
+        st += t;
+    }
+    const double I = block_sum<double>(si, scratch), P = block_sum<double>(sp, scratch),
+                 Tt = block_sum<double>(st, scratch);
+    const double S = P + Tt + eps, num = 2.0 * I + eps;
+    const float dice = static_cast<float>(num / S);
+    float sdm = 0.f;
+    for (int p = tid; p < npix; p += blockDim.x) {
+        const float pr = s_m[p], t = target[pb + p];
+        // loss = scale * (1 - dice): d/dp = -scale * (2 t S - num) / S^2, then through the sigmoid
+        const float dm = -scale * static_cast<float>((2.0 * t * S - num) / (S * S)) * pr * (1.f - pr);
+        dm_out[pb + p] = dm;
+        sdm += dm;
+        const int h = p / W, w = p % W;
+        const float sy = fmaxf((h + 0.5f) * sh - 0.5f, 0.f), sx = fmaxf((w + 0.5f) * sw - 0.5f, 0.f);
+        const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+        const int y1 = min(y0 + 1, Hp - 1), x1 = min(x0 + 1, Wp - 1);
+        const float ly = sy - y0, lx = sx - x0;
+        atomicAdd(&s_q[y0 * Wp + x0], dm * (1.f - ly) * (1.f - lx));
+        atomicAdd(&s_q[y0 * Wp + x1], dm * (1.f - ly) * lx);
+        atomicAdd(&s_q[y1 * Wp + x0], dm * ly * (1.f - lx));
+        atomicAdd(&s_q[y1 * Wp + x1], dm * ly * lx);
+    }
+    const float tot = static_cast<float>(block_sum<double>(sdm, scratch));
+    float extra = 0.f;  // the encoder masks' dice terms: constants for the head, part of the reported loss
+    if (enc_dwi != nullptr) extra += 1.0f - dice_of(enc_dwi + pb, target + pb, npix, eps, scratch);
+    if (enc_dce != nullptr) extra += 1.0f - dice_of(enc_dce + pb, target + pb, npix, eps, scratch);
+    __syncthreads();
+    for (int t = tid; t < T; t += blockDim.x) q_out[b * T + t] = s_q[t];
+    if (tid == 0) {
+        atomicAdd(dc0_out, tot);
+        atomicAdd(loss_out, scale * ((1.0f - dice) + extra));
+    }
+}
+
+// v = pre_w^T out_w, c0 = out_w . pre_b + out_b:  dpre_w = out_w (x) dv, dout_w = pre_w dv + pre_b dc0,
+// dpre_b = out_w dc0, dout_b = dc0.  One CTA.
+__global__ void __launch_bounds__(256)
+mask_head_grads_kernel(const float* __restrict__ dv, const float* __restrict__ dc0, const float* __restrict__ pre_w,
+                       const float* __restrict__ pre_b, const float* __restrict__ out_w, int mid, int C,
+                       float* __restrict__ g_pre_w, float* __restrict__ g_pre_b, float* __restrict__ g_out_w,
+                       float* __restrict__ g_out_b) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const float d0 = dc0[0];
+    for (int i = tid; i < mid * C; i += blockDim.x) g_pre_w[i] += out_w[i / C] * dv[i % C];
+    for (int i = warp; i < mid; i += nwarps) {
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) acc = fmaf(pre_w[i * C + c], dv[c], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            g_out_w[i] += acc + pre_b[i] * d0;
+            g_pre_b[i] += out_w[i] * d0;
+        }
+    }
+    if (tid == 0) g_out_b[0] += d0;
 }
 
 // torch.optim.AdamW (decoupled weight decay, no amsgrad) on a flat buffer; g is scaled by grad_scale first
@@ -682,11 +896,15 @@ extern "C" int b200_head_loss(const b200_head_train* args, int B, void* stream) 
     const b200_head_train& a = *args;
     if (a.C <= 0 || a.T <= 0 || a.num_classes < 2 || a.num_classes > HEAD_MAX_K) return -2;
     if (a.use_se && a.se_mid <= 0) return -2;
-    if (a.tok_dwi == nullptr || a.tok_dce == nullptr || a.labels == nullptr || a.gate_w == nullptr ||
-        a.gate_b == nullptr || a.cls_w == nullptr || a.cls_b == nullptr || a.loss_out == nullptr ||
-        a.dlogits_out == nullptr || a.z_out == nullptr || a.gf_out == nullptr || a.gx_out == nullptr ||
-        a.dgl_out == nullptr || a.dpd_out == nullptr || a.dpc_out == nullptr)
+    if (a.tok_dwi == nullptr || a.tok_dce == nullptr || a.gate_w == nullptr || a.gate_b == nullptr ||
+        a.cls_w == nullptr || a.cls_b == nullptr || a.z_out == nullptr || a.gf_out == nullptr || a.gx_out == nullptr)
         return -3;
+    if (!a.forward_only && (a.labels == nullptr || a.loss_out == nullptr || a.dlogits_out == nullptr ||
+                            a.dgl_out == nullptr || a.dpd_out == nullptr || a.dpc_out == nullptr))
+        return -3;
+    if (a.mk_tmpd != nullptr && (a.mask_v == nullptr || a.mk_tmpc == nullptr || a.mk_q == nullptr ||
+                                 a.dug_out == nullptr || a.aud_out == nullptr || a.auc_out == nullptr))
+        return -8;
     if (a.use_mask_attention && (a.mask_dwi == nullptr || a.mask_dce == nullptr || a.npix_mask <= 0)) return -4;
     if (a.use_se && (a.se_w1 == nullptr || a.se_b1 == nullptr || a.se_w2 == nullptr || a.se_b2 == nullptr ||
                      a.h_out == nullptr || a.da1_out == nullptr || a.da2_out == nullptr))
@@ -696,6 +914,60 @@ extern "C" int b200_head_loss(const b200_head_train* args, int B, void* stream) 
     const size_t smem = (static_cast<size_t>(6) * a.C + 3 * a.se_mid + HEAD_MAX_K + 8) * sizeof(float);
     if (smem > 48 * 1024) return -7;
     head_loss_kernel<<<B, 128, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    return launch_status();
+}
+
+extern "C" int b200_mask_dot(const void* f3, const float* omega, int B, int npix, int Cin, float* D, void* stream) {
+    if (B < 0 || npix <= 0 || Cin <= 0 || Cin % 8 != 0 || Cin > 1024) return -1;
+    if (B == 0) return 0;
+    if (f3 == nullptr || omega == nullptr || D == nullptr) return -2;
+    int gx = (npix + 63) / 64;  // 8 warps x 8 pixels per CTA
+    if (gx > 16) gx = 16;
+    mask_dot_kernel<<<dim3(gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(f3), omega, npix, Cin, D);
+    return launch_status();
+}
+
+extern "C" int b200_mask_wsum(const void* f3, const float* dm, int B, int npix, int Cin, float* s, void* stream) {
+    if (B < 0 || npix <= 0 || Cin <= 0 || Cin % 8 != 0) return -1;
+    if (B == 0) return 0;
+    if (f3 == nullptr || dm == nullptr || s == nullptr) return -2;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(s, 0, static_cast<size_t>(B) * Cin * sizeof(float), st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    int chunks = B >= 148 ? 4 : (592 + B - 1) / B;  // >= 4 CTAs per SM in flight; 64 threads of a CTA carry loads
+    if (chunks > npix) chunks = npix;
+    mask_wsum_kernel<<<dim3(chunks, B), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(f3), dm, npix, Cin, s);
+    return launch_status();
+}
+
+extern "C" int b200_mask_dice(const float* D_dwi, const float* D_dce, const float* gating, const float* u,
+                              const float* lowres, const float* pre_b, const float* out_w, const float* out_b,
+                              int mid, const float* target, const float* enc_mask_dwi, const float* enc_mask_dce,
+                              int B, int H, int W, int Hp, int Wp, int C, float scale, float eps, float* m_out,
+                              float* dm_out, float* q_out, float* dc0_out, float* loss_out, void* stream) {
+    if (B < 0 || H <= 0 || W <= 0 || Hp <= 0 || Wp <= 0 || C <= 0 || mid <= 0 || H * W > 8192 || Hp * Wp > 64) return -1;
+    if (B == 0) return 0;
+    if (D_dwi == nullptr || D_dce == nullptr || gating == nullptr || u == nullptr || pre_b == nullptr ||
+        out_w == nullptr || out_b == nullptr || target == nullptr || m_out == nullptr || dm_out == nullptr ||
+        q_out == nullptr || dc0_out == nullptr || loss_out == nullptr)
+        return -2;
+    const size_t smem = (static_cast<size_t>(H) * W + 2 * Hp * Wp) * sizeof(float);
+    mask_dice_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        D_dwi, D_dce, gating, u, lowres, pre_b, out_w, out_b, mid, target, enc_mask_dwi, enc_mask_dce, H, W, Hp, Wp, C,
+        scale, eps, m_out, dm_out, q_out, dc0_out, loss_out);
+    return launch_status();
+}
+
+extern "C" int b200_mask_head_grads(const float* dv, const float* dc0, const float* pre_w, const float* pre_b,
+                                    const float* out_w, int mid, int C, float* g_pre_w, float* g_pre_b,
+                                    float* g_out_w, float* g_out_b, void* stream) {
+    if (mid <= 0 || C <= 0) return -1;
+    if (dv == nullptr || dc0 == nullptr || pre_w == nullptr || pre_b == nullptr || out_w == nullptr ||
+        g_pre_w == nullptr || g_pre_b == nullptr || g_out_w == nullptr || g_out_b == nullptr)
+        return -2;
+    mask_head_grads_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(dv, dc0, pre_w, pre_b, out_w, mid, C,
+                                                                             g_pre_w, g_pre_b, g_out_w, g_out_b);
     return launch_status();
 }
 

@@ -18,8 +18,15 @@ tests of the host logic) and one fused AdamW launch.  Parameters off the logits 
 head, projector, the reference's dead reduce/refine branch) get no gradient and are left untouched, exactly like
 torch.optim.AdamW skips parameters whose .grad is None.
 
-Not built: the mask / reconstruction / mimic terms of the reference's total loss (they need the training-mode
-BatchNorm backward of the mask, reconstruction and projector heads) and unfrozen encoders.  There is no CPU path.
+Optional second term (lambda_mask > 0): the reference's mask dice term, lambda_mask * (dice(dwi mask) + dice(dce
+mask) + dice(fused mask)) / 3 (train_fusion.py:245-255, loss.py:45-62).  Only the fused mask reaches the head's
+parameters; at the mask size MaskHeadResize is two 1x1 convolutions with nothing in between, so the fused mask logits
+are linear in fused_refined and cost two more passes over each f3 map (a per-case 512-vector dot product forward, a
+dmask-weighted pixel sum backward) - no 128-channel full-resolution map is ever materialised.  mask_head.pre / .out
+then join the trainable set (24 tensors).
+
+Not built: the reconstruction / mimic terms of the reference's total loss (they need the training-mode BatchNorm
+backward of the reconstruction and projector heads) and unfrozen encoders.  There is no CPU path.
 """
 from __future__ import annotations
 
@@ -30,16 +37,26 @@ import torch.nn as nn
 import b200_native as nat
 from model_module import _as_nhwc_bf16, _bilinear_axis_weights
 
-__all__ = ["FusionHeadTrainer", "flat_views", "average_gradients"]
+__all__ = ["FusionHeadTrainer", "flat_views", "flat_size", "average_gradients"]
 
 
-def flat_views(tensors, flat):
-    """Views of `flat` with the shapes of `tensors`, packed back to back (the layout of both flat buffers)."""
+ALIGN = 64  # elements: every tensor starts on a 256-byte boundary of the flat buffers (kernels that consume the
+            # parameters elsewhere - the inference path - use 16-byte vector loads)
+
+
+def flat_size(tensors, align=ALIGN):
+    """Elements of a flat buffer holding `tensors`, each padded to a multiple of `align` elements."""
+    return sum((t.numel() + align - 1) // align * align for t in tensors)
+
+
+def flat_views(tensors, flat, align=ALIGN):
+    """Views of `flat` with the shapes of `tensors`, in order, each starting on an `align`-element boundary (the
+    layout of the parameter, gradient and moment buffers; the padding stays zero)."""
     out, off = [], 0
     for t in tensors:
         n = t.numel()
         out.append(flat[off:off + n].view(t.shape))
-        off += n
+        off += (n + align - 1) // align * align
     return out
 
 
@@ -67,7 +84,7 @@ class FusionHeadTrainer:
     Soft(Weighted)FocalLoss (code/selector_helpers.py:14-46)."""
 
     def __init__(self, fusion_model, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=4e-5, smoothing=0.1,
-                 gamma=1.5, class_weights=None, process_group=None):
+                 gamma=1.5, class_weights=None, lambda_mask=0.0, process_group=None):
         fm = fusion_model
         if not fm.use_cross_attention:
             raise NotImplementedError("fusion-head training without the cross-attention block is not built")
@@ -80,6 +97,7 @@ class FusionHeadTrainer:
         self.lr, self.betas, self.eps, self.weight_decay = lr, tuple(betas), eps, weight_decay
         self.smoothing, self.gamma = float(smoothing), float(gamma)
         self.class_weights = class_weights
+        self.lambda_mask = float(lambda_mask)  # > 0: + lambda_mask * mean of the three mask dice terms
         self.group = process_group
         self.step_count = 0
         ca = fm.cross_attn_block
@@ -100,9 +118,14 @@ class FusionHeadTrainer:
             named += [("fusion_se.fc.1.weight", se.fc[1].weight), ("fusion_se.fc.1.bias", se.fc[1].bias),
                       ("fusion_se.fc.3.weight", se.fc[3].weight), ("fusion_se.fc.3.bias", se.fc[3].bias)]
         named += [("classifier.2.weight", fm.classifier[2].weight), ("classifier.2.bias", fm.classifier[2].bias)]
+        if self.lambda_mask > 0:  # the fused mask head joins the trainable set (its logits enter the loss)
+            mh = fm.mask_head
+            named += [("mask_head.pre.weight", mh.pre.weight), ("mask_head.pre.bias", mh.pre.bias),
+                      ("mask_head.out.weight", mh.out.weight), ("mask_head.out.bias", mh.out.bias)]
         self.names = [n for n, _ in named]
         self.params = [p for _, p in named]
-        self.numel = sum(p.numel() for p in self.params)
+        self.numel = sum(p.numel() for p in self.params)   # trainable parameters
+        self.flat_numel = flat_size(self.params)            # elements of the flat buffers (with alignment padding)
         self._flat = None
         self._ws = {}
 
@@ -114,17 +137,16 @@ class FusionHeadTrainer:
             raise nat.B200NativeError("FusionHeadTrainer needs the fusion model on a CUDA device (no CPU path)")
         bound = self._flat is not None and self._flat["p"].device == dev
         if bound:
-            base, off = self._flat["p"].data_ptr(), 0
-            for p in self.params:
-                bound = bound and p.data_ptr() == base + 4 * off and p.dtype == torch.float32
-                off += p.numel()
+            for p, view in zip(self.params, flat_views(self.params, self._flat["p"])):
+                bound = bound and p.data_ptr() == view.data_ptr() and p.dtype == torch.float32
         if bound:
             return self._flat
         old = self._flat
-        flat = {"p": torch.empty(self.numel, dtype=torch.float32, device=dev),
-                "g": torch.zeros(self.numel + 1, dtype=torch.float32, device=dev),  # last element: the loss
-                "m": torch.zeros(self.numel, dtype=torch.float32, device=dev),
-                "v": torch.zeros(self.numel, dtype=torch.float32, device=dev)}
+        n = self.flat_numel
+        flat = {"p": torch.zeros(n, dtype=torch.float32, device=dev),
+                "g": torch.zeros(n + 1, dtype=torch.float32, device=dev),  # last element: the loss
+                "m": torch.zeros(n, dtype=torch.float32, device=dev),
+                "v": torch.zeros(n, dtype=torch.float32, device=dev)}
         if old is not None:  # the model was moved / reloaded: keep the optimiser state
             flat["m"].copy_(old["m"])
             flat["v"].copy_(old["v"])
@@ -165,6 +187,11 @@ class FusionHeadTrainer:
               "dpd": z(B, C), "dpc": z(B, C), "dLOW": z(R, C), "dG1": z(R, C), "dH1": z(R, C), "dLN": z(R, C),
               "dAO": z(R, C), "tmp": z(R, C), "dCTX": z(R, C), "dQ": z(R, C), "dKV": z(R, 2 * C), "dTd": z(R, C),
               "dTc": z(R, C)}
+        if self.lambda_mask > 0:
+            ws.update({"v": z(1, C), "gate": z(B, C), "u": z(B, C), "omd": z(B, fm.dwi_ch), "omc": z(B, fm.dce_ch),
+                       "Dd": z(B, H * W), "Dc": z(B, H * W), "m": z(B, 1, H, W), "dm": z(B, H * W), "q": z(B, T),
+                       "sd": z(B, fm.dwi_ch), "sc": z(B, fm.dce_ch), "tmpd": z(B, C), "tmpc": z(B, C), "dug": z(B, C),
+                       "aud": z(B, C), "auc": z(B, C), "dv": z(C + 1)})  # dv[C] = dc0
         ah, aw = _bilinear_axis_weights(hp, H), _bilinear_axis_weights(wp, W)
         ws["up"] = torch.tensor([ah[i] * aw[j] for i in range(hp) for j in range(wp)], dtype=torch.float32,
                                 device=dev)
@@ -175,11 +202,12 @@ class FusionHeadTrainer:
     def zero_grad(self):
         self._bind()["g"].zero_()
 
-    def loss_and_grads(self, f3_dwi, f3_dce, dwi_mask_pred, dce_mask_pred, labels):
-        """Forward + backward of the classification objective on one batch; ACCUMULATES into the flat gradient
-        buffer (call zero_grad first).  f3_* are the encoders' deepest maps ([B,C,H,W]-shaped, bf16 channels-last as
-        the B200 encoders emit them), *_mask_pred their mask logits.  Returns (loss, logits) - device tensors, the
-        loss being this rank's batch mean."""
+    def loss_and_grads(self, f3_dwi, f3_dce, dwi_mask_pred, dce_mask_pred, labels, masks=None):
+        """Forward + backward of the objective on one batch; ACCUMULATES into the flat gradient buffer (call
+        zero_grad first).  f3_* are the encoders' deepest maps ([B,C,H,W]-shaped, bf16 channels-last as the B200
+        encoders emit them), *_mask_pred their mask logits, `masks` the [B,1,H,W] target masks (needed when
+        lambda_mask > 0).  Returns (loss, logits) - device tensors, the loss being this rank's batch mean; with the
+        mask term `self.fused_mask_logits` holds the fused mask logits of the step."""
         fm = self.model
         flat = self._bind()
         f3d, f3c = _as_nhwc_bf16(f3_dwi), _as_nhwc_bf16(f3_dce)
@@ -191,6 +219,15 @@ class FusionHeadTrainer:
             raise RuntimeError("use_mask_attention needs both encoder mask predictions")
         T, C, NH = hp * wp, fm.fusion_channels, fm.mha_heads
         R = B * T
+        use_mask_term = self.lambda_mask > 0
+        if use_mask_term:
+            if masks is None:
+                raise ValueError("lambda_mask > 0 needs the target masks")
+            if H != fm.mask_size or W != fm.mask_size:
+                raise NotImplementedError("the mask dice term is built for maps of the mask size (MaskHeadResize's "
+                                          "identity dispatch); other sizes put convolutions / interpolation in between")
+            if tuple(masks.shape[-2:]) != (H, W) or masks.shape[0] != B:
+                raise ValueError("target masks must be [B,1,H,W] at the mask size")
         ws = self._workspace(B, H, W)
         par = dict(zip(self.names, self.params))
         grd = dict(zip(self.names, self.grads))
@@ -230,8 +267,9 @@ class FusionHeadTrainer:
         if flat["cw"] is not None:
             a.class_weights = ptr(flat["cw"])
         a.tok_dwi, a.tok_dce, a.lowres = ptr(ws["Td"]), ptr(ws["Tc"]), ptr(ws["LOW"])
+        md = dwi_mask_pred.contiguous().float() if dwi_mask_pred is not None else None
+        mc = dce_mask_pred.contiguous().float() if dce_mask_pred is not None else None
         if fm.use_mask_attention:
-            md, mc = dwi_mask_pred.contiguous().float(), dce_mask_pred.contiguous().float()
             a.npix_mask = md[0].numel()
             a.mask_dwi, a.mask_dce = ptr(md), ptr(mc)
         lab = labels.to(device=f3d.device, dtype=torch.int64).contiguous()
@@ -246,12 +284,45 @@ class FusionHeadTrainer:
             a.se_w2, a.se_b2 = ptr(par["fusion_se.fc.3.weight"]), ptr(par["fusion_se.fc.3.bias"])
             a.h_out, a.da1_out, a.da2_out = ptr(ws["h"]), ptr(ws["da1"]), ptr(ws["da2"])
         a.cls_w, a.cls_b = ptr(par["classifier.2.weight"]), ptr(par["classifier.2.bias"])
-        loss = flat["g"][self.numel:]
+        loss = flat["g"][self.flat_numel:]
         a.loss_out, a.logits_out, a.gating_out = ptr(loss), ptr(ws["logits"]), ptr(ws["gating"])
         a.dlogits_out, a.z_out, a.gf_out = ptr(ws["dlogits"]), ptr(ws["zvec"]), ptr(ws["gf"])
         a.gx_out, a.dgl_out = ptr(ws["gx"]), ptr(ws["dgl"])
         a.dpd_out, a.dpc_out, a.dlowres_out = ptr(ws["dpd"]), ptr(ws["dpc"]), ptr(ws["dLOW"])
+        if use_mask_term:
+            # fused mask logit = c0 + v . fused_refined (pre and out are both 1x1, nothing in between at this size)
+            pre_w = par["mask_head.pre.weight"].view(par["mask_head.pre.weight"].shape[0], C)
+            pre_b, out_w = par["mask_head.pre.bias"], par["mask_head.out.weight"].view(1, -1)
+            out_b = par["mask_head.out.bias"]
+            nat.sgemm(out_w, pre_w, ws["v"])
+            a.mask_v, a.gate_out, a.u_out = ptr(ws["v"]), ptr(ws["gate"]), ptr(ws["u"])
+            a.forward_only = 1
+            nat.head_loss(a, B)                                   # gating, SE gate, u = v * gate
+            a.forward_only = 0
+            nat.sgemm(ws["u"], Wd, ws["omd"])                     # omega = W^T u: one 512-vector per case
+            nat.sgemm(ws["u"], Wc, ws["omc"])
+            nat.mask_dot(f3d, ws["omd"], ws["Dd"])                # second pass over the maps
+            nat.mask_dot(f3c, ws["omc"], ws["Dc"])
+            tgt = masks.to(device=f3d.device, dtype=torch.float32).contiguous()
+            ws["dv"].zero_()
+            if md is None or mc is None or md[0].numel() != H * W or mc[0].numel() != H * W:
+                raise ValueError("the mask term needs both encoder mask predictions at the mask size "
+                                 "(train_fusion.py:249-251)")
+            nat.mask_dice(ws["Dd"], ws["Dc"], ws["gating"], ws["u"], ws["LOW"], pre_b, out_w, out_b, tgt, md, mc,
+                          H, W, hp, wp, self.lambda_mask / (3.0 * B), 1e-6, ws["m"], ws["dm"], ws["q"], ws["dv"][C:],
+                          loss)
+            nat.mask_wsum(f3d, ws["dm"], ws["sd"])                # third pass: dmask-weighted pixel sums
+            nat.mask_wsum(f3c, ws["dm"], ws["sc"])
+            nat.sgemm(ws["sd"], Wd, ws["tmpd"], trans_b=True)
+            nat.sgemm(ws["sc"], Wc, ws["tmpc"], trans_b=True)
+            a.mk_tmpd, a.mk_tmpc, a.mk_q = ptr(ws["tmpd"]), ptr(ws["tmpc"]), ptr(ws["q"])
+            a.dug_out, a.aud_out, a.auc_out = ptr(ws["dug"]), ptr(ws["aud"]), ptr(ws["auc"])
+            self.fused_mask_logits = ws["m"]
         nat.head_loss(a, B)
+        if use_mask_term:
+            nat.colsum(ws["dug"], ws["dv"][:C])
+            nat.mask_head_grads(ws["dv"][:C], ws["dv"][C:], pre_w, pre_b, out_w, grd["mask_head.pre.weight"],
+                                grd["mask_head.pre.bias"], grd["mask_head.out.weight"], grd["mask_head.out.bias"])
 
         def wgrad(dy, x, name, rows=None):
             g = grd[name] if rows is None else grd[name][rows]
@@ -297,6 +368,9 @@ class FusionHeadTrainer:
         nat.sgemm(ws["dKV"], Win[C:], ws["dTc"], res=ws["dpc"], res_div=T)
         wgrad(ws["dTd"], ws["Xd"], "proj_in_dwi.weight")
         wgrad(ws["dTc"], ws["Xc"], "proj_in_dce.weight")
+        if use_mask_term:  # the full-resolution path of the mask logits into proj_in_*
+            wgrad(ws["aud"], ws["sd"], "proj_in_dwi.weight")
+            wgrad(ws["auc"], ws["sc"], "proj_in_dce.weight")
         return loss, ws["logits"]
 
     def step(self):
@@ -304,16 +378,16 @@ class FusionHeadTrainer:
         flat = self._bind()
         scale = average_gradients(flat["g"], self.group)
         self.step_count += 1
-        nat.adamw(flat["p"], flat["g"][:self.numel], flat["m"], flat["v"], lr=self.lr, betas=self.betas, eps=self.eps,
+        nat.adamw(flat["p"], flat["g"][:self.flat_numel], flat["m"], flat["v"], lr=self.lr, betas=self.betas, eps=self.eps,
                   weight_decay=self.weight_decay, step=self.step_count, grad_scale=scale)
         for p in self.params:  # the kernel wrote through raw pointers: tell torch (packed-weight caches key on it)
             torch.autograd.graph.increment_version(p)
-        return flat["g"][self.numel:] * scale  # the loss averaged over ranks
+        return flat["g"][self.flat_numel:] * scale  # the loss averaged over ranks
 
-    def train_step(self, f3_dwi, f3_dce, dwi_mask_pred, dce_mask_pred, labels):
+    def train_step(self, f3_dwi, f3_dce, dwi_mask_pred, dce_mask_pred, labels, masks=None):
         """zero_grad -> loss_and_grads -> all-reduce -> AdamW.  Returns (loss averaged over ranks, logits)."""
         self.zero_grad()
-        _, logits = self.loss_and_grads(f3_dwi, f3_dce, dwi_mask_pred, dce_mask_pred, labels)
+        _, logits = self.loss_and_grads(f3_dwi, f3_dce, dwi_mask_pred, dce_mask_pred, labels, masks)
         return self.step(), logits
 
     # torch.optim-like surface for harnesses that treat the object returned by configure_optimizers as one

@@ -3,8 +3,8 @@ one object, `forward` / `forward_from_inputs` (:200-201, :670-677) and the predi
 `predict_tta`, `predict_mc_dropout`, `predict_tta_mc`, `predict_custom` (:484-632, :682-702; the default test mode
 is "tta_mc": 4 flips x 10 dropout passes).  Same method names, arguments and return structure; no Lightning
 dependency.  Training: `_shared_step("train")` / `training_step` / `configure_optimizers` run the fusion-head
-fine-tuning step of the frozen-encoder phase under the classification objective (fusion_train.FusionHeadTrainer);
-the mask / reconstruction / mimic loss terms and unfrozen encoders are not built and raise.
+fine-tuning step of the frozen-encoder phase - classification + mask dice terms (fusion_train.FusionHeadTrainer);
+the reconstruction / mimic loss terms and unfrozen encoders are not built and raise.
 
 MC dropout follows the reference's switch exactly: `enable_dropout` puts the nn.Dropout sub-modules of the two
 encoders in train mode, `set_batchnorm_eval` keeps BatchNorm frozen, and the encoders' forward then arms the
@@ -148,17 +148,23 @@ class LightningFusionModel(nn.Module):
                       ("mimic_enabled", "mimic (train_fusion.py:287-292)"),
                       ("attn_reg_enabled", "attention regularisation (train_fusion.py:259-262)"))
 
+    def _lambda_mask(self):
+        mp = self.parameters_dict.get("fusion_model_parameters", {}).get("mask_parameters", {})
+        if self.parameters_dict.get("b200_classification_objective_only", False) or not mp.get("mask", False):
+            return 0.0
+        return float(mp.get("lambda_mask", 0.0))
+
     def _objective_check(self):
-        """The B200 step computes the classification term of the reference's total loss (train_fusion.py:238-242).
-        Anything else the configuration enables raises unless the caller opted into the classification-only
-        objective with parameters_dict["b200_classification_objective_only"] = True."""
+        """The B200 step computes the classification term (train_fusion.py:238-242) and the mask dice term
+        (:245-255) of the reference's total loss.  Anything else the configuration enables raises unless the caller
+        opted into the classification-only objective with parameters_dict["b200_classification_objective_only"]."""
         if self.parameters_dict.get("b200_classification_objective_only", False):
             return
         fp = self.parameters_dict.get("fusion_model_parameters", {})
         on = [what for key, what in self._UNBUILT_TERMS if fp.get(key, False)]
         mp = fp.get("mask_parameters", {})
-        if mp.get("mask", False) and mp.get("lambda_mask", 0.0):
-            on.append("mask dice (train_fusion.py:245-255)")
+        if mp.get("mask", False) and mp.get("lambda_mask", 0.0) and mp.get("mask_loss_type", "dice") != "dice":
+            on.append("mask loss type dice_bce (loss.py:11-43; only 'dice' is built)")
         if on:
             raise NotImplementedError(
                 "loss terms not built in the B200 training step: " + "; ".join(on) + " - disable them or set "
@@ -183,7 +189,8 @@ class LightningFusionModel(nn.Module):
         self.head_trainer = FusionHeadTrainer(
             self.fusion_model, lr=op.get("lr", 1e-4), betas=op.get("betas", (0.9, 0.999)), eps=op.get("eps", 1e-8),
             weight_decay=op.get("weight_decay", 4e-5), smoothing=fp.get("label_smoothing_alpha", 0.1),
-            gamma=2 if gamma is None else gamma, class_weights=getattr(self, "_class_weights", None))
+            gamma=2 if gamma is None else gamma, class_weights=getattr(self, "_class_weights", None),
+            lambda_mask=self._lambda_mask())
         return self.head_trainer
 
     def set_class_weights(self, train_labels):
@@ -193,19 +200,20 @@ class LightningFusionModel(nn.Module):
         return self._class_weights
 
     def _unpack(self, batch):
+        masks = None
         if len(batch) == 4:
-            dwi, dce, _masks, labels = batch
+            dwi, dce, masks, labels = batch
         else:
             dwi, dce, labels = batch
         dev = self.device
-        return dwi.to(dev), dce.to(dev), labels.long().to(dev)
+        return dwi.to(dev), dce.to(dev), (masks.to(dev) if masks is not None else None), labels.long().to(dev)
 
     def _shared_step(self, batch, phase="train", return_preds=False):
         """train: frozen encoders (eval-mode BatchNorm, no dropout) -> fusion head forward + backward; the gradients
         are left in the trainer's flat buffer (there is no autograd graph: `optimizer_step` / `fit_batch` apply
         them).  val / test: inference forward and the hard-label loss (train_fusion.py:241)."""
         self._objective_check()
-        dwi, dce, labels = self._unpack(batch)
+        dwi, dce, masks, labels = self._unpack(batch)
         if phase == "train":
             if getattr(self, "head_trainer", None) is None:
                 self.configure_optimizers()
@@ -217,10 +225,11 @@ class LightningFusionModel(nn.Module):
                 _, dce_aux, dce_mask = self.dce_model(dce)
             self.head_trainer.zero_grad()
             loss, logits = self.head_trainer.loss_and_grads(dwi_aux["raw_feats"][-1], dce_aux["raw_feats"][-1],
-                                                            dwi_mask, dce_mask, labels)
+                                                            dwi_mask, dce_mask, labels, masks)
             loss = loss.clone().squeeze(0)
             if return_preds:
-                return loss, logits.clone(), None, None
+                fused_mask = getattr(self.head_trainer, "fused_mask_logits", None)
+                return loss, logits.clone(), None, fused_mask.clone() if fused_mask is not None else None
             return loss
         with torch.no_grad():
             logits, fused_mask, aux = self.forward_from_inputs(dwi, dce)

@@ -415,12 +415,45 @@ typedef struct b200_head_train {
     float* dpd_out;             /* [B,C]   gradient of each DWI token coming through the pooled vector (already / T) */
     float* dpc_out;             /* [B,C]   same for DCE */
     float* dlowres_out;         /* [B,T,C] gradient of lowres, or NULL with lowres */
+    /* --- fused-mask dice term (NULL / 0 when the term is off) --- */
+    int forward_only;           /* 1: stop after the logits (writes gating_out, gate_out, u_out, logits_out only) */
+    const float* mask_v;        /* [C] v = mask_head.pre.weight^T mask_head.out.weight: fused mask logit = v . fused_refined + c0 */
+    const float* mk_tmpd;       /* [B,C] proj_in_dwi.weight s_dwi, s = sum_pixels dmask * f3 (b200_mask_wsum) */
+    const float* mk_tmpc;       /* [B,C] same for DCE */
+    const float* mk_q;          /* [B,T] transposed bilinear up-sample of dmask (b200_mask_dice) */
+    float* gate_out;            /* [B,C] SE gate, or NULL */
+    float* u_out;               /* [B,C] v * gate (forward_only) */
+    float* dug_out;             /* [B,C] (gradient of u) * gate -> column sums = gradient of v */
+    float* aud_out;             /* [B,C] alpha_dwi * u -> proj_in_dwi weight gradient with s_dwi */
+    float* auc_out;             /* [B,C] alpha_dce * u */
 } b200_head_train;
 
 /* FusionModel.forward tail (code/model_module.py:942-986: gating :952-958, GAP of the fused map, fusion_se :977,
  * classifier :986) + LabelSmoothing and Soft(Weighted)FocalLoss with mean reduction (code/train_fusion.py:238-242)
  * + the backward of that chain, one CTA per case. */
 int b200_head_loss(const b200_head_train* args, int B, void* stream);
+
+/* Fused-mask dice term of the reference's training loss (code/train_fusion.py:245-255: lambda_mask * mean of three
+ * SoftDiceLoss terms, code/loss.py:45-62) for maps of the mask size, where MaskHeadResize is pre (1x1) -> out (1x1)
+ * with nothing in between (code/model_module.py:153-215, the `32: None` dispatch): the fused mask logit is LINEAR
+ * in fused_refined, m = c0 + v . fused_refined, so with u = v * gate
+ *   m[b,p] = c0 + a_dwi (W_dwi^T u_b) . f3_dwi[b,p] + a_dce (W_dce^T u_b) . f3_dce[b,p] + sum_t U[p,t] (u_b . lowres[b,t]).
+ * b200_mask_dot: D[b,p] = omega[b] . f3[b,p,:] (f3 NHWC bf16 [B,npix,Cin], omega fp32 [B,Cin]).
+ * b200_mask_dice: builds m, the dice losses of the fused mask and (for the reported loss value only) of the two
+ *   encoder masks, ACCUMULATES scale * (sum of the (1 - dice_b)) into loss_out, and writes the fused logits, dm =
+ *   dloss/dm, q[b,t] = sum_p U[p,t] dm[b,p] and ACCUMULATES sum dm into dc0_out.  scale = lambda_mask / (3 B).
+ * b200_mask_wsum: s[b,:] = sum_p dm[b,p] f3[b,p,:].
+ * b200_mask_head_grads: gradients of mask_head.pre / .out from dv [C] and dc0 (ACCUMULATED into the outputs). */
+int b200_mask_dot(const void* f3, const float* omega, int B, int npix, int Cin, float* D, void* stream);
+int b200_mask_dice(const float* D_dwi, const float* D_dce, const float* gating, const float* u, const float* lowres,
+                   const float* pre_b, const float* out_w, const float* out_b, int mid, const float* target,
+                   const float* enc_mask_dwi, const float* enc_mask_dce, int B, int H, int W, int Hp, int Wp, int C,
+                   float scale, float eps, float* m_out, float* dm_out, float* q_out, float* dc0_out, float* loss_out,
+                   void* stream);
+int b200_mask_wsum(const void* f3, const float* dm, int B, int npix, int Cin, float* s, void* stream);
+int b200_mask_head_grads(const float* dv, const float* dc0, const float* pre_w, const float* pre_b,
+                         const float* out_w, int mid, int C, float* g_pre_w, float* g_pre_b, float* g_out_w,
+                         float* g_out_b, void* stream);
 
 /* torch.optim.AdamW step (code/selector_helpers.py:222-229) on flat fp32 buffers; g is multiplied by grad_scale
  * first (1 / world_size after the summing gradient all-reduce).  step >= 1 is the update count. */

@@ -28,7 +28,7 @@ HP = {"n": 8, "seed": 11, "smoothing": 0.1, "gamma": 1.5, "class_weights": [0.7,
       "betas": [0.9, 0.999], "eps": 1e-8, "weight_decay": 1e-2, "steps": 3, "weight_seed": 7}
 
 
-def main():
+def main(lambda_mask=0.0, out_name="train_head.npz"):
     import loss as ref_loss
     import model_module as mm
 
@@ -42,16 +42,21 @@ def main():
     crit = ref_loss.SoftWeightedFocalLoss(HP["gamma"], torch.tensor(HP["class_weights"]))
     opt = torch.optim.AdamW(model.parameters(), lr=HP["lr"], betas=tuple(HP["betas"]), eps=HP["eps"],
                             weight_decay=HP["weight_decay"], amsgrad=False)
+    masks = op.synthetic_raw(HP["n"], seed=HP["seed"] + 1, kind="S")[2]  # [n,1,32,32] in {0,1}
+    dice = ref_loss.SoftDiceLoss()
     before = {k: v.detach().clone() for k, v in model.named_parameters()}
     out, losses = {}, []
     for it in range(HP["steps"]):
         opt.zero_grad(set_to_none=True)
-        logits, _, _ = model([f3d], [f3c], md, mc)
+        logits, fused_mask, _ = model([f3d], [f3c], md, mc)
         loss = crit(logits, smoother(logits, labels))
+        if lambda_mask > 0:  # train_fusion.py:245-255 (safe_mask_loss = the criterion at equal sizes)
+            loss = loss + lambda_mask * (dice(md, masks) + dice(mc, masks) + dice(fused_mask, masks)) / 3
         loss.backward()
         losses.append(float(loss))
         if it == 0:
             mg.flatten("logits", logits, out)
+            mg.flatten("fused_mask", fused_mask, out)
             for k, v in model.named_parameters():
                 if v.grad is not None:
                     mg.flatten(f"grad/{k}", v.grad, out)
@@ -61,11 +66,12 @@ def main():
         if k in updated:
             mg.flatten(f"param/{k}", v, out)
     out["losses"] = np.array(losses, dtype=np.float64)
-    out["hp"] = np.array(json.dumps(dict(HP, updated=updated)))
-    np.savez_compressed(os.path.join(mg.GOLD, "train_head.npz"), **out)
+    out["hp"] = np.array(json.dumps(dict(HP, updated=updated, lambda_mask=lambda_mask)))
+    np.savez_compressed(os.path.join(mg.GOLD, out_name), **out)
     print("losses", losses)
     print("updated", len(updated), "parameters:", updated)
 
 
 if __name__ == "__main__":
     main()
+    main(lambda_mask=0.2, out_name="train_head_mask.npz")

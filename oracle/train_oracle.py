@@ -8,6 +8,7 @@ the classification objective:
   * LabelSmoothing                           /root/reference/code/loss.py:190-213
   * SoftFocalLoss / SoftWeightedFocalLoss    /root/reference/code/loss.py:133-188 (reduction "mean")
   * cls_loss = criterion(logits, smoothed)   /root/reference/code/train_fusion.py:238-242
+  * mask term: lambda_mask * mean of three SoftDiceLoss   train_fusion.py:245-255, /root/reference/code/loss.py:45-62
   * torch.optim.AdamW (no amsgrad)           /root/reference/code/selector_helpers.py:222-229
 
 Gradients come from torch autograd over the restated full-resolution forward (NOT the pooled-token shortcut the
@@ -40,15 +41,30 @@ def soft_focal_loss(logits, targets, gamma, class_weights=None):
     return (-(targets * fw * log_probs).sum(dim=1)).mean()
 
 
-def head_loss_and_grads(sd, params, f3_dwi, f3_dce, mask_dwi, mask_dce, labels, smoothing, gamma, class_weights=None):
-    """-> (loss, logits, {name: grad}) for every fusion-head parameter that receives a gradient."""
+def soft_dice_loss(logits, targets, eps=1e-6):
+    """SoftDiceLoss, loss.py:45-62."""
+    probs = torch.sigmoid(logits)
+    dims = tuple(range(2, probs.ndim))
+    inter = (probs * targets).sum(dims)
+    union = probs.sum(dims) + targets.sum(dims)
+    return 1.0 - ((2.0 * inter + eps) / (union + eps)).mean()
+
+
+def head_loss_and_grads(sd, params, f3_dwi, f3_dce, mask_dwi, mask_dce, labels, smoothing, gamma, class_weights=None,
+                        masks=None, lambda_mask=0.0):
+    """-> (loss, logits, {name: grad}) for every fusion-head parameter that receives a gradient.  With lambda_mask > 0
+    the mask term of train_fusion.py:245-255 is added: lambda_mask * mean of the dice losses of the two encoder masks
+    (constants here) and the fused mask."""
     def is_param(k, v):  # BatchNorm running statistics are buffers
         return v.is_floating_point() and k.rsplit(".", 1)[-1] not in ("running_mean", "running_var")
 
     leaf = {k: (v.detach().clone().requires_grad_(True) if is_param(k, v) else v) for k, v in sd.items()}
-    logits, _, _ = mo.fusion_forward(leaf, params, [f3_dwi], [f3_dce], mask_dwi, mask_dce)
+    logits, fused_mask, _ = mo.fusion_forward(leaf, params, [f3_dwi], [f3_dce], mask_dwi, mask_dce)
     targets = smoothed_targets(labels, logits.shape[1], smoothing)
     loss = soft_focal_loss(logits, targets, gamma, class_weights)
+    if lambda_mask > 0:
+        loss = loss + lambda_mask * (soft_dice_loss(mask_dwi, masks) + soft_dice_loss(mask_dce, masks) +
+                                     soft_dice_loss(fused_mask, masks)) / 3
     loss.backward()
     grads = {k: v.grad for k, v in leaf.items() if is_param(k, v) and v.grad is not None}
     return loss.detach(), logits.detach(), grads
@@ -65,13 +81,14 @@ def adamw_step(p, g, m, v, step, lr, betas, eps, weight_decay):
     return p - (lr / bc1) * (m / denom), m, v
 
 
-def train_steps(sd, params, batch, steps, smoothing, gamma, class_weights, lr, betas, eps, weight_decay):
+def train_steps(sd, params, batch, steps, smoothing, gamma, class_weights, lr, betas, eps, weight_decay, masks=None,
+                lambda_mask=0.0):
     """`steps` AdamW steps on one batch.  -> (losses, final state dict, names that were updated)."""
     sd = {k: v.clone() for k, v in sd.items()}
     state = {}
     losses, names = [], []
     for it in range(1, steps + 1):
-        loss, _, grads = head_loss_and_grads(sd, params, *batch, smoothing, gamma, class_weights)
+        loss, _, grads = head_loss_and_grads(sd, params, *batch, smoothing, gamma, class_weights, masks, lambda_mask)
         losses.append(float(loss))
         names = sorted(grads)
         for k, g in grads.items():

@@ -17,8 +17,8 @@ from oracle import train_oracle as to
 ROOT = b200path.ROOT
 
 
-def _setup():
-    gold = gu.load("train_head.npz")
+def _setup(name="train_head.npz"):
+    gold = gu.load(name)
     hp = json.loads(str(gold["hp"]))
     import parameters_default as pd
 
@@ -71,16 +71,39 @@ def test_oracle_adamw_steps_match_the_reference():
     assert untouched and all(torch.equal(sd[k], new_sd[k]) for k in untouched)
 
 
-def test_flat_views_pack_back_to_back():
-    from fusion_train import flat_views
+def test_oracle_mask_term_matches_the_reference():
+    """classification + lambda_mask * mean of three dice terms (train_fusion.py:238-255): 24 tensors get a gradient."""
+    gold, hp, params, sd, batch = _setup("train_head_mask.npz")
+    masks = op.synthetic_raw(hp["n"], seed=hp["seed"] + 1, kind="S")[2]
+    cw = torch.tensor(hp["class_weights"])
+    loss, logits, grads = to.head_loss_and_grads(sd, params, *batch, hp["smoothing"], hp["gamma"], cw, masks,
+                                                 hp["lambda_mask"])
+    assert abs(float(loss) - gold["losses"][0]) <= 1e-5 * abs(gold["losses"][0])
+    assert sorted(grads) == sorted(hp["updated"]) and len(grads) == 24
+    for k in grads:
+        gu.check(gold, f"grad/{k}", grads[k], 2e-4, what="gradient ")
+    losses, new_sd, names = to.train_steps(sd, params, batch, hp["steps"], hp["smoothing"], hp["gamma"], cw, hp["lr"],
+                                           tuple(hp["betas"]), hp["eps"], hp["weight_decay"], masks, hp["lambda_mask"])
+    for a, b in zip(losses, gold["losses"]):
+        assert abs(a - b) <= 2e-4 * abs(b)
+    for k in names:
+        check_updated_parameter(gold, k, new_sd[k], 1e-4)
 
-    ts = [torch.zeros(2, 3), torch.zeros(5), torch.zeros(1, 1, 4)]
-    flat = torch.arange(15, dtype=torch.float32)
+
+def test_flat_views_are_aligned_views():
+    from fusion_train import ALIGN, flat_size, flat_views
+
+    ts = [torch.zeros(2, 3), torch.zeros(70), torch.zeros(1, 1, 4)]
+    assert flat_size(ts) == 4 * ALIGN and flat_size(ts, align=1) == 80
+    flat = torch.arange(4 * ALIGN, dtype=torch.float32)
     v = flat_views(ts, flat)
-    assert [tuple(x.shape) for x in v] == [(2, 3), (5,), (1, 1, 4)]
-    assert v[1][0] == 6 and v[2].flatten()[0] == 11
+    assert [tuple(x.shape) for x in v] == [(2, 3), (70,), (1, 1, 4)]
+    assert v[1][0] == ALIGN and v[2].flatten()[0] == 3 * ALIGN      # every tensor starts on a 256-byte boundary
+    assert all(x.data_ptr() % (4 * ALIGN) == flat.data_ptr() % (4 * ALIGN) for x in v)
     v[0].zero_()
     assert flat[:6].abs().sum() == 0  # views, not copies
+    packed = flat_views(ts, torch.arange(80, dtype=torch.float32), align=1)
+    assert packed[1][0] == 6 and packed[2].flatten()[0] == 76
 
 
 def test_split_k_fills_the_machine_without_empty_slices():
@@ -99,7 +122,7 @@ def test_trainer_refuses_cpu_and_unbuilt_configurations():
 
     params = pd.default_parameters()
     tr = FusionHeadTrainer(mm.FusionModel(params))
-    assert len(tr.names) == 20 and tr.numel == sum(p.numel() for p in tr.params)
+    assert len(tr.names) == 20 and tr.numel == sum(p.numel() for p in tr.params) and tr.flat_numel >= tr.numel
     with pytest.raises(nat.B200NativeError):
         tr.zero_grad()  # parameters live on the CPU: no CPU path
     params["fusion_model_parameters"]["fusion_specific_parameters"]["use_cross_attention"] = False
@@ -113,6 +136,7 @@ def test_shared_step_rejects_unbuilt_loss_terms():
     from train_fusion import LightningFusionModel
 
     params = pd.default_parameters()
+    assert LightningFusionModel(None, None, mm.FusionModel(params), params)._lambda_mask() == 0.2
     params["fusion_model_parameters"]["recon_enabled"] = True
     lm = LightningFusionModel(mm.ModelMaskHeadBackbone("dwi", params), mm.ModelMaskHeadBackbone("dce", params),
                               mm.FusionModel(params), params)
@@ -130,18 +154,20 @@ def test_shared_step_rejects_unbuilt_loss_terms():
 _WORKER = r"""
 import sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1]); import b200path
-from fusion_train import average_gradients, flat_views
+from fusion_train import average_gradients, flat_size, flat_views
 rank = int(sys.argv[3])
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=2)
 shapes = [torch.zeros(3, 2), torch.zeros(4)]
-flat = torch.zeros(11)                      # 10 gradient elements + the loss slot
+n = flat_size(shapes)
+flat = torch.zeros(n + 1)                   # aligned gradient slots + the loss slot
 g = flat_views(shapes, flat)
-g[0].fill_(1.0 + rank); g[1].fill_(10.0 * (1 + rank)); flat[10] = 0.5 + rank
+g[0].fill_(1.0 + rank); g[1].fill_(10.0 * (1 + rank)); flat[n] = 0.5 + rank
 scale = average_gradients(flat)
 assert scale == 0.5
-avg = flat * scale
-assert torch.allclose(avg[:6], torch.full((6,), 1.5)) and torch.allclose(avg[6:10], torch.full((4,), 15.0))
-assert abs(float(avg[10]) - 1.0) < 1e-6     # the loss is averaged by the same collective
+avg = flat_views(shapes, flat * scale)
+assert torch.allclose(avg[0], torch.full((3, 2), 1.5)) and torch.allclose(avg[1], torch.full((4,), 15.0))
+assert abs(float(flat[n]) * scale - 1.0) < 1e-6     # the loss is averaged by the same collective
+assert float((flat * scale).sum()) == 1.5 * 6 + 15.0 * 4 + 1.0   # the padding stays zero
 dist.destroy_process_group()
 print("ok")
 """

@@ -200,6 +200,51 @@ def test_head_step_matches_reference_fixture_and_oracle():
             assert torch.equal(t.cpu(), sd[name]), name
 
 
+def test_mask_dice_term_matches_reference_fixture_and_oracle():
+    """classification + mask dice terms (train_fusion.py:238-255): loss, fused mask logits, all 24 gradients and the
+    three-step trajectory against the reference fixture and the oracle."""
+    from fusion_train import FusionHeadTrainer
+
+    gold = gu.load("train_head_mask.npz")
+    hp = json.loads(str(gold["hp"]))
+    params, fm, sd = _head(hp["weight_seed"])
+    batch = op.synthetic_head_batch(hp["n"], seed=hp["seed"])
+    masks = op.synthetic_raw(hp["n"], seed=hp["seed"] + 1, kind="S")[2]
+    tr = FusionHeadTrainer(fm, lr=hp["lr"], betas=hp["betas"], eps=hp["eps"], weight_decay=hp["weight_decay"],
+                           smoothing=hp["smoothing"], gamma=hp["gamma"], class_weights=hp["class_weights"],
+                           lambda_mask=hp["lambda_mask"])
+    assert sorted(tr.names) == sorted(hp["updated"]) and len(tr.names) == 24
+    dbatch = _to_dev(batch)
+    tr.zero_grad()
+    loss, logits = tr.loss_and_grads(*dbatch, masks.to(DEV))
+    assert abs(loss.item() - gold["losses"][0]) <= 2e-5 * abs(gold["losses"][0])
+    gu.check(gold, "logits", logits, 2e-5)
+    gu.check(gold, "fused_mask", tr.fused_mask_logits, 1e-4)
+    _, _, o_grads = to.head_loss_and_grads(sd, params, *batch, hp["smoothing"], hp["gamma"],
+                                           torch.tensor(hp["class_weights"]), masks, hp["lambda_mask"])
+    for name, g in zip(tr.names, tr.grads):
+        scale = o_grads[name].abs().max().item()
+        assert (g.cpu() - o_grads[name]).abs().max().item() <= 2e-4 * scale + 1e-8, name
+        if not name.endswith("in_proj_bias"):
+            gu.check(gold, f"grad/{name}", g, 4e-4, what="gradient ")
+    losses = [loss.item()]
+    tr.step()
+    for _ in range(hp["steps"] - 1):
+        l, _ = tr.train_step(*dbatch, masks.to(DEV))
+        losses.append(l.item())
+    for a, b in zip(losses, gold["losses"]):
+        assert abs(a - b) <= 5e-4 * abs(b), (losses, list(gold["losses"]))
+    state = fm.state_dict()
+    for name in tr.names:
+        check_updated_parameter(gold, name, state[name], 2e-3)
+    # the inference path (bf16 maps, its own mask-head kernels) produces the same fused mask logits
+    fm.eval()
+    _, mask_inf, _ = fm([dbatch[0]], [dbatch[1]], dbatch[2], dbatch[3])
+    tr.zero_grad()
+    tr.loss_and_grads(*dbatch, masks.to(DEV))
+    assert _rel(mask_inf, tr.fused_mask_logits) < 2e-2
+
+
 def test_larger_batch_gradients_match_oracle_and_training_reduces_the_loss():
     from fusion_train import FusionHeadTrainer
 
@@ -238,6 +283,8 @@ def test_lightning_surface_trains_and_inference_sees_the_new_weights():
     for k in ("dwi", "dce"):
         for p in mods[k].parameters():
             p.requires_grad = False
+    import copy
+    fresh_head = copy.deepcopy(mods["fusion"])
     lm = LightningFusionModel(mods["dwi"], mods["dce"], mods["fusion"], params)
     dwi_raw, dce, _, labels = op.synthetic_raw(16, seed=3, kind="S")
     dwi = dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)
@@ -252,6 +299,15 @@ def test_lightning_surface_trains_and_inference_sees_the_new_weights():
     assert (logits1 - logits0).abs().max().item() > 1e-3
     assert _rel(logits1, tr_logits) < 2e-2
     assert lm.validation_step(batch).item() < before
+    # default objective of the reference minus its unbuilt terms: classification + mask dice, 4-tuple batches
+    params2 = pd.default_parameters()
+    params2["fusion_model_parameters"]["optimizer_parameters"] = params["fusion_model_parameters"]["optimizer_parameters"]
+    lm2 = LightningFusionModel(mods["dwi"], mods["dce"], fresh_head, params2)
+    masks = op.synthetic_raw(16, seed=3, kind="S")[2]
+    batch4 = (dwi, dce, masks, labels)
+    l2 = [lm2.fit_batch(batch4).item() for _ in range(12)]
+    assert lm2.head_trainer.lambda_mask == 0.2 and len(lm2.head_trainer.names) == 24
+    assert l2[-1] < l2[0]
     for p in mods["dwi"].parameters():
         p.requires_grad = True
     with pytest.raises(NotImplementedError):
