@@ -284,7 +284,7 @@ def reference_arm(args):
 
 # --------------------------------------------------------------- fusion-head fine-tuning (C5 slice) ----
 WORKLOAD_C5 = ("C5 (frozen-encoder phase): DWI 16x64x64 + DCE 6x64x64 -> normalise -> frozen CNN encoders -> "
-               "fusion-head forward + backward (smoothed focal loss) -> gradient all-reduce -> AdamW")
+               "fusion-head forward + backward (smoothed focal loss + mask dice) -> gradient all-reduce -> AdamW")
 METRIC_C5 = "fusion-head fine-tuning cases/sec"
 
 
@@ -307,14 +307,18 @@ def train_arm(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     params, pipe, cpu_state, nyul = build_product(device, "logits", False, "c3")
-    trainer = FusionHeadTrainer(pipe.fusion_model, lr=1e-4, weight_decay=4e-5, smoothing=0.1, gamma=1.5)
+    lam = 0.2 if args.objective == "cls+mask" else 0.0   # lambda_mask, parameters_generate.py:125
+    trainer = FusionHeadTrainer(pipe.fusion_model, lr=1e-4, weight_decay=4e-5, smoothing=0.1, gamma=1.5,
+                                lambda_mask=lam)
     B = args.batch
     dwi_h, dce_h = make_inputs(B, rank)
-    lab_h = torch.randint(0, 4, (B,), generator=torch.Generator().manual_seed(99 + rank))
-    dwi_d, dce_d, lab_d = dwi_h.to(device), dce_h.to(device), lab_h.to(device)
+    gen = torch.Generator().manual_seed(99 + rank)
+    lab_h = torch.randint(0, 4, (B,), generator=gen)
+    msk_h = (torch.rand(B, 1, 32, 32, generator=gen) > 0.5).float()
+    dwi_d, dce_d, lab_d, msk_d = dwi_h.to(device), dce_h.to(device), lab_h.to(device), msk_h.to(device)
 
     def step():
-        loss, _ = trainer.train_step(*pipe.encode_raw(dwi_d, dce_d), lab_d)
+        loss, _ = trainer.train_step(*pipe.encode_raw(dwi_d, dce_d), lab_d, msk_d if lam > 0 else None)
         return loss
 
     def barrier():
@@ -339,11 +343,12 @@ def train_arm(args):
     launches = nat.LAUNCH_COUNT - launches0
     ms = e0.elapsed_time(e1)
     # end to end: pinned host batch (inputs + labels) uploaded every step, the loss read back every step
-    dwi_p, dce_p, lab_p = dwi_h.pin_memory(), dce_h.pin_memory(), lab_h.pin_memory()
-    pipe.fit_host([(dwi_p, dce_p, lab_p)] * 2, trainer)
+    dwi_p, dce_p, lab_p, msk_p = dwi_h.pin_memory(), dce_h.pin_memory(), lab_h.pin_memory(), msk_h.pin_memory()
+    host_batch = (dwi_p, dce_p, lab_p, msk_p) if lam > 0 else (dwi_p, dce_p, lab_p)
+    pipe.fit_host([host_batch] * 2, trainer)
     barrier()
     e0.record()
-    pipe.fit_host([(dwi_p, dce_p, lab_p)] * args.steps, trainer)
+    pipe.fit_host([host_batch] * args.steps, trainer)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -362,7 +367,8 @@ def train_arm(args):
         prof = nat.stop_profile()
         total_ms = sum(sum(t) for t in prof.values())
         head = {n: 0.0 for n in ("b200_sgemm", "b200_colsum", "b200_mha_fwd", "b200_mha_bwd", "b200_ln_fwd",
-                                 "b200_ln_bwd", "b200_gelu_bwd", "b200_head_loss", "b200_adamw", "b200_fusion_tokens")}
+                                 "b200_ln_bwd", "b200_gelu_bwd", "b200_head_loss", "b200_adamw", "b200_fusion_tokens",
+                                 "b200_mask_dot", "b200_mask_wsum", "b200_mask_dice", "b200_mask_head_grads")}
         sg_flops = sg_ms = 0.0
         for (n, k), t in prof.items():
             if n in head:
@@ -386,14 +392,15 @@ def train_arm(args):
             "vs_baseline": None, "dtype": "bf16 encoders (frozen) / f32 head forward, backward and optimiser",
             "data": "synthetic",
             "config": {"workload": WORKLOAD_C5, "batch_per_gpu": B, "global_batch": B * world,
-                       "objective": "classification term only (label smoothing 0.1, focal gamma 1.5)",
+                       "objective": "classification (label smoothing 0.1, focal gamma 1.5)" +
+                       (" + 0.2 x mean of the three mask dice terms" if lam > 0 else " only"),
                        "trainable_parameters": trainer.numel, "allreduce_bytes_per_step": 4 * (trainer.flat_numel + 1),
                        "l2": "no flush needed: per-step inputs and activations exceed the 126 MB L2",
                        "parallelism": f"data parallel x{world}, one NCCL all-reduce of the flat gradient buffer per step"
                        if world > 1 else "single GPU"},
             "clocks": clocks.summary(),
             "e2e": {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": UNIT,
-                    "h2d_bytes_per_step": dwi_p.numel() * 4 + dce_p.numel() * 4 + lab_p.numel() * 8,
+                    "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host_batch),
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
                     "api": "FusionPipeline.fit_host (pinned host batch incl. labels, upload overlapped on a copy stream, "
                     "loss read back every step)"},
@@ -406,7 +413,7 @@ def train_arm(args):
             "cpu_baseline": None,
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = run_cpu_train_baseline(params, cpu_state, nyul, args.ref_batch)
+            line["cpu_baseline"] = run_cpu_train_baseline(params, cpu_state, nyul, args.ref_batch, lam)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -414,7 +421,7 @@ def train_arm(args):
         print(json.dumps(line))
 
 
-def run_cpu_train_baseline(params, cpu_state, nyul, batch, steps=3):
+def run_cpu_train_baseline(params, cpu_state, nyul, batch, lambda_mask=0.0, steps=3):
     """The same step on the host cores: oracle encoders (eval, no grad) + oracle/train_oracle.py (autograd over the
     full-resolution FusionModel forward + AdamW)."""
     import numpy as np
@@ -426,7 +433,9 @@ def run_cpu_train_baseline(params, cpu_state, nyul, batch, steps=3):
     torch.set_num_threads(threads)
     lm = np.stack([nyul.channel_landmarks[c] for c in range(6)])
     dwi, dce = make_inputs(batch, 777)
-    labels = torch.randint(0, 4, (batch,), generator=torch.Generator().manual_seed(5))
+    gen = torch.Generator().manual_seed(5)
+    labels = torch.randint(0, 4, (batch,), generator=gen)
+    masks = (torch.rand(batch, 1, 32, 32, generator=gen) > 0.5).float()
     sd = {k: v.clone() for k, v in cpu_state[2].items()}
 
     def one(sd):
@@ -435,7 +444,7 @@ def run_cpu_train_baseline(params, cpu_state, nyul, batch, steps=3):
             _, aux_d, m_d = mo.encoder_forward(cpu_state[0], "dwi", params, x_d)
             _, aux_c, m_c = mo.encoder_forward(cpu_state[1], "dce", params, x_c)
         b = (aux_d["raw_feats"][-1], aux_c["raw_feats"][-1], m_d, m_c, labels)
-        return to.train_steps(sd, params, b, 1, 0.1, 1.5, None, 1e-4, (0.9, 0.999), 1e-8, 4e-5)[1]
+        return to.train_steps(sd, params, b, 1, 0.1, 1.5, None, 1e-4, (0.9, 0.999), 1e-8, 4e-5, masks, lambda_mask)[1]
 
     sd = one(sd)
     t0 = time.perf_counter()
@@ -458,6 +467,9 @@ def main():
                     help="c3 = the headline CNN-encoder configuration; c4 = ViT-B/16 backbone encoders at 224x224; "
                          "resnet = ResNet-50 (RadImageNet branch, output stride 8) backbone encoders at 224x224")
     ap.add_argument("--aux", default="full", choices=["full", "logits"])
+    ap.add_argument("--objective", default="cls+mask", choices=["cls", "cls+mask"],
+                    help="--workload c5: loss terms of the fine-tuning step (the reference's total loss minus its "
+                         "reconstruction / mimic terms, or the classification term alone)")
     ap.add_argument("--ref-batch", type=int, default=32)
     ap.add_argument("--cpu-cases", type=int, default=256, help="bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

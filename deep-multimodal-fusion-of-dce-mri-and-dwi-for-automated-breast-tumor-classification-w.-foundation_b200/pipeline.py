@@ -123,14 +123,16 @@ class FusionPipeline:
         return out_d[1]["raw_feats"][-1], out_c[1]["raw_feats"][-1], out_d[2], out_c[2]
 
     def fit_host(self, batches, trainer, device="cuda"):
-        """End-to-end fine-tuning of the fusion head: iterable of (dwi_host, dce_host, labels_host) PINNED CPU
-        tensors, one optimisation step per batch with `trainer` (fusion_train.FusionHeadTrainer: forward, backward,
-        gradient all-reduce over the data-parallel ranks, AdamW).  Returns the per-step rank-averaged losses as
-        pinned host tensors; the upload of batch i+1 overlaps the step on batch i."""
+        """End-to-end fine-tuning of the fusion head: iterable of (dwi_host, dce_host, labels_host[, masks_host])
+        PINNED CPU tensors, one optimisation step per batch with `trainer` (fusion_train.FusionHeadTrainer: forward,
+        backward, gradient all-reduce over the data-parallel ranks, AdamW).  Returns the per-step rank-averaged
+        losses as pinned host tensors; the upload of batch i+1 overlaps the step on batch i."""
         dev = torch.device(device)
         losses = []
-        for d, c, lab in self._staged(batches, dev):
-            loss, _ = trainer.train_step(*self.encode_raw(d, c), lab)
+        for items in self._staged(batches, dev):
+            d, c, lab = items[:3]
+            masks = items[3] if len(items) > 3 else None
+            loss, _ = trainer.train_step(*self.encode_raw(d, c), lab, masks)
             host = torch.empty(1, dtype=torch.float32, pin_memory=True)
             host.copy_(loss, non_blocking=True)
             losses.append(host)
