@@ -678,12 +678,21 @@ extern "C" int b200_dwi_normalize(const float* x, float* out, int planes, int C,
         if (sms <= 0) sms = 148;
     }
     // persistent grid = resident CTAs (64 / 114 registers per thread -> 4 / 2 CTAs of 256 threads per SM)
-    int grid = planes < sms * 4 ? planes : sms * 4;
+    // With skip_last every C-th plane is a zero fill (half the traffic, no read).  Planes are dealt round-robin, so a
+    // grid sharing a factor with C (592 = 16 * 37) would hand some CTAs nothing but cheap planes and leave the rest
+    // 4-5 % more work than the average: make the grid coprime with C.
+    auto coprime_grid = [&](int g) {
+        if (!skip_last || g >= planes) return g < planes ? g : planes;
+        auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+        while (g > 1 && gcd(g, C) != 1) --g;
+        return g;
+    };
+    int grid = coprime_grid(sms * 4);
     if (aligned && n <= kNormThreads * 4 * 4)
         dwi_normalize_reg_kernel<4><<<grid, kNormThreads, 0, s>>>(x, out, planes, C, n, skip_last, z_lo, z_hi,
                                                                   plane_mean);
     else if (aligned && n <= kNormThreads * 4 * 8)
-        dwi_normalize_reg_kernel<8><<<(grid = planes < sms * 2 ? planes : sms * 2), kNormThreads, 0, s>>>(x, out, planes, C, n, skip_last, z_lo, z_hi,
+        dwi_normalize_reg_kernel<8><<<(grid = coprime_grid(sms * 2)), kNormThreads, 0, s>>>(x, out, planes, C, n, skip_last, z_lo, z_hi,
                                                                   plane_mean);
     else
         dwi_normalize_stream_kernel<<<planes, kNormThreads, 0, s>>>(x, out, C, n, skip_last, z_lo, z_hi, plane_mean);

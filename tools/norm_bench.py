@@ -37,8 +37,26 @@ def timed(fn, iters=10):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--sweep", action="store_true",
+                    help="DWI normaliser against a device-to-device copy of the SAME number of bytes, at several batch "
+                         "sizes: how much of the gap to the large-copy peak is the size of the launch")
     a = ap.parse_args()
     B = a.batch
+    if a.sweep:
+        peak = 6531.9
+        norm = ds.DWINormalize()
+        for b in (256, 1024, 4096, 16384):
+            x = (torch.rand(b, 16, 64, 64, device="cuda") * 1000 + 1)
+            pm = torch.empty(b * 16, device="cuda")
+            ms = timed(lambda: norm.batch(x, plane_mean=pm))
+            nbytes = b * 507904
+            src = torch.empty(nbytes // 8, dtype=torch.float32, device="cuda").normal_()
+            dst = torch.empty_like(src)
+            ms_c = timed(lambda: dst.copy_(src))
+            print(f"B={b:6d}  dwi_normalize {ms:7.3f} ms {nbytes / ms / 1e6:6.0f} GB/s ({100 * nbytes / ms / 1e6 / peak:4.1f} %)   "
+                  f"same-bytes copy {ms_c:7.3f} ms {nbytes / ms_c / 1e6:6.0f} GB/s ({100 * nbytes / ms_c / 1e6 / peak:4.1f} %)   "
+                  f"normaliser / copy = {ms_c / ms:4.2f}")
+        return
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     g = torch.Generator().manual_seed(0)
     dwi = (torch.rand(B, 16, 64, 64, generator=g) * 1000 + 1).cuda()
