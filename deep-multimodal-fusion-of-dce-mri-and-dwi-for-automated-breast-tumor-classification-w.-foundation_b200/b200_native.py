@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 _lib = None
 
@@ -121,6 +121,7 @@ SIGNATURES = {
     "b200_maxpool3x3_s2": [_P, _I, _I, _I, _I, _P, _P],
     "b200_im2col7x7_s2": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "b200_flip_planes": [_P, _P, _LL, _I, _I, _I, _I, _P],
+    "b200_augment": [_P, _P, _I, _I, _I, _I, _P, _P, _F, _P],
     "b200_fusion_tokens": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "b200_fusion_core": [C.POINTER(FusionWeights), _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "b200_fusion_mix": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
@@ -664,3 +665,17 @@ def mask_head_grads(dv, dc0, pre_w, pre_b, out_w, g_pre_w, g_pre_b, g_out_w, g_o
     mid, C_ = pre_b.numel(), dv.numel()
     _call("b200_mask_head_grads", None, _ptr(dv), _ptr(dc0), _ptr(pre_w), _ptr(pre_b), _ptr(out_w), mid, C_,
           _ptr(g_pre_w), _ptr(g_pre_b), _ptr(g_out_w), _ptr(g_out_b), _stream())
+
+
+def augment(x, theta, flips, out, fill=0.0):
+    """x, out [B,C,H,W] fp32; theta [B,6] fp32 inverse affine matrices; flips [B] int32 (bit 0 horizontal, bit 1
+    vertical) or None."""
+    if x.dtype != torch.float32 or not x.is_contiguous() or out.shape != x.shape or not out.is_contiguous():
+        raise B200NativeError("augment needs contiguous float32 [B,C,H,W] tensors of equal shape")
+    B, C_, H, W = x.shape
+    if theta.shape != (B, 6) or theta.dtype != torch.float32 or not theta.is_contiguous():
+        raise B200NativeError("theta must be a contiguous float32 [B,6] tensor")
+    if flips is not None and (flips.dtype != torch.int32 or flips.numel() != B):
+        raise B200NativeError("flips must be an int32 [B] tensor")
+    _call("b200_augment", None, _ptr(x), _ptr(out), B, C_, H, W, _ptr(theta), _ptr(flips), float(fill), _stream())
+    return out

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 import b200_native as nat
 
-__all__ = ["DWINormalize", "DCENormalize", "Resize", "SingleInputDataset", "LoadedFusionDataset", "data_segmentation",
+__all__ = ["DWINormalize", "DCENormalize", "Resize", "BatchAugment", "SingleInputDataset", "LoadedFusionDataset", "data_segmentation",
            "data_segmentation_mask"]
 
 
@@ -73,6 +73,91 @@ class Resize(object):
         x = x.contiguous().float()
         out = torch.empty((B, C, S0, S1), dtype=torch.float32, device=x.device)
         nat.resize_bilinear_c1(x.view(B * C, H, W), out.view(B * C, S0, S1))
+        return out
+
+    def __call__(self, img):
+        dev_img, home = _to_device(img)
+        out = self.batch(dev_img.unsqueeze(0))[0]
+        return out if home is None else out.to(home)
+
+
+class BatchAugment(object):
+    """The reference's training augmentation (code/prepare_single_model.py:107-113) -
+    `transforms.RandomAffine(degrees=90, translate=(0.1, 0.1), shear=(0.1, 0.1))`, `RandomHorizontalFlip()`,
+    `RandomVerticalFlip()` - for a whole batch in one kernel pass on the device.
+
+    Parameters are drawn on the host exactly as torchvision draws them, sample by sample and in the Compose order
+    (RandomAffine.get_params: angle, tx, ty, [scale], shear_x[, shear_y]; then one `torch.rand(1)` per flip), from
+    torch's global CPU generator - so under the same seed a batch gets the parameters the reference's per-sample
+    pipeline would give the same images.  `inverse_matrix` restates
+    torchvision.transforms.functional._get_inverse_affine_matrix for the tensor backend (centre at the image centre).
+    Nearest-neighbour interpolation and zero fill, torchvision's defaults."""
+
+    def __init__(self, degrees=90, translate=(0.1, 0.1), scale=None, shear=(0.1, 0.1), hflip_p=0.5, vflip_p=0.5,
+                 fill=0.0):
+        self.degrees = (-float(degrees), float(degrees)) if isinstance(degrees, (int, float)) else tuple(degrees)
+        self.translate, self.scale = translate, scale
+        if isinstance(shear, (int, float)):
+            shear = (-float(shear), float(shear))
+        self.shear = None if shear is None else tuple(float(s) for s in shear)
+        if self.shear is not None and len(self.shear) not in (2, 4):
+            raise ValueError("shear must hold 2 or 4 values")
+        self.hflip_p, self.vflip_p, self.fill = hflip_p, vflip_p, float(fill)
+
+    def sample_params(self, n, height, width):
+        """-> list of n (angle, (tx, ty), scale, (shear_x, shear_y), hflip, vflip), torchvision's draw order."""
+        out = []
+        for _ in range(n):
+            angle = float(torch.empty(1).uniform_(self.degrees[0], self.degrees[1]).item())
+            tx = ty = 0
+            if self.translate is not None:
+                max_dx, max_dy = float(self.translate[0] * width), float(self.translate[1] * height)
+                tx = int(round(torch.empty(1).uniform_(-max_dx, max_dx).item()))
+                ty = int(round(torch.empty(1).uniform_(-max_dy, max_dy).item()))
+            sc = 1.0
+            if self.scale is not None:
+                sc = float(torch.empty(1).uniform_(self.scale[0], self.scale[1]).item())
+            shx = shy = 0.0
+            if self.shear is not None:
+                shx = float(torch.empty(1).uniform_(self.shear[0], self.shear[1]).item())
+                if len(self.shear) == 4:
+                    shy = float(torch.empty(1).uniform_(self.shear[2], self.shear[3]).item())
+            hf = bool(torch.rand(1) < self.hflip_p) if self.hflip_p is not None else False
+            vf = bool(torch.rand(1) < self.vflip_p) if self.vflip_p is not None else False
+            out.append((angle, (tx, ty), sc, (shx, shy), hf, vf))
+        return out
+
+    @staticmethod
+    def inverse_matrix(angle, translate, scale, shear):
+        """Inverse affine matrix (output -> input pixel, centred coordinates): rotation-scale-shear inverse times the
+        inverse translation, float64 arithmetic like torchvision's."""
+        import math
+
+        rot, sx, sy = math.radians(angle), math.radians(shear[0]), math.radians(shear[1])
+        tx, ty = float(translate[0]), float(translate[1])
+        a = math.cos(rot - sy) / math.cos(sy)
+        b = -math.cos(rot - sy) * math.tan(sx) / math.cos(sy) - math.sin(rot)
+        c = math.sin(rot - sy) / math.cos(sy)
+        d = -math.sin(rot - sy) * math.tan(sx) / math.cos(sy) + math.cos(rot)
+        m = [d / scale, -b / scale, 0.0, -c / scale, a / scale, 0.0]
+        m[2] += m[0] * (-tx) + m[1] * (-ty)
+        m[5] += m[3] * (-tx) + m[4] * (-ty)
+        return m
+
+    def batch(self, x, params=None):
+        """x [B,C,H,W] fp32 CUDA -> augmented copy.  `params` (from sample_params) may be passed to reuse a draw."""
+        if x.dim() != 4:
+            raise ValueError("expected [B,C,H,W]")
+        if not x.is_cuda:
+            raise nat.B200NativeError("BatchAugment.batch needs a CUDA tensor (no CPU path)")
+        B, C, H, W = x.shape
+        if params is None:
+            params = self.sample_params(B, H, W)
+        theta = torch.tensor([self.inverse_matrix(p[0], p[1], p[2], p[3]) for p in params], dtype=torch.float32)
+        flips = torch.tensor([int(p[4]) | (int(p[5]) << 1) for p in params], dtype=torch.int32)
+        x = x.contiguous().float()
+        out = torch.empty_like(x)
+        nat.augment(x, theta.to(x.device), flips.to(x.device), out, self.fill)
         return out
 
     def __call__(self, img):

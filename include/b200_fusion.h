@@ -294,6 +294,14 @@ int b200_adc_map(const float* x, int B, int C, int n, const float* bvals, float 
 int b200_flip_planes(const float* x, float* out, long long planes, int H, int W, int flip_w, int flip_h,
                      void* stream);
 
+/* Training-time augmentation, batched (code/prepare_single_model.py:107-113: torchvision RandomAffine(degrees=90,
+ * translate=(0.1,0.1), shear=(0.1,0.1)) -> RandomHorizontalFlip -> RandomVerticalFlip, per sample on the CPU in the
+ * reference).  x, out [B,C,H,W] fp32 (out of place); theta [B,6] = torchvision's INVERSE affine matrix of each case
+ * (output pixel -> input pixel, centred coordinates; identity = {1,0,0,0,1,0}); flips [B] or NULL: bit 0 = horizontal,
+ * bit 1 = vertical flip applied after the affine map.  Nearest-neighbour sampling, `fill` outside the image. */
+int b200_augment(const float* x, float* out, int B, int C, int H, int W, const float* theta, const int* flips,
+                 float fill, void* stream);
+
 /* FusionModel._to_tokens (code/model_module.py:903-917): adaptive average pool to Hp x Wp tokens, fp32 [B,Hp*Wp,C]. */
 int b200_fusion_tokens(const void* p, int B, int H, int W, int C, int Hp, int Wp, float* tokens, void* stream);
 

@@ -260,3 +260,30 @@ def test_reference_arm_prints_one_json_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "cases/s" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_batch_augment_draws_torchvision_parameters():
+    """dataset.BatchAugment samples what the reference's Compose (RandomAffine -> HFlip -> VFlip,
+    code/prepare_single_model.py:107-113) would draw for the same images under the same seed, and restates
+    torchvision's inverse affine matrix exactly."""
+    import dataset as ds
+    from torchvision import transforms as T
+    from torchvision.transforms import functional as TF
+
+    aug = ds.BatchAugment(degrees=90, translate=(0.1, 0.1), shear=(0.1, 0.1))
+    torch.manual_seed(11)
+    mine = aug.sample_params(6, 64, 48)
+    torch.manual_seed(11)
+    ra = T.RandomAffine(degrees=90, translate=(0.1, 0.1), shear=(0.1, 0.1))
+    for k in range(6):
+        angle, tr, sc, sh = ra.get_params(ra.degrees, ra.translate, ra.scale, ra.shear, [48, 64])
+        hf, vf = bool(torch.rand(1) < 0.5), bool(torch.rand(1) < 0.5)
+        assert mine[k] == (angle, tr, sc, sh, hf, vf)
+        want = TF._get_inverse_affine_matrix([0.0, 0.0], angle, [float(t) for t in tr], sc, list(sh))
+        assert aug.inverse_matrix(angle, tr, sc, sh) == want
+    assert aug.inverse_matrix(0.0, (0, 0), 1.0, (0.0, 0.0)) == [1.0, 0.0, 0.0, 0.0, 1.0, 0.0]
+    import b200_native as nat
+    with pytest.raises(nat.B200NativeError):
+        aug.batch(torch.zeros(2, 3, 8, 8))  # CPU tensor: no CPU path
+    assert nat.lib().b200_augment(None, None, 0, 3, 8, 8, None, None, 0.0, None) == 0
+    assert nat.lib().b200_augment(None, None, 2, 3, 8, 8, None, None, 0.0, None) < 0

@@ -447,3 +447,38 @@ def test_resnet_stem_kernels_and_dilated_relu_conv():
     # a channel slice as the A operand
     o2 = nat.conv_gemm(buf[..., 128:], (torch.randn(64, 256, generator=g) / 16).to(DEV).bfloat16(), taps=1)
     assert tuple(o2.shape) == (2, 28, 28, 64)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(8, 16, 64, 64), (5, 6, 48, 80)])
+def test_batch_augment_matches_torchvision(B, C, H, W):
+    """b200_augment against torchvision's own RandomAffine / flips applied per sample on the CPU with the same
+    drawn parameters (code/prepare_single_model.py:107-113).  Index work: exact, except where a source coordinate
+    lands within rounding of a pixel boundary (fp32 grid arithmetic in a different order) - at most 1e-4 of pixels."""
+    import dataset as ds
+    from torchvision.transforms import functional as TF
+    from torchvision.transforms import InterpolationMode
+
+    g = torch.Generator().manual_seed(B * 100 + H)
+    x = torch.rand(B, C, H, W, generator=g)
+    aug = ds.BatchAugment()
+    torch.manual_seed(17)
+    params = aug.sample_params(B, H, W)
+    assert any(p[4] for p in params) or any(p[5] for p in params)
+    got = aug.batch(x.to(DEV), params=params).cpu()
+    bad = 0
+    for b, (angle, tr, sc, sh, hf, vf) in enumerate(params):
+        ref = TF.affine(x[b], angle, list(tr), sc, list(sh), interpolation=InterpolationMode.NEAREST, fill=[0.0] * C)
+        if hf:
+            ref = TF.hflip(ref)
+        if vf:
+            ref = TF.vflip(ref)
+        bad += int((ref != got[b]).any(dim=0).sum())
+    assert bad <= 1e-4 * B * H * W, f"{bad} of {B * H * W} pixels differ"
+    # identity parameters copy the input; flips alone are exact
+    ident = [(0.0, (0, 0), 1.0, (0.0, 0.0), False, False)] * B
+    assert torch.equal(aug.batch(x.to(DEV), params=ident).cpu(), x)
+    fl = [(0.0, (0, 0), 1.0, (0.0, 0.0), True, b % 2 == 0) for b in range(B)]
+    out = aug.batch(x.to(DEV), params=fl).cpu()
+    for b in range(B):
+        want = torch.flip(x[b], dims=[2, 1] if b % 2 == 0 else [2])
+        assert torch.equal(out[b], want)
