@@ -357,6 +357,14 @@ def train_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms = t[0].item(), t[1].item()
     value = world * B * args.steps / (ms / 1e3)
+    # data-parallel invariant: after the same number of steps every replica holds bit-identical parameters
+    in_sync = True
+    if world > 1:
+        flat_p = trainer._bind()["p"]
+        lo, hi = flat_p.clone(), flat_p.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.equal(lo, hi))
     line = None
     if rank == 0:
         peaks = load_peaks()
@@ -404,7 +412,7 @@ def train_arm(args):
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
                     "api": "FusionPipeline.fit_host (pinned host batch incl. labels, upload overlapped on a copy stream, "
                     "loss read back every step)"},
-            "gpu_launches": launches, "final_loss": float(loss.item()),
+            "gpu_launches": launches, "final_loss": float(loss.item()), "replicas_in_sync": in_sync,
             "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated(device) / 1e9,
             "roofline": roofline,
             "step_model": {"head_kernels_ms_per_step": {k: round(v, 4) for k, v in head.items()},
