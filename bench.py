@@ -384,6 +384,17 @@ def train_arm(args):
             if n == "b200_sgemm" and k is not None:
                 sg_flops += 2.0 * k[0] * k[1] * k[2] * len(t) / nsp
                 sg_ms += sum(t) / nsp
+        # the map-sized passes of the head are HBM bound: algorithmic bytes = one read of the bf16 f3 map per launch
+        hbm_rows = []
+        f3_bytes = B * 32 * 32 * 512 * 2
+        for n in ("b200_fusion_tokens", "b200_mask_dot", "b200_mask_wsum"):
+            times = [x for (nn_, _), t in prof.items() if nn_ == n for x in t]
+            if times:
+                ms_l = statistics.mean(times)
+                gbs = f3_bytes / (ms_l / 1e3) / 1e9
+                hbm_rows.append({"bound": "hbm", "kernel": n, "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": gbs / peaks["hbm_gbs"], "ms_per_launch": ms_l, "traffic": None,
+                                 "algorithmic_bytes_per_launch": f3_bytes})
         dom_key = ("b200_conv_gemm_ex", (B, 32, 32, 256, 256, 9))
         roofline = None
         if dom_key in prof:
@@ -415,6 +426,7 @@ def train_arm(args):
             "gpu_launches": launches, "final_loss": float(loss.item()), "replicas_in_sync": in_sync,
             "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated(device) / 1e9,
             "roofline": roofline,
+            "roofline_hbm_kernels": hbm_rows,
             "step_model": {"head_kernels_ms_per_step": {k: round(v, 4) for k, v in head.items()},
                            "head_share_of_step": sum(head.values()) / (total_ms / nsp) if total_ms else None,
                            "sgemm_fp32_tflops": sg_flops / (sg_ms / 1e3) / 1e12 if sg_ms else None},

@@ -14,27 +14,88 @@
 
 namespace b200 {
 
-__global__ void fusion_tokens_kernel(const __nv_bfloat16* __restrict__ p, int H, int W, int C, int Hp, int Wp,
-                                     float* __restrict__ tokens) {
+// One CTA per (token, case): 16-byte loads (8 channels per thread), the bin's pixels split over the thread groups that
+// do not fit the channel vectors, 4 loads in flight per thread, partial sums combined through shared memory.
+constexpr int kTokThreads = 128;
+__global__ void __launch_bounds__(kTokThreads)
+fusion_tokens_kernel(const __nv_bfloat16* __restrict__ p, int H, int W, int C, int Hp, int Wp,
+                     float* __restrict__ tokens) {
+    __shared__ float part[kTokThreads][9];
     const int b = blockIdx.y;
     const int t = blockIdx.x;
     const int ti = t / Wp, tj = t % Wp;
     const int h0 = (ti * H) / Hp, h1 = ((ti + 1) * H + Hp - 1) / Hp;
     const int w0 = (tj * W) / Wp, w1 = ((tj + 1) * W + Wp - 1) / Wp;
-    const float inv = 1.0f / static_cast<float>((h1 - h0) * (w1 - w0));
-    for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
-        float a0 = 0.f, a1 = 0.f;
-        for (int h = h0; h < h1; ++h)
-            for (int w = w0; w < w1; ++w) {
-                const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(
-                    p + ((static_cast<size_t>(b) * H + h) * W + w) * C + c);
-                a0 += __low2float(v);
-                a1 += __high2float(v);
+    const int bw = w1 - w0, npx = (h1 - h0) * bw;
+    const float inv = 1.0f / static_cast<float>(npx);
+    const int nvec = C >> 3;
+    float* dst = tokens + (static_cast<size_t>(b) * Hp * Wp + t) * C;
+    for (int v0 = 0; v0 < nvec; v0 += kTokThreads) {  // one trip unless C > 1024
+        const int nv = min(nvec - v0, kTokThreads);
+        const int groups = kTokThreads / nv;           // pixel slices working on the same channel vectors
+        const int vi = threadIdx.x % nv, grp = threadIdx.x / nv;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        if (grp < groups) {
+#pragma unroll 4
+            for (int q = grp; q < npx; q += groups) {
+                const int h = h0 + q / bw, w = w0 + q % bw;
+                float f[8];
+                unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p + ((static_cast<size_t>(b) * H + h) * W + w) * C) +
+                                    v0 + vi), f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += f[k];
             }
-        float* dst = tokens + (static_cast<size_t>(b) * Hp * Wp + t) * C + c;
-        dst[0] = a0 * inv;
-        dst[1] = a1 * inv;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) part[threadIdx.x][k] = acc[k];
+        __syncthreads();
+        if (grp == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float s = 0.f;
+                for (int g = 0; g < groups; ++g) s += part[g * nv + vi][k];
+                dst[(v0 + vi) * 8 + k] = s * inv;
+            }
+        }
+        __syncthreads();
     }
+}
+
+// Equal, non-overlapping bins (H % Hp == 0, W % Wp == 0): one CTA per (token row, case) streams the bin rows' contiguous
+// H/Hp * W * C region; a thread owns (token column, 8 channels), so no cross-thread reduction is needed.
+__global__ void __launch_bounds__(256)
+fusion_tokens_rows_kernel(const __nv_bfloat16* __restrict__ p, int H, int W, int C, int Hp, int Wp,
+                          float* __restrict__ tokens) {
+    const int b = blockIdx.y, ti = blockIdx.x;
+    const int nvec = C >> 3, bh = H / Hp, bw = W / Wp;
+    const int vi = threadIdx.x % nvec, tj = threadIdx.x / nvec;
+    const uint4* base = reinterpret_cast<const uint4*>(p + ((static_cast<size_t>(b) * H + ti * bh) * W + tj * bw) * C) + vi;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int h = 0; h < bh; ++h) {
+        const uint4* row = base + static_cast<size_t>(h) * W * nvec;
+        for (int w0 = 0; w0 < bw; w0 += 8) {  // 8 independent 16-byte loads issued before the first use
+            uint4 r[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (w0 + u < bw) r[u] = __ldg(row + static_cast<size_t>(w0 + u) * nvec);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (w0 + u < bw) {
+                    float f[8];
+                    unpack_bf16x8(r[u], f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] += f[k];
+                }
+        }
+    }
+    const float inv = 1.0f / static_cast<float>(bh * bw);
+    float4* dst = reinterpret_cast<float4*>(tokens + (static_cast<size_t>(b) * Hp * Wp + ti * Wp + tj) * C + vi * 8);
+    dst[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+    dst[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
 }
 
 // Y[t][o] = act(sum_i X[t][i] * Wt[i][o] + bias[o]) for T <= 16 tokens held in shared memory.
@@ -289,12 +350,18 @@ using namespace b200;
 
 extern "C" int b200_fusion_tokens(const void* p, int B, int H, int W, int C, int Hp, int Wp, float* tokens,
                                   void* stream) {
-    if (B < 0 || C % 2 != 0 || Hp <= 0 || Wp <= 0 || H < Hp || W < Wp) return -1;
+    if (B < 0 || C <= 0 || C % 8 != 0 || Hp <= 0 || Wp <= 0 || H < Hp || W < Wp) return -1;
     if (B == 0) return 0;
     if (p == nullptr || tokens == nullptr) return -2;
+    const int row_threads = (C / 8) * Wp;
+    if (H % Hp == 0 && W % Wp == 0 && row_threads >= 32 && row_threads <= 256) {
+        fusion_tokens_rows_kernel<<<dim3(Hp, B), row_threads, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(p), H, W, C, Hp, Wp, tokens);
+        return launch_status();
+    }
     dim3 grid(Hp * Wp, B);
-    fusion_tokens_kernel<<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(p), H,
-                                                                             W, C, Hp, Wp, tokens);
+    fusion_tokens_kernel<<<grid, kTokThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(p), H, W, C, Hp, Wp, tokens);
     return launch_status();
 }
 

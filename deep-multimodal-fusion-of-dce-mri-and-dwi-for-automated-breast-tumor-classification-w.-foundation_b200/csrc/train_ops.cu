@@ -571,33 +571,49 @@ __global__ void __launch_bounds__(128) head_loss_kernel(const b200_head_train a)
 // --------------------------------------------------------------------------------------------------------------
 // fused-mask dice term (see b200_fusion.h)
 // --------------------------------------------------------------------------------------------------------------
-// D[b,p] = omega[b] . f3[b,p,:]; one warp per pixel, omega[b] in registers (Cin <= 1024)
+// D[b,p] = omega[b] . f3[b,p,:]; one warp per pixel, omega[b] in registers (8 * 32 * NJ channels)
+template <int NJ>
 __global__ void __launch_bounds__(256)
 mask_dot_kernel(const __nv_bfloat16* __restrict__ f3, const float* __restrict__ omega, int npix, int Cin,
                 float* __restrict__ D) {
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int nvec = Cin >> 3;  // uint4 = 8 channels
-    float w[4][8];
+    float w[NJ][8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NJ; ++j)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int c = (lane + 32 * j) * 8 + k;
             w[j][k] = (lane + 32 * j) < nvec ? omega[static_cast<long long>(b) * Cin + c] : 0.f;
         }
-    for (int p = blockIdx.x * nwarps + warp; p < npix; p += gridDim.x * nwarps) {
-        const uint4* row = reinterpret_cast<const uint4*>(f3 + (static_cast<long long>(b) * npix + p) * Cin);
-        float acc = 0.f;
+    // two pixels per trip (four cost occupancy: 77 registers, measured slower): loads of both rows precede the reductions
+    constexpr int NP = 2;
+    const int stride = gridDim.x * nwarps;
+    for (int p = blockIdx.x * nwarps + warp; p < npix; p += NP * stride) {
+        uint4 r[NP][NJ];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (lane + 32 * j < nvec) {
-                float f[8];
-                unpack_bf16x8(__ldg(row + lane + 32 * j), f);
+        for (int u = 0; u < NP; ++u) {
+            const int q = min(p + u * stride, npix - 1);
+            const uint4* row = reinterpret_cast<const uint4*>(f3 + (static_cast<long long>(b) * npix + q) * Cin);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc = fmaf(w[j][k], f[k], acc);
-            }
-        acc = warp_sum(acc);
-        if (lane == 0) D[static_cast<long long>(b) * npix + p] = acc;
+            for (int j = 0; j < NJ; ++j)
+                if (lane + 32 * j < nvec) r[u][j] = __ldg(row + lane + 32 * j);
+        }
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+                if (lane + 32 * j < nvec) {
+                    float f[8];
+                    unpack_bf16x8(r[u][j], f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc = fmaf(w[j][k], f[k], acc);
+                }
+            acc = warp_sum(acc);
+            const int q = p + u * stride;
+            if (lane == 0 && q < npix) D[static_cast<long long>(b) * npix + q] = acc;
+        }
     }
 }
 
@@ -623,6 +639,44 @@ mask_wsum_kernel(const __nv_bfloat16* __restrict__ f3, const float* __restrict__
 #pragma unroll
         for (int k = 0; k < 8; ++k) atomicAdd(s + static_cast<long long>(b) * Cin + vi * 8 + k, acc[k]);
     }
+}
+
+// Same sum for Cin / 8 <= 256: a thread owns 8 channels of one pixel slice (blockDim = nvec * slices, no idle lanes),
+// 8 independent 16-byte loads in flight per thread.
+__global__ void __launch_bounds__(256)
+mask_wsum_vec_kernel(const __nv_bfloat16* __restrict__ f3, const float* __restrict__ dm, int npix, int Cin,
+                     float* __restrict__ s) {
+    const int b = blockIdx.y, nvec = Cin >> 3;
+    const int vi = threadIdx.x % nvec, pg = threadIdx.x / nvec, npg = blockDim.x / nvec;
+    const int per = (npix + gridDim.x - 1) / gridDim.x;
+    const int p0 = blockIdx.x * per, p1 = min(npix, p0 + per);
+    const uint4* base = reinterpret_cast<const uint4*>(f3 + static_cast<long long>(b) * npix * Cin) + vi;
+    const float* d = dm + static_cast<long long>(b) * npix;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int p = p0 + pg; p < p1; p += 8 * npg) {
+        uint4 r[8];
+        float w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int q = p + u * npg;
+            if (q < p1) {
+                r[u] = __ldg(base + static_cast<long long>(q) * nvec);
+                w[u] = __ldg(d + q);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (p + u * npg < p1) {
+                float f[8];
+                unpack_bf16x8(r[u], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(w[u], f[k], acc[k]);
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(s + static_cast<long long>(b) * Cin + vi * 8 + k, acc[k]);
 }
 
 __device__ __forceinline__ float dice_of(const float* __restrict__ logits, const float* __restrict__ target, int npix,
@@ -923,8 +977,12 @@ extern "C" int b200_mask_dot(const void* f3, const float* omega, int B, int npix
     if (f3 == nullptr || omega == nullptr || D == nullptr) return -2;
     int gx = (npix + 63) / 64;  // 8 warps x 8 pixels per CTA
     if (gx > 16) gx = 16;
-    mask_dot_kernel<<<dim3(gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(f3), omega, npix, Cin, D);
+    if (Cin <= 512)
+        mask_dot_kernel<2><<<dim3(gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(f3), omega, npix, Cin, D);
+    else
+        mask_dot_kernel<4><<<dim3(gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(f3), omega, npix, Cin, D);
     return launch_status();
 }
 
@@ -937,7 +995,13 @@ extern "C" int b200_mask_wsum(const void* f3, const float* dm, int B, int npix, 
     if (e != cudaSuccess) return static_cast<int>(e);
     int chunks = B >= 148 ? 4 : (592 + B - 1) / B;  // >= 4 CTAs per SM in flight; 64 threads of a CTA carry loads
     if (chunks > npix) chunks = npix;
-    mask_wsum_kernel<<<dim3(chunks, B), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(f3), dm, npix, Cin, s);
+    const int nvec = Cin / 8;
+    if (nvec <= 256) {
+        const int threads = nvec * (256 / nvec);
+        mask_wsum_vec_kernel<<<dim3(chunks, B), threads, 0, st>>>(static_cast<const __nv_bfloat16*>(f3), dm, npix, Cin, s);
+    } else {
+        mask_wsum_kernel<<<dim3(chunks, B), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(f3), dm, npix, Cin, s);
+    }
     return launch_status();
 }
 

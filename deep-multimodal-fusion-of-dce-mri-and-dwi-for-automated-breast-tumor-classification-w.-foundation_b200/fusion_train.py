@@ -212,6 +212,10 @@ class FusionHeadTrainer:
         flat = self._bind()
         f3d, f3c = _as_nhwc_bf16(f3_dwi), _as_nhwc_bf16(f3_dce)
         B, H, W, _ = f3d.shape
+        if B == 0:
+            raise ValueError("empty batch: the mean-reduced loss is undefined")
+        if f3c.shape[:3] != f3d.shape[:3]:
+            raise ValueError("the two encoders' maps must have the same batch and spatial size")
         hp, wp = fm.token_pool
         if H % hp or W % wp:
             raise NotImplementedError("token pooling with unequal bins (map size not a multiple of token_pool)")

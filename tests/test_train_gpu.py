@@ -245,6 +245,27 @@ def test_mask_dice_term_matches_reference_fixture_and_oracle():
     assert _rel(mask_inf, tr.fused_mask_logits) < 2e-2
 
 
+@pytest.mark.parametrize("n", [1, 3])
+def test_odd_batch_sizes_match_the_oracle(n):
+    """Ragged tiles everywhere (B*16 = 16 / 48 token rows, B rows for the per-case weight gradients), both terms."""
+    from fusion_train import FusionHeadTrainer
+
+    params, fm, sd = _head(5)
+    batch = op.synthetic_head_batch(n, seed=70 + n)
+    masks = op.synthetic_raw(n, seed=80 + n, kind="S")[2]
+    tr = FusionHeadTrainer(fm, smoothing=0.1, gamma=2.0, lambda_mask=0.2)
+    tr.zero_grad()
+    loss, _ = tr.loss_and_grads(*_to_dev(batch), masks.to(DEV))
+    o_loss, _, o_grads = to.head_loss_and_grads(sd, params, *batch, 0.1, 2.0, None, masks, 0.2)
+    assert abs(loss.item() - float(o_loss)) <= 2e-5 * abs(float(o_loss))
+    for name, g in zip(tr.names, tr.grads):
+        scale = o_grads[name].abs().max().item()
+        assert (g.cpu() - o_grads[name]).abs().max().item() <= 2e-4 * scale + 1e-8, name
+    empty = tuple(t[:0] for t in _to_dev(batch))
+    with pytest.raises(ValueError):
+        tr.loss_and_grads(*empty, masks[:0].to(DEV))
+
+
 def test_larger_batch_gradients_match_oracle_and_training_reduces_the_loss():
     from fusion_train import FusionHeadTrainer
 
