@@ -387,13 +387,16 @@ def train_arm(args):
         # the map-sized passes of the head are HBM bound: algorithmic bytes = one read of the bf16 f3 map per launch
         hbm_rows = []
         f3_bytes = B * 32 * 32 * 512 * 2
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 1024 (profiles/r1_c5_hbm_kernels_ncu.csv)
+        ncu_traffic = {"b200_fusion_tokens": 1.0738e9 + 32.3e6, "b200_mask_dot": 1.0758e9 + 9.0e6}
         for n in ("b200_fusion_tokens", "b200_mask_dot", "b200_mask_wsum"):
             times = [x for (nn_, _), t in prof.items() if nn_ == n for x in t]
             if times:
                 ms_l = statistics.mean(times)
                 gbs = f3_bytes / (ms_l / 1e3) / 1e9
                 hbm_rows.append({"bound": "hbm", "kernel": n, "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                 "frac": gbs / peaks["hbm_gbs"], "ms_per_launch": ms_l, "traffic": None,
+                                 "frac": gbs / peaks["hbm_gbs"], "ms_per_launch": ms_l,
+                                 "traffic": ncu_traffic[n] * B / 1024 if n in ncu_traffic else None,
                                  "algorithmic_bytes_per_launch": f3_bytes})
         dom_key = ("b200_conv_gemm_ex", (B, 32, 32, 256, 256, 9))
         roofline = None

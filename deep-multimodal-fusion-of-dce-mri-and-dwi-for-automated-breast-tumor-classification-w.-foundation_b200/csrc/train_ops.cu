@@ -37,24 +37,27 @@ struct SgemmArgs {
     int M, N, K, res_div, act, beta, kchunk;
 };
 
-constexpr int SG_BN = 64, SG_BK = 16;
+constexpr int SG_BK = 16;
 
-template <int TM, bool TA, bool TB>
+// Tile (16 TM) x (16 TN), 256 threads, each a TM x TN register block (TN = 8: two 4-wide column groups 64 apart, so a
+// warp's B reads stay one contiguous 256-byte segment); (TM, TN) = (4, 4) for small / split-K problems, (8, 8) for the
+// token-matrix products.
+template <int TM, int TN, bool TA, bool TB>
 __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs a) {
-    constexpr int BM = 16 * TM;
+    constexpr int BM = 16 * TM, BN = 16 * TN;
     __shared__ __align__(16) float As[SG_BK][BM + 4];
-    __shared__ __align__(16) float Bs[SG_BK][SG_BN + 4];
+    __shared__ __align__(16) float Bs[SG_BK][BN + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * SG_BN;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kbeg = blockIdx.z * a.kchunk, kend = min(a.K, kbeg + a.kchunk);
-    float acc[TM][4];
+    float acc[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
     // global -> register prefetch of the next k-slab while the current one is consumed from shared memory
-    constexpr int NA = BM * SG_BK / 256, NB = SG_BN * SG_BK / 256;
+    constexpr int NA = BM * SG_BK / 256, NB = BN * SG_BK / 256;
     float ra[NA], rb[NB];
     auto fetch = [&](int k0) {
 #pragma unroll
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs a) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
             const int idx = tid + i * 256;
-            const int n = TB ? idx / SG_BK : idx % SG_BN, k = TB ? idx % SG_BK : idx / SG_BN;
+            const int n = TB ? idx / SG_BK : idx % BN, k = TB ? idx % SG_BK : idx / BN;
             const int gn = n0 + n, gk = k0 + k;
             rb[i] = (gn < a.N && gk < kend) ? (TB ? __ldg(a.B + gn * a.ldb + gk) : __ldg(a.B + gk * a.ldb + gn)) : 0.f;
         }
@@ -83,27 +86,28 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs a) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
             const int idx = tid + i * 256;
-            const int n = TB ? idx / SG_BK : idx % SG_BN, k = TB ? idx % SG_BK : idx / SG_BN;
+            const int n = TB ? idx / SG_BK : idx % BN, k = TB ? idx % SG_BK : idx / BN;
             Bs[k][n] = rb[i];
         }
         __syncthreads();
         if (k0 + SG_BK < kend) fetch(k0 + SG_BK);
 #pragma unroll
         for (int k = 0; k < SG_BK; ++k) {
-            float av[TM];
+            float av[TM], bv[TN];
 #pragma unroll
             for (int i = 0; i < TM; i += 4) {
                 const float4 t = *reinterpret_cast<const float4*>(&As[k][ty * TM + i]);
                 av[i] = t.x, av[i + 1] = t.y, av[i + 2] = t.z, av[i + 3] = t.w;
             }
-            const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
 #pragma unroll
-            for (int i = 0; i < TM; ++i) {
-                acc[i][0] = fmaf(av[i], bv.x, acc[i][0]);
-                acc[i][1] = fmaf(av[i], bv.y, acc[i][1]);
-                acc[i][2] = fmaf(av[i], bv.z, acc[i][2]);
-                acc[i][3] = fmaf(av[i], bv.w, acc[i][3]);
+            for (int j = 0; j < TN; j += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(&Bs[k][(j >> 2) * 64 + tx * 4]);
+                bv[j] = t.x, bv[j + 1] = t.y, bv[j + 2] = t.z, bv[j + 3] = t.w;
             }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
     }
@@ -113,8 +117,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs a) {
         const int row = m0 + ty * TM + i;
         if (row >= a.M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = n0 + tx * 4 + j;
+        for (int j = 0; j < TN; ++j) {
+            const int col = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
             if (col >= a.N) continue;
             float v = acc[i][j];
             float* dst = a.C + row * a.ldc + col;
@@ -822,16 +826,16 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     }
 }
 
-template <int TM>
+template <int TM, int TN>
 static int launch_sgemm(const SgemmArgs& a, int ta, int tb, dim3 grid, cudaStream_t s) {
     if (ta && tb)
-        sgemm_kernel<TM, true, true><<<grid, 256, 0, s>>>(a);
+        sgemm_kernel<TM, TN, true, true><<<grid, 256, 0, s>>>(a);
     else if (ta)
-        sgemm_kernel<TM, true, false><<<grid, 256, 0, s>>>(a);
+        sgemm_kernel<TM, TN, true, false><<<grid, 256, 0, s>>>(a);
     else if (tb)
-        sgemm_kernel<TM, false, true><<<grid, 256, 0, s>>>(a);
+        sgemm_kernel<TM, TN, false, true><<<grid, 256, 0, s>>>(a);
     else
-        sgemm_kernel<TM, false, false><<<grid, 256, 0, s>>>(a);
+        sgemm_kernel<TM, TN, false, false><<<grid, 256, 0, s>>>(a);
     return launch_status();
 }
 
@@ -858,11 +862,15 @@ extern "C" int b200_sgemm(const float* A, long long lda, int trans_a, const floa
     a.kchunk = kchunk;
     const int splits = K == 0 ? 1 : (K + kchunk - 1) / kchunk;
     if (splits > 1 && split_k == 1) return -6;
-    // 128-row tiles only when they still fill the machine several times over (4 CTAs per SM)
-    const bool big = static_cast<long long>((M + 127) / 128) * ((N + SG_BN - 1) / SG_BN) >= 4 * 148;
-    dim3 grid((N + SG_BN - 1) / SG_BN, (M + (big ? 128 : 64) - 1) / (big ? 128 : 64), splits);
+    // 64 x 64 tiles (3-4 CTAs per SM hide the per-slab barrier) unless 128 x 128 tiles (8 x 8 register blocks, one
+    // 160-register CTA per SM) still give every SM several tiles.  Measured on the head's [16384, 128..512] products:
+    // 128 one-per-SM tiles run at 15 TFLOP/s, 512 small tiles at 18.6 - so the large tile is for larger problems only.
+    const long long big_tiles = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128);
+    const bool big = splits == 1 && N >= 128 && big_tiles >= 4 * 148;
+    const int bm = big ? 128 : 64, bn = big ? 128 : 64;
+    dim3 grid((N + bn - 1) / bn, (M + bm - 1) / bm, splits);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    return big ? launch_sgemm<8>(a, trans_a, trans_b, grid, s) : launch_sgemm<4>(a, trans_a, trans_b, grid, s);
+    return big ? launch_sgemm<8, 8>(a, trans_a, trans_b, grid, s) : launch_sgemm<4, 4>(a, trans_a, trans_b, grid, s);
 }
 
 extern "C" int b200_colsum(const float* X, long long ld, int R, int N, float* out, void* stream) {

@@ -23,7 +23,8 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("M,N,K,ta,tb", [(64, 64, 64, 0, 0), (100, 37, 53, 0, 1), (37, 130, 300, 1, 0),
                                          (16384, 128, 512, 0, 1), (128, 512, 4096, 1, 0), (2500, 70, 129, 1, 1),
-                                         (4, 258, 1000, 1, 0)])
+                                         (4, 258, 1000, 1, 0), (13000, 200, 77, 0, 0), (12900, 130, 100, 1, 1),
+                                         (40000, 256, 128, 0, 1), (39000, 257, 64, 1, 0)])
 def test_sgemm_matches_matmul(M, N, K, ta, tb):
     g = torch.Generator(device=DEV).manual_seed(M * 7 + N)
     a = torch.randn((K, M) if ta else (M, K), generator=g, device=DEV)
