@@ -214,30 +214,44 @@ se_dense_kernel(const float* __restrict__ in, float in_scale, int B, int K, int 
 // ------------------------------------------------- channel / pixel scale ---
 // y[b,p,c] = x[b,p,c] * gate[b,c] * (1 + gamma * attn[b,p]); either factor optional.
 // SE rescale (model_module.py:43) and mask-guided modulation (:96).
-__global__ void scale_map_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int npix,
-                                 size_t total_vec, const float* __restrict__ gate, const float* __restrict__ attn,
-                                 const float* __restrict__ gamma_ptr) {
-    const int cv = C >> 3;
+// grid (chunks, B): a CTA owns 4 * blockDim consecutive 8-channel vectors of one case; every thread issues its four
+// 16-byte loads before the first use, and all index arithmetic is 32-bit.
+constexpr int kScaleUnroll = 4;
+__global__ void __launch_bounds__(256)
+scale_map_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int npix,
+                 const float* __restrict__ gate, const float* __restrict__ attn, const float* __restrict__ gamma_ptr) {
+    const int cv = C >> 3, nvc = npix * cv, b = blockIdx.y;
     const float gamma = gamma_ptr != nullptr ? *gamma_ptr : 0.f;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total_vec;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>(i % cv) << 3;
-        const size_t bp = i / cv;
-        const size_t b = bp / npix;
+    const size_t case_off = static_cast<size_t>(b) * nvc;
+    const uint4* xs = reinterpret_cast<const uint4*>(x) + case_off;
+    uint4* ys = reinterpret_cast<uint4*>(y) + case_off;
+    const float* gr = gate != nullptr ? gate + static_cast<size_t>(b) * C : nullptr;
+    const float* ar = attn != nullptr ? attn + static_cast<size_t>(b) * npix : nullptr;
+    const int i0 = blockIdx.x * (kScaleUnroll * blockDim.x) + threadIdx.x;
+    uint4 r[kScaleUnroll];
+#pragma unroll
+    for (int u = 0; u < kScaleUnroll; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < nvc) r[u] = __ldcs(xs + i);
+    }
+#pragma unroll
+    for (int u = 0; u < kScaleUnroll; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i >= nvc) continue;
+        const int c0 = (i % cv) << 3, px = i / cv;
         float f[8];
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
-        float m = 1.f;
-        if (attn != nullptr) m = 1.f + gamma * attn[bp];
-        if (gate != nullptr) {
-            const float4 g0 = *reinterpret_cast<const float4*>(gate + b * C + c0);
-            const float4 g1 = *reinterpret_cast<const float4*>(gate + b * C + c0 + 4);
+        unpack_bf16x8(r[u], f);
+        const float m = ar != nullptr ? 1.f + gamma * __ldg(ar + px) : 1.f;
+        if (gr != nullptr) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gr + c0));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gr + c0 + 4));
             f[0] *= g0.x * m; f[1] *= g0.y * m; f[2] *= g0.z * m; f[3] *= g0.w * m;
             f[4] *= g1.x * m; f[5] *= g1.y * m; f[6] *= g1.z * m; f[7] *= g1.w * m;
         } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] *= m;
         }
-        reinterpret_cast<uint4*>(y)[i] = pack_bf16x8(f);
+        ys[i] = pack_bf16x8(f);
     }
 }
 
@@ -528,9 +542,11 @@ extern "C" int b200_scale_map(const void* x, void* y, int B, int npix, int C, co
     if (B < 0 || C % 8 != 0 || npix <= 0) return -1;
     if (B == 0) return 0;
     if (x == nullptr || y == nullptr) return -2;
-    const size_t total_vec = static_cast<size_t>(B) * npix * (C / 8);
-    scale_map_kernel<<<grid_for(total_vec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), C, npix, total_vec, gate, attn, gamma);
+    const long long nvc = static_cast<long long>(npix) * (C / 8);
+    if (nvc > 0x7fffffff / 2 || B > 65535) return -3;
+    const unsigned chunks = static_cast<unsigned>((nvc + kScaleUnroll * 256 - 1) / (kScaleUnroll * 256));
+    scale_map_kernel<<<dim3(chunks, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), C, npix, gate, attn, gamma);
     return launch_status();
 }
 

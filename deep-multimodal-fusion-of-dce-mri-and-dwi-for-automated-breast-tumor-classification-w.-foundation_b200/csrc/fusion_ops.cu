@@ -302,45 +302,73 @@ fusion_core_kernel(const b200_fusion_weights wts, const float* __restrict__ pvec
     }
 }
 
-__global__ void fusion_mix_kernel(const __nv_bfloat16* __restrict__ p_dwi, const __nv_bfloat16* __restrict__ p_dce,
-                                  const float* __restrict__ gating, const float* __restrict__ lowres,
-                                  const float* __restrict__ gate, int H, int W, int C, int Hp, int Wp,
-                                  size_t total_vec, __nv_bfloat16* __restrict__ out) {
-    const int cv = C >> 3;
+// grid (chunks, B), 32-bit index arithmetic; a thread handles kMixUnroll vectors (8 channels of one pixel each) and
+// issues all its map loads before the first use.
+constexpr int kMixUnroll = 2;
+__global__ void __launch_bounds__(256)
+fusion_mix_kernel(const __nv_bfloat16* __restrict__ p_dwi, const __nv_bfloat16* __restrict__ p_dce,
+                  const float* __restrict__ gating, const float* __restrict__ lowres, const float* __restrict__ gate,
+                  int H, int W, int C, int Hp, int Wp, __nv_bfloat16* __restrict__ out) {
+    const int cv = C >> 3, nvc = H * W * cv, b = blockIdx.y;
     const float sh = static_cast<float>(Hp) / H, sw = static_cast<float>(Wp) / W;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total_vec;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>(i % cv) << 3;
-        const size_t bp = i / cv;
-        const int w = static_cast<int>(bp % W);
-        const int h = static_cast<int>((bp / W) % H);
-        const size_t b = bp / (static_cast<size_t>(W) * H);
-        const float a0 = gating[b * 2], a1 = gating[b * 2 + 1];
+    const size_t case_off = static_cast<size_t>(b) * nvc;
+    const uint4* xd = reinterpret_cast<const uint4*>(p_dwi) + case_off;
+    const uint4* xc = reinterpret_cast<const uint4*>(p_dce) + case_off;
+    uint4* ys = reinterpret_cast<uint4*>(out) + case_off;
+    const float a0 = gating[b * 2], a1 = gating[b * 2 + 1];
+    const float* low = lowres != nullptr ? lowres + static_cast<size_t>(b) * Hp * Wp * C : nullptr;
+    const int i0 = blockIdx.x * (kMixUnroll * blockDim.x) + threadIdx.x;
+    uint4 rd[kMixUnroll], rc[kMixUnroll];
+#pragma unroll
+    for (int u = 0; u < kMixUnroll; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < nvc) {
+            rd[u] = __ldcs(xd + i);
+            rc[u] = __ldcs(xc + i);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kMixUnroll; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i >= nvc) continue;
+        const int c0 = (i % cv) << 3, px = i / cv, w = px % W, h = px / W;
         float fd[8], fc[8], r[8];
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p_dwi) + i), fd);
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p_dce) + i), fc);
+        unpack_bf16x8(rd[u], fd);
+        unpack_bf16x8(rc[u], fc);
 #pragma unroll
         for (int k = 0; k < 8; ++k) r[k] = a0 * fd[k] + a1 * fc[k];
-        if (lowres != nullptr) {
+        if (low != nullptr) {
             // F.interpolate(mode='bilinear', align_corners=False) source coordinates
             const float sy = fmaxf((h + 0.5f) * sh - 0.5f, 0.f), sx = fmaxf((w + 0.5f) * sw - 0.5f, 0.f);
             const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
             const int y1 = min(y0 + 1, Hp - 1), x1 = min(x0 + 1, Wp - 1);
             const float ly = sy - y0, lx = sx - x0;
-            const float* base = lowres + b * Hp * Wp * C + c0;
+            const float* base = low + c0;
             const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
             const float* q00 = base + (y0 * Wp + x0) * C;
             const float* q01 = base + (y0 * Wp + x1) * C;
             const float* q10 = base + (y1 * Wp + x0) * C;
             const float* q11 = base + (y1 * Wp + x1) * C;
+            // 16-byte loads of the four taps (c0 is a multiple of 8 floats); same arithmetic order as before
 #pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] += w00 * q00[k] + w01 * q01[k] + w10 * q10[k] + w11 * q11[k];
+            for (int half = 0; half < 2; ++half) {
+                const float4 t00 = __ldg(reinterpret_cast<const float4*>(q00) + half);
+                const float4 t01 = __ldg(reinterpret_cast<const float4*>(q01) + half);
+                const float4 t10 = __ldg(reinterpret_cast<const float4*>(q10) + half);
+                const float4 t11 = __ldg(reinterpret_cast<const float4*>(q11) + half);
+                r[4 * half + 0] += w00 * t00.x + w01 * t01.x + w10 * t10.x + w11 * t11.x;
+                r[4 * half + 1] += w00 * t00.y + w01 * t01.y + w10 * t10.y + w11 * t11.y;
+                r[4 * half + 2] += w00 * t00.z + w01 * t01.z + w10 * t10.z + w11 * t11.z;
+                r[4 * half + 3] += w00 * t00.w + w01 * t01.w + w10 * t10.w + w11 * t11.w;
+            }
         }
         if (gate != nullptr) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] *= gate[b * C + c0 + k];
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(b) * C + c0));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(b) * C + c0) + 1);
+            r[0] *= g0.x; r[1] *= g0.y; r[2] *= g0.z; r[3] *= g0.w;
+            r[4] *= g1.x; r[5] *= g1.y; r[6] *= g1.z; r[7] *= g1.w;
         }
-        reinterpret_cast<uint4*>(out)[i] = pack_bf16x8(r);
+        ys[i] = pack_bf16x8(r);
     }
 }
 
@@ -402,11 +430,11 @@ extern "C" int b200_fusion_mix(const void* p_dwi, const void* p_dce, const float
     if (B < 0 || C % 8 != 0 || H <= 0 || W <= 0) return -1;
     if (B == 0) return 0;
     if (p_dwi == nullptr || p_dce == nullptr || gating == nullptr || out == nullptr) return -2;
-    const size_t total_vec = static_cast<size_t>(B) * H * W * (C / 8);
-    size_t g = (total_vec + 255) / 256;
-    if (g > 148 * 16) g = 148 * 16;
-    fusion_mix_kernel<<<static_cast<unsigned>(g), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    const long long nvc = static_cast<long long>(H) * W * (C / 8);
+    if (nvc > 0x7fffffff / 2 || B > 65535) return -3;
+    const unsigned chunks = static_cast<unsigned>((nvc + kMixUnroll * 256 - 1) / (kMixUnroll * 256));
+    fusion_mix_kernel<<<dim3(chunks, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(p_dwi), static_cast<const __nv_bfloat16*>(p_dce), gating, lowres, gate, H, W,
-        C, Hp, Wp, total_vec, static_cast<__nv_bfloat16*>(out));
+        C, Hp, Wp, static_cast<__nv_bfloat16*>(out));
     return launch_status();
 }
