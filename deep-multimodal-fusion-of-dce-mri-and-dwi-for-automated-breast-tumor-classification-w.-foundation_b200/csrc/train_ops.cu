@@ -683,18 +683,26 @@ mask_wsum_vec_kernel(const __nv_bfloat16* __restrict__ f3, const float* __restri
     for (int k = 0; k < 8; ++k) atomicAdd(s + static_cast<long long>(b) * Cin + vi * 8 + k, acc[k]);
 }
 
-__device__ __forceinline__ float dice_of(const float* __restrict__ logits, const float* __restrict__ target, int npix,
-                                         float eps, double* scratch) {
-    float si = 0.f, sp = 0.f, st = 0.f;
+__device__ __forceinline__ float bce_logits(float m, float t) {  // F.binary_cross_entropy_with_logits, one element
+    return fmaxf(m, 0.f) - m * t + log1pf(expf(-fabsf(m)));
+}
+
+// One case's mask loss: loss_type 0 = SoftDiceLoss (loss.py:45-62: eps in numerator and denominator),
+// 1 = DiceBCELoss(1, 1) (loss.py:11-43: mean BCE-with-logits + dice with eps in the denominator only).
+__device__ __forceinline__ float mask_loss_of(const float* __restrict__ logits, const float* __restrict__ target,
+                                              int npix, float eps, int loss_type, double* scratch) {
+    float si = 0.f, sp = 0.f, st = 0.f, sb = 0.f;
     for (int p = threadIdx.x; p < npix; p += blockDim.x) {
-        const float pr = sigmoidf_(logits[p]), t = target[p];
+        const float m = logits[p], pr = sigmoidf_(m), t = target[p];
         si = fmaf(pr, t, si);
         sp += pr;
         st += t;
+        if (loss_type == 1) sb += bce_logits(m, t);
     }
     const double I = block_sum<double>(si, scratch), P = block_sum<double>(sp, scratch),
-                 Tt = block_sum<double>(st, scratch);
-    return static_cast<float>((2.0 * I + eps) / (P + Tt + eps));
+                 Tt = block_sum<double>(st, scratch), Bc = block_sum<double>(sb, scratch);
+    const double num = 2.0 * I + (loss_type == 0 ? eps : 0.0);
+    return static_cast<float>(1.0 - num / (P + Tt + eps) + Bc / npix);
 }
 
 __global__ void __launch_bounds__(256)
@@ -703,7 +711,7 @@ mask_dice_kernel(const float* __restrict__ D_dwi, const float* __restrict__ D_dc
                  const float* __restrict__ out_w, const float* __restrict__ out_b, int mid,
                  const float* __restrict__ target, const float* __restrict__ enc_dwi,
                  const float* __restrict__ enc_dce, int H, int W, int Hp, int Wp, int C, float scale, float eps,
-                 float* __restrict__ m_out, float* __restrict__ dm_out, float* __restrict__ q_out,
+                 int loss_type, float* __restrict__ m_out, float* __restrict__ dm_out, float* __restrict__ q_out,
                  float* __restrict__ dc0_out, float* __restrict__ loss_out) {
     extern __shared__ float sm[];
     const int npix = H * W, T = Hp * Wp;
@@ -734,7 +742,7 @@ mask_dice_kernel(const float* __restrict__ D_dwi, const float* __restrict__ D_dc
     __syncthreads();
     const float a0 = gating[b * 2], a1 = gating[b * 2 + 1], c0 = s_c0;
     const float sh = static_cast<float>(Hp) / H, sw = static_cast<float>(Wp) / W;
-    float si = 0.f, sp = 0.f, st = 0.f;
+    float si = 0.f, sp = 0.f, st = 0.f, sb = 0.f;
     for (int p = tid; p < npix; p += blockDim.x) {
         const int h = p / W, w = p % W;
         // F.interpolate(mode='bilinear', align_corners=False) source coordinates (model_module.py:972-973)
@@ -751,16 +759,18 @@ mask_dice_kernel(const float* __restrict__ D_dwi, const float* __restrict__ D_dc
         si = fmaf(pr, t, si);
         sp += pr;
         st += t;
+        if (loss_type == 1) sb += bce_logits(m, t);
     }
     const double I = block_sum<double>(si, scratch), P = block_sum<double>(sp, scratch),
-                 Tt = block_sum<double>(st, scratch);
-    const double S = P + Tt + eps, num = 2.0 * I + eps;
-    const float dice = static_cast<float>(num / S);
+                 Tt = block_sum<double>(st, scratch), Bc = block_sum<double>(sb, scratch);
+    const double S = P + Tt + eps, num = 2.0 * I + (loss_type == 0 ? eps : 0.0);
+    const float own = static_cast<float>(1.0 - num / S + Bc / npix);  // this case's fused-mask loss
+    const float bce_g = loss_type == 1 ? scale / npix : 0.f;
     float sdm = 0.f;
     for (int p = tid; p < npix; p += blockDim.x) {
         const float pr = s_m[p], t = target[pb + p];
         // loss = scale * (1 - dice): d/dp = -scale * (2 t S - num) / S^2, then through the sigmoid
-        const float dm = -scale * static_cast<float>((2.0 * t * S - num) / (S * S)) * pr * (1.f - pr);
+        const float dm = -scale * static_cast<float>((2.0 * t * S - num) / (S * S)) * pr * (1.f - pr) + bce_g * (pr - t);
         dm_out[pb + p] = dm;
         sdm += dm;
         const int h = p / W, w = p % W;
@@ -775,13 +785,13 @@ mask_dice_kernel(const float* __restrict__ D_dwi, const float* __restrict__ D_dc
     }
     const float tot = static_cast<float>(block_sum<double>(sdm, scratch));
     float extra = 0.f;  // the encoder masks' dice terms: constants for the head, part of the reported loss
-    if (enc_dwi != nullptr) extra += 1.0f - dice_of(enc_dwi + pb, target + pb, npix, eps, scratch);
-    if (enc_dce != nullptr) extra += 1.0f - dice_of(enc_dce + pb, target + pb, npix, eps, scratch);
+    if (enc_dwi != nullptr) extra += mask_loss_of(enc_dwi + pb, target + pb, npix, eps, loss_type, scratch);
+    if (enc_dce != nullptr) extra += mask_loss_of(enc_dce + pb, target + pb, npix, eps, loss_type, scratch);
     __syncthreads();
     for (int t = tid; t < T; t += blockDim.x) q_out[b * T + t] = s_q[t];
     if (tid == 0) {
         atomicAdd(dc0_out, tot);
-        atomicAdd(loss_out, scale * ((1.0f - dice) + extra));
+        atomicAdd(loss_out, scale * (own + extra));
     }
 }
 
@@ -1016,8 +1026,10 @@ extern "C" int b200_mask_wsum(const void* f3, const float* dm, int B, int npix, 
 extern "C" int b200_mask_dice(const float* D_dwi, const float* D_dce, const float* gating, const float* u,
                               const float* lowres, const float* pre_b, const float* out_w, const float* out_b,
                               int mid, const float* target, const float* enc_mask_dwi, const float* enc_mask_dce,
-                              int B, int H, int W, int Hp, int Wp, int C, float scale, float eps, float* m_out,
-                              float* dm_out, float* q_out, float* dc0_out, float* loss_out, void* stream) {
+                              int B, int H, int W, int Hp, int Wp, int C, float scale, float eps, int loss_type,
+                              float* m_out, float* dm_out, float* q_out, float* dc0_out, float* loss_out,
+                              void* stream) {
+    if (loss_type != 0 && loss_type != 1) return -1;
     if (B < 0 || H <= 0 || W <= 0 || Hp <= 0 || Wp <= 0 || C <= 0 || mid <= 0 || H * W > 8192 || Hp * Wp > 64) return -1;
     if (B == 0) return 0;
     if (D_dwi == nullptr || D_dce == nullptr || gating == nullptr || u == nullptr || pre_b == nullptr ||
@@ -1027,7 +1039,7 @@ extern "C" int b200_mask_dice(const float* D_dwi, const float* D_dce, const floa
     const size_t smem = (static_cast<size_t>(H) * W + 2 * Hp * Wp) * sizeof(float);
     mask_dice_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(
         D_dwi, D_dce, gating, u, lowres, pre_b, out_w, out_b, mid, target, enc_mask_dwi, enc_mask_dce, H, W, Hp, Wp, C,
-        scale, eps, m_out, dm_out, q_out, dc0_out, loss_out);
+        scale, eps, loss_type, m_out, dm_out, q_out, dc0_out, loss_out);
     return launch_status();
 }
 

@@ -84,7 +84,7 @@ class FusionHeadTrainer:
     Soft(Weighted)FocalLoss (code/selector_helpers.py:14-46)."""
 
     def __init__(self, fusion_model, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=4e-5, smoothing=0.1,
-                 gamma=1.5, class_weights=None, lambda_mask=0.0, process_group=None):
+                 gamma=1.5, class_weights=None, lambda_mask=0.0, mask_loss_type="dice", process_group=None):
         fm = fusion_model
         if not fm.use_cross_attention:
             raise NotImplementedError("fusion-head training without the cross-attention block is not built")
@@ -97,7 +97,10 @@ class FusionHeadTrainer:
         self.lr, self.betas, self.eps, self.weight_decay = lr, tuple(betas), eps, weight_decay
         self.smoothing, self.gamma = float(smoothing), float(gamma)
         self.class_weights = class_weights
-        self.lambda_mask = float(lambda_mask)  # > 0: + lambda_mask * mean of the three mask dice terms
+        self.lambda_mask = float(lambda_mask)  # > 0: + lambda_mask * mean of the three mask loss terms
+        if mask_loss_type not in ("dice", "dice_bce"):  # mask_criterion_selector, code/selector_helpers.py:95-114
+            raise ValueError(f"Invalid mask loss: {mask_loss_type}")
+        self.mask_loss_type = mask_loss_type
         self.group = process_group
         self.step_count = 0
         ca = fm.cross_attn_block
@@ -313,8 +316,8 @@ class FusionHeadTrainer:
                 raise ValueError("the mask term needs both encoder mask predictions at the mask size "
                                  "(train_fusion.py:249-251)")
             nat.mask_dice(ws["Dd"], ws["Dc"], ws["gating"], ws["u"], ws["LOW"], pre_b, out_w, out_b, tgt, md, mc,
-                          H, W, hp, wp, self.lambda_mask / (3.0 * B), 1e-6, ws["m"], ws["dm"], ws["q"], ws["dv"][C:],
-                          loss)
+                          H, W, hp, wp, self.lambda_mask / (3.0 * B), 1e-6, int(self.mask_loss_type == "dice_bce"),
+                          ws["m"], ws["dm"], ws["q"], ws["dv"][C:], loss)
             nat.mask_wsum(f3d, ws["dm"], ws["sd"])                # third pass: dmask-weighted pixel sums
             nat.mask_wsum(f3c, ws["dm"], ws["sc"])
             nat.sgemm(ws["sd"], Wd, ws["tmpd"], trans_b=True)

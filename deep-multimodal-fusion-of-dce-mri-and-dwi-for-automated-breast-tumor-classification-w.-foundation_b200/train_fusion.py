@@ -163,8 +163,8 @@ class LightningFusionModel(nn.Module):
         fp = self.parameters_dict.get("fusion_model_parameters", {})
         on = [what for key, what in self._UNBUILT_TERMS if fp.get(key, False)]
         mp = fp.get("mask_parameters", {})
-        if mp.get("mask", False) and mp.get("lambda_mask", 0.0) and mp.get("mask_loss_type", "dice") != "dice":
-            on.append("mask loss type dice_bce (loss.py:11-43; only 'dice' is built)")
+        if mp.get("mask", False) and mp.get("mask_loss_type", "dice") not in ("dice", "dice_bce"):
+            raise ValueError(f"Invalid mask loss: {mp.get('mask_loss_type')}")  # selector_helpers.py:109
         if on:
             raise NotImplementedError(
                 "loss terms not built in the B200 training step: " + "; ".join(on) + " - disable them or set "
@@ -190,7 +190,8 @@ class LightningFusionModel(nn.Module):
             self.fusion_model, lr=op.get("lr", 1e-4), betas=op.get("betas", (0.9, 0.999)), eps=op.get("eps", 1e-8),
             weight_decay=op.get("weight_decay", 4e-5), smoothing=fp.get("label_smoothing_alpha", 0.1),
             gamma=2 if gamma is None else gamma, class_weights=getattr(self, "_class_weights", None),
-            lambda_mask=self._lambda_mask())
+            lambda_mask=self._lambda_mask(),
+            mask_loss_type=fp.get("mask_parameters", {}).get("mask_loss_type", "dice"))
         return self.head_trainer
 
     def set_class_weights(self, train_labels):

@@ -28,7 +28,7 @@ HP = {"n": 8, "seed": 11, "smoothing": 0.1, "gamma": 1.5, "class_weights": [0.7,
       "betas": [0.9, 0.999], "eps": 1e-8, "weight_decay": 1e-2, "steps": 3, "weight_seed": 7}
 
 
-def main(lambda_mask=0.0, out_name="train_head.npz"):
+def main(lambda_mask=0.0, out_name="train_head.npz", mask_loss_type="dice"):
     import loss as ref_loss
     import model_module as mm
 
@@ -43,7 +43,7 @@ def main(lambda_mask=0.0, out_name="train_head.npz"):
     opt = torch.optim.AdamW(model.parameters(), lr=HP["lr"], betas=tuple(HP["betas"]), eps=HP["eps"],
                             weight_decay=HP["weight_decay"], amsgrad=False)
     masks = op.synthetic_raw(HP["n"], seed=HP["seed"] + 1, kind="S")[2]  # [n,1,32,32] in {0,1}
-    dice = ref_loss.SoftDiceLoss()
+    dice = ref_loss.SoftDiceLoss() if mask_loss_type == "dice" else ref_loss.DiceBCELoss(bce_weight=1.0, dice_weight=1.0)
     before = {k: v.detach().clone() for k, v in model.named_parameters()}
     out, losses = {}, []
     for it in range(HP["steps"]):
@@ -66,7 +66,7 @@ def main(lambda_mask=0.0, out_name="train_head.npz"):
         if k in updated:
             mg.flatten(f"param/{k}", v, out)
     out["losses"] = np.array(losses, dtype=np.float64)
-    out["hp"] = np.array(json.dumps(dict(HP, updated=updated, lambda_mask=lambda_mask)))
+    out["hp"] = np.array(json.dumps(dict(HP, updated=updated, lambda_mask=lambda_mask, mask_loss_type=mask_loss_type)))
     np.savez_compressed(os.path.join(mg.GOLD, out_name), **out)
     print("losses", losses)
     print("updated", len(updated), "parameters:", updated)
@@ -75,3 +75,4 @@ def main(lambda_mask=0.0, out_name="train_head.npz"):
 if __name__ == "__main__":
     main()
     main(lambda_mask=0.2, out_name="train_head_mask.npz")
+    main(lambda_mask=0.2, out_name="train_head_mask_bce.npz", mask_loss_type="dice_bce")

@@ -50,8 +50,17 @@ def soft_dice_loss(logits, targets, eps=1e-6):
     return 1.0 - ((2.0 * inter + eps) / (union + eps)).mean()
 
 
+def dice_bce_loss(logits, targets, eps=1e-6):
+    """DiceBCELoss(bce_weight=1, dice_weight=1), loss.py:11-43."""
+    bce = F.binary_cross_entropy_with_logits(logits, targets)
+    p = torch.sigmoid(logits).flatten(1)
+    t = targets.flatten(1)
+    dice = (2.0 * (p * t).sum(1)) / (p.sum(1) + t.sum(1) + eps)
+    return bce + (1.0 - dice.mean())
+
+
 def head_loss_and_grads(sd, params, f3_dwi, f3_dce, mask_dwi, mask_dce, labels, smoothing, gamma, class_weights=None,
-                        masks=None, lambda_mask=0.0):
+                        masks=None, lambda_mask=0.0, mask_loss_type="dice"):
     """-> (loss, logits, {name: grad}) for every fusion-head parameter that receives a gradient.  With lambda_mask > 0
     the mask term of train_fusion.py:245-255 is added: lambda_mask * mean of the dice losses of the two encoder masks
     (constants here) and the fused mask."""
@@ -63,8 +72,8 @@ def head_loss_and_grads(sd, params, f3_dwi, f3_dce, mask_dwi, mask_dce, labels, 
     targets = smoothed_targets(labels, logits.shape[1], smoothing)
     loss = soft_focal_loss(logits, targets, gamma, class_weights)
     if lambda_mask > 0:
-        loss = loss + lambda_mask * (soft_dice_loss(mask_dwi, masks) + soft_dice_loss(mask_dce, masks) +
-                                     soft_dice_loss(fused_mask, masks)) / 3
+        crit = soft_dice_loss if mask_loss_type == "dice" else dice_bce_loss  # selector_helpers.py:103-106
+        loss = loss + lambda_mask * (crit(mask_dwi, masks) + crit(mask_dce, masks) + crit(fused_mask, masks)) / 3
     loss.backward()
     grads = {k: v.grad for k, v in leaf.items() if is_param(k, v) and v.grad is not None}
     return loss.detach(), logits.detach(), grads
@@ -82,13 +91,14 @@ def adamw_step(p, g, m, v, step, lr, betas, eps, weight_decay):
 
 
 def train_steps(sd, params, batch, steps, smoothing, gamma, class_weights, lr, betas, eps, weight_decay, masks=None,
-                lambda_mask=0.0):
+                lambda_mask=0.0, mask_loss_type="dice"):
     """`steps` AdamW steps on one batch.  -> (losses, final state dict, names that were updated)."""
     sd = {k: v.clone() for k, v in sd.items()}
     state = {}
     losses, names = [], []
     for it in range(1, steps + 1):
-        loss, _, grads = head_loss_and_grads(sd, params, *batch, smoothing, gamma, class_weights, masks, lambda_mask)
+        loss, _, grads = head_loss_and_grads(sd, params, *batch, smoothing, gamma, class_weights, masks, lambda_mask,
+                                             mask_loss_type)
         losses.append(float(loss))
         names = sorted(grads)
         for k, g in grads.items():

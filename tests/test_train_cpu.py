@@ -71,19 +71,22 @@ def test_oracle_adamw_steps_match_the_reference():
     assert untouched and all(torch.equal(sd[k], new_sd[k]) for k in untouched)
 
 
-def test_oracle_mask_term_matches_the_reference():
-    """classification + lambda_mask * mean of three dice terms (train_fusion.py:238-255): 24 tensors get a gradient."""
-    gold, hp, params, sd, batch = _setup("train_head_mask.npz")
+@pytest.mark.parametrize("fixture", ["train_head_mask.npz", "train_head_mask_bce.npz"])
+def test_oracle_mask_term_matches_the_reference(fixture):
+    """classification + lambda_mask * mean of three mask terms (train_fusion.py:238-255; SoftDiceLoss or DiceBCELoss,
+    selector_helpers.py:95-114): 24 tensors get a gradient."""
+    gold, hp, params, sd, batch = _setup(fixture)
     masks = op.synthetic_raw(hp["n"], seed=hp["seed"] + 1, kind="S")[2]
     cw = torch.tensor(hp["class_weights"])
     loss, logits, grads = to.head_loss_and_grads(sd, params, *batch, hp["smoothing"], hp["gamma"], cw, masks,
-                                                 hp["lambda_mask"])
+                                                 hp["lambda_mask"], hp["mask_loss_type"])
     assert abs(float(loss) - gold["losses"][0]) <= 1e-5 * abs(gold["losses"][0])
     assert sorted(grads) == sorted(hp["updated"]) and len(grads) == 24
     for k in grads:
         gu.check(gold, f"grad/{k}", grads[k], 2e-4, what="gradient ")
     losses, new_sd, names = to.train_steps(sd, params, batch, hp["steps"], hp["smoothing"], hp["gamma"], cw, hp["lr"],
-                                           tuple(hp["betas"]), hp["eps"], hp["weight_decay"], masks, hp["lambda_mask"])
+                                           tuple(hp["betas"]), hp["eps"], hp["weight_decay"], masks, hp["lambda_mask"],
+                                           hp["mask_loss_type"])
     for a, b in zip(losses, gold["losses"]):
         assert abs(a - b) <= 2e-4 * abs(b)
     for k in names:

@@ -201,19 +201,20 @@ def test_head_step_matches_reference_fixture_and_oracle():
             assert torch.equal(t.cpu(), sd[name]), name
 
 
-def test_mask_dice_term_matches_reference_fixture_and_oracle():
-    """classification + mask dice terms (train_fusion.py:238-255): loss, fused mask logits, all 24 gradients and the
-    three-step trajectory against the reference fixture and the oracle."""
+@pytest.mark.parametrize("fixture", ["train_head_mask.npz", "train_head_mask_bce.npz"])
+def test_mask_dice_term_matches_reference_fixture_and_oracle(fixture):
+    """classification + mask terms (train_fusion.py:238-255; "dice" and "dice_bce" mask losses): loss, fused mask
+    logits, all 24 gradients and the three-step trajectory against the reference fixture and the oracle."""
     from fusion_train import FusionHeadTrainer
 
-    gold = gu.load("train_head_mask.npz")
+    gold = gu.load(fixture)
     hp = json.loads(str(gold["hp"]))
     params, fm, sd = _head(hp["weight_seed"])
     batch = op.synthetic_head_batch(hp["n"], seed=hp["seed"])
     masks = op.synthetic_raw(hp["n"], seed=hp["seed"] + 1, kind="S")[2]
     tr = FusionHeadTrainer(fm, lr=hp["lr"], betas=hp["betas"], eps=hp["eps"], weight_decay=hp["weight_decay"],
                            smoothing=hp["smoothing"], gamma=hp["gamma"], class_weights=hp["class_weights"],
-                           lambda_mask=hp["lambda_mask"])
+                           lambda_mask=hp["lambda_mask"], mask_loss_type=hp["mask_loss_type"])
     assert sorted(tr.names) == sorted(hp["updated"]) and len(tr.names) == 24
     dbatch = _to_dev(batch)
     tr.zero_grad()
@@ -222,7 +223,8 @@ def test_mask_dice_term_matches_reference_fixture_and_oracle():
     gu.check(gold, "logits", logits, 2e-5)
     gu.check(gold, "fused_mask", tr.fused_mask_logits, 1e-4)
     _, _, o_grads = to.head_loss_and_grads(sd, params, *batch, hp["smoothing"], hp["gamma"],
-                                           torch.tensor(hp["class_weights"]), masks, hp["lambda_mask"])
+                                           torch.tensor(hp["class_weights"]), masks, hp["lambda_mask"],
+                                           hp["mask_loss_type"])
     for name, g in zip(tr.names, tr.grads):
         scale = o_grads[name].abs().max().item()
         assert (g.cpu() - o_grads[name]).abs().max().item() <= 2e-4 * scale + 1e-8, name
