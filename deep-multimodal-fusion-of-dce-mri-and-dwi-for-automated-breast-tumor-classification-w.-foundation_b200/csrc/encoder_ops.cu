@@ -419,24 +419,32 @@ __global__ void mask_tail_kernel(const __nv_bfloat16* __restrict__ pre, int Cm, 
 // ----------------------------------------------- 1 -> C pointwise lift -----
 // First layer of Projector(1, proj_dim) (model_module.py:338-340) on a 1-channel fp32
 // map: y[p, n] = gelu(r[p] * w[n] * scale[n] + bias[n]) as NHWC bf16.
-__global__ void lift_c1_kernel(const float* __restrict__ r, size_t total_pix, int N, const float* __restrict__ w,
-                               const float* __restrict__ scale, const float* __restrict__ bias,
-                               __nv_bfloat16* __restrict__ y) {
+// A thread keeps its 8 output channels' folded weights in registers and walks pixels (blockDim / nv pixels per CTA
+// trip), 32-bit indices; requires blockDim % nv == 0.
+__global__ void __launch_bounds__(256)
+lift_c1_kernel(const float* __restrict__ r, int total_pix, int N, const float* __restrict__ w,
+               const float* __restrict__ scale, const float* __restrict__ bias, __nv_bfloat16* __restrict__ y) {
     const int nv = N >> 3;
-    const size_t total = total_pix * nv;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int n0 = static_cast<int>(i % nv) << 3;
-        const float rv = r[i / nv];
+    const int vi = threadIdx.x % nv, pl = threadIdx.x / nv, ppb = blockDim.x / nv;
+    const int n0 = vi << 3;
+    float wr[8], sr[8], bs[8];  // ((r * w) * scale) + bias keeps the rounding order of the unfolded form
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        wr[k] = w[n0 + k];
+        sr[k] = scale[n0 + k];
+        bs[k] = bias[n0 + k];
+    }
+    uint4* out = reinterpret_cast<uint4*>(y);
+    for (int p = blockIdx.x * ppb + pl; p < total_pix; p += gridDim.x * ppb) {
+        const float rv = __ldg(r + p);
         float f[8];
 #pragma unroll
         for (int k = 0; k < 8; k += 2) {
-            const float2 g = gelu_poly2(make_float2(rv * w[n0 + k] * scale[n0 + k] + bias[n0 + k],
-                                                    rv * w[n0 + k + 1] * scale[n0 + k + 1] + bias[n0 + k + 1]));
+            const float2 g = gelu_poly2(make_float2(rv * wr[k] * sr[k] + bs[k], rv * wr[k + 1] * sr[k + 1] + bs[k + 1]));
             f[k] = g.x;
             f[k + 1] = g.y;
         }
-        reinterpret_cast<uint4*>(y)[i] = pack_bf16x8(f);
+        out[static_cast<size_t>(p) * nv + vi] = pack_bf16x8(f);
     }
 }
 
@@ -615,12 +623,14 @@ extern "C" int b200_resize_bilinear_c1(const float* in, int B, int h, int w, flo
 
 extern "C" int b200_lift_c1(const float* r, long long total_pix, int N, const float* w, const float* scale,
                             const float* bias, void* y, void* stream) {
-    if (total_pix < 0 || N % 8 != 0) return -1;
+    if (total_pix < 0 || N <= 0 || N % 8 != 0 || N > 2048 || total_pix > 0x7fffffffLL) return -1;
     if (total_pix == 0) return 0;
     if (r == nullptr || w == nullptr || scale == nullptr || bias == nullptr || y == nullptr) return -2;
-    lift_c1_kernel<<<grid_for(static_cast<size_t>(total_pix) * (N / 8), 256), 256, 0,
-                     static_cast<cudaStream_t>(stream)>>>(r, static_cast<size_t>(total_pix), N, w, scale, bias,
-                                                          static_cast<__nv_bfloat16*>(y));
+    const int nv = N / 8, threads = nv * (256 / nv), ppb = threads / nv;
+    long long blocks = (total_pix + ppb - 1) / ppb;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    lift_c1_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        r, static_cast<int>(total_pix), N, w, scale, bias, static_cast<__nv_bfloat16*>(y));
     return launch_status();
 }
 
