@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 _lib = None
 
@@ -81,6 +81,7 @@ class HeadTrain(C.Structure):
         ("forward_only", C.c_int), ("mask_v", C.c_void_p), ("mk_tmpd", C.c_void_p), ("mk_tmpc", C.c_void_p),
         ("mk_q", C.c_void_p), ("gate_out", C.c_void_p), ("u_out", C.c_void_p), ("dug_out", C.c_void_p),
         ("aud_out", C.c_void_p), ("auc_out", C.c_void_p),
+        ("pvec_dwi", C.c_void_p), ("pvec_dce", C.c_void_p), ("pvec_scale", C.c_float),
     ]
 
 

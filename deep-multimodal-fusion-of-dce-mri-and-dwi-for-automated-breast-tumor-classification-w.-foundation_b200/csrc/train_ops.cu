@@ -360,7 +360,14 @@ __global__ void __launch_bounds__(128) head_loss_kernel(const b200_head_train a)
     const long long tokbase = static_cast<long long>(b) * T * C;
     const float invT = 1.0f / T;
 
+    const bool given_pvec = a.pvec_dwi != nullptr && a.pvec_dce != nullptr;
+    const float pscale = given_pvec ? a.pvec_scale : invT;  // factor on the pooled-vector gradients
     for (int c = tid; c < C; c += blockDim.x) {
+        if (given_pvec) {
+            s_pd[c] = a.pvec_dwi[static_cast<long long>(b) * C + c] * a.pvec_scale;
+            s_pc[c] = a.pvec_dce[static_cast<long long>(b) * C + c] * a.pvec_scale;
+            continue;
+        }
         float sd = 0.f, sc = 0.f;
         for (int t = 0; t < T; ++t) {
             sd += a.tok_dwi[tokbase + t * C + c];
@@ -560,9 +567,9 @@ __global__ void __launch_bounds__(128) head_loss_kernel(const b200_head_train a)
     for (int c = tid; c < C; c += blockDim.x) {
         const float dgf = s_dgf[c];
         a.dpd_out[static_cast<long long>(b) * C + c] =
-            (al0 * dgf + a.gate_w[c] * dgl0 + a.gate_w[in_dim + c] * dgl1) * invT;
+            (al0 * dgf + a.gate_w[c] * dgl0 + a.gate_w[in_dim + c] * dgl1) * pscale;
         a.dpc_out[static_cast<long long>(b) * C + c] =
-            (al1 * dgf + a.gate_w[C + c] * dgl0 + a.gate_w[in_dim + C + c] * dgl1) * invT;
+            (al1 * dgf + a.gate_w[C + c] * dgl0 + a.gate_w[in_dim + C + c] * dgl1) * pscale;
         if (a.dlowres_out != nullptr) {
             const float u = mask_term ? a.mask_v[c] * s_g[c] : 0.f;
             for (int t = 0; t < T; ++t)

@@ -220,8 +220,9 @@ class FusionHeadTrainer:
         if f3c.shape[:3] != f3d.shape[:3]:
             raise ValueError("the two encoders' maps must have the same batch and spatial size")
         hp, wp = fm.token_pool
-        if H % hp or W % wp:
-            raise NotImplementedError("token pooling with unequal bins (map size not a multiple of token_pool)")
+        # equal bins: GAP(p) is the mean of the tokens.  Otherwise (14 x 14 ViT maps -> 4 x 4 overlapping bins) the
+        # pooled vectors get their own pass over the maps (per-case channel sums) and their own projection.
+        gap_rows = bool(H % hp or W % wp)
         if fm.use_mask_attention and (dwi_mask_pred is None or dce_mask_pred is None):
             raise RuntimeError("use_mask_attention needs both encoder mask predictions")
         T, C, NH = hp * wp, fm.fusion_channels, fm.mha_heads
@@ -251,6 +252,15 @@ class FusionHeadTrainer:
         nat.fusion_tokens(f3c, hp, wp, ws["Xc"])
         nat.sgemm(ws["Xd"], Wd, ws["Td"], trans_b=True)
         nat.sgemm(ws["Xc"], Wc, ws["Tc"], trans_b=True)
+        if gap_rows:
+            for k in ("Gd", "Gc", "Pd", "Pc"):
+                if k not in ws:
+                    ws[k] = torch.empty((B, fm.dwi_ch if k == "Gd" else fm.dce_ch if k == "Gc" else C),
+                                        dtype=torch.float32, device=f3d.device)
+            nat.channel_sums(f3d, ws["Gd"])
+            nat.channel_sums(f3c, ws["Gc"])
+            nat.sgemm(ws["Gd"], Wd, ws["Pd"], trans_b=True)
+            nat.sgemm(ws["Gc"], Wc, ws["Pc"], trans_b=True)
         nat.sgemm(ws["Td"], Win[:C], ws["Q"], trans_b=True, bias=b_in[:C])
         nat.sgemm(ws["Tc"], Win[C:], ws["KV"], trans_b=True, bias=b_in[C:])
         Kt, Vt = ws["KV"][:, :C], ws["KV"][:, C:]
@@ -274,6 +284,8 @@ class FusionHeadTrainer:
         if flat["cw"] is not None:
             a.class_weights = ptr(flat["cw"])
         a.tok_dwi, a.tok_dce, a.lowres = ptr(ws["Td"]), ptr(ws["Tc"]), ptr(ws["LOW"])
+        if gap_rows:
+            a.pvec_dwi, a.pvec_dce, a.pvec_scale = ptr(ws["Pd"]), ptr(ws["Pc"]), 1.0 / (H * W)
         md = dwi_mask_pred.contiguous().float() if dwi_mask_pred is not None else None
         mc = dce_mask_pred.contiguous().float() if dce_mask_pred is not None else None
         if fm.use_mask_attention:
@@ -371,8 +383,14 @@ class FusionHeadTrainer:
         bgrad(ws["dQ"], ca + "cross_attn.in_proj_bias", q_rows)
         wgrad(ws["dKV"], ws["Tc"], ca + "cross_attn.in_proj_weight", kv_rows)
         bgrad(ws["dKV"], ca + "cross_attn.in_proj_bias", kv_rows)
-        nat.sgemm(ws["dQ"], Win[:C], ws["dTd"], res=ws["dpd"], res_div=T)
-        nat.sgemm(ws["dKV"], Win[C:], ws["dTc"], res=ws["dpc"], res_div=T)
+        if gap_rows:  # the pooled vectors' gradients reach proj_in_* through the channel sums, not the tokens
+            nat.sgemm(ws["dQ"], Win[:C], ws["dTd"])
+            nat.sgemm(ws["dKV"], Win[C:], ws["dTc"])
+            wgrad(ws["dpd"], ws["Gd"], "proj_in_dwi.weight")
+            wgrad(ws["dpc"], ws["Gc"], "proj_in_dce.weight")
+        else:
+            nat.sgemm(ws["dQ"], Win[:C], ws["dTd"], res=ws["dpd"], res_div=T)
+            nat.sgemm(ws["dKV"], Win[C:], ws["dTc"], res=ws["dpc"], res_div=T)
         wgrad(ws["dTd"], ws["Xd"], "proj_in_dwi.weight")
         wgrad(ws["dTc"], ws["Xc"], "proj_in_dce.weight")
         if use_mask_term:  # the full-resolution path of the mask logits into proj_in_*

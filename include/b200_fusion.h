@@ -434,6 +434,11 @@ typedef struct b200_head_train {
     float* dug_out;             /* [B,C] (gradient of u) * gate -> column sums = gradient of v */
     float* aud_out;             /* [B,C] alpha_dwi * u -> proj_in_dwi weight gradient with s_dwi */
     float* auc_out;             /* [B,C] alpha_dce * u */
+    /* --- pooled vectors given explicitly (token bins that overlap / differ in size: GAP(p) is then NOT the mean of
+     * the tokens).  NULL: pooled vector = mean of the tokens, and dpd / dpc come back divided by T. --- */
+    const float* pvec_dwi;      /* [B,C] proj_in applied to the per-case channel SUMS of f3 */
+    const float* pvec_dce;
+    float pvec_scale;           /* 1 / pixels; dpd / dpc then come back multiplied by it (gradient w.r.t. the sums) */
 } b200_head_train;
 
 /* FusionModel.forward tail (code/model_module.py:942-986: gating :952-958, GAP of the fused map, fusion_se :977,

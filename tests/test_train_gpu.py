@@ -269,6 +269,34 @@ def test_odd_batch_sizes_match_the_oracle(n):
         tr.loss_and_grads(*empty, masks[:0].to(DEV))
 
 
+def test_vit_geometry_with_overlapping_token_bins_matches_the_oracle():
+    """768-channel 14 x 14 maps (the ViT-B/16 encoders, C4): adaptive 4 x 4 pooling has overlapping bins, so GAP(p) is
+    not the mean of the tokens - the pooled vectors take their own pass (channel sums) and projection."""
+    import model_module as mm
+    import parameters_default as pd
+    from fusion_train import FusionHeadTrainer
+
+    params = pd.default_parameters()
+    fs = params["fusion_model_parameters"]["fusion_specific_parameters"]
+    fs["dwi_out_channels"] = fs["dce_out_channels"] = 768
+    fm = mm.FusionModel(params)
+    sd = op.seeded_state_dict(op.shapes_of(fm.state_dict()), seed=9)
+    fm.load_state_dict(sd)
+    fm.to(DEV).eval()
+    batch = op.synthetic_head_batch(5, seed=55, channels=768, size=14)
+    tr = FusionHeadTrainer(fm, smoothing=0.1, gamma=1.5, class_weights=[1.2, 0.8, 1.0, 1.1])
+    tr.zero_grad()
+    loss, logits = tr.loss_and_grads(*_to_dev(batch))
+    o_loss, o_logits, o_grads = to.head_loss_and_grads(sd, params, *batch, 0.1, 1.5, torch.tensor([1.2, 0.8, 1.0, 1.1]))
+    assert abs(loss.item() - float(o_loss)) <= 2e-5 * abs(float(o_loss))
+    assert _rel(logits.cpu(), o_logits) < 2e-5
+    for name, g in zip(tr.names, tr.grads):
+        scale = o_grads[name].abs().max().item()
+        assert (g.cpu() - o_grads[name]).abs().max().item() <= 2e-4 * scale + 1e-8, name
+    with pytest.raises(NotImplementedError):   # the mask term needs maps of the mask size
+        FusionHeadTrainer(fm, lambda_mask=0.2).loss_and_grads(*_to_dev(batch), torch.zeros(5, 1, 14, 14, device=DEV))
+
+
 def test_larger_batch_gradients_match_oracle_and_training_reduces_the_loss():
     from fusion_train import FusionHeadTrainer
 
