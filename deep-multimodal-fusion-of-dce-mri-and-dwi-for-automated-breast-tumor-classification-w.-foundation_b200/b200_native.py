@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 _lib = None
 
@@ -136,8 +136,8 @@ SIGNATURES = {
     "b200_head_loss": [C.POINTER(HeadTrain), _I, _P],
     "b200_adamw": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P],
     "b200_mask_dot": [_P, _P, _I, _I, _I, _P, _P],
-    "b200_mask_dice": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P,
-                       _P, _P, _P],
+    "b200_mask_dice": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P,
+                       _P, _P, _P, _P, _P],
     "b200_mask_wsum": [_P, _P, _I, _I, _I, _P, _P],
     "b200_mask_head_grads": [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
 }
@@ -654,11 +654,11 @@ def mask_wsum(f3, dm, out):
     return out
 
 
-def mask_dice(D_dwi, D_dce, gating, u, lowres, pre_b, out_w, out_b, target, enc_dwi, enc_dce, H, W, hp, wp, scale,
-              eps, loss_type, m_out, dm_out, q_out, dc0_out, loss_out):
+def mask_dice(D_dwi, D_dce, gating, u, lowres, pre_b, out_w, out_b, target, enc_dwi, enc_dce, H, W, Ho, Wo, hp, wp,
+              scale, eps, loss_type, m_out, dm_out, q_out, dc0_out, loss_out):
     B, C_ = u.shape
     _call("b200_mask_dice", None, _ptr(D_dwi), _ptr(D_dce), _ptr(gating), _ptr(u), _ptr(lowres), _ptr(pre_b),
-          _ptr(out_w), _ptr(out_b), pre_b.numel(), _ptr(target), _ptr(enc_dwi), _ptr(enc_dce), B, H, W, hp, wp, C_,
+          _ptr(out_w), _ptr(out_b), pre_b.numel(), _ptr(target), _ptr(enc_dwi), _ptr(enc_dce), B, H, W, Ho, Wo, hp, wp, C_,
           float(scale), float(eps), int(loss_type), _ptr(m_out), _ptr(dm_out), _ptr(q_out), _ptr(dc0_out), _ptr(loss_out), _stream())
 
 

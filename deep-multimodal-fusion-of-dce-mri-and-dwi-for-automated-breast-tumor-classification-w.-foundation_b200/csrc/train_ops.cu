@@ -712,23 +712,37 @@ __device__ __forceinline__ float mask_loss_of(const float* __restrict__ logits, 
     return static_cast<float>(1.0 - num / (P + Tt + eps) + Bc / npix);
 }
 
+// bilinear source taps of F.interpolate(align_corners=False): n_in -> n_out along one axis
+__device__ __forceinline__ void bilinear_taps(int o, int n_in, float ratio, int& i0, int& i1, float& lam) {
+    const float s = fmaxf((o + 0.5f) * ratio - 0.5f, 0.f);
+    i0 = min(static_cast<int>(s), n_in - 1);
+    i1 = min(i0 + 1, n_in - 1);
+    lam = s - i0;
+}
+
+// One CTA per case.  Map resolution H x W (D_*, dm_out), mask resolution Ho x Wo (target, encoder masks, m_out).
+// Ho x Wo != H x W is MaskHeadResize's interpolation dispatch (code/model_module.py:197-211): pre -> bilinear resize ->
+// out, still linear, = bilinear resize of the map-resolution logit; its gradient returns through the transposed resize.
 __global__ void __launch_bounds__(256)
 mask_dice_kernel(const float* __restrict__ D_dwi, const float* __restrict__ D_dce, const float* __restrict__ gating,
                  const float* __restrict__ u, const float* __restrict__ lowres, const float* __restrict__ pre_b,
                  const float* __restrict__ out_w, const float* __restrict__ out_b, int mid,
                  const float* __restrict__ target, const float* __restrict__ enc_dwi,
-                 const float* __restrict__ enc_dce, int H, int W, int Hp, int Wp, int C, float scale, float eps,
-                 int loss_type, float* __restrict__ m_out, float* __restrict__ dm_out, float* __restrict__ q_out,
-                 float* __restrict__ dc0_out, float* __restrict__ loss_out) {
+                 const float* __restrict__ enc_dce, int H, int W, int Ho, int Wo, int Hp, int Wp, int C, float scale,
+                 float eps, int loss_type, float* __restrict__ m_out, float* __restrict__ dm_out,
+                 float* __restrict__ q_out, float* __restrict__ dc0_out, float* __restrict__ loss_out) {
     extern __shared__ float sm[];
-    const int npix = H * W, T = Hp * Wp;
-    float* s_m = sm;          // [npix] logits, then probabilities
-    float* s_r = s_m + npix;  // [T] u . lowres[t]
-    float* s_q = s_r + T;     // [T]
+    const int npix = H * W, npo = Ho * Wo, T = Hp * Wp;
+    const bool same = (Ho == H && Wo == W);
+    float* s_mh = sm;            // [npix] map-resolution logits
+    float* s_dmh = s_mh + npix;  // [npix] gradient at the map-resolution logits
+    float* s_p = s_dmh + npix;   // [npo] probabilities at the mask resolution
+    float* s_r = s_p + npo;      // [T] u . lowres[t]
+    float* s_q = s_r + T;        // [T]
     __shared__ double scratch[33];
     __shared__ float s_c0;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const long long pb = static_cast<long long>(b) * npix;
+    const long long pb = static_cast<long long>(b) * npix, po = static_cast<long long>(b) * npo;
     for (int t = warp; t < T; t += nwarps) {
         float acc = 0.f;
         if (lowres != nullptr)
@@ -749,20 +763,36 @@ mask_dice_kernel(const float* __restrict__ D_dwi, const float* __restrict__ D_dc
     __syncthreads();
     const float a0 = gating[b * 2], a1 = gating[b * 2 + 1], c0 = s_c0;
     const float sh = static_cast<float>(Hp) / H, sw = static_cast<float>(Wp) / W;
-    float si = 0.f, sp = 0.f, st = 0.f, sb = 0.f;
+    // ---- logits at the map resolution: the cross-attention tokens are up-sampled bilinearly (model_module.py:972) ----
     for (int p = tid; p < npix; p += blockDim.x) {
-        const int h = p / W, w = p % W;
-        // F.interpolate(mode='bilinear', align_corners=False) source coordinates (model_module.py:972-973)
-        const float sy = fmaxf((h + 0.5f) * sh - 0.5f, 0.f), sx = fmaxf((w + 0.5f) * sw - 0.5f, 0.f);
-        const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-        const int y1 = min(y0 + 1, Hp - 1), x1 = min(x0 + 1, Wp - 1);
-        const float ly = sy - y0, lx = sx - x0;
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bilinear_taps(p / W, Hp, sh, y0, y1, ly);
+        bilinear_taps(p % W, Wp, sw, x0, x1, lx);
         const float up = (1.f - ly) * ((1.f - lx) * s_r[y0 * Wp + x0] + lx * s_r[y0 * Wp + x1]) +
                          ly * ((1.f - lx) * s_r[y1 * Wp + x0] + lx * s_r[y1 * Wp + x1]);
-        const float m = c0 + a0 * D_dwi[pb + p] + a1 * D_dce[pb + p] + up;
-        m_out[pb + p] = m;
-        const float pr = sigmoidf_(m), t = target[pb + p];
-        s_m[p] = pr;
+        s_mh[p] = c0 + a0 * D_dwi[pb + p] + a1 * D_dce[pb + p] + up;
+        s_dmh[p] = 0.f;
+    }
+    __syncthreads();
+    // ---- logits and loss sums at the mask resolution ----
+    const float rh = static_cast<float>(H) / Ho, rw = static_cast<float>(W) / Wo;
+    float si = 0.f, sp = 0.f, st = 0.f, sb = 0.f;
+    for (int o = tid; o < npo; o += blockDim.x) {
+        float m;
+        if (same) {
+            m = s_mh[o];
+        } else {
+            int y0, y1, x0, x1;
+            float ly, lx;
+            bilinear_taps(o / Wo, H, rh, y0, y1, ly);
+            bilinear_taps(o % Wo, W, rw, x0, x1, lx);
+            m = (1.f - ly) * ((1.f - lx) * s_mh[y0 * W + x0] + lx * s_mh[y0 * W + x1]) +
+                ly * ((1.f - lx) * s_mh[y1 * W + x0] + lx * s_mh[y1 * W + x1]);
+        }
+        m_out[po + o] = m;
+        const float pr = sigmoidf_(m), t = target[po + o];
+        s_p[o] = pr;
         si = fmaf(pr, t, si);
         sp += pr;
         st += t;
@@ -771,29 +801,45 @@ mask_dice_kernel(const float* __restrict__ D_dwi, const float* __restrict__ D_dc
     const double I = block_sum<double>(si, scratch), P = block_sum<double>(sp, scratch),
                  Tt = block_sum<double>(st, scratch), Bc = block_sum<double>(sb, scratch);
     const double S = P + Tt + eps, num = 2.0 * I + (loss_type == 0 ? eps : 0.0);
-    const float own = static_cast<float>(1.0 - num / S + Bc / npix);  // this case's fused-mask loss
-    const float bce_g = loss_type == 1 ? scale / npix : 0.f;
-    float sdm = 0.f;
-    for (int p = tid; p < npix; p += blockDim.x) {
-        const float pr = s_m[p], t = target[pb + p];
+    const float own = static_cast<float>(1.0 - num / S + Bc / npo);  // this case's fused-mask loss
+    const float bce_g = loss_type == 1 ? scale / npo : 0.f;
+    // ---- gradient at the mask resolution, carried back to the map resolution (transposed resize) ----
+    for (int o = tid; o < npo; o += blockDim.x) {
+        const float pr = s_p[o], t = target[po + o];
         // loss = scale * (1 - dice): d/dp = -scale * (2 t S - num) / S^2, then through the sigmoid
         const float dm = -scale * static_cast<float>((2.0 * t * S - num) / (S * S)) * pr * (1.f - pr) + bce_g * (pr - t);
+        if (same) {
+            s_dmh[o] = dm;
+        } else {
+            int y0, y1, x0, x1;
+            float ly, lx;
+            bilinear_taps(o / Wo, H, rh, y0, y1, ly);
+            bilinear_taps(o % Wo, W, rw, x0, x1, lx);
+            atomicAdd(&s_dmh[y0 * W + x0], dm * (1.f - ly) * (1.f - lx));
+            atomicAdd(&s_dmh[y0 * W + x1], dm * (1.f - ly) * lx);
+            atomicAdd(&s_dmh[y1 * W + x0], dm * ly * (1.f - lx));
+            atomicAdd(&s_dmh[y1 * W + x1], dm * ly * lx);
+        }
+    }
+    __syncthreads();
+    float sdm = 0.f;
+    for (int p = tid; p < npix; p += blockDim.x) {
+        const float dm = s_dmh[p];
         dm_out[pb + p] = dm;
         sdm += dm;
-        const int h = p / W, w = p % W;
-        const float sy = fmaxf((h + 0.5f) * sh - 0.5f, 0.f), sx = fmaxf((w + 0.5f) * sw - 0.5f, 0.f);
-        const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-        const int y1 = min(y0 + 1, Hp - 1), x1 = min(x0 + 1, Wp - 1);
-        const float ly = sy - y0, lx = sx - x0;
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bilinear_taps(p / W, Hp, sh, y0, y1, ly);
+        bilinear_taps(p % W, Wp, sw, x0, x1, lx);
         atomicAdd(&s_q[y0 * Wp + x0], dm * (1.f - ly) * (1.f - lx));
         atomicAdd(&s_q[y0 * Wp + x1], dm * (1.f - ly) * lx);
         atomicAdd(&s_q[y1 * Wp + x0], dm * ly * (1.f - lx));
         atomicAdd(&s_q[y1 * Wp + x1], dm * ly * lx);
     }
     const float tot = static_cast<float>(block_sum<double>(sdm, scratch));
-    float extra = 0.f;  // the encoder masks' dice terms: constants for the head, part of the reported loss
-    if (enc_dwi != nullptr) extra += mask_loss_of(enc_dwi + pb, target + pb, npix, eps, loss_type, scratch);
-    if (enc_dce != nullptr) extra += mask_loss_of(enc_dce + pb, target + pb, npix, eps, loss_type, scratch);
+    float extra = 0.f;  // the encoder masks' loss terms: constants for the head, part of the reported loss
+    if (enc_dwi != nullptr) extra += mask_loss_of(enc_dwi + po, target + po, npo, eps, loss_type, scratch);
+    if (enc_dce != nullptr) extra += mask_loss_of(enc_dce + po, target + po, npo, eps, loss_type, scratch);
     __syncthreads();
     for (int t = tid; t < T; t += blockDim.x) q_out[b * T + t] = s_q[t];
     if (tid == 0) {
@@ -1033,20 +1079,23 @@ extern "C" int b200_mask_wsum(const void* f3, const float* dm, int B, int npix, 
 extern "C" int b200_mask_dice(const float* D_dwi, const float* D_dce, const float* gating, const float* u,
                               const float* lowres, const float* pre_b, const float* out_w, const float* out_b,
                               int mid, const float* target, const float* enc_mask_dwi, const float* enc_mask_dce,
-                              int B, int H, int W, int Hp, int Wp, int C, float scale, float eps, int loss_type,
-                              float* m_out, float* dm_out, float* q_out, float* dc0_out, float* loss_out,
-                              void* stream) {
+                              int B, int H, int W, int Ho, int Wo, int Hp, int Wp, int C, float scale, float eps,
+                              int loss_type, float* m_out, float* dm_out, float* q_out, float* dc0_out,
+                              float* loss_out, void* stream) {
     if (loss_type != 0 && loss_type != 1) return -1;
-    if (B < 0 || H <= 0 || W <= 0 || Hp <= 0 || Wp <= 0 || C <= 0 || mid <= 0 || H * W > 8192 || Hp * Wp > 64) return -1;
+    if (B < 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || Hp <= 0 || Wp <= 0 || C <= 0 || mid <= 0 ||
+        H * W > 4096 || Ho * Wo > 4096 || Hp * Wp > 64)
+        return -1;
     if (B == 0) return 0;
     if (D_dwi == nullptr || D_dce == nullptr || gating == nullptr || u == nullptr || pre_b == nullptr ||
         out_w == nullptr || out_b == nullptr || target == nullptr || m_out == nullptr || dm_out == nullptr ||
         q_out == nullptr || dc0_out == nullptr || loss_out == nullptr)
         return -2;
-    const size_t smem = (static_cast<size_t>(H) * W + 2 * Hp * Wp) * sizeof(float);
+    const size_t smem = (static_cast<size_t>(2) * H * W + static_cast<size_t>(Ho) * Wo + 2 * Hp * Wp) * sizeof(float);
+    if (smem > 48 * 1024) return -3;
     mask_dice_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-        D_dwi, D_dce, gating, u, lowres, pre_b, out_w, out_b, mid, target, enc_mask_dwi, enc_mask_dce, H, W, Hp, Wp, C,
-        scale, eps, loss_type, m_out, dm_out, q_out, dc0_out, loss_out);
+        D_dwi, D_dce, gating, u, lowres, pre_b, out_w, out_b, mid, target, enc_mask_dwi, enc_mask_dce, H, W, Ho, Wo, Hp,
+        Wp, C, scale, eps, loss_type, m_out, dm_out, q_out, dc0_out, loss_out);
     return launch_status();
 }
 

@@ -192,7 +192,8 @@ class FusionHeadTrainer:
               "dTc": z(R, C)}
         if self.lambda_mask > 0:
             ws.update({"v": z(1, C), "gate": z(B, C), "u": z(B, C), "omd": z(B, fm.dwi_ch), "omc": z(B, fm.dce_ch),
-                       "Dd": z(B, H * W), "Dc": z(B, H * W), "m": z(B, 1, H, W), "dm": z(B, H * W), "q": z(B, T),
+                       "Dd": z(B, H * W), "Dc": z(B, H * W), "m": z(B, 1, fm.mask_size, fm.mask_size), "dm": z(B, H * W),
+                       "q": z(B, T),
                        "sd": z(B, fm.dwi_ch), "sc": z(B, fm.dce_ch), "tmpd": z(B, C), "tmpc": z(B, C), "dug": z(B, C),
                        "aud": z(B, C), "auc": z(B, C), "dv": z(C + 1)})  # dv[C] = dc0
         ah, aw = _bilinear_axis_weights(hp, H), _bilinear_axis_weights(wp, W)
@@ -231,10 +232,11 @@ class FusionHeadTrainer:
         if use_mask_term:
             if masks is None:
                 raise ValueError("lambda_mask > 0 needs the target masks")
-            if H != fm.mask_size or W != fm.mask_size:
-                raise NotImplementedError("the mask dice term is built for maps of the mask size (MaskHeadResize's "
-                                          "identity dispatch); other sizes put convolutions / interpolation in between")
-            if tuple(masks.shape[-2:]) != (H, W) or masks.shape[0] != B:
+            ms = fm.mask_size
+            if H != W or H in (64, 128, 256, 512):
+                raise NotImplementedError("the mask term is built for MaskHeadResize's identity (32) and interpolation "
+                                          "dispatches; 64 / 128 / 256 / 512-pixel maps go through GELU convolutions")
+            if tuple(masks.shape[-2:]) != (ms, ms) or masks.shape[0] != B:
                 raise ValueError("target masks must be [B,1,H,W] at the mask size")
         ws = self._workspace(B, H, W)
         par = dict(zip(self.names, self.params))
@@ -324,11 +326,11 @@ class FusionHeadTrainer:
             nat.mask_dot(f3c, ws["omc"], ws["Dc"])
             tgt = masks.to(device=f3d.device, dtype=torch.float32).contiguous()
             ws["dv"].zero_()
-            if md is None or mc is None or md[0].numel() != H * W or mc[0].numel() != H * W:
+            if md is None or mc is None or md[0].numel() != ms * ms or mc[0].numel() != ms * ms:
                 raise ValueError("the mask term needs both encoder mask predictions at the mask size "
                                  "(train_fusion.py:249-251)")
             nat.mask_dice(ws["Dd"], ws["Dc"], ws["gating"], ws["u"], ws["LOW"], pre_b, out_w, out_b, tgt, md, mc,
-                          H, W, hp, wp, self.lambda_mask / (3.0 * B), 1e-6, int(self.mask_loss_type == "dice_bce"),
+                          H, W, ms, ms, hp, wp, self.lambda_mask / (3.0 * B), 1e-6, int(self.mask_loss_type == "dice_bce"),
                           ws["m"], ws["dm"], ws["q"], ws["dv"][C:], loss)
             nat.mask_wsum(f3d, ws["dm"], ws["sd"])                # third pass: dmask-weighted pixel sums
             nat.mask_wsum(f3c, ws["dm"], ws["sc"])

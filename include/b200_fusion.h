@@ -460,8 +460,8 @@ int b200_head_loss(const b200_head_train* args, int B, void* stream);
 int b200_mask_dot(const void* f3, const float* omega, int B, int npix, int Cin, float* D, void* stream);
 int b200_mask_dice(const float* D_dwi, const float* D_dce, const float* gating, const float* u, const float* lowres,
                    const float* pre_b, const float* out_w, const float* out_b, int mid, const float* target,
-                   const float* enc_mask_dwi, const float* enc_mask_dce, int B, int H, int W, int Hp, int Wp, int C,
-                   float scale, float eps, int loss_type, float* m_out, float* dm_out, float* q_out, float* dc0_out,
+                   const float* enc_mask_dwi, const float* enc_mask_dce, int B, int H, int W, int Ho, int Wo, int Hp,
+                   int Wp, int C, float scale, float eps, int loss_type, float* m_out, float* dm_out, float* q_out, float* dc0_out,
                    float* loss_out, void* stream);
 int b200_mask_wsum(const void* f3, const float* dm, int B, int npix, int Cin, float* s, void* stream);
 int b200_mask_head_grads(const float* dv, const float* dc0, const float* pre_w, const float* pre_b,

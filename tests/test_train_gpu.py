@@ -293,8 +293,29 @@ def test_vit_geometry_with_overlapping_token_bins_matches_the_oracle():
     for name, g in zip(tr.names, tr.grads):
         scale = o_grads[name].abs().max().item()
         assert (g.cpu() - o_grads[name]).abs().max().item() <= 2e-4 * scale + 1e-8, name
-    with pytest.raises(NotImplementedError):   # the mask term needs maps of the mask size
-        FusionHeadTrainer(fm, lambda_mask=0.2).loss_and_grads(*_to_dev(batch), torch.zeros(5, 1, 14, 14, device=DEV))
+    # mask term on 14 x 14 maps: MaskHeadResize's interpolation dispatch (pre -> bilinear resize to 32 -> out)
+    g = torch.Generator().manual_seed(77)
+    md, mc = torch.randn(5, 1, 32, 32, generator=g), torch.randn(5, 1, 32, 32, generator=g)
+    masks = (torch.rand(5, 1, 32, 32, generator=g) > 0.6).float()
+    batch = (batch[0], batch[1], md, mc, batch[4])
+    for loss_type in ("dice", "dice_bce"):
+        fm.load_state_dict(sd)
+        tr = FusionHeadTrainer(fm, smoothing=0.1, gamma=1.5, lambda_mask=0.2, mask_loss_type=loss_type)
+        tr.zero_grad()
+        loss, _ = tr.loss_and_grads(*_to_dev(batch), masks.to(DEV))
+        o_loss, _, o_grads = to.head_loss_and_grads(sd, params, *batch, 0.1, 1.5, None, masks, 0.2, loss_type)
+        assert abs(loss.item() - float(o_loss)) <= 2e-5 * abs(float(o_loss)), loss_type
+        assert len(tr.names) == 24 and sorted(tr.names) == sorted(o_grads)
+        for name, gr in zip(tr.names, tr.grads):
+            scale = o_grads[name].abs().max().item()
+            assert (gr.cpu() - o_grads[name]).abs().max().item() <= 2e-4 * scale + 1e-8, (loss_type, name)
+        fm.eval()
+        dbatch = _to_dev(batch)
+        _, mask_inf, _ = fm([dbatch[0]], [dbatch[1]], dbatch[2], dbatch[3])
+        assert tuple(tr.fused_mask_logits.shape) == (5, 1, 32, 32) and _rel(mask_inf, tr.fused_mask_logits) < 2e-2
+    with pytest.raises(NotImplementedError):   # 64-pixel maps go through MaskHeadResize's GELU convolutions
+        b64 = op.synthetic_head_batch(2, seed=1, channels=768, size=64)
+        FusionHeadTrainer(fm, lambda_mask=0.2).loss_and_grads(*_to_dev(b64), torch.zeros(2, 1, 32, 32, device=DEV))
 
 
 def test_larger_batch_gradients_match_oracle_and_training_reduces_the_loss():
