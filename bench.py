@@ -282,6 +282,21 @@ def reference_arm(args):
 
 
 
+def gemm_flops(name, key):
+    """2*M*N*K of a GEMM-shaped launch from its profile key (None for everything else)."""
+    if key is None:
+        return None
+    if name == "b200_conv_gemm_ex":      # (B, H, W, Cin, Cout, taps)
+        b_, h_, w_, ci, co, tp = key[:6]
+        st = 2 if tp == 4 else (key[6] if len(key) > 6 else 1)
+        return 2.0 * b_ * (h_ * w_ // (st * st)) * ci * co * tp
+    if name == "b200_linear":            # (M, K, N)
+        return 2.0 * key[0] * key[1] * key[2]
+    if name == "b200_gemm_batched":      # (batch, heads, M, K, N, mode)
+        return 2.0 * key[0] * key[1] * key[2] * key[3] * key[4]
+    return None
+
+
 # --------------------------------------------------------------- fusion-head fine-tuning (C5 slice) ----
 WORKLOAD_C5 = ("C5 (frozen-encoder phase): DWI 16x64x64 + DCE 6x64x64 -> normalise -> frozen CNN encoders -> "
                "fusion-head forward + backward (smoothed focal loss + mask dice) -> gradient all-reduce -> AdamW")
@@ -306,7 +321,8 @@ def train_arm(args):
         import datetime
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
-    params, pipe, cpu_state, nyul = build_product(device, "logits", False, "c3")
+    enc = args.encoders
+    params, pipe, cpu_state, nyul = build_product(device, "logits", False, enc)
     lam = 0.2 if args.objective == "cls+mask" else 0.0   # lambda_mask, parameters_generate.py:125
     trainer = FusionHeadTrainer(pipe.fusion_model, lr=1e-4, weight_decay=4e-5, smoothing=0.1, gamma=1.5,
                                 lambda_mask=lam)
@@ -386,7 +402,8 @@ def train_arm(args):
                 sg_ms += sum(t) / nsp
         # the map-sized passes of the head are HBM bound: algorithmic bytes = one read of the bf16 f3 map per launch
         hbm_rows = []
-        f3_bytes = B * 32 * 32 * 512 * 2
+        f3_shape = (32, 32, 512) if enc == "c3" else (14, 14, 768)
+        f3_bytes = B * f3_shape[0] * f3_shape[1] * f3_shape[2] * 2
         # dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 1024 (profiles/r1_c5_hbm_kernels_ncu.csv)
         ncu_traffic = {"b200_fusion_tokens": 1.0738e9 + 32.3e6, "b200_mask_dot": 1.0758e9 + 9.0e6}
         for n in ("b200_fusion_tokens", "b200_mask_dot", "b200_mask_wsum"):
@@ -396,16 +413,22 @@ def train_arm(args):
                 gbs = f3_bytes / (ms_l / 1e3) / 1e9
                 hbm_rows.append({"bound": "hbm", "kernel": n, "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": gbs / peaks["hbm_gbs"], "ms_per_launch": ms_l,
-                                 "traffic": ncu_traffic[n] * B / 1024 if n in ncu_traffic else None,
+                                 "traffic": ncu_traffic[n] * B / 1024 if n in ncu_traffic and enc == "c3" else None,
                                  "algorithmic_bytes_per_launch": f3_bytes})
-        dom_key = ("b200_conv_gemm_ex", (B, 32, 32, 256, 256, 9))
+        if enc == "c3":
+            dom_key = ("b200_conv_gemm_ex", (B, 32, 32, 256, 256, 9))
+            dom_name = "conv_gemm_kernel<256> 3x3 256->256 @32x32 (frozen encoders: still the dominant launch)"
+        else:  # the GEMM-shaped launch class with the largest share of the step
+            cands = [(sum(t), nk) for nk, t in prof.items() if gemm_flops(*nk) is not None]
+            dom_key = max(cands)[1] if cands else None
+            dom_name = f"conv_gemm_kernel via {dom_key[0]} {list(dom_key[1])} (frozen encoders)" if dom_key else None
         roofline = None
         if dom_key in prof:
             dom_ms = statistics.mean(prof[dom_key])
-            ach = 2.0 * B * 1024 * 256 * 256 * 9 / (dom_ms / 1e3) / 1e12
+            ach = gemm_flops(*dom_key) / (dom_ms / 1e3) / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tf_sustained"], "traffic": 1.034e9 * B / 1024,
-                        "kernel": "conv_gemm_kernel<256> 3x3 256->256 @32x32 (frozen encoders: still the dominant launch)",
+                        "frac": ach / peaks["tf_sustained"], "traffic": 1.034e9 * B / 1024 if enc == "c3" else None,
+                        "kernel": dom_name,
                         "ms_per_launch": dom_ms, "share_of_step": sum(prof[dom_key]) / total_ms if total_ms else None,
                         "peak_source": peaks["source"] + " sustained bf16"}
         line = {
@@ -413,7 +436,9 @@ def train_arm(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 encoders (frozen) / f32 head forward, backward and optimiser",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD_C5, "batch_per_gpu": B, "global_batch": B * world,
+            "config": {"workload": WORKLOAD_C5 if enc == "c3" else WORKLOAD_C5.replace(
+                           "normalise -> frozen CNN encoders", "resize 224 -> normalise -> frozen ViT-B/16 + adapter encoders"),
+                       "batch_per_gpu": B, "global_batch": B * world,
                        "objective": "classification (label smoothing 0.1, focal gamma 1.5)" +
                        (" + 0.2 x mean of the three mask dice terms" if lam > 0 else " only"),
                        "trainable_parameters": trainer.numel, "allreduce_bytes_per_step": 4 * (trainer.flat_numel + 1),
@@ -436,7 +461,8 @@ def train_arm(args):
             "cpu_baseline": None,
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = run_cpu_train_baseline(params, cpu_state, nyul, args.ref_batch, lam)
+            line["cpu_baseline"] = (run_cpu_train_baseline(params, cpu_state, nyul, args.ref_batch, lam)
+                                    if enc == "c3" else None)  # (the C4 CPU forward alone is ~1 s per case)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -490,6 +516,9 @@ def main():
                     help="c3 = the headline CNN-encoder configuration; c4 = ViT-B/16 backbone encoders at 224x224; "
                          "resnet = ResNet-50 (RadImageNet branch, output stride 8) backbone encoders at 224x224")
     ap.add_argument("--aux", default="full", choices=["full", "logits"])
+    ap.add_argument("--encoders", default="c3", choices=["c3", "c4"],
+                    help="--workload c5: frozen encoders feeding the head - c3 = the CNN encoders (headline), c4 = "
+                         "ViT-B/16 backbone + adapter at 224x224 (768-channel 14x14 maps)")
     ap.add_argument("--objective", default="cls+mask", choices=["cls", "cls+mask"],
                     help="--workload c5: loss terms of the fine-tuning step (the reference's total loss minus its "
                          "reconstruction / mimic terms, or the classification term alone)")
@@ -505,7 +534,7 @@ def main():
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.batch is None:
-        args.batch = 1024 if args.workload in ("c3", "c5") else 256
+        args.batch = 1024 if args.workload == "c3" or (args.workload == "c5" and args.encoders == "c3") else 256
     if args.workload not in ("c3", "c5") and args.ref_batch == 32:
         args.ref_batch = 8  # ~1 s per case on the host cores: keep a step / the CPU sample bounded
         args.cpu_cases = min(args.cpu_cases, 16)
@@ -628,19 +657,6 @@ def main():
         for (name, key), times in prof.items():
             table[(name, key)] = (statistics.mean(times), len(times))
             total_ms += sum(times)
-        def gemm_flops(name, key):
-            if key is None:
-                return None
-            if name == "b200_conv_gemm_ex":      # (B, H, W, Cin, Cout, taps)
-                b_, h_, w_, ci, co, tp = key[:6]
-                st = 2 if tp == 4 else (key[6] if len(key) > 6 else 1)
-                return 2.0 * b_ * (h_ * w_ // (st * st)) * ci * co * tp
-            if name == "b200_linear":            # (M, K, N)
-                return 2.0 * key[0] * key[1] * key[2]
-            if name == "b200_gemm_batched":      # (batch, heads, M, K, N, mode)
-                return 2.0 * key[0] * key[1] * key[2] * key[3] * key[4]
-            return None
-
         if args.workload == "c3":
             dom_key = ("b200_conv_gemm_ex", (B, 32, 32, 256, 256, 9))
             dom_name = "conv_gemm_kernel<256> 3x3 256->256 @32x32"
