@@ -86,12 +86,11 @@ class FusionHeadTrainer:
     def __init__(self, fusion_model, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=4e-5, smoothing=0.1,
                  gamma=1.5, class_weights=None, lambda_mask=0.0, mask_loss_type="dice", process_group=None):
         fm = fusion_model
-        if not fm.use_cross_attention:
-            raise NotImplementedError("fusion-head training without the cross-attention block is not built")
         if isinstance(fm.proj_in_dwi, nn.Identity) or isinstance(fm.proj_in_dce, nn.Identity):
             raise NotImplementedError("encoder channels == fusion_channels (identity proj_in) is not built")
         hp, wp = fm.token_pool
-        if hp * wp > 32 or fm.fusion_channels % fm.mha_heads != 0 or fm.fusion_channels // fm.mha_heads > 128:
+        if fm.use_cross_attention and (hp * wp > 32 or fm.fusion_channels % fm.mha_heads != 0 or
+                                       fm.fusion_channels // fm.mha_heads > 128):
             raise NotImplementedError("token_pool / head size outside the attention kernel's range")
         self.model = fm
         self.lr, self.betas, self.eps, self.weight_decay = lr, tuple(betas), eps, weight_decay
@@ -103,19 +102,20 @@ class FusionHeadTrainer:
         self.mask_loss_type = mask_loss_type
         self.group = process_group
         self.step_count = 0
-        ca = fm.cross_attn_block
         named = [("proj_in_dwi.weight", fm.proj_in_dwi.weight), ("proj_in_dce.weight", fm.proj_in_dce.weight),
-                 ("gating.fc.weight", fm.gating.fc.weight), ("gating.fc.bias", fm.gating.fc.bias),
-                 ("cross_attn_block.cross_attn.in_proj_weight", ca.cross_attn.in_proj_weight),
-                 ("cross_attn_block.cross_attn.in_proj_bias", ca.cross_attn.in_proj_bias),
-                 ("cross_attn_block.cross_attn.out_proj.weight", ca.cross_attn.out_proj.weight),
-                 ("cross_attn_block.cross_attn.out_proj.bias", ca.cross_attn.out_proj.bias),
-                 ("cross_attn_block.attn_ffn.0.weight", ca.attn_ffn[0].weight),
-                 ("cross_attn_block.attn_ffn.0.bias", ca.attn_ffn[0].bias),
-                 ("cross_attn_block.attn_ffn.1.weight", ca.attn_ffn[1].weight),
-                 ("cross_attn_block.attn_ffn.1.bias", ca.attn_ffn[1].bias),
-                 ("cross_attn_block.attn_ffn.3.weight", ca.attn_ffn[3].weight),
-                 ("cross_attn_block.attn_ffn.3.bias", ca.attn_ffn[3].bias)]
+                 ("gating.fc.weight", fm.gating.fc.weight), ("gating.fc.bias", fm.gating.fc.bias)]
+        if fm.use_cross_attention:
+            ca = fm.cross_attn_block
+            named += [("cross_attn_block.cross_attn.in_proj_weight", ca.cross_attn.in_proj_weight),
+                      ("cross_attn_block.cross_attn.in_proj_bias", ca.cross_attn.in_proj_bias),
+                      ("cross_attn_block.cross_attn.out_proj.weight", ca.cross_attn.out_proj.weight),
+                      ("cross_attn_block.cross_attn.out_proj.bias", ca.cross_attn.out_proj.bias),
+                      ("cross_attn_block.attn_ffn.0.weight", ca.attn_ffn[0].weight),
+                      ("cross_attn_block.attn_ffn.0.bias", ca.attn_ffn[0].bias),
+                      ("cross_attn_block.attn_ffn.1.weight", ca.attn_ffn[1].weight),
+                      ("cross_attn_block.attn_ffn.1.bias", ca.attn_ffn[1].bias),
+                      ("cross_attn_block.attn_ffn.3.weight", ca.attn_ffn[3].weight),
+                      ("cross_attn_block.attn_ffn.3.bias", ca.attn_ffn[3].bias)]
         if fm.fusion_se is not None:
             se = fm.fusion_se
             named += [("fusion_se.fc.1.weight", se.fc[1].weight), ("fusion_se.fc.1.bias", se.fc[1].bias),
@@ -223,7 +223,8 @@ class FusionHeadTrainer:
         hp, wp = fm.token_pool
         # equal bins: GAP(p) is the mean of the tokens.  Otherwise (14 x 14 ViT maps -> 4 x 4 overlapping bins) the
         # pooled vectors get their own pass over the maps (per-case channel sums) and their own projection.
-        gap_rows = bool(H % hp or W % wp)
+        cross = bool(fm.use_cross_attention)
+        gap_rows = bool(H % hp or W % wp) or not cross  # (without cross-attention the tokens are not needed at all)
         if fm.use_mask_attention and (dwi_mask_pred is None or dce_mask_pred is None):
             raise RuntimeError("use_mask_attention needs both encoder mask predictions")
         T, C, NH = hp * wp, fm.fusion_channels, fm.mha_heads
@@ -243,17 +244,14 @@ class FusionHeadTrainer:
         grd = dict(zip(self.names, self.grads))
         ca = "cross_attn_block."
         Wd, Wc = par["proj_in_dwi.weight"].view(C, -1), par["proj_in_dce.weight"].view(C, -1)
-        Win, b_in = par[ca + "cross_attn.in_proj_weight"], par[ca + "cross_attn.in_proj_bias"]
-        Wo, bo = par[ca + "cross_attn.out_proj.weight"], par[ca + "cross_attn.out_proj.bias"]
-        lnw, lnb = par[ca + "attn_ffn.0.weight"], par[ca + "attn_ffn.0.bias"]
-        W1, b1 = par[ca + "attn_ffn.1.weight"], par[ca + "attn_ffn.1.bias"]
-        W2, b2 = par[ca + "attn_ffn.3.weight"], par[ca + "attn_ffn.3.bias"]
+        if cross:
+            Win, b_in = par[ca + "cross_attn.in_proj_weight"], par[ca + "cross_attn.in_proj_bias"]
+            Wo, bo = par[ca + "cross_attn.out_proj.weight"], par[ca + "cross_attn.out_proj.bias"]
+            lnw, lnb = par[ca + "attn_ffn.0.weight"], par[ca + "attn_ffn.0.bias"]
+            W1, b1 = par[ca + "attn_ffn.1.weight"], par[ca + "attn_ffn.1.bias"]
+            W2, b2 = par[ca + "attn_ffn.3.weight"], par[ca + "attn_ffn.3.bias"]
 
         # ---- forward on pooled tokens ----
-        nat.fusion_tokens(f3d, hp, wp, ws["Xd"])
-        nat.fusion_tokens(f3c, hp, wp, ws["Xc"])
-        nat.sgemm(ws["Xd"], Wd, ws["Td"], trans_b=True)
-        nat.sgemm(ws["Xc"], Wc, ws["Tc"], trans_b=True)
         if gap_rows:
             for k in ("Gd", "Gc", "Pd", "Pc"):
                 if k not in ws:
@@ -263,14 +261,19 @@ class FusionHeadTrainer:
             nat.channel_sums(f3c, ws["Gc"])
             nat.sgemm(ws["Gd"], Wd, ws["Pd"], trans_b=True)
             nat.sgemm(ws["Gc"], Wc, ws["Pc"], trans_b=True)
-        nat.sgemm(ws["Td"], Win[:C], ws["Q"], trans_b=True, bias=b_in[:C])
-        nat.sgemm(ws["Tc"], Win[C:], ws["KV"], trans_b=True, bias=b_in[C:])
-        Kt, Vt = ws["KV"][:, :C], ws["KV"][:, C:]
-        nat.mha_fwd(ws["Q"], Kt, Vt, B, NH, ws["P"], ws["CTX"])
-        nat.sgemm(ws["CTX"], Wo, ws["AO"], trans_b=True, bias=bo)
-        nat.ln_fwd(ws["AO"], lnw, lnb, fm.cross_attn_block.attn_ffn[0].eps, ws["LN"], ws["mean"], ws["rstd"])
-        nat.sgemm(ws["LN"], W1, ws["G1"], trans_b=True, bias=b1, pre=ws["H1"], act=1)
-        nat.sgemm(ws["G1"], W2, ws["LOW"], trans_b=True, bias=b2, res=ws["AO"])
+        if cross:
+            nat.fusion_tokens(f3d, hp, wp, ws["Xd"])
+            nat.fusion_tokens(f3c, hp, wp, ws["Xc"])
+            nat.sgemm(ws["Xd"], Wd, ws["Td"], trans_b=True)
+            nat.sgemm(ws["Xc"], Wc, ws["Tc"], trans_b=True)
+            nat.sgemm(ws["Td"], Win[:C], ws["Q"], trans_b=True, bias=b_in[:C])
+            nat.sgemm(ws["Tc"], Win[C:], ws["KV"], trans_b=True, bias=b_in[C:])
+            Kt, Vt = ws["KV"][:, :C], ws["KV"][:, C:]
+            nat.mha_fwd(ws["Q"], Kt, Vt, B, NH, ws["P"], ws["CTX"])
+            nat.sgemm(ws["CTX"], Wo, ws["AO"], trans_b=True, bias=bo)
+            nat.ln_fwd(ws["AO"], lnw, lnb, fm.cross_attn_block.attn_ffn[0].eps, ws["LN"], ws["mean"], ws["rstd"])
+            nat.sgemm(ws["LN"], W1, ws["G1"], trans_b=True, bias=b1, pre=ws["H1"], act=1)
+            nat.sgemm(ws["G1"], W2, ws["LOW"], trans_b=True, bias=b2, res=ws["AO"])
 
         # ---- per-case tail, loss, and the backward of the tail ----
         a = nat.HeadTrain()
@@ -285,7 +288,9 @@ class FusionHeadTrainer:
 
         if flat["cw"] is not None:
             a.class_weights = ptr(flat["cw"])
-        a.tok_dwi, a.tok_dce, a.lowres = ptr(ws["Td"]), ptr(ws["Tc"]), ptr(ws["LOW"])
+        a.tok_dwi, a.tok_dce = ptr(ws["Td"]), ptr(ws["Tc"])  # (not read when the pooled vectors are given)
+        if cross:
+            a.lowres = ptr(ws["LOW"])
         if gap_rows:
             a.pvec_dwi, a.pvec_dce, a.pvec_scale = ptr(ws["Pd"]), ptr(ws["Pc"]), 1.0 / (H * W)
         md = dwi_mask_pred.contiguous().float() if dwi_mask_pred is not None else None
@@ -309,7 +314,9 @@ class FusionHeadTrainer:
         a.loss_out, a.logits_out, a.gating_out = ptr(loss), ptr(ws["logits"]), ptr(ws["gating"])
         a.dlogits_out, a.z_out, a.gf_out = ptr(ws["dlogits"]), ptr(ws["zvec"]), ptr(ws["gf"])
         a.gx_out, a.dgl_out = ptr(ws["gx"]), ptr(ws["dgl"])
-        a.dpd_out, a.dpc_out, a.dlowres_out = ptr(ws["dpd"]), ptr(ws["dpc"]), ptr(ws["dLOW"])
+        a.dpd_out, a.dpc_out = ptr(ws["dpd"]), ptr(ws["dpc"])
+        if cross:
+            a.dlowres_out = ptr(ws["dLOW"])
         if use_mask_term:
             # fused mask logit = c0 + v . fused_refined (pre and out are both 1x1, nothing in between at this size)
             pre_w = par["mask_head.pre.weight"].view(par["mask_head.pre.weight"].shape[0], C)
@@ -329,7 +336,7 @@ class FusionHeadTrainer:
             if md is None or mc is None or md[0].numel() != ms * ms or mc[0].numel() != ms * ms:
                 raise ValueError("the mask term needs both encoder mask predictions at the mask size "
                                  "(train_fusion.py:249-251)")
-            nat.mask_dice(ws["Dd"], ws["Dc"], ws["gating"], ws["u"], ws["LOW"], pre_b, out_w, out_b, tgt, md, mc,
+            nat.mask_dice(ws["Dd"], ws["Dc"], ws["gating"], ws["u"], ws["LOW"] if cross else None, pre_b, out_w, out_b, tgt, md, mc,
                           H, W, ms, ms, hp, wp, self.lambda_mask / (3.0 * B), 1e-6, int(self.mask_loss_type == "dice_bce"),
                           ws["m"], ws["dm"], ws["q"], ws["dv"][C:], loss)
             nat.mask_wsum(f3d, ws["dm"], ws["sd"])                # third pass: dmask-weighted pixel sums
@@ -364,37 +371,39 @@ class FusionHeadTrainer:
         bgrad(ws["dgl"], "gating.fc.bias")
 
         # ---- backward through the cross-attention block ----
-        dLOW = ws["dLOW"]
-        wgrad(dLOW, ws["G1"], ca + "attn_ffn.3.weight")
-        bgrad(dLOW, ca + "attn_ffn.3.bias")
-        nat.sgemm(dLOW, W2, ws["dG1"])
-        nat.gelu_bwd(ws["H1"], ws["dG1"], ws["dH1"])
-        wgrad(ws["dH1"], ws["LN"], ca + "attn_ffn.1.weight")
-        bgrad(ws["dH1"], ca + "attn_ffn.1.bias")
-        nat.sgemm(ws["dH1"], W1, ws["dLN"])
-        nat.ln_bwd(ws["AO"], ws["dLN"], dLOW, lnw, ws["mean"], ws["rstd"], ws["dAO"], ws["tmp"])
-        bgrad(ws["tmp"], ca + "attn_ffn.0.weight")
-        bgrad(ws["dLN"], ca + "attn_ffn.0.bias")
-        wgrad(ws["dAO"], ws["CTX"], ca + "cross_attn.out_proj.weight")
-        bgrad(ws["dAO"], ca + "cross_attn.out_proj.bias")
-        nat.sgemm(ws["dAO"], Wo, ws["dCTX"])
-        dK, dV = ws["dKV"][:, :C], ws["dKV"][:, C:]
-        nat.mha_bwd(ws["Q"], Kt, Vt, ws["P"], ws["dCTX"], B, NH, ws["dQ"], dK, dV)
-        q_rows, kv_rows = slice(0, C), slice(C, 3 * C)
-        wgrad(ws["dQ"], ws["Td"], ca + "cross_attn.in_proj_weight", q_rows)
-        bgrad(ws["dQ"], ca + "cross_attn.in_proj_bias", q_rows)
-        wgrad(ws["dKV"], ws["Tc"], ca + "cross_attn.in_proj_weight", kv_rows)
-        bgrad(ws["dKV"], ca + "cross_attn.in_proj_bias", kv_rows)
+        if cross:
+            dLOW = ws["dLOW"]
+            wgrad(dLOW, ws["G1"], ca + "attn_ffn.3.weight")
+            bgrad(dLOW, ca + "attn_ffn.3.bias")
+            nat.sgemm(dLOW, W2, ws["dG1"])
+            nat.gelu_bwd(ws["H1"], ws["dG1"], ws["dH1"])
+            wgrad(ws["dH1"], ws["LN"], ca + "attn_ffn.1.weight")
+            bgrad(ws["dH1"], ca + "attn_ffn.1.bias")
+            nat.sgemm(ws["dH1"], W1, ws["dLN"])
+            nat.ln_bwd(ws["AO"], ws["dLN"], dLOW, lnw, ws["mean"], ws["rstd"], ws["dAO"], ws["tmp"])
+            bgrad(ws["tmp"], ca + "attn_ffn.0.weight")
+            bgrad(ws["dLN"], ca + "attn_ffn.0.bias")
+            wgrad(ws["dAO"], ws["CTX"], ca + "cross_attn.out_proj.weight")
+            bgrad(ws["dAO"], ca + "cross_attn.out_proj.bias")
+            nat.sgemm(ws["dAO"], Wo, ws["dCTX"])
+            dK, dV = ws["dKV"][:, :C], ws["dKV"][:, C:]
+            nat.mha_bwd(ws["Q"], Kt, Vt, ws["P"], ws["dCTX"], B, NH, ws["dQ"], dK, dV)
+            q_rows, kv_rows = slice(0, C), slice(C, 3 * C)
+            wgrad(ws["dQ"], ws["Td"], ca + "cross_attn.in_proj_weight", q_rows)
+            bgrad(ws["dQ"], ca + "cross_attn.in_proj_bias", q_rows)
+            wgrad(ws["dKV"], ws["Tc"], ca + "cross_attn.in_proj_weight", kv_rows)
+            bgrad(ws["dKV"], ca + "cross_attn.in_proj_bias", kv_rows)
+            if gap_rows:
+                nat.sgemm(ws["dQ"], Win[:C], ws["dTd"])
+                nat.sgemm(ws["dKV"], Win[C:], ws["dTc"])
+            else:
+                nat.sgemm(ws["dQ"], Win[:C], ws["dTd"], res=ws["dpd"], res_div=T)
+                nat.sgemm(ws["dKV"], Win[C:], ws["dTc"], res=ws["dpc"], res_div=T)
+            wgrad(ws["dTd"], ws["Xd"], "proj_in_dwi.weight")
+            wgrad(ws["dTc"], ws["Xc"], "proj_in_dce.weight")
         if gap_rows:  # the pooled vectors' gradients reach proj_in_* through the channel sums, not the tokens
-            nat.sgemm(ws["dQ"], Win[:C], ws["dTd"])
-            nat.sgemm(ws["dKV"], Win[C:], ws["dTc"])
             wgrad(ws["dpd"], ws["Gd"], "proj_in_dwi.weight")
             wgrad(ws["dpc"], ws["Gc"], "proj_in_dce.weight")
-        else:
-            nat.sgemm(ws["dQ"], Win[:C], ws["dTd"], res=ws["dpd"], res_div=T)
-            nat.sgemm(ws["dKV"], Win[C:], ws["dTc"], res=ws["dpc"], res_div=T)
-        wgrad(ws["dTd"], ws["Xd"], "proj_in_dwi.weight")
-        wgrad(ws["dTc"], ws["Xc"], "proj_in_dce.weight")
         if use_mask_term:  # the full-resolution path of the mask logits into proj_in_*
             wgrad(ws["aud"], ws["sd"], "proj_in_dwi.weight")
             wgrad(ws["auc"], ws["sc"], "proj_in_dce.weight")

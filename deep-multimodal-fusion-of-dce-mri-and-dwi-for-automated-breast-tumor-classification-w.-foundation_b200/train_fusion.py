@@ -186,9 +186,14 @@ class LightningFusionModel(nn.Module):
             raise RuntimeError("the reference training step requires label_smoothing_enabled")
         cl = fp.get("classification_loss_parameters", {})
         gamma = cl.get("gamma", None)
+        # the fusion head is the LAST group of the discriminative schedule (selector_helpers.py:490-512): its learning
+        # rate is the base rate (decay exponent 0) and its weight decay reg_base when discriminative_reg is on
+        wd = op.get("weight_decay", 4e-5)
+        if op.get("discriminative_lr", False) and op.get("discriminative_reg", False):
+            wd = op.get("reg_base", wd)
         self.head_trainer = FusionHeadTrainer(
             self.fusion_model, lr=op.get("lr", 1e-4), betas=op.get("betas", (0.9, 0.999)), eps=op.get("eps", 1e-8),
-            weight_decay=op.get("weight_decay", 4e-5), smoothing=fp.get("label_smoothing_alpha", 0.1),
+            weight_decay=wd, smoothing=fp.get("label_smoothing_alpha", 0.1),
             gamma=2 if gamma is None else gamma, class_weights=getattr(self, "_class_weights", None),
             lambda_mask=self._lambda_mask(),
             mask_loss_type=fp.get("mask_parameters", {}).get("mask_loss_type", "dice"))

@@ -129,8 +129,11 @@ def test_trainer_refuses_cpu_and_unbuilt_configurations():
     with pytest.raises(nat.B200NativeError):
         tr.zero_grad()  # parameters live on the CPU: no CPU path
     params["fusion_model_parameters"]["fusion_specific_parameters"]["use_cross_attention"] = False
-    with pytest.raises(NotImplementedError):
-        FusionHeadTrainer(mm.FusionModel(params))
+    params["fusion_model_parameters"]["use_se"] = False
+    small = FusionHeadTrainer(mm.FusionModel(params), lambda_mask=0.2)   # gating + classifier + proj_in + mask head
+    assert len(small.names) == 10 and not any("cross_attn" in n or "fusion_se" in n for n in small.names)
+    with pytest.raises(ValueError):
+        FusionHeadTrainer(mm.FusionModel(params), mask_loss_type="bce")
 
 
 def test_shared_step_rejects_unbuilt_loss_terms():
@@ -150,6 +153,12 @@ def test_shared_step_rejects_unbuilt_loss_terms():
     params["b200_classification_objective_only"] = True
     with pytest.raises(RuntimeError, match="label_smoothing"):
         lm.configure_optimizers()
+    params["fusion_model_parameters"]["label_smoothing_enabled"] = True
+    params["fusion_model_parameters"]["optimizer_parameters"] = {
+        "name": "adamW", "lr": 3e-4, "betas": (0.9, 0.99), "eps": 1e-8, "weight_decay": 4e-5, "discriminative_lr": True,
+        "lr_decay_factor": 1.2, "discriminative_reg": True, "reg_decay_factor": 0.8, "reg_base": 1e-4}
+    tr = lm.configure_optimizers()   # last group of the discriminative schedule: base lr, reg_base weight decay
+    assert (tr.lr, tr.weight_decay, tr.betas) == (3e-4, 1e-4, (0.9, 0.99))
     w = lm.set_class_weights(torch.tensor([0, 0, 1, 2, 3, 3, 3, 3]))
     assert torch.allclose(w, torch.tensor([1.0, 2.0, 2.0, 0.5]), atol=1e-5)
 

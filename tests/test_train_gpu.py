@@ -318,6 +318,40 @@ def test_vit_geometry_with_overlapping_token_bins_matches_the_oracle():
         FusionHeadTrainer(fm, lambda_mask=0.2).loss_and_grads(*_to_dev(b64), torch.zeros(2, 1, 32, 32, device=DEV))
 
 
+@pytest.mark.parametrize("cross,se", [(False, True), (True, False), (False, False)])
+def test_optional_blocks_off_match_the_oracle(cross, se):
+    """FusionModel without its cross-attention block and / or its SE block (use_cross_attention, use_se), both loss
+    terms: the trainable set shrinks accordingly and every gradient still matches autograd over the oracle."""
+    import model_module as mm
+    import parameters_default as pd
+    from fusion_train import FusionHeadTrainer
+
+    params = pd.default_parameters()
+    params["fusion_model_parameters"]["fusion_specific_parameters"]["use_cross_attention"] = cross
+    params["fusion_model_parameters"]["use_se"] = se
+    fm = mm.FusionModel(params)
+    sd = op.seeded_state_dict(op.shapes_of(fm.state_dict()), seed=13)
+    fm.load_state_dict(sd)
+    fm.to(DEV).eval()
+    batch = op.synthetic_head_batch(6, seed=91)
+    masks = op.synthetic_raw(6, seed=92, kind="S")[2]
+    tr = FusionHeadTrainer(fm, smoothing=0.1, gamma=1.5, lambda_mask=0.2)
+    tr.zero_grad()
+    loss, logits = tr.loss_and_grads(*_to_dev(batch), masks.to(DEV))
+    o_loss, o_logits, o_grads = to.head_loss_and_grads(sd, params, *batch, 0.1, 1.5, None, masks, 0.2)
+    assert sorted(tr.names) == sorted(o_grads)
+    assert abs(loss.item() - float(o_loss)) <= 2e-5 * abs(float(o_loss)) and _rel(logits.cpu(), o_logits) < 2e-5
+    for name, g in zip(tr.names, tr.grads):
+        scale = o_grads[name].abs().max().item()
+        assert (g.cpu() - o_grads[name]).abs().max().item() <= 2e-4 * scale + 1e-8, name
+    first = loss.item()
+    tr.lr = 2e-3
+    tr.step()
+    for _ in range(10):
+        last, _ = tr.train_step(*_to_dev(batch), masks.to(DEV))
+    assert last.item() < first
+
+
 def test_larger_batch_gradients_match_oracle_and_training_reduces_the_loss():
     from fusion_train import FusionHeadTrainer
 
