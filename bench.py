@@ -3,6 +3,9 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--aux full|logits]
     python bench.py --impl reference ...      # the reference algorithm on the host CPU cores
+    python bench.py --workload c4|resnet       # ViT-B/16 / ResNet-50 backbone encoders at 224x224 (not the headline)
+    python bench.py --workload c5 [--encoders c4] [--objective cls]   # fusion-head fine-tuning step (forward +
+                                               # backward + gradient all-reduce + AdamW), its own metric line
 
 Workload (BASELINE.json configs[2], the configuration the metric "fused DWI+DCE classify" is
 quoted on): per step one batch of B synthetic cases per GPU - raw DWI [B,16,64,64] and DCE
