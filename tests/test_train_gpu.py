@@ -459,3 +459,29 @@ def test_fit_host_equals_step_by_step_training():
     assert len(losses[0]) == 3
     for a, b in zip(*losses):
         assert abs(a - b) <= 1e-4 * abs(b), losses
+
+
+def test_optimizer_state_roundtrip_and_model_reload():
+    """state_dict / load_state_dict of the trainer (AdamW moments + step count) resume training bit for bit on the same
+    batch order; load_state_dict on the MODEL writes through the flat-buffer views (the parameters stay bound)."""
+    from fusion_train import FusionHeadTrainer
+
+    params, fm, sd = _head(3)
+    batch = _to_dev(op.synthetic_head_batch(4, seed=17))
+    tr = FusionHeadTrainer(fm, lr=1e-3)
+    for _ in range(3):
+        tr.train_step(*batch)
+    opt_state = tr.state_dict()
+    model_state = {k: v.clone() for k, v in fm.state_dict().items()}
+    ref = [tr.train_step(*batch)[0].item() for _ in range(2)]
+    ref_param = fm.state_dict()["classifier.2.weight"].clone()
+    # rewind: reload the model (in place, through the views) and the optimiser state
+    fm.load_state_dict(model_state)
+    assert tr._bind() is tr._flat and fm.classifier[2].weight.data_ptr() == tr.params[-2].data_ptr()
+    tr.load_state_dict(opt_state)
+    again = [tr.train_step(*batch)[0].item() for _ in range(2)]
+    # split-K weight gradients accumulate with float atomics: equal to fp32 round-off, not bitwise
+    assert all(abs(a - b) <= 1e-5 * abs(b) for a, b in zip(again, ref)), (again, ref)
+    assert _rel(fm.state_dict()["classifier.2.weight"], ref_param) < 1e-4
+    with pytest.raises(ValueError):
+        tr.load_state_dict({"step": 1, "names": ["x"], "exp_avg": opt_state["exp_avg"], "exp_avg_sq": opt_state["exp_avg_sq"]})
