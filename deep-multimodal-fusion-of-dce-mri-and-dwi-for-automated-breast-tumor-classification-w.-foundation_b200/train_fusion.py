@@ -85,8 +85,12 @@ class LightningFusionModel(nn.Module):
         self.mc_enable(self.dce_model)
         preds, gating = [], []
         dwi_aux = dce_aux = None
+        modes = self._aux_modes()
         try:
-            for _ in range(passes):
+            for i in range(passes):
+                # only the LAST pass's encoder aux is returned (train_fusion.py:536): the other passes skip every
+                # output the logits do not depend on (reconstruction heads, projectors, encoder class heads)
+                self._set_aux_modes(modes if i == passes - 1 else ("logits", "logits", "logits"), fusion="logits")
                 _, dwi_aux, dwi_mask = self.dwi_model(dwi_inputs)
                 _, dce_aux, dce_mask = self.dce_model(dce_inputs)
                 logits, _, aux = self.forward(dwi_aux["raw_feats"], dce_aux["raw_feats"], dwi_mask, dce_mask)
@@ -95,21 +99,36 @@ class LightningFusionModel(nn.Module):
                     gating.append(_collapse_gating(gw))
                 preds.append(torch.softmax(logits, dim=1))
         finally:
+            self._set_aux_modes(modes)
             self._restore_module_train_states(self.dwi_model, states_dwi)
             self._restore_module_train_states(self.dce_model, states_dce)
         stack = torch.stack(preds, dim=0)
         mean_gating = torch.stack(gating, dim=0).mean(0).cpu() if gating else None
         return stack.mean(0), stack.std(0), {"gating_weights": mean_gating, "dwi_aux": dwi_aux, "dce_aux": dce_aux}
 
+    def _aux_modes(self):
+        return tuple(getattr(m, "aux_mode", "full") for m in (self.dwi_model, self.dce_model, self.fusion_model))
+
+    def _set_aux_modes(self, modes, fusion=None):
+        for m, mode in zip((self.dwi_model, self.dce_model, self.fusion_model), modes):
+            m.aux_mode = mode
+        if fusion is not None:
+            self.fusion_model.aux_mode = fusion
+
     # -------------------------------------------------------------------- TTA ----
     @torch.no_grad()
     def predict_tta(self, dwi_inputs, dce_inputs, masks=None, transforms=None):
         transforms = self.transforms_list if transforms is None else transforms
         preds, gating = [], []
-        for t in transforms:
-            logits, _, aux = self.forward_from_inputs(t(x=dwi_inputs), t(x=dce_inputs), masks)
-            preds.append(torch.softmax(logits, dim=1))
-            gating.append(_collapse_gating(aux["gating_weights"]))
+        modes = self._aux_modes()
+        self._set_aux_modes(("logits", "logits", "logits"))  # nothing but logits and gating weights is returned
+        try:
+            for t in transforms:
+                logits, _, aux = self.forward_from_inputs(t(x=dwi_inputs), t(x=dce_inputs), masks)
+                preds.append(torch.softmax(logits, dim=1))
+                gating.append(_collapse_gating(aux["gating_weights"]))
+        finally:
+            self._set_aux_modes(modes)
         stack = torch.stack(preds, dim=0)
         mean_gating = torch.stack(gating, dim=0).mean(0).cpu() if gating else None
         # (the reference reads aux.get("dwi_aux") from the fusion aux, which never holds it: None)
