@@ -245,9 +245,14 @@ class LightningFusionModel(nn.Module):
             if any(p.requires_grad for m in (self.dwi_model, self.dce_model) for p in m.parameters()):
                 raise NotImplementedError("training with unfrozen encoders is not built (freeze them: "
                                           "backbone_freeze_on_start)")
-            with torch.no_grad():
-                _, dwi_aux, dwi_mask = self.dwi_model(dwi)
-                _, dce_aux, dce_mask = self.dce_model(dce)
+            modes = self._aux_modes()
+            self._set_aux_modes(("logits", "logits", modes[2]))  # the step needs f3 and the mask logits only
+            try:
+                with torch.no_grad():
+                    _, dwi_aux, dwi_mask = self.dwi_model(dwi)
+                    _, dce_aux, dce_mask = self.dce_model(dce)
+            finally:
+                self._set_aux_modes(modes)
             self.head_trainer.zero_grad()
             loss, logits = self.head_trainer.loss_and_grads(dwi_aux["raw_feats"][-1], dce_aux["raw_feats"][-1],
                                                             dwi_mask, dce_mask, labels, masks)
