@@ -258,7 +258,7 @@ def test_hybrid_transformer_encoders_vs_golden_and_oracle():
             lf, mf, af = mods["fusion"](ad["raw_feats"], ac["raw_feats"], md, mc)  # 16x16 encoder maps
         torch.cuda.synchronize()
         # The fusion head on these 16x16 maps amplifies input perturbations ~5x for this seeded weight draw
-        # (fed identical inputs it matches the oracle to 1.7e-3 - tools/dbg_hybrid.py): the encoders' 0.7 %
+        # (fed identical inputs it matches the oracle to 1.7e-3 - tests/tools/dbg_hybrid.py): the encoders' 0.7 %
         # bf16 error on f3 becomes up to 3.5 % on the fused logits.  Encoder outputs keep the 2e-2 bound above;
         # the fused outputs of this non-default configuration are held to 5e-2.
         for prefix, obj in {f"{kind}/fusion/logits": lf, f"{kind}/fusion/mask": mf, f"{kind}/fusion/aux": af}.items():
@@ -324,7 +324,7 @@ def test_vit_backbone_features_vs_oracle():
 
 # Tolerance of the ViT-adapter path.  With the seeded random weights the two GroupNorm(C, C) backbone mixes
 # (per-channel instance norms over 196 pixels) and the heavy-tailed maps they feed (max/rms ~ 25) amplify bf16
-# operand rounding: the fp32 oracle with nothing but its GEMM operands rounded to bf16 (tools/bf16_floor.py)
+# operand rounding: the fp32 oracle with nothing but its GEMM operands rounded to bf16 (tests/tools/bf16_floor.py)
 # already deviates from itself by 1.2-1.7 % on f1, 3-7 % on f2 / f3, 2.7 % on the DWI logits and 3.7 % on the
 # DWI mask.  The product is held to that floor: 8e-2 of the tensor's max on maps downstream of a mix, and the
 # usual 2e-2 on everything upstream of the first one.
@@ -600,7 +600,7 @@ def test_resnet_backbone_and_adapter_path_vs_golden_reference():
     assert len(worst) == 34
     # 53 bf16 convolutions put the backbone features themselves at 1.0-1.3 % of their range (above); the necks,
     # the instance-norm backbone mixes and the heads amplify that as on the ViT path.  The floor of THIS fixture -
-    # the fp32 oracle with nothing but its GEMM operands rounded to bf16, `python tools/bf16_floor.py resnet` - is
+    # the fp32 oracle with nothing but its GEMM operands rounded to bf16, `python tests/tools/bf16_floor.py resnet` - is
     # 12.7-13.7 % on the DWI f3, 8-10 % on p_dwi, 6.7 % on the fusion mask, 4.5-4.8 % on the fusion logits; the product
     # measures 5.7 %, 4.4 %, 7.2-8.6 %, 4.1 %.  Held to 1.5e-1.
     bad = {k: v for k, v in worst.items() if v > 1.5e-1}

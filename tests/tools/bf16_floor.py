@@ -7,8 +7,8 @@ weights the two GroupNorm(C, C) backbone mixes (instance norms over 196 pixels) 
 maps they produce amplify bf16 operand rounding to 2-7 % on the downstream maps; this is the floor the
 tolerance of tests/test_parity_gpu.py::test_vit_adapter_pipeline_vs_golden_reference is set against.
 
-    python tools/bf16_floor.py            # ViT-adapter fixture (model_vit.npz configuration)
-    python tools/bf16_floor.py resnet     # ResNet-50 fixture (model_resnet.npz configuration)
+    python tests/tools/bf16_floor.py            # ViT-adapter fixture (model_vit.npz configuration)
+    python tests/tools/bf16_floor.py resnet     # ResNet-50 fixture (model_resnet.npz configuration)
 """
 import os
 import sys
@@ -16,7 +16,7 @@ import sys
 import torch
 import torch.nn.functional as F
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import b200path, golden_util as gu
 from oracle import model_oracle as mo, params as op, backbone_oracle as bo
