@@ -1132,10 +1132,10 @@ class FusionModel(nn.Module):
             npix_mask = md[0].numel()
         nat.fusion_core(pk["w"], B, pv_d, pv_c, H * W, md, mc, npix_mask, tok_d, tok_c, gating, attn_w, lowres, gate,
                         logits)
-        fused = torch.empty((B, H, W, c), dtype=torch.bfloat16, device=dev)
-        nat.fusion_mix(p_dwi, p_dce, gating, lowres, gate if self.fusion_se is not None else None, hp, wp, fused)
         mask_logits = recon = proj = None
-        if full:
+        if full:  # (the logits come from the pooled vectors: the fused map only feeds the mask / recon / projector heads)
+            fused = torch.empty((B, H, W, c), dtype=torch.bfloat16, device=dev)
+            nat.fusion_mix(p_dwi, p_dce, gating, lowres, gate if self.fusion_se is not None else None, hp, wp, fused)
             mask_logits = _mask_head(pk["mask"], fused, self.mask_size)
             recon = _recon(pk["recon"], fused).unsqueeze(1)
             pj = pk["projF"]
