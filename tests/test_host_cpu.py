@@ -287,3 +287,49 @@ def test_batch_augment_draws_torchvision_parameters():
         aug.batch(torch.zeros(2, 3, 8, 8))  # CPU tensor: no CPU path
     assert nat.lib().b200_augment(None, None, 0, 3, 8, 8, None, None, 0.0, None) == 0
     assert nat.lib().b200_augment(None, None, 2, 3, 8, 8, None, None, 0.0, None) < 0
+
+
+def test_reference_checkpoint_layouts_roundtrip(tmp_path):
+    """The reference's two on-disk layouts (run_training.py:316-326 dictionary file, Lightning .ckpt state dicts) load
+    into the B200 modules: same parameter names and shapes."""
+    import checkpoints as ck
+    import model_module as mm
+    import parameters_default as pd
+    from oracle import params as op
+
+    params = pd.default_parameters()
+    mods = {"dwi": mm.ModelMaskHeadBackbone("dwi", params), "dce": mm.ModelMaskHeadBackbone("dce", params),
+            "fusion": mm.FusionModel(params)}
+    want = {}
+    for i, (k, m) in enumerate(mods.items()):
+        want[k] = op.seeded_state_dict(op.shapes_of(m.state_dict()), seed=20 + i)
+        m.load_state_dict(want[k])
+    path = str(tmp_path / "fusion_model_dict.pth")
+    ck.save_model_dict(path, 0, mods["dwi"], mods["dce"], mods["fusion"])
+    ck.save_model_dict(path, 1, mods["dwi"], mods["dce"], mods["fusion"])      # merges, like the reference
+    assert sorted(torch.load(path)) == ["dce_0", "dce_1", "dwi_0", "dwi_1", "fusion_0", "fusion_1"]
+    fresh = {"dwi": mm.ModelMaskHeadBackbone("dwi", params), "dce": mm.ModelMaskHeadBackbone("dce", params),
+             "fusion": mm.FusionModel(params)}
+    report = ck.apply_states(ck.load_model_dict(path, 1), **fresh)
+    assert all(r == ([], []) for r in report.values())
+    for k in fresh:
+        got = fresh[k].state_dict()
+        assert all(torch.equal(got[n], want[k][n]) for n in want[k])
+    with pytest.raises(KeyError):
+        ck.load_model_dict(path, 7)
+    # Lightning checkpoint of the fusion module: prefixed parameters + foreign entries (metrics) that are dropped
+    sd = {}
+    for k, prefix in (("dwi", "dwi_model."), ("dce", "dce_model."), ("fusion", "fusion_model.")):
+        sd.update({prefix + n: t for n, t in want[k].items()})
+    sd["train_acc.mean_value"] = torch.zeros(())
+    ckpt = str(tmp_path / "best-v0.ckpt")
+    torch.save({"state_dict": sd, "epoch": 3}, ckpt)
+    states = ck.load_lightning_checkpoint(ckpt)
+    assert sorted(states) == ["dce", "dwi", "fusion"] and set(states["fusion"]) == set(want["fusion"])
+    # ... and of a single-modality module (prefix `model.`, prepare_single_model.py:215)
+    torch.save({"state_dict": {"model." + n: t for n, t in want["dwi"].items()}}, ckpt)
+    single = ck.load_lightning_checkpoint(ckpt)
+    assert list(single) == ["model"]
+    assert ck.apply_states(single, model=mm.ModelMaskHeadBackbone("dwi", params))["model"] == ([], [])
+    with pytest.raises(ValueError):
+        ck.split_lightning_state_dict({"foo.bar": torch.zeros(1)})
