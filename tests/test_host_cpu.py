@@ -333,3 +333,26 @@ def test_reference_checkpoint_layouts_roundtrip(tmp_path):
     assert ck.apply_states(single, model=mm.ModelMaskHeadBackbone("dwi", params))["model"] == ([], [])
     with pytest.raises(ValueError):
         ck.split_lightning_state_dict({"foo.bar": torch.zeros(1)})
+
+
+@pytest.mark.parametrize("name", ["r1_bench_c3.json", "r1_bench_c5.json", "r1_bench_c4.json"])
+def test_committed_bench_lines_keep_the_driver_contract(name):
+    """The JSON lines bench.py printed on the B200 boxes (profiles/) carry every key of the bench contract."""
+    with open(os.path.join(ROOT, "profiles", name)) as f:
+        line = json.loads(f.read().strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["unit"] == "cases/s" and line["higher_is_better"] is True and line["scaling"] == "weak"
+    assert line["vs_baseline"] is None and line["data"] == "synthetic" and "workload" in line["config"]
+    assert line["value"] > 0 and line["gpu_launches"] > 0 and line["warmup"] >= 3
+    e2e = line["e2e"]
+    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
+    assert e2e["value"] <= 1.02 * line["value"]            # host copies inside the timed region never make it faster
+    roof = line["roofline"]
+    assert roof["bound"] in ("hbm", "tensor") and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+    assert 0.0 < roof["frac"] < 1.0
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"])
+    cpu = line["cpu_baseline"]
+    assert cpu is None or ({"value", "unit", "cores", "kind", "sample"} <= set(cpu) and cpu["kind"] in ("port", "reference"))
