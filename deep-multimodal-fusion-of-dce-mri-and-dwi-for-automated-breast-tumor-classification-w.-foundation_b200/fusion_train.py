@@ -77,11 +77,17 @@ def _split_k(m, n, k):
     return max(1, min((2 * 148 + tiles - 1) // tiles, max(1, k // 64)))
 
 
-class FusionHeadTrainer:
+class FusionHeadTrainer(torch.optim.Optimizer):
     """Owns the flat parameter / gradient / AdamW-moment buffers of a `model_module.FusionModel` and runs its
-    classification fine-tuning step.  `lr`, `betas`, `eps`, `weight_decay` as torch.optim.AdamW
-    (code/selector_helpers.py:222-229); `smoothing` = label_smoothing_alpha, `gamma` / `class_weights` as
-    Soft(Weighted)FocalLoss (code/selector_helpers.py:14-46)."""
+    fine-tuning step.  `lr`, `betas`, `eps`, `weight_decay` as torch.optim.AdamW (code/selector_helpers.py:222-229);
+    `smoothing` = label_smoothing_alpha, `gamma` / `class_weights` as Soft(Weighted)FocalLoss
+    (code/selector_helpers.py:14-46).
+
+    It IS a `torch.optim.Optimizer` (one parameter group, the fusion head): torch's learning-rate schedulers - the
+    ones the reference's `_build_scheduler` creates (code/selector_helpers.py:692-728) - and harnesses that expect an
+    optimizer from `configure_optimizers` drive it unchanged; `step()` launches the fused AdamW kernel with the
+    group's current `lr` / `weight_decay`, `zero_grad()` clears the flat gradient buffer (the `.grad` views are never
+    dropped, whatever `set_to_none` says)."""
 
     def __init__(self, fusion_model, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=4e-5, smoothing=0.1,
                  gamma=1.5, class_weights=None, lambda_mask=0.0, mask_loss_type="dice", process_group=None):
@@ -93,7 +99,6 @@ class FusionHeadTrainer:
                                        fm.fusion_channels // fm.mha_heads > 128):
             raise NotImplementedError("token_pool / head size outside the attention kernel's range")
         self.model = fm
-        self.lr, self.betas, self.eps, self.weight_decay = lr, tuple(betas), eps, weight_decay
         self.smoothing, self.gamma = float(smoothing), float(gamma)
         self.class_weights = class_weights
         self.lambda_mask = float(lambda_mask)  # > 0: + lambda_mask * mean of the three mask loss terms
@@ -131,6 +136,16 @@ class FusionHeadTrainer:
         self.flat_numel = flat_size(self.params)            # elements of the flat buffers (with alignment padding)
         self._flat = None
         self._ws = {}
+        super().__init__(self.params, dict(lr=float(lr), betas=tuple(betas), eps=float(eps),
+                                           weight_decay=float(weight_decay)))
+
+    # hyper-parameters live in the (single) parameter group, where torch's schedulers read and write them
+    def _hp(name):  # noqa: N805
+        return property(lambda self: self.param_groups[0][name],
+                        lambda self, value: self.param_groups[0].__setitem__(name, value))
+
+    lr, betas, eps, weight_decay = _hp("lr"), _hp("betas"), _hp("eps"), _hp("weight_decay")
+    del _hp
 
     # ------------------------------------------------------------------------------------------ buffers ----
     def _bind(self):
@@ -203,7 +218,7 @@ class FusionHeadTrainer:
         return ws
 
     # ---------------------------------------------------------------------------------------- the step ----
-    def zero_grad(self):
+    def zero_grad(self, set_to_none=False):
         self._bind()["g"].zero_()
 
     def loss_and_grads(self, f3_dwi, f3_dce, dwi_mask_pred, dce_mask_pred, labels, masks=None):
@@ -409,13 +424,15 @@ class FusionHeadTrainer:
             wgrad(ws["auc"], ws["sc"], "proj_in_dce.weight")
         return loss, ws["logits"]
 
-    def step(self):
+    def step(self, closure=None):
         """Gradient all-reduce (when torch.distributed is initialised) + one fused AdamW launch."""
+        if closure is not None:
+            raise NotImplementedError("closures are not supported: the step has no autograd graph to re-evaluate")
         flat = self._bind()
         scale = average_gradients(flat["g"], self.group)
         self.step_count += 1
-        nat.adamw(flat["p"], flat["g"][:self.flat_numel], flat["m"], flat["v"], lr=self.lr, betas=self.betas, eps=self.eps,
-                  weight_decay=self.weight_decay, step=self.step_count, grad_scale=scale)
+        nat.adamw(flat["p"], flat["g"][:self.flat_numel], flat["m"], flat["v"], lr=float(self.lr), betas=self.betas,
+                  eps=self.eps, weight_decay=self.weight_decay, step=self.step_count, grad_scale=scale)
         for p in self.params:  # the kernel wrote through raw pointers: tell torch (packed-weight caches key on it)
             torch.autograd.graph.increment_version(p)
         return flat["g"][self.flat_numel:] * scale  # the loss averaged over ranks
@@ -430,7 +447,8 @@ class FusionHeadTrainer:
     def state_dict(self):
         flat = self._bind()
         return {"step": self.step_count, "names": list(self.names), "exp_avg": flat["m"].clone(),
-                "exp_avg_sq": flat["v"].clone()}
+                "exp_avg_sq": flat["v"].clone(),
+                "hyper": {k: self.param_groups[0][k] for k in ("lr", "betas", "eps", "weight_decay")}}
 
     def load_state_dict(self, sd):
         flat = self._bind()
@@ -439,3 +457,4 @@ class FusionHeadTrainer:
         self.step_count = int(sd["step"])
         flat["m"].copy_(sd["exp_avg"])
         flat["v"].copy_(sd["exp_avg_sq"])
+        self.param_groups[0].update(sd.get("hyper", {}))

@@ -216,7 +216,38 @@ class LightningFusionModel(nn.Module):
             gamma=2 if gamma is None else gamma, class_weights=getattr(self, "_class_weights", None),
             lambda_mask=self._lambda_mask(),
             mask_loss_type=fp.get("mask_parameters", {}).get("mask_loss_type", "dice"))
-        return self.head_trainer
+        sched = self._build_scheduler(fp.get("scheduler", None), self.head_trainer)
+        if sched is None:
+            return self.head_trainer
+        return {"optimizer": self.head_trainer, "lr_scheduler": sched}   # train_fusion.py:151-161
+
+    @staticmethod
+    def _build_scheduler(cfg, optimizer):
+        """LightningFusionOptimizerFactory._build_scheduler (selector_helpers.py:692-728): torch's own schedulers on
+        the trainer, which is a torch.optim.Optimizer."""
+        if cfg is None:
+            return None
+        import math
+
+        name = cfg["name"].lower()
+        if name == "reduce_lr_on_plateau":
+            sch = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, mode="min", factor=cfg["factor"],
+                                                             patience=cfg["patience"], min_lr=cfg["min_lr"],
+                                                             threshold=cfg["threshold"])
+            return {"scheduler": sch, "monitor": cfg["monitor"], "interval": "epoch"}
+        if name == "cosine":
+            sch = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=cfg["T_max"], eta_min=cfg["eta_min"])
+            return {"scheduler": sch, "interval": "epoch"}
+        if name == "cosine_with_warmup":
+            warmup, max_steps = cfg.get("warmup_steps", 500), cfg.get("max_steps", 10000)
+
+            def lr_lambda(step):
+                if step < warmup:
+                    return float(step) / float(warmup)
+                return 0.5 * (1 + math.cos(math.pi * (step - warmup) / float(max_steps - warmup)))
+
+            return {"scheduler": torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda), "interval": "step"}
+        raise ValueError(f"Unknown scheduler: {cfg['name']}")
 
     def set_class_weights(self, train_labels):
         """Inverse class frequency weights of the 'wfl' loss (selector_helpers.py:25-41)."""

@@ -159,6 +159,30 @@ def test_shared_step_rejects_unbuilt_loss_terms():
         "lr_decay_factor": 1.2, "discriminative_reg": True, "reg_decay_factor": 0.8, "reg_base": 1e-4}
     tr = lm.configure_optimizers()   # last group of the discriminative schedule: base lr, reg_base weight decay
     assert (tr.lr, tr.weight_decay, tr.betas) == (3e-4, 1e-4, (0.9, 0.99))
+    # the trainer is a torch.optim.Optimizer: the reference's scheduler choices (selector_helpers.py:692-728) drive it
+    assert isinstance(tr, torch.optim.Optimizer) and len(tr.param_groups) == 1
+    params["fusion_model_parameters"]["scheduler"] = {"name": "cosine", "T_max": 10, "eta_min": 1e-6}
+    both = lm.configure_optimizers()
+    tr, sch = both["optimizer"], both["lr_scheduler"]["scheduler"]
+    twin = torch.optim.AdamW([torch.nn.Parameter(torch.zeros(1))], lr=3e-4)
+    twin_sch = torch.optim.lr_scheduler.CosineAnnealingLR(twin, T_max=10, eta_min=1e-6)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")      # (scheduler.step() before optimizer.step(): no GPU here)
+        for _ in range(4):
+            sch.step()
+            twin_sch.step()
+    assert tr.lr == twin.param_groups[0]["lr"] and both["lr_scheduler"]["interval"] == "epoch"
+    params["fusion_model_parameters"]["scheduler"] = {"name": "reduce_lr_on_plateau", "factor": 0.5, "patience": 0,
+                                                      "min_lr": 1e-7, "threshold": 1e-4, "monitor": "val_loss"}
+    both = lm.configure_optimizers()
+    both["lr_scheduler"]["scheduler"].step(1.0)
+    both["lr_scheduler"]["scheduler"].step(2.0)
+    assert both["optimizer"].lr == 1.5e-4 and both["lr_scheduler"]["monitor"] == "val_loss"
+    params["fusion_model_parameters"]["scheduler"] = {"name": "nope"}
+    with pytest.raises(ValueError):
+        lm.configure_optimizers()
+    params["fusion_model_parameters"].pop("scheduler")
     w = lm.set_class_weights(torch.tensor([0, 0, 1, 2, 3, 3, 3, 3]))
     assert torch.allclose(w, torch.tensor([1.0, 2.0, 2.0, 0.5]), atol=1e-5)
 
