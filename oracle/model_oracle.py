@@ -37,7 +37,12 @@ class SD:
         return (self.prefix + name) in self.sd
 
 
+BN_BATCH_STATS = False  # train-mode BatchNorm (batch statistics); set by oracle.train_oracle around its forward only
+
+
 def _bn(x, s: SD):
+    if BN_BATCH_STATS:  # nn.BatchNorm2d in train mode: normalise with the batch statistics (running stats untouched here)
+        return F.batch_norm(x, None, None, s["weight"], s["bias"], True, 0.0, BN_EPS)
     return F.batch_norm(x, s["running_mean"], s["running_var"], s["weight"], s["bias"], False, 0.0, BN_EPS)
 
 

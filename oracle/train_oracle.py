@@ -106,3 +106,60 @@ def train_steps(sd, params, batch, steps, smoothing, gamma, class_weights, lr, b
             sd[k], m, v = adamw_step(sd[k], g, m, v, it, lr, betas, eps, weight_decay)
             state[k] = (m, v)
     return losses, sd, names
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the rest of the reference's frozen-phase objective (NOT built in the CUDA path yet: this pins the oracle ahead of it)
+# ----------------------------------------------------------------------------------------------------------------
+def charbonnier_loss(pred, target, eps=1e-3):
+    """train.py:1041-1042."""
+    return torch.mean(torch.sqrt((pred - target) ** 2 + eps ** 2))
+
+
+def recon_list_loss(recon, input_img):
+    """compute_recon_list_loss for one reconstruction tensor (train_fusion.py:709-745) with recon_image_loss
+    (train.py:1043-1048): bilinear up-sample to the input size, channel means when the channel counts differ,
+    sigmoid -> clamp -> Charbonnier."""
+    if recon is None:
+        return torch.zeros(())
+    r_up = F.interpolate(recon, size=input_img.shape[-2:], mode="bilinear", align_corners=False)
+    target = input_img
+    if r_up.size(1) != input_img.size(1):
+        r_up, target = r_up.mean(dim=1, keepdim=True), input_img.mean(dim=1, keepdim=True)
+    return charbonnier_loss(torch.sigmoid(r_up).clamp(0, 1), target.clamp(0, 1))
+
+
+def mimic_feat_loss(s_feat, t_feat, eps=1e-6):
+    """train.py:1033-1038 (teacher detached)."""
+    s = F.normalize(s_feat.flatten(1), dim=1)
+    t = F.normalize(t_feat.detach().flatten(1), dim=1)
+    return (1.0 - (s * t).sum(dim=1).clamp(-1 + eps, 1 - eps)).mean()
+
+
+def full_objective_and_grads(sd, params, f3_dwi, f3_dce, mask_dwi, mask_dce, labels, masks, dwi_in, dce_in, smoothing,
+                             gamma, class_weights, lambda_mask, lambda_recon, lambda_mimic, aux_w=1.0):
+    """Total training loss of LightningFusionModel._shared_step (train_fusion.py:238-292) as far as it depends on the
+    fusion head, FusionModel in TRAIN mode (batch-statistic BatchNorm in the reconstruction head and the projector):
+    classification + lambda_mask * mean of three dice terms + lambda_recon * recon_fused / 3 + lambda_mimic * mimic
+    (the encoders' own reconstruction lists are taken as absent, which compute_recon_list_loss maps to 0).  The
+    reference's mimic term unpacks `proj_fused[:4]` - the FIRST FOUR CASES of the fused projection - as
+    (p1, p1_r, p2, p2_r) (train_fusion.py:287-290): reproduced as is.  -> (loss, parts, {name: grad})."""
+    def is_param(k, v):
+        return v.is_floating_point() and k.rsplit(".", 1)[-1] not in ("running_mean", "running_var")
+
+    leaf = {k: (v.detach().clone().requires_grad_(True) if is_param(k, v) else v) for k, v in sd.items()}
+    mo.BN_BATCH_STATS = True
+    try:
+        logits, fused_mask, aux = mo.fusion_forward(leaf, params, [f3_dwi], [f3_dce], mask_dwi, mask_dce)
+    finally:
+        mo.BN_BATCH_STATS = False
+    cls = soft_focal_loss(logits, smoothed_targets(labels, logits.shape[1], smoothing), gamma, class_weights)
+    mask = (soft_dice_loss(mask_dwi, masks) + soft_dice_loss(mask_dce, masks) + soft_dice_loss(fused_mask, masks)) / 3
+    recon = recon_list_loss(aux["recon_fused"], torch.cat([dwi_in, dce_in], dim=1)) / 3
+    p1, p1_r, p2, p2_r = aux["proj_fused"][:4]
+    mimic = (mimic_feat_loss(p1, p1_r) + mimic_feat_loss(p2, p2_r)) / 2
+    loss = cls + lambda_mask * mask + lambda_recon * recon * aux_w + lambda_mimic * mimic * aux_w
+    loss.backward()
+    grads = {k: v.grad for k, v in leaf.items() if is_param(k, v) and v.grad is not None}
+    parts = {"cls": cls.item(), "mask": mask.item(), "recon": recon.item(), "mimic": mimic.item()}
+    return loss.detach(), parts, grads

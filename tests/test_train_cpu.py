@@ -230,3 +230,23 @@ def test_training_entry_points_reject_bad_arguments_without_a_gpu():
     assert lib.b200_adamw(None, None, None, None, 8, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0, 1.0, None) < 0  # step < 1
     assert lib.b200_head_loss(None, 4, None) < 0
     assert lib.b200_colsum(None, 1, 0, 4, None, None) == 0
+
+
+def test_oracle_full_frozen_phase_objective_matches_the_reference():
+    """classification + mask dice + fused reconstruction + mimic (train_fusion.py:238-292) with FusionModel in train
+    mode (batch-statistic BatchNorm in ReconHead / Projector), computed by the reference's OWN loss functions
+    (oracle/make_golden_train.py::main_full): the oracle restatement reproduces the total, every term and all 35
+    gradients.  (The CUDA path builds the first two terms; this pins the oracle for the other two.)"""
+    gold, hp, params, sd, batch = _setup("train_head_full.npz")
+    dwi_in, dce_in, masks, _ = op.synthetic_raw(hp["n"], seed=hp["seed"] + 1, kind="S")
+    dwi_in = dwi_in / dwi_in.amax(dim=(1, 2, 3), keepdim=True)
+    loss, parts, grads = to.full_objective_and_grads(
+        sd, params, *batch, masks, dwi_in, dce_in, hp["smoothing"], hp["gamma"], torch.tensor(hp["class_weights"]),
+        hp["lambda_mask"], hp["lambda_recon"], hp["lambda_mimic"])
+    total, cls, mask, recon, mimic = gold["parts"]
+    assert abs(float(loss) - total) <= 1e-5 * abs(total)
+    for got, want in ((parts["cls"], cls), (parts["mask"], mask), (parts["recon"], recon), (parts["mimic"], mimic)):
+        assert abs(got - want) <= 1e-5 * abs(want), parts
+    assert sorted(grads) == sorted(hp["with_grad"]) and len(grads) == 35
+    for k in grads:
+        gu.check(gold, f"grad/{k}", grads[k], 5e-4, what="gradient ")
