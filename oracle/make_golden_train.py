@@ -174,8 +174,56 @@ def main_full(out_name="train_head_full.npz"):
     print("full objective", out["parts"], len(names), "tensors with a gradient")
 
 
+def main_c1(out_name="train_c1_dwi.npz", n=8):
+    """BASELINE config C1: the DWI CNN encoder's forward + training loss + backward on the CPU, by the reference's
+    own modules and loss functions (code/train.py behind the import stubs), dropouts at p = 0 so that the train-mode
+    forward is deterministic.  Composed exactly as LightningSingleModel._shared_step does (train.py:294-400)."""
+    import types
+
+    stub_harness_modules()
+    import loss as ref_loss
+    import model_module as mm
+    import train as ref_train
+
+    p = mg.configure(mg.reference_parameters())
+    mp = p["dwi_model_parameters"]
+    mp["dropout"] = 0.0
+    lam = {"lambda_mask": mp["mask_parameters"]["lambda_mask"], "lambda_recon": mp["lambda_recon"],
+           "lambda_mimic": mp["lambda_mimic"], "lambda_feat_norm": mp["lambda_feat_norm"]}
+    torch.manual_seed(0)
+    model = mm.ModelMaskHeadBackbone("dwi", p, None)
+    model.load_state_dict(op.seeded_state_dict(op.shapes_of(model.state_dict()), seed=HP["weight_seed"]))
+    model.train()
+    dwi_raw, _, masks, labels = op.synthetic_raw(n, seed=1234, kind="S")
+    x = dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)
+    outputs, aux, mask_output = model(x, masks)
+    smoother = ref_loss.LabelSmoothing(p["class_num"], HP["smoothing"])
+    crit = ref_loss.SoftWeightedFocalLoss(HP["gamma"], torch.tensor(HP["class_weights"]))
+    cls = crit(outputs, smoother(outputs, labels))
+    feat_norm = ref_train.compute_feat_norm_loss(aux, x.device)
+    mask = ref_loss.SoftDiceLoss()(mask_output, masks)
+    ns = types.SimpleNamespace(device=x.device, mimic_enabled=True, lambda_recon=lam["lambda_recon"],
+                               lambda_mimic=lam["lambda_mimic"])
+    recon_w, mimic_w = ref_train.LightningSingleModel.compute_aux_losses(ns, aux, x, aux["proj_pairs"], 1.0, True)
+    total = (cls + lam["lambda_feat_norm"] * feat_norm + lam["lambda_mask"] * mask +
+             lam["lambda_recon"] * recon_w * 1.0 + lam["lambda_mimic"] * mimic_w * 1.0)       # train.py:396-399
+    total.backward()
+    out, names = {}, []
+    mg.flatten("logits", outputs, out)
+    mg.flatten("mask", mask_output, out)
+    for k, v in model.named_parameters():
+        if v.grad is not None:
+            mg.flatten(f"grad/{k}", v.grad, out)
+            names.append(k)
+    out["parts"] = np.array([t.item() for t in (total, cls, feat_norm, mask, recon_w, mimic_w)], dtype=np.float64)
+    out["hp"] = np.array(json.dumps(dict(HP, **lam, n=n, with_grad=names)))
+    np.savez_compressed(os.path.join(mg.GOLD, out_name), **out)
+    print("C1 objective", out["parts"], len(names), "tensors with a gradient")
+
+
 if __name__ == "__main__":
     main()
     main(lambda_mask=0.2, out_name="train_head_mask.npz")
     main(lambda_mask=0.2, out_name="train_head_mask_bce.npz", mask_loss_type="dice_bce")
     main_full()
+    main_c1()

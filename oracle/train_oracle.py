@@ -163,3 +163,42 @@ def full_objective_and_grads(sd, params, f3_dwi, f3_dce, mask_dwi, mask_dce, lab
     grads = {k: v.grad for k, v in leaf.items() if is_param(k, v) and v.grad is not None}
     parts = {"cls": cls.item(), "mask": mask.item(), "recon": recon.item(), "mimic": mimic.item()}
     return loss.detach(), parts, grads
+
+
+def single_model_objective_and_grads(sd, params, method, x, masks, labels, smoothing, gamma, class_weights, lambda_mask,
+                                     lambda_recon, lambda_mimic, lambda_feat_norm, aux_w=1.0):
+    """Training loss of LightningSingleModel._shared_step (train.py:294-400, :434-466) for one modality's encoder in
+    TRAIN mode with its dropouts at p = 0 (BASELINE config C1: the DWI CNN forward + train step on the CPU):
+    classification + lambda_feat_norm * sum_f mean(f^2) + lambda_mask * dice(mask logits) + recon + mimic, where the
+    reference weights the last two TWICE - compute_aux_losses already multiplies by lambda * aux_w (:462-464) and
+    _shared_step multiplies again (:396-399): reproduced as is.  -> (loss, parts, {name: grad})."""
+    def is_param(k, v):
+        return v.is_floating_point() and k.rsplit(".", 1)[-1] not in ("running_mean", "running_var")
+
+    leaf = {k: (v.detach().clone().requires_grad_(True) if is_param(k, v) else v) for k, v in sd.items()}
+    mo.BN_BATCH_STATS = True
+    try:
+        logits, aux, mask_pred = mo.encoder_forward(leaf, method, params, x)
+    finally:
+        mo.BN_BATCH_STATS = False
+    cls = soft_focal_loss(logits, smoothed_targets(labels, logits.shape[1], smoothing), gamma, class_weights)
+    feat_norm = sum(f.pow(2).mean() for f in aux["raw_feats"])                            # train.py:1021-1030
+    mask = soft_dice_loss(mask_pred, masks)                                               # train.py:373-374
+    recon = torch.zeros(())
+    for r in aux["recon_feats"]:                                                          # train.py:446-454
+        if r is None:
+            continue
+        target = x
+        r_up = F.interpolate(r, size=target.shape[-2:], mode="bilinear", align_corners=False)
+        if r_up.size(1) == 1 and target.size(1) > 1:
+            target = target.mean(dim=1, keepdim=True)
+        recon = recon + charbonnier_loss(torch.sigmoid(r_up).clamp(0, 1), target.clamp(0, 1))
+    p1, p1_r, p2, p2_r = aux["proj_pairs"][:4]
+    mimic = mimic_feat_loss(p1, p1_r) + mimic_feat_loss(p2, p2_r)                         # train.py:457-459
+    loss = (cls + lambda_feat_norm * feat_norm + lambda_mask * mask +
+            lambda_recon * (recon * lambda_recon * aux_w) * aux_w + lambda_mimic * (mimic * lambda_mimic * aux_w) * aux_w)
+    loss.backward()
+    grads = {k: v.grad for k, v in leaf.items() if is_param(k, v) and v.grad is not None}
+    parts = {"cls": cls.item(), "feat_norm": feat_norm.item(), "mask": mask.item(), "recon": recon.item(),
+             "mimic": mimic.item()}
+    return loss.detach(), parts, grads

@@ -250,3 +250,29 @@ def test_oracle_full_frozen_phase_objective_matches_the_reference():
     assert sorted(grads) == sorted(hp["with_grad"]) and len(grads) == 35
     for k in grads:
         gu.check(gold, f"grad/{k}", grads[k], 5e-4, what="gradient ")
+
+
+def test_oracle_c1_single_modality_train_step_matches_the_reference():
+    """BASELINE config C1 (DWI CNN forward + train step on the CPU): the reference's own modules and loss functions
+    (oracle/make_golden_train.py::main_c1; train mode, dropout p = 0) against the oracle restatement - total, terms
+    and all 89 parameter gradients.  (The CUDA path does not train encoders; this pins the oracle for it.)"""
+    gold = gu.load("train_c1_dwi.npz")
+    hp = json.loads(str(gold["hp"]))
+    import parameters_default as pd
+
+    params = pd.default_parameters()
+    params["dwi_model_parameters"]["dropout"] = 0.0
+    sd = op.seeded_state_dict(gu.load_shapes("cnn")["dwi"], seed=hp["weight_seed"])
+    dwi_raw, _, masks, labels = op.synthetic_raw(hp["n"], seed=1234, kind="S")
+    x = dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)
+    loss, parts, grads = to.single_model_objective_and_grads(
+        sd, params, "dwi", x, masks, labels, hp["smoothing"], hp["gamma"], torch.tensor(hp["class_weights"]),
+        hp["lambda_mask"], hp["lambda_recon"], hp["lambda_mimic"], hp["lambda_feat_norm"])
+    total, cls, feat_norm, mask, recon_w, mimic_w = gold["parts"]
+    assert abs(float(loss) - total) <= 2e-5 * abs(total)
+    for got, want in ((parts["cls"], cls), (parts["feat_norm"], feat_norm), (parts["mask"], mask),
+                      (parts["recon"] * hp["lambda_recon"], recon_w), (parts["mimic"] * hp["lambda_mimic"], mimic_w)):
+        assert abs(got - want) <= 2e-5 * abs(want), (parts, gold["parts"])
+    assert sorted(grads) == sorted(hp["with_grad"]) and len(grads) == 89
+    worst = max(gu.check(gold, f"grad/{k}", grads[k], 1e-5, what="gradient ") for k in grads)
+    assert worst <= 1e-5   # (same torch operators in the same order: bit-identical in the authoring container)
