@@ -13,7 +13,9 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200fusion.so")
+# csrc/build.sh links the library at <repo>/lib/libb200fusion.so: a short path without the dots and dashes of the
+# package directory name, which is the path string dlopen sees.
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200fusion.so")
 ABI_VERSION = 17
 
 _lib = None
@@ -151,7 +153,12 @@ def lib():
             raise B200NativeError(
                 f"{LIB_PATH} is missing: build it with csrc/build.sh (or __graft_entry__.build()); "
                 "this package has no CPU or PyTorch fallback")
-        handle = C.CDLL(LIB_PATH)
+        path = LIB_PATH
+        # a checkout reached through the /root/repo symlink is opened under that name (same file, plain path)
+        alias = "/root/repo/lib/libb200fusion.so"
+        if path != alias and os.path.exists(alias) and os.path.samefile(alias, path):
+            path = alias
+        handle = C.CDLL(path)
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.argtypes = argtypes

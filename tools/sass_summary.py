@@ -15,8 +15,7 @@ sys.path.insert(0, ROOT)
 import b200path  # noqa: F401,E402
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
-so = os.path.join(b200path.PKG if hasattr(b200path, "PKG") else
-                  [os.path.join(ROOT, d) for d in os.listdir(ROOT) if d.endswith("_b200")][0], "libb200fusion.so")
+so = os.path.join(ROOT, "lib", "libb200fusion.so")
 out_dir = os.path.join(ROOT, "profiles", "sass")
 os.makedirs(out_dir, exist_ok=True)
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
