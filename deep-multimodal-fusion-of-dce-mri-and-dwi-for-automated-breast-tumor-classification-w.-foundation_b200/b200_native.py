@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # csrc/build.sh links the library at <repo>/lib/libb200fusion.so: a short path without the dots and dashes of the
 # package directory name, which is the path string dlopen sees.
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200fusion.so")
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 _lib = None
 
@@ -106,6 +106,7 @@ SIGNATURES = {
     "b200_linear": [_P, _LL, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _P],
     "b200_dwi_normalize": [_P, _P, _I, _I, _I, _I, _F, _F, _P, _P],
     "b200_nyul_transform": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "b200_nyul_transform_ex": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "b200_plane_mean": [_P, _I, _I, _P, _P],
     "b200_stem": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P],
     "b200_se_gate": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
@@ -142,6 +143,33 @@ SIGNATURES = {
                        _P, _P, _P, _P, _P],
     "b200_mask_wsum": [_P, _P, _I, _I, _I, _P, _P],
     "b200_mask_head_grads": [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
+    "b200_conv_wgrad": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b200_pack_conv_weights": [_P, _I, _I, _I, _P, _P, _P],
+    "b200_bn_stats": [_P, _LL, _I, _I, _P, _P, _P],
+    "b200_bn_finalize": [_P, _P, _I, C.c_double, _F, _F, _P, _P, _P, _P, _P],
+    "b200_bn_act_fwd": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _F, C.c_ulonglong, _LL, _I, _P, _I, _P],
+    "b200_bn_act_bwd": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _F, C.c_ulonglong, _LL, _I, _P, _I, _I, _P, _P, _I, _P, _I,
+                        _P, _P, _P],
+    "b200_map_dot": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "b200_map_scale_add": [_P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _P],
+    "b200_map_axpby": [_P, _I, _F, _P, _I, _F, _LL, _I, _P, _I, _P],
+    "b200_map_sumsq": [_P, _I, _LL, _I, _P, _P],
+    "b200_se_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "b200_se_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
+    "b200_convc1_fwd": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "b200_convc1_bwd": [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P],
+    "b200_lift_fwd": [_P, _LL, _I, _P, _P, _P],
+    "b200_lift_bwd": [_P, _P, _LL, _I, _P, _P, _P, _P],
+    "b200_modulate_bwd": [_P, _I, _P, _I, _P, _P, _LL, _I, _P, _I, _P, _P, _P],
+    "b200_mask_attn_bwd": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P],
+    "b200_stem_bwd": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P],
+    "b200_cls_head_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "b200_focal_loss": [_P, _P, _I, _I, _F, _F, _P, _F, _P, _P, _P],
+    "b200_dice_loss": [_P, _P, _I, _I, _F, _F, _P, _P, _P],
+    "b200_recon_loss": [_P, _I, _I, _I, _P, _I, _I, _I, _F, _F, _P, _P, _P],
+    "b200_mimic_loss": [_P, _P, _I, _LL, _F, _P, _P, _P],
+    "b200_up2_bwd": [_P, _I, _I, _I, _I, _P, _P],
+    "b200_vec_axpby": [_P, _F, _F, _LL, _P, _P],
 }
 
 
@@ -396,12 +424,13 @@ def dwi_normalize(x, out, C_, n, skip_last, z_lo, z_hi, plane_mean=None):
     return out
 
 
-def nyul_transform(x, out, C_, n, avg_landmarks, standard_scale, prev_index, gamma, plane_mean=None):
+def nyul_transform(x, out, C_, n, avg_landmarks, standard_scale, prev_index, gamma, plane_mean=None, exact=False):
+    """exact=False: composed piece-wise linear table per plane (<= 1 fp32 ulp from numpy); exact=True: numpy's own
+    fp64 operation order (bit-identical on > 99.9 % of the samples, ~6x the instructions)."""
     planes = x.numel() // n
     L = standard_scale.numel()
-    _call("b200_nyul_transform", None, _ptr(x), _ptr(out), planes, C_, n, L, _ptr(avg_landmarks),
-                                     _ptr(standard_scale), _ptr(prev_index), _ptr(gamma), _ptr(plane_mean),
-                                     _stream())
+    _call("b200_nyul_transform_ex", None, _ptr(x), _ptr(out), planes, C_, n, L, _ptr(avg_landmarks),
+          _ptr(standard_scale), _ptr(prev_index), _ptr(gamma), _ptr(plane_mean), 1 if exact else 0, _stream())
     return out
 
 

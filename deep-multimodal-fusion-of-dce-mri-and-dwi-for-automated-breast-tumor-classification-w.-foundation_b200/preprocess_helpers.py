@@ -51,8 +51,9 @@ class NyulStandardizer:
                 torch.from_numpy(prev.astype(np.int32)).to(dev), torch.from_numpy(virt - prev).to(dev))
         return self._dev_cache[key]
 
-    def transform_batch(self, x, num_channels=None, plane_mean=None):
-        """x [B,C,H,W] fp32 CUDA -> standardised fp32 [B,C,H,W]."""
+    def transform_batch(self, x, num_channels=None, plane_mean=None, exact=False):
+        """x [B,C,H,W] fp32 CUDA -> standardised fp32 [B,C,H,W].  `exact=True` reproduces numpy's fp64 operation
+        order bit for bit; the default composes the two interpolations into one table per plane (<= 1 fp32 ulp)."""
         if not self.fitted:
             raise RuntimeError("Call fit() first")
         x = x.contiguous().float()
@@ -62,7 +63,7 @@ class NyulStandardizer:
             raise ValueError("transform_batch standardises every channel of the batch")
         avg, scale, prev, gamma = self._device_tables(x.device, H * W, C)
         out = torch.empty_like(x)
-        nat.nyul_transform(x, out, C, H * W, avg, scale, prev, gamma, plane_mean)
+        nat.nyul_transform(x, out, C, H * W, avg, scale, prev, gamma, plane_mean, exact=exact)
         return out
 
     def transform(self, img, num_channels=6):

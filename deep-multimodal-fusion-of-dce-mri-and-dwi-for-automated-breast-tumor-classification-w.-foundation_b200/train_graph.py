@@ -1,0 +1,563 @@
+"""Training-mode forward + explicit backward of the encoders on the sm_100a kernels (BASELINE configs C1 / C5).
+
+The reference trains `ModelMaskHeadBackbone` through torch autograd (code/train.py:294-428, code/train_fusion.py:203-321):
+train-mode BatchNorm (batch statistics, running-statistics update), active nn.Dropout, every parameter receiving a
+gradient.  Here the same arithmetic is an explicit tape:
+
+* every tensor-core convolution = three launches of hand-written kernels - forward `b200_conv_gemm` on the bf16
+  packed weights, data gradient `b200_conv_gemm` on the flipped / transposed packing, weight gradient
+  `b200_conv_wgrad` (tcgen05 with MN-major operands straight from the NHWC maps; csrc/conv_wgrad.cu);
+* BatchNorm statistics / apply / backward, activations, residual adds, dropout (Philox, regenerated in the backward
+  pass), squeeze-excite, the mask head and mask-guided attention, the 1-channel convolutions, the stem, the
+  classifier and every loss term are the SIMT kernels of csrc/train_elem.cu;
+* PyTorch provides device memory, the parameter objects and (optionally) torch.distributed - no ATen arithmetic on
+  maps, no autograd engine.
+
+Activations and their gradients are NHWC bf16, parameter gradients fp32 accumulated straight into `param.grad` in the
+parameter's own layout, BatchNorm buffers updated in place like nn.BatchNorm2d does.  Covers the CNN encoder
+configuration of BASELINE.json (block1 reading the raw <= 32-channel input with stride 2, stride-1 block2 / block3,
+one bottleneck per block, mask head on f2): anything else raises.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+import b200_native as nat
+
+_P = nat._ptr
+
+
+def _s():
+    return nat._stream()
+
+
+def _call(name, *args):
+    nat._call(name, None, *args)
+
+
+class Tape:
+    """Reverse-mode bookkeeping: `grads` maps a tensor's id to the gradient accumulated so far (bf16 maps / fp32
+    vectors); `steps` are closures run in reverse order by `backward`."""
+
+    def __init__(self):
+        self.steps = []
+        self.grads = {}
+        self.keep = []  # tensors referenced by id must stay alive
+
+    def record(self, fn):
+        self.steps.append(fn)
+
+    def grad_of(self, t):
+        return self.grads.pop(id(t), None)
+
+    def add_grad(self, t, g):
+        """Accumulate gradient g for tensor t (takes ownership of g on first use)."""
+        self.keep.append(t)
+        cur = self.grads.get(id(t))
+        if cur is None:
+            self.grads[id(t)] = g
+        elif g.dtype == torch.bfloat16:
+            C = g.shape[-1]
+            _call("b200_map_axpby", _P(cur), nat._ld(cur), 1.0, _P(g), nat._ld(g), 1.0, g.numel() // C, C, _P(cur),
+                  nat._ld(cur), _s())
+        else:
+            _call("b200_vec_axpby", _P(g), 1.0, 1.0, g.numel(), _P(cur), _s())
+
+    def backward(self):
+        for fn in reversed(self.steps):
+            fn()
+        self.steps.clear()
+        self.grads.clear()
+        self.keep.clear()
+
+
+def _grad_buf(p):
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, dtype=torch.float32)
+    return p.grad
+
+
+def _rows(t):
+    return t.numel() // t.shape[-1]
+
+
+class _Scratch:
+    """Reusable device scratch (fp64 reduction buffers)."""
+
+    def __init__(self, dev):
+        self.d2c = torch.zeros(2 * 2048, dtype=torch.float64, device=dev)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# differentiable building blocks
+# ------------------------------------------------------------------------------------------------------------------
+class TrainOps:
+    def __init__(self, dev, drop_seed=0x5EED):
+        self.dev = dev
+        self.tape = Tape()
+        self.scratch = _Scratch(dev)
+        self._packs = {}
+        self._seed = int(drop_seed)
+        self._launch = 0
+
+    def next_seed(self):
+        self._launch += 1
+        return (self._seed * 0x9E3779B97F4A7C15 + self._launch * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+
+    # ---- weights ------------------------------------------------------------------------------------------------
+    def packed(self, conv, need_dgrad=True):
+        """bf16 operands of a tensor-core conv, repacked from the fp32 master weights (once per step)."""
+        key = id(conv)
+        if key in self._packs:
+            return self._packs[key]
+        w = conv.weight
+        cout, cin, kh, kw = w.shape
+        taps = kh * kw
+        if taps not in (1, 9) or conv.stride != (1, 1) or cin % 64 or cout % 64:
+            raise NotImplementedError(f"training path: conv {tuple(w.shape)} stride {conv.stride}")
+        wf = torch.empty((cout, taps * cin), dtype=torch.bfloat16, device=self.dev)
+        wd = torch.empty((cin, taps * cout), dtype=torch.bfloat16, device=self.dev) if need_dgrad else None
+        _call("b200_pack_conv_weights", _P(w.detach()), cout, cin, taps, _P(wf), _P(wd), _s())
+        self._packs[key] = (wf, wd, taps)
+        return self._packs[key]
+
+    def new_step(self):
+        self._packs.clear()
+
+    # ---- convolution (tensor cores) -------------------------------------------------------------------------------
+    def conv(self, x, conv, x_needs_grad=True):
+        """z = conv(x) without bias (the bias, if any, is applied by bn_act as `beta`).  x NHWC bf16."""
+        wf, wd, taps = self.packed(conv, x_needs_grad)
+        z = nat.conv_gemm(x, wf, taps=taps)
+        tape = self.tape
+
+        def bwd():
+            dz = tape.grad_of(z)
+            if dz is None:
+                return
+            B, H, W, cin = x.shape
+            cout = z.shape[-1]
+            if conv.weight.requires_grad:
+                _call("b200_conv_wgrad", _P(dz), nat._ld(dz), _P(x), nat._ld(x), _P(_grad_buf(conv.weight)), B, H, W, cin,
+                      cout, taps, _s())
+            if x_needs_grad:
+                tape.add_grad(x, nat.conv_gemm(dz, wd, taps=taps))
+
+        tape.record(bwd)
+        return z
+
+    # ---- BatchNorm (batch statistics) + residual + activation + dropout ---------------------------------------------
+    def bn_act(self, z, bn=None, bias=None, act=0, res=None, drop_p=0.0, train_bn=True):
+        """a = dropout(act(BN(z) + res)); `bn` an nn.BatchNorm2d in training mode (or None: `bias` only)."""
+        R, C = _rows(z), z.shape[-1]
+        dev = self.dev
+        mean = invstd = gamma = beta = None
+        if bn is not None:
+            st = self.scratch.d2c[:2 * C]
+            st.zero_()
+            _call("b200_bn_stats", _P(z), R, C, nat._ld(z), _P(st), _P(st[C:]), _s())
+            mean = torch.empty(C, dtype=torch.float32, device=dev)
+            invstd = torch.empty(C, dtype=torch.float32, device=dev)
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            _call("b200_bn_finalize", _P(st), _P(st[C:]), C, float(R), float(bn.eps), float(mom),
+                  _P(bn.running_mean) if bn.track_running_stats else None,
+                  _P(bn.running_var) if bn.track_running_stats else None, _P(mean), _P(invstd), _s())
+            if bn.track_running_stats:
+                bn.num_batches_tracked += 1
+            gamma, beta = bn.weight, bn.bias
+        elif bias is not None:
+            beta = bias
+        seed = self.next_seed() if drop_p > 0 else 0
+        a = torch.empty(z.shape, dtype=torch.bfloat16, device=dev)
+        _call("b200_bn_act_fwd", _P(z), nat._ld(z), _P(res), nat._ld(res) if res is not None else 0, _P(mean), _P(invstd),
+              _P(gamma.detach()) if gamma is not None else None, _P(beta.detach()) if beta is not None else None, act,
+              float(drop_p), seed, R, C, _P(a), nat._ld(a), _s())
+        tape = self.tape
+
+        def bwd():
+            da = tape.grad_of(a)
+            if da is None:
+                return
+            dz = torch.empty(z.shape, dtype=torch.bfloat16, device=dev)
+            dres = torch.empty(res.shape, dtype=torch.bfloat16, device=dev) if res is not None else None
+            dg = _grad_buf(gamma) if (gamma is not None and gamma.requires_grad) else None
+            db = _grad_buf(beta) if (beta is not None and beta.requires_grad) else None
+            _call("b200_bn_act_bwd", _P(z), nat._ld(z), _P(res), nat._ld(res) if res is not None else 0, _P(mean),
+                  _P(invstd), _P(gamma.detach()) if gamma is not None else None,
+                  _P(beta.detach()) if beta is not None else None, act, float(drop_p), seed, R, C, _P(da), nat._ld(da),
+                  1 if bn is not None else 0, _P(self.scratch.d2c), _P(dz), nat._ld(dz), _P(dres),
+                  nat._ld(dres) if dres is not None else 0, _P(dg), _P(db), _s())
+            tape.add_grad(z, dz)
+            if res is not None:
+                tape.add_grad(res, dres)
+
+        tape.record(bwd)
+        return a
+
+    # ---- squeeze-excite on a map -----------------------------------------------------------------------------------
+    def se(self, x, se_mod):
+        """SEBlock (reference model_module.py:25-43): returns x * gate, gate."""
+        B, H, W, C = x.shape
+        npix = H * W
+        dev = self.dev
+        c1, c2 = se_mod.fc[1], se_mod.fc[3]
+        M = c1.out_channels
+        sums = torch.empty((B, C), dtype=torch.float32, device=dev)
+        _call("b200_map_dot", _P(x), nat._ld(x), None, 0, B, npix, C, _P(sums), _s())
+        pooled = torch.empty((B, C), dtype=torch.float32, device=dev)
+        gate = torch.empty((B, C), dtype=torch.float32, device=dev)
+        _call("b200_se_fwd", _P(sums), B, C, M, npix, _P(c1.weight.detach()), _P(c1.bias.detach()), _P(c2.weight.detach()),
+              _P(c2.bias.detach()), _P(pooled), _P(gate), _s())
+        y = torch.empty(x.shape, dtype=torch.bfloat16, device=dev)
+        _call("b200_map_scale_add", _P(x), nat._ld(x), _P(gate), None, B, npix, C, _P(y), nat._ld(y), 0, _s())
+        tape = self.tape
+
+        def bwd():
+            dy = tape.grad_of(y)
+            if dy is None:
+                return
+            dgate = torch.empty((B, C), dtype=torch.float32, device=dev)
+            _call("b200_map_dot", _P(dy), nat._ld(dy), _P(x), nat._ld(x), B, npix, C, _P(dgate), _s())
+            dpooled = torch.empty((B, C), dtype=torch.float32, device=dev)
+            da2 = torch.empty((B, C), dtype=torch.float32, device=dev)
+            da1 = torch.empty((B, M), dtype=torch.float32, device=dev)
+            h = torch.empty((B, M), dtype=torch.float32, device=dev)
+            _call("b200_se_bwd", _P(pooled), _P(c1.weight.detach()), _P(c1.bias.detach()), _P(c2.weight.detach()),
+                  _P(c2.bias.detach()), _P(dgate), B, C, M, _P(dpooled), _P(da2), _P(da1), _P(h), _s())
+            # weight gradients: dW2 [C,M] += da2^T h, dW1 [M,C] += da1^T pooled, biases = column sums
+            nat.sgemm(da2, h, _grad_buf(c2.weight).view(C, M), trans_a=True, beta=1)
+            nat.sgemm(da1, pooled, _grad_buf(c1.weight).view(M, C), trans_a=True, beta=1)
+            nat.colsum(da2, _grad_buf(c2.bias))
+            nat.colsum(da1, _grad_buf(c1.bias))
+            # dx = dy * gate + dpooled / npix
+            _call("b200_vec_axpby", _P(dpooled), 1.0 / npix, 0.0, dpooled.numel(), _P(dpooled), _s())
+            dx = torch.empty(x.shape, dtype=torch.bfloat16, device=dev)
+            _call("b200_map_scale_add", _P(dy), nat._ld(dy), _P(gate), _P(dpooled), B, npix, C, _P(dx), nat._ld(dx), 0, _s())
+            tape.add_grad(x, dx)
+
+        tape.record(bwd)
+        return y, gate
+
+    # ---- C -> 1 convolution ---------------------------------------------------------------------------------------------
+    def conv_c1(self, x, conv):
+        B, H, W, C = x.shape
+        taps = conv.kernel_size[0] * conv.kernel_size[1]
+        out = torch.empty((B, H, W), dtype=torch.float32, device=self.dev)
+        _call("b200_convc1_fwd", _P(x), nat._ld(x), B, H, W, C, taps, _P(conv.weight.detach()),
+              _P(conv.bias.detach()) if conv.bias is not None else None, _P(out), _s())
+        tape = self.tape
+
+        def bwd():
+            do = tape.grad_of(out)
+            if do is None:
+                return
+            dx = torch.empty(x.shape, dtype=torch.bfloat16, device=self.dev)
+            _call("b200_convc1_bwd", _P(x), nat._ld(x), _P(do), B, H, W, C, taps, _P(conv.weight.detach()), _P(dx),
+                  nat._ld(dx), 0, _P(_grad_buf(conv.weight)), _P(_grad_buf(conv.bias)) if conv.bias is not None else None,
+                  _s())
+            tape.add_grad(x, dx)
+
+        tape.record(bwd)
+        return out
+
+    # ---- 1 -> N convolution of a 1-channel fp32 map ------------------------------------------------------------------------
+    def lift(self, r, conv, r_needs_grad=True):
+        N = conv.out_channels
+        z = torch.empty((*r.shape, N), dtype=torch.bfloat16, device=self.dev)
+        _call("b200_lift_fwd", _P(r), r.numel(), N, _P(conv.weight.detach()), _P(z), _s())
+        tape = self.tape
+
+        def bwd():
+            dz = tape.grad_of(z)
+            if dz is None:
+                return
+            dr = torch.empty(r.shape, dtype=torch.float32, device=self.dev) if r_needs_grad else None
+            _call("b200_lift_bwd", _P(dz), _P(r), r.numel(), N, _P(conv.weight.detach()), _P(_grad_buf(conv.weight)), _P(dr),
+                  _s())
+            if r_needs_grad:
+                tape.add_grad(r, dr)
+
+        tape.record(bwd)
+        return z
+
+    # ---- map arithmetic -----------------------------------------------------------------------------------------------------
+    def add(self, a, b):
+        y = nat.add_maps(a, b)
+        tape = self.tape
+
+        def bwd():
+            dy = tape.grad_of(y)
+            if dy is None:
+                return
+            tape.add_grad(a, dy)
+            tape.add_grad(b, _copy_map(dy))
+
+        tape.record(bwd)
+        return y
+
+    def mask_modulate(self, f, mask_pred, ma):
+        """MaskGuidedSpatialAttention at the map's own size (reference :75-97): returns f * (1 + gamma A), A."""
+        B, H, W, C = f.shape
+        dev = self.dev
+        mp = ma.mask_processor
+        K = mp[0].out_channels
+        wa, gw, gb, wb, bb = (mp[0].weight, mp[1].weight, mp[1].bias, mp[3].weight, mp[3].bias)
+        A = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        nat.mask_attention(mask_pred, (K, wa.detach().flatten(), gw.detach(), gb.detach(), wb.detach().flatten(),
+                                       bb.detach(), mp[1].eps), A)
+        gamma = ma.gamma.detach().reshape(1)
+        y = torch.empty(f.shape, dtype=torch.bfloat16, device=dev)
+        nat.scale_map(f, y, attn=A, gamma=gamma)
+        tape = self.tape
+
+        def bwd():
+            dy = tape.grad_of(y)
+            if dy is None:
+                return
+            df = torch.empty(f.shape, dtype=torch.bfloat16, device=dev)
+            dA = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+            _call("b200_modulate_bwd", _P(dy), nat._ld(dy), _P(f), nat._ld(f), _P(A), _P(gamma), B * H * W, C, _P(df),
+                  nat._ld(df), _P(dA), _P(_grad_buf(ma.gamma)), _s())
+            tape.add_grad(f, df)
+            dm = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+            _call("b200_mask_attn_bwd", _P(mask_pred), _P(dA), B, H * W, K, _P(wa.detach()), _P(gw.detach()),
+                  _P(gb.detach()), _P(wb.detach()), _P(bb.detach()), float(mp[1].eps), _P(dm), _P(_grad_buf(wa)),
+                  _P(_grad_buf(gw)), _P(_grad_buf(gb)), _P(_grad_buf(wb)), _P(_grad_buf(bb)), _s())
+            tape.add_grad(mask_pred, dm)
+
+        tape.record(bwd)
+        return y, A
+
+
+def _copy_map(t):
+    out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+    C = t.shape[-1]
+    _call("b200_map_axpby", _P(t), nat._ld(t), 1.0, None, 0, 0.0, t.numel() // C, C, _P(out), nat._ld(out), _s())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# encoder
+# ------------------------------------------------------------------------------------------------------------------
+def _check_supported(m):
+    if m.use_backbone or m.use_hybrid_transformer:
+        raise NotImplementedError("training path: CNN encoders only (no backbone adapter / hybrid transformer stage)")
+    if tuple(m.num_repeats) != (1, 1, 1) or m.mask_stage != "f2" or not m.mask_enabled or not m.use_se:
+        raise NotImplementedError("training path: repeat_blocks (1,1,1), mask head on f2, squeeze-excite on")
+    if m.block1.stride != 2 or m.block2.stride != 1 or m.block3.stride != 1:
+        raise NotImplementedError("training path: downsample=(True, False, False)")
+    if m.modality_attention is None:
+        raise NotImplementedError("training path: modality attention on")
+
+
+def _block_tail(ops, blk, t2, identity, p_drop):
+    """conv 1x1 -> BN, + identity, GELU, Dropout, SE, ReconHead (reference :298-316)."""
+    bt = blk.bottlenecks[0]
+    z3 = ops.conv(t2, bt[7])
+    out = ops.bn_act(z3, bn=bt[8], act=1, res=identity, drop_p=p_drop)
+    out, _ = ops.se(out, blk.se)
+    rec = None
+    if blk.reconstruct is not None:
+        rh = blk.reconstruct.conv
+        ar = ops.bn_act(ops.conv(out, rh[0]), bn=rh[1], act=1)
+        rec = ops.conv_c1(ar, rh[3])
+    return out, rec
+
+
+def _block_from_map(ops, blk, x, p_drop):
+    bt = blk.bottlenecks[0]
+    identity = ops.bn_act(ops.conv(x, blk.skip[0]), bn=blk.skip[1]) if blk.skip is not None else x
+    t1 = ops.bn_act(ops.conv(x, bt[0]), bn=bt[1], act=1, drop_p=p_drop)
+    t2 = ops.bn_act(ops.conv(t1, bt[4]), bn=bt[5], act=1)
+    return _block_tail(ops, blk, t2, identity, p_drop)
+
+
+def _projector(ops, pr, src):
+    g = ops.bn_act(ops.conv(src, pr.proj[0]), bn=pr.proj[1], act=1)
+    return ops.bn_act(ops.conv(g, pr.proj[3]), bn=pr.proj[4], act=1)
+
+
+def _projector_c1(ops, pr, r):
+    g = ops.bn_act(ops.lift(r, pr.proj[0], r_needs_grad=False), bn=pr.proj[1], act=1)
+    return ops.bn_act(ops.conv(g, pr.proj[3]), bn=pr.proj[4], act=1)
+
+
+def encoder_forward_train(ops, m, x):
+    """Train-mode ModelMaskHeadBackbone.forward (reference :645-733) on the tape of `ops`.
+
+    x [B,C,H,W] fp32 normalised input.  Returns a dict: logits [B,K] fp32, f1 / f2 / f3 NHWC bf16, r1 / r2 fp32
+    [B,h,w], p1 / p1_r / p2 / p2_r NHWC bf16 at the MAP resolution (the reference's AdaptiveAvgPool2d to 2x the size
+    replicates every pixel 2 x 2, which changes neither the BatchNorm statistics nor the cosine / mean losses taken on
+    the result), mask_pred [B,h,w] fp32, mask_attn_map, mod_attn_map, pooled3 (the classifier's GAP input)."""
+    _check_supported(m)
+    dev = x.device
+    tape = ops.tape
+    x = x.contiguous().float()
+    B, C, H, W = x.shape
+    p_drop = float(m.dropout)
+    b1 = m.block1
+    stride = b1.stride
+    Ho, Wo = H // stride, W // stride
+    # ---- modality attention + the two strided 1x1 convolutions that read the raw input (fp32 SIMT "stem") ----
+    se0 = m.modality_attention
+    pm = torch.empty(B * C, dtype=torch.float32, device=dev)
+    nat.plane_mean(x, B * C, H * W, pm)
+    skip_conv, mid_conv = b1.skip[0], b1.bottlenecks[0][0]
+    n_skip, n_mid = skip_conv.out_channels, mid_conv.out_channels
+    n_cat = n_skip + n_mid
+    wcat = torch.cat([skip_conv.weight.detach().flatten(1), mid_conv.weight.detach().flatten(1)], 0).contiguous()
+    ones = torch.ones(n_cat, dtype=torch.float32, device=dev)
+    zeros = torch.zeros(n_cat, dtype=torch.float32, device=dev)
+    zcat = torch.empty((B, Ho, Wo, n_cat), dtype=torch.bfloat16, device=dev)
+    dummy = torch.empty(8, dtype=torch.bfloat16, device=dev)
+    gate0 = torch.empty((B, C), dtype=torch.float32, device=dev)
+    c1, c2 = se0.fc[1], se0.fc[3]
+    nat.stem(x, stride, pm, (c1.weight.detach().flatten(1), c1.bias.detach(), c2.weight.detach().flatten(1), c2.bias.detach()),
+             wcat, ones, zeros, n_cat, 0, zcat, dummy, gate0)
+    z_skip, z_mid = zcat[..., :n_skip], zcat[..., n_skip:]
+
+    def stem_bwd():
+        dzs, dzm = tape.grad_of(z_skip), tape.grad_of(z_mid)
+        if dzs is None and dzm is None:
+            return
+        dz = torch.zeros((B, Ho, Wo, n_cat), dtype=torch.bfloat16, device=dev)
+        for part, g in ((dz[..., :n_skip], dzs), (dz[..., n_skip:], dzm)):
+            if g is not None:
+                _call("b200_map_axpby", _P(g), nat._ld(g), 1.0, None, 0, 0.0, _rows(g), g.shape[-1], _P(part), n_cat, _s())
+        dw = torch.zeros((n_cat, C), dtype=torch.float32, device=dev)
+        dgate = torch.zeros((B, C), dtype=torch.float32, device=dev)
+        _call("b200_stem_bwd", _P(x), B, C, H, W, stride, _P(gate0), _P(dz), n_cat, _P(wcat), _P(dw), _P(dgate), _s())
+        _call("b200_vec_axpby", _P(dw[:n_skip]), 1.0, 1.0, n_skip * C, _P(_grad_buf(skip_conv.weight)), _s())
+        _call("b200_vec_axpby", _P(dw[n_skip:]), 1.0, 1.0, n_mid * C, _P(_grad_buf(mid_conv.weight)), _s())
+        # modality SE: gate = sigmoid(W2 gelu(W1 pm + b1) + b2) with pm the plane means
+        M = c1.out_channels
+        dpooled = torch.empty((B, C), dtype=torch.float32, device=dev)
+        da2 = torch.empty((B, C), dtype=torch.float32, device=dev)
+        da1 = torch.empty((B, M), dtype=torch.float32, device=dev)
+        h = torch.empty((B, M), dtype=torch.float32, device=dev)
+        pooled = pm.view(B, C)
+        _call("b200_se_bwd", _P(pooled), _P(c1.weight.detach()), _P(c1.bias.detach()), _P(c2.weight.detach()),
+              _P(c2.bias.detach()), _P(dgate), B, C, M, _P(dpooled), _P(da2), _P(da1), _P(h), _s())
+        nat.sgemm(da2, h, _grad_buf(c2.weight).view(C, M), trans_a=True, beta=1)
+        nat.sgemm(da1, pooled, _grad_buf(c1.weight).view(M, C), trans_a=True, beta=1)
+        nat.colsum(da2, _grad_buf(c2.bias))
+        nat.colsum(da1, _grad_buf(c1.bias))
+
+    tape.record(stem_bwd)
+    bt1 = b1.bottlenecks[0]
+    identity1 = ops.bn_act(z_skip, bn=b1.skip[1])
+    t1 = ops.bn_act(z_mid, bn=bt1[1], act=1, drop_p=p_drop)
+    t2 = ops.bn_act(ops.conv(t1, bt1[4]), bn=bt1[5], act=1)
+    f1, r1 = _block_tail(ops, b1, t2, identity1, p_drop)
+    # ---- block2, mask head on f2 (+ aligned f1), mask-guided modulation -------------------------------------------
+    f2_pre, r2 = _block_from_map(ops, m.block2, f1, p_drop)
+    al = m.f1_to_f2.proj
+    if isinstance(al, nn.Identity):
+        f1_aligned = f1
+    else:
+        f1_aligned = ops.bn_act(ops.conv(f1, al[0]), bn=al[1], act=1)
+    m_in = ops.add(f2_pre, f1_aligned)
+    mh = m.mask_head
+    if m_in.shape[1] != m.mask_size:
+        raise NotImplementedError("training path: mask head at the mask size (32 x 32 maps)")
+    t64 = ops.bn_act(ops.conv(m_in, mh.pre), bias=mh.pre.bias)
+    mask_pred = ops.conv_c1(t64, mh.out)
+    f2, attn_map = ops.mask_modulate(f2_pre, mask_pred, m.mask_spatial_attention)
+    # ---- block3, classifier, projectors ------------------------------------------------------------------------------
+    f3, _ = _block_from_map(ops, m.block3, f2, p_drop)
+    npix3 = f3.shape[1] * f3.shape[2]
+    C3 = f3.shape[-1]
+    sums3 = torch.empty((B, C3), dtype=torch.float32, device=dev)
+    _call("b200_map_dot", _P(f3), nat._ld(f3), None, 0, B, npix3, C3, _P(sums3), _s())
+    head = m.classification_head
+    K = head.fc.out_features
+    logits = torch.empty((B, K), dtype=torch.float32, device=dev)
+    pooled3 = torch.empty((B, C3), dtype=torch.float32, device=dev)
+    _call("b200_vec_axpby", _P(sums3), 1.0 / npix3, 0.0, sums3.numel(), _P(pooled3), _s())  # GAP mean (pre-normalise)
+    nat.cls_head(sums3, None, npix3, head.fc.weight.detach(), head.fc.bias.detach(), head.normalize, logits)
+
+    def head_bwd():
+        dl = tape.grad_of(logits)
+        if dl is None:
+            return
+        dpooled = torch.empty((B, C3), dtype=torch.float32, device=dev)
+        _call("b200_cls_head_bwd", _P(pooled3), _P(dl), _P(head.fc.weight.detach()), B, C3, K, 1 if head.normalize else 0,
+              _P(_grad_buf(head.fc.weight)), _P(_grad_buf(head.fc.bias)), _P(dpooled), _s())
+        _call("b200_vec_axpby", _P(dpooled), 1.0 / npix3, 0.0, dpooled.numel(), _P(dpooled), _s())
+        df3 = torch.empty(f3.shape, dtype=torch.bfloat16, device=dev)
+        _call("b200_map_scale_add", None, 0, None, _P(dpooled), B, npix3, C3, _P(df3), nat._ld(df3), 0, _s())  # broadcast
+        tape.add_grad(f3, df3)
+
+    tape.record(head_bwd)
+    p1 = _projector(ops, m.proj_f1, f1)
+    p2 = _projector(ops, m.proj_f2, f2)
+    p1_r = _projector_c1(ops, m.proj_r1, r1)
+    p2_r = _projector_c1(ops, m.proj_r2, r2)
+    return {"logits": logits, "f1": f1, "f2": f2, "f3": f3, "r1": r1, "r2": r2, "p1": p1, "p1_r": p1_r, "p2": p2,
+            "p2_r": p2_r, "mask_pred": mask_pred, "mask_attn_map": attn_map, "mod_attn_map": gate0, "pooled3": pooled3,
+            "x": x}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the single-modality objective (BASELINE config C1): LightningSingleModel._shared_step, code/train.py:294-400
+# ------------------------------------------------------------------------------------------------------------------
+def single_model_loss(ops, out, masks, labels, *, smoothing, gamma, class_weights, lambda_mask, lambda_recon,
+                      lambda_mimic, lambda_feat_norm, aux_w=1.0):
+    """Seeds the tape with the gradients of
+        cls + lambda_feat_norm * sum_f mean(f^2) + lambda_mask * dice + lambda_recon * (recon * lambda_recon * aux_w) * aux_w
+            + lambda_mimic * (mimic * lambda_mimic * aux_w) * aux_w
+    (the reference weights the last two twice, train.py:396-399 and :462-464 - reproduced) and returns
+    (total [1] fp32 device tensor, parts dict of device scalars)."""
+    tape, dev = ops.tape, ops.dev
+    logits = out["logits"]
+    B, K = logits.shape
+    parts = {k: torch.zeros(1, dtype=torch.float32, device=dev) for k in ("cls", "feat_norm", "mask", "recon", "mimic")}
+    dl = torch.empty_like(logits)
+    cw = class_weights.to(dev).float().contiguous() if class_weights is not None else None
+    _call("b200_focal_loss", _P(logits), _P(labels), B, K, float(smoothing), float(gamma), _P(cw), 1.0 / B, _P(parts["cls"]),
+          _P(dl), _s())
+    tape.add_grad(logits, dl)
+    # feature-norm regulariser: sum_f mean(f^2), gradient 2 f / numel
+    fn64 = torch.zeros(3, dtype=torch.float64, device=dev)
+    for i, key in enumerate(("f1", "f2", "f3")):
+        f = out[key]
+        C = f.shape[-1]
+        _call("b200_map_sumsq", _P(f), nat._ld(f), _rows(f), C, _P(fn64[i:]), _s())
+        if lambda_feat_norm != 0:
+            g = torch.empty(f.shape, dtype=torch.bfloat16, device=dev)
+            _call("b200_map_axpby", _P(f), nat._ld(f), 2.0 * lambda_feat_norm / f.numel(), None, 0, 0.0, _rows(f), C, _P(g),
+                  nat._ld(g), _s())
+            tape.add_grad(f, g)
+    numels = torch.tensor([out[k].numel() for k in ("f1", "f2", "f3")], dtype=torch.float64, device=dev)
+    parts["feat_norm"] = (fn64 / numels).sum().float().reshape(1)
+    # mask dice
+    mp = out["mask_pred"]
+    n = mp[0].numel()
+    dm = torch.empty_like(mp)
+    _call("b200_dice_loss", _P(mp), _P(masks.contiguous().float()), B, n, 1e-6, 1.0 / B, _P(parts["mask"]), _P(dm), _s())
+    _call("b200_vec_axpby", _P(dm), float(lambda_mask), 0.0, dm.numel(), _P(dm), _s())
+    tape.add_grad(mp, dm)
+    # reconstruction (both heads) and mimic (both pairs)
+    x = out["x"]
+    _, C, H, W = x.shape
+    w_recon = lambda_recon * lambda_recon * aux_w * aux_w
+    for key in ("r1", "r2"):
+        r = out[key]
+        dr = torch.empty_like(r)
+        one = torch.zeros(1, dtype=torch.float32, device=dev)
+        _call("b200_recon_loss", _P(r), B, r.shape[1], r.shape[2], _P(x), C, H, W, 1e-3, 1.0 / (B * H * W), _P(one), _P(dr), _s())
+        _call("b200_vec_axpby", _P(one), 1.0, 1.0, 1, _P(parts["recon"]), _s())
+        _call("b200_vec_axpby", _P(dr), float(w_recon), 0.0, dr.numel(), _P(dr), _s())
+        tape.add_grad(r, dr)
+    w_mimic = lambda_mimic * lambda_mimic * aux_w * aux_w
+    for s_key, t_key in (("p1", "p1_r"), ("p2", "p2_r")):
+        s_map, t_map = out[s_key], out[t_key]
+        ds = torch.empty(s_map.shape, dtype=torch.bfloat16, device=dev)
+        _call("b200_mimic_loss", _P(s_map), _P(t_map), B, s_map[0].numel(), float(w_mimic) / B, _P(parts["mimic"]), _P(ds), _s())
+        tape.add_grad(s_map, ds)
+    if w_mimic != 0:
+        parts["mimic"] = parts["mimic"] / w_mimic
+    total = (parts["cls"] + lambda_feat_norm * parts["feat_norm"] + lambda_mask * parts["mask"] +
+             w_recon * parts["recon"] + w_mimic * parts["mimic"])
+    return total, parts

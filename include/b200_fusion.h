@@ -174,11 +174,22 @@ int b200_dwi_normalize(const float* x, float* out, int planes, int C, int n, int
  *   standard_scale fp64 [L]     np.linspace(target_range) (:60)
  *   prev_index int32 [L], gamma fp64 [L]: floor and fractional part of q/100*(n-1), the
  *   "linear" percentile rule of np.percentile (:100), computed on the host in float64.
- * n must be <= 32768 samples per plane in this version.
+ * Planes above 32 768 samples (224 x 224) take the radix-select kernel.
  */
 int b200_nyul_transform(const float* x, float* out, int planes, int C, int n, int L, const double* avg_landmarks,
                         const double* standard_scale, const int* prev_index, const double* gamma,
                         float* plane_mean, void* stream);
+
+/*
+ * Same transform with the arithmetic mode chosen by the caller.  exact = 0 (what b200_nyul_transform runs): the two
+ * chained np.interp maps are composed once per plane, in fp64, into one <= L-segment piece-wise linear table
+ * (np.interp's tie / fill semantics folded in) and every sample costs an fp32 segment search plus one fp64 fma -
+ * equal to numpy within 1 fp32 ulp, i.e. far inside the 1e-5 contract.  exact = 1: numpy's own operation order in
+ * fp64 without FMA contraction, bit-identical to the reference on > 99.9 % of the samples, ~6x the instructions.
+ */
+int b200_nyul_transform_ex(const float* x, float* out, int planes, int C, int n, int L, const double* avg_landmarks,
+                           const double* standard_scale, const int* prev_index, const double* gamma,
+                           float* plane_mean, int exact, void* stream);
 
 /* Mean of each fp32 plane (AdaptiveAvgPool2d(1) of SEBlock, code/model_module.py:35). */
 int b200_plane_mean(const float* x, int planes, int n, float* plane_mean, void* stream);
@@ -472,6 +483,118 @@ int b200_mask_head_grads(const float* dv, const float* dc0, const float* pre_w, 
  * first (1 / world_size after the summing gradient all-reduce).  step >= 1 is the update count. */
 int b200_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Training step of the encoders / the whole fusion objective (BASELINE configs C1 and C5 with the encoders
+ * unfrozen): torch autograd over code/model_module.py in train mode, restated as explicit backward kernels.
+ * Maps are NHWC bf16 [rows, ld]; gradients of maps bf16; parameter gradients fp32, ACCUMULATED into the given
+ * buffers (the caller zeroes them once per step) in the parameter's own nn.Module layout.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* Weight gradient of a stride-1 1x1 / 3x3 (padding 1) nn.Conv2d on the tensor cores (csrc/conv_wgrad.cu):
+ * dw[co, ci, tap] += sum_pixels dy[p, co] * x[p + offset(tap), ci]; dw is the fp32 gradient in the nn.Conv2d layout
+ * [Cout, Cin, kh, kw].  Both NHWC maps are consumed as MN-major tcgen05 operands straight from their TMA boxes.
+ * W must divide 64 or be a multiple of 64, H a multiple of 64 / min(W, 64). */
+int b200_conv_wgrad(const void* dy, int dy_ld, const void* x, int x_ld, float* dw, int B, int H, int W, int Cin,
+                    int Cout, int taps, void* stream);
+
+/* fp32 master weights [Cout, Cin, kh, kw] -> bf16 [Cout, taps*Cin] (forward operand of b200_conv_gemm) and / or
+ * bf16 [Cin, taps*Cout] with flipped taps (operand of the data gradient: dX = conv(dY, w_dgrad)).  Either may be NULL. */
+int b200_pack_conv_weights(const float* w, int Cout, int Cin, int taps, void* w_fwd, void* w_dgrad, void* stream);
+
+/* nn.BatchNorm2d in training mode on a conv output z [R, C]: per-channel sum / sum of squares (fp64, accumulated
+ * into zeroed buffers), then mean / 1/sqrt(biased var + eps) and the momentum update of the running statistics
+ * (unbiased variance), as torch does. */
+int b200_bn_stats(const void* z, long long R, int C, int ld, double* sum, double* sumsq, void* stream);
+int b200_bn_finalize(const double* sum, const double* sumsq, int C, double count, float eps, float momentum,
+                     float* running_mean, float* running_var, float* mean_out, float* invstd_out, void* stream);
+
+/* out = dropout(act((z - mean) * invstd * gamma + beta + res)): BatchNorm apply + residual + activation (0 none,
+ * 1 exact GELU, 2 ReLU) + nn.Dropout(drop_p) with Philox4x32-7 keyed by (seed, element index).  Any of mean / invstd /
+ * gamma / beta / res may be NULL (0, 1, 1, 0, none): a conv bias is `beta` alone.
+ * (code/model_module.py:259-269, :298-306: conv -> BN -> GELU -> Dropout; GELU(out + identity) -> Dropout.) */
+int b200_bn_act_fwd(const void* z, int ldz, const void* res, int ldres, const float* mean, const float* invstd,
+                    const float* gamma, const float* beta, int act, float drop_p, unsigned long long seed, long long R,
+                    int C, void* out, int ldo, void* stream);
+
+/* Backward of the above from dA (gradient of `out`): dY = dA * dropout mask * act'(.);
+ * batch_stats = 1: dz = gamma * invstd * (dY - mean(dY) - xhat * mean(dY * xhat)) (training-mode BatchNorm);
+ * batch_stats = 0: dz = gamma * invstd * dY.  dres = dY (NULL when there is no residual branch); dgamma += sum dY*xhat,
+ * dbeta += sum dY (NULL to skip).  scratch2C: 2*C doubles of workspace. */
+int b200_bn_act_bwd(const void* z, int ldz, const void* res, int ldres, const float* mean, const float* invstd,
+                    const float* gamma, const float* beta, int act, float drop_p, unsigned long long seed, long long R,
+                    int C, const void* dA, int ldd, int batch_stats, double* scratch2C, void* dz, int lddz, void* dres,
+                    int lddres, float* dgamma, float* dbeta, void* stream);
+
+/* out[b, c] = sum_p a[b,p,c] * b[b,p,c] (b NULL: channel sums) - SE gate gradient / global average pools. */
+int b200_map_dot(const void* a, int lda, const void* b, int ldb, int B, int npix, int C, float* out, void* stream);
+/* out[b,p,c] (+)= x[b,p,c] * gate[b,c] + add[b,c] (x NULL: 1; gate / add NULL: 1 / 0): SE rescale and its backward,
+ * broadcast of a pooled-vector gradient over the pixels. */
+int b200_map_scale_add(const void* x, int ldx, const float* gate, const float* add, int B, int npix, int C, void* out,
+                       int ldo, int accumulate, void* stream);
+/* y = alpha * a + beta * b on bf16 maps (b NULL: y = alpha * a): gradient accumulation, feature-norm gradient. */
+int b200_map_axpby(const void* a, int lda, float alpha, const void* b, int ldb, float beta, long long R, int C, void* y,
+                   int ldy, void* stream);
+/* *out += sum of squares of a bf16 map (fp64): compute_feat_norm_loss, code/train.py:1021-1030. */
+int b200_map_sumsq(const void* a, int lda, long long R, int C, double* out, void* stream);
+
+/* SEBlock (code/model_module.py:25-43) with the weights in their nn.Conv2d layouts w1 [M,C], w2 [C,M]:
+ * forward from per-case channel SUMS (pooled = sums / npix is written too); backward from dgate [B,C] through the
+ * MLP: dpooled, and da2 [B,C], da1 [B,M], h [B,M] whose outer products with h / pooled are the weight gradients. */
+int b200_se_fwd(const float* sums, int B, int C, int M, int npix, const float* w1, const float* b1, const float* w2,
+                const float* b2, float* pooled, float* gate, void* stream);
+int b200_se_bwd(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2,
+                const float* dgate, int B, int C, int M, float* dpooled, float* da2, float* da1, float* h, void* stream);
+
+/* C -> 1 convolutions, 1x1 or 3x3 padding 1 (ReconHead.conv[3], MaskHeadResize.out; code/model_module.py:117, :187):
+ * w fp32 in the nn.Conv2d layout [1, C, kh, kw]; out / dout fp32 [B,H,W]; dx bf16 (optionally accumulated). */
+int b200_convc1_fwd(const void* x, int ldx, int B, int H, int W, int C, int taps, const float* w, const float* bias,
+                    float* out, void* stream);
+int b200_convc1_bwd(const void* x, int ldx, const float* dout, int B, int H, int W, int C, int taps, const float* w,
+                    void* dx, int lddx, int accumulate_dx, float* dw, float* dbias, void* stream);
+
+/* 1 -> N convolution of a 1-channel fp32 map (Projector.proj[0] on a reconstruction, code/model_module.py:338):
+ * z[p, n] = r[p] * w[n]; backward dw[n] += sum_p dz r, dr[p] = sum_n dz w (dr NULL to skip). */
+int b200_lift_fwd(const float* r, long long P, int N, const float* w, void* z, void* stream);
+int b200_lift_bwd(const void* dz, const float* r, long long P, int N, const float* w, float* dw, float* dr, void* stream);
+
+/* MaskGuidedSpatialAttention (code/model_module.py:49-97) backward.  b200_modulate_bwd: y = f * (1 + gamma * A):
+ * df = dy * (1 + gamma A), dA[b,p] = gamma * sum_c dy f, dgamma += sum dy f A.  b200_mask_attn_bwd: through
+ * clamp(sigmoid(conv(gelu(GroupNorm(1,K)(conv(mask)))))) to dmask and the five small parameter gradients. */
+int b200_modulate_bwd(const void* dy, int lddy, const void* f, int ldf, const float* A, const float* gamma, long long P,
+                      int C, void* df, int lddf, float* dA, float* dgamma, void* stream);
+int b200_mask_attn_bwd(const float* mask, const float* dA, int B, int npix, int K, const float* wa, const float* gnw,
+                       const float* gnb, const float* wb, const float* bb, float eps, float* dm, float* dwa, float* dgnw,
+                       float* dgnb, float* dwb, float* dbb, void* stream);
+
+/* Backward of b200_stem run with every output channel un-activated (training: BatchNorm follows): from dz
+ * [B, npix, N] bf16 to dwcat [N, C] and the modality-attention gate gradient dgate [B, C]. */
+int b200_stem_bwd(const float* x, int B, int C, int H, int W, int stride, const float* gate, const void* dz, int N,
+                  const float* wcat, float* dwcat, float* dgate, void* stream);
+
+/* ClassificationHead backward (code/model_module.py:355-369): pooled [B,C] = GAP mean; dfcw / dfcb accumulated. */
+int b200_cls_head_bwd(const float* pooled, const float* dlogits, const float* fcw, int B, int C, int K, int normalize,
+                      float* dfcw, float* dfcb, float* dpooled, void* stream);
+
+/* Loss terms with their gradients; each ACCUMULATES scale * (sum over cases) into *loss.
+ *   b200_focal_loss  LabelSmoothing + Soft(Weighted)FocalLoss (code/loss.py:133-213), scale = 1 / B
+ *   b200_dice_loss   SoftDiceLoss (code/loss.py:45-62) on logits [B,n], scale = weight / B
+ *   b200_recon_loss  bilinear up-sample -> sigmoid -> Charbonnier against the clamped channel mean of the input
+ *                    (code/train.py:1041-1048, :446-454), scale = weight / (B*H*W)
+ *   b200_mimic_loss  1 - cos(student, detached teacher) per case (code/train.py:1033-1038), scale = weight / B */
+int b200_focal_loss(const float* logits, const long long* labels, int B, int K, float smoothing, float gamma,
+                    const float* class_weights, float scale, float* loss, float* dlogits, void* stream);
+int b200_dice_loss(const float* logits, const float* target, int B, int n, float eps, float scale, float* loss,
+                   float* dlogits, void* stream);
+int b200_recon_loss(const float* r, int B, int h, int w, const float* x, int C, int H, int W, float eps, float scale,
+                    float* loss, float* dr, void* stream);
+int b200_mimic_loss(const void* s, const void* t, int B, long long n, float scale, float* loss, void* ds, void* stream);
+
+/* din = sum of the four 2x2 replicas of dout [B,2H,2W,C] (backward of AdaptiveAvgPool2d to twice the size). */
+int b200_up2_bwd(const void* dout, int B, int H, int W, int C, void* din, void* stream);
+/* y = alpha * a + beta * y on fp32 vectors. */
+int b200_vec_axpby(const float* a, float alpha, float beta, long long n, float* y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -111,3 +111,40 @@ def synthetic_head_batch(n, seed=11, channels=512, size=32, num_classes=4):
     mc = torch.randn(n, 1, size, size, generator=g)
     labels = torch.randint(0, num_classes, (n,), generator=g)
     return f3d, f3c, md, mc, labels
+
+
+# ------------------------------------------------ briefly trained weights (tests/golden/trained_cnn.npz) ----
+def structured_targets(dwi_raw):
+    """Labels and 32 x 32 target masks that are functions of the structured ("S") ROI itself, so a few optimisation
+    steps make the predictions vary over cases: class = 2 * (lesion area above the median) + (lesion centre in the
+    right half); mask = the lesion (pixels above half of the first b-value image's maximum), 2 x 2 pooled."""
+    d0 = dwi_raw[:, 0]
+    hot = (d0 > 0.5 * d0.amax(dim=(1, 2), keepdim=True)).float()
+    area = hot.mean(dim=(1, 2))
+    xx = torch.linspace(-1, 1, d0.shape[-1]).view(1, 1, -1)
+    w = d0 - d0.amin(dim=(1, 2), keepdim=True)
+    cx = (w * xx).sum(dim=(1, 2)) / w.sum(dim=(1, 2))
+    labels = 2 * (area > 0.13).long() + (cx > -0.03).long()
+    masks = (torch.nn.functional.adaptive_avg_pool2d(hot.unsqueeze(1), 32) > 0.5).float()
+    return labels, masks
+
+
+def apply_delta(base, q, scale):
+    """fixture weight = seeded + q * scale, elementwise in fp32 (bit-reproducible on any machine)."""
+    return (base.float() + q.float() * torch.tensor(float(scale), dtype=torch.float32)).to(base.dtype)
+
+
+def trained_state_dicts(npz, shapes, seed=7):
+    """{"dwi" | "dce" | "fusion": state_dict} of the briefly trained fixture: `npz` = the loaded
+    tests/golden/trained_cnn.npz (int8 deltas + per-tensor scales), `shapes` = {module: {name: shape}}."""
+    out = {}
+    for name, sh in shapes.items():
+        sd = seeded_state_dict(sh, seed)
+        for k in sd:
+            key = f"{name}/{k}/q"
+            if key in npz.files:
+                sd[k] = apply_delta(sd[k], torch.from_numpy(npz[key]), npz[f"{name}/{k}/scale"])
+            elif f"{name}/{k}/exact" in npz.files:
+                sd[k] = torch.from_numpy(npz[f"{name}/{k}/exact"]).to(sd[k].dtype).reshape(sd[k].shape)
+        out[name] = sd
+    return out

@@ -275,3 +275,35 @@ def test_resize_oracle_is_torchvision_resize():
     # for an upsample the antialias filter degenerates to plain bilinear interpolation (what the kernel does)
     plain = torch.nn.functional.interpolate(x, size=(224, 224), mode="bilinear", align_corners=False)
     assert torch.allclose(ref, plain, rtol=0, atol=1e-5)  # the separable antialias code path rounds differently
+
+
+def test_oracle_on_trained_weights_matches_reference_pipeline():
+    """The briefly trained fixture (tests/golden/trained_cnn.npz: int8 deltas on the seeded weights) and the
+    reference pipeline's outputs on it (model_cnn_trained.npz): the oracle - numpy normalisers + functional
+    networks - reproduces the first 8 of the 1 024 held-out cases, and the fixture itself is non-degenerate
+    (every class predicted, top-2 margins reaching down to ~0)."""
+    import json
+
+    import parameters_default as pd
+
+    gold = gu.load("model_cnn_trained.npz")
+    hp = json.loads(str(gold["hp"]))
+    sds = op.trained_state_dicts(gu.load("trained_cnn.npz"), gu.load_shapes("cnn"), seed=hp["weight_seed"])
+    n = 8
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(hp["n_eval"], seed=hp["eval_seed"], kind="S")
+    labels, _ = op.structured_targets(dwi_raw)
+    assert np.array_equal(labels.numpy(), gold["labels"])
+    lm = gold["landmarks"]
+    dwi, dce = no.dwi_normalize_batch(dwi_raw[:n]), no.nyul_transform_batch(dce_raw[:n], lm)
+    with torch.no_grad():
+        lf, mf, af = mo.pipeline_forward(sds, pd.default_parameters(), dwi, dce)
+    ref = torch.from_numpy(gold["fusion_logits"][:n])
+    assert (lf - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+    assert (af["gating_weights"] - torch.from_numpy(gold["gating"][:n])).abs().max().item() <= 1e-4
+    ref_m = torch.from_numpy(gold["fusion_mask_sum"][:n])
+    assert (mf.sum((1, 2, 3)) - ref_m).abs().max().item() <= 2e-4 * ref_m.abs().max().item()
+    full = torch.from_numpy(gold["fusion_logits"])
+    hist = torch.bincount(full.argmax(1), minlength=4)
+    assert hist.min().item() >= 0.1 * hp["n_eval"], hist
+    top = full.topk(2, dim=1).values
+    assert (top[:, 0] - top[:, 1]).min().item() < 0.02

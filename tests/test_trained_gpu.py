@@ -1,0 +1,95 @@
+"""Parity on briefly TRAINED weights over 1 024 held-out structured cases (VERDICT r1 weak-1 / SURVEY.md 8d).
+
+tests/golden/trained_cnn.npz holds weights the unmodified reference produced with AdamW steps of its own objectives
+(oracle/make_golden_trained.py); tests/golden/model_cnn_trained.npz holds the unmodified reference pipeline's outputs
+(DWINormalize / NyulStandardizer -> encoders -> FusionModel) on 1 024 held-out cases whose predictions spread over all
+four classes with top-2 margins reaching down to ~0.  The product runs the same raw ROIs through
+FusionPipeline.forward_raw (normaliser kernels included) and is held to north_star's bars: logits <= 2e-2 of the
+reference's max |logit|, argmax agreement >= 99.9 %.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import b200path  # noqa: F401
+import golden_util as gu
+from oracle import params as op
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-2     # north_star: logits to 2e-2 relative in bf16 (max|d| / max|ref| over the batch)
+ARGMAX_MIN = 0.999   # north_star: argmax class >= 99.9 % agreement
+
+
+def _load():
+    import model_module as mm
+    import parameters_default as pd
+    import preprocess_helpers as pre
+    from pipeline import FusionPipeline
+
+    gold = gu.load("model_cnn_trained.npz")
+    hp = json.loads(str(gold["hp"]))
+    sds = op.trained_state_dicts(gu.load("trained_cnn.npz"), gu.load_shapes("cnn"), seed=hp["weight_seed"])
+    p = pd.default_parameters()
+    mods = {"dwi": mm.ModelMaskHeadBackbone("dwi", p), "dce": mm.ModelMaskHeadBackbone("dce", p), "fusion": mm.FusionModel(p)}
+    for k, m in mods.items():
+        m.load_state_dict(sds[k])
+        m.cuda().eval()
+    nyul = pre.NyulStandardizer()
+    _, dce_train, _, _ = op.synthetic_raw(hp["n_train"], seed=hp["train_seed"], kind="S")
+    nyul.fit(list(dce_train), num_channels=6)
+    lm = np.stack([nyul.channel_landmarks[c] for c in range(6)])
+    assert np.array_equal(lm, gold["landmarks"]), "Nyul.fit landmarks differ from the reference's"
+    return gold, hp, FusionPipeline(mods["dwi"], mods["dce"], mods["fusion"], nyul).eval()
+
+
+def _margins(lg):
+    top = lg.topk(2, dim=1).values
+    return top[:, 0] - top[:, 1]
+
+
+def test_1024_structured_cases_logits_and_argmax_vs_reference():
+    gold, hp, pipe = _load()
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(hp["n_eval"], seed=hp["eval_seed"], kind="S")
+    got = {k: [] for k in ("dwi_logits", "dce_logits", "fusion_logits", "gating", "dwi_mask_sum", "dce_mask_sum",
+                           "fusion_mask_sum", "f3_dwi_sum", "f3_dce_sum")}
+    for i in range(0, hp["n_eval"], 256):
+        o_d, o_c, o_f = pipe.forward_raw(dwi_raw[i:i + 256].cuda(), dce_raw[i:i + 256].cuda(), return_all=True)
+        got["dwi_logits"].append(o_d[0]), got["dce_logits"].append(o_c[0]), got["fusion_logits"].append(o_f[0])
+        got["gating"].append(o_f[2]["gating_weights"])
+        got["dwi_mask_sum"].append(o_d[2].sum((1, 2, 3))), got["dce_mask_sum"].append(o_c[2].sum((1, 2, 3)))
+        got["fusion_mask_sum"].append(o_f[1].sum((1, 2, 3)))
+        got["f3_dwi_sum"].append(o_d[1]["raw_feats"][-1].float().sum((1, 2, 3)))
+        got["f3_dce_sum"].append(o_c[1]["raw_feats"][-1].float().sum((1, 2, 3)))
+    got = {k: torch.cat(v).float().cpu() for k, v in got.items()}
+    report = {}
+    for k in ("dwi_logits", "dce_logits", "fusion_logits"):
+        ref = torch.from_numpy(gold[k])
+        err = (got[k] - ref).abs().max().item() / ref.abs().max().item()
+        med = ((got[k] - ref).abs() / ref.abs().clamp_min(1e-3)).median().item()
+        agree = (got[k].argmax(1) == ref.argmax(1)).float().mean().item()
+        m = _margins(ref)
+        flips = (got[k].argmax(1) != ref.argmax(1)).nonzero().flatten().tolist()
+        report[k] = {"max_rel": err, "median_elementwise_rel": med, "argmax_agreement": agree,
+                     "class_histogram": torch.bincount(ref.argmax(1), minlength=4).tolist(),
+                     "margin_quantiles_0_1_10_50": [round(v, 4) for v in
+                                                    torch.quantile(m, torch.tensor([0.0, 0.01, 0.1, 0.5])).tolist()],
+                     "margins_of_flipped_cases": [round(m[i].item(), 5) for i in flips]}
+    for k in ("gating", "dwi_mask_sum", "dce_mask_sum", "fusion_mask_sum", "f3_dwi_sum", "f3_dce_sum"):
+        ref = torch.from_numpy(gold[k])
+        report[k] = {"max_rel": (got[k] - ref).abs().max().item() / ref.abs().max().item()}
+    print(json.dumps(report, indent=1))
+    out_dir = os.path.join(b200path.ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "trained_parity_report.json"), "w") as f:
+            json.dump(report, f, indent=1)
+    hist = report["fusion_logits"]["class_histogram"]
+    assert min(hist) >= 0.1 * hp["n_eval"], f"fixture degenerate: fusion class histogram {hist}"
+    for k in ("dwi_logits", "dce_logits", "fusion_logits"):
+        assert report[k]["max_rel"] <= LOGIT_TOL, (k, report[k])
+        assert report[k]["argmax_agreement"] >= ARGMAX_MIN, (k, report[k])
+    for k in ("gating", "dwi_mask_sum", "dce_mask_sum", "fusion_mask_sum", "f3_dwi_sum", "f3_dce_sum"):
+        assert report[k]["max_rel"] <= LOGIT_TOL, (k, report[k])
