@@ -166,10 +166,16 @@ SIGNATURES = {
     "b200_cls_head_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
     "b200_focal_loss": [_P, _P, _I, _I, _F, _F, _P, _F, _P, _P, _P],
     "b200_dice_loss": [_P, _P, _I, _I, _F, _F, _P, _P, _P],
-    "b200_recon_loss": [_P, _I, _I, _I, _P, _I, _I, _I, _F, _F, _P, _P, _P],
+    "b200_recon_loss": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _F, _F, _P, _P, _P],
+    "b200_gating_fwd": [_P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P],
+    "b200_gating_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "b200_fused_pool": [_P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P],
+    "b200_fusion_mix_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "b200_mimic_pairs": [_P, _I, _I, _I, _F, _P, _P, _P],
     "b200_mimic_loss": [_P, _P, _I, _LL, _F, _P, _P, _P],
     "b200_up2_bwd": [_P, _I, _I, _I, _I, _P, _P],
     "b200_vec_axpby": [_P, _F, _F, _LL, _P, _P],
+    "b200_row_bcast": [_P, _I, _F, _I, _I, _P, _P],
 }
 
 

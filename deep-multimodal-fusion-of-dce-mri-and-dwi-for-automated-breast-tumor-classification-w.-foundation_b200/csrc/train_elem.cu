@@ -914,8 +914,8 @@ dice_loss_kernel(const float* __restrict__ logits, const float* __restrict__ tar
 // clamp(0,1) channel-MEAN of the fp32 input x [B,C,H,W]:  loss += scale * sum sqrt((s - t)^2 + eps^2)
 // (scale = weight / (B H W)).  dr[b,i,j] = scale * sum over the output pixels it feeds.  One CTA per case; h*w <= 4096.
 __global__ void __launch_bounds__(kTeThreads)
-recon_loss_kernel(const float* __restrict__ r, int h, int w, const float* __restrict__ x, int C, int H, int W, float eps,
-                  float scale, float* __restrict__ loss, float* __restrict__ dr) {
+recon_loss_kernel(const float* __restrict__ r, int h, int w, const float* __restrict__ x, int C, const float* __restrict__ x2,
+                  int C2, int H, int W, float eps, float scale, float* __restrict__ loss, float* __restrict__ dr) {
     extern __shared__ float s_dr[];  // [h*w]
     __shared__ double scratch[33];
     const int b = blockIdx.x;
@@ -934,7 +934,8 @@ recon_loss_kernel(const float* __restrict__ r, int h, int w, const float* __rest
         const float v = w00 * rb[y0 * w + x0] + w01 * rb[y0 * w + x1] + w10 * rb[y1 * w + x0] + w11 * rb[y1 * w + x1];
         float t = 0.f;
         for (int c = 0; c < C; ++c) t += x[((static_cast<long long>(b) * C + c) * H + oy) * W + ox];
-        t = fminf(fmaxf(t / C, 0.f), 1.f);
+        for (int c = 0; c < C2; ++c) t += x2[((static_cast<long long>(b) * C2 + c) * H + oy) * W + ox];
+        t = fminf(fmaxf(t / (C + C2), 0.f), 1.f);
         const float s = sigmoidf_(v);
         const float d = s - t;
         const float e = sqrtf(d * d + eps * eps);
@@ -996,6 +997,217 @@ mimic_loss_kernel(const __nv_bfloat16* __restrict__ s, const __nv_bfloat16* __re
     }
 }
 
+
+// ------------------------------------------------------------------------------------------- fusion head ---------
+// GatingAttention (code/model_module.py:745-780): gx = [pvec_dwi, pvec_dce, mean(mask_dwi), mean(mask_dce)],
+// alpha = softmax(W gx + b) over the two modalities.  One CTA per case.  pvec_* are per-case channel SUMS (x inv_npix).
+__global__ void __launch_bounds__(kTeThreads)
+gating_fwd_kernel(const float* __restrict__ sum_d, const float* __restrict__ sum_c, float inv_npix,
+                  const float* __restrict__ mask_d, const float* __restrict__ mask_c, int npix_mask, int C,
+                  const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ gx,
+                  float* __restrict__ alpha) {
+    __shared__ double scratch[33];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int D = 2 * C + (mask_d != nullptr ? 2 : 0);
+    float* g = gx + static_cast<long long>(b) * D;
+    float md = 0.f, mc = 0.f;
+    if (mask_d != nullptr) {
+        for (int i = tid; i < npix_mask; i += kTeThreads) {
+            md += mask_d[static_cast<long long>(b) * npix_mask + i];
+            mc += mask_c[static_cast<long long>(b) * npix_mask + i];
+        }
+        md = static_cast<float>(block_sum<double>(static_cast<double>(md), scratch) / npix_mask);
+        mc = static_cast<float>(block_sum<double>(static_cast<double>(mc), scratch) / npix_mask);
+    }
+    float a0 = 0.f, a1 = 0.f;
+    for (int i = tid; i < D; i += kTeThreads) {
+        float v;
+        if (i < C) v = sum_d[static_cast<long long>(b) * C + i] * inv_npix;
+        else if (i < 2 * C) v = sum_c[static_cast<long long>(b) * C + i - C] * inv_npix;
+        else v = i == 2 * C ? md : mc;
+        g[i] = v;
+        a0 = fmaf(w[i], v, a0);
+        a1 = fmaf(w[D + i], v, a1);
+    }
+    const float l0 = static_cast<float>(block_sum<double>(static_cast<double>(a0), scratch)) + bias[0];
+    const float l1 = static_cast<float>(block_sum<double>(static_cast<double>(a1), scratch)) + bias[1];
+    if (tid == 0) {
+        const float m = fmaxf(l0, l1);
+        const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+        alpha[b * 2 + 0] = e0 / (e0 + e1);
+        alpha[b * 2 + 1] = e1 / (e0 + e1);
+    }
+}
+// softmax backward + input gradient: dgl = alpha * (dalpha - <alpha, dalpha>), dgx = dgl W.  (dW = dgl^T gx and db =
+// column sums of dgl are taken by b200_sgemm / b200_colsum.)
+__global__ void gating_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ dalpha,
+                                  const float* __restrict__ w, int C, int D, float inv_npix, float* __restrict__ dgl,
+                                  float* __restrict__ dgx, float* __restrict__ dpv_d, float* __restrict__ dpv_c) {
+    const int b = blockIdx.x;
+    const float a0 = alpha[b * 2], a1 = alpha[b * 2 + 1];
+    const float d0 = dalpha[b * 2], d1 = dalpha[b * 2 + 1];
+    const float dot = a0 * d0 + a1 * d1;
+    const float g0 = a0 * (d0 - dot), g1 = a1 * (d1 - dot);
+    if (threadIdx.x == 0) {
+        dgl[b * 2] = g0;
+        dgl[b * 2 + 1] = g1;
+    }
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const float v = g0 * w[i] + g1 * w[D + i];
+        dgx[static_cast<long long>(b) * D + i] = v;
+        // gradient w.r.t. the per-case channel SUMS' pixels: the pooled vectors are means over npix pixels
+        if (i < C) dpv_d[static_cast<long long>(b) * C + i] = v * inv_npix;
+        else if (i < 2 * C) dpv_c[static_cast<long long>(b) * C + i - C] = v * inv_npix;
+    }
+}
+
+// pooled fused vector (GAP of alpha0 p_dwi + alpha1 p_dce + bilinear_up(lowres)), as channel "sums" with npix = 1:
+// out[b,c] = alpha0 pvec_d + alpha1 pvec_c + sum_t up[t] lowres[b,t,c]
+__global__ void fused_pool_kernel(const float* __restrict__ sum_d, const float* __restrict__ sum_c, float inv_npix,
+                                  const float* __restrict__ alpha, const float* __restrict__ lowres,
+                                  const float* __restrict__ up, int T, int C, float* __restrict__ out) {
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float v = (alpha[b * 2] * sum_d[static_cast<long long>(b) * C + c] + alpha[b * 2 + 1] * sum_c[static_cast<long long>(b) * C + c]) * inv_npix;
+        if (lowres != nullptr)
+            for (int t = 0; t < T; ++t) v = fmaf(up[t], lowres[(static_cast<long long>(b) * T + t) * C + c], v);
+        out[static_cast<long long>(b) * C + c] = v;
+    }
+}
+
+// Backward of fused = alpha0 p_dwi + alpha1 p_dce + bilinear_up(lowres) from dfused [B,H,W,C] bf16.
+// reduce pass: dalpha[b,m] += sum dfused * p_m;  dlowres[b,t,c] += sum_p U[p,t] dfused[b,p,c]   (grid: (slabs, B))
+__global__ void __launch_bounds__(kTeThreads)
+fusion_mix_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ df, const __nv_bfloat16* __restrict__ pd,
+                             const __nv_bfloat16* __restrict__ pc, int H, int W, int C, int Hp, int Wp,
+                             float* __restrict__ dalpha, float* __restrict__ dlowres) {
+    extern __shared__ float s_low[];  // [Hp*Wp][C]
+    __shared__ double scratch[33];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int T = Hp * Wp, CG = C / 8, npix = H * W;
+    for (int i = tid; i < T * C; i += kTeThreads) s_low[i] = 0.f;
+    __syncthreads();
+    float ad = 0.f, ac = 0.f;
+    const int per = (npix + gridDim.x - 1) / gridDim.x;
+    const int p0 = blockIdx.x * per, p1 = min(p0 + per, npix);
+    const float sy = static_cast<float>(Hp) / H, sx = static_cast<float>(Wp) / W;
+    for (int i = p0 * CG + tid; i < p1 * CG; i += kTeThreads) {
+        const int pix = i / CG, c0 = (i - pix * CG) * 8;
+        const long long off = (static_cast<long long>(b) * npix + pix) * C + c0;
+        float g[8], u[8], v[8];
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(df + off)), g);
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(pd + off)), u);
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(pc + off)), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            ad = fmaf(g[k], u[k], ad);
+            ac = fmaf(g[k], v[k], ac);
+        }
+        if (dlowres != nullptr) {
+            const int oy = pix / W, ox = pix - oy * W;
+            const float fy = fmaxf((oy + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sx - 0.5f, 0.f);
+            const int y0 = min(static_cast<int>(fy), Hp - 1), x0 = min(static_cast<int>(fx), Wp - 1);
+            const int y1 = min(y0 + 1, Hp - 1), x1 = min(x0 + 1, Wp - 1);
+            const float ly = fy - y0, lx = fx - x0;
+            const float wt[4] = {(1.f - ly) * (1.f - lx), (1.f - ly) * lx, ly * (1.f - lx), ly * lx};
+            const int tk[4] = {y0 * Wp + x0, y0 * Wp + x1, y1 * Wp + x0, y1 * Wp + x1};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (wt[q] != 0.f) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) atomicAdd(&s_low[tk[q] * C + c0 + k], wt[q] * g[k]);
+                }
+            }
+        }
+    }
+    const double AD = block_sum<double>(static_cast<double>(ad), scratch);
+    const double AC = block_sum<double>(static_cast<double>(ac), scratch);
+    if (tid == 0) {
+        atomicAdd(dalpha + b * 2, static_cast<float>(AD));
+        atomicAdd(dalpha + b * 2 + 1, static_cast<float>(AC));
+    }
+    __syncthreads();
+    if (dlowres != nullptr)
+        for (int i = tid; i < T * C; i += kTeThreads) atomicAdd(dlowres + static_cast<long long>(b) * T * C + i, s_low[i]);
+}
+// apply pass: dp_m[b,p,c] = alpha_m dfused + dtok_m[b, bin(p), c] + dpvec_m[b,c]   (dtok already / bin size, dpvec / npix)
+__global__ void __launch_bounds__(kTeThreads)
+fusion_mix_bwd_apply_kernel(const __nv_bfloat16* __restrict__ df, const float* __restrict__ alpha,
+                            const float* __restrict__ dtok_d, const float* __restrict__ dtok_c,
+                            const float* __restrict__ dpv_d, const float* __restrict__ dpv_c, int B, int H, int W, int C,
+                            int Hp, int Wp, __nv_bfloat16* __restrict__ dpd, __nv_bfloat16* __restrict__ dpc) {
+    const int CG = C / 8, npix = H * W, T = Hp * Wp;
+    const long long total = static_cast<long long>(B) * npix * CG;
+    for (long long i = blockIdx.x * static_cast<long long>(kTeThreads) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * kTeThreads) {
+        const int c0 = static_cast<int>(i % CG) * 8;
+        const long long r = i / CG;
+        const int pix = static_cast<int>(r % npix);
+        const long long b = r / npix;
+        const int oy = pix / W, ox = pix - oy * W;
+        const int t = (oy * Hp / H) * Wp + (ox * Wp / W);
+        float g[8], o0[8], o1[8];
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(df + r * C + c0)), g);
+        const float a0 = alpha[b * 2], a1 = alpha[b * 2 + 1];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float e0 = a0 * g[k], e1 = a1 * g[k];
+            if (dtok_d != nullptr) {
+                e0 += dtok_d[(b * T + t) * C + c0 + k];
+                e1 += dtok_c[(b * T + t) * C + c0 + k];
+            }
+            if (dpv_d != nullptr) {
+                e0 += dpv_d[b * C + c0 + k];
+                e1 += dpv_c[b * C + c0 + k];
+            }
+            o0[k] = e0;
+            o1[k] = e1;
+        }
+        *reinterpret_cast<uint4*>(dpd + r * C + c0) = pack_bf16x8(o0);
+        *reinterpret_cast<uint4*>(dpc + r * C + c0) = pack_bf16x8(o1);
+    }
+}
+
+// The fusion step's mimic term as the reference writes it (code/train_fusion.py:287-296): `proj_fused[:4]` unpacks the
+// first four CASES of the fused projection as (p1, p1_r, p2, p2_r); mimic_feat_loss flattens a [C,H,W] tensor from dim
+// 1, so the cosine is taken per CHANNEL over the pixels and averaged over channels.  map [B, npix, C] bf16 (B >= 4).
+// loss += scale * (mean_c(1 - cos_c(case0, case1)) + mean_c(1 - cos_c(case2, case3))) / 2; dmap is zero except for
+// the student cases 0 and 2.  grid = 2 (one CTA per pair), thread = channel.
+__global__ void mimic_pairs_kernel(const __nv_bfloat16* __restrict__ map, int npix, int C, float scale,
+                                   float* __restrict__ loss, __nv_bfloat16* __restrict__ dmap) {
+    __shared__ double scratch[33];
+    const int pair = blockIdx.x;
+    const __nv_bfloat16* s = map + static_cast<long long>(2 * pair) * npix * C;
+    const __nv_bfloat16* t = map + static_cast<long long>(2 * pair + 1) * npix * C;
+    float acc = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float st = 0.f, ss = 0.f, tt = 0.f;
+        for (int p = 0; p < npix; ++p) {
+            const float u = __bfloat162float(s[static_cast<long long>(p) * C + c]);
+            const float v = __bfloat162float(t[static_cast<long long>(p) * C + c]);
+            st = fmaf(u, v, st);
+            ss = fmaf(u, u, ss);
+            tt = fmaf(v, v, tt);
+        }
+        const float ns = fmaxf(sqrtf(ss), 1e-12f), nt = fmaxf(sqrtf(tt), 1e-12f);
+        const float cosv = st / (ns * nt);
+        const bool inside = cosv > -1.f + 1e-6f && cosv < 1.f - 1e-6f;
+        acc += 1.f - fminf(fmaxf(cosv, -1.f + 1e-6f), 1.f - 1e-6f);
+        if (dmap != nullptr) {
+            const float w = scale * 0.5f / C;
+            const float k1 = inside ? -w / (ns * nt) : 0.f, k2 = inside ? w * cosv / (ns * ns) : 0.f;
+            __nv_bfloat16* d = dmap + static_cast<long long>(2 * pair) * npix * C;
+            for (int p = 0; p < npix; ++p) {
+                const float u = __bfloat162float(s[static_cast<long long>(p) * C + c]);
+                const float v = __bfloat162float(t[static_cast<long long>(p) * C + c]);
+                d[static_cast<long long>(p) * C + c] = __float2bfloat16_rn(k1 * v + k2 * u);
+            }
+        }
+    }
+    const double A = block_sum<double>(static_cast<double>(acc), scratch);
+    if (threadIdx.x == 0) atomicAdd(loss, scale * 0.5f * static_cast<float>(A) / C);
+}
+
 // 2x2 replication (AdaptiveAvgPool2d to twice the size) backward: din[b,h,w,c] = sum of the four replicas of dout
 __global__ void __launch_bounds__(kTeThreads)
 up2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int B, int H, int W, int C, __nv_bfloat16* __restrict__ din) {
@@ -1020,6 +1232,13 @@ up2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int B, int H, int W, int 
         }
         *reinterpret_cast<uint4*>(din + pix * C + cg * 8) = pack_bf16x8(o);
     }
+}
+
+// out[b, i] = v[b * v_stride] * scale for i < n (gradient of a per-case mean of an fp32 map)
+__global__ void row_bcast_kernel(const float* __restrict__ v, int v_stride, float scale, int n, float* __restrict__ out) {
+    const int b = blockIdx.x;
+    const float s = v[static_cast<long long>(b) * v_stride] * scale;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[static_cast<long long>(b) * n + i] = s;
 }
 
 // fp32 vector helpers for the tiny per-case tensors: y = alpha * a + beta * y
@@ -1285,11 +1504,11 @@ extern "C" int b200_dice_loss(const float* logits, const float* target, int B, i
     return launch_status();
 }
 
-extern "C" int b200_recon_loss(const float* r, int B, int h, int w, const float* x, int C, int H, int W, float eps,
-                               float scale, float* loss, float* dr, void* stream) {
-    if (r == nullptr || x == nullptr || loss == nullptr || B <= 0 || h * w > 8192) return -1;
-    recon_loss_kernel<<<B, kTeThreads, static_cast<size_t>(h) * w * sizeof(float), TE_STREAM>>>(r, h, w, x, C, H, W, eps,
-                                                                                               scale, loss, dr);
+extern "C" int b200_recon_loss(const float* r, int B, int h, int w, const float* x, int C, const float* x2, int C2, int H,
+                               int W, float eps, float scale, float* loss, float* dr, void* stream) {
+    if (r == nullptr || x == nullptr || loss == nullptr || B <= 0 || h * w > 8192 || (x2 == nullptr && C2 != 0)) return -1;
+    recon_loss_kernel<<<B, kTeThreads, static_cast<size_t>(h) * w * sizeof(float), TE_STREAM>>>(r, h, w, x, C, x2, C2, H, W,
+                                                                                               eps, scale, loss, dr);
     return launch_status();
 }
 
@@ -1302,10 +1521,70 @@ extern "C" int b200_mimic_loss(const void* s, const void* t, int B, long long n,
     return launch_status();
 }
 
+
+extern "C" int b200_gating_fwd(const float* sum_d, const float* sum_c, int B, int C, int npix, const float* mask_d,
+                               const float* mask_c, int npix_mask, const float* w, const float* bias, float* gx,
+                               float* alpha, void* stream) {
+    if (sum_d == nullptr || sum_c == nullptr || w == nullptr || bias == nullptr || gx == nullptr || alpha == nullptr || B <= 0) return -1;
+    gating_fwd_kernel<<<B, kTeThreads, 0, TE_STREAM>>>(sum_d, sum_c, 1.0f / npix, mask_d, mask_c, npix_mask, C, w, bias, gx, alpha);
+    return launch_status();
+}
+extern "C" int b200_gating_bwd(const float* alpha, const float* dalpha, const float* w, int B, int C, int D, int npix,
+                               float* dgl, float* dgx, float* dpv_d, float* dpv_c, void* stream) {
+    if (alpha == nullptr || dalpha == nullptr || w == nullptr || dgl == nullptr || dgx == nullptr || dpv_d == nullptr ||
+        dpv_c == nullptr || B <= 0 || npix <= 0)
+        return -1;
+    gating_bwd_kernel<<<B, 128, 0, TE_STREAM>>>(alpha, dalpha, w, C, D, 1.0f / npix, dgl, dgx, dpv_d, dpv_c);
+    return launch_status();
+}
+extern "C" int b200_fused_pool(const float* sum_d, const float* sum_c, int B, int C, int npix, const float* alpha,
+                               const float* lowres, const float* up, int T, float* out, void* stream) {
+    if (sum_d == nullptr || sum_c == nullptr || alpha == nullptr || out == nullptr || B <= 0) return -1;
+    fused_pool_kernel<<<B, 128, 0, TE_STREAM>>>(sum_d, sum_c, 1.0f / npix, alpha, lowres, up, T, C, out);
+    return launch_status();
+}
+extern "C" int b200_fusion_mix_bwd(const void* dfused, const void* p_dwi, const void* p_dce, const float* alpha, int B, int H,
+                                   int W, int C, int Hp, int Wp, float* dalpha, float* dlowres, const float* dtok_d,
+                                   const float* dtok_c, const float* dpv_d, const float* dpv_c, void* dp_dwi, void* dp_dce,
+                                   int phase, void* stream) {
+    if (dfused == nullptr || B <= 0 || C % 8 != 0) return -1;
+    if (phase == 0) {  // reductions: dalpha, dlowres (caller zeroes both)
+        if (p_dwi == nullptr || p_dce == nullptr || dalpha == nullptr) return -2;
+        const size_t smem = static_cast<size_t>(Hp) * Wp * C * sizeof(float);
+        if (smem > 48 * 1024) return -3;
+        int slabs = (148 * 2 + B - 1) / B;
+        if (slabs < 1) slabs = 1;
+        if (slabs > 16) slabs = 16;
+        fusion_mix_bwd_reduce_kernel<<<dim3(slabs, B), kTeThreads, smem, TE_STREAM>>>(
+            static_cast<const __nv_bfloat16*>(dfused), static_cast<const __nv_bfloat16*>(p_dwi),
+            static_cast<const __nv_bfloat16*>(p_dce), H, W, C, Hp, Wp, dalpha, dlowres);
+    } else {
+        if (alpha == nullptr || dp_dwi == nullptr || dp_dce == nullptr) return -2;
+        if (dtok_d != nullptr && (H % Hp != 0 || W % Wp != 0)) return -4;
+        fusion_mix_bwd_apply_kernel<<<blocks_for(static_cast<long long>(B) * H * W * (C / 8)), kTeThreads, 0, TE_STREAM>>>(
+            static_cast<const __nv_bfloat16*>(dfused), alpha, dtok_d, dtok_c, dpv_d, dpv_c, B, H, W, C, Hp, Wp,
+            static_cast<__nv_bfloat16*>(dp_dwi), static_cast<__nv_bfloat16*>(dp_dce));
+    }
+    return launch_status();
+}
+extern "C" int b200_mimic_pairs(const void* map, int B, int npix, int C, float scale, float* loss, void* dmap, void* stream) {
+    if (map == nullptr || loss == nullptr || B < 4 || C <= 0) return -1;
+    if (dmap != nullptr) cudaMemsetAsync(dmap, 0, static_cast<size_t>(B) * npix * C * 2, TE_STREAM);
+    mimic_pairs_kernel<<<2, 128, 0, TE_STREAM>>>(static_cast<const __nv_bfloat16*>(map), npix, C, scale, loss,
+                                                static_cast<__nv_bfloat16*>(dmap));
+    return launch_status();
+}
+
 extern "C" int b200_up2_bwd(const void* dout, int B, int H, int W, int C, void* din, void* stream) {
     if (dout == nullptr || din == nullptr || C % 8 != 0) return -1;
     up2_bwd_kernel<<<blocks_for(static_cast<long long>(B) * H * W * (C / 8)), kTeThreads, 0, TE_STREAM>>>(
         static_cast<const __nv_bfloat16*>(dout), B, H, W, C, static_cast<__nv_bfloat16*>(din));
+    return launch_status();
+}
+
+extern "C" int b200_row_bcast(const float* v, int v_stride, float scale, int B, int n, float* out, void* stream) {
+    if (v == nullptr || out == nullptr || B <= 0 || n <= 0) return -1;
+    row_bcast_kernel<<<B, 256, 0, TE_STREAM>>>(v, v_stride, scale, n, out);
     return launch_status();
 }
 

@@ -98,6 +98,7 @@ class TrainOps:
         self.tape = Tape()
         self.scratch = _Scratch(dev)
         self._packs = {}
+        self._bucket_marks = None
         self._seed = int(drop_seed)
         self._launch = 0
 
@@ -383,13 +384,15 @@ def _projector_c1(ops, pr, r):
     return ops.bn_act(ops.conv(g, pr.proj[3]), bn=pr.proj[4], act=1)
 
 
-def encoder_forward_train(ops, m, x):
+def encoder_forward_train(ops, m, x, heads=True):
     """Train-mode ModelMaskHeadBackbone.forward (reference :645-733) on the tape of `ops`.
 
     x [B,C,H,W] fp32 normalised input.  Returns a dict: logits [B,K] fp32, f1 / f2 / f3 NHWC bf16, r1 / r2 fp32
     [B,h,w], p1 / p1_r / p2 / p2_r NHWC bf16 at the MAP resolution (the reference's AdaptiveAvgPool2d to 2x the size
     replicates every pixel 2 x 2, which changes neither the BatchNorm statistics nor the cosine / mean losses taken on
-    the result), mask_pred [B,h,w] fp32, mask_attn_map, mod_attn_map, pooled3 (the classifier's GAP input)."""
+    the result), mask_pred [B,h,w] fp32, mask_attn_map, mod_attn_map, pooled3 (the classifier's GAP input).
+    heads=False skips the encoder's own classifier and projectors (the fusion step's loss does not read them, so the
+    reference's autograd leaves their parameters without a gradient too)."""
     _check_supported(m)
     dev = x.device
     tape = ops.tape
@@ -399,6 +402,9 @@ def encoder_forward_train(ops, m, x):
     b1 = m.block1
     stride = b1.stride
     Ho, Wo = H // stride, W // stride
+    marks = getattr(ops, "_bucket_marks", None) or [None, None, None]
+    if marks[0] is not None:
+        tape.record(marks[0])
     # ---- modality attention + the two strided 1x1 convolutions that read the raw input (fp32 SIMT "stem") ----
     se0 = m.modality_attention
     pm = torch.empty(B * C, dtype=torch.float32, device=dev)
@@ -451,6 +457,8 @@ def encoder_forward_train(ops, m, x):
     t2 = ops.bn_act(ops.conv(t1, bt1[4]), bn=bt1[5], act=1)
     f1, r1 = _block_tail(ops, b1, t2, identity1, p_drop)
     # ---- block2, mask head on f2 (+ aligned f1), mask-guided modulation -------------------------------------------
+    if marks[1] is not None:
+        tape.record(marks[1])
     f2_pre, r2 = _block_from_map(ops, m.block2, f1, p_drop)
     al = m.f1_to_f2.proj
     if isinstance(al, nn.Identity):
@@ -465,35 +473,39 @@ def encoder_forward_train(ops, m, x):
     mask_pred = ops.conv_c1(t64, mh.out)
     f2, attn_map = ops.mask_modulate(f2_pre, mask_pred, m.mask_spatial_attention)
     # ---- block3, classifier, projectors ------------------------------------------------------------------------------
+    if marks[2] is not None:
+        tape.record(marks[2])
     f3, _ = _block_from_map(ops, m.block3, f2, p_drop)
-    npix3 = f3.shape[1] * f3.shape[2]
-    C3 = f3.shape[-1]
-    sums3 = torch.empty((B, C3), dtype=torch.float32, device=dev)
-    _call("b200_map_dot", _P(f3), nat._ld(f3), None, 0, B, npix3, C3, _P(sums3), _s())
-    head = m.classification_head
-    K = head.fc.out_features
-    logits = torch.empty((B, K), dtype=torch.float32, device=dev)
-    pooled3 = torch.empty((B, C3), dtype=torch.float32, device=dev)
-    _call("b200_vec_axpby", _P(sums3), 1.0 / npix3, 0.0, sums3.numel(), _P(pooled3), _s())  # GAP mean (pre-normalise)
-    nat.cls_head(sums3, None, npix3, head.fc.weight.detach(), head.fc.bias.detach(), head.normalize, logits)
+    logits = pooled3 = p1 = p2 = p1_r = p2_r = None
+    if heads:
+        npix3 = f3.shape[1] * f3.shape[2]
+        C3 = f3.shape[-1]
+        sums3 = torch.empty((B, C3), dtype=torch.float32, device=dev)
+        _call("b200_map_dot", _P(f3), nat._ld(f3), None, 0, B, npix3, C3, _P(sums3), _s())
+        head = m.classification_head
+        K = head.fc.out_features
+        logits = torch.empty((B, K), dtype=torch.float32, device=dev)
+        pooled3 = torch.empty((B, C3), dtype=torch.float32, device=dev)
+        _call("b200_vec_axpby", _P(sums3), 1.0 / npix3, 0.0, sums3.numel(), _P(pooled3), _s())  # GAP mean (pre-normalise)
+        nat.cls_head(sums3, None, npix3, head.fc.weight.detach(), head.fc.bias.detach(), head.normalize, logits)
 
-    def head_bwd():
-        dl = tape.grad_of(logits)
-        if dl is None:
-            return
-        dpooled = torch.empty((B, C3), dtype=torch.float32, device=dev)
-        _call("b200_cls_head_bwd", _P(pooled3), _P(dl), _P(head.fc.weight.detach()), B, C3, K, 1 if head.normalize else 0,
-              _P(_grad_buf(head.fc.weight)), _P(_grad_buf(head.fc.bias)), _P(dpooled), _s())
-        _call("b200_vec_axpby", _P(dpooled), 1.0 / npix3, 0.0, dpooled.numel(), _P(dpooled), _s())
-        df3 = torch.empty(f3.shape, dtype=torch.bfloat16, device=dev)
-        _call("b200_map_scale_add", None, 0, None, _P(dpooled), B, npix3, C3, _P(df3), nat._ld(df3), 0, _s())  # broadcast
-        tape.add_grad(f3, df3)
+        def head_bwd():
+            dl = tape.grad_of(logits)
+            if dl is None:
+                return
+            dpooled = torch.empty((B, C3), dtype=torch.float32, device=dev)
+            _call("b200_cls_head_bwd", _P(pooled3), _P(dl), _P(head.fc.weight.detach()), B, C3, K, 1 if head.normalize else 0,
+                  _P(_grad_buf(head.fc.weight)), _P(_grad_buf(head.fc.bias)), _P(dpooled), _s())
+            _call("b200_vec_axpby", _P(dpooled), 1.0 / npix3, 0.0, dpooled.numel(), _P(dpooled), _s())
+            df3 = torch.empty(f3.shape, dtype=torch.bfloat16, device=dev)
+            _call("b200_map_scale_add", None, 0, None, _P(dpooled), B, npix3, C3, _P(df3), nat._ld(df3), 0, _s())  # broadcast
+            tape.add_grad(f3, df3)
 
-    tape.record(head_bwd)
-    p1 = _projector(ops, m.proj_f1, f1)
-    p2 = _projector(ops, m.proj_f2, f2)
-    p1_r = _projector_c1(ops, m.proj_r1, r1)
-    p2_r = _projector_c1(ops, m.proj_r2, r2)
+        tape.record(head_bwd)
+        p1 = _projector(ops, m.proj_f1, f1)
+        p2 = _projector(ops, m.proj_f2, f2)
+        p1_r = _projector_c1(ops, m.proj_r1, r1)
+        p2_r = _projector_c1(ops, m.proj_r2, r2)
     return {"logits": logits, "f1": f1, "f2": f2, "f3": f3, "r1": r1, "r2": r2, "p1": p1, "p1_r": p1_r, "p2": p2,
             "p2_r": p2_r, "mask_pred": mask_pred, "mask_attn_map": attn_map, "mod_attn_map": gate0, "pooled3": pooled3,
             "x": x}
@@ -546,7 +558,7 @@ def single_model_loss(ops, out, masks, labels, *, smoothing, gamma, class_weight
         r = out[key]
         dr = torch.empty_like(r)
         one = torch.zeros(1, dtype=torch.float32, device=dev)
-        _call("b200_recon_loss", _P(r), B, r.shape[1], r.shape[2], _P(x), C, H, W, 1e-3, 1.0 / (B * H * W), _P(one), _P(dr), _s())
+        _call("b200_recon_loss", _P(r), B, r.shape[1], r.shape[2], _P(x), C, None, 0, H, W, 1e-3, 1.0 / (B * H * W), _P(one), _P(dr), _s())
         _call("b200_vec_axpby", _P(one), 1.0, 1.0, 1, _P(parts["recon"]), _s())
         _call("b200_vec_axpby", _P(dr), float(w_recon), 0.0, dr.numel(), _P(dr), _s())
         tape.add_grad(r, dr)
@@ -561,3 +573,408 @@ def single_model_loss(ops, out, masks, labels, *, smoothing, gamma, class_weight
     total = (parts["cls"] + lambda_feat_norm * parts["feat_norm"] + lambda_mask * parts["mask"] +
              w_recon * parts["recon"] + w_mimic * parts["mimic"])
     return total, parts
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fusion head at full resolution (reference model_module.py:919-1000, train mode)
+# ------------------------------------------------------------------------------------------------------------------
+def _split_k(m, n, k):
+    tiles = ((m + 63) // 64) * ((n + 63) // 64)
+    return max(1, min((2 * 148 + tiles - 1) // tiles, max(1, k // 64)))
+
+
+def _wgrad32(dy, x, param, rows=None):
+    """param.grad[rows] += dy^T x (fp32 token / vector matrices)."""
+    g = _grad_buf(param) if rows is None else _grad_buf(param)[rows]
+    g = g.view(g.shape[0], -1)
+    nat.sgemm(dy, x, g, trans_a=True, beta=1, split_k=_split_k(g.shape[0], g.shape[1], dy.shape[0]))
+
+
+def _bgrad32(dy, param, rows=None):
+    nat.colsum(dy, _grad_buf(param) if rows is None else _grad_buf(param)[rows])
+
+
+def fusion_forward_train(ops, fm, f3d, f3c, md, mc):
+    """Train-mode FusionModel.forward on the tape of `ops`.  f3d / f3c: NHWC bf16 encoder maps (tape tensors when the
+    encoders train too), md / mc: [B,h,w] fp32 encoder mask logits (or None without use_mask_attention).  The
+    reference's dead cat -> reduce -> refine branch (:935-940) is not evaluated.  Returns a dict: logits, fused_mask
+    [B,h,w] fp32, recon [B,h,w] fp32, proj NHWC bf16, gating [B,2], attn_weights, p_dwi, p_dce."""
+    from model_module import _bilinear_axis_weights
+
+    if isinstance(fm.proj_in_dwi, nn.Identity) or isinstance(fm.proj_in_dce, nn.Identity) or fm.fusion_se is None:
+        raise NotImplementedError("training path: proj_in convolutions and fusion_se present")
+    if not fm.use_cross_attention:
+        raise NotImplementedError("training path: use_cross_attention")
+    tape, dev = ops.tape, ops.dev
+    B, H, W, _ = f3d.shape
+    C, (hp, wp), NH = fm.fusion_channels, fm.token_pool, fm.mha_heads
+    T, npix, R = hp * wp, H * W, B * hp * wp
+    if H % hp or W % wp:
+        raise NotImplementedError("training path: token bins that tile the map")
+
+    def z(*shape):
+        return torch.empty(shape, dtype=torch.float32, device=dev)
+
+    p_d = ops.conv(f3d, fm.proj_in_dwi)
+    p_c = ops.conv(f3c, fm.proj_in_dce)
+    sum_d, sum_c = z(B, C), z(B, C)
+    _call("b200_map_dot", _P(p_d), nat._ld(p_d), None, 0, B, npix, C, _P(sum_d), _s())
+    _call("b200_map_dot", _P(p_c), nat._ld(p_c), None, 0, B, npix, C, _P(sum_c), _s())
+    Td, Tc = z(R, C), z(R, C)
+    nat.fusion_tokens(p_d, hp, wp, Td.view(B, T, C))
+    nat.fusion_tokens(p_c, hp, wp, Tc.view(B, T, C))
+    # ---- cross-attention block on the pooled tokens (fp32) ----
+    ca = fm.cross_attn_block
+    Win, b_in = ca.cross_attn.in_proj_weight.detach(), ca.cross_attn.in_proj_bias.detach()
+    Wo, bo = ca.cross_attn.out_proj.weight.detach(), ca.cross_attn.out_proj.bias.detach()
+    ln = ca.attn_ffn[0]
+    W1, b1 = ca.attn_ffn[1].weight.detach(), ca.attn_ffn[1].bias.detach()
+    W2, b2 = ca.attn_ffn[3].weight.detach(), ca.attn_ffn[3].bias.detach()
+    Q, KV, Pm, CTX, AO, LN = z(R, C), z(R, 2 * C), z(B, NH, T, T), z(R, C), z(R, C), z(R, C)
+    mean, rstd, H1, G1, LOW = z(R), z(R), z(R, C), z(R, C), z(R, C)
+    nat.sgemm(Td, Win[:C], Q, trans_b=True, bias=b_in[:C])
+    nat.sgemm(Tc, Win[C:], KV, trans_b=True, bias=b_in[C:])
+    Kt, Vt = KV[:, :C], KV[:, C:]
+    nat.mha_fwd(Q, Kt, Vt, B, NH, Pm, CTX)
+    nat.sgemm(CTX, Wo, AO, trans_b=True, bias=bo)
+    nat.ln_fwd(AO, ln.weight.detach(), ln.bias.detach(), ln.eps, LN, mean, rstd)
+    nat.sgemm(LN, W1, G1, trans_b=True, bias=b1, pre=H1, act=1)
+    nat.sgemm(G1, W2, LOW, trans_b=True, bias=b2, res=AO)
+    # ---- gating ----
+    use_ma = bool(fm.use_mask_attention)
+    if use_ma and (md is None or mc is None):
+        raise RuntimeError("use_mask_attention needs both encoder mask predictions")
+    D = 2 * C + (2 if use_ma else 0)
+    gx, alpha = z(B, D), z(B, 2)
+    npm = md[0].numel() if use_ma else 0
+    gw, gb = fm.gating.fc.weight, fm.gating.fc.bias
+    _call("b200_gating_fwd", _P(sum_d), _P(sum_c), B, C, npix, _P(md) if use_ma else None, _P(mc) if use_ma else None, npm,
+          _P(gw.detach()), _P(gb.detach()), _P(gx), _P(alpha), _s())
+    # ---- fused = alpha0 p_dwi + alpha1 p_dce + up(lowres) ----
+    fused = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dev)
+    nat.fusion_mix(p_d, p_c, alpha, LOW.view(B, T, C), None, hp, wp, fused)
+    attn_w = None  # (the head-averaged attention weights are an eval-path output; training does not need them)
+
+    def mix_bwd():
+        df = tape.grad_of(fused)
+        if df is None:
+            return
+        dalpha = torch.zeros((B, 2), dtype=torch.float32, device=dev)
+        dLOW = torch.zeros((R, C), dtype=torch.float32, device=dev)
+        _call("b200_fusion_mix_bwd", _P(df), _P(p_d), _P(p_c), None, B, H, W, C, hp, wp, _P(dalpha), _P(dLOW), None, None,
+              None, None, None, None, 0, _s())
+        # cross-attention block backward (same sequence as the fusion-head trainer, csrc/train_ops.cu kernels)
+        dG1, dH1, dLN, dAO, tmp, dCTX, dQ, dKV = z(R, C), z(R, C), z(R, C), z(R, C), z(R, C), z(R, C), z(R, C), z(R, 2 * C)
+        _wgrad32(dLOW, G1, ca.attn_ffn[3].weight)
+        _bgrad32(dLOW, ca.attn_ffn[3].bias)
+        nat.sgemm(dLOW, W2, dG1)
+        nat.gelu_bwd(H1, dG1, dH1)
+        _wgrad32(dH1, LN, ca.attn_ffn[1].weight)
+        _bgrad32(dH1, ca.attn_ffn[1].bias)
+        nat.sgemm(dH1, W1, dLN)
+        nat.ln_bwd(AO, dLN, dLOW, ln.weight.detach(), mean, rstd, dAO, tmp)
+        _bgrad32(tmp, ln.weight)
+        _bgrad32(dLN, ln.bias)
+        _wgrad32(dAO, CTX, ca.cross_attn.out_proj.weight)
+        _bgrad32(dAO, ca.cross_attn.out_proj.bias)
+        nat.sgemm(dAO, Wo, dCTX)
+        nat.mha_bwd(Q, Kt, Vt, Pm, dCTX, B, NH, dQ, dKV[:, :C], dKV[:, C:])
+        _wgrad32(dQ, Td, ca.cross_attn.in_proj_weight, slice(0, C))
+        _bgrad32(dQ, ca.cross_attn.in_proj_bias, slice(0, C))
+        _wgrad32(dKV, Tc, ca.cross_attn.in_proj_weight, slice(C, 3 * C))
+        _bgrad32(dKV, ca.cross_attn.in_proj_bias, slice(C, 3 * C))
+        dTd, dTc = z(R, C), z(R, C)
+        nat.sgemm(dQ, Win[:C], dTd)
+        nat.sgemm(dKV, Win[C:], dTc)
+        bin_px = (H // hp) * (W // wp)
+        _call("b200_vec_axpby", _P(dTd), 1.0 / bin_px, 0.0, dTd.numel(), _P(dTd), _s())
+        _call("b200_vec_axpby", _P(dTc), 1.0 / bin_px, 0.0, dTc.numel(), _P(dTc), _s())
+        # gating backward
+        dgl, dgx, dpv_d, dpv_c = z(B, 2), z(B, D), z(B, C), z(B, C)
+        _call("b200_gating_bwd", _P(alpha), _P(dalpha), _P(gw.detach()), B, C, D, npix, _P(dgl), _P(dgx), _P(dpv_d),
+              _P(dpv_c), _s())
+        _wgrad32(dgl, gx, gw)
+        _bgrad32(dgl, gb)
+        if use_ma:
+            for m_, col in ((md, 2 * C), (mc, 2 * C + 1)):
+                dm_ = torch.empty(m_.shape, dtype=torch.float32, device=dev)
+                _call("b200_row_bcast", _P(dgx[:, col:]), D, 1.0 / npm, B, npm, _P(dm_), _s())
+                tape.add_grad(m_, dm_)
+        dpd = torch.empty(p_d.shape, dtype=torch.bfloat16, device=dev)
+        dpc = torch.empty(p_c.shape, dtype=torch.bfloat16, device=dev)
+        _call("b200_fusion_mix_bwd", _P(df), None, None, _P(alpha), B, H, W, C, hp, wp, None, None, _P(dTd), _P(dTc),
+              _P(dpv_d), _P(dpv_c), _P(dpd), _P(dpc), 1, _s())
+        tape.add_grad(p_d, dpd)
+        tape.add_grad(p_c, dpc)
+
+    tape.record(mix_bwd)
+    fr, gate = ops.se(fused, fm.fusion_se)
+    # ---- heads on fused_refined ----
+    mh = fm.mask_head
+    if H != fm.mask_size:
+        raise NotImplementedError("training path: mask head at the mask size (32 x 32 maps)")
+    t64 = ops.bn_act(ops.conv(fr, mh.pre), bias=mh.pre.bias)
+    fused_mask = ops.conv_c1(t64, mh.out)
+    sums = z(B, C)
+    _call("b200_map_dot", _P(fr), nat._ld(fr), None, 0, B, npix, C, _P(sums), _s())
+    pooled = z(B, C)
+    _call("b200_vec_axpby", _P(sums), 1.0 / npix, 0.0, sums.numel(), _P(pooled), _s())
+    fc = fm.classifier[2]
+    K = fc.out_features
+    logits = z(B, K)
+    nat.cls_head(sums, None, npix, fc.weight.detach(), fc.bias.detach(), False, logits)
+
+    def cls_bwd():
+        dl = tape.grad_of(logits)
+        if dl is None:
+            return
+        dpooled = z(B, C)
+        _call("b200_cls_head_bwd", _P(pooled), _P(dl), _P(fc.weight.detach()), B, C, K, 0, _P(_grad_buf(fc.weight)),
+              _P(_grad_buf(fc.bias)), _P(dpooled), _s())
+        _call("b200_vec_axpby", _P(dpooled), 1.0 / npix, 0.0, dpooled.numel(), _P(dpooled), _s())
+        dfr = torch.empty(fr.shape, dtype=torch.bfloat16, device=dev)
+        _call("b200_map_scale_add", None, 0, None, _P(dpooled), B, npix, C, _P(dfr), nat._ld(dfr), 0, _s())
+        tape.add_grad(fr, dfr)
+
+    tape.record(cls_bwd)
+    rh = fm.fusion_reconstruct.conv
+    recon = ops.conv_c1(ops.bn_act(ops.conv(fr, rh[0]), bn=rh[1], act=1), rh[3])
+    proj = _projector(ops, fm.projF, fr)
+    return {"logits": logits, "fused_mask": fused_mask, "recon": recon, "proj": proj, "gating": alpha, "attn_weights": attn_w,
+            "p_dwi": p_d, "p_dce": p_c, "fused_refined": fr}
+
+
+def fusion_objective(ops, fo, enc_d, enc_c, masks, labels, dwi_in, dce_in, *, smoothing, gamma, class_weights, lambda_mask,
+                     lambda_recon, lambda_mimic, aux_w=1.0, md=None, mc=None):
+    """Total loss of LightningFusionModel._shared_step (code/train_fusion.py:238-296) with its gradients seeded on the
+    tape:  cls + lambda_mask * (dice(md) + dice(mc) + dice(fused)) / 3
+               + lambda_recon * aux_w * (recon_list(dwi) + recon_list(dce) + recon(fused)) / 3
+               + lambda_mimic * aux_w * mimic(proj_fused[:4]).
+    `fo` = fusion_forward_train's dict; enc_d / enc_c = the encoders' train-forward dicts (their r1 / r2 and mask_pred
+    join the loss) or None when the encoders are frozen (then md / mc are the constant mask logits and the encoder
+    reconstruction lists count as absent, i.e. 0, as compute_recon_list_loss does).  Returns (total, parts)."""
+    tape, dev = ops.tape, ops.dev
+    logits = fo["logits"]
+    B, K = logits.shape
+    parts = {k: torch.zeros(1, dtype=torch.float32, device=dev) for k in ("cls", "mask", "recon", "mimic")}
+    dl = torch.empty_like(logits)
+    cw = class_weights.to(dev).float().contiguous() if class_weights is not None else None
+    _call("b200_focal_loss", _P(logits), _P(labels), B, K, float(smoothing), float(gamma), _P(cw), 1.0 / B, _P(parts["cls"]),
+          _P(dl), _s())
+    tape.add_grad(logits, dl)
+    tgt = masks.contiguous().float()
+    md = enc_d["mask_pred"] if enc_d is not None else md
+    mc = enc_c["mask_pred"] if enc_c is not None else mc
+    for m_, trainable in ((md, enc_d is not None), (mc, enc_c is not None), (fo["fused_mask"], True)):
+        n = m_[0].numel()
+        dm = torch.empty(m_.shape, dtype=torch.float32, device=dev) if trainable else None
+        _call("b200_dice_loss", _P(m_), _P(tgt), B, n, 1e-6, 1.0 / (3 * B), _P(parts["mask"]), _P(dm), _s())
+        if trainable and lambda_mask != 0:
+            _call("b200_vec_axpby", _P(dm), float(lambda_mask), 0.0, dm.numel(), _P(dm), _s())
+            tape.add_grad(m_, dm)
+    _, Cd, H, W = dwi_in.shape
+    Cc = dce_in.shape[1]
+    wr = lambda_recon * aux_w
+    scale = 1.0 / (3 * B * H * W)
+    for enc, x in ((enc_d, dwi_in), (enc_c, dce_in)):
+        if enc is None:
+            continue
+        for key in ("r1", "r2"):  # compute_recon_list_loss: mean over the list's reconstructions
+            r = enc[key]
+            dr = torch.empty_like(r)
+            _call("b200_recon_loss", _P(r), B, r.shape[1], r.shape[2], _P(x), x.shape[1], None, 0, H, W, 1e-3, 0.5 * scale,
+                  _P(parts["recon"]), _P(dr), _s())
+            _call("b200_vec_axpby", _P(dr), float(wr), 0.0, dr.numel(), _P(dr), _s())
+            tape.add_grad(r, dr)
+    r = fo["recon"]
+    dr = torch.empty_like(r)
+    _call("b200_recon_loss", _P(r), B, r.shape[1], r.shape[2], _P(dwi_in), Cd, _P(dce_in), Cc, H, W, 1e-3, scale,
+          _P(parts["recon"]), _P(dr), _s())
+    _call("b200_vec_axpby", _P(dr), float(wr), 0.0, dr.numel(), _P(dr), _s())
+    tape.add_grad(r, dr)
+    proj = fo["proj"]
+    if B >= 4:
+        wm = lambda_mimic * aux_w
+        dpj = torch.empty(proj.shape, dtype=torch.bfloat16, device=dev)
+        one = torch.zeros(1, dtype=torch.float32, device=dev)
+        _call("b200_mimic_pairs", _P(proj), B, proj.shape[1] * proj.shape[2], proj.shape[3], 1.0, _P(one), None, _s())
+        _call("b200_mimic_pairs", _P(proj), B, proj.shape[1] * proj.shape[2], proj.shape[3], float(wm), _P(parts["mimic"]),
+              _P(dpj), _s())
+        parts["mimic"] = one
+        tape.add_grad(proj, dpj)
+    total = parts["cls"] + lambda_mask * parts["mask"] + lambda_recon * aux_w * parts["recon"] + lambda_mimic * aux_w * parts["mimic"]
+    return total, parts
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# data-parallel training step of the whole model (BASELINE config C5: backbone unfrozen, bf16, NCCL all-reduce)
+# ------------------------------------------------------------------------------------------------------------------
+_NO_GRAD_PREFIXES_ENC = ("classification_head.", "proj_f1.", "proj_f2.", "proj_r1.", "proj_r2.", "f2_to_f3.", "f2_weight",
+                         "f3_weight", "norm_f2.", "norm_f3.", "mask_head.down_")
+_NO_GRAD_PREFIXES_FUS = ("fusion_conv_reduce.", "refine.", "mask_head.down_")
+
+
+class FullFusionTrainer:
+    """One optimisation step of LightningFusionModel with everything unfrozen (code/train_fusion.py:203-321,
+    optimiser code/selector_helpers.py:356-742 reduced to one AdamW group): train-mode forward of both encoders and
+    the fusion head, the full objective, explicit backward, bucketed gradient all-reduce overlapped with the rest of
+    the backward pass, one fused AdamW launch over the flat parameter buffer.
+
+    Parameters the fusion objective cannot reach (the reference's autograd leaves their .grad None and AdamW skips
+    them, SURVEY.md App. A-2: encoder classifier / projectors, unused mask-head down-samplers, the dead reduce / refine
+    branch ...) stay outside the flat buffers and are never touched.  Every other parameter becomes a view of ONE fp32
+    buffer, its gradient a view of a second one; the gradient buffer is cut into buckets in backward order and bucket
+    i's all-reduce (NCCL over NVLink) is issued on a side stream as soon as the tape has passed the forward position
+    where its last gradient is produced.  `encoders_trainable=False` is the reference's frozen phase: the encoders run
+    their eval forward and only the head is in the buffers."""
+
+    def __init__(self, dwi_model, dce_model, fusion_model, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=4e-5,
+                 smoothing=0.1, gamma=1.5, class_weights=None, lambda_mask=0.2, lambda_recon=0.1, lambda_mimic=0.2,
+                 encoders_trainable=True, process_group=None, bucket_mb=8.0, seed=0x5EED):
+        from fusion_train import flat_size, flat_views
+
+        self.dwi, self.dce, self.fusion = dwi_model, dce_model, fusion_model
+        self.hp = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.loss_hp = dict(smoothing=smoothing, gamma=gamma, class_weights=class_weights, lambda_mask=lambda_mask,
+                            lambda_recon=lambda_recon, lambda_mimic=lambda_mimic)
+        self.encoders_trainable = bool(encoders_trainable)
+        self.group = process_group
+        self.step_count = 0
+        dev = next(fusion_model.parameters()).device
+        if dev.type != "cuda":
+            raise nat.B200NativeError("FullFusionTrainer needs the models on a CUDA device (no CPU path)")
+        self.dev = dev
+        self.ops = TrainOps(dev, drop_seed=seed)
+        # ---- trainable parameters in FORWARD order, segment by segment (a segment = one all-reduce bucket unit) ----
+        def seg(module, prefixes, names_filter):
+            return [(n, p) for n, p in module.named_parameters()
+                    if p.requires_grad and not n.startswith(prefixes) and names_filter(n)]
+
+        segments = []
+        if self.encoders_trainable:
+            for tag, m in (("dwi", dwi_model), ("dce", dce_model)):
+                _check_supported(m)
+                b1 = lambda n: n.startswith(("modality_attention.", "block1."))
+                b2 = lambda n: n.startswith(("block2.", "f1_to_f2.", "mask_head.", "mask_spatial_attention."))
+                b3 = lambda n: n.startswith("block3.")
+                for filt in (b1, b2, b3):
+                    segments.append([(f"{tag}.{n}", p) for n, p in seg(m, _NO_GRAD_PREFIXES_ENC, filt)])
+        segments.append([(f"fusion.{n}", p) for n, p in seg(fusion_model, _NO_GRAD_PREFIXES_FUS, lambda n: True)])
+        self.segments = segments
+        named = [np_ for s in segments for np_ in s]
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        n = flat_size(self.params)
+        self.flat_numel = n
+        self.flat = {k: torch.zeros(n + (1 if k == "g" else 0), dtype=torch.float32, device=dev) for k in ("p", "g", "m", "v")}
+        for p, view in zip(self.params, flat_views(self.params, self.flat["p"])):
+            view.copy_(p.data.float())
+            p.data = view
+        for p, g in zip(self.params, flat_views(self.params, self.flat["g"])):
+            p.grad = g
+        # bucket boundaries (element offsets into the flat buffers) at segment ends, merged up to bucket_mb
+        ends, off = [], 0
+        for s in segments:
+            off += flat_size([p for _, p in s])
+            ends.append(off)
+        self.seg_ends = ends
+        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self._comm = None
+        self._pending = []
+        self.numel = sum(p.numel() for p in self.params)
+
+    # ---- gradient exchange ---------------------------------------------------------------------------------------------
+    def _world(self):
+        import torch.distributed as dist
+
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def _reduce_range(self, lo, hi):
+        """SUM all-reduce of flat_g[lo:hi] on the communication stream, ordered after everything recorded so far on the
+        compute stream."""
+        import torch.distributed as dist
+
+        if self._world() == 1 or hi <= lo:
+            return
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=self.dev)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ev)
+            self._pending.append(dist.all_reduce(self.flat["g"][lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _marker(self, seg_index):
+        """Tape step recorded BEFORE segment seg_index's forward: in the backward pass it runs right after that
+        segment's last gradient has been produced, i.e. gradients [seg start, end of buffer) are final."""
+        def fire():
+            lo = self.seg_ends[seg_index - 1] if seg_index > 0 else 0
+            hi = self._reduced_from
+            if hi - lo >= self.bucket_elems or seg_index == 0:
+                self._reduce_range(lo, hi)
+                self._reduced_from = lo
+        return fire
+
+    # ---- the step ----------------------------------------------------------------------------------------------------------
+    def zero_grad(self):
+        self.flat["g"].zero_()
+
+    def forward_backward(self, dwi_in, dce_in, masks, labels, md=None, mc=None, f3d=None, f3c=None):
+        """Forward + loss + backward on one batch (gradients ACCUMULATE into the flat buffer: call zero_grad first).
+        dwi_in / dce_in: normalised fp32 [B,C,H,W].  With frozen encoders pass their eval outputs f3d / f3c (NHWC bf16)
+        and md / mc.  Returns (total, parts)."""
+        ops = self.ops
+        ops.new_step()
+        self._reduced_from = self.flat_numel
+        self._pending = []
+        labels = labels.to(self.dev, torch.int64).contiguous()
+        masks = masks.to(self.dev).float().contiguous()
+        enc_d = enc_c = None
+        si = 0
+        if self.encoders_trainable:
+            outs = []
+            for m, x in ((self.dwi, dwi_in), (self.dce, dce_in)):
+                # three bucket markers per encoder: they sit at the forward positions of block1 / block2 / block3
+                marks = [self._marker(si), self._marker(si + 1), self._marker(si + 2)]
+                outs.append(_encoder_with_markers(ops, m, x, marks))
+                si += 3
+            enc_d, enc_c = outs
+            f3d, f3c, md, mc = enc_d["f3"], enc_c["f3"], enc_d["mask_pred"], enc_c["mask_pred"]
+        ops.tape.record(self._marker(si))
+        fo = fusion_forward_train(ops, self.fusion, f3d, f3c, md, mc)
+        total, parts = fusion_objective(ops, fo, enc_d, enc_c, masks, labels, dwi_in, dce_in, md=md, mc=mc, **self.loss_hp)
+        self.flat["g"][self.flat_numel:].copy_(total)   # the loss rides along with the gradients
+        ops.tape.backward()
+        if self._reduced_from > 0:  # whatever is left (including the loss slot with the first bucket of the buffer)
+            self._reduce_range(0, self._reduced_from)
+        if self._world() > 1:
+            self._reduce_range(self.flat_numel, self.flat_numel + 1)
+        self.logits = fo["logits"]
+        return total, parts
+
+    def step(self):
+        """Wait for the gradient exchange, then one fused AdamW launch (grad_scale folds the 1 / world average)."""
+        world = self._world()
+        if self._comm is not None:
+            for w in self._pending:
+                w.wait()
+            torch.cuda.current_stream(self.dev).wait_stream(self._comm)
+        self.step_count += 1
+        f = self.flat
+        nat.adamw(f["p"], f["g"][:self.flat_numel], f["m"], f["v"], lr=self.hp["lr"], betas=self.hp["betas"],
+                  eps=self.hp["eps"], weight_decay=self.hp["weight_decay"], step=self.step_count, grad_scale=1.0 / world)
+
+    def train_step(self, dwi_in, dce_in, masks, labels, **kw):
+        self.zero_grad()
+        total, parts = self.forward_backward(dwi_in, dce_in, masks, labels, **kw)
+        self.step()
+        return total, parts
+
+
+def _encoder_with_markers(ops, m, x, marks):
+    """encoder_forward_train with all-reduce bucket markers at the forward positions of block1 / block2 / block3."""
+    ops._bucket_marks = list(marks)
+    try:
+        return encoder_forward_train(ops, m, x, heads=False)
+    finally:
+        ops._bucket_marks = None

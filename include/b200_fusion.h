@@ -581,18 +581,44 @@ int b200_cls_head_bwd(const float* pooled, const float* dlogits, const float* fc
  *   b200_focal_loss  LabelSmoothing + Soft(Weighted)FocalLoss (code/loss.py:133-213), scale = 1 / B
  *   b200_dice_loss   SoftDiceLoss (code/loss.py:45-62) on logits [B,n], scale = weight / B
  *   b200_recon_loss  bilinear up-sample -> sigmoid -> Charbonnier against the clamped channel mean of the input
- *                    (code/train.py:1041-1048, :446-454), scale = weight / (B*H*W)
+ *                    (code/train.py:1041-1048, :446-454), scale = weight / (B*H*W); x2 / C2: a second input tensor
+ *                    whose channels join the mean (the fusion step's cat([dwi, dce]), code/train_fusion.py:276-285)
  *   b200_mimic_loss  1 - cos(student, detached teacher) per case (code/train.py:1033-1038), scale = weight / B */
 int b200_focal_loss(const float* logits, const long long* labels, int B, int K, float smoothing, float gamma,
                     const float* class_weights, float scale, float* loss, float* dlogits, void* stream);
 int b200_dice_loss(const float* logits, const float* target, int B, int n, float eps, float scale, float* loss,
                    float* dlogits, void* stream);
-int b200_recon_loss(const float* r, int B, int h, int w, const float* x, int C, int H, int W, float eps, float scale,
-                    float* loss, float* dr, void* stream);
+int b200_recon_loss(const float* r, int B, int h, int w, const float* x, int C, const float* x2, int C2, int H, int W,
+                    float eps, float scale, float* loss, float* dr, void* stream);
 int b200_mimic_loss(const void* s, const void* t, int B, long long n, float scale, float* loss, void* ds, void* stream);
+
+/* Full-resolution training of FusionModel (code/model_module.py:919-1000) - the pieces between the tensor-core layers:
+ *   b200_gating_fwd     GatingAttention (:745-780) from per-case channel SUMS of p_dwi / p_dce (+ encoder mask logits):
+ *                       gx [B, 2C(+2)] (the Linear's input, kept for its weight gradient), alpha [B,2] = softmax
+ *   b200_gating_bwd     dalpha -> dgl [B,2] (logit gradients), dgx [B, 2C(+2)] = dgl W, and dpv_* [B,C] = the pooled
+ *                       vectors' share of dgx / npix (what every pixel of p_dwi / p_dce receives)
+ *   b200_fused_pool     GAP of the fused map, analytically: alpha0 pvec_dwi + alpha1 pvec_dce + sum_t up[t] lowres[:,t]
+ *   b200_fusion_mix_bwd backward of fused = alpha0 p_dwi + alpha1 p_dce + bilinear_up(lowres): phase 0 accumulates
+ *                       dalpha [B,2] and dlowres [B,T,C]; phase 1 writes dp_m = alpha_m dfused + dtok_m (token-pool
+ *                       backward, already / bin size) + dpvec_m (already / npix)
+ *   b200_mimic_pairs    the fusion step's mimic term over `proj_fused[:4]` exactly as the reference unpacks it
+ *                       (code/train_fusion.py:287-296: the first four CASES; per-channel cosines) */
+int b200_gating_fwd(const float* sum_d, const float* sum_c, int B, int C, int npix, const float* mask_d,
+                    const float* mask_c, int npix_mask, const float* w, const float* bias, float* gx, float* alpha,
+                    void* stream);
+int b200_gating_bwd(const float* alpha, const float* dalpha, const float* w, int B, int C, int D, int npix, float* dgl,
+                    float* dgx, float* dpv_d, float* dpv_c, void* stream);
+int b200_fused_pool(const float* sum_d, const float* sum_c, int B, int C, int npix, const float* alpha,
+                    const float* lowres, const float* up, int T, float* out, void* stream);
+int b200_fusion_mix_bwd(const void* dfused, const void* p_dwi, const void* p_dce, const float* alpha, int B, int H, int W,
+                        int C, int Hp, int Wp, float* dalpha, float* dlowres, const float* dtok_d, const float* dtok_c,
+                        const float* dpv_d, const float* dpv_c, void* dp_dwi, void* dp_dce, int phase, void* stream);
+int b200_mimic_pairs(const void* map, int B, int npix, int C, float scale, float* loss, void* dmap, void* stream);
 
 /* din = sum of the four 2x2 replicas of dout [B,2H,2W,C] (backward of AdaptiveAvgPool2d to twice the size). */
 int b200_up2_bwd(const void* dout, int B, int H, int W, int C, void* din, void* stream);
+/* out[b, 0..n) = v[b * v_stride] * scale (gradient of the per-case mean of an fp32 map). */
+int b200_row_bcast(const float* v, int v_stride, float scale, int B, int n, float* out, void* stream);
 /* y = alpha * a + beta * y on fp32 vectors. */
 int b200_vec_axpby(const float* a, float alpha, float beta, long long n, float* y, void* stream);
 
