@@ -473,6 +473,291 @@ def train_arm(args):
         print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# --workload c5 --unfrozen / --objective full, and --workload c1: the training step on the training kernels
+# ------------------------------------------------------------------------------------------------------------------
+WORKLOAD_C5_FULL = ("C5: fusion fine-tuning step, backbone (both CNN encoders) UNFROZEN, bf16 activations and gradient maps, "
+                    "fp32 master weights: normalise -> train-mode DWI / DCE encoders + fusion head (batch-statistic "
+                    "BatchNorm, dropout 0.2) -> classification + 3 dice + 3 reconstruction + mimic terms -> explicit "
+                    "backward (dgrad / wgrad on tcgen05) -> bucketed NCCL gradient all-reduce -> fused AdamW")
+WORKLOAD_C1 = ("C1: DWI-only model_module CNN forward + train step on synthetic 16-b-value 64x64 ROIs, batch 32 "
+               "(LightningSingleModel._shared_step objective: classification + feature norm + mask dice + reconstruction "
+               "+ mimic) -> backward -> AdamW")
+
+
+def _train_flops_per_case(unfrozen):
+    """Algorithmic FLOPs of one training step per case: forward of the graph that is evaluated + dgrad + wgrad of every
+    convolution whose input / weight needs a gradient (2 MAC = 2 FLOP).  Encoder logit-path + reconstruction heads
+    (no encoder classifier / projectors in the fusion step): 4.06 GF forward per encoder (4.40 minus
+    0.34 of projectors); fusion head 0.616 GF.  Training = 3x the forward of everything trainable (the stem's data
+    gradient is not needed, < 0.1 %)."""
+    enc = 4.06e9
+    fus = 0.616e9
+    return 3 * (2 * enc + fus) if unfrozen else (2 * 2.545e9 + 3 * fus)
+
+
+def train_full_arm(args):
+    """--workload c5 --unfrozen (BASELINE configs[4]) or --objective full with frozen encoders: one optimisation step per
+    batch on train_graph.FullFusionTrainer."""
+    import b200_native as nat
+    import train_graph as tg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import datetime
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
+    unfrozen = bool(args.unfrozen)
+    params, pipe, cpu_state, nyul = build_product(device, "logits", False, "c3")
+    for m in (pipe.dwi_model, pipe.dce_model, pipe.fusion_model):
+        for q in m.parameters():
+            q.requires_grad_(True)
+        m.train() if (unfrozen or m is pipe.fusion_model) else m.eval()
+    trainer = tg.FullFusionTrainer(pipe.dwi_model, pipe.dce_model, pipe.fusion_model, lr=1e-4, weight_decay=4e-5,
+                                   smoothing=0.1, gamma=1.5, lambda_mask=0.2, lambda_recon=0.1, lambda_mimic=0.2,
+                                   encoders_trainable=unfrozen)
+    B = args.batch
+    dwi_h, dce_h = make_inputs(B, rank)
+    gen = torch.Generator().manual_seed(99 + rank)
+    lab_h = torch.randint(0, 4, (B,), generator=gen)
+    msk_h = (torch.rand(B, 1, 32, 32, generator=gen) > 0.5).float()
+    dwi_d, dce_d, lab_d, msk_d = dwi_h.to(device), dce_h.to(device), lab_h.to(device), msk_h.to(device)
+
+    def step_on(dwi_raw, dce_raw, lab, msk):
+        dwi = pipe.dwi_norm.batch(dwi_raw)
+        dce = pipe.dce_norm.batch(dce_raw)
+        if unfrozen:
+            return trainer.train_step(dwi, dce, msk, lab)[0]
+        with torch.no_grad():
+            o_d = pipe.dwi_model(dwi, None)
+            o_c = pipe.dce_model(dce, None)
+        f3d = o_d[1]["raw_feats"][-1].permute(0, 2, 3, 1)
+        f3c = o_c[1]["raw_feats"][-1].permute(0, 2, 3, 1)
+        return trainer.train_step(dwi, dce, msk, lab, md=o_d[2][:, 0].contiguous(), mc=o_c[2][:, 0].contiguous(),
+                                  f3d=f3d, f3c=f3c)[0]
+
+    def step():
+        return step_on(dwi_d, dce_d, lab_d, msk_d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = nat.LAUNCH_COUNT
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        torch.cuda.nvtx.range_push("timed")
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        barrier()
+        torch.cuda.nvtx.range_pop()
+    launches = nat.LAUNCH_COUNT - launches0
+    ms = e0.elapsed_time(e1)
+    # end to end: pinned host batch uploaded every step (copy stream, overlapped with the previous step), loss read back
+    host_batch = tuple(t.pin_memory() for t in (dwi_h, dce_h, lab_h, msk_h))
+
+    def fit_host(n):
+        losses = []
+        for d, c, lab, msk in pipe._staged([host_batch] * n, device):
+            l_ = step_on(d, c, lab, msk)
+            h = torch.empty(1, dtype=torch.float32, pin_memory=True)
+            h.copy_(l_, non_blocking=True)
+            losses.append(h)
+        torch.cuda.current_stream(device).synchronize()
+        return losses
+
+    fit_host(2)
+    barrier()
+    e0.record()
+    fit_host(args.steps)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t[0].item(), t[1].item()
+    value = world * B * args.steps / (ms / 1e3)
+    in_sync = True
+    if world > 1:
+        lo, hi = trainer.flat["p"].clone(), trainer.flat["p"].clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.equal(lo, hi))
+    line = None
+    if rank == 0:
+        peaks = load_peaks()
+        nsp = 2
+        prof = {}
+        if world == 1:
+            nat.start_profile()
+            for _ in range(nsp):
+                step()
+            prof = nat.stop_profile()
+        total_ms = sum(sum(t) for t in prof.values())
+        by_name = {}
+        for (n, k), t in prof.items():
+            by_name[n] = by_name.get(n, 0.0) + sum(t) / nsp
+        # dominant launches: forward / data-gradient GEMMs (b200_conv_gemm_ex) and the weight-gradient kernel
+        roofline = None
+        wg = [(sum(t), t) for (n, k), t in prof.items() if n == "b200_conv_wgrad"]
+        cands = [(sum(t), nk) for nk, t in prof.items() if gemm_flops(*nk) is not None]
+        if cands:
+            dom_key = max(cands)[1]
+            dom_ms = statistics.mean(prof[dom_key])
+            ach = gemm_flops(*dom_key) / (dom_ms / 1e3) / 1e12
+            roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["tf_sustained"], "frac_of_burst_peak": ach / peaks["tf_burst"], "traffic": None,
+                        "kernel": f"conv_gemm_kernel via {dom_key[0]} {list(dom_key[1])} (forward and data-gradient launches "
+                                  "of this shape)", "ms_per_launch": dom_ms,
+                        "share_of_step": sum(prof[dom_key]) / total_ms if total_ms else None,
+                        "peak_source": peaks["source"] + " sustained bf16"}
+        flop_case = _train_flops_per_case(unfrozen)
+        line = {
+            "metric": METRIC_C5, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 activations / gradient maps, fp32 accumulation, master weights and optimiser", "data": "synthetic",
+            "config": {"workload": WORKLOAD_C5_FULL if unfrozen else WORKLOAD_C5_FULL.replace(
+                           "backbone (both CNN encoders) UNFROZEN", "frozen-encoder phase (eval-mode encoders), full objective"),
+                       "batch_per_gpu": B, "global_batch": B * world, "trainable_parameters": trainer.numel,
+                       "allreduce_bytes_per_step": 4 * (trainer.flat_numel + 1),
+                       "allreduce_buckets": "cut at block boundaries in backward order, >= 8 MB each, issued on a side "
+                                            "stream while the rest of the backward pass runs",
+                       "l2": "no flush needed: per-step inputs and activations exceed the 126 MB L2",
+                       "parallelism": f"data parallel x{world} (NCCL)" if world > 1 else "single GPU"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host_batch), "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "api": "pinned host batch (raw ROIs, labels, target masks) -> FusionPipeline normalisers -> "
+                           "FullFusionTrainer.train_step, upload overlapped on a copy stream, loss read back every step"},
+            "gpu_launches": launches, "final_loss": float(loss.item()), "replicas_in_sync": in_sync,
+            "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated(device) / 1e9,
+            "roofline": roofline,
+            "step_model": {"algorithmic_gflop_per_case": flop_case / 1e9,
+                           "achieved_tflops_whole_step": value / world * flop_case / 1e12,
+                           "frac_of_sustained_peak": value / world * flop_case / 1e12 / peaks["tf_sustained"],
+                           "ms_per_step_by_entry_point": {k: round(v, 3) for k, v in sorted(by_name.items(), key=lambda kv: -kv[1])},
+                           "wgrad_launches_ms": round(sum(s for s, _ in wg) / nsp, 3) if wg else None},
+            "cpu_baseline": None,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def c1_arm(args):
+    """--workload c1 (BASELINE configs[0]): DWI CNN forward + train step at batch 32 - on the GPU through
+    train_graph (forward, single-model objective, backward, AdamW) and, beside it, the reference's CPU path (oracle
+    restatement of LightningSingleModel._shared_step + backward + AdamW, pinned by tests/golden/train_c1_dwi.npz) on the
+    host cores."""
+    import b200_native as nat
+    import model_module as mm
+    import parameters_default as pd
+    import train_graph as tg
+    from oracle import params as op
+    from oracle import train_oracle as to
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    device = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    B = args.batch
+    p = pd.default_parameters()
+    model = mm.ModelMaskHeadBackbone("dwi", p)
+    sd = op.seeded_state_dict(op.shapes_of(model.state_dict()), seed=7)
+    model.load_state_dict(sd)
+    model.to(device).train()
+    for q in model.parameters():
+        q.requires_grad_(True)
+    lam = dict(lambda_mask=0.2, lambda_recon=0.1, lambda_mimic=0.2, lambda_feat_norm=4e-5)
+    tr = tg.SingleModelTrainer(model, lr=1e-4, weight_decay=4e-5, smoothing=0.1, gamma=1.5, **lam)
+    dwi_raw, _, masks, labels = op.synthetic_raw(B, seed=1234, kind="S")
+    x_h = (dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)).pin_memory()
+    x_d, m_d, l_d = x_h.to(device), masks.to(device), labels.to(device)
+    for _ in range(args.warmup):
+        tr.train_step(x_d, m_d, l_d)
+    torch.cuda.synchronize()
+    l0 = nat.LAUNCH_COUNT
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            loss = tr.train_step(x_d, m_d, l_d)[0]
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = nat.LAUNCH_COUNT - l0
+    m_h, l_h = masks.pin_memory(), labels.pin_memory()
+    e0.record()
+    for _ in range(args.steps):
+        loss_h = tr.train_step(x_h.to(device, non_blocking=True), m_h.to(device, non_blocking=True),
+                               l_h.to(device, non_blocking=True))[0].cpu()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    # the reference's CPU path: same batch, same seeded weights
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cw = None
+    pc = pd.default_parameters()
+
+    def cpu_step(state, mom, it):
+        _, _, grads = to.single_model_objective_and_grads(state, pc, "dwi", x_h, masks, labels, 0.1, 1.5, cw, **lam)
+        for k, g in grads.items():
+            mm_, vv_ = mom.get(k, (torch.zeros_like(g), torch.zeros_like(g)))
+            state[k], mm_, vv_ = to.adamw_step(state[k], g, mm_, vv_, it, 1e-4, (0.9, 0.999), 1e-8, 4e-5)
+            mom[k] = (mm_, vv_)
+
+    state, mom = {k: v.clone() for k, v in sd.items()}, {}
+    cpu_step(state, mom, 1)
+    n_cpu = 3
+    t0 = time.perf_counter()
+    for it in range(n_cpu):
+        cpu_step(state, mom, it + 2)
+    dt = time.perf_counter() - t0
+    peaks = load_peaks()
+    flop_case = 3 * 4.403e9
+    value = B * args.steps / (ms / 1e3)
+    line = {
+        "metric": "DWI CNN train-step cases/sec", "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16 activations / gradient maps, fp32 master weights", "data": "synthetic",
+        "config": {"workload": WORKLOAD_C1, "batch_per_gpu": B, "global_batch": B, "trainable_parameters": tr.numel,
+                   "note": "batch 32 is the reference's CPU-runnable case: a launch-latency-bound size on a B200 "
+                           f"({launches // max(args.steps, 1)} launches per step)"},
+        "clocks": clocks.summary(),
+        "e2e": {"value": B * args.steps / (e2e_ms / 1e3), "unit": UNIT,
+                "h2d_bytes_per_step": x_h.numel() * 4 + m_h.numel() * 4 + l_h.numel() * 8, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / args.steps, "api": "SingleModelTrainer.train_step on pinned host tensors, loss read back"},
+        "gpu_launches": launches, "final_loss": float(loss.item()),
+        "roofline": None,
+        "step_model": {"algorithmic_gflop_per_case": flop_case / 1e9, "achieved_tflops_whole_step": value * flop_case / 1e12,
+                       "frac_of_sustained_peak": value * flop_case / 1e12 / peaks["tf_sustained"]},
+        "cpu_baseline": {"value": n_cpu * B / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n_cpu} optimisation steps of {B} cases (forward + backward + AdamW), fp32, torch CPU "
+                                   f"threads={threads}, 1 warm-up step, {dt:.1f} s"},
+    }
+    print(json.dumps(line))
+
+
 def run_cpu_train_baseline(params, cpu_state, nyul, batch, lambda_mask=0.0, steps=3):
     """The same step on the host cores: oracle encoders (eval, no grad) + oracle/train_oracle.py (autograd over the
     full-resolution FusionModel forward + AdamW)."""
@@ -515,14 +800,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="cases per GPU per step (default 1024; 256 for c4)")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "resnet", "c5"],
+    ap.add_argument("--unfrozen", action="store_true",
+                    help="--workload c5: BASELINE configs[4] proper - both CNN encoders train too (train-mode BatchNorm, "
+                         "dropout, dgrad / wgrad on the tensor cores, bucketed all-reduce); implies --objective full")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "resnet", "c5", "c1"],
                     help="c3 = the headline CNN-encoder configuration; c4 = ViT-B/16 backbone encoders at 224x224; "
                          "resnet = ResNet-50 (RadImageNet branch, output stride 8) backbone encoders at 224x224")
     ap.add_argument("--aux", default="full", choices=["full", "logits"])
     ap.add_argument("--encoders", default="c3", choices=["c3", "c4"],
                     help="--workload c5: frozen encoders feeding the head - c3 = the CNN encoders (headline), c4 = "
                          "ViT-B/16 backbone + adapter at 224x224 (768-channel 14x14 maps)")
-    ap.add_argument("--objective", default="cls+mask", choices=["cls", "cls+mask"],
+    ap.add_argument("--objective", default="cls+mask", choices=["cls", "cls+mask", "full"],
                     help="--workload c5: loss terms of the fine-tuning step (the reference's total loss minus its "
                          "reconstruction / mimic terms, or the classification term alone)")
     ap.add_argument("--ref-batch", type=int, default=32)
@@ -536,6 +824,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.workload == "c1":
+        args.batch = args.batch or 32
+        c1_arm(args)
+        return
+    if args.batch is None and args.workload == "c5" and (args.unfrozen or args.objective == "full"):
+        args.batch = 512
     if args.batch is None:
         args.batch = 1024 if args.workload == "c3" or (args.workload == "c5" and args.encoders == "c3") else 256
     if args.workload not in ("c3", "c5") and args.ref_batch == 32:
@@ -546,7 +840,10 @@ def main():
         if args.impl == "reference":
             raise SystemExit("--impl reference times the headline inference workload; the c5 line carries its own "
                              "cpu_baseline")
-        train_arm(args)
+        if args.unfrozen or args.objective == "full":
+            train_full_arm(args)
+        else:
+            train_arm(args)
         return
     if args.impl == "reference":
         reference_arm(args)
@@ -679,9 +976,14 @@ def main():
             if args.workload == "c4" and dom_key[0] == "b200_conv_gemm_ex" and tuple(dom_key[1][3:]) == (768, 3072, 1):
                 traffic = 334.5e6 * dom_key[1][2] / 50432
             roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tf_sustained"], "traffic": traffic,
+                        "frac": ach / peaks["tf_sustained"], "frac_of_burst_peak": ach / peaks["tf_burst"],
+                        "traffic": traffic,
+                        "traffic_source": ("profiles/r1_conv_gemm_ncu_full.csv: one ncu --set full capture of this kernel "
+                                           "(dram__bytes_read.sum + dram__bytes_write.sum), scaled by the batch - a static "
+                                           "figure, not re-measured in this run") if traffic is not None else None,
                         "kernel": dom_name,
-                        "ms_per_launch": dom_ms, "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
+                        "ms_per_launch": dom_ms, "peak_source": peaks["source"] + " sustained bf16 (the kernel runs inside "
+                        "a step of back-to-back GEMM launches; frac_of_burst_peak is against the burst figure)",
                         "share_of_step": sum(prof[dom_key]) / total_ms if total_ms else None}
         # the HBM-bound side of the path: the DWI normaliser against the measured copy bandwidth
         # (algorithmic bytes per case: 15 planes read + 16 written, SURVEY.md section 8(d) / DESIGN.md 4.2)

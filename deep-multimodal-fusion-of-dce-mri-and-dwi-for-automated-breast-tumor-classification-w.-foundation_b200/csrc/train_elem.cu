@@ -114,164 +114,188 @@ struct BnAct {
     int C;
 };
 
-__device__ __forceinline__ void bnact_coeffs(const BnAct& p, int c0, float (&a)[8], float (&b)[8]) {
+// Per-thread constants of one 8-channel group: y = z * a + b, xhat = (z - mu) * is.
+struct BnCoef {
+    float a[8], b[8], mu[8], is[8];
+};
+__device__ __forceinline__ void bnact_coeffs(const BnAct& p, int c0, BnCoef& k) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const float is = p.invstd != nullptr ? p.invstd[c0 + i] : 1.f;
         const float g = p.gamma != nullptr ? p.gamma[c0 + i] : 1.f;
         const float m = p.mean != nullptr ? p.mean[c0 + i] : 0.f;
         const float be = p.beta != nullptr ? p.beta[c0 + i] : 0.f;
-        a[i] = is * g;
-        b[i] = be - m * is * g;
+        k.a[i] = is * g;
+        k.b[i] = be - m * is * g;
+        k.mu[i] = m;
+        k.is[i] = is;
     }
+}
+
+// erf(z) ~= z * P(z^2) on |z| <= 3 (the 8-term odd minimax polynomial of the GEMM epilogue's GELU, |err| < 9e-5)
+__device__ __forceinline__ float erf_poly(float zc) {
+    const float t = zc * zc;
+    float q = -3.901667185e-07f;
+    q = fmaf(q, t, 1.668003461e-05f);
+    q = fmaf(q, t, -3.086500801e-04f);
+    q = fmaf(q, t, 3.281538375e-03f);
+    q = fmaf(q, t, -2.256273106e-02f);
+    q = fmaf(q, t, 1.075116023e-01f);
+    q = fmaf(q, t, -3.730817735e-01f);
+    q = fmaf(q, t, 1.127865076e+00f);
+    return zc * q;
+}
+__device__ __forceinline__ float act_fwd_fast(float y, int act) {
+    if (act == 1) {
+        const float zc = fminf(fmaxf(y * 0.70710678118654752f, -3.0f), 3.0f);
+        const float h = 0.5f * y;
+        return fmaf(h, erf_poly(zc), h);
+    }
+    return act == 2 ? fmaxf(y, 0.f) : y;
+}
+__device__ __forceinline__ float act_bwd_fast(float y, int act) {
+    if (act == 1) {
+        const float zc = fminf(fmaxf(y * 0.70710678118654752f, -3.0f), 3.0f);
+        // 0.5 (1 + erf) + y phi(y);  phi = exp(-y^2 / 2) / sqrt(2 pi) = 2^(-y^2 * log2(e) / 2) / sqrt(2 pi)
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044448170f * y * y));
+        return fmaf(0.5f, erf_poly(zc), 0.5f) + y * 0.3989422804014327f * e;
+    }
+    return act == 2 ? (y > 0.f ? 1.f : 0.f) : 1.f;
+}
+
+// Thread layout shared by the three BN kernels: a thread owns ONE 8-channel group (its BatchNorm constants stay in
+// registers) and walks rows r = first, first + stride, ...; a warp's 32 lanes cover 32 consecutive 16-byte groups.
+#define BN_ROW_WALK(CG_)                                                                             \
+    const int CG = (CG_);                                                                              \
+    const int rows_par = kTeThreads / CG;                                                              \
+    const int cg = threadIdx.x % CG, rp = threadIdx.x / CG;                                            \
+    const int c0 = cg * 8;                                                                             \
+    const long long row_first = static_cast<long long>(blockIdx.x) * rows_par + rp;                    \
+    const long long row_step = static_cast<long long>(gridDim.x) * rows_par;
+
+__device__ __forceinline__ void drop_bits(const BnAct& p, long long r, int c0, unsigned int (&rn)[8]) {
+    const unsigned long long e = (static_cast<unsigned long long>(r) * p.C + c0) / 4;
+    const uint4 r0 = philox4x32_7(e, p.seed_lo, p.seed_hi), r1 = philox4x32_7(e + 1, p.seed_lo, p.seed_hi);
+    rn[0] = r0.x; rn[1] = r0.y; rn[2] = r0.z; rn[3] = r0.w;
+    rn[4] = r1.x; rn[5] = r1.y; rn[6] = r1.z; rn[7] = r1.w;
 }
 
 // out = dropout(act(bn(z) + res))
 __global__ void __launch_bounds__(kTeThreads)
 bn_act_fwd_kernel(const BnAct p, __nv_bfloat16* __restrict__ out, int ldo) {
-    const int CG = p.C / 8;
-    const long long total = p.R * CG;
-    for (long long i = blockIdx.x * static_cast<long long>(kTeThreads) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * kTeThreads) {
-        const long long r = i / CG;
-        const int c0 = static_cast<int>(i - r * CG) * 8;
-        float a[8], b[8], f[8], rr[8];
-        bnact_coeffs(p, c0, a, b);
+    BN_ROW_WALK(p.C / 8)
+    if (rp >= rows_par) return;
+    BnCoef k;
+    bnact_coeffs(p, c0, k);
+    for (long long r = row_first; r < p.R; r += row_step) {
+        float f[8], rr[8];
         unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.z + r * p.ldz + c0)), f);
         if (p.res != nullptr) unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.res + r * p.ldres + c0)), rr);
-        uint4 rnd0 = make_uint4(0, 0, 0, 0), rnd1 = rnd0;
-        if (p.drop_thresh != 0u) {
-            const unsigned long long e = (static_cast<unsigned long long>(r) * p.C + c0) / 4;
-            rnd0 = philox4x32_7(e, p.seed_lo, p.seed_hi);
-            rnd1 = philox4x32_7(e + 1, p.seed_lo, p.seed_hi);
-        }
-        const unsigned int rn[8] = {rnd0.x, rnd0.y, rnd0.z, rnd0.w, rnd1.x, rnd1.y, rnd1.z, rnd1.w};
+        unsigned int rn[8];
+        if (p.drop_thresh != 0u) drop_bits(p, r, c0, rn);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float y = fmaf(f[k], a[k], b[k]);
-            if (p.res != nullptr) y += rr[k];
-            y = act_fwd(y, p.act);
-            if (p.drop_thresh != 0u) y = rn[k] < p.drop_thresh ? 0.f : y * p.drop_scale;
-            f[k] = y;
+        for (int j = 0; j < 8; ++j) {
+            float y = fmaf(f[j], k.a[j], k.b[j]);
+            if (p.res != nullptr) y += rr[j];
+            y = act_fwd_fast(y, p.act);
+            if (p.drop_thresh != 0u) y = rn[j] < p.drop_thresh ? 0.f : y * p.drop_scale;
+            f[j] = y;
         }
         *reinterpret_cast<uint4*>(out + r * ldo + c0) = pack_bf16x8(f);
     }
 }
 
-// Backward, pass 1: dY = dA * dropout_mask * act'(y), y = bn(z) + res;  s1[c] += sum dY, s2[c] += sum dY * xhat.
+// Backward, pass 1: dY = dA * dropout_mask * act'(y), y = bn(z) + res, WRITTEN to dy_out (and dy_out2: the residual
+// branch's gradient); with batch statistics s1[c] += sum dY, s2[c] += sum dY * xhat; without them dy_out receives
+// dz = a * dY directly and only s1 / s2 (when requested) feed dbeta / dgamma.
 __global__ void __launch_bounds__(kTeThreads)
-bn_act_bwd_reduce_kernel(const BnAct p, const __nv_bfloat16* __restrict__ dA, int ldd, double* __restrict__ s1,
-                         double* __restrict__ s2) {
+bn_act_bwd_pass1_kernel(const BnAct p, const __nv_bfloat16* __restrict__ dA, int ldd, int batch_stats,
+                        __nv_bfloat16* __restrict__ dy_out, int ldo, __nv_bfloat16* __restrict__ dy_out2, int ldo2,
+                        double* __restrict__ s1, double* __restrict__ s2) {
     extern __shared__ float s_part[];
-    const int CG = p.C / 8;
-    const int rows_par = kTeThreads / CG;
-    const int tid = threadIdx.x;
-    const int cg = tid % CG, rp = tid / CG;
+    BN_ROW_WALK(p.C / 8)
     float u[8], v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) u[i] = v[i] = 0.f;
     if (rp < rows_par) {
-        const int c0 = cg * 8;
-        float a[8], b[8], mu[8], is[8];
-        bnact_coeffs(p, c0, a, b);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            mu[i] = p.mean != nullptr ? p.mean[c0 + i] : 0.f;
-            is[i] = p.invstd != nullptr ? p.invstd[c0 + i] : 1.f;
-        }
-        for (long long r = static_cast<long long>(blockIdx.x) * rows_par + rp; r < p.R;
-             r += static_cast<long long>(gridDim.x) * rows_par) {
-            float f[8], d[8], rr[8];
+        BnCoef k;
+        bnact_coeffs(p, c0, k);
+        for (long long r = row_first; r < p.R; r += row_step) {
+            float f[8], d[8], rr[8], o[8], o2[8];
             unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.z + r * p.ldz + c0)), f);
             unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(dA + r * ldd + c0)), d);
             if (p.res != nullptr) unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.res + r * p.ldres + c0)), rr);
-            uint4 rnd0 = make_uint4(0, 0, 0, 0), rnd1 = rnd0;
-            if (p.drop_thresh != 0u) {
-                const unsigned long long e = (static_cast<unsigned long long>(r) * p.C + c0) / 4;
-                rnd0 = philox4x32_7(e, p.seed_lo, p.seed_hi);
-                rnd1 = philox4x32_7(e + 1, p.seed_lo, p.seed_hi);
-            }
-            const unsigned int rn[8] = {rnd0.x, rnd0.y, rnd0.z, rnd0.w, rnd1.x, rnd1.y, rnd1.z, rnd1.w};
+            unsigned int rn[8];
+            if (p.drop_thresh != 0u) drop_bits(p, r, c0, rn);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float y = fmaf(f[k], a[k], b[k]);
-                if (p.res != nullptr) y += rr[k];
-                float g = d[k];
-                if (p.drop_thresh != 0u) g = rn[k] < p.drop_thresh ? 0.f : g * p.drop_scale;
-                g *= act_bwd(y, p.act);
-                u[k] += g;
-                v[k] = fmaf(g, (f[k] - mu[k]) * is[k], v[k]);
+            for (int j = 0; j < 8; ++j) {
+                float g = d[j];
+                if (p.drop_thresh != 0u) g = rn[j] < p.drop_thresh ? 0.f : g * p.drop_scale;
+                if (p.act != 0) {
+                    float y = fmaf(f[j], k.a[j], k.b[j]);
+                    if (p.res != nullptr) y += rr[j];
+                    g *= act_bwd_fast(y, p.act);
+                }
+                u[j] += g;
+                v[j] = fmaf(g, (f[j] - k.mu[j]) * k.is[j], v[j]);
+                o2[j] = g;
+                o[j] = batch_stats ? g : g * k.a[j];
             }
+            if (dy_out != nullptr) *reinterpret_cast<uint4*>(dy_out + r * ldo + c0) = pack_bf16x8(o);
+            if (dy_out2 != nullptr) *reinterpret_cast<uint4*>(dy_out2 + r * ldo2 + c0) = pack_bf16x8(o2);
         }
+        if (s1 != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            s_part[(rp * p.C + c0 + i) * 2 + 0] = u[i];
-            s_part[(rp * p.C + c0 + i) * 2 + 1] = v[i];
+            for (int i = 0; i < 8; ++i) {
+                s_part[(rp * p.C + c0 + i) * 2 + 0] = u[i];
+                s_part[(rp * p.C + c0 + i) * 2 + 1] = v[i];
+            }
         }
     }
+    if (s1 == nullptr) return;
     __syncthreads();
-    for (int c = tid; c < p.C; c += kTeThreads) {
+    for (int c = threadIdx.x; c < p.C; c += kTeThreads) {
         double a = 0.0, b = 0.0;
-        for (int k = 0; k < rows_par; ++k) {
-            a += static_cast<double>(s_part[(k * p.C + c) * 2 + 0]);
-            b += static_cast<double>(s_part[(k * p.C + c) * 2 + 1]);
+        for (int kk = 0; kk < rows_par; ++kk) {
+            a += static_cast<double>(s_part[(kk * p.C + c) * 2 + 0]);
+            b += static_cast<double>(s_part[(kk * p.C + c) * 2 + 1]);
         }
         atomicAdd(s1 + c, a);
         atomicAdd(s2 + c, b);
     }
 }
 
-// Backward, pass 2: dz = gamma * invstd * (dY - s1/N - xhat * s2/N) (batch-statistic BN), or dz = dY * gamma * invstd
-// when the statistics are constants (s1 == nullptr: eval-mode BN, bias-only layers); dres = dY.  Block 0 also
-// accumulates dgamma += s2, dbeta += s1.
+// Backward, pass 2 (batch statistics only), in place on the dY map pass 1 wrote:
+// dz = gamma * invstd * (dY - s1/N - xhat * s2/N).  Block 0 also accumulates dgamma += s2, dbeta += s1.
 __global__ void __launch_bounds__(kTeThreads)
-bn_act_bwd_apply_kernel(const BnAct p, const __nv_bfloat16* __restrict__ dA, int ldd, const double* __restrict__ s1,
-                        const double* __restrict__ s2, double count, __nv_bfloat16* __restrict__ dz, int lddz,
-                        __nv_bfloat16* __restrict__ dres, int lddres, float* __restrict__ dgamma,
-                        float* __restrict__ dbeta) {
-    const int CG = p.C / 8;
-    const long long total = p.R * CG;
-    if (blockIdx.x == 0 && s1 != nullptr) {
+bn_act_bwd_pass2_kernel(const BnAct p, const double* __restrict__ s1, const double* __restrict__ s2, double count,
+                        __nv_bfloat16* __restrict__ dz, int lddz, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                        int map_pass) {
+    if (blockIdx.x == 0) {
         for (int c = threadIdx.x; c < p.C; c += kTeThreads) {
             if (dgamma != nullptr) dgamma[c] += static_cast<float>(s2[c]);
             if (dbeta != nullptr) dbeta[c] += static_cast<float>(s1[c]);
         }
     }
-    for (long long i = blockIdx.x * static_cast<long long>(kTeThreads) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * kTeThreads) {
-        const long long r = i / CG;
-        const int c0 = static_cast<int>(i - r * CG) * 8;
-        float a[8], b[8], f[8], d[8], rr[8], o[8], dy[8];
-        bnact_coeffs(p, c0, a, b);
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.z + r * p.ldz + c0)), f);
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(dA + r * ldd + c0)), d);
-        if (p.res != nullptr) unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.res + r * p.ldres + c0)), rr);
-        uint4 rnd0 = make_uint4(0, 0, 0, 0), rnd1 = rnd0;
-        if (p.drop_thresh != 0u) {
-            const unsigned long long e = (static_cast<unsigned long long>(r) * p.C + c0) / 4;
-            rnd0 = philox4x32_7(e, p.seed_lo, p.seed_hi);
-            rnd1 = philox4x32_7(e + 1, p.seed_lo, p.seed_hi);
-        }
-        const unsigned int rn[8] = {rnd0.x, rnd0.y, rnd0.z, rnd0.w, rnd1.x, rnd1.y, rnd1.z, rnd1.w};
+    if (!map_pass) return;
+    BN_ROW_WALK(p.C / 8)
+    if (rp >= rows_par) return;
+    BnCoef k;
+    bnact_coeffs(p, c0, k);
+    float k1[8], k2[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float y = fmaf(f[k], a[k], b[k]);
-            if (p.res != nullptr) y += rr[k];
-            float g = d[k];
-            if (p.drop_thresh != 0u) g = rn[k] < p.drop_thresh ? 0.f : g * p.drop_scale;
-            g *= act_bwd(y, p.act);
-            dy[k] = g;
-            if (s1 != nullptr) {
-                const float mu = p.mean != nullptr ? p.mean[c0 + k] : 0.f;
-                const float is = p.invstd != nullptr ? p.invstd[c0 + k] : 1.f;
-                const float xh = (f[k] - mu) * is;
-                o[k] = a[k] * (g - static_cast<float>(s1[c0 + k] / count) - xh * static_cast<float>(s2[c0 + k] / count));
-            } else {
-                o[k] = a[k] * g;
-            }
-        }
-        if (dz != nullptr) *reinterpret_cast<uint4*>(dz + r * lddz + c0) = pack_bf16x8(o);
-        if (dres != nullptr) *reinterpret_cast<uint4*>(dres + r * lddres + c0) = pack_bf16x8(dy);
+    for (int i = 0; i < 8; ++i) {
+        k1[i] = static_cast<float>(s1[c0 + i] / count);
+        k2[i] = static_cast<float>(s2[c0 + i] / count);
+    }
+    for (long long r = row_first; r < p.R; r += row_step) {
+        float f[8], g[8];
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.z + r * p.ldz + c0)), f);
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(dz + r * lddz + c0), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = k.a[j] * (g[j] - k1[j] - (f[j] - k.mu[j]) * k.is[j] * k2[j]);
+        *reinterpret_cast<uint4*>(dz + r * lddz + c0) = pack_bf16x8(g);
     }
 }
 
@@ -1298,13 +1322,21 @@ static int fill_bnact(BnAct& p, const void* z, int ldz, const void* res, int ldr
     return 0;
 }
 
+static int bn_grid(long long R, int C, int& rows_par) {
+    rows_par = kTeThreads / (C / 8);
+    long long want = (R + rows_par * 4 - 1) / (rows_par * 4);
+    return static_cast<int>(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+}
+
 extern "C" int b200_bn_act_fwd(const void* z, int ldz, const void* res, int ldres, const float* mean, const float* invstd,
                                const float* gamma, const float* beta, int act, float drop_p, unsigned long long seed,
                                long long R, int C, void* out, int ldo, void* stream) {
     BnAct p;
     int rc = fill_bnact(p, z, ldz, res, ldres, mean, invstd, gamma, beta, act, drop_p, seed, R, C);
-    if (rc != 0 || out == nullptr || ldo % 8 != 0) return rc != 0 ? rc : -3;
-    bn_act_fwd_kernel<<<blocks_for(R * (C / 8)), kTeThreads, 0, TE_STREAM>>>(p, static_cast<__nv_bfloat16*>(out), ldo);
+    if (rc != 0 || out == nullptr || ldo % 8 != 0 || C > 2048) return rc != 0 ? rc : -3;
+    int rows_par;
+    const int grid = bn_grid(R, C, rows_par);
+    bn_act_fwd_kernel<<<grid, kTeThreads, 0, TE_STREAM>>>(p, static_cast<__nv_bfloat16*>(out), ldo);
     return launch_status();
 }
 
@@ -1314,40 +1346,26 @@ extern "C" int b200_bn_act_bwd(const void* z, int ldz, const void* res, int ldre
                                void* dz, int lddz, void* dres, int lddres, float* dgamma, float* dbeta, void* stream) {
     BnAct p;
     int rc = fill_bnact(p, z, ldz, res, ldres, mean, invstd, gamma, beta, act, drop_p, seed, R, C);
-    if (rc != 0 || dA == nullptr || ldd % 8 != 0) return rc != 0 ? rc : -3;
+    if (rc != 0 || dA == nullptr || ldd % 8 != 0 || C > 2048) return rc != 0 ? rc : -3;
+    if (batch_stats && dz == nullptr) return -5;  // pass 2 works in place on dz
     const bool need_sums = batch_stats || dgamma != nullptr || dbeta != nullptr;
     double *s1 = nullptr, *s2 = nullptr;
+    int rows_par;
+    const int grid = bn_grid(R, C, rows_par);
+    size_t smem = 0;
     if (need_sums) {
-        if (scratch2C == nullptr || C > 2048) return -4;
+        if (scratch2C == nullptr) return -4;
         s1 = scratch2C;
         s2 = scratch2C + C;
         cudaMemsetAsync(scratch2C, 0, 2 * C * sizeof(double), TE_STREAM);
-        const int CG = C / 8, rows_par = kTeThreads / CG;
-        if (rows_par < 1) return -2;
-        const size_t smem = static_cast<size_t>(rows_par) * C * 2 * sizeof(float);
-        long long want = (R + rows_par * 16 - 1) / (rows_par * 16);
-        const int grid = static_cast<int>(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
-        bn_act_bwd_reduce_kernel<<<grid, kTeThreads, smem, TE_STREAM>>>(p, static_cast<const __nv_bfloat16*>(dA), ldd, s1, s2);
+        smem = static_cast<size_t>(rows_par) * C * 2 * sizeof(float);
     }
-    if (dz != nullptr || dres != nullptr || need_sums) {
-        // constants-statistics mode still wants dgamma / dbeta from the sums: block 0 adds them; the map pass uses
-        // s1 == nullptr to skip the batch-statistic correction
-        if (need_sums && !batch_stats) {
-            // accumulate dgamma / dbeta with a tiny launch, then the plain apply
-            bn_act_bwd_apply_kernel<<<1, kTeThreads, 0, TE_STREAM>>>(BnAct{p.z, p.ldz, p.res, p.ldres, p.mean, p.invstd,
-                                                                           p.gamma, p.beta, p.act, p.drop_thresh,
-                                                                           p.drop_scale, p.seed_lo, p.seed_hi, 0, p.C},
-                                                                     static_cast<const __nv_bfloat16*>(dA), ldd, s1, s2,
-                                                                     1.0, nullptr, 0, nullptr, 0, dgamma, dbeta);
-            bn_act_bwd_apply_kernel<<<blocks_for(R * (C / 8)), kTeThreads, 0, TE_STREAM>>>(
-                p, static_cast<const __nv_bfloat16*>(dA), ldd, nullptr, nullptr, 1.0, static_cast<__nv_bfloat16*>(dz),
-                lddz, static_cast<__nv_bfloat16*>(dres), lddres, nullptr, nullptr);
-        } else {
-            bn_act_bwd_apply_kernel<<<blocks_for(R * (C / 8)), kTeThreads, 0, TE_STREAM>>>(
-                p, static_cast<const __nv_bfloat16*>(dA), ldd, batch_stats ? s1 : nullptr, batch_stats ? s2 : nullptr,
-                static_cast<double>(R), static_cast<__nv_bfloat16*>(dz), lddz, static_cast<__nv_bfloat16*>(dres), lddres,
-                dgamma, dbeta);
-        }
+    bn_act_bwd_pass1_kernel<<<grid, kTeThreads, smem, TE_STREAM>>>(p, static_cast<const __nv_bfloat16*>(dA), ldd,
+                                                                  batch_stats ? 1 : 0, static_cast<__nv_bfloat16*>(dz), lddz,
+                                                                  static_cast<__nv_bfloat16*>(dres), lddres, s1, s2);
+    if (need_sums) {
+        bn_act_bwd_pass2_kernel<<<batch_stats ? grid : 1, kTeThreads, 0, TE_STREAM>>>(
+            p, s1, s2, static_cast<double>(R), static_cast<__nv_bfloat16*>(dz), lddz, dgamma, dbeta, batch_stats ? 1 : 0);
     }
     return launch_status();
 }

@@ -978,3 +978,57 @@ def _encoder_with_markers(ops, m, x, marks):
         return encoder_forward_train(ops, m, x, heads=False)
     finally:
         ops._bucket_marks = None
+
+
+_NO_GRAD_PREFIXES_SINGLE = ("proj_r1.", "proj_r2.", "f2_to_f3.", "f2_weight", "f3_weight", "norm_f2.", "norm_f3.",
+                            "mask_head.down_")
+
+
+class SingleModelTrainer:
+    """One optimisation step of LightningSingleModel (BASELINE config C1; code/train.py:294-428, AdamW
+    code/selector_helpers.py:222-229) for one encoder: train-mode forward, the single-modality objective, explicit
+    backward, one fused AdamW launch over a flat parameter buffer.  Parameters the objective cannot reach (the teacher
+    projectors - the mimic term detaches them -, the unused aligner / backbone-mix parameters / mask-head
+    down-samplers) stay outside the buffers, as torch.optim.AdamW skips parameters whose .grad is None."""
+
+    def __init__(self, model, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=4e-5, smoothing=0.1, gamma=1.5,
+                 class_weights=None, lambda_mask=0.2, lambda_recon=0.1, lambda_mimic=0.2, lambda_feat_norm=4e-5, seed=0x5EED):
+        from fusion_train import flat_size, flat_views
+
+        _check_supported(model)
+        self.model = model
+        self.hp = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.loss_hp = dict(smoothing=smoothing, gamma=gamma, class_weights=class_weights, lambda_mask=lambda_mask,
+                            lambda_recon=lambda_recon, lambda_mimic=lambda_mimic, lambda_feat_norm=lambda_feat_norm)
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise nat.B200NativeError("SingleModelTrainer needs the model on a CUDA device (no CPU path)")
+        self.dev = dev
+        self.ops = TrainOps(dev, drop_seed=seed)
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and not n.startswith(_NO_GRAD_PREFIXES_SINGLE)]
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        self.numel = sum(p.numel() for p in self.params)
+        n = flat_size(self.params)
+        self.flat_numel = n
+        self.flat = {k: torch.zeros(n, dtype=torch.float32, device=dev) for k in ("p", "g", "m", "v")}
+        for p, view in zip(self.params, flat_views(self.params, self.flat["p"])):
+            view.copy_(p.data.float())
+            p.data = view
+        for p, g in zip(self.params, flat_views(self.params, self.flat["g"])):
+            p.grad = g
+        self.step_count = 0
+
+    def train_step(self, x, masks, labels):
+        self.flat["g"].zero_()
+        self.ops.new_step()
+        out = encoder_forward_train(self.ops, self.model, x)
+        total, parts = single_model_loss(self.ops, out, masks.to(self.dev).float(), labels.to(self.dev, torch.int64).contiguous(),
+                                         **self.loss_hp)
+        self.ops.tape.backward()
+        self.step_count += 1
+        f = self.flat
+        nat.adamw(f["p"], f["g"], f["m"], f["v"], lr=self.hp["lr"], betas=self.hp["betas"], eps=self.hp["eps"],
+                  weight_decay=self.hp["weight_decay"], step=self.step_count)
+        self.logits = out["logits"]
+        return total, parts

@@ -195,5 +195,11 @@ def test_c1_single_modality_train_step_vs_oracle_and_reference_fixture():
     assert max(rest.values()) <= 4e-2, sorted(rest.items(), key=lambda kv: -kv[1])[:5]
     assert max(noisy.values()) <= 2.5e-1, noisy
     assert np.median([v for _, v in worst]) <= 1.5e-2
-    for k in [n for n in hp["with_grad"] if n not in noisy][:24]:  # and directly against the reference fixture
-        gu.check(gold, f"grad/{k}", named[k].grad, rtol=4e-2)
+    # ... and directly against the reference fixture (full tensors where the fixture stores them, i.e. <= 8 192 elements)
+    n_direct = 0
+    for k in hp["with_grad"]:
+        if k in noisy or f"grad/{k}/full" not in gold.files:
+            continue
+        assert _rel(named[k].grad, torch.from_numpy(gold[f"grad/{k}/full"])) <= 4e-2, k
+        n_direct += 1
+    assert n_direct >= 30
