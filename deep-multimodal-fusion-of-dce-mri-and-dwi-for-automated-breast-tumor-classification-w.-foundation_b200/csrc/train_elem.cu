@@ -40,7 +40,7 @@ static inline int blocks_for(long long items, int threads = kTeThreads, int cap 
 // sum / sum of squares per channel of a bf16 map, accumulated into fp64 [C] buffers (caller zeroes them).
 // Thread = one 8-channel group x a strided set of rows; partials are combined across the row-threads of the CTA in
 // shared memory and leave with one fp64 atomic per channel and CTA.
-__global__ void __launch_bounds__(kTeThreads)
+__global__ void __launch_bounds__(kTeThreads, 4)
 bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long long R, int C, int ld, double* __restrict__ sum,
                 double* __restrict__ sumsq) {
     extern __shared__ float s_part[];  // [rows_par][C][2]
@@ -114,24 +114,6 @@ struct BnAct {
     int C;
 };
 
-// Per-thread constants of one 8-channel group: y = z * a + b, xhat = (z - mu) * is.
-struct BnCoef {
-    float a[8], b[8], mu[8], is[8];
-};
-__device__ __forceinline__ void bnact_coeffs(const BnAct& p, int c0, BnCoef& k) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float is = p.invstd != nullptr ? p.invstd[c0 + i] : 1.f;
-        const float g = p.gamma != nullptr ? p.gamma[c0 + i] : 1.f;
-        const float m = p.mean != nullptr ? p.mean[c0 + i] : 0.f;
-        const float be = p.beta != nullptr ? p.beta[c0 + i] : 0.f;
-        k.a[i] = is * g;
-        k.b[i] = be - m * is * g;
-        k.mu[i] = m;
-        k.is[i] = is;
-    }
-}
-
 // erf(z) ~= z * P(z^2) on |z| <= 3 (the 8-term odd minimax polynomial of the GEMM epilogue's GELU, |err| < 9e-5)
 __device__ __forceinline__ float erf_poly(float zc) {
     const float t = zc * zc;
@@ -164,90 +146,149 @@ __device__ __forceinline__ float act_bwd_fast(float y, int act) {
     return act == 2 ? (y > 0.f ? 1.f : 0.f) : 1.f;
 }
 
-// Thread layout shared by the three BN kernels: a thread owns ONE 8-channel group (its BatchNorm constants stay in
-// registers) and walks rows r = first, first + stride, ...; a warp's 32 lanes cover 32 consecutive 16-byte groups.
+// Thread layout shared by the BN kernels: a thread owns ONE 4-channel group (its BatchNorm constants stay in a handful
+// of registers: the kernels run at 5-6 CTAs per SM - at 8 channels per thread and 80-130 registers ncu showed 24 % of
+// the warp slots active and the kernels latency bound) and walks rows r = first, first + stride, ...; a warp's 32
+// lanes cover 32 consecutive 8-byte groups.  One Philox call yields the 4 dropout decisions of the group.
 #define BN_ROW_WALK(CG_)                                                                             \
     const int CG = (CG_);                                                                              \
     const int rows_par = kTeThreads / CG;                                                              \
     const int cg = threadIdx.x % CG, rp = threadIdx.x / CG;                                            \
-    const int c0 = cg * 8;                                                                             \
+    const int c0 = cg * 4;                                                                             \
     const long long row_first = static_cast<long long>(blockIdx.x) * rows_par + rp;                    \
     const long long row_step = static_cast<long long>(gridDim.x) * rows_par;
 
-__device__ __forceinline__ void drop_bits(const BnAct& p, long long r, int c0, unsigned int (&rn)[8]) {
-    const unsigned long long e = (static_cast<unsigned long long>(r) * p.C + c0) / 4;
-    const uint4 r0 = philox4x32_7(e, p.seed_lo, p.seed_hi), r1 = philox4x32_7(e + 1, p.seed_lo, p.seed_hi);
-    rn[0] = r0.x; rn[1] = r0.y; rn[2] = r0.z; rn[3] = r0.w;
-    rn[4] = r1.x; rn[5] = r1.y; rn[6] = r1.z; rn[7] = r1.w;
+__device__ __forceinline__ void unpack_bf16x4(const uint2& u, float (&f)[4]) {
+    f[0] = __uint_as_float(u.x << 16);
+    f[1] = __uint_as_float(u.x & 0xffff0000u);
+    f[2] = __uint_as_float(u.y << 16);
+    f[3] = __uint_as_float(u.y & 0xffff0000u);
+}
+__device__ __forceinline__ uint2 pack_bf16x4(const float (&f)[4]) {
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+}
+// y = z * a + b per channel (BatchNorm folded with its batch statistics)
+__device__ __forceinline__ void bnact_ab(const BnAct& p, int c0, float (&a)[4], float (&b)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float is = p.invstd != nullptr ? p.invstd[c0 + i] : 1.f;
+        const float g = p.gamma != nullptr ? p.gamma[c0 + i] : 1.f;
+        const float m = p.mean != nullptr ? p.mean[c0 + i] : 0.f;
+        const float be = p.beta != nullptr ? p.beta[c0 + i] : 0.f;
+        a[i] = is * g;
+        b[i] = be - m * is * g;
+    }
+}
+__device__ __forceinline__ uint4 drop_bits4(const BnAct& p, long long r, int c0) {
+    return philox4x32_7((static_cast<unsigned long long>(r) * p.C + c0) / 4, p.seed_lo, p.seed_hi);
 }
 
 // out = dropout(act(bn(z) + res))
-__global__ void __launch_bounds__(kTeThreads)
+__global__ void __launch_bounds__(kTeThreads, 4)
 bn_act_fwd_kernel(const BnAct p, __nv_bfloat16* __restrict__ out, int ldo) {
-    BN_ROW_WALK(p.C / 8)
+    BN_ROW_WALK(p.C / 4)
     if (rp >= rows_par) return;
-    BnCoef k;
-    bnact_coeffs(p, c0, k);
-    for (long long r = row_first; r < p.R; r += row_step) {
-        float f[8], rr[8];
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.z + r * p.ldz + c0)), f);
-        if (p.res != nullptr) unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.res + r * p.ldres + c0)), rr);
-        unsigned int rn[8];
-        if (p.drop_thresh != 0u) drop_bits(p, r, c0, rn);
+    float ka[4], kb[4];
+    bnact_ab(p, c0, ka, kb);
+    constexpr int NR = 4;  // rows per trip: all loads of a trip are issued before its arithmetic
+    for (long long r = row_first; r < p.R; r += NR * row_step) {
+        uint2 zq[NR], rq[NR];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float y = fmaf(f[j], k.a[j], k.b[j]);
-            if (p.res != nullptr) y += rr[j];
-            y = act_fwd_fast(y, p.act);
-            if (p.drop_thresh != 0u) y = rn[j] < p.drop_thresh ? 0.f : y * p.drop_scale;
-            f[j] = y;
+        for (int h = 0; h < NR; ++h) {
+            const long long rh = r + h * row_step;
+            if (rh < p.R) {
+                zq[h] = __ldg(reinterpret_cast<const uint2*>(p.z + rh * p.ldz + c0));
+                if (p.res != nullptr) rq[h] = __ldg(reinterpret_cast<const uint2*>(p.res + rh * p.ldres + c0));
+            }
         }
-        *reinterpret_cast<uint4*>(out + r * ldo + c0) = pack_bf16x8(f);
+#pragma unroll
+        for (int h = 0; h < NR; ++h) {
+            const long long rh = r + h * row_step;
+            if (rh >= p.R) break;
+            float f[4], rr[4];
+            unpack_bf16x4(zq[h], f);
+            if (p.res != nullptr) unpack_bf16x4(rq[h], rr);
+            uint4 rn = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            if (p.drop_thresh != 0u) rn = drop_bits4(p, rh, c0);
+            const unsigned int rnv[4] = {rn.x, rn.y, rn.z, rn.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float y = fmaf(f[j], ka[j], kb[j]);
+                if (p.res != nullptr) y += rr[j];
+                y = act_fwd_fast(y, p.act);
+                if (p.drop_thresh != 0u) y = rnv[j] < p.drop_thresh ? 0.f : y * p.drop_scale;
+                f[j] = y;
+            }
+            *reinterpret_cast<uint2*>(out + rh * ldo + c0) = pack_bf16x4(f);
+        }
     }
 }
 
 // Backward, pass 1: dY = dA * dropout_mask * act'(y), y = bn(z) + res, WRITTEN to dy_out (and dy_out2: the residual
 // branch's gradient); with batch statistics s1[c] += sum dY, s2[c] += sum dY * xhat; without them dy_out receives
 // dz = a * dY directly and only s1 / s2 (when requested) feed dbeta / dgamma.
-__global__ void __launch_bounds__(kTeThreads)
+__global__ void __launch_bounds__(kTeThreads, 4)
 bn_act_bwd_pass1_kernel(const BnAct p, const __nv_bfloat16* __restrict__ dA, int ldd, int batch_stats,
                         __nv_bfloat16* __restrict__ dy_out, int ldo, __nv_bfloat16* __restrict__ dy_out2, int ldo2,
                         double* __restrict__ s1, double* __restrict__ s2) {
     extern __shared__ float s_part[];
-    BN_ROW_WALK(p.C / 8)
-    float u[8], v[8];
+    BN_ROW_WALK(p.C / 4)
+    float u[4], v[4];  // sum dY, sum dY * z (xhat = (z - mu) * invstd is applied once, after the reduction)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) u[i] = v[i] = 0.f;
+    for (int i = 0; i < 4; ++i) u[i] = v[i] = 0.f;
     if (rp < rows_par) {
-        BnCoef k;
-        bnact_coeffs(p, c0, k);
-        for (long long r = row_first; r < p.R; r += row_step) {
-            float f[8], d[8], rr[8], o[8], o2[8];
-            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.z + r * p.ldz + c0)), f);
-            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(dA + r * ldd + c0)), d);
-            if (p.res != nullptr) unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.res + r * p.ldres + c0)), rr);
-            unsigned int rn[8];
-            if (p.drop_thresh != 0u) drop_bits(p, r, c0, rn);
+        float ka[4], kb[4];
+        bnact_ab(p, c0, ka, kb);
+        constexpr int NR = 2;
+        for (long long r = row_first; r < p.R; r += NR * row_step) {
+            uint2 zq[NR], dq[NR], rq[NR];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float g = d[j];
-                if (p.drop_thresh != 0u) g = rn[j] < p.drop_thresh ? 0.f : g * p.drop_scale;
-                if (p.act != 0) {
-                    float y = fmaf(f[j], k.a[j], k.b[j]);
-                    if (p.res != nullptr) y += rr[j];
-                    g *= act_bwd_fast(y, p.act);
+            for (int h = 0; h < NR; ++h) {
+                const long long rh = r + h * row_step;
+                if (rh < p.R) {
+                    zq[h] = __ldg(reinterpret_cast<const uint2*>(p.z + rh * p.ldz + c0));
+                    dq[h] = __ldg(reinterpret_cast<const uint2*>(dA + rh * ldd + c0));
+                    if (p.res != nullptr) rq[h] = __ldg(reinterpret_cast<const uint2*>(p.res + rh * p.ldres + c0));
                 }
-                u[j] += g;
-                v[j] = fmaf(g, (f[j] - k.mu[j]) * k.is[j], v[j]);
-                o2[j] = g;
-                o[j] = batch_stats ? g : g * k.a[j];
             }
-            if (dy_out != nullptr) *reinterpret_cast<uint4*>(dy_out + r * ldo + c0) = pack_bf16x8(o);
-            if (dy_out2 != nullptr) *reinterpret_cast<uint4*>(dy_out2 + r * ldo2 + c0) = pack_bf16x8(o2);
+#pragma unroll
+            for (int h = 0; h < NR; ++h) {
+                const long long rh = r + h * row_step;
+                if (rh >= p.R) break;
+                float f[4], d[4], rr[4];
+                unpack_bf16x4(zq[h], f);
+                unpack_bf16x4(dq[h], d);
+                if (p.res != nullptr) unpack_bf16x4(rq[h], rr);
+                uint4 rn = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                if (p.drop_thresh != 0u) rn = drop_bits4(p, rh, c0);
+                const unsigned int rnv[4] = {rn.x, rn.y, rn.z, rn.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float g = d[j];
+                    if (p.drop_thresh != 0u) g = rnv[j] < p.drop_thresh ? 0.f : g * p.drop_scale;
+                    if (p.act != 0) {
+                        float y = fmaf(f[j], ka[j], kb[j]);
+                        if (p.res != nullptr) y += rr[j];
+                        g *= act_bwd_fast(y, p.act);
+                    }
+                    u[j] += g;
+                    v[j] = fmaf(g, f[j], v[j]);
+                    d[j] = g;
+                }
+                if (dy_out2 != nullptr) *reinterpret_cast<uint2*>(dy_out2 + rh * ldo2 + c0) = pack_bf16x4(d);
+                if (dy_out != nullptr) {
+                    if (!batch_stats) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) d[j] *= ka[j];
+                    }
+                    *reinterpret_cast<uint2*>(dy_out + rh * ldo + c0) = pack_bf16x4(d);
+                }
+            }
         }
         if (s1 != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 s_part[(rp * p.C + c0 + i) * 2 + 0] = u[i];
                 s_part[(rp * p.C + c0 + i) * 2 + 1] = v[i];
             }
@@ -261,14 +302,16 @@ bn_act_bwd_pass1_kernel(const BnAct p, const __nv_bfloat16* __restrict__ dA, int
             a += static_cast<double>(s_part[(kk * p.C + c) * 2 + 0]);
             b += static_cast<double>(s_part[(kk * p.C + c) * 2 + 1]);
         }
+        const double mu = p.mean != nullptr ? static_cast<double>(p.mean[c]) : 0.0;
+        const double is = p.invstd != nullptr ? static_cast<double>(p.invstd[c]) : 1.0;
         atomicAdd(s1 + c, a);
-        atomicAdd(s2 + c, b);
+        atomicAdd(s2 + c, (b - mu * a) * is);  // sum dY * xhat
     }
 }
 
 // Backward, pass 2 (batch statistics only), in place on the dY map pass 1 wrote:
 // dz = gamma * invstd * (dY - s1/N - xhat * s2/N).  Block 0 also accumulates dgamma += s2, dbeta += s1.
-__global__ void __launch_bounds__(kTeThreads)
+__global__ void __launch_bounds__(kTeThreads, 4)
 bn_act_bwd_pass2_kernel(const BnAct p, const double* __restrict__ s1, const double* __restrict__ s2, double count,
                         __nv_bfloat16* __restrict__ dz, int lddz, float* __restrict__ dgamma, float* __restrict__ dbeta,
                         int map_pass) {
@@ -279,29 +322,48 @@ bn_act_bwd_pass2_kernel(const BnAct p, const double* __restrict__ s1, const doub
         }
     }
     if (!map_pass) return;
-    BN_ROW_WALK(p.C / 8)
+    BN_ROW_WALK(p.C / 4)
     if (rp >= rows_par) return;
-    BnCoef k;
-    bnact_coeffs(p, c0, k);
-    float k1[8], k2[8];
+    // dz = a (dY - k1 - (z - mu) is k2) = A dY + Bz z + Cc with A = a, Bz = -a is k2, Cc = a (is k2 mu - k1)
+    float kA[4], kB[4], kC[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        k1[i] = static_cast<float>(s1[c0 + i] / count);
-        k2[i] = static_cast<float>(s2[c0 + i] / count);
+    for (int i = 0; i < 4; ++i) {
+        const float is = p.invstd != nullptr ? p.invstd[c0 + i] : 1.f;
+        const float g = p.gamma != nullptr ? p.gamma[c0 + i] : 1.f;
+        const float mu = p.mean != nullptr ? p.mean[c0 + i] : 0.f;
+        const float k1 = static_cast<float>(s1[c0 + i] / count), k2 = static_cast<float>(s2[c0 + i] / count);
+        kA[i] = is * g;
+        kB[i] = -kA[i] * is * k2;
+        kC[i] = kA[i] * (is * k2 * mu - k1);
     }
-    for (long long r = row_first; r < p.R; r += row_step) {
-        float f[8], g[8];
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.z + r * p.ldz + c0)), f);
-        unpack_bf16x8(*reinterpret_cast<const uint4*>(dz + r * lddz + c0), g);
+    constexpr int NR = 4;
+    for (long long r = row_first; r < p.R; r += NR * row_step) {
+        uint2 zq[NR], gq[NR];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = k.a[j] * (g[j] - k1[j] - (f[j] - k.mu[j]) * k.is[j] * k2[j]);
-        *reinterpret_cast<uint4*>(dz + r * lddz + c0) = pack_bf16x8(g);
+        for (int h = 0; h < NR; ++h) {
+            const long long rh = r + h * row_step;
+            if (rh < p.R) {
+                zq[h] = __ldg(reinterpret_cast<const uint2*>(p.z + rh * p.ldz + c0));
+                gq[h] = *reinterpret_cast<const uint2*>(dz + rh * lddz + c0);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < NR; ++h) {
+            const long long rh = r + h * row_step;
+            if (rh >= p.R) break;
+            float f[4], g[4];
+            unpack_bf16x4(zq[h], f);
+            unpack_bf16x4(gq[h], g);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g[j] = fmaf(kA[j], g[j], fmaf(kB[j], f[j], kC[j]));
+            *reinterpret_cast<uint2*>(dz + rh * lddz + c0) = pack_bf16x4(g);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------- generic map helpers -------
 // out[b, c] = sum_p a[b, p, c] * b[b, p, c]   (b == nullptr: plain channel sums)       [fp32, overwritten]
-__global__ void __launch_bounds__(kTeThreads)
+__global__ void __launch_bounds__(kTeThreads, 4)
 map_dot_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ bmap, int ldb, int npix,
                int C, float* __restrict__ out) {
     extern __shared__ float s_part[];  // [rows_par][C]
@@ -338,28 +400,45 @@ map_dot_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16
 }
 
 // out[b,p,c] = x[b,p,c] * gate[b,c] + add[b,c]  (x NULL: the gate alone, or 0 without a gate -> a pure broadcast of add)
-__global__ void __launch_bounds__(kTeThreads)
+__global__ void __launch_bounds__(kTeThreads, 4)
 map_scale_add_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gate,
                      const float* __restrict__ add, long long R, int npix, int C, __nv_bfloat16* __restrict__ out,
                      int ldo, int accumulate) {
     const int CG = C / 8;
     const long long total = R * CG;
-    for (long long i = blockIdx.x * static_cast<long long>(kTeThreads) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * kTeThreads) {
-        const long long r = i / CG;
-        const int c0 = static_cast<int>(i - r * CG) * 8;
-        const long long bc = (r / npix) * C + c0;
-        float f[8], o[8];
-        if (x != nullptr) unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(x + r * ldx + c0)), f);
-        if (accumulate) unpack_bf16x8(*reinterpret_cast<const uint4*>(out + r * ldo + c0), o);
+    constexpr int NI = 1;
+    const long long step = static_cast<long long>(gridDim.x) * kTeThreads;
+    for (long long i0 = blockIdx.x * static_cast<long long>(kTeThreads) + threadIdx.x; i0 < total; i0 += NI * step) {
+        uint4 xq[NI], oq[NI];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float v = x != nullptr ? f[k] : (gate != nullptr ? 1.f : 0.f);
-            if (gate != nullptr) v *= gate[bc + k];
-            if (add != nullptr) v += add[bc + k];
-            o[k] = accumulate ? o[k] + v : v;
+        for (int h = 0; h < NI; ++h) {
+            const long long i = i0 + h * step;
+            if (i < total) {
+                const long long r = i / CG;
+                const int c0 = static_cast<int>(i - r * CG) * 8;
+                if (x != nullptr) xq[h] = __ldg(reinterpret_cast<const uint4*>(x + r * ldx + c0));
+                if (accumulate) oq[h] = *reinterpret_cast<const uint4*>(out + r * ldo + c0);
+            }
         }
-        *reinterpret_cast<uint4*>(out + r * ldo + c0) = pack_bf16x8(o);
+#pragma unroll
+        for (int h = 0; h < NI; ++h) {
+            const long long i = i0 + h * step;
+            if (i >= total) break;
+            const long long r = i / CG;
+            const int c0 = static_cast<int>(i - r * CG) * 8;
+            const long long bc = (r / npix) * C + c0;
+            float f[8], o[8];
+            if (x != nullptr) unpack_bf16x8(xq[h], f);
+            if (accumulate) unpack_bf16x8(oq[h], o);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float v = x != nullptr ? f[k] : (gate != nullptr ? 1.f : 0.f);
+                if (gate != nullptr) v *= gate[bc + k];
+                if (add != nullptr) v += add[bc + k];
+                o[k] = accumulate ? o[k] + v : v;
+            }
+            *reinterpret_cast<uint4*>(out + r * ldo + c0) = pack_bf16x8(o);
+        }
     }
 }
 
@@ -403,6 +482,19 @@ map_sumsq_kernel(const __nv_bfloat16* __restrict__ a, int lda, long long R, int 
 }
 
 // ------------------------------------------------------------------------------------------- squeeze-excite ------
+// y[i] = bias[i] + sum_j W[i * n_in + j] * v[j] for i < n_out, one warp per output row (coalesced weight reads)
+template <typename F>
+__device__ __forceinline__ void rows_dot(const float* __restrict__ Wm, const float* __restrict__ bias, const float* v,
+                                         int n_out, int n_in, F store) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = warp; i < n_out; i += nw) {
+        float a = 0.f;
+        for (int j = lane; j < n_in; j += 32) a = fmaf(__ldg(Wm + static_cast<long long>(i) * n_in + j), v[j], a);
+        a = warp_sum(a);
+        if (lane == 0) store(i, a + (bias != nullptr ? bias[i] : 0.f));
+    }
+}
+
 // Forward with the weights in their nn.Conv2d layouts (the training step re-reads the fp32 master weights every step,
 // so nothing is pre-transposed): pooled = sums / npix (also written out), gate = sigmoid(W2 gelu(W1 pooled + b1) + b2).
 __global__ void __launch_bounds__(kTeThreads)
@@ -418,17 +510,9 @@ se_fwd_kernel(const float* __restrict__ sums, float inv_npix, const float* __res
         if (pooled != nullptr) pooled[static_cast<long long>(b) * C + c] = s_p[c];
     }
     __syncthreads();
-    for (int m = tid; m < M; m += kTeThreads) {
-        float a = b1[m];
-        for (int c = 0; c < C; ++c) a = fmaf(w1[m * C + c], s_p[c], a);
-        s_h[m] = gelu_exact(a);
-    }
+    rows_dot(w1, b1, s_p, M, C, [&](int m, float a) { s_h[m] = gelu_exact(a); });
     __syncthreads();
-    for (int c = tid; c < C; c += kTeThreads) {
-        float a = b2[c];
-        for (int m = 0; m < M; ++m) a = fmaf(w2[c * M + m], s_h[m], a);
-        gate[static_cast<long long>(b) * C + c] = sigmoidf_(a);
-    }
+    rows_dot(w2, b2, s_h, C, M, [&](int c, float a) { gate[static_cast<long long>(b) * C + c] = sigmoidf_(a); });
 }
 
 // One CTA per case: recomputes the SE MLP from the pooled vector and back-propagates dgate through it.
@@ -447,22 +531,18 @@ se_bwd_kernel(const float* __restrict__ pooled, const float* __restrict__ w1, co
     const int b = blockIdx.x, tid = threadIdx.x;
     for (int c = tid; c < C; c += kTeThreads) s_p[c] = pooled[static_cast<long long>(b) * C + c];
     __syncthreads();
-    for (int m = tid; m < M; m += kTeThreads) {
-        float a = b1[m];
-        for (int c = 0; c < C; ++c) a = fmaf(w1[m * C + c], s_p[c], a);
+    rows_dot(w1, b1, s_p, M, C, [&](int m, float a) {
         s_a1[m] = a;
         s_h[m] = gelu_exact(a);
         h_out[static_cast<long long>(b) * M + m] = s_h[m];
-    }
+    });
     __syncthreads();
-    for (int c = tid; c < C; c += kTeThreads) {
-        float a = b2[c];
-        for (int m = 0; m < M; ++m) a = fmaf(w2[c * M + m], s_h[m], a);
+    rows_dot(w2, b2, s_h, C, M, [&](int c, float a) {
         const float g = sigmoidf_(a);
         const float d = dgate[static_cast<long long>(b) * C + c] * g * (1.f - g);
         s_da2[c] = d;
         da2[static_cast<long long>(b) * C + c] = d;
-    }
+    });
     __syncthreads();
     for (int m = tid; m < M; m += kTeThreads) {
         float a = 0.f;
@@ -481,98 +561,178 @@ se_bwd_kernel(const float* __restrict__ pooled, const float* __restrict__ w1, co
 
 // --------------------------------------------------------------------------- C -> 1 convolutions (1x1 / 3x3) -----
 // out[b,h,w] = bias + sum_{tap,c} x[b, h+dy, w+dx, c] * w[c * taps + tap]   (weights in the nn.Conv2d layout [1,C,kh,kw])
-// One warp per output pixel.
+//
+// One CTA per case.  A group of C/8 lanes owns a pixel: every lane loads 8 channels (one 16-byte load) and keeps its
+// 8 x TAPS weights in registers.  Forward: the TAPS per-pixel dot products d[p][tap] go to shared memory, then
+// out[q] = bias + sum_tap d[q + off(tap)][tap] - the map is read from HBM exactly once.  Backward: dout of the case sits
+// in shared memory; dx[p][c] = sum_tap dout[p - off(tap)] w[c][tap] is written once, dw[c][tap] += sum_p dout[p - off] x[p][c]
+// accumulates in registers over the CTA's pixels and leaves through shared memory with one atomic per (c, tap) and CTA.
+template <int TAPS>
 __global__ void __launch_bounds__(kTeThreads)
-convc1_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int B, int H, int W, int C, int taps,
-                  const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out) {
+convc1_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int H, int W, int C, const float* __restrict__ w,
+                  const float* __restrict__ bias, float* __restrict__ out) {
+    extern __shared__ float s_d[];  // [H*W][TAPS]
+    const int b = blockIdx.x, npix = H * W;
+    const int lpp = C / 8;                      // lanes per pixel (power of two, <= 32: C <= 256) or 32 (C > 256: loop)
+    const int gl = lpp < 32 ? lpp : 32;
     const int lane = threadIdx.x & 31;
-    const long long warp = (blockIdx.x * static_cast<long long>(kTeThreads) + threadIdx.x) >> 5;
-    const long long nwarps = (static_cast<long long>(gridDim.x) * kTeThreads) >> 5;
-    const long long total = static_cast<long long>(B) * H * W;
-    for (long long pix = warp; pix < total; pix += nwarps) {
-        const int wq = static_cast<int>(pix % W), hq = static_cast<int>((pix / W) % H);
-        const long long b = pix / (static_cast<long long>(W) * H);
-        float acc = 0.f;
-        for (int tap = 0; tap < taps; ++tap) {
-            const int dy = taps == 9 ? tap / 3 - 1 : 0, dx = taps == 9 ? tap % 3 - 1 : 0;
-            const int hh = hq + dy, ww = wq + dx;
-            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-            const __nv_bfloat16* row = x + ((b * H + hh) * W + ww) * ldx;
-            for (int c = lane * 2; c < C; c += 64) {
-                const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(row + c);
-                acc = fmaf(__low2float(v), w[c * taps + tap], acc);
-                acc = fmaf(__high2float(v), w[(c + 1) * taps + tap], acc);
+    const int sub = lane % gl, grp = lane / gl;  // lane's channel slice / pixel slot inside the warp
+    const int ppw = 32 / gl;                     // pixels per warp and trip
+    const int slot = (threadIdx.x >> 5) * ppw + grp, nslots = (kTeThreads >> 5) * ppw;
+    for (int c0 = sub * 8; c0 < C; c0 += 256) {
+        float wr[8][TAPS];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int t = 0; t < TAPS; ++t) wr[k][t] = __ldg(w + (c0 + k) * TAPS + t);
+        }
+        constexpr int NP = 4;  // pixels per trip: their loads are issued together (the loop is latency bound otherwise)
+        for (int pix0 = slot; pix0 < npix; pix0 += NP * nslots) {
+            uint4 q[NP];
+#pragma unroll
+            for (int h = 0; h < NP; ++h) {
+                const int pix = pix0 + h * nslots;
+                if (pix < npix) q[h] = __ldg(reinterpret_cast<const uint4*>(x + (static_cast<long long>(b) * npix + pix) * ldx + c0));
+            }
+#pragma unroll
+            for (int h = 0; h < NP; ++h) {
+                const int pix = pix0 + h * nslots;
+                if (pix >= npix) break;
+                float acc[TAPS];
+#pragma unroll
+                for (int t = 0; t < TAPS; ++t) acc[t] = 0.f;
+                float f[8];
+                unpack_bf16x8(q[h], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                    for (int t = 0; t < TAPS; ++t) acc[t] = fmaf(f[k], wr[k][t], acc[t]);
+                }
+#pragma unroll
+                for (int t = 0; t < TAPS; ++t) {
+                    float v = acc[t];
+                    for (int o = gl >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    acc[t] = v;
+                }
+                if (sub == 0) {  // (C > 256: the same lane revisits the pixel with the next 256 channels)
+#pragma unroll
+                    for (int t = 0; t < TAPS; ++t) s_d[pix * TAPS + t] = (c0 < 256 ? 0.f : s_d[pix * TAPS + t]) + acc[t];
+                }
             }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) out[pix] = acc + (bias != nullptr ? bias[0] : 0.f);
+    }
+    __syncthreads();
+    const float bv = bias != nullptr ? bias[0] : 0.f;
+    for (int q = threadIdx.x; q < npix; q += kTeThreads) {
+        float v = bv;
+        if (TAPS == 1) {
+            v += s_d[q];
+        } else {
+            const int hq = q / W, wq = q - hq * W;
+#pragma unroll
+            for (int t = 0; t < TAPS; ++t) {
+                const int hh = hq + t / 3 - 1, ww = wq + t % 3 - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) v += s_d[(hh * W + ww) * TAPS + t];
+            }
+        }
+        out[static_cast<long long>(b) * npix + q] = v;
     }
 }
 
-// dx[b,h,w,c] = sum_tap dout[b, h-dy, w-dx] * w[c*taps+tap];  dw[c*taps+tap] += sum dout[p] * x[p+off, c];  dbias += sum dout
-// One CTA per (case, row group): dx by one warp per pixel; dw by per-thread partial sums over the CTA's pixels.
+template <int TAPS>
 __global__ void __launch_bounds__(kTeThreads)
-convc1_bwd_dx_kernel(const float* __restrict__ dout, int B, int H, int W, int C, int taps, const float* __restrict__ w,
-                     __nv_bfloat16* __restrict__ dx, int lddx, int accumulate) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = (blockIdx.x * static_cast<long long>(kTeThreads) + threadIdx.x) >> 5;
-    const long long nwarps = (static_cast<long long>(gridDim.x) * kTeThreads) >> 5;
-    const long long total = static_cast<long long>(B) * H * W;
-    for (long long pix = warp; pix < total; pix += nwarps) {
-        const int wq = static_cast<int>(pix % W), hq = static_cast<int>((pix / W) % H);
-        const long long b = pix / (static_cast<long long>(W) * H);
-        float g[9];
-        for (int tap = 0; tap < taps; ++tap) {
-            const int dy = taps == 9 ? tap / 3 - 1 : 0, dxo = taps == 9 ? tap % 3 - 1 : 0;
-            const int hh = hq - dy, ww = wq - dxo;
-            g[tap] = (hh < 0 || hh >= H || ww < 0 || ww >= W) ? 0.f : dout[(b * H + hh) * W + ww];
-        }
-        __nv_bfloat16* row = dx + pix * lddx;
-        for (int c = lane * 2; c < C; c += 64) {
-            float a0 = 0.f, a1 = 0.f;
-            for (int tap = 0; tap < taps; ++tap) {
-                a0 = fmaf(g[tap], w[c * taps + tap], a0);
-                a1 = fmaf(g[tap], w[(c + 1) * taps + tap], a1);
-            }
-            if (accumulate) {
-                const __nv_bfloat162 o = *reinterpret_cast<const __nv_bfloat162*>(row + c);
-                a0 += __low2float(o);
-                a1 += __high2float(o);
-            }
-            *reinterpret_cast<__nv_bfloat162*>(row + c) = __floats2bfloat162_rn(a0, a1);
-        }
-    }
-}
-
-// dw[c*taps+tap] += sum_p dout[p] * x[p + off(tap), c]; grid = (row slabs, channel pairs handled by threads)
-__global__ void __launch_bounds__(kTeThreads)
-convc1_bwd_dw_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ x, int ldx, int B, int H, int W,
-                     int C, int taps, float* __restrict__ dw, float* __restrict__ dbias) {
-    // thread = one channel (c = threadIdx.x + k * 256); loop over the CTA's pixels; 9 partial sums in registers
-    const long long total = static_cast<long long>(B) * H * W;
-    const long long per = (total + gridDim.x - 1) / gridDim.x;
-    const long long p0 = blockIdx.x * per, p1 = min(p0 + per, total);
+convc1_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ x, int ldx, int H, int W, int C,
+                  const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, int lddx, int accumulate,
+                  float* __restrict__ dw, float* __restrict__ dbias) {
+    extern __shared__ float s_g[];  // [H*W] dout of this case | [C*TAPS] dw partials
     __shared__ double scratch[33];
-    for (int c = threadIdx.x; c < C; c += kTeThreads) {
-        float acc[9];
-        for (int t = 0; t < 9; ++t) acc[t] = 0.f;
-        for (long long pix = p0; pix < p1; ++pix) {
-            const float xv = __bfloat162float(x[pix * ldx + c]);
-            const int wq = static_cast<int>(pix % W), hq = static_cast<int>((pix / W) % H);
-            // x[pix] contributes to dw[tap] with dout[pix - off(tap)]
-            for (int tap = 0; tap < taps; ++tap) {
-                const int dy = taps == 9 ? tap / 3 - 1 : 0, dxo = taps == 9 ? tap % 3 - 1 : 0;
-                const int hh = hq - dy, ww = wq - dxo;
-                if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-                acc[tap] = fmaf(dout[pix - static_cast<long long>(dy) * W - dxo], xv, acc[tap]);
+    const int b = blockIdx.x, npix = H * W;
+    float* s_dw = s_g + npix;
+    float bsum = 0.f;
+    for (int i = threadIdx.x; i < npix; i += kTeThreads) {
+        const float g = dout[static_cast<long long>(b) * npix + i];
+        s_g[i] = g;
+        bsum += g;
+    }
+    for (int i = threadIdx.x; i < C * TAPS; i += kTeThreads) s_dw[i] = 0.f;
+    __syncthreads();
+    const int lpp = C / 8;
+    const int gl = lpp < 32 ? lpp : 32;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % gl, grp = lane / gl;
+    const int ppw = 32 / gl;
+    const int slot = (threadIdx.x >> 5) * ppw + grp, nslots = (kTeThreads >> 5) * ppw;
+    for (int c0 = sub * 8; c0 < C; c0 += 256) {
+        float wr[8][TAPS], acc[8][TAPS];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int t = 0; t < TAPS; ++t) {
+                wr[k][t] = __ldg(w + (c0 + k) * TAPS + t);
+                acc[k][t] = 0.f;
             }
         }
-        for (int tap = 0; tap < taps; ++tap) atomicAdd(dw + c * taps + tap, acc[tap]);
+        constexpr int NP = 4;
+        for (int pix0 = slot; pix0 < npix; pix0 += NP * nslots) {
+            uint4 q[NP], oq[NP];
+#pragma unroll
+            for (int h = 0; h < NP; ++h) {
+                const int pix = pix0 + h * nslots;
+                if (pix < npix) {
+                    const long long row = static_cast<long long>(b) * npix + pix;
+                    if (dw != nullptr) q[h] = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + c0));
+                    if (dx != nullptr && accumulate) oq[h] = *reinterpret_cast<const uint4*>(dx + row * lddx + c0);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < NP; ++h) {
+                const int pix = pix0 + h * nslots;
+                if (pix >= npix) break;
+                const int hq = pix / W, wq = pix - hq * W;
+                float g[TAPS];
+#pragma unroll
+                for (int t = 0; t < TAPS; ++t) {
+                    const int hh = TAPS == 9 ? hq - (t / 3 - 1) : hq, ww = TAPS == 9 ? wq - (t % 3 - 1) : wq;
+                    g[t] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? s_g[hh * W + ww] : 0.f;
+                }
+                const long long row = static_cast<long long>(b) * npix + pix;
+                if (dw != nullptr) {
+                    float f[8];
+                    unpack_bf16x8(q[h], f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                        for (int t = 0; t < TAPS; ++t) acc[k][t] = fmaf(g[t], f[k], acc[k][t]);
+                    }
+                }
+                if (dx != nullptr) {
+                    float o[8];
+                    if (accumulate) unpack_bf16x8(oq[h], o);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float v = accumulate ? o[k] : 0.f;
+#pragma unroll
+                        for (int t = 0; t < TAPS; ++t) v = fmaf(g[t], wr[k][t], v);
+                        o[k] = v;
+                    }
+                    *reinterpret_cast<uint4*>(dx + row * lddx + c0) = pack_bf16x8(o);
+                }
+            }
+        }
+        if (dw != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                for (int t = 0; t < TAPS; ++t) atomicAdd(&s_dw[(c0 + k) * TAPS + t], acc[k][t]);
+            }
+        }
+    }
+    if (dw != nullptr) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < C * TAPS; i += kTeThreads) atomicAdd(dw + i, s_dw[i]);
     }
     if (dbias != nullptr) {
-        float s = 0.f;
-        for (long long pix = p0 + threadIdx.x; pix < p1; pix += kTeThreads) s += dout[pix];
-        const double t = block_sum<double>(static_cast<double>(s), scratch);
+        const double t = block_sum<double>(static_cast<double>(bsum), scratch);
         if (threadIdx.x == 0) atomicAdd(dbias, static_cast<float>(t));
     }
 }
@@ -779,57 +939,95 @@ mask_attn_bwd_kernel(const float* __restrict__ mask, const float* __restrict__ d
 
 // ---------------------------------------------------------------------------------------------- stem backward ----
 // Forward (b200_stem with every output channel in the un-activated segment): z[b,p,n] = sum_c wcat[n,c] x[b,c,s*p] gate[b,c].
-// Backward from dz [B, npix, N] bf16:  dwcat[n,c] += sum_{b,p} dz[b,p,n] x[b,c,sp] gate[b,c];
-//   dgate[b,c] = sum_p x[b,c,sp] * sum_n dz[b,p,n] wcat[n,c].   One CTA per (case, pixel slab); C <= 32, N <= 256.
+// Backward from dz [B, npix, N] bf16:  dwcat[n,c] += gate[b,c] * sum_p dz[b,p,n] x[b,c,sp];
+//   dgate[b,c] = sum_p x[b,c,sp] * sum_n dz[b,p,n] wcat[n,c].
+// One CTA per case, 256-pixel tiles of x staged in shared memory (channels padded to CP).  Phase A: thread = pixel,
+// t[c] = sum_n dz[p,n] w[n,c] with the weights broadcast from shared memory.  Phase B: thread = output channel n,
+// acc[c] += dz[p,n] x[p,c] with dz read coalesced across n and x broadcast from shared memory.
+template <int CP>
 __global__ void __launch_bounds__(kTeThreads)
 stem_bwd_kernel(const float* __restrict__ x, int C, int H, int W, int stride, const float* __restrict__ gate,
                 const __nv_bfloat16* __restrict__ dz, int N, const float* __restrict__ wcat, float* __restrict__ dwcat,
                 float* __restrict__ dgate) {
-    extern __shared__ float s_st[];  // dzs[64][N+1] | xs[64][C] | dw_acc[N][C]
-    const int b = blockIdx.y;
+    extern __shared__ float s_st[];  // w[N][CP] | x[256][CP] | dg[CP]
+    float* s_w = s_st;
+    float* s_x = s_w + N * CP;
+    float* s_dg = s_x + kTeThreads * CP;
+    const int b = blockIdx.x, tid = threadIdx.x;
     const int Ho = H / stride, Wo = W / stride, npix = Ho * Wo;
-    float* s_dz = s_st;
-    float* s_x = s_dz + 64 * (N + 1);
-    float* s_dw = s_x + 64 * C;
-    float* s_dg = s_dw + N * C;  // [C]
-    const int tid = threadIdx.x;
-    for (int i = tid; i < N * C; i += kTeThreads) s_dw[i] = 0.f;
-    if (tid < C) s_dg[tid] = 0.f;
+    for (int i = tid; i < N * CP; i += kTeThreads) {
+        const int n = i / CP, c = i - n * CP;
+        s_w[i] = c < C ? wcat[n * C + c] : 0.f;
+    }
+    if (tid < CP) s_dg[tid] = 0.f;
+    float dg[CP], acc[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) dg[c] = acc[c] = 0.f;
+    const __nv_bfloat16* dzb = dz + static_cast<long long>(b) * npix * N;
+    for (int pix0 = 0; pix0 < npix; pix0 += kTeThreads) {
+        const int np = min(kTeThreads, npix - pix0);
+        __syncthreads();  // previous tile's readers are done with s_x
+        for (int i = tid; i < kTeThreads * CP; i += kTeThreads) {
+            const int c = i / kTeThreads, pp = i - c * kTeThreads;
+            float v = 0.f;
+            if (c < C && pp < np) {
+                const int pix = pix0 + pp;
+                const int ho = pix / Wo, wo = pix - ho * Wo;
+                v = __ldg(x + ((static_cast<long long>(b) * C + c) * H + ho * stride) * W + wo * stride);
+            }
+            s_x[pp * CP + c] = v;
+        }
+        __syncthreads();
+        if (tid < np) {  // phase A
+            float t[CP];
+#pragma unroll
+            for (int c = 0; c < CP; ++c) t[c] = 0.f;
+            const __nv_bfloat16* row = dzb + static_cast<long long>(pix0 + tid) * N;
+            for (int n0 = 0; n0 < N; n0 += 8) {
+                float f[8];
+                unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(row + n0)), f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4* w4 = reinterpret_cast<const float4*>(s_w + (n0 + k) * CP);
+#pragma unroll
+                    for (int c4 = 0; c4 < CP / 4; ++c4) {
+                        const float4 wv = w4[c4];
+                        t[4 * c4 + 0] = fmaf(f[k], wv.x, t[4 * c4 + 0]);
+                        t[4 * c4 + 1] = fmaf(f[k], wv.y, t[4 * c4 + 1]);
+                        t[4 * c4 + 2] = fmaf(f[k], wv.z, t[4 * c4 + 2]);
+                        t[4 * c4 + 3] = fmaf(f[k], wv.w, t[4 * c4 + 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CP; ++c) dg[c] = fmaf(t[c], s_x[tid * CP + c], dg[c]);
+        }
+        if (tid < N) {  // phase B
+            for (int pp = 0; pp < np; ++pp) {
+                const float v = __bfloat162float(dzb[static_cast<long long>(pix0 + pp) * N + tid]);
+                const float4* x4 = reinterpret_cast<const float4*>(s_x + pp * CP);
+#pragma unroll
+                for (int c4 = 0; c4 < CP / 4; ++c4) {
+                    const float4 xv = x4[c4];
+                    acc[4 * c4 + 0] = fmaf(v, xv.x, acc[4 * c4 + 0]);
+                    acc[4 * c4 + 1] = fmaf(v, xv.y, acc[4 * c4 + 1]);
+                    acc[4 * c4 + 2] = fmaf(v, xv.z, acc[4 * c4 + 2]);
+                    acc[4 * c4 + 3] = fmaf(v, xv.w, acc[4 * c4 + 3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+        const float v = warp_sum(dg[c]);
+        if ((tid & 31) == 0 && c < C) atomicAdd(&s_dg[c], v);
+    }
+    if (tid < N) {
+#pragma unroll
+        for (int c = 0; c < CP; ++c)
+            if (c < C) atomicAdd(dwcat + tid * C + c, acc[c] * (gate != nullptr ? gate[static_cast<long long>(b) * C + c] : 1.f));
+    }
     __syncthreads();
-    for (int pix0 = blockIdx.x * 64; pix0 < npix; pix0 += gridDim.x * 64) {
-        const int np = min(64, npix - pix0);
-        for (int i = tid; i < np * N; i += kTeThreads) {
-            const int pp = i / N, n = i - pp * N;
-            s_dz[pp * (N + 1) + n] = __bfloat162float(dz[(static_cast<long long>(b) * npix + pix0 + pp) * N + n]);
-        }
-        for (int i = tid; i < np * C; i += kTeThreads) {
-            const int c = i / np, pp = i - c * np;
-            const int pix = pix0 + pp;
-            const int ho = pix / Wo, wo = pix - ho * Wo;
-            s_x[pp * C + c] = x[((static_cast<long long>(b) * C + c) * H + ho * stride) * W + wo * stride];
-        }
-        __syncthreads();
-        // dw partials: thread -> (n, c) pairs
-        for (int i = tid; i < N * C; i += kTeThreads) {
-            const int n = i / C, c = i - n * C;
-            float a = 0.f;
-            for (int pp = 0; pp < np; ++pp) a = fmaf(s_dz[pp * (N + 1) + n], s_x[pp * C + c], a);
-            s_dw[i] += a;
-        }
-        // dgate partials: thread -> (pp, c) pairs: t = sum_n dz[pp,n] w[n,c]
-        for (int i = tid; i < np * C; i += kTeThreads) {
-            const int pp = i / C, c = i - pp * C;
-            float t = 0.f;
-            for (int n = 0; n < N; ++n) t = fmaf(s_dz[pp * (N + 1) + n], wcat[n * C + c], t);
-            atomicAdd(&s_dg[c], t * s_x[pp * C + c]);
-        }
-        __syncthreads();
-    }
-    const float* g = gate != nullptr ? gate + static_cast<long long>(b) * C : nullptr;
-    for (int i = tid; i < N * C; i += kTeThreads) {
-        const int c = i % C;
-        atomicAdd(dwcat + i, s_dw[i] * (g != nullptr ? g[c] : 1.f));
-    }
     if (dgate != nullptr && tid < C) atomicAdd(dgate + static_cast<long long>(b) * C + tid, s_dg[tid]);
 }
 
@@ -1323,7 +1521,7 @@ static int fill_bnact(BnAct& p, const void* z, int ldz, const void* res, int ldr
 }
 
 static int bn_grid(long long R, int C, int& rows_par) {
-    rows_par = kTeThreads / (C / 8);
+    rows_par = kTeThreads / (C / 4);
     long long want = (R + rows_par * 4 - 1) / (rows_par * 4);
     return static_cast<int>(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
 }
@@ -1333,7 +1531,7 @@ extern "C" int b200_bn_act_fwd(const void* z, int ldz, const void* res, int ldre
                                long long R, int C, void* out, int ldo, void* stream) {
     BnAct p;
     int rc = fill_bnact(p, z, ldz, res, ldres, mean, invstd, gamma, beta, act, drop_p, seed, R, C);
-    if (rc != 0 || out == nullptr || ldo % 8 != 0 || C > 2048) return rc != 0 ? rc : -3;
+    if (rc != 0 || out == nullptr || ldo % 8 != 0 || C > 1024) return rc != 0 ? rc : -3;
     int rows_par;
     const int grid = bn_grid(R, C, rows_par);
     bn_act_fwd_kernel<<<grid, kTeThreads, 0, TE_STREAM>>>(p, static_cast<__nv_bfloat16*>(out), ldo);
@@ -1346,7 +1544,7 @@ extern "C" int b200_bn_act_bwd(const void* z, int ldz, const void* res, int ldre
                                void* dz, int lddz, void* dres, int lddres, float* dgamma, float* dbeta, void* stream) {
     BnAct p;
     int rc = fill_bnact(p, z, ldz, res, ldres, mean, invstd, gamma, beta, act, drop_p, seed, R, C);
-    if (rc != 0 || dA == nullptr || ldd % 8 != 0 || C > 2048) return rc != 0 ? rc : -3;
+    if (rc != 0 || dA == nullptr || ldd % 8 != 0 || C > 1024) return rc != 0 ? rc : -3;
     if (batch_stats && dz == nullptr) return -5;  // pass 2 works in place on dz
     const bool need_sums = batch_stats || dgamma != nullptr || dbeta != nullptr;
     double *s1 = nullptr, *s2 = nullptr;
@@ -1423,30 +1621,43 @@ extern "C" int b200_se_bwd(const float* pooled, const float* w1, const float* b1
     return launch_status();
 }
 
+static bool convc1_shape_ok(int H, int W, int C, int taps) {
+    const int lpp = C / 8;
+    return C % 8 == 0 && (lpp >= 32 ? C % 256 == 0 : (lpp & (lpp - 1)) == 0) && (taps == 1 || taps == 9) &&
+           static_cast<size_t>(H) * W * taps * sizeof(float) <= 200 * 1024;
+}
+
 extern "C" int b200_convc1_fwd(const void* x, int ldx, int B, int H, int W, int C, int taps, const float* w,
                                const float* bias, float* out, void* stream) {
-    if (x == nullptr || w == nullptr || out == nullptr || (taps != 1 && taps != 9) || C % 2 != 0) return -1;
-    const long long total = static_cast<long long>(B) * H * W;
-    convc1_fwd_kernel<<<blocks_for(total * 32), kTeThreads, 0, TE_STREAM>>>(static_cast<const __nv_bfloat16*>(x), ldx, B, H,
-                                                                           W, C, taps, w, bias, out);
-    return launch_status();
+    if (x == nullptr || w == nullptr || out == nullptr || B <= 0 || !convc1_shape_ok(H, W, C, taps) || ldx % 8 != 0) return -1;
+    const size_t smem = static_cast<size_t>(H) * W * taps * sizeof(float);
+    auto go = [&](auto kern) -> int {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return static_cast<int>(e);
+        }
+        kern<<<B, kTeThreads, smem, TE_STREAM>>>(static_cast<const __nv_bfloat16*>(x), ldx, H, W, C, w, bias, out);
+        return launch_status();
+    };
+    return taps == 9 ? go(convc1_fwd_kernel<9>) : go(convc1_fwd_kernel<1>);
 }
 
 extern "C" int b200_convc1_bwd(const void* x, int ldx, const float* dout, int B, int H, int W, int C, int taps,
                                const float* w, void* dx, int lddx, int accumulate_dx, float* dw, float* dbias,
                                void* stream) {
-    if (x == nullptr || w == nullptr || dout == nullptr || (taps != 1 && taps != 9) || C % 2 != 0) return -1;
-    const long long total = static_cast<long long>(B) * H * W;
-    if (dx != nullptr)
-        convc1_bwd_dx_kernel<<<blocks_for(total * 32), kTeThreads, 0, TE_STREAM>>>(dout, B, H, W, C, taps, w,
-                                                                                  static_cast<__nv_bfloat16*>(dx), lddx,
-                                                                                  accumulate_dx);
-    if (dw != nullptr) {
-        const int grid = static_cast<int>(total / 256 < 1 ? 1 : (total / 256 > 148 * 4 ? 148 * 4 : total / 256));
-        convc1_bwd_dw_kernel<<<grid, kTeThreads, 0, TE_STREAM>>>(dout, static_cast<const __nv_bfloat16*>(x), ldx, B, H, W,
-                                                                C, taps, dw, dbias);
-    }
-    return launch_status();
+    if (x == nullptr || w == nullptr || dout == nullptr || B <= 0 || !convc1_shape_ok(H, W, C, taps) || ldx % 8 != 0) return -1;
+    const size_t smem = (static_cast<size_t>(H) * W + static_cast<size_t>(C) * taps) * sizeof(float);
+    if (smem > 200 * 1024) return -2;
+    auto go = [&](auto kern) -> int {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return static_cast<int>(e);
+        }
+        kern<<<B, kTeThreads, smem, TE_STREAM>>>(dout, static_cast<const __nv_bfloat16*>(x), ldx, H, W, C, w,
+                                                static_cast<__nv_bfloat16*>(dx), lddx, accumulate_dx, dw, dbias);
+        return launch_status();
+    };
+    return taps == 9 ? go(convc1_bwd_kernel<9>) : go(convc1_bwd_kernel<1>);
 }
 
 extern "C" int b200_lift_fwd(const float* r, long long P, int N, const float* w, void* z, void* stream) {
@@ -1483,20 +1694,22 @@ extern "C" int b200_mask_attn_bwd(const float* mask, const float* dA, int B, int
 
 extern "C" int b200_stem_bwd(const float* x, int B, int C, int H, int W, int stride, const float* gate, const void* dz,
                              int N, const float* wcat, float* dwcat, float* dgate, void* stream) {
-    if (x == nullptr || dz == nullptr || wcat == nullptr || dwcat == nullptr || C > 32 || N > 256 || B <= 0) return -1;
-    const size_t smem = (static_cast<size_t>(64) * (N + 1) + 64 * C + static_cast<size_t>(N) * C + C) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(stem_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return static_cast<int>(e);
-        configured = smem;
-    }
-    const int npix = (H / stride) * (W / stride);
-    int gx = (npix + 63) / 64;
-    while (gx > 1 && static_cast<long long>(gx / 2) * B >= 148LL * 4) gx = (gx + 1) / 2;
-    stem_bwd_kernel<<<dim3(gx, B), kTeThreads, smem, TE_STREAM>>>(x, C, H, W, stride, gate,
-                                                                 static_cast<const __nv_bfloat16*>(dz), N, wcat, dwcat, dgate);
-    return launch_status();
+    if (x == nullptr || dz == nullptr || wcat == nullptr || dwcat == nullptr || C > 32 || N > kTeThreads || N % 8 != 0 || B <= 0)
+        return -1;
+    const int CP = C <= 8 ? 8 : (C <= 16 ? 16 : 32);
+    const size_t smem = (static_cast<size_t>(N) * CP + static_cast<size_t>(kTeThreads) * CP + CP) * sizeof(float);
+    auto go = [&](auto kern) -> int {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return static_cast<int>(e);
+        }
+        kern<<<B, kTeThreads, smem, TE_STREAM>>>(x, C, H, W, stride, gate, static_cast<const __nv_bfloat16*>(dz), N, wcat, dwcat,
+                                                dgate);
+        return launch_status();
+    };
+    if (CP == 8) return go(stem_bwd_kernel<8>);
+    if (CP == 16) return go(stem_bwd_kernel<16>);
+    return go(stem_bwd_kernel<32>);
 }
 
 extern "C" int b200_cls_head_bwd(const float* pooled, const float* dlogits, const float* fcw, int B, int C, int K,
