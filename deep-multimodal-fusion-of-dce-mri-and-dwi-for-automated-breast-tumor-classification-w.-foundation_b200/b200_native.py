@@ -108,6 +108,7 @@ SIGNATURES = {
     "b200_nyul_transform": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "b200_nyul_transform_ex": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "b200_plane_mean": [_P, _I, _I, _P, _P],
+    "b200_case_max_scale": [_P, _I, _LL, _P, _P],
     "b200_stem": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P],
     "b200_se_gate": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "b200_scale_map": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
@@ -138,6 +139,7 @@ SIGNATURES = {
     "b200_gelu_bwd": [_P, _P, _LL, _P, _P],
     "b200_head_loss": [C.POINTER(HeadTrain), _I, _P],
     "b200_adamw": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P],
+    "b200_adamw_groups": [_P, _P, _P, _P, _LL, _P, _P, _P, _F, _F, _F, _F, _I, _F, _P],
     "b200_mask_dot": [_P, _P, _I, _I, _I, _P, _P],
     "b200_mask_dice": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P,
                        _P, _P, _P, _P, _P],

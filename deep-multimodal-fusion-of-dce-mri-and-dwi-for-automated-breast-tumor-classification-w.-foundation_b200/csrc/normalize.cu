@@ -810,3 +810,48 @@ extern "C" int b200_adc_map(const float* x, int B, int C, int n, const float* bv
                      static_cast<cudaStream_t>(stream)>>>(x, bvals, C, n, eps, out, total);
     return launch_status();
 }
+
+// DCE pre-scale of prep_data_by_mod (reference prepare_single_model.py:337-343): every case divided by its maximum over
+// all channels and pixels.  One CTA per case: a max reduction over the case (which then sits in L2), then the IEEE
+// division per element, exactly what torch's `imgs / imgs_max` computes.
+namespace b200 {
+__global__ void __launch_bounds__(kNormThreads)
+case_max_scale_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+    __shared__ float s_red[kNormThreads / 32];
+    const float* src = x + static_cast<long long>(blockIdx.x) * n;
+    float* dst = out + static_cast<long long>(blockIdx.x) * n;
+    const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    float m = -FLT_MAX;
+    if (vec) {
+        for (long long i = threadIdx.x; i < (n >> 2); i += kNormThreads) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(src) + i);
+            m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+        }
+    } else {
+        for (long long i = threadIdx.x; i < n; i += kNormThreads) m = fmaxf(m, __ldg(src + i));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = s_red[0];
+    for (int w = 1; w < kNormThreads / 32; ++w) m = fmaxf(m, s_red[w]);
+    if (vec) {
+        for (long long i = threadIdx.x; i < (n >> 2); i += kNormThreads) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(src) + i);
+            __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(__fdiv_rn(q.x, m), __fdiv_rn(q.y, m), __fdiv_rn(q.z, m), __fdiv_rn(q.w, m)));
+        }
+    } else {
+        for (long long i = threadIdx.x; i < n; i += kNormThreads) dst[i] = __fdiv_rn(__ldg(src + i), m);
+    }
+}
+}  // namespace b200
+
+extern "C" int b200_case_max_scale(const float* x, int B, long long n, float* out, void* stream) {
+    using namespace b200;
+    if (B < 0 || n <= 0) return -1;
+    if (B == 0) return 0;
+    if (x == nullptr || out == nullptr) return -2;
+    case_max_scale_kernel<<<B, kNormThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out);
+    return launch_status();
+}

@@ -889,6 +889,31 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     }
 }
 
+// The same update with PER-ELEMENT learning rate, weight decay and first step (parameter groups of
+// LightningFusionOptimizerFactory, code/selector_helpers.py:456-518: discriminative learning rates / regularisation by
+// depth; groups that join the optimiser later - gradual unfreezing - start their own bias-correction count).
+__global__ void adamw_groups_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                    float* __restrict__ v, long long n, const float* __restrict__ lr_vec,
+                                    const float* __restrict__ wd_vec, const int* __restrict__ step0, float lr_mult,
+                                    float beta1, float beta2, float eps, int step, float grad_scale) {
+    const float l1 = logf(beta1), l2 = logf(beta2);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float lr = lr_vec[i] * lr_mult;
+        if (lr == 0.f) continue;  // alignment padding / parameters parked outside every group
+        const float k = static_cast<float>(step - (step0 != nullptr ? step0[i] : 0));
+        const float bc1 = 1.0f - expf(k * l1), bc2_sqrt = sqrtf(1.0f - expf(k * l2));
+        const float gi = g[i] * grad_scale;
+        float pi = p[i] * (1.0f - lr * wd_vec[i]);
+        const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        pi -= (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+        p[i] = pi;
+    }
+}
+
 template <int TM, int TN>
 static int launch_sgemm(const SgemmArgs& a, int ta, int tb, dim3 grid, cudaStream_t s) {
     if (ta && tb)
@@ -1123,5 +1148,18 @@ extern "C" int b200_adamw(float* p, const float* g, float* m, float* v, long lon
     adamw_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
         grad_scale);
+    return launch_status();
+}
+
+extern "C" int b200_adamw_groups(float* p, const float* g, float* m, float* v, long long n, const float* lr_vec,
+                                 const float* wd_vec, const int* step0, float lr_mult, float beta1, float beta2, float eps,
+                                 int step, float grad_scale, void* stream) {
+    if (n < 0 || step < 1) return -1;
+    if (n == 0) return 0;
+    if (p == nullptr || g == nullptr || m == nullptr || v == nullptr || lr_vec == nullptr || wd_vec == nullptr) return -2;
+    long long grid = (n + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    adamw_groups_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, g, m, v, n, lr_vec, wd_vec, step0, lr_mult, beta1, beta2, eps, step, grad_scale);
     return launch_status();
 }

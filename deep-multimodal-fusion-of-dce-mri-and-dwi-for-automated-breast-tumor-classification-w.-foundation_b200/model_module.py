@@ -16,8 +16,10 @@ live in HBM as NHWC bf16; the feature maps handed back in ``aux`` are zero-copy 
 (channels_last) bf16 views of those buffers, 1-channel maps / gates / logits are fp32.
 
 There is no CPU or PyTorch fallback: a forward on a non-CUDA tensor, or without the
-compiled library, raises.  Training-mode forward (batch-statistics BatchNorm, dropout,
-autograd) is not built yet and raises NotImplementedError - see DESIGN.md.
+compiled library, raises.  In training mode (`.train()`) the forward runs train_graph's
+train-mode arithmetic (batch-statistic BatchNorm with running-statistics update, dropout) and
+returns tensors that carry a torch-autograd node: `loss.backward()` runs the explicit backward
+pass on the training kernels (CNN encoder configuration; see train_graph.py).
 """
 from __future__ import annotations
 
@@ -61,6 +63,14 @@ def _container_only(name):
         "ModelMaskHeadBackbone.forward / FusionModel.forward")
 
 
+def _standalone_eval(mod, name):
+    """Stand-alone sub-module forwards run the eval-mode kernels (folded BatchNorm, no dropout); in training mode the
+    sub-modules are driven through their parent's train-mode forward (train_graph)."""
+    if mod.training:
+        raise NotImplementedError(f"{name}.forward in training mode: call the parent model (ModelMaskHeadBackbone / "
+                                  "FusionModel) in train mode, or .eval() for the stand-alone inference forward")
+
+
 # --------------------------------------------------------------------------------------
 # parameter containers (names mirror the reference so state_dict keys are identical)
 # --------------------------------------------------------------------------------------
@@ -75,7 +85,16 @@ class SEBlock(nn.Module):
                                 nn.Conv2d(mid, channels, 1), nn.Sigmoid())
 
     def forward(self, x):
-        _container_only("SEBlock")
+        """x [B,C,H,W] -> (x * w, w [B,C,1,1]) (reference :41-43) on b200_channel_sums / b200_se_gate / b200_scale_map."""
+        _standalone_eval(self, "SEBlock")
+        xm = _as_nhwc_bf16(x)
+        B, H, W, C = xm.shape
+        se = _se_pack(self, xm.device)
+        gate = torch.empty((B, C), dtype=torch.float32, device=xm.device)
+        nat.se_gate(nat.channel_sums(xm), H * W, se["w1t"], se["b1"], se["w2t"], se["b2"], gate)
+        y = torch.empty_like(xm)
+        nat.scale_map(xm, y, gate=gate)
+        return _nchw(y), gate.view(B, C, 1, 1)
 
 
 class TemporalAttention(SEBlock):
@@ -100,7 +119,23 @@ class MaskGuidedSpatialAttention(nn.Module):
             nn.Conv2d(hidden_channels, 1, 1), nn.Sigmoid())
 
     def forward(self, img_features, mask_features):
-        _container_only("MaskGuidedSpatialAttention")
+        """(img [B,C,H,W], mask logits [B,1,h,w]) -> (img * (1 + gamma * A), A [B,1,H,W]) (reference :75-97)."""
+        _standalone_eval(self, "MaskGuidedSpatialAttention")
+        f = _as_nhwc_bf16(img_features)
+        B, H, W, _ = f.shape
+        dev = f.device
+        m = mask_features.contiguous().float()
+        if m.shape[-2:] != (H, W):
+            up = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+            nat.resize_bilinear_c1(m.view(B, *m.shape[-2:]), up.view(B, H, W))
+            m = up
+        mp = self.mask_processor
+        attn = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+        nat.mask_attention(m, (mp[0].out_channels, _f32(mp[0].weight.flatten(), dev), _f32(mp[1].weight, dev),
+                               _f32(mp[1].bias, dev), _f32(mp[3].weight.flatten(), dev), _f32(mp[3].bias, dev), mp[1].eps), attn)
+        y = torch.empty_like(f)
+        nat.scale_map(f, y, attn=attn, gamma=_f32(self.gamma, dev).reshape(1))
+        return _nchw(y), attn
 
 
 class ReconHead(nn.Module):
@@ -114,7 +149,12 @@ class ReconHead(nn.Module):
                                   nn.Conv2d(in_ch, recon_ch, 3, padding=1))
 
     def forward(self, x):
-        _container_only("ReconHead")
+        """x [B,C,H,W] -> reconstruction [B,1,H,W] fp32 (reference :113-125; recon_ch = 1, no up-sampling)."""
+        _standalone_eval(self, "ReconHead")
+        if self.upsample:
+            raise NotImplementedError("ReconHead(upsample=True) (unused by the reference models)")
+        xm = _as_nhwc_bf16(x)
+        return _recon(_recon_pack(self, xm.device), xm).unsqueeze(1)
 
 
 class MaskHeadResize(nn.Module):
@@ -137,7 +177,13 @@ class MaskHeadResize(nn.Module):
         self.out = nn.Conv2d(mid_ch, out_ch, 1)
 
     def forward(self, x):
-        _container_only("MaskHeadResize")
+        """x [B,C,H,W] -> mask logits [B,1,out,out] fp32 (reference :197-215)."""
+        _standalone_eval(self, "MaskHeadResize")
+        xm = _as_nhwc_bf16(x)
+        dev = xm.device
+        mk = {"pre_w": _conv_w_bf16(self.pre, dev), "pre_b": _f32(self.pre.bias, dev), "down": _mask_down_pack(self, dev),
+              "out_w": _f32(self.out.weight.flatten(), dev), "out_b_host": float(self.out.bias.detach().float().cpu().item())}
+        return _mask_head(mk, xm, self.out_size)
 
 
 class ResNetLiteBlock_withRecon(nn.Module):
@@ -172,7 +218,29 @@ class ResNetLiteBlock_withRecon(nn.Module):
         self.reconstruct = ReconHead(out_ch, recon_ch, upsample=False, dim=dim) if self.recon_ch > 0 else None
 
     def forward(self, x):
-        _container_only("ResNetLiteBlock_withRecon")
+        """x [B,Cin,H,W] (Cin a multiple of 64) -> (out [B,Cout,H/s,W/s], recon [B,1,H/s,W/s] | None) (reference :298-316)."""
+        _standalone_eval(self, "ResNetLiteBlock_withRecon")
+        xm = _as_nhwc_bf16(x)
+        if xm.shape[-1] % 64:
+            raise NotImplementedError("stand-alone block forward needs >= 64 input channels (block1 reads the raw input "
+                                      "through the encoder's fused stem)")
+        dev = xm.device
+        pk = _block_pack(self, dev)
+        pk["stride"], pk["downsample_each_repeat"] = self.stride, bool(self.downsample_each_repeat) and len(self.bottlenecks) > 1
+        for bt in pk["bott"]:
+            bt["w0"] = _conv_w_bf16(bt["conv0"], dev)
+        st = self.stride
+        b0 = pk["bott"][0]
+        if "skip" in pk:
+            skip = nat.conv_gemm(xm, _conv_w_bf16(pk["skip"]["conv"], dev), taps=1, scale=pk["skip"]["s"], bias=pk["skip"]["b"],
+                                 stride=st)
+        else:
+            skip = xm
+        mid = nat.conv_gemm(xm, b0["w0"], taps=1, scale=b0["s1"], bias=b0["b1"], act=1, stride=st)
+        host = ModelMaskHeadBackbone.__new__(ModelMaskHeadBackbone)
+        host._drop = None
+        out, rec, _, _ = ModelMaskHeadBackbone._run_block(host, pk, mid, skip, True)
+        return _nchw(out), (rec.unsqueeze(1) if rec is not None else None)
 
 
 class Projector(nn.Module):
@@ -186,7 +254,18 @@ class Projector(nn.Module):
                                   nn.Conv2d(proj_dim, proj_dim, 1, bias=False), nn.BatchNorm2d(proj_dim), nn.GELU())
 
     def forward(self, x):
-        _container_only("Projector")
+        """x [B,C,H,W] (C >= 64, or a 1-channel fp32 map) -> [B,proj_dim,H,W] (reference :346-348)."""
+        _standalone_eval(self, "Projector")
+        if x.shape[1] == 1:
+            src = x[:, 0].contiguous().float()
+            pp = _proj_pack(self, src.device)
+            g = torch.empty((*src.shape, pp["w0_vec"].numel()), dtype=torch.bfloat16, device=src.device)
+            nat.lift_c1(src, pp["w0_vec"], pp["s0"], pp["b0"], g)
+        else:
+            xm = _as_nhwc_bf16(x)
+            pp = _proj_pack(self, xm.device)
+            g = nat.conv_gemm(xm, pp["w0"], taps=1, scale=pp["s0"], bias=pp["b0"], act=1)
+        return _nchw(nat.conv_gemm(g, pp["w3"], taps=1, scale=pp["s3"], bias=pp["b3"], act=1))
 
 
 class ClassificationHead(nn.Module):
@@ -200,7 +279,14 @@ class ClassificationHead(nn.Module):
         self.normalize = normalize
 
     def forward(self, x):
-        _container_only("ClassificationHead")
+        """x [B,C,H,W] -> logits [B,K] fp32: GAP, L2-normalise, Linear (reference :364-369)."""
+        _standalone_eval(self, "ClassificationHead")
+        xm = _as_nhwc_bf16(x)
+        B, H, W, _ = xm.shape
+        logits = torch.empty((B, self.fc.out_features), dtype=torch.float32, device=xm.device)
+        nat.cls_head(nat.channel_sums(xm), None, H * W, _f32(self.fc.weight, xm.device), _f32(self.fc.bias, xm.device),
+                     self.normalize, logits)
+        return logits
 
 
 class FeatureDownAlign(nn.Module):
@@ -218,7 +304,14 @@ class FeatureDownAlign(nn.Module):
             self.proj = nn.Identity()
 
     def forward(self, x):
-        _container_only("FeatureDownAlign")
+        """x [B,Cin,H,W] -> conv + BN + GELU (1x1, or 3x3 stride 2 when `downsample`) (reference :393-396)."""
+        _standalone_eval(self, "FeatureDownAlign")
+        if isinstance(self.proj, nn.Identity):
+            return x
+        xm = _as_nhwc_bf16(x)
+        s, b = _bn_fold(self.proj[1], xm.device)
+        taps, st = (9, 2) if self.downsample else (1, 1)
+        return _nchw(nat.conv_gemm(xm, _conv_w_bf16(self.proj[0], xm.device), taps=taps, scale=s, bias=b, act=1, stride=st))
 
 
 class _DynamoDisabled(nn.Module):
@@ -261,7 +354,20 @@ class BackboneAdapter(nn.Module):
                 nn.Conv2d(cout, cout, 3, padding=1), nn.BatchNorm2d(cout), nn.GELU())
 
     def forward(self, x):
-        _container_only("BackboneAdapter")
+        """x [B,C,H,W] normalised input -> (f1_b, f2_b, f3_b) (reference :449-476): backbone chains + the two 3x3
+        conv + BN + GELU necks."""
+        _standalone_eval(self, "BackboneAdapter")
+        if not hasattr(self.backbone, "forward_chains"):
+            raise NotImplementedError("BackboneAdapter needs a backbone from foundation_model.build_medical_backbone")
+        dev = x.device
+        outs = []
+        for i, cat in enumerate(self.backbone.forward_chains(x.contiguous().float(), self.selected_indices_chains, None)):
+            nk = self.necks[f"f{i + 1}"]
+            s0, b0 = _bn_fold(nk[1], dev, nk[0].bias)
+            s3, b3 = _bn_fold(nk[4], dev, nk[3].bias)
+            t = nat.conv_gemm(cat, _conv_w_bf16(nk[0], dev), taps=9, scale=s0, bias=b0, act=1)
+            outs.append(_nchw(nat.conv_gemm(t, _conv_w_bf16(nk[3], dev), taps=9, scale=s3, bias=b3, act=1)))
+        return tuple(outs)
 
 
 class GatingAttention(nn.Module):
@@ -273,7 +379,23 @@ class GatingAttention(nn.Module):
         self.fc = nn.Linear(feat_dim * 2 + (2 if use_mask_attention else 0), 2)
 
     def forward(self, pvec_dwi, pvec_dce, dwi_mask=None, dce_mask=None):
-        _container_only("GatingAttention")
+        """pooled vectors [B,C] (+ encoder mask logits) -> softmax gating weights [B,2] (reference :758-780)."""
+        pd_, pc_ = pvec_dwi.contiguous().float(), pvec_dce.contiguous().float()
+        if not pd_.is_cuda:
+            raise nat.B200NativeError("GatingAttention.forward needs CUDA tensors (no CPU path)")
+        B, C = pd_.shape
+        use = self.use_mask_attention and dwi_mask is not None and dce_mask is not None
+        md = dwi_mask.contiguous().float() if use else None
+        mc = dce_mask.contiguous().float() if use else None
+        D = 2 * C + (2 if use else 0)
+        if self.fc.in_features != D:
+            raise RuntimeError("GatingAttention: the Linear expects the mask confidences it was built with")
+        gx = torch.empty((B, D), dtype=torch.float32, device=pd_.device)
+        alpha = torch.empty((B, 2), dtype=torch.float32, device=pd_.device)
+        nat._call("b200_gating_fwd", None, nat._ptr(pd_), nat._ptr(pc_), B, C, 1, nat._ptr(md), nat._ptr(mc),
+                  md[0].numel() if use else 0, nat._ptr(_f32(self.fc.weight, pd_.device)), nat._ptr(_f32(self.fc.bias, pd_.device)),
+                  nat._ptr(gx), nat._ptr(alpha), nat._stream())
+        return alpha
 
 
 class FusionReduce(nn.Module):
@@ -285,7 +407,11 @@ class FusionReduce(nn.Module):
         self.reduce = nn.Sequential(nn.Conv2d(in_ch, out_ch, 1, bias=False), nn.BatchNorm2d(out_ch), nn.GELU())
 
     def forward(self, x):
-        _container_only("FusionReduce")
+        """x [B,2C,H,W] -> 1x1 conv + BN + GELU (reference :793-794)."""
+        _standalone_eval(self, "FusionReduce")
+        xm = _as_nhwc_bf16(x)
+        s, b = _bn_fold(self.reduce[1], xm.device)
+        return _nchw(nat.conv_gemm(xm, _conv_w_bf16(self.reduce[0], xm.device), taps=1, scale=s, bias=b, act=1))
 
 
 class CrossAttentionBlock(nn.Module):
@@ -298,7 +424,25 @@ class CrossAttentionBlock(nn.Module):
                                       nn.Linear(channels, channels))
 
     def forward(self, query_tokens, key_value_tokens):
-        _container_only("CrossAttentionBlock")
+        """(q tokens [B,T,C], kv tokens [B,T,C]) -> (attn_out + FFN(attn_out) [B,T,C], head-averaged weights [B,T,T])
+        (reference :814-818) on the fp32 token kernels (b200_sgemm / b200_mha_fwd / b200_ln_fwd)."""
+        q_, kv_ = query_tokens.contiguous().float(), key_value_tokens.contiguous().float()
+        if not q_.is_cuda:
+            raise nat.B200NativeError("CrossAttentionBlock.forward needs CUDA tensors (no CPU path)")
+        B, T, C = q_.shape
+        dev, R, NH = q_.device, B * T, self.cross_attn.num_heads
+        z = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+        Win, b_in = _f32(self.cross_attn.in_proj_weight, dev), _f32(self.cross_attn.in_proj_bias, dev)
+        Q, KV, P, CTX, AO, LN, G1, LOW = z(R, C), z(R, 2 * C), z(B, NH, T, T), z(R, C), z(R, C), z(R, C), z(R, C), z(R, C)
+        nat.sgemm(q_.view(R, C), Win[:C], Q, trans_b=True, bias=b_in[:C])
+        nat.sgemm(kv_.view(R, C), Win[C:], KV, trans_b=True, bias=b_in[C:])
+        nat.mha_fwd(Q, KV[:, :C], KV[:, C:], B, NH, P, CTX)
+        nat.sgemm(CTX, _f32(self.cross_attn.out_proj.weight, dev), AO, trans_b=True, bias=_f32(self.cross_attn.out_proj.bias, dev))
+        ln = self.attn_ffn[0]
+        nat.ln_fwd(AO, _f32(ln.weight, dev), _f32(ln.bias, dev), ln.eps, LN, z(R), z(R))
+        nat.sgemm(LN, _f32(self.attn_ffn[1].weight, dev), G1, trans_b=True, bias=_f32(self.attn_ffn[1].bias, dev), act=1)
+        nat.sgemm(G1, _f32(self.attn_ffn[3].weight, dev), LOW, trans_b=True, bias=_f32(self.attn_ffn[3].bias, dev), res=AO)
+        return LOW.view(B, T, C), P.mean(dim=1)
 
 
 # --------------------------------------------------------------------------------------
@@ -888,10 +1032,15 @@ class ModelMaskHeadBackbone(nn.Module):
     def forward(self, x, masks=None, plane_mean=None):
         """x [B,C,H,W] normalised fp32.  `plane_mean` (optional, [B*C] fp32) is the per-plane mean the
         normaliser kernels can emit, which saves one pass over x."""
-        if self.training:
-            raise NotImplementedError("training-mode forward is not built in the B200 path yet; call .eval()")
         if not x.is_cuda:
             raise nat.B200NativeError("ModelMaskHeadBackbone.forward needs a CUDA tensor (no CPU path)")
+        if self.training:
+            # train mode (reference :298-316, :645-733 under nn.Module.train()): batch-statistic BatchNorm with
+            # running-statistics update, active dropout, and a torch-autograd node whose backward runs the explicit
+            # backward pass of train_graph on the training kernels
+            from train_graph import encoder_train_forward_autograd
+
+            return encoder_train_forward_autograd(self, x)
         p_drop = self._mc_dropout_p()
         if p_drop > 0 and self.use_hybrid_transformer:
             raise NotImplementedError("MC dropout with the hybrid transformer stage (its attention / MLP dropouts)")
@@ -1100,7 +1249,11 @@ class FusionModel(nn.Module):
 
     def forward(self, raw_feats_dwi, raw_feats_dce, dwi_mask_pred=None, dce_mask_pred=None):
         if self.training:
-            raise NotImplementedError("training-mode forward is not built in the B200 path yet; call .eval()")
+            if not raw_feats_dwi[-1].is_cuda:
+                raise nat.B200NativeError("feature maps must be CUDA tensors (no CPU path)")
+            from train_graph import fusion_train_forward_autograd
+
+            return fusion_train_forward_autograd(self, raw_feats_dwi, raw_feats_dce, dwi_mask_pred, dce_mask_pred)
         f3d, f3c = _as_nhwc_bf16(raw_feats_dwi[-1]), _as_nhwc_bf16(raw_feats_dce[-1])
         B, H, W, _ = f3d.shape
         dev = f3d.device

@@ -13,7 +13,7 @@ import torch
 
 import b200_native as nat
 
-__all__ = ["NyulStandardizer", "preprocess_dce", "zero_to_one_adc", "normalize_adc", "preprocess_adc",
+__all__ = ["NyulStandardizer", "preprocess_dce", "prescale_dce", "prep_data_by_mod", "zero_to_one_adc", "normalize_adc", "preprocess_adc",
            "compute_adc_map"]
 
 
@@ -129,3 +129,24 @@ def compute_adc_map(dwi_imgs, bvals, eps=1e-6):
 def compute_adc_map_batch(dwi, bvals, eps=1e-6):
     """Batched form: dwi [B,C,H,W] CUDA -> [B,1,H,W] (one launch)."""
     return nat.adc_map(dwi, torch.as_tensor(bvals, dtype=torch.float32).to(dwi.device), eps)
+
+
+def prescale_dce(imgs):
+    """DCE pre-scale of `prep_data_by_mod` (reference prepare_single_model.py:337-343): every case [N,C,H,W] divided by
+    its maximum over all channels and pixels - `imgs / imgs_max[:, None, None, None]`.  Runs on the GPU
+    (b200_case_max_scale, one CTA per case); a CPU tensor raises (no CPU path)."""
+    if not imgs.is_cuda:
+        raise nat.B200NativeError("prescale_dce needs a CUDA tensor (no CPU path)")
+    x = imgs.contiguous().float()
+    out = torch.empty_like(x)
+    nat._call("b200_case_max_scale", None, nat._ptr(x), x.shape[0], x[0].numel(), nat._ptr(out), nat._stream())
+    return out
+
+
+def prep_data_by_mod(method, bvals, imgs, test_imgs, parameters):
+    """The DCE branch of the reference's `prep_data_by_mod` (prepare_single_model.py:311-343): both splits pre-scaled per
+    case; returns (imgs, test_imgs, None) like the reference.  (The DWI branch - ADC maps - is `compute_adc_map` +
+    `preprocess_adc` + `zero_to_one_adc` above.)"""
+    if method != "dce":
+        raise NotImplementedError("prep_data_by_mod: the DCE pre-scale; DWI's ADC maps go through compute_adc_map")
+    return prescale_dce(imgs), prescale_dce(test_imgs), None

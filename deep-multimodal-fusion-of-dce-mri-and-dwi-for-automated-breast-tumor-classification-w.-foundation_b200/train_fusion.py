@@ -2,9 +2,12 @@
 one object, `forward` / `forward_from_inputs` (:200-201, :670-677) and the prediction modes its test loop runs -
 `predict_tta`, `predict_mc_dropout`, `predict_tta_mc`, `predict_custom` (:484-632, :682-702; the default test mode
 is "tta_mc": 4 flips x 10 dropout passes).  Same method names, arguments and return structure; no Lightning
-dependency.  Training: `_shared_step("train")` / `training_step` / `configure_optimizers` run the fusion-head
-fine-tuning step of the frozen-encoder phase - classification + mask dice terms (fusion_train.FusionHeadTrainer);
-the reconstruction / mimic loss terms and unfrozen encoders are not built and raise.
+dependency.  Training: `_shared_step("train")` / `training_step` / `configure_optimizers` / `on_train_epoch_start` run
+the reference's optimisation step - classification + three mask + three reconstruction + mimic terms
+(train_fusion.py:238-296), frozen encoders (train-mode BatchNorm / dropout like Lightning's fit loop, or eval mode with
+parameters_dict["b200_frozen_encoder_mode"] = "eval") or unfrozen ones with the reference's depth-wise parameter
+groups - on train_graph.FullFusionTrainer (explicit backward on the training kernels); the classification + mask
+objective on eval-mode frozen encoders can also run on the fp32 token-shortcut trainer fusion_train.FusionHeadTrainer.
 
 MC dropout follows the reference's switch exactly: `enable_dropout` puts the nn.Dropout sub-modules of the two
 encoders in train mode, `set_batchnorm_eval` keeps BatchNorm frozen, and the encoders' forward then arms the
@@ -163,39 +166,72 @@ class LightningFusionModel(nn.Module):
         raise ValueError(f"Unknown predict mode: {mode}")
 
     # --------------------------------------------------------------- training ----
-    _UNBUILT_TERMS = (("recon_enabled", "reconstruction (train_fusion.py:271-284)"),
-                      ("mimic_enabled", "mimic (train_fusion.py:287-292)"),
-                      ("attn_reg_enabled", "attention regularisation (train_fusion.py:259-262)"))
-
     def _lambda_mask(self):
         mp = self.parameters_dict.get("fusion_model_parameters", {}).get("mask_parameters", {})
         if self.parameters_dict.get("b200_classification_objective_only", False) or not mp.get("mask", False):
             return 0.0
         return float(mp.get("lambda_mask", 0.0))
 
-    def _objective_check(self):
-        """The B200 step computes the classification term (train_fusion.py:238-242) and the mask dice term
-        (:245-255) of the reference's total loss.  Anything else the configuration enables raises unless the caller
-        opted into the classification-only objective with parameters_dict["b200_classification_objective_only"]."""
-        if self.parameters_dict.get("b200_classification_objective_only", False):
-            return
+    def _objective(self):
+        """Which of the reference's loss terms (train_fusion.py:238-296) the configuration turns on.  Everything the
+        reference's default configuration enables is built: classification, the three mask terms, the three
+        reconstruction terms and the mimic term.  Attention-energy / feature-consistency regularisation
+        (`attn_reg_enabled`, off by default; it calls a 2-argument function with 3 arguments in the reference, SURVEY
+        App. A-11) raises; the fusion step's feature-norm term is identically 0 in the reference (its `aux` holds no
+        `raw_feats`, train.py:1021-1030)."""
         fp = self.parameters_dict.get("fusion_model_parameters", {})
-        on = [what for key, what in self._UNBUILT_TERMS if fp.get(key, False)]
+        if fp.get("attn_reg_enabled", False):
+            raise NotImplementedError("attn_reg_enabled: attention-energy / feature-consistency regularisation is not built")
         mp = fp.get("mask_parameters", {})
         if mp.get("mask", False) and mp.get("mask_loss_type", "dice") not in ("dice", "dice_bce"):
             raise ValueError(f"Invalid mask loss: {mp.get('mask_loss_type')}")  # selector_helpers.py:109
-        if on:
-            raise NotImplementedError(
-                "loss terms not built in the B200 training step: " + "; ".join(on) + " - disable them or set "
-                "parameters_dict['b200_classification_objective_only'] = True")
+        cls_only = self.parameters_dict.get("b200_classification_objective_only", False)
+        return {"recon": bool(fp.get("recon_enabled", False)) and not cls_only,
+                "mimic": bool(fp.get("mimic_enabled", False)) and not cls_only,
+                "lambda_recon": float(fp.get("lambda_recon", 0.0)), "lambda_mimic": float(fp.get("lambda_mimic", 0.0))}
+
+    def _encoders_trainable(self):
+        return any(p.requires_grad for m in (self.dwi_model, self.dce_model) for p in m.parameters())
+
+    def _needs_full_trainer(self):
+        obj = self._objective()
+        mode = self.parameters_dict.get("b200_frozen_encoder_mode", "train")
+        return obj["recon"] or obj["mimic"] or self._encoders_trainable() or mode == "train"
+
+    def _group_hparams(self):
+        """(lr, weight_decay) per parameter name, as LightningFusionOptimizerFactory._build_optimizer assigns them
+        (selector_helpers.py:456-518): without `discriminative_lr` one group; with it the depth groups [block1],
+        [block2], [block3 + everything else of the encoders], [fusion head] get lr = base / decay^(depth from the
+        head) and, with `discriminative_reg`, weight decay reg_base * reg_decay^(depth from the head)."""
+        fp = self.parameters_dict.get("fusion_model_parameters", {})
+        op = fp.get("optimizer_parameters", {})
+        base_lr, wd = op.get("lr", 1e-4), op.get("weight_decay", 4e-5)
+        if not op.get("discriminative_lr", False):
+            return lambda name: (base_lr, wd)
+        decay, use_reg = op.get("lr_decay_factor", 2.0), op.get("discriminative_reg", False)
+        reg_base, reg_decay = op.get("reg_base", wd), op.get("reg_decay_factor", 2.0)
+
+        def fn(name):
+            if name.startswith("fusion."):
+                depth = 0
+            elif ".block1." in name:
+                depth = 3
+            elif ".block2." in name:
+                depth = 2
+            else:
+                depth = 1
+            return base_lr / decay ** depth, (reg_base * reg_decay ** depth) if use_reg else wd
+
+        return fn
 
     def configure_optimizers(self):
-        """The fusion-head parameter group of LightningFusionOptimizerFactory (selector_helpers.py:356-520, the only
-        group in the optimiser while `backbone_freeze_on_start`), as a FusionHeadTrainer (flat buffers + fused
-        AdamW).  Loss settings: label_smoothing_alpha, classification_loss_parameters.gamma; `class_weights` (the
-        'wfl' inverse-frequency weights of selector_helpers.py:25-41) via set_class_weights."""
-        from fusion_train import FusionHeadTrainer
-
+        """The optimiser of the fit: the fusion-head group alone while the encoders are frozen
+        (`backbone_freeze_on_start`), every reachable parameter once they are unfrozen.  Loss settings:
+        label_smoothing_alpha, classification_loss_parameters.gamma; `class_weights` (the 'wfl' inverse-frequency
+        weights of selector_helpers.py:25-41) via set_class_weights.  Two implementations behind one interface:
+        train_graph.FullFusionTrainer (any objective, trainable or train-mode encoders - the reference's behaviour) and
+        fusion_train.FusionHeadTrainer (classification + mask terms on eval-mode frozen encoders, fp32 token shortcut;
+        chosen with parameters_dict["b200_frozen_encoder_mode"] = "eval" when recon / mimic are off)."""
         fp = self.parameters_dict.get("fusion_model_parameters", {})
         op = fp.get("optimizer_parameters", {})
         if op.get("name", "adamw").lower() != "adamw" or op.get("amsgrad", False):
@@ -205,21 +241,46 @@ class LightningFusionModel(nn.Module):
             raise RuntimeError("the reference training step requires label_smoothing_enabled")
         cl = fp.get("classification_loss_parameters", {})
         gamma = cl.get("gamma", None)
-        # the fusion head is the LAST group of the discriminative schedule (selector_helpers.py:490-512): its learning
-        # rate is the base rate (decay exponent 0) and its weight decay reg_base when discriminative_reg is on
         wd = op.get("weight_decay", 4e-5)
         if op.get("discriminative_lr", False) and op.get("discriminative_reg", False):
             wd = op.get("reg_base", wd)
+        common = dict(lr=op.get("lr", 1e-4), betas=op.get("betas", (0.9, 0.999)), eps=op.get("eps", 1e-8), weight_decay=wd,
+                      smoothing=fp.get("label_smoothing_alpha", 0.1), gamma=2 if gamma is None else gamma,
+                      class_weights=getattr(self, "_class_weights", None), lambda_mask=self._lambda_mask())
+        self.head_trainer = self.full_trainer = None
+        if self._needs_full_trainer():
+            from train_graph import FullFusionTrainer
+
+            obj = self._objective()
+            if fp.get("mask_parameters", {}).get("mask_loss_type", "dice") != "dice":
+                raise NotImplementedError("the full objective is built with SoftDiceLoss mask terms (mask_loss_type='dice')")
+            self.full_trainer = FullFusionTrainer(
+                self.dwi_model, self.dce_model, self.fusion_model, lambda_recon=obj["lambda_recon"] if obj["recon"] else 0.0,
+                lambda_mimic=obj["lambda_mimic"] if obj["mimic"] else 0.0, group_fn=self._group_hparams(),
+                encoder_mode=self.parameters_dict.get("b200_frozen_encoder_mode", "train"), **common)
+            return self.full_trainer
+        from fusion_train import FusionHeadTrainer
+
         self.head_trainer = FusionHeadTrainer(
-            self.fusion_model, lr=op.get("lr", 1e-4), betas=op.get("betas", (0.9, 0.999)), eps=op.get("eps", 1e-8),
-            weight_decay=wd, smoothing=fp.get("label_smoothing_alpha", 0.1),
-            gamma=2 if gamma is None else gamma, class_weights=getattr(self, "_class_weights", None),
-            lambda_mask=self._lambda_mask(),
-            mask_loss_type=fp.get("mask_parameters", {}).get("mask_loss_type", "dice"))
+            self.fusion_model, mask_loss_type=fp.get("mask_parameters", {}).get("mask_loss_type", "dice"), **common)
         sched = self._build_scheduler(fp.get("scheduler", None), self.head_trainer)
         if sched is None:
             return self.head_trainer
         return {"optimizer": self.head_trainer, "lr_scheduler": sched}   # train_fusion.py:151-161
+
+    def on_train_epoch_start(self):
+        """Gradual unfreezing (train_fusion.py:155-169 -> selector_helpers.py:523-620): after the caller (or the
+        reference's factory) has flipped requires_grad flags, the flat buffers are re-bound to the new trainable set."""
+        tr = getattr(self, "full_trainer", None)
+        if tr is not None:
+            tr.aux_w = self._aux_w()
+            tr.refresh()
+
+    def _aux_w(self):
+        if self.parameters_dict.get("use_simple_aux_loss_scheduling", False):
+            limit = self.parameters_dict.get("aux_loss_weight_epoch_limit", 1)
+            return max(0.0, 1 - getattr(self, "current_epoch", 0) / limit)
+        return 1.0
 
     @staticmethod
     def _build_scheduler(cfg, optimizer):
@@ -265,25 +326,41 @@ class LightningFusionModel(nn.Module):
         return dwi.to(dev), dce.to(dev), (masks.to(dev) if masks is not None else None), labels.long().to(dev)
 
     def _shared_step(self, batch, phase="train", return_preds=False):
-        """train: frozen encoders (eval-mode BatchNorm, no dropout) -> fusion head forward + backward; the gradients
-        are left in the trainer's flat buffer (there is no autograd graph: `optimizer_step` / `fit_batch` apply
-        them).  val / test: inference forward and the hard-label loss (train_fusion.py:241)."""
-        self._objective_check()
+        """train: forward + loss + explicit backward of the configured objective; the gradients are left in the
+        trainer's flat buffer (there is no autograd graph: `optimizer_step` / `fit_batch` apply them).  val / test:
+        inference forward and the hard-label loss (train_fusion.py:241)."""
+        self._objective()
         dwi, dce, masks, labels = self._unpack(batch)
         if phase == "train":
-            if getattr(self, "head_trainer", None) is None:
+            if getattr(self, "head_trainer", None) is None and getattr(self, "full_trainer", None) is None:
                 self.configure_optimizers()
-            if any(p.requires_grad for m in (self.dwi_model, self.dce_model) for p in m.parameters()):
-                raise NotImplementedError("training with unfrozen encoders is not built (freeze them: "
-                                          "backbone_freeze_on_start)")
+            if self.full_trainer is not None:
+                tr = self.full_trainer
+                if tr.encoders_trainable != self._encoders_trainable():
+                    tr.refresh()
+                if masks is None:
+                    raise ValueError("the fusion objective needs the target masks (mask_enabled)")
+                tr.aux_w = self._aux_w()
+                tr.zero_grad()
+                total, _ = tr.forward_backward(dwi, dce, masks, labels)
+                loss = total.clone().squeeze(0)
+                if return_preds:
+                    return loss, tr.logits.clone(), None, tr.fused_mask_logits.unsqueeze(1).clone()
+                return loss
+            if self._encoders_trainable():
+                raise NotImplementedError("unfrozen encoders need the full trainer (configure_optimizers picks it)")
             modes = self._aux_modes()
             self._set_aux_modes(("logits", "logits", modes[2]))  # the step needs f3 and the mask logits only
+            states = [self._get_module_train_states(m) for m in (self.dwi_model, self.dce_model)]
             try:
+                self.dwi_model.eval(), self.dce_model.eval()
                 with torch.no_grad():
                     _, dwi_aux, dwi_mask = self.dwi_model(dwi)
                     _, dce_aux, dce_mask = self.dce_model(dce)
             finally:
                 self._set_aux_modes(modes)
+                for m, st in zip((self.dwi_model, self.dce_model), states):
+                    self._restore_module_train_states(m, st)
             self.head_trainer.zero_grad()
             loss, logits = self.head_trainer.loss_and_grads(dwi_aux["raw_feats"][-1], dce_aux["raw_feats"][-1],
                                                             dwi_mask, dce_mask, labels, masks)
@@ -295,7 +372,8 @@ class LightningFusionModel(nn.Module):
         with torch.no_grad():
             logits, fused_mask, aux = self.forward_from_inputs(dwi, dce)
             tr = getattr(self, "head_trainer", None)
-            gamma = tr.gamma if tr is not None else 2.0
+            ft = getattr(self, "full_trainer", None)
+            gamma = tr.gamma if tr is not None else (ft.loss_hp["gamma"] if ft is not None else 2.0)
             lp = torch.log_softmax(logits, dim=1)  # [B, K] metric arithmetic on the logits
             fw = (1 - lp.exp()) ** gamma
             if getattr(self, "_class_weights", None) is not None:
@@ -317,7 +395,8 @@ class LightningFusionModel(nn.Module):
 
     def optimizer_step(self):
         """Gradient all-reduce over the data-parallel ranks + AdamW; returns the rank-averaged loss."""
-        return self.head_trainer.step()
+        tr = self.full_trainer if getattr(self, "full_trainer", None) is not None else self.head_trainer
+        return tr.step()
 
     def fit_batch(self, batch):
         """One whole optimisation step: training_step + optimizer_step."""

@@ -64,12 +64,16 @@ class Tape:
         else:
             _call("b200_vec_axpby", _P(g), 1.0, 1.0, g.numel(), _P(cur), _s())
 
-    def backward(self):
+    def backward(self, want=()):
+        """Run the recorded steps in reverse.  `want`: input tensors whose accumulated gradient is returned (None where
+        nothing reached them)."""
         for fn in reversed(self.steps):
             fn()
+        out = [self.grads.get(id(t)) for t in want]
         self.steps.clear()
         self.grads.clear()
         self.keep.clear()
+        return out
 
 
 def _grad_buf(p):
@@ -745,7 +749,7 @@ def fusion_forward_train(ops, fm, f3d, f3c, md, mc):
 
 
 def fusion_objective(ops, fo, enc_d, enc_c, masks, labels, dwi_in, dce_in, *, smoothing, gamma, class_weights, lambda_mask,
-                     lambda_recon, lambda_mimic, aux_w=1.0, md=None, mc=None):
+                     lambda_recon, lambda_mimic, aux_w=1.0, md=None, mc=None, frozen_d=None, frozen_c=None):
     """Total loss of LightningFusionModel._shared_step (code/train_fusion.py:238-296) with its gradients seeded on the
     tape:  cls + lambda_mask * (dice(md) + dice(mc) + dice(fused)) / 3
                + lambda_recon * aux_w * (recon_list(dwi) + recon_list(dce) + recon(fused)) / 3
@@ -776,16 +780,18 @@ def fusion_objective(ops, fo, enc_d, enc_c, masks, labels, dwi_in, dce_in, *, sm
     Cc = dce_in.shape[1]
     wr = lambda_recon * aux_w
     scale = 1.0 / (3 * B * H * W)
-    for enc, x in ((enc_d, dwi_in), (enc_c, dce_in)):
-        if enc is None:
-            continue
+    for enc, frozen, x in ((enc_d, frozen_d, dwi_in), (enc_c, frozen_c, dce_in)):
+        src = enc if enc is not None else frozen
+        if src is None or src.get("r1") is None:
+            continue  # no reconstruction list: compute_recon_list_loss returns 0
         for key in ("r1", "r2"):  # compute_recon_list_loss: mean over the list's reconstructions
-            r = enc[key]
-            dr = torch.empty_like(r)
+            r = src[key]
+            dr = torch.empty_like(r) if enc is not None else None  # (a frozen encoder's term is a constant of the loss)
             _call("b200_recon_loss", _P(r), B, r.shape[1], r.shape[2], _P(x), x.shape[1], None, 0, H, W, 1e-3, 0.5 * scale,
                   _P(parts["recon"]), _P(dr), _s())
-            _call("b200_vec_axpby", _P(dr), float(wr), 0.0, dr.numel(), _P(dr), _s())
-            tape.add_grad(r, dr)
+            if enc is not None:
+                _call("b200_vec_axpby", _P(dr), float(wr), 0.0, dr.numel(), _P(dr), _s())
+                tape.add_grad(r, dr)
     r = fo["recon"]
     dr = torch.empty_like(r)
     _call("b200_recon_loss", _P(r), B, r.shape[1], r.shape[2], _P(dwi_in), Cd, _P(dce_in), Cc, H, W, 1e-3, scale,
@@ -815,73 +821,118 @@ _NO_GRAD_PREFIXES_FUS = ("fusion_conv_reduce.", "refine.", "mask_head.down_")
 
 
 class FullFusionTrainer:
-    """One optimisation step of LightningFusionModel with everything unfrozen (code/train_fusion.py:203-321,
-    optimiser code/selector_helpers.py:356-742 reduced to one AdamW group): train-mode forward of both encoders and
-    the fusion head, the full objective, explicit backward, bucketed gradient all-reduce overlapped with the rest of
-    the backward pass, one fused AdamW launch over the flat parameter buffer.
+    """One optimisation step of LightningFusionModel (code/train_fusion.py:203-321; optimiser
+    code/selector_helpers.py:356-742): train-mode forward of the encoders and the fusion head, the full objective,
+    explicit backward, bucketed gradient all-reduce overlapped with the rest of the backward pass, one fused AdamW
+    launch over the flat parameter buffer.
 
-    Parameters the fusion objective cannot reach (the reference's autograd leaves their .grad None and AdamW skips
-    them, SURVEY.md App. A-2: encoder classifier / projectors, unused mask-head down-samplers, the dead reduce / refine
-    branch ...) stay outside the flat buffers and are never touched.  Every other parameter becomes a view of ONE fp32
-    buffer, its gradient a view of a second one; the gradient buffer is cut into buckets in backward order and bucket
-    i's all-reduce (NCCL over NVLink) is issued on a side stream as soon as the tape has passed the forward position
-    where its last gradient is produced.  `encoders_trainable=False` is the reference's frozen phase: the encoders run
-    their eval forward and only the head is in the buffers."""
+    The trainable set is what the reference's optimiser would hold: every parameter with requires_grad that the fusion
+    objective can reach (the reference's autograd leaves .grad None on the rest and AdamW skips them, SURVEY.md App.
+    A-2: encoder classifier / projectors, unused mask-head down-samplers, the dead reduce / refine branch ...).  Frozen
+    encoders (`backbone_freeze_on_start`) therefore put the head alone in the buffers; `refresh()` re-binds the buffers
+    after a gradual-unfreeze event (selector_helpers.py:523-620), keeping the Adam moments of the parameters that were
+    already in and starting the new ones at step 1.  Every trainable parameter is a view of ONE fp32 buffer, its
+    gradient a view of a second one; the gradient buffer is cut into buckets in backward order and bucket i's
+    all-reduce (NCCL over NVLink) is issued on a side stream as soon as the tape has passed the forward position where
+    its last gradient is produced.  `group_fn(name) -> (lr, weight_decay)` gives per-parameter hyper-parameters
+    (discriminative learning rates); `encoder_mode` "train" (what Lightning's fit loop does to the frozen encoders too:
+    batch-statistic BatchNorm with running-statistics update, active dropout) or "eval" for the frozen phase."""
 
     def __init__(self, dwi_model, dce_model, fusion_model, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=4e-5,
                  smoothing=0.1, gamma=1.5, class_weights=None, lambda_mask=0.2, lambda_recon=0.1, lambda_mimic=0.2,
-                 encoders_trainable=True, process_group=None, bucket_mb=8.0, seed=0x5EED):
-        from fusion_train import flat_size, flat_views
-
+                 encoders_trainable=None, encoder_mode="train", group_fn=None, process_group=None, bucket_mb=8.0,
+                 seed=0x5EED):
         self.dwi, self.dce, self.fusion = dwi_model, dce_model, fusion_model
         self.hp = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         self.loss_hp = dict(smoothing=smoothing, gamma=gamma, class_weights=class_weights, lambda_mask=lambda_mask,
                             lambda_recon=lambda_recon, lambda_mimic=lambda_mimic)
-        self.encoders_trainable = bool(encoders_trainable)
+        if encoders_trainable is False:
+            for m in (dwi_model, dce_model):
+                if m is not None:
+                    for q in m.parameters():
+                        q.requires_grad_(False)
+        self.encoder_mode = encoder_mode
+        self.group_fn = group_fn
         self.group = process_group
         self.step_count = 0
+        self.lr_mult = 1.0   # schedulers scale every group's rate through this factor
+        self.aux_w = 1.0     # auxiliary-loss weight schedule (train_fusion.py:220-224)
         dev = next(fusion_model.parameters()).device
         if dev.type != "cuda":
             raise nat.B200NativeError("FullFusionTrainer needs the models on a CUDA device (no CPU path)")
         self.dev = dev
         self.ops = TrainOps(dev, drop_seed=seed)
-        # ---- trainable parameters in FORWARD order, segment by segment (a segment = one all-reduce bucket unit) ----
+        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self._comm = None
+        self._pending = []
+        self.flat = None
+        self.names = []
+        self.refresh()
+
+    # ---- trainable set / flat buffers ---------------------------------------------------------------------------------
+    def _segments(self):
+        """Trainable parameters in FORWARD order, segment by segment (a segment = one all-reduce bucket unit)."""
         def seg(module, prefixes, names_filter):
             return [(n, p) for n, p in module.named_parameters()
                     if p.requires_grad and not n.startswith(prefixes) and names_filter(n)]
 
         segments = []
-        if self.encoders_trainable:
-            for tag, m in (("dwi", dwi_model), ("dce", dce_model)):
-                _check_supported(m)
-                b1 = lambda n: n.startswith(("modality_attention.", "block1."))
-                b2 = lambda n: n.startswith(("block2.", "f1_to_f2.", "mask_head.", "mask_spatial_attention."))
-                b3 = lambda n: n.startswith("block3.")
-                for filt in (b1, b2, b3):
-                    segments.append([(f"{tag}.{n}", p) for n, p in seg(m, _NO_GRAD_PREFIXES_ENC, filt)])
-        segments.append([(f"fusion.{n}", p) for n, p in seg(fusion_model, _NO_GRAD_PREFIXES_FUS, lambda n: True)])
-        self.segments = segments
-        named = [np_ for s in segments for np_ in s]
+        for tag, m in (("dwi", self.dwi), ("dce", self.dce)):
+            if m is None or not any(p.requires_grad for p in m.parameters()):
+                segments += [[], [], []]
+                continue
+            _check_supported(m)
+            b1 = lambda n: n.startswith(("modality_attention.", "block1."))
+            b2 = lambda n: n.startswith(("block2.", "f1_to_f2.", "mask_head.", "mask_spatial_attention."))
+            b3 = lambda n: n.startswith("block3.")
+            for filt in (b1, b2, b3):
+                segments.append([(f"{tag}.{n}", p) for n, p in seg(m, _NO_GRAD_PREFIXES_ENC, filt)])
+        segments.append([(f"fusion.{n}", p) for n, p in seg(self.fusion, _NO_GRAD_PREFIXES_FUS, lambda n: True)])
+        return segments
+
+    def refresh(self):
+        """(Re)bind the flat buffers to the current trainable set (call after requires_grad flags change)."""
+        from fusion_train import flat_size, flat_views
+
+        dev = self.dev
+        old = None
+        if self.flat is not None:
+            old = {n: (m_.clone(), v_.clone(), int(s0.flatten()[0].item()))
+                   for n, m_, v_, s0 in zip(self.names, flat_views(self.params, self.flat["m"]),
+                                            flat_views(self.params, self.flat["v"]),
+                                            flat_views(self.params, self.flat["step0"]))}
+            for p_ in self.params:  # detach the old views so that freed parameters keep their values
+                p_.data = p_.data.clone()
+                p_.grad = None
+        self.segments = self._segments()
+        named = [np_ for s_ in self.segments for np_ in s_]
         self.names = [n for n, _ in named]
-        self.params = [p for _, p in named]
+        self.params = [p_ for _, p_ in named]
+        self.encoders_trainable = any(n.startswith(("dwi.", "dce.")) for n in self.names)
         n = flat_size(self.params)
         self.flat_numel = n
-        self.flat = {k: torch.zeros(n + (1 if k == "g" else 0), dtype=torch.float32, device=dev) for k in ("p", "g", "m", "v")}
-        for p, view in zip(self.params, flat_views(self.params, self.flat["p"])):
-            view.copy_(p.data.float())
-            p.data = view
-        for p, g in zip(self.params, flat_views(self.params, self.flat["g"])):
-            p.grad = g
-        # bucket boundaries (element offsets into the flat buffers) at segment ends, merged up to bucket_mb
+        self.flat = {k: torch.zeros(n + (1 if k == "g" else 0), dtype=torch.float32, device=dev) for k in ("p", "g", "m", "v", "lr", "wd")}
+        self.flat["step0"] = torch.zeros(n, dtype=torch.int32, device=dev)
+        views = {k: flat_views(self.params, self.flat[k]) for k in ("p", "g", "m", "v", "lr", "wd", "step0")}
+        for i, (name, p_) in enumerate(named):
+            views["p"][i].copy_(p_.data.float())
+            p_.data = views["p"][i]
+            p_.grad = views["g"][i]
+            lr_, wd_ = self.group_fn(name) if self.group_fn is not None else (self.hp["lr"], self.hp["weight_decay"])
+            views["lr"][i].fill_(float(lr_))
+            views["wd"][i].fill_(float(wd_))
+            if old is not None and name in old and old[name][0].shape == views["m"][i].shape:
+                views["m"][i].copy_(old[name][0])
+                views["v"][i].copy_(old[name][1])
+                views["step0"][i].fill_(old[name][2])
+            else:
+                views["step0"][i].fill_(self.step_count)  # a parameter that joins now counts its Adam steps from here
         ends, off = [], 0
-        for s in segments:
-            off += flat_size([p for _, p in s])
+        for s_ in self.segments:
+            off += flat_size([p_ for _, p_ in s_])
             ends.append(off)
         self.seg_ends = ends
-        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
-        self._comm = None
-        self._pending = []
-        self.numel = sum(p.numel() for p in self.params)
+        self.numel = sum(p_.numel() for p_ in self.params)
 
     # ---- gradient exchange ---------------------------------------------------------------------------------------------
     def _world(self):
@@ -919,10 +970,30 @@ class FullFusionTrainer:
     def zero_grad(self):
         self.flat["g"].zero_()
 
+    def _frozen_encoder_outputs(self, m, x):
+        """f3 (NHWC bf16) and mask logits [B,h,w] of a frozen encoder: its train-mode forward (batch statistics, dropout,
+        running statistics updated - what the reference's fit loop does to frozen encoders) with the tape discarded, or
+        its eval forward."""
+        if self.encoder_mode == "train":
+            ops = TrainOps(self.dev, drop_seed=self.ops.next_seed())
+            out = encoder_forward_train(ops, m, x, heads=False)
+            ops.tape.steps.clear()
+            return out["f3"], out["mask_pred"], out["r1"], out["r2"]
+        was = m.training
+        m.eval()
+        try:
+            with torch.no_grad():
+                o = m(x, None)
+        finally:
+            m.train(was)
+        rf = o[1].get("recon_feats") or [None, None]
+        r1, r2 = (r[:, 0].contiguous() if r is not None else None for r in rf)
+        return o[1]["raw_feats"][-1].permute(0, 2, 3, 1), o[2][:, 0].contiguous(), r1, r2
+
     def forward_backward(self, dwi_in, dce_in, masks, labels, md=None, mc=None, f3d=None, f3c=None):
         """Forward + loss + backward on one batch (gradients ACCUMULATE into the flat buffer: call zero_grad first).
-        dwi_in / dce_in: normalised fp32 [B,C,H,W].  With frozen encoders pass their eval outputs f3d / f3c (NHWC bf16)
-        and md / mc.  Returns (total, parts)."""
+        dwi_in / dce_in: normalised fp32 [B,C,H,W].  Pre-computed frozen-encoder outputs may be passed as f3d / f3c
+        (NHWC bf16) and md / mc.  Returns (total, parts)."""
         ops = self.ops
         ops.new_step()
         self._reduced_from = self.flat_numel
@@ -930,30 +1001,38 @@ class FullFusionTrainer:
         labels = labels.to(self.dev, torch.int64).contiguous()
         masks = masks.to(self.dev).float().contiguous()
         enc_d = enc_c = None
-        si = 0
-        if self.encoders_trainable:
-            outs = []
-            for m, x in ((self.dwi, dwi_in), (self.dce, dce_in)):
-                # three bucket markers per encoder: they sit at the forward positions of block1 / block2 / block3
-                marks = [self._marker(si), self._marker(si + 1), self._marker(si + 2)]
-                outs.append(_encoder_with_markers(ops, m, x, marks))
-                si += 3
-            enc_d, enc_c = outs
-            f3d, f3c, md, mc = enc_d["f3"], enc_c["f3"], enc_d["mask_pred"], enc_c["mask_pred"]
-        ops.tape.record(self._marker(si))
+        trainable = {"dwi": any(n.startswith("dwi.") for n in self.names), "dce": any(n.startswith("dce.") for n in self.names)}
+        outs = {}
+        for si, (tag, m, x, pre) in enumerate((("dwi", self.dwi, dwi_in, (f3d, md)), ("dce", self.dce, dce_in, (f3c, mc)))):
+            if trainable[tag]:
+                marks = [self._marker(3 * si), self._marker(3 * si + 1), self._marker(3 * si + 2)]
+                outs[tag] = _encoder_with_markers(ops, m, x, marks)
+            elif pre[0] is None:
+                outs[tag] = dict(zip(("f3", "mask_pred", "r1", "r2"), self._frozen_encoder_outputs(m, x)))
+                outs[tag]["frozen"] = True
+            else:
+                outs[tag] = {"f3": pre[0], "mask_pred": pre[1], "frozen": True}
+        enc_d = outs["dwi"] if trainable["dwi"] else None
+        enc_c = outs["dce"] if trainable["dce"] else None
+        f3d, f3c, md, mc = outs["dwi"]["f3"], outs["dce"]["f3"], outs["dwi"]["mask_pred"], outs["dce"]["mask_pred"]
+        ops.tape.record(self._marker(6))
         fo = fusion_forward_train(ops, self.fusion, f3d, f3c, md, mc)
-        total, parts = fusion_objective(ops, fo, enc_d, enc_c, masks, labels, dwi_in, dce_in, md=md, mc=mc, **self.loss_hp)
+        total, parts = fusion_objective(ops, fo, enc_d, enc_c, masks, labels, dwi_in, dce_in, md=md, mc=mc, aux_w=self.aux_w,
+                                        frozen_d=None if trainable["dwi"] else outs["dwi"],
+                                        frozen_c=None if trainable["dce"] else outs["dce"], **self.loss_hp)
         self.flat["g"][self.flat_numel:].copy_(total)   # the loss rides along with the gradients
         ops.tape.backward()
-        if self._reduced_from > 0:  # whatever is left (including the loss slot with the first bucket of the buffer)
+        if self._reduced_from > 0:  # whatever is left
             self._reduce_range(0, self._reduced_from)
         if self._world() > 1:
             self._reduce_range(self.flat_numel, self.flat_numel + 1)
         self.logits = fo["logits"]
+        self.fused_mask_logits = fo["fused_mask"]
         return total, parts
 
     def step(self):
-        """Wait for the gradient exchange, then one fused AdamW launch (grad_scale folds the 1 / world average)."""
+        """Wait for the gradient exchange, then one fused AdamW launch over the flat buffer (per-element learning rate /
+        weight decay / first step; grad_scale folds the 1 / world average).  Returns the rank-averaged loss."""
         world = self._world()
         if self._comm is not None:
             for w in self._pending:
@@ -961,8 +1040,10 @@ class FullFusionTrainer:
             torch.cuda.current_stream(self.dev).wait_stream(self._comm)
         self.step_count += 1
         f = self.flat
-        nat.adamw(f["p"], f["g"][:self.flat_numel], f["m"], f["v"], lr=self.hp["lr"], betas=self.hp["betas"],
-                  eps=self.hp["eps"], weight_decay=self.hp["weight_decay"], step=self.step_count, grad_scale=1.0 / world)
+        _call("b200_adamw_groups", _P(f["p"]), _P(f["g"]), _P(f["m"]), _P(f["v"]), self.flat_numel, _P(f["lr"]), _P(f["wd"]),
+              _P(f["step0"]), float(self.lr_mult), float(self.hp["betas"][0]), float(self.hp["betas"][1]),
+              float(self.hp["eps"]), self.step_count, 1.0 / world, _s())
+        return f["g"][self.flat_numel:] / world
 
     def train_step(self, dwi_in, dce_in, masks, labels, **kw):
         self.zero_grad()
@@ -1032,3 +1113,112 @@ class SingleModelTrainer:
                   weight_decay=self.hp["weight_decay"], step=self.step_count)
         self.logits = out["logits"]
         return total, parts
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# torch.autograd bridge: lets code written against the reference modules - `loss = f(model(x)); loss.backward()`, i.e.
+# the reference's own train.py / train_fusion.py `_shared_step` - drive the training kernels.  One autograd node per
+# module forward; its backward seeds the tape with the incoming gradients and runs it.  Parameter gradients are
+# accumulated by the kernels straight into `param.grad` (the node returns None for them).
+# ------------------------------------------------------------------------------------------------------------------
+def _to_map_grad(g, like):
+    """Incoming autograd gradient -> the layout / dtype of the tape tensor `like` (NHWC bf16 map or fp32 vector)."""
+    if g is None:
+        return None
+    return g.to(like.dtype).contiguous() if g.shape == like.shape else g.reshape(like.shape).to(like.dtype).contiguous()
+
+
+class _EncoderTrainFn(torch.autograd.Function):
+    KEYS = ("logits", "f1", "f2", "f3", "r1", "r2", "p1", "p1_r", "p2", "p2_r", "mask_pred")
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        ops = TrainOps(x.device, drop_seed=getattr(module, "_train_seed", 0x5EED))
+        module._train_seed = (getattr(module, "_train_seed", 0x5EED) * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFF
+        out = encoder_forward_train(ops, module, x)
+        ctx.ops, ctx.out, ctx.n_params = ops, out, len(params)
+        res = tuple(out[k] for k in _EncoderTrainFn.KEYS) + (out["mask_attn_map"], out["mod_attn_map"])
+        ctx.mark_non_differentiable(res[-2], res[-1])
+        return res
+
+    @staticmethod
+    def backward(ctx, *grads):
+        tape = ctx.ops.tape
+        for k, g in zip(_EncoderTrainFn.KEYS, grads):
+            if g is not None:
+                tape.add_grad(ctx.out[k], _to_map_grad(g, ctx.out[k]))
+        tape.backward()
+        return (None, None) + (None,) * ctx.n_params
+
+
+class _FusionTrainFn(torch.autograd.Function):
+    KEYS = ("logits", "fused_mask", "recon", "proj", "p_dwi", "p_dce")
+
+    @staticmethod
+    def forward(ctx, module, f3d, f3c, md, mc, *params):
+        ops = TrainOps(f3d.device)
+        fo = fusion_forward_train(ops, module, f3d, f3c, md, mc)
+        ctx.ops, ctx.fo, ctx.inputs, ctx.n_params = ops, fo, (f3d, f3c, md, mc), len(params)
+        res = tuple(fo[k] for k in _FusionTrainFn.KEYS) + (fo["gating"],)
+        ctx.mark_non_differentiable(res[-1])
+        return res
+
+    @staticmethod
+    def backward(ctx, *grads):
+        tape = ctx.ops.tape
+        for k, g in zip(_FusionTrainFn.KEYS, grads):
+            if g is not None:
+                tape.add_grad(ctx.fo[k], _to_map_grad(g, ctx.fo[k]))
+        want = [t for t in ctx.inputs if t is not None]
+        got = iter(tape.backward(want))
+        gin = tuple(next(got) if t is not None else None for t in ctx.inputs)
+        return (None,) + gin + (None,) * ctx.n_params
+
+
+def encoder_train_forward_autograd(module, x):
+    """ModelMaskHeadBackbone.forward in training mode with torch-autograd semantics: returns the reference's
+    (logits, aux, mask_pred) whose tensors carry a grad_fn."""
+    params = [p for p in module.parameters() if p.requires_grad]
+    x = x.contiguous().float()
+    if not params:  # nothing to differentiate: still the train-mode arithmetic (batch statistics, dropout)
+        ops = TrainOps(x.device)
+        out = encoder_forward_train(ops, module, x)
+        ops.tape.steps.clear()
+        res = tuple(out[k] for k in _EncoderTrainFn.KEYS) + (out["mask_attn_map"], out["mod_attn_map"])
+    else:
+        res = _EncoderTrainFn.apply(module, x, *params)
+    logits, f1, f2, f3, r1, r2, p1, p1_r, p2, p2_r, mask_pred, attn, mod = res
+    nchw = lambda t: t.permute(0, 3, 1, 2)
+    pd = module.proj_dim
+
+    def pooled(t):  # AdaptiveAvgPool2d((proj_dim, proj_dim)) of the reference ahead of the projector: a 2x2 replication
+        t = nchw(t)
+        if t.shape[-1] == pd:
+            return t
+        if pd == 2 * t.shape[-1]:
+            return t.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+        raise NotImplementedError("training path: proj_dim equal to or twice the map size")
+
+    B, C = x.shape[:2]
+    aux = {"raw_feats": [nchw(f1), nchw(f2), nchw(f3)], "recon_feats": [r1.unsqueeze(1), r2.unsqueeze(1)],
+           "proj_pairs": [pooled(p1), pooled(p1_r), pooled(p2), pooled(p2_r)], "mask_attn_map": attn.unsqueeze(1),
+           "mod_attn_map": mod.view(B, C, 1, 1)}
+    return logits, aux, mask_pred.unsqueeze(1)
+
+
+def fusion_train_forward_autograd(module, raw_feats_dwi, raw_feats_dce, dwi_mask_pred, dce_mask_pred):
+    """FusionModel.forward in training mode with torch-autograd semantics."""
+    def nhwc(t):
+        v = t.permute(0, 2, 3, 1)
+        return v if (v.dtype == torch.bfloat16 and v.is_contiguous()) else v.to(torch.bfloat16).contiguous()
+
+    f3d, f3c = nhwc(raw_feats_dwi[-1]), nhwc(raw_feats_dce[-1])
+    md = dwi_mask_pred[:, 0].contiguous().float() if dwi_mask_pred is not None else None
+    mc = dce_mask_pred[:, 0].contiguous().float() if dce_mask_pred is not None else None
+    params = [p for p in module.parameters() if p.requires_grad]
+    res = _FusionTrainFn.apply(module, f3d, f3c, md, mc, *params)
+    logits, fused_mask, recon, proj, p_dwi, p_dce, gating = res
+    nchw = lambda t: t.permute(0, 3, 1, 2)
+    aux = {"proj_fused": nchw(proj), "recon_fused": recon.unsqueeze(1), "gating_weights": gating, "attn_weights": None,
+           "p_dwi": nchw(p_dwi), "p_dce": nchw(p_dce)}
+    return logits, fused_mask.unsqueeze(1), aux

@@ -191,6 +191,10 @@ int b200_nyul_transform_ex(const float* x, float* out, int planes, int C, int n,
                            const double* standard_scale, const int* prev_index, const double* gamma,
                            float* plane_mean, int exact, void* stream);
 
+/* DCE pre-scale of prep_data_by_mod (code/prepare_single_model.py:337-343): out[b] = x[b] / max(x[b]) over all the
+ * channels and pixels of case b (n = C*H*W elements per case; IEEE division, as torch's `imgs / imgs_max`). */
+int b200_case_max_scale(const float* x, int B, long long n, float* out, void* stream);
+
 /* Mean of each fp32 plane (AdaptiveAvgPool2d(1) of SEBlock, code/model_module.py:35). */
 int b200_plane_mean(const float* x, int planes, int n, float* plane_mean, void* stream);
 
@@ -484,6 +488,14 @@ int b200_mask_head_grads(const float* dv, const float* dc0, const float* pre_w, 
 int b200_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+
+/* The same update with per-element hyper-parameters: lr_vec / wd_vec [n] fp32 (learning rate x lr_mult; 0 = skip the
+ * element), step0 [n] int32 or NULL (the element's bias correction counts from step - step0).  Parameter groups of
+ * LightningFusionOptimizerFactory (code/selector_helpers.py:456-518): discriminative learning rates / regularisation
+ * by depth, and groups added later by gradual unfreezing (:523-620) that start their own Adam step count. */
+int b200_adamw_groups(float* p, const float* g, float* m, float* v, long long n, const float* lr_vec, const float* wd_vec,
+                      const int* step0, float lr_mult, float beta1, float beta2, float eps, int step, float grad_scale,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Training step of the encoders / the whole fusion objective (BASELINE configs C1 and C5 with the encoders

@@ -128,14 +128,19 @@ def test_no_cpu_fallback():
     enc = mm.ModelMaskHeadBackbone("dwi", p).eval()
     with pytest.raises(nat.B200NativeError):
         enc(torch.zeros(1, 16, 64, 64))
-    enc.train()
-    with pytest.raises(NotImplementedError):
+    enc.train()   # the train-mode forward runs on the training kernels: still no CPU path
+    with pytest.raises(nat.B200NativeError):
         enc(torch.zeros(1, 16, 64, 64))
     if not torch.cuda.is_available():
         with pytest.raises(nat.B200NativeError):
             ds.DWINormalize()(torch.zeros(4, 8, 8))
-    with pytest.raises(NotImplementedError):
-        mm.SEBlock(8)(torch.zeros(1, 8, 4, 4))
+    with pytest.raises(nat.B200NativeError):   # stand-alone sub-module forwards are kernel-backed too
+        mm.SEBlock(8).eval()(torch.zeros(1, 8, 4, 4))
+    with pytest.raises(NotImplementedError):   # ... and in training mode they are driven through their parent
+        mm.SEBlock(8).train()(torch.zeros(1, 8, 4, 4))
+    fm = mm.FusionModel(p).train()
+    with pytest.raises(nat.B200NativeError):
+        fm([torch.zeros(1, 512, 32, 32)], [torch.zeros(1, 512, 32, 32)], torch.zeros(1, 1, 32, 32), torch.zeros(1, 1, 32, 32))
 
 
 def test_initialize_model_rules():

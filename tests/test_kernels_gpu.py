@@ -482,3 +482,70 @@ def test_batch_augment_matches_torchvision(B, C, H, W):
     for b in range(B):
         want = torch.flip(x[b], dims=[2, 1] if b % 2 == 0 else [2])
         assert torch.equal(out[b], want)
+
+
+def test_standalone_submodule_forwards_vs_oracle():
+    """SEBlock, ReconHead, Projector, ClassificationHead, FeatureDownAlign, MaskHeadResize, MaskGuidedSpatialAttention,
+    ResNetLiteBlock_withRecon, FusionReduce, GatingAttention, CrossAttentionBlock called on their own (reference
+    model_module.py:25-43, :49-97, :100-125, :131-215, :220-316, :323-396, :745-818) against the oracle's functional
+    restatements with the same seeded weights."""
+    import torch.nn.functional as F
+
+    import model_module as mm
+    from oracle import model_oracle as mo
+    from oracle import params as op
+
+    g = torch.Generator().manual_seed(21)
+    dev = "cuda"
+
+    def seeded(mod):
+        sd = op.seeded_state_dict(op.shapes_of(mod.state_dict()), seed=13)
+        mod.load_state_dict(sd)
+        return mod.to(dev).eval(), mo.SD(sd)
+
+    def rel(a, b):
+        return (a.float().cpu() - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
+
+    x = torch.randn(3, 128, 32, 32, generator=g).bfloat16().float()
+    se, sd = seeded(mm.SEBlock(128))
+    y, w = se(x.to(dev))
+    ry, rw = mo.se_block(x, sd)
+    assert rel(y, ry) <= 1e-2 and rel(w, rw) <= 1e-3
+    rh, sd = seeded(mm.ReconHead(128))
+    assert rel(rh(x.to(dev)), mo.recon_head(x, sd)) <= 2e-2
+    pr, sd = seeded(mm.Projector(128, 64))
+    assert rel(pr(x.to(dev)), mo.projector(x, sd)) <= 2e-2
+    ch, sd = seeded(mm.ClassificationHead(128, 4))
+    assert rel(ch(x.to(dev)), mo.classification_head(x, sd)) <= 5e-3
+    fa, sd = seeded(mm.FeatureDownAlign(128, 256, downsample=False))
+    assert rel(fa(x.to(dev)), mo.feature_down_align(x, sd)) <= 2e-2
+    mh, sd = seeded(mm.MaskHeadResize(128))
+    mlog = mh(x.to(dev))
+    assert rel(mlog, mo.mask_head(x, sd)) <= 2e-2
+    ma, sd = seeded(mm.MaskGuidedSpatialAttention(128, 1))
+    mref = mo.mask_head(x, mo.SD(op.seeded_state_dict(op.shapes_of(mm.MaskHeadResize(128).state_dict()), seed=13)))
+    ym, am = ma(x.to(dev), mref.to(dev))
+    rym, ram = mo.mask_spatial_attention(x, mref, sd)
+    assert rel(ym, rym) <= 1e-2 and rel(am, ram) <= 1e-3
+    blk, sd = seeded(mm.ResNetLiteBlock_withRecon(128, 256, recon_ch=1, use_se=True, dropout=0.2))
+    out, rec = blk(x.to(dev))
+    rout, rrec = mo.res_block(x, sd, 1, 1, False, True)
+    assert rel(out, rout) <= 2e-2 and rel(rec, rrec) <= 2e-2
+    fr, sd = seeded(mm.FusionReduce(128, 64))
+    assert rel(fr(x.to(dev)), F.gelu(mo._bn(mo._conv(x, sd.sub("reduce.0")), sd.sub("reduce.1")))) <= 2e-2
+    # per-case vector blocks of the fusion head
+    ga, sd = seeded(mm.GatingAttention(128, use_mask_attention=True))
+    pd_, pc_ = torch.randn(5, 128, generator=g), torch.randn(5, 128, generator=g)
+    md, mc = torch.randn(5, 1, 32, 32, generator=g), torch.randn(5, 1, 32, 32, generator=g)
+    xin = torch.cat([pd_, pc_, md.mean(dim=(2, 3)), mc.mean(dim=(2, 3))], dim=1)
+    ref = torch.softmax(F.linear(xin, sd["fc.weight"], sd["fc.bias"]), dim=1)
+    assert rel(ga(pd_.to(dev), pc_.to(dev), md.to(dev), mc.to(dev)), ref) <= 1e-4
+    ca = mm.CrossAttentionBlock(128, num_heads=4)
+    ca.load_state_dict(op.seeded_state_dict(op.shapes_of(ca.state_dict()), seed=13))
+    q, kv = torch.randn(5, 16, 128, generator=g), torch.randn(5, 16, 128, generator=g)
+    with torch.no_grad():
+        ao, aw = ca.cross_attn(q, kv, kv, need_weights=True)
+        ref_out = ao + ca.attn_ffn(ao)
+    ca.to(dev)
+    got_out, got_w = ca(q.to(dev), kv.to(dev))
+    assert rel(got_out, ref_out) <= 1e-4 and rel(got_w, aw) <= 1e-4

@@ -297,9 +297,14 @@ def test_cpu_input_fails_loudly():
     p, sds, mods = _build()
     with pytest.raises(Exception):
         mods["dwi"](torch.zeros(1, 16, 64, 64))
-    mods["dwi"].train()
-    with pytest.raises(NotImplementedError):
-        mods["dwi"](torch.zeros(1, 16, 64, 64, device=DEV))
+    mods["dwi"].train()   # train mode: batch-statistic BatchNorm on the training kernels, outputs carry a grad_fn
+    x = torch.rand(4, 16, 64, 64, device=DEV)
+    logits, aux, mask = mods["dwi"](x)
+    assert logits.shape == (4, 4) and logits.requires_grad and mask.shape == (4, 1, 32, 32)
+    assert aux["raw_feats"][2].shape == (4, 512, 32, 32) and aux["proj_pairs"][0].shape == (4, 64, 64, 64)
+    with pytest.raises(Exception):
+        mods["dwi"](torch.zeros(1, 16, 64, 64))
+    mods["dwi"].eval()
 
 
 def test_vit_backbone_features_vs_oracle():
@@ -615,3 +620,15 @@ def test_resnet_backbone_and_adapter_path_vs_golden_reference():
     bad = {k: v for k, v in worst.items() if v > 1.5e-1}
     assert not bad, bad
     assert worst["S/dwi/aux.mod_attn_map"] < 1e-5 and worst["S/fusion/aux.gating_weights"] < 5e-3
+
+
+def test_dce_prescale_matches_torch_division():
+    """prep_data_by_mod's per-case max division (prepare_single_model.py:337-343), bit for bit."""
+    g = torch.Generator().manual_seed(3)
+    for shape in ((5, 6, 64, 64), (3, 6, 17, 9)):
+        x = torch.rand(shape, generator=g) * 37.0 + 0.01
+        ref = x / x.reshape(x.size(0), -1).max(dim=1)[0].view(-1, 1, 1, 1)
+        got = b_pre.prescale_dce(x.to(DEV)).cpu()
+        assert torch.equal(got, ref)
+    tr, te, none = b_pre.prep_data_by_mod("dce", None, x.to(DEV), x[:2].to(DEV), {})
+    assert none is None and torch.equal(tr.cpu(), ref) and torch.equal(te.cpu(), ref[:2])

@@ -138,19 +138,41 @@ def test_trainer_refuses_cpu_and_unbuilt_configurations():
         FusionHeadTrainer(mm.FusionModel(params), mask_loss_type="bce")
 
 
-def test_shared_step_rejects_unbuilt_loss_terms():
+def test_shared_step_objective_selection_and_loud_cpu_failure():
+    import b200_native as nat
     import model_module as mm
     import parameters_default as pd
     from train_fusion import LightningFusionModel
 
     params = pd.default_parameters()
     assert LightningFusionModel(None, None, mm.FusionModel(params), params)._lambda_mask() == 0.2
-    params["fusion_model_parameters"]["recon_enabled"] = True
+    params["fusion_model_parameters"].update(recon_enabled=True, lambda_recon=0.1, mimic_enabled=True, lambda_mimic=0.2)
     lm = LightningFusionModel(mm.ModelMaskHeadBackbone("dwi", params), mm.ModelMaskHeadBackbone("dce", params),
                               mm.FusionModel(params), params)
-    batch = (torch.zeros(2, 16, 64, 64), torch.zeros(2, 6, 64, 64), torch.zeros(2, dtype=torch.long))
-    with pytest.raises(NotImplementedError, match="reconstruction"):
+    obj = lm._objective()   # the reference's default objective is built in full ...
+    assert obj == {"recon": True, "mimic": True, "lambda_recon": 0.1, "lambda_mimic": 0.2} and lm._needs_full_trainer()
+    batch = (torch.zeros(2, 16, 64, 64), torch.zeros(2, 6, 64, 64), torch.zeros(2, 1, 32, 32), torch.zeros(2, dtype=torch.long))
+    with pytest.raises(nat.B200NativeError):   # ... on the training kernels: no CPU path
         lm.training_step(batch)
+    params["fusion_model_parameters"]["attn_reg_enabled"] = True
+    with pytest.raises(NotImplementedError, match="attn_reg"):
+        lm.training_step(batch)
+    params["fusion_model_parameters"]["attn_reg_enabled"] = False
+    # depth-wise parameter groups of LightningFusionOptimizerFactory (selector_helpers.py:456-518)
+    params["fusion_model_parameters"]["optimizer_parameters"] = {
+        "name": "adamW", "lr": 3e-4, "weight_decay": 4e-5, "discriminative_lr": True, "lr_decay_factor": 2.0,
+        "discriminative_reg": True, "reg_decay_factor": 0.5, "reg_base": 1e-4}
+    fn = lm._group_hparams()
+    assert fn("fusion.classifier.2.weight") == (3e-4, 1e-4)
+    assert fn("dwi.block3.skip.0.weight") == (1.5e-4, 5e-5) and fn("dce.mask_head.pre.weight") == (1.5e-4, 5e-5)
+    assert fn("dwi.block2.se.fc.1.weight") == (7.5e-5, 2.5e-5) and fn("dce.block1.skip.1.bias") == (3.75e-5, 1.25e-5)
+    # the token-shortcut head trainer serves the classification (+ mask) objective on eval-mode frozen encoders
+    params["b200_frozen_encoder_mode"] = "eval"
+    params["fusion_model_parameters"].update(recon_enabled=False, mimic_enabled=False)
+    for m in (lm.dwi_model, lm.dce_model):
+        for q in m.parameters():
+            q.requires_grad = False
+    assert not lm._needs_full_trainer()
     params["fusion_model_parameters"]["label_smoothing_enabled"] = False
     params["b200_classification_objective_only"] = True
     with pytest.raises(RuntimeError, match="label_smoothing"):

@@ -166,3 +166,59 @@ def test_c5_unfrozen_step_vs_oracle():
         for k, v in m.named_parameters():
             if f"{tag}.{k}" not in named:
                 assert torch.equal(v.detach().cpu(), sds[tag][k]), k
+
+
+def test_reference_style_autograd_loop_drives_the_training_kernels():
+    """The drop-in claim for training: code written against the reference modules - `model.train()`, forward,
+    a torch loss on the outputs, `loss.backward()` (the shape of train.py / train_fusion.py's `_shared_step`) - runs the
+    explicit backward pass through the modules' autograd bridge.  Same objective as test_c5_unfrozen_step_vs_oracle,
+    losses written with torch operators on the module outputs; gradients against the CPU oracle."""
+    import model_module as mm
+    import parameters_default as pd
+
+    hp = {"smoothing": 0.1, "gamma": 1.5, "class_weights": [0.7, 1.3, 1.0, 0.9], "lambda_mask": 0.2, "lambda_recon": 0.1,
+          "lambda_mimic": 0.2}
+    p = pd.default_parameters()
+    for m in ("dwi", "dce", "fusion"):
+        p[f"{m}_model_parameters"]["dropout"] = 0.0
+    mods = {"dwi": mm.ModelMaskHeadBackbone("dwi", p), "dce": mm.ModelMaskHeadBackbone("dce", p), "fusion": mm.FusionModel(p)}
+    sds = {}
+    for k, m in mods.items():
+        sds[k] = op.seeded_state_dict(op.shapes_of(m.state_dict()), seed=7)
+        m.load_state_dict(sds[k])
+        m.to(DEV).train()
+    n = 6
+    dwi_raw, dce, masks, labels = op.synthetic_raw(n, seed=99, kind="S")
+    dwi = dwi_raw / dwi_raw.amax(dim=(1, 2, 3), keepdim=True)
+    x_d, x_c, mk, lb = dwi.to(DEV), dce.to(DEV), masks.to(DEV), labels.to(DEV)
+    # ---- what LightningFusionModel._shared_step does (train_fusion.py:226-296), with torch operators ----
+    _, dwi_aux, dwi_mask = mods["dwi"](x_d)
+    _, dce_aux, dce_mask = mods["dce"](x_c)
+    assert dwi_aux["raw_feats"][2].requires_grad and dwi_mask.requires_grad and dwi_aux["proj_pairs"][0].shape[-1] == 64
+    logits, fused_mask, aux = mods["fusion"](dwi_aux["raw_feats"], dce_aux["raw_feats"], dwi_mask, dce_mask)
+    cw = torch.tensor(hp["class_weights"], device=DEV)
+    tgt = to.smoothed_targets(labels, 4, hp["smoothing"]).to(DEV)
+    cls = to.soft_focal_loss(logits, tgt, hp["gamma"], cw)
+    mask = (to.soft_dice_loss(dwi_mask, mk) + to.soft_dice_loss(dce_mask, mk) + to.soft_dice_loss(fused_mask, mk)) / 3
+
+    def rlist(rs, x):
+        return sum(to.recon_list_loss(r, x) for r in rs) / len(rs)
+
+    recon = (rlist(dwi_aux["recon_feats"], x_d) + rlist(dce_aux["recon_feats"], x_c) +
+             to.recon_list_loss(aux["recon_fused"], torch.cat([x_d, x_c], dim=1))) / 3
+    p1, p1_r, p2, p2_r = aux["proj_fused"][:4]
+    mimic = (to.mimic_feat_loss(p1.float(), p1_r.float()) + to.mimic_feat_loss(p2.float(), p2_r.float())) / 2
+    total = cls + hp["lambda_mask"] * mask + hp["lambda_recon"] * recon + hp["lambda_mimic"] * mimic
+    total.backward()
+    torch.cuda.synchronize()
+    o_total, o_parts, o_grads = _oracle_full_step(sds, p, dwi, dce, masks, labels, hp)
+    assert abs(total.item() - o_total) <= 1e-2 * abs(o_total), (total.item(), o_total)
+    named = {f"{tag}.{k}": v for tag, m in mods.items() for k, v in m.named_parameters()}
+    errs = {k: _rel(named[k].grad, g) for k, g in o_grads.items() if named[k].grad is not None}
+    missing = [k for k, g in o_grads.items() if named[k].grad is None and g.abs().max().item() > 0]
+    assert not missing, missing
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])
+    print(len(errs), "gradients through the autograd bridge; worst:", [(k, f"{v:.2e}") for k, v in worst[:8]])
+    noisy = {k: v for k, v in errs.items() if ".mask_spatial_attention." in k or ".cross_attn_block." in k}
+    rest = {k: v for k, v in errs.items() if k not in noisy}
+    assert np.median(list(errs.values())) <= 2e-2 and max(rest.values()) <= 8e-2 and max(noisy.values()) <= 3e-1, worst[:6]

@@ -380,6 +380,7 @@ def test_lightning_surface_trains_and_inference_sees_the_new_weights():
 
     params = pd.default_parameters()
     params["b200_classification_objective_only"] = True
+    params["b200_frozen_encoder_mode"] = "eval"   # eval-mode frozen encoders + cls (+ mask) objective: the head trainer
     params["fusion_model_parameters"]["optimizer_parameters"] = {"name": "adamW", "lr": 2e-3, "betas": (0.9, 0.999),
                                                                  "eps": 1e-8, "weight_decay": 4e-5}
     mods = {"dwi": mm.ModelMaskHeadBackbone("dwi", params), "dce": mm.ModelMaskHeadBackbone("dce", params),
@@ -408,6 +409,7 @@ def test_lightning_surface_trains_and_inference_sees_the_new_weights():
     assert lm.validation_step(batch).item() < before
     # default objective of the reference minus its unbuilt terms: classification + mask dice, 4-tuple batches
     params2 = pd.default_parameters()
+    params2["b200_frozen_encoder_mode"] = "eval"
     params2["fusion_model_parameters"]["optimizer_parameters"] = params["fusion_model_parameters"]["optimizer_parameters"]
     lm2 = LightningFusionModel(mods["dwi"], mods["dce"], fresh_head, params2)
     masks = op.synthetic_raw(16, seed=3, kind="S")[2]
@@ -415,10 +417,30 @@ def test_lightning_surface_trains_and_inference_sees_the_new_weights():
     l2 = [lm2.fit_batch(batch4).item() for _ in range(12)]
     assert lm2.head_trainer.lambda_mask == 0.2 and len(lm2.head_trainer.names) == 24
     assert l2[-1] < l2[0]
-    for p in mods["dwi"].parameters():
-        p.requires_grad = True
-    with pytest.raises(NotImplementedError):
-        lm.training_step(batch)
+    # the reference's own configuration: reconstruction + mimic terms on, encoders in train mode (frozen first, then
+    # unfrozen through the gradual-unfreeze hook) -> train_graph.FullFusionTrainer behind the same surface
+    params3 = pd.default_parameters()
+    params3["fusion_model_parameters"].update(recon_enabled=True, lambda_recon=0.1, mimic_enabled=True, lambda_mimic=0.2,
+                                              optimizer_parameters=dict(params["fusion_model_parameters"]["optimizer_parameters"],
+                                                                        lr=5e-4))
+    head3 = copy.deepcopy(fresh_head)
+    for m in (mods["dwi"], mods["dce"], head3):
+        m.train()
+    lm3 = LightningFusionModel(mods["dwi"], mods["dce"], head3, params3)
+    l3 = [lm3.fit_batch(batch4).item() for _ in range(8)]
+    assert lm3.full_trainer is not None and not lm3.full_trainer.encoders_trainable
+    assert all(n.startswith("fusion.") for n in lm3.full_trainer.names) and len(lm3.full_trainer.names) == 35
+    assert l3[-1] < l3[0]
+    w_before = mods["dwi"].block3.skip[0].weight.detach().clone()
+    for m in (mods["dwi"], mods["dce"]):
+        for p in m.parameters():
+            p.requires_grad = True
+    lm3.on_train_epoch_start()                      # gradual unfreeze: the flat buffers are re-bound
+    assert lm3.full_trainer.encoders_trainable and len(lm3.full_trainer.names) > 150
+    l4 = [lm3.fit_batch(batch4).item() for _ in range(6)]
+    assert l4[-1] < l4[0] * 1.05 and not torch.equal(mods["dwi"].block3.skip[0].weight.detach(), w_before)
+    for m in (mods["dwi"], mods["dce"]):
+        m.eval()
 
 
 def test_fit_host_equals_step_by_step_training():
