@@ -105,6 +105,9 @@ SIGNATURES = {
     "b200_vit_feature": [_P, _I, _I, _I, _P, _I, _P],
     "b200_linear": [_P, _LL, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _P],
     "b200_dwi_normalize": [_P, _P, _I, _I, _I, _I, _F, _F, _P, _P],
+    "b200_dwi_normalize_ex": [_P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P],
+    "b200_nyul_transform_ex2": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P],
+    "b200_stem_ex": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _F, _F, _P, _I, _P],
     "b200_nyul_transform": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "b200_nyul_transform_ex": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "b200_plane_mean": [_P, _I, _I, _P, _P],
@@ -497,15 +500,25 @@ def flip_planes(x, flip_w, flip_h):
     return out
 
 
-def stem(x, stride, pm, se, wcat, scale, bias, n_skip, n_mid, skip_out, mid_out, mod_attn, dropout=None):
+def stem(x, stride, pm, se, wcat, scale, bias, n_skip, n_mid, skip_out, mid_out, mod_attn, dropout=None, input_norm=None):
+    """input_norm: None (x is normalised), ("dwi", stats [B*C,4] fp32, z_lo, z_hi) or ("nyul", tables [B*C,56] fp64, L):
+    x is the RAW input and the normalisation is applied in the operand load (b200_stem_ex)."""
     if dropout is not None:
         set_dropout(dropout[0], dropout[1], 1)
     B, C_, H, W = x.shape
     w1, b1, w2, b2 = se if se is not None else (None, None, None, None)
     cm = w1.shape[0] if w1 is not None else 0
-    _call("b200_stem", None, _ptr(x), B, C_, H, W, stride, _ptr(pm), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), cm,
-                           _ptr(wcat), _ptr(scale), _ptr(bias), n_skip, n_mid, _ptr(skip_out), _ptr(mid_out),
-                           _ptr(mod_attn), _stream())
+    aff = tab = None
+    z_lo = z_hi = 0.0
+    L = 0
+    if input_norm is not None:
+        if input_norm[0] == "dwi":
+            _, aff, z_lo, z_hi = input_norm
+        else:
+            _, tab, L = input_norm
+    _call("b200_stem_ex", None, _ptr(x), B, C_, H, W, stride, _ptr(pm), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), cm,
+          _ptr(wcat), _ptr(scale), _ptr(bias), n_skip, n_mid, _ptr(skip_out), _ptr(mid_out), _ptr(mod_attn), _ptr(aff),
+          float(z_lo), float(z_hi), _ptr(tab), int(L), _stream())
 
 
 def se_gate(gap_sum, npix, w1t, b1, w2t, b2, gate):

@@ -33,7 +33,12 @@ stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
             const float* __restrict__ scale,  // [n_out]
             const float* __restrict__ bias, int n_skip, int n_mid, __nv_bfloat16* __restrict__ skip_out,
             __nv_bfloat16* __restrict__ mid_out, float* __restrict__ mod_attn, unsigned int drop_thresh,
-            float drop_scale, unsigned int seed_lo, unsigned int seed_hi) {
+            float drop_scale, unsigned int seed_lo, unsigned int seed_hi,
+            // normalisation fused into the operand load (x is then the RAW input):
+            const float* __restrict__ in_affine,  // [B*C][4] {mean, 1/std, scale, offset} from b200_dwi_normalize_ex
+            float z_lo, float z_hi,
+            const double* __restrict__ in_table,  // [B*C][56] composed Nyul table from b200_nyul_transform_ex2
+            int L) {
     extern __shared__ float s_dyn[];
     __shared__ float s_gate[kStemMaxC];
     __shared__ float s_hidden[kStemMaxC];
@@ -43,6 +48,11 @@ stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
     float* s_sc = s_w + C * n_out;          // [n_out]
     float* s_bi = s_sc + n_out;             // [n_out]
     uint32_t* s_out = reinterpret_cast<uint32_t*>(s_bi + n_out);  // [kStemPix][row_words]
+    // per-plane normaliser parameters of this case (8-byte aligned: after an even number of words)
+    constexpr int kTabD = 3 * 16 + 8;  // doubles per plane: orig[16] | slope[16] | value[16] | up[16] as floats
+    double* s_tab = reinterpret_cast<double*>(s_out + ((kStemPix * row_words + 1) & ~1));
+    __shared__ float4 s_aff[kStemMaxC];
+    __shared__ float s_in[kStemMaxC * kStemPix];
     const int b = blockIdx.y;
     const int Ho = H / stride, Wo = W / stride;
     const int npix = Ho * Wo;
@@ -73,6 +83,9 @@ stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
         s_sc[i] = scale[i];
         s_bi[i] = bias[i];
     }
+    if (in_affine != nullptr && tid < C) s_aff[tid] = reinterpret_cast<const float4*>(in_affine)[b * C + tid];
+    if (in_table != nullptr)
+        for (int i = tid; i < C * kTabD; i += kStemThreads) s_tab[i] = in_table[static_cast<size_t>(b) * C * kTabD + i];
     __syncthreads();
 
     const int pp = tid % kStemPix;
@@ -83,15 +96,38 @@ stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int pix0 = tile * kStemPix;
     const int pix = pix0 + pp;
-    float2 xv[CMAX];  // the pixel's gated input, duplicated into both halves of a packed operand
-    {
-        const int ho = pix / Wo, wo = pix - ho * Wo;
-        const float* src = x + (static_cast<size_t>(b) * C * H + static_cast<size_t>(ho) * stride) * W + wo * stride;
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c) {
-            const float v = (c < C && pix < npix) ? __ldg(src + static_cast<size_t>(c) * H * W) * s_gate[c] : 0.f;
-            xv[c] = make_float2(v, v);
+    // the tile's inputs - normalised (when fused) and gated - are staged in shared memory ONCE per (pixel, channel);
+    // the four threads that share a pixel then read them from there (they used to load and transform 4 x each)
+    __syncthreads();  // the previous tile's readers are done with s_in
+    for (int i = tid; i < C * kStemPix; i += kStemThreads) {
+        const int c = i / kStemPix, q = i - c * kStemPix;
+        const int px = pix0 + q;
+        float v = 0.f;
+        if (px < npix) {
+            const int ho = px / Wo, wo = px - ho * Wo;
+            v = __ldg(x + ((static_cast<size_t>(b) * C + c) * H + static_cast<size_t>(ho) * stride) * W + wo * stride);
+            if (in_affine != nullptr) {  // DWINormalize, the instructions of dwi_normalize_reg_kernel's apply step
+                const float4 st = s_aff[c];
+                v = fmaf(fminf(fmaxf((v - st.x) * st.y, z_lo), z_hi), st.z, st.w);
+            } else if (in_table != nullptr) {  // Nyul: the composed piece-wise linear table (nyul_apply, fast path)
+                const double* tb = s_tab + c * kTabD;
+                const float* up = reinterpret_cast<const float*>(tb + 48);
+                int j = 0;
+                for (int t = 1; t < L; ++t) j += (v >= up[t]) ? 1 : 0;
+                const double d = static_cast<double>(v) - tb[j];
+                const float o = static_cast<float>(fma(tb[16 + j], d > 0.0 ? d : 0.0, tb[32 + j]));
+                v = v != v ? v : o;
+            }
+            v *= s_gate[c];
         }
+        s_in[c * kStemPix + q] = v;
+    }
+    __syncthreads();
+    float2 xv[CMAX];  // the pixel's gated input, duplicated into both halves of a packed operand
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        const float v = c < C ? s_in[c * kStemPix + pp] : 0.f;
+        xv[c] = make_float2(v, v);
     }
     const int per_quarter = n_out / 4;
     for (int n0 = quarter * per_quarter; n0 < (quarter + 1) * per_quarter; n0 += kStemCB) {
@@ -496,10 +532,11 @@ static inline int grid_for(size_t work_items, int threads, int max_blocks = 148 
 
 using namespace b200;
 
-extern "C" int b200_stem(const float* x, int B, int C, int H, int W, int stride, const float* plane_mean,
-                         const float* se_w1, const float* se_b1, const float* se_w2, const float* se_b2, int Cm,
-                         const float* wcat, const float* scale, const float* bias, int n_skip, int n_mid,
-                         void* skip_out, void* mid_out, float* mod_attn, void* stream) {
+extern "C" int b200_stem_ex(const float* x, int B, int C, int H, int W, int stride, const float* plane_mean,
+                            const float* se_w1, const float* se_b1, const float* se_w2, const float* se_b2, int Cm,
+                            const float* wcat, const float* scale, const float* bias, int n_skip, int n_mid,
+                            void* skip_out, void* mid_out, float* mod_attn, const float* in_affine, float z_lo, float z_hi,
+                            const double* in_table, int L, void* stream) {
     const b200::PendingDropout drop = b200::take_pending_dropout();  // one shot, consumed even if validation fails
     if (B < 0 || C <= 0 || C > kStemMaxC || Cm > kStemMaxC || H % stride != 0 || W % stride != 0) return -1;
     if (B == 0) return 0;
@@ -511,8 +548,12 @@ extern "C" int b200_stem(const float* x, int B, int C, int H, int W, int stride,
         return -4;
     if (skip_out == nullptr || mid_out == nullptr) return -5;
     const int npix = (H / stride) * (W / stride);
-    const size_t smem = (static_cast<size_t>(C) * n_out + 2 * n_out) * sizeof(float) +
-                        static_cast<size_t>(kStemPix) * (n_out / 2 + 1) * sizeof(uint32_t);
+    if (in_affine != nullptr && in_table != nullptr) return -7;
+    if (in_table != nullptr && (L < 2 || L > 16)) return -7;
+    const size_t out_words = (static_cast<size_t>(kStemPix) * (n_out / 2 + 1) + 1) & ~static_cast<size_t>(1);
+    const size_t smem = (static_cast<size_t>(C) * n_out + 2 * n_out) * sizeof(float) + out_words * sizeof(uint32_t) +
+                        (in_table != nullptr ? static_cast<size_t>(C) * 56 * sizeof(double) : 0);
+    if (((static_cast<size_t>(C) * n_out + 2 * n_out) & 1) != 0) return -6;  // keeps the table 8-byte aligned
     if (smem > 48 * 1024) return -6;  // all supported shapes stay inside the default dynamic limit
     const int n_tiles = (npix + kStemPix - 1) / kStemPix;
     // tiles per CTA: as many as keeps >= ~8 CTAs per SM in the grid
@@ -525,12 +566,21 @@ extern "C" int b200_stem(const float* x, int B, int C, int H, int W, int stride,
         kern<<<grid, kStemThreads, smem, static_cast<cudaStream_t>(stream)>>>(
             x, C, H, W, stride, plane_mean, se_w1, se_b1, se_w2, se_b2, Cm, wcat, scale, bias, n_skip, n_mid,
             static_cast<__nv_bfloat16*>(skip_out), static_cast<__nv_bfloat16*>(mid_out), mod_attn, thresh, dscale,
-            static_cast<unsigned int>(drop.seed), static_cast<unsigned int>(drop.seed >> 32));
+            static_cast<unsigned int>(drop.seed), static_cast<unsigned int>(drop.seed >> 32), in_affine, z_lo, z_hi,
+            in_table, L);
     };
     if (C <= 8) go(stem_kernel<8>);
     else if (C <= 16) go(stem_kernel<16>);
     else go(stem_kernel<32>);
     return launch_status();
+}
+
+extern "C" int b200_stem(const float* x, int B, int C, int H, int W, int stride, const float* plane_mean,
+                         const float* se_w1, const float* se_b1, const float* se_w2, const float* se_b2, int Cm,
+                         const float* wcat, const float* scale, const float* bias, int n_skip, int n_mid,
+                         void* skip_out, void* mid_out, float* mod_attn, void* stream) {
+    return b200_stem_ex(x, B, C, H, W, stride, plane_mean, se_w1, se_b1, se_w2, se_b2, Cm, wcat, scale, bias, n_skip, n_mid,
+                        skip_out, mid_out, mod_attn, nullptr, 0.f, 0.f, nullptr, 0, stream);
 }
 
 extern "C" int b200_se_gate(const float* gap_sum, int B, int C, int Cm, int npix, const float* w1t, const float* b1,

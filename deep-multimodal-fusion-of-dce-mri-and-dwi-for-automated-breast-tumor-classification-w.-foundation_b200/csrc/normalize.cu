@@ -25,7 +25,11 @@ constexpr int kNormThreads = 256;
 template <int VEC>
 __global__ void __launch_bounds__(kNormThreads)
 dwi_normalize_reg_kernel(const float* __restrict__ x, float* __restrict__ out, int planes, int C, int n,
-                         int skip_last, float z_lo, float z_hi, float* __restrict__ plane_mean) {
+                         int skip_last, float z_lo, float z_hi, float* __restrict__ plane_mean,
+                         float* __restrict__ stats_out) {
+    // out == nullptr: statistics only (the consumer applies the map while loading the raw plane: stats_out[plane] =
+    // {mean, 1/std, scale, offset} with y = fma(clamp((x - mean) * (1/std), z_lo, z_hi), scale, offset); a skipped
+    // plane carries {0, 0, 0, 0}, i.e. y = 0).  The arithmetic below and the consumer's are the same instructions.
     // One block-wide barrier per plane.  Each thread accumulates sum(d) and sum(d^2) of d = x - pivot in fp64
     // (pivot = the plane's first sample: shifting makes the one-pass variance as safe as the reference's two
     // passes; fp64 removes what cancellation is left), the block reduces both together with the OUTPUT sum of
@@ -58,23 +62,29 @@ dwi_normalize_reg_kernel(const float* __restrict__ x, float* __restrict__ out, i
         // the next plane's loads are issued before this plane's barrier, so HBM reads stay in flight across it
         const int next = plane + gridDim.x;
         if (next < planes && !skipped(next)) load(next, vn, pivot_n);
-        float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(plane) * n);
+        float4* dst = out != nullptr ? reinterpret_cast<float4*>(out + static_cast<size_t>(plane) * n) : nullptr;
         const bool skip = skipped(plane);
         double sd = 0.0, sq = 0.0;
         if (!skip) {
-            const double pv = static_cast<double>(pivot);
+            // per-thread partial sums of d = x - pivot in fp32 (<= 32 samples per thread: ~1e-7 relative error, the
+            // shift keeps the variance well conditioned); fp64 only across threads.  The fp64 per-element form made
+            // the kernel issue bound (ncu: 67 % issue-active, 4 200 warp instructions per plane).
+            float fs = 0.f, fq = 0.f;
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                const double a = static_cast<double>(v[j].x) - pv, b = static_cast<double>(v[j].y) - pv;
-                const double c = static_cast<double>(v[j].z) - pv, d = static_cast<double>(v[j].w) - pv;
-                sd += (a + b) + (c + d);
-                sq = fma(a, a, sq);
-                sq = fma(b, b, sq);
-                sq = fma(c, c, sq);
-                sq = fma(d, d, sq);
+                const float a = v[j].x - pivot, b = v[j].y - pivot, c = v[j].z - pivot, d = v[j].w - pivot;
+                fs += (a + b) + (c + d);
+                fq = fmaf(a, a, fq);
+                fq = fmaf(b, b, fq);
+                fq = fmaf(c, c, fq);
+                fq = fmaf(d, d, fq);
             }
+            sd = static_cast<double>(fs);
+            sq = static_cast<double>(fq);
         }
-        double r0 = warp_sum(sd), r1 = warp_sum(sq), r2 = warp_sum(osum_prev);
+        // fp32 shuffles inside the warp (32 partials of <= 32 samples each), fp64 across the warps
+        double r0 = static_cast<double>(warp_sum(static_cast<float>(sd))), r1 = static_cast<double>(warp_sum(static_cast<float>(sq)));
+        double r2 = static_cast<double>(warp_sum(static_cast<float>(osum_prev)));
         if (lane == 0) {
             red[buf][warp][0] = r0;
             red[buf][warp][1] = r1;
@@ -92,7 +102,10 @@ dwi_normalize_reg_kernel(const float* __restrict__ x, float* __restrict__ out, i
         if (plane_mean != nullptr && threadIdx.x == 0 && prev_plane >= 0) plane_mean[prev_plane] = static_cast<float>(r2 / n);
         float osum = 0.f;
         if (skip) {
-            for (int i = threadIdx.x; i < n4; i += kNormThreads) __stcs(dst + i, make_float4(0.f, 0.f, 0.f, 0.f));
+            if (dst != nullptr)
+                for (int i = threadIdx.x; i < n4; i += kNormThreads) __stcs(dst + i, make_float4(0.f, 0.f, 0.f, 0.f));
+            if (stats_out != nullptr && threadIdx.x == 0)
+                *reinterpret_cast<float4*>(stats_out + 4 * static_cast<size_t>(plane)) = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
             const double md = r0 / n;
             const float mean = static_cast<float>(static_cast<double>(pivot) + md);
@@ -103,17 +116,28 @@ dwi_normalize_reg_kernel(const float* __restrict__ x, float* __restrict__ out, i
             // (<= 2 ulp from the divided form, far inside the 1e-5 tolerance): IEEE fp32 division costs ~10
             // issue slots and would make this HBM-bound kernel ALU-bound.
             const float inv_sd = 1.0f / sdev;
+            if (stats_out != nullptr && threadIdx.x == 0)
+                *reinterpret_cast<float4*>(stats_out + 4 * static_cast<size_t>(plane)) = make_float4(mean, inv_sd, inv_range, off);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 const int i = threadIdx.x + j * kNormThreads;
                 if (i < n4) {
                     float4 o;
-                    o.x = fmaf(fminf(fmaxf((v[j].x - mean) * inv_sd, z_lo), z_hi), inv_range, off);
-                    o.y = fmaf(fminf(fmaxf((v[j].y - mean) * inv_sd, z_lo), z_hi), inv_range, off);
-                    o.z = fmaf(fminf(fmaxf((v[j].z - mean) * inv_sd, z_lo), z_hi), inv_range, off);
-                    o.w = fmaf(fminf(fmaxf((v[j].w - mean) * inv_sd, z_lo), z_hi), inv_range, off);
-                    osum += (o.x + o.y) + (o.z + o.w);
-                    __stcs(dst + i, o);
+                    // (x - mean) * inv_sd as packed fp32x2 (FADD2 / FMUL2 / FFMA2 round exactly like the scalar forms)
+                    const float2 nm = make_float2(-mean, -mean), is2 = make_float2(inv_sd, inv_sd);
+                    const float2 ir2 = make_float2(inv_range, inv_range), of2 = make_float2(off, off);
+                    float2 a = __fmul2_rn(__fadd2_rn(make_float2(v[j].x, v[j].y), nm), is2);
+                    float2 b = __fmul2_rn(__fadd2_rn(make_float2(v[j].z, v[j].w), nm), is2);
+                    a.x = fminf(fmaxf(a.x, z_lo), z_hi);
+                    a.y = fminf(fmaxf(a.y, z_lo), z_hi);
+                    b.x = fminf(fmaxf(b.x, z_lo), z_hi);
+                    b.y = fminf(fmaxf(b.y, z_lo), z_hi);
+                    a = __ffma2_rn(a, ir2, of2);
+                    b = __ffma2_rn(b, ir2, of2);
+                    o = make_float4(a.x, a.y, b.x, b.y);
+                    const float2 s2 = __fadd2_rn(a, b);
+                    osum += s2.x + s2.y;
+                    if (dst != nullptr) __stcs(dst + i, o);
                 }
             }
         }
@@ -257,7 +281,8 @@ __device__ __forceinline__ void nyul_apply(const float* s_val, int L, int c, int
                                            const double* __restrict__ avg_landmarks,
                                            const double* __restrict__ standard_scale,
                                            const double* __restrict__ gamma, Load load, float* __restrict__ dst,
-                                           float* __restrict__ plane_mean, const float* __restrict__ gsrc = nullptr) {
+                                           float* __restrict__ plane_mean, const float* __restrict__ gsrc = nullptr,
+                                           double* __restrict__ table_out = nullptr) {
     __shared__ double s_orig[kMaxLandmarks], s_avg[kMaxLandmarks], s_std[kMaxLandmarks];
     __shared__ double s_slope1[kMaxLandmarks], s_slope2[kMaxLandmarks];
     __shared__ float s_origf[kMaxLandmarks], s_avgf[kMaxLandmarks];
@@ -298,6 +323,13 @@ __device__ __forceinline__ void nyul_apply(const float* s_val, int L, int c, int
                 m = __ddiv_rn(__dadd_rn(s_std[t + 1], -s_std[t]), __dadd_rn(s_orig[t + 1], -s_orig[t]));
             s_tm[t] = m;
             s_up[t] = __double2float_ru(s_orig[t]);
+            if (table_out != nullptr) {  // per plane: orig[16] | slope[16] | value[16] (fp64) | up[16] (fp32, in 8 doubles)
+                double* tb = table_out + static_cast<size_t>(plane) * (3 * kMaxLandmarks + kMaxLandmarks / 2);
+                tb[t] = s_orig[t];
+                tb[kMaxLandmarks + t] = m;
+                tb[2 * kMaxLandmarks + t] = s_tc[t];
+                reinterpret_cast<float*>(tb + 3 * kMaxLandmarks)[t] = s_up[t];
+            }
         }
         __syncthreads();
     }
@@ -320,19 +352,20 @@ __device__ __forceinline__ void nyul_apply(const float* s_val, int L, int c, int
         const float o = static_cast<float>(fma(s_tm[j], d > 0.0 ? d : 0.0, s_tc[j]));
         return v != v ? v : o;
     };
+    if (plane_mean == nullptr && dst == nullptr) return;  // tables only
     if (gsrc != nullptr && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(gsrc) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
         // plane read straight from global / L2: 16-byte loads and stores, four independent interpolations per trip
         for (int i = tid; i < (n >> 2); i += blockDim.x) {
             const float4 q4 = __ldg(reinterpret_cast<const float4*>(gsrc) + i);
             const float4 o = make_float4(map(q4.x), map(q4.y), map(q4.z), map(q4.w));
             osum += (static_cast<double>(o.x) + static_cast<double>(o.y)) + (static_cast<double>(o.z) + static_cast<double>(o.w));
-            __stcs(reinterpret_cast<float4*>(dst) + i, o);
+            if (dst != nullptr) __stcs(reinterpret_cast<float4*>(dst) + i, o);
         }
     } else {
         for (int i = tid; i < n; i += blockDim.x) {
             const float o = map(load(i));
             osum += static_cast<double>(o);
-            __stcs(dst + i, o);
+            if (dst != nullptr) __stcs(dst + i, o);
         }
     }
     if (plane_mean != nullptr) {
@@ -355,7 +388,7 @@ nyul_transform_kernel(const float* __restrict__ x, float* __restrict__ out, int 
                       const double* __restrict__ standard_scale,  // [L]
                       const int* __restrict__ prev_index,         // [L] floor(q*(n-1))
                       const double* __restrict__ gamma,           // [L] fractional part
-                      float* __restrict__ plane_mean) {
+                      float* __restrict__ plane_mean, double* __restrict__ table_out) {
     extern __shared__ float s_x[];  // npad floats: the plane (later sorted in place on the fallback path)
     __shared__ int s_hist[kNyulBins];
     __shared__ unsigned char s_mark[kNyulBins];
@@ -370,7 +403,7 @@ nyul_transform_kernel(const float* __restrict__ x, float* __restrict__ out, int 
     const int c = plane % C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* src = x + static_cast<size_t>(plane) * n;
-    float* dst = out + static_cast<size_t>(plane) * n;
+    float* dst = out != nullptr ? out + static_cast<size_t>(plane) * n : nullptr;
     const int R = 2 * L;
 
     // ---- load, min / max ----
@@ -520,7 +553,7 @@ nyul_transform_kernel(const float* __restrict__ x, float* __restrict__ out, int 
     __syncthreads();
     // the sort fallback permuted the shared copy: re-read the plane (an L2 hit) on that path only
     nyul_apply<EXACT>(s_val, L, c, n, plane, avg_landmarks, standard_scale, gamma,
-                      [&](int i) { return fallback ? src[i] : s_x[i]; }, dst, plane_mean);
+                      [&](int i) { return fallback ? src[i] : s_x[i]; }, dst, plane_mean, nullptr, table_out);
 }
 
 // Planes too large to stage in shared memory (224 x 224 after the C4 resize = 50 176 samples): the 2L order
@@ -541,7 +574,7 @@ __global__ void __launch_bounds__(kNyulThreads)
 nyul_transform_large_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int n, int L,
                             const double* __restrict__ avg_landmarks, const double* __restrict__ standard_scale,
                             const int* __restrict__ prev_index, const double* __restrict__ gamma,
-                            float* __restrict__ plane_mean) {
+                            float* __restrict__ plane_mean, double* __restrict__ table_out) {
     __shared__ int s_hist[kNyulMaxRanks][256];
     __shared__ uint32_t s_prefix[kNyulMaxRanks], s_uprefix[kNyulMaxRanks];
     __shared__ int s_rem[kNyulMaxRanks], s_uid[kNyulMaxRanks];
@@ -551,7 +584,7 @@ nyul_transform_large_kernel(const float* __restrict__ x, float* __restrict__ out
     const int c = plane % C;
     const int tid = threadIdx.x, lane = tid & 31;
     const float* src = x + static_cast<size_t>(plane) * n;
-    float* dst = out + static_cast<size_t>(plane) * n;
+    float* dst = out != nullptr ? out + static_cast<size_t>(plane) * n : nullptr;
     const int R = 2 * L;
     if (tid < R) {
         const int lo = prev_index[tid >> 1];
@@ -651,7 +684,7 @@ nyul_transform_large_kernel(const float* __restrict__ x, float* __restrict__ out
     if (tid < R) s_val[tid] = nyul_ordkey_inv(s_prefix[tid]);
     __syncthreads();
     nyul_apply<EXACT>(s_val, L, c, n, plane, avg_landmarks, standard_scale, gamma, [&](int i) { return __ldg(src + i); },
-                      dst, plane_mean, src);
+                      dst, plane_mean, src, table_out);
 }
 
 // ADC map (reference preprocess_helpers.py:133-167): per pixel, minus the least-squares slope of log(max(S, eps))
@@ -704,15 +737,17 @@ plane_mean_kernel(const float* __restrict__ x, int n, float* __restrict__ plane_
 
 }  // namespace b200
 
-extern "C" int b200_dwi_normalize(const float* x, float* out, int planes, int C, int n, int skip_last, float z_lo,
-                                  float z_hi, float* plane_mean, void* stream) {
+extern "C" int b200_dwi_normalize_ex(const float* x, float* out, int planes, int C, int n, int skip_last, float z_lo,
+                                     float z_hi, float* plane_mean, float* stats_out, void* stream) {
     using namespace b200;
     if (planes < 0 || C <= 0 || n <= 0 || planes % C != 0) return -1;
     if (planes == 0) return 0;
-    if (x == nullptr || out == nullptr) return -2;
+    if (x == nullptr || (out == nullptr && stats_out == nullptr)) return -2;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool aligned = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if ((out == nullptr || stats_out != nullptr) && !(aligned && n <= kNormThreads * 4 * 8)) return -3;  // statistics-only
+    // mode exists for register-resident planes (<= 8 192 samples, 16-byte aligned): the ROI sizes of the CNN encoders
     static int sms = 0;
     if (sms == 0) {
         int dev = 0;
@@ -733,27 +768,33 @@ extern "C" int b200_dwi_normalize(const float* x, float* out, int planes, int C,
     int grid = coprime_grid(sms * 4);
     if (aligned && n <= kNormThreads * 4 * 4)
         dwi_normalize_reg_kernel<4><<<grid, kNormThreads, 0, s>>>(x, out, planes, C, n, skip_last, z_lo, z_hi,
-                                                                  plane_mean);
+                                                                  plane_mean, stats_out);
     else if (aligned && n <= kNormThreads * 4 * 8)
         dwi_normalize_reg_kernel<8><<<(grid = coprime_grid(sms * 2)), kNormThreads, 0, s>>>(x, out, planes, C, n, skip_last, z_lo, z_hi,
-                                                                  plane_mean);
+                                                                  plane_mean, stats_out);
     else
         dwi_normalize_stream_kernel<<<planes, kNormThreads, 0, s>>>(x, out, C, n, skip_last, z_lo, z_hi, plane_mean);
     return launch_status();
+}
+
+extern "C" int b200_dwi_normalize(const float* x, float* out, int planes, int C, int n, int skip_last, float z_lo,
+                                  float z_hi, float* plane_mean, void* stream) {
+    if (out == nullptr) return -2;
+    return b200_dwi_normalize_ex(x, out, planes, C, n, skip_last, z_lo, z_hi, plane_mean, nullptr, stream);
 }
 
 namespace b200 {
 template <bool EXACT>
 static int nyul_launch(const float* x, float* out, int planes, int C, int n, int L, const double* avg_landmarks,
                        const double* standard_scale, const int* prev_index, const double* gamma, float* plane_mean,
-                       cudaStream_t stream) {
+                       double* table_out, cudaStream_t stream) {
     int npad = 2;
     while (npad < n) npad <<= 1;
     const size_t smem = static_cast<size_t>(npad) * sizeof(float);
     static const bool force_large = std::getenv("B200_NYUL_LARGE") != nullptr;  // test hook
     if (smem > 128 * 1024 || force_large) {  // > 32 768 samples: radix select straight from global / L2
         nyul_transform_large_kernel<EXACT><<<planes, kNyulThreads, 0, stream>>>(
-            x, out, C, n, L, avg_landmarks, standard_scale, prev_index, gamma, plane_mean);
+            x, out, C, n, L, avg_landmarks, standard_scale, prev_index, gamma, plane_mean, table_out);
         return launch_status();
     }
     static size_t configured = 0;
@@ -764,24 +805,34 @@ static int nyul_launch(const float* x, float* out, int planes, int C, int n, int
         configured = smem;
     }
     nyul_transform_kernel<EXACT><<<planes, kNyulThreads, smem, stream>>>(
-        x, out, C, n, npad, L, avg_landmarks, standard_scale, prev_index, gamma, plane_mean);
+        x, out, C, n, npad, L, avg_landmarks, standard_scale, prev_index, gamma, plane_mean, table_out);
     return launch_status();
 }
 }  // namespace b200
 
-extern "C" int b200_nyul_transform_ex(const float* x, float* out, int planes, int C, int n, int L,
-                                      const double* avg_landmarks, const double* standard_scale, const int* prev_index,
-                                      const double* gamma, float* plane_mean, int exact, void* stream) {
+extern "C" int b200_nyul_transform_ex2(const float* x, float* out, int planes, int C, int n, int L,
+                                       const double* avg_landmarks, const double* standard_scale, const int* prev_index,
+                                       const double* gamma, float* plane_mean, int exact, double* table_out, void* stream) {
     using namespace b200;
     if (planes < 0 || C <= 0 || n <= 0 || planes % C != 0 || L < 2 || L > kMaxLandmarks) return -1;
     if (planes == 0) return 0;
-    if (x == nullptr || out == nullptr || avg_landmarks == nullptr || standard_scale == nullptr ||
-        prev_index == nullptr || gamma == nullptr)
+    if (x == nullptr || avg_landmarks == nullptr || standard_scale == nullptr || prev_index == nullptr || gamma == nullptr)
         return -2;
+    if (out == nullptr && table_out == nullptr) return -2;
+    if (table_out != nullptr && exact) return -3;  // the per-plane table IS the composed (fast) form
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    return exact ? nyul_launch<true>(x, out, planes, C, n, L, avg_landmarks, standard_scale, prev_index, gamma, plane_mean, s)
+    return exact ? nyul_launch<true>(x, out, planes, C, n, L, avg_landmarks, standard_scale, prev_index, gamma, plane_mean,
+                                     nullptr, s)
                  : nyul_launch<false>(x, out, planes, C, n, L, avg_landmarks, standard_scale, prev_index, gamma,
-                                      plane_mean, s);
+                                      plane_mean, table_out, s);
+}
+
+extern "C" int b200_nyul_transform_ex(const float* x, float* out, int planes, int C, int n, int L,
+                                      const double* avg_landmarks, const double* standard_scale, const int* prev_index,
+                                      const double* gamma, float* plane_mean, int exact, void* stream) {
+    if (out == nullptr) return -2;
+    return b200_nyul_transform_ex2(x, out, planes, C, n, L, avg_landmarks, standard_scale, prev_index, gamma, plane_mean,
+                                   exact, nullptr, stream);
 }
 
 extern "C" int b200_nyul_transform(const float* x, float* out, int planes, int C, int n, int L,

