@@ -79,6 +79,7 @@ struct ConvGemmParams {
     int n_valid;           // MODE 1: number of real columns (keys); the rest are masked out
     int res_f32, out_f32;  // residual / output are fp32 row-major (transformer residual stream); direct path
     int stages;            // operand ring depth
+    int pair;              // BN = 128: two M tiles per CTA iteration share one weight slab (conv_gemm_kernel<..., PAIR>)
     int off_ring, off_bar, off_union, off_rbox, off_sm;  // shared-memory plan (bytes from the 1 KB-aligned base)
 };
 
@@ -103,6 +104,7 @@ template <int BN>
 struct Tile {
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kTmemCols = 2 * BN;             // two accumulator stages: 128 / 256 / 512 columns
+    static constexpr int kTmemColsPair = 4 * BN;         // PAIR (BN = 128): four stages = 512 columns
     static constexpr int kColsPerWarp = BN / 2;           // each epilogue warp: 32 rows x BN/2 columns
     static constexpr int kChunksPerWarp = kColsPerWarp / kChunk;
     static constexpr int kBoxCols = kColsPerWarp < 64 ? kColsPerWarp : 64;  // TMA box width (<= 128 B rows)
@@ -156,7 +158,12 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
 //   GAP  per-case channel sums          NDOT 0, or 1 / 9 fused per-pixel dot products (no map store)
 //   MODE 0 standard; 1 row softmax numerator: out = exp(alpha*acc - rowmax) as bf16, 1/rowsum to rowsum_inv
 //        (the whole row lives in one N tile; the division is deferred to the consumer GEMM's rowscale)
-template <int BN, bool WS, int RES, bool GAP, int NDOT, int MODE>
+//   PAIR (BN = 128 only): a CTA works on TWO consecutive M tiles of the same N tile at once - 256 x 128 outputs: per
+//        64-deep k-block the weight slab is loaded once and feeds two MMAs (one per M tile, each with its own TMEM
+//        accumulator), so a stage moves 48 KB for 2 x (128 x 128 x 64) MACs instead of 64 KB.  128 x 128 tiles were
+//        shared-memory-feed bound (0.64 PFLOP/s on 3x3 128->128 against 1.24 for the 128 x 256 tiles); four accumulator
+//        stages (512 TMEM columns) keep the epilogue of one pair overlapped with the MMAs of the next.
+template <int BN, bool WS, int RES, bool GAP, int NDOT, int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
@@ -169,12 +176,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = smem_raw + ((1024u - (static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw)) & 1023u)) & 1023u);
     uint8_t* sW = smem;  // resident weights [k_blocks][BN x 64] (WS only)
     uint8_t* sRing = smem + p.off_ring;
-    constexpr int kStageBytes = WS ? kABytes : kABytes + T::kBBytes;
+    static_assert(!PAIR || (BN == 128 && !WS && MODE == 0), "PAIR: BN = 128, streamed weights, standard epilogue");
+    constexpr int kStageBytes = WS ? kABytes : (PAIR ? 2 * kABytes : kABytes) + T::kBBytes;
+    constexpr int kAcc = PAIR ? 4 : 2;             // accumulator stages in TMEM
+    constexpr int kTmemCols = PAIR ? T::kTmemColsPair : T::kTmemCols;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
     uint64_t* empty = full + kMaxStages;
     uint64_t* tfull = empty + kMaxStages;
-    uint64_t* tempty = tfull + 2;
-    uint64_t* resbar = tempty + 2;  // [kNumEpiWarps][2] residual-box arrival, one per epilogue warp and box
+    uint64_t* tempty = tfull + 4;
+    uint64_t* resbar = tempty + 4;  // [kNumEpiWarps][2] residual-box arrival, one per epilogue warp and box
     uint64_t* wbar = resbar + 2 * kNumEpiWarps;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
     uint8_t* s_union = smem + p.off_union;
@@ -188,7 +198,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int my_n = WS ? static_cast<int>(blockIdx.x) % p.n_tiles : 0;
     const int m_first = WS ? static_cast<int>(blockIdx.x) / p.n_tiles : 0;
     const int m_step = WS ? static_cast<int>(gridDim.x) / p.n_tiles : 0;
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int total_tiles = PAIR ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles;  // PAIR: super-tiles
     const int n_iters = WS ? (p.m_tiles > m_first ? (p.m_tiles - m_first + m_step - 1) / m_step : 0)
                            : (total_tiles > static_cast<int>(blockIdx.x)
                                   ? (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
@@ -209,7 +219,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < kAcc; ++s) {
             mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], MODE == 1 ? kNumEpiWarps / 2 : kNumEpiWarps);  // mode 1: one warp set per stage
         }
@@ -217,7 +227,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_init(wbar, 1);
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<T::kTmemCols>(tmem_slot);
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
     if (DOT && warp >= kEpiWarp0) {
         for (int i = threadIdx.x - kEpiWarp0 * 32; i < NDOT * BN; i += kNumEpiWarps * 32) s_dotw[i] = p.dot_w[i];
     }
@@ -238,10 +248,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int tile = blockIdx.x, m_tile = m_first;
             for (int it = 0; it < n_iters; ++it, tile += gridDim.x, m_tile += m_step) {
                 const int n_tile = WS ? my_n : tile % p.n_tiles;
-                const int mt = WS ? m_tile : tile / p.n_tiles;
+                const int mt = WS ? m_tile : (PAIR ? 2 * (tile / p.n_tiles) : tile / p.n_tiles);
                 const int w0 = (mt % p.tiles_w) * p.BW;
                 const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.BH;
                 const int b = mt / (p.tiles_w * p.tiles_h);
+                // PAIR: the second M tile of the pair (absent only for the last tile of an odd count)
+                const bool has2 = PAIR && mt + 1 < p.m_tiles;
+                const int w1 = ((mt + 1) % p.tiles_w) * p.BW;
+                const int h1 = (((mt + 1) / p.tiles_w) % p.tiles_h) * p.BH;
+                const int b1 = (mt + 1) / (p.tiles_w * p.tiles_h);
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     const int tap = kb / p.kc;
                     const int c0 = (kb - tap * p.kc) * kBlockK;
@@ -254,13 +269,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         dx = tap & 1;
                     }
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], p.a_box_bytes + (WS ? 0 : T::kBBytes));
+                    mbar_arrive_expect_tx(&full[stage], p.a_box_bytes * (has2 ? 2 : 1) + (WS ? 0 : T::kBBytes));
                     uint8_t* dst = sRing + stage * kStageBytes;
                     if (p.a_batched) tma_load_4d(dst, &tmA, &full[stage], c0, p.cstride * w0 + dx, p.cstride * h0 + dy, b);
                     else tma_load_4d(dst, &tmA, &full[stage], c0, w0, 0, 0);
+                    if (has2) tma_load_4d(dst + kABytes, &tmA, &full[stage], c0, p.cstride * w1 + dx, p.cstride * h1 + dy, b1);
+                    constexpr int kBOff = PAIR ? 2 * kABytes : kABytes;
                     if (!WS) {
-                        if (p.b_mode == 0) tma_load_2d(dst + kABytes, &tmB, &full[stage], kb * kBlockK, n_tile * BN);
-                        else tma_load_4d(dst + kABytes, &tmB, &full[stage], kb * kBlockK, n_tile * BN, h0, b);
+                        if (p.b_mode == 0) tma_load_2d(dst + kBOff, &tmB, &full[stage], kb * kBlockK, n_tile * BN);
+                        else tma_load_4d(dst + kBOff, &tmB, &full[stage], kb * kBlockK, n_tile * BN, h0, b);
                     }
                     if (++stage == stages) {
                         stage = 0;
@@ -277,8 +294,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int acc = 0;
             uint32_t acc_phase = 0;
             if (WS) mbar_wait(wbar, 0);
-            for (int it = 0; it < n_iters; ++it) {
+            int tile = blockIdx.x;
+            for (int it = 0; it < n_iters; ++it, tile += gridDim.x) {
+                const bool has2 = PAIR && 2 * (tile / p.n_tiles) + 1 < p.m_tiles;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
+                if (has2) mbar_wait(&tempty[acc + 1], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -286,11 +306,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_after();
                     const uint8_t* a_src = sRing + stage * kStageBytes;
                     const uint64_t da = umma_desc_sw128(smem_u32(a_src));
-                    const uint64_t db = umma_desc_sw128(smem_u32(WS ? sW + kb * T::kBBytes : a_src + kABytes));
+                    const uint64_t db = umma_desc_sw128(smem_u32(WS ? sW + kb * T::kBBytes : a_src + (PAIR ? 2 * kABytes : kABytes)));
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // 16 bf16 = 32 bytes along K inside the 128-byte swizzle row -> +2 in 16-byte units
                         umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    if (has2) {  // the pair's second M tile: its own A box and accumulator, the SAME weight slab
+                        const uint64_t da1 = umma_desc_sw128(smem_u32(a_src + kABytes));
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16(d_tmem + BN, da1 + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);
                     if (++stage == stages) {
@@ -299,8 +325,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
                 umma_commit(&tfull[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                if (has2) umma_commit(&tfull[acc + 1]);
+                acc += PAIR ? 2 : 1;
+                if (acc == kAcc) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
             }
         }
     } else if (MODE == 1 && warp >= kEpiWarp0) {
@@ -445,22 +475,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int tile = blockIdx.x, m_walk = m_first;
         // Residual boxes are fetched one tile ahead: box bx of tile i+1 is requested as soon as the last lane
         // has read box bx of tile i, so its DRAM latency hides behind the rest of tile i's epilogue.
-        auto res_fetch = [&](int t_idx, int m_idx, int bx) {
-            const int nt = WS ? my_n : t_idx % p.n_tiles;
-            const int mt = WS ? m_idx : t_idx / p.n_tiles;
+        auto res_fetch = [&](int nt, int mt, int bx) {
             const int fw = (mt % p.tiles_w) * p.BW + (q * 32) % p.BW;
             const int fh = ((mt / p.tiles_w) % p.tiles_h) * p.BH + (q * 32) / p.BW;
             const int fb = mt / (p.tiles_w * p.tiles_h);
             mbar_arrive_expect_tx(&rbar[bx], T::kBoxBytes);
             tma_load_4d(rbuf + bx * T::kBoxBytes, &tmRes, &rbar[bx], nt * BN + colw0 + bx * T::kBoxCols, fw, fh, fb);
         };
+        // the CTA's tile sequence: (tile index, sub) -> (N tile, M tile); PAIR walks super-tiles of two M tiles
+        auto tile_nm = [&](int t_idx, int m_idx, int sub, int& nt, int& mt) {
+            nt = WS ? my_n : t_idx % p.n_tiles;
+            mt = WS ? m_idx : (PAIR ? 2 * (t_idx / p.n_tiles) + sub : t_idx / p.n_tiles);
+            return mt < p.m_tiles;
+        };
         if (RES != 0 && tma_epi && lane == 0 && n_iters > 0) {
+            int nt0, mt0;
+            tile_nm(tile, m_walk, 0, nt0, mt0);
 #pragma unroll
-            for (int bx = 0; bx < T::kBoxesPerWarp; ++bx) res_fetch(tile, m_walk, bx);
+            for (int bx = 0; bx < T::kBoxesPerWarp; ++bx) res_fetch(nt0, mt0, bx);
         }
         for (int it = 0; it < n_iters; ++it, tile += gridDim.x, m_walk += m_step) {
-            const int n_tile = WS ? my_n : tile % p.n_tiles;
-            const int m_tile = WS ? m_walk : tile / p.n_tiles;
+          for (int sub = 0; sub < (PAIR ? 2 : 1); ++sub) {
+            int n_tile, m_tile;
+            if (!tile_nm(tile, m_walk, sub, n_tile, m_tile)) {  // (PAIR) the absent second tile of an odd count
+                if (++acc == kAcc) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+                continue;
+            }
+            // the tile this warp handles next (its residual boxes are prefetched while this one is in flight)
+            int n_next = 0, m_next = 0;
+            bool have_next = false;
+            if (PAIR && sub == 0) have_next = tile_nm(tile, m_walk, 1, n_next, m_next);
+            if (!have_next && it + 1 < n_iters) have_next = tile_nm(tile + gridDim.x, m_walk + m_step, 0, n_next, m_next);
             // tile -> (w0, h0, b); this warp's slab = 32 consecutive rows of the tile = a {bw, bh} box in (w, h)
             const int w0 = (m_tile % p.tiles_w) * p.BW;
             const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.BH;
@@ -673,7 +721,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                                        (((c16 + j) ^ swz) << 4));
                             if (ch % kChunksPerBox == kChunksPerBox - 1) {  // last use: refill it for the next tile
                                 __syncwarp();
-                                if (lane == 0 && it + 1 < n_iters) res_fetch(tile + gridDim.x, m_walk + m_step, bx);
+                                if (lane == 0 && have_next) res_fetch(n_next, m_next, bx);
                             }
                         } else if (valid) {
                             const uint4* r4 = reinterpret_cast<const uint4*>(p.res + static_cast<long long>(pix) * p.res_ld + n0);
@@ -904,7 +952,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // The two column halves of a row live in different warps: half 1 parks its 9 partial sums in
                 // shared memory (double buffered by accumulator stage), one named barrier over the 8 epilogue
                 // warps, half 0 adds its own and writes the row.  Deterministic, no atomics.
-                float* buf = s_dots + (acc * kBlockM + q * 32 + lane) * NDOT;
+                float* buf = s_dots + ((acc & 1) * kBlockM + q * 32 + lane) * NDOT;
                 if (half == 1) {
 #pragma unroll
                     for (int k = 0; k < NDOT; ++k) buf[k] = dsum[k];
@@ -916,8 +964,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int k = 0; k < NDOT; ++k) dst[k] = dsum[k] + buf[k] + p.dot_bias;
                 }
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (++acc == kAcc) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+          }
         }
         if (tma_epi && lane == 0) tma_store_wait_all<0>();  // global writes done before the CTA retires
     }
@@ -926,7 +977,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<T::kTmemCols>(tmem_base);
+        tmem_dealloc<kTmemCols>(tmem_base);
     }
 }
 
@@ -951,17 +1002,17 @@ static EncodeTiledFn get_encode_fn() {
 static int g_num_sms = 0;
 constexpr int kSmemLimit = 227 * 1024;
 
-template <int BN, bool WS, int RES, bool GAP, int NDOT, int MODE>
+template <int BN, bool WS, int RES, bool GAP, int NDOT, int MODE, bool PAIR = false>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmOut2,
                   const CUtensorMap& tmRes, const ConvGemmParams& p, int smem_bytes, int grid, cudaStream_t stream) {
     static int configured = 0;
     if (smem_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, WS, RES, GAP, NDOT, MODE>,
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, WS, RES, GAP, NDOT, MODE, PAIR>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return static_cast<int>(e);
         configured = smem_bytes;
     }
-    conv_gemm_kernel<BN, WS, RES, GAP, NDOT, MODE>
+    conv_gemm_kernel<BN, WS, RES, GAP, NDOT, MODE, PAIR>
         <<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmOut, tmOut2, tmRes, p);
     return static_cast<int>(cudaGetLastError());
 }
@@ -1006,6 +1057,19 @@ static int dispatch(int res_mode, bool gap, int ndot, int mode, const CUtensorMa
         }
         return -14;
     }
+    if constexpr (BN == 128 && !WS) {
+        if (p.pair) {
+#define B200_GO_PAIR(RES, GAP) \
+    return launch<BN, WS, RES, GAP, 0, 0, true>(tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s)
+            if (res_mode == 0 && gap) B200_GO_PAIR(0, true);
+            if (res_mode == 0) B200_GO_PAIR(0, false);
+            if (res_mode == 1 && gap) B200_GO_PAIR(1, true);
+            if (res_mode == 1) B200_GO_PAIR(1, false);
+            if (res_mode == 2 && !gap) B200_GO_PAIR(2, false);
+#undef B200_GO_PAIR
+            return -14;
+        }
+    }
     if (res_mode == 0) {
         if (gap) B200_GO(0, true, 0, 0);
         B200_GO(0, false, 0, 0);
@@ -1043,9 +1107,9 @@ static inline int align1k(int v) { return (v + 1023) & ~1023; }
 // Lays out shared memory for (BN, weight-stationary?) and returns the total dynamic size, or -1 if the
 // configuration does not fit / leaves fewer than 3 ring stages.
 static int plan_smem(ConvGemmParams& p, int BN, bool ws, bool has_out, bool has_res, int ndot, int mode,
-                     bool share_box = false) {
+                     bool share_box = false, bool pair = false) {
     const int b_bytes = BN * kBlockK * 2;
-    const int stage_bytes = ws ? kABytes : kABytes + b_bytes;
+    const int stage_bytes = ws ? kABytes : (pair ? 2 * kABytes : kABytes) + b_bytes;
     const int box_all = kBlockM * BN * 2;  // 8 warps x (32 rows x BN/2 columns) of bf16
     const int dot_bytes = ndot * BN * 4 + 2 * kBlockM * ndot * 4;
     // mode 2 (fp32 epilogue) needs only the eight 32 x 33-word transposition blocks
@@ -1151,7 +1215,13 @@ static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, 
                                mode == 0 && !p.up2 && !no_share;
             // staging boxes exist only for the TMA epilogue (mode 2 keeps its transposition blocks)
             const bool st_out = has_out && (p.tma_epi || mode == 2), st_res = has_res && p.tma_epi;
-            smem_bytes = plan_smem(p, bn, false, st_out, st_res, ndot, mode, share);
+            // BN = 128: pair two M tiles per iteration when there is enough work to keep every SM busy with pairs
+            static const bool no_pair = std::getenv("B200_NO_PAIR") != nullptr;  // A/B measurements
+            const bool pair = bn == 128 && mode == 0 && ndot == 0 && p.a_batched && p.b_mode == 0 && !no_pair &&
+                              (p.m_tiles / 2) * (Cout / bn) >= g_num_sms;
+            smem_bytes = plan_smem(p, bn, false, st_out, st_res, ndot, mode, share, pair);
+            p.pair = (pair && smem_bytes > 0) ? 1 : 0;
+            if (pair && smem_bytes <= 0) smem_bytes = plan_smem(p, bn, false, st_out, st_res, ndot, mode, share, false);
             if (smem_bytes > 0) {
                 BN = bn;
                 p.share_box = share ? 1 : 0;
@@ -1215,7 +1285,7 @@ static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, 
         if (has_res && (rc = encode_view(encode, &tmRes, j.res, rbox, one, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE)) != 0)
             return rc - 5000;
     }
-    const int total = p.m_tiles * p.n_tiles;
+    const int total = p.pair ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
     int grid = total < g_num_sms ? total : g_num_sms;
     if (ws) {  // every CTA keeps one N tile: the grid is a whole number of N-tile groups
         const int groups = g_num_sms / p.n_tiles < p.m_tiles ? g_num_sms / p.n_tiles : p.m_tiles;

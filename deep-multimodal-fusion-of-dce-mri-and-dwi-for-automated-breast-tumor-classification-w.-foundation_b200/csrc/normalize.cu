@@ -783,7 +783,7 @@ extern "C" int b200_dwi_normalize_ex(const float* x, float* out, int planes, int
 
 extern "C" int b200_dwi_normalize(const float* x, float* out, int planes, int C, int n, int skip_last, float z_lo,
                                   float z_hi, float* plane_mean, void* stream) {
-    if (out == nullptr) return -2;
+    if (out == nullptr && planes > 0) return -2;
     return b200_dwi_normalize_ex(x, out, planes, C, n, skip_last, z_lo, z_hi, plane_mean, nullptr, stream);
 }
 

@@ -549,3 +549,25 @@ def test_standalone_submodule_forwards_vs_oracle():
     ca.to(dev)
     got_out, got_w = ca(q.to(dev), kv.to(dev))
     assert rel(got_out, ref_out) <= 1e-4 and rel(got_w, aw) <= 1e-4
+
+
+def test_paired_tiles_are_bitwise_the_unpaired_result():
+    """conv_gemm_kernel<128, ..., PAIR> (two M tiles per CTA iteration sharing one weight slab, used once a launch has
+    >= 2 x 148 M tiles) against the unpaired kernel on the same maps: the accumulation order per tile is the same, so the
+    bf16 outputs must be bit-identical.  3x3 and 1x1, plain and residual + GELU epilogues, odd tile counts."""
+    import b200_native as nat
+
+    g = torch.Generator().manual_seed(8)
+    for taps, cin, cout, res in ((9, 128, 128, False), (1, 128, 128, True), (1, 512, 128, False), (1, 128, 384, False)):
+        B = 41  # 41 cases x 8 tiles = 328 M tiles (>= 296: paired; odd pair count per N tile walk)
+        x = torch.randn(B, 32, 32, cin, generator=g).bfloat16().to(DEV)
+        w = (torch.randn(cout, taps * cin, generator=g) / (taps * cin) ** 0.5).bfloat16().to(DEV)
+        sc = (1 + 0.1 * torch.randn(cout, generator=g)).to(DEV)
+        bi = (0.1 * torch.randn(cout, generator=g)).to(DEV)
+        r = torch.randn(B, 32, 32, cout, generator=g).bfloat16().to(DEV) if res else None
+        kw = dict(taps=taps, scale=sc, bias=bi, act=1, res=r, res_mode=1 if res else 0)
+        big = nat.conv_gemm(x, w, **kw)
+        for lo in (0, 17, 33):  # 8-case launches: 64 M tiles, below the pairing threshold
+            kw_s = dict(kw, res=r[lo:lo + 8].contiguous() if res else None)
+            small = nat.conv_gemm(x[lo:lo + 8].contiguous(), w, **kw_s)
+            assert torch.equal(big[lo:lo + 8], small), (taps, cin, cout, res, lo)

@@ -409,8 +409,12 @@ def test_full_size_batch_is_the_small_batches_stacked():
         # parity tolerance, not bitwise
         assert _relmax(big_f[0][sl], s_f[0]) <= 2e-3
         assert _relmax(big_f[1][sl], s_f[1]) <= 1e-2
-        assert _relmax(big_d[1]["raw_feats"][2][sl], s_d[1]["raw_feats"][2]) <= 1e-2
-        assert _relmax(big_d[2][sl], s_d[2]) <= 1e-2
+        # Stage-3 maps sit behind the SE gate, whose channel means are float atomics: their summation order follows the
+        # tile schedule, which differs between a 512-case and a 16-case launch (the big one also pairs M tiles; that
+        # kernel is bit-identical per tile, test_paired_tiles_are_bitwise_the_unpaired_result).  1.33e-2 of the map's
+        # max was observed once (two bf16 ulps of one element); 1.6e-2 = two ulps.
+        assert _relmax(big_d[1]["raw_feats"][2][sl], s_d[1]["raw_feats"][2]) <= 1.6e-2
+        assert _relmax(big_d[2][sl], s_d[2]) <= 1.6e-2
         assert _relmax(big_c[0][sl], s_c[0]) <= 2e-3
 
 
