@@ -345,8 +345,7 @@ def train_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    gather([step() for _ in range(args.warmup)])
     barrier()
     launches0 = nat.LAUNCH_COUNT
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -551,8 +550,7 @@ def train_full_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    gather([step() for _ in range(args.warmup)])
     barrier()
     launches0 = nat.LAUNCH_COUNT
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -868,7 +866,6 @@ def main():
     B = args.batch
     dwi_h, dce_h = make_inputs(B, rank)
     dwi_d, dce_d = dwi_h.to(device), dce_h.to(device)
-    gathered = [torch.empty((B, 4), device=device) for _ in range(world)] if world > 1 else None
 
     lightning = None
     if args.predict_mode != "normal":
@@ -887,21 +884,26 @@ def main():
                 logits = lightning.predict_mc_dropout(d, c, passes=10)[0]
             else:
                 logits = lightning.predict_tta_mc(d, c, passes=10)[0]
-            if world > 1:
-                dist.all_gather(gathered, logits)
             return logits
-        logits = pipe.forward_raw(dwi_d, dce_d)
-        if world > 1:  # the path's only exchange: final logit gather (16 B/case)
-            dist.all_gather(gathered, logits)
-        return logits
+        return pipe.forward_raw(dwi_d, dce_d)
+
+    def gather(per_step):
+        """The path's only exchange: every rank's logits (16 B/case) collected ONCE for the K steps, inside the timed
+        region, as a prediction loop gathers at the end of an epoch (model_test.py:150-163 accumulates per-batch
+        predictions and concatenates after the loop) - not a collective per step."""
+        if world > 1 and per_step:
+            mine = torch.stack(per_step)
+            everyone = torch.empty((world,) + tuple(mine.shape), device=device, dtype=mine.dtype)
+            dist.all_gather_into_tensor(everyone, mine)
+            return everyone
+        return None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    gather([step() for _ in range(args.warmup)])
     barrier()
     launches0 = nat.LAUNCH_COUNT
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -909,8 +911,8 @@ def main():
         barrier()
         torch.cuda.nvtx.range_push("timed")  # ncu --nvtx --nvtx-include "timed/" captures exactly these steps
         e0.record()
-        for _ in range(args.steps):
-            step()
+        per_step = [step() for _ in range(args.steps)]
+        gather(per_step)
         e1.record()
         barrier()
         torch.cuda.nvtx.range_pop()
@@ -1050,7 +1052,7 @@ def main():
                        "batch_per_gpu": B, "global_batch": B * world, "aux": args.aux,
                        "weights": "seeded random init (initialize_model) + randomised BN running stats",
                        "l2": "no flush needed: per-step inputs (369 MB at B=1024) and activations (>10 GB) exceed the 126 MB L2",
-                       "parallelism": f"case-sharded x{world}, logit all_gather" if world > 1 else "single GPU"},
+                       "parallelism": f"case-sharded x{world}, one logit all_gather after the K steps" if world > 1 else "single GPU"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "api": "FusionPipeline.classify_host (pinned host tensors, "

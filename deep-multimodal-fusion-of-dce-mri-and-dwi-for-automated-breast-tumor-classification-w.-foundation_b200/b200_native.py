@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # csrc/build.sh links the library at <repo>/lib/libb200fusion.so: a short path without the dots and dashes of the
 # package directory name, which is the path string dlopen sees.
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200fusion.so")
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 _lib = None
 
@@ -95,6 +95,8 @@ SIGNATURES = {
     "b200_conv_gemm": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_conv_gemm_ex": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _F, _P, _I, _I, _I,
                           _I, _I, _I, _I, _I, _P],
+    "b200_conv_gemm_mc": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _F, _P, _I, _I, _I,
+                          _I, _I, _I, _I, _I, _F, C.c_ulonglong, _I, _P],
     "b200_resize_bilinear_c1": [_P, _I, _I, _I, _P, _I, _I, _P],
     "b200_mask_attention": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P],
     "b200_tapsum": [_P, _I, _I, _I, _P, _P, _P],
@@ -108,6 +110,8 @@ SIGNATURES = {
     "b200_dwi_normalize_ex": [_P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P],
     "b200_nyul_transform_ex2": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P],
     "b200_stem_ex": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _F, _F, _P, _I, _P],
+    "b200_stem_mc": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _F, _F, _P, _I, _F,
+                     C.c_ulonglong, _P],
     "b200_nyul_transform": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "b200_nyul_transform_ex": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "b200_plane_mean": [_P, _I, _I, _P, _P],
@@ -123,7 +127,6 @@ SIGNATURES = {
     "b200_mix_instnorm": [_P, _P, _I, _I, _I, _P, _P, _P, _F, _P, _P],
     "b200_adaptive_pool": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "b200_add_maps": [_P, _P, _LL, _P, _P],
-    "b200_set_dropout": [_F, C.c_ulonglong, _I],
     "b200_adc_map": [_P, _I, _I, _I, _P, _F, _P, _P],
     "b200_conv7x7_s2": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "b200_maxpool3x3_s2": [_P, _I, _I, _I, _I, _P, _P],
@@ -306,13 +309,16 @@ def conv_gemm(x, w, *, taps, scale=None, bias=None, res=None, res_mode=0, act=0,
         _bf16_map(out2, "out2", allow_slice=True)
     if res is not None:
         _bf16_map(res, "res")
-    if dropout is not None:  # (p, seed, segments): arms the one-shot MC-dropout epilogue of this launch
-        set_dropout(*dropout)
-    _call("b200_conv_gemm_ex", (B, H, W, cin, cout, taps) if stride == 1 else (B, H, W, cin, cout, taps, stride), _ptr(x), x_ld, _ptr(w), _ptr(scale), _ptr(bias), _ptr(res),
-          res.shape[-1] if res is not None else 0, res_mode, act, _ptr(out), out_ld,
-          1 if up2 else 0, _ptr(gap), n1, _ptr(out2), _ld(out2) if out2 is not None else 0, act2,
-          _ptr(dot_w), dot_w.shape[0] if dot_w is not None else 0, float(dot_bias), _ptr(dot_out), B, H, W, cin, cout,
-          taps, stride, dilation, _stream())
+    key = (B, H, W, cin, cout, taps) if stride == 1 else (B, H, W, cin, cout, taps, stride)
+    args = (_ptr(x), x_ld, _ptr(w), _ptr(scale), _ptr(bias), _ptr(res), res.shape[-1] if res is not None else 0,
+            res_mode, act, _ptr(out), out_ld, 1 if up2 else 0, _ptr(gap), n1, _ptr(out2),
+            _ld(out2) if out2 is not None else 0, act2, _ptr(dot_w), dot_w.shape[0] if dot_w is not None else 0,
+            float(dot_bias), _ptr(dot_out), B, H, W, cin, cout, taps, stride, dilation)
+    if dropout is not None:  # (p, seed, segments): the MC-dropout epilogue, part of this launch's argument list
+        p_drop, seed, segments = dropout
+        _call("b200_conv_gemm_mc", key, *args, float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, int(segments), _stream())
+    else:
+        _call("b200_conv_gemm_ex", key, *args, _stream())
     return out if n_split is None else (out, out2)
 
 
@@ -450,13 +456,6 @@ def plane_mean(x, planes, n, out):
     return out
 
 
-def set_dropout(p, seed, segments=1):
-    """One-shot: the next conv_gemm / stem launch drops elements of the selected output segments with probability p."""
-    rc = lib().b200_set_dropout(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(segments))
-    if rc:
-        raise B200NativeError(f"b200_set_dropout -> {rc}")
-
-
 def adc_map(x, bvals, eps=1e-6):
     """x [B,C,H,W] fp32 CUDA, bvals [C] fp32 CUDA -> [B,1,H,W] ADC maps."""
     x = x.contiguous().float()
@@ -503,8 +502,6 @@ def flip_planes(x, flip_w, flip_h):
 def stem(x, stride, pm, se, wcat, scale, bias, n_skip, n_mid, skip_out, mid_out, mod_attn, dropout=None, input_norm=None):
     """input_norm: None (x is normalised), ("dwi", stats [B*C,4] fp32, z_lo, z_hi) or ("nyul", tables [B*C,56] fp64, L):
     x is the RAW input and the normalisation is applied in the operand load (b200_stem_ex)."""
-    if dropout is not None:
-        set_dropout(dropout[0], dropout[1], 1)
     B, C_, H, W = x.shape
     w1, b1, w2, b2 = se if se is not None else (None, None, None, None)
     cm = w1.shape[0] if w1 is not None else 0
@@ -516,9 +513,13 @@ def stem(x, stride, pm, se, wcat, scale, bias, n_skip, n_mid, skip_out, mid_out,
             _, aff, z_lo, z_hi = input_norm
         else:
             _, tab, L = input_norm
-    _call("b200_stem_ex", None, _ptr(x), B, C_, H, W, stride, _ptr(pm), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), cm,
-          _ptr(wcat), _ptr(scale), _ptr(bias), n_skip, n_mid, _ptr(skip_out), _ptr(mid_out), _ptr(mod_attn), _ptr(aff),
-          float(z_lo), float(z_hi), _ptr(tab), int(L), _stream())
+    args = (_ptr(x), B, C_, H, W, stride, _ptr(pm), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), cm, _ptr(wcat), _ptr(scale),
+            _ptr(bias), n_skip, n_mid, _ptr(skip_out), _ptr(mid_out), _ptr(mod_attn), _ptr(aff), float(z_lo), float(z_hi),
+            _ptr(tab), int(L))
+    if dropout is not None:  # (p, seed): MC dropout on the bottleneck output
+        _call("b200_stem_mc", None, *args, float(dropout[0]), int(dropout[1]) & 0xFFFFFFFFFFFFFFFF, _stream())
+    else:
+        _call("b200_stem_ex", None, *args, _stream())
 
 
 def se_gate(gap_sum, npix, w1t, b1, w2t, b2, gate):

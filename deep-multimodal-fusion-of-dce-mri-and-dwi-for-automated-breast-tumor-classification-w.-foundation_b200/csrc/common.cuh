@@ -105,14 +105,14 @@ __device__ __forceinline__ uint4 philox4x32_7(unsigned long long ctr, uint32_t k
     return make_uint4(c0, c1, c2, c3);
 }
 
-// Host side of b200_set_dropout: the one-shot request armed for the next dropout-capable launch of this thread
-// (defined in conv_gemm.cu; taking it clears it).
-struct PendingDropout {
+// MC-dropout request of one launch (b200_conv_gemm_mc / b200_stem_mc): probability, Philox seed, and which output
+// segments it applies to (0 = none).  Passed by value in the argument list; there is no ambient state.
+struct DropoutArgs {
     float p = 0.f;
     unsigned long long seed = 0;
     int seg = 0;
 };
-PendingDropout take_pending_dropout();
+inline bool dropout_args_valid(float p, int segments) { return p >= 0.f && p < 1.f && segments >= 0 && segments <= 3; }
 inline unsigned int dropout_threshold(float p) {
     const double t = static_cast<double>(p) * 4294967296.0;
     return t >= 4294967295.0 ? 4294967295u : static_cast<unsigned int>(t);

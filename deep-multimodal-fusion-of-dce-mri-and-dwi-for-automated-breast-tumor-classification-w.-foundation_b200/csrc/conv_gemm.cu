@@ -3,19 +3,23 @@
 //   out[pixel, n] = epilogue( sum_{tap, c} x[pixel + offset(tap), c] * w[n, tap*Cin + c] )
 //
 // Activations are NHWC bf16, weights are [Cout, taps*Cin] bf16 (K-major), the accumulator lives in
-// TMEM (fp32).  One persistent CTA per SM, warp-specialised, 640 threads:
+// TMEM (fp32).  One persistent CTA per SM, warp-specialised, 384 threads (kThreads):
 //   warp 0      TMA producer: one 4-D box {64 ch, BW, BH, 1} of the input per (tap, 64-channel slice) -
 //               the tap shift is a coordinate offset, the zero padding is the TMA out-of-bounds fill -
-//               plus one 2-D box {64, BLOCK_N} of the weights, both written with the 128-byte swizzle
-//   warp 1      tcgen05.mma issuer (single thread), M=128, N=BLOCK_N, K=16 per instruction
-//   warp 2      TMEM allocation / release (2 accumulator stages: the epilogue of tile i overlaps the
-//               MMAs of tile i+1)
-//   warps 4-19  epilogue (4 warps per scheduler so fixed-latency stalls are covered): each warp owns 32
-//               accumulator rows (its TMEM lane quadrant) x BLOCK_N/4 columns and walks them in
-//               16-column chunks: tcgen05.ld -> folded-BN FMA -> residual (TMA-loaded box) -> GELU ->
-//               bf16 -> swizzled shared-memory box -> TMA store.  Optional fused products: per-case
-//               channel sums, a second output segment with its own activation, the 9 per-tap dot
-//               products of a following 3x3 C->1 convolution, 2x2-replicated (strided TMA) stores.
+//               plus one 2-D box {64, BLOCK_N} of the weights, both written with the 128-byte swizzle.
+//               PAIR (BLOCK_N = 128 layers with >= 2 x 148 M tiles): a second input box per stage, so
+//               one weight slab feeds two M tiles.
+//   warp 1      tcgen05.mma issuer (single thread), M=128, N=BLOCK_N, K=16 per instruction; PAIR issues
+//               the second tile's MMAs into the next BLOCK_N TMEM columns off the same B descriptor
+//   warp 2      TMEM allocation / release: 2 accumulator stages (4 with PAIR) - the epilogue of tile i
+//               overlaps the MMAs of tile i+1
+//   warp 3      idle (keeps the epilogue warps aligned to TMEM lane quadrants: quadrant = warp % 4)
+//   warps 4-11  epilogue (kNumEpiWarps = 8, two per TMEM lane quadrant): each warp owns 32 accumulator
+//               rows x BLOCK_N/2 columns and walks them in 32-column chunks (tcgen05.ld.32x32b.x32):
+//               folded-BN FMA -> residual (its own TMA-loaded box, prefetched one tile ahead) -> GELU ->
+//               (Philox dropout) -> bf16 -> swizzled shared-memory box -> TMA store.  Optional fused products: per-case channel
+//               sums, a second output segment with its own activation, the 9 per-tap dot products of a
+//               following 3x3 C->1 convolution, 2x2-replicated (strided TMA) stores.
 //
 // Covers the reference's conv/BN/GELU stacks (model_module.py:259-269, :113-118, :150, :337-345,
 // :386-390, :857-858) and nn.Linear layers (transformer_model.py:93-125).
@@ -1314,32 +1318,12 @@ extern "C" int b200_conv_gemm(const void* x, int x_ld, const void* w, const floa
                              0, 0, nullptr, 0, 0.f, nullptr, B, H, W, Cin, Cout, taps, 1, 1, stream);
 }
 
-// One-shot MC-dropout request for the next dropout-capable launch of this thread (see b200_fusion.h).
-namespace b200 {
-static thread_local PendingDropout g_pending_dropout;
-PendingDropout take_pending_dropout() {
-    const PendingDropout d = g_pending_dropout;
-    g_pending_dropout = PendingDropout{};
-    return d;
-}
-}  // namespace b200
-
-extern "C" int b200_set_dropout(float p, unsigned long long seed, int segments) {
-    if (!(p >= 0.f && p < 1.f) || segments < 0 || segments > 3) return -1;
-    b200::g_pending_dropout.p = p;
-    b200::g_pending_dropout.seed = seed;
-    b200::g_pending_dropout.seg = p > 0.f ? segments : 0;
-    return 0;
-}
-
-extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
-                                 const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
-                                 float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w,
-                                 int ndot, float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout,
-                                 int taps, int stride, int dilation, void* stream) {
+static int conv_gemm_launch(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
+                            const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
+                            float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w, int ndot,
+                            float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout, int taps,
+                            int stride, int dilation, b200::DropoutArgs drop, void* stream) {
     using namespace b200;
-    // consume the one-shot dropout request first: a call that fails validation must not leave it armed for the next
-    const PendingDropout drop = take_pending_dropout();
     if (dilation < 1 || dilation > 8 || (dilation != 1 && taps != 9)) return -6;
     if (dot_w == nullptr) ndot = 0;
     if (ndot != 0 && ndot != 1 && ndot != 9) return -18;
@@ -1442,6 +1426,33 @@ extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const f
         p.drop_seg = drop.seg;
     }
     return run_job(p, j, mode, mode == 0 && want_ws, static_cast<cudaStream_t>(stream));
+}
+extern "C" int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
+                                 const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
+                                 float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w,
+                                 int ndot, float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout,
+                                 int taps, int stride, int dilation, void* stream) {
+    return conv_gemm_launch(x, x_ld, w, scale, bias, res, res_ld, res_mode, act, out, out_ld, up2, gap, n_split, out2,
+                            out2_ld, act2, dot_w, ndot, dot_bias, dot_out, B, H, W, Cin, Cout, taps, stride, dilation,
+                            b200::DropoutArgs{}, stream);
+}
+
+// b200_conv_gemm_ex with the MC-dropout epilogue: elements of the selected output segments (bit 0: out, bit 1: out2)
+// are zeroed with probability drop_p and the survivors scaled by 1 / (1 - drop_p) after the activation.
+extern "C" int b200_conv_gemm_mc(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
+                                 const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
+                                 float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w,
+                                 int ndot, float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout,
+                                 int taps, int stride, int dilation, float drop_p, unsigned long long drop_seed,
+                                 int drop_segments, void* stream) {
+    if (!b200::dropout_args_valid(drop_p, drop_segments)) return -19;
+    b200::DropoutArgs d;
+    d.p = drop_p;
+    d.seed = drop_seed;
+    d.seg = drop_p > 0.f ? drop_segments : 0;
+    return conv_gemm_launch(x, x_ld, w, scale, bias, res, res_ld, res_mode, act, out, out_ld, up2, gap, n_split, out2,
+                            out2_ld, act2, dot_w, ndot, dot_bias, dot_out, B, H, W, Cin, Cout, taps, stride, dilation, d,
+                            stream);
 }
 
 extern "C" int b200_linear(const void* x, long long M, int K, const void* w, int N, const float* scale, const float* bias,

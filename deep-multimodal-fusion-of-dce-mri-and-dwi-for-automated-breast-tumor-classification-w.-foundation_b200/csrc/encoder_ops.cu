@@ -532,12 +532,11 @@ static inline int grid_for(size_t work_items, int threads, int max_blocks = 148 
 
 using namespace b200;
 
-extern "C" int b200_stem_ex(const float* x, int B, int C, int H, int W, int stride, const float* plane_mean,
-                            const float* se_w1, const float* se_b1, const float* se_w2, const float* se_b2, int Cm,
-                            const float* wcat, const float* scale, const float* bias, int n_skip, int n_mid,
-                            void* skip_out, void* mid_out, float* mod_attn, const float* in_affine, float z_lo, float z_hi,
-                            const double* in_table, int L, void* stream) {
-    const b200::PendingDropout drop = b200::take_pending_dropout();  // one shot, consumed even if validation fails
+static int stem_launch(const float* x, int B, int C, int H, int W, int stride, const float* plane_mean,
+                       const float* se_w1, const float* se_b1, const float* se_w2, const float* se_b2, int Cm,
+                       const float* wcat, const float* scale, const float* bias, int n_skip, int n_mid, void* skip_out,
+                       void* mid_out, float* mod_attn, const float* in_affine, float z_lo, float z_hi,
+                       const double* in_table, int L, b200::DropoutArgs drop, void* stream) {
     if (B < 0 || C <= 0 || C > kStemMaxC || Cm > kStemMaxC || H % stride != 0 || W % stride != 0) return -1;
     if (B == 0) return 0;
     if (x == nullptr || wcat == nullptr || scale == nullptr || bias == nullptr) return -2;
@@ -573,6 +572,31 @@ extern "C" int b200_stem_ex(const float* x, int B, int C, int H, int W, int stri
     else if (C <= 16) go(stem_kernel<16>);
     else go(stem_kernel<32>);
     return launch_status();
+}
+
+extern "C" int b200_stem_ex(const float* x, int B, int C, int H, int W, int stride, const float* plane_mean,
+                            const float* se_w1, const float* se_b1, const float* se_w2, const float* se_b2, int Cm,
+                            const float* wcat, const float* scale, const float* bias, int n_skip, int n_mid,
+                            void* skip_out, void* mid_out, float* mod_attn, const float* in_affine, float z_lo, float z_hi,
+                            const double* in_table, int L, void* stream) {
+    return stem_launch(x, B, C, H, W, stride, plane_mean, se_w1, se_b1, se_w2, se_b2, Cm, wcat, scale, bias, n_skip,
+                       n_mid, skip_out, mid_out, mod_attn, in_affine, z_lo, z_hi, in_table, L, b200::DropoutArgs{}, stream);
+}
+
+// b200_stem_ex with MC dropout (probability drop_p, Philox seed drop_seed) on the bottleneck (mid) output, where the
+// reference's first nn.Dropout sits (model_module.py:262).
+extern "C" int b200_stem_mc(const float* x, int B, int C, int H, int W, int stride, const float* plane_mean,
+                            const float* se_w1, const float* se_b1, const float* se_w2, const float* se_b2, int Cm,
+                            const float* wcat, const float* scale, const float* bias, int n_skip, int n_mid,
+                            void* skip_out, void* mid_out, float* mod_attn, const float* in_affine, float z_lo, float z_hi,
+                            const double* in_table, int L, float drop_p, unsigned long long drop_seed, void* stream) {
+    if (!b200::dropout_args_valid(drop_p, 1)) return -19;
+    b200::DropoutArgs d;
+    d.p = drop_p;
+    d.seed = drop_seed;
+    d.seg = drop_p > 0.f ? 1 : 0;
+    return stem_launch(x, B, C, H, W, stride, plane_mean, se_w1, se_b1, se_w2, se_b2, Cm, wcat, scale, bias, n_skip,
+                       n_mid, skip_out, mid_out, mod_attn, in_affine, z_lo, z_hi, in_table, L, d, stream);
 }
 
 extern "C" int b200_stem(const float* x, int B, int C, int H, int W, int stride, const float* plane_mean,

@@ -641,6 +641,25 @@ def _state_signature(module):
     return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
 
 
+class _PackedWeightsMixin:
+    """Owner of a packed-weight cache (bf16 [Cout, taps*Cin] slabs, folded BatchNorm affines).  The cache key is
+    (data_ptr, version) of every parameter and buffer, which in-place writes through `.data` do not change
+    (init_parameter below writes that way, as the reference's does, and so do EMA / SWA swaps): every entry point that
+    can rewrite weights behind the version counter drops the cache instead - `initialize_model`, `load_state_dict`,
+    `_apply` (.to / .half / .cuda) - and `invalidate_packed()` is public for callers that poke `.data` themselves."""
+
+    def invalidate_packed(self):
+        self._pack_cache = None
+
+    def _apply(self, fn, *a, **k):
+        self._pack_cache = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._pack_cache = None
+        return super().load_state_dict(*a, **k)
+
+
 def _as_nhwc_bf16(t):
     """NCHW-shaped tensor -> NHWC bf16 contiguous buffer (zero-copy for our own channels_last views)."""
     if not t.is_cuda:
@@ -696,7 +715,7 @@ def _recon(rc, x):
 # --------------------------------------------------------------------------------------
 # encoder
 # --------------------------------------------------------------------------------------
-class ModelMaskHeadBackbone(nn.Module):
+class ModelMaskHeadBackbone(_PackedWeightsMixin, nn.Module):
     """DWI / DCE encoder (reference :481-733).  ``aux_mode``: "full" materialises every output of
     the reference API; "logits" skips what the fusion logits do not depend on (reconstruction heads,
     projectors, the encoder's own classifier) and returns None for those entries."""
@@ -1158,7 +1177,7 @@ def _bilinear_axis_weights(n_in, n_out):
     return w
 
 
-class FusionModel(nn.Module):
+class FusionModel(_PackedWeightsMixin, nn.Module):
     """Late-fusion head (reference :821-1000).  The reference's cat -> fusion_conv_reduce -> refine
     branch (:935-940) never reaches an output, so it is not evaluated (its parameters exist for
     state_dict compatibility)."""
@@ -1326,4 +1345,7 @@ def initialize_model(model, requires_grad):
     for param in model.parameters():
         param.requires_grad = requires_grad
     model.apply(init_parameter)
+    for mod in model.modules():  # init_parameter writes through .data: the packed copies are stale now
+        if isinstance(mod, _PackedWeightsMixin):
+            mod.invalidate_packed()
     return model

@@ -56,16 +56,6 @@ int b200_conv_gemm(const void* x, int x_ld, const void* w, const float* scale, c
                    float* gap, int B, int H, int W, int Cin, int Cout, int taps, void* stream);
 
 /*
- * MC-dropout inference (code/train_fusion.py:478-536: nn.Dropout modules in train mode, BatchNorm frozen; the
- * dropouts of ResNetLiteBlock_withRecon, code/model_module.py:260, :271, :306).  One-shot: arms the NEXT
- * b200_conv_gemm_ex or b200_stem call of the calling thread (b200_stem drops its `mid` map), whose epilogue then zeroes each element of the selected output
- * segments (bit 0 = first, bit 1 = second) with probability p and scales the survivors by 1 / (1 - p), after the
- * activation and before the store / channel sums.  Decisions are Philox4x32-7(seed; pixel * Cout + channel):
- * reproducible for a given seed, statistically (not bitwise) comparable with torch's generator.
- */
-int b200_set_dropout(float p, unsigned long long seed, int segments);
-
-/*
  * b200_conv_gemm with two extensions used to fuse neighbouring layers of the reference graph:
  *   n_split/out2/out2_ld/act2: output channels [n_split, Cout) are a second layer that reads the same
  *     input (e.g. a block's skip conv and first bottleneck conv, code/model_module.py:299 and :303) and
@@ -88,6 +78,22 @@ int b200_conv_gemm_ex(const void* x, int x_ld, const void* w, const float* scale
                       float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w, int ndot,
                       float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout, int taps,
                       int stride, int dilation, void* stream);
+
+/*
+ * b200_conv_gemm_ex with the MC-dropout epilogue (code/train_fusion.py:478-536: nn.Dropout modules in train mode,
+ * BatchNorm frozen; the dropouts of ResNetLiteBlock_withRecon, code/model_module.py:260, :271, :306).  The request is
+ * part of the argument list - there is no ambient or per-thread state: each element of the selected output segments
+ * (drop_segments bit 0 = out, bit 1 = out2) is zeroed with probability drop_p and the survivors are scaled by
+ * 1 / (1 - drop_p), after the activation and before the store / channel sums.  Decisions are
+ * Philox4x32-7(drop_seed; pixel * Cout + channel): reproducible for a given seed, statistically (not bitwise)
+ * comparable with torch's generator.  drop_p outside [0, 1) or drop_segments outside [0, 3] -> -19.
+ */
+int b200_conv_gemm_mc(const void* x, int x_ld, const void* w, const float* scale, const float* bias,
+                      const void* res, int res_ld, int res_mode, int act, void* out, int out_ld, int up2,
+                      float* gap, int n_split, void* out2, int out2_ld, int act2, const float* dot_w, int ndot,
+                      float dot_bias, float* dot_out, int B, int H, int W, int Cin, int Cout, int taps,
+                      int stride, int dilation, float drop_p, unsigned long long drop_seed, int drop_segments,
+                      void* stream);
 
 /*
  * Batched GEMM on the same tcgen05 kernel: for every (batch, head)
@@ -240,6 +246,13 @@ int b200_stem_ex(const float* x, int B, int C, int H, int W, int stride, const f
                  const float* scale, const float* bias, int n_skip, int n_mid, void* skip_out, void* mid_out,
                  float* mod_attn, const float* in_affine, float z_lo, float z_hi, const double* in_table, int L,
                  void* stream);
+
+/* b200_stem_ex with MC dropout on the bottleneck (`mid`) map, the reference's first nn.Dropout (code/model_module.py:260). */
+int b200_stem_mc(const float* x, int B, int C, int H, int W, int stride, const float* plane_mean, const float* se_w1,
+                 const float* se_b1, const float* se_w2, const float* se_b2, int Cm, const float* wcat,
+                 const float* scale, const float* bias, int n_skip, int n_mid, void* skip_out, void* mid_out,
+                 float* mod_attn, const float* in_affine, float z_lo, float z_hi, const double* in_table, int L,
+                 float drop_p, unsigned long long drop_seed, void* stream);
 
 /*
  * SEBlock.fc on pooled sums (code/model_module.py:34-40): gate[b,:] =

@@ -153,6 +153,21 @@ def test_initialize_model_rules():
     assert abs(bn.weight.mean().item() - 1) < 0.05
 
 
+def test_packed_weight_cache_is_dropped_by_every_weight_rewriting_entry_point():
+    """The packed-weight cache keys on (data_ptr, version); writes through `.data` change neither, so
+    initialize_model / load_state_dict / .to() and the public invalidate_packed() drop it explicitly."""
+    import model_module as mm
+    import parameters_default as pd
+
+    p = pd.default_parameters()
+    for m in (mm.ModelMaskHeadBackbone("dce", p), mm.FusionModel(p)):
+        for poke in (lambda: mm.initialize_model(m, True), lambda: m.load_state_dict(m.state_dict()),
+                     lambda: m.to(torch.float32), m.invalidate_packed):
+            m._pack_cache = ("sig", "stale")
+            poke()
+            assert m._pack_cache is None
+
+
 def test_bilinear_axis_weights_equal_gap_of_interpolate():
     import model_module as mm
 

@@ -571,3 +571,23 @@ def test_paired_tiles_are_bitwise_the_unpaired_result():
             kw_s = dict(kw, res=r[lo:lo + 8].contiguous() if res else None)
             small = nat.conv_gemm(x[lo:lo + 8].contiguous(), w, **kw_s)
             assert torch.equal(big[lo:lo + 8], small), (taps, cin, cout, res, lo)
+
+
+def test_reinitialised_weights_are_repacked():
+    """forward -> initialize_model (in-place `.data` writes, version counters untouched) -> forward must use the new
+    weights: the second result differs from the first and equals a fresh module holding the same state."""
+    import model_module as mm
+    import parameters_default as pd
+
+    p = pd.default_parameters()
+    torch.manual_seed(3)
+    m = mm.ModelMaskHeadBackbone("dce", p).to(DEV).eval()
+    x = torch.rand(2, 6, 64, 64, device=DEV)
+    with torch.no_grad():
+        a = m(x)[0].clone()
+        mm.initialize_model(m, True)
+        b = m(x)[0].clone()
+        fresh = mm.ModelMaskHeadBackbone("dce", p)
+        fresh.load_state_dict(m.state_dict())
+        c = fresh.to(DEV).eval()(x)[0]
+    assert not torch.equal(a, b) and torch.equal(b, c)
