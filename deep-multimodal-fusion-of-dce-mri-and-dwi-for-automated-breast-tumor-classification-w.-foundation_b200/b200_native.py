@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # csrc/build.sh links the library at <repo>/lib/libb200fusion.so: a short path without the dots and dashes of the
 # package directory name, which is the path string dlopen sees.
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200fusion.so")
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 _lib = None
 
@@ -97,6 +97,7 @@ SIGNATURES = {
                           _I, _I, _I, _I, _I, _P],
     "b200_conv_gemm_mc": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _F, _P, _I, _I, _I,
                           _I, _I, _I, _I, _I, _F, C.c_ulonglong, _I, _P],
+    "b200_attention": [_P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
     "b200_resize_bilinear_c1": [_P, _I, _I, _I, _P, _I, _I, _P],
     "b200_mask_attention": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P],
     "b200_tapsum": [_P, _I, _I, _I, _P, _P, _P],
@@ -448,6 +449,15 @@ def nyul_transform(x, out, C_, n, avg_landmarks, standard_scale, prev_index, gam
     L = standard_scale.numel()
     _call("b200_nyul_transform_ex", None, _ptr(x), _ptr(out), planes, C_, n, L, _ptr(avg_landmarks),
           _ptr(standard_scale), _ptr(prev_index), _ptr(gamma), _ptr(plane_mean), 1 if exact else 0, _stream())
+    return out
+
+
+def attention(qkv, out, B, N, heads, dh, scale=None):
+    """Fused softmax(q k^T * scale) v over the packed qkv rows [B*N, 3*heads*dh] bf16 -> out [B*N, heads*dh] bf16
+    (b200_attention; transformer_model.py:101-112)."""
+    assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and qkv.stride(-1) == 1 and out.stride(-1) == 1
+    _call("b200_attention", (B, N, heads, dh), _ptr(qkv), qkv.stride(0), _ptr(out), out.stride(0), B, N, heads, dh,
+          float(dh ** -0.5 if scale is None else scale), _stream())
     return out
 
 

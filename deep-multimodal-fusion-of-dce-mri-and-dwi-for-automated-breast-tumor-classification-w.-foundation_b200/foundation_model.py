@@ -124,8 +124,7 @@ class B200ViTBackbone(nn.Module):
                 "heads": blk.attn.num_heads, "dh": E // blk.attn.num_heads,
                 "ln1": (_f32(blk.norm1.weight, dev), _f32(blk.norm1.bias, dev), blk.norm1.eps),
                 "ln2": (_f32(blk.norm2.weight, dev), _f32(blk.norm2.bias, dev), blk.norm2.eps),
-                "wqk": _bf16(wqkv[:2 * E], dev), "bqk": _f32(bqkv[:2 * E], dev),
-                "wv": _bf16(wqkv[2 * E:], dev), "bv": _f32(bqkv[2 * E:], dev),
+                "wqkv": _bf16(wqkv, dev), "bqkv": _f32(bqkv, dev),
                 "wproj": _bf16(blk.attn.proj.weight, dev), "bproj": _f32(blk.attn.proj.bias, dev),
                 "wfc1": _bf16(blk.mlp.fc1.weight, dev), "bfc1": _f32(blk.mlp.fc1.bias, dev),
                 "wfc2": _bf16(blk.mlp.fc2.weight, dev), "bfc2": _f32(blk.mlp.fc2.bias, dev)})
@@ -158,7 +157,7 @@ class B200ViTBackbone(nn.Module):
         n = g * g          # patch tokens
         N = n + 1          # + cls
         if N > 256:
-            raise NotImplementedError("more than 256 tokens per image (the fused softmax tile is 256 keys wide)")
+            raise NotImplementedError("more than 256 tokens per image (b200_attention holds one 256-key score tile)")
         dev = x.device
         pk = self._packed(dev)
         K0 = C * P * P
@@ -171,34 +170,19 @@ class B200ViTBackbone(nn.Module):
         nat.vit_tokens(emb, pk["cls"], pk["pos"], B, n, E, t)
         M = B * N
         h = torch.empty((M, E), dtype=torch.bfloat16, device=dev)
-        qk = torch.empty((M, 2 * E), dtype=torch.bfloat16, device=dev)
-        vt = torch.empty((B, E, 256), dtype=torch.bfloat16, device=dev)   # V^T, key axis padded to the tile
+        qkv = torch.empty((M, 3 * E), dtype=torch.bfloat16, device=dev)
         o = torch.empty((M, E), dtype=torch.bfloat16, device=dev)
         u = torch.empty((M, pk["layers"][0]["wfc1"].shape[0]), dtype=torch.bfloat16, device=dev)
         heads, dh = pk["layers"][0]["heads"], pk["layers"][0]["dh"]
-        p_buf = torch.empty((B, heads, N, 256), dtype=torch.bfloat16, device=dev)
-        rs = torch.empty((B, heads, N), dtype=torch.float32, device=dev)
         feats = []
         bufs = None
         if chains is not None:
             bufs = [torch.empty((B, g, g, len(c) * E), dtype=torch.bfloat16, device=dev) for c in chains]
         for i, ly in enumerate(pk["layers"]):
             nat.layernorm(t, *ly["ln1"], out=h)
-            nat.linear(h, ly["wqk"], bias=ly["bqk"], out=qk)
-            # V^T[b] = W_v h[b]^T (weights on the A side); token rows >= N of the B operand are zero-filled
-            nat.gemm_batched(M=E, N=256, K=E, heads=1, batch=B, a=ly["wv"].data_ptr(), a_strides=(E, 0, 0),
-                             a_shared=True, b=h.data_ptr(), b_strides=(E, 0, N * E), b_rows=N, out=vt.data_ptr(),
-                             out_strides=(256, 0, E * 256))
-            # P = exp(q.k^T / sqrt(d) - rowmax) over the N real keys of a 256-wide tile; rs = 1 / rowsum
-            nat.gemm_batched(M=N, N=256, K=dh, heads=heads, batch=B, a=qk.data_ptr(),
-                             a_strides=(2 * E, dh, N * 2 * E), b=qk.data_ptr() + 2 * E,
-                             b_strides=(2 * E, dh, N * 2 * E), b_rows=N, out=p_buf.data_ptr(),
-                             out_strides=(256, N * 256, heads * N * 256), mode=1, alpha=dh ** -0.5, n_valid=N,
-                             rowsum_inv=rs)
-            # O = (P V) * rs + b_v  (the V bias commutes past the row-stochastic attention matrix)
-            nat.gemm_batched(M=N, N=dh, K=256, heads=heads, batch=B, a=p_buf.data_ptr(),
-                             a_strides=(256, N * 256, heads * N * 256), b=vt.data_ptr(), b_strides=(256, dh * 256, E * 256),
-                             out=o.data_ptr(), out_strides=(E, dh, N * E), rowscale=rs, bias=ly["bv"], vec_h_stride=dh)
+            nat.linear(h, ly["wqkv"], bias=ly["bqkv"], out=qkv)
+            # softmax(q k^T / sqrt(d)) v per (case, head) in one launch: scores in TMEM, probabilities in shared memory
+            nat.attention(qkv, o, B, N, heads, dh)
             t2 = nat.linear_f32(o, ly["wproj"], bias=ly["bproj"], res=t, res_mode=2, out_dtype=torch.float32)
             nat.layernorm(t2, *ly["ln2"], out=h)
             nat.linear(h, ly["wfc1"], bias=ly["bfc1"], act=1, out=u)

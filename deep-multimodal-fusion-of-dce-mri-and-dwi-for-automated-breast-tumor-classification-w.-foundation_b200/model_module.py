@@ -573,8 +573,7 @@ def _transformer_pack(stage, out_proj, dev):
             "heads": at.num_heads, "dh": at.head_dim,
             "ln1": (_f32(blk.norm1.weight, dev), _f32(blk.norm1.bias, dev), blk.norm1.eps),
             "ln2": (_f32(blk.norm2.weight, dev), _f32(blk.norm2.bias, dev), blk.norm2.eps),
-            "wqk": wqkv[:2 * E].to(torch.bfloat16).contiguous(), "bqk": bqkv[:2 * E].contiguous(),
-            "wv": wqkv[2 * E:].to(torch.bfloat16).contiguous(), "bv": bqkv[2 * E:].contiguous(),
+            "wqkv": wqkv.to(torch.bfloat16).contiguous(), "bqkv": bqkv.contiguous(),
             # x + gamma * (W y + b)  ==  (acc * gamma + gamma * b) + x : LayerScale folds into the epilogue affine
             "wproj": at.proj.weight.detach().to(dev, torch.bfloat16).contiguous(), "sproj": g1,
             "bproj": (g1 * _f32(at.proj.bias, dev)).contiguous(),
@@ -599,31 +598,21 @@ def _transformer_stage(tr, x):
     tok = nat.conv_gemm(x, tr["pe_w"], taps=4, bias=tr["pe_b"])  # [B, H/2, W/2, E]
     Ht, Wt = tok.shape[1], tok.shape[2]
     N = Ht * Wt
-    if N != 256:
-        raise NotImplementedError("the fused softmax epilogue needs 256 tokens per case (32x32 maps, patch 2)")
+    if N > 256:
+        raise NotImplementedError("b200_attention holds one 256-key score tile per (case, head): at most 256 tokens")
     M = B * N
     # the residual stream t is kept in fp32 across the blocks (12 bf16 roundings of it would dominate the error);
     # everything that feeds a tensor-core GEMM is bf16
     t = nat.layernorm(tok.view(M, E), *tr["pe_ln"], out_dtype=torch.float32)
     h = torch.empty((M, E), dtype=torch.bfloat16, device=dev)
-    qk = torch.empty((M, 2 * E), dtype=torch.bfloat16, device=dev)
-    vt = torch.empty((B, E, N), dtype=torch.bfloat16, device=dev)
+    qkv = torch.empty((M, 3 * E), dtype=torch.bfloat16, device=dev)
     o = torch.empty((M, E), dtype=torch.bfloat16, device=dev)
     u = torch.empty((M, 4 * E), dtype=torch.bfloat16, device=dev)
     for ly in tr["layers"]:
         heads, dh = ly["heads"], ly["dh"]
-        p_buf = torch.empty((B, heads, N, N), dtype=torch.bfloat16, device=dev)
-        rs = torch.empty((B, heads, N), dtype=torch.float32, device=dev)
         nat.layernorm(t, *ly["ln1"], out=h)
-        nat.linear(h, ly["wqk"], bias=ly["bqk"], out=qk)
-        nat.gemm_batched(M=E, N=N, K=E, heads=1, batch=B, a=ly["wv"].data_ptr(), a_strides=(E, 0, 0), a_shared=True,
-                         b=h.data_ptr(), b_strides=(E, 0, N * E), out=vt.data_ptr(), out_strides=(N, 0, E * N))
-        nat.gemm_batched(M=N, N=N, K=dh, heads=heads, batch=B, a=qk.data_ptr(), a_strides=(2 * E, dh, N * 2 * E),
-                         b=qk.data_ptr() + 2 * E, b_strides=(2 * E, dh, N * 2 * E), out=p_buf.data_ptr(),
-                         out_strides=(N, N * N, heads * N * N), mode=1, alpha=dh ** -0.5, n_valid=N, rowsum_inv=rs)
-        nat.gemm_batched(M=N, N=dh, K=N, heads=heads, batch=B, a=p_buf.data_ptr(),
-                         a_strides=(N, N * N, heads * N * N), b=vt.data_ptr(), b_strides=(N, dh * N, E * N),
-                         out=o.data_ptr(), out_strides=(E, dh, N * E), rowscale=rs, bias=ly["bv"], vec_h_stride=dh)
+        nat.linear(h, ly["wqkv"], bias=ly["bqkv"], out=qkv)
+        nat.attention(qkv, o, B, N, heads, dh)  # transformer_model.py:101-112 in one launch
         last = ly is tr["layers"][-1]
         t2 = nat.linear_f32(o, ly["wproj"], scale=ly["sproj"], bias=ly["bproj"], res=t, res_mode=2,
                             out_dtype=torch.float32)

@@ -96,6 +96,19 @@ int b200_conv_gemm_mc(const void* x, int x_ld, const void* w, const float* scale
                       void* stream);
 
 /*
+ * Fused multi-head self-attention: out[b, n, h*dh : (h+1)*dh] = softmax(q k^T * scale) v for every case b and head h,
+ * from the packed rows qkv[b*N + n, :] = q | k | v (each [heads, dh]) that `Linear(E, 3E)` produces - the reference's
+ * MultiHeadSelfAttention.forward between its qkv and proj layers (code/transformer_model.py:101-112; attn_drop is
+ * identity in eval mode) and the timm ViT-B/16 attention of the backbone (code/foundation_model.py:371-431).
+ * One launch, no score / probability buffer in HBM: S in TMEM -> softmax in registers -> P in shared memory -> P V.
+ * bf16 in / out, fp32 accumulation and softmax.  N <= 256 tokens, dh in {64, 128}; qkv_ld >= 3*heads*dh, out_ld >=
+ * heads*dh, both multiples of 8 elements, 16-byte aligned bases.  Returns 0, -1 unsupported shape, -2 null pointer,
+ * -3 leading dimensions, -5 alignment.
+ */
+int b200_attention(const void* qkv, int qkv_ld, void* out, int out_ld, int B, int N, int heads, int dh, float scale,
+                   void* stream);
+
+/*
  * Batched GEMM on the same tcgen05 kernel: for every (batch, head)
  *     out[m, n] = epilogue( sum_k A[m, k] * B[n, k] ),   A, B bf16 K-major, fp32 accumulation.
  * This is how the transformer blocks run (code/transformer_model.py:98-116): Q.K^T per head

@@ -32,14 +32,16 @@ def check(gold, key, t, rtol, atol_frac=None, what=""):
     meta = gold[key + "/meta"]
     shape = tuple(int(v) for v in meta[:-1])
     assert tuple(t.shape) == shape, f"{key}: shape {tuple(t.shape)} != {shape}"
-    ref_s = torch.from_numpy(gold[key + "/samples"]).double()
-    got_s = t.double().reshape(-1)[::PROBE_STRIDE][:PROBE_N]
-    denom = max(ref_s.abs().max().item(), 1e-12)
-    err = (got_s - ref_s).abs().max().item() / denom
     if key + "/full" in gold.files:
+        # the whole tensor is stored: the metric is exact.  (The strided probe of a tensor smaller than the stride
+        # is its first element alone, and max|d| / |ref[0]| is not the metric - a 2 x 1 x 14 x 14 map whose first
+        # element is near zero reads as 20 % off while every element is within 2 % of the map's range.)
         ref_f = torch.from_numpy(gold[key + "/full"]).double()
-        denom_f = max(ref_f.abs().max().item(), 1e-12)
-        err = max(err, (t.double() - ref_f).abs().max().item() / denom_f)
+        err = (t.double() - ref_f).abs().max().item() / max(ref_f.abs().max().item(), 1e-12)
+    else:
+        ref_s = torch.from_numpy(gold[key + "/samples"]).double()
+        got_s = t.double().reshape(-1)[::PROBE_STRIDE][:PROBE_N]
+        err = (got_s - ref_s).abs().max().item() / max(ref_s.abs().max().item(), 1e-12)
     assert err <= rtol, f"{what}{key}: max|d|/max|ref| = {err:.3e} > {rtol:.1e}"
     ref_sum, ref_abs = gold[key + "/sums"]
     assert abs(t.double().sum().item() - ref_sum) <= 4 * rtol * max(ref_abs, 1e-12) + 1e-9, f"{key}: sum mismatch"

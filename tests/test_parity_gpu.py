@@ -340,9 +340,10 @@ def test_vit_backbone_features_vs_oracle():
 # (per-channel instance norms over 196 pixels) and the heavy-tailed maps they feed (max/rms ~ 25) amplify bf16
 # operand rounding: the fp32 oracle with nothing but its GEMM operands rounded to bf16 (tests/tools/bf16_floor.py)
 # already deviates from itself by 1.2-1.7 % on f1, 3-7 % on f2 / f3, 2.7 % on the DWI logits and 3.7 % on the
-# DWI mask.  The product is held to that floor: 8e-2 of the tensor's max on maps downstream of a mix, and the
+# DWI mask.  The product (fused attention: fp32 softmax, probabilities rounded once) measures <= 4.0 % on every
+# output (tests/tools/vit_err.py); it is held to 5e-2 of the tensor's max on maps downstream of a mix, and the
 # usual 2e-2 on everything upstream of the first one.
-VIT_TOL = 8e-2
+VIT_TOL = 5e-2
 VIT_UPSTREAM = ("aux.raw_feats.0", "aux.recon_feats.0", "aux.proj_pairs.0", "aux.proj_pairs.1", "aux.mod_attn_map")
 
 
