@@ -138,6 +138,11 @@ def test_no_cpu_fallback():
         mm.SEBlock(8).eval()(torch.zeros(1, 8, 4, 4))
     with pytest.raises(NotImplementedError):   # ... and in training mode they are driven through their parent
         mm.SEBlock(8).train()(torch.zeros(1, 8, 4, 4))
+    import transformer_model as tm
+    with pytest.raises(nat.B200NativeError):  # the transformer sub-modules too: CUDA only
+        tm.MLP(64).eval()(torch.zeros(1, 4, 64))
+    with pytest.raises(nat.B200NativeError):
+        tm.TransformerStage(64, 128, depth=1, heads=2).eval()(torch.zeros(1, 64, 8, 8))
     fm = mm.FusionModel(p).train()
     with pytest.raises(nat.B200NativeError):
         fm([torch.zeros(1, 512, 32, 32)], [torch.zeros(1, 512, 32, 32)], torch.zeros(1, 1, 32, 32), torch.zeros(1, 1, 32, 32))

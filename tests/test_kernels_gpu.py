@@ -641,3 +641,55 @@ def test_reinitialised_weights_are_repacked():
         c = fresh.to(DEV).eval()(x)[0]
     # channel sums are float atomics: two runs agree to rounding, not bitwise
     assert not torch.allclose(a, b, rtol=1e-2, atol=1e-4) and torch.allclose(b, c, rtol=1e-3, atol=1e-5)
+
+
+def test_standalone_transformer_forwards_vs_fp32_torch():
+    """PatchEmbed, MultiHeadSelfAttention, MLP, TransformerBlock, TransformerEncoder and TransformerStage called on
+    their own (transformer_model.py:7-175) against an fp32 torch evaluation of the same formulas with the same
+    parameters (eval mode: the dropouts are identity)."""
+    import transformer_model as tm
+
+    def ref_attn(at, x):
+        B, N, C = x.shape
+        qkv = F.linear(x, at.qkv.weight, at.qkv.bias).reshape(B, N, 3, at.num_heads, at.head_dim).permute(2, 0, 3, 1, 4)
+        a = (qkv[0] @ qkv[1].transpose(-2, -1) * at.scale).softmax(-1)
+        return F.linear((a @ qkv[2]).transpose(1, 2).reshape(B, N, C), at.proj.weight, at.proj.bias)
+
+    def ref_mlp(m, x):
+        return F.linear(F.gelu(F.linear(x, m.fc1.weight, m.fc1.bias)), m.fc2.weight, m.fc2.bias)
+
+    def ref_block(b, x):
+        x = x + ref_attn(b.attn, F.layer_norm(x, (x.shape[-1],), b.norm1.weight, b.norm1.bias, b.norm1.eps)) * b.gamma1
+        return x + ref_mlp(b.mlp, F.layer_norm(x, (x.shape[-1],), b.norm2.weight, b.norm2.bias, b.norm2.eps)) * b.gamma2
+
+    def ref_stage(st, x):
+        t = st.patch_embed.proj(x)
+        hw = t.shape[-2:]
+        t = t.flatten(2).transpose(1, 2)
+        t = F.layer_norm(t, (t.shape[-1],), st.patch_embed.norm.weight, st.patch_embed.norm.bias, st.patch_embed.norm.eps)
+        for b in st.transformer.layers:
+            t = ref_block(b, t)
+        return t.transpose(1, 2).reshape(x.shape[0], -1, *hw)
+
+    torch.manual_seed(5)
+    stage = tm.TransformerStage(in_ch=256, embed_dim=512, depth=2, heads=4).to(DEV).eval()
+    with torch.no_grad():
+        for p_ in stage.parameters():  # non-trivial LayerNorm / LayerScale parameters
+            if p_.dim() == 1:
+                p_.add_(0.2 * torch.randn_like(p_))
+        x = torch.randn(3, 256, 16, 16, device=DEV)          # -> 64 tokens
+        tok = torch.randn(3, 64, 512, device=DEV)
+        blk = stage.transformer.layers[0]
+        tokens, hw = stage.patch_embed(x)
+        assert tuple(tokens.shape) == (3, 64, 512) and tuple(hw) == (8, 8) and tokens.dtype == torch.float32
+        cases = {"attn": (blk.attn(tok), ref_attn(blk.attn, tok)), "mlp": (blk.mlp(tok), ref_mlp(blk.mlp, tok)),
+                 "block": (blk(tok), ref_block(blk, tok)),
+                 "encoder": (stage.transformer(tok), ref_block(stage.transformer.layers[1], ref_block(blk, tok))),
+                 "stage": (stage(x), ref_stage(stage, x))}
+        torch.cuda.synchronize()
+        for name, (got, ref) in cases.items():
+            assert got.shape == ref.shape and got.dtype == torch.float32, name
+            assert _rel(got, ref) < 1.5e-2, (name, _rel(got, ref))
+        stage.train()
+        with pytest.raises(NotImplementedError):
+            stage(x)
