@@ -39,6 +39,8 @@ namespace b200 {
 struct ConvGemmParams {
     int H, W, Cout;
     int BH, BW;            // TMA box over (h, w); BH*BW == 128
+    int BB, B;             // cases per M tile (box extent over the batch dimension; 1 unless the planner packs several
+                           // cases of a small map into one tile) and the number of cases
     int tiles_w, tiles_h;  // tiles per image row / column
     int n_tiles, m_tiles;
     int kc;                // Cin / 64
@@ -255,12 +257,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int mt = WS ? m_tile : (PAIR ? 2 * (tile / p.n_tiles) : tile / p.n_tiles);
                 const int w0 = (mt % p.tiles_w) * p.BW;
                 const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.BH;
-                const int b = mt / (p.tiles_w * p.tiles_h);
+                const int b = mt / (p.tiles_w * p.tiles_h) * p.BB;
                 // PAIR: the second M tile of the pair (absent only for the last tile of an odd count)
                 const bool has2 = PAIR && mt + 1 < p.m_tiles;
                 const int w1 = ((mt + 1) % p.tiles_w) * p.BW;
                 const int h1 = (((mt + 1) / p.tiles_w) % p.tiles_h) * p.BH;
-                const int b1 = (mt + 1) / (p.tiles_w * p.tiles_h);
+                const int b1 = (mt + 1) / (p.tiles_w * p.tiles_h) * p.BB;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     const int tap = kb / p.kc;
                     const int c0 = (kb - tap * p.kc) * kBlockK;
@@ -516,12 +518,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // tile -> (w0, h0, b); this warp's slab = 32 consecutive rows of the tile = a {bw, bh} box in (w, h)
             const int w0 = (m_tile % p.tiles_w) * p.BW;
             const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.BH;
-            const int b = m_tile / (p.tiles_w * p.tiles_h);
-            const int slab_w = w0 + (q * 32) % p.BW, slab_h = h0 + (q * 32) / p.BW;
+            const int b = m_tile / (p.tiles_w * p.tiles_h) * p.BB;
+            const int slab_w = w0 + (q * 32) % p.BW, slab_h = h0 + (q * 32) / p.BW;  // (staged epilogue: BB = 1)
             const int trow = q * 32 + lane;
-            const int pw = w0 + trow % p.BW, ph = h0 + trow / p.BW;
-            const bool valid = trow < p.BW * p.BH && pw < p.W && ph < p.H;
-            const long long pix = (static_cast<long long>(b) * p.H + ph) * p.W + pw;
+            // tile row -> (w, h, case): the TMA box is {64 ch, BW, BH, BB}, rows in that order
+            const int pw = w0 + trow % p.BW, ph = h0 + (trow / p.BW) % p.BH, pb = b + trow / (p.BW * p.BH);
+            const bool valid = trow < p.BW * p.BH * p.BB && pw < p.W && ph < p.H && pb < p.B;
+            const long long pix = (static_cast<long long>(pb) * p.H + ph) * p.W + pw;
             // pixel index of tile row r, or -1 when that row does not exist (ragged tiles / tails)
             // (used by the fp32 epilogue, i.e. b200_linear only: H = 1 and a tile is 128 consecutive rows)
             auto row_pix = [&](int r) -> long long { return w0 + r < p.W ? static_cast<long long>(w0 + r) : -1; };
@@ -1205,7 +1208,7 @@ static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, 
     }
     // TMA-staged epilogue?  Needs the warp's 32-row slab to be a {bw, bh} box and bf16 output / residual.
     static const bool no_tma_up2 = std::getenv("B200_NO_TMA_UP2") != nullptr;
-    const bool slab_is_box = p.BW * p.BH == kBlockM && (p.BW % 32 == 0 || 32 % p.BW == 0) &&
+    const bool slab_is_box = p.BB == 1 && p.BW * p.BH == kBlockM && (p.BW % 32 == 0 || 32 % p.BW == 0) &&
                              (p.H == 1 || p.b_mode == 1 || p.H % p.BH == 0);
     p.tma_epi = ((p.up2 && no_tma_up2) || p.res_f32 || p.out_f32 || !slab_is_box) ? 0 : 1;
     p.share_box = 0;
@@ -1244,7 +1247,7 @@ static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, 
     int rc;
     {
         const int s = p.cstride;
-        const int box[4] = {64, p.BW * s, p.BH * s, 1};
+        const int box[4] = {64, p.BW * s, p.BH * s, p.BB};
         const int estr[4] = {1, s, s, 1};
         if ((rc = encode_view(encode, &tmA, j.a, box, estr, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != 0)
@@ -1272,7 +1275,7 @@ static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, 
     tmOut = tmA;
     tmOut2 = tmA;
     tmRes = tmA;
-    p.a_box_bytes = p.BW * p.BH * kBlockK * 2;
+    p.a_box_bytes = p.BW * p.BH * p.BB * kBlockK * 2;
     if (p.tma_epi) {
         const int cw = BN / 2 < 64 ? BN / 2 : 64;
         const CUtensorMapSwizzle swz = cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -1336,7 +1339,11 @@ static int conv_gemm_launch(const void* x, int x_ld, const void* w, const float*
         return -5;
 
     ConvGemmParams p{};
+    p.BB = 1;
+    p.B = B;
     if (stride != 1 && stride != 2) return -6;
+    if (n_split <= 0 || n_split > Cout || n_split % 64 != 0) return -10;
+    const bool two = n_split < Cout;
     // taps == 4: 2x2 kernel, stride 2, no padding (patch embedding); taps 1 / 9 with stride 2: the strided 1x1 and
     // 3x3 (padding 1) convolutions of down-sampling blocks and of the mask head (input pixel 2*o + tap - pad)
     const int cs = taps == 4 ? 2 : stride;
@@ -1359,18 +1366,39 @@ static int conv_gemm_launch(const void* x, int x_ld, const void* w, const float*
         p.tiles_h = (Ho + p.BH - 1) / p.BH;
         const bool ragged = p.BW * p.BH != 128 || Ho % p.BH != 0;
         if (ragged && (up2 || gap != nullptr)) return -7;
+        // Small ragged maps: a tile may span several cases (the 4th box dimension).  14 x 14 (ViT grid) as 9-row tiles
+        // fills 196 of every 256 MMA rows; one image row of 9 consecutive cases per tile fills 126 of 128.  Pick the
+        // (rows, cases) box with the best fill; plain stride-1 convolutions with the direct epilogue only.
+        static const bool no_multi = std::getenv("B200_NO_MULTICASE") != nullptr;  // A/B measurements
+        if (ragged && cs == 1 && !two && dot_w == nullptr && B > 1 && !no_multi) {
+            double best = static_cast<double>(Ho) * Wo / (p.tiles_h * 128.0);
+            int best_bh = p.BH, best_bb = 1;
+            for (int bh = 1; bh <= Ho && bh * Wo <= 128; ++bh) {
+                int bb = 128 / (bh * Wo);
+                if (bb > B) bb = B;
+                if (bb > 256) bb = 256;
+                const int groups = (B + bb - 1) / bb;
+                const double fill = static_cast<double>(B) * Ho * Wo / (static_cast<double>(groups) * ((Ho + bh - 1) / bh) * 128.0);
+                if (fill > best + 0.02) {
+                    best = fill;
+                    best_bh = bh;
+                    best_bb = bb;
+                }
+            }
+            p.BH = best_bh;
+            p.BB = best_bb;
+            p.tiles_h = (Ho + p.BH - 1) / p.BH;
+        }
     }
     p.H = Ho;
     p.W = Wo;
     p.Cout = Cout;
-    if (n_split <= 0 || n_split > Cout || n_split % 64 != 0) return -10;
-    const bool two = n_split < Cout;
     if (two && (out2 == nullptr || out2_ld % 8 != 0 || (reinterpret_cast<uintptr_t>(out2) & 15) || gap != nullptr ||
                 up2 || dot_w != nullptr || res_mode != 0))
         return -11;
     if (gap != nullptr && (out == nullptr || up2)) return -17;  // channel sums are taken from the staged output boxes
     if (dot_w != nullptr && (dot_out == nullptr || H == 1 || out != nullptr)) return -12;
-    p.m_tiles = B * p.tiles_w * p.tiles_h;
+    p.m_tiles = ((B + p.BB - 1) / p.BB) * p.tiles_w * p.tiles_h;
     p.kc = Cin / 64;
     p.taps = taps;
     p.k_blocks = taps * p.kc;
@@ -1463,6 +1491,8 @@ extern "C" int b200_linear(const void* x, long long M, int K, const void* w, int
     if (K % 64 != 0 || N % 64 != 0) return -2;
     if (res_mode != 0 && res == nullptr) return -4;
     ConvGemmParams p{};
+    p.BB = 1;
+    p.B = 1;
     p.H = 1;
     p.W = static_cast<int>(M);
     p.BW = 128;
@@ -1506,6 +1536,8 @@ extern "C" int b200_gemm_batched(const b200_gemm_desc* d, void* stream) {
     if (d->mode == 1 && (d->N != 256 || d->rowsum_inv == nullptr || d->out == nullptr || !(d->alpha > 0.f))) return -3;
     if (d->res_mode != 0 && d->res == nullptr) return -4;
     ConvGemmParams p{};
+    p.BB = 1;
+    p.B = d->batch;
     p.H = d->heads;
     p.W = d->M;
     p.BW = 128;

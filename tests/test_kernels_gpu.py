@@ -693,3 +693,33 @@ def test_standalone_transformer_forwards_vs_fp32_torch():
         stage.train()
         with pytest.raises(NotImplementedError):
             stage(x)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps,res_mode", [(20, 14, 14, 128, 256, 9, 0), (9, 14, 14, 64, 128, 1, 1),
+                                                         (5, 7, 7, 128, 64, 9, 2), (37, 14, 14, 192, 768, 9, 0),
+                                                         (163, 14, 14, 128, 128, 9, 1)])
+def test_conv_gemm_tiles_spanning_cases(B, H, W, Cin, Cout, taps, res_mode):
+    """Small ragged maps are tiled across cases (14 x 14: one image row of 9 consecutive cases per 128-row tile, 126 rows
+    filled, instead of 9-row tiles of one case): same results as a per-case launch (which cannot span cases) bit for
+    bit, and as fp32 torch within bf16 rounding; batch sizes that leave a partial last group, and the paired kernel."""
+    g = torch.Generator().manual_seed(B + H)
+    x = torch.randn(B, H, W, Cin, generator=g).bfloat16().to(DEV)
+    w = (torch.randn(Cout, taps * Cin, generator=g) / (taps * Cin) ** 0.5).bfloat16().to(DEV)
+    sc = (1 + 0.1 * torch.randn(Cout, generator=g)).to(DEV)
+    bi = (0.1 * torch.randn(Cout, generator=g)).to(DEV)
+    r = torch.randn(B, H, W, Cout, generator=g).bfloat16().to(DEV) if res_mode else None
+    y = nat.conv_gemm(x, w, taps=taps, scale=sc, bias=bi, act=1, res=r, res_mode=res_mode)
+    for b in (0, B // 2, B - 1):
+        one = nat.conv_gemm(x[b:b + 1].contiguous(), w, taps=taps, scale=sc, bias=bi, act=1,
+                            res=None if r is None else r[b:b + 1].contiguous(), res_mode=res_mode)
+        assert torch.equal(y[b:b + 1], one), (b,)
+    k = int(taps ** 0.5)
+    wt = w.float().view(Cout, k, k, Cin).permute(0, 3, 1, 2)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt, padding=k // 2) * sc.view(1, -1, 1, 1) + bi.view(1, -1, 1, 1)
+    if res_mode == 1:
+        ref = F.gelu(ref + r.float().permute(0, 3, 1, 2))
+    else:
+        ref = F.gelu(ref)
+        if res_mode == 2:
+            ref = ref + r.float().permute(0, 3, 1, 2)
+    assert _rel(y.permute(0, 3, 1, 2), ref) < 1.5e-2
