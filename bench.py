@@ -345,7 +345,8 @@ def train_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    gather([step() for _ in range(args.warmup)])
+    for _ in range(args.warmup):
+        step()
     barrier()
     launches0 = nat.LAUNCH_COUNT
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -550,7 +551,8 @@ def train_full_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    gather([step() for _ in range(args.warmup)])
+    for _ in range(args.warmup):
+        step()
     barrier()
     launches0 = nat.LAUNCH_COUNT
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -947,6 +947,9 @@ class FullFusionTrainer:
 
         if self._world() == 1 or hi <= lo:
             return
+        if torch.device(self.dev).type != "cuda":  # host-side tests of the bucket plan (gloo): no streams to order
+            dist.all_reduce(self.flat["g"][lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+            return
         if self._comm is None:
             self._comm = torch.cuda.Stream(device=self.dev)
         ev = torch.cuda.Event()

@@ -244,6 +244,57 @@ def test_gradient_allreduce_two_ranks_gloo(tmp_path):
     assert all("ok" in o for o in outs)
 
 
+_BUCKET_WORKER = r"""
+import sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); import b200path
+from train_graph import FullFusionTrainer
+rank = int(sys.argv[3])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=2)
+# the bucket plan of the all-unfrozen step on the host: 7 segments in forward order (3 per encoder + the fusion head),
+# sizes in elements; the backward pass fires the markers last segment first
+sizes = [900, 5000, 30000, 700, 5200, 31000, 4000]
+ends, off = [], 0
+for s in sizes:
+    off += s; ends.append(off)
+t = FullFusionTrainer.__new__(FullFusionTrainer)
+t.dev, t.group, t._comm, t._pending = torch.device("cpu"), None, None, []
+t.seg_ends, t.flat_numel, t.bucket_elems = ends, off, 8192
+t.flat = {"g": torch.arange(off + 1, dtype=torch.float32) * (1 + rank)}      # + the loss slot, which no bucket covers
+calls = []
+orig = t._reduce_range
+def spy(lo, hi):
+    calls.append((lo, hi)); orig(lo, hi)
+t._reduce_range = spy
+t._reduced_from = t.flat_numel
+for seg in reversed(range(len(sizes))):
+    t._marker(seg)()
+# every gradient element reduced exactly once, in backward order, buckets >= 8192 elements except the one that
+# closes the buffer at segment 0
+assert calls[0][1] == off and calls[-1][0] == 0 and all(a[0] == b[1] for a, b in zip(calls, calls[1:])), calls
+assert all(hi - lo >= 8192 for lo, hi in calls[:-1]), calls
+assert calls == [(41800, 76800), (5900, 41800), (0, 5900)], calls
+want = torch.arange(off + 1, dtype=torch.float32) * 3.0                       # rank 0 + rank 1
+want[off] = float(off) * (1 + rank)                                            # the loss slot stays local
+assert torch.equal(t.flat["g"], want)
+dist.destroy_process_group()
+print("ok", calls)
+"""
+
+
+def test_full_trainer_bucket_plan_two_ranks_gloo(tmp_path):
+    """FullFusionTrainer's gradient exchange (train_graph._marker / _reduce_range): tape markers fire in backward order,
+    each closes a bucket once >= bucket_elems gradients are final, the first segment's marker flushes the rest; under
+    gloo with two ranks every element of the flat gradient buffer is summed exactly once."""
+    script = tmp_path / "bucket_worker.py"
+    script.write_text(_BUCKET_WORKER)
+    port = str(30700 + os.getpid() % 500)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
 def test_training_entry_points_reject_bad_arguments_without_a_gpu():
     import b200_native as nat
 
