@@ -38,17 +38,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait blocks in hardware for a bounded, implementation-defined time, then reports the phase.
+// try_wait blocks in hardware until the phase completes or the suspend-time hint (ns) runs out, then reports the
+// phase.  A generous hint costs no latency (completion wakes the thread at once) and keeps the waiting producer /
+// MMA / epilogue warps from spending issue slots on poll loops: with the default (short) limit 18 % of the
+// instructions the block-tail kernels issued were SYNCS / BRA / YIELD polls (profiles/r2_tail_opmix.txt).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
     return ok != 0;
 }
