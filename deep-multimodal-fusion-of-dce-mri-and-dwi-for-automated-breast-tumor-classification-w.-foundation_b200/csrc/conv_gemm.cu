@@ -39,6 +39,13 @@ namespace b200 {
 struct ConvGemmParams {
     int H, W, Cout;
     int BH, BW;            // TMA box over (h, w); BH*BW == 128
+    // exact division by launch constants without the 25-instruction software divide (the tile -> coordinate maps run per
+    // tile in every role; they were 14 % of the instructions the block-tail kernels issued): q = umulhi(n, m) [+ n when
+    // d == 1], m = floor(2^32 / d) + 1, exact while n * d < 2^32
+    struct FastDiv {
+        uint32_t d, m;
+    };
+    FastDiv fd_ntiles, fd_tw, fd_th, fd_twth;
     int BB, B;             // cases per M tile (box extent over the batch dimension; 1 unless the planner packs several
                            // cases of a small map into one tile) and the number of cases
     int tiles_w, tiles_h;  // tiles per image row / column
@@ -88,6 +95,21 @@ struct ConvGemmParams {
     int pair;              // BN = 128: two M tiles per CTA iteration share one weight slab (conv_gemm_kernel<..., PAIR>)
     int off_ring, off_bar, off_union, off_rbox, off_sm;  // shared-memory plan (bytes from the 1 KB-aligned base)
 };
+
+__device__ __forceinline__ int fd_div(const ConvGemmParams::FastDiv& f, int n) {
+    return static_cast<int>(__umulhi(static_cast<uint32_t>(n), f.m) + (f.d == 1 ? static_cast<uint32_t>(n) : 0u));
+}
+__device__ __forceinline__ int fd_mod(const ConvGemmParams::FastDiv& f, int n) {
+    return n - fd_div(f, n) * static_cast<int>(f.d);
+}
+// M tile index -> (w0 tile, h0 tile, case group) indices
+__device__ __forceinline__ void tile_whb(const ConvGemmParams& p, int mt, int& tw, int& th, int& tb) {
+    const int a = fd_div(p.fd_tw, mt);
+    tw = mt - a * static_cast<int>(p.fd_tw.d);
+    tb = fd_div(p.fd_twth, mt);
+    th = a - tb * static_cast<int>(p.fd_th.d);
+}
+
 
 constexpr int kBlockM = 128;
 constexpr int kF32BlockBytes = 32 * 33 * 4;  // one warp's padded 32 x 32 fp32 transposition block (fp32 epilogue)
@@ -253,16 +275,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t phase = 0;
             int tile = blockIdx.x, m_tile = m_first;
             for (int it = 0; it < n_iters; ++it, tile += gridDim.x, m_tile += m_step) {
-                const int n_tile = WS ? my_n : tile % p.n_tiles;
-                const int mt = WS ? m_tile : (PAIR ? 2 * (tile / p.n_tiles) : tile / p.n_tiles);
-                const int w0 = (mt % p.tiles_w) * p.BW;
-                const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.BH;
-                const int b = mt / (p.tiles_w * p.tiles_h) * p.BB;
+                const int tq = fd_div(p.fd_ntiles, tile);
+                const int n_tile = WS ? my_n : tile - tq * p.n_tiles;
+                const int mt = WS ? m_tile : (PAIR ? 2 * tq : tq);
+                int tw0, th0, tb0, tw1 = 0, th1 = 0, tb1 = 0;
+                tile_whb(p, mt, tw0, th0, tb0);
+                const int w0 = tw0 * p.BW, h0 = th0 * p.BH, b = tb0 * p.BB;
                 // PAIR: the second M tile of the pair (absent only for the last tile of an odd count)
                 const bool has2 = PAIR && mt + 1 < p.m_tiles;
-                const int w1 = ((mt + 1) % p.tiles_w) * p.BW;
-                const int h1 = (((mt + 1) / p.tiles_w) % p.tiles_h) * p.BH;
-                const int b1 = (mt + 1) / (p.tiles_w * p.tiles_h) * p.BB;
+                if (PAIR) tile_whb(p, mt + 1, tw1, th1, tb1);
+                const int w1 = tw1 * p.BW, h1 = th1 * p.BH, b1 = tb1 * p.BB;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     const int tap = kb / p.kc;
                     const int c0 = (kb - tap * p.kc) * kBlockK;
@@ -302,7 +324,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (WS) mbar_wait(wbar, 0);
             int tile = blockIdx.x;
             for (int it = 0; it < n_iters; ++it, tile += gridDim.x) {
-                const bool has2 = PAIR && 2 * (tile / p.n_tiles) + 1 < p.m_tiles;
+                const bool has2 = PAIR && 2 * fd_div(p.fd_ntiles, tile) + 1 < p.m_tiles;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 if (has2) mbar_wait(&tempty[acc + 1], acc_phase ^ 1);
                 tc_fence_after();
@@ -360,10 +382,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int tile = blockIdx.x;
         for (int it = 0; it < n_iters; ++it, tile += gridDim.x) {
             if (acc == set) {
-                const int m_tile = tile / p.n_tiles;
-                const int w0 = (m_tile % p.tiles_w) * p.BW;
-                const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.BH;
-                const int b = m_tile / (p.tiles_w * p.tiles_h);
+                const int m_tile = fd_div(p.fd_ntiles, tile);
+                int tw0, th0, b;
+                tile_whb(p, m_tile, tw0, th0, b);
+                const int w0 = tw0 * p.BW, h0 = th0 * p.BH;
                 const int slab_w = w0 + (q * 32) % p.BW, slab_h = h0 + (q * 32) / p.BW;
                 const int trow = q * 32 + lane;
                 const int pw = w0 + trow % p.BW, ph = h0 + trow / p.BW;
@@ -479,19 +501,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int acc = 0;
         uint32_t acc_phase = 0;
         int tile = blockIdx.x, m_walk = m_first;
+        // tile-invariant pieces of the row -> pixel map (the TMA box is {64 ch, BW, BH, BB}, rows in that order)
+        const int trow = q * 32 + lane;
+        const int r_w = trow % p.BW, r_h = (trow / p.BW) % p.BH, r_b = trow / (p.BW * p.BH);
+        const int q_w = (q * 32) % p.BW, q_h = (q * 32) / p.BW;
+        const bool row_in_box = trow < p.BW * p.BH * p.BB;
         // Residual boxes are fetched one tile ahead: box bx of tile i+1 is requested as soon as the last lane
         // has read box bx of tile i, so its DRAM latency hides behind the rest of tile i's epilogue.
         auto res_fetch = [&](int nt, int mt, int bx) {
-            const int fw = (mt % p.tiles_w) * p.BW + (q * 32) % p.BW;
-            const int fh = ((mt / p.tiles_w) % p.tiles_h) * p.BH + (q * 32) / p.BW;
-            const int fb = mt / (p.tiles_w * p.tiles_h);
+            int ftw, fth, fb;
+            tile_whb(p, mt, ftw, fth, fb);
+            const int fw = ftw * p.BW + q_w, fh = fth * p.BH + q_h;
             mbar_arrive_expect_tx(&rbar[bx], T::kBoxBytes);
             tma_load_4d(rbuf + bx * T::kBoxBytes, &tmRes, &rbar[bx], nt * BN + colw0 + bx * T::kBoxCols, fw, fh, fb);
         };
         // the CTA's tile sequence: (tile index, sub) -> (N tile, M tile); PAIR walks super-tiles of two M tiles
         auto tile_nm = [&](int t_idx, int m_idx, int sub, int& nt, int& mt) {
-            nt = WS ? my_n : t_idx % p.n_tiles;
-            mt = WS ? m_idx : (PAIR ? 2 * (t_idx / p.n_tiles) + sub : t_idx / p.n_tiles);
+            const int tq = fd_div(p.fd_ntiles, t_idx);
+            nt = WS ? my_n : t_idx - tq * p.n_tiles;
+            mt = WS ? m_idx : (PAIR ? 2 * tq + sub : tq);
             return mt < p.m_tiles;
         };
         if (RES != 0 && tma_epi && lane == 0 && n_iters > 0) {
@@ -516,14 +544,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (PAIR && sub == 0) have_next = tile_nm(tile, m_walk, 1, n_next, m_next);
             if (!have_next && it + 1 < n_iters) have_next = tile_nm(tile + gridDim.x, m_walk + m_step, 0, n_next, m_next);
             // tile -> (w0, h0, b); this warp's slab = 32 consecutive rows of the tile = a {bw, bh} box in (w, h)
-            const int w0 = (m_tile % p.tiles_w) * p.BW;
-            const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.BH;
-            const int b = m_tile / (p.tiles_w * p.tiles_h) * p.BB;
-            const int slab_w = w0 + (q * 32) % p.BW, slab_h = h0 + (q * 32) / p.BW;  // (staged epilogue: BB = 1)
-            const int trow = q * 32 + lane;
-            // tile row -> (w, h, case): the TMA box is {64 ch, BW, BH, BB}, rows in that order
-            const int pw = w0 + trow % p.BW, ph = h0 + (trow / p.BW) % p.BH, pb = b + trow / (p.BW * p.BH);
-            const bool valid = trow < p.BW * p.BH * p.BB && pw < p.W && ph < p.H && pb < p.B;
+            int tw0, th0, tb0;
+            tile_whb(p, m_tile, tw0, th0, tb0);
+            const int w0 = tw0 * p.BW, h0 = th0 * p.BH, b = tb0 * p.BB;
+            const int slab_w = w0 + q_w, slab_h = h0 + q_h;  // (staged epilogue: BB = 1)
+            const int pw = w0 + r_w, ph = h0 + r_h, pb = b + r_b;
+            const bool valid = row_in_box && pw < p.W && ph < p.H && pb < p.B;
             const long long pix = (static_cast<long long>(pb) * p.H + ph) * p.W + pw;
             // pixel index of tile row r, or -1 when that row does not exist (ragged tiles / tails)
             // (used by the fp32 epilogue, i.e. b200_linear only: H = 1 and a tile is 128 consecutive rows)
@@ -1238,6 +1264,23 @@ static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, 
     }
     if (BN == 0) return -13;
     p.n_tiles = Cout / BN;
+    {
+        auto fd = [](int d) {
+            ConvGemmParams::FastDiv f;
+            f.d = static_cast<uint32_t>(d);
+            f.m = d == 1 ? 0u : static_cast<uint32_t>((1ull << 32) / static_cast<uint32_t>(d)) + 1u;
+            return f;
+        };
+        p.fd_ntiles = fd(p.n_tiles);
+        p.fd_tw = fd(p.tiles_w);
+        p.fd_th = fd(p.tiles_h);
+        p.fd_twth = fd(p.tiles_w * p.tiles_h);
+        // exactness bound of the multiply-high division: n * d < 2^32 for every n the kernel divides
+        const unsigned long long n_max = static_cast<unsigned long long>(p.m_tiles + 2) * p.n_tiles + 2ull * g_num_sms;
+        if (n_max * static_cast<unsigned long long>(p.tiles_w) * p.tiles_h >= (1ull << 32) ||
+            n_max * p.n_tiles >= (1ull << 32))
+            return -21;
+    }
     if (Cout > 8192) return -15;
     if (p.scale == nullptr) p.scale = identity_affine(true);
     if (p.bias == nullptr) p.bias = identity_affine(false);
