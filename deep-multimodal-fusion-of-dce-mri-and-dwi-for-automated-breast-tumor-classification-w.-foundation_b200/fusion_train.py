@@ -445,16 +445,40 @@ class FusionHeadTrainer(torch.optim.Optimizer):
 
     # torch.optim-like surface for harnesses that treat the object returned by configure_optimizers as one
     def state_dict(self):
+        """torch.optim.AdamW-shaped: {"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [{..., "params":
+        [0..n-1]}]} (what generic checkpoint code and `torch.optim.Optimizer.load_state_dict` consumers index), plus
+        "names" / "flat_numel" so that a state saved for another parameter set is refused with a clear message."""
         flat = self._bind()
-        return {"step": self.step_count, "names": list(self.names), "exp_avg": flat["m"].clone(),
-                "exp_avg_sq": flat["v"].clone(),
-                "hyper": {k: self.param_groups[0][k] for k in ("lr", "betas", "eps", "weight_decay")}}
+        step = torch.tensor(float(self.step_count))
+        state = {i: {"step": step.clone(), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
+                 for i, (m, v) in enumerate(zip(flat_views(self.params, flat["m"]), flat_views(self.params, flat["v"])))}
+        group = {k: self.param_groups[0][k] for k in ("lr", "betas", "eps", "weight_decay")}
+        group["params"] = list(range(len(self.params)))
+        return {"state": state, "param_groups": [group], "names": list(self.names), "flat_numel": self.flat_numel}
 
     def load_state_dict(self, sd):
+        """Accepts the dict above or the flat form earlier checkpoints hold ({"step", "names", "exp_avg", "exp_avg_sq",
+        "hyper"})."""
         flat = self._bind()
-        if list(sd["names"]) != list(self.names):
+        if "names" in sd and list(sd["names"]) != list(self.names):
             raise ValueError("optimizer state was saved for a different parameter set")
-        self.step_count = int(sd["step"])
-        flat["m"].copy_(sd["exp_avg"])
-        flat["v"].copy_(sd["exp_avg_sq"])
-        self.param_groups[0].update(sd.get("hyper", {}))
+        if "state" in sd:
+            if len(sd["state"]) != len(self.params):
+                raise ValueError(f"optimizer state holds {len(sd['state'])} tensors, this trainer {len(self.params)}")
+            ms, vs = flat_views(self.params, flat["m"]), flat_views(self.params, flat["v"])
+            for i, (m, v) in enumerate(zip(ms, vs)):
+                st = sd["state"][i]
+                if tuple(st["exp_avg"].shape) != tuple(m.shape):
+                    raise ValueError(f"optimizer state {i} ({self.names[i]}): shape {tuple(st['exp_avg'].shape)} != {tuple(m.shape)}")
+                m.copy_(st["exp_avg"])
+                v.copy_(st["exp_avg_sq"])
+            self.step_count = int(float(sd["state"][0]["step"])) if len(sd["state"]) else 0
+            hyper = {k: v for k, v in sd["param_groups"][0].items() if k != "params"}
+        else:
+            if sd["exp_avg"].numel() != self.flat_numel:
+                raise ValueError(f"optimizer state holds {sd['exp_avg'].numel()} moment elements, this trainer {self.flat_numel}")
+            self.step_count = int(sd["step"])
+            flat["m"].copy_(sd["exp_avg"])
+            flat["v"].copy_(sd["exp_avg_sq"])
+            hyper = sd.get("hyper", {})
+        self.param_groups[0].update(hyper)

@@ -505,5 +505,16 @@ def test_optimizer_state_roundtrip_and_model_reload():
     # split-K weight gradients accumulate with float atomics: equal to fp32 round-off, not bitwise
     assert all(abs(a - b) <= 1e-5 * abs(b) for a, b in zip(again, ref)), (again, ref)
     assert _rel(fm.state_dict()["classifier.2.weight"], ref_param) < 1e-4
+    # the dict has torch.optim.AdamW's shape (generic checkpoint code indexes "state" / "param_groups")
+    assert set(opt_state) >= {"state", "param_groups"} and opt_state["param_groups"][0]["params"] == list(range(len(tr.params)))
+    assert all(set(st) == {"step", "exp_avg", "exp_avg_sq"} for st in opt_state["state"].values())
+    assert tuple(opt_state["state"][0]["exp_avg"].shape) == tuple(tr.params[0].shape)
+    flat = tr._bind()
+    legacy = {"step": 3, "names": list(tr.names), "exp_avg": flat["m"].clone(), "exp_avg_sq": flat["v"].clone()}
+    tr.load_state_dict(legacy)                                  # the flat form of earlier checkpoints still loads
     with pytest.raises(ValueError):
-        tr.load_state_dict({"step": 1, "names": ["x"], "exp_avg": opt_state["exp_avg"], "exp_avg_sq": opt_state["exp_avg_sq"]})
+        tr.load_state_dict(dict(legacy, names=["x"]))
+    with pytest.raises(ValueError):
+        tr.load_state_dict(dict(legacy, exp_avg=legacy["exp_avg"][:-8]))
+    with pytest.raises(ValueError):
+        tr.load_state_dict(dict(opt_state, state={0: opt_state["state"][0]}))
