@@ -430,7 +430,7 @@ def train_arm(args):
             dom_ms = statistics.mean(prof[dom_key])
             ach = gemm_flops(*dom_key) / (dom_ms / 1e3) / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tf_sustained"], "traffic": 1.034e9 * B / 1024 if enc == "c3" else None,
+                        "frac": ach / peaks["tf_sustained"], "traffic": 1.032e9 * B / 1024 if enc == "c3" else None,
                         "kernel": dom_name,
                         "ms_per_launch": dom_ms, "share_of_step": sum(prof[dom_key]) / total_ms if total_ms else None,
                         "peak_source": peaks["source"] + " sustained bf16"}
@@ -975,14 +975,14 @@ def main():
             ach = flops / (dom_ms / 1e3) / 1e12
             # DRAM bytes of this launch from the committed ncu --set full captures (dram__bytes_read.sum +
             # dram__bytes_write.sum, scaled by the batch)
-            # profiles/r1_conv_gemm_ncu_full.csv: 539 + 495 MB (C3 conv, B = 1024); 82 + 252 MB (C4 fc1, 50 432 rows)
-            traffic = 1.034e9 * B / 1024 if args.workload == "c3" else None
+            # profiles/r2_ncu_full.csv: 538 + 494 MB (C3 conv, B = 1024); 82 + 252 MB (C4 fc1, 50 432 rows)
+            traffic = 1.032e9 * B / 1024 if args.workload == "c3" else None
             if args.workload == "c4" and dom_key[0] == "b200_conv_gemm_ex" and tuple(dom_key[1][3:]) == (768, 3072, 1):
                 traffic = 334.5e6 * dom_key[1][2] / 50432
             roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                         "frac": ach / peaks["tf_sustained"], "frac_of_burst_peak": ach / peaks["tf_burst"],
                         "traffic": traffic,
-                        "traffic_source": ("profiles/r1_conv_gemm_ncu_full.csv: one ncu --set full capture of this kernel "
+                        "traffic_source": ("profiles/r2_ncu_full.csv (r2_conv256): one ncu --set full capture of this kernel "
                                            "(dram__bytes_read.sum + dram__bytes_write.sum), scaled by the batch - a static "
                                            "figure, not re-measured in this run") if traffic is not None else None,
                         "kernel": dom_name,

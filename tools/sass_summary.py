@@ -51,12 +51,13 @@ with open(os.path.join(out_dir, f"{tag}_sass_summary.md"), "w") as f:
             "count and the count of the mnemonics that identify the Blackwell-native paths (UTCHMMA = tcgen05.mma, "
             "LDTM = tcgen05.ld, UTMALDG/UTMASTG = TMA load/store, SYNCS = mbarrier, FFMA2/FMUL2/FADD2 = packed fp32x2; "
             "LD/ST = generic-space accesses, which the hot kernels should not have).  No HMMA (legacy mma.sync) anywhere.  "
-            f"The complete listing of every kernel is `{tag}_all_kernels.sass.gz`; three representative kernels are also "
+            f"The complete listing of every kernel is `{tag}_all_kernels.sass.gz`; six representative kernels are also "
             "stored uncompressed next to this file.\n\n")
     f.write("| kernel | instr | " + " | ".join(COLS) + " |\n|---|---|" + "---|" * len(COLS) + "\n")
     for d, n, ops, _ in rows:
         f.write(f"| `{d}` | {n} | " + " | ".join(str(ops[c]) if ops[c] else "" for c in COLS) + " |\n")
-wanted = ("conv_gemm_kernel<256, false, 0, false, 0, 0>", "dwi_normalize_reg_kernel<4>", "nyul_transform_kernel")
+wanted = ("conv_gemm_kernel<256, false, 0, false, 0, 0, false>", "conv_gemm_kernel<128, false, 0, false, 0, 0, true>",
+          "conv_wgrad_kernel<256>", "attn_fused_kernel<64>", "dwi_normalize_reg_kernel<4>", "nyul_transform_kernel<false>")
 for old in os.listdir(out_dir):
     if old.endswith(".sass"):
         os.remove(os.path.join(out_dir, old))
