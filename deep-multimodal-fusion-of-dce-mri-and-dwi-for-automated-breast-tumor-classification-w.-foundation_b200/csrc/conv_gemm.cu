@@ -204,7 +204,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = smem_raw + ((1024u - (static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw)) & 1023u)) & 1023u);
     uint8_t* sW = smem;  // resident weights [k_blocks][BN x 64] (WS only)
     uint8_t* sRing = smem + p.off_ring;
-    static_assert(!PAIR || (BN == 128 && !WS && MODE == 0), "PAIR: BN = 128, streamed weights, standard epilogue");
+    static_assert(!PAIR || ((BN == 128 || BN == 64) && !WS && MODE == 0), "PAIR: BN = 128 / 64, streamed weights, standard epilogue");
     constexpr int kStageBytes = WS ? kABytes : (PAIR ? 2 * kABytes : kABytes) + T::kBBytes;
     constexpr int kAcc = PAIR ? 4 : 2;             // accumulator stages in TMEM
     constexpr int kTmemCols = PAIR ? T::kTmemColsPair : T::kTmemCols;
@@ -1090,7 +1090,7 @@ static int dispatch(int res_mode, bool gap, int ndot, int mode, const CUtensorMa
         }
         return -14;
     }
-    if constexpr (BN == 128 && !WS) {
+    if constexpr ((BN == 128 || BN == 64) && !WS) {
         if (p.pair) {
 #define B200_GO_PAIR(RES, GAP) \
     return launch<BN, WS, RES, GAP, 0, 0, true>(tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s)
@@ -1250,7 +1250,9 @@ static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, 
             const bool st_out = has_out && (p.tma_epi || mode == 2), st_res = has_res && p.tma_epi;
             // BN = 128: pair two M tiles per iteration when there is enough work to keep every SM busy with pairs
             static const bool no_pair = std::getenv("B200_NO_PAIR") != nullptr;  // A/B measurements
-            const bool pair = bn == 128 && mode == 0 && ndot == 0 && p.a_batched && p.b_mode == 0 && !no_pair &&
+            static const bool no_pair64 = std::getenv("B200_NO_PAIR64") != nullptr;
+            // (N = 64: only the 3x3 layers gain - 64->64 0.211 -> 0.158 ms; the 1x1 layers lose 5-9 %)
+            const bool pair = (bn == 128 || (bn == 64 && p.k_blocks >= 8 && !no_pair64)) && mode == 0 && ndot == 0 && p.a_batched && p.b_mode == 0 && !no_pair &&
                               (p.m_tiles / 2) * (Cout / bn) >= g_num_sms;
             smem_bytes = plan_smem(p, bn, false, st_out, st_res, ndot, mode, share, pair);
             p.pair = (pair && smem_bytes > 0) ? 1 : 0;

@@ -605,7 +605,9 @@ def test_paired_tiles_are_bitwise_the_unpaired_result():
 
     g = torch.Generator().manual_seed(8)
     for taps, cin, cout, res, hw in ((9, 128, 128, False, 32), (1, 128, 128, True, 32), (1, 512, 128, False, 32),
-                                     (1, 128, 384, False, 32), (9, 128, 128, False, 14), (1, 256, 128, True, 14)):
+                                     (1, 128, 384, False, 32), (9, 128, 128, False, 14), (1, 256, 128, True, 14),
+                                     (1, 64, 64, False, 32), (9, 64, 64, False, 32), (1, 128, 64, True, 32),
+                                     (1, 256, 192, False, 32)):  # N = 64 tiles pair too
         # 32 x 32 maps: 41 cases x 8 tiles = 328 M tiles (>= 296: paired; odd pair count per N tile walk);
         # 14 x 14 maps (ragged 126-row tiles, two per case, direct epilogue): 163 cases = 326 M tiles
         B = 41 if hw == 32 else 163
