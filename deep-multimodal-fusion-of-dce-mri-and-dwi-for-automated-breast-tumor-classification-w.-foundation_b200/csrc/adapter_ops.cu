@@ -147,7 +147,7 @@ __global__ void adaptive_pool_kernel(const __nv_bfloat16* __restrict__ x, int H,
 #pragma unroll
     for (int k = 0; k < 8; k += 2) {
         float2 v = make_float2(s[k] * inv, s[k + 1] * inv);
-        if (act == 1) v = gelu_poly2(v);
+        if (act == 1) v = gelu_fast2(v);
         s[k] = v.x;
         s[k + 1] = v.y;
     }

@@ -58,7 +58,7 @@ struct ConvGemmParams {
     const __nv_bfloat16* res;
     int res_ld;
     int res_mode;          // 0 none, 1 add before activation, 2 add after activation
-    int act;               // 0 none, 1 GELU(erf)
+    int act;               // 0 none, 1 GELU (gelu_fast2), 2 ReLU
     __nv_bfloat16* out;
     int out_ld;
     int up2;               // replicate every output pixel into a 2x2 block of a [B,2H,2W,ld] map
@@ -143,43 +143,7 @@ struct Tile {
     static constexpr int kDotBytes = 9 * BN * 4 + 2 * kBlockM * 9 * 4;
 };
 
-// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf(z) ~= z * P(z^2) on |z| <= 3 (odd minimax polynomial,
-// 8 terms, |erf error| < 9e-5, P(9)*3 == 1 so the clamp is continuous with +-1).  The result is rounded to
-// bf16 (relative step 4e-3), so the 1.8e-4 worst-case absolute deviation from the exact-erf GELU is below
-// one output ulp for |x| >= 0.05; it costs 15 issue slots against ~30 for erff().
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fminf(fmaxf(x * 0.70710678118654752f, -3.0f), 3.0f);
-    const float t = z * z;
-    float p = -3.901667185e-07f;
-    p = fmaf(p, t, 1.668003461e-05f);
-    p = fmaf(p, t, -3.086500801e-04f);
-    p = fmaf(p, t, 3.281538375e-03f);
-    p = fmaf(p, t, -2.256273106e-02f);
-    p = fmaf(p, t, 1.075116023e-01f);
-    p = fmaf(p, t, -3.730817735e-01f);
-    p = fmaf(p, t, 1.127865076e+00f);
-    const float h = 0.5f * x;
-    return fmaf(h, z * p, h);
-}
-
-// Two elements at a time on the packed fp32x2 pipe (FFMA2 / FMUL2, new in sm_100): the polynomial, the
-// scaling and the final blend are packed, only the clamp stays scalar - 8 issue slots per element.
-__device__ __forceinline__ float2 gelu_erf2(float2 x) {
-    float2 z = __fmul2_rn(x, make_float2(0.70710678118654752f, 0.70710678118654752f));
-    z.x = fminf(fmaxf(z.x, -3.0f), 3.0f);
-    z.y = fminf(fmaxf(z.y, -3.0f), 3.0f);
-    const float2 t = __fmul2_rn(z, z);
-    float2 p = make_float2(-3.901667185e-07f, -3.901667185e-07f);
-    p = __ffma2_rn(p, t, make_float2(1.668003461e-05f, 1.668003461e-05f));
-    p = __ffma2_rn(p, t, make_float2(-3.086500801e-04f, -3.086500801e-04f));
-    p = __ffma2_rn(p, t, make_float2(3.281538375e-03f, 3.281538375e-03f));
-    p = __ffma2_rn(p, t, make_float2(-2.256273106e-02f, -2.256273106e-02f));
-    p = __ffma2_rn(p, t, make_float2(1.075116023e-01f, 1.075116023e-01f));
-    p = __ffma2_rn(p, t, make_float2(-3.730817735e-01f, -3.730817735e-01f));
-    p = __ffma2_rn(p, t, make_float2(1.127865076e+00f, 1.127865076e+00f));
-    const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
-    return __ffma2_rn(h, __fmul2_rn(z, p), h);
-}
+// The epilogue GELU is common.cuh's gelu_fast2 (tanh form on MUFU.TANH, two elements per packed instruction).
 
 // Epilogue features are compile-time so that the per-element instruction stream carries no flag tests:
 //   RES  0 none, 1 residual added before the activation, 2 after it
@@ -687,7 +651,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (act == 1) {
 #pragma unroll
 
-                                for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+                                for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_fast2(v2[j]);
 
                             } else {  // act == 2: ReLU (ResNet backbones)
 #pragma unroll
@@ -731,7 +695,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (act == 1) {
 #pragma unroll
 
-                                for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+                                for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_fast2(v2[j]);
 
                             } else {  // act == 2: ReLU (ResNet backbones)
 #pragma unroll
@@ -769,7 +733,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (act == 1) {
 #pragma unroll
 
-                                for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+                                for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_fast2(v2[j]);
 
                             } else {  // act == 2: ReLU (ResNet backbones)
 #pragma unroll
@@ -791,7 +755,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (act == 1) {
 #pragma unroll
 
-                                for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+                                for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_fast2(v2[j]);
 
                             } else {  // act == 2: ReLU (ResNet backbones)
 #pragma unroll
@@ -805,7 +769,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (act == 1) {
 #pragma unroll
 
-                            for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+                            for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_fast2(v2[j]);
 
                         } else {  // act == 2: ReLU (ResNet backbones)
 #pragma unroll
@@ -819,7 +783,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (act == 1) {
 #pragma unroll
 
-                        for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+                        for (int j = 0; j < kChunk / 2; ++j) v2[j] = gelu_fast2(v2[j]);
 
                     } else {  // act == 2: ReLU (ResNet backbones)
 #pragma unroll

@@ -154,7 +154,7 @@ stem_kernel(const float* __restrict__ x, int C, int H, int W, int stride,
             const float2 sc = *reinterpret_cast<const float2*>(s_sc + n0 + 2 * j);
             const float2 bi = *reinterpret_cast<const float2*>(s_bi + n0 + 2 * j);
             float2 y = __ffma2_rn(acc[j], sc, bi);
-            if (is_mid) y = gelu_poly2(y);
+            if (is_mid) y = gelu_fast2(y);
             if (is_mid && drop_thresh != 0u) {
                 const uint4 rnd = philox4x32_7(e0 / 4 + (j >> 1), seed_lo, seed_hi);  // 4 channels per call
                 const unsigned int r0 = (j & 1) ? rnd.z : rnd.x, r1 = (j & 1) ? rnd.w : rnd.y;
@@ -442,7 +442,7 @@ __global__ void mask_tail_kernel(const __nv_bfloat16* __restrict__ pre, int Cm, 
         const float m = s_m[p];
         float a = bb[0];
         for (int c = 0; c + 1 < Hc; c += 2) {
-            const float2 g = gelu_poly2(make_float2((wa[c] * m - muf) * rstd * gn_w[c] + gn_b[c],
+            const float2 g = gelu_fast2(make_float2((wa[c] * m - muf) * rstd * gn_w[c] + gn_b[c],
                                                     (wa[c + 1] * m - muf) * rstd * gn_w[c + 1] + gn_b[c + 1]));
             a += wb[c] * g.x + wb[c + 1] * g.y;
         }
@@ -476,7 +476,7 @@ lift_c1_kernel(const float* __restrict__ r, int total_pix, int N, const float* _
         float f[8];
 #pragma unroll
         for (int k = 0; k < 8; k += 2) {
-            const float2 g = gelu_poly2(make_float2(rv * wr[k] * sr[k] + bs[k], rv * wr[k + 1] * sr[k + 1] + bs[k + 1]));
+            const float2 g = gelu_fast2(make_float2(rv * wr[k] * sr[k] + bs[k], rv * wr[k + 1] * sr[k + 1] + bs[k + 1]));
             f[k] = g.x;
             f[k + 1] = g.y;
         }

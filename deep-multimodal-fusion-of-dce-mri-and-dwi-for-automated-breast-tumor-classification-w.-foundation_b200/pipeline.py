@@ -119,9 +119,13 @@ class FusionPipeline:
         Upload of batch i+1 runs on a copy stream while batch i computes."""
         dev = torch.device(device)
         results = []
-        for d, c in self._staged(batches, dev):
+        pool, n = None, (len(batches) if hasattr(batches, "__len__") else 0)
+        for i, (d, c) in enumerate(self._staged(batches, dev)):
             logits = self.forward_raw(d, c)
-            host = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
+            if i == 0 and n > 0:  # one pinned allocation for the whole sequence instead of one per step
+                pool = torch.empty((n,) + tuple(logits.shape), dtype=logits.dtype, pin_memory=True)
+            host = pool[i] if pool is not None and i < n and pool.shape[1:] == logits.shape else \
+                torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
             host.copy_(logits, non_blocking=True)
             results.append(host)
         torch.cuda.current_stream(dev).synchronize()

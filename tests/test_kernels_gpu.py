@@ -123,9 +123,11 @@ def test_recon_head_fused_tap_dots(B, C):
     assert _rel(out2, ref2) < 1e-3
 
 
-def test_fast_gelu_deviation_is_below_bf16_resolution():
-    """The epilogue GELU uses an 8-term odd polynomial for erf: compare with exact GELU through an
-    identity 1x1 'convolution' (weights = I)."""
+def test_fast_gelu_deviation_from_erf_gelu():
+    """The epilogue GELU is 0.5 x (1 + tanh(x (c0 + c1 x^2))) on MUFU.TANH (common.cuh gelu_fast2): compared with
+    nn.GELU()'s erf form through an identity 1x1 'convolution' (weights = I) over [-9, 9].  Bound: the bf16 rounding of
+    the output (4e-3 relative) plus 1.2e-3 absolute (4.7e-4 from the tanh form, the rest from MUFU.TANH's 2^-11
+    relative error on 1 + tanh); exact zero / identity far from the origin."""
     C = 64
     xs = torch.linspace(-9, 9, 2 * 32 * 32 * C).view(2, 32, 32, C).to(DEV).bfloat16()
     w = torch.eye(C, device=DEV).bfloat16()
@@ -133,7 +135,10 @@ def test_fast_gelu_deviation_is_below_bf16_resolution():
     torch.cuda.synchronize()
     ref = F.gelu(xs.float())
     err = (y.float() - ref).abs()
-    assert (err <= 4e-3 * ref.abs() + 2.5e-4).all(), err.max()
+    print("fast GELU: max |d| =", err.max().item(), "at x =", xs.float().flatten()[err.argmax()].item())
+    assert (err <= 4e-3 * ref.abs() + 1.2e-3).all(), err.max()
+    far = xs.float().abs() > 6.5
+    assert (err[far] <= 4e-3 * ref[far].abs() + 2e-4).all(), err[far].max()   # saturated: 0 or x, no tanh residue
 
 
 def test_fused_single_dot_is_a_following_1x1_conv_to_one_channel():
