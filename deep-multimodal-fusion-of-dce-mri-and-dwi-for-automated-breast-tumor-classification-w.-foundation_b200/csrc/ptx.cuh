@@ -60,7 +60,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > 40000000u) __trap();  // seconds of waiting: a protocol bug, not a slow tile
+        if (++spins > 8000000u) __trap();  // each failed try sleeps up to 20 us: seconds to minutes of waiting - a protocol bug, not a slow tile
     }
 }
 

@@ -1037,6 +1037,11 @@ class ModelMaskHeadBackbone(_PackedWeightsMixin, nn.Module):
             outs.append(nat.conv_gemm(t, nk["w3"], taps=9, scale=nk["s3"], bias=nk["b3"], act=1))
         return outs[0], outs[1], outs[2], gate
 
+    # The reference wraps its models in torch.compile(backend='inductor') when parameters['compile'] is set
+    # (code/run_training.py:90-91, :242-244).  The forward below is a schedule of C-ABI launches, nothing Dynamo could
+    # trace: it is marked opaque, so a compiled wrapper of the module runs exactly this code (no graph breaks to
+    # discover, no recompilations).
+    @torch.compiler.disable
     def forward(self, x, masks=None, plane_mean=None, input_norm=None):
         """x [B,C,H,W] normalised fp32.  `plane_mean` (optional, [B*C] fp32) is the per-plane mean the
         normaliser kernels can emit, which saves one pass over x.  `input_norm` (with plane_mean): x is the RAW
@@ -1261,6 +1266,7 @@ class FusionModel(_PackedWeightsMixin, nn.Module):
         self._pack_cache = (sig, pk)
         return pk
 
+    @torch.compiler.disable  # see ModelMaskHeadBackbone.forward
     def forward(self, raw_feats_dwi, raw_feats_dce, dwi_mask_pred=None, dce_mask_pred=None):
         if self.training:
             if not raw_feats_dwi[-1].is_cuda:

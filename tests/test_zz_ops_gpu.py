@@ -53,3 +53,24 @@ def test_torch_compile_traces_through_the_operators():
     want = fn(x)
     got = torch.compile(fn, backend="eager", fullgraph=True)(x)
     assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+
+
+def test_torch_compile_of_the_models_runs_the_kernels():
+    """`torch.compile(model, backend='inductor')`, as the reference applies with parameters['compile']
+    (run_training.py:90-91, :242-244): the compiled wrappers of both encoders and the fusion head return what the plain
+    modules return (their forwards are opaque to Dynamo)."""
+    import model_module as mm
+    import parameters_default as pd
+
+    torch.manual_seed(0)
+    p = pd.default_parameters()
+    enc = mm.ModelMaskHeadBackbone("dce", p).to("cuda").eval()
+    fus = mm.FusionModel(p).to("cuda").eval()
+    x = torch.rand(2, 6, 64, 64, device="cuda")
+    with torch.no_grad():
+        l0, a0, m0 = enc(x)
+        l1, a1, m1 = torch.compile(enc, backend="inductor")(x)
+        f0 = fus(a0["raw_feats"], a0["raw_feats"], m0, m0)
+        f1 = torch.compile(fus, backend="inductor")(a1["raw_feats"], a1["raw_feats"], m1, m1)
+    assert torch.allclose(l0, l1, rtol=1e-3, atol=1e-5) and torch.allclose(m0.float(), m1.float(), rtol=1e-3, atol=1e-4)
+    assert torch.allclose(f0[0], f1[0], rtol=1e-3, atol=1e-5)
