@@ -270,17 +270,27 @@ scale_map_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict_
         const int i = i0 + u * blockDim.x;
         if (i < nvc) r[u] = __ldcs(xs + i);
     }
+    // C / 8 a power of two that divides the block size (every CNN width: 128 / 256 / 512 channels): the thread's four
+    // vectors share one channel offset - one pair of gate loads instead of four, shifts instead of divisions
+    const bool pow2 = (cv & (cv - 1)) == 0 && (blockDim.x % cv) == 0;
+    const int sh = 31 - __clz(cv);
+    float4 gs0 = make_float4(1.f, 1.f, 1.f, 1.f), gs1 = gs0;
+    if (pow2 && gr != nullptr) {
+        const int c0 = (i0 & (cv - 1)) << 3;
+        gs0 = __ldg(reinterpret_cast<const float4*>(gr + c0));
+        gs1 = __ldg(reinterpret_cast<const float4*>(gr + c0 + 4));
+    }
 #pragma unroll
     for (int u = 0; u < kScaleUnroll; ++u) {
         const int i = i0 + u * blockDim.x;
         if (i >= nvc) continue;
-        const int c0 = (i % cv) << 3, px = i / cv;
+        const int c0 = (pow2 ? (i & (cv - 1)) : (i % cv)) << 3, px = pow2 ? (i >> sh) : (i / cv);
         float f[8];
         unpack_bf16x8(r[u], f);
         const float m = ar != nullptr ? 1.f + gamma * __ldg(ar + px) : 1.f;
         if (gr != nullptr) {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gr + c0));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gr + c0 + 4));
+            const float4 g0 = pow2 ? gs0 : __ldg(reinterpret_cast<const float4*>(gr + c0));
+            const float4 g1 = pow2 ? gs1 : __ldg(reinterpret_cast<const float4*>(gr + c0 + 4));
             f[0] *= g0.x * m; f[1] *= g0.y * m; f[2] *= g0.z * m; f[3] *= g0.w * m;
             f[4] *= g1.x * m; f[5] *= g1.y * m; f[6] *= g1.z * m; f[7] *= g1.w * m;
         } else {

@@ -730,3 +730,23 @@ def test_conv_gemm_tiles_spanning_cases(B, H, W, Cin, Cout, taps, res_mode):
         if res_mode == 2:
             ref = ref + r.float().permute(0, 3, 1, 2)
     assert _rel(y.permute(0, 3, 1, 2), ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("B,H,W,C", [(5, 32, 32, 128), (3, 32, 32, 512), (4, 14, 14, 768), (2, 7, 9, 24), (3, 16, 16, 256)])
+def test_scale_map_channel_gate_and_pixel_attention(B, H, W, C):
+    """y = x * gate[b, c] * (1 + gamma * attn[b, p]) (SE rescale model_module.py:43, mask-guided modulation :96): both index
+    paths of the kernel (C / 8 a power of two dividing the block: shared gate registers and shifts; any other C), each
+    factor alone and together, against fp32 torch."""
+    g = torch.Generator().manual_seed(C + B)
+    x = torch.randn(B, H, W, C, generator=g).bfloat16().to(DEV)
+    gate = torch.rand(B, C, generator=g).to(DEV)
+    attn = torch.rand(B, H * W, generator=g).to(DEV)
+    gamma = torch.tensor([0.7], device=DEV)
+    xf = x.float()
+    cases = {"gate": (gate, None, None, xf * gate.view(B, 1, 1, C)),
+             "attn": (None, attn, gamma, xf * (1 + 0.7 * attn.view(B, H, W, 1))),
+             "both": (gate, attn, gamma, xf * gate.view(B, 1, 1, C) * (1 + 0.7 * attn.view(B, H, W, 1)))}
+    for name, (ga, at, gm, ref) in cases.items():
+        y = nat.scale_map(x, torch.empty_like(x), gate=ga, attn=at, gamma=gm)
+        torch.cuda.synchronize()
+        assert _rel(y, ref) < 6e-3, (name, _rel(y, ref))
