@@ -92,6 +92,8 @@ struct ConvGemmParams {
     int n_valid;           // MODE 1: number of real columns (keys); the rest are masked out
     int res_f32, out_f32;  // residual / output are fp32 row-major (transformer residual stream); direct path
     int stages;            // operand ring depth
+    int obuf2;             // output staging double-buffered per epilogue warp (tile i+1 is staged while the TMA store of
+                           // tile i still reads its boxes); 0: one set of boxes, the store is waited for at the next tile
     int pair;              // BN = 128: two M tiles per CTA iteration share one weight slab (conv_gemm_kernel<..., PAIR>)
     int off_ring, off_bar, off_union, off_rbox, off_sm;  // shared-memory plan (bytes from the 1 KB-aligned base)
 };
@@ -450,7 +452,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int half = ew >> 2;  // column half: columns [half*BN/2, (half+1)*BN/2)
         const int colw0 = half * T::kColsPerWarp;
         const bool share = p.share_box != 0;  // warp-uniform; set by the host for BN = 256 plain-output launches only
-        uint8_t* const obuf = s_union + ew * (MODE == 2 ? kF32BlockBytes : (share ? T::kBoxBytes : T::kWarpBoxBytes));
+        uint8_t* const obuf0 = s_union + ew * (MODE == 2 ? kF32BlockBytes : (share ? T::kBoxBytes : T::kWarpBoxBytes));
+        const int obuf_flip = p.obuf2 ? 8 * T::kWarpBoxBytes : 0;  // second set of boxes (all 8 warps') behind the first
+        int obuf_sel = 0;
         uint8_t* const rbuf = smem + p.off_rbox + ew * T::kWarpBoxBytes;
         uint64_t* const rbar = &resbar[2 * ew];  // one barrier per staged residual box
         uint32_t rphase = 0;                     // bit bx = phase of box bx
@@ -531,8 +535,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int k = 0; k < NDOT; ++k) dsum[k] = 0.f;
             }
-            if (!DOT && tma_epi && out_ptr != nullptr) {  // last tile's store has finished reading this warp's boxes
-                if (lane == 0) tma_store_wait_read<0>();
+            uint8_t* const obuf = obuf0 + obuf_sel * obuf_flip;
+            obuf_sel ^= 1;
+            if (!DOT && tma_epi && out_ptr != nullptr) {
+                // the store that last read THESE boxes has finished reading them: the previous tile's with one set of
+                // boxes, the one before it with two (the previous tile's store may still be in flight)
+                if (lane == 0) {
+                    if (p.obuf2) tma_store_wait_read<1>();
+                    else tma_store_wait_read<0>();
+                }
                 __syncwarp();
             }
             if (kF32 && RES != 0 && p.res_f32) {
@@ -1110,7 +1121,21 @@ static int plan_smem(ConvGemmParams& p, int BN, bool ws, bool has_out, bool has_
     const int box_all = kBlockM * BN * 2;  // 8 warps x (32 rows x BN/2 columns) of bf16
     const int dot_bytes = ndot * BN * 4 + 2 * kBlockM * ndot * 4;
     // mode 2 (fp32 epilogue) needs only the eight 32 x 33-word transposition blocks
-    const int out_stage = mode == 2 ? 8 * kF32BlockBytes : (share_box ? box_all / 2 : box_all);
+    // One-k-block-deep layers (1x1, Cin <= 256) are epilogue bound, and with one set of staging boxes every tile's
+    // epilogue starts by waiting for the previous tile's TMA store to finish reading them: a second set hides that.
+    static const bool no_obuf2 = std::getenv("B200_NO_OBUF2") != nullptr;  // A/B measurements
+    const bool want2 = !no_obuf2 && !ws && BN <= 128 && (mode == 0 || mode == 3) && has_out && !share_box && ndot == 0 &&
+                       p.tma_epi && p.k_blocks <= 4;
+    int out_stage = mode == 2 ? 8 * kF32BlockBytes : (share_box ? box_all / 2 : box_all);
+    p.obuf2 = 0;
+    if (want2) {
+        const int fixed2 = (ws ? align1k(p.k_blocks * b_bytes) : 0) + align1k(kBarBytes) + align1k(2 * box_all) +
+                           (has_res ? align1k(box_all) : 0) + 1024;
+        if ((kSmemLimit - fixed2) / stage_bytes >= 4) {
+            out_stage = 2 * box_all;
+            p.obuf2 = 1;
+        }
+    }
     const int union_bytes = align1k(ndot ? dot_bytes : (has_out ? out_stage : 0));
     const int rbox_bytes = has_res ? align1k(box_all) : 0;
     const int sm_bytes = mode == 1 ? align1k(8 * kBlockM * 4) : 0;  // row max / row sum exchange
