@@ -96,8 +96,8 @@ struct ConvGemmParams {
                            // tile i still reads its boxes); 0: one set of boxes, the store is waited for at the next tile
     int pair;              // BN = 128: two M tiles per CTA iteration share one weight slab (conv_gemm_kernel<..., PAIR>)
     int off_ring, off_bar, off_union, off_rbox, off_sm;  // shared-memory plan (bytes from the 1 KB-aligned base)
-    int off_aff;           // >= 0: single-N-tile launches keep each epilogue warp's scale | bias columns in shared memory
-                           // (loaded once per CTA); -1: they are read from global memory per chunk
+    int off_aff;           // >= 0: [scale Cout | bias Cout] parked in shared memory once per CTA (BN <= 128 launches);
+                           // -1: they are read from global memory per chunk
 };
 
 __device__ __forceinline__ int fd_div(const ConvGemmParams::FastDiv& f, int n) {
@@ -476,19 +476,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int r_w = trow % p.BW, r_h = (trow / p.BW) % p.BH, r_b = trow / (p.BW * p.BH);
         const int q_w = (q * 32) % p.BW, q_h = (q * 32) / p.BW;
         const bool row_in_box = trow < p.BW * p.BH * p.BB;
-        // Cout == BN (one N tile: the projector / mask-head / 3x3 128 layers): every tile uses the same folded-BN scale |
-        // bias columns, so each epilogue warp parks its kColsPerWarp of them in shared memory once.  Per 32-column chunk
-        // that replaces 16 LDG.128 + 32 descriptor moves (R2UR) by 16 LDS.128 - 15 % of the instructions a BN = 64 tile
-        // costs (profiles/r2_ncu_full.csv, capture r2_k64).
-        float* const s_aff = (MODE != 1 && p.off_aff >= 0)
-                                 ? reinterpret_cast<float*>(smem + p.off_aff) + ew * (2 * T::kColsPerWarp) : nullptr;
+        // Folded-BN scale | bias of ALL output channels, parked in shared memory once per CTA by the epilogue warps
+        // ([scale Cout | bias Cout] fp32): per 32-column chunk every lane needs the same 32 + 32 floats, which cost 16
+        // LDG.128 + 32 descriptor moves (R2UR) per chunk and lane when read from global memory - 15 % of the instructions
+        // of a BN = 64 tile (profiles/r2_ncu_full.csv, capture r2_k64).  BN <= 128 launches only (the host plans it).
+        float* const s_aff = (MODE != 1 && p.off_aff >= 0) ? reinterpret_cast<float*>(smem + p.off_aff) : nullptr;
         if (s_aff != nullptr) {
-            constexpr int kVec = T::kColsPerWarp / 4;  // float4 per array: 8 / 16 / 32
-            if (lane < kVec) {
-                reinterpret_cast<float4*>(s_aff)[lane] = __ldg(reinterpret_cast<const float4*>(p.scale + colw0) + lane);
-                reinterpret_cast<float4*>(s_aff)[kVec + lane] = __ldg(reinterpret_cast<const float4*>(p.bias + colw0) + lane);
+            const int et = threadIdx.x - kEpiWarp0 * 32;  // 0 .. 255 over the epilogue warps
+            for (int i = et; i < p.Cout / 4; i += kNumEpiWarps * 32) {
+                reinterpret_cast<float4*>(s_aff)[i] = __ldg(reinterpret_cast<const float4*>(p.scale) + i);
+                reinterpret_cast<float4*>(s_aff + p.Cout)[i] = __ldg(reinterpret_cast<const float4*>(p.bias) + i);
             }
-            __syncwarp();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         // Residual boxes are fetched one tile ahead: box bx of tile i+1 is requested as soon as the last lane
         // has read box bx of tile i, so its DRAM latency hides behind the rest of tile i's epilogue.
@@ -657,8 +656,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int j = 0; j < kChunk; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * row_mul);
                     }
                     if (s_aff != nullptr) {
-                        const float4* s4 = reinterpret_cast<const float4*>(s_aff + ch * kChunk);
-                        const float4* b4 = reinterpret_cast<const float4*>(s_aff + T::kColsPerWarp + ch * kChunk);
+                        const float4* s4 = reinterpret_cast<const float4*>(s_aff + n0);
+                        const float4* b4 = reinterpret_cast<const float4*>(s_aff + p.Cout + n0);
 #pragma unroll
                         for (int j = 0; j < kChunk / 4; ++j) {
                             const float4 s = s4[j], t = b4[j];
@@ -1170,7 +1169,7 @@ static int plan_smem(ConvGemmParams& p, int BN, bool ws, bool has_out, bool has_
     const int sm_bytes = mode == 1 ? align1k(8 * kBlockM * 4) : 0;  // row max / row sum exchange
     const int resident = ws ? align1k(p.k_blocks * b_bytes) : 0;
     static const bool no_aff = std::getenv("B200_NO_AFF_SMEM") != nullptr;  // A/B measurements
-    const int aff_bytes = (BN <= 128 && p.Cout == BN && mode != 1 && p.bias_h_stride == 0 && !no_aff) ? align1k(8 * BN * 4) : 0;
+    const int aff_bytes = (BN <= 128 && p.Cout <= 2048 && mode != 1 && p.bias_h_stride == 0 && !no_aff) ? align1k(2 * p.Cout * 4) : 0;
     const int fixed = resident + align1k(kBarBytes) + union_bytes + rbox_bytes + sm_bytes + aff_bytes + 1024 /*alignment slack*/;
     int stages = (kSmemLimit - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
