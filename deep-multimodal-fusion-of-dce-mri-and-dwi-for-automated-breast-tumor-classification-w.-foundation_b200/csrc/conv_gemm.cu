@@ -1169,7 +1169,7 @@ static int plan_smem(ConvGemmParams& p, int BN, bool ws, bool has_out, bool has_
     const int sm_bytes = mode == 1 ? align1k(8 * kBlockM * 4) : 0;  // row max / row sum exchange
     const int resident = ws ? align1k(p.k_blocks * b_bytes) : 0;
     static const bool no_aff = std::getenv("B200_NO_AFF_SMEM") != nullptr;  // A/B measurements
-    const int aff_bytes = (BN <= 128 && p.Cout <= 2048 && mode != 1 && p.bias_h_stride == 0 && !no_aff) ? align1k(2 * p.Cout * 4) : 0;
+    const int aff_bytes = ((BN <= 128 || p.k_blocks <= 4) && p.Cout <= 2048 && mode != 1 && p.bias_h_stride == 0 && !no_aff) ? align1k(2 * p.Cout * 4) : 0;
     const int fixed = resident + align1k(kBarBytes) + union_bytes + rbox_bytes + sm_bytes + aff_bytes + 1024 /*alignment slack*/;
     int stages = (kSmemLimit - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
