@@ -267,12 +267,13 @@ def test_hybrid_transformer_encoders_vs_golden_and_oracle():
             lf, mf, af = mods["fusion"](ad["raw_feats"], ac["raw_feats"], md, mc)  # 16x16 encoder maps
         torch.cuda.synchronize()
         # The fusion head on these 16x16 maps amplifies input perturbations ~5x for this seeded weight draw
-        # (fed identical inputs it matches the oracle to 1.7e-3 - tests/tools/dbg_hybrid.py): the encoders' 0.7 %
-        # bf16 error on f3 becomes up to 3.5 % on the fused logits.  Encoder outputs keep the 2e-2 bound above;
-        # the fused outputs of this non-default configuration are held to 5e-2.
+        # (fed identical inputs it matches the oracle to 1.7e-3 - tests/tools/dbg_hybrid.py).  With round 2's fused
+        # attention (fp32 softmax, probabilities rounded once) the worst fused output is the mask at 2.0 % (it was
+        # 3.5 % on the fused logits with the three-GEMM attention).  Encoder outputs keep the 2e-2 bound above;
+        # the fused outputs of this non-default configuration are held to 3e-2.
         for prefix, obj in {f"{kind}/fusion/logits": lf, f"{kind}/fusion/mask": mf, f"{kind}/fusion/aux": af}.items():
             for key, t in gu.walk(prefix, obj):
-                worst[key] = gu.check(gold, key, t, rtol=5e-2)
+                worst[key] = gu.check(gold, key, t, rtol=3e-2)
     assert tuple(ad["raw_feats"][2].shape) == (2, 512, 16, 16) and tuple(mf.shape) == (2, 1, 32, 32)
     print("hybrid worst relative errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:6])
     with torch.no_grad():
@@ -341,9 +342,10 @@ def test_vit_backbone_features_vs_oracle():
 # operand rounding: the fp32 oracle with nothing but its GEMM operands rounded to bf16 (tests/tools/bf16_floor.py)
 # already deviates from itself by 1.2-1.7 % on f1, 3-7 % on f2 / f3, 2.7 % on the DWI logits and 3.7 % on the
 # DWI mask.  The product (fused attention: fp32 softmax, probabilities rounded once) measures <= 4.0 % on every
-# output (tests/tools/vit_err.py); it is held to 5e-2 of the tensor's max on maps downstream of a mix, and the
-# usual 2e-2 on everything upstream of the first one.
-VIT_TOL = 5e-2
+# output in most runs and up to 4.9 % in some (tests/tools/vit_err.py; the SE gates are fed by float-atomic channel sums,
+# so WHICH bf16 roundings flip varies run to run); it is held to 6e-2 of the tensor's max on maps downstream of a mix,
+# and the usual 2e-2 on everything upstream of the first one.
+VIT_TOL = 6e-2
 VIT_UPSTREAM = ("aux.raw_feats.0", "aux.recon_feats.0", "aux.proj_pairs.0", "aux.proj_pairs.1", "aux.mod_attn_map")
 
 
