@@ -18,6 +18,7 @@ Operators (all functional, outputs freshly allocated):
   conv_gemm(x[B,H,W,Cin] bf16, w[Cout,taps*Cin] bf16, scale[Cout]?, bias[Cout]?, res?, res_mode, act, taps)
       -> [B,H,W,Cout] bf16                                                           code/model_module.py:259-269 etc.
   fusion_tokens(p[B,H,W,C] bf16, hp, wp) -> [B,hp*wp,C] f32                          code/model_module.py:903-917
+  attention(qkv[B*N,3*heads*d] bf16, B, N, heads, d) -> [B*N,heads*d] bf16           code/transformer_model.py:101-112
 """
 from __future__ import annotations
 
@@ -28,7 +29,7 @@ from torch.library import custom_op
 
 import b200_native as nat
 
-__all__ = ["dwi_normalize", "nyul_transform", "resize_bilinear", "augment", "conv_gemm", "fusion_tokens"]
+__all__ = ["dwi_normalize", "nyul_transform", "resize_bilinear", "augment", "conv_gemm", "fusion_tokens", "attention"]
 
 
 def _need_cuda(t, name):
@@ -125,3 +126,18 @@ def fusion_tokens(p: torch.Tensor, hp: int, wp: int) -> torch.Tensor:
 @fusion_tokens.register_fake
 def _(p, hp, wp):
     return p.new_empty((p.shape[0], hp * wp, p.shape[3]), dtype=torch.float32)
+
+
+@custom_op("b200::attention", mutates_args=())
+def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: int) -> torch.Tensor:
+    """softmax(q k^T / sqrt d) v per (case, head) from the packed rows `Linear(E, 3E)` writes (b200_attention)."""
+    _need_cuda(qkv, "attention")
+    qkv = qkv.contiguous()
+    out = torch.empty((batch * tokens, heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
+    nat.attention(qkv, out, batch, tokens, heads, head_dim)
+    return out
+
+
+@attention.register_fake
+def _(qkv, batch, tokens, heads, head_dim):
+    return qkv.new_empty((batch * tokens, heads * head_dim), dtype=torch.bfloat16)

@@ -29,6 +29,9 @@ def test_operators_are_registered_with_shape_correct_fakes():
         assert y.shape == (4, 32, 32, 128) and y.dtype == torch.bfloat16
         t = ops.fusion_tokens(y, 4, 4)
         assert t.shape == (4, 16, 128) and t.dtype == torch.float32
+        qkv = torch.empty(3 * 197, 3 * 768, device="cuda", dtype=torch.bfloat16)
+        o = ops.attention(qkv, 3, 197, 12, 64)
+        assert o.shape == (3 * 197, 768) and o.dtype == torch.bfloat16
 
 
 def test_graph_capture_sees_opaque_b200_nodes():

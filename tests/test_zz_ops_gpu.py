@@ -42,6 +42,10 @@ def test_operators_equal_the_direct_call_path():
     ref = torch.empty(2, 16, 128, device=DEV)
     nat.fusion_tokens(y, 4, 4, ref)
     assert torch.equal(tok, ref)
+    qkv = (torch.randn(2 * 197, 3 * 768, generator=g, device=DEV) * 0.8).to(torch.bfloat16)
+    o_ref = torch.empty(2 * 197, 768, device=DEV, dtype=torch.bfloat16)
+    nat.attention(qkv, o_ref, 2, 197, 12, 64)
+    assert torch.equal(ops.attention(qkv, 2, 197, 12, 64), o_ref)
 
 
 def test_torch_compile_traces_through_the_operators():
