@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # csrc/build.sh links the library at <repo>/lib/libb200fusion.so: a short path without the dots and dashes of the
 # package directory name, which is the path string dlopen sees.
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200fusion.so")
-ABI_VERSION = 20
+ABI_VERSION = 21
 
 _lib = None
 
@@ -99,6 +99,7 @@ SIGNATURES = {
                           _I, _I, _I, _I, _I, _F, C.c_ulonglong, _I, _P],
     "b200_attention": [_P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
     "b200_resize_bilinear_c1": [_P, _I, _I, _I, _P, _I, _I, _P],
+    "b200_resize_aa_c1": [_P, _I, _I, _I, _P, _I, _I, _P],
     "b200_mask_attention": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _P],
     "b200_tapsum": [_P, _I, _I, _I, _P, _P, _P],
     "b200_gemm_batched": [C.POINTER(GemmDesc), _P],
@@ -576,6 +577,13 @@ def resize_bilinear_c1(src, out):
     """src [B,h,w] fp32 -> out [B,H,W] fp32, F.interpolate(bilinear, align_corners=False)."""
     B, h, w = src.shape
     _call("b200_resize_bilinear_c1", None, _ptr(src), B, h, w, _ptr(out), out.shape[-2], out.shape[-1], _stream())
+    return out
+
+
+def resize_aa_c1(src, out):
+    """src [B,h,w] fp32 -> out [B,H,W] fp32, F.interpolate(bilinear, align_corners=False, antialias=True)."""
+    B, h, w = src.shape
+    _call("b200_resize_aa_c1", None, _ptr(src), B, h, w, _ptr(out), out.shape[-2], out.shape[-1], _stream())
     return out
 
 

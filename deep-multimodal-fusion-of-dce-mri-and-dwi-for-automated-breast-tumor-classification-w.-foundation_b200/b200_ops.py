@@ -78,7 +78,9 @@ def resize_bilinear(x: torch.Tensor, height: int, width: int) -> torch.Tensor:
     x = x.contiguous().float()
     B, C, h, w = x.shape
     out = torch.empty((B, C, height, width), dtype=torch.float32, device=x.device)
-    nat.resize_bilinear_c1(x.view(B * C, h, w), out.view(B * C, height, width))
+    # a shrinking side takes the antialiased triangle filter, as torchvision's Resize does for tensors
+    kernel = nat.resize_aa_c1 if (height < h or width < w) else nat.resize_bilinear_c1
+    kernel(x.view(B * C, h, w), out.view(B * C, height, width))
     return out
 
 

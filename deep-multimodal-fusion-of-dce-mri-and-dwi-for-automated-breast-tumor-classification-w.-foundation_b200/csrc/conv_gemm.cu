@@ -1087,6 +1087,13 @@ static int dispatch(int res_mode, bool gap, int ndot, int mode, const CUtensorMa
         return -14;
     }
     if (ndot != 0) {
+        if constexpr (BN == 128 && !WS) {
+            // paired M tiles for the N = 128 tap-dot layers too (3x3 128->128 + GELU + nine dots, the reconstruction
+            // heads): the unpaired 128 x 128 tiles were shared-memory-feed bound like the plain ones
+            if (p.pair && res_mode == 0 && !gap && ndot == 9)
+                return launch<BN, WS, 0, false, 9, 0, true>(tmA, tmB, tmOut, tmOut2, tmRes, p, smem_bytes, grid, s);
+            if (p.pair) return -14;
+        }
         if constexpr (!WS) {
             if (res_mode == 0 && !gap && ndot == 9) B200_GO(0, false, 9, 0);
             if (res_mode == 0 && !gap && ndot == 1) B200_GO(0, false, 1, 0);
@@ -1272,7 +1279,10 @@ static int run_job(ConvGemmParams& p, const GemmJob& j, int mode, bool want_ws, 
             static const bool no_pair = std::getenv("B200_NO_PAIR") != nullptr;  // A/B measurements
             static const bool no_pair64 = std::getenv("B200_NO_PAIR64") != nullptr;
             // (N = 64: only the 3x3 layers gain - 64->64 0.211 -> 0.158 ms; the 1x1 layers lose 5-9 %)
-            const bool pair = (bn == 128 || (bn == 64 && p.k_blocks >= 8 && !no_pair64)) && mode == 0 && ndot == 0 && p.a_batched && p.b_mode == 0 && !no_pair &&
+            static const bool no_pair_dot = std::getenv("B200_NO_PAIR_DOT") != nullptr;
+            const bool pair = ((bn == 128 && (ndot == 0 || (ndot == 9 && !no_pair_dot))) ||
+                               (bn == 64 && ndot == 0 && p.k_blocks >= 8 && !no_pair64)) &&
+                              mode == 0 && p.a_batched && p.b_mode == 0 && !no_pair &&
                               (p.m_tiles / 2) * (Cout / bn) >= g_num_sms;
             smem_bytes = plan_smem(p, bn, false, st_out, st_res, ndot, mode, share, pair);
             p.pair = (pair && smem_bytes > 0) ? 1 : 0;

@@ -391,6 +391,57 @@ resize_bilinear_c1_kernel(const float* __restrict__ in, int h, int w, float* __r
     }
 }
 
+// --------------------------------- 1-channel antialiased bilinear resize ----
+// torchvision `transforms.Resize(input_size)` / F.interpolate(mode='bilinear', align_corners=False, antialias=True)
+// where a side SHRINKS (code/prepare_single_model.py:112-120 with ROIs larger than `input_size`): ATen's separable
+// triangle filter (UpSampleKernel.cpp, `_compute_indices_min_size_weights_aa`) - per output index i:
+//   scale = in / out,  support = max(scale, 1),  centre = scale (i + 0.5),
+//   first = max(int(centre - support + 0.5), 0),  count = min(int(centre + support + 0.5), in) - first,
+//   w_j = max(0, 1 - |(j + first - centre + 0.5) / max(scale, 1)|) / sum_j(...)
+// horizontal pass first, then vertical, both accumulated in fp32 in tap order as ATen does.  A side that grows gets
+// support 1, i.e. the plain bilinear taps, so mixed shrink / grow shapes go through the same code.
+// block (64, 4): thread (tx, ty) produces output x = blockIdx.x * 64 + tx of row blockIdx.y * 4 + ty of plane
+// blockIdx.z; the <= 2 support + 1 source rows / columns of neighbouring outputs overlap and are served by L1.
+struct AaTaps {
+    int first, count;
+    float centre, inv, norm;
+    __device__ __forceinline__ float weight(int j) const {
+        return fmaxf(0.f, 1.f - fabsf((static_cast<float>(j + first) - centre + 0.5f) * inv)) * norm;
+    }
+};
+
+__device__ __forceinline__ AaTaps aa_taps(int i, int in_size, int out_size) {
+    const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+    const float support = scale >= 1.f ? scale : 1.f;
+    AaTaps t;
+    t.centre = scale * (static_cast<float>(i) + 0.5f);
+    t.inv = scale >= 1.f ? 1.f / scale : 1.f;
+    t.first = max(static_cast<int>(t.centre - support + 0.5f), 0);
+    t.count = min(static_cast<int>(t.centre + support + 0.5f), in_size) - t.first;
+    t.norm = 1.f;
+    float total = 0.f;
+    for (int j = 0; j < t.count; ++j) total += t.weight(j);
+    t.norm = total != 0.f ? 1.f / total : 1.f;
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+resize_aa_c1_kernel(const float* __restrict__ in, int h, int w, float* __restrict__ out, int H, int W) {
+    const int oy = blockIdx.y * 4 + threadIdx.y;
+    const int ox = blockIdx.x * 64 + threadIdx.x;
+    if (oy >= H || ox >= W) return;
+    const size_t plane = blockIdx.z;
+    const AaTaps ty = aa_taps(oy, h, H), tx = aa_taps(ox, w, W);
+    const float* src = in + (plane * h + ty.first) * w + tx.first;
+    float acc = 0.f;
+    for (int r = 0; r < ty.count; ++r, src += w) {
+        float row = __ldg(src) * tx.weight(0);
+        for (int c = 1; c < tx.count; ++c) row = fmaf(__ldg(src + c), tx.weight(c), row);
+        acc = r == 0 ? row * ty.weight(0) : fmaf(row, ty.weight(r), acc);
+    }
+    __stcs(out + (plane * H + oy) * W + ox, acc);
+}
+
 // ------------------------------------------- mask head tail + attention ----
 // MaskHeadResize.out (model_module.py:187, 1x1 Cm->1 + bias) on the `pre` activations, then
 // MaskGuidedSpatialAttention.mask_processor (:67-73, :92-93): 1x1 1->Hc (no bias),
@@ -700,6 +751,20 @@ extern "C" int b200_resize_bilinear_c1(const float* in, int B, int h, int w, flo
         const int nb = B - b0 < 65535 ? B - b0 : 65535;
         const dim3 grid((W + 255) / 256, (H + 3) / 4, nb);
         resize_bilinear_c1_kernel<<<grid, dim3(64, 4), 0, static_cast<cudaStream_t>(stream)>>>(
+            in + static_cast<size_t>(b0) * h * w, h, w, out + static_cast<size_t>(b0) * H * W, H, W);
+    }
+    return launch_status();
+}
+
+extern "C" int b200_resize_aa_c1(const float* in, int B, int h, int w, float* out, int H, int W, void* stream) {
+    if (B < 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return -1;
+    if (B == 0) return 0;
+    if (in == nullptr || out == nullptr) return -2;
+    if (B > 65535 * 64 || (H + 3) / 4 > 65535) return -3;
+    for (int b0 = 0; b0 < B; b0 += 65535) {  // gridDim.z limit
+        const int nb = B - b0 < 65535 ? B - b0 : 65535;
+        const dim3 grid((W + 63) / 64, (H + 3) / 4, nb);
+        resize_aa_c1_kernel<<<grid, dim3(64, 4), 0, static_cast<cudaStream_t>(stream)>>>(
             in + static_cast<size_t>(b0) * h * w, h, w, out + static_cast<size_t>(b0) * H * W, H, W);
     }
     return launch_status();

@@ -66,8 +66,9 @@ class DWINormalize(object):
 class Resize(object):
     """torchvision `transforms.Resize(input_size)` as the reference applies it BEFORE the normaliser
     (code/prepare_single_model.py:112-120): bilinear, align_corners=False, antialias on.  For an upsample
-    (64 -> 224, config C4) the antialias filter is the plain bilinear kernel, which is what is built;
-    downsampling (where antialiasing widens the filter) is not."""
+    (64 -> 224, config C4) the antialias filter is the plain bilinear kernel (`b200_resize_bilinear_c1`); where a
+    side shrinks (ROIs larger than `input_size`) the filter widens to ATen's triangle of support in / out
+    (`b200_resize_aa_c1`).  An int `size` is a square target here, as every ROI of the path is square."""
 
     def __init__(self, size):
         self.size = (size, size) if isinstance(size, int) else tuple(size)
@@ -80,11 +81,10 @@ class Resize(object):
         S0, S1 = self.size
         if (S0, S1) == (H, W):
             return x
-        if S0 < H or S1 < W:
-            raise NotImplementedError("Resize: antialiased downsampling is not built (the path only upsamples)")
         x = x.contiguous().float()
         out = torch.empty((B, C, S0, S1), dtype=torch.float32, device=x.device)
-        nat.resize_bilinear_c1(x.view(B * C, H, W), out.view(B * C, S0, S1))
+        kernel = nat.resize_aa_c1 if (S0 < H or S1 < W) else nat.resize_bilinear_c1
+        kernel(x.view(B * C, H, W), out.view(B * C, S0, S1))
         return out
 
     def __call__(self, img):

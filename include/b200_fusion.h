@@ -304,6 +304,12 @@ int b200_mask_attention(const float* mask, int B, int npix, int Hc, const float*
  * (MaskHeadResize fallback, code/model_module.py:205-211, commuted past the 1x1 `out` conv). */
 int b200_resize_bilinear_c1(const float* in, int B, int h, int w, float* out, int H, int W, void* stream);
 
+/* torchvision `transforms.Resize(input_size)` = F.interpolate(bilinear, align_corners=False, antialias=True) of
+ * fp32 planes [B,h,w] -> [B,H,W] where a side shrinks (code/prepare_single_model.py:112, :116, :120 with ROIs larger
+ * than `input_size`; code/parameters_generate.py:68).  ATen's separable triangle filter of support max(in/out, 1),
+ * horizontal pass then vertical, fp32.  Growing sides reduce to the plain bilinear taps. */
+int b200_resize_aa_c1(const float* in, int B, int h, int w, float* out, int H, int W, void* stream);
+
 int b200_mask_tail(const void* pre, int B, int npix, int Cm, const float* w_out, const float* b_out,
                    float* mask_pred, int Hc, const float* wa, const float* gn_w, const float* gn_b, const float* wb,
                    const float* bb, float gn_eps, float* attn, void* stream);

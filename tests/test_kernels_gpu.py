@@ -627,6 +627,22 @@ def test_paired_tiles_are_bitwise_the_unpaired_result():
             kw_s = dict(kw, res=r[lo:lo + 8].contiguous() if res else None)
             small = nat.conv_gemm(x[lo:lo + 8].contiguous(), w, **kw_s)
             assert torch.equal(big[lo:lo + 8], small), (taps, cin, cout, res, hw, lo)
+    # the tap-dot epilogue (3x3 128->128 + GELU + nine per-pixel dots, no map store: the reconstruction heads) pairs too
+    B = 41
+    x = torch.randn(B, 32, 32, 128, generator=g).bfloat16().to(DEV)
+    w = (torch.randn(128, 9 * 128, generator=g) / (9 * 128) ** 0.5).bfloat16().to(DEV)
+    sc, bi = (1 + 0.1 * torch.randn(128, generator=g)).to(DEV), (0.1 * torch.randn(128, generator=g)).to(DEV)
+    dw = torch.randn(9, 128, generator=g).to(DEV)
+    big = torch.full((B, 32, 32, 9), float("nan"), device=DEV)
+    nat.conv_gemm(x, w, taps=9, scale=sc, bias=bi, act=1, store=False, dot_w=dw, dot_out=big, dot_bias=0.25)
+    ref_map = nat.conv_gemm(x, w, taps=9, scale=sc, bias=bi, act=1).float()   # the stored (bf16-rounded) map
+    ref = torch.einsum("bhwc,kc->bhwk", ref_map, dw) + 0.25
+    assert (big - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()     # dots of the un-rounded fp32 values
+    for lo in (0, 17, 33):
+        small = torch.empty((8, 32, 32, 9), device=DEV)
+        nat.conv_gemm(x[lo:lo + 8].contiguous(), w, taps=9, scale=sc, bias=bi, act=1, store=False, dot_w=dw,
+                      dot_out=small, dot_bias=0.25)
+        assert torch.equal(big[lo:lo + 8], small), ("tap-dot", lo)
 
 
 def test_reinitialised_weights_are_repacked():

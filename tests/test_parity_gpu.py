@@ -167,8 +167,29 @@ def test_resize_then_normalise_matches_oracle():
     y = b_dataset.DWINormalize().batch(d224)
     assert _relmax(y, no.dwi_normalize_batch(no.resize(dwi_raw, 224))) <= NORM_TOL
     assert torch.allclose(rz(dce_raw[0]), no.resize(dce_raw[0], 224), atol=1e-5)  # per-image CPU-in/CPU-out call
-    with pytest.raises(NotImplementedError):
-        b_dataset.Resize(32).batch(dwi_raw.to(DEV))
+
+
+def test_antialiased_downsampling_resize_matches_oracle():
+    """a5 where a side shrinks (ROIs larger than `input_size`, code/prepare_single_model.py:112-120 with
+    code/parameters_generate.py:68): torchvision's Resize antialiases tensors, i.e. ATen's triangle filter of support
+    in / out.  Integer and ragged ratios, mixed shrink / grow shapes, a 1-pixel target and the normaliser on top."""
+    dwi_raw, dce_raw, _, _ = op.synthetic_raw(2, seed=98, kind="S")
+    assert _relmax(b_dataset.Resize(32).batch(dwi_raw.to(DEV)), no.resize(dwi_raw, 32)) <= NORM_TOL
+    g = torch.Generator().manual_seed(5)
+    interp = lambda x, hw: torch.nn.functional.interpolate(x, size=hw, mode="bilinear", align_corners=False,
+                                                           antialias=True)
+    for (h, w), (H, W) in (((128, 128), (64, 64)), ((100, 77), (64, 64)), ((512, 512), (256, 256)),
+                           ((300, 200), (224, 224)), ((65, 130), (64, 64)), ((64, 64), (7, 5)), ((33, 91), (64, 64)),
+                           ((97, 97), (1, 1)), ((257, 64), (64, 64))):
+        x = torch.rand(3, 2, h, w, generator=g) * 3000.0 + torch.randn(3, 2, 1, 1, generator=g) * 100.0
+        y = b_dataset.Resize((H, W)).batch(x.to(DEV))
+        assert tuple(y.shape) == (3, 2, H, W) and _relmax(y, interp(x, (H, W))) <= NORM_TOL, ((h, w), (H, W))
+    big = torch.rand(2, 16, 160, 160, generator=g) * 2000.0
+    small = b_dataset.Resize(64).batch(big.to(DEV))
+    assert _relmax(b_dataset.DWINormalize().batch(small), no.dwi_normalize_batch(no.resize(big, 64))) <= NORM_TOL
+    one = b_dataset.Resize(64)(big[0])  # per-image CPU-in / CPU-out call, as a torchvision transform is used
+    assert one.device.type == "cpu" and torch.allclose(one, no.resize(big[0], 64), rtol=NORM_TOL, atol=1e-3)
+    assert b_dataset.Resize(64).batch(torch.empty(0, 16, 128, 128, device=DEV)).shape == (0, 16, 64, 64)
 
 
 # ----------------------------------------------------------------------- models ----

@@ -26,6 +26,7 @@ def test_operators_equal_the_direct_call_path():
     o2, _ = ops.nyul_transform(dce, *tabs)
     assert torch.equal(o2, nyul.transform_batch(dce))
     assert torch.equal(ops.resize_bilinear(dwi, 224, 224), ds.Resize(224).batch(dwi))
+    assert torch.equal(ops.resize_bilinear(dwi, 48, 40), ds.Resize((48, 40)).batch(dwi))  # shrinking: antialiased
     aug = ds.BatchAugment()
     torch.manual_seed(2)
     params = aug.sample_params(4, 64, 64)
