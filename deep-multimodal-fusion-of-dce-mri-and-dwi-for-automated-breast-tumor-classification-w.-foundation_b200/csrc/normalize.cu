@@ -587,6 +587,10 @@ nyul_transform_large_kernel(const float* __restrict__ x, float* __restrict__ out
     __shared__ int s_rem[kNyulMaxRanks], s_uid[kNyulMaxRanks];
     __shared__ int s_nu;
     __shared__ float s_val[kNyulMaxRanks];
+    // alive-prefix lookup of the current pass: last digit of a prefix -> first alive prefix id carrying it, then a
+    // chain through the ids that share that digit (one LDS for the samples that match nothing, i.e. most of them
+    // from the third pass on, instead of a scan over all <= 2L prefixes)
+    __shared__ int s_lut[256], s_chain[kNyulMaxRanks];
     const int plane = blockIdx.x;
     const int c = plane % C;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -608,7 +612,18 @@ nyul_transform_large_kernel(const float* __restrict__ x, float* __restrict__ out
         const int shift = 24 - 8 * pass;
         const int nu = s_nu;
         for (int i = tid; i < nu * 256; i += kNyulThreads) (&s_hist[0][0])[i] = 0;
+        if (tid < 256) s_lut[tid] = -1;
         __syncthreads();
+        if (pass != 0) {
+            if (tid == 0) {
+                for (int q = nu - 1; q >= 0; --q) {
+                    const int d = static_cast<int>(s_uprefix[q] & 255u);
+                    s_chain[q] = s_lut[d];
+                    s_lut[d] = q;
+                }
+            }
+            __syncthreads();
+        }
         // four samples per thread and trip (one 16-byte load when the plane allows it): the passes are bound by the
         // L2 round trip of the load, not by arithmetic
         const bool vec = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
@@ -631,12 +646,8 @@ nyul_transform_large_kernel(const float* __restrict__ x, float* __restrict__ out
                     int u = 0;
                     if (pass != 0) {
                         const uint32_t hi = key >> (shift + 8);
-                        u = -1;
-                        for (int q = 0; q < nu; ++q)
-                            if (s_uprefix[q] == hi) {
-                                u = q;
-                                break;
-                            }
+                        u = s_lut[hi & 255u];
+                        while (u >= 0 && s_uprefix[u] != hi) u = s_chain[u];
                     }
                     if (u >= 0) slot = u * 256 + static_cast<int>((key >> shift) & 255u);
                 }
