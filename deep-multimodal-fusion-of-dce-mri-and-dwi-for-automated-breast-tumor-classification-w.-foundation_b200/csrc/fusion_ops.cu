@@ -108,12 +108,32 @@ __device__ __forceinline__ void linear_tokens(const float* X, int ldx, const flo
         float acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-#pragma unroll 8
-        for (int i = 0; i < Cin; ++i) {
-            const float w = __ldg(Wt + static_cast<size_t>(i) * ldw + o);
+        if (((Cin | ldx) & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+            // four input channels per trip: the token rows are read as one broadcast LDS.128 instead of four LDS.32
+            // (the loop was shared-memory-issue bound: one LDS per FMA), four weight loads in flight; the
+            // accumulation order over i is unchanged
+#pragma unroll 2
+            for (int i = 0; i < Cin; i += 4) {
+                const float* wp = Wt + static_cast<size_t>(i) * ldw + o;
+                const float w0 = __ldg(wp), w1 = __ldg(wp + ldw), w2 = __ldg(wp + 2 * ldw), w3 = __ldg(wp + 3 * ldw);
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (k < TG && t0 + k < T) acc[k] += w * X[(t0 + k) * ldx + i];
+                for (int k = 0; k < 8; ++k)
+                    if (k < TG && t0 + k < T) {
+                        const float4 xv = *reinterpret_cast<const float4*>(X + (t0 + k) * ldx + i);
+                        acc[k] = fmaf(w0, xv.x, acc[k]);
+                        acc[k] = fmaf(w1, xv.y, acc[k]);
+                        acc[k] = fmaf(w2, xv.z, acc[k]);
+                        acc[k] = fmaf(w3, xv.w, acc[k]);
+                    }
+            }
+        } else {
+#pragma unroll 8
+            for (int i = 0; i < Cin; ++i) {
+                const float w = __ldg(Wt + static_cast<size_t>(i) * ldw + o);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k < TG && t0 + k < T) acc[k] += w * X[(t0 + k) * ldx + i];
+            }
         }
         const float bv = bias != nullptr ? bias[o] : 0.f;
 #pragma unroll
