@@ -24,3 +24,5 @@ try:
 except Exception as e: print(sys.argv[1], "ERR", e)
 P
 done
+python tools/stem_bench.py > $o/r2_stem_bench.txt 2>&1
+python tools/norm_bench.py > $o/r2_norm_bench.txt 2>&1
