@@ -7,8 +7,8 @@
 //   warp 0      TMA producer: one 4-D box {64 ch, BW, BH, 1} of the input per (tap, 64-channel slice) -
 //               the tap shift is a coordinate offset, the zero padding is the TMA out-of-bounds fill -
 //               plus one 2-D box {64, BLOCK_N} of the weights, both written with the 128-byte swizzle.
-//               PAIR (BLOCK_N = 128 layers with >= 2 x 148 M tiles): a second input box per stage, so
-//               one weight slab feeds two M tiles.
+//               PAIR (BLOCK_N = 128 layers, plain and tap-dot epilogues, and 3x3 BLOCK_N = 64 layers, with
+//               >= 2 x 148 M tiles): a second input box per stage, so one weight slab feeds two M tiles.
 //   warp 1      tcgen05.mma issuer (single thread), M=128, N=BLOCK_N, K=16 per instruction; PAIR issues
 //               the second tile's MMAs into the next BLOCK_N TMEM columns off the same B descriptor
 //   warp 2      TMEM allocation / release: 2 accumulator stages (4 with PAIR) - the epilogue of tile i
