@@ -275,6 +275,13 @@ def test_resize_oracle_is_torchvision_resize():
     # for an upsample the antialias filter degenerates to plain bilinear interpolation (what the kernel does)
     plain = torch.nn.functional.interpolate(x, size=(224, 224), mode="bilinear", align_corners=False)
     assert torch.allclose(ref, plain, rtol=0, atol=1e-5)  # the separable antialias code path rounds differently
+    # shrinking (ROIs larger than input_size): torchvision antialiases tensors, and so does the oracle - what
+    # b200_resize_aa_c1 is held to; the plain bilinear taps would differ visibly here
+    big = torch.rand(2, 6, 160, 160, generator=torch.Generator().manual_seed(6))
+    ref_small = torch.stack([transforms.Resize(64)(c) for c in big])
+    assert torch.equal(no.resize(big, 64), ref_small)
+    plain_small = torch.nn.functional.interpolate(big, size=(64, 64), mode="bilinear", align_corners=False)
+    assert (ref_small - plain_small).abs().max().item() > 1e-2
 
 
 def test_oracle_on_trained_weights_matches_reference_pipeline():
