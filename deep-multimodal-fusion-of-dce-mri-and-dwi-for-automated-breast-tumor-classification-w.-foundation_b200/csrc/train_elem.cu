@@ -13,6 +13,8 @@
 #include <cfloat>
 #include <cstdint>
 
+#include <type_traits>
+
 #include "b200_fusion.h"
 #include "common.cuh"
 
@@ -184,7 +186,9 @@ __device__ __forceinline__ uint4 drop_bits4(const BnAct& p, long long r, int c0)
     return philox4x32_7((static_cast<unsigned long long>(r) * p.C + c0) / 4, p.seed_lo, p.seed_hi);
 }
 
-// out = dropout(act(bn(z) + res))
+// out = dropout(act(bn(z) + res)).  The activation / residual / dropout options are template parameters: as run-time
+// fields they sat in the per-element loop as uniform branches (cf. the first-layer kernel).
+template <int ACT, bool RES, bool DROP>
 __global__ void __launch_bounds__(kTeThreads, 4)
 bn_act_fwd_kernel(const BnAct p, __nv_bfloat16* __restrict__ out, int ldo) {
     BN_ROW_WALK(p.C / 4)
@@ -199,7 +203,7 @@ bn_act_fwd_kernel(const BnAct p, __nv_bfloat16* __restrict__ out, int ldo) {
             const long long rh = r + h * row_step;
             if (rh < p.R) {
                 zq[h] = __ldg(reinterpret_cast<const uint2*>(p.z + rh * p.ldz + c0));
-                if (p.res != nullptr) rq[h] = __ldg(reinterpret_cast<const uint2*>(p.res + rh * p.ldres + c0));
+                if (RES) rq[h] = __ldg(reinterpret_cast<const uint2*>(p.res + rh * p.ldres + c0));
             }
         }
 #pragma unroll
@@ -208,16 +212,16 @@ bn_act_fwd_kernel(const BnAct p, __nv_bfloat16* __restrict__ out, int ldo) {
             if (rh >= p.R) break;
             float f[4], rr[4];
             unpack_bf16x4(zq[h], f);
-            if (p.res != nullptr) unpack_bf16x4(rq[h], rr);
+            if (RES) unpack_bf16x4(rq[h], rr);
             uint4 rn = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-            if (p.drop_thresh != 0u) rn = drop_bits4(p, rh, c0);
+            if (DROP) rn = drop_bits4(p, rh, c0);
             const unsigned int rnv[4] = {rn.x, rn.y, rn.z, rn.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float y = fmaf(f[j], ka[j], kb[j]);
-                if (p.res != nullptr) y += rr[j];
-                y = act_fwd_fast(y, p.act);
-                if (p.drop_thresh != 0u) y = rnv[j] < p.drop_thresh ? 0.f : y * p.drop_scale;
+                if (RES) y += rr[j];
+                y = act_fwd_fast(y, ACT);
+                if (DROP) y = rnv[j] < p.drop_thresh ? 0.f : y * p.drop_scale;
                 f[j] = y;
             }
             *reinterpret_cast<uint2*>(out + rh * ldo + c0) = pack_bf16x4(f);
@@ -228,6 +232,7 @@ bn_act_fwd_kernel(const BnAct p, __nv_bfloat16* __restrict__ out, int ldo) {
 // Backward, pass 1: dY = dA * dropout_mask * act'(y), y = bn(z) + res, WRITTEN to dy_out (and dy_out2: the residual
 // branch's gradient); with batch statistics s1[c] += sum dY, s2[c] += sum dY * xhat; without them dy_out receives
 // dz = a * dY directly and only s1 / s2 (when requested) feed dbeta / dgamma.
+template <int ACT, bool RES, bool DROP>
 __global__ void __launch_bounds__(kTeThreads, 4)
 bn_act_bwd_pass1_kernel(const BnAct p, const __nv_bfloat16* __restrict__ dA, int ldd, int batch_stats,
                         __nv_bfloat16* __restrict__ dy_out, int ldo, __nv_bfloat16* __restrict__ dy_out2, int ldo2,
@@ -249,7 +254,7 @@ bn_act_bwd_pass1_kernel(const BnAct p, const __nv_bfloat16* __restrict__ dA, int
                 if (rh < p.R) {
                     zq[h] = __ldg(reinterpret_cast<const uint2*>(p.z + rh * p.ldz + c0));
                     dq[h] = __ldg(reinterpret_cast<const uint2*>(dA + rh * ldd + c0));
-                    if (p.res != nullptr) rq[h] = __ldg(reinterpret_cast<const uint2*>(p.res + rh * p.ldres + c0));
+                    if (RES) rq[h] = __ldg(reinterpret_cast<const uint2*>(p.res + rh * p.ldres + c0));
                 }
             }
 #pragma unroll
@@ -259,18 +264,18 @@ bn_act_bwd_pass1_kernel(const BnAct p, const __nv_bfloat16* __restrict__ dA, int
                 float f[4], d[4], rr[4];
                 unpack_bf16x4(zq[h], f);
                 unpack_bf16x4(dq[h], d);
-                if (p.res != nullptr) unpack_bf16x4(rq[h], rr);
+                if (RES) unpack_bf16x4(rq[h], rr);
                 uint4 rn = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-                if (p.drop_thresh != 0u) rn = drop_bits4(p, rh, c0);
+                if (DROP) rn = drop_bits4(p, rh, c0);
                 const unsigned int rnv[4] = {rn.x, rn.y, rn.z, rn.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float g = d[j];
-                    if (p.drop_thresh != 0u) g = rnv[j] < p.drop_thresh ? 0.f : g * p.drop_scale;
-                    if (p.act != 0) {
+                    if (DROP) g = rnv[j] < p.drop_thresh ? 0.f : g * p.drop_scale;
+                    if (ACT != 0) {
                         float y = fmaf(f[j], ka[j], kb[j]);
-                        if (p.res != nullptr) y += rr[j];
-                        g *= act_bwd_fast(y, p.act);
+                        if (RES) y += rr[j];
+                        g *= act_bwd_fast(y, ACT);
                     }
                     u[j] += g;
                     v[j] = fmaf(g, f[j], v[j]);
@@ -1520,6 +1525,21 @@ static int fill_bnact(BnAct& p, const void* z, int ldz, const void* res, int ldr
     return 0;
 }
 
+// (act, residual?, dropout?) -> compile-time kernel options
+template <typename F>
+static void bn_dispatch(const BnAct& p, F&& f) {
+    auto with_act = [&](auto act) {
+        const bool res = p.res != nullptr, drop = p.drop_thresh != 0u;
+        if (res && drop) f(act, std::true_type{}, std::true_type{});
+        else if (res) f(act, std::true_type{}, std::false_type{});
+        else if (drop) f(act, std::false_type{}, std::true_type{});
+        else f(act, std::false_type{}, std::false_type{});
+    };
+    if (p.act == 1) with_act(std::integral_constant<int, 1>{});
+    else if (p.act == 2) with_act(std::integral_constant<int, 2>{});
+    else with_act(std::integral_constant<int, 0>{});
+}
+
 static int bn_grid(long long R, int C, int& rows_par) {
     rows_par = kTeThreads / (C / 4);
     long long want = (R + rows_par * 4 - 1) / (rows_par * 4);
@@ -1534,7 +1554,10 @@ extern "C" int b200_bn_act_fwd(const void* z, int ldz, const void* res, int ldre
     if (rc != 0 || out == nullptr || ldo % 8 != 0 || C > 1024) return rc != 0 ? rc : -3;
     int rows_par;
     const int grid = bn_grid(R, C, rows_par);
-    bn_act_fwd_kernel<<<grid, kTeThreads, 0, TE_STREAM>>>(p, static_cast<__nv_bfloat16*>(out), ldo);
+    bn_dispatch(p, [&](auto act, auto res, auto drop) {
+        bn_act_fwd_kernel<decltype(act)::value, decltype(res)::value, decltype(drop)::value>
+            <<<grid, kTeThreads, 0, TE_STREAM>>>(p, static_cast<__nv_bfloat16*>(out), ldo);
+    });
     return launch_status();
 }
 
@@ -1558,9 +1581,12 @@ extern "C" int b200_bn_act_bwd(const void* z, int ldz, const void* res, int ldre
         cudaMemsetAsync(scratch2C, 0, 2 * C * sizeof(double), TE_STREAM);
         smem = static_cast<size_t>(rows_par) * C * 2 * sizeof(float);
     }
-    bn_act_bwd_pass1_kernel<<<grid, kTeThreads, smem, TE_STREAM>>>(p, static_cast<const __nv_bfloat16*>(dA), ldd,
-                                                                  batch_stats ? 1 : 0, static_cast<__nv_bfloat16*>(dz), lddz,
-                                                                  static_cast<__nv_bfloat16*>(dres), lddres, s1, s2);
+    bn_dispatch(p, [&](auto act, auto res, auto drop) {
+        bn_act_bwd_pass1_kernel<decltype(act)::value, decltype(res)::value, decltype(drop)::value>
+            <<<grid, kTeThreads, smem, TE_STREAM>>>(p, static_cast<const __nv_bfloat16*>(dA), ldd, batch_stats ? 1 : 0,
+                                                    static_cast<__nv_bfloat16*>(dz), lddz,
+                                                    static_cast<__nv_bfloat16*>(dres), lddres, s1, s2);
+    });
     if (need_sums) {
         bn_act_bwd_pass2_kernel<<<batch_stats ? grid : 1, kTeThreads, 0, TE_STREAM>>>(
             p, s1, s2, static_cast<double>(R), static_cast<__nv_bfloat16*>(dz), lddz, dgamma, dbeta, batch_stats ? 1 : 0);
