@@ -54,14 +54,24 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long long R, int C, int ld,
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
     if (rp < rows_par) {
-        for (long long r = static_cast<long long>(blockIdx.x) * rows_par + rp; r < R;
-             r += static_cast<long long>(gridDim.x) * rows_par) {
-            float f[8];
-            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(z + r * ld + cg * 8)), f);
+        // four rows per trip with all loads issued first (same pattern and reason as map_dot_kernel below)
+        constexpr int NR = 4;
+        const long long step = static_cast<long long>(gridDim.x) * rows_par;
+        for (long long r = static_cast<long long>(blockIdx.x) * rows_par + rp; r < R; r += NR * step) {
+            uint4 zq[NR];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                s[i] += f[i];
-                q[i] = fmaf(f[i], f[i], q[i]);
+            for (int h = 0; h < NR; ++h)
+                if (r + h * step < R) zq[h] = __ldg(reinterpret_cast<const uint4*>(z + (r + h * step) * ld + cg * 8));
+#pragma unroll
+            for (int h = 0; h < NR; ++h) {
+                if (r + h * step >= R) break;
+                float f[8];
+                unpack_bf16x8(zq[h], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    s[i] += f[i];
+                    q[i] = fmaf(f[i], f[i], q[i]);
+                }
             }
         }
 #pragma unroll
@@ -380,17 +390,33 @@ map_dot_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = 0.f;
     if (rp < rows_par) {
-        for (int pp = rp; pp < npix; pp += rows_par) {
-            const long long r = static_cast<long long>(bcase) * npix + pp;
-            float f[8], g[8];
-            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(a + r * lda + cg * 8)), f);
-            if (bmap != nullptr) {
-                unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(bmap + r * ldb + cg * 8)), g);
+        // four rows per trip, every load issued before the first use (one 16-byte load in flight per thread left the
+        // kernel latency bound at 40-57 % of the HBM peak); the accumulation order over the rows is unchanged
+        constexpr int NR = 4;
+        const long long row0 = static_cast<long long>(bcase) * npix;
+        for (int pp = rp; pp < npix; pp += NR * rows_par) {
+            uint4 aq[NR], bq[NR];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) s[i] = fmaf(f[i], g[i], s[i]);
-            } else {
+            for (int h = 0; h < NR; ++h) {
+                const int ph = pp + h * rows_par;
+                if (ph < npix) {
+                    aq[h] = __ldg(reinterpret_cast<const uint4*>(a + (row0 + ph) * lda + cg * 8));
+                    if (bmap != nullptr) bq[h] = __ldg(reinterpret_cast<const uint4*>(bmap + (row0 + ph) * ldb + cg * 8));
+                }
+            }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) s[i] += f[i];
+            for (int h = 0; h < NR; ++h) {
+                if (pp + h * rows_par >= npix) break;
+                float f[8], g[8];
+                unpack_bf16x8(aq[h], f);
+                if (bmap != nullptr) {
+                    unpack_bf16x8(bq[h], g);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) s[i] = fmaf(f[i], g[i], s[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) s[i] += f[i];
+                }
             }
         }
 #pragma unroll
