@@ -381,3 +381,25 @@ def test_committed_bench_lines_keep_the_driver_contract(name):
     assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"])
     cpu = line["cpu_baseline"]
     assert cpu is None or ({"value", "unit", "cores", "kind", "sample"} <= set(cpu) and cpu["kind"] in ("port", "reference"))
+
+
+def test_resize_dispatches_the_antialiased_kernel_only_when_a_side_shrinks(monkeypatch):
+    """Host logic of dataset.Resize (reference: transforms.Resize(input_size), code/prepare_single_model.py:112-120):
+    torchvision antialiases tensors, which differs from plain bilinear taps only where a side shrinks - that, and only
+    that, goes to b200_resize_aa_c1; the same size is a no-op; shapes follow (size, size) / (h, w)."""
+    import dataset as ds
+
+    calls = []
+    monkeypatch.setattr(ds.nat, "resize_aa_c1", lambda src, out: calls.append(("aa", tuple(src.shape), tuple(out.shape))))
+    monkeypatch.setattr(ds.nat, "resize_bilinear_c1",
+                        lambda src, out: calls.append(("bilinear", tuple(src.shape), tuple(out.shape))))
+    x = torch.zeros(2, 3, 64, 64)
+    assert ds.Resize(64).batch(x) is x and calls == []
+    assert ds.Resize(224).batch(x).shape == (2, 3, 224, 224)
+    assert ds.Resize(32).batch(x).shape == (2, 3, 32, 32)
+    assert ds.Resize((48, 100)).batch(x).shape == (2, 3, 48, 100)      # one side shrinks, one grows
+    assert ds.Resize((64, 100)).batch(x).shape == (2, 3, 64, 100)      # nothing shrinks
+    assert calls == [("bilinear", (6, 64, 64), (6, 224, 224)), ("aa", (6, 64, 64), (6, 32, 32)),
+                     ("aa", (6, 64, 64), (6, 48, 100)), ("bilinear", (6, 64, 64), (6, 64, 100))]
+    with pytest.raises(ValueError):
+        ds.Resize(32).batch(torch.zeros(3, 64, 64))
